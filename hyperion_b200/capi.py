@@ -1,0 +1,252 @@
+"""ctypes binding of ``include/hyperion_b200.h``.
+
+This is the host side of the drop-in boundary: where the reference launches a
+Fortran binary (``hyperion/model/model.py:1053-1080``), this module loads
+``libhyperion_b200.so`` and drives the CUDA engine through its C ABI.  There is
+no CPU fallback: if the shared library (or a CUDA device) is missing the load
+fails loudly.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from .flatmodel import FlatConf, FlatDust, FlatModel, FlatSource, apply_model
+
+_dp = C.POINTER(C.c_double)
+
+
+class DustTables(C.Structure):
+    _fields_ = [
+        ("version", C.c_int32), ("is_lte", C.c_int32), ("sublimation_mode", C.c_int32),
+        ("sublimation_specific_energy", C.c_double),
+        ("n_nu", C.c_int32), ("nu", _dp), ("albedo", _dp), ("chi", _dp),
+        ("n_mu", C.c_int32), ("mu", _dp),
+        ("P1", _dp), ("P2", _dp), ("P3", _dp), ("P4", _dp),
+        ("n_e", C.c_int32), ("specific_energy", _dp),
+        ("chi_planck", _dp), ("kappa_planck", _dp),
+        ("chi_inv_planck", _dp), ("kappa_inv_planck", _dp),
+        ("chi_rosseland", _dp), ("kappa_rosseland", _dp),
+        ("n_emiss_nu", C.c_int32), ("emiss_nu", _dp),
+        ("n_jnu", C.c_int32), ("emiss_jnu", _dp), ("jnu_var", _dp),
+    ]
+
+
+class Source(C.Structure):
+    _fields_ = [
+        ("type", C.c_int32), ("peeloff", C.c_int32), ("luminosity", C.c_double),
+        ("x", C.c_double), ("y", C.c_double), ("z", C.c_double),
+        ("radius", C.c_double), ("limb_darkening", C.c_int32),
+        ("spectrum_type", C.c_int32), ("temperature", C.c_double),
+        ("n_spec", C.c_int32), ("spec_nu", _dp), ("spec_fnu", _dp),
+    ]
+
+
+class RunConf(C.Structure):
+    _fields_ = [
+        ("seed", C.c_int64), ("n_inter_max", C.c_int64), ("n_reabs_max", C.c_int64),
+        ("kill_on_absorb", C.c_int32), ("kill_on_scatter", C.c_int32),
+        ("sample_sources_evenly", C.c_int32), ("enforce_energy_range", C.c_int32),
+        ("use_mrw", C.c_int32), ("mrw_gamma", C.c_double), ("n_mrw_max", C.c_int64),
+        ("propagation_check_frequency", C.c_double),
+    ]
+
+
+class IterStats(C.Structure):
+    _fields_ = [
+        ("energy_emitted", C.c_double), ("n_photons", C.c_int64),
+        ("killed_geo", C.c_int64), ("killed_int", C.c_int64),
+        ("n_crossings", C.c_int64), ("n_absorptions", C.c_int64),
+        ("n_scatterings", C.c_int64), ("n_escaped", C.c_int64),
+        ("kernel_ms", C.c_double), ("epilogue_ms", C.c_double),
+    ]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+def _ptr(a):
+    return a.ctypes.data_as(_dp)
+
+
+class HyperionError(RuntimeError):
+    pass
+
+
+class CApi:
+    """Thin object wrapper over a shared library exporting ``<prefix>*``
+    functions with the signatures of ``include/hyperion_b200.h``."""
+
+    def __init__(self, lib, prefix):
+        self.lib = lib
+        self.prefix = prefix
+        self._keep = []
+        f = self._fn
+        f("last_error").restype = C.c_char_p
+        for name in ("set_grid_cartesian", "add_dust", "add_source", "set_run_conf", "set_density",
+                     "set_specific_energy", "lucy_begin", "lucy_finish", "get_specific_energy",
+                     "get_density", "get_energy_sum"):
+            f(name).restype = C.c_int
+
+    def _fn(self, name):
+        return getattr(self.lib, self.prefix + name)
+
+    def check(self, rc):
+        if rc != 0:
+            msg = self._fn("last_error")()
+            raise HyperionError((msg or b"unknown error").decode("utf-8", "replace"))
+
+    # -- setters -----------------------------------------------------------
+    def set_grid_cartesian(self, ctx, n1, n2, n3, w1, w2, w3):
+        self.check(self._fn("set_grid_cartesian")(ctx, C.c_int32(n1), C.c_int32(n2), C.c_int32(n3),
+                                                  _ptr(w1), _ptr(w2), _ptr(w3)))
+
+    def add_dust(self, ctx, d: FlatDust):
+        t = DustTables()
+        t.version, t.is_lte, t.sublimation_mode = d.version, int(d.is_lte), d.sublimation_mode
+        t.sublimation_specific_energy = d.sublimation_specific_energy
+        t.n_nu, t.n_mu, t.n_e = len(d.nu), len(d.mu), len(d.specific_energy)
+        t.n_emiss_nu, t.n_jnu = len(d.emiss_nu), len(d.jnu_var)
+        for k in ("nu", "albedo", "chi", "mu", "P1", "P2", "P3", "P4", "specific_energy", "chi_planck",
+                  "kappa_planck", "chi_inv_planck", "kappa_inv_planck", "chi_rosseland", "kappa_rosseland",
+                  "emiss_nu", "emiss_jnu", "jnu_var"):
+            setattr(t, k, _ptr(getattr(d, k)))
+        self.check(self._fn("add_dust")(ctx, C.byref(t)))
+
+    def add_source(self, ctx, s: FlatSource):
+        t = Source()
+        t.type, t.peeloff, t.luminosity = s.type, int(s.peeloff), s.luminosity
+        t.x, t.y, t.z = [float(v) for v in s.position]
+        t.radius, t.limb_darkening = s.radius, int(s.limb_darkening)
+        keep = None
+        if s.temperature is not None:
+            t.spectrum_type, t.temperature = 2, float(s.temperature)
+        else:
+            nu = np.ascontiguousarray(s.spectrum_nu, dtype=np.float64)
+            fnu = np.ascontiguousarray(s.spectrum_fnu, dtype=np.float64)
+            keep = (nu, fnu)
+            t.spectrum_type, t.n_spec, t.spec_nu, t.spec_fnu = 1, len(nu), _ptr(nu), _ptr(fnu)
+        self.check(self._fn("add_source")(ctx, C.byref(t)))
+        del keep
+
+    def set_run_conf(self, ctx, c: FlatConf):
+        t = RunConf()
+        t.seed, t.n_inter_max, t.n_reabs_max = c.seed, c.n_inter_max, c.n_reabs_max
+        t.kill_on_absorb, t.kill_on_scatter = int(c.kill_on_absorb), int(c.kill_on_scatter)
+        t.sample_sources_evenly, t.enforce_energy_range = int(c.sample_sources_evenly), int(c.enforce_energy_range)
+        t.use_mrw, t.mrw_gamma, t.n_mrw_max = int(c.use_mrw), c.mrw_gamma, c.n_mrw_max
+        t.propagation_check_frequency = c.propagation_check_frequency
+        self.check(self._fn("set_run_conf")(ctx, C.byref(t)))
+
+    def set_density(self, ctx, n_dust, density):
+        density = np.ascontiguousarray(density, dtype=np.float64)
+        self.check(self._fn("set_density")(ctx, C.c_int32(n_dust), _ptr(density)))
+
+    def set_specific_energy(self, ctx, se, min_e):
+        se_p = None if se is None else _ptr(np.ascontiguousarray(se, dtype=np.float64))
+        me_p = None if min_e is None else _ptr(np.ascontiguousarray(min_e, dtype=np.float64))
+        self.check(self._fn("set_specific_energy")(ctx, se_p, me_p))
+
+
+# ---------------------------------------------------------------------------
+# the product library
+# ---------------------------------------------------------------------------
+_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "libhyperion_b200.so")
+_lib = None
+
+
+def load_library(path=None):
+    """Load ``libhyperion_b200.so``; raises if it has not been built
+    (``python -c 'import __graft_entry__ as g; g.build()'``)."""
+    global _lib
+    if _lib is None or path is not None:
+        p = path or _LIB_PATH
+        if not os.path.exists(p):
+            raise HyperionError("%s not found: build it with __graft_entry__.build(); "
+                                "there is no CPU fallback" % p)
+        _lib = C.CDLL(p)
+    return _lib
+
+
+class Engine(CApi):
+    """One GPU's photon-propagation context (``hyp_ctx``)."""
+
+    def __init__(self, device_id=0, lib=None):
+        super().__init__(lib or load_library(), "hyp_")
+        L = self.lib
+        L.hyp_ctx_create.restype = C.c_int
+        L.hyp_ctx_destroy.restype = None
+        L.hyp_stream.restype = C.c_void_p
+        for n in ("hyp_finalize_setup", "hyp_lucy_photons", "hyp_lucy_device_buffers",
+                  "hyp_run_lucy_iteration"):
+            getattr(L, n).restype = C.c_int
+        self.ctx = C.c_void_p()
+        self.check(L.hyp_ctx_create(C.c_int(device_id), C.byref(self.ctx)))
+        self.n_dust = 0
+        self.n_cells = 0
+        self.shape = None
+
+    def close(self):
+        if self.ctx:
+            self.lib.hyp_ctx_destroy(self.ctx)
+            self.ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def load_model(self, model: FlatModel):
+        apply_model(self, self.ctx, model)
+        self.n_dust = len(model.dust)
+        self.shape = model.shape
+        self.n_cells = model.n_cells
+        self.check(self.lib.hyp_finalize_setup(self.ctx))
+
+    def update_density(self, density):
+        self.set_density(self.ctx, self.n_dust, density)
+
+    def lucy_begin(self):
+        self.check(self.lib.hyp_lucy_begin(self.ctx))
+
+    def lucy_photons(self, first_id, n, iteration):
+        self.check(self.lib.hyp_lucy_photons(self.ctx, C.c_int64(first_id), C.c_int64(n), C.c_int64(iteration)))
+
+    def lucy_device_buffers(self):
+        p = C.c_void_p()
+        n = C.c_int64()
+        self.check(self.lib.hyp_lucy_device_buffers(self.ctx, C.byref(p), C.byref(n)))
+        return p.value, n.value
+
+    def lucy_finish(self):
+        st = IterStats()
+        self.check(self.lib.hyp_lucy_finish(self.ctx, C.byref(st)))
+        return st
+
+    def run_lucy_iteration(self, n_photons, iteration=1):
+        st = IterStats()
+        self.check(self.lib.hyp_run_lucy_iteration(self.ctx, C.c_int64(n_photons), C.c_int64(iteration),
+                                                   C.byref(st)))
+        return st
+
+    def _get(self, fn, out=None):
+        if out is None:
+            out = np.empty((self.n_dust,) + tuple(self.shape), dtype=np.float64)
+        self.check(fn(self.ctx, _ptr(out)))
+        return out
+
+    def get_specific_energy(self, out=None):
+        return self._get(self.lib.hyp_get_specific_energy, out)
+
+    def get_density(self, out=None):
+        return self._get(self.lib.hyp_get_density, out)
+
+    def get_energy_sum(self, out=None):
+        return self._get(self.lib.hyp_get_energy_sum, out)
+
+    @property
+    def stream(self):
+        return self.lib.hyp_stream(self.ctx)

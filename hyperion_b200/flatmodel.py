@@ -1,0 +1,183 @@
+"""Neutral in-memory model: what the .rtin file holds for the photon path.
+
+The reference keeps this state in Fortran module globals filled by
+``setup_initial`` (``src/main/setup_rt.f90:27-304``).  Here it is a handful of
+numpy arrays that both the CUDA engine (through the C ABI) and the test oracle
+consume, so that kernels can be exercised without any HDF5 file.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import List, Optional
+
+import numpy as np
+
+
+def _f8(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+@dataclass
+class FlatDust:
+    """One dust type: the columns of a Hyperion dust file
+    (``src/dust/dust_type_4elem.f90:94-277``)."""
+    nu: np.ndarray
+    albedo: np.ndarray
+    chi: np.ndarray
+    mu: np.ndarray
+    P1: np.ndarray  # [n_nu, n_mu]
+    P2: np.ndarray
+    P3: np.ndarray
+    P4: np.ndarray
+    specific_energy: np.ndarray
+    chi_planck: np.ndarray
+    kappa_planck: np.ndarray
+    chi_inv_planck: np.ndarray
+    kappa_inv_planck: np.ndarray
+    chi_rosseland: np.ndarray
+    kappa_rosseland: np.ndarray
+    emiss_nu: np.ndarray
+    emiss_jnu: np.ndarray  # [n_emiss_nu, n_jnu]
+    jnu_var: np.ndarray
+    version: int = 2
+    is_lte: bool = True
+    sublimation_mode: int = 0
+    sublimation_specific_energy: float = 0.0
+
+    def __post_init__(self):
+        for k in ("nu", "albedo", "chi", "mu", "P1", "P2", "P3", "P4", "specific_energy", "chi_planck",
+                  "kappa_planck", "chi_inv_planck", "kappa_inv_planck", "chi_rosseland", "kappa_rosseland",
+                  "emiss_nu", "emiss_jnu", "jnu_var"):
+            setattr(self, k, _f8(getattr(self, k)))
+        n_nu, n_mu = len(self.nu), len(self.mu)
+        for k in ("P1", "P2", "P3", "P4"):
+            if getattr(self, k).shape != (n_nu, n_mu):
+                raise ValueError("%s should have shape (n_nu, n_mu)" % k)
+        if self.emiss_jnu.shape != (len(self.emiss_nu), len(self.jnu_var)):
+            raise ValueError("emiss_jnu should have shape (n_emiss_nu, n_jnu)")
+
+    @classmethod
+    def from_hdf5_group(cls, g):
+        """Read a dust group (``Dust/dust_%03i`` or the root of a dust file)."""
+        sub = {b"no": 0, b"fast": 1, b"slow": 2, b"cap": 3}
+        attrs = g.attrs
+        version = int(attrs["version"])
+        op = g["optical_properties"][...]
+        mo = g["mean_opacities"][...]
+        em = g["emissivities"][...]
+        ev = g["emissivity_variable"][...]
+        mu = g["scattering_angles"][...]["mu"]
+        if version == 1:
+            # dust_type_4elem.f90:232-238: version-1 files hold the inverse Planck
+            # means in the *_rosseland columns
+            chi_inv, kap_inv = mo["chi_rosseland"], mo["kappa_rosseland"]
+        else:
+            chi_inv, kap_inv = mo["chi_inv_planck"], mo["kappa_inv_planck"]
+        mode = bytes(attrs["sublimation_mode"]).strip()
+        return cls(nu=op["nu"], albedo=op["albedo"], chi=op["chi"], mu=mu,
+                   P1=op["P1"], P2=op["P2"], P3=op["P3"], P4=op["P4"],
+                   specific_energy=mo["specific_energy"], chi_planck=mo["chi_planck"],
+                   kappa_planck=mo["kappa_planck"], chi_inv_planck=chi_inv, kappa_inv_planck=kap_inv,
+                   chi_rosseland=mo["chi_rosseland"], kappa_rosseland=mo["kappa_rosseland"],
+                   emiss_nu=em["nu"], emiss_jnu=em["jnu"], jnu_var=ev["specific_energy"],
+                   version=version, is_lte=bytes(attrs["lte"]).strip().lower() in (b"yes", b"y", b"true"),
+                   sublimation_mode=sub[mode],
+                   sublimation_specific_energy=float(attrs.get("sublimation_specific_energy", 0.0)))
+
+    def to_npz_dict(self, prefix):
+        d = {}
+        for k, v in self.__dict__.items():
+            d[prefix + k] = np.asarray(v)
+        return d
+
+    @classmethod
+    def from_npz_dict(cls, z, prefix):
+        kw = {}
+        for k in cls.__dataclass_fields__:
+            v = z[prefix + k]
+            kw[k] = v if v.ndim else v.item()
+        return cls(**kw)
+
+
+@dataclass
+class FlatSource:
+    """One source (``src/sources/source_type.f90:102-282``)."""
+    type: int = 1              # 1 point, 2 sphere
+    luminosity: float = 0.0
+    position: tuple = (0.0, 0.0, 0.0)
+    temperature: Optional[float] = None   # blackbody
+    spectrum_nu: Optional[np.ndarray] = None
+    spectrum_fnu: Optional[np.ndarray] = None
+    radius: float = 0.0
+    limb_darkening: bool = False
+    peeloff: bool = True
+
+
+@dataclass
+class FlatConf:
+    """Run configuration (``hyperion/conf/conf_files.py:48-73``)."""
+    seed: int = -124902
+    n_inter_max: int = 1000000
+    n_reabs_max: int = 1000000
+    kill_on_absorb: bool = False
+    kill_on_scatter: bool = False
+    sample_sources_evenly: bool = False
+    enforce_energy_range: bool = True
+    use_mrw: bool = False
+    mrw_gamma: float = 1.0
+    n_mrw_max: int = 1000
+    propagation_check_frequency: float = 1.e-3
+    n_initial_iter: int = 5
+    n_initial_photons: int = 0
+
+
+@dataclass
+class FlatModel:
+    w1: np.ndarray
+    w2: np.ndarray
+    w3: np.ndarray
+    density: np.ndarray                 # [n_dust, n3, n2, n1]
+    dust: List[FlatDust]
+    sources: List[FlatSource]
+    conf: FlatConf = field(default_factory=FlatConf)
+    specific_energy: Optional[np.ndarray] = None
+    minimum_specific_energy: Optional[np.ndarray] = None
+
+    def __post_init__(self):
+        self.w1, self.w2, self.w3 = _f8(self.w1), _f8(self.w2), _f8(self.w3)
+        self.density = _f8(self.density)
+        n1, n2, n3 = len(self.w1) - 1, len(self.w2) - 1, len(self.w3) - 1
+        if self.density.ndim == 3:
+            self.density = self.density[None]
+        if self.density.shape != (len(self.dust), n3, n2, n1):
+            raise ValueError("density should have shape (n_dust, n3, n2, n1) = %s, got %s" %
+                             ((len(self.dust), n3, n2, n1), self.density.shape))
+
+    @property
+    def shape(self):
+        return (len(self.w3) - 1, len(self.w2) - 1, len(self.w1) - 1)
+
+    @property
+    def n_cells(self):
+        s = self.shape
+        return s[0] * s[1] * s[2]
+
+    def volumes(self):
+        dx, dy, dz = np.diff(self.w1), np.diff(self.w2), np.diff(self.w3)
+        return (dx[None, None, :] * dy[None, :, None]) * dz[:, None, None]
+
+
+def apply_model(api, ctx, model: FlatModel):
+    """Push a FlatModel through a C API object exposing the hyp_*/orc_* setters.
+
+    ``api`` is a binding object with methods named like the header's functions
+    minus the prefix (see :mod:`hyperion_b200.capi`)."""
+    n3, n2, n1 = model.shape
+    api.set_grid_cartesian(ctx, n1, n2, n3, model.w1, model.w2, model.w3)
+    for d in model.dust:
+        api.add_dust(ctx, d)
+    for s in model.sources:
+        api.add_source(ctx, s)
+    api.set_run_conf(ctx, model.conf)
+    api.set_density(ctx, len(model.dust), model.density)
+    api.set_specific_energy(ctx, model.specific_energy, model.minimum_specific_energy)

@@ -1,0 +1,176 @@
+/*
+ * hyperion_b200.h -- C ABI of the B200-native photon-packet propagation engine.
+ *
+ * The reference (hyperion-rt/hyperion) has no FFI on this path: the Python
+ * front end writes an .rtin file and shells out to a Fortran binary
+ * (hyperion/model/model.py:1025-1080, scripts/hyperion:39-92, program main
+ * src/main/main.f90:1).  This header is the seam a maintainer would bind
+ * instead of that process boundary.  Each entry point
+ * cites the reference routine whose job it takes over.
+ *
+ * Conventions
+ *   - plain C, no C++ / torch types; all arrays are caller-owned, contiguous,
+ *     C-ordered HOST buffers unless a name says "device"
+ *   - every function returns 0 on success, <0 on error; the message is
+ *     available from hyp_last_error() (thread-local); nothing calls exit()
+ *   - one hyp_ctx drives ONE GPU (one process per GPU); multi-GPU runs shard
+ *     photon packets across processes and all-reduce the deposit grid
+ *     (hyp_lucy_device_buffers + NCCL, replacing src/mpi/mpi_routines.f90)
+ *   - grids use the .rtin layout: density[n_dust][n3][n2][n1] (x fastest),
+ *     identical in bytes to the Fortran (n_cells, n_dust) column-major arrays
+ *     (src/core/type_cell_id_3d.f90:97-102)
+ */
+#ifndef HYPERION_B200_H
+#define HYPERION_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct hyp_ctx hyp_ctx;
+
+/* error codes */
+#define HYP_OK 0
+#define HYP_ERR_INVALID -1      /* bad argument / inconsistent model */
+#define HYP_ERR_CUDA -2         /* CUDA runtime failure */
+#define HYP_ERR_STATE -3        /* call out of order */
+#define HYP_ERR_PHYSICS -4      /* reference error() condition hit (message matches the reference text) */
+
+/* Dust tables for one dust type, exactly the columns of a Hyperion dust file
+ * (read by dust_setup, src/dust/dust_type_4elem.f90:78-293).  2-D tables are
+ * in file (C) order. */
+typedef struct {
+  int32_t version;                 /* root attr 'version' (1 or 2) */
+  int32_t is_lte;                  /* root attr 'lte' */
+  int32_t sublimation_mode;        /* 0 no, 1 fast, 2 slow, 3 cap */
+  double sublimation_specific_energy;
+  int32_t n_nu;                    /* optical_properties rows */
+  const double *nu, *albedo, *chi; /* [n_nu] */
+  int32_t n_mu;                    /* scattering_angles rows */
+  const double *mu;                /* [n_mu] */
+  const double *P1, *P2, *P3, *P4; /* [n_nu][n_mu] */
+  int32_t n_e;                     /* mean_opacities rows */
+  const double *specific_energy;   /* [n_e] */
+  const double *chi_planck, *kappa_planck;
+  const double *chi_inv_planck, *kappa_inv_planck; /* version 1 files: pass the rosseland columns (dust_type_4elem.f90:232-238) */
+  const double *chi_rosseland, *kappa_rosseland;
+  int32_t n_emiss_nu;              /* emissivities rows */
+  const double *emiss_nu;          /* [n_emiss_nu] */
+  int32_t n_jnu;                   /* emissivity_variable rows */
+  const double *emiss_jnu;         /* [n_emiss_nu][n_jnu] */
+  const double *jnu_var;           /* [n_jnu] specific energies */
+} hyp_dust_tables;
+
+/* One source (source_read, src/sources/source_type.f90:102-282). */
+#define HYP_SOURCE_POINT 1
+#define HYP_SOURCE_SPHERE 2
+#define HYP_SPECTRUM_TABLE 1
+#define HYP_SPECTRUM_BLACKBODY 2
+typedef struct {
+  int32_t type;            /* HYP_SOURCE_* */
+  int32_t peeloff;
+  double luminosity;
+  double x, y, z;
+  double radius;           /* sphere only */
+  int32_t limb_darkening;  /* sphere only */
+  int32_t spectrum_type;   /* HYP_SPECTRUM_* */
+  double temperature;      /* blackbody */
+  int32_t n_spec;          /* tabulated spectrum */
+  const double *spec_nu, *spec_fnu;
+} hyp_source;
+
+/* Run configuration: the root attributes of the .rtin file
+ * (setup_initial, src/main/setup_rt.f90:38-157; defaults
+ * hyperion/conf/conf_files.py:48-73). */
+typedef struct {
+  int64_t seed;                    /* 'seed' (default -124902) */
+  int64_t n_inter_max;             /* 'n_inter_max' */
+  int64_t n_reabs_max;             /* 'n_reabs_max' */
+  int32_t kill_on_absorb;
+  int32_t kill_on_scatter;
+  int32_t sample_sources_evenly;
+  int32_t enforce_energy_range;
+  int32_t use_mrw;                 /* not yet implemented on the device: rejected */
+  double mrw_gamma;
+  int64_t n_mrw_max;
+  double propagation_check_frequency; /* reference self-check rate; see DESIGN.md */
+} hyp_run_conf;
+
+/* Per-iteration counters (killed_photons_* attrs of main.f90:225-230 plus the
+ * work counters the roofline needs). */
+typedef struct {
+  double energy_emitted;      /* sum of emitted packet weights (energy_current, source.f90:163) */
+  int64_t n_photons;          /* packets run by this ctx */
+  int64_t killed_geo;
+  int64_t killed_int;
+  int64_t n_crossings;        /* cell crossings in grid_integrate */
+  int64_t n_absorptions;      /* absorb + re-emit events */
+  int64_t n_scatterings;
+  int64_t n_escaped;
+  double kernel_ms;           /* device time of the photon kernel (CUDA events) */
+  double epilogue_ms;         /* device time of scale/clamp/jnu_var kernels */
+} hyp_iter_stats;
+
+const char *hyp_last_error(void);
+int hyp_version(void);
+
+/* replaces: program start-up, mp_initialize (src/mpi/mpi_core.f90:35) */
+int hyp_ctx_create(int device_id, hyp_ctx **out);
+void hyp_ctx_destroy(hyp_ctx *ctx);
+
+/* replaces: setup_grid_geometry (src/grid/grid_geometry_cartesian_3d.f90:77-135).
+ * w1/w2/w3 are the n+1 wall positions (Grid/Geometry walls_1..3). */
+int hyp_set_grid_cartesian(hyp_ctx *ctx, int32_t n1, int32_t n2, int32_t n3,
+                           const double *w1, const double *w2, const double *w3);
+
+/* replaces: dust_setup (src/dust/dust_type_4elem.f90:78-293); call once per dust type, in order */
+int hyp_add_dust(hyp_ctx *ctx, const hyp_dust_tables *dust);
+
+/* replaces: source_read / setup_sources (src/sources/source.f90:48-80) */
+int hyp_add_source(hyp_ctx *ctx, const hyp_source *src);
+
+/* replaces: the root-attribute block of setup_initial (src/main/setup_rt.f90:38-157) */
+int hyp_set_run_conf(hyp_ctx *ctx, const hyp_run_conf *conf);
+
+/* replaces: setup_grid_physics (src/grid/grid_physics_3d.f90:111-322).
+ * density: [n_dust][n_cells]; specific_energy may be NULL (then the minimum is
+ * used); minimum_specific_energy: [n_dust] or NULL (zeros). */
+int hyp_set_density(hyp_ctx *ctx, int32_t n_dust, const double *density);
+int hyp_set_specific_energy(hyp_ctx *ctx, const double *specific_energy,
+                            const double *minimum_specific_energy);
+
+/* Builds the sampling tables and uploads everything to the device; after this
+ * the model is frozen except for density / specific_energy. */
+int hyp_finalize_setup(hyp_ctx *ctx);
+
+/* replaces: do_lucy (src/main/iter_lucy.f90:66-237) in three steps so that a
+ * multi-process host can all-reduce between the photon loop and the scaling:
+ *   begin   = grid_reset_energy + precompute_jnu_var        (iter_lucy.f90:101-107)
+ *   photons = the photon loop for packets [first_id, first_id+n)   (iter_lucy.f90:119-209)
+ *   finish  = update_energy_abs(energy_total/energy_current) + sublimate_dust (iter_lucy.f90:224-235)
+ * hyp_run_lucy_iteration does all three for a single process. */
+int hyp_lucy_begin(hyp_ctx *ctx);
+int hyp_lucy_photons(hyp_ctx *ctx, int64_t first_id, int64_t n_photons, int64_t iteration);
+/* Device pointers for the host's collective: sum grid [n_dust*n_cells] fp64 followed
+ * directly by 8 fp64 scalars (energy_emitted, killed_geo, killed_int, crossings,
+ * absorptions, scatterings, escaped, photons); n_values = n_dust*n_cells + 8.
+ * replaces: mp_collect_physical_arrays + mp_sync (src/mpi/mpi_routines.f90:272-361) */
+int hyp_lucy_device_buffers(hyp_ctx *ctx, void **sum_and_scalars, int64_t *n_values);
+int hyp_lucy_finish(hyp_ctx *ctx, hyp_iter_stats *stats);
+int hyp_run_lucy_iteration(hyp_ctx *ctx, int64_t n_photons, int64_t iteration, hyp_iter_stats *stats);
+
+/* replaces: output_grid 'specific_energy' (src/grid/grid_generic.f90:50-63): [n_dust][n_cells] */
+int hyp_get_specific_energy(hyp_ctx *ctx, double *out);
+int hyp_get_density(hyp_ctx *ctx, double *out);
+/* raw deposit sums of the last iteration (specific_energy_sum, grid_physics_3d.f90:40) */
+int hyp_get_energy_sum(hyp_ctx *ctx, double *out);
+
+/* stream handle (cudaStream_t) the ctx launches on, for callers that time with events */
+void *hyp_stream(hyp_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HYPERION_B200_H */

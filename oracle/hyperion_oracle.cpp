@@ -1,0 +1,1518 @@
+/*
+ * hyperion_oracle.cpp -- CPU restatement of the reference's photon path.
+ *
+ * TEST INFRASTRUCTURE ONLY.  This file is the parity oracle: a plain, scalar,
+ * single-stream fp64 restatement of the Fortran algorithm, including the
+ * reference's Marsaglia-Tsang generator and its exact draw order, so that it
+ * can be pinned bit-for-bit (to the reference's own 1000-ULP criterion) against
+ * the golden .rtout files in hyperion/model/tests/data/.  Only tests/,
+ * __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs
+ * may load it.  The product (hyperion_b200/csrc) never links or calls it.
+ *
+ * Every routine cites the reference file:line it restates (paths relative to
+ * the reference checkout).  Arithmetic is written in the same operand order as
+ * the Fortran and must be compiled with -ffp-contract=off (no FMA), because
+ * the goldens were produced by gfortran on baseline x86-64.
+ */
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <string>
+#include <vector>
+
+#include "../include/hyperion_b200.h"
+
+namespace {
+
+const double PI = 3.14159265358979323846;
+const double TWOPI = PI + PI;  // lib_random.f90:51
+
+// ---------------------------------------------------------------------------
+// RNG: fortranlib/src/lib_random.f90
+// ---------------------------------------------------------------------------
+struct Rng {
+  double u[98];
+  int i = 97, j = 33;
+  double c = 0.0;
+  uint64_t n_draws = 0;
+
+  // set_seed (lib_random.f90:100-107) -> set_seed_64 (:109-127)
+  void set_seed(int seed) {
+    int a = seed < 0 ? -seed : seed;
+    int32_t x = a, y = 987654321;
+    for (int ii = 1; ii <= 97; ii++) {
+      double s = 0.0, t = 0.5;
+      for (int jj = 1; jj <= 53; jj++) {
+        x = (6969 * x) % 65543;
+        y = (8888 * x) % 65579;
+        if (((x ^ y) & 32) > 0) s = s + t;
+        t = 0.5 * t;
+      }
+      u[ii] = s;
+    }
+    (void)y;
+  }
+
+  // random_dp (lib_random.f90:172-197)
+  double random() {
+    const double r = 9007199254740881.0 / 9007199254740992.0;
+    const double d = 362436069876.0 / 9007199254740992.0;
+    double x = u[i] - u[j];
+    if (x < 0.0) x = x + 1.0;
+    u[i] = x;
+    i = i - 1;
+    if (i == 0) i = 97;
+    j = j - 1;
+    if (j == 0) j = 97;
+    c = c - d;
+    if (c < 0.0) c = c + r;
+    x = x - c;
+    n_draws++;
+    if (x < 0.0) return x + 1.0;
+    return x;
+  }
+
+  // random_uni_dp (lib_random.f90:200-207)
+  double random_uni(double a, double b) {
+    double xi = random();
+    return a + (b - a) * xi;
+  }
+
+  // random_exp_dp (lib_random.f90:227-236)
+  double random_exp() {
+    double xi;
+    do {
+      xi = random();
+    } while (!(xi < 1.0));
+    return -std::log(1.0 - xi);
+  }
+
+  // random_planck_frequency_dp (lib_random.f90:297-347)
+  double random_planck_frequency(double T) {
+    const double k = 1.3806503e-23;
+    const double h = 6.626068e-34;
+    double r;
+    for (;;) {
+      double r1 = random();
+      double r2 = random();
+      double r3 = random();
+      double r4 = random();
+      r = r1 * r2 * r3 * r4;
+      if (r > 0.0) break;
+    }
+    double x = -std::log(r);
+    double a = 1.0, y = 1.0, z = 1.0;
+    double r1 = random();
+    for (;;) {
+      if (1.08232 * r1 <= a) break;
+      y = y + 1.0;
+      z = 1.0 / y;
+      a = a + z * z * z * z;
+    }
+    x = x * z;
+    return x * k * T / h;
+  }
+};
+
+// ---------------------------------------------------------------------------
+// lib_array.f90 numerics (1-based indices returned, as in the Fortran)
+// ---------------------------------------------------------------------------
+
+// locate_dp (lib_array.f90:917-950)
+int locate(const double *xx, int n, double x) {
+  bool ascnd = (xx[n - 1] >= xx[0]);
+  int jl = 0, ju = n + 1;
+  for (;;) {
+    if (ju - jl <= 1) break;
+    int jm = (ju + jl) / 2;
+    if (ascnd == (x >= xx[jm - 1]))
+      jl = jm;
+    else
+      ju = jm;
+  }
+  if (x == xx[0]) return 1;
+  if (x == xx[n - 1]) return n - 1;
+  if (ascnd && (x > xx[n - 1] || x < xx[0])) return -1;
+  if (!ascnd && (x < xx[n - 1] || x > xx[0])) return -1;
+  return jl;
+}
+
+// ipos_dp (lib_array.f90:954-998)
+int ipos(double xmin, double xmax, double x, int nbin) {
+  if (xmax > xmin) {
+    if (x < xmin) return 0;
+    if (x > xmax) return nbin + 1;
+    if (x < xmax) {
+      double frac = (x - xmin) / (xmax - xmin);
+      return (int)(frac * (double)nbin) + 1;
+    }
+    return nbin;
+  } else {
+    if (x > xmin) return 0;
+    if (x < xmax) return nbin + 1;
+    if (x > xmax) {
+      double frac = (x - xmin) / (xmax - xmin);
+      return (int)(frac * (double)nbin) + 1;
+    }
+    return nbin;
+  }
+}
+
+// trapezium_dp (lib_array.f90:528-532)
+double trapezium(double x1, double y1, double x2, double y2) {
+  return 0.5 * (y1 + y2) * (x2 - x1);
+}
+
+// trapezium_linlog_dp (lib_array.f90:548-560)
+double trapezium_linlog(double x1, double y1, double x2, double y2) {
+  if (x1 == x2) return 0.0;
+  if (y1 == y2) return y1 * (x2 - x1);
+  return (y2 - y1) * (x2 - x1) / std::log(10.0) / std::log10(y2 / y1);
+}
+
+// trapezium_loglog_dp (lib_array.f90:562-578)
+double trapezium_loglog(double x1, double y1, double x2, double y2) {
+  if (x1 == x2) return 0.0;
+  if (y1 == 0.0 || y2 == 0.0) return 0.0;
+  double b = std::log10(y1 / y2) / std::log10(x1 / x2);
+  // note: the Fortran compares with the single-precision literal 1e-10
+  if (std::fabs(b + 1.0) < (double)1e-10f) return x1 * y1 * std::log(x2 / x1);
+  return y1 * (x2 * std::pow(x2 / x1, b) - x1) / (b + 1);
+}
+
+typedef double (*chunk_fn)(double, double, double, double);
+
+// integral_general_dp (lib_array.f90:413-429)
+double integral_general(const double *x, const double *y, int n, chunk_fn f) {
+  double sum = 0.0;
+  for (int j = 0; j < n - 1; j++) sum = sum + f(x[j], y[j], x[j + 1], y[j + 1]);
+  return sum;
+}
+
+// cumulative_integral_general_dp (lib_array.f90:431-448)
+void cumulative_integral_general(const double *x, const double *y, int n, chunk_fn f, double *c) {
+  c[0] = 0.0;
+  for (int j = 0; j < n - 1; j++) c[j + 1] = c[j] + f(x[j], y[j], x[j + 1], y[j + 1]);
+}
+
+// interp1d_single_loglog_dp (lib_array.f90:605-614)
+double interp1d_single_loglog(double x1, double y1, double x2, double y2, double xval) {
+  if (y1 == 0.0 || y2 == 0.0) return 0.0;
+  double frac = (std::log10(xval) - std::log10(x1)) / (std::log10(x2) - std::log10(x1));
+  return std::pow(10.0, std::log10(y1) + frac * (std::log10(y2) - std::log10(y1)));
+}
+
+// interp1d_single_linlog_dp (lib_array.f90:587-596)
+double interp1d_single_linlog(double x1, double y1, double x2, double y2, double xval) {
+  if (y1 == 0.0 || y2 == 0.0) return 0.0;
+  double frac = (xval - x1) / (x2 - x1);
+  return std::pow(10.0, std::log10(y1) + frac * (std::log10(y2) - std::log10(y1)));
+}
+
+struct OracleError {
+  std::string msg;
+};
+
+// interp1d_general_dp with loglog chunks (lib_array.f90:682-689,704-778)
+double interp1d_loglog(const double *x, const double *y, int n, double xval, bool bounds_error = true,
+                       double fill_value = 0.0) {
+  int ip = locate(x, n, xval);
+  if (ip == -1) {
+    if (bounds_error) throw OracleError{"Interpolation out of bounds"};
+    return fill_value;
+  }
+  if (ip < n && ip > 0) return interp1d_single_loglog(x[ip - 1], y[ip - 1], x[ip], y[ip], xval);
+  if (ip == n) return y[n - 1];
+  if (ip == 0) return y[0];
+  throw OracleError{"Unexpected value of ipos"};
+}
+
+// interp2d_dp (lib_array.f90:780-846); array(i,j) stored as a[(j-1)*nx + (i-1)]
+double interp2d(const double *x, int nx, const double *y, int ny, const double *a, double x0, double y0) {
+  int i1 = locate(x, nx, x0), i2 = i1 + 1;
+  int j1 = locate(y, ny, y0), j2 = j1 + 1;
+  if (i1 == -1 || j1 == -1) throw OracleError{"Interpolation out of bounds"};
+  double norm = 1.0 / (x[i2 - 1] - x[i1 - 1]) / (y[j2 - 1] - y[j1 - 1]);
+#define A(i, j) a[(size_t)((j)-1) * nx + ((i)-1)]
+  double value = A(i1, j1) * (x[i2 - 1] - x0) * (y[j2 - 1] - y0) * norm +
+                 A(i2, j1) * (x0 - x[i1 - 1]) * (y[j2 - 1] - y0) * norm +
+                 A(i1, j2) * (x[i2 - 1] - x0) * (y0 - y[j1 - 1]) * norm +
+                 A(i2, j2) * (x0 - x[i1 - 1]) * (y0 - y[j1 - 1]) * norm;
+#undef A
+  return value;
+}
+
+// ---------------------------------------------------------------------------
+// type_pdf.f90
+// ---------------------------------------------------------------------------
+struct PdfDiscrete {
+  int n = 0;
+  std::vector<double> pdf, cdf;
+
+  // find_cdf_discrete_dp (type_pdf.f90:167-180)
+  void find_cdf() {
+    cdf[0] = pdf[0];
+    for (int i = 1; i < n; i++) cdf[i] = cdf[i - 1] + pdf[i];
+    double norm = cdf[n - 1];
+    if (norm == 0.0) throw OracleError{"[find_cdf_discrete] all PDF elements are zero"};
+    for (int i = 0; i < n; i++) cdf[i] = cdf[i] / norm;
+  }
+  // set_pdf_discrete_dp (type_pdf.f90:222-231) + normalize (:200-209)
+  void set(const double *y, int nn) {
+    n = nn;
+    pdf.assign(y, y + nn);
+    cdf.assign(nn, 0.0);
+    double norm = 0.0;
+    for (int i = 0; i < n; i++) norm = norm + pdf[i];
+    if (norm == 0.0) throw OracleError{"[normalize_pdf_discrete] all PDF elements are zero"};
+    for (int i = 0; i < n; i++) pdf[i] = pdf[i] / norm;
+    find_cdf();
+  }
+  // sample_pdf_discrete_dp (type_pdf.f90:313-337)
+  int sample(Rng &rng) const {
+    double xi = rng.random();
+    if (xi <= cdf[0]) return 1;
+    if (xi >= cdf[n - 1]) return n;
+    int jmin = 1, jmax = n;
+    for (;;) {
+      int j = (jmax + jmin) / 2;
+      if (xi > cdf[j - 1])
+        jmin = j;
+      else
+        jmax = j;
+      if (jmax == jmin + 1) break;
+    }
+    return jmax;
+  }
+};
+
+struct PdfCont {
+  int n = 0;
+  bool log = false;
+  std::vector<double> x, pdf, cdf, a, b, r, rx, rc;
+
+  // set_pdf_cont_dp (type_pdf.f90:233-248) -> normalize (:211-220) -> find_cdf (:279-311)
+  void set(const double *xs, const double *ys, int nn, bool is_log) {
+    n = nn;
+    log = is_log;
+    x.assign(xs, xs + nn);
+    pdf.assign(ys, ys + nn);
+    cdf.assign(nn, 0.0);
+    double norm = log ? integral_general(x.data(), pdf.data(), n, trapezium_loglog)
+                      : integral_general(x.data(), pdf.data(), n, trapezium);
+    for (int i = 0; i < n; i++) pdf[i] = pdf[i] / norm;
+    for (int i = 1; i < n; i++)
+      if (!(x[i] > x[i - 1])) throw OracleError{"[check_pdf] PDF x array is not sorted"};
+    if (log)
+      cumulative_integral_general(x.data(), pdf.data(), n, trapezium_loglog, cdf.data());
+    else
+      cumulative_integral_general(x.data(), pdf.data(), n, trapezium, cdf.data());
+    double last = cdf[n - 1];
+    for (int i = 0; i < n; i++) cdf[i] = cdf[i] / last;
+    if (log) {
+      b.assign(n - 1, 0.0);
+      r.assign(n - 1, 0.0);
+      for (int i = 0; i < n - 1; i++) {
+        b[i] = std::log10(pdf[i] / pdf[i + 1]) / std::log10(x[i] / x[i + 1]);
+        r[i] = std::pow(x[i + 1] / x[i], b[i] + 1.0);
+      }
+    } else {
+      a.assign(n - 1, 0.0);
+      b.assign(n - 1, 0.0);
+      rx.assign(n - 1, 0.0);
+      rc.assign(n - 1, 0.0);
+      for (int i = 0; i < n - 1; i++) {
+        a[i] = (pdf[i] - pdf[i + 1]) / (x[i] - x[i + 1]);
+        b[i] = pdf[i] - a[i] * x[i];
+        rx[i] = x[i + 1] / x[i];
+        rc[i] = b[i] / a[i];
+      }
+    }
+  }
+
+  // sample_pdf_cont_dp (type_pdf.f90:339-381), non-"simple" branch
+  double sample_xi(double xi) const {
+    if (xi <= cdf[0]) return x[0];
+    if (xi >= cdf[n - 1]) return x[n - 1];
+    int i = locate(cdf.data(), n, xi);
+    xi = (xi - cdf[i - 1]) / (cdf[i] - cdf[i - 1]);
+    if (log) {
+      return std::pow(xi * (r[i - 1] - 1.0) + 1.0, 1.0 / (b[i - 1] + 1.0)) * x[i - 1];
+    } else {
+      double A = a[i - 1], RC = rc[i - 1], X = x[i - 1], X1 = x[i], RX = rx[i - 1];
+      if (A == 0.0) return xi * (X1 - X) + X;
+      if (X == 0.0) return -RC + std::copysign(std::sqrt(RC * RC + xi * X1 * X1 + 2.0 * RC * xi * X1), A);
+      return -RC + std::copysign(std::sqrt(RC * RC + X * X * (xi * (RX * RX - 1.0) + 1.0) +
+                                           2.0 * RC * X * (xi * (RX - 1.0) + 1.0)),
+                                 A);
+    }
+  }
+  double sample(Rng &rng) const { return sample_xi(rng.random()); }
+};
+
+// ---------------------------------------------------------------------------
+// type_angle3d.f90 / type_vector3d.f90 / type_stokes
+// ---------------------------------------------------------------------------
+struct Angle {
+  double cost, sint, cosp, sinp;
+};
+struct Vec {
+  double x, y, z;
+};
+struct Stokes {
+  double I, Q, U, V;
+};
+
+// random_sphere_angle3d_dp (type_angle3d.f90:431-441); random_sphere_dp (lib_random.f90:239-245)
+Angle random_sphere_angle3d(Rng &rng) {
+  Angle a;
+  a.cost = rng.random_uni(-1.0, +1.0);
+  double phi = rng.random_uni(0.0, TWOPI);
+  a.sint = std::sqrt(1.0 - a.cost * a.cost);
+  a.cosp = std::cos(phi);
+  a.sinp = std::sin(phi);
+  return a;
+}
+
+// angle3d_to_vector3d_dp (type_vector3d.f90:301-317)
+Vec angle3d_to_vector3d(const Angle &a) { return Vec{a.sint * a.cosp, a.sint * a.sinp, a.cost}; }
+
+// sin2cos_dp (type_angle3d.f90:421-429)
+double sin2cos(double x) { return (x * x < 1.0) ? std::sqrt(1.0 - x * x) : 0.0; }
+
+Angle angle3d_deg(double theta, double phi) {
+  const double deg2rad = PI / 180.0;
+  return Angle{std::cos(theta * deg2rad), std::sin(theta * deg2rad), std::cos(phi * deg2rad),
+               std::sin(phi * deg2rad)};
+}
+
+// rotate_angle3d_dp (type_angle3d.f90:160-281)
+Angle rotate_angle3d(const Angle &a_local, const Angle &a_coord) {
+  Angle f;
+  if (std::fabs(a_coord.sint) < 1.e-10) {
+    f = a_local;
+    if (a_coord.cost > 0.0) {
+      f.cosp = +a_local.cosp * a_coord.cosp + a_local.sinp * a_coord.sinp;
+      f.sinp = +a_local.cosp * a_coord.sinp - a_local.sinp * a_coord.cosp;
+    } else {
+      f.cost = -a_local.cost;
+      f.cosp = +a_local.cosp * a_coord.cosp - a_local.sinp * a_coord.sinp;
+      f.sinp = +a_local.cosp * a_coord.sinp + a_local.sinp * a_coord.cosp;
+    }
+    return f;
+  }
+  double cos_a = a_coord.cost, sin_a = a_coord.sint;
+  double cos_b = a_local.cost, sin_b = a_local.sint;
+  double cos_big_c, sin_big_c;
+  if (a_local.sinp < 0.0) {
+    cos_big_c = +a_local.cosp;
+    sin_big_c = -a_local.sinp;
+  } else {
+    cos_big_c = +a_local.cosp;
+    sin_big_c = +a_local.sinp;
+  }
+  bool same_sign;
+  double delta;
+  if (std::fabs(sin_a) > std::fabs(cos_a)) {
+    same_sign = (sin_a > 0.0) == (sin_b > 0.0);
+    delta = cos_b - cos_a;
+  } else {
+    same_sign = (cos_a > 0.0) == (cos_b > 0.0);
+    delta = sin_b - sin_a;
+  }
+  double cos_c, sin_c;
+  if (same_sign && std::fabs(delta) < 1.e-5 && sin_big_c < 1.e-5 && cos_big_c > 0.0) {
+    if (std::fabs(sin_a) > std::fabs(cos_a)) {
+      double q = cos_a / sin_a;
+      sin_c = std::sqrt(delta * delta * (1.0 + q * q) + sin_a * sin_b * sin_big_c * sin_big_c);
+    } else {
+      double q = sin_a / cos_a;
+      sin_c = std::sqrt(delta * delta * (1.0 + q * q) + sin_a * sin_b * sin_big_c * sin_big_c);
+    }
+    cos_c = sin2cos(sin_c);
+  } else {
+    cos_c = cos_a * cos_b + sin_a * sin_b * cos_big_c;
+    sin_c = sin2cos(cos_c);
+  }
+  if (std::fabs(sin_c) < 1.e-10) {
+    if (cos_c > 0.0) return angle3d_deg(0.0, 0.0);
+    return angle3d_deg(180.0, 0.0);
+  }
+  double cos_big_b = (cos_b - cos_a * cos_c) / (sin_a * sin_c);
+  double sin_big_b = +sin_big_c * sin_b / sin_c;
+  f.cost = cos_c;
+  f.sint = sin_c;
+  if (a_local.sinp < 0.0) {
+    f.cosp = +cos_big_b * a_coord.cosp + sin_big_b * a_coord.sinp;
+    f.sinp = +cos_big_b * a_coord.sinp - sin_big_b * a_coord.cosp;
+  } else {
+    f.cosp = +cos_big_b * a_coord.cosp - sin_big_b * a_coord.sinp;
+    f.sinp = +cos_big_b * a_coord.sinp + sin_big_b * a_coord.cosp;
+  }
+  return f;
+}
+
+// ---------------------------------------------------------------------------
+// dust: src/dust/dust_type_4elem.f90
+// ---------------------------------------------------------------------------
+struct Dust {
+  int version = 2, sublimation_mode = 0;
+  double sublimation_specific_energy = 0.0;
+  int n_nu = 0, n_mu = 0, n_e = 0, n_jnu = 0;
+  std::vector<double> nu, albedo_nu, chi_nu, kappa_nu;
+  std::vector<double> mu;
+  std::vector<double> P1, P2, P3, P4, P1_cdf, P2_cdf, P3_cdf, P4_cdf;  // (imu, inu) at [inu*n_mu+imu]
+  double mu_min = -1, mu_max = 1;
+  std::vector<double> specific_energy, chi_planck, kappa_planck, chi_inv_planck, kappa_inv_planck,
+      chi_rosseland, kappa_rosseland;
+  std::vector<double> j_nu_var, log10_j_nu_var;
+  std::vector<PdfCont> j_nu;
+  bool zero_p2 = true;
+
+  // dust_setup (dust_type_4elem.f90:78-293)
+  void setup(const hyp_dust_tables &t) {
+    version = t.version;
+    sublimation_mode = t.sublimation_mode;
+    sublimation_specific_energy = t.sublimation_specific_energy;
+    n_nu = t.n_nu;
+    n_mu = t.n_mu;
+    nu.assign(t.nu, t.nu + n_nu);
+    albedo_nu.assign(t.albedo, t.albedo + n_nu);
+    chi_nu.assign(t.chi, t.chi + n_nu);
+    size_t np = (size_t)n_nu * n_mu;
+    P1.assign(t.P1, t.P1 + np);
+    P2.assign(t.P2, t.P2 + np);
+    P3.assign(t.P3, t.P3 + np);
+    P4.assign(t.P4, t.P4 + np);
+    zero_p2 = true;
+    for (size_t i = 0; i < np; i++)
+      if (P2[i] != 0.0) zero_p2 = false;
+    kappa_nu.resize(n_nu);
+    for (int j = 0; j < n_nu; j++) kappa_nu[j] = chi_nu[j] * (1.0 - albedo_nu[j]);
+    mu.assign(t.mu, t.mu + n_mu);
+    mu_min = mu[0];
+    mu_max = mu[n_mu - 1];
+    double dmu = mu_max - mu_min;
+    // normalise so that the integral over mu is dmu (:193-203)
+    for (int j = 0; j < n_nu; j++) {
+      double *p1 = &P1[(size_t)j * n_mu];
+      double norm = integral_general(mu.data(), p1, n_mu, trapezium_linlog);
+      if (norm == 0.0) throw OracleError{"P1 matrix normalization is zero"};
+      for (int i = 0; i < n_mu; i++) {
+        size_t k = (size_t)j * n_mu + i;
+        P1[k] = P1[k] / norm * dmu;
+        P2[k] = P2[k] / norm * dmu;
+        P3[k] = P3[k] / norm * dmu;
+        P4[k] = P4[k] / norm * dmu;
+      }
+    }
+    P1_cdf.assign(np, 0.0);
+    P2_cdf.assign(np, 0.0);
+    P3_cdf.assign(np, 0.0);
+    P4_cdf.assign(np, 0.0);
+    std::vector<double> *Ps[4] = {&P1, &P2, &P3, &P4};
+    std::vector<double> *Cs[4] = {&P1_cdf, &P2_cdf, &P3_cdf, &P4_cdf};
+    for (int j = 0; j < n_nu; j++) {
+      for (int q = 0; q < 4; q++) {
+        double *c = &(*Cs[q])[(size_t)j * n_mu];
+        cumulative_integral_general(mu.data(), &(*Ps[q])[(size_t)j * n_mu], n_mu, trapezium, c);
+        bool all_zero = true;
+        for (int i = 0; i < n_mu; i++)
+          if (c[i] != 0.0) all_zero = false;
+        if (!all_zero) {
+          double last = c[n_mu - 1];
+          for (int i = 0; i < n_mu; i++) c[i] = c[i] / last;
+        }
+      }
+    }
+    n_e = t.n_e;
+    specific_energy.assign(t.specific_energy, t.specific_energy + n_e);
+    chi_planck.assign(t.chi_planck, t.chi_planck + n_e);
+    kappa_planck.assign(t.kappa_planck, t.kappa_planck + n_e);
+    chi_inv_planck.assign(t.chi_inv_planck, t.chi_inv_planck + n_e);
+    kappa_inv_planck.assign(t.kappa_inv_planck, t.kappa_inv_planck + n_e);
+    chi_rosseland.assign(t.chi_rosseland, t.chi_rosseland + n_e);
+    kappa_rosseland.assign(t.kappa_rosseland, t.kappa_rosseland + n_e);
+    for (int i = 1; i < n_e; i++)
+      if (specific_energy[i] < specific_energy[i - 1])
+        throw OracleError{"energy per unit mass is not monotonically increasing"};
+    n_jnu = t.n_jnu;
+    j_nu_var.assign(t.jnu_var, t.jnu_var + n_jnu);
+    log10_j_nu_var.resize(n_jnu);
+    for (int i = 0; i < n_jnu; i++) log10_j_nu_var[i] = std::log10(j_nu_var[i]);
+    j_nu.resize(n_jnu);
+    std::vector<double> col(t.n_emiss_nu);
+    for (int i = 0; i < n_jnu; i++) {
+      for (int k = 0; k < t.n_emiss_nu; k++) col[k] = t.emiss_jnu[(size_t)k * n_jnu + i];
+      j_nu[i].set(t.emiss_nu, col.data(), t.n_emiss_nu, true);
+    }
+  }
+
+  // dust_jnu_var_pos_frac (dust_type_4elem.f90:295-320)
+  void jnu_var_pos_frac(double se, int &id, double &frac) const {
+    double v = se;
+    if (v < j_nu_var[0]) {
+      id = 1;
+      frac = 0.0;
+    } else if (v > j_nu_var[n_jnu - 1]) {
+      id = n_jnu - 1;
+      frac = 1.0;
+    } else {
+      id = locate(j_nu_var.data(), n_jnu, v);
+      frac = (std::log10(v) - log10_j_nu_var[id - 1]) / (log10_j_nu_var[id] - log10_j_nu_var[id - 1]);
+    }
+  }
+
+  // dust_sample_j_nu (dust_type_4elem.f90:379-398)
+  double sample_j_nu(Rng &rng, int id, double frac) const {
+    double xi = rng.random();
+    double nu1 = j_nu[id - 1].sample_xi(xi);
+    double nu2 = j_nu[id].sample_xi(xi);
+    double v = std::log10(nu1) + frac * (std::log10(nu2) - std::log10(nu1));
+    return std::pow(10.0, v);
+  }
+};
+
+// scatter_stokes (dust_type_4elem.f90:603-690)
+void scatter_stokes(Stokes &s, const Angle &a_coord, const Angle &a_scat, const Angle &a_final, double P1,
+                    double P2, double P3, double P4) {
+  const double tiny = std::numeric_limits<double>::min();
+  double cos_a = a_coord.cost, sin_a = a_coord.sint;
+  double cos_b = a_scat.cost, sin_b = a_scat.sint;
+  double cos_c = a_final.cost, sin_c = a_final.sint;
+  double cos_big_b = a_coord.cosp * a_final.cosp + a_coord.sinp * a_final.sinp;
+  double cos_big_c = a_scat.cosp;
+  double sin_big_c = std::fabs(a_scat.sinp);
+  double cos_big_a, sin_big_a;
+  if (sin_big_c < 10. * tiny && sin_c < 10. * tiny) {
+    cos_big_a = -cos_big_b * cos_big_c;
+    sin_big_a = std::sqrt(1.0 - cos_big_a * cos_big_a);
+  } else {
+    cos_big_a = (cos_a - cos_b * cos_c) / (sin_b * sin_c);
+    sin_big_a = +sin_big_c * sin_a / sin_c;
+  }
+  double cos_i2 = cos_big_a, sin_i2 = sin_big_a;
+  double cos_2_i2 = 1.0 - 2.0 * sin_i2 * sin_i2;
+  double sin_2_i2 = 2.0 * sin_i2 * cos_i2;
+  double cos_2_alpha = 1.0 - 2.0 * a_scat.sinp * a_scat.sinp;
+  double sin_2_alpha = -2.0 * a_scat.sinp * a_scat.cosp;
+  double cos_2_beta, sin_2_beta;
+  if (a_scat.sinp < 0.) {
+    cos_2_beta = cos_2_i2;
+    sin_2_beta = sin_2_i2;
+  } else {
+    cos_2_beta = cos_2_i2;
+    sin_2_beta = -sin_2_i2;
+  }
+  double RLS1 = P1 * s.I + P2 * (+cos_2_alpha * s.Q + sin_2_alpha * s.U);
+  double RLS2 = P2 * s.I + P1 * (+cos_2_alpha * s.Q + sin_2_alpha * s.U);
+  double RLS3 = -P4 * s.V + P3 * (-sin_2_alpha * s.Q + cos_2_alpha * s.U);
+  double RLS4 = P3 * s.V + P4 * (-sin_2_alpha * s.Q + cos_2_alpha * s.U);
+  s.I = RLS1;
+  s.Q = +cos_2_beta * RLS2 + sin_2_beta * RLS3;
+  s.U = -sin_2_beta * RLS2 + cos_2_beta * RLS3;
+  s.V = RLS4;
+}
+
+// dust_scatter (dust_type_4elem.f90:446-566)
+void dust_scatter(const Dust &d, Rng &rng, double nu, Angle &a, Stokes &s) {
+  Angle a_scat = random_sphere_angle3d(rng);
+  double sin_2_i1 = 2.0 * a_scat.sinp * a_scat.cosp;
+  double cos_2_i1 = 1.0 - 2.0 * a_scat.sinp * a_scat.sinp;
+  double c1 = s.I;
+  double c2 = (cos_2_i1 * s.Q - sin_2_i1 * s.U);
+  double ctot = c1 + c2;
+  c1 = c1 / ctot;
+  c2 = c2 / ctot;
+  int imin = 1, imax = d.n_mu;
+  int inu = locate(d.nu.data(), d.n_nu, nu);
+  double P1, P2, P3, P4;
+  if (inu == -1) {
+    P1 = 1.0;
+    P2 = 0.0;
+    P3 = 1.0;
+    P4 = 0.0;
+  } else {
+    double xi = rng.random();
+    int imu = 0;
+    double cdf1 = 0, cdf2 = 0;
+    const double *c1p = &d.P1_cdf[(size_t)(inu - 1) * d.n_mu];
+    const double *c2p = &d.P2_cdf[(size_t)(inu - 1) * d.n_mu];
+    for (int iter = 1; iter <= 1000000; iter++) {
+      imu = (imax + imin) / 2;
+      if (d.zero_p2) {
+        cdf1 = c1p[imu - 1];
+        cdf2 = c1p[imu];
+      } else {
+        cdf1 = c1 * c1p[imu - 1] + c2 * c2p[imu - 1];
+        cdf2 = c1 * c1p[imu] + c2 * c2p[imu];
+      }
+      if (xi > cdf2)
+        imin = imu;
+      else if (xi < cdf1)
+        imax = imu;
+      else
+        break;
+      if (imin == imax) throw OracleError{"ERROR: in sampling mu for scattering"};
+    }
+    a_scat.cost = (xi - cdf1) / (cdf2 - cdf1) * (d.mu[imu] - d.mu[imu - 1]) + d.mu[imu - 1];
+    a_scat.sint = std::sqrt(1.0 - a_scat.cost * a_scat.cost);
+    P1 = interp2d(d.mu.data(), d.n_mu, d.nu.data(), d.n_nu, d.P1.data(), a_scat.cost, nu);
+    P2 = interp2d(d.mu.data(), d.n_mu, d.nu.data(), d.n_nu, d.P2.data(), a_scat.cost, nu);
+    P3 = interp2d(d.mu.data(), d.n_mu, d.nu.data(), d.n_nu, d.P3.data(), a_scat.cost, nu);
+    P4 = interp2d(d.mu.data(), d.n_mu, d.nu.data(), d.n_nu, d.P4.data(), a_scat.cost, nu);
+  }
+  Angle a_final = rotate_angle3d(a_scat, a);
+  scatter_stokes(s, a, a_scat, a_final, P1, P2, P3, P4);
+  a = a_final;
+  double norm = 1.0 / s.I;
+  s.I = 1.0;
+  s.Q = s.Q * norm;
+  s.U = s.U * norm;
+  s.V = s.V * norm;
+}
+
+// ---------------------------------------------------------------------------
+// photon: src/core/type_photon.f90:14-73
+// ---------------------------------------------------------------------------
+struct WallId {
+  int w1 = 0, w2 = 0, w3 = 0;
+};
+struct Cell {
+  int i1 = 0, i2 = 0, i3 = 0, ic = 0;
+};
+const int MAX_DUST = 16;
+struct Photon {
+  Vec r{0, 0, 0}, v{0, 0, 0};
+  Angle a{0, 0, 0, 0};
+  Stokes s{0, 0, 0, 0};
+  double nu = 0, energy = 0;
+  bool in_cell = false, on_wall = false;
+  WallId on_wall_id;
+  bool killed = false, reabsorbed = false;
+  int reabsorbed_id = 0;
+  double current_chi[MAX_DUST], current_albedo[MAX_DUST], current_kappa[MAX_DUST];
+  Cell icell;
+  bool last_isotropic = false, scattered = false, reprocessed = false;
+  int n_scat = 0, source_id = 0, dust_id = 0;
+  char last[3] = "  ";
+};
+
+struct Source {
+  int type = 1;
+  bool peeloff = true;
+  double luminosity = 0;
+  Vec position{0, 0, 0};
+  double radius = 0;
+  bool limb_darkening = false;
+  int freq_type = 2;
+  double temperature = 0;
+  PdfCont spectrum;
+  bool intersect = false;
+};
+
+}  // namespace
+
+// ---------------------------------------------------------------------------
+// context: the module-level state of the Fortran program
+// ---------------------------------------------------------------------------
+struct orc_ctx {
+  Rng rng;
+  hyp_run_conf conf;
+  // geometry (grid_geometry_cartesian_3d.f90:77-135)
+  int n1 = 0, n2 = 0, n3 = 0, n_cells = 0;
+  std::vector<double> w1, w2, w3, ew1, ew2, ew3, dx, dy, dz, volume;
+  // find_wall scratch (:29-30)
+  double tmin = 0, emin = 0;
+  WallId imin;
+  // dust
+  int n_dust = 0;
+  std::vector<Dust> d;
+  // grid physics (grid_physics_3d.f90:34-63): (ic, id) stored at [id*n_cells + ic]
+  std::vector<double> density, specific_energy, specific_energy_sum, jnu_var_frac, minimum_specific_energy;
+  std::vector<int> jnu_var_id;
+  std::vector<double> energy_abs_tot;
+  PdfDiscrete absorption;
+  // sources (source.f90:25-44)
+  std::vector<Source> s;
+  PdfDiscrete luminosity;
+  double energy_total = 0, energy_current = 0;
+  bool any_intersect = false;
+  // counters
+  int64_t killed_photons_geo = 0, killed_photons_int = 0;
+  int64_t n_crossings = 0, n_absorptions = 0, n_scatterings = 0, n_escaped = 0, n_photons_run = 0;
+  bool setup_done = false;
+  std::string error;
+};
+
+namespace {
+
+thread_local std::string g_last_error;
+
+double spacing(double x) {
+  // Fortran SPACING(x): distance to the next representable number of larger magnitude
+  if (x == 0.0) return std::numeric_limits<double>::min();
+  double ax = std::fabs(x);
+  return std::nextafter(ax, std::numeric_limits<double>::infinity()) - ax;
+}
+
+// new_grid_cell_3d (type_cell_id_3d.f90:67-75,97-102)
+Cell new_grid_cell(const orc_ctx &g, int i1, int i2, int i3) {
+  Cell c;
+  c.i1 = i1;
+  c.i2 = i2;
+  c.i3 = i3;
+  c.ic = (i3 - 1) * g.n1 * g.n2 + (i2 - 1) * g.n1 + i1;
+  return c;
+}
+
+// escaped_cell (grid_geometry_cartesian_3d.f90:267-275)
+bool escaped(const orc_ctx &g, const Cell &c) {
+  if (c.i1 < 1 || c.i1 > g.n1) return true;
+  if (c.i2 < 1 || c.i2 > g.n2) return true;
+  if (c.i3 < 1 || c.i3 > g.n3) return true;
+  return false;
+}
+
+// find_cell (grid_geometry_cartesian_3d.f90:143-167); returns false for invalid_cell
+bool find_cell(const orc_ctx &g, const Photon &p, Cell &out) {
+  int i1 = locate(g.w1.data(), g.n1 + 1, p.r.x);
+  int i2 = locate(g.w2.data(), g.n2 + 1, p.r.y);
+  int i3 = locate(g.w3.data(), g.n3 + 1, p.r.z);
+  if (i1 < 1 || i1 > g.n1) return false;
+  if (i2 < 1 || i2 > g.n2) return false;
+  if (i3 < 1 || i3 > g.n3) return false;
+  out = new_grid_cell(g, i1, i2, i3);
+  return true;
+}
+
+// adjust_wall (grid_geometry_cartesian_3d.f90:169-237)
+void adjust_wall(const orc_ctx &g, Photon &p) {
+  p.on_wall = false;
+  p.on_wall_id = WallId();
+#define ADJ(V, R, W, I, WID)                   \
+  if (V > 0.0) {                               \
+    if (R == W[I - 1]) {                       \
+      WID = -1;                                \
+    } else if (R == W[I]) {                    \
+      WID = -1;                                \
+      I = I + 1;                               \
+    }                                          \
+  } else if (V < 0.0) {                        \
+    if (R == W[I - 1]) {                       \
+      WID = +1;                                \
+      I = I - 1;                               \
+    } else if (R == W[I]) {                    \
+      WID = +1;                                \
+    }                                          \
+  }
+  ADJ(p.v.x, p.r.x, g.w1, p.icell.i1, p.on_wall_id.w1)
+  ADJ(p.v.y, p.r.y, g.w2, p.icell.i2, p.on_wall_id.w2)
+  ADJ(p.v.z, p.r.z, g.w3, p.icell.i3, p.on_wall_id.w3)
+#undef ADJ
+  // NB: the reference does not refresh icell%ic here (only i1/i2/i3 change).
+  p.on_wall = p.on_wall_id.w1 != 0 || p.on_wall_id.w2 != 0 || p.on_wall_id.w3 != 0;
+}
+
+// place_in_cell (grid_geometry_cartesian_3d.f90:239-259)
+void place_in_cell(orc_ctx &g, Photon &p) {
+  Cell c;
+  if (!find_cell(g, p, c)) {
+    g.killed_photons_geo++;
+    p.killed = true;
+  } else {
+    p.icell = c;
+    p.in_cell = true;
+    adjust_wall(g, p);
+  }
+}
+
+// in_correct_cell (grid_geometry_cartesian_3d.f90:330-381)
+bool in_correct_cell(const orc_ctx &g, const Photon &p) {
+  const double threshold = 1.e-3;
+  Cell act;
+  bool valid = find_cell(g, p, act);
+  if (!valid) act = Cell{-1, -1, -1, -1};  // invalid_cell
+  if (p.on_wall) {
+    bool ok = true;
+    double frac;
+#define CHK(WID, R, W, I, IA)                              \
+  if (WID == -1) {                                         \
+    frac = (R - W[I - 1]) / (W[I] - W[I - 1]);             \
+    ok = ok && std::fabs(frac) < threshold;                \
+  } else if (WID == +1) {                                  \
+    frac = (R - W[I]) / (W[I] - W[I - 1]);                 \
+    ok = ok && std::fabs(frac) < threshold;                \
+  } else {                                                 \
+    ok = ok && IA == I;                                    \
+  }
+    CHK(p.on_wall_id.w1, p.r.x, g.w1, p.icell.i1, act.i1)
+    CHK(p.on_wall_id.w2, p.r.y, g.w2, p.icell.i2, act.i2)
+    CHK(p.on_wall_id.w3, p.r.z, g.w3, p.icell.i3, act.i3)
+#undef CHK
+    return ok;
+  }
+  return act.i1 == p.icell.i1 && act.i2 == p.icell.i2 && act.i3 == p.icell.i3;
+}
+
+// insert_t (grid_geometry_cartesian_3d.f90:482-512)
+inline void insert_t(orc_ctx &g, double t, int iw, int i, double e) {
+  if (t > 0.0) {
+    double emax = e > g.emin ? e : g.emin;
+    if (t < g.tmin - emax) {
+      g.tmin = t;
+      g.imin = WallId();
+      g.emin = emax;
+      if (iw == 1)
+        g.imin.w1 = i;
+      else if (iw == 2)
+        g.imin.w2 = i;
+      else
+        g.imin.w3 = i;
+    } else if (t < g.tmin + emax) {
+      g.emin = emax;
+      if (iw == 1)
+        g.imin.w1 = i;
+      else if (iw == 2)
+        g.imin.w2 = i;
+      else
+        g.imin.w3 = i;
+    }
+  }
+}
+
+// find_wall (grid_geometry_cartesian_3d.f90:424-472), reset_t (:474-480), find_next_wall (:514-521)
+void find_wall(orc_ctx &g, const Photon &p, double &tnearest, WallId &id_min) {
+  g.tmin = std::numeric_limits<double>::max();
+  g.emin = 0.0;
+  g.imin = WallId();
+  if (p.on_wall_id.w1 != -1) {
+    double t1 = (g.w1[p.icell.i1 - 1] - p.r.x) / p.v.x;
+    insert_t(g, t1, 1, -1, g.ew1[p.icell.i1 - 1]);
+  }
+  if (p.on_wall_id.w1 != +1) {
+    double t2 = (g.w1[p.icell.i1] - p.r.x) / p.v.x;
+    insert_t(g, t2, 1, +1, g.ew1[p.icell.i1]);
+  }
+  if (p.on_wall_id.w2 != -1) {
+    double t1 = (g.w2[p.icell.i2 - 1] - p.r.y) / p.v.y;
+    insert_t(g, t1, 2, -1, g.ew2[p.icell.i2 - 1]);
+  }
+  if (p.on_wall_id.w2 != +1) {
+    double t2 = (g.w2[p.icell.i2] - p.r.y) / p.v.y;
+    insert_t(g, t2, 2, +1, g.ew2[p.icell.i2]);
+  }
+  if (p.on_wall_id.w3 != -1) {
+    double t1 = (g.w3[p.icell.i3 - 1] - p.r.z) / p.v.z;
+    insert_t(g, t1, 3, -1, g.ew3[p.icell.i3 - 1]);
+  }
+  if (p.on_wall_id.w3 != +1) {
+    double t2 = (g.w3[p.icell.i3] - p.r.z) / p.v.z;
+    insert_t(g, t2, 3, +1, g.ew3[p.icell.i3]);
+  }
+  tnearest = g.tmin;
+  id_min = g.imin;
+}
+
+// next_cell_wall_id (grid_geometry_cartesian_3d.f90:303-328)
+Cell next_cell(const orc_ctx &g, const Cell &c, const WallId &dir) {
+  int i1 = c.i1, i2 = c.i2, i3 = c.i3;
+  if (dir.w1 == -1)
+    i1 = i1 - 1;
+  else if (dir.w1 == +1)
+    i1 = i1 + 1;
+  if (dir.w2 == -1)
+    i2 = i2 - 1;
+  else if (dir.w2 == +1)
+    i2 = i2 + 1;
+  if (dir.w3 == -1)
+    i3 = i3 - 1;
+  else if (dir.w3 == +1)
+    i3 = i3 + 1;
+  return new_grid_cell(g, i1, i2, i3);
+}
+
+// update_optconsts (dust.f90:64-79)
+void update_optconsts(orc_ctx &g, Photon &p) {
+  for (int id = 0; id < g.n_dust; id++) {
+    const Dust &d = g.d[id];
+    if (p.nu < d.nu[0] || p.nu > d.nu[d.n_nu - 1]) {
+      char buf[256];
+      snprintf(buf, sizeof buf,
+               "photon frequency (%10.4E Hz) is outside the range defined for the dust optical properties "
+               "(%10.4E to %10.4E Hz)",
+               p.nu, d.nu[0], d.nu[d.n_nu - 1]);
+      throw OracleError{buf};
+    }
+    p.current_chi[id] = interp1d_loglog(d.nu.data(), d.chi_nu.data(), d.n_nu, p.nu);
+    p.current_albedo[id] = interp1d_loglog(d.nu.data(), d.albedo_nu.data(), d.n_nu, p.nu);
+    p.current_kappa[id] = p.current_chi[id] * (1.0 - p.current_albedo[id]);
+  }
+}
+
+// quadratic_pascal_reduced_dp (fortranlib/src/lib_algebra.f90:145-164): x^2 + b x + c = 0
+void quadratic_pascal_reduced(double b, double c, double &x1, double &x2) {
+  const double huge = std::numeric_limits<double>::max();
+  double delta = b * b - 4.0 * c;
+  if (delta > 0) {
+    delta = std::sqrt(delta);
+    delta = std::copysign(delta, b);
+    double q = -0.5 * (b + delta);
+    x1 = q;
+    x2 = c / q;
+  } else if (delta < 0) {
+    x1 = -huge;
+    x2 = -huge;
+  } else {
+    x1 = -2.0 * c / b;
+    x2 = -huge;
+  }
+}
+
+// find_nearest_source (source.f90:206-227)
+void find_nearest_source(const orc_ctx &g, const Vec &r, const Vec &v, double &nearest, int &nearest_id) {
+  (void)r;
+  (void)v;
+  nearest_id = 0;
+  nearest = std::numeric_limits<double>::infinity();
+  if (!g.any_intersect) return;
+  // spherical sources are not part of the pinned Cartesian slice yet
+}
+
+// emit_from_point (source_type.f90:539-564)
+void emit_from_point(orc_ctx &g, const Source &src, Photon &p) {
+  p.r = src.position;
+  p.a = random_sphere_angle3d(g.rng);
+  p.s = Stokes{1.0, 0.0, 0.0, 0.0};
+  p.last_isotropic = true;
+}
+
+// emit (source.f90:100-179) + source_emit (source_type.f90:398-511)
+void emit(orc_ctx &g, Photon &p) {
+  p = Photon();
+  int n_sources = (int)g.s.size();
+  if (n_sources == 0) throw OracleError{"no sources to emit from"};
+  if (n_sources > 1) {
+    if (g.conf.sample_sources_evenly) {
+      double xi = g.rng.random();
+      p.source_id = (int)(xi * n_sources) + 1;
+    } else {
+      p.source_id = g.luminosity.sample(g.rng);
+    }
+  } else {
+    p.source_id = 1;
+  }
+  const Source &src = g.s[p.source_id - 1];
+  switch (src.type) {
+    case HYP_SOURCE_POINT:
+      emit_from_point(g, src, p);
+      break;
+    default:
+      throw OracleError{"source type not restated in the oracle"};
+  }
+  p.energy = 1.0;
+  if (src.freq_type == 1)
+    p.nu = src.spectrum.sample(g.rng);
+  else if (src.freq_type == 2)
+    p.nu = g.rng.random_planck_frequency(src.temperature);
+  else
+    throw OracleError{"unknown spectrum type"};
+  p.v = angle3d_to_vector3d(p.a);
+  if (g.conf.sample_sources_evenly) p.energy = p.energy * g.luminosity.pdf[p.source_id - 1] * n_sources;
+  g.energy_current = g.energy_current + p.energy;
+  update_optconsts(g, p);
+  p.last[0] = 's';
+  p.last[1] = 'r';
+  place_in_cell(g, p);
+  if (p.killed)
+    throw OracleError{
+        "photon was not emitted inside a cell - this usually indicates that a source is not inside the grid"};
+}
+
+// grid_integrate (grid_propagate_3d.f90:35-234)
+void grid_integrate(orc_ctx &g, Photon &p, double tau_required, double &tau_achieved) {
+  const double frac_check = g.conf.propagation_check_frequency;
+  tau_achieved = 0.0;
+  if (!p.in_cell) throw OracleError{"photon has not been placed in a cell"};
+  if (escaped(g, p.icell)) return;
+  if (tau_required == 0.0) return;
+  double t_source;
+  int source_id;
+  find_nearest_source(g, p.r, p.v, t_source, source_id);
+  double t_achieved = 0.0;
+  const int nc = g.n_cells;
+  for (;;) {
+    double xi = g.rng.random();
+    if (xi < frac_check) {
+      if (!in_correct_cell(g, p)) {
+        g.killed_photons_geo++;
+        p.killed = true;
+        return;
+      }
+    }
+    double tau_needed = tau_required - tau_achieved;
+    double tmin;
+    WallId id_min;
+    find_wall(g, p, tmin, id_min);
+    if (id_min.w1 == 0 && id_min.w2 == 0 && id_min.w3 == 0) {
+      g.killed_photons_geo++;
+      p.killed = true;
+      return;
+    }
+    // density(p%icell%ic, id): the STORED 1-D id.  adjust_wall changes i1/i2/i3 without
+    // refreshing ic (grid_geometry_cartesian_3d.f90:184-232), so for a photon emitted exactly
+    // on a wall the first segment reads/deposits in the cell find_cell returned.  Restated as is.
+    int ic = p.icell.ic;
+    double chi_rho_total = 0.0;
+    for (int id = 0; id < g.n_dust; id++)
+      chi_rho_total = chi_rho_total + p.current_chi[id] * g.density[(size_t)id * nc + ic - 1];
+    double tau_cell = chi_rho_total * tmin;
+    g.n_crossings++;
+    if (tau_cell < tau_needed) {
+      t_achieved = t_achieved + tmin;
+      if (t_achieved > t_source) {
+        p.reabsorbed = true;
+        p.reabsorbed_id = source_id;
+        return;
+      }
+      p.r.x = p.r.x + tmin * p.v.x;
+      p.r.y = p.r.y + tmin * p.v.y;
+      p.r.z = p.r.z + tmin * p.v.z;
+      tau_achieved = tau_achieved + tau_cell;
+      for (int id = 0; id < g.n_dust; id++) {
+        size_t k = (size_t)id * nc + ic - 1;
+        if (g.density[k] > 0.0)
+          g.specific_energy_sum[k] = g.specific_energy_sum[k] + tmin * p.current_kappa[id] * p.energy;
+      }
+      p.on_wall = true;
+      p.icell = next_cell(g, p.icell, id_min);
+      p.on_wall_id = WallId{-id_min.w1, -id_min.w2, -id_min.w3};  // opposite_wall (grid_geometry_common_3d.f90:40-45)
+      if (escaped(g, p.icell)) return;
+    } else {
+      double tact = tmin * (tau_needed / tau_cell);
+      t_achieved = t_achieved + tact;
+      if (t_achieved > t_source) {
+        p.reabsorbed = true;
+        p.reabsorbed_id = source_id;
+        return;
+      }
+      p.r.x = p.r.x + tact * p.v.x;
+      p.r.y = p.r.y + tact * p.v.y;
+      p.r.z = p.r.z + tact * p.v.z;
+      tau_achieved = tau_achieved + tau_needed;
+      p.on_wall = false;
+      p.on_wall_id = WallId();
+      for (int id = 0; id < g.n_dust; id++) {
+        size_t k = (size_t)id * nc + ic - 1;
+        if (g.density[k] > 0.0)
+          g.specific_energy_sum[k] = g.specific_energy_sum[k] + tact * p.current_kappa[id] * p.energy;
+      }
+      return;
+    }
+  }
+}
+
+// select_dust_chi_rho (grid_physics_3d.f90:87-99)
+int select_dust_chi_rho(orc_ctx &g, const Photon &p) {
+  if (g.n_dust == 1) return 1;
+  int ic = p.icell.ic;
+  for (int id = 0; id < g.n_dust; id++)
+    g.absorption.pdf[id] = p.current_chi[id] * g.density[(size_t)id * g.n_cells + ic - 1];
+  g.absorption.find_cdf();
+  return g.absorption.sample(g.rng);
+}
+
+// interact (dust_interact.f90:22-79)
+void interact(orc_ctx &g, Photon &p) {
+  int id = select_dust_chi_rho(g, p);
+  double albedo = p.current_albedo[id - 1];
+  double xi = g.rng.random();
+  const Dust &d = g.d[id - 1];
+  if (xi > albedo) {
+    // dust_emit (dust_type_4elem.f90:334-354)
+    int ic = p.icell.ic;
+    size_t k = (size_t)(id - 1) * g.n_cells + ic - 1;
+    p.nu = d.sample_j_nu(g.rng, g.jnu_var_id[k], g.jnu_var_frac[k]);
+    p.s = Stokes{1.0, 0.0, 0.0, 0.0};
+    p.a = random_sphere_angle3d(g.rng);
+    p.energy = p.energy * 1.0;
+    update_optconsts(g, p);
+    p.scattered = false;
+    p.reprocessed = true;
+    p.last_isotropic = true;
+    p.dust_id = id;
+    p.last[0] = 'd';
+    p.last[1] = 'e';
+    g.n_absorptions++;
+  } else {
+    dust_scatter(d, g.rng, p.nu, p.a, p.s);
+    p.scattered = true;
+    p.last_isotropic = false;
+    p.dust_id = id;
+    p.last[0] = 'd';
+    p.last[1] = 's';
+    p.n_scat = p.n_scat + 1;
+    g.n_scatterings++;
+  }
+  p.v = angle3d_to_vector3d(p.a);
+}
+
+// update_energy_abs_tot (grid_physics_3d.f90:605-611)
+void update_energy_abs_tot(orc_ctx &g) {
+  for (int id = 0; id < g.n_dust; id++) {
+    double sum = 0.0;
+    for (int ic = 0; ic < g.n_cells; ic++) {
+      size_t k = (size_t)id * g.n_cells + ic;
+      sum = sum + g.specific_energy[k] * g.density[k] * g.volume[ic];
+    }
+    g.energy_abs_tot[id] = sum;
+  }
+}
+
+// check_energy_abs (grid_physics_3d.f90:555-603)
+void check_energy_abs(orc_ctx &g) {
+  for (int id = 0; id < g.n_dust; id++) {
+    const Dust &d = g.d[id];
+    double *e = &g.specific_energy[(size_t)id * g.n_cells];
+    double mn = g.minimum_specific_energy[id];
+    for (int ic = 0; ic < g.n_cells; ic++)
+      if (e[ic] < mn) e[ic] = mn;
+    if (g.conf.enforce_energy_range) {
+      double lo = d.specific_energy[0], hi = d.specific_energy[d.n_e - 1];
+      for (int ic = 0; ic < g.n_cells; ic++)
+        if (e[ic] < lo) e[ic] = lo;
+      for (int ic = 0; ic < g.n_cells; ic++)
+        if (e[ic] > hi) e[ic] = hi;
+    }
+  }
+  update_energy_abs_tot(g);
+}
+
+// update_energy_abs (grid_physics_3d.f90:500-553)
+void update_energy_abs(orc_ctx &g, double scale) {
+  for (int id = 0; id < g.n_dust; id++)
+    for (int ic = 0; ic < g.n_cells; ic++) {
+      size_t k = (size_t)id * g.n_cells + ic;
+      g.specific_energy[k] = g.specific_energy_sum[k] * scale / g.volume[ic];
+      if (g.volume[ic] == 0.0) g.specific_energy[k] = 0.0;
+    }
+  update_energy_abs_tot(g);
+  check_energy_abs(g);
+}
+
+// sublimate_dust (grid_physics_3d.f90:420-498)
+void sublimate_dust(orc_ctx &g) {
+  for (int id = 0; id < g.n_dust; id++) {
+    const Dust &d = g.d[id];
+    double *e = &g.specific_energy[(size_t)id * g.n_cells];
+    double *rho = &g.density[(size_t)id * g.n_cells];
+    switch (d.sublimation_mode) {
+      case 1:
+        for (int ic = 0; ic < g.n_cells; ic++)
+          if (e[ic] > d.sublimation_specific_energy) {
+            rho[ic] = 0.;
+            e[ic] = g.minimum_specific_energy[id];
+          }
+        break;
+      case 2:
+        for (int ic = 0; ic < g.n_cells; ic++)
+          if (e[ic] > d.sublimation_specific_energy) {
+            double cr1 = interp1d_loglog(d.specific_energy.data(), d.chi_rosseland.data(), d.n_e, e[ic]);
+            double cr2 = interp1d_loglog(d.specific_energy.data(), d.chi_rosseland.data(), d.n_e,
+                                         d.sublimation_specific_energy);
+            double q = cr1 / cr2;
+            rho[ic] = rho[ic] * d.sublimation_specific_energy / e[ic] * (q * q);
+            e[ic] = d.sublimation_specific_energy;
+          }
+        break;
+      case 3:
+        for (int ic = 0; ic < g.n_cells; ic++)
+          if (e[ic] > d.sublimation_specific_energy) e[ic] = d.sublimation_specific_energy;
+        break;
+      default:
+        break;
+    }
+  }
+  update_energy_abs_tot(g);
+  check_energy_abs(g);
+}
+
+// precompute_jnu_var (grid_physics_3d.f90:613-629)
+void precompute_jnu_var(orc_ctx &g) {
+  for (int ic = 0; ic < g.n_cells; ic++)
+    for (int id = 0; id < g.n_dust; id++) {
+      size_t k = (size_t)id * g.n_cells + ic;
+      g.d[id].jnu_var_pos_frac(g.specific_energy[k], g.jnu_var_id[k], g.jnu_var_frac[k]);
+    }
+}
+
+// the photon loop of do_lucy (iter_lucy.f90:127-205)
+void lucy_photons(orc_ctx &g, int64_t n_photons) {
+  Photon p;
+  const int64_t n_inter_max = g.conf.n_inter_max;
+  for (int64_t ip = 1; ip <= n_photons; ip++) {
+    emit(g, p);
+    g.n_photons_run++;
+    for (int64_t interactions = 1; interactions <= n_inter_max + 1; interactions++) {
+      double tau = g.rng.random_exp();
+      double tau_achieved;
+      grid_integrate(g, p, tau, tau_achieved);
+      if (p.reabsorbed) throw OracleError{"source re-absorption not restated in the oracle"};
+      if (p.killed || escaped(g, p.icell)) {
+        if (!p.killed) g.n_escaped++;
+        break;
+      }
+      if (interactions == n_inter_max + 1) {
+        g.killed_photons_int++;
+        p.killed = true;
+        break;
+      }
+      interact(g, p);
+      p.killed = (g.conf.kill_on_scatter && p.scattered) || (g.conf.kill_on_absorb && !p.scattered);
+      if (p.killed) break;
+    }
+  }
+}
+
+int fail(orc_ctx *g, const std::string &m) {
+  g_last_error = m;
+  if (g) g->error = m;
+  return HYP_ERR_INVALID;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------
+// C API (mirrors include/hyperion_b200.h with the orc_ prefix)
+// ---------------------------------------------------------------------------
+extern "C" {
+
+const char *orc_last_error(void) { return g_last_error.c_str(); }
+
+int orc_ctx_create(orc_ctx **out) {
+  *out = new orc_ctx();
+  hyp_run_conf &c = (*out)->conf;
+  memset(&c, 0, sizeof c);
+  c.seed = -124902;
+  c.n_inter_max = 1000000;
+  c.n_reabs_max = 1000000;
+  c.enforce_energy_range = 1;
+  c.propagation_check_frequency = 1.e-3;
+  return 0;
+}
+
+void orc_ctx_destroy(orc_ctx *g) { delete g; }
+
+int orc_set_grid_cartesian(orc_ctx *g, int32_t n1, int32_t n2, int32_t n3, const double *w1, const double *w2,
+                           const double *w3) {
+  g->n1 = n1;
+  g->n2 = n2;
+  g->n3 = n3;
+  g->n_cells = n1 * n2 * n3;
+  g->w1.assign(w1, w1 + n1 + 1);
+  g->w2.assign(w2, w2 + n2 + 1);
+  g->w3.assign(w3, w3 + n3 + 1);
+  g->dx.resize(n1);
+  g->dy.resize(n2);
+  g->dz.resize(n3);
+  for (int i = 0; i < n1; i++) g->dx[i] = w1[i + 1] - w1[i];
+  for (int i = 0; i < n2; i++) g->dy[i] = w2[i + 1] - w2[i];
+  for (int i = 0; i < n3; i++) g->dz[i] = w3[i + 1] - w3[i];
+  g->volume.resize(g->n_cells);
+  for (int i3 = 0; i3 < n3; i3++)
+    for (int i2 = 0; i2 < n2; i2++)
+      for (int i1 = 0; i1 < n1; i1++)
+        g->volume[(size_t)i3 * n1 * n2 + i2 * n1 + i1] = g->dx[i1] * g->dy[i2] * g->dz[i3];
+  g->ew1.resize(n1 + 1);
+  g->ew2.resize(n2 + 1);
+  g->ew3.resize(n3 + 1);
+  for (int i = 0; i <= n1; i++) g->ew1[i] = 3 * spacing(w1[i]);
+  for (int i = 0; i <= n2; i++) g->ew2[i] = 3 * spacing(w2[i]);
+  for (int i = 0; i <= n3; i++) g->ew3[i] = 3 * spacing(w3[i]);
+  return 0;
+}
+
+int orc_add_dust(orc_ctx *g, const hyp_dust_tables *t) {
+  try {
+    g->d.emplace_back();
+    g->d.back().setup(*t);
+    g->n_dust = (int)g->d.size();
+    if (g->n_dust > MAX_DUST) return fail(g, "too many dust types");
+  } catch (OracleError &e) {
+    return fail(g, e.msg);
+  }
+  return 0;
+}
+
+int orc_add_source(orc_ctx *g, const hyp_source *s) {
+  try {
+    Source src;
+    src.type = s->type;
+    src.peeloff = s->peeloff != 0;
+    src.luminosity = s->luminosity;
+    src.position = Vec{s->x, s->y, s->z};
+    src.radius = s->radius;
+    src.limb_darkening = s->limb_darkening != 0;
+    src.freq_type = s->spectrum_type;
+    src.temperature = s->temperature;
+    if (s->spectrum_type == HYP_SPECTRUM_TABLE) {
+      for (int i = 0; i + 1 < s->n_spec; i++)
+        if (s->spec_nu[i + 1] < s->spec_nu[i])
+          return fail(g, "spectrum frequency should be monotonically increasing");
+      src.spectrum.set(s->spec_nu, s->spec_fnu, s->n_spec, true);
+    }
+    src.intersect = (s->type == HYP_SOURCE_SPHERE);
+    if (src.intersect) g->any_intersect = true;
+    g->s.push_back(src);
+  } catch (OracleError &e) {
+    return fail(g, e.msg);
+  }
+  return 0;
+}
+
+int orc_set_run_conf(orc_ctx *g, const hyp_run_conf *c) {
+  g->conf = *c;
+  return 0;
+}
+
+int orc_set_density(orc_ctx *g, int32_t n_dust, const double *density) {
+  if (n_dust != g->n_dust) return fail(g, "density array has wrong number of dust types");
+  g->density.assign(density, density + (size_t)n_dust * g->n_cells);
+  return 0;
+}
+
+int orc_set_specific_energy(orc_ctx *g, const double *se, const double *min_e) {
+  size_t n = (size_t)g->n_dust * g->n_cells;
+  g->minimum_specific_energy.assign(g->n_dust, 0.0);
+  if (min_e)
+    for (int id = 0; id < g->n_dust; id++) g->minimum_specific_energy[id] = min_e[id];
+  g->specific_energy.resize(n);
+  if (se) {
+    g->specific_energy.assign(se, se + n);
+  } else {
+    for (int id = 0; id < g->n_dust; id++)
+      for (int ic = 0; ic < g->n_cells; ic++)
+        g->specific_energy[(size_t)id * g->n_cells + ic] = g->minimum_specific_energy[id];
+  }
+  return 0;
+}
+
+// the remaining steps of setup_initial (setup_rt.f90:27-304) and main.f90:157-167
+int orc_finalize_setup(orc_ctx *g, int32_t rank) {
+  try {
+    size_t n = (size_t)g->n_dust * g->n_cells;
+    if (g->density.size() != n) return fail(g, "density not set");
+    if (g->specific_energy.size() != n) orc_set_specific_energy(g, nullptr, nullptr);
+    g->specific_energy_sum.assign(n, 0.0);
+    g->jnu_var_id.assign(n, 0);
+    g->jnu_var_frac.assign(n, 0.0);
+    g->energy_abs_tot.assign(g->n_dust, 0.0);
+    g->absorption.n = g->n_dust;
+    g->absorption.pdf.assign(g->n_dust, 0.0);
+    g->absorption.cdf.assign(g->n_dust, 0.0);
+    check_energy_abs(*g);  // setup_grid_physics (grid_physics_3d.f90:291)
+    if (!g->s.empty()) {
+      std::vector<double> lum;
+      for (auto &s : g->s) lum.push_back(s.luminosity);
+      g->luminosity.set(lum.data(), (int)lum.size());
+      double tot = 0.0;
+      for (double l : lum) tot = tot + l;
+      g->energy_total = tot;
+    }
+    g->rng.set_seed((int)(g->conf.seed + rank));  // mp_set_random_seed (mpi_routines.f90:266-270)
+    g->setup_done = true;
+  } catch (OracleError &e) {
+    return fail(g, e.msg);
+  }
+  return 0;
+}
+
+// do_lucy, first part (iter_lucy.f90:99-112)
+int orc_lucy_begin(orc_ctx *g) {
+  std::fill(g->specific_energy_sum.begin(), g->specific_energy_sum.end(), 0.0);
+  g->energy_current = 0.0;
+  g->killed_photons_geo = g->killed_photons_int = 0;
+  g->n_crossings = g->n_absorptions = g->n_scatterings = g->n_escaped = g->n_photons_run = 0;
+  precompute_jnu_var(*g);
+  return 0;
+}
+
+int orc_lucy_photons(orc_ctx *g, int64_t n_photons) {
+  try {
+    lucy_photons(*g, n_photons);
+  } catch (OracleError &e) {
+    g_last_error = e.msg;
+    g->error = e.msg;
+    return HYP_ERR_PHYSICS;
+  }
+  return 0;
+}
+
+// accessors used to emulate mp_collect_physical_arrays / mp_sync across oracle "ranks"
+double *orc_energy_sum_ptr(orc_ctx *g) { return g->specific_energy_sum.data(); }
+double orc_get_energy_current(orc_ctx *g) { return g->energy_current; }
+void orc_set_energy_current(orc_ctx *g, double e) { g->energy_current = e; }
+
+// do_lucy, last part (iter_lucy.f90:224-235)
+int orc_lucy_finish(orc_ctx *g, hyp_iter_stats *st) {
+  try {
+    update_energy_abs(*g, g->energy_total / g->energy_current);
+    sublimate_dust(*g);
+  } catch (OracleError &e) {
+    return fail(g, e.msg);
+  }
+  if (st) {
+    memset(st, 0, sizeof *st);
+    st->energy_emitted = g->energy_current;
+    st->n_photons = g->n_photons_run;
+    st->killed_geo = g->killed_photons_geo;
+    st->killed_int = g->killed_photons_int;
+    st->n_crossings = g->n_crossings;
+    st->n_absorptions = g->n_absorptions;
+    st->n_scatterings = g->n_scatterings;
+    st->n_escaped = g->n_escaped;
+  }
+  return 0;
+}
+
+int orc_run_lucy_iteration(orc_ctx *g, int64_t n_photons, hyp_iter_stats *st) {
+  int rc = orc_lucy_begin(g);
+  if (rc) return rc;
+  rc = orc_lucy_photons(g, n_photons);
+  if (rc) return rc;
+  return orc_lucy_finish(g, st);
+}
+
+int orc_get_specific_energy(orc_ctx *g, double *out) {
+  memcpy(out, g->specific_energy.data(), g->specific_energy.size() * sizeof(double));
+  return 0;
+}
+int orc_get_density(orc_ctx *g, double *out) {
+  memcpy(out, g->density.data(), g->density.size() * sizeof(double));
+  return 0;
+}
+int orc_get_energy_sum(orc_ctx *g, double *out) {
+  memcpy(out, g->specific_energy_sum.data(), g->specific_energy_sum.size() * sizeof(double));
+  return 0;
+}
+int orc_set_energy_sum(orc_ctx *g, const double *in) {
+  memcpy(g->specific_energy_sum.data(), in, g->specific_energy_sum.size() * sizeof(double));
+  return 0;
+}
+
+// unit-test hooks for the numerics
+double orc_test_random(orc_ctx *g) { return g->rng.random(); }
+int orc_test_locate(const double *xx, int n, double x) { return locate(xx, n, x); }
+double orc_test_interp1d_loglog(const double *x, const double *y, int n, double xv) {
+  try {
+    return interp1d_loglog(x, y, n, xv);
+  } catch (OracleError &) {
+    return std::nan("");
+  }
+}
+double orc_test_planck(orc_ctx *g, double T) { return g->rng.random_planck_frequency(T); }
+uint64_t orc_rng_draws(orc_ctx *g) { return g->rng.n_draws; }
+
+}  // extern "C"

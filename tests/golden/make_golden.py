@@ -1,0 +1,87 @@
+"""Regenerate the committed golden fixtures from the reference checkout.
+
+Run in the build container (needs /root/reference; never at test time):
+
+    python tests/golden/make_golden.py
+
+Writes tests/golden/bitlevel_car.npz holding
+  * the inputs of hyperion/model/tests/test_bit_level.py::TestBasic::test_specific_energy
+    for grid_type='car' (walls, the three random density grids, five random point
+    sources -- regenerated with the same numpy legacy seeds 141412 / 12345 the
+    reference test uses, test_bit_level.py:37-42,141-155),
+  * the dust tables of hyperion/model/tests/data/kmh_lite.hdf5,
+  * the reference's own outputs: specific_energy of all 5 Lucy iterations from the
+    four golden files test_specific_energy.grid_type=car.*.rtout.
+"""
+import os
+import runpy
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "..", ".."))
+
+from hyperion_b200.io import h5min  # noqa: E402
+from hyperion_b200.flatmodel import FlatDust  # noqa: E402
+
+REF = "/root/reference"
+DATA = os.path.join(REF, "hyperion/model/tests/data")
+const = runpy.run_path(os.path.join(REF, "hyperion/util/constants.py"))
+pc, lsun = const["pc"], const["lsun"]
+
+
+def setup_all_grid_types(u, d):
+    """test_bit_level.py:37-113 (only the random-number consumption order matters)."""
+    np.random.seed(141412)
+    out = {}
+    # AMR level 1 and 2 quantities come first
+    for shape in [(4, 6, 8)] * 3 + [(20, 6, 4)] * 3:
+        np.random.random(shape)
+    shapes = {"car": (3, 5, 7), "cyl": (5, 3, 7), "sph": (3, 7, 5), "oct": (25,)}
+    for k in ("density", "density_2", "density_3"):
+        for g in ("car", "cyl", "sph"):
+            out[(k, g)] = np.random.random(shapes[g]) * d
+        out[(k, "oct")] = np.random.random(25) * d
+    return out
+
+
+def sources():
+    """test_bit_level.py:141-155"""
+    np.random.seed(12345)
+    src = []
+    for i in range(5):
+        lum = np.random.random() * lsun
+        temp = np.random.uniform(2000., 10000.)
+        pos = np.random.uniform(-pc, pc, 3)
+        src.append((lum, temp, pos))
+    return src
+
+
+def main():
+    dens = setup_all_grid_types(pc, 1.e-20)
+    out = {
+        "w1": np.linspace(-pc, pc, 8), "w2": np.linspace(-pc, pc, 6), "w3": np.linspace(-pc, pc, 4),
+        "density_1": dens[("density", "car")], "density_2": dens[("density_2", "car")],
+        "density_3": dens[("density_3", "car")],
+    }
+    src = sources()
+    out["source_luminosity"] = np.array([s[0] for s in src])
+    out["source_temperature"] = np.array([s[1] for s in src])
+    out["source_position"] = np.array([s[2] for s in src])
+    dust = FlatDust.from_hdf5_group(h5min.File(os.path.join(DATA, "kmh_lite.hdf5")))
+    out.update(dust.to_npz_dict("dust_"))
+    for evenly in (False, True):
+        for multi in (False, True):
+            fn = ("test_specific_energy.grid_type=car.sample_sources_evenly=%s."
+                  "multiple_densities=%s.rtout" % (evenly, multi))
+            f = h5min.File(os.path.join(DATA, fn))
+            se = np.array([f["iteration_%05d/specific_energy" % i][...] for i in range(1, 6)])
+            out["expected_evenly=%s_multi=%s" % (evenly, multi)] = se
+            assert int(f.attrs["iterations"]) == 5
+    np.savez_compressed(os.path.join(HERE, "bitlevel_car.npz"), **out)
+    print("wrote", os.path.join(HERE, "bitlevel_car.npz"))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,31 @@
+"""Shared model builders for the tests."""
+import os
+
+import numpy as np
+
+from hyperion_b200.flatmodel import FlatConf, FlatDust, FlatModel, FlatSource
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+pc = 3.08568025e18     # hyperion/util/constants.py
+lsun = 3.846e33
+
+
+def kmh_dust(z):
+    return FlatDust.from_npz_dict(z, "dust_")
+
+
+def bitlevel_model(z, evenly, multi):
+    """hyperion/model/tests/test_bit_level.py::TestBasic::test_specific_energy, grid_type='car'."""
+    dust = kmh_dust(z)
+    dens = [z["density_1"]] + ([z["density_2"], z["density_3"]] if multi else [])
+    srcs = [FlatSource(type=1, luminosity=float(l), temperature=float(t), position=tuple(p))
+            for l, t, p in zip(z["source_luminosity"], z["source_temperature"], z["source_position"])]
+    return FlatModel(z["w1"], z["w2"], z["w3"], np.array(dens), [dust] * len(dens), srcs,
+                     FlatConf(sample_sources_evenly=evenly))
+
+
+def ulp_diff(a, b):
+    """Distance in units in the last place, as hyperion/model/tests/test_helpers.py:59-144 measures it."""
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    return np.abs(a - b) / np.spacing(np.maximum(np.abs(a), np.abs(b)))
