@@ -1,0 +1,335 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: photon packets/sec for one Lucy iteration on a 256^3
+Cartesian grid (BASELINE.json metric), one process per GPU.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+A "step" is one Lucy iteration (src/main/iter_lucy.f90:66-237) over a fixed batch of
+synthetic photon packets per GPU (weak scaling): reset + jnu_var precompute, the photon
+kernel, the all-reduce of the deposit grid (N > 1), the scale/clamp epilogue.
+
+Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for how each field is derived.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from hyperion_b200 import synthetic as syn  # noqa: E402
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--grid", type=int, default=256, help="cells per axis")
+    ap.add_argument("--photons", type=float, default=2.0e7, help="packets per GPU per step")
+    ap.add_argument("--tau", type=float, default=1.0, help="centre-to-face optical depth at 0.5 micron")
+    ap.add_argument("--cpu-photons", type=float, default=0, help="packets for the CPU sample (0 = auto)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def workload_name(a):
+    return "cartesian_%d^3_point_source_6000K_isotropic_dust_tau%.3g" % (a.grid, a.tau)
+
+
+def build_model(a):
+    dust = syn.realistic_dust(n_temp=1200)
+    return syn.cartesian_point_source_model(n=a.grid, tau_edge=a.tau, dust=dust, seed=1)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clock/throttle sampling during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                       "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.f:
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                mx.append(float(parts[2]))
+            except ValueError:
+                continue
+            for nme, v in zip(names, parts[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nme)
+        os.unlink(self.f.name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+class DevBuf:
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (ptr, False), "version": 2}
+
+
+def cpu_sample(model, n_photons, cores):
+    """Time the CPU restatement of the Fortran path (oracle/) the way the reference runs under
+    MPI: `cores` ranks seeded seed+r, equal split, deposit grids summed (src/mpi/mpi_routines.f90)."""
+    from oracle import oracle
+    oracle.build()
+    t0 = time.time()
+    ranks = [oracle.Oracle(model, rank=r) for r in range(cores)]
+    t_setup = time.time() - t0
+    from concurrent.futures import ThreadPoolExecutor
+    split = [n_photons // cores + (1 if r < n_photons % cores else 0) for r in range(cores)]
+    for o in ranks:
+        o.lucy_begin()
+    t0 = time.time()
+    with ThreadPoolExecutor(max_workers=cores) as pool:
+        list(pool.map(lambda x: x[0].lucy_photons(x[1]), zip(ranks, split)))
+    dt = time.time() - t0
+    cross = 0
+    e_cur = sum(o.energy_current for o in ranks)
+    for o in ranks:
+        o.energy_current = e_cur
+        cross += o.lucy_finish().n_crossings
+    return n_photons / dt, dt, t_setup, cross
+
+
+def run_reference(a):
+    """--impl reference: the reference's CPU implementation of the path, all host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    model = build_model(a)
+    n = int(a.cpu_photons) if a.cpu_photons else 0
+    if n == 0:
+        rate, dt, _, _ = cpu_sample(model, 20000 * cores, cores)
+        n = int(max(20000 * cores, min(rate * 15.0, 5e7)))
+    times, cross = [], 0
+    for i in range(a.warmup + a.steps):
+        rate, dt, t_setup, cr = cpu_sample(model, n, cores)
+        if i >= a.warmup:
+            times.append(dt)
+            cross += cr
+        if sum(times) > 240:
+            break
+    steps = len(times)
+    T = sum(times)
+    value = n * steps / T
+    line = {
+        "impl": "reference", "metric": "photon_packets_per_sec", "value": value, "unit": "packets/s",
+        "n_gpus": a.gpus, "steps": steps, "warmup": a.warmup, "ms_per_step": 1e3 * T / steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(a), "grid": [a.grid] * 3, "n_dust": 1,
+                   "photons_per_step": n, "note": "bounded CPU sample of the same model"},
+        "cpu_baseline": {"value": value, "unit": "packets/s", "cores": cores, "kind": "port",
+                         "sample": "%d packets/step x %d steps on %d threads (rank r seeded seed+r, grids summed)"
+                                   % (n, steps, cores)},
+        "e2e": {"value": value, "unit": "packets/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "crossings_per_packet": cross / (n * steps),
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+        return
+    import torch
+    import torch.distributed as dist
+    import __graft_entry__ as ge
+    from hyperion_b200.capi import Engine
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the engine has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if rank == 0:
+        ge.build()
+    if world > 1:
+        dist.barrier()
+
+    model = build_model(a)
+    P = int(a.photons)
+    eng = Engine(local)
+    eng.load_model(model)
+    stream = torch.cuda.ExternalStream(eng.stream, device=torch.device("cuda", local))
+    ptr, nval = eng.lucy_device_buffers()
+    sums = torch.as_tensor(DevBuf(ptr, nval), device=torch.device("cuda", local))
+    launches = {"n": 0}
+
+    def step(it):
+        eng.lucy_begin()
+        eng.lucy_photons(rank * P + it * world * P, P, it + 1)
+        launches["n"] += 2
+        if world > 1:
+            eng.lucy_device_buffers()   # gathers the record-interleaved sums into the contiguous buffer
+            with torch.cuda.stream(stream):
+                dist.all_reduce(sums)
+            stream.synchronize()
+        st = eng.lucy_finish()
+        launches["n"] += 2              # gather + finish kernels
+        return st
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for it in range(a.warmup):
+        step(it)
+    sync_all()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches["n"] = 0
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    stats = []
+    for it in range(a.steps):
+        stats.append(step(a.warmup + it))
+    e1.record(stream)
+    sync_all()
+    clocks = sampler.stop() if rank == 0 else None
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    total_ms = float(ms.item())
+    gpu_launches = launches["n"]
+
+    # roofline of the photon kernel (this rank; after the all-reduce the counters are global)
+    cross = sum(s.n_crossings for s in stats)
+    nabs = sum(s.n_absorptions for s in stats)
+    nscat = sum(s.n_scatterings for s in stats)
+    kern_ms = sum(s.kernel_ms for s in stats)
+    div = world if world > 1 else 1   # counters were all-reduced with the grid
+    alg_bytes = (24.0 * eng.n_dust * cross + 12.0 * nabs) / div
+    peak, peak_kind = peaks()
+    achieved = alg_bytes / (kern_ms * 1e-3) / 1e9 if kern_ms > 0 else 0.0
+
+    # end-to-end through the public API with host buffers (H2D density, D2H specific_energy)
+    e2e = None
+    if not a.no_e2e:
+        n_el = eng.n_dust * eng.n_cells
+        h_rho = torch.empty(n_el, dtype=torch.float64).pin_memory()
+        h_rho.numpy()[:] = model.density.ravel()
+        h_out = torch.empty(n_el, dtype=torch.float64).pin_memory()
+        out_np = h_out.numpy().reshape((eng.n_dust,) + tuple(eng.shape))
+
+        def e2e_step(it):
+            eng.update_density(h_rho.numpy())
+            step(it)
+            eng.get_specific_energy(out_np)
+
+        e2e_step(10_000)
+        sync_all()
+        t0 = torch.cuda.Event(enable_timing=True)
+        t1 = torch.cuda.Event(enable_timing=True)
+        k2 = max(1, min(a.steps, 3))
+        t0.record(stream)
+        for it in range(k2):
+            e2e_step(20_000 + it)
+        t1.record(stream)
+        sync_all()
+        ms2 = torch.tensor([t0.elapsed_time(t1)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
+        e2e = {"value": P * world * k2 / (float(ms2.item()) * 1e-3), "unit": "packets/s",
+               "h2d_bytes_per_step": int(n_el * 8), "d2h_bytes_per_step": int(n_el * 8), "steps": k2}
+
+    cpu = None
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        n = int(a.cpu_photons) if a.cpu_photons else 0
+        if n == 0:
+            rate, _, _, _ = cpu_sample(model, 10000 * cores, cores)
+            n = int(max(10000 * cores, min(rate * 15.0, 5e7)))
+        rate, dt, t_setup, cr = cpu_sample(model, n, cores)
+        cpu = {"value": rate, "unit": "packets/s", "cores": cores, "kind": "port",
+               "sample": "%d packets of the same model in %.1f s on %d threads (rank r seeded seed+r, grids summed)"
+                         % (n, dt, cores),
+               "crossings_per_packet": cr / n}
+
+    if rank == 0:
+        value = P * world * a.steps / (total_ms * 1e-3)
+        line = {
+            "metric": "photon_packets_per_sec", "value": value, "unit": "packets/s",
+            "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": total_ms / a.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": workload_name(a), "grid": [a.grid] * 3, "n_dust": eng.n_dust,
+                       "photons_per_gpu_per_step": P, "tau_centre_to_face": a.tau,
+                       "dust": "9-point realistic table, isotropic, LTE emissivities 1200 states",
+                       "cache": "cell records 16 B x n_cells = %.0f MB > 126 MB L2 (no flush needed)"
+                                % (16e-6 * eng.n_cells * eng.n_dust)
+                       if 16 * eng.n_cells * eng.n_dust > 126e6 else "working set fits L2"},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": None, "peak_kind": peak_kind,
+                         "bytes_per_crossing": 24 * eng.n_dust, "kernel": "lucy_photon_kernel",
+                         "kernel_ms_per_step": kern_ms / a.steps},
+            "crossings_per_packet": cross / div / (P * a.steps),
+            "absorptions_per_packet": nabs / div / (P * a.steps),
+            "scatterings_per_packet": nscat / div / (P * a.steps),
+            "gpu_launches": gpu_launches,
+            "clocks": clocks,
+        }
+        if e2e:
+            line["e2e"] = e2e
+        if cpu:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line), flush=True)
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

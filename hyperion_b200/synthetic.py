@@ -1,0 +1,189 @@
+"""Synthetic inputs for tests and benchmarks (no HDF5, no astropy needed).
+
+Produces the same kind of tables the reference's Python front end writes into a
+dust file, following the published recipe:
+
+* isotropic / Henyey-Greenstein scattering matrices
+  (``hyperion/dust/dust_type.py:35-40,525-585``),
+* Planck / reciprocal-Planck / Rosseland mean opacities and
+  ``specific_energy = 4 sigma T^4 kappa_P`` (``hyperion/dust/mean_opacities.py:30-110``),
+* LTE emissivities ``j_nu = kappa_nu B_nu(T)`` on the merged frequency grid
+  (``hyperion/dust/emissivities.py:33-65``, ``hyperion/util/functions.py:111-152``).
+
+and the synthetic grids BASELINE.json names.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from .flatmodel import FlatConf, FlatDust, FlatModel, FlatSource
+
+# cgs constants, hyperion/util/constants.py
+h = 6.626068e-27
+k = 1.3806503e-16
+c = 2.99792458e10
+sigma = 5.67051e-5
+pc = 3.08568025e18
+lsun = 3.846e33
+rsun = 6.95508e10
+au = 1.49598e13
+
+
+def planck_nu_range(tmin, tmax):
+    alpha = 2.821439
+    nu_min = np.log10(alpha / h * k * tmin / 100.)
+    nu_max = np.log10(alpha / h * k * tmax * 10.)
+    n_nu = int((nu_max - nu_min) * 100.)
+    return np.logspace(nu_min, nu_max, n_nu)
+
+
+def nu_common(nu1, nu2):
+    nu = np.sort(np.hstack([nu1, nu2]))
+    keep = np.hstack([(nu[1:] - nu[:-1]) / nu[:-1] > 1.e-10, True])
+    return nu[keep]
+
+
+def B_nu(nu, T):
+    x = h * nu / k / T
+    f = np.zeros(nu.shape)
+    main = (1.e-8 <= x) & (x < 700.)
+    f[main] = 2. * h * nu[main] ** 3. / c ** 2. / np.expm1(x[main])
+    small = x < 1.e-8
+    f[small] = 2. * h * nu[small] ** 3. / c ** 2. / x[small]
+    return f
+
+
+def dB_nu_dT(nu, T):
+    b = B_nu(nu, T)
+    x = h * nu / k / T
+    f = np.zeros(nu.shape)
+    main = x >= 1.e-14
+    f[main] = x[main] / T / (-np.expm1(-x[main])) * b[main]
+    f[~main] = b[~main] / T
+    return f
+
+
+def interp_loglog(x, y, xv):
+    with np.errstate(divide="ignore"):
+        ly = np.log10(y)
+    out = 10. ** np.interp(np.log10(xv), np.log10(x), ly)
+    return out
+
+
+def integrate_loglog(x, y):
+    """Integral of a piecewise power law (zero segments where y is zero)."""
+    x1, x2, y1, y2 = x[:-1], x[1:], y[:-1], y[1:]
+    ok = (y1 > 0) & (y2 > 0) & (x2 > x1)
+    out = np.zeros(len(x) - 1)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        b = np.log10(y1[ok] / y2[ok]) / np.log10(x1[ok] / x2[ok])
+        near = np.abs(b + 1.) < 1.e-10
+        seg = np.where(near, x1[ok] * y1[ok] * np.log(x2[ok] / x1[ok]),
+                       y1[ok] * (x2[ok] * (x2[ok] / x1[ok]) ** b - x1[ok]) / (b + 1.))
+    out[ok] = seg
+    return out.sum()
+
+
+def make_dust(nu, albedo, chi, g=None, p_lin_max=None, n_temp=1200, temp_min=0.1, temp_max=100000.,
+              sublimation_mode=0, sublimation_specific_energy=0.0):
+    """IsotropicDust (g is None) or HenyeyGreensteinDust with LTE emissivities."""
+    nu = np.asarray(nu, dtype=float)
+    albedo = np.asarray(albedo, dtype=float)
+    chi = np.asarray(chi, dtype=float)
+    order = np.argsort(nu)
+    nu, albedo, chi = nu[order], albedo[order], chi[order]
+    if g is None:
+        mu = np.linspace(-1., 1., 2)
+        P1 = np.ones((len(nu), 2))
+        P2 = np.zeros((len(nu), 2))
+        P3 = np.ones((len(nu), 2))
+        P4 = np.zeros((len(nu), 2))
+    else:
+        gg = np.broadcast_to(np.asarray(g, dtype=float), nu.shape)[order][:, None]
+        pl = np.broadcast_to(np.asarray(p_lin_max, dtype=float), nu.shape)[order][:, None]
+        mu = np.linspace(-1., 1., 100)
+        m = mu[None, :]
+        P1 = (1. - gg * gg) / (1. + gg * gg - 2. * gg * m) ** 1.5
+        P2 = -pl * P1 * (1. - m * m) / (1. + m * m)
+        P3 = P1 * 2. * m / (1. + m * m)
+        P4 = np.zeros_like(P1)
+    kappa = chi * (1. - albedo)
+
+    temperatures = np.logspace(np.log10(temp_min), np.log10(temp_max), n_temp)
+    temperatures[0], temperatures[-1] = temp_min, temp_max
+    pn = planck_nu_range(temp_min, temp_max)
+    nuc = nu_common(pn, nu)
+    nuc = nuc[(nuc >= nu.min()) & (nuc <= nu.max())]
+    chi_c = interp_loglog(nu, chi, nuc)
+    kap_c = interp_loglog(nu, kappa, nuc)
+    n = len(temperatures)
+    chi_p, kap_p, chi_ip, kap_ip, chi_r, kap_r = (np.zeros(n) for _ in range(6))
+    jnu = np.zeros((len(nuc), n))
+    with np.errstate(divide="ignore", invalid="ignore"):
+        for it, T in enumerate(temperatures):
+            b = B_nu(nuc, T)
+            db = dB_nu_dT(nuc, T)
+            ib = integrate_loglog(nuc, b)
+            chi_p[it] = integrate_loglog(nuc, b * chi_c) / ib
+            kap_p[it] = integrate_loglog(nuc, b * kap_c) / ib
+            chi_ip[it] = ib / integrate_loglog(nuc, np.where(chi_c > 0, b / chi_c, 0.))
+            kap_ip[it] = ib / integrate_loglog(nuc, np.where(kap_c > 0, b / kap_c, 0.))
+            idb = integrate_loglog(nuc, db)
+            chi_r[it] = idb / integrate_loglog(nuc, np.where(chi_c > 0, db / chi_c, 0.))
+            kap_r[it] = idb / integrate_loglog(nuc, np.where(kap_c > 0, db / kap_c, 0.))
+            jnu[:, it] = kap_c * b
+    specific_energy = 4. * sigma * temperatures ** 4. * kap_p
+    d = FlatDust(nu=nu, albedo=albedo, chi=chi, mu=mu, P1=P1, P2=P2, P3=P3, P4=P4,
+                 specific_energy=specific_energy, chi_planck=chi_p, kappa_planck=kap_p,
+                 chi_inv_planck=chi_ip, kappa_inv_planck=kap_ip, chi_rosseland=chi_r, kappa_rosseland=kap_r,
+                 emiss_nu=nuc, emiss_jnu=jnu, jnu_var=specific_energy, version=2, is_lte=True,
+                 sublimation_mode=sublimation_mode, sublimation_specific_energy=sublimation_specific_energy)
+    d.temperature = temperatures
+    return d
+
+
+def grey_dust(n_temp=10, **kw):
+    """hyperion/model/tests/test_helpers.py:14-18: albedo 0.5, chi = 1 cm^2/g."""
+    return make_dust([3.e9, 3.e16], [0.5, 0.5], [1., 1.], n_temp=n_temp, temp_min=0.1, temp_max=1600., **kw)
+
+
+REALISTIC_NU = [3.e7, 1.e10, 2.e11, 2.e12, 2.e13, 2.e14, 2.e15, 2.e16, 2.e17]
+REALISTIC_CHI = [1.e-11, 2.e-6, 2.e-3, 0.2, 13., 90., 1000., 700., 700.]
+REALISTIC_ALBEDO = [0., 0., 0., 0., 0.1, 0.5, 0.4, 0.4, 0.4]
+
+
+def realistic_dust(n_temp=40, **kw):
+    """hyperion/model/tests/test_helpers.py:21-30 (isotropic scattering)."""
+    return make_dust(REALISTIC_NU, REALISTIC_ALBEDO, REALISTIC_CHI, n_temp=n_temp, **kw)
+
+
+def hg_dust(g=0.6, p_lin_max=0.5, n_temp=40, **kw):
+    """The realistic table with Henyey-Greenstein scattering tabulated at 100 mu points."""
+    return make_dust(REALISTIC_NU, REALISTIC_ALBEDO, REALISTIC_CHI, g=g, p_lin_max=p_lin_max, n_temp=n_temp, **kw)
+
+
+def chi_at(dust: FlatDust, nu0):
+    return float(interp_loglog(dust.nu, dust.chi, np.array([nu0]))[0])
+
+
+def cartesian_point_source_model(n=256, tau_edge=1.0, dust=None, temperature=6000., seed=1,
+                                 uniform=False, n_photons=0, n_iter=1, lam_ref_um=0.5):
+    """SURVEY.md section 8d 'C1' / 'C-headline': n^3 Cartesian grid over [-pc, pc]^3, density
+    1+U(0,1) times a base value chosen so that the optical depth from the centre to the
+    face centre at ``lam_ref_um`` microns is ``tau_edge``; one 6000 K point source at the origin."""
+    if dust is None:
+        dust = realistic_dust(n_temp=1200)
+    w = np.linspace(-pc, pc, n + 1)
+    chi0 = chi_at(dust, c / (lam_ref_um * 1.e-4))
+    mean_factor = 1.0 if uniform else 1.5
+    rho0 = tau_edge / (chi0 * pc * mean_factor)
+    if uniform:
+        rho = np.full((1, n, n, n), rho0)
+    else:
+        rng = np.random.default_rng(seed)
+        rho = rng.random((1, n, n, n), dtype=np.float64)
+        rho += 1.0
+        rho *= rho0
+    src = FlatSource(type=1, luminosity=lsun, temperature=temperature, position=(0., 0., 0.))
+    conf = FlatConf(n_initial_iter=n_iter, n_initial_photons=n_photons)
+    return FlatModel(w, w, w, rho, [dust], [src], conf)

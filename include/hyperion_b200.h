@@ -115,6 +115,9 @@ typedef struct {
 
 const char *hyp_last_error(void);
 int hyp_version(void);
+/* sizeof() of the ABI structs as compiled: 0 hyp_dust_tables, 1 hyp_source, 2 hyp_run_conf, 3 hyp_iter_stats
+ * (lets a binding verify its mirror of this header) */
+int hyp_sizeof(int which);
 
 /* replaces: program start-up, mp_initialize (src/mpi/mpi_core.f90:35) */
 int hyp_ctx_create(int device_id, hyp_ctx **out);
