@@ -162,7 +162,7 @@ def load_library(path=None):
     (``python -c 'import __graft_entry__ as g; g.build()'``)."""
     global _lib
     if _lib is None or path is not None:
-        p = path or _LIB_PATH
+        p = path or os.environ.get("HYPERION_B200_LIB") or _LIB_PATH
         if not os.path.exists(p):
             raise HyperionError("%s not found: build it with __graft_entry__.build(); "
                                 "there is no CPU fallback" % p)

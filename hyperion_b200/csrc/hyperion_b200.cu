@@ -68,6 +68,7 @@ struct Photon {
   // flight origin, direction, path length travelled from the origin
   double r0x, r0y, r0z;
   double vx, vy, vz;
+  double ivx, ivy, ivz;  // 1/v, +-Inf for a ray parallel to the walls of that axis
   double t;
   // distance (from the flight origin) at which the next x / y / z wall is reached
   double tnx, tny, tnz;
@@ -103,15 +104,21 @@ __device__ __forceinline__ bool update_optconsts(const ModelDev &M, Photon<ND> &
 }
 
 // Set up the wall-distance table for a new straight flight from (r0, v) in cell (ix,iy,iz).
+// W holds the three wall arrays back to back: w1 at 0, w2 at o2, w3 at o3.
 template <int ND>
-__device__ __forceinline__ void start_flight(const ModelDev &M, Photon<ND> &p, Rng &rng) {
+__device__ __forceinline__ void start_flight(const double *__restrict__ W, int o2, int o3, Photon<ND> &p, Rng &rng) {
   // random_exp (lib_random.f90:227-236)
   p.tau_left = -log(1.0 - rng.next());
   p.t = 0.0;
   const double inf = __longlong_as_double(0x7ff0000000000000LL);
-  p.tnx = p.vx > 0.0 ? (__ldg(M.w1 + p.ix + 1) - p.r0x) / p.vx : (p.vx < 0.0 ? (__ldg(M.w1 + p.ix) - p.r0x) / p.vx : inf);
-  p.tny = p.vy > 0.0 ? (__ldg(M.w2 + p.iy + 1) - p.r0y) / p.vy : (p.vy < 0.0 ? (__ldg(M.w2 + p.iy) - p.r0y) / p.vy : inf);
-  p.tnz = p.vz > 0.0 ? (__ldg(M.w3 + p.iz + 1) - p.r0z) / p.vz : (p.vz < 0.0 ? (__ldg(M.w3 + p.iz) - p.r0z) / p.vz : inf);
+  p.ivx = 1.0 / p.vx;
+  p.ivy = 1.0 / p.vy;
+  p.ivz = 1.0 / p.vz;
+  // distance to the wall ahead on each axis; a ray parallel to an axis never reaches its walls
+  p.tnx = p.vx != 0.0 ? (W[p.ix + (p.vx > 0.0 ? 1 : 0)] - p.r0x) * p.ivx : inf;
+  p.tny = p.vy != 0.0 ? (W[o2 + p.iy + (p.vy > 0.0 ? 1 : 0)] - p.r0y) * p.ivy : inf;
+  p.tnz = p.vz != 0.0 ? (W[o3 + p.iz + (p.vz > 0.0 ? 1 : 0)] - p.r0z) * p.ivz : inf;
+  // rounding at an interaction point can leave it a few ulp behind the wall it faces
   p.tnx = fmax(p.tnx, 0.0);
   p.tny = fmax(p.tny, 0.0);
   p.tnz = fmax(p.tnz, 0.0);
@@ -357,13 +364,31 @@ __device__ int interact_photon(const ModelDev &M, Photon<ND> &p, Rng &rng, uint3
 // the photon kernel
 // =============================================================================================
 constexpr int LUCY_THREADS = 256;
-constexpr int STEPS_PER_ROUND = 32;  // crossings a lane may take before the warp re-votes
-constexpr int SERVICE_THRESHOLD = 8; // waiting lanes that trigger an EMIT/INTERACT service pass
+#ifndef LUCY_MIN_BLOCKS
+#define LUCY_MIN_BLOCKS 3
+#endif
+#ifndef LUCY_STEPS_PER_ROUND
+#define LUCY_STEPS_PER_ROUND 32   // crossings a lane may take before the warp re-votes
+#endif
+#ifndef LUCY_SERVICE_THRESHOLD
+#define LUCY_SERVICE_THRESHOLD 8  // waiting lanes that trigger an EMIT/INTERACT service pass
+#endif
 
 template <int ND>
-__global__ void __launch_bounds__(LUCY_THREADS)
+__global__ void __launch_bounds__(LUCY_THREADS, LUCY_MIN_BLOCKS)
 lucy_photon_kernel(const ModelDev M, const unsigned long long first_id, const unsigned long long n_photons,
-                   const uint32_t iteration) {
+                   const uint32_t iteration, const int walls_in_smem) {
+  extern __shared__ double s_walls[];
+  const int n1 = M.n1, n2 = M.n2, n3 = M.n3;
+  const int o2 = n1 + 1, o3 = n1 + n2 + 2;
+  // wall table: shared memory when it fits (always for the grids of BASELINE.json), else global
+  const double *__restrict__ W = M.w1;  // w1|w2|w3 are contiguous in global memory as well
+  if (walls_in_smem) {
+    for (int i = threadIdx.x; i < n1 + n2 + n3 + 3; i += blockDim.x) s_walls[i] = M.w1[i];
+    __syncthreads();
+    W = s_walls;
+  }
+
   Photon<ND> p;
   Rng rng;
   int state = ST_EMIT;
@@ -371,25 +396,21 @@ lucy_photon_kernel(const ModelDev M, const unsigned long long first_id, const un
   uint32_t n_cross = 0, n_abs = 0, n_scat = 0, n_esc = 0, n_kill_int = 0, n_run = 0;
   unsigned long long cross_hi = 0;
   const unsigned lane = threadIdx.x & 31;
-  const int n1 = M.n1, n2 = M.n2, n3 = M.n3;
   CellRec *__restrict__ cells = M.cells;
-  const double *__restrict__ w1 = M.w1;
-  const double *__restrict__ w2 = M.w2;
-  const double *__restrict__ w3 = M.w3;
 
   for (;;) {
     const unsigned m_flight = __ballot_sync(0xffffffffu, state == ST_FLIGHT);
     const unsigned m_wait = __ballot_sync(0xffffffffu, state == ST_EMIT || state == ST_INTERACT);
     if (m_flight == 0 && m_wait == 0) break;
 
-    if (m_wait != 0 && (__popc(m_wait) >= SERVICE_THRESHOLD || m_flight == 0)) {
+    if (m_wait != 0 && (__popc(m_wait) >= LUCY_SERVICE_THRESHOLD || m_flight == 0)) {
       // ---------------- service pass: divergent, rare ----------------
       if (state == ST_INTERACT) {
         int fin = interact_photon<ND>(M, p, rng, n_abs, n_scat, n_kill_int);
         if (fin) {
           state = ST_EMIT;
         } else {
-          start_flight<ND>(M, p, rng);
+          start_flight<ND>(W, o2, o3, p, rng);
           state = ST_FLIGHT;
         }
       }
@@ -413,7 +434,7 @@ lucy_photon_kernel(const ModelDev M, const unsigned long long first_id, const un
                 ++n_esc;
                 state = ST_EMIT;
               } else {
-                start_flight<ND>(M, p, rng);
+                start_flight<ND>(W, o2, o3, p, rng);
                 state = ST_FLIGHT;
               }
             } else {
@@ -426,68 +447,56 @@ lucy_photon_kernel(const ModelDev M, const unsigned long long first_id, const un
     }
 
     // ---------------- flight pass: cell crossings (grid_integrate) ----------------
+    // Branch-free DDA step: the axis whose wall is reached first is picked with selects, so all
+    // lanes of the warp execute the same instruction stream whatever their direction.
     if (state == ST_FLIGHT) {
 #pragma unroll 1
-      for (int step = 0; step < STEPS_PER_ROUND; ++step) {
-        const double t_exit = fmin(p.tnx, fmin(p.tny, p.tnz));
-        const double ds = t_exit - p.t;
+      for (int step = 0; step < LUCY_STEPS_PER_ROUND; ++step) {
         CellRec *rec = cells + (size_t)p.ic * ND;
         double rho[ND];
+#pragma unroll
+        for (int id = 0; id < ND; ++id) rho[id] = rec[id].rho;
+
+        const bool bx = (p.tnx <= p.tny) & (p.tnx <= p.tnz);
+        const bool by = (!bx) & (p.tny <= p.tnz);
+        const double t_exit = bx ? p.tnx : (by ? p.tny : p.tnz);
+        const double ds = t_exit - p.t;
+        // geometry of the step (does not depend on the density): next cell and its far wall
+        const double v_ax = bx ? p.vx : (by ? p.vy : p.vz);
+        const int fwd = v_ax > 0.0 ? 1 : 0;
+        const int i_new = (bx ? p.ix : (by ? p.iy : p.iz)) + 2 * fwd - 1;
+        const int n_ax = bx ? n1 : (by ? n2 : n3);
+        const bool out = (unsigned)i_new >= (unsigned)n_ax;
+        const int woff = bx ? 0 : (by ? o2 : o3);
+        const double wall = W[woff + (out ? 0 : i_new + fwd)];
+        const double tn_new = (wall - (bx ? p.r0x : (by ? p.r0y : p.r0z))) * (bx ? p.ivx : (by ? p.ivy : p.ivz));
+
         double chi_rho = 0.0;
 #pragma unroll
-        for (int id = 0; id < ND; ++id) {
-          rho[id] = rec[id].rho;
-          chi_rho += p.chi[id] * rho[id];
-        }
+        for (int id = 0; id < ND; ++id) chi_rho += p.chi[id] * rho[id];
         const double tau_cell = chi_rho * ds;
         ++n_cross;
         if (tau_cell < p.tau_left) {
-          // cross the whole cell
+          // cross the whole cell: deposit tmin * kappa * E (grid_propagate_3d.f90:148-160)
 #pragma unroll
           for (int id = 0; id < ND; ++id)
             if (rho[id] > 0.0) atomicAdd(&rec[id].esum, ds * p.kE[id]);
           p.tau_left -= tau_cell;
           p.t = t_exit;
-          bool out;
-          if (p.tnx <= p.tny && p.tnx <= p.tnz) {
-            if (p.vx > 0.0) {
-              ++p.ix;
-              out = p.ix >= n1;
-              if (!out) p.tnx = (__ldg(w1 + p.ix + 1) - p.r0x) / p.vx;
-            } else {
-              --p.ix;
-              out = p.ix < 0;
-              if (!out) p.tnx = (__ldg(w1 + p.ix) - p.r0x) / p.vx;
-            }
-          } else if (p.tny <= p.tnz) {
-            if (p.vy > 0.0) {
-              ++p.iy;
-              out = p.iy >= n2;
-              if (!out) p.tny = (__ldg(w2 + p.iy + 1) - p.r0y) / p.vy;
-            } else {
-              --p.iy;
-              out = p.iy < 0;
-              if (!out) p.tny = (__ldg(w2 + p.iy) - p.r0y) / p.vy;
-            }
-          } else {
-            if (p.vz > 0.0) {
-              ++p.iz;
-              out = p.iz >= n3;
-              if (!out) p.tnz = (__ldg(w3 + p.iz + 1) - p.r0z) / p.vz;
-            } else {
-              --p.iz;
-              out = p.iz < 0;
-              if (!out) p.tnz = (__ldg(w3 + p.iz) - p.r0z) / p.vz;
-            }
-          }
           if (out) {
             ++n_esc;
             state = ST_EMIT;
             break;
           }
+          p.ix = bx ? i_new : p.ix;
+          p.iy = by ? i_new : p.iy;
+          p.iz = (bx | by) ? p.iz : i_new;
+          p.tnx = bx ? tn_new : p.tnx;
+          p.tny = by ? tn_new : p.tny;
+          p.tnz = (bx | by) ? p.tnz : tn_new;
           p.ic = (p.iz * n2 + p.iy) * n1 + p.ix;
         } else {
-          // interaction inside this cell
+          // interaction inside this cell (grid_propagate_3d.f90:186-228)
           const double tact = tau_cell > 0.0 ? ds * (p.tau_left / tau_cell) : 0.0;
 #pragma unroll
           for (int id = 0; id < ND; ++id)
@@ -1099,16 +1108,26 @@ int hyp_lucy_photons(hyp_ctx *c, int64_t first_id, int64_t n_photons, int64_t it
   CUDA_TRY(cudaMemsetAsync(c->d_work, 0, sizeof(unsigned long long), c->stream));
   int per_sm = 0;
   const int nd = c->M.n_dust;
+  // the three wall arrays go to shared memory when they fit next to 3+ resident blocks
+  size_t wall_bytes = (size_t)(c->n1 + c->n2 + c->n3 + 3) * sizeof(double);
+  int walls_smem = 1;
+  if (wall_bytes > 48 * 1024) {
+    wall_bytes = 0;
+    walls_smem = 0;
+  }
 #define LAUNCH(ND)                                                                                              \
   do {                                                                                                          \
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lucy_photon_kernel<ND>, LUCY_THREADS, 0));  \
+    CUDA_TRY(cudaFuncSetAttribute(lucy_photon_kernel<ND>, cudaFuncAttributeMaxDynamicSharedMemorySize,         \
+                                  (int)wall_bytes));                                                            \
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lucy_photon_kernel<ND>, LUCY_THREADS,       \
+                                                           wall_bytes));                                        \
     int64_t blocks = (int64_t)per_sm * c->sm_count;                                                             \
     int64_t need = (n_photons + LUCY_THREADS - 1) / LUCY_THREADS;                                               \
     if (blocks > need) blocks = need;                                                                           \
     if (blocks < 1) blocks = 1;                                                                                 \
     CUDA_TRY(cudaEventRecord(c->ev0, c->stream));                                                               \
-    lucy_photon_kernel<ND><<<(int)blocks, LUCY_THREADS, 0, c->stream>>>(                                        \
-        c->M, (unsigned long long)first_id, (unsigned long long)n_photons, (uint32_t)iteration);                \
+    lucy_photon_kernel<ND><<<(int)blocks, LUCY_THREADS, wall_bytes, c->stream>>>(                               \
+        c->M, (unsigned long long)first_id, (unsigned long long)n_photons, (uint32_t)iteration, walls_smem);    \
     CUDA_TRY(cudaGetLastError());                                                                               \
     CUDA_TRY(cudaEventRecord(c->ev1, c->stream));                                                               \
   } while (0)
