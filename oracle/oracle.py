@@ -112,12 +112,12 @@ class Oracle(CApi):
         self.lib.orc_set_energy_current(self.ctx, C.c_double(v))
 
 
-def run_lucy_ranks(model: FlatModel, n_photons, n_ranks=1, n_iter=1):
+def run_lucy_ranks(model: FlatModel, n_photons, n_ranks=1, n_iter=1, first_rank=0):
     """Emulate ``mpirun -n n_ranks`` of the reference: equal photon split,
     rank r seeded seed+r, deposit grids and energy_current summed, every rank
     continues from the same scaled grid.  Returns (specific_energy per
     iteration, list of per-iteration stats dicts)."""
-    ranks = [Oracle(model, rank=r) for r in range(n_ranks)]
+    ranks = [Oracle(model, rank=first_rank + r) for r in range(n_ranks)]
     split = [n_photons // n_ranks + (1 if r < n_photons % n_ranks else 0) for r in range(n_ranks)]
     out, stats = [], []
     with ThreadPoolExecutor(max_workers=n_ranks) as pool:

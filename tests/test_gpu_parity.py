@@ -96,21 +96,32 @@ def test_deposits_match_oracle_bitlevel_model(golden_car, evenly, multi):
 
 def test_converged_temperature_matches_oracle(golden_car):
     """Five Lucy iterations (test_bit_level.py: n_initial_iter = 5): the converged
-    specific_energy agrees with the oracle within Monte-Carlo noise; BASELINE.json asks for
-    1 % RMS in temperature, i.e. about 4-6 % RMS in specific_energy."""
+    specific_energy agrees with the oracle within Monte-Carlo noise.  The noise level is
+    measured, not assumed: two oracle runs with disjoint RNG streams (ranks 0-7 and 8-15 of
+    the emulated MPI job, src/mpi/mpi_routines.f90:266-270) give the run-to-run RMS of the
+    reference itself; the engine must sit no further from either of them than they sit from
+    each other (x1.5), and within the 1 % RMS temperature target of BASELINE.json, i.e.
+    about 4-6 % RMS in specific_energy."""
     from oracle import oracle
     model = bitlevel_model(golden_car, False, False)
     N = 1000000
     eng = _engine(model)
     for it in range(5):
-        st = eng.run_lucy_iteration(N, iteration=it + 1)
+        eng.run_lucy_iteration(N, iteration=it + 1)
     got = eng.get_specific_energy()
     eng.close()
-    ref, _ = oracle.run_lucy_ranks(model, N, n_ranks=8, n_iter=5)
-    rel = got / ref[-1] - 1
-    rms = np.sqrt((rel ** 2).mean())
-    assert rms < 0.02, rms      # specific_energy RMS -> < 0.5 % in temperature
-    assert np.abs(rel).max() < 0.1
+    ref_a, _ = oracle.run_lucy_ranks(model, N, n_ranks=8, n_iter=5)
+    ref_b, _ = oracle.run_lucy_ranks(model, N, n_ranks=8, n_iter=5, first_rank=8)
+
+    def rms(a, b):
+        return float(np.sqrt(((a / b - 1) ** 2).mean()))
+
+    noise = rms(ref_a[-1], ref_b[-1])
+    d_a, d_b = rms(got, ref_a[-1]), rms(got, ref_b[-1])
+    assert max(d_a, d_b) < 1.5 * noise + 1e-3, (d_a, d_b, noise)
+    assert max(d_a, d_b) < 0.04, (d_a, d_b)     # < 1 % RMS in temperature
+    mean_ref = 0.5 * (ref_a[-1] + ref_b[-1])
+    assert abs(float((got / mean_ref).mean()) - 1) < 0.02
 
 
 def test_source_on_cell_vertex_keeps_reference_cell_id(golden_car):
