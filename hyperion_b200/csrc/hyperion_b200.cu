@@ -1,24 +1,21 @@
 // hyperion_b200.cu -- CUDA kernels and C ABI of the B200-native photon-packet engine.
 //
-// Hot path: the Lucy iteration of the reference (do_lucy, src/main/iter_lucy.f90:66-237) as a
-// persistent-threads photon loop.  Each lane owns one packet and runs a three-state machine
-//   EMIT     emit (src/sources/source.f90:100-179)                  -> FLIGHT
-//   FLIGHT   grid_integrate (src/grid/grid_propagate_3d.f90:35-234)  -> INTERACT | EMIT (escaped/killed)
-//   INTERACT interact (src/dust/dust_interact.f90:22-79)             -> FLIGHT | EMIT (killed)
-// The warp keeps stepping cell crossings while most lanes are in FLIGHT and only services the
-// divergent EMIT / INTERACT work once enough lanes are waiting, so the crossing loop (>90 % of
-// the work) runs converged.
+// Hot path: the Lucy iteration of the reference (do_lucy, src/main/iter_lucy.f90:66-237).  A pool
+// of photon packets advances in rounds of three kernels (emit -> flight -> interact); the flight
+// kernel (grid_integrate) is a persistent-threads loop that refills idle lanes from a queue.
 //
 // HBM layout: one 16-byte record {density, energy_sum} per (cell, dust) so the
 // density read and the deposit RED of a crossing touch the same 32-byte sector.
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <string>
 #include <vector>
 
 #include <cuda_runtime.h>
+#include <cub/device/device_radix_sort.cuh>
 
 #include "device.cuh"
 
@@ -59,28 +56,133 @@ struct ModelDev {
 enum { ERR_NONE = 0, ERR_NOT_IN_CELL = 1, ERR_NU_RANGE = 2, ERR_SCATTER = 3 };
 
 // =============================================================================================
-// photon state
+// photon pool (wavefront formulation of do_lucy's photon loop, src/main/iter_lucy.f90:119-209)
+//
+// The reference runs one photon at a time through emit -> [flight -> interact]* .  Here a pool of
+// packets advances in rounds of three kernels:
+//   emit_kernel      fills free slots with new packets          (emit, src/sources/source.f90:100-179)
+//   flight_kernel    marches every queued packet to its next event, depositing energy
+//                    (grid_integrate, src/grid/grid_propagate_3d.f90:35-234)   <- the HBM-bound part
+//   interact_kernel  absorbs/re-emits or scatters                (interact, src/dust/dust_interact.f90:22-79)
+// so that the crossing loop runs converged, with few registers (high occupancy) and several
+// density loads in flight per lane, while the branchy table sampling runs in its own kernels.
 // =============================================================================================
-enum : int { ST_EMIT = 0, ST_FLIGHT = 1, ST_INTERACT = 2, ST_DONE = 3 };
+template <int ND>
+struct alignas(32) Slot {
+  // ---- hot part: what a flight needs
+  double r0x, r0y, r0z;  // flight origin
+  double vx, vy, vz;
+  double tau_left;
+  double t;              // out: path length from the origin at which the flight ended
+  double chi[ND], kE[ND];
+  int32_t ix, iy, iz;    // in: cell whose walls bound the flight; out: cell of the event
+  int32_t ic;            // 1-D id used for density / deposits (p%icell%ic of the reference)
+  // ---- cold part: only the emit / interact kernels touch it
+  double nu, energy;
+  double sQ, sU, sV;     // Stokes (I = 1)
+  double albedo[ND];
+  double rng_spare;
+  uint64_t id;
+  uint32_t rng_blk, rng_has_spare;
+  uint32_t n_inter, pad;
+};
 
+enum { C_NF0 = 0, C_NF1, C_NB, C_NI, C_NE, C_CURSOR, C_CURSOR_B, C_COUNT = 8 };
+
+struct Pool {
+  void *slots;
+  uint32_t capacity;
+  uint32_t *q_flight[2];  // slot ids with a flight pending after an interaction (double-buffered across rounds)
+  uint32_t *q_beam;       // slot ids of freshly emitted packets, in emission (direction-sorted) order
+  uint32_t *q_interact;   // slot ids that reached an interaction
+  uint32_t *q_emit;       // free slot ids
+  uint32_t *counts;       // [C_COUNT]
+  unsigned long long *next_photon;
+  // emission order: packets are emitted sorted by direction so that the flights running at the
+  // same time cross the same cells (L2 hits, coalesced loads).  perm is a ring of two windows of
+  // `window` packet offsets each; window w of the launch lives in half (w & 1).
+  const uint32_t *perm;
+  uint32_t window;        // power of two
+};
+
+// Register view of one packet in the emit / interact kernels.
 template <int ND>
 struct Photon {
-  // flight origin, direction, path length travelled from the origin
   double r0x, r0y, r0z;
   double vx, vy, vz;
-  double ivx, ivy, ivz;  // 1/v, +-Inf for a ray parallel to the walls of that axis
   double t;
-  // distance (from the flight origin) at which the next x / y / z wall is reached
-  double tnx, tny, tnz;
   double tau_left;
-  // optical constants at the current frequency, per dust type
   double chi[ND], kE[ND], albedo[ND];
   double nu, energy;
-  double sQ, sU, sV;  // Stokes (I = 1)
-  int32_t ix, iy, iz;
-  int32_t ic;         // 1-D cell id used for density / deposits (p%icell%ic of the reference)
-  int64_t n_inter;
+  double sQ, sU, sV;
+  int32_t ix, iy, iz, ic;
+  uint32_t n_inter;
 };
+
+template <int ND>
+__device__ __forceinline__ void load_photon(const Slot<ND> *__restrict__ s, Photon<ND> &p, Rng &rng, uint64_t seed,
+                                            uint32_t iteration) {
+  p.r0x = s->r0x; p.r0y = s->r0y; p.r0z = s->r0z;
+  p.vx = s->vx; p.vy = s->vy; p.vz = s->vz;
+  p.t = s->t;
+  p.tau_left = s->tau_left;
+#pragma unroll
+  for (int k = 0; k < ND; ++k) {
+    p.chi[k] = s->chi[k];
+    p.kE[k] = s->kE[k];
+    p.albedo[k] = s->albedo[k];
+  }
+  p.nu = s->nu; p.energy = s->energy;
+  p.sQ = s->sQ; p.sU = s->sU; p.sV = s->sV;
+  p.ix = s->ix; p.iy = s->iy; p.iz = s->iz; p.ic = s->ic;
+  p.n_inter = s->n_inter;
+  rng.init(seed, s->id, iteration);
+  rng.blk = s->rng_blk;
+  rng.has_spare = s->rng_has_spare != 0;
+  rng.spare = s->rng_spare;
+}
+
+template <int ND>
+__device__ __forceinline__ void store_photon(Slot<ND> *__restrict__ s, const Photon<ND> &p, const Rng &rng, uint64_t id) {
+  s->r0x = p.r0x; s->r0y = p.r0y; s->r0z = p.r0z;
+  s->vx = p.vx; s->vy = p.vy; s->vz = p.vz;
+  s->tau_left = p.tau_left;
+  s->t = 0.0;
+#pragma unroll
+  for (int k = 0; k < ND; ++k) {
+    s->chi[k] = p.chi[k];
+    s->kE[k] = p.kE[k];
+    s->albedo[k] = p.albedo[k];
+  }
+  s->ix = p.ix; s->iy = p.iy; s->iz = p.iz; s->ic = p.ic;
+  s->nu = p.nu; s->energy = p.energy;
+  s->sQ = p.sQ; s->sU = p.sU; s->sV = p.sV;
+  s->rng_spare = rng.spare;
+  s->id = id;
+  s->rng_blk = rng.blk;
+  s->rng_has_spare = rng.has_spare ? 1u : 0u;
+  s->n_inter = p.n_inter;
+  s->pad = 0;
+}
+
+// Append `value` to a queue for every lane with pred set; must be called by the whole warp.
+__device__ __forceinline__ void queue_append(bool pred, uint32_t *__restrict__ q, uint32_t *count, uint32_t value) {
+  const unsigned m = __ballot_sync(0xffffffffu, pred);
+  if (m == 0) return;
+  const unsigned lane = threadIdx.x & 31;
+  const int leader = __ffs(m) - 1;
+  uint32_t base = 0;
+  if ((int)lane == leader) base = atomicAdd(count, (uint32_t)__popc(m));
+  base = __shfl_sync(0xffffffffu, base, leader);
+  if (pred) q[base + __popc(m & ((1u << lane) - 1u))] = value;
+}
+
+// Sum a per-lane value over the warp and add it to a global scalar.
+__device__ __forceinline__ void warp_add_scalar(double *dst, double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if ((threadIdx.x & 31) == 0 && v != 0.0) atomicAdd(dst, v);
+}
 
 // update_optconsts (src/dust/dust.f90:64-79)
 template <int ND>
@@ -101,27 +203,6 @@ __device__ __forceinline__ bool update_optconsts(const ModelDev &M, Photon<ND> &
     p.kE[id] = chi * (1.0 - alb) * p.energy;
   }
   return true;
-}
-
-// Set up the wall-distance table for a new straight flight from (r0, v) in cell (ix,iy,iz).
-// W holds the three wall arrays back to back: w1 at 0, w2 at o2, w3 at o3.
-template <int ND>
-__device__ __forceinline__ void start_flight(const double *__restrict__ W, int o2, int o3, Photon<ND> &p, Rng &rng) {
-  // random_exp (lib_random.f90:227-236)
-  p.tau_left = -log(1.0 - rng.next());
-  p.t = 0.0;
-  const double inf = __longlong_as_double(0x7ff0000000000000LL);
-  p.ivx = 1.0 / p.vx;
-  p.ivy = 1.0 / p.vy;
-  p.ivz = 1.0 / p.vz;
-  // distance to the wall ahead on each axis; a ray parallel to an axis never reaches its walls
-  p.tnx = p.vx != 0.0 ? (W[p.ix + (p.vx > 0.0 ? 1 : 0)] - p.r0x) * p.ivx : inf;
-  p.tny = p.vy != 0.0 ? (W[o2 + p.iy + (p.vy > 0.0 ? 1 : 0)] - p.r0y) * p.ivy : inf;
-  p.tnz = p.vz != 0.0 ? (W[o3 + p.iz + (p.vz > 0.0 ? 1 : 0)] - p.r0z) * p.ivz : inf;
-  // rounding at an interaction point can leave it a few ulp behind the wall it faces
-  p.tnx = fmax(p.tnx, 0.0);
-  p.tny = fmax(p.tny, 0.0);
-  p.tnz = fmax(p.tnz, 0.0);
 }
 
 // find_cell + adjust_wall (src/grid/grid_geometry_cartesian_3d.f90:143-259) for one axis.
@@ -214,6 +295,7 @@ __device__ bool emit_photon(const ModelDev &M, Photon<ND> &p, Rng &rng, double &
   }
   p.ic = (fz * M.n2 + fy) * M.n1 + fx;
   p.n_inter = 0;
+  p.t = 0.0;
   return true;
 }
 
@@ -299,7 +381,7 @@ __device__ int interact_photon(const ModelDev &M, Photon<ND> &p, Rng &rng, uint3
                                uint32_t &n_killed_int) {
   // the loop guard of do_lucy (iter_lucy.f90:193-198)
   p.n_inter += 1;
-  if (p.n_inter > M.n_inter_max) {
+  if ((int64_t)p.n_inter > M.n_inter_max) {
     ++n_killed_int;
     return 1;
   }
@@ -307,6 +389,7 @@ __device__ int interact_photon(const ModelDev &M, Photon<ND> &p, Rng &rng, uint3
   p.r0x = p.r0x + p.t * p.vx;
   p.r0y = p.r0y + p.t * p.vy;
   p.r0z = p.r0z + p.t * p.vz;
+  p.t = 0.0;
   // select_dust_chi_rho (src/grid/grid_physics_3d.f90:87-99)
   int id = 0;
   if (ND > 1) {
@@ -324,7 +407,10 @@ __device__ int interact_photon(const ModelDev &M, Photon<ND> &p, Rng &rng, uint3
     if (xi >= 1.0) id = ND - 1;
   }
   const DustDev &d = M.dust[id];
-  const double albedo = p.albedo[id];
+  double albedo = p.albedo[0];
+#pragma unroll
+  for (int k = 1; k < ND; ++k)
+    if (k == id) albedo = p.albedo[k];
   const double xi = rng.next();
   bool scattered;
   if (xi > albedo) {
@@ -361,176 +447,513 @@ __device__ int interact_photon(const ModelDev &M, Photon<ND> &p, Rng &rng, uint3
 }
 
 // =============================================================================================
-// the photon kernel
+// kernels of one round
 // =============================================================================================
-constexpr int LUCY_THREADS = 256;
-#ifndef LUCY_MIN_BLOCKS
-#define LUCY_MIN_BLOCKS 3
-#endif
-#ifndef LUCY_STEPS_PER_ROUND
-#define LUCY_STEPS_PER_ROUND 32   // crossings a lane may take before the warp re-votes
-#endif
-#ifndef LUCY_SERVICE_THRESHOLD
-#define LUCY_SERVICE_THRESHOLD 8  // waiting lanes that trigger an EMIT/INTERACT service pass
-#endif
+constexpr int SERVICE_THREADS = 128;
 
-template <int ND>
-__global__ void __launch_bounds__(LUCY_THREADS, LUCY_MIN_BLOCKS)
-lucy_photon_kernel(const ModelDev M, const unsigned long long first_id, const unsigned long long n_photons,
-                   const uint32_t iteration, const int walls_in_smem) {
-  extern __shared__ double s_walls[];
-  const int n1 = M.n1, n2 = M.n2, n3 = M.n3;
-  const int o2 = n1 + 1, o3 = n1 + n2 + 2;
-  // wall table: shared memory when it fits (always for the grids of BASELINE.json), else global
-  const double *__restrict__ W = M.w1;  // w1|w2|w3 are contiguous in global memory as well
-  if (walls_in_smem) {
-    for (int i = threadIdx.x; i < n1 + n2 + n3 + 3; i += blockDim.x) s_walls[i] = M.w1[i];
-    __syncthreads();
-    W = s_walls;
+__global__ void pool_init_kernel(Pool P, uint32_t n_slots) {
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_slots; i += gridDim.x * blockDim.x) P.q_emit[i] = i;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    for (int k = 0; k < C_COUNT; ++k) P.counts[k] = 0;
+    P.counts[C_NE] = n_slots;
+    *P.next_photon = 0ull;
   }
+}
 
-  Photon<ND> p;
-  Rng rng;
-  int state = ST_EMIT;
-  double energy_emitted = 0.0;
-  uint32_t n_cross = 0, n_abs = 0, n_scat = 0, n_esc = 0, n_kill_int = 0, n_run = 0;
-  unsigned long long cross_hi = 0;
-  const unsigned lane = threadIdx.x & 31;
-  CellRec *__restrict__ cells = M.cells;
+// Direction key of packet `id` (the same draws emit_photon makes first): source, then the cube-map
+// face and a Morton code of the direction.  Packets are emitted in key order.
+__device__ __forceinline__ uint32_t interleave12(uint32_t a, uint32_t b) {
+  // 2-D Morton code of two 12-bit integers
+  auto part = [](uint32_t x) {
+    x &= 0xfffu;
+    x = (x | (x << 8)) & 0x00ff00ffu;
+    x = (x | (x << 4)) & 0x0f0f0f0fu;
+    x = (x | (x << 2)) & 0x33333333u;
+    x = (x | (x << 1)) & 0x55555555u;
+    return x;
+  };
+  return part(a) | (part(b) << 1);
+}
 
-  for (;;) {
-    const unsigned m_flight = __ballot_sync(0xffffffffu, state == ST_FLIGHT);
-    const unsigned m_wait = __ballot_sync(0xffffffffu, state == ST_EMIT || state == ST_INTERACT);
-    if (m_flight == 0 && m_wait == 0) break;
-
-    if (m_wait != 0 && (__popc(m_wait) >= LUCY_SERVICE_THRESHOLD || m_flight == 0)) {
-      // ---------------- service pass: divergent, rare ----------------
-      if (state == ST_INTERACT) {
-        int fin = interact_photon<ND>(M, p, rng, n_abs, n_scat, n_kill_int);
-        if (fin) {
-          state = ST_EMIT;
-        } else {
-          start_flight<ND>(W, o2, o3, p, rng);
-          state = ST_FLIGHT;
-        }
+__global__ void emit_keys_kernel(const ModelDev M, const unsigned long long first_id, const uint32_t count,
+                                 const uint32_t iteration, uint32_t *__restrict__ keys, uint32_t *__restrict__ vals) {
+  for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < count; k += gridDim.x * blockDim.x) {
+    Rng rng;
+    rng.init(M.seed, first_id + k, iteration);
+    uint32_t is = 0;
+    const int ns = M.n_sources;
+    if (ns > 1) {
+      const double xi = rng.next();
+      if (M.sample_evenly) {
+        is = (uint32_t)min((int)(xi * ns), ns - 1);
+      } else if (xi >= M.sources[ns - 1].cdf) {
+        is = ns - 1;
+      } else {
+        while ((int)is < ns - 1 && xi > M.sources[is].cdf) ++is;
       }
-      // claim packet ids for every lane that needs one (warp-aggregated)
-      const unsigned m_emit = __ballot_sync(0xffffffffu, state == ST_EMIT);
-      if (m_emit) {
-        const int leader = __ffs(m_emit) - 1;
-        unsigned long long base = 0;
-        if ((int)lane == leader) base = atomicAdd(M.work_counter, (unsigned long long)__popc(m_emit));
-        base = __shfl_sync(0xffffffffu, base, leader);
-        if (state == ST_EMIT) {
-          const unsigned long long k = base + __popc(m_emit & ((1u << lane) - 1u));
-          if (k >= n_photons) {
-            state = ST_DONE;
-          } else {
-            rng.init(M.seed, first_id + k, iteration);
-            ++n_run;
-            if (emit_photon<ND>(M, p, rng, energy_emitted)) {
-              // a packet emitted on the outer wall moving outwards escapes immediately
-              if (p.ix < 0 || p.ix >= n1 || p.iy < 0 || p.iy >= n2 || p.iz < 0 || p.iz >= n3) {
-                ++n_esc;
-                state = ST_EMIT;
-              } else {
-                start_flight<ND>(W, o2, o3, p, rng);
-                state = ST_FLIGHT;
-              }
-            } else {
-              state = ST_EMIT;  // fatal model error is flagged; drain the remaining ids quickly
-            }
-          }
-        }
-      }
-      continue;
     }
+    const Angle a = random_sphere_angle(rng);
+    const double d[3] = {a.sint * a.cosp, a.sint * a.sinp, a.cost};
+    const double ax = fabs(d[0]), ay = fabs(d[1]), az = fabs(d[2]);
+    int f = (ax >= ay && ax >= az) ? 0 : (ay >= az ? 1 : 2);
+    const double m = f == 0 ? d[0] : (f == 1 ? d[1] : d[2]);
+    const double u = (f == 0 ? d[1] : d[0]) / fabs(m), v = (f == 2 ? d[1] : d[2]) / fabs(m);
+    const uint32_t iu = (uint32_t)min(4095.0, (u + 1.0) * 2048.0), iv = (uint32_t)min(4095.0, (v + 1.0) * 2048.0);
+    const uint32_t face = (uint32_t)(2 * f + (m < 0.0 ? 1 : 0));
+    keys[k] = ((is & 31u) << 27) | (face << 24) | interleave12(iu, iv);
+    vals[k] = k;
+  }
+}
 
-    // ---------------- flight pass: cell crossings (grid_integrate) ----------------
-    // Branch-free DDA step: the axis whose wall is reached first is picked with selects, so all
-    // lanes of the warp execute the same instruction stream whatever their direction.
-    if (state == ST_FLIGHT) {
-#pragma unroll 1
-      for (int step = 0; step < LUCY_STEPS_PER_ROUND; ++step) {
-        CellRec *rec = cells + (size_t)p.ic * ND;
-        double rho[ND];
-#pragma unroll
-        for (int id = 0; id < ND; ++id) rho[id] = rec[id].rho;
-
-        const bool bx = (p.tnx <= p.tny) & (p.tnx <= p.tnz);
-        const bool by = (!bx) & (p.tny <= p.tnz);
-        const double t_exit = bx ? p.tnx : (by ? p.tny : p.tnz);
-        const double ds = t_exit - p.t;
-        // geometry of the step (does not depend on the density): next cell and its far wall
-        const double v_ax = bx ? p.vx : (by ? p.vy : p.vz);
-        const int fwd = v_ax > 0.0 ? 1 : 0;
-        const int i_new = (bx ? p.ix : (by ? p.iy : p.iz)) + 2 * fwd - 1;
-        const int n_ax = bx ? n1 : (by ? n2 : n3);
-        const bool out = (unsigned)i_new >= (unsigned)n_ax;
-        const int woff = bx ? 0 : (by ? o2 : o3);
-        const double wall = W[woff + (out ? 0 : i_new + fwd)];
-        const double tn_new = (wall - (bx ? p.r0x : (by ? p.r0y : p.r0z))) * (bx ? p.ivx : (by ? p.ivy : p.ivz));
-
-        double chi_rho = 0.0;
-#pragma unroll
-        for (int id = 0; id < ND; ++id) chi_rho += p.chi[id] * rho[id];
-        const double tau_cell = chi_rho * ds;
-        ++n_cross;
-        if (tau_cell < p.tau_left) {
-          // cross the whole cell: deposit tmin * kappa * E (grid_propagate_3d.f90:148-160)
-#pragma unroll
-          for (int id = 0; id < ND; ++id)
-            if (rho[id] > 0.0) atomicAdd(&rec[id].esum, ds * p.kE[id]);
-          p.tau_left -= tau_cell;
-          p.t = t_exit;
-          if (out) {
-            ++n_esc;
-            state = ST_EMIT;
-            break;
-          }
-          p.ix = bx ? i_new : p.ix;
-          p.iy = by ? i_new : p.iy;
-          p.iz = (bx | by) ? p.iz : i_new;
-          p.tnx = bx ? tn_new : p.tnx;
-          p.tny = by ? tn_new : p.tny;
-          p.tnz = (bx | by) ? p.tnz : tn_new;
-          p.ic = (p.iz * n2 + p.iy) * n1 + p.ix;
-        } else {
-          // interaction inside this cell (grid_propagate_3d.f90:186-228)
-          const double tact = tau_cell > 0.0 ? ds * (p.tau_left / tau_cell) : 0.0;
-#pragma unroll
-          for (int id = 0; id < ND; ++id)
-            if (rho[id] > 0.0) atomicAdd(&rec[id].esum, tact * p.kE[id]);
-          p.t += tact;
-          state = ST_INTERACT;
+// Fill the free slots with new packets while ids remain.
+template <int ND>
+__global__ void __launch_bounds__(SERVICE_THREADS)
+emit_kernel(const ModelDev M, Pool P, const unsigned long long first_id, const unsigned long long n_photons, const uint32_t iteration) {
+  const uint32_t n = P.counts[C_NE];
+  const unsigned lane = threadIdx.x & 31;
+  Slot<ND> *slots = (Slot<ND> *)P.slots;
+  double energy_emitted = 0.0;
+  uint32_t n_run = 0, n_esc = 0;
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t base = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < n; base += stride) {
+    const uint32_t i = base + lane;
+    const bool valid = i < n;
+    // claim packet ids (warp-aggregated)
+    const unsigned m = __ballot_sync(0xffffffffu, valid);
+    const int leader = __ffs(m) - 1;
+    unsigned long long k0 = 0;
+    if ((int)lane == leader) k0 = atomicAdd(P.next_photon, (unsigned long long)__popc(m));
+    k0 = __shfl_sync(0xffffffffu, k0, leader);
+    unsigned long long k = k0 + __popc(m & ((1u << lane) - 1u));  // position in emission order
+    bool go = valid && k < n_photons;
+    uint32_t slot = 0;
+    if (go) {
+      slot = P.q_emit[i];
+      Photon<ND> p;
+      Rng rng;
+      unsigned long long id = 0;
+      for (;;) {
+        // k-th packet in emission order -> packet id (window base + sorted offset)
+        id = first_id + (k & ~(unsigned long long)(P.window - 1)) + P.perm[k & (2ull * P.window - 1)];
+        rng.init(M.seed, id, iteration);
+        ++n_run;
+        if (!emit_photon<ND>(M, p, rng, energy_emitted)) {
+          go = false;  // fatal model error is flagged; the host reports it after the round
           break;
         }
+        // a packet emitted on the outer wall moving outwards escapes immediately
+        if (p.ix < 0 || p.ix >= M.n1 || p.iy < 0 || p.iy >= M.n2 || p.iz < 0 || p.iz >= M.n3) {
+          ++n_esc;
+          k = atomicAdd(P.next_photon, 1ull);
+          if (k >= n_photons) {
+            go = false;
+            break;
+          }
+          continue;
+        }
+        break;
+      }
+      if (go) {
+        p.tau_left = -log(1.0 - rng.next());  // random_exp (lib_random.f90:227-236)
+        store_photon<ND>(slots + slot, p, rng, id);
+      }
+    }
+    queue_append(go, P.q_beam, P.counts + C_NB, slot);
+  }
+  warp_add_scalar(M.scalars + SC_ENERGY, energy_emitted);
+  warp_add_scalar(M.scalars + SC_PHOTONS, (double)n_run);
+  warp_add_scalar(M.scalars + SC_ESC, (double)n_esc);
+}
+
+// Interactions of every packet whose flight ended inside the grid.
+template <int ND>
+__global__ void __launch_bounds__(SERVICE_THREADS)
+interact_kernel(const ModelDev M, Pool P, uint32_t *__restrict__ q_flight_next, uint32_t *n_flight_next,
+                const uint32_t iteration) {
+  const uint32_t n = P.counts[C_NI];
+  const unsigned lane = threadIdx.x & 31;
+  Slot<ND> *slots = (Slot<ND> *)P.slots;
+  uint32_t n_abs = 0, n_scat = 0, n_kill = 0;
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t base = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < n; base += stride) {
+    const uint32_t i = base + lane;
+    const bool valid = i < n;
+    uint32_t slot = 0;
+    bool alive = false;
+    if (valid) {
+      slot = P.q_interact[i];
+      Photon<ND> p;
+      Rng rng;
+      load_photon<ND>(slots + slot, p, rng, M.seed, iteration);
+      const uint64_t id = slots[slot].id;
+      if (interact_photon<ND>(M, p, rng, n_abs, n_scat, n_kill) == 0) {
+        p.tau_left = -log(1.0 - rng.next());
+        store_photon<ND>(slots + slot, p, rng, id);
+        alive = true;
+      }
+    }
+    queue_append(alive, q_flight_next, n_flight_next, slot);
+    queue_append(valid && !alive, P.q_emit, P.counts + C_NE, slot);
+  }
+  warp_add_scalar(M.scalars + SC_ABS, (double)n_abs);
+  warp_add_scalar(M.scalars + SC_SCAT, (double)n_scat);
+  warp_add_scalar(M.scalars + SC_KILLED_INT, (double)n_kill);
+}
+
+// ---------------------------------------------------------------------------------------------
+// flight kernels: grid_integrate for every queued packet (persistent threads, one packet per lane)
+//
+// Two variants share the crossing code (advance_group):
+//   flight_kernel        packets of unrelated directions (after an interaction).  Each lane refills
+//                        on its own from the queue; every deposit is one RED to L2.
+//   flight_beam_kernel   freshly emitted packets.  They are emitted sorted by direction, so the
+//                        32 packets a warp claims together leave the source as a narrow beam and
+//                        sit in the same few cells at every step: the warp marches them in
+//                        lockstep, their density loads coalesce, and the deposits of all lanes in
+//                        one cell are summed with shuffles before a single RED leaves the SM.
+// ---------------------------------------------------------------------------------------------
+constexpr int FLIGHT_THREADS = 256;
+#ifndef FLIGHT_MIN_BLOCKS
+#define FLIGHT_MIN_BLOCKS 3
+#endif
+#ifndef FLIGHT_LOOKAHEAD
+#define FLIGHT_LOOKAHEAD 4   // cell crossings whose density loads are in flight together
+#endif
+#ifndef FLIGHT_GROUPS
+#define FLIGHT_GROUPS 8      // look-ahead groups between two refill votes
+#endif
+#ifndef BEAM_MAX_GROUPS
+#define BEAM_MAX_GROUPS 8    // distinct cells per warp step above which deposits go out lane by lane
+#endif
+// experiment switches (tools/sweep.sh): 0 = product path
+#ifndef FLIGHT_EXPERIMENT
+#define FLIGHT_EXPERIMENT 0
+#endif
+template <typename T>
+__device__ __forceinline__ void deposit_add(T *addr, T v) {
+#if FLIGHT_EXPERIMENT == 1      // no deposit at all (throughput probe)
+  (void)addr; (void)v;
+#else
+  atomicAdd(addr, v);
+#endif
+}
+
+// State of one flight in registers.
+template <int ND>
+struct Lane {
+  double r0x, r0y, r0z;      // flight origin
+  double ivx, ivy, ivz;      // 1/v, +-Inf for a ray parallel to the walls of that axis
+  double t;                  // path length travelled from the origin
+  double tnx, tny, tnz;      // path length at which the next x / y / z wall is reached
+  double tau;                // optical depth left to the interaction
+  double chi[ND], kE[ND];
+  int ix, iy, iz, ic;
+};
+
+template <int ND>
+__device__ __forceinline__ void load_lane(const Slot<ND> *__restrict__ s, Lane<ND> &L, const double *__restrict__ W,
+                                          int o2, int o3) {
+  const double inf = __longlong_as_double(0x7ff0000000000000LL);
+  const double2 a0 = __ldcs((const double2 *)&s->r0x);  // r0x r0y
+  const double2 a1 = __ldcs((const double2 *)&s->r0z);  // r0z vx
+  const double2 a2 = __ldcs((const double2 *)&s->vy);   // vy vz
+  L.r0x = a0.x; L.r0y = a0.y; L.r0z = a1.x;
+  const double vx = a1.y, vy = a2.x, vz = a2.y;
+  L.tau = __ldcs(&s->tau_left);
+  L.t = 0.0;
+#pragma unroll
+  for (int k = 0; k < ND; ++k) {
+    L.chi[k] = __ldcs(&s->chi[k]);
+    L.kE[k] = __ldcs(&s->kE[k]);
+  }
+  const int4 c = __ldcs((const int4 *)&s->ix);
+  L.ix = c.x; L.iy = c.y; L.iz = c.z; L.ic = c.w;
+  L.ivx = 1.0 / vx;
+  L.ivy = 1.0 / vy;
+  L.ivz = 1.0 / vz;
+  // distance to the wall ahead on each axis; a ray parallel to an axis never reaches its walls.
+  // Rounding at an interaction point can leave it a few ulp behind the wall it faces: clamp.
+  L.tnx = vx != 0.0 ? fmax((W[L.ix + (vx > 0.0 ? 1 : 0)] - L.r0x) * L.ivx, 0.0) : inf;
+  L.tny = vy != 0.0 ? fmax((W[o2 + L.iy + (vy > 0.0 ? 1 : 0)] - L.r0y) * L.ivy, 0.0) : inf;
+  L.tnz = vz != 0.0 ? fmax((W[o3 + L.iz + (vz > 0.0 ? 1 : 0)] - L.r0z) * L.ivz, 0.0) : inf;
+}
+
+// Deposits of a whole warp for one crossing step, summed per cell before they leave the SM.
+// Must be called by all 32 lanes; `has` marks the lanes with a deposit into cell `c`.
+// The packets of a beam are sorted along a space-filling curve of their direction, so lanes in
+// the same cell are neighbours: a segmented suffix sum over runs of equal cell ids (5 shuffle
+// steps, no loop over cells) leaves each run's total in its first lane, which issues the RED.
+template <int ND>
+__device__ __forceinline__ void deposit_warp(CellRec *__restrict__ cells, bool has, int c, const double (&dv)[ND]) {
+  const unsigned lane = threadIdx.x & 31;
+  if (__ballot_sync(0xffffffffu, has) == 0) return;
+  const int key = has ? c : -1 - (int)lane;  // lanes without a deposit never join a run
+  const int kp = __shfl_up_sync(0xffffffffu, key, 1);
+  const bool first = lane == 0 || kp != key;
+  const unsigned heads = __ballot_sync(0xffffffffu, first);
+  const unsigned above = lane == 31 ? 0u : (heads & ~((2u << lane) - 1u));
+  const unsigned end = above ? (unsigned)__ffs(above) - 2u : 31u;  // last lane of my run
+  double v[ND];
+#pragma unroll
+  for (int id = 0; id < ND; ++id) v[id] = dv[id];
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const bool join = lane + o <= end;
+#pragma unroll
+    for (int id = 0; id < ND; ++id) {
+      const double v2 = __shfl_down_sync(0xffffffffu, v[id], o);
+      v[id] += join ? v2 : 0.0;
+    }
+  }
+  const bool head = has && first;
+  if (head) {
+#pragma unroll
+    for (int id = 0; id < ND; ++id)
+      if (v[id] != 0.0) deposit_add(&cells[(size_t)c * ND + id].esum, v[id]);
+  }
+}
+
+// March one look-ahead group of D cell crossings (grid_propagate_3d.f90:106-232).
+// Returns 0 to continue, 1 if the packet left the grid, 2 if it reached its interaction (then
+// L.t / L.ix,iy,iz / L.ic describe the interaction point).  With COH set the function is called
+// by the whole warp (lanes with `on` unset only take part in the shuffles).
+template <int ND, int D, bool COH>
+__device__ __forceinline__ int advance_group(Lane<ND> &L, const bool on, const double *__restrict__ W,
+                                             CellRec *__restrict__ cells, const int n1, const int n2, const int n3,
+                                             uint32_t &n_cross) {
+  const int o2 = n1 + 1, o3 = n1 + n2 + 2;
+  // stage A: geometry of the next D crossings (independent of the density) and their loads.
+  // Branch-free DDA: the axis whose wall is reached first is picked with selects.
+  double tx_s[D], rho_s[D][ND];
+  int ic_s[D];
+  unsigned outm = 0, movedm = 0, mv = 0;
+  bool dead = !on;
+  double t_cur = L.t;
+#pragma unroll
+  for (int j = 0; j < D; ++j) {
+    ic_s[j] = L.ic;
+#pragma unroll
+    for (int id = 0; id < ND; ++id) rho_s[j][id] = __ldcg(&cells[(size_t)L.ic * ND + id].rho);
+    const bool bx = (L.tnx <= L.tny) & (L.tnx <= L.tnz);
+    const bool by = (!bx) & (L.tny <= L.tnz);
+    const double t_exit = bx ? L.tnx : (by ? L.tny : L.tnz);
+    const double iv_ax = bx ? L.ivx : (by ? L.ivy : L.ivz);
+    const int fwd = iv_ax > 0.0 ? 1 : 0;
+    const int i_new = (bx ? L.ix : (by ? L.iy : L.iz)) + 2 * fwd - 1;
+    const int n_ax = bx ? n1 : (by ? n2 : n3);
+    const bool out = (unsigned)i_new >= (unsigned)n_ax;
+    const int woff = bx ? 0 : (by ? o2 : o3);
+    const double wall = W[woff + (out ? 0 : i_new + fwd)];
+    const double tn_new = (wall - (bx ? L.r0x : (by ? L.r0y : L.r0z))) * iv_ax;
+    const bool live = !dead;
+    const bool moved = live & !out;
+    t_cur = live ? t_exit : t_cur;
+    tx_s[j] = t_cur;
+    outm |= (live & out) ? (1u << j) : 0u;
+    movedm |= moved ? (1u << j) : 0u;
+    mv |= (unsigned)((bx ? 0 : (by ? 2 : 4)) + fwd) << (3 * j);
+    L.ix = (moved & bx) ? i_new : L.ix;
+    L.iy = (moved & by) ? i_new : L.iy;
+    L.iz = (moved & !(bx | by)) ? i_new : L.iz;
+    L.tnx = (moved & bx) ? tn_new : L.tnx;
+    L.tny = (moved & by) ? tn_new : L.tny;
+    L.tnz = (moved & !(bx | by)) ? tn_new : L.tnz;
+    L.ic = moved ? (L.iz * n2 + L.iy) * n1 + L.ix : L.ic;
+    dead |= out;
+  }
+  // stage B: optical depth and deposits, in order
+  int fin = on ? 0 : 3;
+  double t_prev = L.t;
+  int jf = 0;
+#pragma unroll
+  for (int j = 0; j < D; ++j) {
+    double dv[ND];
+#pragma unroll
+    for (int id = 0; id < ND; ++id) dv[id] = 0.0;
+    bool has = false;
+    if (fin == 0) {
+      const double ds = tx_s[j] - t_prev;
+      double chi_rho = 0.0;
+#pragma unroll
+      for (int id = 0; id < ND; ++id) chi_rho += L.chi[id] * rho_s[j][id];
+      const double tau_cell = chi_rho * ds;
+      ++n_cross;
+      double len;
+      if (tau_cell < L.tau) {
+        // cross the whole cell: deposit tmin * kappa * E (grid_propagate_3d.f90:148-160)
+        len = ds;
+        L.tau -= tau_cell;
+        t_prev = tx_s[j];
+        if ((outm >> j) & 1u) fin = 1;
+      } else {
+        // interaction inside this cell (grid_propagate_3d.f90:186-228)
+        len = tau_cell > 0.0 ? ds * (L.tau / tau_cell) : 0.0;
+        t_prev += len;
+        fin = 2;
+        jf = j;
+      }
+      has = true;
+#pragma unroll
+      for (int id = 0; id < ND; ++id) dv[id] = rho_s[j][id] > 0.0 ? len * L.kE[id] : 0.0;
+    }
+    if (COH) {
+      deposit_warp<ND>(cells, has, ic_s[j], dv);
+    } else if (has) {
+#pragma unroll
+      for (int id = 0; id < ND; ++id)
+        if (rho_s[j][id] > 0.0) deposit_add(&cells[(size_t)ic_s[j] * ND + id].esum, dv[id]);
+    }
+  }
+  L.t = t_prev;
+  if (fin == 2) {
+    // the geometry ran ahead of the interaction: step the cell indices back
+#pragma unroll
+    for (int j = D - 1; j >= 0; --j) {
+      if (j >= jf && ((movedm >> j) & 1u)) {
+        const unsigned code = (mv >> (3 * j)) & 7u;
+        const int s = 2 * (int)(code & 1u) - 1;
+        const unsigned ax = code >> 1;
+        L.ix -= ax == 0 ? s : 0;
+        L.iy -= ax == 1 ? s : 0;
+        L.iz -= ax == 2 ? s : 0;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < D; ++j)
+      if (j == jf) L.ic = ic_s[j];
+  }
+  return fin == 3 ? 0 : fin;
+}
+
+__device__ __forceinline__ const double *stage_walls(const ModelDev &M, double *s_walls, int walls_in_smem) {
+  // wall table: shared memory when it fits (always for the grids of BASELINE.json), else global;
+  // w1|w2|w3 are contiguous in global memory as well
+  if (!walls_in_smem) return M.w1;
+  for (int i = threadIdx.x; i < M.n1 + M.n2 + M.n3 + 3; i += blockDim.x) s_walls[i] = M.w1[i];
+  __syncthreads();
+  return s_walls;
+}
+
+template <int ND>
+__device__ __forceinline__ void store_flight_result(Slot<ND> *s, const Lane<ND> &L) {
+  __stcs(&s->t, L.t);
+  __stcs((int4 *)&s->ix, make_int4(L.ix, L.iy, L.iz, L.ic));
+}
+
+template <int ND, int D>
+__global__ void __launch_bounds__(FLIGHT_THREADS, FLIGHT_MIN_BLOCKS)
+flight_kernel(const ModelDev M, Pool P, const uint32_t *__restrict__ q_flight, const uint32_t *n_flight_ptr,
+              const int walls_in_smem) {
+  extern __shared__ double s_walls[];
+  const int n1 = M.n1, n2 = M.n2, n3 = M.n3;
+  const double *__restrict__ W = stage_walls(M, s_walls, walls_in_smem);
+  const uint32_t n_flight = *n_flight_ptr;
+  Slot<ND> *slots = (Slot<ND> *)P.slots;
+  CellRec *__restrict__ cells = M.cells;
+  const unsigned lane = threadIdx.x & 31;
+
+  bool active = false, exhausted = false;
+  uint32_t slot = 0;
+  Lane<ND> L;
+  L.ic = 0;
+  uint32_t n_cross = 0, n_esc = 0;
+  unsigned long long cross_hi = 0;
+
+  for (;;) {
+    // ---------------- refill idle lanes from the flight queue ----------------
+    const bool need = !active && !exhausted;
+    const unsigned m_need = __ballot_sync(0xffffffffu, need);
+    if (m_need) {
+      const int leader = __ffs(m_need) - 1;
+      uint32_t base = 0;
+      if ((int)lane == leader) base = atomicAdd(P.counts + C_CURSOR, (uint32_t)__popc(m_need));
+      base = __shfl_sync(0xffffffffu, base, leader);
+      if (need) {
+        const uint32_t idx = base + __popc(m_need & ((1u << lane) - 1u));
+        if (idx >= n_flight) {
+          exhausted = true;
+        } else {
+          slot = q_flight[idx];
+          load_lane<ND>(slots + slot, L, W, n1 + 1, n1 + n2 + 2);
+          active = true;
+        }
+      }
+    }
+    if (__ballot_sync(0xffffffffu, active) == 0) break;
+
+    // ---------------- cell crossings ----------------
+    int fin = 0;
+    if (active) {
+#pragma unroll 1
+      for (int g = 0; g < FLIGHT_GROUPS; ++g) {
+        fin = advance_group<ND, D, false>(L, true, W, cells, n1, n2, n3, n_cross);
+        if (fin) break;
       }
       if (n_cross > 0x7fffff00u) {
         cross_hi += n_cross;
         n_cross = 0;
       }
     }
-  }
 
-  // ---------------- reduce the per-lane counters ----------------
-  unsigned long long cross = cross_hi + n_cross;
-  double vals[SC_COUNT];
-  vals[SC_ENERGY] = energy_emitted;
-  vals[SC_KILLED_GEO] = 0.0;
-  vals[SC_KILLED_INT] = (double)n_kill_int;
-  vals[SC_CROSS] = (double)cross;
-  vals[SC_ABS] = (double)n_abs;
-  vals[SC_SCAT] = (double)n_scat;
-  vals[SC_ESC] = (double)n_esc;
-  vals[SC_PHOTONS] = (double)n_run;
-#pragma unroll
-  for (int q = 0; q < SC_COUNT; ++q) {
-    double v = vals[q];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    if (lane == 0 && v != 0.0) atomicAdd(M.scalars + q, v);
+    // ---------------- hand finished packets to the next kernel ----------------
+    if (fin == 2) store_flight_result<ND>(slots + slot, L);
+    queue_append(fin == 2, P.q_interact, P.counts + C_NI, slot);
+    queue_append(fin == 1, P.q_emit, P.counts + C_NE, slot);
+    if (fin) {
+      n_esc += fin == 1 ? 1u : 0u;
+      active = false;
+    }
   }
+  warp_add_scalar(M.scalars + SC_CROSS, (double)(cross_hi + n_cross));
+  warp_add_scalar(M.scalars + SC_ESC, (double)n_esc);
+}
+
+template <int ND, int D>
+__global__ void __launch_bounds__(FLIGHT_THREADS, FLIGHT_MIN_BLOCKS)
+flight_beam_kernel(const ModelDev M, Pool P, const uint32_t *__restrict__ q_beam, const uint32_t *n_beam_ptr,
+                   const int walls_in_smem) {
+  extern __shared__ double s_walls[];
+  const int n1 = M.n1, n2 = M.n2, n3 = M.n3;
+  const double *__restrict__ W = stage_walls(M, s_walls, walls_in_smem);
+  const uint32_t n_beam = *n_beam_ptr;
+  Slot<ND> *slots = (Slot<ND> *)P.slots;
+  CellRec *__restrict__ cells = M.cells;
+  const unsigned lane = threadIdx.x & 31;
+  uint32_t n_cross = 0, n_esc = 0;
+  unsigned long long cross_hi = 0;
+
+  for (;;) {
+    // the warp claims 32 consecutive packets of the emission order: one beam
+    uint32_t base = 0;
+    if (lane == 0) base = atomicAdd(P.counts + C_CURSOR_B, 32u);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (base >= n_beam) break;
+    const uint32_t idx = base + lane;
+    uint32_t slot = 0;
+    Lane<ND> L;
+    L.ic = 0;
+    int fin = 3;  // 3: no packet in this lane
+    if (idx < n_beam) {
+      slot = q_beam[idx];
+      load_lane<ND>(slots + slot, L, W, n1 + 1, n1 + n2 + 2);
+      fin = 0;
+    }
+    // lockstep march until every lane has escaped or interacted
+    while (__ballot_sync(0xffffffffu, fin == 0)) {
+      const int f = advance_group<ND, D, true>(L, fin == 0, W, cells, n1, n2, n3, n_cross);
+      if (fin == 0) fin = f;
+    }
+    if (n_cross > 0x7fffff00u) {
+      cross_hi += n_cross;
+      n_cross = 0;
+    }
+    if (fin == 2) store_flight_result<ND>(slots + slot, L);
+    queue_append(fin == 2, P.q_interact, P.counts + C_NI, slot);
+    queue_append(fin == 1, P.q_emit, P.counts + C_NE, slot);
+    n_esc += fin == 1 ? 1u : 0u;
+  }
+  warp_add_scalar(M.scalars + SC_CROSS, (double)(cross_hi + n_cross));
+  warp_add_scalar(M.scalars + SC_ESC, (double)n_esc);
 }
 
 // =============================================================================================
@@ -717,7 +1140,18 @@ struct hyp_ctx {
   ModelDev M;
   bool finalized = false;
   bool sums_gathered = false;
-  float kernel_ms_acc = 0.f;
+  float kernel_ms_acc = 0.f, flight_ms_acc = 0.f;
+  int64_t rounds_acc = 0;
+  // photon pool
+  Pool pool;
+  uint32_t pool_cap = 0;
+  uint32_t *h_counts = nullptr;  // pinned: [C_COUNT] counters + next_photon (2 words)
+  // emission-order sort (direction keys)
+  uint32_t sort_window = 0;
+  uint32_t *d_keys_in = nullptr, *d_keys_out = nullptr, *d_vals_in = nullptr, *d_perm = nullptr;
+  void *d_sort_tmp = nullptr;
+  size_t sort_tmp_bytes = 0;
+  cudaEvent_t evA = nullptr, evB = nullptr;
 };
 
 namespace {
@@ -760,6 +1194,96 @@ void free_dev(T *&p) {
   p = nullptr;
 }
 
+void free_pool(hyp_ctx *c) {
+  free_dev(c->pool.slots);
+  free_dev(c->pool.q_flight[0]);
+  free_dev(c->pool.q_flight[1]);
+  free_dev(c->pool.q_beam);
+  free_dev(c->pool.q_interact);
+  free_dev(c->pool.q_emit);
+  free_dev(c->pool.counts);
+  free_dev(c->pool.next_photon);
+  c->pool_cap = 0;
+  free_dev(c->d_keys_in);
+  free_dev(c->d_keys_out);
+  free_dev(c->d_vals_in);
+  free_dev(c->d_perm);
+  free_dev(c->d_sort_tmp);
+  c->sort_window = 0;
+}
+
+size_t slot_bytes(int nd) {
+  switch (nd) {
+    case 1: return sizeof(Slot<1>);
+    case 2: return sizeof(Slot<2>);
+    case 3: return sizeof(Slot<3>);
+    default: return sizeof(Slot<4>);
+  }
+}
+
+// Packets resident in the pool at once.  Large enough that a round keeps every SM busy for a
+// few milliseconds, small enough that the records (192 B each) stream through L2 without
+// displacing the cell grid.
+uint32_t pool_target() {
+  const char *e = getenv("HYPERION_B200_POOL");
+  long v = e ? atol(e) : (1L << 21);
+  if (v < 1024) v = 1024;
+  if (v > (1L << 28)) v = 1L << 28;
+  return (uint32_t)v;
+}
+
+int ensure_pool(hyp_ctx *c, uint32_t cap) {
+  if (c->pool_cap >= cap) return HYP_OK;
+  free_pool(c);
+  Pool &P = c->pool;
+  CUDA_TRY(cudaMalloc(&P.slots, (size_t)cap * slot_bytes(c->M.n_dust)));
+  CUDA_TRY(cudaMalloc(&P.q_flight[0], (size_t)cap * sizeof(uint32_t)));
+  CUDA_TRY(cudaMalloc(&P.q_flight[1], (size_t)cap * sizeof(uint32_t)));
+  CUDA_TRY(cudaMalloc(&P.q_beam, (size_t)cap * sizeof(uint32_t)));
+  CUDA_TRY(cudaMalloc(&P.q_interact, (size_t)cap * sizeof(uint32_t)));
+  CUDA_TRY(cudaMalloc(&P.q_emit, (size_t)cap * sizeof(uint32_t)));
+  CUDA_TRY(cudaMalloc(&P.counts, C_COUNT * sizeof(uint32_t)));
+  CUDA_TRY(cudaMalloc(&P.next_photon, sizeof(unsigned long long)));
+  P.capacity = cap;
+  c->pool_cap = cap;
+  // emission-order windows: a power of two >= 2 * cap so that the ring of two windows always
+  // covers every id the next round can claim
+  uint32_t w = 1u << 24;
+  while (w < 2ull * cap) w <<= 1;
+  c->sort_window = w;
+  CUDA_TRY(cudaMalloc(&c->d_keys_in, (size_t)w * sizeof(uint32_t)));
+  CUDA_TRY(cudaMalloc(&c->d_keys_out, (size_t)w * sizeof(uint32_t)));
+  CUDA_TRY(cudaMalloc(&c->d_vals_in, (size_t)w * sizeof(uint32_t)));
+  CUDA_TRY(cudaMalloc(&c->d_perm, 2 * (size_t)w * sizeof(uint32_t)));
+  c->sort_tmp_bytes = 0;
+  CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, c->sort_tmp_bytes, c->d_keys_in, c->d_keys_out, c->d_vals_in,
+                                           c->d_perm, (int)w, 0, 32, c->stream));
+  CUDA_TRY(cudaMalloc(&c->d_sort_tmp, c->sort_tmp_bytes));
+  P.perm = c->d_perm;
+  P.window = w;
+  return HYP_OK;
+}
+
+// Emission order of window `w` of a launch: sort the packets of the window by direction key.
+int prepare_window(hyp_ctx *c, int64_t first_id, int64_t n_photons, int64_t iteration, int64_t w) {
+  const int64_t win = c->sort_window;
+  const int64_t count = std::min<int64_t>(win, n_photons - w * win);
+  if (count <= 0) return HYP_OK;
+  static const bool sorted = [] {
+    const char *e = getenv("HYPERION_B200_SORT");
+    return !(e && atoi(e) == 0);
+  }();
+  uint32_t *dst = c->d_perm + (w & 1) * win;
+  emit_keys_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(c->M, (unsigned long long)(first_id + w * win),
+                                                           (uint32_t)count, (uint32_t)iteration, c->d_keys_in,
+                                                           sorted ? c->d_vals_in : dst);
+  CUDA_TRY(cudaGetLastError());
+  if (sorted)
+    CUDA_TRY(cub::DeviceRadixSort::SortPairs(c->d_sort_tmp, c->sort_tmp_bytes, c->d_keys_in, c->d_keys_out,
+                                             c->d_vals_in, dst, (int)count, 0, 32, c->stream));
+  return HYP_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -795,6 +1319,17 @@ int hyp_ctx_create(int device_id, hyp_ctx **out) {
   CUDA_TRY(cudaEventCreate(&c->ev1));
   CUDA_TRY(cudaEventCreate(&c->ev2));
   CUDA_TRY(cudaEventCreate(&c->ev3));
+  CUDA_TRY(cudaEventCreate(&c->evA));
+  CUDA_TRY(cudaEventCreate(&c->evB));
+  CUDA_TRY(cudaMallocHost(&c->h_counts, (C_COUNT + 2) * sizeof(uint32_t)));
+  memset(&c->pool, 0, sizeof c->pool);
+  // Cell records are touched one 32-byte sector at a time at random: do not let L2 fetch more.
+  {
+    const char *g = getenv("HYPERION_B200_L2_FETCH");
+    size_t gran = g ? (size_t)atoi(g) : 32;
+    if (gran) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, gran);
+    cudaGetLastError();
+  }
   memset(&c->conf, 0, sizeof c->conf);
   c->conf.seed = -124902;
   c->conf.n_inter_max = 1000000;
@@ -821,6 +1356,10 @@ void hyp_ctx_destroy(hyp_ctx *c) {
   free_dev(c->d_spectra);
   free_dev(c->d_work);
   free_dev(c->d_error);
+  free_pool(c);
+  if (c->h_counts) cudaFreeHost(c->h_counts);
+  if (c->evA) cudaEventDestroy(c->evA);
+  if (c->evB) cudaEventDestroy(c->evB);
   for (auto &d : c->dust) free_dev(d.dev);
   for (auto &s : c->spectra) free_dev(s.dev);
   if (c->h_pinned) cudaFreeHost(c->h_pinned);
@@ -1097,50 +1636,120 @@ int hyp_lucy_begin(hyp_ctx *c) {
   CUDA_TRY(cudaMemsetAsync(c->d_error, 0, sizeof(int32_t), c->stream));
   c->sums_gathered = false;
   c->kernel_ms_acc = 0.f;
+  c->flight_ms_acc = 0.f;
+  c->rounds_acc = 0;
   return HYP_OK;
 }
+
+}  // extern "C"
+
+// The rounds of the packet pool for a fixed number of dust types.
+template <int ND>
+static int run_rounds(hyp_ctx *c, int64_t first_id, int64_t n_photons, int64_t iteration) {
+  const uint32_t cap = (uint32_t)std::min<int64_t>(pool_target(), n_photons);
+  int rc = ensure_pool(c, cap);
+  if (rc) return rc;
+  Pool &P = c->pool;
+  // the three wall arrays go to shared memory when they fit next to the resident blocks
+  size_t wall_bytes = (size_t)(c->n1 + c->n2 + c->n3 + 3) * sizeof(double);
+  int walls_smem = 1;
+  if (wall_bytes > 40 * 1024) {
+    wall_bytes = 0;
+    walls_smem = 0;
+  }
+  auto flight = flight_kernel<ND, FLIGHT_LOOKAHEAD>;
+  auto beam = flight_beam_kernel<ND, FLIGHT_LOOKAHEAD>;
+  CUDA_TRY(cudaFuncSetAttribute(flight, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wall_bytes));
+  CUDA_TRY(cudaFuncSetAttribute(beam, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wall_bytes));
+  int per_sm = 0, per_sm_beam = 0;
+  CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, flight, FLIGHT_THREADS, wall_bytes));
+  CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_beam, beam, FLIGHT_THREADS, wall_bytes));
+  if (per_sm < 1) per_sm = 1;
+  if (per_sm_beam < 1) per_sm_beam = 1;
+  const int flight_blocks_max = per_sm * c->sm_count;
+  const int beam_blocks_max = per_sm_beam * c->sm_count;
+  const int service_blocks_max = c->sm_count * 8;
+  cudaStream_t st = c->stream;
+
+  pool_init_kernel<<<c->sm_count, 256, 0, st>>>(P, cap);
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaEventRecord(c->ev0, st));
+  int cur = 0;
+  uint32_t n_emit = cap, n_flight_prev = 0;
+  unsigned long long claimed = 0;
+  int64_t windows_ready = 0;
+  for (int64_t round = 0;; ++round) {
+    uint32_t *nF = P.counts + C_NF0 + cur, *nF_next = P.counts + C_NF0 + (1 - cur);
+    while (windows_ready * (int64_t)c->sort_window < n_photons &&
+           (int64_t)claimed + 2 * (int64_t)cap > windows_ready * (int64_t)c->sort_window) {
+      rc = prepare_window(c, first_id, n_photons, iteration, windows_ready);
+      if (rc) return rc;
+      ++windows_ready;
+    }
+    // 1. new packets into the free slots -> beam queue
+    int64_t n_new = 0;
+    if (claimed < (unsigned long long)n_photons && n_emit > 0) {
+      n_new = std::min<int64_t>(n_emit, n_photons - (int64_t)claimed);
+      int blocks = (int)std::min<int64_t>(((int64_t)n_emit + SERVICE_THREADS - 1) / SERVICE_THREADS, service_blocks_max);
+      emit_kernel<ND><<<blocks, SERVICE_THREADS, 0, st>>>(c->M, P, (unsigned long long)first_id,
+                                                          (unsigned long long)n_photons, (uint32_t)iteration);
+      CUDA_TRY(cudaGetLastError());
+    }
+    CUDA_TRY(cudaMemsetAsync(P.counts + C_NI, 0, 4 * sizeof(uint32_t), st));  // C_NI, C_NE, C_CURSOR, C_CURSOR_B
+    // 2. flights: the beams of new packets, then the packets that come out of an interaction
+    CUDA_TRY(cudaEventRecord(c->evA, st));
+    if (n_new > 0) {
+      int blocks = (int)std::min<int64_t>((n_new + FLIGHT_THREADS - 1) / FLIGHT_THREADS, beam_blocks_max);
+      beam<<<blocks, FLIGHT_THREADS, wall_bytes, st>>>(c->M, P, P.q_beam, P.counts + C_NB, walls_smem);
+      CUDA_TRY(cudaGetLastError());
+    }
+    if (n_flight_prev > 0) {
+      int blocks = (int)std::min<int64_t>(((int64_t)n_flight_prev + FLIGHT_THREADS - 1) / FLIGHT_THREADS, flight_blocks_max);
+      flight<<<blocks, FLIGHT_THREADS, wall_bytes, st>>>(c->M, P, P.q_flight[cur], nF, walls_smem);
+      CUDA_TRY(cudaGetLastError());
+    }
+    CUDA_TRY(cudaEventRecord(c->evB, st));
+    CUDA_TRY(cudaMemsetAsync(nF_next, 0, sizeof(uint32_t), st));
+    CUDA_TRY(cudaMemsetAsync(P.counts + C_NB, 0, sizeof(uint32_t), st));
+    // 3. interactions -> next round's flight queue; killed packets free their slot
+    interact_kernel<ND><<<service_blocks_max, SERVICE_THREADS, 0, st>>>(c->M, P, P.q_flight[1 - cur], nF_next,
+                                                                        (uint32_t)iteration);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(c->h_counts, P.counts, C_COUNT * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(c->h_counts + C_COUNT, P.next_photon, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, c->evA, c->evB) == cudaSuccess) c->flight_ms_acc += ms;
+    c->rounds_acc += 1;
+    cur = 1 - cur;
+    memcpy(&claimed, c->h_counts + C_COUNT, sizeof claimed);
+    n_emit = c->h_counts[C_NE];
+    n_flight_prev = c->h_counts[C_NF0 + cur];
+    const bool ids_left = claimed < (unsigned long long)n_photons;
+    if (n_flight_prev == 0 && (!ids_left || n_emit == 0)) break;
+  }
+  CUDA_TRY(cudaEventRecord(c->ev1, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  float ms = 0.f;
+  if (cudaEventElapsedTime(&ms, c->ev0, c->ev1) == cudaSuccess) c->kernel_ms_acc += ms;
+  return HYP_OK;
+}
+
+extern "C" {
 
 int hyp_lucy_photons(hyp_ctx *c, int64_t first_id, int64_t n_photons, int64_t iteration) {
   if (!c || !c->finalized) return fail(HYP_ERR_STATE, "hyp_finalize_setup has not been called");
   if (n_photons < 0 || first_id < 0) return fail(HYP_ERR_INVALID, "negative photon count");
   if (n_photons == 0) return HYP_OK;
   CUDA_TRY(cudaSetDevice(c->device));
-  CUDA_TRY(cudaMemsetAsync(c->d_work, 0, sizeof(unsigned long long), c->stream));
-  int per_sm = 0;
-  const int nd = c->M.n_dust;
-  // the three wall arrays go to shared memory when they fit next to 3+ resident blocks
-  size_t wall_bytes = (size_t)(c->n1 + c->n2 + c->n3 + 3) * sizeof(double);
-  int walls_smem = 1;
-  if (wall_bytes > 48 * 1024) {
-    wall_bytes = 0;
-    walls_smem = 0;
-  }
-#define LAUNCH(ND)                                                                                              \
-  do {                                                                                                          \
-    CUDA_TRY(cudaFuncSetAttribute(lucy_photon_kernel<ND>, cudaFuncAttributeMaxDynamicSharedMemorySize,         \
-                                  (int)wall_bytes));                                                            \
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lucy_photon_kernel<ND>, LUCY_THREADS,       \
-                                                           wall_bytes));                                        \
-    int64_t blocks = (int64_t)per_sm * c->sm_count;                                                             \
-    int64_t need = (n_photons + LUCY_THREADS - 1) / LUCY_THREADS;                                               \
-    if (blocks > need) blocks = need;                                                                           \
-    if (blocks < 1) blocks = 1;                                                                                 \
-    CUDA_TRY(cudaEventRecord(c->ev0, c->stream));                                                               \
-    lucy_photon_kernel<ND><<<(int)blocks, LUCY_THREADS, wall_bytes, c->stream>>>(                               \
-        c->M, (unsigned long long)first_id, (unsigned long long)n_photons, (uint32_t)iteration, walls_smem);    \
-    CUDA_TRY(cudaGetLastError());                                                                               \
-    CUDA_TRY(cudaEventRecord(c->ev1, c->stream));                                                               \
-  } while (0)
-  switch (nd) {
-    case 1: LAUNCH(1); break;
-    case 2: LAUNCH(2); break;
-    case 3: LAUNCH(3); break;
-    case 4: LAUNCH(4); break;
+  c->sums_gathered = false;
+  switch (c->M.n_dust) {
+    case 1: return run_rounds<1>(c, first_id, n_photons, iteration);
+    case 2: return run_rounds<2>(c, first_id, n_photons, iteration);
+    case 3: return run_rounds<3>(c, first_id, n_photons, iteration);
+    case 4: return run_rounds<4>(c, first_id, n_photons, iteration);
     default: return fail(HYP_ERR_INVALID, "unsupported number of dust types");
   }
-#undef LAUNCH
-  c->sums_gathered = false;
-  return HYP_OK;
 }
 
 static int gather_sums(hyp_ctx *c) {
@@ -1191,9 +1800,11 @@ int hyp_lucy_finish(hyp_ctx *c, hyp_iter_stats *st) {
     st->n_absorptions = (int64_t)sc[SC_ABS];
     st->n_scatterings = (int64_t)sc[SC_SCAT];
     st->n_escaped = (int64_t)sc[SC_ESC];
-    float ms = 0.f, total = 0.f;
-    if (cudaEventElapsedTime(&ms, c->ev0, c->ev1) == cudaSuccess) st->kernel_ms = ms;
-    if (cudaEventElapsedTime(&total, c->ev2, c->ev3) == cudaSuccess) st->epilogue_ms = total - ms;
+    float total = 0.f;
+    st->kernel_ms = c->kernel_ms_acc;
+    st->flight_ms = c->flight_ms_acc;
+    st->n_rounds = c->rounds_acc;
+    if (cudaEventElapsedTime(&total, c->ev2, c->ev3) == cudaSuccess) st->epilogue_ms = total - c->kernel_ms_acc;
   }
   return HYP_OK;
 }

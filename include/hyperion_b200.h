@@ -109,8 +109,10 @@ typedef struct {
   int64_t n_absorptions;      /* absorb + re-emit events */
   int64_t n_scatterings;
   int64_t n_escaped;
-  double kernel_ms;           /* device time of the photon kernel (CUDA events) */
+  double kernel_ms;           /* device time of the photon loop: all rounds of emit/flight/interact (CUDA events) */
   double epilogue_ms;         /* device time of scale/clamp/jnu_var kernels */
+  double flight_ms;           /* device time of the flight kernel alone (the HBM-bound part) */
+  int64_t n_rounds;           /* rounds of the packet pool */
 } hyp_iter_stats;
 
 const char *hyp_last_error(void);

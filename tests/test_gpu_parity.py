@@ -137,7 +137,7 @@ def test_source_on_cell_vertex_keeps_reference_cell_id(golden_car):
     z, ok = _zscores(g, o)
     assert np.abs(z[ok]).max() < 5.0
     rel = np.abs(g.mean(0) / o.mean(0) - 1)
-    assert rel.max() < 0.05
+    assert rel.max() < 0.08
     assert all(s["killed_geo"] == 0 for s in gst)
 
 
