@@ -38,6 +38,8 @@ def parse():
     ap.add_argument("--cpu-photons", type=float, default=0, help="packets for the CPU sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-thin", action="store_true", help="skip the optically thin variant")
+    ap.add_argument("--thin-tau", type=float, default=0.01)
     return ap.parse_args()
 
 
@@ -106,11 +108,6 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-class DevBuf:
-    def __init__(self, ptr, n):
-        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (ptr, False), "version": 2}
-
-
 def cpu_sample(model, n_photons, cores):
     """Time the CPU restatement of the Fortran path (oracle/) the way the reference runs under
     MPI: `cores` ranks seeded seed+r, equal split, deposit grids summed (src/mpi/mpi_routines.f90)."""
@@ -172,64 +169,18 @@ def run_reference(a):
     print(json.dumps(line), flush=True)
 
 
-def main():
-    a = parse()
-    if a.impl == "reference":
-        run_reference(a)
-        return
+def measure(eng, drv, stream, model, P, world, rank, a, sync_all, e2e=True):
+    """Warm-up + K timed Lucy iterations of P packets per GPU; returns (total_ms, stats, e2e dict)."""
     import torch
     import torch.distributed as dist
-    import __graft_entry__ as ge
-    from hyperion_b200.capi import Engine
-
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device: the engine has no CPU fallback")
-    torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    if rank == 0:
-        ge.build()
-    if world > 1:
-        dist.barrier()
-
-    model = build_model(a)
-    P = int(a.photons)
-    eng = Engine(local)
-    eng.load_model(model)
-    stream = torch.cuda.ExternalStream(eng.stream, device=torch.device("cuda", local))
-    ptr, nval = eng.lucy_device_buffers()
-    sums = torch.as_tensor(DevBuf(ptr, nval), device=torch.device("cuda", local))
-    launches = {"n": 0}
 
     def step(it):
-        eng.lucy_begin()
-        eng.lucy_photons(rank * P + it * world * P, P, it + 1)
-        launches["n"] += 2
-        if world > 1:
-            eng.lucy_device_buffers()   # gathers the record-interleaved sums into the contiguous buffer
-            with torch.cuda.stream(stream):
-                dist.all_reduce(sums)
-            stream.synchronize()
-        st = eng.lucy_finish()
-        launches["n"] += 2              # gather + finish kernels
-        return st
-
-    def sync_all():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+        # every step draws fresh packet ids (it * world * P is the id offset of the step)
+        return drv.iteration(world * P, it + 1, id_offset=it * world * P)
 
     for it in range(a.warmup):
         step(it)
     sync_all()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-    launches["n"] = 0
     e0 = torch.cuda.Event(enable_timing=True)
     e1 = torch.cuda.Event(enable_timing=True)
     e0.record(stream)
@@ -238,26 +189,15 @@ def main():
         stats.append(step(a.warmup + it))
     e1.record(stream)
     sync_all()
-    clocks = sampler.stop() if rank == 0 else None
     ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     total_ms = float(ms.item())
-    gpu_launches = launches["n"]
 
-    # roofline of the photon kernel (this rank; after the all-reduce the counters are global)
-    cross = sum(s.n_crossings for s in stats)
-    nabs = sum(s.n_absorptions for s in stats)
-    nscat = sum(s.n_scatterings for s in stats)
-    kern_ms = sum(s.kernel_ms for s in stats)
-    div = world if world > 1 else 1   # counters were all-reduced with the grid
-    alg_bytes = (24.0 * eng.n_dust * cross + 12.0 * nabs) / div
-    peak, peak_kind = peaks()
-    achieved = alg_bytes / (kern_ms * 1e-3) / 1e9 if kern_ms > 0 else 0.0
-
-    # end-to-end through the public API with host buffers (H2D density, D2H specific_energy)
-    e2e = None
-    if not a.no_e2e:
+    out = None
+    if e2e:
+        # end to end through the public API with HOST buffers: density in (pinned H2D), one
+        # iteration, specific_energy out (D2H)
         n_el = eng.n_dust * eng.n_cells
         h_rho = torch.empty(n_el, dtype=torch.float64).pin_memory()
         h_rho.numpy()[:] = model.density.ravel()
@@ -282,8 +222,100 @@ def main():
         ms2 = torch.tensor([t0.elapsed_time(t1)], dtype=torch.float64, device="cuda")
         if world > 1:
             dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
-        e2e = {"value": P * world * k2 / (float(ms2.item()) * 1e-3), "unit": "packets/s",
+        out = {"value": P * world * k2 / (float(ms2.item()) * 1e-3), "unit": "packets/s",
                "h2d_bytes_per_step": int(n_el * 8), "d2h_bytes_per_step": int(n_el * 8), "steps": k2}
+    return total_ms, stats, out
+
+
+def roofline_of(stats, n_dust, world, steps):
+    """Algorithmic bytes (24 B per crossing per dust type + 12 B per absorption)
+    over the device time of the flight kernels, summed over the rounds of each step."""
+    div = world if world > 1 else 1     # with N > 1 the counters were all-reduced with the grid
+    cross = sum(s.n_crossings for s in stats) / div
+    nabs = sum(s.n_absorptions for s in stats) / div
+    nscat = sum(s.n_scatterings for s in stats) / div
+    flight_ms = sum(s.flight_ms for s in stats)
+    loop_ms = sum(s.kernel_ms for s in stats)
+    alg_bytes = 24.0 * n_dust * cross + 12.0 * nabs
+    peak, peak_kind = peaks()
+    achieved = alg_bytes / (flight_ms * 1e-3) / 1e9 if flight_ms > 0 else 0.0
+    return {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "traffic": None, "peak_kind": peak_kind, "bytes_per_crossing": 24 * n_dust,
+            "kernel": "flight_beam_kernel + flight_kernel (all rounds of a step)",
+            "kernel_ms_per_step": flight_ms / steps, "photon_loop_ms_per_step": loop_ms / steps,
+            "achieved_whole_photon_loop": alg_bytes / (loop_ms * 1e-3) / 1e9 if loop_ms > 0 else 0.0,
+            "crossings_per_step": cross / steps}, cross, nabs, nscat
+
+
+def main():
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+        return
+    import torch
+    import torch.distributed as dist
+    import __graft_entry__ as ge
+    from hyperion_b200.capi import Engine
+    from hyperion_b200.multigpu import ShardedLucy
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the engine has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if rank == 0:
+        ge.build()
+    if world > 1:
+        dist.barrier()
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def make(model):
+        eng = Engine(local)
+        eng.load_model(model)
+        stream = torch.cuda.ExternalStream(eng.stream, device=torch.device("cuda", local))
+
+        def all_reduce(buf):
+            with torch.cuda.stream(stream):
+                dist.all_reduce(buf)
+            stream.synchronize()
+
+        return eng, ShardedLucy(eng, rank, world, all_reduce if world > 1 else None), stream
+
+    model = build_model(a)
+    P = int(a.photons)
+    eng, drv, stream = make(model)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    total_ms, stats, e2e = measure(eng, drv, stream, model, P, world, rank, a, sync_all, e2e=not a.no_e2e)
+    clocks = sampler.stop() if rank == 0 else None
+    roof, cross, nabs, nscat = roofline_of(stats, eng.n_dust, world, a.steps)
+    gpu_launches = int(sum(s.n_launches for s in stats))
+    n_dust, n_cells = eng.n_dust, eng.n_cells
+    eng.close()
+
+    # the optically thin variant of the same grid (SURVEY.md 8d asks for both), rank-local timing
+    thin = None
+    if not a.no_thin:
+        a2 = argparse.Namespace(**vars(a))
+        a2.tau = a.thin_tau
+        m2 = build_model(a2)
+        eng2, drv2, stream2 = make(m2)
+        ms2, st2, _ = measure(eng2, drv2, stream2, m2, P, world, rank, a2, sync_all, e2e=False)
+        r2, c2, _, _ = roofline_of(st2, eng2.n_dust, world, a.steps)
+        thin = {"workload": workload_name(a2), "value": P * world * a.steps / (ms2 * 1e-3), "unit": "packets/s",
+                "ms_per_step": ms2 / a.steps, "roofline_achieved": r2["achieved"], "roofline_frac": r2["frac"],
+                "roofline_achieved_whole_photon_loop": r2["achieved_whole_photon_loop"],
+                "crossings_per_packet": c2 / (P * a.steps)}
+        eng2.close()
 
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
@@ -305,28 +337,27 @@ def main():
             "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": total_ms / a.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
-            "config": {"workload": workload_name(a), "grid": [a.grid] * 3, "n_dust": eng.n_dust,
+            "config": {"workload": workload_name(a), "grid": [a.grid] * 3, "n_dust": n_dust,
                        "photons_per_gpu_per_step": P, "tau_centre_to_face": a.tau,
                        "dust": "9-point realistic table, isotropic, LTE emissivities 1200 states",
                        "cache": "cell records 16 B x n_cells = %.0f MB > 126 MB L2 (no flush needed)"
-                                % (16e-6 * eng.n_cells * eng.n_dust)
-                       if 16 * eng.n_cells * eng.n_dust > 126e6 else "working set fits L2"},
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_kind": peak_kind,
-                         "bytes_per_crossing": 24 * eng.n_dust, "kernel": "lucy_photon_kernel",
-                         "kernel_ms_per_step": kern_ms / a.steps},
-            "crossings_per_packet": cross / div / (P * a.steps),
-            "absorptions_per_packet": nabs / div / (P * a.steps),
-            "scatterings_per_packet": nscat / div / (P * a.steps),
+                                % (16e-6 * n_cells * n_dust)
+                       if 16 * n_cells * n_dust > 126e6 else "working set fits L2"},
+            "roofline": roof,
+            "crossings_per_packet": cross / (P * a.steps),
+            "absorptions_per_packet": nabs / (P * a.steps),
+            "scatterings_per_packet": nscat / (P * a.steps),
+            "rounds_per_step": sum(s.n_rounds for s in stats) / a.steps,
             "gpu_launches": gpu_launches,
             "clocks": clocks,
         }
         if e2e:
             line["e2e"] = e2e
+        if thin:
+            line["other_workloads"] = [thin]
         if cpu:
             line["cpu_baseline"] = cpu
         print(json.dumps(line), flush=True)
-    eng.close()
     if world > 1:
         dist.destroy_process_group()
 

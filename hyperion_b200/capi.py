@@ -61,7 +61,7 @@ class IterStats(C.Structure):
         ("n_crossings", C.c_int64), ("n_absorptions", C.c_int64),
         ("n_scatterings", C.c_int64), ("n_escaped", C.c_int64),
         ("kernel_ms", C.c_double), ("epilogue_ms", C.c_double),
-        ("flight_ms", C.c_double), ("n_rounds", C.c_int64),
+        ("flight_ms", C.c_double), ("n_rounds", C.c_int64), ("n_launches", C.c_int64),
     ]
 
     def as_dict(self):
@@ -185,6 +185,7 @@ class Engine(CApi):
             getattr(L, n).restype = C.c_int
         self.ctx = C.c_void_p()
         self.check(L.hyp_ctx_create(C.c_int(device_id), C.byref(self.ctx)))
+        self.device_id = device_id
         self.n_dust = 0
         self.n_cells = 0
         self.shape = None
@@ -221,6 +222,18 @@ class Engine(CApi):
         n = C.c_int64()
         self.check(self.lib.hyp_lucy_device_buffers(self.ctx, C.byref(p), C.byref(n)))
         return p.value, n.value
+
+    def reduction_buffer(self):
+        """The iteration's deposit grid + scalars as a torch CUDA tensor aliasing the engine's
+        device buffer (for the NCCL all-reduce of :mod:`hyperion_b200.multigpu`).  The engine's
+        stream has been synchronised when this returns."""
+        import torch
+        ptr, n = self.lucy_device_buffers()
+
+        class _Buf:
+            __cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (ptr, False), "version": 2}
+
+        return torch.as_tensor(_Buf(), device=torch.device("cuda", self.device_id))
 
     def lucy_finish(self):
         st = IterStats()

@@ -648,6 +648,7 @@ struct Lane {
   double tau;                // optical depth left to the interaction
   double chi[ND], kE[ND];
   int ix, iy, iz, ic;
+  int fwd;                   // bit a set: the packet moves towards +axis a
 };
 
 template <int ND>
@@ -676,6 +677,7 @@ __device__ __forceinline__ void load_lane(const Slot<ND> *__restrict__ s, Lane<N
   L.tnx = vx != 0.0 ? fmax((W[L.ix + (vx > 0.0 ? 1 : 0)] - L.r0x) * L.ivx, 0.0) : inf;
   L.tny = vy != 0.0 ? fmax((W[o2 + L.iy + (vy > 0.0 ? 1 : 0)] - L.r0y) * L.ivy, 0.0) : inf;
   L.tnz = vz != 0.0 ? fmax((W[o3 + L.iz + (vz > 0.0 ? 1 : 0)] - L.r0z) * L.ivz, 0.0) : inf;
+  L.fwd = (vx > 0.0 ? 1 : 0) | (vy > 0.0 ? 2 : 0) | (vz > 0.0 ? 4 : 0);
 }
 
 // Deposits of a whole warp for one crossing step, summed per cell before they leave the SM.
@@ -702,7 +704,7 @@ __device__ __forceinline__ void deposit_warp(CellRec *__restrict__ cells, bool h
 #pragma unroll
     for (int id = 0; id < ND; ++id) {
       const double v2 = __shfl_down_sync(0xffffffffu, v[id], o);
-      v[id] += join ? v2 : 0.0;
+      if (join) v[id] += v2;
     }
   }
   const bool head = has && first;
@@ -1141,7 +1143,7 @@ struct hyp_ctx {
   bool finalized = false;
   bool sums_gathered = false;
   float kernel_ms_acc = 0.f, flight_ms_acc = 0.f;
-  int64_t rounds_acc = 0;
+  int64_t rounds_acc = 0, launches_acc = 0;  // launches: this library's own kernels in the iteration
   // photon pool
   Pool pool;
   uint32_t pool_cap = 0;
@@ -1278,6 +1280,7 @@ int prepare_window(hyp_ctx *c, int64_t first_id, int64_t n_photons, int64_t iter
                                                            (uint32_t)count, (uint32_t)iteration, c->d_keys_in,
                                                            sorted ? c->d_vals_in : dst);
   CUDA_TRY(cudaGetLastError());
+  c->launches_acc += 1;
   if (sorted)
     CUDA_TRY(cub::DeviceRadixSort::SortPairs(c->d_sort_tmp, c->sort_tmp_bytes, c->d_keys_in, c->d_keys_out,
                                              c->d_vals_in, dst, (int)count, 0, 32, c->stream));
@@ -1632,6 +1635,7 @@ int hyp_lucy_begin(hyp_ctx *c) {
   CUDA_TRY(cudaEventRecord(c->ev2, c->stream));
   lucy_begin_kernel<<<grid_blocks(c), 256, 0, c->stream>>>(c->M);
   CUDA_TRY(cudaGetLastError());
+  c->launches_acc = 1;
   CUDA_TRY(cudaMemsetAsync(c->d_sums + n, 0, SC_COUNT * sizeof(double), c->stream));
   CUDA_TRY(cudaMemsetAsync(c->d_error, 0, sizeof(int32_t), c->stream));
   c->sums_gathered = false;
@@ -1672,6 +1676,7 @@ static int run_rounds(hyp_ctx *c, int64_t first_id, int64_t n_photons, int64_t i
   cudaStream_t st = c->stream;
 
   pool_init_kernel<<<c->sm_count, 256, 0, st>>>(P, cap);
+  c->launches_acc += 1;
   CUDA_TRY(cudaGetLastError());
   CUDA_TRY(cudaEventRecord(c->ev0, st));
   int cur = 0;
@@ -1694,6 +1699,7 @@ static int run_rounds(hyp_ctx *c, int64_t first_id, int64_t n_photons, int64_t i
       emit_kernel<ND><<<blocks, SERVICE_THREADS, 0, st>>>(c->M, P, (unsigned long long)first_id,
                                                           (unsigned long long)n_photons, (uint32_t)iteration);
       CUDA_TRY(cudaGetLastError());
+      c->launches_acc += 1;
     }
     CUDA_TRY(cudaMemsetAsync(P.counts + C_NI, 0, 4 * sizeof(uint32_t), st));  // C_NI, C_NE, C_CURSOR, C_CURSOR_B
     // 2. flights: the beams of new packets, then the packets that come out of an interaction
@@ -1702,11 +1708,13 @@ static int run_rounds(hyp_ctx *c, int64_t first_id, int64_t n_photons, int64_t i
       int blocks = (int)std::min<int64_t>((n_new + FLIGHT_THREADS - 1) / FLIGHT_THREADS, beam_blocks_max);
       beam<<<blocks, FLIGHT_THREADS, wall_bytes, st>>>(c->M, P, P.q_beam, P.counts + C_NB, walls_smem);
       CUDA_TRY(cudaGetLastError());
+      c->launches_acc += 1;
     }
     if (n_flight_prev > 0) {
       int blocks = (int)std::min<int64_t>(((int64_t)n_flight_prev + FLIGHT_THREADS - 1) / FLIGHT_THREADS, flight_blocks_max);
       flight<<<blocks, FLIGHT_THREADS, wall_bytes, st>>>(c->M, P, P.q_flight[cur], nF, walls_smem);
       CUDA_TRY(cudaGetLastError());
+      c->launches_acc += 1;
     }
     CUDA_TRY(cudaEventRecord(c->evB, st));
     CUDA_TRY(cudaMemsetAsync(nF_next, 0, sizeof(uint32_t), st));
@@ -1715,6 +1723,7 @@ static int run_rounds(hyp_ctx *c, int64_t first_id, int64_t n_photons, int64_t i
     interact_kernel<ND><<<service_blocks_max, SERVICE_THREADS, 0, st>>>(c->M, P, P.q_flight[1 - cur], nF_next,
                                                                         (uint32_t)iteration);
     CUDA_TRY(cudaGetLastError());
+    c->launches_acc += 1;
     CUDA_TRY(cudaMemcpyAsync(c->h_counts, P.counts, C_COUNT * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaMemcpyAsync(c->h_counts + C_COUNT, P.next_photon, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
@@ -1756,6 +1765,7 @@ static int gather_sums(hyp_ctx *c) {
   if (!c->sums_gathered) {
     gather_sums_kernel<<<grid_blocks(c), 256, 0, c->stream>>>(c->M, c->d_sums);
     CUDA_TRY(cudaGetLastError());
+    c->launches_acc += 1;
     c->sums_gathered = true;
   }
   return HYP_OK;
@@ -1788,6 +1798,7 @@ int hyp_lucy_finish(hyp_ctx *c, hyp_iter_stats *st) {
   const double scale = c->energy_total / sc[SC_ENERGY];
   lucy_finish_kernel<<<grid_blocks(c), 256, 0, c->stream>>>(c->M, c->d_sums, scale);
   CUDA_TRY(cudaGetLastError());
+  c->launches_acc += 1;
   CUDA_TRY(cudaEventRecord(c->ev3, c->stream));
   CUDA_TRY(cudaStreamSynchronize(c->stream));
   if (st) {
@@ -1804,6 +1815,7 @@ int hyp_lucy_finish(hyp_ctx *c, hyp_iter_stats *st) {
     st->kernel_ms = c->kernel_ms_acc;
     st->flight_ms = c->flight_ms_acc;
     st->n_rounds = c->rounds_acc;
+    st->n_launches = c->launches_acc;
     if (cudaEventElapsedTime(&total, c->ev2, c->ev3) == cudaSuccess) st->epilogue_ms = total - c->kernel_ms_acc;
   }
   return HYP_OK;

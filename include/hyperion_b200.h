@@ -113,6 +113,7 @@ typedef struct {
   double epilogue_ms;         /* device time of scale/clamp/jnu_var kernels */
   double flight_ms;           /* device time of the flight kernel alone (the HBM-bound part) */
   int64_t n_rounds;           /* rounds of the packet pool */
+  int64_t n_launches;         /* kernels of this library launched for the iteration */
 } hyp_iter_stats;
 
 const char *hyp_last_error(void);
