@@ -61,7 +61,7 @@ class FlatDust:
         """Read a dust group (``Dust/dust_%03i`` or the root of a dust file)."""
         sub = {b"no": 0, b"fast": 1, b"slow": 2, b"cap": 3}
         attrs = g.attrs
-        version = int(attrs["version"])
+        version = int(np.asarray(attrs["version"]).ravel()[0])
         op = g["optical_properties"][...]
         mo = g["mean_opacities"][...]
         em = g["emissivities"][...]

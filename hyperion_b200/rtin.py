@@ -1,0 +1,243 @@
+"""Parse a Hyperion ``.rtin`` model file into the neutral in-memory model.
+
+Host-side replacement of ``setup_initial`` (``src/main/setup_rt.f90:27-304``) and the readers
+it calls (``setup_dust`` ``src/dust/dust.f90:30``, ``setup_grid_geometry``
+``src/grid/grid_geometry_cartesian_3d.f90:77-135``, ``setup_grid_physics``
+``src/grid/grid_physics_3d.f90:111-322``, ``setup_sources`` ``src/sources/source.f90:48-80``).
+The file layout is the one ``hyperion.model.Model.write`` produces
+(``hyperion/model/model.py:513-740``; ``docs/advanced/model_file.rst``).
+
+Errors use the reference's wording where its tests look for it
+(``hyperion/model/tests/test_fortran.py``).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Optional
+
+import numpy as np
+
+from .flatmodel import FlatConf, FlatDust, FlatModel, FlatSource
+from .io import h5min
+
+
+class ModelError(RuntimeError):
+    """A condition the reference reports through ``error()`` (``fortranlib/src/lib_messages.f90:126-179``)."""
+
+
+def _s(v):
+    """HDF5 string attribute -> python str."""
+    if isinstance(v, np.ndarray):
+        v = v.reshape(-1)[0] if v.size else b""
+    if isinstance(v, bytes):
+        return v.split(b"\x00")[0].decode("utf-8").strip()
+    return str(v).strip()
+
+
+def _yes(v):
+    """Booleans are the strings yes/no (``hyperion/util/functions.py:28-33``; accepted spellings
+    ``fortranlib/src/lib_hdf5_110.f90:2880-2884``)."""
+    t = _s(v).lower()
+    if t in ("yes", "y", "true"):
+        return True
+    if t in ("no", "n", "false"):
+        return False
+    raise ModelError("Unknown logical value: %s" % t)
+
+
+def _num(v):
+    a = np.asarray(v).reshape(-1)
+    return a[0]
+
+
+@dataclass
+class RunSettings:
+    """Root / Output attributes beyond what the photon kernels need (``setup_rt.f90:38-157``)."""
+    n_initial_iter: int = 0
+    n_initial_photons: int = 0
+    n_last_photons: int = 0
+    n_ray_photons_sources: int = 0
+    n_ray_photons_dust: int = 0
+    n_stats: int = 0
+    raytracing: bool = False
+    monochromatic: bool = False
+    pda: bool = False
+    forced_first_interaction: bool = True
+    forced_first_interaction_algorithm: str = "wr99"
+    baes16_xi: float = 0.5
+    check_convergence: bool = False
+    convergence_absolute: float = 0.0
+    convergence_relative: float = 0.0
+    convergence_percentile: float = 100.0
+    specific_energy_type: str = "initial"
+    physics_io_bytes: int = 8
+    copy_input: bool = True
+    output_specific_energy: str = "last"
+    output_density: str = "none"
+    output_density_diff: str = "none"
+    output_n_photons: str = "none"
+    geometry_id: str = ""
+    grid_type: str = "car"
+    extra: dict = field(default_factory=dict)
+
+
+def _attr(attrs, name, default=None, required=False):
+    if name in attrs:
+        return attrs[name]
+    if required:
+        raise ModelError("attribute %s is missing from the input file" % name)
+    return default
+
+
+def read_rtin(filename):
+    """Returns (FlatModel, RunSettings, h5min.File).  Only what the implemented hot path needs is
+    interpreted; unsupported options raise ModelError instead of being silently ignored."""
+    f = h5min.File(filename)
+    A = f.attrs
+    if "python_version" not in A:
+        raise ModelError("cannot read files made with the Python module before version 0.8.7")
+
+    rs = RunSettings()
+    rs.monochromatic = _yes(_attr(A, "monochromatic", b"no"))
+    rs.raytracing = _yes(_attr(A, "raytracing", b"no"))
+    rs.n_stats = int(_num(_attr(A, "n_stats", 0)))
+    rs.pda = _yes(_attr(A, "pda", b"no"))
+    conf = FlatConf()
+    conf.seed = int(_num(_attr(A, "seed", -124902)))
+    conf.n_inter_max = int(_num(_attr(A, "n_inter_max", required=True)))
+    conf.n_reabs_max = int(_num(_attr(A, "n_reabs_max", required=True)))
+    conf.use_mrw = _yes(_attr(A, "mrw", b"no"))
+    if conf.use_mrw:
+        conf.mrw_gamma = float(_num(_attr(A, "mrw_gamma", required=True)))
+        conf.n_mrw_max = int(_num(_attr(A, "n_inter_mrw_max", required=True)))
+    conf.kill_on_absorb = _yes(_attr(A, "kill_on_absorb", b"no"))
+    conf.kill_on_scatter = _yes(_attr(A, "kill_on_scatter", b"no"))
+    if "forced_first_scattering" in A:
+        rs.forced_first_interaction = _yes(A["forced_first_scattering"])
+    else:
+        rs.forced_first_interaction = _yes(_attr(A, "forced_first_interaction", b"yes"))
+        rs.forced_first_interaction_algorithm = _s(_attr(A, "forced_first_interaction_algorithm", b"wr99")).lower()
+        if rs.forced_first_interaction_algorithm == "baes16":
+            rs.baes16_xi = float(_num(_attr(A, "forced_first_interaction_baes16_xi", required=True)))
+        elif rs.forced_first_interaction_algorithm != "wr99":
+            raise ModelError("Unknown forced first interaction algorithm: " + rs.forced_first_interaction_algorithm)
+    conf.propagation_check_frequency = float(_num(_attr(A, "propagation_check_frequency", 1.e-3)))
+    conf.sample_sources_evenly = _yes(_attr(A, "sample_sources_evenly", b"no"))
+    conf.enforce_energy_range = _yes(_attr(A, "enforce_energy_range", b"yes"))
+
+    # photon counts may be stored as floats (hyperion/conf/conf_files.py:142-227)
+    rs.n_initial_iter = int(_num(_attr(A, "n_initial_iter", 0)))
+    if rs.n_initial_iter > 0:
+        rs.n_initial_photons = int(float(_num(_attr(A, "n_initial_photons", required=True))))
+        if rs.n_initial_photons == 0:
+            raise ModelError("Number of initial iterations is non-zero, but number of specific_energy photons is zero")
+    rs.n_last_photons = int(float(_num(_attr(A, "n_last_photons", 0))))
+    if rs.raytracing:
+        rs.n_ray_photons_sources = int(float(_num(_attr(A, "n_ray_photons_sources", 0))))
+        rs.n_ray_photons_dust = int(float(_num(_attr(A, "n_ray_photons_dust", 0))))
+    conf.n_initial_iter = rs.n_initial_iter
+    conf.n_initial_photons = rs.n_initial_photons
+    rs.specific_energy_type = _s(_attr(A, "specific_energy_type", b"initial"))
+    if rs.specific_energy_type not in ("initial", "additional"):
+        raise ModelError("specific_energy_type should be 'additional' or 'initial'")
+    rs.physics_io_bytes = int(_num(_attr(A, "physics_io_bytes", 8)))
+    if rs.physics_io_bytes not in (4, 8):
+        raise ModelError("unexpected value of physics_io_bytes (should be 4 or 8)")
+    rs.copy_input = _yes(_attr(A, "copy_input", b"yes"))
+    if rs.n_initial_iter > 0:
+        rs.check_convergence = _yes(_attr(A, "check_convergence", b"no"))
+        if rs.check_convergence:
+            rs.convergence_absolute = float(_num(A["convergence_absolute"]))
+            rs.convergence_relative = float(_num(A["convergence_relative"]))
+            rs.convergence_percentile = float(_num(A["convergence_percentile"]))
+
+    # ---- dust
+    dust = []
+    if "Dust" in f:
+        g_dust = f["Dust"]
+        for name in sorted(g_dust.keys()):
+            dust.append(FlatDust.from_hdf5_group(g_dust[name]))
+
+    # ---- grid geometry
+    geo = f["Grid/Geometry"]
+    rs.grid_type = _s(geo.attrs["grid_type"])
+    rs.geometry_id = _s(geo.attrs["geometry"])
+    if rs.grid_type != "car":
+        raise ModelError("grid type '%s' is not implemented by this engine yet (Cartesian only)" % rs.grid_type)
+    w1 = np.asarray(geo["walls_1"][...]["x"], dtype=np.float64)
+    w2 = np.asarray(geo["walls_2"][...]["y"], dtype=np.float64)
+    w3 = np.asarray(geo["walls_3"][...]["z"], dtype=np.float64)
+    for w, nm in ((w1, "dx"), (w2, "dy"), (w3, "dz")):
+        if np.any(np.diff(w) <= 0):
+            raise ModelError("all %s values should be greater than zero" % nm)
+
+    # ---- grid physics
+    q = f["Grid/Quantities"]
+    n3, n2, n1 = len(w3) - 1, len(w2) - 1, len(w1) - 1
+    if "density" in q:
+        dset = q["density"]
+        if "geometry" in dset.attrs and _s(dset.attrs["geometry"]) != rs.geometry_id:
+            raise ModelError("geometry id of density does not match that of the grid")
+        density = np.asarray(dset[...], dtype=np.float64)
+        if density.shape[1:] != (n3, n2, n1):
+            raise ModelError("density array has wrong shape")
+        if density.shape[0] != len(dust):
+            raise ModelError("density array has wrong number of dust types")
+        if np.any(density < 0):
+            raise ModelError("density should be positive")
+    else:
+        density = np.zeros((0, n3, n2, n1))
+    se = None
+    if "specific_energy" in q:
+        se = np.asarray(q["specific_energy"][...], dtype=np.float64)
+        if np.any(se < 0):
+            raise ModelError("specific_energy should be positive")
+    min_e = None
+    if "minimum_specific_energy" in q.attrs:
+        min_e = np.asarray(q.attrs["minimum_specific_energy"], dtype=np.float64).reshape(-1)
+
+    # ---- sources
+    sources = []
+    if "Sources" in f:
+        g_src = f["Sources"]
+        for name in sorted(g_src.keys()):
+            g = g_src[name]
+            a = g.attrs
+            stype = _s(a["type"])
+            if stype not in ("point", "sphere"):
+                raise ModelError("source type '%s' is not implemented by this engine yet" % stype)
+            spec = _s(a["spectrum"])
+            kw = dict(type=1 if stype == "point" else 2, luminosity=float(_num(a["luminosity"])),
+                      position=(float(_num(a["x"])), float(_num(a["y"])), float(_num(a["z"]))),
+                      peeloff=_yes(a["peeloff"]))
+            if stype == "sphere":
+                kw["radius"] = float(_num(a["r"]))
+                kw["limb_darkening"] = _yes(a["limb"])
+            if spec == "temperature":
+                kw["temperature"] = float(_num(a["temperature"]))
+            elif spec == "spectrum":
+                t = g["spectrum"][...]
+                nu, fnu = np.asarray(t["nu"], dtype=np.float64), np.asarray(t["fnu"], dtype=np.float64)
+                if np.any(np.diff(nu) < 0):
+                    raise ModelError("spectrum frequency should be monotonically increasing")
+                kw["spectrum_nu"], kw["spectrum_fnu"] = nu, fnu
+            elif spec == "lte":
+                raise ModelError("Point source cannot have LTE spectrum" if stype == "point"
+                                 else "Spherical source cannot have LTE spectrum")
+            else:
+                raise ModelError("unknown spectrum specifier: " + spec)
+            sources.append(FlatSource(**kw))
+    if not sources and rs.n_initial_iter > 0:
+        raise ModelError("no sources set up - need sources for initial iteration(s)")
+
+    # ---- output switches
+    out = f["Output"].attrs if "Output" in f else {}
+    for key in ("output_density", "output_density_diff", "output_specific_energy", "output_n_photons"):
+        if key in out:
+            val = _s(out[key])
+            if val not in ("all", "last", "none"):
+                raise ModelError("%s should be one of all/last/none" % key)
+            setattr(rs, key, val)
+
+    model = FlatModel(w1, w2, w3, density, dust, sources, conf, specific_energy=se, minimum_specific_energy=min_e)
+    return model, rs, f

@@ -1,0 +1,157 @@
+"""Write a FlatModel as a ``.rtin`` file in the layout ``hyperion.model.Model.write`` produces
+(``hyperion/model/model.py:513-740``, ``hyperion/grid/cartesian_grid.py:295-358``,
+``hyperion/sources/source.py:264-284``, ``hyperion/dust/dust_type.py:377-443``,
+``hyperion/conf/conf_files.py:795-822``).
+
+The reference front end needs h5py + astropy to do this; where those are missing (this engine's
+test and benchmark boxes) this writer produces the same file so that the drop-in binary can be
+exercised end to end on synthetic models.
+"""
+from __future__ import annotations
+
+import hashlib
+
+import numpy as np
+
+from .flatmodel import FlatModel
+from .io import h5write
+
+
+def _yn(b):
+    return b"yes" if b else b"no"
+
+
+def _table(cols):
+    dt = []
+    n = None
+    for name, a in cols:
+        a = np.asarray(a)
+        n = len(a)
+        dt.append((name, a.dtype.str) if a.ndim == 1 else (name, a.dtype.str, a.shape[1:]))
+    t = np.zeros(n, dtype=dt)
+    for name, a in cols:
+        t[name] = a
+    return t
+
+
+def write_dust(g, d):
+    """``SphericalDust.write`` (``hyperion/dust/dust_type.py:377-443``): a version-2 dust group."""
+    g.attrs["version"] = np.int32(2 if d.version != 1 else 1)
+    g.attrs["type"] = np.int32(1)
+    g.attrs["python_version"] = "0.9.12"
+    g.attrs["emissvar"] = "E"
+    g.attrs["lte"] = _yn(d.is_lte)
+    g.attrs["sublimation_mode"] = {0: "no", 1: "fast", 2: "slow", 3: "cap"}[d.sublimation_mode]
+    if d.sublimation_mode:
+        g.attrs["sublimation_specific_energy"] = float(d.sublimation_specific_energy)
+    g.create_dataset("optical_properties", _table([("nu", d.nu), ("albedo", d.albedo), ("chi", d.chi),
+                                                   ("P1", d.P1), ("P2", d.P2), ("P3", d.P3), ("P4", d.P4)]))
+    g.create_dataset("scattering_angles", _table([("mu", d.mu)]))
+    temperature = getattr(d, "temperature", np.zeros_like(d.specific_energy))
+    if d.version == 1:
+        cols = [("specific_energy", d.specific_energy), ("chi_planck", d.chi_planck), ("kappa_planck", d.kappa_planck),
+                ("chi_rosseland", d.chi_inv_planck), ("kappa_rosseland", d.kappa_inv_planck)]
+    else:
+        cols = [("temperature", temperature), ("specific_energy", d.specific_energy),
+                ("chi_planck", d.chi_planck), ("kappa_planck", d.kappa_planck),
+                ("chi_inv_planck", d.chi_inv_planck), ("kappa_inv_planck", d.kappa_inv_planck),
+                ("chi_rosseland", d.chi_rosseland), ("kappa_rosseland", d.kappa_rosseland)]
+    g.create_dataset("mean_opacities", _table(cols))
+    g.create_dataset("emissivities", _table([("nu", d.emiss_nu), ("jnu", d.emiss_jnu)]))
+    g.create_dataset("emissivity_variable", _table([("specific_energy", d.jnu_var)]))
+
+
+def write_rtin(filename, model: FlatModel, n_initial_iter=5, n_initial_photons=10000, n_last_photons=0,
+               output_specific_energy="last", copy_input=True, check_convergence=None, physics_io_bytes=8,
+               raytracing=False, extra_root_attrs=None):
+    f = h5write.File()
+    c = model.conf
+    A = f.attrs
+    A["python_version"] = "0.9.12"
+    A["monochromatic"] = b"no"
+    A["raytracing"] = _yn(raytracing)
+    A["n_stats"] = np.int64(0)
+    A["n_inter_max"] = np.int64(c.n_inter_max)
+    A["n_reabs_max"] = np.int64(c.n_reabs_max)
+    A["pda"] = b"no"
+    A["mrw"] = _yn(c.use_mrw)
+    if c.use_mrw:
+        A["mrw_gamma"] = float(c.mrw_gamma)
+        A["n_inter_mrw_max"] = np.int64(c.n_mrw_max)
+    A["kill_on_absorb"] = _yn(c.kill_on_absorb)
+    A["kill_on_scatter"] = _yn(c.kill_on_scatter)
+    A["forced_first_interaction"] = b"yes"
+    A["forced_first_interaction_algorithm"] = "wr99"
+    A["propagation_check_frequency"] = float(c.propagation_check_frequency)
+    A["sample_sources_evenly"] = _yn(c.sample_sources_evenly)
+    A["enforce_energy_range"] = _yn(c.enforce_energy_range)
+    A["seed"] = np.int32(c.seed)
+    A["n_initial_iter"] = np.int64(n_initial_iter)
+    A["n_initial_photons"] = float(n_initial_photons)     # the front end stores what the user passed
+    A["n_last_photons"] = float(n_last_photons)
+    A["specific_energy_type"] = "initial"
+    A["physics_io_bytes"] = np.int32(physics_io_bytes)
+    A["copy_input"] = _yn(copy_input)
+    if check_convergence is None:
+        A["check_convergence"] = b"no"
+    else:
+        A["check_convergence"] = b"yes"
+        A["convergence_absolute"], A["convergence_relative"], A["convergence_percentile"] = \
+            [float(x) for x in check_convergence]
+    for k, v in (extra_root_attrs or {}).items():
+        A[k] = v
+
+    geo = f.create_group("Grid/Geometry")
+    h = hashlib.md5()
+    for w in (model.w1, model.w2, model.w3):
+        h.update(np.ascontiguousarray(w).tobytes())
+    gid = h.hexdigest()
+    geo.attrs["geometry"] = gid
+    geo.attrs["grid_type"] = "car"
+    geo.create_dataset("walls_1", _table([("x", model.w1)]))
+    geo.create_dataset("walls_2", _table([("y", model.w2)]))
+    geo.create_dataset("walls_3", _table([("z", model.w3)]))
+    q = f.create_group("Grid/Quantities")
+    d = q.create_dataset("density", model.density)
+    d.attrs["geometry"] = gid
+    if model.specific_energy is not None:
+        d = q.create_dataset("specific_energy", model.specific_energy)
+        d.attrs["geometry"] = gid
+    if model.minimum_specific_energy is not None:
+        q.attrs["minimum_specific_energy"] = np.asarray(model.minimum_specific_energy, dtype=np.float64)
+
+    gd = f.create_group("Dust")
+    for i, dust in enumerate(model.dust):
+        name = "dust_%03i" % (i + 1)
+        first = next(j for j, other in enumerate(model.dust) if other is dust)
+        if first < i:
+            gd[name] = h5write.SoftLink("/Dust/dust_%03i" % (first + 1))   # model.py:654-660
+        else:
+            write_dust(gd.create_group(name), dust)
+
+    gs = f.create_group("Sources")
+    for i, s in enumerate(model.sources):
+        g = gs.create_group("source_%05i" % (i + 1))
+        g.attrs["type"] = "point" if s.type == 1 else "sphere"
+        g.attrs["luminosity"] = float(s.luminosity)
+        g.attrs["peeloff"] = _yn(s.peeloff)
+        g.attrs["x"], g.attrs["y"], g.attrs["z"] = [float(v) for v in s.position]
+        if s.type == 2:
+            g.attrs["r"] = float(s.radius)
+            g.attrs["limb"] = _yn(s.limb_darkening)
+        if s.temperature is not None:
+            g.attrs["spectrum"] = "temperature"
+            g.attrs["temperature"] = float(s.temperature)
+        else:
+            g.attrs["spectrum"] = "spectrum"
+            g.create_dataset("spectrum", _table([("nu", s.spectrum_nu), ("fnu", s.spectrum_fnu)]))
+
+    go = f.create_group("Output")
+    go.attrs["output_density"] = "none"
+    go.attrs["output_density_diff"] = "none"
+    go.attrs["output_specific_energy"] = output_specific_energy
+    go.attrs["output_n_photons"] = "none"
+    go.create_group("Binned")
+    go.create_group("Peeled")
+    f.write(filename)
+    return gid

@@ -1,0 +1,272 @@
+"""Drop-in replacement of the reference back-end program: ``hyperion_car [-f] input output``.
+
+Mirrors ``program main`` (``src/main/main.f90:74-345``): open the ``.rtin``, copy or link
+``/Input``, run the Lucy iterations with the convergence test and per-iteration grid output
+(``output_grid``, ``src/grid/grid_generic.f90:29-130``), write the ``.rtout`` attributes the
+Python front end expects (``hyperion/model/helpers.py:10``, ``hyperion/model/model_output.py``)
+and ``date_ended`` only on success (the launcher treats its absence as failure,
+``scripts/hyperion:94-104``).
+
+The photon loop itself runs on the GPU through the C ABI (``hyperion_b200.capi``); there is no
+CPU path.  Under ``torchrun`` (WORLD_SIZE > 1) every rank drives one GPU, the packets are
+sharded by id and the deposit grid is all-reduced over NCCL once per iteration
+(``hyperion_b200.multigpu``); rank 0 writes the output.
+"""
+from __future__ import annotations
+
+import datetime
+import os
+import sys
+import time
+
+import numpy as np
+
+from . import __version__
+from .io import h5min, h5write
+from .multigpu import ShardedLucy
+from .rtin import ModelError, read_rtin
+
+
+def boxed_error(where, text, stream=None):
+    """Same shape as ``error()`` of ``fortranlib/src/lib_messages.f90:126-179`` (stderr)."""
+    stream = stream or sys.stderr
+    line = "ERROR: %s [%s]" % (text, where)
+    bar = "-" * min(max(len(line) + 2, 20), 100)
+    stream.write(" %s\n %s\n %s\n" % (bar, line, bar))
+    stream.flush()
+
+
+class ConvergenceCheck:
+    """``specific_energy_converged`` (``src/grid/grid_physics_3d.f90:630-689``)."""
+
+    def __init__(self, absolute, relative, percentile, log=lambda s: None):
+        self.absolute, self.relative, self.percentile = absolute, relative, percentile
+        self.prev = None
+        self.value_prev = None
+        self.log = log
+
+    @staticmethod
+    def quantile(x, percent):
+        """``quantile_dp`` (``fortranlib/src/lib_statistics.f90:102-125``)."""
+        xs = np.sort(x)
+        n = len(xs)
+        if percent >= 100.0:
+            ipos = n
+        elif percent <= 0.0:
+            ipos = 1
+        else:
+            ipos = int(np.floor(percent / 100.0 * (n - 1) + 0.5)) + 1   # Fortran nint for positive values
+        return xs[ipos - 1]
+
+    def __call__(self, se):
+        se = np.asarray(se, dtype=np.float64).ravel()
+        self.log(" [specific_energy_converged] checking convergence")
+        if self.prev is None:
+            self.prev = se.copy()
+            return False
+        prev = self.prev
+        if np.array_equal(prev, se):
+            value = 0.0
+        elif np.all((prev == se) | (prev == 0) | (se == 0)):
+            self.log(" [specific_energy_converged] could not check for convergence, as the only cells that "
+                     "changed had zero value before or after")
+            return False
+        else:
+            mask = (prev > 0) & (se > 0) & (prev != se)
+            a, b = prev[mask], se[mask]
+            value = self.quantile(np.maximum(a / b, b / a), self.percentile)
+        self.log("     -> Percentile: %7.2f" % self.percentile)
+        self.log("     -> Value @ Percentile: %10.3E" % value)
+        converged = False
+        if self.value_prev is not None:
+            if value == 0.0:
+                self.log("     -> Exact convergence")
+                converged = True
+            else:
+                ratio = max(self.value_prev / value, value / self.value_prev) if self.value_prev > 0 else np.inf
+                self.log("     -> Difference from previous iteration: %10.2f" % ratio)
+                converged = bool(value < self.absolute and abs(ratio) < self.relative)
+        self.prev = se.copy()
+        self.value_prev = value
+        return converged
+
+
+def _copy_tree(src, dst):
+    """Copy an h5min group into an h5write group (``mp_copy_group``, ``main.f90:145-147``)."""
+    for k, v in src.attrs.items():
+        dst.attrs[k] = v
+    for name in src.keys():
+        link = src.get_link(name)
+        if isinstance(link, h5min.ExternalLink):
+            dst[name] = h5write.ExternalLink(link.filename, link.path)
+            continue
+        if isinstance(link, h5min.SoftLink):
+            dst[name] = h5write.SoftLink(link.path)
+            continue
+        child = src[name]
+        if isinstance(child, h5min.Dataset):
+            ds = dst.create_dataset(name, child.read())
+            for k, v in child.attrs.items():
+                ds.attrs[k] = v
+        else:
+            _copy_tree(child, dst.create_group(name))
+
+
+def run(input_file, output_file, overwrite=False, device=None, log=None):
+    """Run the model in ``input_file`` and write ``output_file``.  Returns 0 on success; raises
+    ModelError / HyperionError for the conditions the reference reports through ``error()``."""
+    from .capi import Engine
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0")) if device is None else device
+    main = rank == 0
+    if log is None:
+        def log(s):
+            if main:
+                print(s, flush=True)
+
+    started = datetime.datetime.now().strftime("%d %B %Y at %H:%M:%S")
+    log(" " + "-" * 60)
+    log(" hyperion_b200 v%s (CUDA photon engine behind the Hyperion file interface)" % __version__)
+    log(" Started on %s" % started)
+    log(" Input:  %s" % input_file)
+    log(" Output: %s" % output_file)
+    log(" " + "-" * 60)
+    if not os.path.exists(input_file):
+        raise ModelError("File does not exist: %s" % input_file)
+    if main and os.path.exists(output_file):
+        if not overwrite:
+            raise ModelError("File exists: %s (use -f to overwrite)" % output_file)
+        os.remove(output_file)
+
+    t_start = time.time()
+    model, rs, fin = read_rtin(input_file)
+    log(" [main] using random seed = %d" % model.conf.seed)
+    if rs.monochromatic:
+        raise ModelError("the monochromatic final iteration is not implemented by this engine yet")
+    if rs.pda:
+        raise ModelError("the partial diffusion approximation is not implemented by this engine yet")
+    if rs.specific_energy_type == "additional":
+        raise ModelError("specific_energy_type='additional' is not implemented by this engine yet")
+
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        if not dist.is_initialized():
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    eng = Engine(local)
+    eng.load_model(model)
+    all_reduce = None
+    if world > 1:
+        import torch
+        stream = torch.cuda.ExternalStream(eng.stream, device=torch.device("cuda", local))
+
+        def all_reduce(buf):
+            with torch.cuda.stream(stream):
+                dist.all_reduce(buf)
+            stream.synchronize()
+    drv = ShardedLucy(eng, rank, world, all_reduce)
+
+    out = h5write.File()
+    out.attrs["date_started"] = started
+    out.attrs["fortran_version"] = "hyperion_b200 " + __version__
+    if rs.copy_input:
+        _copy_tree(fin, out.create_group("Input"))
+    else:
+        out["Input"] = h5write.ExternalLink(input_file, "/")
+
+    check = ConvergenceCheck(rs.convergence_absolute, rs.convergence_relative, rs.convergence_percentile, log) \
+        if rs.check_convergence else None
+    io_dtype = np.float32 if rs.physics_io_bytes == 4 else np.float64
+    density0 = model.density.copy() if rs.output_density_diff != "none" else None
+    converged = False
+    n_done = rs.n_initial_iter
+    for it in range(1, rs.n_initial_iter + 1):
+        log(" [main] starting Lucy iteration %d" % it)
+        st = drv.iteration(rs.n_initial_photons, it)
+        log(" [main] exiting Lucy iteration")
+        se = None
+        if check is not None:
+            se = eng.get_specific_energy()
+            converged = check(se)
+            if converged:
+                log("      ------ Specific energy calculation converged -----")
+        g = out.create_group("iteration_%05d" % it)
+        n_iter = it if (check is not None and converged) else rs.n_initial_iter
+
+        def wanted(mode):
+            return mode == "all" or (mode == "last" and it == n_iter)
+
+        log(" [output_grid] outputting grid arrays for iteration")
+        if wanted(rs.output_n_photons):
+            log(" WARNING: n_photons array is not allocated [output_grid]")
+        if wanted(rs.output_specific_energy):
+            if se is None:
+                se = eng.get_specific_energy()
+            d = g.create_dataset("specific_energy", se.astype(io_dtype))
+            d.attrs["geometry"] = rs.geometry_id
+        if wanted(rs.output_density):
+            d = g.create_dataset("density", eng.get_density().astype(io_dtype))
+            d.attrs["geometry"] = rs.geometry_id
+        if wanted(rs.output_density_diff):
+            d = g.create_dataset("density_diff", (eng.get_density() - density0).astype(io_dtype))
+            d.attrs["geometry"] = rs.geometry_id
+        g.attrs["killed_photons_geo"] = np.int64(st.killed_geo)
+        g.attrs["killed_photons_int"] = np.int64(st.killed_int)
+        if check is not None and converged:
+            n_done = it
+            break
+
+    out.attrs["converged"] = "yes" if converged else "no"
+    out.attrs["iterations"] = np.int32(n_done)
+
+    # final / raytracing iterations: no image groups are produced yet ("next" rows)
+    has_images = False
+    if "Output" in fin:
+        o = fin["Output"]
+        has_images = ("Binned" in o and len(o["Binned"].keys()) > 0) or ("Peeled" in o and len(o["Peeled"].keys()) > 0)
+    if has_images and (rs.n_last_photons > 0 or rs.raytracing):
+        raise ModelError("image / SED output (final and raytracing iterations) is not implemented by this engine yet")
+    for key in ("final", "raytracing"):
+        out.attrs["killed_photons_geo_" + key] = np.int64(0)
+        out.attrs["killed_photons_int_" + key] = np.int64(0)
+
+    eng.close()
+    out.attrs["cpu_time"] = float(time.time() - t_start)
+    ended = datetime.datetime.now().strftime("%d %B %Y at %H:%M:%S")
+    out.attrs["date_ended"] = ended
+    if main:
+        out.write(output_file)
+    log(" " + "-" * 60)
+    log(" Total time elapsed: %16.2f" % (time.time() - t_start))
+    log(" Ended on %s" % ended)
+    log(" " + "-" * 60)
+    if world > 1:
+        dist.barrier()
+    return 0
+
+
+def main(argv=None):
+    """``hyperion_car [-f] input_file output_file`` (``src/main/main.f90:74-106``)."""
+    argv = list(sys.argv[1:] if argv is None else argv)
+    overwrite = False
+    if argv and argv[0] == "-f":
+        overwrite = True
+        argv = argv[1:]
+    if len(argv) != 2:
+        sys.stderr.write("Usage: hyperion_car [-f] input_file output_file\n")
+        return 2
+    from .capi import HyperionError
+    try:
+        return run(argv[0], argv[1], overwrite=overwrite)
+    except (ModelError, HyperionError, h5min.H5Error) as e:
+        boxed_error("main", str(e))
+        return 1
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,90 @@
+"""Host side of the drop-in boundary: .rtin parsing, the convergence test, error wording."""
+import numpy as np
+import pytest
+
+from helpers import bitlevel_model
+from hyperion_b200 import rtin, rtin_write, runner
+from hyperion_b200.io import h5min, h5write
+
+
+def test_rtin_roundtrip(golden_car, tmp_path):
+    m = bitlevel_model(golden_car, True, True)
+    m.minimum_specific_energy = np.array([1.0, 2.0, 3.0])
+    fn = str(tmp_path / "m.rtin")
+    rtin_write.write_rtin(fn, m, n_initial_iter=5, n_initial_photons=1e4, check_convergence=(2., 1.02, 99.))
+    got, rs, _ = rtin.read_rtin(fn)
+    assert rs.n_initial_iter == 5 and rs.n_initial_photons == 10000 and rs.grid_type == "car"
+    assert rs.check_convergence and rs.convergence_percentile == 99.
+    assert got.conf.sample_sources_evenly and got.conf.seed == -124902
+    for k in ("w1", "w2", "w3", "density"):
+        assert np.array_equal(getattr(got, k), getattr(m, k))
+    assert len(got.dust) == 3 and len(got.sources) == 5
+    for k in ("nu", "chi", "albedo", "P2", "emiss_jnu", "jnu_var", "chi_inv_planck"):
+        assert np.array_equal(getattr(got.dust[2], k), getattr(m.dust[0], k)), k
+    assert got.dust[0].version == m.dust[0].version
+    assert np.array_equal(got.minimum_specific_energy, [1., 2., 3.])
+    for a, b in zip(got.sources, m.sources):
+        assert a.luminosity == b.luminosity and a.temperature == b.temperature and tuple(a.position) == tuple(b.position)
+
+
+def test_reference_error_phrases(golden_car, tmp_path):
+    """hyperion/model/tests/test_fortran.py: the log is searched for these phrases."""
+    m = bitlevel_model(golden_car, False, False)
+    fn = str(tmp_path / "m.rtin")
+    rtin_write.write_rtin(fn, m, n_initial_iter=1, n_initial_photons=0)
+    with pytest.raises(rtin.ModelError, match="number of specific_energy photons is zero"):
+        rtin.read_rtin(fn)
+    m.sources[0].temperature = None
+    m.sources[0].spectrum_nu = np.array([3e10, 2e10, 1e11])
+    m.sources[0].spectrum_fnu = np.ones(3)
+    rtin_write.write_rtin(fn, m)
+    with pytest.raises(rtin.ModelError, match="spectrum frequency should be monotonically increasing"):
+        rtin.read_rtin(fn)
+    m.sources.clear()
+    rtin_write.write_rtin(fn, m)
+    with pytest.raises(rtin.ModelError, match="no sources set up"):
+        rtin.read_rtin(fn)
+
+
+def test_convergence_check_follows_reference():
+    """specific_energy_converged (grid_physics_3d.f90:637-689): first call stores, second call
+    has no previous value, third may converge; quantile uses nint(p/100*(n-1))+1."""
+    q = runner.ConvergenceCheck.quantile
+    x = np.arange(1., 11.)
+    assert q(x, 100.) == 10. and q(x, 0.) == 1. and q(x, 50.) == 6. and q(x, 99.) == 10.
+    c = runner.ConvergenceCheck(absolute=2., relative=1.5, percentile=100.)
+    a = np.array([1., 2., 4.])
+    assert c(a) is False
+    assert c(a * np.array([1.1, 1., 1.])) is False          # value 1.1, no previous value
+    assert c(a * np.array([1.1, 1.2, 1.])) is True           # value 1.2, ratio 1.09
+    assert c(a * 100.) is False                               # value way above 'absolute'
+    same = a * 100.
+    assert c(same) is True                                    # exact convergence
+
+
+@pytest.mark.gpu
+def test_runner_end_to_end_writes_reference_layout(golden_car, tmp_path):
+    """python -m hyperion_b200 input output: the .rtout has what ModelOutput reads
+    (hyperion/model/helpers.py:10 find_last_iteration, model_output.py:975 get_quantities)."""
+    m = bitlevel_model(golden_car, False, True)
+    fin, fout = str(tmp_path / "m.rtin"), str(tmp_path / "m.rtout")
+    gid = rtin_write.write_rtin(fin, m, n_initial_iter=3, n_initial_photons=20000, output_specific_energy="all",
+                                copy_input=False)
+    assert runner.main([fin, fout]) == 0
+    assert runner.main([fin, fout]) == 1                      # exists, no -f
+    assert runner.main(["-f", fin, fout]) == 0
+    r = h5min.File(fout)
+    assert "date_ended" in r.attrs and "date_started" in r.attrs and "cpu_time" in r.attrs
+    assert int(np.asarray(r.attrs["iterations"]).ravel()[0]) == 3
+    assert bytes(np.asarray(r.attrs["converged"]).ravel()[0]).strip(b"\x00") == b"no"
+    for k in ("killed_photons_geo_final", "killed_photons_int_final", "killed_photons_geo_raytracing",
+              "killed_photons_int_raytracing"):
+        assert k in r.attrs
+    assert isinstance(r.get_link("Input"), h5min.ExternalLink)
+    for it in (1, 2, 3):
+        g = r["iteration_%05d" % it]
+        se = g["specific_energy"]
+        assert se.shape == (3, 3, 5, 7) and se.dtype == np.float64
+        assert bytes(np.asarray(se.attrs["geometry"]).ravel()[0]).decode().strip("\x00") == gid
+        assert int(np.asarray(g.attrs["killed_photons_geo"]).ravel()[0]) == 0
+        assert np.all(se[...] > 0)
