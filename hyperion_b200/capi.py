@@ -51,6 +51,23 @@ class RunConf(C.Structure):
         ("sample_sources_evenly", C.c_int32), ("enforce_energy_range", C.c_int32),
         ("use_mrw", C.c_int32), ("mrw_gamma", C.c_double), ("n_mrw_max", C.c_int64),
         ("propagation_check_frequency", C.c_double),
+        ("forced_first_interaction", C.c_int32), ("forced_first_interaction_algorithm", C.c_int32),
+        ("baes16_xi", C.c_double),
+    ]
+
+
+class ImageConf(C.Structure):
+    _fields_ = [
+        ("n_view", C.c_int32), ("theta", _dp), ("phi", _dp),
+        ("inside_observer", C.c_int32), ("ignore_optical_depth", C.c_int32),
+        ("peeloff_x", C.c_double), ("peeloff_y", C.c_double), ("peeloff_z", C.c_double),
+        ("d_min", C.c_double), ("d_max", C.c_double),
+        ("compute_image", C.c_int32), ("n_x", C.c_int32), ("n_y", C.c_int32),
+        ("x_min", C.c_double), ("x_max", C.c_double), ("y_min", C.c_double), ("y_max", C.c_double),
+        ("compute_sed", C.c_int32), ("n_ap", C.c_int32), ("ap_min", C.c_double), ("ap_max", C.c_double),
+        ("n_wav", C.c_int32), ("wav_min", C.c_double), ("wav_max", C.c_double),
+        ("track_origin", C.c_int32), ("track_n_scat", C.c_int32),
+        ("uncertainties", C.c_int32), ("compute_stokes", C.c_int32), ("io_bytes", C.c_int32),
     ]
 
 
@@ -61,7 +78,7 @@ class IterStats(C.Structure):
         ("n_crossings", C.c_int64), ("n_absorptions", C.c_int64),
         ("n_scatterings", C.c_int64), ("n_escaped", C.c_int64),
         ("kernel_ms", C.c_double), ("epilogue_ms", C.c_double),
-        ("flight_ms", C.c_double), ("n_rounds", C.c_int64), ("n_launches", C.c_int64),
+        ("flight_ms", C.c_double), ("n_rounds", C.c_int64), ("n_launches", C.c_int64), ("n_peel_crossings", C.c_int64), ("n_peeloffs", C.c_int64),
     ]
 
     def as_dict(self):
@@ -88,7 +105,8 @@ class CApi:
         f("last_error").restype = C.c_char_p
         for name in ("set_grid_cartesian", "add_dust", "add_source", "set_run_conf", "set_density",
                      "set_specific_energy", "lucy_begin", "lucy_finish", "get_specific_energy",
-                     "get_density", "get_energy_sum"):
+                     "get_density", "get_energy_sum", "add_peeled_group", "final_begin", "final_photons",
+                     "final_finish", "raytracing_photons", "image_shape", "get_sed", "get_image"):
             f(name).restype = C.c_int
 
     def _fn(self, name):
@@ -139,7 +157,51 @@ class CApi:
         t.sample_sources_evenly, t.enforce_energy_range = int(c.sample_sources_evenly), int(c.enforce_energy_range)
         t.use_mrw, t.mrw_gamma, t.n_mrw_max = int(c.use_mrw), c.mrw_gamma, c.n_mrw_max
         t.propagation_check_frequency = c.propagation_check_frequency
+        t.forced_first_interaction = int(c.forced_first_interaction)
+        t.forced_first_interaction_algorithm = {"wr99": 1, "baes16": 2}[c.forced_first_interaction_algorithm]
+        t.baes16_xi = c.baes16_xi
         self.check(self._fn("set_run_conf")(ctx, C.byref(t)))
+
+    def add_peeled_group(self, ctx, g):
+        """g: :class:`hyperion_b200.flatmodel.FlatPeeledGroup`"""
+        t = ImageConf()
+        theta = np.ascontiguousarray(g.theta, dtype=np.float64)
+        phi = np.ascontiguousarray(g.phi, dtype=np.float64)
+        t.n_view, t.theta, t.phi = len(theta), _ptr(theta), _ptr(phi)
+        t.inside_observer, t.ignore_optical_depth = int(g.inside_observer), int(g.ignore_optical_depth)
+        t.peeloff_x, t.peeloff_y, t.peeloff_z = [float(v) for v in g.peeloff_origin]
+        t.d_min, t.d_max = g.d_min, g.d_max
+        t.compute_image = int(g.image is not None)
+        if g.image is not None:
+            t.n_x, t.n_y, t.x_min, t.x_max, t.y_min, t.y_max = g.image
+        t.compute_sed = int(g.sed is not None)
+        if g.sed is not None:
+            t.n_ap, t.ap_min, t.ap_max = g.sed
+        t.n_wav, t.wav_min, t.wav_max = g.wavelengths
+        t.track_origin = {"no": 0, "basic": 1, "yes": 1, "detailed": 2, "scatterings": 3}[g.track_origin]
+        t.track_n_scat = g.track_n_scat
+        t.uncertainties, t.compute_stokes, t.io_bytes = int(g.uncertainties), int(g.stokes), g.io_bytes
+        self.check(self._fn("add_peeled_group")(ctx, C.byref(t)))
+
+    def image_shape(self, ctx, group, which):
+        dims = (C.c_int64 * 6)()
+        nd = C.c_int32()
+        self.check(self._fn("image_shape")(ctx, C.c_int32(group), C.c_int32(which), dims, C.byref(nd)))
+        return tuple(dims[i] for i in range(nd.value))
+
+    def _get_cube(self, ctx, group, which, uncertainties=False):
+        shape = self.image_shape(ctx, group, which)
+        out = np.zeros(shape, dtype=np.float64)
+        unc = np.zeros(shape, dtype=np.float64) if uncertainties else None
+        fn = self._fn("get_sed" if which == 0 else "get_image")
+        self.check(fn(ctx, C.c_int32(group), _ptr(out), None if unc is None else _ptr(unc)))
+        return (out, unc) if uncertainties else out
+
+    def get_sed(self, ctx, group, uncertainties=False):
+        return self._get_cube(ctx, group, 0, uncertainties)
+
+    def get_image(self, ctx, group, uncertainties=False):
+        return self._get_cube(ctx, group, 1, uncertainties)
 
     def set_density(self, ctx, n_dust, density):
         density = np.ascontiguousarray(density, dtype=np.float64)

@@ -129,6 +129,30 @@ class FlatConf:
     propagation_check_frequency: float = 1.e-3
     n_initial_iter: int = 5
     n_initial_photons: int = 0
+    forced_first_interaction: bool = True
+    forced_first_interaction_algorithm: str = "wr99"
+    baes16_xi: float = 0.5
+
+
+@dataclass
+class FlatPeeledGroup:
+    """One ``Output/Peeled/group_%05i`` (``hyperion/conf/conf_files.py`` PeeledImageConf;
+    ``src/images/images_peeled.f90:272-382``, ``src/images/image_type.f90:153-335``)."""
+    theta: np.ndarray = None            # degrees
+    phi: np.ndarray = None
+    wavelengths: tuple = (1, 1.0, 1000.0)          # (n_wav, wav_min, wav_max) microns
+    image: Optional[tuple] = None       # (n_x, n_y, x_min, x_max, y_min, y_max)
+    sed: Optional[tuple] = None         # (n_ap, ap_min, ap_max)
+    track_origin: str = "no"
+    track_n_scat: int = 0
+    uncertainties: bool = False
+    stokes: bool = True
+    io_bytes: int = 8
+    inside_observer: bool = False
+    ignore_optical_depth: bool = False
+    peeloff_origin: tuple = (0.0, 0.0, 0.0)
+    d_min: float = -np.inf
+    d_max: float = np.inf
 
 
 @dataclass
@@ -142,6 +166,7 @@ class FlatModel:
     conf: FlatConf = field(default_factory=FlatConf)
     specific_energy: Optional[np.ndarray] = None
     minimum_specific_energy: Optional[np.ndarray] = None
+    peeled: List["FlatPeeledGroup"] = field(default_factory=list)
 
     def __post_init__(self):
         self.w1, self.w2, self.w3 = _f8(self.w1), _f8(self.w2), _f8(self.w3)
@@ -181,3 +206,5 @@ def apply_model(api, ctx, model: FlatModel):
     api.set_run_conf(ctx, model.conf)
     api.set_density(ctx, len(model.dust), model.density)
     api.set_specific_energy(ctx, model.specific_energy, model.minimum_specific_energy)
+    for g in model.peeled:
+        api.add_peeled_group(ctx, g)

@@ -96,7 +96,41 @@ typedef struct {
   double mrw_gamma;
   int64_t n_mrw_max;
   double propagation_check_frequency; /* reference self-check rate; see DESIGN.md */
+  /* final iteration (src/main/iter_final.f90:191-209, src/main/forced_interaction.f90) */
+  int32_t forced_first_interaction;            /* default on (hyperion/conf/conf_files.py:66) */
+  int32_t forced_first_interaction_algorithm;  /* HYP_FFI_WR99 / HYP_FFI_BAES16 */
+  double baes16_xi;
 } hyp_run_conf;
+
+#define HYP_FFI_WR99 1
+#define HYP_FFI_BAES16 2
+
+/* One peeled image / SED group: the attributes of Output/Peeled/group_%05i in the .rtin file
+ * (peeled_images_setup, src/images/images_peeled.f90:272-382; image_setup,
+ * src/images/image_type.f90:153-335; written by hyperion/conf/conf_files.py PeeledImageConf). */
+#define HYP_TRACK_NO 0
+#define HYP_TRACK_BASIC 1
+#define HYP_TRACK_DETAILED 2
+#define HYP_TRACK_SCATTERINGS 3
+typedef struct {
+  int32_t n_view;
+  const double *theta, *phi;                 /* [n_view] viewing angles, degrees (table 'angles') */
+  int32_t inside_observer;                   /* not implemented: rejected */
+  int32_t ignore_optical_depth;
+  double peeloff_x, peeloff_y, peeloff_z;    /* peeloff origin */
+  double d_min, d_max;                       /* depth cut along the line of sight (+-inf: none) */
+  int32_t compute_image, n_x, n_y;
+  double x_min, x_max, y_min, y_max;
+  int32_t compute_sed, n_ap;
+  double ap_min, ap_max;
+  int32_t n_wav;
+  double wav_min, wav_max;                   /* microns */
+  int32_t track_origin;                      /* HYP_TRACK_* */
+  int32_t track_n_scat;
+  int32_t uncertainties;
+  int32_t compute_stokes;
+  int32_t io_bytes;                          /* 4 or 8: precision the caller will store */
+} hyp_image_conf;
 
 /* Per-iteration counters (killed_photons_* attrs of main.f90:225-230 plus the
  * work counters the roofline needs). */
@@ -114,6 +148,8 @@ typedef struct {
   double flight_ms;           /* device time of the flight kernel alone (the HBM-bound part) */
   int64_t n_rounds;           /* rounds of the packet pool */
   int64_t n_launches;         /* kernels of this library launched for the iteration */
+  int64_t n_peel_crossings;   /* cell crossings of peel-off marches (grid_escape_tau / _column_density) */
+  int64_t n_peeloffs;         /* peel-off contributions binned */
 } hyp_iter_stats;
 
 const char *hyp_last_error(void);
@@ -172,6 +208,33 @@ int hyp_get_specific_energy(hyp_ctx *ctx, double *out);
 int hyp_get_density(hyp_ctx *ctx, double *out);
 /* raw deposit sums of the last iteration (specific_energy_sum, grid_physics_3d.f90:40) */
 int hyp_get_energy_sum(hyp_ctx *ctx, double *out);
+
+/* ---- final (imaging) and raytracing iterations ------------------------------------------------
+ * replaces: setup_final_iteration (src/main/setup_rt.f90:306-347) -- call once per peeled group,
+ * in file order, any time before hyp_run_final. */
+int hyp_add_peeled_group(hyp_ctx *ctx, const hyp_image_conf *conf);
+/* replaces: do_final (src/main/iter_final.f90:60-145) for packets [first_id, first_id+n).
+ * peeloff_scattering_only is main.f90:274's use_raytracing.  Images accumulate in device memory;
+ * hyp_final_finish applies peeled_images_adjust_scale(energy_total / energy_current)
+ * (iter_final.f90:140-143) after the host has all-reduced hyp_image_device_buffers. */
+int hyp_final_begin(hyp_ctx *ctx);
+int hyp_final_photons(hyp_ctx *ctx, int64_t first_id, int64_t n_photons, int32_t peeloff_scattering_only);
+int hyp_final_finish(hyp_ctx *ctx, hyp_iter_stats *stats);
+/* replaces: do_raytracing (src/main/iter_raytracing.f90:31-141): n_sources packets from the
+ * sources [first_source_id ...) and n_dust packets from random cells [first_dust_id ...), each
+ * peeled off polychromatically.  n_total_* are the whole job's counts (the weights divide by them). */
+int hyp_raytracing_photons(hyp_ctx *ctx, int64_t first_source_id, int64_t n_sources, int64_t n_total_sources,
+                           int64_t first_dust_id, int64_t n_dust, int64_t n_total_dust, hyp_iter_stats *stats);
+/* All image / SED accumulators of all groups as one contiguous device buffer (fp64) followed by
+ * 8 scalars, for the host's collective.  replaces: mp_collect_images (src/mpi/mpi_routines.f90:363-471) */
+int hyp_image_device_buffers(hyp_ctx *ctx, void **buffer, int64_t *n_values);
+/* Shapes in file order: seds (n_stokes, n_orig, n_view, n_ap, n_wav), images (n_stokes, n_orig,
+ * n_view, n_y, n_x, n_wav) (src/images/image_type.f90:291,299 reversed, as HDF5 stores them). */
+int hyp_image_shape(hyp_ctx *ctx, int32_t group, int32_t which /* 0 sed, 1 image */, int64_t dims[6], int32_t *ndim);
+/* replaces: image_write (src/images/image_type.f90:608-788): values as the reference writes them
+ * (divided by the relative bin width, apertures cumulative); unc may be NULL. */
+int hyp_get_sed(hyp_ctx *ctx, int32_t group, double *sed, double *unc);
+int hyp_get_image(hyp_ctx *ctx, int32_t group, double *image, double *unc);
 
 /* stream handle (cudaStream_t) the ctx launches on, for callers that time with events */
 void *hyp_stream(hyp_ctx *ctx);

@@ -698,6 +698,12 @@ struct Photon {
   bool last_isotropic = false, scattered = false, reprocessed = false;
   int n_scat = 0, source_id = 0, dust_id = 0;
   char last[3] = "  ";
+  // state before the last interaction, used by peel-off (type_photon.f90:44-46)
+  Angle a_prev{0, 0, 0, 0};
+  Stokes s_prev{0, 0, 0, 0};
+  Vec v_prev{0, 0, 0};
+  int emiss_type = 0, emiss_var_id = 0;
+  double emiss_var_frac = 0.0;
 };
 
 struct Source {
@@ -712,6 +718,295 @@ struct Source {
   PdfCont spectrum;
   bool intersect = false;
 };
+
+// ---------------------------------------------------------------------------
+// final iteration, peel-off and raytracing
+// ---------------------------------------------------------------------------
+
+// integral_general_subset_dp with loglog pieces (lib_array.f90:362-366,450-526)
+double integral_loglog_subset(const double *x, const double *y, int n, double x1, double x2) {
+  if (x1 > x[n - 1] || x2 < x[0]) return 0.0;
+  int i1, i2;
+  double f1, f2, xx1, xx2;
+  if (x1 > x[0]) {
+    i1 = locate(x, n, x1);
+    f1 = interp1d_loglog(x, y, n, x1);
+    xx1 = x1;
+  } else {
+    i1 = 0;
+    f1 = y[0];
+    xx1 = x[0];
+  }
+  if (x2 < x[n - 1]) {
+    i2 = locate(x, n, x2);
+    f2 = interp1d_loglog(x, y, n, x2);
+    xx2 = x2;
+  } else {
+    i2 = n;
+    f2 = y[n - 1];
+    xx2 = x[n - 1];
+  }
+  double sum;
+  if (i2 > i1) {
+    if (i2 > i1 + 1)
+      sum = integral_general(x + i1, y + i1, i2 - i1, trapezium_loglog);  // x(i1+1:i2)
+    else
+      sum = 0.0;
+    sum = sum + trapezium_loglog(xx1, f1, x[i1], y[i1]);          // x(i1+1)
+    sum = sum + trapezium_loglog(x[i2 - 1], y[i2 - 1], xx2, f2);  // x(i2)
+  } else {
+    sum = trapezium_loglog(xx1, f1, xx2, f2);
+  }
+  return sum;
+}
+
+// difference_angle3d_dp (type_angle3d.f90:283-419)
+Angle difference_angle3d(const Angle &a_coord, const Angle &a_final) {
+  Angle l;
+  if (std::fabs(a_coord.sint) < 1.e-10) {
+    l = a_final;
+    if (a_coord.cost > 0.0) {
+      l.cosp = +a_coord.cosp * a_final.cosp + a_coord.sinp * a_final.sinp;
+      l.sinp = -a_coord.cosp * a_final.sinp + a_coord.sinp * a_final.cosp;
+    } else {
+      l.cost = -l.cost;
+      l.cosp = +a_coord.cosp * a_final.cosp + a_coord.sinp * a_final.sinp;
+      l.sinp = +a_coord.cosp * a_final.sinp - a_coord.sinp * a_final.cosp;
+    }
+    return l;
+  }
+  double cos_a = a_coord.cost, sin_a = a_coord.sint, cos_c = a_final.cost, sin_c = a_final.sint;
+  double cos_big_b = a_coord.cosp * a_final.cosp + a_coord.sinp * a_final.sinp;
+  double sin_big_b = a_coord.sinp * a_final.cosp - a_coord.cosp * a_final.sinp;
+  double cos_b = cos_a * cos_c + sin_a * sin_c * cos_big_b;
+  double sin_b = sin2cos(cos_b);  // cos2sin is the same expression
+  if (std::fabs(cos_b + 1.0) < 1.e-10) return angle3d_deg(180.0, 0.0);
+  if (std::fabs(cos_b - 1.0) < 1.e-10) return angle3d_deg(0.0, 0.0);
+  // Fortran precedence: .eqv. binds weaker than .and.:  A .eqv. (B .and. C) .eqv. D
+  bool same_sign = ((cos_a > 0.0) == ((cos_b > 0.0) && (sin_a > 0.0))) == (sin_b > 0.0);
+  double delta;
+  if (std::fabs(sin_a) > std::fabs(cos_a))
+    delta = cos_b - cos_a;
+  else
+    delta = sin_b - sin_a;
+  double sin_big_c, cos_big_c;
+  if (same_sign && std::fabs(delta) < 1.e-5 && sin_c < 1.e-5) {
+    double diff;
+    if (std::fabs(sin_a) > std::fabs(cos_a))
+      diff = (sin_c * sin_c - delta * delta * (1.0 + (cos_a / sin_a) * (cos_a / sin_a))) / (sin_a * sin_b);
+    else
+      diff = (sin_c * sin_c - delta * delta * (1.0 + (sin_a / cos_a) * (sin_a / cos_a))) / (sin_a * sin_b);
+    sin_big_c = diff >= 0.0 ? std::sqrt(diff) : 0.0;
+    cos_big_c = cos_c > 0.0 ? sin2cos(sin_big_c) : -sin2cos(sin_big_c);
+  } else {
+    sin_big_c = +std::fabs(sin_big_b) * sin_c / sin_b;
+    cos_big_c = (cos_c - cos_a * cos_b) / (sin_a * sin_b);
+  }
+  if (sin_big_c == 0.0) sin_big_c = std::numeric_limits<double>::min();
+  l.cost = cos_b;
+  l.sint = sin_b;
+  l.cosp = cos_big_c;
+  l.sinp = sin_big_b < 0.0 ? sin_big_c : -sin_big_c;
+  return l;
+}
+
+// type image (image_type.f90:44-115); arrays in Fortran order, first index fastest
+struct Image {
+  hyp_image_conf c;
+  int n_nu = 0, n_stokes = 4, n_orig = 1, n_sources = 0, n_dust = 0;
+  double nu_min = 0, nu_max = 0, log10_nu_min = 0, log10_nu_max = 0, log10_ap_min = 0, log10_ap_max = 0;
+  std::vector<double> img, img2, imgn, sed, sed2, sedn;
+  size_t img_index(int inu, int ix, int iy, int iv, int io, int is) const {
+    return (size_t)(inu - 1) +
+           (size_t)n_nu * ((ix - 1) + (size_t)c.n_x * ((iy - 1) + (size_t)c.n_y * ((iv - 1) + (size_t)c.n_view * ((io - 1) + (size_t)n_orig * is))));
+  }
+  size_t sed_index(int inu, int ir, int iv, int io, int is) const {
+    return (size_t)(inu - 1) + (size_t)n_nu * ((ir - 1) + (size_t)c.n_ap * ((iv - 1) + (size_t)c.n_view * ((io - 1) + (size_t)n_orig * is)));
+  }
+};
+
+struct PeeledState {
+  std::vector<Image> image;                 // per group
+  std::vector<int> group_id, view_id;       // per peeled view, 1-based
+  std::vector<Angle> viewing_angles;
+  std::vector<Vec> r_peeloff;               // per group
+  // raytracing caches (images_peeled.f90:423-530), per (group, source / dust)
+  std::vector<std::vector<std::vector<double>>> source_spectra, dust_extinction;
+  std::vector<std::vector<std::vector<double>>> dust_log10_emissivity;  // [ig][id][ijnu*n_nu + inu]
+};
+
+// image_setup (image_type.f90:153-335)
+void image_setup(Image &im, const hyp_image_conf &c, int n_sources, int n_dust) {
+  im.c = c;
+  im.n_sources = n_sources;
+  im.n_dust = n_dust;
+  im.n_nu = c.n_wav;
+  if (im.n_nu < 1) throw OracleError{"n_nu should be >= 1"};
+  im.n_stokes = c.compute_stokes ? 4 : 1;
+  if (c.compute_sed) {
+    im.log10_ap_min = std::log10(c.ap_min);
+    im.log10_ap_max = std::log10(c.ap_max);
+  }
+  switch (c.track_origin) {
+    case HYP_TRACK_SCATTERINGS: im.n_orig = 4 + 2 * c.track_n_scat; break;
+    case HYP_TRACK_DETAILED: im.n_orig = 2 * (n_sources + n_dust); break;
+    case HYP_TRACK_BASIC: im.n_orig = 4; break;
+    case HYP_TRACK_NO: im.n_orig = 1; break;
+    default: throw OracleError{"unknown track_origin flag"};
+  }
+  const double c_cgs = 2.99792458e10;
+  // "1.e-4" is a default-real (single precision) literal in image_type.f90:262-263
+  const double micron = (double)1.e-4f;
+  im.nu_min = c_cgs / (c.wav_max * micron);
+  im.nu_max = c_cgs / (c.wav_min * micron);
+  im.log10_nu_min = std::log10(im.nu_min);
+  im.log10_nu_max = std::log10(im.nu_max);
+  if (c.compute_image) {
+    size_t n = (size_t)im.n_nu * c.n_x * c.n_y * c.n_view * im.n_orig * im.n_stokes;
+    im.img.assign(n, 0.0);
+    if (c.uncertainties) {
+      im.img2.assign(n, 0.0);
+      im.imgn.assign(n, 0.0);
+    }
+  }
+  if (c.compute_sed) {
+    size_t n = (size_t)im.n_nu * c.n_ap * c.n_view * im.n_orig * im.n_stokes;
+    im.sed.assign(n, 0.0);
+    if (c.uncertainties) {
+      im.sed2.assign(n, 0.0);
+      im.sedn.assign(n, 0.0);
+    }
+  }
+  if (c.io_bytes != 4 && c.io_bytes != 8) throw OracleError{"unexpected value of io_bytes (should be 4 or 8)"};
+}
+
+// orig (image_type.f90:117-134)
+int orig(const Photon &p) {
+  if (p.scattered) return p.reprocessed ? 4 : 3;
+  return p.reprocessed ? 2 : 1;
+}
+
+// origin slice shared by image_bin / image_bin_raytraced (image_type.f90:440-460)
+int origin_slice(const Image &im, const Photon &p) {
+  if (im.c.track_origin == HYP_TRACK_DETAILED) {
+    int iorig = orig(p);
+    // mod(iorig,2), mod(iorig+1,2) as in the Fortran
+    int io = ((iorig - iorig % 2) * im.n_sources + (iorig - (iorig + 1) % 2 - 1) * im.n_dust) / 2;
+    if (iorig % 2 == 0)
+      io = io + p.dust_id;
+    else
+      io = io + p.source_id;
+    return io;
+  }
+  if (im.c.track_origin == HYP_TRACK_SCATTERINGS) {
+    int io = p.n_scat > im.c.track_n_scat ? im.c.track_n_scat + 2 : p.n_scat + 1;
+    if (p.reprocessed) io = io + (im.c.track_n_scat + 2);
+    return io;
+  }
+  if (im.c.track_origin == HYP_TRACK_BASIC) return orig(p);
+  return 1;
+}
+
+// find_sed_bin (image_type.f90:337-354)
+int find_sed_bin(const Image &im, double x_image, double y_image) {
+  double log10_r = std::log10(std::sqrt(x_image * x_image + y_image * y_image));
+  if (log10_r < im.log10_ap_min || im.c.n_ap == 1) return 1;
+  return ipos(im.log10_ap_min, im.log10_ap_max, log10_r, im.c.n_ap - 1) + 1;
+}
+
+// in_image (image_type.f90:369-406)
+bool in_image(const Image &im, double x, double y) {
+  const hyp_image_conf &c = im.c;
+  if (c.compute_image) {
+    if ((x >= c.x_min && x <= c.x_max) || (x <= c.x_min && x >= c.x_max))
+      if ((y >= c.y_min && y <= c.y_max) || (y <= c.y_min && y >= c.y_max)) return true;
+  }
+  if (c.compute_sed) {
+    if (x * x + y * y <= c.ap_max * c.ap_max) return true;
+  }
+  return false;
+}
+
+// image_bin + image_bin_single (image_type.f90:408-524), no filters
+void image_bin(Image &im, const Photon &p, double x_image, double y_image, int iv) {
+  if (std::isnan(p.energy) || std::isnan(p.s.I)) return;
+  int inu = ipos(im.log10_nu_min, im.log10_nu_max, std::log10(p.nu), im.n_nu);
+  int io = origin_slice(im, p);
+  const double st[4] = {p.s.I, p.s.Q, p.s.U, p.s.V};
+  if (inu >= 1 && inu <= im.n_nu) {
+    if (im.c.compute_image) {
+      int ix = ipos(im.c.x_min, im.c.x_max, x_image, im.c.n_x);
+      int iy = ipos(im.c.y_min, im.c.y_max, y_image, im.c.n_y);
+      if (ix >= 1 && ix <= im.c.n_x && iy >= 1 && iy <= im.c.n_y) {
+        for (int is = 0; is < im.n_stokes; is++) {
+          size_t k = im.img_index(inu, ix, iy, iv, io, is);
+          double v = st[is] * p.energy * 1.0;
+          im.img[k] = im.img[k] + v;
+          if (im.c.uncertainties) {
+            im.img2[k] = im.img2[k] + v * v;
+            im.imgn[k] = im.imgn[k] + 1.0;
+          }
+        }
+      }
+    }
+    if (im.c.compute_sed) {
+      int ir = find_sed_bin(im, x_image, y_image);
+      if (ir >= 1 && ir <= im.c.n_ap) {
+        for (int is = 0; is < im.n_stokes; is++) {
+          size_t k = im.sed_index(inu, ir, iv, io, is);
+          double v = st[is] * p.energy * 1.0;
+          im.sed[k] = im.sed[k] + v;
+          if (im.c.uncertainties) {
+            im.sed2[k] = im.sed2[k] + v * v;
+            im.sedn[k] = im.sedn[k] + 1.0;
+          }
+        }
+      }
+    }
+  }
+}
+
+// image_bin_raytraced (image_type.f90:526-606)
+void image_bin_raytraced(Image &im, const Photon &p, double x_image, double y_image, int iv,
+                         const std::vector<double> &spectrum) {
+  if (std::isnan(p.energy) || std::isnan(p.s.I)) return;
+  int io = origin_slice(im, p);
+  if (im.c.compute_image) {
+    int ix = ipos(im.c.x_min, im.c.x_max, x_image, im.c.n_x);
+    int iy = ipos(im.c.y_min, im.c.y_max, y_image, im.c.n_y);
+    if (ix >= 1 && ix <= im.c.n_x && iy >= 1 && iy <= im.c.n_y) {
+      for (int iw = 1; iw <= im.n_nu; iw++) {
+        size_t k = im.img_index(iw, ix, iy, iv, io, 0);
+        im.img[k] = im.img[k] + spectrum[iw - 1];
+        if (im.c.uncertainties) {
+          im.img2[k] = im.img2[k] + spectrum[iw - 1] * spectrum[iw - 1];
+          im.imgn[k] = im.imgn[k] + 1.0;
+        }
+      }
+    }
+  }
+  if (im.c.compute_sed) {
+    int ir = find_sed_bin(im, x_image, y_image);
+    if (ir >= 1 && ir <= im.c.n_ap) {
+      for (int iw = 1; iw <= im.n_nu; iw++) {
+        size_t k = im.sed_index(iw, ir, iv, io, 0);
+        im.sed[k] = im.sed[k] + spectrum[iw - 1];
+        if (im.c.uncertainties) {
+          im.sed2[k] = im.sed2[k] + spectrum[iw - 1] * spectrum[iw - 1];
+          im.sedn[k] = im.sedn[k] + 1.0;
+        }
+      }
+    }
+  }
+}
+
+// image_scale (image_type.f90:136-151)
+void image_scale(Image &im, double scale) {
+  for (auto &v : im.img) v = v * scale;
+  for (auto &v : im.sed) v = v * scale;
+  for (auto &v : im.img2) v = v * (scale * scale);
+  for (auto &v : im.sed2) v = v * (scale * scale);
+}
 
 }  // namespace
 
@@ -743,6 +1038,8 @@ struct orc_ctx {
   // counters
   int64_t killed_photons_geo = 0, killed_photons_int = 0;
   int64_t n_crossings = 0, n_absorptions = 0, n_scatterings = 0, n_escaped = 0, n_photons_run = 0;
+  int64_t n_peel_crossings = 0, n_peeloffs = 0;
+  PeeledState peeled;
   bool setup_done = false;
   std::string error;
 };
@@ -1023,6 +1320,7 @@ void emit(orc_ctx &g, Photon &p) {
   if (g.conf.sample_sources_evenly) p.energy = p.energy * g.luminosity.pdf[p.source_id - 1] * n_sources;
   g.energy_current = g.energy_current + p.energy;
   update_optconsts(g, p);
+  p.emiss_type = src.freq_type;
   p.last[0] = 's';
   p.last[1] = 'r';
   place_in_cell(g, p);
@@ -1128,6 +1426,9 @@ int select_dust_chi_rho(orc_ctx &g, const Photon &p) {
 void interact(orc_ctx &g, Photon &p) {
   int id = select_dust_chi_rho(g, p);
   double albedo = p.current_albedo[id - 1];
+  p.a_prev = p.a;
+  p.v_prev = p.v;
+  p.s_prev = p.s;
   double xi = g.rng.random();
   const Dust &d = g.d[id - 1];
   if (xi > albedo) {
@@ -1273,6 +1574,485 @@ void lucy_photons(orc_ctx &g, int64_t n_photons) {
       p.killed = (g.conf.kill_on_scatter && p.scattered) || (g.conf.kill_on_absorb && !p.scattered);
       if (p.killed) break;
     }
+  }
+}
+
+
+// grid_integrate_noenergy (grid_propagate_3d.f90:237-375)
+void grid_integrate_noenergy(orc_ctx &g, Photon &p, double tau_required, double &tau_achieved) {
+  const double frac_check = g.conf.propagation_check_frequency;
+  tau_achieved = 0.0;
+  if (!p.in_cell) throw OracleError{"photon has not been placed in a cell"};
+  if (escaped(g, p.icell)) return;
+  if (tau_required == 0.0) return;
+  double t_source;
+  int source_id;
+  find_nearest_source(g, p.r, p.v, t_source, source_id);
+  double t_achieved = 0.0;
+  const int nc = g.n_cells;
+  for (;;) {
+    double xi = g.rng.random();
+    if (xi < frac_check) {
+      if (!in_correct_cell(g, p)) {
+        g.killed_photons_geo++;
+        p.killed = true;
+        return;
+      }
+    }
+    double tau_needed = tau_required - tau_achieved;
+    double tmin;
+    WallId id_min;
+    find_wall(g, p, tmin, id_min);
+    if (id_min.w1 == 0 && id_min.w2 == 0 && id_min.w3 == 0) {
+      g.killed_photons_geo++;
+      p.killed = true;
+      return;
+    }
+    int ic = p.icell.ic;
+    double chi_rho_total = 0.0;
+    for (int id = 0; id < g.n_dust; id++)
+      chi_rho_total = chi_rho_total + p.current_chi[id] * g.density[(size_t)id * nc + ic - 1];
+    double tau_cell = chi_rho_total * tmin;
+    g.n_crossings++;
+    if (tau_cell < tau_needed) {
+      t_achieved = t_achieved + tmin;
+      if (t_achieved > t_source) {
+        p.reabsorbed = true;
+        p.reabsorbed_id = source_id;
+        return;
+      }
+      p.r.x = p.r.x + tmin * p.v.x;
+      p.r.y = p.r.y + tmin * p.v.y;
+      p.r.z = p.r.z + tmin * p.v.z;
+      tau_achieved = tau_achieved + tau_cell;
+      p.on_wall = true;
+      p.icell = next_cell(g, p.icell, id_min);
+      p.on_wall_id = WallId{-id_min.w1, -id_min.w2, -id_min.w3};
+      if (escaped(g, p.icell)) return;
+    } else {
+      double tact = tmin * (tau_needed / tau_cell);
+      t_achieved = t_achieved + tact;
+      if (t_achieved > t_source) {
+        p.reabsorbed = true;
+        p.reabsorbed_id = source_id;
+        return;
+      }
+      p.r.x = p.r.x + tact * p.v.x;
+      p.r.y = p.r.y + tact * p.v.y;
+      p.r.z = p.r.z + tact * p.v.z;
+      tau_achieved = tau_achieved + tau_needed;
+      p.on_wall = false;
+      p.on_wall_id = WallId();
+      return;
+    }
+  }
+}
+
+// grid_escape_tau (grid_propagate_3d.f90:377-480) and grid_escape_column_density (:482-582):
+// march a COPY of the photon to tmax / the grid edge.  column == nullptr: optical depth.
+void grid_escape(orc_ctx &g, const Photon &p_orig, double tmax, double &tau, double *column, bool &killed) {
+  const double frac_check = g.conf.propagation_check_frequency;
+  Photon p = p_orig;
+  killed = false;
+  if (!p.in_cell) throw OracleError{"photon has not been placed in a cell"};
+  if (escaped(g, p.icell)) {
+    tau = 0.0;
+    if (column)
+      for (int id = 0; id < g.n_dust; id++) column[id] = 0.0;
+    return;
+  }
+  double t_source;
+  int source_id;
+  find_nearest_source(g, p.r, p.v, t_source, source_id);
+  if (t_source < tmax) {
+    killed = true;
+    return;
+  }
+  tau = 0.0;
+  if (column)
+    for (int id = 0; id < g.n_dust; id++) column[id] = 0.0;
+  double t_current = 0.0;
+  bool finished = false;
+  const int nc = g.n_cells;
+  for (;;) {
+    double xi = g.rng.random();
+    if (xi < frac_check) {
+      if (!in_correct_cell(g, p)) {
+        g.killed_photons_geo++;
+        killed = true;
+        return;
+      }
+    }
+    double tmin;
+    WallId id_min;
+    find_wall(g, p, tmin, id_min);
+    if (id_min.w1 == 0 && id_min.w2 == 0 && id_min.w3 == 0) {
+      g.killed_photons_geo++;
+      killed = true;
+      return;
+    }
+    if (t_current + tmin > tmax) {
+      tmin = tmax - t_current;
+      finished = true;
+    }
+    p.r.x = p.r.x + tmin * p.v.x;
+    p.r.y = p.r.y + tmin * p.v.y;
+    p.r.z = p.r.z + tmin * p.v.z;
+    t_current = t_current + tmin;
+    g.n_peel_crossings++;
+    int ic = p.icell.ic;
+    if (column) {
+      for (int id = 0; id < g.n_dust; id++) column[id] = column[id] + g.density[(size_t)id * nc + ic - 1] * tmin;
+    } else {
+      for (int id = 0; id < g.n_dust; id++)
+        tau = tau + p.current_chi[id] * g.density[(size_t)id * nc + ic - 1] * tmin;
+    }
+    if (finished) return;
+    p.on_wall = true;
+    p.icell = next_cell(g, p.icell, id_min);
+    p.on_wall_id = WallId{-id_min.w1, -id_min.w2, -id_min.w3};
+    if (escaped(g, p.icell)) return;
+  }
+}
+
+// forced_interaction_wr99 / _baes16 (src/main/forced_interaction.f90:23-133)
+void forced_interaction(orc_ctx &g, double tau_escape, double &tau, double &weight) {
+  const double TAU_THRES = 1.e-7;
+  if (g.conf.forced_first_interaction_algorithm == HYP_FFI_BAES16) {
+    double one_minus_exp = tau_escape > TAU_THRES ? 1.0 - std::exp(-tau_escape) : tau_escape;
+    double alpha = (1.0 - g.conf.baes16_xi) / one_minus_exp;
+    double beta = g.conf.baes16_xi / tau_escape;
+    double tau_min = 0.0, tau_max = tau_escape;
+    double xi = g.rng.random();
+    for (int i = 1; i <= 60; i++) {
+      tau = 0.5 * (tau_min + tau_max);
+      double xi_test;
+      if (tau > TAU_THRES)
+        xi_test = alpha * (1.0 - std::exp(-tau)) + beta * tau;
+      else
+        xi_test = alpha * tau + beta * tau;
+      if (xi_test > xi)
+        tau_max = tau;
+      else
+        tau_min = tau;
+    }
+    tau = 0.5 * (tau_min + tau_max);
+    weight = 1.0 / (alpha + beta * std::exp(tau));
+  } else {
+    double xi = g.rng.random();
+    double one_minus_exp = tau_escape > TAU_THRES ? (1.0 - std::exp(-tau_escape)) : tau_escape;
+    tau = -std::log(1.0 - xi * one_minus_exp);
+    weight = one_minus_exp;
+  }
+}
+
+// dust_scatter_peeloff (dust_type_4elem.f90:421-444)
+void dust_scatter_peeloff(const Dust &d, double nu, Angle &a, Stokes &s, const Angle &a_req) {
+  Angle a_scat = difference_angle3d(a, a_req);
+  if (a_scat.cost < d.mu_min || a_scat.cost > d.mu_max) {
+    s = Stokes{0.0, 0.0, 0.0, 0.0};
+  } else {
+    double P1 = interp2d(d.mu.data(), d.n_mu, d.nu.data(), d.n_nu, d.P1.data(), a_scat.cost, nu);
+    double P2 = interp2d(d.mu.data(), d.n_mu, d.nu.data(), d.n_nu, d.P2.data(), a_scat.cost, nu);
+    double P3 = interp2d(d.mu.data(), d.n_mu, d.nu.data(), d.n_nu, d.P3.data(), a_scat.cost, nu);
+    double P4 = interp2d(d.mu.data(), d.n_mu, d.nu.data(), d.n_nu, d.P4.data(), a_scat.cost, nu);
+    scatter_stokes(s, a, a_scat, a_req, P1, P2, P3, P4);
+  }
+  a = a_req;
+}
+
+// normalized_B_nu (source_type.f90:1088-1096)
+double normalized_B_nu(double nu, double T) {
+  const double h_cgs = 6.6260689633e-27, c_cgs = 2.99792458e10, k_cgs = 1.380650424e-16, stef_boltz = 5.670400e-5;  // lib_constants.f90:52-96
+  const double a = 2.0 * h_cgs / c_cgs / c_cgs / stef_boltz * PI;
+  const double b = h_cgs / k_cgs;
+  double T4 = T * T * T * T;
+  return a * nu * nu * nu / (std::exp(b * nu / T) - 1.0) / T4;
+}
+
+void bin_edges(const Image &im, int inu, double &numin, double &numax) {
+  numin = std::pow(10.0, im.log10_nu_min + (im.log10_nu_max - im.log10_nu_min) * (double)(inu - 1) / (double)im.n_nu);
+  numax = std::pow(10.0, im.log10_nu_min + (im.log10_nu_max - im.log10_nu_min) * (double)inu / (double)im.n_nu);
+}
+
+// get_spectrum_binned (source_type.f90:1118-1165)
+std::vector<double> get_spectrum_binned(const Source &src, const Image &im) {
+  std::vector<double> nu, fnu;
+  if (src.freq_type == 1) {
+    nu = src.spectrum.x;
+    fnu = src.spectrum.pdf;
+  } else {
+    double lmin = std::log10(3.e9), lmax = std::log10(3.e16);
+    int n = (int)std::ceil((lmax - lmin) * 100000);
+    nu.resize(n);
+    fnu.resize(n);
+    for (int i = 1; i <= n; i++) {
+      nu[i - 1] = std::pow(10.0, (double)(i - 1) / (double)(n - 1) * (lmax - lmin) + lmin);
+      fnu[i - 1] = normalized_B_nu(nu[i - 1], src.temperature);
+    }
+  }
+  std::vector<double> sp(im.n_nu);
+  for (int inu = 1; inu <= im.n_nu; inu++) {
+    double numin, numax;
+    bin_edges(im, inu, numin, numax);
+    sp[inu - 1] = integral_loglog_subset(nu.data(), fnu.data(), (int)nu.size(), numin, numax);
+  }
+  double tot = integral_general(nu.data(), fnu.data(), (int)nu.size(), trapezium_loglog);
+  for (auto &v : sp) v = v / tot;
+  return sp;
+}
+
+// get_j_nu_binned (dust_type_4elem.f90:722-741)
+std::vector<double> get_j_nu_binned(const Dust &d, const Image &im, int ijnu) {
+  const PdfCont &j = d.j_nu[ijnu - 1];
+  std::vector<double> sp(im.n_nu);
+  for (int inu = 1; inu <= im.n_nu; inu++) {
+    double numin, numax;
+    bin_edges(im, inu, numin, numax);
+    sp[inu - 1] = integral_loglog_subset(j.x.data(), j.pdf.data(), j.n, numin, numax);
+  }
+  double tot = integral_general(j.x.data(), j.pdf.data(), j.n, trapezium_loglog);
+  for (auto &v : sp) v = v / tot;
+  return sp;
+}
+
+// get_chi_nu_binned (dust_type_4elem.f90:793-811)
+std::vector<double> get_chi_nu_binned(const Dust &d, const Image &im) {
+  std::vector<double> chi(im.n_nu);
+  for (int inu = 1; inu <= im.n_nu; inu++) {
+    double numin, numax;
+    bin_edges(im, inu, numin, numax);
+    chi[inu - 1] = integral_loglog_subset(d.nu.data(), d.chi_nu.data(), d.n_nu, numin, numax) / (numax - numin);
+  }
+  return chi;
+}
+
+// peeloff_photon (images_peeled.f90:95-270); inside observers are not restated
+void peeloff_photon(orc_ctx &g, const Photon &p_orig, bool polychromatic) {
+  PeeledState &P = g.peeled;
+  const int n_peeled = (int)P.group_id.size();
+  std::vector<double> column(g.n_dust), spectrum;
+  for (int ip = 1; ip <= n_peeled; ip++) {
+    const int ig = P.group_id[ip - 1], iv = P.view_id[ip - 1];
+    Image &im = P.image[ig - 1];
+    Photon p = p_orig;
+    p.s = p.s_prev;
+    p.a = p.a_prev;
+    p.v = p.v_prev;
+    const Angle a_req = P.viewing_angles[ip - 1];  // a_peeloff (:410-421), outside observer
+    const Vec v_req = angle3d_to_vector3d(a_req);
+    if (p.last_isotropic) {
+      p.s = Stokes{1.0, 0.0, 0.0, 0.0};
+      p.a = a_req;
+      p.v = v_req;
+    } else {
+      if (p.last[0] == 's' && p.last[1] == 'r') {
+        // source_emit_peeloff (source_type.f90:513-537): point sources are always isotropic
+        throw OracleError{"anisotropic source peel-off not restated in the oracle"};
+      } else if (p.last[0] == 'd' && p.last[1] == 's') {
+        dust_scatter_peeloff(g.d[p.dust_id - 1], p.nu, p.a, p.s, a_req);
+        p.v = angle3d_to_vector3d(p.a);
+      } else if (p.last[0] == 'd' && p.last[1] == 'e') {
+        p.a = a_req;  // dust_emit_peeloff (dust_type_4elem.f90:322-332)
+        p.v = angle3d_to_vector3d(p.a);
+      } else {
+        throw OracleError{"unexpected p%last flag"};
+      }
+    }
+    place_in_cell(g, p);
+    const Vec rp = P.r_peeloff[ig - 1];
+    double d = -(v_req.x * p.r.x + v_req.y * p.r.y + v_req.z * p.r.z);
+    double tmax = std::numeric_limits<double>::max();
+    if (d < im.c.d_min || d > im.c.d_max) continue;
+    Vec dr{p.r.x - rp.x, p.r.y - rp.y, p.r.z - rp.z};
+    double x_image = dr.y * p.a.cosp - dr.x * p.a.sinp;
+    double y_image = dr.z * p.a.sint - dr.y * p.a.cost * p.a.sinp - dr.x * p.a.cost * p.a.cosp;
+    if (!in_image(im, x_image, y_image)) continue;
+    double tau = 0.0;
+    bool killed = false;
+    if (im.c.ignore_optical_depth) {
+      for (auto &c : column) c = 0.0;
+    } else {
+      grid_escape(g, p, tmax, tau, polychromatic ? column.data() : nullptr, killed);
+    }
+    if (killed) continue;
+    g.n_peeloffs++;
+    if (polychromatic) {
+      if (p.emiss_type == 1 || p.emiss_type == 2) {
+        auto &cache = P.source_spectra[ig - 1][p.source_id - 1];
+        if (cache.empty()) cache = get_spectrum_binned(g.s[p.source_id - 1], im);
+        spectrum = cache;
+      } else if (p.emiss_type == 3) {
+        // get_dust_emissivity (images_peeled.f90:454-500)
+        auto &cache = P.dust_log10_emissivity[ig - 1][p.dust_id - 1];
+        const Dust &dd = g.d[p.dust_id - 1];
+        if (cache.empty()) {
+          cache.resize((size_t)dd.n_jnu * im.n_nu);
+          for (int ij = 1; ij <= dd.n_jnu; ij++) {
+            std::vector<double> sp = get_j_nu_binned(dd, im, ij);
+            for (int inu = 0; inu < im.n_nu; inu++) cache[(size_t)(ij - 1) * im.n_nu + inu] = std::log10(sp[inu]);
+          }
+        }
+        spectrum.resize(im.n_nu);
+        for (int inu = 0; inu < im.n_nu; inu++) {
+          double l0 = cache[(size_t)(p.emiss_var_id - 1) * im.n_nu + inu];
+          double l1 = cache[(size_t)p.emiss_var_id * im.n_nu + inu];
+          double v = std::pow(10.0, (l1 - l0) * p.emiss_var_frac + l0);
+          spectrum[inu] = std::isnan(v) ? 0.0 : v;
+        }
+      } else {
+        throw OracleError{"unknown emiss_type"};
+      }
+      for (auto &v : spectrum) v = v * p.s.I * p.energy;
+      for (int id = 1; id <= g.n_dust; id++) {
+        auto &chi = P.dust_extinction[ig - 1][id - 1];
+        if (chi.empty()) chi = get_chi_nu_binned(g.d[id - 1], im);
+        for (int inu = 0; inu < im.n_nu; inu++) spectrum[inu] = spectrum[inu] * std::exp(-column[id - 1] * chi[inu]);
+      }
+      image_bin_raytraced(im, p, x_image, y_image, iv, spectrum);
+    } else {
+      double e = std::exp(-tau);
+      p.s = Stokes{p.s.I * e, p.s.Q * e, p.s.U * e, p.s.V * e};
+      image_bin(im, p, x_image, y_image, iv);
+    }
+  }
+}
+
+// propagate (iter_final.f90:147-273); MRW and source re-absorption are not restated
+void propagate_final(orc_ctx &g, Photon &p, bool peeloff_scattering_only) {
+  const int64_t n_inter_max = g.conf.n_inter_max;
+  const bool make_peeled = !g.peeled.image.empty();
+  for (int64_t interactions = 1; interactions <= n_inter_max + 1; interactions++) {
+    double tau;
+    if (interactions == 1 && g.conf.forced_first_interaction) {
+      double tau_escape;
+      bool killed;
+      grid_escape(g, p, std::numeric_limits<double>::max(), tau_escape, nullptr, killed);
+      if (tau_escape > 1.e-10 && !killed) {
+        double weight;
+        forced_interaction(g, tau_escape, tau, weight);
+        p.energy = p.energy * weight;
+      } else {
+        tau = g.rng.random_exp();
+      }
+    } else {
+      tau = g.rng.random_exp();
+    }
+    double tau_achieved;
+    grid_integrate_noenergy(g, p, tau, tau_achieved);
+    if (p.reabsorbed) throw OracleError{"source re-absorption not restated in the oracle"};
+    if (p.killed || escaped(g, p.icell)) {
+      if (!p.killed) g.n_escaped++;
+      break;
+    }
+    if (interactions == n_inter_max + 1) {
+      g.killed_photons_int++;
+      p.killed = true;
+      break;
+    }
+    interact(g, p);
+    p.killed = (g.conf.kill_on_scatter && p.scattered) || (g.conf.kill_on_absorb && !p.scattered);
+    if (p.killed) break;
+    if (make_peeled) {
+      if (p.scattered || !peeloff_scattering_only) peeloff_photon(g, p, false);
+    }
+  }
+}
+
+// do_final (iter_final.f90:60-145), photon loop only
+void final_photons(orc_ctx &g, int64_t n_photons, bool peeloff_scattering_only) {
+  const bool make_peeled = !g.peeled.image.empty();
+  Photon p;
+  for (int64_t ip = 1; ip <= n_photons; ip++) {
+    emit(g, p);
+    g.n_photons_run++;
+    if (make_peeled && !peeloff_scattering_only) peeloff_photon(g, p, false);
+    propagate_final(g, p, peeloff_scattering_only);
+  }
+}
+
+// emit_from_grid (grid_physics_3d.f90:691-753), polychromatic form
+Photon emit_from_grid(orc_ctx &g) {
+  Photon p;
+  double xi = g.rng.random();
+  p.dust_id = std::max((int)std::ceil(xi * (double)g.n_dust), 1);
+  // random_masked_cell (grid_geometry_common_3d.f90:104-115): Cartesian grids have no mask
+  xi = g.rng.random();
+  int ic = std::max((int)std::ceil(xi * g.n_cells), 1);
+  int i3 = (ic - 1) / (g.n1 * g.n2) + 1;
+  int i2 = (ic - 1 - (i3 - 1) * g.n1 * g.n2) / g.n1 + 1;
+  int i1 = ic - (i3 - 1) * g.n1 * g.n2 - (i2 - 1) * g.n1;
+  p.icell = new_grid_cell(g, i1, i2, i3);
+  p.in_cell = true;
+  // random_position_cell (grid_geometry_cartesian_3d.f90:383-394)
+  double x = g.rng.random(), y = g.rng.random(), z = g.rng.random();
+  p.r.x = x * (g.w1[i1] - g.w1[i1 - 1]) + g.w1[i1 - 1];
+  p.r.y = y * (g.w2[i2] - g.w2[i2 - 1]) + g.w2[i2 - 1];
+  p.r.z = z * (g.w3[i3] - g.w3[i3 - 1]) + g.w3[i3 - 1];
+  p.a = random_sphere_angle3d(g.rng);
+  p.v = angle3d_to_vector3d(p.a);
+  p.s = Stokes{1.0, 0.0, 0.0, 0.0};
+  size_t k = (size_t)(p.dust_id - 1) * g.n_cells + ic - 1;
+  if (g.energy_abs_tot[p.dust_id - 1] > 0.0) {
+    double mass = g.density[k] * g.volume[ic - 1];
+    p.energy = g.specific_energy[k] * mass * (double)g.n_cells / g.energy_abs_tot[p.dust_id - 1];
+  } else {
+    p.energy = 0.0;
+  }
+  p.emiss_type = 3;
+  p.emiss_var_id = g.jnu_var_id[k];
+  p.emiss_var_frac = g.jnu_var_frac[k];
+  p.scattered = false;
+  p.reprocessed = true;
+  p.last_isotropic = true;
+  p.last[0] = 'd';
+  p.last[1] = 'e';
+  return p;
+}
+
+// do_raytracing (iter_raytracing.f90:31-141)
+void raytracing_photons(orc_ctx &g, int64_t n_sources, int64_t n_thermal) {
+  precompute_jnu_var(g);
+  Photon p;
+  for (int64_t ip = 1; ip <= n_sources; ip++) {
+    emit(g, p);
+    p.energy = p.energy * g.energy_total / (double)n_sources;
+    peeloff_photon(g, p, true);
+  }
+  if (g.n_dust == 0) return;
+  for (int64_t ip = 1; ip <= n_thermal; ip++) {
+    p = emit_from_grid(g);
+    if (p.energy > 0.0) {
+      p.energy = p.energy * g.energy_abs_tot[p.dust_id - 1] / (double)n_thermal * (double)g.n_dust;
+      peeloff_photon(g, p, true);
+    }
+  }
+}
+
+// image_write (image_type.f90:608-788): the arrays as written, in memory order
+void image_written(const Image &im, bool sed, std::vector<double> &out, std::vector<double> &unc) {
+  double dnunorm = std::pow(im.nu_max / im.nu_min, +0.5 / (double)im.n_nu) -
+                   std::pow(im.nu_max / im.nu_min, -0.5 / (double)im.n_nu);
+  out = sed ? im.sed : im.img;
+  if (im.c.uncertainties) {
+    const std::vector<double> &s2 = sed ? im.sed2 : im.img2;
+    unc.resize(s2.size());
+    for (size_t i = 0; i < s2.size(); i++) unc[i] = std::sqrt(s2[i]);
+  } else {
+    unc.clear();
+  }
+  for (auto &v : out) v = v / dnunorm;
+  for (auto &v : unc) v = v / dnunorm;
+  if (sed) {
+    const size_t n_nu = im.n_nu, n_ap = im.c.n_ap;
+    const size_t outer = out.size() / (n_nu * n_ap);
+    for (size_t o = 0; o < outer; o++)
+      for (size_t ia = 1; ia < n_ap; ia++)
+        for (size_t inu = 0; inu < n_nu; inu++) {
+          size_t k = inu + n_nu * (ia + n_ap * o), km = inu + n_nu * (ia - 1 + n_ap * o);
+          out[k] = out[km] + out[k];
+          if (!unc.empty()) unc[k] = std::sqrt(unc[km] * unc[km] + unc[k] * unc[k]);
+        }
   }
 }
 
@@ -1503,6 +2283,121 @@ int orc_set_energy_sum(orc_ctx *g, const double *in) {
 }
 
 // unit-test hooks for the numerics
+
+// ---- final / raytracing iterations ------------------------------------------------------------
+// peeled_images_setup (images_peeled.f90:272-382)
+int orc_add_peeled_group(orc_ctx *g, const hyp_image_conf *c) {
+  try {
+    if (c->inside_observer) return fail(g, "inside observers are not restated in the oracle");
+    if (!(c->n_view > 0)) return fail(g, "n_view should be a positive integer");
+    Image im;
+    image_setup(im, *c, (int)g->s.size(), g->n_dust);
+    PeeledState &P = g->peeled;
+    P.image.push_back(im);
+    const int ig = (int)P.image.size();
+    P.r_peeloff.push_back(Vec{c->peeloff_x, c->peeloff_y, c->peeloff_z});
+    for (int iv = 1; iv <= c->n_view; iv++) {
+      P.group_id.push_back(ig);
+      P.view_id.push_back(iv);
+      P.viewing_angles.push_back(angle3d_deg(c->theta[iv - 1], c->phi[iv - 1]));
+    }
+    P.image.back().c.theta = nullptr;
+    P.image.back().c.phi = nullptr;
+    P.source_spectra.emplace_back(g->s.size());
+    P.dust_extinction.emplace_back(g->n_dust);
+    P.dust_log10_emissivity.emplace_back(g->n_dust);
+  } catch (OracleError &e) {
+    return fail(g, e.msg);
+  }
+  return 0;
+}
+
+// do_final, first part (iter_final.f90:84-100)
+int orc_final_begin(orc_ctx *g) {
+  g->energy_current = 0.0;
+  g->killed_photons_geo = g->killed_photons_int = 0;
+  g->n_crossings = g->n_absorptions = g->n_scatterings = g->n_escaped = g->n_photons_run = 0;
+  g->n_peel_crossings = g->n_peeloffs = 0;
+  try {
+    precompute_jnu_var(*g);
+  } catch (OracleError &e) {
+    return fail(g, e.msg);
+  }
+  return 0;
+}
+
+int orc_final_photons(orc_ctx *g, int64_t n_photons, int32_t peeloff_scattering_only) {
+  try {
+    final_photons(*g, n_photons, peeloff_scattering_only != 0);
+  } catch (OracleError &e) {
+    return fail(g, e.msg);
+  }
+  return 0;
+}
+
+static void fill_stats(orc_ctx *g, hyp_iter_stats *st) {
+  if (!st) return;
+  std::memset(st, 0, sizeof *st);
+  st->energy_emitted = g->energy_current;
+  st->n_photons = g->n_photons_run;
+  st->killed_geo = g->killed_photons_geo;
+  st->killed_int = g->killed_photons_int;
+  st->n_crossings = g->n_crossings;
+  st->n_absorptions = g->n_absorptions;
+  st->n_scatterings = g->n_scatterings;
+  st->n_escaped = g->n_escaped;
+  st->n_peel_crossings = g->n_peel_crossings;
+  st->n_peeloffs = g->n_peeloffs;
+}
+
+// do_final, last part (iter_final.f90:136-143)
+int orc_final_finish(orc_ctx *g, hyp_iter_stats *st) {
+  if (!(g->energy_current > 0.0)) return fail(g, "no photons were emitted in this iteration");
+  for (auto &im : g->peeled.image) image_scale(im, g->energy_total / g->energy_current);
+  fill_stats(g, st);
+  return 0;
+}
+
+int orc_raytracing_photons(orc_ctx *g, int64_t n_sources, int64_t n_thermal, hyp_iter_stats *st) {
+  g->killed_photons_geo = g->killed_photons_int = 0;
+  g->n_peel_crossings = g->n_peeloffs = 0;
+  try {
+    raytracing_photons(*g, n_sources, n_thermal);
+  } catch (OracleError &e) {
+    return fail(g, e.msg);
+  }
+  fill_stats(g, st);
+  return 0;
+}
+
+int orc_image_shape(orc_ctx *g, int32_t group, int32_t which, int64_t dims[6], int32_t *ndim) {
+  if (group < 0 || group >= (int)g->peeled.image.size()) return fail(g, "no such image group");
+  const Image &im = g->peeled.image[group];
+  if (which == 0) {
+    if (!im.c.compute_sed) return fail(g, "group has no SED");
+    int64_t d[5] = {im.n_stokes, im.n_orig, im.c.n_view, im.c.n_ap, im.n_nu};
+    for (int i = 0; i < 5; i++) dims[i] = d[i];
+    *ndim = 5;
+  } else {
+    if (!im.c.compute_image) return fail(g, "group has no image");
+    int64_t d[6] = {im.n_stokes, im.n_orig, im.c.n_view, im.c.n_y, im.c.n_x, im.n_nu};
+    for (int i = 0; i < 6; i++) dims[i] = d[i];
+    *ndim = 6;
+  }
+  return 0;
+}
+
+static int get_written(orc_ctx *g, int32_t group, bool sed, double *out, double *unc) {
+  if (group < 0 || group >= (int)g->peeled.image.size()) return fail(g, "no such image group");
+  std::vector<double> a, u;
+  image_written(g->peeled.image[group], sed, a, u);
+  std::copy(a.begin(), a.end(), out);
+  if (unc && !u.empty()) std::copy(u.begin(), u.end(), unc);
+  return 0;
+}
+int orc_get_sed(orc_ctx *g, int32_t group, double *sed, double *unc) { return get_written(g, group, true, sed, unc); }
+int orc_get_image(orc_ctx *g, int32_t group, double *img, double *unc) { return get_written(g, group, false, img, unc); }
+
 double orc_test_random(orc_ctx *g) { return g->rng.random(); }
 int orc_test_locate(const double *xx, int n, double x) { return locate(xx, n, x); }
 double orc_test_interp1d_loglog(const double *x, const double *y, int n, double xv) {

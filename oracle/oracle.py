@@ -37,8 +37,7 @@ def build(force=False):
 def load():
     global _lib
     if _lib is None:
-        if not os.path.exists(_LIB):
-            build()
+        build()   # no-op unless the source is newer than the library
         _lib = C.CDLL(_LIB)
         _lib.orc_ctx_create.restype = C.c_int
         _lib.orc_finalize_setup.restype = C.c_int
@@ -50,6 +49,8 @@ def load():
         _lib.orc_test_interp1d_loglog.restype = C.c_double
         _lib.orc_test_planck.restype = C.c_double
         _lib.orc_rng_draws.restype = C.c_uint64
+        for n in ("orc_final_begin", "orc_final_photons", "orc_final_finish", "orc_raytracing_photons"):
+            getattr(_lib, n).restype = C.c_int
     return _lib
 
 
@@ -88,6 +89,29 @@ class Oracle(CApi):
         st = IterStats()
         self.check(self.lib.orc_lucy_finish(self.ctx, C.byref(st)))
         return st
+
+    # -- final / raytracing iterations (do_final, do_raytracing) -------------------------------
+    def final_begin(self):
+        self.check(self.lib.orc_final_begin(self.ctx))
+
+    def final_photons(self, n, peeloff_scattering_only=False):
+        self.check(self.lib.orc_final_photons(self.ctx, C.c_int64(n), C.c_int32(int(peeloff_scattering_only))))
+
+    def final_finish(self):
+        st = IterStats()
+        self.check(self.lib.orc_final_finish(self.ctx, C.byref(st)))
+        return st
+
+    def raytracing_photons(self, n_sources, n_dust):
+        st = IterStats()
+        self.check(self.lib.orc_raytracing_photons(self.ctx, C.c_int64(n_sources), C.c_int64(n_dust), C.byref(st)))
+        return st
+
+    def sed(self, group, uncertainties=False):
+        return self.get_sed(self.ctx, group, uncertainties)
+
+    def image(self, group, uncertainties=False):
+        return self.get_image(self.ctx, group, uncertainties)
 
     def get_specific_energy(self):
         out = self._grid()

@@ -79,6 +79,17 @@ def main():
             se = np.array([f["iteration_%05d/specific_energy" % i][...] for i in range(1, 6)])
             out["expected_evenly=%s_multi=%s" % (evenly, multi)] = se
             assert int(f.attrs["iterations"]) == 5
+    # test_peeloff (test_bit_level.py:175-236): seds + images of the three peeled groups
+    for ray in (False, True):
+        for evenly in (False, True):
+            fn = ("test_peeloff.grid_type=car.raytracing=%s.sample_sources_evenly=%s.rtout" % (ray, evenly))
+            f = h5min.File(os.path.join(DATA, fn))
+            for ig in (1, 2, 3):
+                for kind in ("seds", "images"):
+                    d = f["Peeled/group_%05d/%s" % (ig, kind)]
+                    out["peeloff_ray=%s_evenly=%s_g%d_%s" % (ray, evenly, ig, kind)] = d[...]
+            for k in ("killed_photons_geo_final", "killed_photons_int_final"):
+                assert int(np.asarray(f.attrs[k]).ravel()[0]) == 0
     np.savez_compressed(os.path.join(HERE, "bitlevel_car.npz"), **out)
     print("wrote", os.path.join(HERE, "bitlevel_car.npz"))
 

@@ -3,7 +3,7 @@ import os
 
 import numpy as np
 
-from hyperion_b200.flatmodel import FlatConf, FlatDust, FlatModel, FlatSource
+from hyperion_b200.flatmodel import FlatConf, FlatDust, FlatModel, FlatPeeledGroup, FlatSource
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 pc = 3.08568025e18     # hyperion/util/constants.py
@@ -29,3 +29,20 @@ def ulp_diff(a, b):
     a = np.asarray(a, dtype=np.float64)
     b = np.asarray(b, dtype=np.float64)
     return np.abs(a - b) / np.spacing(np.maximum(np.abs(a), np.abs(b)))
+
+
+def peeloff_groups():
+    """The three peeled image groups of test_bit_level.py::TestBasic::test_peeloff (:198-224)."""
+    g1 = FlatPeeledGroup(theta=[33.4, 110.], phi=[65.4, 103.2], wavelengths=(5, 0.05, 200.),
+                         image=(4, 5, -0.8 * pc, 0.8 * pc, -pc, pc), sed=(5, 0.1 * pc, pc), track_origin="no")
+    g2 = FlatPeeledGroup(theta=[22.1], phi=[203.2], wavelengths=(4, 0.05, 200.),
+                         image=(6, 6, -pc, pc, -pc, pc), sed=(2, 0.5 * pc, pc), track_origin="basic")
+    g3 = FlatPeeledGroup(theta=[22.1], phi=[203.2], wavelengths=(4, 0.05, 200.),
+                         image=(6, 6, -pc, pc, -pc, pc), sed=(2, 0.5 * pc, pc), track_origin="detailed")
+    return [g1, g2, g3]
+
+
+def peeloff_model(z, evenly):
+    m = bitlevel_model(z, evenly, False)
+    m.peeled = peeloff_groups()
+    return m

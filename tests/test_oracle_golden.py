@@ -9,7 +9,7 @@ import numpy as np
 import pytest
 
 from oracle import oracle
-from helpers import bitlevel_model, ulp_diff
+from helpers import bitlevel_model, peeloff_model, ulp_diff
 
 
 @pytest.mark.parametrize("evenly", [False, True])
@@ -26,6 +26,35 @@ def test_specific_energy_bitlevel_car(golden_car, evenly, multi):
         assert ulp_diff(got, expected[it]).max() <= 1000, "iteration %d" % (it + 1)
         # in fact bit-identical on this platform; keep the stronger statement visible
         assert np.array_equal(got, expected[it])
+
+
+@pytest.mark.parametrize("raytracing", [False, True])
+@pytest.mark.parametrize("evenly", [False, True])
+def test_peeloff_bitlevel_car(golden_car, raytracing, evenly):
+    """hyperion/model/tests/test_bit_level.py::TestBasic::test_peeloff, grid_type='car': 5 Lucy
+    iterations of 1000 packets, 5000 imaging packets (forced first interaction, peel-off of
+    scattered light only when raytracing is on), then 2000 + 3000 raytracing packets; SEDs and
+    images of three peeled groups (no / basic / detailed origin tracking, all Stokes components)
+    against the stored .rtout, to the reference's own 1000-ULP criterion."""
+    z = golden_car
+    o = oracle.Oracle(peeloff_model(z, evenly))
+    for it in range(5):
+        o.run_lucy_iteration(1000)
+    o.final_begin()
+    o.final_photons(5000, peeloff_scattering_only=raytracing)
+    st = o.final_finish()
+    assert st.killed_geo == 0 and st.killed_int == 0
+    if raytracing:
+        o.raytracing_photons(2000, 3000)
+    for ig in (1, 2, 3):
+        for kind, get in (("seds", o.sed), ("images", o.image)):
+            expected = z["peeloff_ray=%s_evenly=%s_g%d_%s" % (raytracing, evenly, ig, kind)]
+            got = get(ig - 1)
+            assert got.shape == expected.shape
+            nz = (expected != 0) | (got != 0)
+            assert nz.any()
+            assert np.array_equal(got == 0, expected == 0), (ig, kind)
+            assert ulp_diff(got[nz], expected[nz]).max() <= 1000, (ig, kind, ulp_diff(got[nz], expected[nz]).max())
 
 
 def test_rng_known_stream():
