@@ -243,7 +243,7 @@ class Engine(CApi):
         L.hyp_ctx_destroy.restype = None
         L.hyp_stream.restype = C.c_void_p
         for n in ("hyp_finalize_setup", "hyp_lucy_photons", "hyp_lucy_device_buffers",
-                  "hyp_run_lucy_iteration"):
+                  "hyp_run_lucy_iteration", "hyp_image_device_buffers"):
             getattr(L, n).restype = C.c_int
         self.ctx = C.c_void_p()
         self.check(L.hyp_ctx_create(C.c_int(device_id), C.byref(self.ctx)))
@@ -307,6 +307,54 @@ class Engine(CApi):
         self.check(self.lib.hyp_run_lucy_iteration(self.ctx, C.c_int64(n_photons), C.c_int64(iteration),
                                                    C.byref(st)))
         return st
+
+    # -- final (imaging) and raytracing iterations: do_final, do_raytracing ---------------------
+    def final_begin(self):
+        self.check(self.lib.hyp_final_begin(self.ctx))
+
+    def final_photons(self, first_id, n, peeloff_scattering_only=False):
+        self.check(self.lib.hyp_final_photons(self.ctx, C.c_int64(first_id), C.c_int64(n),
+                                              C.c_int32(int(peeloff_scattering_only))))
+
+    def final_finish(self):
+        st = IterStats()
+        self.check(self.lib.hyp_final_finish(self.ctx, C.byref(st)))
+        return st
+
+    def raytracing_photons(self, n_sources, n_dust, first_source_id=0, n_total_sources=None,
+                           first_dust_id=0, n_total_dust=None):
+        """Packets [first_*_id, first_*_id + n_*) of a raytracing iteration of n_total_* packets
+        (defaults: this call is the whole iteration)."""
+        st = IterStats()
+        self.check(self.lib.hyp_raytracing_photons(
+            self.ctx, C.c_int64(first_source_id), C.c_int64(n_sources),
+            C.c_int64(n_sources if n_total_sources is None else n_total_sources),
+            C.c_int64(first_dust_id), C.c_int64(n_dust),
+            C.c_int64(n_dust if n_total_dust is None else n_total_dust), C.byref(st)))
+        return st
+
+    def image_device_buffers(self):
+        p = C.c_void_p()
+        n = C.c_int64()
+        self.check(self.lib.hyp_image_device_buffers(self.ctx, C.byref(p), C.byref(n)))
+        return p.value, n.value
+
+    def image_buffer(self):
+        """All image / SED accumulators + scalars as a torch CUDA tensor aliasing device memory
+        (for the end-of-run reduction, mp_collect_images src/mpi/mpi_routines.f90:363-471)."""
+        import torch
+        ptr, n = self.image_device_buffers()
+
+        class _Buf:
+            __cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (ptr, False), "version": 2}
+
+        return torch.as_tensor(_Buf(), device=torch.device("cuda", self.device_id))
+
+    def sed(self, group, uncertainties=False):
+        return self.get_sed(self.ctx, group, uncertainties)
+
+    def image(self, group, uncertainties=False):
+        return self.get_image(self.ctx, group, uncertainties)
 
     def _get(self, fn, out=None):
         if out is None:

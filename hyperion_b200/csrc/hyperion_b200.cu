@@ -29,7 +29,8 @@ struct CellRec {
   double esum;
 };
 
-enum { SC_ENERGY = 0, SC_KILLED_GEO, SC_KILLED_INT, SC_CROSS, SC_ABS, SC_SCAT, SC_ESC, SC_PHOTONS, SC_COUNT };
+enum { SC_ENERGY = 0, SC_KILLED_GEO, SC_KILLED_INT, SC_CROSS, SC_ABS, SC_SCAT, SC_ESC, SC_PHOTONS, SC_PEEL_CROSS, SC_PEELOFFS,
+       SC_COUNT };
 
 struct ModelDev {
   int32_t n1, n2, n3, n_dust, n_sources;
@@ -84,7 +85,8 @@ struct alignas(32) Slot {
   double rng_spare;
   uint64_t id;
   uint32_t rng_blk, rng_has_spare;
-  uint32_t n_inter, pad;
+  uint32_t n_inter;
+  uint32_t tag;          // final iteration: source id | scattered | reprocessed | n_scat (see imaging.cuh)
 };
 
 enum { C_NF0 = 0, C_NF1, C_NB, C_NI, C_NE, C_CURSOR, C_CURSOR_B, C_COUNT = 8 };
@@ -117,6 +119,7 @@ struct Photon {
   double sQ, sU, sV;
   int32_t ix, iy, iz, ic;
   uint32_t n_inter;
+  uint32_t tag;
 };
 
 template <int ND>
@@ -136,6 +139,7 @@ __device__ __forceinline__ void load_photon(const Slot<ND> *__restrict__ s, Phot
   p.sQ = s->sQ; p.sU = s->sU; p.sV = s->sV;
   p.ix = s->ix; p.iy = s->iy; p.iz = s->iz; p.ic = s->ic;
   p.n_inter = s->n_inter;
+  p.tag = s->tag;
   rng.init(seed, s->id, iteration);
   rng.blk = s->rng_blk;
   rng.has_spare = s->rng_has_spare != 0;
@@ -162,7 +166,7 @@ __device__ __forceinline__ void store_photon(Slot<ND> *__restrict__ s, const Pho
   s->rng_blk = rng.blk;
   s->rng_has_spare = rng.has_spare ? 1u : 0u;
   s->n_inter = p.n_inter;
-  s->pad = 0;
+  s->tag = p.tag;
 }
 
 // Append `value` to a queue for every lane with pred set; must be called by the whole warp.
@@ -264,6 +268,7 @@ __device__ bool emit_photon(const ModelDev &M, Photon<ND> &p, Rng &rng, double &
     }
   }
   const SourceDev &S = M.sources[is];
+  p.tag = (uint32_t)(is + 1);
   // emit_from_point (source_type.f90:539-564)
   p.r0x = S.x;
   p.r0y = S.y;
@@ -378,7 +383,7 @@ __device__ bool scatter_photon(const ModelDev &M, const DustDev &d, Photon<ND> &
 // interact (src/dust/dust_interact.f90:22-79).  Returns: 0 continue, 1 packet finished (killed).
 template <int ND>
 __device__ int interact_photon(const ModelDev &M, Photon<ND> &p, Rng &rng, uint32_t &n_abs, uint32_t &n_scat,
-                               uint32_t &n_killed_int) {
+                               uint32_t &n_killed_int, int &dust_id, bool &was_scattered) {
   // the loop guard of do_lucy (iter_lucy.f90:193-198)
   p.n_inter += 1;
   if ((int64_t)p.n_inter > M.n_inter_max) {
@@ -407,6 +412,7 @@ __device__ int interact_photon(const ModelDev &M, Photon<ND> &p, Rng &rng, uint3
     if (xi >= 1.0) id = ND - 1;
   }
   const DustDev &d = M.dust[id];
+  dust_id = id;
   double albedo = p.albedo[0];
 #pragma unroll
   for (int k = 1; k < ND; ++k)
@@ -442,6 +448,7 @@ __device__ int interact_photon(const ModelDev &M, Photon<ND> &p, Rng &rng, uint3
     scattered = true;
     ++n_scat;
   }
+  was_scattered = scattered;
   if ((M.kill_on_scatter && scattered) || (M.kill_on_absorb && !scattered)) return 1;
   return 0;
 }
@@ -586,7 +593,9 @@ interact_kernel(const ModelDev M, Pool P, uint32_t *__restrict__ q_flight_next, 
       Rng rng;
       load_photon<ND>(slots + slot, p, rng, M.seed, iteration);
       const uint64_t id = slots[slot].id;
-      if (interact_photon<ND>(M, p, rng, n_abs, n_scat, n_kill) == 0) {
+      int dust_id = 0;
+      bool scattered = false;
+      if (interact_photon<ND>(M, p, rng, n_abs, n_scat, n_kill, dust_id, scattered) == 0) {
         p.tau_left = -log(1.0 - rng.next());
         store_photon<ND>(slots + slot, p, rng, id);
         alive = true;
@@ -651,24 +660,15 @@ struct Lane {
   int fwd;                   // bit a set: the packet moves towards +axis a
 };
 
+// Geometry of a flight that starts at r0 in cell (ix, iy, iz) with direction v.
 template <int ND>
-__device__ __forceinline__ void load_lane(const Slot<ND> *__restrict__ s, Lane<ND> &L, const double *__restrict__ W,
+__device__ __forceinline__ void init_lane(Lane<ND> &L, double r0x, double r0y, double r0z, double vx, double vy,
+                                          double vz, int ix, int iy, int iz, int ic, const double *__restrict__ W,
                                           int o2, int o3) {
   const double inf = __longlong_as_double(0x7ff0000000000000LL);
-  const double2 a0 = __ldcs((const double2 *)&s->r0x);  // r0x r0y
-  const double2 a1 = __ldcs((const double2 *)&s->r0z);  // r0z vx
-  const double2 a2 = __ldcs((const double2 *)&s->vy);   // vy vz
-  L.r0x = a0.x; L.r0y = a0.y; L.r0z = a1.x;
-  const double vx = a1.y, vy = a2.x, vz = a2.y;
-  L.tau = __ldcs(&s->tau_left);
+  L.r0x = r0x; L.r0y = r0y; L.r0z = r0z;
   L.t = 0.0;
-#pragma unroll
-  for (int k = 0; k < ND; ++k) {
-    L.chi[k] = __ldcs(&s->chi[k]);
-    L.kE[k] = __ldcs(&s->kE[k]);
-  }
-  const int4 c = __ldcs((const int4 *)&s->ix);
-  L.ix = c.x; L.iy = c.y; L.iz = c.z; L.ic = c.w;
+  L.ix = ix; L.iy = iy; L.iz = iz; L.ic = ic;
   L.ivx = 1.0 / vx;
   L.ivy = 1.0 / vy;
   L.ivz = 1.0 / vz;
@@ -678,6 +678,22 @@ __device__ __forceinline__ void load_lane(const Slot<ND> *__restrict__ s, Lane<N
   L.tny = vy != 0.0 ? fmax((W[o2 + L.iy + (vy > 0.0 ? 1 : 0)] - L.r0y) * L.ivy, 0.0) : inf;
   L.tnz = vz != 0.0 ? fmax((W[o3 + L.iz + (vz > 0.0 ? 1 : 0)] - L.r0z) * L.ivz, 0.0) : inf;
   L.fwd = (vx > 0.0 ? 1 : 0) | (vy > 0.0 ? 2 : 0) | (vz > 0.0 ? 4 : 0);
+}
+
+template <int ND>
+__device__ __forceinline__ void load_lane(const Slot<ND> *__restrict__ s, Lane<ND> &L, const double *__restrict__ W,
+                                          int o2, int o3) {
+  const double2 a0 = __ldcs((const double2 *)&s->r0x);  // r0x r0y
+  const double2 a1 = __ldcs((const double2 *)&s->r0z);  // r0z vx
+  const double2 a2 = __ldcs((const double2 *)&s->vy);   // vy vz
+  const int4 c = __ldcs((const int4 *)&s->ix);
+  init_lane<ND>(L, a0.x, a0.y, a1.x, a1.y, a2.x, a2.y, c.x, c.y, c.z, c.w, W, o2, o3);
+  L.tau = __ldcs(&s->tau_left);
+#pragma unroll
+  for (int k = 0; k < ND; ++k) {
+    L.chi[k] = __ldcs(&s->chi[k]);
+    L.kE[k] = __ldcs(&s->kE[k]);
+  }
 }
 
 // Deposits of a whole warp for one crossing step, summed per cell before they leave the SM.
@@ -719,7 +735,7 @@ __device__ __forceinline__ void deposit_warp(CellRec *__restrict__ cells, bool h
 // Returns 0 to continue, 1 if the packet left the grid, 2 if it reached its interaction (then
 // L.t / L.ix,iy,iz / L.ic describe the interaction point).  With COH set the function is called
 // by the whole warp (lanes with `on` unset only take part in the shuffles).
-template <int ND, int D, bool COH>
+template <int ND, int D, bool COH, bool DEP = true>
 __device__ __forceinline__ int advance_group(Lane<ND> &L, const bool on, const double *__restrict__ W,
                                              CellRec *__restrict__ cells, const int n1, const int n2, const int n3,
                                              uint32_t &n_cross) {
@@ -798,7 +814,9 @@ __device__ __forceinline__ int advance_group(Lane<ND> &L, const bool on, const d
 #pragma unroll
       for (int id = 0; id < ND; ++id) dv[id] = rho_s[j][id] > 0.0 ? len * L.kE[id] : 0.0;
     }
-    if (COH) {
+    if (!DEP) {
+      // imaging iterations march without depositing (grid_integrate_noenergy, grid_propagate_3d.f90:237-375)
+    } else if (COH) {
       deposit_warp<ND>(cells, has, ic_s[j], dv);
     } else if (has) {
 #pragma unroll
@@ -964,11 +982,11 @@ flight_beam_kernel(const ModelDev M, Pool P, const uint32_t *__restrict__ q_beam
 
 // grid_reset_energy (src/grid/grid_generic.f90:21-27) + precompute_jnu_var
 // (src/grid/grid_physics_3d.f90:613-629, dust_jnu_var_pos_frac dust_type_4elem.f90:295-320)
-__global__ void lucy_begin_kernel(ModelDev M) {
+__global__ void lucy_begin_kernel(ModelDev M, const int reset_sums) {
   const int nd = M.n_dust;
   const int64_t n = M.n_cells * nd;
   for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x) {
-    M.cells[k].esum = 0.0;
+    if (reset_sums) M.cells[k].esum = 0.0;
     const int id = (int)(k % nd);
     const DustDev &d = M.dust[id];
     const double e = M.specific_energy[k];
@@ -1092,6 +1110,8 @@ __global__ void to_file_order_kernel(ModelDev M, int which, const double *__rest
   }
 }
 
+#include "imaging.cuh"
+
 // =============================================================================================
 // host side: context + C ABI
 // =============================================================================================
@@ -1103,11 +1123,24 @@ struct HostDust {
   DustLayout L;
   std::vector<double> buf;
   double *dev = nullptr;
+  // raw columns kept for the raytracing spectra (get_chi_nu_binned / get_j_nu_binned)
+  std::vector<double> nu, chi, emiss_nu, emiss_jnu;
+  int n_jnu = 0;
 };
 struct HostSpectrum {
   SpectrumLayout L;
   std::vector<double> buf;
   double *dev = nullptr;
+  std::vector<double> nu, fnu;  // raw table (get_spectrum_binned)
+};
+// one peeled group (peeled_images_setup, src/images/images_peeled.f90:272-382)
+struct HostImage {
+  hyp_image_conf conf;
+  std::vector<double> theta, phi;
+  int n_orig = 1, n_stokes = 4;
+  double nu_min = 0, nu_max = 0;
+  size_t n_sed = 0, n_img = 0;     // elements of one SED / image cube
+  size_t o_sed = 0, o_img = 0;     // offsets into the image buffer: [val | sum of squares | count] each
 };
 
 }  // namespace
@@ -1154,6 +1187,21 @@ struct hyp_ctx {
   void *d_sort_tmp = nullptr;
   size_t sort_tmp_bytes = 0;
   cudaEvent_t evA = nullptr, evB = nullptr;
+  // imaging (final / raytracing iterations)
+  std::vector<HostImage> groups;
+  double *d_imgbuf = nullptr;       // all cubes of all groups, then SC_COUNT scalars
+  size_t imgbuf_n = 0;
+  ImageDev *d_images = nullptr;
+  ViewDev *d_views = nullptr;
+  int n_views = 0;
+  std::vector<ImageDev> h_images;
+  void *d_jobs = nullptr;
+  uint32_t *d_njobs = nullptr;
+  uint32_t job_cap = 0;
+  double *d_eabs = nullptr;
+  std::vector<double *> ray_tables;  // device copies of the binned raytracing spectra
+  bool images_ready = false, ray_ready = false;
+  int64_t peel_launches = 0;
 };
 
 namespace {
@@ -1359,6 +1407,13 @@ void hyp_ctx_destroy(hyp_ctx *c) {
   free_dev(c->d_spectra);
   free_dev(c->d_work);
   free_dev(c->d_error);
+  free_dev(c->d_imgbuf);
+  free_dev(c->d_images);
+  free_dev(c->d_views);
+  free_dev(c->d_jobs);
+  free_dev(c->d_njobs);
+  free_dev(c->d_eabs);
+  for (auto &t : c->ray_tables) free_dev(t);
   free_pool(c);
   if (c->h_counts) cudaFreeHost(c->h_counts);
   if (c->evA) cudaEventDestroy(c->evA);
@@ -1406,6 +1461,11 @@ int hyp_add_dust(hyp_ctx *c, const hyp_dust_tables *t) {
   try {
     HostDust d;
     build_dust(*t, d.L, d.buf);
+    d.nu.assign(t->nu, t->nu + t->n_nu);
+    d.chi.assign(t->chi, t->chi + t->n_nu);
+    d.emiss_nu.assign(t->emiss_nu, t->emiss_nu + t->n_emiss_nu);
+    d.emiss_jnu.assign(t->emiss_jnu, t->emiss_jnu + (size_t)t->n_emiss_nu * t->n_jnu);
+    d.n_jnu = t->n_jnu;
     c->dust.push_back(std::move(d));
   } catch (std::exception &e) {
     return fail(HYP_ERR_INVALID, e.what());
@@ -1424,6 +1484,8 @@ int hyp_add_source(hyp_ctx *c, const hyp_source *s) {
     try {
       HostSpectrum sp;
       build_spectrum(s->spec_nu, s->spec_fnu, s->n_spec, sp.L, sp.buf);
+      sp.nu.assign(s->spec_nu, s->spec_nu + s->n_spec);
+      sp.fnu.assign(s->spec_fnu, s->spec_fnu + s->n_spec);
       spec = (int)c->spectra.size();
       c->spectra.push_back(std::move(sp));
     } catch (std::exception &e) {
@@ -1633,7 +1695,7 @@ int hyp_lucy_begin(hyp_ctx *c) {
   CUDA_TRY(cudaSetDevice(c->device));
   const size_t n = (size_t)c->n_cells * c->dust.size();
   CUDA_TRY(cudaEventRecord(c->ev2, c->stream));
-  lucy_begin_kernel<<<grid_blocks(c), 256, 0, c->stream>>>(c->M);
+  lucy_begin_kernel<<<grid_blocks(c), 256, 0, c->stream>>>(c->M, 1);
   CUDA_TRY(cudaGetLastError());
   c->launches_acc = 1;
   CUDA_TRY(cudaMemsetAsync(c->d_sums + n, 0, SC_COUNT * sizeof(double), c->stream));
@@ -1848,5 +1910,564 @@ static int get_grid(hyp_ctx *c, int which, double *out) {
 int hyp_get_specific_energy(hyp_ctx *c, double *out) { return get_grid(c, 0, out); }
 int hyp_get_density(hyp_ctx *c, double *out) { return get_grid(c, 1, out); }
 int hyp_get_energy_sum(hyp_ctx *c, double *out) { return get_grid(c, 2, out); }
+
+}  // extern "C"
+
+// =============================================================================================
+// final (imaging) and raytracing iterations: host side
+// =============================================================================================
+namespace {
+
+int n_orig_of(const hyp_image_conf &g, int n_sources, int n_dust) {
+  switch (g.track_origin) {
+    case HYP_TRACK_SCATTERINGS: return 4 + 2 * g.track_n_scat;
+    case HYP_TRACK_DETAILED: return 2 * (n_sources + n_dust);
+    case HYP_TRACK_BASIC: return 4;
+    default: return 1;
+  }
+}
+
+// Allocate the image cubes of every group in ONE buffer (so that one collective reduces them) and
+// build the device descriptors.  Cubes start at zero and accumulate over calls, as in the reference.
+int ensure_images(hyp_ctx *c) {
+  if (c->images_ready) return HYP_OK;
+  const int ns = (int)c->sources.size(), nd = (int)c->dust.size();
+  size_t off = 0;
+  int n_views = 0;
+  for (auto &g : c->groups) {
+    const hyp_image_conf &k = g.conf;
+    g.n_orig = n_orig_of(k, ns, nd);
+    g.n_stokes = k.compute_stokes ? 4 : 1;
+    const double c_cgs = 2.99792458e10, micron = (double)1.e-4f;  // single-precision literal in image_type.f90:262-263
+    g.nu_min = c_cgs / (k.wav_max * micron);
+    g.nu_max = c_cgs / (k.wav_min * micron);
+    const size_t outer = (size_t)k.n_view * g.n_orig * g.n_stokes;
+    g.n_sed = k.compute_sed ? (size_t)k.n_wav * k.n_ap * outer : 0;
+    g.n_img = k.compute_image ? (size_t)k.n_wav * k.n_x * k.n_y * outer : 0;
+    const int copies = k.uncertainties ? 3 : 1;
+    g.o_sed = off;
+    off += g.n_sed * copies;
+    g.o_img = off;
+    off += g.n_img * copies;
+    n_views += k.n_view;
+  }
+  c->imgbuf_n = off;
+  CUDA_TRY(cudaMalloc(&c->d_imgbuf, (off + SC_COUNT) * sizeof(double)));
+  CUDA_TRY(cudaMemset(c->d_imgbuf, 0, (off + SC_COUNT) * sizeof(double)));
+  CUDA_TRY(cudaMalloc(&c->d_eabs, MAX_DUST * sizeof(double)));
+  std::vector<ViewDev> views;
+  c->h_images.assign(c->groups.size(), ImageDev());
+  const double deg = 3.14159265358979323846264338327950288419 / 180.0;
+  for (size_t ig = 0; ig < c->groups.size(); ++ig) {
+    const HostImage &g = c->groups[ig];
+    const hyp_image_conf &k = g.conf;
+    ImageDev &d = c->h_images[ig];
+    memset(&d, 0, sizeof d);
+    d.n_view = k.n_view; d.n_nu = k.n_wav; d.n_x = k.n_x; d.n_y = k.n_y; d.n_ap = k.n_ap;
+    d.n_orig = g.n_orig; d.n_stokes = g.n_stokes;
+    d.compute_image = k.compute_image; d.compute_sed = k.compute_sed;
+    d.track_origin = k.track_origin; d.track_n_scat = k.track_n_scat;
+    d.uncertainties = k.uncertainties; d.ignore_optical_depth = k.ignore_optical_depth;
+    d.n_sources = ns; d.n_dust = nd;
+    d.x_min = k.x_min; d.x_max = k.x_max; d.y_min = k.y_min; d.y_max = k.y_max;
+    d.ap_min = k.ap_min; d.ap_max = k.ap_max;
+    if (k.compute_sed) {
+      d.log10_ap_min = std::log10(k.ap_min);
+      d.log10_ap_max = std::log10(k.ap_max);
+    }
+    d.log10_nu_min = std::log10(g.nu_min);
+    d.log10_nu_max = std::log10(g.nu_max);
+    d.d_min = k.d_min; d.d_max = k.d_max;
+    d.rpx = k.peeloff_x; d.rpy = k.peeloff_y; d.rpz = k.peeloff_z;
+    double *b = c->d_imgbuf;
+    if (g.n_sed) {
+      d.sed = b + g.o_sed;
+      if (k.uncertainties) { d.sed2 = d.sed + g.n_sed; d.sedn = d.sed2 + g.n_sed; }
+    }
+    if (g.n_img) {
+      d.img = b + g.o_img;
+      if (k.uncertainties) { d.img2 = d.img + g.n_img; d.imgn = d.img2 + g.n_img; }
+    }
+    for (int iv = 0; iv < k.n_view; ++iv) {
+      ViewDev v;
+      v.group = (int)ig;
+      v.view = iv;
+      // angle3d_deg (type_angle3d.f90:127-147)
+      v.a.cost = std::cos(g.theta[iv] * deg);
+      v.a.sint = std::sin(g.theta[iv] * deg);
+      v.a.cosp = std::cos(g.phi[iv] * deg);
+      v.a.sinp = std::sin(g.phi[iv] * deg);
+      views.push_back(v);
+    }
+  }
+  c->n_views = n_views;
+  if (!c->groups.empty()) {
+    CUDA_TRY(cudaMalloc(&c->d_images, c->h_images.size() * sizeof(ImageDev)));
+    CUDA_TRY(cudaMemcpy(c->d_images, c->h_images.data(), c->h_images.size() * sizeof(ImageDev), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMalloc(&c->d_views, views.size() * sizeof(ViewDev)));
+    CUDA_TRY(cudaMemcpy(c->d_views, views.data(), views.size() * sizeof(ViewDev), cudaMemcpyHostToDevice));
+  }
+  c->images_ready = true;
+  return HYP_OK;
+}
+
+// Spectra of every source and dust type on every group's frequency grid (the lazily filled caches of
+// images_peeled.f90:423-530, computed up front here).
+int ensure_ray_tables(hyp_ctx *c) {
+  if (c->ray_ready) return HYP_OK;
+  const int ns = (int)c->sources.size(), nd = (int)c->dust.size();
+  auto upload = [&](const std::vector<double> &h, const double **dst) -> int {
+    double *d = nullptr;
+    CUDA_TRY(cudaMalloc(&d, std::max<size_t>(h.size(), 1) * sizeof(double)));
+    CUDA_TRY(cudaMemcpy(d, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice));
+    c->ray_tables.push_back(d);
+    *dst = d;
+    return HYP_OK;
+  };
+  for (size_t ig = 0; ig < c->groups.size(); ++ig) {
+    ImageDev &d = c->h_images[ig];
+    const int n_nu = d.n_nu;
+    const double l0 = d.log10_nu_min, l1 = d.log10_nu_max;
+    std::vector<double> spec((size_t)ns * n_nu), chi((size_t)nd * n_nu);
+    std::vector<double> bnu, bfnu;
+    for (int is = 0; is < ns; ++is) {
+      const int sp = c->source_spectrum[is];
+      if (sp >= 0) {
+        const HostSpectrum &S = c->spectra[sp];
+        binned_fraction(S.nu.data(), S.fnu.data(), (int)S.nu.size(), l0, l1, n_nu, &spec[(size_t)is * n_nu]);
+      } else {
+        blackbody_table(c->sources[is].temperature, bnu, bfnu);
+        binned_fraction(bnu.data(), bfnu.data(), (int)bnu.size(), l0, l1, n_nu, &spec[(size_t)is * n_nu]);
+      }
+    }
+    int rc = upload(spec, &d.src_spec);
+    if (rc) return rc;
+    for (int id = 0; id < nd; ++id) {
+      const HostDust &D = c->dust[id];
+      binned_chi(D.nu.data(), D.chi.data(), (int)D.nu.size(), l0, l1, n_nu, &chi[(size_t)id * n_nu]);
+      const int ne = (int)D.emiss_nu.size();
+      std::vector<double> logj((size_t)D.n_jnu * n_nu), col(ne);
+      for (int s = 0; s < D.n_jnu; ++s) {
+        for (int k = 0; k < ne; ++k) col[k] = D.emiss_jnu[(size_t)k * D.n_jnu + s];
+        double *o = &logj[(size_t)s * n_nu];
+        binned_fraction(D.emiss_nu.data(), col.data(), ne, l0, l1, n_nu, o);
+        for (int i = 0; i < n_nu; ++i) o[i] = std::log10(o[i]);
+      }
+      rc = upload(logj, &d.dust_logj[id]);
+      if (rc) return rc;
+    }
+    rc = upload(chi, &d.dust_chi);
+    if (rc) return rc;
+  }
+  if (!c->groups.empty())
+    CUDA_TRY(cudaMemcpy(c->d_images, c->h_images.data(), c->h_images.size() * sizeof(ImageDev), cudaMemcpyHostToDevice));
+  c->ray_ready = true;
+  return HYP_OK;
+}
+
+size_t job_bytes(int nd) {
+  switch (nd) {
+    case 1: return sizeof(PeelJob<1>);
+    case 2: return sizeof(PeelJob<2>);
+    case 3: return sizeof(PeelJob<3>);
+    default: return sizeof(PeelJob<4>);
+  }
+}
+
+int ensure_jobs(hyp_ctx *c, uint32_t cap) {
+  if (c->job_cap >= cap) return HYP_OK;
+  free_dev(c->d_jobs);
+  free_dev(c->d_njobs);
+  CUDA_TRY(cudaMalloc(&c->d_jobs, (size_t)cap * job_bytes(c->M.n_dust)));
+  CUDA_TRY(cudaMalloc(&c->d_njobs, sizeof(uint32_t)));
+  CUDA_TRY(cudaMemset(c->d_njobs, 0, sizeof(uint32_t)));
+  c->job_cap = cap;
+  return HYP_OK;
+}
+
+struct WallSmem {
+  size_t bytes;
+  int on;
+};
+WallSmem wall_smem(const hyp_ctx *c) {
+  size_t b = (size_t)(c->n1 + c->n2 + c->n3 + 3) * sizeof(double);
+  if (b > 40 * 1024) return {0, 0};
+  return {b, 1};
+}
+
+template <int ND, bool POLY>
+int launch_peel(hyp_ctx *c, const ModelDev &M, uint32_t n_jobs_max) {
+  if (c->n_views == 0 || n_jobs_max == 0) return HYP_OK;
+  const WallSmem ws = wall_smem(c);
+  auto k = peel_kernel<ND, POLY>;
+  CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ws.bytes));
+  ImagingDev I{c->d_images, c->d_views, (int)c->groups.size(), c->n_views};
+  const int64_t work = (int64_t)n_jobs_max * c->n_views;
+  const int blocks = (int)std::min<int64_t>((work + PEEL_THREADS - 1) / PEEL_THREADS, (int64_t)c->sm_count * 8);
+  k<<<blocks, PEEL_THREADS, ws.bytes, c->stream>>>(M, I, (const PeelJob<ND> *)c->d_jobs, c->d_njobs, ws.on);
+  CUDA_TRY(cudaGetLastError());
+  c->launches_acc += 1;
+  return HYP_OK;
+}
+
+ModelDev imaging_model(hyp_ctx *c) {
+  ModelDev M = c->M;
+  M.scalars = c->d_imgbuf + c->imgbuf_n;
+  return M;
+}
+
+// rounds of the packet pool for the imaging iteration (propagate, iter_final.f90:147-273)
+template <int ND>
+int run_final_rounds(hyp_ctx *c, int64_t first_id, int64_t n_photons, int scattering_only) {
+  const uint32_t cap = (uint32_t)std::min<int64_t>(pool_target(), n_photons);
+  int rc = ensure_pool(c, cap);
+  if (rc) return rc;
+  rc = ensure_jobs(c, 2 * c->pool_cap);
+  if (rc) return rc;
+  Pool &P = c->pool;
+  const WallSmem ws = wall_smem(c);
+  auto flight = flight_final_kernel<ND, FLIGHT_LOOKAHEAD>;
+  CUDA_TRY(cudaFuncSetAttribute(flight, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ws.bytes));
+  int per_sm = 0;
+  CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, flight, FLIGHT_THREADS, ws.bytes));
+  if (per_sm < 1) per_sm = 1;
+  const int flight_blocks_max = per_sm * c->sm_count;
+  const int service_blocks_max = c->sm_count * 8;
+  cudaStream_t st = c->stream;
+  const ModelDev M = imaging_model(c);
+  FinalArgs F;
+  F.jobs = c->d_jobs;
+  F.n_jobs = c->d_njobs;
+  F.job_capacity = c->job_cap;
+  F.scattering_only = scattering_only;
+  F.forced = c->conf.forced_first_interaction;
+  F.algorithm = c->conf.forced_first_interaction_algorithm;
+  F.baes16_xi = c->conf.baes16_xi;
+  F.make_peeled = c->n_views > 0;
+  const uint32_t iteration = ITER_FINAL;
+
+  pool_init_kernel<<<c->sm_count, 256, 0, st>>>(P, cap);
+  c->launches_acc += 1;
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaMemsetAsync(c->d_njobs, 0, sizeof(uint32_t), st));
+  CUDA_TRY(cudaEventRecord(c->ev0, st));
+  int cur = 0;
+  uint32_t n_emit = cap, n_flight_prev = 0;
+  unsigned long long claimed = 0;
+  int64_t windows_ready = 0;
+  for (int64_t round = 0;; ++round) {
+    uint32_t *nF = P.counts + C_NF0 + cur, *nF_next = P.counts + C_NF0 + (1 - cur);
+    while (windows_ready * (int64_t)c->sort_window < n_photons &&
+           (int64_t)claimed + 2 * (int64_t)cap > windows_ready * (int64_t)c->sort_window) {
+      rc = prepare_window(c, first_id, n_photons, iteration, windows_ready);
+      if (rc) return rc;
+      ++windows_ready;
+    }
+    int64_t n_new = 0;
+    if (claimed < (unsigned long long)n_photons && n_emit > 0) {
+      n_new = std::min<int64_t>(n_emit, n_photons - (int64_t)claimed);
+      int blocks = (int)std::min<int64_t>(((int64_t)n_emit + SERVICE_THREADS - 1) / SERVICE_THREADS, service_blocks_max);
+      emit_final_kernel<ND><<<blocks, SERVICE_THREADS, 0, st>>>(M, P, F, (unsigned long long)first_id,
+                                                                (unsigned long long)n_photons, iteration);
+      CUDA_TRY(cudaGetLastError());
+      c->launches_acc += 1;
+    }
+    CUDA_TRY(cudaMemsetAsync(P.counts + C_NI, 0, 4 * sizeof(uint32_t), st));  // C_NI, C_NE, C_CURSOR, C_CURSOR_B
+    CUDA_TRY(cudaEventRecord(c->evA, st));
+    if (n_new > 0) {
+      int blocks = (int)std::min<int64_t>((n_new + FLIGHT_THREADS - 1) / FLIGHT_THREADS, flight_blocks_max);
+      flight<<<blocks, FLIGHT_THREADS, ws.bytes, st>>>(M, P, F, P.q_beam, P.counts + C_NB, P.counts + C_CURSOR_B, ws.on, iteration);
+      CUDA_TRY(cudaGetLastError());
+      c->launches_acc += 1;
+    }
+    if (n_flight_prev > 0) {
+      int blocks = (int)std::min<int64_t>(((int64_t)n_flight_prev + FLIGHT_THREADS - 1) / FLIGHT_THREADS, flight_blocks_max);
+      flight<<<blocks, FLIGHT_THREADS, ws.bytes, st>>>(M, P, F, P.q_flight[cur], nF, P.counts + C_CURSOR, ws.on, iteration);
+      CUDA_TRY(cudaGetLastError());
+      c->launches_acc += 1;
+    }
+    CUDA_TRY(cudaEventRecord(c->evB, st));
+    CUDA_TRY(cudaMemsetAsync(nF_next, 0, sizeof(uint32_t), st));
+    CUDA_TRY(cudaMemsetAsync(P.counts + C_NB, 0, sizeof(uint32_t), st));
+    interact_final_kernel<ND><<<service_blocks_max, SERVICE_THREADS, 0, st>>>(M, P, F, P.q_flight[1 - cur], nF_next, iteration);
+    CUDA_TRY(cudaGetLastError());
+    c->launches_acc += 1;
+    // peel-offs of this round's emissions and interactions
+    rc = launch_peel<ND, false>(c, M, (uint32_t)std::min<int64_t>((int64_t)c->job_cap, n_new + (int64_t)cap));
+    if (rc) return rc;
+    CUDA_TRY(cudaMemsetAsync(c->d_njobs, 0, sizeof(uint32_t), st));
+    CUDA_TRY(cudaMemcpyAsync(c->h_counts, P.counts, C_COUNT * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(c->h_counts + C_COUNT, P.next_photon, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, c->evA, c->evB) == cudaSuccess) c->flight_ms_acc += ms;
+    c->rounds_acc += 1;
+    cur = 1 - cur;
+    memcpy(&claimed, c->h_counts + C_COUNT, sizeof claimed);
+    n_emit = c->h_counts[C_NE];
+    n_flight_prev = c->h_counts[C_NF0 + cur];
+    const bool ids_left = claimed < (unsigned long long)n_photons;
+    if (n_flight_prev == 0 && (!ids_left || n_emit == 0)) break;
+  }
+  CUDA_TRY(cudaEventRecord(c->ev1, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  float ms = 0.f;
+  if (cudaEventElapsedTime(&ms, c->ev0, c->ev1) == cudaSuccess) c->kernel_ms_acc += ms;
+  return HYP_OK;
+}
+
+template <int ND>
+int run_raytracing(hyp_ctx *c, int64_t first_source_id, int64_t n_sources, int64_t n_total_sources,
+                   int64_t first_dust_id, int64_t n_thermal, int64_t n_total_dust) {
+  const ModelDev M = imaging_model(c);
+  cudaStream_t st = c->stream;
+  // do_raytracing starts with precompute_jnu_var (iter_raytracing.f90:60)
+  lucy_begin_kernel<<<grid_blocks(c), 256, 0, st>>>(c->M, 0);
+  CUDA_TRY(cudaMemsetAsync(c->d_eabs, 0, MAX_DUST * sizeof(double), st));
+  energy_abs_tot_kernel<<<grid_blocks(c), 256, 0, st>>>(c->M, c->d_eabs);
+  CUDA_TRY(cudaGetLastError());
+  c->launches_acc += 2;
+  const uint32_t chunk = 1u << 20;
+  int rc = ensure_jobs(c, chunk);
+  if (rc) return rc;
+  const double source_weight = n_total_sources > 0 ? c->energy_total / (double)n_total_sources : 0.0;
+  const double dust_weight = n_total_dust > 0 ? (double)ND / (double)n_total_dust : 0.0;
+  int64_t done_s = 0, done_d = 0;
+  while (done_s < n_sources || done_d < n_thermal) {
+    const uint32_t ns = (uint32_t)std::min<int64_t>(chunk, n_sources - done_s);
+    const uint32_t nt = (uint32_t)std::min<int64_t>(chunk - ns, n_thermal - done_d);
+    CUDA_TRY(cudaMemsetAsync(c->d_njobs, 0, sizeof(uint32_t), st));
+    const int blocks = (int)std::min<int64_t>(((int64_t)ns + nt + 255) / 256, (int64_t)c->sm_count * 8);
+    raytrace_emit_kernel<ND><<<blocks, 256, 0, st>>>(M, (PeelJob<ND> *)c->d_jobs, c->d_njobs,
+                                                     (unsigned long long)(first_source_id + done_s), ns, source_weight,
+                                                     (unsigned long long)(first_dust_id + done_d), nt, dust_weight,
+                                                     c->d_eabs);
+    CUDA_TRY(cudaGetLastError());
+    c->launches_acc += 1;
+    rc = launch_peel<ND, true>(c, M, ns + nt);
+    if (rc) return rc;
+    done_s += ns;
+    done_d += nt;
+  }
+  CUDA_TRY(cudaStreamSynchronize(st));
+  return HYP_OK;
+}
+
+int read_image_scalars(hyp_ctx *c, double *sc) {
+  CUDA_TRY(cudaMemcpyAsync(sc, c->d_imgbuf + c->imgbuf_n, SC_COUNT * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  return HYP_OK;
+}
+
+void fill_image_stats(hyp_ctx *c, const double *sc, hyp_iter_stats *st) {
+  if (!st) return;
+  memset(st, 0, sizeof *st);
+  st->energy_emitted = sc[SC_ENERGY];
+  st->n_photons = (int64_t)sc[SC_PHOTONS];
+  st->killed_geo = (int64_t)sc[SC_KILLED_GEO];
+  st->killed_int = (int64_t)sc[SC_KILLED_INT];
+  st->n_crossings = (int64_t)sc[SC_CROSS];
+  st->n_absorptions = (int64_t)sc[SC_ABS];
+  st->n_scatterings = (int64_t)sc[SC_SCAT];
+  st->n_escaped = (int64_t)sc[SC_ESC];
+  st->n_peel_crossings = (int64_t)sc[SC_PEEL_CROSS];
+  st->n_peeloffs = (int64_t)sc[SC_PEELOFFS];
+  st->kernel_ms = c->kernel_ms_acc;
+  st->flight_ms = c->flight_ms_acc;
+  st->n_rounds = c->rounds_acc;
+  st->n_launches = c->launches_acc;
+}
+
+}  // namespace
+
+extern "C" {
+
+int hyp_add_peeled_group(hyp_ctx *c, const hyp_image_conf *g) {
+  if (!c || !g) return fail(HYP_ERR_INVALID, "NULL argument");
+  if (c->images_ready) return fail(HYP_ERR_STATE, "image groups are frozen once an imaging iteration has started");
+  if (g->inside_observer) return fail(HYP_ERR_INVALID, "inside observers are not implemented on the device yet");
+  if (!(g->n_view > 0) || !g->theta || !g->phi) return fail(HYP_ERR_INVALID, "n_view should be a positive integer");
+  if (g->n_wav < 1) return fail(HYP_ERR_INVALID, "n_nu should be >= 1");
+  if (g->io_bytes != 4 && g->io_bytes != 8) return fail(HYP_ERR_INVALID, "unexpected value of io_bytes (should be 4 or 8)");
+  if (g->track_origin < HYP_TRACK_NO || g->track_origin > HYP_TRACK_SCATTERINGS)
+    return fail(HYP_ERR_INVALID, "unknown track_origin flag");
+  if (g->compute_image && (g->n_x < 1 || g->n_y < 1)) return fail(HYP_ERR_INVALID, "image needs at least one pixel");
+  if (g->compute_sed && g->n_ap < 1) return fail(HYP_ERR_INVALID, "SED needs at least one aperture");
+  HostImage h;
+  h.conf = *g;
+  h.theta.assign(g->theta, g->theta + g->n_view);
+  h.phi.assign(g->phi, g->phi + g->n_view);
+  h.conf.theta = h.conf.phi = nullptr;
+  c->groups.push_back(std::move(h));
+  return HYP_OK;
+}
+
+int hyp_final_begin(hyp_ctx *c) {
+  if (!c || !c->finalized) return fail(HYP_ERR_STATE, "hyp_finalize_setup has not been called");
+  CUDA_TRY(cudaSetDevice(c->device));
+  int rc = ensure_images(c);
+  if (rc) return rc;
+  CUDA_TRY(cudaEventRecord(c->ev2, c->stream));
+  // precompute_jnu_var (iter_final.f90:99); the deposit grid is left alone
+  lucy_begin_kernel<<<grid_blocks(c), 256, 0, c->stream>>>(c->M, 0);
+  CUDA_TRY(cudaGetLastError());
+  c->launches_acc = 1;
+  CUDA_TRY(cudaMemsetAsync(c->d_imgbuf + c->imgbuf_n, 0, SC_COUNT * sizeof(double), c->stream));
+  CUDA_TRY(cudaMemsetAsync(c->d_error, 0, sizeof(int32_t), c->stream));
+  c->kernel_ms_acc = 0.f;
+  c->flight_ms_acc = 0.f;
+  c->rounds_acc = 0;
+  return HYP_OK;
+}
+
+int hyp_final_photons(hyp_ctx *c, int64_t first_id, int64_t n_photons, int32_t peeloff_scattering_only) {
+  if (!c || !c->finalized) return fail(HYP_ERR_STATE, "hyp_finalize_setup has not been called");
+  if (!c->images_ready) return fail(HYP_ERR_STATE, "hyp_final_begin has not been called");
+  if (n_photons < 0 || first_id < 0) return fail(HYP_ERR_INVALID, "negative photon count");
+  if (n_photons == 0) return HYP_OK;
+  CUDA_TRY(cudaSetDevice(c->device));
+  switch (c->M.n_dust) {
+    case 1: return run_final_rounds<1>(c, first_id, n_photons, peeloff_scattering_only);
+    case 2: return run_final_rounds<2>(c, first_id, n_photons, peeloff_scattering_only);
+    case 3: return run_final_rounds<3>(c, first_id, n_photons, peeloff_scattering_only);
+    case 4: return run_final_rounds<4>(c, first_id, n_photons, peeloff_scattering_only);
+    default: return fail(HYP_ERR_INVALID, "unsupported number of dust types");
+  }
+}
+
+int hyp_image_device_buffers(hyp_ctx *c, void **buffer, int64_t *n_values) {
+  if (!c || !c->finalized) return fail(HYP_ERR_STATE, "hyp_finalize_setup has not been called");
+  CUDA_TRY(cudaSetDevice(c->device));
+  int rc = ensure_images(c);
+  if (rc) return rc;
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  if (buffer) *buffer = c->d_imgbuf;
+  if (n_values) *n_values = (int64_t)c->imgbuf_n + SC_COUNT;
+  return HYP_OK;
+}
+
+int hyp_final_finish(hyp_ctx *c, hyp_iter_stats *st) {
+  if (!c || !c->images_ready) return fail(HYP_ERR_STATE, "hyp_final_begin has not been called");
+  CUDA_TRY(cudaSetDevice(c->device));
+  double sc[SC_COUNT];
+  int rc = read_image_scalars(c, sc);
+  if (rc) return rc;
+  rc = device_error_to_status(c);
+  if (rc) return rc;
+  if (!(sc[SC_ENERGY] > 0.0)) return fail(HYP_ERR_STATE, "no photons were emitted in this iteration");
+  // peeled_images_adjust_scale(energy_total / energy_current) (iter_final.f90:140-143)
+  const double scale = c->energy_total / sc[SC_ENERGY];
+  for (auto &g : c->groups) {
+    const size_t ns[2] = {g.n_sed, g.n_img}, os[2] = {g.o_sed, g.o_img};
+    for (int w = 0; w < 2; ++w) {
+      if (!ns[w]) continue;
+      image_scale_kernel<<<grid_blocks(c), 256, 0, c->stream>>>(c->d_imgbuf + os[w], (int64_t)ns[w], scale);
+      if (g.conf.uncertainties)
+        image_scale_kernel<<<grid_blocks(c), 256, 0, c->stream>>>(c->d_imgbuf + os[w] + ns[w], (int64_t)ns[w], scale * scale);
+      c->launches_acc += g.conf.uncertainties ? 2 : 1;
+    }
+  }
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaEventRecord(c->ev3, c->stream));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  fill_image_stats(c, sc, st);
+  if (st) {
+    float total = 0.f;
+    if (cudaEventElapsedTime(&total, c->ev2, c->ev3) == cudaSuccess) st->epilogue_ms = total - c->kernel_ms_acc;
+  }
+  return HYP_OK;
+}
+
+int hyp_raytracing_photons(hyp_ctx *c, int64_t first_source_id, int64_t n_sources, int64_t n_total_sources,
+                           int64_t first_dust_id, int64_t n_dust, int64_t n_total_dust, hyp_iter_stats *st) {
+  if (!c || !c->finalized) return fail(HYP_ERR_STATE, "hyp_finalize_setup has not been called");
+  if (n_sources < 0 || n_dust < 0 || first_source_id < 0 || first_dust_id < 0)
+    return fail(HYP_ERR_INVALID, "negative photon count");
+  CUDA_TRY(cudaSetDevice(c->device));
+  int rc = ensure_images(c);
+  if (rc) return rc;
+  rc = ensure_ray_tables(c);
+  if (rc) return rc;
+  CUDA_TRY(cudaMemsetAsync(c->d_imgbuf + c->imgbuf_n, 0, SC_COUNT * sizeof(double), c->stream));
+  CUDA_TRY(cudaMemsetAsync(c->d_error, 0, sizeof(int32_t), c->stream));
+  c->launches_acc = 0;
+  c->kernel_ms_acc = c->flight_ms_acc = 0.f;
+  c->rounds_acc = 0;
+  CUDA_TRY(cudaEventRecord(c->ev0, c->stream));
+  switch (c->M.n_dust) {
+    case 1: rc = run_raytracing<1>(c, first_source_id, n_sources, n_total_sources, first_dust_id, n_dust, n_total_dust); break;
+    case 2: rc = run_raytracing<2>(c, first_source_id, n_sources, n_total_sources, first_dust_id, n_dust, n_total_dust); break;
+    case 3: rc = run_raytracing<3>(c, first_source_id, n_sources, n_total_sources, first_dust_id, n_dust, n_total_dust); break;
+    case 4: rc = run_raytracing<4>(c, first_source_id, n_sources, n_total_sources, first_dust_id, n_dust, n_total_dust); break;
+    default: return fail(HYP_ERR_INVALID, "unsupported number of dust types");
+  }
+  if (rc) return rc;
+  CUDA_TRY(cudaEventRecord(c->ev1, c->stream));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  float ms = 0.f;
+  if (cudaEventElapsedTime(&ms, c->ev0, c->ev1) == cudaSuccess) c->kernel_ms_acc = ms;
+  double sc[SC_COUNT];
+  rc = read_image_scalars(c, sc);
+  if (rc) return rc;
+  rc = device_error_to_status(c);
+  if (rc) return rc;
+  fill_image_stats(c, sc, st);
+  return HYP_OK;
+}
+
+int hyp_image_shape(hyp_ctx *c, int32_t group, int32_t which, int64_t dims[6], int32_t *ndim) {
+  if (!c || !dims || !ndim) return fail(HYP_ERR_INVALID, "NULL argument");
+  if (group < 0 || group >= (int)c->groups.size()) return fail(HYP_ERR_INVALID, "no such image group");
+  const HostImage &g = c->groups[group];
+  const int n_orig = n_orig_of(g.conf, (int)c->sources.size(), (int)c->dust.size());
+  const int n_stokes = g.conf.compute_stokes ? 4 : 1;
+  if (which == 0) {
+    if (!g.conf.compute_sed) return fail(HYP_ERR_INVALID, "group has no SED");
+    const int64_t d[5] = {n_stokes, n_orig, g.conf.n_view, g.conf.n_ap, g.conf.n_wav};
+    for (int i = 0; i < 5; ++i) dims[i] = d[i];
+    *ndim = 5;
+  } else {
+    if (!g.conf.compute_image) return fail(HYP_ERR_INVALID, "group has no image");
+    const int64_t d[6] = {n_stokes, n_orig, g.conf.n_view, g.conf.n_y, g.conf.n_x, g.conf.n_wav};
+    for (int i = 0; i < 6; ++i) dims[i] = d[i];
+    *ndim = 6;
+  }
+  return HYP_OK;
+}
+
+// image_write (image_type.f90:608-788): divide by the relative bin width, make the apertures cumulative
+static int get_cube(hyp_ctx *c, int32_t group, bool sed, double *out, double *unc) {
+  if (!c || !out) return fail(HYP_ERR_INVALID, "NULL argument");
+  if (group < 0 || group >= (int)c->groups.size()) return fail(HYP_ERR_INVALID, "no such image group");
+  CUDA_TRY(cudaSetDevice(c->device));
+  int rc = ensure_images(c);
+  if (rc) return rc;
+  const HostImage &g = c->groups[group];
+  const size_t n = sed ? g.n_sed : g.n_img, off = sed ? g.o_sed : g.o_img;
+  if (!n) return fail(HYP_ERR_INVALID, sed ? "group has no SED" : "group has no image");
+  CUDA_TRY(cudaMemcpyAsync(out, c->d_imgbuf + off, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  const bool have_unc = unc && g.conf.uncertainties;
+  if (have_unc) CUDA_TRY(cudaMemcpyAsync(unc, c->d_imgbuf + off + n, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  const int n_nu = g.conf.n_wav;
+  const double dnunorm = std::pow(g.nu_max / g.nu_min, +0.5 / (double)n_nu) - std::pow(g.nu_max / g.nu_min, -0.5 / (double)n_nu);
+  for (size_t i = 0; i < n; ++i) out[i] = out[i] / dnunorm;
+  if (have_unc)
+    for (size_t i = 0; i < n; ++i) unc[i] = std::sqrt(unc[i]) / dnunorm;
+  if (sed) {
+    const size_t n_ap = g.conf.n_ap, outer = n / ((size_t)n_nu * n_ap);
+    for (size_t o = 0; o < outer; ++o)
+      for (size_t ia = 1; ia < n_ap; ++ia)
+        for (size_t inu = 0; inu < (size_t)n_nu; ++inu) {
+          const size_t k = inu + n_nu * (ia + n_ap * o), km = inu + n_nu * (ia - 1 + n_ap * o);
+          out[k] = out[km] + out[k];
+          if (have_unc) unc[k] = std::sqrt(unc[km] * unc[km] + unc[k] * unc[k]);
+        }
+  }
+  return HYP_OK;
+}
+
+int hyp_get_sed(hyp_ctx *c, int32_t group, double *sed, double *unc) { return get_cube(c, group, true, sed, unc); }
+int hyp_get_image(hyp_ctx *c, int32_t group, double *image, double *unc) { return get_cube(c, group, false, image, unc); }
 
 }  // extern "C"

@@ -1,0 +1,719 @@
+// imaging.cuh -- device side of the final (imaging) and raytracing iterations.
+//
+// Reference routines restated here for the GPU: do_final / propagate (src/main/iter_final.f90:60-273),
+// forced first interaction (src/main/forced_interaction.f90:23-133), peeloff_photon
+// (src/images/images_peeled.f90:95-270), grid_escape_tau / grid_escape_column_density
+// (src/grid/grid_propagate_3d.f90:377-582), image_bin / image_bin_raytraced
+// (src/images/image_type.f90:408-606), do_raytracing (src/main/iter_raytracing.f90:31-141) and
+// emit_from_grid (src/grid/grid_physics_3d.f90:691-753).
+//
+// The imaging iteration reuses the packet pool of the Lucy iteration.  A round is
+//   emit_final -> peel -> flight_final -> interact_final
+// Every event that the reference peels off (an emission, and each interaction that survives) is
+// written as a self-contained PeelJob; the peel kernel runs one thread per (job, viewing angle),
+// marches the ray to the grid edge (8 B of density per crossing, no deposit) and adds the
+// attenuated packet into the image / SED cubes with fp64 REDs.
+//
+// Included by hyperion_b200.cu after the Lucy kernels (it uses ModelDev, Slot, Photon, Lane, ...).
+#pragma once
+
+// ---------------------------------------------------------------------------------------------
+// image cubes on the device
+// ---------------------------------------------------------------------------------------------
+struct ImageDev {
+  int32_t n_view, n_nu, n_x, n_y, n_ap, n_orig, n_stokes;
+  int32_t compute_image, compute_sed, track_origin, track_n_scat, uncertainties, ignore_optical_depth;
+  int32_t n_sources, n_dust;
+  double x_min, x_max, y_min, y_max, ap_min, ap_max;
+  double log10_ap_min, log10_ap_max, log10_nu_min, log10_nu_max;
+  double d_min, d_max;
+  double rpx, rpy, rpz;  // peeloff origin
+  // accumulators, Fortran order (first index fastest): sed(n_nu, n_ap, n_view, n_orig, n_stokes),
+  // img(n_nu, n_x, n_y, n_view, n_orig, n_stokes)  (image_type.f90:291,299); 2 = sum of squares, n = counts
+  double *sed, *sed2, *sedn, *img, *img2, *imgn;
+  // raytracing spectra on this group's frequency grid (images_peeled.f90:423-530)
+  const double *src_spec;               // [n_sources][n_nu]
+  const double *dust_chi;               // [n_dust][n_nu]
+  const double *dust_logj[MAX_DUST];    // [n_jnu][n_nu] log10 of the binned emissivities
+};
+
+struct ViewDev {
+  int32_t group, view;  // 0-based group, 0-based view inside the group
+  Angle a;
+};
+
+struct ImagingDev {
+  const ImageDev *images;
+  const ViewDev *views;
+  int32_t n_groups, n_views;
+};
+
+// One peel-off event.  kind 0: the last event was isotropic (emission from a point source, thermal
+// re-emission); kind 1: a scattering -- the direction and Stokes vector BEFORE the scattering are kept so
+// that the phase matrix can be evaluated towards each observer (dust_scatter_peeloff,
+// src/dust/dust_type_4elem.f90:421-444).
+template <int ND>
+struct PeelJob {
+  double rx, ry, rz, nu, energy;
+  double chi[ND];
+  double vpx, vpy, vpz, sQ, sU, sV;
+  double emiss_var_frac;
+  int32_t kind, source_id, dust_id, n_scat;      // ids are 1-based as in the reference
+  int32_t scattered, reprocessed, emiss_type, emiss_var_id;
+};
+
+// bits of Slot::tag / Photon::tag during the final iteration
+constexpr uint32_t TAG_SRC_MASK = 0xffu, TAG_SCATTERED = 0x100u, TAG_REPROCESSED = 0x200u;
+constexpr int TAG_NSCAT_SHIFT = 16;
+
+// ipos_dp (fortranlib/src/lib_array.f90:954-998): 1-based bin, 0 / nbin+1 outside
+__device__ __forceinline__ int ipos_bin(double xmin, double xmax, double x, int nbin) {
+  if (xmax > xmin) {
+    if (x < xmin) return 0;
+    if (x > xmax) return nbin + 1;
+    if (x < xmax) return (int)((x - xmin) / (xmax - xmin) * (double)nbin) + 1;
+    return nbin;
+  }
+  if (x > xmin) return 0;
+  if (x < xmax) return nbin + 1;
+  if (x > xmax) return (int)((x - xmin) / (xmax - xmin) * (double)nbin) + 1;
+  return nbin;
+}
+
+__device__ __forceinline__ Angle angle_of(double vx, double vy, double vz) {
+  Angle a;
+  a.cost = vz;
+  a.sint = sqrt(vx * vx + vy * vy);
+  if (a.sint > 0.0) {
+    a.cosp = vx / a.sint;
+    a.sinp = vy / a.sint;
+  } else {
+    a.cosp = 1.0;
+    a.sinp = 0.0;
+  }
+  return a;
+}
+
+// difference_angle3d_dp (fortranlib/src/type_angle3d.f90:283-419): the local angle that takes
+// a_coord into a_final, i.e. the inverse of rotate_angle.
+__device__ inline Angle difference_angle(const Angle &c, const Angle &f) {
+  Angle l;
+  if (fabs(c.sint) < 1.e-10) {
+    l = f;
+    if (c.cost > 0.0) {
+      l.cosp = c.cosp * f.cosp + c.sinp * f.sinp;
+      l.sinp = -c.cosp * f.sinp + c.sinp * f.cosp;
+    } else {
+      l.cost = -l.cost;
+      l.cosp = c.cosp * f.cosp + c.sinp * f.sinp;
+      l.sinp = c.cosp * f.sinp - c.sinp * f.cosp;
+    }
+    return l;
+  }
+  const double cos_a = c.cost, sin_a = c.sint, cos_c = f.cost, sin_c = f.sint;
+  const double cos_B = c.cosp * f.cosp + c.sinp * f.sinp;
+  const double sin_B = c.sinp * f.cosp - c.cosp * f.sinp;
+  const double cos_b = cos_a * cos_c + sin_a * sin_c * cos_B;
+  const double sin_b = sin2cos(cos_b);
+  if (fabs(cos_b + 1.0) < 1.e-10) return Angle{-1.0, 0.0, 1.0, 0.0};  // angle3d_deg(180, 0) up to rounding of sin(pi)
+  if (fabs(cos_b - 1.0) < 1.e-10) return Angle{1.0, 0.0, 1.0, 0.0};
+  // the reference's logical expression parses as  A .eqv. (B .and. C) .eqv. D
+  const bool same_sign = ((cos_a > 0.0) == ((cos_b > 0.0) && (sin_a > 0.0))) == (sin_b > 0.0);
+  const bool sin_dom = fabs(sin_a) > fabs(cos_a);
+  const double delta = sin_dom ? cos_b - cos_a : sin_b - sin_a;
+  double sin_C, cos_C;
+  if (same_sign && fabs(delta) < 1.e-5 && sin_c < 1.e-5) {
+    const double q = sin_dom ? cos_a / sin_a : sin_a / cos_a;
+    const double diff = (sin_c * sin_c - delta * delta * (1.0 + q * q)) / (sin_a * sin_b);
+    sin_C = diff >= 0.0 ? sqrt(diff) : 0.0;
+    cos_C = cos_c > 0.0 ? sin2cos(sin_C) : -sin2cos(sin_C);
+  } else {
+    sin_C = fabs(sin_B) * sin_c / sin_b;
+    cos_C = (cos_c - cos_a * cos_b) / (sin_a * sin_b);
+  }
+  if (sin_C == 0.0) sin_C = 2.2250738585072014e-308;
+  l.cost = cos_b;
+  l.sint = sin_b;
+  l.cosp = cos_C;
+  l.sinp = sin_B < 0.0 ? sin_C : -sin_C;
+  return l;
+}
+
+// find_cell + adjust_wall for all three axes (grid_geometry_cartesian_3d.f90:143-259).  ic is the 1-D id
+// find_cell reports; the reference keeps it for the first segment even when adjust_wall moved an index.
+__device__ __forceinline__ bool place_in_grid(const ModelDev &M, double rx, double ry, double rz, double vx, double vy,
+                                              double vz, int &ix, int &iy, int &iz, int &ic) {
+  int fx, fy, fz;
+  bool ok = place_axis(M.w1, M.n1, rx, vx, ix, fx);
+  ok = place_axis(M.w2, M.n2, ry, vy, iy, fy) && ok;
+  ok = place_axis(M.w3, M.n3, rz, vz, iz, fz) && ok;
+  if (!ok) return false;
+  ic = (fz * M.n2 + fy) * M.n1 + fx;
+  return true;
+}
+
+__device__ __forceinline__ bool lane_outside(int ix, int iy, int iz, int n1, int n2, int n3) {
+  return (unsigned)ix >= (unsigned)n1 || (unsigned)iy >= (unsigned)n2 || (unsigned)iz >= (unsigned)n3;
+}
+
+// March a ray from its current cell to the edge of the grid (grid_escape_tau with tmax = huge /
+// grid_escape_column_density).  COLUMN: accumulate the column density of every dust type instead of the
+// optical depth.  D crossings are resolved geometrically before their densities are consumed, so D loads
+// are in flight per lane (the cell sequence does not depend on the density).
+template <int ND, bool COLUMN, int D>
+__device__ __forceinline__ void escape_march(Lane<ND> &L, const double *__restrict__ W,
+                                             const CellRec *__restrict__ cells, const int n1, const int n2,
+                                             const int n3, double &tau, double (&col)[ND], uint32_t &n_cross) {
+  const int o2 = n1 + 1, o3 = n1 + n2 + 2;
+  bool dead = lane_outside(L.ix, L.iy, L.iz, n1, n2, n3);
+  while (!dead) {
+    double ds_s[D], rho_s[D][ND];
+#pragma unroll
+    for (int j = 0; j < D; ++j) {
+#pragma unroll
+      for (int id = 0; id < ND; ++id) rho_s[j][id] = __ldg(&cells[(size_t)L.ic * ND + id].rho);
+      const bool bx = (L.tnx <= L.tny) & (L.tnx <= L.tnz);
+      const bool by = (!bx) & (L.tny <= L.tnz);
+      const double t_exit = bx ? L.tnx : (by ? L.tny : L.tnz);
+      const double iv_ax = bx ? L.ivx : (by ? L.ivy : L.ivz);
+      const int fwd = iv_ax > 0.0 ? 1 : 0;
+      const int i_new = (bx ? L.ix : (by ? L.iy : L.iz)) + 2 * fwd - 1;
+      const int n_ax = bx ? n1 : (by ? n2 : n3);
+      const bool out = (unsigned)i_new >= (unsigned)n_ax;
+      const int woff = bx ? 0 : (by ? o2 : o3);
+      const double wall = W[woff + (out ? 0 : i_new + fwd)];
+      const double tn_new = (wall - (bx ? L.r0x : (by ? L.r0y : L.r0z))) * iv_ax;
+      const bool live = !dead;
+      const bool moved = live & !out;
+      ds_s[j] = live ? t_exit - L.t : -1.0;
+      L.t = live ? t_exit : L.t;
+      L.ix = (moved & bx) ? i_new : L.ix;
+      L.iy = (moved & by) ? i_new : L.iy;
+      L.iz = (moved & !(bx | by)) ? i_new : L.iz;
+      L.tnx = (moved & bx) ? tn_new : L.tnx;
+      L.tny = (moved & by) ? tn_new : L.tny;
+      L.tnz = (moved & !(bx | by)) ? tn_new : L.tnz;
+      L.ic = moved ? (L.iz * n2 + L.iy) * n1 + L.ix : L.ic;
+      dead |= out;
+    }
+#pragma unroll
+    for (int j = 0; j < D; ++j) {
+      if (ds_s[j] >= 0.0) {
+        ++n_cross;
+#pragma unroll
+        for (int id = 0; id < ND; ++id) {
+          if (COLUMN)
+            col[id] = col[id] + rho_s[j][id] * ds_s[j];
+          else
+            tau = tau + L.chi[id] * rho_s[j][id] * ds_s[j];
+        }
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// binning (image_type.f90:117-134, 337-606)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ int origin_slice(const ImageDev &im, int scattered, int reprocessed, int source_id,
+                                            int dust_id, int n_scat) {
+  const int iorig = scattered ? (reprocessed ? 4 : 3) : (reprocessed ? 2 : 1);
+  if (im.track_origin == HYP_TRACK_DETAILED) {
+    int io = ((iorig - iorig % 2) * im.n_sources + (iorig - (iorig + 1) % 2 - 1) * im.n_dust) / 2;
+    return io + (iorig % 2 == 0 ? dust_id : source_id);
+  }
+  if (im.track_origin == HYP_TRACK_SCATTERINGS) {
+    int io = n_scat > im.track_n_scat ? im.track_n_scat + 2 : n_scat + 1;
+    if (reprocessed) io += im.track_n_scat + 2;
+    return io;
+  }
+  if (im.track_origin == HYP_TRACK_BASIC) return iorig;
+  return 1;
+}
+
+__device__ __forceinline__ bool in_image(const ImageDev &im, double x, double y) {
+  if (im.compute_image) {
+    if ((x >= im.x_min && x <= im.x_max) || (x <= im.x_min && x >= im.x_max))
+      if ((y >= im.y_min && y <= im.y_max) || (y <= im.y_min && y >= im.y_max)) return true;
+  }
+  if (im.compute_sed && x * x + y * y <= im.ap_max * im.ap_max) return true;
+  return false;
+}
+
+__device__ __forceinline__ int find_sed_bin(const ImageDev &im, double x, double y) {
+  const double log10_r = log10(sqrt(x * x + y * y));
+  if (log10_r < im.log10_ap_min || im.n_ap == 1) return 1;
+  return ipos_bin(im.log10_ap_min, im.log10_ap_max, log10_r, im.n_ap - 1) + 1;
+}
+
+__device__ __forceinline__ void bin_add(double *a, double *a2, double *an, size_t k, double v, bool unc) {
+  atomicAdd(a + k, v);
+  if (unc) {
+    atomicAdd(a2 + k, v * v);
+    atomicAdd(an + k, 1.0);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// the peel-off kernel: one thread per (job, view); threads of a warp share the view
+// ---------------------------------------------------------------------------------------------
+constexpr int PEEL_THREADS = 256;
+constexpr int PEEL_LOOKAHEAD = 4;
+
+template <int ND, bool POLY>
+__global__ void __launch_bounds__(PEEL_THREADS)
+peel_kernel(const ModelDev M, const ImagingDev I, const PeelJob<ND> *__restrict__ jobs,
+            const uint32_t *__restrict__ n_jobs_ptr, const int walls_in_smem) {
+  extern __shared__ double s_walls[];
+  const int n1 = M.n1, n2 = M.n2, n3 = M.n3;
+  const double *__restrict__ W = stage_walls(M, s_walls, walls_in_smem);
+  const uint32_t n_jobs = *n_jobs_ptr;
+  const unsigned long long total = (unsigned long long)n_jobs * (unsigned)I.n_views;
+  uint32_t n_cross = 0, n_peel = 0;
+  const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+  for (unsigned long long idx = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; idx < total; idx += stride) {
+    const uint32_t ip = (uint32_t)(idx / n_jobs), ij = (uint32_t)(idx % n_jobs);
+    const PeelJob<ND> &J = jobs[ij];
+    const ViewDev &V = I.views[ip];
+    const ImageDev &im = I.images[V.group];
+    const Angle a_req = V.a;
+    Stokes S{1.0, 0.0, 0.0, 0.0};
+    if (J.kind == 1) {
+      // dust_scatter_peeloff (dust_type_4elem.f90:421-444)
+      const DustDev &d = M.dust[J.dust_id - 1];
+      const Angle a_prev = angle_of(J.vpx, J.vpy, J.vpz);
+      const Angle as = difference_angle(a_prev, a_req);
+      S = Stokes{1.0, J.sQ, J.sU, J.sV};
+      if (as.cost < d.L.mu_min || as.cost > d.L.mu_max) {
+        S = Stokes{0.0, 0.0, 0.0, 0.0};
+      } else {
+        const double *nu = d.B + d.L.o_nu;
+        const double *mu = d.B + d.L.o_mu;
+        const int n_mu = d.L.n_mu;
+        const int j = lower_interval(nu, d.L.n_nu, J.nu);
+        const int i = lower_interval(mu, n_mu, as.cost);
+        const double x0 = __ldg(mu + i), x1 = __ldg(mu + i + 1);
+        const double y0 = __ldg(nu + j), y1 = __ldg(nu + j + 1);
+        const double norm = 1.0 / (x1 - x0) / (y1 - y0);
+        const double wx0 = as.cost - x0, wx1 = x1 - as.cost, wy0 = J.nu - y0, wy1 = y1 - J.nu;
+        const double P1 = interp_phase(d.B + d.L.o_P1, n_mu, i, j, wx0, wx1, wy0, wy1, norm);
+        const double P2 = interp_phase(d.B + d.L.o_P2, n_mu, i, j, wx0, wx1, wy0, wy1, norm);
+        const double P3 = interp_phase(d.B + d.L.o_P3, n_mu, i, j, wx0, wx1, wy0, wy1, norm);
+        const double P4 = interp_phase(d.B + d.L.o_P4, n_mu, i, j, wx0, wx1, wy0, wy1, norm);
+        scatter_stokes(S, a_prev, as, a_req, P1, P2, P3, P4);
+      }
+    }
+    // angle3d_to_vector3d of the viewing direction
+    const double vx = a_req.sint * a_req.cosp, vy = a_req.sint * a_req.sinp, vz = a_req.cost;
+    int ix, iy, iz, ic;
+    if (!place_in_grid(M, J.rx, J.ry, J.rz, vx, vy, vz, ix, iy, iz, ic)) continue;
+    // depth along the line of sight and image-plane coordinates (images_peeled.f90:196-211)
+    const double depth = -(vx * J.rx + vy * J.ry + vz * J.rz);
+    if (depth < im.d_min || depth > im.d_max) continue;
+    const double dx = J.rx - im.rpx, dy = J.ry - im.rpy, dz = J.rz - im.rpz;
+    const double x_image = dy * a_req.cosp - dx * a_req.sinp;
+    const double y_image = dz * a_req.sint - dy * a_req.cost * a_req.sinp - dx * a_req.cost * a_req.cosp;
+    if (!in_image(im, x_image, y_image)) continue;
+    double tau = 0.0, col[ND];
+#pragma unroll
+    for (int id = 0; id < ND; ++id) col[id] = 0.0;
+    if (!im.ignore_optical_depth) {
+      Lane<ND> L;
+      init_lane<ND>(L, J.rx, J.ry, J.rz, vx, vy, vz, ix, iy, iz, ic, W, n1 + 1, n1 + n2 + 2);
+#pragma unroll
+      for (int id = 0; id < ND; ++id) L.chi[id] = J.chi[id];
+      escape_march<ND, POLY, PEEL_LOOKAHEAD>(L, W, M.cells, n1, n2, n3, tau, col, n_cross);
+    }
+    ++n_peel;
+    if (isnan(J.energy) || isnan(S.I)) continue;
+    const int io = origin_slice(im, J.scattered, J.reprocessed, J.source_id, J.dust_id, J.n_scat);
+    const bool unc = im.uncertainties != 0;
+    int ixp = 0, iyp = 0, ir = 0;
+    bool in_img = false, in_sed = false;
+    if (im.compute_image) {
+      ixp = ipos_bin(im.x_min, im.x_max, x_image, im.n_x);
+      iyp = ipos_bin(im.y_min, im.y_max, y_image, im.n_y);
+      in_img = ixp >= 1 && ixp <= im.n_x && iyp >= 1 && iyp <= im.n_y;
+    }
+    if (im.compute_sed) {
+      ir = find_sed_bin(im, x_image, y_image);
+      in_sed = ir >= 1 && ir <= im.n_ap;
+    }
+    const size_t nn = (size_t)im.n_nu;
+    // offsets of (inu = 1, stokes 0) in the two cubes
+    const size_t k_img = nn * ((ixp - 1) + (size_t)im.n_x * ((iyp - 1) + (size_t)im.n_y * (V.view + (size_t)im.n_view * (io - 1))));
+    const size_t s_img = nn * im.n_x * im.n_y * im.n_view * im.n_orig;
+    const size_t k_sed = nn * ((ir - 1) + (size_t)im.n_ap * (V.view + (size_t)im.n_view * (io - 1)));
+    const size_t s_sed = nn * im.n_ap * im.n_view * im.n_orig;
+    if (POLY) {
+      // image_bin_raytraced: the whole spectrum of the ray goes into the cube, attenuated per bin
+      const double w = S.I * J.energy;
+      const double *base0 = nullptr, *base1 = nullptr;
+      if (J.emiss_type == 3) {
+        base0 = im.dust_logj[J.dust_id - 1] + (size_t)(J.emiss_var_id) * nn;      // emiss_var_id is 0-based here
+        base1 = base0 + nn;
+      } else {
+        base0 = im.src_spec + (size_t)(J.source_id - 1) * nn;
+      }
+      for (int inu = 0; inu < im.n_nu; ++inu) {
+        double v;
+        if (J.emiss_type == 3) {
+          const double l0 = __ldg(base0 + inu), l1 = __ldg(base1 + inu);
+          v = pow(10.0, (l1 - l0) * J.emiss_var_frac + l0);
+          if (isnan(v)) v = 0.0;
+        } else {
+          v = __ldg(base0 + inu);
+        }
+        v = v * w;
+#pragma unroll
+        for (int id = 0; id < ND; ++id) v = v * exp(-col[id] * __ldg(im.dust_chi + (size_t)id * nn + inu));
+        if (in_img) bin_add(im.img, im.img2, im.imgn, k_img + inu, v, unc);
+        if (in_sed) bin_add(im.sed, im.sed2, im.sedn, k_sed + inu, v, unc);
+      }
+    } else {
+      const int inu = ipos_bin(im.log10_nu_min, im.log10_nu_max, log10(J.nu), im.n_nu);
+      if (inu < 1 || inu > im.n_nu) continue;
+      const double e = exp(-tau);
+      const double st[4] = {S.I * e, S.Q * e, S.U * e, S.V * e};
+      for (int is = 0; is < im.n_stokes; ++is) {
+        const double v = st[is] * J.energy * 1.0;
+        if (in_img) bin_add(im.img, im.img2, im.imgn, k_img + (inu - 1) + is * s_img, v, unc);
+        if (in_sed) bin_add(im.sed, im.sed2, im.sedn, k_sed + (inu - 1) + is * s_sed, v, unc);
+      }
+    }
+  }
+  warp_add_scalar(M.scalars + SC_PEEL_CROSS, (double)n_cross);
+  warp_add_scalar(M.scalars + SC_PEELOFFS, (double)n_peel);
+}
+
+// ---------------------------------------------------------------------------------------------
+// kernels of one round of the final iteration
+// ---------------------------------------------------------------------------------------------
+struct FinalArgs {
+  void *jobs;            // PeelJob<ND>[job_capacity]
+  uint32_t *n_jobs;
+  uint32_t job_capacity;
+  int32_t scattering_only;   // main.f90:274: with raytracing on, only scattered light is peeled here
+  int32_t forced, algorithm; // forced first interaction (iter_final.f90:191-209)
+  double baes16_xi;
+  int32_t make_peeled;
+};
+
+// Append one job per lane with pred set; whole-warp call.
+template <int ND>
+__device__ __forceinline__ PeelJob<ND> *job_append(bool pred, const FinalArgs &F) {
+  const unsigned m = __ballot_sync(0xffffffffu, pred);
+  if (m == 0) return nullptr;
+  const unsigned lane = threadIdx.x & 31;
+  const int leader = __ffs(m) - 1;
+  uint32_t base = 0;
+  if ((int)lane == leader) base = atomicAdd(F.n_jobs, (uint32_t)__popc(m));
+  base = __shfl_sync(0xffffffffu, base, leader);
+  if (!pred) return nullptr;
+  const uint32_t k = base + __popc(m & ((1u << lane) - 1u));
+  return k < F.job_capacity ? (PeelJob<ND> *)F.jobs + k : nullptr;
+}
+
+template <int ND>
+__device__ __forceinline__ void fill_job(PeelJob<ND> *J, const Photon<ND> &p, int kind, double vpx, double vpy,
+                                         double vpz, double sQ, double sU, double sV, int dust_id) {
+  J->rx = p.r0x; J->ry = p.r0y; J->rz = p.r0z;
+  J->nu = p.nu;
+  J->energy = p.energy;
+#pragma unroll
+  for (int k = 0; k < ND; ++k) J->chi[k] = p.chi[k];
+  J->vpx = vpx; J->vpy = vpy; J->vpz = vpz;
+  J->sQ = sQ; J->sU = sU; J->sV = sV;
+  J->emiss_var_frac = 0.0;
+  J->kind = kind;
+  J->source_id = (int)(p.tag & TAG_SRC_MASK);
+  J->dust_id = dust_id;
+  J->n_scat = (int)(p.tag >> TAG_NSCAT_SHIFT);
+  J->scattered = (p.tag & TAG_SCATTERED) ? 1 : 0;
+  J->reprocessed = (p.tag & TAG_REPROCESSED) ? 1 : 0;
+  J->emiss_type = 0;
+  J->emiss_var_id = 0;
+}
+
+// emit + the peel-off of the fresh packet (iter_final.f90:113-123)
+template <int ND>
+__global__ void __launch_bounds__(SERVICE_THREADS)
+emit_final_kernel(const ModelDev M, Pool P, const FinalArgs F, const unsigned long long first_id,
+                  const unsigned long long n_photons, const uint32_t iteration) {
+  const uint32_t n = P.counts[C_NE];
+  const unsigned lane = threadIdx.x & 31;
+  Slot<ND> *slots = (Slot<ND> *)P.slots;
+  double energy_emitted = 0.0;
+  uint32_t n_run = 0;
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t base = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < n; base += stride) {
+    const uint32_t i = base + lane;
+    const bool valid = i < n;
+    const unsigned m = __ballot_sync(0xffffffffu, valid);
+    const int leader = __ffs(m) - 1;
+    unsigned long long k0 = 0;
+    if ((int)lane == leader) k0 = atomicAdd(P.next_photon, (unsigned long long)__popc(m));
+    k0 = __shfl_sync(0xffffffffu, k0, leader);
+    const unsigned long long k = k0 + __popc(m & ((1u << lane) - 1u));
+    bool go = valid && k < n_photons;
+    uint32_t slot = 0;
+    Photon<ND> p;
+    Rng rng;
+    unsigned long long id = 0;
+    if (go) {
+      slot = P.q_emit[i];
+      id = first_id + (k & ~(unsigned long long)(P.window - 1)) + P.perm[k & (2ull * P.window - 1)];
+      rng.init(M.seed, id, iteration);
+      ++n_run;
+      go = emit_photon<ND>(M, p, rng, energy_emitted);
+    }
+    PeelJob<ND> *J = job_append<ND>(go && F.make_peeled && !F.scattering_only, F);
+    if (J) fill_job<ND>(J, p, 0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0);
+    if (go) {
+      // with a forced first interaction the optical depth is drawn by the flight kernel once the
+      // optical depth to the grid edge is known
+      p.tau_left = F.forced ? -1.0 : -log(1.0 - rng.next());
+      store_photon<ND>(slots + slot, p, rng, id);
+    }
+    queue_append(go, P.q_beam, P.counts + C_NB, slot);
+  }
+  warp_add_scalar(M.scalars + SC_ENERGY, energy_emitted);
+  warp_add_scalar(M.scalars + SC_PHOTONS, (double)n_run);
+}
+
+// interact + the peel-off of the surviving packet (iter_final.f90:247-269)
+template <int ND>
+__global__ void __launch_bounds__(SERVICE_THREADS)
+interact_final_kernel(const ModelDev M, Pool P, const FinalArgs F, uint32_t *__restrict__ q_flight_next,
+                      uint32_t *n_flight_next, const uint32_t iteration) {
+  const uint32_t n = P.counts[C_NI];
+  const unsigned lane = threadIdx.x & 31;
+  Slot<ND> *slots = (Slot<ND> *)P.slots;
+  uint32_t n_abs = 0, n_scat = 0, n_kill = 0;
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t base = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < n; base += stride) {
+    const uint32_t i = base + lane;
+    const bool valid = i < n;
+    uint32_t slot = 0;
+    bool alive = false, peel = false, scattered = false;
+    Photon<ND> p;
+    Rng rng;
+    double vpx = 0, vpy = 0, vpz = 0, sQ = 0, sU = 0, sV = 0;
+    int dust_id = 0;
+    uint64_t id = 0;
+    if (valid) {
+      slot = P.q_interact[i];
+      load_photon<ND>(slots + slot, p, rng, M.seed, iteration);
+      id = slots[slot].id;
+      vpx = p.vx; vpy = p.vy; vpz = p.vz;
+      sQ = p.sQ; sU = p.sU; sV = p.sV;
+      if (interact_photon<ND>(M, p, rng, n_abs, n_scat, n_kill, dust_id, scattered) == 0) {
+        alive = true;
+        if (scattered) {
+          uint32_t ns = p.tag >> TAG_NSCAT_SHIFT;
+          if (ns < 0xffffu) ++ns;
+          p.tag = (p.tag & 0xffffu) | (ns << TAG_NSCAT_SHIFT) | TAG_SCATTERED;
+        } else {
+          p.tag = (p.tag & ~TAG_SCATTERED) | TAG_REPROCESSED;
+        }
+        peel = F.make_peeled && (scattered || !F.scattering_only);
+      }
+    }
+    PeelJob<ND> *J = job_append<ND>(peel, F);
+    if (J) fill_job<ND>(J, p, scattered ? 1 : 0, vpx, vpy, vpz, sQ, sU, sV, dust_id + 1);
+    if (alive) {
+      p.tau_left = -log(1.0 - rng.next());
+      store_photon<ND>(slots + slot, p, rng, id);
+    }
+    queue_append(alive, q_flight_next, n_flight_next, slot);
+    queue_append(valid && !alive, P.q_emit, P.counts + C_NE, slot);
+  }
+  warp_add_scalar(M.scalars + SC_ABS, (double)n_abs);
+  warp_add_scalar(M.scalars + SC_SCAT, (double)n_scat);
+  warp_add_scalar(M.scalars + SC_KILLED_INT, (double)n_kill);
+}
+
+// grid_integrate_noenergy for every queued packet.  A packet on its first flight with a forced first
+// interaction first has its optical depth to the grid edge measured, then draws tau from the truncated
+// exponential and carries the weight (forced_interaction.f90:23-133).
+template <int ND, int D>
+__global__ void __launch_bounds__(FLIGHT_THREADS, FLIGHT_MIN_BLOCKS)
+flight_final_kernel(const ModelDev M, Pool P, const FinalArgs F, const uint32_t *__restrict__ q_flight,
+                    const uint32_t *n_flight_ptr, uint32_t *cursor, const int walls_in_smem, const uint32_t iteration) {
+  extern __shared__ double s_walls[];
+  const int n1 = M.n1, n2 = M.n2, n3 = M.n3;
+  const double *__restrict__ W = stage_walls(M, s_walls, walls_in_smem);
+  const uint32_t n_flight = *n_flight_ptr;
+  Slot<ND> *slots = (Slot<ND> *)P.slots;
+  CellRec *__restrict__ cells = M.cells;
+  const unsigned lane = threadIdx.x & 31;
+  bool active = false, exhausted = false;
+  uint32_t slot = 0;
+  Lane<ND> L;
+  L.ic = 0;
+  uint32_t n_cross = 0, n_esc = 0, n_peel_cross = 0;
+  unsigned long long cross_hi = 0;
+  for (;;) {
+    const bool need = !active && !exhausted;
+    const unsigned m_need = __ballot_sync(0xffffffffu, need);
+    int fin = 0;
+    if (m_need) {
+      const int leader = __ffs(m_need) - 1;
+      uint32_t base = 0;
+      if ((int)lane == leader) base = atomicAdd(cursor, (uint32_t)__popc(m_need));
+      base = __shfl_sync(0xffffffffu, base, leader);
+      if (need) {
+        const uint32_t idx = base + __popc(m_need & ((1u << lane) - 1u));
+        if (idx >= n_flight) {
+          exhausted = true;
+        } else {
+          slot = q_flight[idx];
+          load_lane<ND>(slots + slot, L, W, n1 + 1, n1 + n2 + 2);
+          active = true;
+          if (lane_outside(L.ix, L.iy, L.iz, n1, n2, n3)) {
+            fin = 1;  // emitted on the outer wall moving outwards (escaped_cell before the first step)
+          } else if (L.tau < 0.0) {
+            Lane<ND> E = L;
+            double tau_escape = 0.0, col[ND];
+            escape_march<ND, false, D>(E, W, cells, n1, n2, n3, tau_escape, col, n_peel_cross);
+            Slot<ND> *s = slots + slot;
+            Rng rng;
+            rng.init(M.seed, s->id, iteration);
+            rng.blk = s->rng_blk;
+            rng.has_spare = s->rng_has_spare != 0;
+            rng.spare = s->rng_spare;
+            double tau, weight = 1.0;
+            if (tau_escape > 1.e-10) {
+              const double TAU_THRES = 1.e-7;
+              const double one_minus_exp = tau_escape > TAU_THRES ? 1.0 - exp(-tau_escape) : tau_escape;
+              if (F.algorithm == HYP_FFI_BAES16) {
+                const double alpha = (1.0 - F.baes16_xi) / one_minus_exp, beta = F.baes16_xi / tau_escape;
+                double tau_min = 0.0, tau_max = tau_escape;
+                const double xi = rng.next();
+                for (int it = 0; it < 60; ++it) {
+                  tau = 0.5 * (tau_min + tau_max);
+                  const double xt = tau > TAU_THRES ? alpha * (1.0 - exp(-tau)) + beta * tau : alpha * tau + beta * tau;
+                  if (xt > xi) tau_max = tau; else tau_min = tau;
+                }
+                tau = 0.5 * (tau_min + tau_max);
+                weight = 1.0 / (alpha + beta * exp(tau));
+              } else {
+                tau = -log(1.0 - rng.next() * one_minus_exp);
+                weight = one_minus_exp;
+              }
+              s->energy = s->energy * weight;
+            } else {
+              tau = -log(1.0 - rng.next());
+            }
+            L.tau = tau;
+            s->rng_blk = rng.blk;
+            s->rng_has_spare = rng.has_spare ? 1u : 0u;
+            s->rng_spare = rng.spare;
+          }
+        }
+      }
+    }
+    if (__ballot_sync(0xffffffffu, active) == 0) break;
+    if (active && fin == 0) {
+#pragma unroll 1
+      for (int g = 0; g < FLIGHT_GROUPS; ++g) {
+        fin = advance_group<ND, D, false, false>(L, true, W, cells, n1, n2, n3, n_cross);
+        if (fin) break;
+      }
+      if (n_cross > 0x7fffff00u) {
+        cross_hi += n_cross;
+        n_cross = 0;
+      }
+    }
+    if (fin == 2) store_flight_result<ND>(slots + slot, L);
+    queue_append(fin == 2, P.q_interact, P.counts + C_NI, slot);
+    queue_append(fin == 1, P.q_emit, P.counts + C_NE, slot);
+    if (fin) {
+      n_esc += fin == 1 ? 1u : 0u;
+      active = false;
+    }
+  }
+  warp_add_scalar(M.scalars + SC_CROSS, (double)(cross_hi + n_cross));
+  warp_add_scalar(M.scalars + SC_ESC, (double)n_esc);
+  warp_add_scalar(M.scalars + SC_PEEL_CROSS, (double)n_peel_cross);
+}
+
+// ---------------------------------------------------------------------------------------------
+// raytracing iteration (iter_raytracing.f90:31-141): packets that are only peeled off
+// ---------------------------------------------------------------------------------------------
+// energy_abs_tot(d) = sum over cells of E * rho * V (update_energy_abs_tot, grid_physics_3d.f90:605-611)
+__global__ void energy_abs_tot_kernel(const ModelDev M, double *__restrict__ out) {
+  const int nd = M.n_dust;
+  const int64_t n = M.n_cells * nd;
+  double acc[MAX_DUST] = {0.0, 0.0, 0.0, 0.0};
+  for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x) {
+    const int id = (int)(k % nd);
+    const int64_t ic = k / nd;
+    const int i1 = (int)(ic % M.n1), i2 = (int)((ic / M.n1) % M.n2), i3 = (int)(ic / ((int64_t)M.n1 * M.n2));
+    const double vol = ((M.w1[i1 + 1] - M.w1[i1]) * (M.w2[i2 + 1] - M.w2[i2])) * (M.w3[i3 + 1] - M.w3[i3]);
+    const double v = M.specific_energy[k] * M.cells[k].rho * vol;
+#pragma unroll
+    for (int d = 0; d < MAX_DUST; ++d) acc[d] += d == id ? v : 0.0;
+  }
+#pragma unroll
+  for (int d = 0; d < MAX_DUST; ++d) warp_add_scalar(out + d, acc[d]);
+}
+
+constexpr uint32_t ITER_FINAL = 0x7fffff00u, ITER_RAY_SOURCE = 0x7fffff01u, ITER_RAY_DUST = 0x7fffff02u;
+
+// jobs [0, n_src) come from the sources, jobs [n_src, n_src + n_thermal) from random cells
+template <int ND>
+__global__ void raytrace_emit_kernel(const ModelDev M, PeelJob<ND> *__restrict__ jobs, uint32_t *n_jobs,
+                                     const unsigned long long first_source_id, const uint32_t n_src,
+                                     const double source_weight, const unsigned long long first_dust_id,
+                                     const uint32_t n_thermal, const double dust_weight,
+                                     const double *__restrict__ energy_abs_tot) {
+  const uint32_t total = n_src + n_thermal;
+  double dummy = 0.0;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    Photon<ND> p;
+    Rng rng;
+    PeelJob<ND> J;
+    bool ok = true;
+    if (i < n_src) {
+      rng.init(M.seed, first_source_id + i, ITER_RAY_SOURCE);
+      ok = emit_photon<ND>(M, p, rng, dummy);
+      p.energy = p.energy * source_weight;  // energy_total / n_photons_sources (iter_raytracing.f90:79)
+      fill_job<ND>(&J, p, 0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0);
+      J.emiss_type = M.sources[(p.tag & TAG_SRC_MASK) - 1].freq_type;
+    } else {
+      // emit_from_grid (grid_physics_3d.f90:691-753)
+      rng.init(M.seed, first_dust_id + (i - n_src), ITER_RAY_DUST);
+      const int id = max((int)ceil(rng.next() * (double)ND), 1) - 1;
+      const int64_t ic = max((int64_t)ceil(rng.next() * (double)M.n_cells), (int64_t)1) - 1;
+      const int i1 = (int)(ic % M.n1), i2 = (int)((ic / M.n1) % M.n2), i3 = (int)(ic / ((int64_t)M.n1 * M.n2));
+      const double x0 = M.w1[i1], x1 = M.w1[i1 + 1], y0 = M.w2[i2], y1 = M.w2[i2 + 1], z0 = M.w3[i3], z1 = M.w3[i3 + 1];
+      p.r0x = rng.next() * (x1 - x0) + x0;
+      p.r0y = rng.next() * (y1 - y0) + y0;
+      p.r0z = rng.next() * (z1 - z0) + z0;
+      const size_t k = (size_t)ic * ND + id;
+      const double vol = ((x1 - x0) * (y1 - y0)) * (z1 - z0);
+      const double etot = energy_abs_tot[id];
+      p.energy = 0.0;
+      if (etot > 0.0) p.energy = M.specific_energy[k] * (M.cells[k].rho * vol) * (double)M.n_cells / etot;
+      ok = p.energy > 0.0;
+      // energy_abs_tot(dust) / n_photons_thermal * n_dust (iter_raytracing.f90:113)
+      p.energy = p.energy * etot * dust_weight;
+      p.nu = 0.0;
+#pragma unroll
+      for (int q = 0; q < ND; ++q) p.chi[q] = 0.0;
+      p.tag = TAG_REPROCESSED;
+      fill_job<ND>(&J, p, 0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, id + 1);
+      J.emiss_type = 3;
+      J.emiss_var_id = M.jnu_id[k];
+      J.emiss_var_frac = M.jnu_frac[k];
+    }
+    if (ok) jobs[atomicAdd(n_jobs, 1u)] = J;
+  }
+}
+
+// image_scale (image_type.f90:136-151): which = 0 values (x scale), 1 sums of squares (x scale^2)
+__global__ void image_scale_kernel(double *__restrict__ a, int64_t n, double scale) {
+  for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x)
+    a[k] = a[k] * scale;
+}

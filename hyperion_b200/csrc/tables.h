@@ -259,4 +259,121 @@ inline void build_spectrum(const double *nu, const double *fnu, int n, SpectrumL
   detail::build_powerlaw_sampler(nu, fnu, n, buf.data() + L.o_cdf, buf.data() + L.o_invb, buf.data() + L.o_rm1);
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// spectra on an image group's frequency grid, used by the raytracing iteration
+// (get_spectrum_binned src/sources/source_type.f90:1118-1165, get_j_nu_binned / get_chi_nu_binned
+//  src/dust/dust_type_4elem.f90:722-741,793-811, on top of integral_loglog with limits,
+//  fortranlib/src/lib_array.f90:362-366,450-526)
+// ---------------------------------------------------------------------------------------------
+namespace detail {
+
+// value of the piecewise power law through (x, y) at xv (x[0] <= xv <= x[n-1]); j = interval of xv
+inline double powerlaw_at(const double *x, const double *y, int j, double xv) {
+  if (y[j] == 0.0 || y[j + 1] == 0.0) return 0.0;
+  const double f = (std::log10(xv) - std::log10(x[j])) / (std::log10(x[j + 1]) - std::log10(x[j]));
+  return std::pow(10.0, std::log10(y[j]) + f * (std::log10(y[j + 1]) - std::log10(y[j])));
+}
+
+// interval j in [0, n-2] with x[j] <= v < x[j+1] (top edge belongs to the last interval)
+inline int interval_of(const double *x, int n, double v) {
+  int lo = 0, hi = n - 1;
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) / 2;
+    if (x[mid] <= v) lo = mid; else hi = mid;
+  }
+  return lo;
+}
+
+inline double seg_loglog_f32tol(double x1, double y1, double x2, double y2) {
+  // as seg_loglog, with the reference's single-precision tolerance on b = -1 (lib_array.f90:562-578)
+  if (x1 == x2 || y1 == 0.0 || y2 == 0.0) return 0.0;
+  const double b = std::log10(y1 / y2) / std::log10(x1 / x2);
+  if (std::fabs(b + 1.0) < (double)1e-10f) return x1 * y1 * std::log(x2 / x1);
+  return y1 * (x2 * std::pow(x2 / x1, b) - x1) / (b + 1.0);
+}
+
+// integral of the piecewise power law over [a, b] clipped to the table
+inline double integral_loglog_range(const double *x, const double *y, int n, double a, double b) {
+  if (a > x[n - 1] || b < x[0]) return 0.0;
+  // first node strictly above the lower limit, last node strictly below the upper limit
+  int k_lo, k_hi;
+  double xa, ya, xb, yb;
+  if (a > x[0]) {
+    const int j = (a == x[n - 1]) ? n - 2 : interval_of(x, n, a);
+    k_lo = j + 1;
+    xa = a;
+    ya = powerlaw_at(x, y, j, a);
+  } else {
+    k_lo = 0;
+    xa = x[0];
+    ya = y[0];
+  }
+  if (b < x[n - 1]) {
+    const int j = interval_of(x, n, b);
+    k_hi = j;
+    xb = b;
+    yb = powerlaw_at(x, y, j, b);
+  } else {
+    k_hi = n - 1;
+    xb = x[n - 1];
+    yb = y[n - 1];
+  }
+  if (k_hi < k_lo) return seg_loglog_f32tol(xa, ya, xb, yb);  // both limits inside one interval
+  double sum = 0.0;
+  for (int k = k_lo; k < k_hi; ++k) sum += seg_loglog_f32tol(x[k], y[k], x[k + 1], y[k + 1]);
+  sum += seg_loglog_f32tol(xa, ya, x[k_lo], y[k_lo]);
+  sum += seg_loglog_f32tol(x[k_hi], y[k_hi], xb, yb);
+  return sum;
+}
+
+inline double integral_loglog_all(const double *x, const double *y, int n) {
+  double sum = 0.0;
+  for (int k = 0; k + 1 < n; ++k) sum += seg_loglog_f32tol(x[k], y[k], x[k + 1], y[k + 1]);
+  return sum;
+}
+
+}  // namespace detail
+
+// edges of frequency bin inu (0-based) of an image group with n_nu log-spaced bins
+inline void image_bin_edges(double log10_nu_min, double log10_nu_max, int n_nu, int inu, double &lo, double &hi) {
+  lo = std::pow(10.0, log10_nu_min + (log10_nu_max - log10_nu_min) * (double)inu / (double)n_nu);
+  hi = std::pow(10.0, log10_nu_min + (log10_nu_max - log10_nu_min) * (double)(inu + 1) / (double)n_nu);
+}
+
+// fraction of a spectrum (nu, fnu) falling in each bin
+inline void binned_fraction(const double *nu, const double *fnu, int n, double l0, double l1, int n_nu, double *out) {
+  const double tot = detail::integral_loglog_all(nu, fnu, n);
+  for (int i = 0; i < n_nu; ++i) {
+    double lo, hi;
+    image_bin_edges(l0, l1, n_nu, i, lo, hi);
+    out[i] = detail::integral_loglog_range(nu, fnu, n, lo, hi) / tot;
+  }
+}
+
+// normalized_B_nu (source_type.f90:1088-1096) tabulated as get_spectrum_binned does for a blackbody
+inline void blackbody_table(double T, std::vector<double> &nu, std::vector<double> &fnu) {
+  const double h_cgs = 6.6260689633e-27, c_cgs = 2.99792458e10, k_cgs = 1.380650424e-16, stef_boltz = 5.670400e-5;
+  const double pi = 3.14159265358979323846264338327950288419;
+  const double a = 2.0 * h_cgs / c_cgs / c_cgs / stef_boltz * pi, b = h_cgs / k_cgs;
+  const double lmin = std::log10(3.e9), lmax = std::log10(3.e16);
+  const int n = (int)std::ceil((lmax - lmin) * 100000);
+  nu.resize(n);
+  fnu.resize(n);
+  const double T4 = T * T * T * T;
+  for (int i = 0; i < n; ++i) {
+    nu[i] = std::pow(10.0, (double)i / (double)(n - 1) * (lmax - lmin) + lmin);
+    fnu[i] = a * nu[i] * nu[i] * nu[i] / (std::exp(b * nu[i] / T) - 1.0) / T4;
+  }
+}
+
+// mean extinction in each bin
+inline void binned_chi(const double *nu, const double *chi, int n, double l0, double l1, int n_nu, double *out) {
+  for (int i = 0; i < n_nu; ++i) {
+    double lo, hi;
+    image_bin_edges(l0, l1, n_nu, i, lo, hi);
+    out[i] = detail::integral_loglog_range(nu, chi, n, lo, hi) / (hi - lo);
+  }
+}
+
 }  // namespace hyp

@@ -35,7 +35,7 @@ def test_oracle_exports_checker_api():
     olib = oracle.load()
     for n in _declared():
         if n in ("hyp_version", "hyp_sizeof", "hyp_stream", "hyp_lucy_device_buffers", "hyp_lucy_photons", "hyp_ctx_create",
-                 "hyp_finalize_setup", "hyp_run_lucy_iteration"):
+                 "hyp_finalize_setup", "hyp_run_lucy_iteration", "hyp_image_device_buffers"):
             continue
         assert hasattr(olib, "orc_" + n[4:]), n
 

@@ -1,0 +1,152 @@
+"""GPU parity of the final (imaging) and raytracing iterations: CUDA engine vs the CPU oracle.
+
+The oracle reproduces the reference's test_peeloff golden files (tests/test_oracle_golden.py); the
+engine uses per-packet counter RNG streams, so parity is statistical: B independent batches on each
+side, per-bin z-scores of the batch means of every SED / image cube.
+"""
+from concurrent.futures import ThreadPoolExecutor
+
+import numpy as np
+import pytest
+
+from helpers import peeloff_model, bitlevel_model, peeloff_groups, pc
+
+pytestmark = pytest.mark.gpu
+
+
+def _converged_energy(model, n=200000):
+    """Specific energy after the reference's 5 Lucy iterations (oracle), used as the common
+    starting state of both imaging runs."""
+    from oracle import oracle
+    o = oracle.Oracle(model)
+    for _ in range(5):
+        o.run_lucy_iteration(n)
+    return o.get_specific_energy()
+
+
+def _cubes(x, groups):
+    out = {}
+    for ig, g in enumerate(groups):
+        if g.sed is not None:
+            out["g%d_sed" % ig] = x.sed(ig)
+        if g.image is not None:
+            out["g%d_img" % ig] = x.image(ig)
+    return out
+
+
+def _gpu_batch(model, b, n_final, scattering_only, n_ray):
+    from hyperion_b200.capi import Engine
+    eng = Engine(0)
+    eng.load_model(model)
+    eng.final_begin()
+    eng.final_photons(b * n_final, n_final, scattering_only)
+    st = eng.final_finish()
+    st2 = None
+    if n_ray:
+        st2 = eng.raytracing_photons(n_ray[0], n_ray[1], first_source_id=b * n_ray[0], first_dust_id=b * n_ray[1])
+    cubes = _cubes(eng, model.peeled)
+    eng.close()
+    return cubes, st.as_dict(), None if st2 is None else st2.as_dict()
+
+
+def _oracle_batch(model, b, n_final, scattering_only, n_ray):
+    from oracle import oracle
+    o = oracle.Oracle(model, rank=b)
+    o.final_begin()
+    o.final_photons(n_final, scattering_only)
+    st = o.final_finish()
+    st2 = None
+    if n_ray:
+        st2 = o.raytracing_photons(n_ray[0], n_ray[1])
+    return _cubes(o, model.peeled), st.as_dict(), None if st2 is None else st2.as_dict()
+
+
+def _run_both(model, B, n_final, scattering_only, n_ray):
+    gpu = [_gpu_batch(model, b, n_final, scattering_only, n_ray) for b in range(B)]
+    with ThreadPoolExecutor(max_workers=8) as pool:
+        orc = list(pool.map(lambda b: _oracle_batch(model, b, n_final, scattering_only, n_ray), range(B)))
+    return gpu, orc
+
+
+def _compare(gpu, orc, zmax=5.5):
+    keys = gpu[0][0].keys()
+    report = {}
+    for k in keys:
+        a = np.array([g[0][k] for g in gpu])
+        b = np.array([o[0][k] for o in orc])
+        ma, mb = a.mean(0), b.mean(0)
+        sa, sb = a.std(0, ddof=1) / np.sqrt(len(a)), b.std(0, ddof=1) / np.sqrt(len(b))
+        den = np.sqrt(sa ** 2 + sb ** 2)
+        # bins both sides populate in most batches (the z statistic assumes near-normal means)
+        filled = ((a != 0).mean(0) > 0.9) & ((b != 0).mean(0) > 0.9) & (den > 0)
+        assert filled.sum() > 0, k
+        z = (ma[filled] - mb[filled]) / den[filled]
+        report[k] = (float(np.abs(z).max()), float((z ** 2).mean()), int(filled.sum()))
+        assert np.abs(z).max() < zmax, (k, report[k])
+        assert (z ** 2).mean() < 1.8, (k, report[k])
+    return report
+
+
+@pytest.mark.parametrize("raytracing", [False, True])
+def test_peeloff_matches_oracle(golden_car, raytracing):
+    """The reference's test_peeloff model (test_bit_level.py:175-236): three peeled groups (no / basic /
+    detailed origin tracking, Stokes on), forced first interaction; with raytracing the imaging
+    iteration peels scattered light only and the raytracing iteration adds sources + thermal emission."""
+    model = peeloff_model(golden_car, False)
+    model.specific_energy = _converged_energy(model)
+    B = 12
+    gpu, orc = _run_both(model, B, 60000, raytracing, (20000, 30000) if raytracing else None)
+    report = _compare(gpu, orc)
+    print(report)
+    for key in ("n_crossings", "n_absorptions", "n_scatterings", "n_peeloffs", "n_peel_crossings"):
+        a = np.mean([g[1][key] for g in gpu])
+        b = np.mean([o[1][key] for o in orc])
+        assert abs(a / b - 1) < 0.02, (key, a, b)
+    assert all(g[1]["killed_geo"] == 0 and g[1]["killed_int"] == 0 and g[1]["n_photons"] == 60000 for g in gpu)
+    if raytracing:
+        for key in ("n_peeloffs", "n_peel_crossings"):
+            a = np.mean([g[2][key] for g in gpu])
+            b = np.mean([o[2][key] for o in orc])
+            assert abs(a / b - 1) < 0.02, (key, a, b)
+
+
+def test_peeloff_multiple_dust_and_even_sampling(golden_car):
+    """Three dust types, sources sampled evenly, BAES16 forced interaction, uncertainties on."""
+    model = bitlevel_model(golden_car, True, True)
+    groups = peeloff_groups()
+    for g in groups:
+        g.uncertainties = True
+    groups[1].track_origin = "scatterings"
+    groups[1].track_n_scat = 2
+    model.peeled = groups
+    model.conf.forced_first_interaction_algorithm = "baes16"
+    model.specific_energy = _converged_energy(model)
+    gpu, orc = _run_both(model, 12, 40000, False, (10000, 20000))
+    print(_compare(gpu, orc))
+
+
+def test_image_flux_is_additive_and_unattenuated_in_vacuum(golden_car):
+    """Known answers (hyperion/model/tests/test_image.py:635-677, test_sed.py): with no dust every
+    packet reaches the observer, so the SED integrated over frequency bins inside the largest
+    aperture equals the luminosity of the sources; an image holds the same flux as the SED when it
+    covers the aperture."""
+    from hyperion_b200.capi import Engine
+    from hyperion_b200.flatmodel import FlatPeeledGroup
+    model = bitlevel_model(golden_car, False, False)
+    model.density[...] = 0.0
+    model.peeled = [FlatPeeledGroup(theta=[45.], phi=[30.], wavelengths=(20, 0.01, 5000.),
+                                    image=(8, 8, -2 * pc, 2 * pc, -2 * pc, 2 * pc), sed=(1, 3 * pc, 3 * pc),
+                                    stokes=False)]
+    eng = Engine(0)
+    eng.load_model(model)
+    eng.final_begin()
+    eng.final_photons(0, 200000, False)
+    st = eng.final_finish()
+    sed, img = eng.sed(0), eng.image(0)
+    eng.close()
+    assert st.n_escaped == 200000 and st.n_peeloffs == 200000
+    nu_min, nu_max = 2.99792458e10 / (5000. * 1e-4), 2.99792458e10 / (0.01 * 1e-4)
+    dnunorm = (nu_max / nu_min) ** (0.5 / 20) - (nu_max / nu_min) ** (-0.5 / 20)
+    ltot = sum(s.luminosity for s in model.sources)
+    assert abs(sed.sum() * dnunorm / ltot - 1) < 2e-3     # a little flux lies outside 0.01-5000 micron
+    assert abs(img.sum() / sed.sum() - 1) < 1e-12
