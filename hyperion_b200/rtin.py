@@ -17,7 +17,7 @@ from typing import Optional
 
 import numpy as np
 
-from .flatmodel import FlatConf, FlatDust, FlatModel, FlatSource
+from .flatmodel import FlatConf, FlatDust, FlatModel, FlatPeeledGroup, FlatSource
 from .io import h5min
 
 
@@ -239,5 +239,68 @@ def read_rtin(filename):
                 raise ModelError("%s should be one of all/last/none" % key)
             setattr(rs, key, val)
 
+    conf.forced_first_interaction = rs.forced_first_interaction
+    conf.forced_first_interaction_algorithm = rs.forced_first_interaction_algorithm
+    conf.baes16_xi = rs.baes16_xi
+    if sources and not rs.monochromatic and rs.n_last_photons == 0 and "n_last_photons" not in A:
+        raise ModelError("attribute n_last_photons is missing from the input file")
+    if not sources and rs.n_last_photons > 0:
+        raise ModelError("no sources set up - need sources for last iteration")
+
     model = FlatModel(w1, w2, w3, density, dust, sources, conf, specific_energy=se, minimum_specific_energy=min_e)
+    model.peeled = read_peeled_groups(f)
+    if "Output" in f and "Binned" in f["Output"] and len(f["Output"]["Binned"].keys()) > 0:
+        if rs.forced_first_interaction:
+            raise ModelError("can't use binned images with forced first interaction")
+        raise ModelError("binned images are not implemented by this engine yet")
     return model, rs, f
+
+
+def read_peeled_groups(f):
+    """``setup_final_iteration`` / ``peeled_images_setup`` / ``image_setup``
+    (``src/main/setup_rt.f90:306-347``, ``src/images/images_peeled.f90:272-382``,
+    ``src/images/image_type.f90:153-335``): one FlatPeeledGroup per ``Output/Peeled/group_%05i``."""
+    groups = []
+    if "Output" not in f or "Peeled" not in f["Output"]:
+        return groups
+    gp = f["Output"]["Peeled"]
+    for name in sorted(gp.keys()):
+        g = gp[name]
+        a = g.attrs
+        if "use_filters" in a and _yes(a["use_filters"]):
+            raise ModelError("filter convolution is not implemented by this engine yet")
+        if "inu_min" in a:
+            raise ModelError("the monochromatic final iteration is not implemented by this engine yet")
+        n_view = int(_num(_attr(a, "n_view", required=True)))
+        if not n_view > 0:
+            raise ModelError("n_view should be a positive integer")
+        inside = _yes(_attr(a, "inside_observer", required=True))
+        if inside:
+            raise ModelError("inside observers are not implemented by this engine yet")
+        ang = g["angles"][...]
+        kw = dict(theta=np.asarray(ang["theta"], dtype=np.float64), phi=np.asarray(ang["phi"], dtype=np.float64),
+                  inside_observer=inside, ignore_optical_depth=_yes(_attr(a, "ignore_optical_depth", b"no")),
+                  d_min=float(_num(_attr(a, "d_min", required=True))), d_max=float(_num(_attr(a, "d_max", required=True))),
+                  peeloff_origin=tuple(float(_num(_attr(a, k, required=True))) for k in ("peeloff_x", "peeloff_y", "peeloff_z")))
+        if len(kw["theta"]) != n_view:
+            raise ModelError("n_view does not match the length of the angles table")
+        n_wav = int(_num(_attr(a, "n_wav", required=True)))
+        if n_wav < 1:
+            raise ModelError("n_nu should be >= 1")
+        kw["wavelengths"] = (n_wav, float(_num(_attr(a, "wav_min", required=True))), float(_num(_attr(a, "wav_max", required=True))))
+        kw["stokes"] = _yes(a["compute_stokes"]) if "compute_stokes" in a else True
+        if _yes(_attr(a, "compute_image", required=True)):
+            kw["image"] = (int(_num(a["n_x"])), int(_num(a["n_y"])), float(_num(a["x_min"])), float(_num(a["x_max"])),
+                           float(_num(a["y_min"])), float(_num(a["y_max"])))
+        if _yes(_attr(a, "compute_sed", required=True)):
+            kw["sed"] = (int(_num(a["n_ap"])), float(_num(a["ap_min"])), float(_num(a["ap_max"])))
+        kw["track_origin"] = _s(_attr(a, "track_origin", required=True))
+        if kw["track_origin"] not in ("no", "basic", "yes", "detailed", "scatterings"):
+            raise ModelError("unknown track_origin flag: " + kw["track_origin"])
+        kw["track_n_scat"] = int(_num(a["track_n_scat"])) if "track_n_scat" in a else 0
+        kw["uncertainties"] = _yes(_attr(a, "uncertainties", required=True))
+        kw["io_bytes"] = int(_num(_attr(a, "io_bytes", required=True)))
+        if kw["io_bytes"] not in (4, 8):
+            raise ModelError("unexpected value of io_bytes (should be 4 or 8)")
+        groups.append(FlatPeeledGroup(**kw))
+    return groups

@@ -61,9 +61,37 @@ def write_dust(g, d):
     g.create_dataset("emissivity_variable", _table([("specific_energy", d.jnu_var)]))
 
 
+def write_peeled_group(g, p):
+    """``PeeledImageConf.write`` (``hyperion/conf/conf_files.py:795-1130,1293-1345``)."""
+    a = g.attrs
+    a["n_view"] = np.int64(len(p.theta))
+    g.create_dataset("angles", _table([("theta", np.asarray(p.theta, dtype=np.float64)),
+                                       ("phi", np.asarray(p.phi, dtype=np.float64))]))
+    a["inside_observer"] = _yn(p.inside_observer)
+    a["ignore_optical_depth"] = _yn(p.ignore_optical_depth)
+    a["peeloff_x"], a["peeloff_y"], a["peeloff_z"] = [float(v) for v in p.peeloff_origin]
+    a["d_min"], a["d_max"] = float(p.d_min), float(p.d_max)
+    a["compute_image"] = _yn(p.image is not None)
+    if p.image is not None:
+        a["n_x"], a["n_y"] = np.int64(p.image[0]), np.int64(p.image[1])
+        a["x_min"], a["x_max"], a["y_min"], a["y_max"] = [float(v) for v in p.image[2:]]
+    a["compute_sed"] = _yn(p.sed is not None)
+    if p.sed is not None:
+        a["n_ap"] = np.int64(p.sed[0])
+        a["ap_min"], a["ap_max"] = float(p.sed[1]), float(p.sed[2])
+    a["use_filters"] = b"no"
+    a["n_wav"] = np.int64(p.wavelengths[0])
+    a["wav_min"], a["wav_max"] = float(p.wavelengths[1]), float(p.wavelengths[2])
+    a["track_origin"] = p.track_origin
+    a["track_n_scat"] = np.int64(p.track_n_scat)
+    a["uncertainties"] = _yn(p.uncertainties)
+    a["compute_stokes"] = _yn(p.stokes)
+    a["io_bytes"] = np.int64(p.io_bytes)
+
+
 def write_rtin(filename, model: FlatModel, n_initial_iter=5, n_initial_photons=10000, n_last_photons=0,
                output_specific_energy="last", copy_input=True, check_convergence=None, physics_io_bytes=8,
-               raytracing=False, extra_root_attrs=None):
+               raytracing=False, n_ray_photons=(0, 0), extra_root_attrs=None):
     f = h5write.File()
     c = model.conf
     A = f.attrs
@@ -80,8 +108,9 @@ def write_rtin(filename, model: FlatModel, n_initial_iter=5, n_initial_photons=1
         A["n_inter_mrw_max"] = np.int64(c.n_mrw_max)
     A["kill_on_absorb"] = _yn(c.kill_on_absorb)
     A["kill_on_scatter"] = _yn(c.kill_on_scatter)
-    A["forced_first_interaction"] = b"yes"
-    A["forced_first_interaction_algorithm"] = "wr99"
+    A["forced_first_interaction"] = _yn(c.forced_first_interaction)
+    A["forced_first_interaction_algorithm"] = c.forced_first_interaction_algorithm
+    A["forced_first_interaction_baes16_xi"] = float(c.baes16_xi)
     A["propagation_check_frequency"] = float(c.propagation_check_frequency)
     A["sample_sources_evenly"] = _yn(c.sample_sources_evenly)
     A["enforce_energy_range"] = _yn(c.enforce_energy_range)
@@ -89,6 +118,9 @@ def write_rtin(filename, model: FlatModel, n_initial_iter=5, n_initial_photons=1
     A["n_initial_iter"] = np.int64(n_initial_iter)
     A["n_initial_photons"] = float(n_initial_photons)     # the front end stores what the user passed
     A["n_last_photons"] = float(n_last_photons)
+    if raytracing:
+        A["n_ray_photons_sources"] = float(n_ray_photons[0])
+        A["n_ray_photons_dust"] = float(n_ray_photons[1])
     A["specific_energy_type"] = "initial"
     A["physics_io_bytes"] = np.int32(physics_io_bytes)
     A["copy_input"] = _yn(copy_input)
@@ -152,6 +184,8 @@ def write_rtin(filename, model: FlatModel, n_initial_iter=5, n_initial_photons=1
     go.attrs["output_specific_energy"] = output_specific_energy
     go.attrs["output_n_photons"] = "none"
     go.create_group("Binned")
-    go.create_group("Peeled")
+    gp = go.create_group("Peeled")
+    for i, p in enumerate(model.peeled):
+        write_peeled_group(gp.create_group("group_%05i" % (i + 1)), p)
     f.write(filename)
     return gid

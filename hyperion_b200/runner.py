@@ -23,7 +23,7 @@ import numpy as np
 
 from . import __version__
 from .io import h5min, h5write
-from .multigpu import ShardedLucy
+from .multigpu import ShardedLucy, shard
 from .rtin import ModelError, read_rtin
 
 
@@ -110,6 +110,48 @@ def _copy_tree(src, dst):
                 ds.attrs[k] = v
         else:
             _copy_tree(child, dst.create_group(name))
+
+
+def write_peeled_output(g, eng, ig, p, n_sources, n_dust):
+    """``image_write`` + ``peeled_images_write`` (``src/images/image_type.f90:608-788``,
+    ``src/images/images_peeled.f90:384-408``): datasets ``seds`` / ``images`` (+ ``_unc``) with the
+    attributes ``ModelOutput.get_sed`` / ``get_image`` read."""
+    c_cgs = 2.99792458e10
+    micron = float(np.float32(1.e-4))          # single-precision literal in image_type.f90:262-263
+    n_wav, wav_min, wav_max = p.wavelengths
+    nu_min, nu_max = c_cgs / (wav_max * micron), c_cgs / (wav_min * micron)
+    dt = np.float32 if p.io_bytes == 4 else np.float64
+
+    def origin_attrs(d):
+        d.attrs["track_origin"] = p.track_origin
+        if p.track_origin == "detailed":
+            d.attrs["n_sources"] = np.int32(n_sources)
+            d.attrs["n_dust"] = np.int32(n_dust)
+        elif p.track_origin == "scatterings":
+            d.attrs["track_n_scat"] = np.int32(p.track_n_scat)
+
+    if p.sed is not None:
+        res = eng.sed(ig, p.uncertainties)
+        val, unc = res if p.uncertainties else (res, None)
+        d = g.create_dataset("seds", val.astype(dt))
+        if unc is not None:
+            g.create_dataset("seds_unc", unc.astype(dt))
+        d.attrs["numin"], d.attrs["numax"] = float(nu_min), float(nu_max)
+        d.attrs["apmin"], d.attrs["apmax"] = float(p.sed[1]), float(p.sed[2])
+        origin_attrs(d)
+    if p.image is not None:
+        res = eng.image(ig, p.uncertainties)
+        val, unc = res if p.uncertainties else (res, None)
+        d = g.create_dataset("images", val.astype(dt))
+        if unc is not None:
+            g.create_dataset("images_unc", unc.astype(dt))
+        d.attrs["numin"], d.attrs["numax"] = float(nu_min), float(nu_max)
+        d.attrs["xmin"], d.attrs["xmax"] = float(p.image[2]), float(p.image[3])
+        d.attrs["ymin"], d.attrs["ymax"] = float(p.image[4]), float(p.image[5])
+        origin_attrs(d)
+    g.attrs["inside_observer"] = "yes" if p.inside_observer else "no"
+    g.attrs["d_min"] = float(p.d_min)
+    g.attrs["d_max"] = float(p.d_max)
 
 
 def run(input_file, output_file, overwrite=False, device=None, log=None):
@@ -224,16 +266,55 @@ def run(input_file, output_file, overwrite=False, device=None, log=None):
     out.attrs["converged"] = "yes" if converged else "no"
     out.attrs["iterations"] = np.int32(n_done)
 
-    # final / raytracing iterations: no image groups are produced yet ("next" rows)
-    has_images = False
-    if "Output" in fin:
-        o = fin["Output"]
-        has_images = ("Binned" in o and len(o["Binned"].keys()) > 0) or ("Peeled" in o and len(o["Peeled"].keys()) > 0)
-    if has_images and (rs.n_last_photons > 0 or rs.raytracing):
-        raise ModelError("image / SED output (final and raytracing iterations) is not implemented by this engine yet")
-    for key in ("final", "raytracing"):
-        out.attrs["killed_photons_geo_" + key] = np.int64(0)
-        out.attrs["killed_photons_int_" + key] = np.int64(0)
+    # FINAL ITERATION (main.f90:253-290): imaging packets with peel-off; with raytracing on, only
+    # scattered light is peeled here (iter_final.f90:119-121)
+    log(" [main] starting final iteration")
+    killed_final = (0, 0)
+    make_peeled = len(model.peeled) > 0
+    if make_peeled:
+        log(" [peeled_images] setting up %d peeled image groups " % len(model.peeled))
+    if rs.n_last_photons > 0:
+        first, count = shard(rs.n_last_photons, rank, world)
+        eng.final_begin()
+        eng.final_photons(first, count, rs.raytracing)
+    log(" [main] exiting final iteration")
+    n_ray = (0, 0)
+    if rs.raytracing:
+        n_ray = (rs.n_ray_photons_sources if model.sources else 0, rs.n_ray_photons_dust)
+    if rs.n_last_photons > 0:
+        # scale by energy_total / energy_current over ALL ranks (iter_final.f90:136-143): the emitted
+        # energy travels with the cubes, so reduce first, then scale
+        if world > 1:
+            all_reduce(eng.image_buffer())
+        st = eng.final_finish()
+        killed_final = (st.killed_geo, st.killed_int)
+        if world > 1:
+            # every rank applied the scale to the reduced cubes; keep one copy for the final sum below
+            if rank != 0:
+                with torch.cuda.stream(stream):
+                    eng.image_buffer().zero_()
+                stream.synchronize()
+    out.attrs["killed_photons_geo_final"] = np.int64(killed_final[0])
+    out.attrs["killed_photons_int_final"] = np.int64(killed_final[1])
+    killed_ray = (0, 0)
+    if rs.raytracing:
+        log(" [main] starting raytracing iteration")
+        fs, cs = shard(n_ray[0], rank, world)
+        fd, cd = shard(n_ray[1], rank, world)
+        st = eng.raytracing_photons(cs, cd, first_source_id=fs, n_total_sources=n_ray[0],
+                                    first_dust_id=fd, n_total_dust=n_ray[1])
+        killed_ray = (st.killed_geo, st.killed_int)
+        log(" [main] exiting raytracing iteration")
+    out.attrs["killed_photons_geo_raytracing"] = np.int64(killed_ray[0])
+    out.attrs["killed_photons_int_raytracing"] = np.int64(killed_ray[1])
+    # mp_collect_images (mpi_routines.f90:363-471)
+    if make_peeled and world > 1:
+        all_reduce(eng.image_buffer())
+    if make_peeled:
+        gp = out.create_group("Peeled")
+        for ig, p in enumerate(model.peeled):
+            write_peeled_output(gp.create_group("group_%05d" % (ig + 1)), eng, ig, p,
+                                len(model.sources), len(model.dust))
 
     eng.close()
     out.attrs["cpu_time"] = float(time.time() - t_start)

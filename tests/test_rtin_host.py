@@ -88,3 +88,66 @@ def test_runner_end_to_end_writes_reference_layout(golden_car, tmp_path):
         assert bytes(np.asarray(se.attrs["geometry"]).ravel()[0]).decode().strip("\x00") == gid
         assert int(np.asarray(g.attrs["killed_photons_geo"]).ravel()[0]) == 0
         assert np.all(se[...] > 0)
+
+
+def test_rtin_roundtrip_peeled_groups(golden_car, tmp_path):
+    """Output/Peeled/group_%05i as PeeledImageConf.write lays it out (hyperion/conf/conf_files.py)."""
+    from helpers import peeloff_model
+    m = peeloff_model(golden_car, False)
+    m.peeled[1].track_origin, m.peeled[1].track_n_scat = "scatterings", 3
+    m.peeled[2].uncertainties, m.peeled[2].io_bytes, m.peeled[2].stokes = True, 4, False
+    m.peeled[0].d_min, m.peeled[0].peeloff_origin = -1e18, (1e17, 2e17, 3e17)
+    m.conf.forced_first_interaction_algorithm, m.conf.baes16_xi = "baes16", 0.3
+    fn = str(tmp_path / "m.rtin")
+    rtin_write.write_rtin(fn, m, n_last_photons=5000, raytracing=True, n_ray_photons=(2000, 3000))
+    got, rs, _ = rtin.read_rtin(fn)
+    assert rs.n_last_photons == 5000 and rs.raytracing and rs.n_ray_photons_sources == 2000 and rs.n_ray_photons_dust == 3000
+    assert got.conf.forced_first_interaction and got.conf.forced_first_interaction_algorithm == "baes16"
+    assert got.conf.baes16_xi == 0.3
+    assert len(got.peeled) == 3
+    for a, b in zip(got.peeled, m.peeled):
+        assert np.array_equal(a.theta, b.theta) and np.array_equal(a.phi, b.phi)
+        for k in ("wavelengths", "image", "sed", "track_origin", "track_n_scat", "uncertainties", "stokes", "io_bytes",
+                  "inside_observer", "ignore_optical_depth", "d_min", "d_max"):
+            assert getattr(a, k) == getattr(b, k), k
+        assert tuple(a.peeloff_origin) == tuple(b.peeloff_origin)
+
+
+@pytest.mark.gpu
+def test_runner_writes_peeled_groups(golden_car, tmp_path):
+    """End to end through the file boundary: Lucy iterations, imaging iteration, raytracing;
+    /Peeled/group_%05d/{seds,images}[_unc] with the attributes ModelOutput.get_sed/get_image read
+    (hyperion/model/model_output.py:212,539), in the shapes of the reference's golden .rtout."""
+    from helpers import peeloff_model
+    m = peeloff_model(golden_car, False)
+    m.peeled[0].uncertainties = True
+    m.peeled[1].io_bytes = 4
+    fin, fout = str(tmp_path / "m.rtin"), str(tmp_path / "m.rtout")
+    rtin_write.write_rtin(fin, m, n_initial_iter=2, n_initial_photons=20000, n_last_photons=50000, raytracing=True,
+                          n_ray_photons=(20000, 30000))
+    assert runner.main(["-f", fin, fout]) == 0
+    r = h5min.File(fout)
+    assert "date_ended" in r.attrs
+    shapes = {1: ((4, 1, 2, 5, 5), (4, 1, 2, 5, 4, 5)), 2: ((4, 4, 1, 2, 4), (4, 4, 1, 6, 6, 4)),
+              3: ((4, 12, 1, 2, 4), (4, 12, 1, 6, 6, 4))}
+    for ig, (ssed, simg) in shapes.items():
+        g = r["Peeled/group_%05d" % ig]
+        assert g["seds"].shape == ssed and g["images"].shape == simg
+        assert g["seds"].dtype == (np.float32 if ig == 2 else np.float64)
+        for k in ("numin", "numax", "apmin", "apmax", "track_origin"):
+            assert k in g["seds"].attrs
+        for k in ("numin", "numax", "xmin", "xmax", "ymin", "ymax", "track_origin"):
+            assert k in g["images"].attrs
+        for k in ("inside_observer", "d_min", "d_max"):
+            assert k in g.attrs
+        sed = g["seds"][...]
+        assert np.all(np.isfinite(sed)) and sed[0].sum() > 0
+        # apertures are cumulative (image_type.f90:683-686)
+        assert np.all(np.diff(sed[0], axis=-2) >= -1e-30)
+    assert "seds_unc" in r["Peeled/group_00001"] and "images_unc" in r["Peeled/group_00001"]
+    assert "n_sources" in r["Peeled/group_00003/seds"].attrs
+    # total flux: with raytracing the direct + thermal light comes from do_raytracing, the scattered
+    # light from do_final; the largest aperture of group 2 (basic origin tracking) holds all four
+    sed2 = r["Peeled/group_00002/seds"][...]
+    # (re-emitted IR light is practically not scattered by this dust: the oracle leaves slice 4 empty too)
+    assert (sed2[0, :3, 0, -1, :].sum(axis=-1) > 0).all()
