@@ -167,6 +167,7 @@ class FlatModel:
     specific_energy: Optional[np.ndarray] = None
     minimum_specific_energy: Optional[np.ndarray] = None
     peeled: List["FlatPeeledGroup"] = field(default_factory=list)
+    grid_type: str = "car"              # "car" (x, y, z walls) or "sph" (r, theta, phi walls)
 
     def __post_init__(self):
         self.w1, self.w2, self.w3 = _f8(self.w1), _f8(self.w2), _f8(self.w3)
@@ -188,6 +189,10 @@ class FlatModel:
         return s[0] * s[1] * s[2]
 
     def volumes(self):
+        if self.grid_type == "sph":
+            # grid_geometry_spherical_3d.f90:147-160
+            dr3, dcost, dphi = np.diff(self.w1 ** 3), -np.diff(np.cos(self.w2)), np.diff(self.w3)
+            return dr3[None, None, :] * dcost[None, :, None] * dphi[:, None, None] / 3.
         dx, dy, dz = np.diff(self.w1), np.diff(self.w2), np.diff(self.w3)
         return (dx[None, None, :] * dy[None, :, None]) * dz[:, None, None]
 
@@ -198,7 +203,10 @@ def apply_model(api, ctx, model: FlatModel):
     ``api`` is a binding object with methods named like the header's functions
     minus the prefix (see :mod:`hyperion_b200.capi`)."""
     n3, n2, n1 = model.shape
-    api.set_grid_cartesian(ctx, n1, n2, n3, model.w1, model.w2, model.w3)
+    if model.grid_type == "sph":
+        api.set_grid_spherical(ctx, n1, n2, n3, model.w1, model.w2, model.w3)
+    else:
+        api.set_grid_cartesian(ctx, n1, n2, n3, model.w1, model.w2, model.w3)
     for d in model.dust:
         api.add_dust(ctx, d)
     for s in model.sources:

@@ -1021,7 +1021,12 @@ struct orc_ctx {
   std::vector<double> w1, w2, w3, ew1, ew2, ew3, dx, dy, dz, volume;
   // find_wall scratch (:29-30)
   double tmin = 0, emin = 0;
-  WallId imin;
+  WallId imin, iext;
+  // geometry kind: 0 Cartesian, 1 spherical polar (grid_geometry_spherical_3d.f90)
+  int grid_type = 0;
+  bool radial = false;  // the 'radial' argument of the spherical find_wall (grid_propagate_3d.f90:73)
+  std::vector<double> wr2, wtanp, wtant, wcost, wsint, wtant2;  // (:169-185)
+  int midplane = -1;
   // dust
   int n_dust = 0;
   std::vector<Dust> d;
@@ -1068,13 +1073,20 @@ Cell new_grid_cell(const orc_ctx &g, int i1, int i2, int i3) {
 // escaped_cell (grid_geometry_cartesian_3d.f90:267-275)
 bool escaped(const orc_ctx &g, const Cell &c) {
   if (c.i1 < 1 || c.i1 > g.n1) return true;
+  if (g.grid_type == 1) return false;  // spherical: radial escape only (grid_geometry_spherical_3d.f90:493-500)
   if (c.i2 < 1 || c.i2 > g.n2) return true;
   if (c.i3 < 1 || c.i3 > g.n3) return true;
   return false;
 }
 
 // find_cell (grid_geometry_cartesian_3d.f90:143-167); returns false for invalid_cell
+bool sph_find_cell(const orc_ctx &g, const Photon &p, Cell &out);
+void sph_adjust_wall(const orc_ctx &g, Photon &p);
+bool sph_in_correct_cell(const orc_ctx &g, const Photon &p);
+void sph_find_wall(orc_ctx &g, const Photon &p, double &tnearest, WallId &id_min);
+
 bool find_cell(const orc_ctx &g, const Photon &p, Cell &out) {
+  if (g.grid_type == 1) return sph_find_cell(g, p, out);
   int i1 = locate(g.w1.data(), g.n1 + 1, p.r.x);
   int i2 = locate(g.w2.data(), g.n2 + 1, p.r.y);
   int i3 = locate(g.w3.data(), g.n3 + 1, p.r.z);
@@ -1087,6 +1099,10 @@ bool find_cell(const orc_ctx &g, const Photon &p, Cell &out) {
 
 // adjust_wall (grid_geometry_cartesian_3d.f90:169-237)
 void adjust_wall(const orc_ctx &g, Photon &p) {
+  if (g.grid_type == 1) {
+    sph_adjust_wall(g, p);
+    return;
+  }
   p.on_wall = false;
   p.on_wall_id = WallId();
 #define ADJ(V, R, W, I, WID)                   \
@@ -1128,6 +1144,7 @@ void place_in_cell(orc_ctx &g, Photon &p) {
 
 // in_correct_cell (grid_geometry_cartesian_3d.f90:330-381)
 bool in_correct_cell(const orc_ctx &g, const Photon &p) {
+  if (g.grid_type == 1) return sph_in_correct_cell(g, p);
   const double threshold = 1.e-3;
   Cell act;
   bool valid = find_cell(g, p, act);
@@ -1182,6 +1199,10 @@ inline void insert_t(orc_ctx &g, double t, int iw, int i, double e) {
 
 // find_wall (grid_geometry_cartesian_3d.f90:424-472), reset_t (:474-480), find_next_wall (:514-521)
 void find_wall(orc_ctx &g, const Photon &p, double &tnearest, WallId &id_min) {
+  if (g.grid_type == 1) {
+    sph_find_wall(g, p, tnearest, id_min);
+    return;
+  }
   g.tmin = std::numeric_limits<double>::max();
   g.emin = 0.0;
   g.imin = WallId();
@@ -1228,7 +1249,358 @@ Cell next_cell(const orc_ctx &g, const Cell &c, const WallId &dir) {
     i3 = i3 - 1;
   else if (dir.w3 == +1)
     i3 = i3 + 1;
+  if (g.grid_type == 1) {  // phi is periodic (grid_geometry_spherical_3d.f90:549-555)
+    if (i3 == 0) i3 = g.n3;
+    if (i3 == g.n3 + 1) i3 = 1;
+  }
   return new_grid_cell(g, i1, i2, i3);
+}
+
+// ---------------------------------------------------------------------------
+// spherical polar geometry (src/grid/grid_geometry_spherical_3d.f90)
+// ---------------------------------------------------------------------------
+const double PI_F = 3.14159265358979323846;  // lib_constants.f90:66
+const double TWOPI_F = PI_F + PI_F;
+
+// equal_nulp (:48-57)
+bool equal_nulp(double x, double y, int n) {
+  if (x == y) return true;
+  return std::fabs(x - y) <= n * spacing(std::max(x, y));
+}
+
+// theta / phi of a photon as find_cell and adjust_wall compute them (:224-245)
+void sph_angles(const Photon &p, double &r_sq, double &w_sq, double &theta, double &phi) {
+  r_sq = p.r.x * p.r.x + p.r.y * p.r.y + p.r.z * p.r.z;
+  w_sq = p.r.x * p.r.x + p.r.y * p.r.y;
+  if (r_sq == 0.0)
+    theta = std::atan2(std::sqrt(p.v.x * p.v.x + p.v.y * p.v.y), p.v.z);
+  else
+    theta = std::atan2(std::sqrt(p.r.x * p.r.x + p.r.y * p.r.y), p.r.z);
+  if (w_sq == 0.0) {
+    phi = std::atan2(p.v.y, p.v.x);
+    if (phi < 0.0) phi = phi + TWOPI_F;
+  } else {
+    phi = std::atan2(p.r.y, p.r.x);
+    if (phi < 0.0) phi = phi + TWOPI_F;
+  }
+}
+
+// find_cell (:212-276)
+bool sph_find_cell(const orc_ctx &g, const Photon &p, Cell &out) {
+  double r_sq, w_sq, theta, phi;
+  sph_angles(p, r_sq, w_sq, theta, phi);
+  int i1 = locate(g.wr2.data(), g.n1 + 1, r_sq);
+  int i2 = locate(g.w2.data(), g.n2 + 1, theta);
+  int i3 = locate(g.w3.data(), g.n3 + 1, phi);
+  if (i1 < 1 || i1 > g.n1) return false;
+  if (i2 < 1 || i2 > g.n2) return false;
+  if (i3 < 1 || i3 > g.n3) return false;
+  out = new_grid_cell(g, i1, i2, i3);
+  return true;
+}
+
+// adjust_wall (:278-469)
+void sph_adjust_wall(const orc_ctx &g, Photon &p) {
+  const int eps = 3;
+  p.on_wall = false;
+  p.on_wall_id = WallId();
+  double r_sq, w_sq, theta, phi;
+  sph_angles(p, r_sq, w_sq, theta, phi);
+  const double rdotv = p.r.x * p.v.x + p.r.y * p.v.y + p.r.z * p.v.z;
+  // radial walls
+  if (rdotv >= 0.0) {
+    if (equal_nulp(r_sq, g.wr2[p.icell.i1 - 1], eps)) {
+      p.on_wall_id.w1 = -1;
+    } else if (equal_nulp(r_sq, g.wr2[p.icell.i1], eps)) {
+      p.on_wall_id.w1 = -1;
+      p.icell.i1 = p.icell.i1 + 1;
+    }
+  } else {
+    if (equal_nulp(r_sq, g.wr2[p.icell.i1 - 1], eps)) {
+      p.on_wall_id.w1 = +1;
+      p.icell.i1 = p.icell.i1 - 1;
+    } else if (equal_nulp(r_sq, g.wr2[p.icell.i1], eps)) {
+      p.on_wall_id.w1 = +1;
+    }
+  }
+  // theta walls
+  if (r_sq == 0.0) {
+    if (std::fabs(p.v.z) < 1.0) {
+      double theta_v = std::atan2(std::sqrt(p.v.x * p.v.x + p.v.y * p.v.y), p.v.z);
+      if (equal_nulp(theta_v, g.w2[p.icell.i2 - 1], eps))
+        p.on_wall_id.w2 = -1;
+      else if (equal_nulp(theta_v, g.w2[p.icell.i2], eps))
+        p.on_wall_id.w2 = +1;
+    }
+  } else if (p.icell.i2 > 1 && equal_nulp(theta, g.w2[p.icell.i2 - 1], eps)) {
+    if (p.icell.i2 == g.midplane) {
+      if (p.v.z > 0.0) {
+        p.on_wall_id.w2 = +1;
+        p.icell.i2 = p.icell.i2 - 1;
+      } else {
+        p.on_wall_id.w2 = -1;
+      }
+    } else {
+      bool lhs = (std::sqrt(w_sq) * p.v.z * g.wtant[p.icell.i2 - 1] - (p.r.x * p.v.x + p.r.y * p.v.y) < 0.0);
+      if (lhs == (p.r.z > 0.0)) {
+        p.on_wall_id.w2 = -1;
+      } else {
+        p.on_wall_id.w2 = +1;
+        p.icell.i2 = p.icell.i2 - 1;
+      }
+    }
+  } else if (p.icell.i2 + 1 < g.n2 + 1 && equal_nulp(theta, g.w2[p.icell.i2], eps)) {
+    if (p.icell.i2 + 1 == g.midplane) {
+      if (p.v.z > 0.0) {
+        p.on_wall_id.w2 = +1;
+      } else {
+        p.on_wall_id.w2 = -1;
+        p.icell.i2 = p.icell.i2 + 1;
+      }
+    } else {
+      bool lhs = (std::sqrt(w_sq) * p.v.z * g.wtant[p.icell.i2] - (p.r.x * p.v.x + p.r.y * p.v.y) < 0.0);
+      if (lhs == (p.r.z > 0.0)) {
+        p.on_wall_id.w2 = -1;
+        p.icell.i2 = p.icell.i2 + 1;
+      } else {
+        p.on_wall_id.w2 = +1;
+      }
+    }
+  }
+  // phi walls
+  if (p.r.x == 0.0 && p.r.y == 0.0 && p.v.x == 0.0 && p.v.y == 0.0) {
+    // on all phi walls at once: leave alone
+  } else if (equal_nulp(phi, g.w3[p.icell.i3 - 1], eps)) {
+    double phi_v = std::atan2(p.v.y, p.v.x);
+    double dphi = phi_v - g.w3[p.icell.i3 - 1];
+    if (dphi < -PI_F) dphi = dphi + TWOPI_F;
+    if (dphi > 0.0) {
+      p.on_wall_id.w3 = -1;
+    } else {
+      p.on_wall_id.w3 = +1;
+      p.icell.i3 = p.icell.i3 - 1;
+      if (p.icell.i3 == 0) p.icell.i3 = g.n3;
+    }
+  } else if (equal_nulp(phi, g.w3[p.icell.i3], eps)) {
+    double phi_v = std::atan2(p.v.y, p.v.x);
+    double dphi = phi_v - g.w3[p.icell.i3];
+    if (dphi < -PI_F) dphi = dphi + TWOPI_F;
+    if (dphi > 0.0) {
+      p.on_wall_id.w3 = -1;
+      p.icell.i3 = p.icell.i3 + 1;
+      if (p.icell.i3 == g.n3 + 1) p.icell.i3 = 1;
+    } else {
+      p.on_wall_id.w3 = +1;
+    }
+  }
+  p.on_wall = p.on_wall_id.w1 != 0 || p.on_wall_id.w2 != 0 || p.on_wall_id.w3 != 0;
+}
+
+// in_correct_cell (:557-643)
+bool sph_in_correct_cell(const orc_ctx &g, const Photon &p) {
+  const double threshold = 1.e-3;
+  Cell act;
+  bool valid = sph_find_cell(g, p, act);
+  if (!valid) act = Cell{-1, -1, -1, -1};
+  if (!p.on_wall) return act.i1 == p.icell.i1 && act.i2 == p.icell.i2 && act.i3 == p.icell.i3;
+  bool ok = true;
+  double r_sq, w_sq, theta, phi, frac, dphi;
+  r_sq = p.r.x * p.r.x + p.r.y * p.r.y + p.r.z * p.r.z;
+  if (r_sq == 0.0) return true;
+  sph_angles(p, r_sq, w_sq, theta, phi);
+  if (p.on_wall_id.w1 == -1) {
+    if (g.w1[p.icell.i1 - 1] != std::sqrt(r_sq)) {
+      frac = std::sqrt(r_sq) / g.w1[p.icell.i1 - 1] - 1.0;
+      ok = ok && std::fabs(frac) < threshold;
+    }
+  } else if (p.on_wall_id.w1 == +1) {
+    if (g.w1[p.icell.i1] != std::sqrt(r_sq)) {
+      frac = std::sqrt(r_sq) / g.w1[p.icell.i1] - 1.0;
+      ok = ok && std::fabs(frac) < threshold;
+    }
+  } else {
+    ok = ok && act.i1 == p.icell.i1;
+  }
+  if (p.on_wall_id.w2 == -1) {
+    frac = theta / g.w2[p.icell.i2 - 1] - 1.0;
+    ok = ok && std::fabs(frac) < threshold;
+  } else if (p.on_wall_id.w2 == +1) {
+    frac = theta / g.w2[p.icell.i2] - 1.0;
+    ok = ok && std::fabs(frac) < threshold;
+  } else {
+    ok = ok && act.i2 == p.icell.i2;
+  }
+  if (p.on_wall_id.w3 == -1) {
+    dphi = phi - g.w3[p.icell.i3 - 1];
+    if (dphi > PI_F) dphi = dphi - TWOPI_F;
+    if (dphi < -PI_F) dphi = dphi + TWOPI_F;
+    frac = dphi / (g.w3[p.icell.i3] - g.w3[p.icell.i3 - 1]);
+    ok = ok && std::fabs(frac) < threshold;
+  } else if (p.on_wall_id.w3 == +1) {
+    dphi = phi - g.w3[p.icell.i3];
+    if (dphi > PI_F) dphi = dphi - TWOPI_F;
+    if (dphi < -PI_F) dphi = dphi + TWOPI_F;
+    frac = dphi / (g.w3[p.icell.i3] - g.w3[p.icell.i3 - 1]);
+    ok = ok && std::fabs(frac) < threshold;
+  } else {
+    ok = ok && act.i3 == p.icell.i3;
+  }
+  return ok;
+}
+
+// quadratic_dp (fortranlib/src/lib_algebra.f90:107-122)
+void quadratic(double a, double b, double c, double &x1, double &x2) {
+  const double huge = std::numeric_limits<double>::max();
+  double delta = b * b - 4.0 * a * c;
+  if (delta > 0) {
+    delta = std::sqrt(delta);
+    double factor = 0.5 / a;
+    x1 = (-b - delta) * factor;
+    x2 = (-b + delta) * factor;
+  } else {
+    x1 = huge;
+    x2 = huge;
+  }
+}
+
+void quadratic_pascal_reduced(double b, double c, double &x1, double &x2);
+
+// one cone wall of find_wall (:822-962); iw2 is the wall index (1-based), side -1 lower / +1 upper
+void sph_cone_wall(orc_ctx &g, const Photon &p, int iw2, int side, double v2_xy, double v2_z, double rv_xy,
+                   double rv_z, double r2_xy, double r2_z) {
+  const double huge = std::numeric_limits<double>::max();
+  const double wtant = g.wtant[iw2 - 1], wtant2 = g.wtant2[iw2 - 1], ew = g.ew2[iw2 - 1];
+  if (p.on_wall_id.w2 == side && equal_nulp(wtant, std::sqrt(v2_xy) / p.v.z, 10) &&
+      equal_nulp(std::sqrt(r2_xy) * p.v.z * wtant, rv_xy, 10)) {
+    g.iext.w2 = side;
+    return;
+  }
+  if (iw2 == g.midplane && p.v.z != 0) {
+    if (p.on_wall_id.w2 != side) insert_t(g, -p.r.z / p.v.z, 2, side, ew);
+    return;
+  }
+  double pA = v2_xy - v2_z * wtant2;
+  double pB = rv_xy - rv_z * wtant2;
+  pB = pB + pB;
+  double pC = r2_xy - r2_z * wtant2;
+  if (std::fabs(pA) > 0.0) {
+    double t1, t2;
+    quadratic(pA, pB, pC, t1, t2);
+    double z1 = p.r.z + p.v.z * t1;
+    if ((z1 > 0.0) != (wtant > 0.0)) t1 = huge;
+    double z2 = p.r.z + p.v.z * t2;
+    if ((z2 > 0.0) != (wtant > 0.0)) t2 = huge;
+    if (p.on_wall_id.w2 == side) {
+      if (std::fabs(t1) < std::fabs(t2))
+        insert_t(g, t2, 2, side, ew);
+      else
+        insert_t(g, t1, 2, side, ew);
+    } else {
+      insert_t(g, t1, 2, side, ew);
+      insert_t(g, t2, 2, side, ew);
+    }
+  } else if (std::fabs(pB) > 0.0) {
+    if (p.on_wall_id.w2 != side) insert_t(g, -pC / pB, 2, side, ew);
+  }
+}
+
+// find_wall (:741-1073), reset_t (:1075-1081), find_next_wall (:1113-1120)
+void sph_find_wall(orc_ctx &g, const Photon &p, double &tnearest, WallId &id_min) {
+  g.tmin = std::numeric_limits<double>::max();
+  g.emin = 0.0;
+  g.imin = WallId();
+  g.iext = WallId();
+  double v2_xy = p.v.x * p.v.x + p.v.y * p.v.y;
+  double v2_z = p.v.z * p.v.z;
+  double rv_xy = p.r.x * p.v.x + p.r.y * p.v.y;
+  double rv_z = p.r.z * p.v.z;
+  double r2_xy = p.r.x * p.r.x + p.r.y * p.r.y;
+  double r2_z = p.r.z * p.r.z;
+  double pB = rv_xy + rv_z;
+  pB = pB + pB;
+  double pC = r2_xy + r2_z;
+  double t1, t2;
+  // spherical walls
+  if (!g.radial) {
+    double pC_1 = pC - g.wr2[p.icell.i1 - 1];
+    quadratic_pascal_reduced(pB, pC_1, t1, t2);
+    if (p.on_wall_id.w1 == -1) {
+      if (std::fabs(t1) < std::fabs(t2))
+        insert_t(g, t2, 1, -1, g.ew1[p.icell.i1 - 1]);
+      else
+        insert_t(g, t1, 1, -1, g.ew1[p.icell.i1 - 1]);
+    } else {
+      insert_t(g, t1, 1, -1, g.ew1[p.icell.i1 - 1]);
+      insert_t(g, t2, 1, -1, g.ew1[p.icell.i1 - 1]);
+    }
+  }
+  double pC_2 = pC - g.wr2[p.icell.i1];
+  quadratic_pascal_reduced(pB, pC_2, t1, t2);
+  if (p.on_wall_id.w1 == +1) {
+    if (std::fabs(t1) < std::fabs(t2))
+      insert_t(g, t2, 1, +1, g.ew1[p.icell.i1]);
+    else
+      insert_t(g, t1, 1, +1, g.ew1[p.icell.i1]);
+  } else {
+    insert_t(g, t1, 1, +1, g.ew1[p.icell.i1]);
+    insert_t(g, t2, 1, +1, g.ew1[p.icell.i1]);
+  }
+  // cone walls (theta = 0 and theta = pi are not walls)
+  if (p.icell.i2 > 1) sph_cone_wall(g, p, p.icell.i2, -1, v2_xy, v2_z, rv_xy, rv_z, r2_xy, r2_z);
+  if (p.icell.i2 < g.n2) sph_cone_wall(g, p, p.icell.i2 + 1, +1, v2_xy, v2_z, rv_xy, rv_z, r2_xy, r2_z);
+  // phi walls
+  if (g.n3 > 1) {
+    double dphi = 0.0;
+    if (p.on_wall_id.w3 == -1) {
+      dphi = std::atan2(p.v.y, p.v.x) - g.w3[p.icell.i3 - 1];
+      if (dphi > PI_F) dphi = dphi - TWOPI_F;
+      if (dphi < -PI_F) dphi = dphi + TWOPI_F;
+    }
+    if (p.on_wall_id.w3 == +1) {
+      dphi = std::atan2(p.v.y, p.v.x) - g.w3[p.icell.i3];
+      if (dphi > PI_F) dphi = dphi - TWOPI_F;
+      if (dphi < -PI_F) dphi = dphi + TWOPI_F;
+    }
+    if (p.on_wall_id.w3 == +1 && std::fabs(dphi) < g.ew3[p.icell.i3]) {
+      g.iext.w3 = +1;
+    } else if (p.on_wall_id.w3 == -1 && std::fabs(dphi) < g.ew3[p.icell.i3 - 1]) {
+      g.iext.w3 = -1;
+    } else if (r2_xy > 0.0) {
+      if (p.on_wall_id.w3 != -1) {
+        double tp = g.wtanp[p.icell.i3 - 1];
+        t1 = -(tp * p.r.x - p.r.y) / (tp * p.v.x - p.v.y);
+        double x_i = p.r.x + p.v.x * t1, y_i = p.r.y + p.v.y * t1;
+        double phi_i = std::atan2(y_i, x_i);
+        double dp = std::fabs(phi_i - g.w3[p.icell.i3 - 1]);
+        if (dp > PI_F) dp = std::fabs(dp - TWOPI_F);
+        if (dp < 0.5 * PI_F) insert_t(g, t1, 3, -1, 0.0);
+      }
+      if (p.on_wall_id.w3 != +1) {
+        double tp = g.wtanp[p.icell.i3];
+        t2 = -(tp * p.r.x - p.r.y) / (tp * p.v.x - p.v.y);
+        double x_i = p.r.x + p.v.x * t2, y_i = p.r.y + p.v.y * t2;
+        double phi_i = std::atan2(y_i, x_i);
+        double dp = std::fabs(phi_i - g.w3[p.icell.i3]);
+        if (dp > PI_F) dp = std::fabs(dp - TWOPI_F);
+        if (dp < 0.5 * PI_F) insert_t(g, t2, 3, +1, 0.0);
+      }
+    }
+  }
+  tnearest = g.tmin;
+  id_min = WallId{g.imin.w1 + g.iext.w1, g.imin.w2 + g.iext.w2, g.imin.w3 + g.iext.w3};
+}
+
+// random_position_cell (:645-677)
+Vec sph_random_position_cell(orc_ctx &g, const Cell &c) {
+  double r = g.rng.random(), t = g.rng.random(), ph = g.rng.random();
+  double w1a = g.w1[c.i1 - 1], w1b = g.w1[c.i1];
+  r = std::pow(r * (w1b * w1b * w1b - w1a * w1a * w1a) + w1a * w1a * w1a, 1.0 / 3.0);
+  t = std::acos(t * (g.wcost[c.i2] - g.wcost[c.i2 - 1]) + g.wcost[c.i2 - 1]);
+  ph = ph * (g.w3[c.i3] - g.w3[c.i3 - 1]) + g.w3[c.i3 - 1];
+  if (r <= w1a || r >= w1b) r = 0.5 * (w1a + w1b);
+  if (t <= g.w2[c.i2 - 1] || t >= g.w2[c.i2]) t = 0.5 * (g.w2[c.i2 - 1] + g.w2[c.i2]);
+  if (ph <= g.w3[c.i3 - 1] || ph >= g.w3[c.i3]) ph = 0.5 * (g.w3[c.i3 - 1] + g.w3[c.i3]);
+  return Vec{r * std::sin(t) * std::cos(ph), r * std::sin(t) * std::sin(ph), r * std::cos(t)};
 }
 
 // update_optconsts (dust.f90:64-79)
@@ -1339,6 +1711,7 @@ void grid_integrate(orc_ctx &g, Photon &p, double tau_required, double &tau_achi
   double t_source;
   int source_id;
   find_nearest_source(g, p.r, p.v, t_source, source_id);
+  g.radial = (p.r.x * p.v.x + p.r.y * p.v.y + p.r.z * p.v.z) > 0.;  // grid_propagate_3d.f90:73,262
   double t_achieved = 0.0;
   const int nc = g.n_cells;
   for (;;) {
@@ -1588,6 +1961,7 @@ void grid_integrate_noenergy(orc_ctx &g, Photon &p, double tau_required, double 
   double t_source;
   int source_id;
   find_nearest_source(g, p.r, p.v, t_source, source_id);
+  g.radial = (p.r.x * p.v.x + p.r.y * p.v.y + p.r.z * p.v.z) > 0.;  // grid_propagate_3d.f90:73,262
   double t_achieved = 0.0;
   const int nc = g.n_cells;
   for (;;) {
@@ -1664,6 +2038,7 @@ void grid_escape(orc_ctx &g, const Photon &p_orig, double tmax, double &tau, dou
   double t_source;
   int source_id;
   find_nearest_source(g, p.r, p.v, t_source, source_id);
+  g.radial = (p.r.x * p.v.x + p.r.y * p.v.y + p.r.z * p.v.z) > 0.;  // grid_propagate_3d.f90:400,505
   if (t_source < tmax) {
     killed = true;
     return;
@@ -1985,10 +2360,14 @@ Photon emit_from_grid(orc_ctx &g) {
   p.icell = new_grid_cell(g, i1, i2, i3);
   p.in_cell = true;
   // random_position_cell (grid_geometry_cartesian_3d.f90:383-394)
-  double x = g.rng.random(), y = g.rng.random(), z = g.rng.random();
-  p.r.x = x * (g.w1[i1] - g.w1[i1 - 1]) + g.w1[i1 - 1];
-  p.r.y = y * (g.w2[i2] - g.w2[i2 - 1]) + g.w2[i2 - 1];
-  p.r.z = z * (g.w3[i3] - g.w3[i3 - 1]) + g.w3[i3 - 1];
+  if (g.grid_type == 1) {
+    p.r = sph_random_position_cell(g, p.icell);
+  } else {
+    double x = g.rng.random(), y = g.rng.random(), z = g.rng.random();
+    p.r.x = x * (g.w1[i1] - g.w1[i1 - 1]) + g.w1[i1 - 1];
+    p.r.y = y * (g.w2[i2] - g.w2[i2 - 1]) + g.w2[i2 - 1];
+    p.r.z = z * (g.w3[i3] - g.w3[i3 - 1]) + g.w3[i3 - 1];
+  }
   p.a = random_sphere_angle3d(g.rng);
   p.v = angle3d_to_vector3d(p.a);
   p.s = Stokes{1.0, 0.0, 0.0, 0.0};
@@ -2111,6 +2490,65 @@ int orc_set_grid_cartesian(orc_ctx *g, int32_t n1, int32_t n2, int32_t n3, const
   for (int i = 0; i <= n1; i++) g->ew1[i] = 3 * spacing(w1[i]);
   for (int i = 0; i <= n2; i++) g->ew2[i] = 3 * spacing(w2[i]);
   for (int i = 0; i <= n3; i++) g->ew3[i] = 3 * spacing(w3[i]);
+  return 0;
+}
+
+// setup_grid_geometry (grid_geometry_spherical_3d.f90:92-203): w1 = r, w2 = theta, w3 = phi walls
+int orc_set_grid_spherical(orc_ctx *g, int32_t n1, int32_t n2, int32_t n3, const double *w1, const double *w2,
+                           const double *w3) {
+  g->grid_type = 1;
+  g->n1 = n1;
+  g->n2 = n2;
+  g->n3 = n3;
+  g->n_cells = n1 * n2 * n3;
+  g->w1.assign(w1, w1 + n1 + 1);
+  g->w2.assign(w2, w2 + n2 + 1);
+  g->w3.assign(w3, w3 + n3 + 1);
+  for (int i = 0; i <= n1; i++)
+    if (w1[i] < 0.) return fail(g, "r walls should be positive");
+  for (int i = 0; i <= n2; i++)
+    if (w2[i] < 0. || w2[i] > PI_F) return fail(g, "theta walls should be between 0 and pi");
+  for (int i = 0; i <= n3; i++)
+    if (w3[i] < 0. || w3[i] > TWOPI_F) return fail(g, "phi walls should be between 0 and 2*pi");
+  std::vector<double> dr3(n1), dcost(n2), dphi(n3);
+  for (int i = 0; i < n1; i++) dr3[i] = w1[i + 1] * w1[i + 1] * w1[i + 1] - w1[i] * w1[i] * w1[i];
+  for (int i = 0; i < n2; i++) dcost[i] = std::cos(w2[i]) - std::cos(w2[i + 1]);
+  for (int i = 0; i < n3; i++) dphi[i] = w3[i + 1] - w3[i];
+  g->volume.resize(g->n_cells);
+  for (int i3 = 0; i3 < n3; i3++)
+    for (int i2 = 0; i2 < n2; i2++)
+      for (int i1 = 0; i1 < n1; i1++)
+        g->volume[(size_t)i3 * n1 * n2 + i2 * n1 + i1] = dr3[i1] * dcost[i2] * dphi[i3] / 3.0;
+  for (double v : g->volume)
+    if (v == 0.0) return fail(g, "all volumes should be greater than zero");
+  g->wr2.resize(n1 + 1);
+  for (int i = 0; i <= n1; i++) g->wr2[i] = w1[i] * w1[i];
+  g->wtanp.resize(n3 + 1);
+  for (int i = 0; i <= n3; i++) g->wtanp[i] = std::tan(w3[i]);
+  g->wtant.resize(n2 + 1);
+  g->wcost.resize(n2 + 1);
+  g->wsint.resize(n2 + 1);
+  g->wtant2.resize(n2 + 1);
+  for (int i = 0; i <= n2; i++) {
+    g->wtant[i] = std::tan(w2[i]);
+    g->wcost[i] = std::cos(w2[i]);
+    g->wsint[i] = std::sin(w2[i]);
+    g->wtant2[i] = g->wtant[i] * g->wtant[i];
+  }
+  g->midplane = -1;
+  bool any = false;
+  for (int i = 0; i <= n2; i++)
+    if (std::fabs(w2[i] - PI_F / 2.0) < (double)1.e-6f) any = true;
+  if (any) {
+    int best = 0;
+    for (int i = 1; i <= n2; i++)
+      if (std::fabs(w2[i] - PI_F / 2.0) < std::fabs(w2[best] - PI_F / 2.0)) best = i;
+    g->midplane = best + 1;
+  }
+  g->ew1.resize(n1 + 1);
+  g->ew2.assign(n2 + 1, 3 * spacing(1.0));
+  g->ew3.assign(n3 + 1, 3 * spacing(1.0));
+  for (int i = 0; i <= n1; i++) g->ew1[i] = 3 * spacing(w1[i]);
   return 0;
 }
 

@@ -16,3 +16,9 @@ def pytest_configure(config):
 def golden_car():
     import numpy as np
     return np.load(os.path.join(ROOT, "tests", "golden", "bitlevel_car.npz"))
+
+
+@pytest.fixture(scope="session")
+def golden_sph():
+    import numpy as np
+    return np.load(os.path.join(ROOT, "tests", "golden", "bitlevel_sph.npz"))

@@ -92,6 +92,32 @@ def main():
                 assert int(np.asarray(f.attrs[k]).ravel()[0]) == 0
     np.savez_compressed(os.path.join(HERE, "bitlevel_car.npz"), **out)
     print("wrote", os.path.join(HERE, "bitlevel_car.npz"))
+    # spherical polar grid of the same tests (test_bit_level.py:58-62): the dust and sources are shared
+    # with bitlevel_car.npz, only the geometry, densities and expected outputs are stored
+    sph = {"w1": np.linspace(0., 3. * pc, 6), "w2": np.linspace(0., np.pi, 8), "w3": np.linspace(0., 2. * np.pi, 4),
+           "density_1": dens[("density", "sph")], "density_2": dens[("density_2", "sph")],
+           "density_3": dens[("density_3", "sph")]}
+    golden_outputs(sph, "sph")
+    np.savez_compressed(os.path.join(HERE, "bitlevel_sph.npz"), **sph)
+    print("wrote", os.path.join(HERE, "bitlevel_sph.npz"))
+
+
+def golden_outputs(out, grid_type):
+    for evenly in (False, True):
+        for multi in (False, True):
+            fn = ("test_specific_energy.grid_type=%s.sample_sources_evenly=%s."
+                  "multiple_densities=%s.rtout" % (grid_type, evenly, multi))
+            f = h5min.File(os.path.join(DATA, fn))
+            out["expected_evenly=%s_multi=%s" % (evenly, multi)] = \
+                np.array([f["iteration_%05d/specific_energy" % i][...] for i in range(1, 6)])
+    for ray in (False, True):
+        for evenly in (False, True):
+            fn = ("test_peeloff.grid_type=%s.raytracing=%s.sample_sources_evenly=%s.rtout" % (grid_type, ray, evenly))
+            f = h5min.File(os.path.join(DATA, fn))
+            for ig in (1, 2, 3):
+                for kind in ("seds", "images"):
+                    out["peeloff_ray=%s_evenly=%s_g%d_%s" % (ray, evenly, ig, kind)] = \
+                        f["Peeled/group_%05d/%s" % (ig, kind)][...]
 
 
 if __name__ == "__main__":

@@ -24,6 +24,17 @@ def bitlevel_model(z, evenly, multi):
                      FlatConf(sample_sources_evenly=evenly))
 
 
+def bitlevel_model_sph(zc, z, evenly, multi):
+    """Same test on the spherical polar grid (test_bit_level.py:58-62): r, theta, phi walls; the dust
+    and the five point sources are those of the Cartesian fixture ``zc``."""
+    dust = kmh_dust(zc)
+    dens = [z["density_1"]] + ([z["density_2"], z["density_3"]] if multi else [])
+    srcs = [FlatSource(type=1, luminosity=float(l), temperature=float(t), position=tuple(p))
+            for l, t, p in zip(zc["source_luminosity"], zc["source_temperature"], zc["source_position"])]
+    return FlatModel(z["w1"], z["w2"], z["w3"], np.array(dens), [dust] * len(dens), srcs,
+                     FlatConf(sample_sources_evenly=evenly), grid_type="sph")
+
+
 def ulp_diff(a, b):
     """Distance in units in the last place, as hyperion/model/tests/test_helpers.py:59-144 measures it."""
     a = np.asarray(a, dtype=np.float64)
@@ -44,5 +55,11 @@ def peeloff_groups():
 
 def peeloff_model(z, evenly):
     m = bitlevel_model(z, evenly, False)
+    m.peeled = peeloff_groups()
+    return m
+
+
+def peeloff_model_sph(zc, z, evenly):
+    m = bitlevel_model_sph(zc, z, evenly, False)
     m.peeled = peeloff_groups()
     return m
