@@ -1,0 +1,95 @@
+// flight_sph.cuh -- flight kernel for spherical polar grids (Lucy and imaging iterations).
+// Included by hyperion_b200.cu after imaging.cuh (it uses FinalArgs).
+#pragma once
+
+constexpr int SPH_FLIGHT_THREADS = 128;
+
+// grid_integrate (DEP) / grid_integrate_noenergy for every queued packet; persistent threads, each lane
+// refills from the queue on its own.  FINAL: a packet on its first flight with a forced first interaction
+// measures its optical depth to the grid edge first (iter_final.f90:191-209).
+template <int ND, bool DEP, bool FINAL>
+__global__ void __launch_bounds__(SPH_FLIGHT_THREADS)
+flight_sph_kernel(const ModelDev M, Pool P, const FinalArgs F, const uint32_t *__restrict__ q_flight,
+                  const uint32_t *n_flight_ptr, uint32_t *cursor, const uint32_t iteration) {
+  const SphGrid &G = M.sph;
+  const uint32_t n_flight = *n_flight_ptr;
+  Slot<ND> *slots = (Slot<ND> *)P.slots;
+  CellRec *__restrict__ cells = M.cells;
+  const unsigned lane = threadIdx.x & 31;
+  uint32_t n_cross = 0, n_esc = 0, n_peel_cross = 0, n_killed = 0;
+  for (;;) {
+    // the warp claims 32 queue entries at a time
+    uint32_t base = 0;
+    if (lane == 0) base = atomicAdd(cursor, 32u);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (base >= n_flight) break;
+    const uint32_t idx = base + lane;
+    int fin = 0;
+    uint32_t slot = 0;
+    if (idx < n_flight) {
+      slot = q_flight[idx];
+      Slot<ND> *s = slots + slot;
+      SphRay R;
+      sph_start(G, R, s->r0x, s->r0y, s->r0z, s->vx, s->vy, s->vz, s->ix, s->iy, s->iz);
+      double tau = s->tau_left;
+      double chi[ND], kE[ND];
+#pragma unroll
+      for (int k = 0; k < ND; ++k) {
+        chi[k] = s->chi[k];
+        kE[k] = s->kE[k];
+      }
+      if (FINAL && tau < 0.0 && !sph_escaped(G, R)) {
+        SphRay E = R;
+        double tau_escape = 0.0, col[ND];
+        const bool ok = sph_escape<ND, false>(G, E, chi, cells, tau_escape, col, n_peel_cross);
+        if (!ok) ++n_killed;  // grid_escape_tau killed its copy; the packet itself goes on unforced
+        Rng rng;
+        rng.init(M.seed, s->id, iteration);
+        rng.blk = s->rng_blk;
+        rng.has_spare = s->rng_has_spare != 0;
+        rng.spare = s->rng_spare;
+        if (ok && tau_escape > 1.e-10) {
+          const double TAU_THRES = 1.e-7;
+          const double one_minus_exp = tau_escape > TAU_THRES ? 1.0 - exp(-tau_escape) : tau_escape;
+          double weight;
+          if (F.algorithm == HYP_FFI_BAES16) {
+            const double alpha = (1.0 - F.baes16_xi) / one_minus_exp, beta = F.baes16_xi / tau_escape;
+            double tau_min = 0.0, tau_max = tau_escape;
+            const double xi = rng.next();
+            for (int it = 0; it < 60; ++it) {
+              tau = 0.5 * (tau_min + tau_max);
+              const double xt = tau > TAU_THRES ? alpha * (1.0 - exp(-tau)) + beta * tau : alpha * tau + beta * tau;
+              if (xt > xi) tau_max = tau; else tau_min = tau;
+            }
+            tau = 0.5 * (tau_min + tau_max);
+            weight = 1.0 / (alpha + beta * exp(tau));
+          } else {
+            tau = -log(1.0 - rng.next() * one_minus_exp);
+            weight = one_minus_exp;
+          }
+          s->energy = s->energy * weight;
+        } else {
+          tau = -log(1.0 - rng.next());
+        }
+        s->rng_blk = rng.blk;
+        s->rng_has_spare = rng.has_spare ? 1u : 0u;
+        s->rng_spare = rng.spare;
+      } else if (FINAL && tau < 0.0) {
+        tau = 1.0;  // escaped before the first step: the value is never used
+      }
+      fin = sph_march<ND, DEP>(G, R, tau, chi, kE, cells, n_cross);
+      if (fin == MARCH_INTERACT) {
+        s->t = R.t;
+        s->ix = R.i1; s->iy = R.i2; s->iz = R.i3; s->ic = R.ic;
+      }
+      n_esc += fin == MARCH_ESCAPED ? 1u : 0u;
+      n_killed += fin == MARCH_KILLED ? 1u : 0u;
+    }
+    queue_append(fin == MARCH_INTERACT, P.q_interact, P.counts + C_NI, slot);
+    queue_append(fin == MARCH_ESCAPED || fin == MARCH_KILLED, P.q_emit, P.counts + C_NE, slot);
+  }
+  warp_add_scalar(M.scalars + SC_CROSS, (double)n_cross);
+  warp_add_scalar(M.scalars + SC_ESC, (double)n_esc);
+  warp_add_scalar(M.scalars + SC_KILLED_GEO, (double)n_killed);
+  if (FINAL) warp_add_scalar(M.scalars + SC_PEEL_CROSS, (double)n_peel_cross);
+}

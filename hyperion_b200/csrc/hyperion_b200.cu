@@ -18,6 +18,7 @@
 #include <cub/device/device_radix_sort.cuh>
 
 #include "device.cuh"
+#include "geometry_sph.cuh"
 
 using namespace hyp;
 
@@ -32,7 +33,11 @@ struct CellRec {
 enum { SC_ENERGY = 0, SC_KILLED_GEO, SC_KILLED_INT, SC_CROSS, SC_ABS, SC_SCAT, SC_ESC, SC_PHOTONS, SC_PEEL_CROSS, SC_PEELOFFS,
        SC_COUNT };
 
+enum { GEO_CAR = 0, GEO_SPH = 1 };
+
 struct ModelDev {
+  int32_t grid_type;        // GEO_*
+  SphGrid sph;              // spherical polar tables (grid_type == GEO_SPH)
   int32_t n1, n2, n3, n_dust, n_sources;
   int64_t n_cells;
   const double *w1, *w2, *w3;
@@ -291,9 +296,16 @@ __device__ bool emit_photon(const ModelDev &M, Photon<ND> &p, Rng &rng, double &
     return false;
   }
   int fx, fy, fz;
-  bool ok = place_axis(M.w1, M.n1, p.r0x, p.vx, p.ix, fx);
-  ok = place_axis(M.w2, M.n2, p.r0y, p.vy, p.iy, fy) && ok;
-  ok = place_axis(M.w3, M.n3, p.r0z, p.vz, p.iz, fz) && ok;
+  bool ok;
+  if (M.grid_type == GEO_SPH) {
+    // the flight kernel applies adjust_wall when it starts the ray; the slot keeps find_cell's cell
+    ok = sph_find_cell(M.sph, p.r0x, p.r0y, p.r0z, p.vx, p.vy, p.vz, fx, fy, fz);
+    p.ix = fx; p.iy = fy; p.iz = fz;
+  } else {
+    ok = place_axis(M.w1, M.n1, p.r0x, p.vx, p.ix, fx);
+    ok = place_axis(M.w2, M.n2, p.r0y, p.vy, p.iy, fy) && ok;
+    ok = place_axis(M.w3, M.n3, p.r0z, p.vz, p.iz, fz) && ok;
+  }
   if (!ok) {
     atomicMax(M.error_flag, ERR_NOT_IN_CELL);
     return false;
@@ -453,6 +465,38 @@ __device__ int interact_photon(const ModelDev &M, Photon<ND> &p, Rng &rng, uint3
   return 0;
 }
 
+// cell volume (setup_grid_geometry of each geometry module)
+__device__ __forceinline__ double cell_volume(const ModelDev &M, int64_t ic) {
+  if (M.grid_type == GEO_SPH) return sph_volume(M.sph, ic);
+  const int i1 = (int)(ic % M.n1), i2 = (int)((ic / M.n1) % M.n2), i3 = (int)(ic / ((int64_t)M.n1 * M.n2));
+  return ((M.w1[i1 + 1] - M.w1[i1]) * (M.w2[i2 + 1] - M.w2[i2])) * (M.w3[i3 + 1] - M.w3[i3]);
+}
+
+// random_position_cell (grid_geometry_cartesian_3d.f90:383-394, grid_geometry_spherical_3d.f90:645-677)
+__device__ inline void random_position_cell(const ModelDev &M, int64_t ic, Rng &rng, double &x, double &y, double &z) {
+  const int i1 = (int)(ic % M.n1), i2 = (int)((ic / M.n1) % M.n2), i3 = (int)(ic / ((int64_t)M.n1 * M.n2));
+  if (M.grid_type == GEO_SPH) {
+    const SphGrid &G = M.sph;
+    const double *w1 = G.T + G.o_w1, *w2 = G.T + G.o_w2, *w3 = G.T + G.o_w3, *wc = G.T + G.o_wcost;
+    double r = rng.next(), t = rng.next(), ph = rng.next();
+    const double a = w1[i1], b = w1[i1 + 1];
+    r = pow(r * (b * b * b - a * a * a) + a * a * a, 1.0 / 3.0);
+    t = acos(t * (wc[i2 + 1] - wc[i2]) + wc[i2]);
+    ph = ph * (w3[i3 + 1] - w3[i3]) + w3[i3];
+    if (r <= a || r >= b) r = 0.5 * (a + b);
+    if (t <= w2[i2] || t >= w2[i2 + 1]) t = 0.5 * (w2[i2] + w2[i2 + 1]);
+    if (ph <= w3[i3] || ph >= w3[i3 + 1]) ph = 0.5 * (w3[i3] + w3[i3 + 1]);
+    x = r * sin(t) * cos(ph);
+    y = r * sin(t) * sin(ph);
+    z = r * cos(t);
+    return;
+  }
+  const double x0 = M.w1[i1], x1 = M.w1[i1 + 1], y0 = M.w2[i2], y1 = M.w2[i2 + 1], z0 = M.w3[i3], z1 = M.w3[i3 + 1];
+  x = rng.next() * (x1 - x0) + x0;
+  y = rng.next() * (y1 - y0) + y0;
+  z = rng.next() * (z1 - z0) + z0;
+}
+
 // =============================================================================================
 // kernels of one round
 // =============================================================================================
@@ -549,7 +593,7 @@ emit_kernel(const ModelDev M, Pool P, const unsigned long long first_id, const u
           break;
         }
         // a packet emitted on the outer wall moving outwards escapes immediately
-        if (p.ix < 0 || p.ix >= M.n1 || p.iy < 0 || p.iy >= M.n2 || p.iz < 0 || p.iz >= M.n3) {
+        if (M.grid_type == GEO_CAR && (p.ix < 0 || p.ix >= M.n1 || p.iy < 0 || p.iy >= M.n2 || p.iz < 0 || p.iz >= M.n3)) {
           ++n_esc;
           k = atomicAdd(P.next_photon, 1ull);
           if (k >= n_photons) {
@@ -1046,8 +1090,7 @@ __global__ void lucy_finish_kernel(ModelDev M, const double *__restrict__ sums, 
   for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x) {
     const int id = (int)(k % nd);
     const int64_t ic = k / nd;
-    const int i1 = (int)(ic % M.n1), i2 = (int)((ic / M.n1) % M.n2), i3 = (int)(ic / ((int64_t)M.n1 * M.n2));
-    const double vol = ((M.w1[i1 + 1] - M.w1[i1]) * (M.w2[i2 + 1] - M.w2[i2])) * (M.w3[i3 + 1] - M.w3[i3]);
+    const double vol = cell_volume(M, ic);
     const DustDev &d = M.dust[id];
     double e = sums[k] * scale / vol;
     if (vol == 0.0) e = 0.0;
@@ -1110,7 +1153,9 @@ __global__ void to_file_order_kernel(ModelDev M, int which, const double *__rest
   }
 }
 
+#include "march_sph.cuh"
 #include "imaging.cuh"
+#include "flight_sph.cuh"
 
 // =============================================================================================
 // host side: context + C ABI
@@ -1151,6 +1196,8 @@ struct hyp_ctx {
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
   // host model
+  int grid_type = GEO_CAR;
+  double *d_sph = nullptr;  // spherical polar tables
   int n1 = 0, n2 = 0, n3 = 0;
   int64_t n_cells = 0;
   std::vector<double> w1, w2, w3;
@@ -1397,6 +1444,7 @@ void hyp_ctx_destroy(hyp_ctx *c) {
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
   free_dev(c->d_w);
+  free_dev(c->d_sph);
   free_dev(c->d_cells);
   free_dev(c->d_energy);
   free_dev(c->d_jfrac);
@@ -1444,6 +1492,38 @@ int hyp_set_grid_cartesian(hyp_ctx *c, int32_t n1, int32_t n2, int32_t n3, const
     for (int i = 0; i < ns[a]; ++i)
       if (!(ws[a][i + 1] - ws[a][i] > 0.0))
         return fail(HYP_ERR_INVALID, std::string("all ") + names[a] + " values should be greater than zero");
+  c->grid_type = GEO_CAR;
+  c->n1 = n1;
+  c->n2 = n2;
+  c->n3 = n3;
+  c->n_cells = (int64_t)n1 * n2 * n3;
+  c->w1.assign(w1, w1 + n1 + 1);
+  c->w2.assign(w2, w2 + n2 + 1);
+  c->w3.assign(w3, w3 + n3 + 1);
+  return HYP_OK;
+}
+
+int hyp_set_grid_spherical(hyp_ctx *c, int32_t n1, int32_t n2, int32_t n3, const double *w1, const double *w2,
+                           const double *w3) {
+  if (!c || !w1 || !w2 || !w3) return fail(HYP_ERR_INVALID, "NULL argument");
+  if (c->finalized) return fail(HYP_ERR_STATE, "model is frozen");
+  if (n1 < 1 || n2 < 1 || n3 < 1) return fail(HYP_ERR_INVALID, "grid needs at least one cell per axis");
+  if ((int64_t)n1 * n2 * n3 > 2000000000LL) return fail(HYP_ERR_INVALID, "grid too large for 32-bit cell ids");
+  const double pi = SPH_PI;
+  for (int i = 0; i <= n1; ++i)
+    if (w1[i] < 0.) return fail(HYP_ERR_INVALID, "r walls should be positive");
+  for (int i = 0; i <= n2; ++i)
+    if (w2[i] < 0. || w2[i] > pi) return fail(HYP_ERR_INVALID, "theta walls should be between 0 and pi");
+  for (int i = 0; i <= n3; ++i)
+    if (w3[i] < 0. || w3[i] > pi + pi) return fail(HYP_ERR_INVALID, "phi walls should be between 0 and 2*pi");
+  const double *ws[3] = {w1, w2, w3};
+  const int ns[3] = {n1, n2, n3};
+  const char *names[3] = {"dr", "dt", "dphi"};
+  for (int a = 0; a < 3; ++a)
+    for (int i = 0; i < ns[a]; ++i)
+      if (!(ws[a][i + 1] - ws[a][i] > 0.0))
+        return fail(HYP_ERR_INVALID, std::string("all ") + names[a] + " values should be greater than zero");
+  c->grid_type = GEO_SPH;
   c->n1 = n1;
   c->n2 = n2;
   c->n3 = n3;
@@ -1604,6 +1684,59 @@ int hyp_finalize_setup(hyp_ctx *c) {
   M.w1 = c->d_w;
   M.w2 = c->d_w + c->w1.size();
   M.w3 = M.w2 + c->w2.size();
+  M.grid_type = c->grid_type;
+  if (c->grid_type == GEO_SPH) {
+    // derived wall quantities of setup_grid_geometry (grid_geometry_spherical_3d.f90:137-201)
+    const int n1 = c->n1, n2 = c->n2, n3 = c->n3;
+    SphGrid &G = M.sph;
+    G.n1 = n1; G.n2 = n2; G.n3 = n3;
+    int off = 0;
+    auto take = [&](int n) { int o = off; off += n; return o; };
+    G.o_w1 = take(n1 + 1); G.o_wr2 = take(n1 + 1); G.o_ew1 = take(n1 + 1);
+    G.o_w2 = take(n2 + 1); G.o_wtant = take(n2 + 1); G.o_wtant2 = take(n2 + 1); G.o_wcost = take(n2 + 1);
+    G.o_w3 = take(n3 + 1); G.o_wtanp = take(n3 + 1); G.o_wcosp = take(n3 + 1); G.o_wsinp = take(n3 + 1);
+    G.o_dr3 = take(n1); G.o_dcost = take(n2); G.o_dphi = take(n3);
+    std::vector<double> T(off);
+    for (int i = 0; i <= n1; ++i) {
+      const double w = c->w1[i];
+      T[G.o_w1 + i] = w;
+      T[G.o_wr2 + i] = w * w;
+      const double aw = std::fabs(w);
+      T[G.o_ew1 + i] = 3 * (w == 0.0 ? std::numeric_limits<double>::min()
+                                     : std::nextafter(aw, std::numeric_limits<double>::infinity()) - aw);
+    }
+    G.midplane = -1;
+    bool any = false;
+    for (int i = 0; i <= n2; ++i) {
+      const double w = c->w2[i];
+      T[G.o_w2 + i] = w;
+      T[G.o_wtant + i] = std::tan(w);
+      T[G.o_wtant2 + i] = std::tan(w) * std::tan(w);
+      T[G.o_wcost + i] = std::cos(w);
+      if (std::fabs(w - SPH_PI / 2.0) < (double)1.e-6f) any = true;
+    }
+    if (any) {
+      int best = 0;
+      for (int i = 1; i <= n2; ++i)
+        if (std::fabs(c->w2[i] - SPH_PI / 2.0) < std::fabs(c->w2[best] - SPH_PI / 2.0)) best = i;
+      G.midplane = best;
+    }
+    for (int i = 0; i <= n3; ++i) {
+      const double w = c->w3[i];
+      T[G.o_w3 + i] = w;
+      T[G.o_wtanp + i] = std::tan(w);
+      T[G.o_wcosp + i] = std::cos(w);
+      T[G.o_wsinp + i] = std::sin(w);
+    }
+    for (int i = 0; i < n1; ++i) T[G.o_dr3 + i] = c->w1[i + 1] * c->w1[i + 1] * c->w1[i + 1] - c->w1[i] * c->w1[i] * c->w1[i];
+    for (int i = 0; i < n2; ++i) T[G.o_dcost + i] = std::cos(c->w2[i]) - std::cos(c->w2[i + 1]);
+    for (int i = 0; i < n3; ++i) T[G.o_dphi + i] = c->w3[i + 1] - c->w3[i];
+    for (int i2 = 0; i2 < n2; ++i2)
+      if (T[G.o_dcost + i2] == 0.0) return fail(HYP_ERR_INVALID, "all volumes should be greater than zero");
+    CUDA_TRY(cudaMalloc(&c->d_sph, T.size() * sizeof(double)));
+    CUDA_TRY(cudaMemcpy(c->d_sph, T.data(), T.size() * sizeof(double), cudaMemcpyHostToDevice));
+    G.T = c->d_sph;
+  }
   // dust tables
   for (int id = 0; id < nd; ++id) {
     HostDust &d = c->dust[id];
@@ -1766,6 +1899,23 @@ static int run_rounds(hyp_ctx *c, int64_t first_id, int64_t n_photons, int64_t i
     CUDA_TRY(cudaMemsetAsync(P.counts + C_NI, 0, 4 * sizeof(uint32_t), st));  // C_NI, C_NE, C_CURSOR, C_CURSOR_B
     // 2. flights: the beams of new packets, then the packets that come out of an interaction
     CUDA_TRY(cudaEventRecord(c->evA, st));
+    if (c->grid_type == GEO_SPH) {
+      const FinalArgs none = FinalArgs();
+      const int sph_blocks_max = c->sm_count * 12;
+      if (n_new > 0) {
+        int blocks = (int)std::min<int64_t>((n_new + SPH_FLIGHT_THREADS - 1) / SPH_FLIGHT_THREADS, sph_blocks_max);
+        flight_sph_kernel<ND, true, false><<<blocks, SPH_FLIGHT_THREADS, 0, st>>>(c->M, P, none, P.q_beam, P.counts + C_NB,
+                                                                                 P.counts + C_CURSOR_B, (uint32_t)iteration);
+        c->launches_acc += 1;
+      }
+      if (n_flight_prev > 0) {
+        int blocks = (int)std::min<int64_t>(((int64_t)n_flight_prev + SPH_FLIGHT_THREADS - 1) / SPH_FLIGHT_THREADS, sph_blocks_max);
+        flight_sph_kernel<ND, true, false><<<blocks, SPH_FLIGHT_THREADS, 0, st>>>(c->M, P, none, P.q_flight[cur], nF,
+                                                                                 P.counts + C_CURSOR, (uint32_t)iteration);
+        c->launches_acc += 1;
+      }
+      CUDA_TRY(cudaGetLastError());
+    } else {
     if (n_new > 0) {
       int blocks = (int)std::min<int64_t>((n_new + FLIGHT_THREADS - 1) / FLIGHT_THREADS, beam_blocks_max);
       beam<<<blocks, FLIGHT_THREADS, wall_bytes, st>>>(c->M, P, P.q_beam, P.counts + C_NB, walls_smem);
@@ -1777,6 +1927,7 @@ static int run_rounds(hyp_ctx *c, int64_t first_id, int64_t n_photons, int64_t i
       flight<<<blocks, FLIGHT_THREADS, wall_bytes, st>>>(c->M, P, P.q_flight[cur], nF, walls_smem);
       CUDA_TRY(cudaGetLastError());
       c->launches_acc += 1;
+    }
     }
     CUDA_TRY(cudaEventRecord(c->evB, st));
     CUDA_TRY(cudaMemsetAsync(nF_next, 0, sizeof(uint32_t), st));
@@ -2098,8 +2249,12 @@ WallSmem wall_smem(const hyp_ctx *c) {
 template <int ND, bool POLY>
 int launch_peel(hyp_ctx *c, const ModelDev &M, uint32_t n_jobs_max) {
   if (c->n_views == 0 || n_jobs_max == 0) return HYP_OK;
-  const WallSmem ws = wall_smem(c);
-  auto k = peel_kernel<ND, POLY>;
+  WallSmem ws = wall_smem(c);
+  auto k = peel_kernel<ND, POLY, GEO_CAR>;
+  if (c->grid_type == GEO_SPH) {
+    k = peel_kernel<ND, POLY, GEO_SPH>;
+    ws = WallSmem{0, 0};
+  }
   CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ws.bytes));
   ImagingDev I{c->d_images, c->d_views, (int)c->groups.size(), c->n_views};
   const int64_t work = (int64_t)n_jobs_max * c->n_views;
@@ -2174,6 +2329,22 @@ int run_final_rounds(hyp_ctx *c, int64_t first_id, int64_t n_photons, int scatte
     }
     CUDA_TRY(cudaMemsetAsync(P.counts + C_NI, 0, 4 * sizeof(uint32_t), st));  // C_NI, C_NE, C_CURSOR, C_CURSOR_B
     CUDA_TRY(cudaEventRecord(c->evA, st));
+    if (c->grid_type == GEO_SPH) {
+      const int sph_blocks_max = c->sm_count * 12;
+      if (n_new > 0) {
+        int blocks = (int)std::min<int64_t>((n_new + SPH_FLIGHT_THREADS - 1) / SPH_FLIGHT_THREADS, sph_blocks_max);
+        flight_sph_kernel<ND, false, true><<<blocks, SPH_FLIGHT_THREADS, 0, st>>>(M, P, F, P.q_beam, P.counts + C_NB,
+                                                                                 P.counts + C_CURSOR_B, iteration);
+        c->launches_acc += 1;
+      }
+      if (n_flight_prev > 0) {
+        int blocks = (int)std::min<int64_t>(((int64_t)n_flight_prev + SPH_FLIGHT_THREADS - 1) / SPH_FLIGHT_THREADS, sph_blocks_max);
+        flight_sph_kernel<ND, false, true><<<blocks, SPH_FLIGHT_THREADS, 0, st>>>(M, P, F, P.q_flight[cur], nF,
+                                                                                 P.counts + C_CURSOR, iteration);
+        c->launches_acc += 1;
+      }
+      CUDA_TRY(cudaGetLastError());
+    } else {
     if (n_new > 0) {
       int blocks = (int)std::min<int64_t>((n_new + FLIGHT_THREADS - 1) / FLIGHT_THREADS, flight_blocks_max);
       flight<<<blocks, FLIGHT_THREADS, ws.bytes, st>>>(M, P, F, P.q_beam, P.counts + C_NB, P.counts + C_CURSOR_B, ws.on, iteration);
@@ -2185,6 +2356,7 @@ int run_final_rounds(hyp_ctx *c, int64_t first_id, int64_t n_photons, int scatte
       flight<<<blocks, FLIGHT_THREADS, ws.bytes, st>>>(M, P, F, P.q_flight[cur], nF, P.counts + C_CURSOR, ws.on, iteration);
       CUDA_TRY(cudaGetLastError());
       c->launches_acc += 1;
+    }
     }
     CUDA_TRY(cudaEventRecord(c->evB, st));
     CUDA_TRY(cudaMemsetAsync(nF_next, 0, sizeof(uint32_t), st));

@@ -260,16 +260,16 @@ __device__ __forceinline__ void bin_add(double *a, double *a2, double *an, size_
 constexpr int PEEL_THREADS = 256;
 constexpr int PEEL_LOOKAHEAD = 4;
 
-template <int ND, bool POLY>
+template <int ND, bool POLY, int GEO>
 __global__ void __launch_bounds__(PEEL_THREADS)
 peel_kernel(const ModelDev M, const ImagingDev I, const PeelJob<ND> *__restrict__ jobs,
             const uint32_t *__restrict__ n_jobs_ptr, const int walls_in_smem) {
   extern __shared__ double s_walls[];
   const int n1 = M.n1, n2 = M.n2, n3 = M.n3;
-  const double *__restrict__ W = stage_walls(M, s_walls, walls_in_smem);
+  const double *__restrict__ W = GEO == GEO_CAR ? stage_walls(M, s_walls, walls_in_smem) : nullptr;
   const uint32_t n_jobs = *n_jobs_ptr;
   const unsigned long long total = (unsigned long long)n_jobs * (unsigned)I.n_views;
-  uint32_t n_cross = 0, n_peel = 0;
+  uint32_t n_cross = 0, n_peel = 0, n_killed = 0;
   const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
   for (unsigned long long idx = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; idx < total; idx += stride) {
     const uint32_t ip = (uint32_t)(idx / n_jobs), ij = (uint32_t)(idx % n_jobs);
@@ -305,8 +305,12 @@ peel_kernel(const ModelDev M, const ImagingDev I, const PeelJob<ND> *__restrict_
     }
     // angle3d_to_vector3d of the viewing direction
     const double vx = a_req.sint * a_req.cosp, vy = a_req.sint * a_req.sinp, vz = a_req.cost;
-    int ix, iy, iz, ic;
-    if (!place_in_grid(M, J.rx, J.ry, J.rz, vx, vy, vz, ix, iy, iz, ic)) continue;
+    int ix = 0, iy = 0, iz = 0, ic = 0;
+    if (GEO == GEO_CAR) {
+      if (!place_in_grid(M, J.rx, J.ry, J.rz, vx, vy, vz, ix, iy, iz, ic)) continue;
+    } else {
+      if (!sph_find_cell(M.sph, J.rx, J.ry, J.rz, vx, vy, vz, ix, iy, iz)) continue;
+    }
     // depth along the line of sight and image-plane coordinates (images_peeled.f90:196-211)
     const double depth = -(vx * J.rx + vy * J.ry + vz * J.rz);
     if (depth < im.d_min || depth > im.d_max) continue;
@@ -318,11 +322,20 @@ peel_kernel(const ModelDev M, const ImagingDev I, const PeelJob<ND> *__restrict_
 #pragma unroll
     for (int id = 0; id < ND; ++id) col[id] = 0.0;
     if (!im.ignore_optical_depth) {
-      Lane<ND> L;
-      init_lane<ND>(L, J.rx, J.ry, J.rz, vx, vy, vz, ix, iy, iz, ic, W, n1 + 1, n1 + n2 + 2);
+      if (GEO == GEO_CAR) {
+        Lane<ND> L;
+        init_lane<ND>(L, J.rx, J.ry, J.rz, vx, vy, vz, ix, iy, iz, ic, W, n1 + 1, n1 + n2 + 2);
 #pragma unroll
-      for (int id = 0; id < ND; ++id) L.chi[id] = J.chi[id];
-      escape_march<ND, POLY, PEEL_LOOKAHEAD>(L, W, M.cells, n1, n2, n3, tau, col, n_cross);
+        for (int id = 0; id < ND; ++id) L.chi[id] = J.chi[id];
+        escape_march<ND, POLY, PEEL_LOOKAHEAD>(L, W, M.cells, n1, n2, n3, tau, col, n_cross);
+      } else {
+        SphRay R;
+        sph_start(M.sph, R, J.rx, J.ry, J.rz, vx, vy, vz, ix, iy, iz);
+        if (!sph_escape<ND, POLY>(M.sph, R, J.chi, M.cells, tau, col, n_cross)) {
+          ++n_killed;  // no wall found: the reference counts the packet as killed and drops the peel-off
+          continue;
+        }
+      }
     }
     ++n_peel;
     if (isnan(J.energy) || isnan(S.I)) continue;
@@ -384,6 +397,7 @@ peel_kernel(const ModelDev M, const ImagingDev I, const PeelJob<ND> *__restrict_
   }
   warp_add_scalar(M.scalars + SC_PEEL_CROSS, (double)n_cross);
   warp_add_scalar(M.scalars + SC_PEELOFFS, (double)n_peel);
+  if (GEO != GEO_CAR) warp_add_scalar(M.scalars + SC_KILLED_GEO, (double)n_killed);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -649,8 +663,7 @@ __global__ void energy_abs_tot_kernel(const ModelDev M, double *__restrict__ out
   for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x) {
     const int id = (int)(k % nd);
     const int64_t ic = k / nd;
-    const int i1 = (int)(ic % M.n1), i2 = (int)((ic / M.n1) % M.n2), i3 = (int)(ic / ((int64_t)M.n1 * M.n2));
-    const double vol = ((M.w1[i1 + 1] - M.w1[i1]) * (M.w2[i2 + 1] - M.w2[i2])) * (M.w3[i3 + 1] - M.w3[i3]);
+    const double vol = cell_volume(M, ic);
     const double v = M.specific_energy[k] * M.cells[k].rho * vol;
 #pragma unroll
     for (int d = 0; d < MAX_DUST; ++d) acc[d] += d == id ? v : 0.0;
@@ -686,13 +699,9 @@ __global__ void raytrace_emit_kernel(const ModelDev M, PeelJob<ND> *__restrict__
       rng.init(M.seed, first_dust_id + (i - n_src), ITER_RAY_DUST);
       const int id = max((int)ceil(rng.next() * (double)ND), 1) - 1;
       const int64_t ic = max((int64_t)ceil(rng.next() * (double)M.n_cells), (int64_t)1) - 1;
-      const int i1 = (int)(ic % M.n1), i2 = (int)((ic / M.n1) % M.n2), i3 = (int)(ic / ((int64_t)M.n1 * M.n2));
-      const double x0 = M.w1[i1], x1 = M.w1[i1 + 1], y0 = M.w2[i2], y1 = M.w2[i2 + 1], z0 = M.w3[i3], z1 = M.w3[i3 + 1];
-      p.r0x = rng.next() * (x1 - x0) + x0;
-      p.r0y = rng.next() * (y1 - y0) + y0;
-      p.r0z = rng.next() * (z1 - z0) + z0;
+      random_position_cell(M, ic, rng, p.r0x, p.r0y, p.r0z);
       const size_t k = (size_t)ic * ND + id;
-      const double vol = ((x1 - x0) * (y1 - y0)) * (z1 - z0);
+      const double vol = cell_volume(M, ic);
       const double etot = energy_abs_tot[id];
       p.energy = 0.0;
       if (etot > 0.0) p.energy = M.specific_energy[k] * (M.cells[k].rho * vol) * (double)M.n_cells / etot;

@@ -167,6 +167,13 @@ void hyp_ctx_destroy(hyp_ctx *ctx);
 int hyp_set_grid_cartesian(hyp_ctx *ctx, int32_t n1, int32_t n2, int32_t n3,
                            const double *w1, const double *w2, const double *w3);
 
+/* replaces: setup_grid_geometry (src/grid/grid_geometry_spherical_3d.f90:92-203).
+ * w1 = r walls (n1+1), w2 = theta walls in [0, pi] (n2+1), w3 = phi walls in [0, 2 pi] (n3+1)
+ * (Grid/Geometry walls_1 'r', walls_2 't', walls_3 'p' of a 'sph_pol' grid).  Cell ids and the
+ * density layout are as for Cartesian grids: density[n_dust][n3][n2][n1], r fastest. */
+int hyp_set_grid_spherical(hyp_ctx *ctx, int32_t n1, int32_t n2, int32_t n3,
+                           const double *w1, const double *w2, const double *w3);
+
 /* replaces: dust_setup (src/dust/dust_type_4elem.f90:78-293); call once per dust type, in order */
 int hyp_add_dust(hyp_ctx *ctx, const hyp_dust_tables *dust);
 
@@ -196,8 +203,8 @@ int hyp_finalize_setup(hyp_ctx *ctx);
 int hyp_lucy_begin(hyp_ctx *ctx);
 int hyp_lucy_photons(hyp_ctx *ctx, int64_t first_id, int64_t n_photons, int64_t iteration);
 /* Device pointers for the host's collective: sum grid [n_dust*n_cells] fp64 followed
- * directly by 8 fp64 scalars (energy_emitted, killed_geo, killed_int, crossings,
- * absorptions, scatterings, escaped, photons); n_values = n_dust*n_cells + 8.
+ * directly by 10 fp64 scalars (energy_emitted, killed_geo, killed_int, crossings,
+ * absorptions, scatterings, escaped, photons, peel crossings, peel-offs); n_values = n_dust*n_cells + 10.
  * replaces: mp_collect_physical_arrays + mp_sync (src/mpi/mpi_routines.f90:272-361) */
 int hyp_lucy_device_buffers(hyp_ctx *ctx, void **sum_and_scalars, int64_t *n_values);
 int hyp_lucy_finish(hyp_ctx *ctx, hyp_iter_stats *stats);
@@ -226,7 +233,7 @@ int hyp_final_finish(hyp_ctx *ctx, hyp_iter_stats *stats);
 int hyp_raytracing_photons(hyp_ctx *ctx, int64_t first_source_id, int64_t n_sources, int64_t n_total_sources,
                            int64_t first_dust_id, int64_t n_dust, int64_t n_total_dust, hyp_iter_stats *stats);
 /* All image / SED accumulators of all groups as one contiguous device buffer (fp64) followed by
- * 8 scalars, for the host's collective.  replaces: mp_collect_images (src/mpi/mpi_routines.f90:363-471) */
+ * the same 10 scalars, for the host's collective.  replaces: mp_collect_images (src/mpi/mpi_routines.f90:363-471) */
 int hyp_image_device_buffers(hyp_ctx *ctx, void **buffer, int64_t *n_values);
 /* Shapes in file order: seds (n_stokes, n_orig, n_view, n_ap, n_wav), images (n_stokes, n_orig,
  * n_view, n_y, n_x, n_wav) (src/images/image_type.f90:291,299 reversed, as HDF5 stores them). */

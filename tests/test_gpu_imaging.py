@@ -9,7 +9,7 @@ from concurrent.futures import ThreadPoolExecutor
 import numpy as np
 import pytest
 
-from helpers import peeloff_model, bitlevel_model, peeloff_groups, pc
+from helpers import peeloff_model, peeloff_model_sph, bitlevel_model, peeloff_groups, pc
 
 pytestmark = pytest.mark.gpu
 
@@ -108,6 +108,22 @@ def test_peeloff_matches_oracle(golden_car, raytracing):
             a = np.mean([g[2][key] for g in gpu])
             b = np.mean([o[2][key] for o in orc])
             assert abs(a / b - 1) < 0.02, (key, a, b)
+
+
+@pytest.mark.parametrize("raytracing", [False, True])
+def test_peeloff_matches_oracle_spherical_grid(golden_car, golden_sph, raytracing):
+    """test_peeloff on the reference's spherical polar grid: peel-off rays cross spheres, cones and
+    phi planes; the thermal raytracing packets start at random positions of (r, theta, phi) cells."""
+    model = peeloff_model_sph(golden_car, golden_sph, False)
+    model.specific_energy = _converged_energy(model)
+    B = 12
+    gpu, orc = _run_both(model, B, 60000, raytracing, (20000, 30000) if raytracing else None)
+    print(_compare(gpu, orc))
+    for key in ("n_crossings", "n_absorptions", "n_scatterings", "n_peeloffs", "n_peel_crossings"):
+        a = np.mean([g[1][key] for g in gpu])
+        b = np.mean([o[1][key] for o in orc])
+        assert abs(a / b - 1) < 0.02, (key, a, b)
+    assert all(g[1]["killed_geo"] == 0 and g[1]["n_photons"] == 60000 for g in gpu)
 
 
 def test_peeloff_multiple_dust_and_even_sampling(golden_car):

@@ -10,7 +10,7 @@ estimates (|z| bounded, z^2 averaging to 1).
 import numpy as np
 import pytest
 
-from helpers import bitlevel_model, pc, lsun
+from helpers import bitlevel_model, bitlevel_model_sph, kmh_dust, pc, lsun
 
 pytestmark = pytest.mark.gpu
 
@@ -210,3 +210,55 @@ def test_path_length_estimator_consistency_large_grid():
     est = float((sums * model.density).sum())
     assert st.n_photons == N and st.n_escaped + st.killed_int == N
     assert abs(est / st.n_absorptions - 1) < 0.01, (est, st.n_absorptions)
+
+
+@pytest.mark.parametrize("evenly,multi", [(False, False), (True, True)])
+def test_deposits_match_oracle_spherical_grid(golden_car, golden_sph, evenly, multi):
+    """The reference's bit-level model on its spherical polar grid (test_bit_level.py:58-62: 5 x 7 x 3
+    cells in r, theta, phi, sources off-centre): sphere, cone and phi-plane crossings, periodic phi."""
+    model = bitlevel_model_sph(golden_car, golden_sph, evenly, multi)
+    B, N = 16, 100000
+    g, gst = _gpu_batches(model, N, B)
+    o, ost = _oracle_batches(model, N, B)
+    z, ok = _zscores(g, o)
+    assert ok.all()
+    assert np.abs(z).max() < 5.0, np.abs(z).max()
+    assert 0.6 < (z ** 2).mean() < 1.5, (z ** 2).mean()
+    rel = np.abs(g.mean(0) / o.mean(0) - 1)
+    assert np.median(rel) < 0.03
+    for key in ("n_crossings", "n_absorptions", "n_scatterings"):
+        a = np.mean([s[key] for s in gst])
+        b = np.mean([s[key] for s in ost])
+        assert abs(a / b - 1) < 0.01, (key, a, b)
+    assert all(s["killed_geo"] == 0 and s["killed_int"] == 0 for s in gst)
+    assert all(s["n_photons"] == N for s in gst)
+
+
+def test_axisymmetric_grid_with_central_source(golden_car):
+    """The usual YSO set-up: (r, theta) grid with a single phi cell, a theta wall exactly on the
+    midplane (treated as a plane, grid_geometry_spherical_3d.f90:856-861), log-spaced radii starting
+    at r = 0 and the source AT the origin, where theta and phi of the cell come from the direction of
+    flight (:224-245) and the packet starts on the inner radial wall."""
+    from hyperion_b200.flatmodel import FlatConf, FlatModel, FlatSource
+    rng = np.random.default_rng(5)
+    n_r, n_t = 24, 16
+    w1 = np.hstack([0., np.logspace(-2, 0, n_r) * pc])
+    w2 = np.linspace(0., np.pi, n_t + 1)
+    w3 = np.array([0., 2 * np.pi])
+    # flared-disk-like density contrast: dense towards the midplane
+    theta_c = 0.5 * (w2[1:] + w2[:-1])
+    dens = 3e-21 * np.exp(-0.5 * ((theta_c - np.pi / 2) / 0.4) ** 2)[None, :, None] * (1 + rng.random((1, n_t, n_r)))
+    src = [FlatSource(type=1, luminosity=lsun, temperature=5000., position=(0., 0., 0.))]
+    model = FlatModel(w1, w2, w3, dens, [kmh_dust(golden_car)], src, FlatConf(), grid_type="sph")
+    B, N = 12, 100000
+    g, gst = _gpu_batches(model, N, B)
+    o, ost = _oracle_batches(model, N, B)
+    z, ok = _zscores(g, o)
+    assert ok.mean() > 0.95
+    assert np.abs(z[ok]).max() < 5.5, np.abs(z[ok]).max()
+    assert 0.6 < (z[ok] ** 2).mean() < 1.5, (z[ok] ** 2).mean()
+    for key in ("n_crossings", "n_absorptions", "n_scatterings"):
+        a = np.mean([s[key] for s in gst])
+        b = np.mean([s[key] for s in ost])
+        assert abs(a / b - 1) < 0.01, (key, a, b)
+    assert all(s["killed_geo"] == 0 for s in gst) and all(s["killed_geo"] == 0 for s in ost)
