@@ -162,12 +162,25 @@ def read_rtin(filename):
     geo = f["Grid/Geometry"]
     rs.grid_type = _s(geo.attrs["grid_type"])
     rs.geometry_id = _s(geo.attrs["geometry"])
-    if rs.grid_type != "car":
-        raise ModelError("grid type '%s' is not implemented by this engine yet (Cartesian only)" % rs.grid_type)
-    w1 = np.asarray(geo["walls_1"][...]["x"], dtype=np.float64)
-    w2 = np.asarray(geo["walls_2"][...]["y"], dtype=np.float64)
-    w3 = np.asarray(geo["walls_3"][...]["z"], dtype=np.float64)
-    for w, nm in ((w1, "dx"), (w2, "dy"), (w3, "dz")):
+    if rs.grid_type == "car":
+        cols, names, grid_type = ("x", "y", "z"), ("dx", "dy", "dz"), "car"
+    elif rs.grid_type == "sph_pol":
+        # grid_geometry_spherical_3d.f90:111-128
+        cols, names, grid_type = ("r", "t", "p"), ("dr", "dt", "dphi"), "sph"
+    else:
+        raise ModelError("grid type '%s' is not implemented by this engine yet (Cartesian and spherical polar only)"
+                         % rs.grid_type)
+    w1 = np.asarray(geo["walls_1"][...][cols[0]], dtype=np.float64)
+    w2 = np.asarray(geo["walls_2"][...][cols[1]], dtype=np.float64)
+    w3 = np.asarray(geo["walls_3"][...][cols[2]], dtype=np.float64)
+    if grid_type == "sph":
+        if np.any(w1 < 0.):
+            raise ModelError("r walls should be positive")
+        if np.any(w2 < 0.) or np.any(w2 > np.pi):
+            raise ModelError("theta walls should be between 0 and pi")
+        if np.any(w3 < 0.) or np.any(w3 > 2 * np.pi):
+            raise ModelError("phi walls should be between 0 and 2*pi")
+    for w, nm in zip((w1, w2, w3), names):
         if np.any(np.diff(w) <= 0):
             raise ModelError("all %s values should be greater than zero" % nm)
 
@@ -247,7 +260,8 @@ def read_rtin(filename):
     if not sources and rs.n_last_photons > 0:
         raise ModelError("no sources set up - need sources for last iteration")
 
-    model = FlatModel(w1, w2, w3, density, dust, sources, conf, specific_energy=se, minimum_specific_energy=min_e)
+    model = FlatModel(w1, w2, w3, density, dust, sources, conf, specific_energy=se, minimum_specific_energy=min_e,
+                      grid_type=grid_type)
     model.peeled = read_peeled_groups(f)
     if "Output" in f and "Binned" in f["Output"] and len(f["Output"]["Binned"].keys()) > 0:
         if rs.forced_first_interaction:

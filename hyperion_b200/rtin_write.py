@@ -139,10 +139,12 @@ def write_rtin(filename, model: FlatModel, n_initial_iter=5, n_initial_photons=1
         h.update(np.ascontiguousarray(w).tobytes())
     gid = h.hexdigest()
     geo.attrs["geometry"] = gid
-    geo.attrs["grid_type"] = "car"
-    geo.create_dataset("walls_1", _table([("x", model.w1)]))
-    geo.create_dataset("walls_2", _table([("y", model.w2)]))
-    geo.create_dataset("walls_3", _table([("z", model.w3)]))
+    # hyperion/grid/cartesian_grid.py:336-343, hyperion/grid/spherical_polar_grid.py (write)
+    cols = ("r", "t", "p") if model.grid_type == "sph" else ("x", "y", "z")
+    geo.attrs["grid_type"] = "sph_pol" if model.grid_type == "sph" else "car"
+    geo.create_dataset("walls_1", _table([(cols[0], model.w1)]))
+    geo.create_dataset("walls_2", _table([(cols[1], model.w2)]))
+    geo.create_dataset("walls_3", _table([(cols[2], model.w3)]))
     q = f.create_group("Grid/Quantities")
     d = q.create_dataset("density", model.density)
     d.attrs["geometry"] = gid

@@ -339,7 +339,7 @@ def main(argv=None):
         overwrite = True
         argv = argv[1:]
     if len(argv) != 2:
-        sys.stderr.write("Usage: hyperion_car [-f] input_file output_file\n")
+        sys.stderr.write("Usage: hyperion_car|hyperion_sph [-f] input_file output_file\n")
         return 2
     from .capi import HyperionError
     try:

@@ -151,3 +151,36 @@ def test_runner_writes_peeled_groups(golden_car, tmp_path):
     sed2 = r["Peeled/group_00002/seds"][...]
     # (re-emitted IR light is practically not scattered by this dust: the oracle leaves slice 4 empty too)
     assert (sed2[0, :3, 0, -1, :].sum(axis=-1) > 0).all()
+
+
+def test_rtin_roundtrip_spherical_grid(golden_car, golden_sph, tmp_path):
+    """Grid/Geometry of a 'sph_pol' grid: walls_1 'r', walls_2 't', walls_3 'p'
+    (hyperion/grid/spherical_polar_grid.py:371-380, grid_geometry_spherical_3d.f90:111-128)."""
+    from helpers import bitlevel_model_sph
+    m = bitlevel_model_sph(golden_car, golden_sph, False, True)
+    fn = str(tmp_path / "m.rtin")
+    rtin_write.write_rtin(fn, m)
+    got, rs, _ = rtin.read_rtin(fn)
+    assert rs.grid_type == "sph_pol" and got.grid_type == "sph"
+    for k in ("w1", "w2", "w3", "density"):
+        assert np.array_equal(getattr(got, k), getattr(m, k))
+    assert np.allclose(got.volumes().sum(), 4. / 3. * np.pi * m.w1[-1] ** 3, rtol=1e-12)
+    m.w2[0] = -0.1
+    rtin_write.write_rtin(fn, m)
+    with pytest.raises(rtin.ModelError, match="theta walls should be between 0 and pi"):
+        rtin.read_rtin(fn)
+
+
+@pytest.mark.gpu
+def test_runner_spherical_grid(golden_car, golden_sph, tmp_path):
+    """hyperion_sph: the same binary drives spherical polar grids (scripts/hyperion:44-92 picks the
+    back end from grid_type)."""
+    from helpers import peeloff_model_sph
+    m = peeloff_model_sph(golden_car, golden_sph, False)
+    fin, fout = str(tmp_path / "m.rtin"), str(tmp_path / "m.rtout")
+    rtin_write.write_rtin(fin, m, n_initial_iter=2, n_initial_photons=20000, n_last_photons=20000)
+    assert runner.main(["-f", fin, fout]) == 0
+    r = h5min.File(fout)
+    se = r["iteration_00002/specific_energy"][...]
+    assert se.shape == (1, 3, 7, 5) and np.all(se > 0)
+    assert r["Peeled/group_00001/seds"][...][0].sum() > 0
