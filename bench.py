@@ -40,6 +40,8 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-thin", action="store_true", help="skip the optically thin variant")
     ap.add_argument("--thin-tau", type=float, default=0.01)
+    ap.add_argument("--no-imaging", action="store_true", help="skip the imaging-iteration variant")
+    ap.add_argument("--imaging-photons", type=float, default=2.0e6)
     return ap.parse_args()
 
 
@@ -317,6 +319,39 @@ def main():
                 "crossings_per_packet": c2 / (P * a.steps)}
         eng2.close()
 
+    # the imaging iteration on the same grid (do_final + peel-off): every
+    # emission and interaction is peeled towards 4 observers; unit = cell crossings at 8 B each
+    imaging = None
+    if not a.no_imaging:
+        from hyperion_b200.flatmodel import FlatPeeledGroup
+        m3 = build_model(a)
+        half = float(m3.w1[-1])
+        m3.peeled = [FlatPeeledGroup(theta=[30., 60., 90., 140.], phi=[10., 80., 200., 300.],
+                                     wavelengths=(50, 0.1, 1000.), image=(256, 256, -half, half, -half, half),
+                                     sed=(1, 2 * half, 2 * half), stokes=True)]
+        eng3 = Engine(local)
+        eng3.load_model(m3)
+        Pi = int(a.imaging_photons)
+        st3 = None
+        for rep in range(2):       # first pass is the warm-up
+            sync_all()
+            t0 = time.time()
+            eng3.final_begin()
+            eng3.final_photons((rank + world * rep) * Pi, Pi, False)
+            st3 = eng3.final_finish()
+            sync_all()
+            wall = time.time() - t0
+        cr = st3.n_crossings + st3.n_peel_crossings
+        peak, _ = peaks()
+        imaging = {"workload": "imaging_iteration_" + workload_name(a) + "_4_views_256x256x50",
+                   "value": Pi / (st3.kernel_ms * 1e-3), "unit": "packets/s per GPU", "ms_per_step": st3.kernel_ms,
+                   "wall_ms": wall * 1e3, "peeloffs_per_packet": st3.n_peeloffs / Pi,
+                   "crossings_per_packet": cr / Pi, "bytes_per_crossing": 8,
+                   "roofline_achieved": 8.0 * cr / (st3.kernel_ms * 1e-3) / 1e9,
+                   "roofline_frac": 8.0 * cr / (st3.kernel_ms * 1e-3) / 1e9 / peak,
+                   "gpu_launches": int(st3.n_launches)}
+        eng3.close()
+
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
         cores = os.cpu_count() or 1
@@ -353,8 +388,9 @@ def main():
         }
         if e2e:
             line["e2e"] = e2e
-        if thin:
-            line["other_workloads"] = [thin]
+        others = [w for w in (thin, imaging) if w]
+        if others:
+            line["other_workloads"] = others
         if cpu:
             line["cpu_baseline"] = cpu
         print(json.dumps(line), flush=True)

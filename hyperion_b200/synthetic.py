@@ -187,3 +187,47 @@ def cartesian_point_source_model(n=256, tau_edge=1.0, dust=None, temperature=600
     src = FlatSource(type=1, luminosity=lsun, temperature=temperature, position=(0., 0., 0.))
     conf = FlatConf(n_initial_iter=n_iter, n_initial_photons=n_photons)
     return FlatModel(w, w, w, rho, [dust], [src], conf)
+
+
+def spherical_disk_model(n_r=399, n_theta=199, n_phi=1, tau_edge=10.0, dust=None, temperature=4000.,
+                         lam_ref_um=0.5, n_photons=0, n_iter=1):
+    """SURVEY.md section 8d 'C3': spherical polar (r, theta[, phi]) grid of a flared disk as the
+    AnalyticalYSOModel front end lays it out (hyperion/model/analytical_yso_model.py:490-626: r walls
+    [0, rmin, rmin (1 + logspace)], theta walls linspace(0, pi) + sin(2 theta)/6, which concentrates
+    cells towards the midplane; hyperion/densities/flared_disk.py:286-351: rho ~ (r0/w)^(beta-p)
+    exp(-(z/h)^2/2), h = h0 (w/r0)^beta).  The density is scaled so that the midplane optical depth
+    from rmin to rmax at ``lam_ref_um`` is ``tau_edge``.  A point source sits at the origin (the
+    spherical stellar source of the tutorial model is not implemented on the device yet)."""
+    if dust is None:
+        dust = realistic_dust(n_temp=200)
+    rstar = 2. * rsun
+    rmin, rmax = 10. * rstar, 200. * au
+    beta, p, r0, h0 = 1.25, -1.0, 100. * au, 10. * au
+    rnext = rmin * 1.e-3
+    w1 = np.hstack([0., rmin, rmin * (1. + np.logspace(np.log10(rnext / rmin), np.log10((rmax - rmin) / rmin), n_r - 1))])
+    t = np.linspace(0., np.pi, n_theta + 1)
+    w2 = t + np.sin(2. * t) / 6.
+    w2[0], w2[-1] = 0., np.pi
+    if n_theta % 2 == 0:
+        w2[n_theta // 2] = np.pi / 2.
+    w3 = np.linspace(0., 2. * np.pi, n_phi + 1)
+    rc = np.sqrt(np.maximum(w1[:-1], 1e-30) * w1[1:])
+    rc[0] = 0.5 * w1[1]
+    tc = 0.5 * (w2[:-1] + w2[1:])
+    R, T = np.meshgrid(rc, tc)                       # [n_theta, n_r]
+    w = R * np.sin(T)
+    z = R * np.cos(T)
+    with np.errstate(divide="ignore", invalid="ignore", over="ignore"):
+        h = h0 * (w / r0) ** beta
+        rho = (r0 / w) ** (beta - p) * np.exp(-0.5 * (z / h) ** 2)
+    rho[~np.isfinite(rho)] = 0.
+    rho[(w < rmin) | (w > rmax)] = 0.
+    # midplane optical depth: integrate along the row closest to theta = pi/2
+    chi0 = chi_at(dust, c / (lam_ref_um * 1.e-4))
+    imid = int(np.argmin(np.abs(tc - np.pi / 2.)))
+    tau_mid = float((rho[imid] * np.diff(w1)).sum() * chi0)
+    rho *= tau_edge / tau_mid
+    rho = np.broadcast_to(rho[None, None], (1, n_phi, n_theta, n_r)).copy()
+    src = FlatSource(type=1, luminosity=lsun, temperature=temperature, position=(0., 0., 0.))
+    conf = FlatConf(n_initial_iter=n_iter, n_initial_photons=n_photons)
+    return FlatModel(w1, w2, w3, rho, [dust], [src], conf, grid_type="sph")
