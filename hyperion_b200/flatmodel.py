@@ -167,7 +167,7 @@ class FlatModel:
     specific_energy: Optional[np.ndarray] = None
     minimum_specific_energy: Optional[np.ndarray] = None
     peeled: List["FlatPeeledGroup"] = field(default_factory=list)
-    grid_type: str = "car"              # "car" (x, y, z walls) or "sph" (r, theta, phi walls)
+    grid_type: str = "car"              # "car" (x, y, z walls), "sph" (r, theta, phi) or "cyl" (w, z, phi)
 
     def __post_init__(self):
         self.w1, self.w2, self.w3 = _f8(self.w1), _f8(self.w2), _f8(self.w3)
@@ -193,6 +193,10 @@ class FlatModel:
             # grid_geometry_spherical_3d.f90:147-160
             dr3, dcost, dphi = np.diff(self.w1 ** 3), -np.diff(np.cos(self.w2)), np.diff(self.w3)
             return dr3[None, None, :] * dcost[None, :, None] * dphi[:, None, None] / 3.
+        if self.grid_type == "cyl":
+            # grid_geometry_cylindrical_3d.f90:141-147
+            dw2, dz, dphi = np.diff(self.w1 ** 2), np.diff(self.w2), np.diff(self.w3)
+            return dw2[None, None, :] * dz[None, :, None] * dphi[:, None, None] / 2.
         dx, dy, dz = np.diff(self.w1), np.diff(self.w2), np.diff(self.w3)
         return (dx[None, None, :] * dy[None, :, None]) * dz[:, None, None]
 
@@ -205,6 +209,8 @@ def apply_model(api, ctx, model: FlatModel):
     n3, n2, n1 = model.shape
     if model.grid_type == "sph":
         api.set_grid_spherical(ctx, n1, n2, n3, model.w1, model.w2, model.w3)
+    elif model.grid_type == "cyl":
+        api.set_grid_cylindrical(ctx, n1, n2, n3, model.w1, model.w2, model.w3)
     else:
         api.set_grid_cartesian(ctx, n1, n2, n3, model.w1, model.w2, model.w3)
     for d in model.dust:

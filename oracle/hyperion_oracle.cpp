@@ -1022,7 +1022,8 @@ struct orc_ctx {
   // find_wall scratch (:29-30)
   double tmin = 0, emin = 0;
   WallId imin, iext;
-  // geometry kind: 0 Cartesian, 1 spherical polar (grid_geometry_spherical_3d.f90)
+  // geometry kind: 0 Cartesian, 1 spherical polar (grid_geometry_spherical_3d.f90),
+  // 2 cylindrical polar (grid_geometry_cylindrical_3d.f90)
   int grid_type = 0;
   bool radial = false;  // the 'radial' argument of the spherical find_wall (grid_propagate_3d.f90:73)
   std::vector<double> wr2, wtanp, wtant, wcost, wsint, wtant2;  // (:169-185)
@@ -1074,6 +1075,7 @@ Cell new_grid_cell(const orc_ctx &g, int i1, int i2, int i3) {
 bool escaped(const orc_ctx &g, const Cell &c) {
   if (c.i1 < 1 || c.i1 > g.n1) return true;
   if (g.grid_type == 1) return false;  // spherical: radial escape only (grid_geometry_spherical_3d.f90:493-500)
+  if (g.grid_type == 2) return c.i2 < 1 || c.i2 > g.n2;  // cylindrical: w and z (grid_geometry_cylindrical_3d.f90:375-384)
   if (c.i2 < 1 || c.i2 > g.n2) return true;
   if (c.i3 < 1 || c.i3 > g.n3) return true;
   return false;
@@ -1084,9 +1086,14 @@ bool sph_find_cell(const orc_ctx &g, const Photon &p, Cell &out);
 void sph_adjust_wall(const orc_ctx &g, Photon &p);
 bool sph_in_correct_cell(const orc_ctx &g, const Photon &p);
 void sph_find_wall(orc_ctx &g, const Photon &p, double &tnearest, WallId &id_min);
+bool cyl_find_cell(const orc_ctx &g, const Photon &p, Cell &out);
+void cyl_adjust_wall(const orc_ctx &g, Photon &p);
+bool cyl_in_correct_cell(const orc_ctx &g, const Photon &p);
+void cyl_find_wall(orc_ctx &g, const Photon &p, double &tnearest, WallId &id_min);
 
 bool find_cell(const orc_ctx &g, const Photon &p, Cell &out) {
   if (g.grid_type == 1) return sph_find_cell(g, p, out);
+  if (g.grid_type == 2) return cyl_find_cell(g, p, out);
   int i1 = locate(g.w1.data(), g.n1 + 1, p.r.x);
   int i2 = locate(g.w2.data(), g.n2 + 1, p.r.y);
   int i3 = locate(g.w3.data(), g.n3 + 1, p.r.z);
@@ -1101,6 +1108,10 @@ bool find_cell(const orc_ctx &g, const Photon &p, Cell &out) {
 void adjust_wall(const orc_ctx &g, Photon &p) {
   if (g.grid_type == 1) {
     sph_adjust_wall(g, p);
+    return;
+  }
+  if (g.grid_type == 2) {
+    cyl_adjust_wall(g, p);
     return;
   }
   p.on_wall = false;
@@ -1145,6 +1156,7 @@ void place_in_cell(orc_ctx &g, Photon &p) {
 // in_correct_cell (grid_geometry_cartesian_3d.f90:330-381)
 bool in_correct_cell(const orc_ctx &g, const Photon &p) {
   if (g.grid_type == 1) return sph_in_correct_cell(g, p);
+  if (g.grid_type == 2) return cyl_in_correct_cell(g, p);
   const double threshold = 1.e-3;
   Cell act;
   bool valid = find_cell(g, p, act);
@@ -1203,6 +1215,10 @@ void find_wall(orc_ctx &g, const Photon &p, double &tnearest, WallId &id_min) {
     sph_find_wall(g, p, tnearest, id_min);
     return;
   }
+  if (g.grid_type == 2) {
+    cyl_find_wall(g, p, tnearest, id_min);
+    return;
+  }
   g.tmin = std::numeric_limits<double>::max();
   g.emin = 0.0;
   g.imin = WallId();
@@ -1249,7 +1265,7 @@ Cell next_cell(const orc_ctx &g, const Cell &c, const WallId &dir) {
     i3 = i3 - 1;
   else if (dir.w3 == +1)
     i3 = i3 + 1;
-  if (g.grid_type == 1) {  // phi is periodic (grid_geometry_spherical_3d.f90:549-555)
+  if (g.grid_type == 1 || g.grid_type == 2) {  // phi is periodic (grid_geometry_spherical_3d.f90:549-555)
     if (i3 == 0) i3 = g.n3;
     if (i3 == g.n3 + 1) i3 = 1;
   }
@@ -1601,6 +1617,245 @@ Vec sph_random_position_cell(orc_ctx &g, const Cell &c) {
   if (t <= g.w2[c.i2 - 1] || t >= g.w2[c.i2]) t = 0.5 * (g.w2[c.i2 - 1] + g.w2[c.i2]);
   if (ph <= g.w3[c.i3 - 1] || ph >= g.w3[c.i3]) ph = 0.5 * (g.w3[c.i3 - 1] + g.w3[c.i3]);
   return Vec{r * std::sin(t) * std::cos(ph), r * std::sin(t) * std::sin(ph), r * std::cos(t)};
+}
+
+// ---------------------------------------------------------------------------
+// cylindrical polar geometry (src/grid/grid_geometry_cylindrical_3d.f90): walls w (cylinders), z (planes),
+// phi (half-planes)
+// ---------------------------------------------------------------------------
+void cyl_phi(const Photon &p, double &w_sq, double &phi) {
+  w_sq = p.r.x * p.r.x + p.r.y * p.r.y;
+  if (w_sq == 0.0) {
+    phi = std::atan2(p.v.y, p.v.x);
+    if (phi < 0.0) phi = phi + TWOPI_F;
+  } else {
+    phi = std::atan2(p.r.y, p.r.x);
+    if (phi < 0.0) phi = phi + TWOPI_F;
+  }
+}
+
+// find_cell (:184-237)
+bool cyl_find_cell(const orc_ctx &g, const Photon &p, Cell &out) {
+  double w_sq, phi;
+  cyl_phi(p, w_sq, phi);
+  int i1 = locate(g.wr2.data(), g.n1 + 1, w_sq);
+  int i2 = locate(g.w2.data(), g.n2 + 1, p.r.z);
+  int i3 = locate(g.w3.data(), g.n3 + 1, phi);
+  if (i1 < 1 || i1 > g.n1) return false;
+  if (i2 < 1 || i2 > g.n2) return false;
+  if (i3 < 1 || i3 > g.n3) return false;
+  out = new_grid_cell(g, i1, i2, i3);
+  return true;
+}
+
+// adjust_wall (:239-346)
+void cyl_adjust_wall(const orc_ctx &g, Photon &p) {
+  const int eps = 3;
+  p.on_wall = false;
+  p.on_wall_id = WallId();
+  double w_sq, phi;
+  cyl_phi(p, w_sq, phi);
+  if ((p.r.x * p.v.x + p.r.y * p.v.y) >= 0.0) {
+    if (equal_nulp(w_sq, g.wr2[p.icell.i1 - 1], eps)) {
+      p.on_wall_id.w1 = -1;
+    } else if (equal_nulp(w_sq, g.wr2[p.icell.i1], eps)) {
+      p.on_wall_id.w1 = -1;
+      p.icell.i1 = p.icell.i1 + 1;
+    }
+  } else {
+    if (equal_nulp(w_sq, g.wr2[p.icell.i1 - 1], eps)) {
+      p.on_wall_id.w1 = +1;
+      p.icell.i1 = p.icell.i1 - 1;
+    } else if (equal_nulp(w_sq, g.wr2[p.icell.i1], eps)) {
+      p.on_wall_id.w1 = +1;
+    }
+  }
+  if (p.v.z > 0.0) {
+    if (equal_nulp(p.r.z, g.w2[p.icell.i2 - 1], eps)) {
+      p.on_wall_id.w2 = -1;
+    } else if (equal_nulp(p.r.z, g.w2[p.icell.i2], eps)) {
+      p.on_wall_id.w2 = -1;
+      p.icell.i2 = p.icell.i2 + 1;
+    }
+  } else if (p.v.z < 0.0) {
+    if (equal_nulp(p.r.z, g.w2[p.icell.i2 - 1], eps)) {
+      p.on_wall_id.w2 = +1;
+      p.icell.i2 = p.icell.i2 - 1;
+    } else if (equal_nulp(p.r.z, g.w2[p.icell.i2], eps)) {
+      p.on_wall_id.w2 = +1;
+    }
+  }
+  if (p.r.x == 0.0 && p.r.y == 0.0 && p.v.x == 0.0 && p.v.y == 0.0) {
+    // on every phi wall at once
+  } else if (equal_nulp(phi, g.w3[p.icell.i3 - 1], eps)) {
+    double phi_v = std::atan2(p.v.y, p.v.x);
+    double dphi = phi_v - g.w3[p.icell.i3 - 1];
+    if (dphi < -PI_F) dphi = dphi + TWOPI_F;
+    if (dphi > 0.0) {
+      p.on_wall_id.w3 = -1;
+    } else {
+      p.on_wall_id.w3 = +1;
+      p.icell.i3 = p.icell.i3 - 1;
+      if (p.icell.i3 == 0) p.icell.i3 = g.n3;
+    }
+  } else if (equal_nulp(phi, g.w3[p.icell.i3], eps)) {
+    double phi_v = std::atan2(p.v.y, p.v.x);
+    double dphi = phi_v - g.w3[p.icell.i3];
+    if (dphi < -PI_F) dphi = dphi + TWOPI_F;
+    if (dphi > 0.0) {
+      p.on_wall_id.w3 = -1;
+      p.icell.i3 = p.icell.i3 + 1;
+      if (p.icell.i3 == g.n3 + 1) p.icell.i3 = 1;
+    } else {
+      p.on_wall_id.w3 = +1;
+    }
+  }
+  p.on_wall = p.on_wall_id.w1 != 0 || p.on_wall_id.w2 != 0 || p.on_wall_id.w3 != 0;
+}
+
+// in_correct_cell (:443-514)
+bool cyl_in_correct_cell(const orc_ctx &g, const Photon &p) {
+  const double threshold = 1.e-3;
+  Cell act;
+  bool valid = cyl_find_cell(g, p, act);
+  if (!valid) act = Cell{-1, -1, -1, -1};
+  if (!p.on_wall) return act.i1 == p.icell.i1 && act.i2 == p.icell.i2 && act.i3 == p.icell.i3;
+  bool ok = true;
+  double w_sq, phi, frac, dphi;
+  cyl_phi(p, w_sq, phi);
+  if (p.on_wall_id.w1 == -1) {
+    if (g.w1[p.icell.i1 - 1] != std::sqrt(w_sq)) {
+      frac = std::sqrt(w_sq) / g.w1[p.icell.i1 - 1] - 1.0;
+      ok = ok && std::fabs(frac) < threshold;
+    }
+  } else if (p.on_wall_id.w1 == +1) {
+    if (g.w1[p.icell.i1] != std::sqrt(w_sq)) {
+      frac = std::sqrt(w_sq) / g.w1[p.icell.i1] - 1.0;
+      ok = ok && std::fabs(frac) < threshold;
+    }
+  } else {
+    ok = ok && act.i1 == p.icell.i1;
+  }
+  if (p.on_wall_id.w2 == -1) {
+    frac = (p.r.z - g.w2[p.icell.i2 - 1]) / (g.w2[p.icell.i2] - g.w2[p.icell.i2 - 1]);
+    ok = ok && std::fabs(frac) < threshold;
+  } else if (p.on_wall_id.w2 == +1) {
+    frac = (p.r.z - g.w2[p.icell.i2]) / (g.w2[p.icell.i2] - g.w2[p.icell.i2 - 1]);
+    ok = ok && std::fabs(frac) < threshold;
+  } else {
+    ok = ok && act.i2 == p.icell.i2;
+  }
+  if (p.on_wall_id.w3 == -1) {
+    dphi = phi - g.w3[p.icell.i3 - 1];
+    if (dphi > PI_F) dphi = dphi - TWOPI_F;
+    if (dphi < -PI_F) dphi = dphi + TWOPI_F;
+    frac = dphi / (g.w3[p.icell.i3] - g.w3[p.icell.i3 - 1]);
+    ok = ok && std::fabs(frac) < threshold;
+  } else if (p.on_wall_id.w3 == +1) {
+    dphi = phi - g.w3[p.icell.i3];
+    if (dphi > PI_F) dphi = dphi - TWOPI_F;
+    if (dphi < -PI_F) dphi = dphi + TWOPI_F;
+    frac = dphi / (g.w3[p.icell.i3] - g.w3[p.icell.i3 - 1]);
+    ok = ok && std::fabs(frac) < threshold;
+  } else {
+    ok = ok && act.i3 == p.icell.i3;
+  }
+  return ok;
+}
+
+// find_wall (:592-770)
+void cyl_find_wall(orc_ctx &g, const Photon &p, double &tnearest, WallId &id_min) {
+  g.tmin = std::numeric_limits<double>::max();
+  g.emin = 0.0;
+  g.imin = WallId();
+  g.iext = WallId();
+  double v2_xy = p.v.x * p.v.x + p.v.y * p.v.y;
+  double rv_xy = p.r.x * p.v.x + p.r.y * p.v.y;
+  double r2_xy = p.r.x * p.r.x + p.r.y * p.r.y;
+  double pB = rv_xy / v2_xy;
+  pB = pB + pB;
+  double pC = r2_xy / v2_xy;
+  double t1, t2;
+  double pC_1 = pC - g.wr2[p.icell.i1 - 1] / v2_xy;
+  quadratic_pascal_reduced(pB, pC_1, t1, t2);
+  if (p.on_wall_id.w1 == -1) {
+    if (std::fabs(t1) < std::fabs(t2))
+      insert_t(g, t2, 1, -1, g.ew1[p.icell.i1 - 1]);
+    else
+      insert_t(g, t1, 1, -1, g.ew1[p.icell.i1 - 1]);
+  } else {
+    insert_t(g, t1, 1, -1, g.ew1[p.icell.i1 - 1]);
+    insert_t(g, t2, 1, -1, g.ew1[p.icell.i1 - 1]);
+  }
+  double pC_2 = pC - g.wr2[p.icell.i1] / v2_xy;
+  quadratic_pascal_reduced(pB, pC_2, t1, t2);
+  if (p.on_wall_id.w1 == +1) {
+    if (std::fabs(t1) < std::fabs(t2))
+      insert_t(g, t2, 1, +1, g.ew1[p.icell.i1]);
+    else
+      insert_t(g, t1, 1, +1, g.ew1[p.icell.i1]);
+  } else {
+    insert_t(g, t1, 1, +1, g.ew1[p.icell.i1]);
+    insert_t(g, t2, 1, +1, g.ew1[p.icell.i1]);
+  }
+  if (p.on_wall_id.w2 != -1) {
+    t1 = (g.w2[p.icell.i2 - 1] - p.r.z) / p.v.z;
+    insert_t(g, t1, 2, -1, 0.0);
+  }
+  if (p.on_wall_id.w2 != +1) {
+    t2 = (g.w2[p.icell.i2] - p.r.z) / p.v.z;
+    insert_t(g, t2, 2, +1, 0.0);
+  }
+  if (g.n3 > 1) {
+    double dphi = 0.0;
+    if (p.on_wall_id.w3 == -1) {
+      dphi = std::atan2(p.v.y, p.v.x) - g.w3[p.icell.i3 - 1];
+      if (dphi > PI_F) dphi = dphi - TWOPI_F;
+      if (dphi < -PI_F) dphi = dphi + TWOPI_F;
+    }
+    if (p.on_wall_id.w3 == +1) {
+      dphi = std::atan2(p.v.y, p.v.x) - g.w3[p.icell.i3];
+      if (dphi > PI_F) dphi = dphi - TWOPI_F;
+      if (dphi < -PI_F) dphi = dphi + TWOPI_F;
+    }
+    if (p.on_wall_id.w3 == +1 && std::fabs(dphi) < g.ew3[p.icell.i3]) {
+      g.iext.w3 = +1;
+    } else if (p.on_wall_id.w3 == -1 && std::fabs(dphi) < g.ew3[p.icell.i3 - 1]) {
+      g.iext.w3 = -1;
+    } else if (r2_xy > 0.0) {
+      if (p.on_wall_id.w3 != -1) {
+        double tp = g.wtanp[p.icell.i3 - 1];
+        t1 = -(tp * p.r.x - p.r.y) / (tp * p.v.x - p.v.y);
+        double x_i = p.r.x + p.v.x * t1, y_i = p.r.y + p.v.y * t1;
+        double dp = std::fabs(std::atan2(y_i, x_i) - g.w3[p.icell.i3 - 1]);
+        if (dp > PI_F) dp = std::fabs(dp - TWOPI_F);
+        if (dp < 0.5 * PI_F) insert_t(g, t1, 3, -1, 0.0);
+      }
+      if (p.on_wall_id.w3 != +1) {
+        double tp = g.wtanp[p.icell.i3];
+        t2 = -(tp * p.r.x - p.r.y) / (tp * p.v.x - p.v.y);
+        double x_i = p.r.x + p.v.x * t2, y_i = p.r.y + p.v.y * t2;
+        double dp = std::fabs(std::atan2(y_i, x_i) - g.w3[p.icell.i3]);
+        if (dp > PI_F) dp = std::fabs(dp - TWOPI_F);
+        if (dp < 0.5 * PI_F) insert_t(g, t2, 3, +1, 0.0);
+      }
+    }
+  }
+  tnearest = g.tmin;
+  id_min = WallId{g.imin.w1 + g.iext.w1, g.imin.w2 + g.iext.w2, g.imin.w3 + g.iext.w3};
+}
+
+// random_position_cell (:516-547)
+Vec cyl_random_position_cell(orc_ctx &g, const Cell &c) {
+  double r = g.rng.random(), z = g.rng.random(), ph = g.rng.random();
+  double a = g.w1[c.i1 - 1], b = g.w1[c.i1];
+  r = std::sqrt(r * (b * b - a * a) + a * a);
+  z = z * (g.w2[c.i2] - g.w2[c.i2 - 1]) + g.w2[c.i2 - 1];
+  ph = ph * (g.w3[c.i3] - g.w3[c.i3 - 1]) + g.w3[c.i3 - 1];
+  if (r <= a || r >= b) r = 0.5 * (a + b);
+  if (z <= g.w2[c.i2 - 1] || z >= g.w2[c.i2]) z = 0.5 * (g.w2[c.i2 - 1] + g.w2[c.i2]);
+  if (ph <= g.w3[c.i3 - 1] || ph >= g.w3[c.i3]) ph = 0.5 * (g.w3[c.i3 - 1] + g.w3[c.i3]);
+  return Vec{r * std::cos(ph), r * std::sin(ph), z};
 }
 
 // update_optconsts (dust.f90:64-79)
@@ -2362,6 +2617,8 @@ Photon emit_from_grid(orc_ctx &g) {
   // random_position_cell (grid_geometry_cartesian_3d.f90:383-394)
   if (g.grid_type == 1) {
     p.r = sph_random_position_cell(g, p.icell);
+  } else if (g.grid_type == 2) {
+    p.r = cyl_random_position_cell(g, p.icell);
   } else {
     double x = g.rng.random(), y = g.rng.random(), z = g.rng.random();
     p.r.x = x * (g.w1[i1] - g.w1[i1 - 1]) + g.w1[i1 - 1];
@@ -2549,6 +2806,41 @@ int orc_set_grid_spherical(orc_ctx *g, int32_t n1, int32_t n2, int32_t n3, const
   g->ew2.assign(n2 + 1, 3 * spacing(1.0));
   g->ew3.assign(n3 + 1, 3 * spacing(1.0));
   for (int i = 0; i <= n1; i++) g->ew1[i] = 3 * spacing(w1[i]);
+  return 0;
+}
+
+// setup_grid_geometry (grid_geometry_cylindrical_3d.f90:90-177): w1 = w, w2 = z, w3 = phi walls
+int orc_set_grid_cylindrical(orc_ctx *g, int32_t n1, int32_t n2, int32_t n3, const double *w1, const double *w2,
+                             const double *w3) {
+  g->grid_type = 2;
+  g->n1 = n1;
+  g->n2 = n2;
+  g->n3 = n3;
+  g->n_cells = n1 * n2 * n3;
+  g->w1.assign(w1, w1 + n1 + 1);
+  g->w2.assign(w2, w2 + n2 + 1);
+  g->w3.assign(w3, w3 + n3 + 1);
+  for (int i = 0; i <= n1; i++)
+    if (w1[i] < 0.) return fail(g, "w walls should be positive");
+  for (int i = 0; i <= n3; i++)
+    if (w3[i] < 0. || w3[i] > TWOPI_F) return fail(g, "phi walls should be between 0 and 2*pi");
+  g->volume.resize(g->n_cells);
+  for (int i3 = 0; i3 < n3; i3++)
+    for (int i2 = 0; i2 < n2; i2++)
+      for (int i1 = 0; i1 < n1; i1++)
+        g->volume[(size_t)i3 * n1 * n2 + i2 * n1 + i1] =
+            (w1[i1 + 1] * w1[i1 + 1] - w1[i1] * w1[i1]) * (w2[i2 + 1] - w2[i2]) * (w3[i3 + 1] - w3[i3]) / 2.0;
+  for (double v : g->volume)
+    if (v == 0.0) return fail(g, "all volumes should be greater than zero");
+  g->wr2.resize(n1 + 1);
+  for (int i = 0; i <= n1; i++) g->wr2[i] = w1[i] * w1[i];
+  g->wtanp.resize(n3 + 1);
+  for (int i = 0; i <= n3; i++) g->wtanp[i] = std::tan(w3[i]);
+  g->ew1.resize(n1 + 1);
+  g->ew2.resize(n2 + 1);
+  g->ew3.assign(n3 + 1, 3 * spacing(1.0));
+  for (int i = 0; i <= n1; i++) g->ew1[i] = 3 * spacing(w1[i]);
+  for (int i = 0; i <= n2; i++) g->ew2[i] = 3 * spacing(w2[i]);
   return 0;
 }
 

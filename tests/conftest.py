@@ -22,3 +22,9 @@ def golden_car():
 def golden_sph():
     import numpy as np
     return np.load(os.path.join(ROOT, "tests", "golden", "bitlevel_sph.npz"))
+
+
+@pytest.fixture(scope="session")
+def golden_cyl():
+    import numpy as np
+    return np.load(os.path.join(ROOT, "tests", "golden", "bitlevel_cyl.npz"))

@@ -100,6 +100,13 @@ def main():
     golden_outputs(sph, "sph")
     np.savez_compressed(os.path.join(HERE, "bitlevel_sph.npz"), **sph)
     print("wrote", os.path.join(HERE, "bitlevel_sph.npz"))
+    # cylindrical polar grid (test_bit_level.py:52-56)
+    cyl = {"w1": np.linspace(0., 2. * pc, 8), "w2": np.linspace(-pc, pc, 4), "w3": np.linspace(0., 2. * np.pi, 6),
+           "density_1": dens[("density", "cyl")], "density_2": dens[("density_2", "cyl")],
+           "density_3": dens[("density_3", "cyl")]}
+    golden_outputs(cyl, "cyl")
+    np.savez_compressed(os.path.join(HERE, "bitlevel_cyl.npz"), **cyl)
+    print("wrote", os.path.join(HERE, "bitlevel_cyl.npz"))
 
 
 def golden_outputs(out, grid_type):

@@ -24,15 +24,16 @@ def bitlevel_model(z, evenly, multi):
                      FlatConf(sample_sources_evenly=evenly))
 
 
-def bitlevel_model_sph(zc, z, evenly, multi):
-    """Same test on the spherical polar grid (test_bit_level.py:58-62): r, theta, phi walls; the dust
-    and the five point sources are those of the Cartesian fixture ``zc``."""
+def bitlevel_model_sph(zc, z, evenly, multi, grid_type="sph"):
+    """Same test on the spherical polar grid (test_bit_level.py:58-62): r, theta, phi walls (or, with
+    grid_type="cyl", the cylindrical polar grid of :52-56: w, z, phi walls); the dust and the five
+    point sources are those of the Cartesian fixture ``zc``."""
     dust = kmh_dust(zc)
     dens = [z["density_1"]] + ([z["density_2"], z["density_3"]] if multi else [])
     srcs = [FlatSource(type=1, luminosity=float(l), temperature=float(t), position=tuple(p))
             for l, t, p in zip(zc["source_luminosity"], zc["source_temperature"], zc["source_position"])]
     return FlatModel(z["w1"], z["w2"], z["w3"], np.array(dens), [dust] * len(dens), srcs,
-                     FlatConf(sample_sources_evenly=evenly), grid_type="sph")
+                     FlatConf(sample_sources_evenly=evenly), grid_type=grid_type)
 
 
 def ulp_diff(a, b):
@@ -59,7 +60,7 @@ def peeloff_model(z, evenly):
     return m
 
 
-def peeloff_model_sph(zc, z, evenly):
-    m = bitlevel_model_sph(zc, z, evenly, False)
+def peeloff_model_sph(zc, z, evenly, grid_type="sph"):
+    m = bitlevel_model_sph(zc, z, evenly, False, grid_type)
     m.peeled = peeloff_groups()
     return m
