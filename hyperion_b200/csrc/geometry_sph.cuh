@@ -12,14 +12,21 @@
 namespace hyp {
 
 // Tables of a spherical polar grid in one device buffer (offsets in doubles).
+// The same structure also carries a cylindrical polar grid (kind == POLAR_CYL,
+// src/grid/grid_geometry_cylindrical_3d.f90): w1 = cylinder radii, w2 = z planes, w3 = phi half-planes;
+// o_ew2 then holds 3*spacing(z walls) and the theta tables are unused.
+enum { POLAR_SPH = 1, POLAR_CYL = 2 };
+
 struct SphGrid {
   const double *T;
+  int32_t kind;                  // POLAR_SPH / POLAR_CYL
   int32_t n1, n2, n3, midplane;  // midplane: 0-based index of the theta wall at pi/2, or -1
   int32_t o_w1, o_wr2, o_ew1;    // [n1+1] r walls, squared, 3*spacing
   int32_t o_w2, o_wtant, o_wtant2;  // [n2+1] theta walls, tan, tan^2
   int32_t o_w3, o_wtanp, o_wcosp, o_wsinp;  // [n3+1] phi walls, tan, cos, sin
   int32_t o_dr3, o_dcost, o_dphi;   // [n1], [n2], [n3] for the cell volumes
   int32_t o_wcost;                  // [n2+1] cos(theta walls)
+  int32_t o_ew2;                    // [n2+1] cylindrical: 3*spacing(z walls)
 };
 
 constexpr double SPH_PI = 3.14159265358979323846;
@@ -72,8 +79,14 @@ __device__ inline bool sph_find_cell(const SphGrid &G, double rx, double ry, dou
                                      int &i1, int &i2, int &i3) {
   double r_sq, w_sq, theta, phi;
   sph_angles(rx, ry, rz, vx, vy, vz, r_sq, w_sq, theta, phi);
-  i1 = locate0(G.T + G.o_wr2, G.n1 + 1, r_sq);
-  i2 = locate0(G.T + G.o_w2, G.n2 + 1, theta);
+  if (G.kind == POLAR_CYL) {
+    // grid_geometry_cylindrical_3d.f90:184-237
+    i1 = locate0(G.T + G.o_wr2, G.n1 + 1, w_sq);
+    i2 = locate0(G.T + G.o_w2, G.n2 + 1, rz);
+  } else {
+    i1 = locate0(G.T + G.o_wr2, G.n1 + 1, r_sq);
+    i2 = locate0(G.T + G.o_w2, G.n2 + 1, theta);
+  }
   i3 = locate0(G.T + G.o_w3, G.n3 + 1, phi);
   return i1 >= 0 && i2 >= 0 && i3 >= 0;
 }
@@ -98,6 +111,24 @@ __device__ inline void sph_start(const SphGrid &G, SphRay &R, double rx, double 
   double r_sq, w_sq, theta, phi;
   sph_angles(rx, ry, rz, vx, vy, vz, r_sq, w_sq, theta, phi);
   const double *wr2 = G.T + G.o_wr2, *w2 = G.T + G.o_w2, *w3 = G.T + G.o_w3, *wtant = G.T + G.o_wtant;
+  if (G.kind == POLAR_CYL) {
+    // adjust_wall of the cylindrical grid (grid_geometry_cylindrical_3d.f90:239-346)
+    R.radial = false;  // the cylindrical find_wall always tests the inner wall
+    if (rx * vx + ry * vy >= 0.0) {
+      if (equal_nulp(w_sq, wr2[i1], eps)) { R.ow1 = -1; }
+      else if (equal_nulp(w_sq, wr2[i1 + 1], eps)) { R.ow1 = -1; i1 += 1; }
+    } else {
+      if (equal_nulp(w_sq, wr2[i1], eps)) { R.ow1 = +1; i1 -= 1; }
+      else if (equal_nulp(w_sq, wr2[i1 + 1], eps)) { R.ow1 = +1; }
+    }
+    if (vz > 0.0) {
+      if (equal_nulp(rz, w2[i2], eps)) { R.ow2 = -1; }
+      else if (equal_nulp(rz, w2[i2 + 1], eps)) { R.ow2 = -1; i2 += 1; }
+    } else if (vz < 0.0) {
+      if (equal_nulp(rz, w2[i2], eps)) { R.ow2 = +1; i2 -= 1; }
+      else if (equal_nulp(rz, w2[i2 + 1], eps)) { R.ow2 = +1; }
+    }
+  } else {
   // radial walls
   if (rx * vx + ry * vy + rz * vz >= 0.0) {
     if (equal_nulp(r_sq, wr2[i1], eps)) {
@@ -136,6 +167,7 @@ __device__ inline void sph_start(const SphGrid &G, SphRay &R, double rx, double 
       if (lhs == (rz > 0.0)) { R.ow2 = -1; i2 += 1; } else { R.ow2 = +1; }
     }
   }
+  }
   // phi walls
   if (rx == 0.0 && ry == 0.0 && vx == 0.0 && vy == 0.0) {
     // on the axis moving along it: on every phi wall at once, leave alone
@@ -152,7 +184,8 @@ __device__ inline void sph_start(const SphGrid &G, SphRay &R, double rx, double 
 }
 
 __device__ __forceinline__ bool sph_escaped(const SphGrid &G, const SphRay &R) {
-  return (unsigned)R.i1 >= (unsigned)G.n1;
+  // spherical: radial only (:493-500); cylindrical: w and z (grid_geometry_cylindrical_3d.f90:375-384)
+  return (unsigned)R.i1 >= (unsigned)G.n1 || (G.kind == POLAR_CYL && (unsigned)R.i2 >= (unsigned)G.n2);
 }
 
 // nearest-wall search state (reset_t / insert_t / find_next_wall)
@@ -261,11 +294,34 @@ __device__ inline bool sph_find_wall(const SphGrid &G, const SphRay &R, double &
   int iext2 = 0, iext3 = 0;
   const double t0 = R.t;
   const double *wr2 = G.T + G.o_wr2, *ew1 = G.T + G.o_ew1;
+  double t1, t2;
+  if (G.kind == POLAR_CYL) {
+    // cylinders and z planes (grid_geometry_cylindrical_3d.f90:592-680)
+    double qB = R.rv_xy / R.v2_xy;
+    qB = qB + qB;
+    const double qC = R.r2_xy / R.v2_xy;
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+      const int side = s == 0 ? -1 : +1;
+      quad_pascal_reduced(qB, qC - __ldg(wr2 + R.i1 + s) / R.v2_xy, t1, t2);
+      t1 -= t0;
+      t2 -= t0;
+      const double e = __ldg(ew1 + R.i1 + s);
+      if (R.ow1 == side) {
+        S.insert(fabs(t1) < fabs(t2) ? t2 : t1, 1, side, e);
+      } else {
+        S.insert(t1, 1, side, e);
+        S.insert(t2, 1, side, e);
+      }
+    }
+    const double *w2 = G.T + G.o_w2;
+    if (R.ow2 != -1) S.insert((__ldg(w2 + R.i2) - R.r0z) / R.vz - t0, 2, -1, 0.0);
+    if (R.ow2 != +1) S.insert((__ldg(w2 + R.i2 + 1) - R.r0z) / R.vz - t0, 2, +1, 0.0);
+  } else {
   // spheres: |r0 + t v|^2 = R^2
   double pB = R.rv_xy + R.rv_z;
   pB = pB + pB;
   const double pC = R.r2_xy + R.r2_z;
-  double t1, t2;
   if (!R.radial) {
     quad_pascal_reduced(pB, pC - __ldg(wr2 + R.i1), t1, t2);
     t1 -= t0;
@@ -293,6 +349,7 @@ __device__ inline bool sph_find_wall(const SphGrid &G, const SphRay &R, double &
   // cones (theta = 0 and theta = pi are not walls)
   if (R.i2 > 0) sph_cone(G, R, S, iext2, R.i2, -1);
   if (R.i2 < G.n2 - 1) sph_cone(G, R, S, iext2, R.i2 + 1, +1);
+  }
   // half-planes of constant phi
   if (G.n3 > 1) {
     const double *w3 = G.T + G.o_w3;
@@ -341,9 +398,11 @@ __device__ __forceinline__ void sph_step(const SphGrid &G, SphRay &R, int d1, in
   R.ic = (R.i3 * G.n2 + R.i2) * G.n1 + R.i1;
 }
 
+// spherical: dr3 * dcost * dphi / 3; cylindrical: the same slots hold dw2, dz, dphi and the divisor is 2
 __device__ __forceinline__ double sph_volume(const SphGrid &G, int64_t ic) {
   const int i1 = (int)(ic % G.n1), i2 = (int)((ic / G.n1) % G.n2), i3 = (int)(ic / ((int64_t)G.n1 * G.n2));
-  return __ldg(G.T + G.o_dr3 + i1) * __ldg(G.T + G.o_dcost + i2) * __ldg(G.T + G.o_dphi + i3) / 3.0;
+  const double v = __ldg(G.T + G.o_dr3 + i1) * __ldg(G.T + G.o_dcost + i2) * __ldg(G.T + G.o_dphi + i3);
+  return G.kind == POLAR_CYL ? v / 2.0 : v / 3.0;
 }
 
 }  // namespace hyp

@@ -475,6 +475,23 @@ __device__ __forceinline__ double cell_volume(const ModelDev &M, int64_t ic) {
 // random_position_cell (grid_geometry_cartesian_3d.f90:383-394, grid_geometry_spherical_3d.f90:645-677)
 __device__ inline void random_position_cell(const ModelDev &M, int64_t ic, Rng &rng, double &x, double &y, double &z) {
   const int i1 = (int)(ic % M.n1), i2 = (int)((ic / M.n1) % M.n2), i3 = (int)(ic / ((int64_t)M.n1 * M.n2));
+  if (M.grid_type == GEO_SPH && M.sph.kind == POLAR_CYL) {
+    // grid_geometry_cylindrical_3d.f90:516-547
+    const SphGrid &G = M.sph;
+    const double *w1 = G.T + G.o_w1, *w2 = G.T + G.o_w2, *w3 = G.T + G.o_w3;
+    double r = rng.next(), zz = rng.next(), ph = rng.next();
+    const double a = w1[i1], b = w1[i1 + 1];
+    r = sqrt(r * (b * b - a * a) + a * a);
+    zz = zz * (w2[i2 + 1] - w2[i2]) + w2[i2];
+    ph = ph * (w3[i3 + 1] - w3[i3]) + w3[i3];
+    if (r <= a || r >= b) r = 0.5 * (a + b);
+    if (zz <= w2[i2] || zz >= w2[i2 + 1]) zz = 0.5 * (w2[i2] + w2[i2 + 1]);
+    if (ph <= w3[i3] || ph >= w3[i3 + 1]) ph = 0.5 * (w3[i3] + w3[i3 + 1]);
+    x = r * cos(ph);
+    y = r * sin(ph);
+    z = zz;
+    return;
+  }
   if (M.grid_type == GEO_SPH) {
     const SphGrid &G = M.sph;
     const double *w1 = G.T + G.o_w1, *w2 = G.T + G.o_w2, *w3 = G.T + G.o_w3, *wc = G.T + G.o_wcost;
@@ -1197,6 +1214,7 @@ struct hyp_ctx {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
   // host model
   int grid_type = GEO_CAR;
+  int polar_kind = POLAR_SPH;  // grid_type == GEO_SPH: spherical or cylindrical polar
   double *d_sph = nullptr;  // spherical polar tables
   int n1 = 0, n2 = 0, n3 = 0;
   int64_t n_cells = 0;
@@ -1524,6 +1542,36 @@ int hyp_set_grid_spherical(hyp_ctx *c, int32_t n1, int32_t n2, int32_t n3, const
       if (!(ws[a][i + 1] - ws[a][i] > 0.0))
         return fail(HYP_ERR_INVALID, std::string("all ") + names[a] + " values should be greater than zero");
   c->grid_type = GEO_SPH;
+  c->polar_kind = POLAR_SPH;
+  c->n1 = n1;
+  c->n2 = n2;
+  c->n3 = n3;
+  c->n_cells = (int64_t)n1 * n2 * n3;
+  c->w1.assign(w1, w1 + n1 + 1);
+  c->w2.assign(w2, w2 + n2 + 1);
+  c->w3.assign(w3, w3 + n3 + 1);
+  return HYP_OK;
+}
+
+int hyp_set_grid_cylindrical(hyp_ctx *c, int32_t n1, int32_t n2, int32_t n3, const double *w1, const double *w2,
+                             const double *w3) {
+  if (!c || !w1 || !w2 || !w3) return fail(HYP_ERR_INVALID, "NULL argument");
+  if (c->finalized) return fail(HYP_ERR_STATE, "model is frozen");
+  if (n1 < 1 || n2 < 1 || n3 < 1) return fail(HYP_ERR_INVALID, "grid needs at least one cell per axis");
+  if ((int64_t)n1 * n2 * n3 > 2000000000LL) return fail(HYP_ERR_INVALID, "grid too large for 32-bit cell ids");
+  for (int i = 0; i <= n1; ++i)
+    if (w1[i] < 0.) return fail(HYP_ERR_INVALID, "w walls should be positive");
+  for (int i = 0; i <= n3; ++i)
+    if (w3[i] < 0. || w3[i] > SPH_TWOPI) return fail(HYP_ERR_INVALID, "phi walls should be between 0 and 2*pi");
+  const double *ws[3] = {w1, w2, w3};
+  const int ns[3] = {n1, n2, n3};
+  const char *names[3] = {"dw", "dz", "dphi"};
+  for (int a = 0; a < 3; ++a)
+    for (int i = 0; i < ns[a]; ++i)
+      if (!(ws[a][i + 1] - ws[a][i] > 0.0))
+        return fail(HYP_ERR_INVALID, std::string("all ") + names[a] + " values should be greater than zero");
+  c->grid_type = GEO_SPH;
+  c->polar_kind = POLAR_CYL;
   c->n1 = n1;
   c->n2 = n2;
   c->n3 = n3;
@@ -1689,6 +1737,8 @@ int hyp_finalize_setup(hyp_ctx *c) {
     // derived wall quantities of setup_grid_geometry (grid_geometry_spherical_3d.f90:137-201)
     const int n1 = c->n1, n2 = c->n2, n3 = c->n3;
     SphGrid &G = M.sph;
+    G.kind = c->polar_kind;
+    const bool cyl = c->polar_kind == POLAR_CYL;
     G.n1 = n1; G.n2 = n2; G.n3 = n3;
     int off = 0;
     auto take = [&](int n) { int o = off; off += n; return o; };
@@ -1696,6 +1746,7 @@ int hyp_finalize_setup(hyp_ctx *c) {
     G.o_w2 = take(n2 + 1); G.o_wtant = take(n2 + 1); G.o_wtant2 = take(n2 + 1); G.o_wcost = take(n2 + 1);
     G.o_w3 = take(n3 + 1); G.o_wtanp = take(n3 + 1); G.o_wcosp = take(n3 + 1); G.o_wsinp = take(n3 + 1);
     G.o_dr3 = take(n1); G.o_dcost = take(n2); G.o_dphi = take(n3);
+    G.o_ew2 = take(n2 + 1);
     std::vector<double> T(off);
     for (int i = 0; i <= n1; ++i) {
       const double w = c->w1[i];
@@ -1714,8 +1765,11 @@ int hyp_finalize_setup(hyp_ctx *c) {
       T[G.o_wtant2 + i] = std::tan(w) * std::tan(w);
       T[G.o_wcost + i] = std::cos(w);
       if (std::fabs(w - SPH_PI / 2.0) < (double)1.e-6f) any = true;
+      const double aw = std::fabs(w);
+      T[G.o_ew2 + i] = 3 * (w == 0.0 ? std::numeric_limits<double>::min()
+                                     : std::nextafter(aw, std::numeric_limits<double>::infinity()) - aw);
     }
-    if (any) {
+    if (any && !cyl) {
       int best = 0;
       for (int i = 1; i <= n2; ++i)
         if (std::fabs(c->w2[i] - SPH_PI / 2.0) < std::fabs(c->w2[best] - SPH_PI / 2.0)) best = i;
@@ -1728,8 +1782,10 @@ int hyp_finalize_setup(hyp_ctx *c) {
       T[G.o_wcosp + i] = std::cos(w);
       T[G.o_wsinp + i] = std::sin(w);
     }
-    for (int i = 0; i < n1; ++i) T[G.o_dr3 + i] = c->w1[i + 1] * c->w1[i + 1] * c->w1[i + 1] - c->w1[i] * c->w1[i] * c->w1[i];
-    for (int i = 0; i < n2; ++i) T[G.o_dcost + i] = std::cos(c->w2[i]) - std::cos(c->w2[i + 1]);
+    for (int i = 0; i < n1; ++i)
+      T[G.o_dr3 + i] = cyl ? c->w1[i + 1] * c->w1[i + 1] - c->w1[i] * c->w1[i]
+                           : c->w1[i + 1] * c->w1[i + 1] * c->w1[i + 1] - c->w1[i] * c->w1[i] * c->w1[i];
+    for (int i = 0; i < n2; ++i) T[G.o_dcost + i] = cyl ? c->w2[i + 1] - c->w2[i] : std::cos(c->w2[i]) - std::cos(c->w2[i + 1]);
     for (int i = 0; i < n3; ++i) T[G.o_dphi + i] = c->w3[i + 1] - c->w3[i];
     for (int i2 = 0; i2 < n2; ++i2)
       if (T[G.o_dcost + i2] == 0.0) return fail(HYP_ERR_INVALID, "all volumes should be greater than zero");

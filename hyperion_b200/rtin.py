@@ -167,9 +167,12 @@ def read_rtin(filename):
     elif rs.grid_type == "sph_pol":
         # grid_geometry_spherical_3d.f90:111-128
         cols, names, grid_type = ("r", "t", "p"), ("dr", "dt", "dphi"), "sph"
+    elif rs.grid_type == "cyl_pol":
+        # grid_geometry_cylindrical_3d.f90:109-121
+        cols, names, grid_type = ("w", "z", "p"), ("dw", "dz", "dphi"), "cyl"
     else:
-        raise ModelError("grid type '%s' is not implemented by this engine yet (Cartesian and spherical polar only)"
-                         % rs.grid_type)
+        raise ModelError("grid type '%s' is not implemented by this engine yet (Cartesian, spherical polar and "
+                         "cylindrical polar only)" % rs.grid_type)
     w1 = np.asarray(geo["walls_1"][...][cols[0]], dtype=np.float64)
     w2 = np.asarray(geo["walls_2"][...][cols[1]], dtype=np.float64)
     w3 = np.asarray(geo["walls_3"][...][cols[2]], dtype=np.float64)
@@ -178,6 +181,11 @@ def read_rtin(filename):
             raise ModelError("r walls should be positive")
         if np.any(w2 < 0.) or np.any(w2 > np.pi):
             raise ModelError("theta walls should be between 0 and pi")
+        if np.any(w3 < 0.) or np.any(w3 > 2 * np.pi):
+            raise ModelError("phi walls should be between 0 and 2*pi")
+    if grid_type == "cyl":
+        if np.any(w1 < 0.):
+            raise ModelError("w walls should be positive")
         if np.any(w3 < 0.) or np.any(w3 > 2 * np.pi):
             raise ModelError("phi walls should be between 0 and 2*pi")
     for w, nm in zip((w1, w2, w3), names):

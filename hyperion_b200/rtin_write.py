@@ -140,8 +140,8 @@ def write_rtin(filename, model: FlatModel, n_initial_iter=5, n_initial_photons=1
     gid = h.hexdigest()
     geo.attrs["geometry"] = gid
     # hyperion/grid/cartesian_grid.py:336-343, hyperion/grid/spherical_polar_grid.py (write)
-    cols = ("r", "t", "p") if model.grid_type == "sph" else ("x", "y", "z")
-    geo.attrs["grid_type"] = "sph_pol" if model.grid_type == "sph" else "car"
+    cols = {"sph": ("r", "t", "p"), "cyl": ("w", "z", "p"), "car": ("x", "y", "z")}[model.grid_type]
+    geo.attrs["grid_type"] = {"sph": "sph_pol", "cyl": "cyl_pol", "car": "car"}[model.grid_type]
     geo.create_dataset("walls_1", _table([(cols[0], model.w1)]))
     geo.create_dataset("walls_2", _table([(cols[1], model.w2)]))
     geo.create_dataset("walls_3", _table([(cols[2], model.w3)]))

@@ -174,6 +174,12 @@ int hyp_set_grid_cartesian(hyp_ctx *ctx, int32_t n1, int32_t n2, int32_t n3,
 int hyp_set_grid_spherical(hyp_ctx *ctx, int32_t n1, int32_t n2, int32_t n3,
                            const double *w1, const double *w2, const double *w3);
 
+/* replaces: setup_grid_geometry (src/grid/grid_geometry_cylindrical_3d.f90:90-177).
+ * w1 = cylindrical radius walls (n1+1), w2 = z walls (n2+1), w3 = phi walls in [0, 2 pi] (n3+1)
+ * (walls_1 'w', walls_2 'z', walls_3 'p' of a 'cyl_pol' grid); density[n_dust][n3][n2][n1]. */
+int hyp_set_grid_cylindrical(hyp_ctx *ctx, int32_t n1, int32_t n2, int32_t n3,
+                             const double *w1, const double *w2, const double *w3);
+
 /* replaces: dust_setup (src/dust/dust_type_4elem.f90:78-293); call once per dust type, in order */
 int hyp_add_dust(hyp_ctx *ctx, const hyp_dust_tables *dust);
 

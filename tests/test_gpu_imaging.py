@@ -110,11 +110,12 @@ def test_peeloff_matches_oracle(golden_car, raytracing):
             assert abs(a / b - 1) < 0.02, (key, a, b)
 
 
-@pytest.mark.parametrize("raytracing", [False, True])
-def test_peeloff_matches_oracle_spherical_grid(golden_car, golden_sph, raytracing):
+@pytest.mark.parametrize("raytracing,geometry", [(False, "sph"), (True, "sph"), (True, "cyl")])
+def test_peeloff_matches_oracle_spherical_grid(golden_car, golden_sph, golden_cyl, raytracing, geometry):
     """test_peeloff on the reference's spherical polar grid: peel-off rays cross spheres, cones and
-    phi planes; the thermal raytracing packets start at random positions of (r, theta, phi) cells."""
-    model = peeloff_model_sph(golden_car, golden_sph, False)
+    phi planes; the thermal raytracing packets start at random positions of (r, theta, phi) cells.
+    Same on the cylindrical polar grid."""
+    model = peeloff_model_sph(golden_car, golden_sph if geometry == "sph" else golden_cyl, False, geometry)
     model.specific_energy = _converged_energy(model)
     B = 12
     gpu, orc = _run_both(model, B, 60000, raytracing, (20000, 30000) if raytracing else None)

@@ -212,11 +212,13 @@ def test_path_length_estimator_consistency_large_grid():
     assert abs(est / st.n_absorptions - 1) < 0.01, (est, st.n_absorptions)
 
 
-@pytest.mark.parametrize("evenly,multi", [(False, False), (True, True)])
-def test_deposits_match_oracle_spherical_grid(golden_car, golden_sph, evenly, multi):
+@pytest.mark.parametrize("evenly,multi,geometry", [(False, False, "sph"), (True, True, "sph"),
+                                                    (False, False, "cyl"), (True, True, "cyl")])
+def test_deposits_match_oracle_spherical_grid(golden_car, golden_sph, golden_cyl, evenly, multi, geometry):
     """The reference's bit-level model on its spherical polar grid (test_bit_level.py:58-62: 5 x 7 x 3
-    cells in r, theta, phi, sources off-centre): sphere, cone and phi-plane crossings, periodic phi."""
-    model = bitlevel_model_sph(golden_car, golden_sph, evenly, multi)
+    cells in r, theta, phi, sources off-centre): sphere, cone and phi-plane crossings, periodic phi;
+    and on its cylindrical polar grid (:52-56: 7 x 3 x 5 cells in w, z, phi)."""
+    model = bitlevel_model_sph(golden_car, golden_sph if geometry == "sph" else golden_cyl, evenly, multi, geometry)
     B, N = 16, 100000
     g, gst = _gpu_batches(model, N, B)
     o, ost = _oracle_batches(model, N, B)

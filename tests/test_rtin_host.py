@@ -184,3 +184,16 @@ def test_runner_spherical_grid(golden_car, golden_sph, tmp_path):
     se = r["iteration_00002/specific_energy"][...]
     assert se.shape == (1, 3, 7, 5) and np.all(se > 0)
     assert r["Peeled/group_00001/seds"][...][0].sum() > 0
+
+
+def test_rtin_roundtrip_cylindrical_grid(golden_car, golden_cyl, tmp_path):
+    """'cyl_pol' grids: walls_1 'w', walls_2 'z', walls_3 'p' (grid_geometry_cylindrical_3d.f90:109-121)."""
+    from helpers import bitlevel_model_sph
+    m = bitlevel_model_sph(golden_car, golden_cyl, False, False, "cyl")
+    fn = str(tmp_path / "m.rtin")
+    rtin_write.write_rtin(fn, m)
+    got, rs, _ = rtin.read_rtin(fn)
+    assert rs.grid_type == "cyl_pol" and got.grid_type == "cyl"
+    for k in ("w1", "w2", "w3", "density"):
+        assert np.array_equal(getattr(got, k), getattr(m, k))
+    assert np.allclose(got.volumes().sum(), np.pi * m.w1[-1] ** 2 * (m.w2[-1] - m.w2[0]), rtol=1e-12)
