@@ -103,7 +103,7 @@ class CApi:
         self._keep = []
         f = self._fn
         f("last_error").restype = C.c_char_p
-        for name in ("set_grid_cartesian", "set_grid_spherical", "set_grid_cylindrical", "add_dust", "add_source", "set_run_conf", "set_density",
+        for name in ("set_grid_cartesian", "set_grid_spherical", "set_grid_cylindrical", "set_grid_octree", "add_dust", "add_source", "set_run_conf", "set_density",
                      "set_specific_energy", "lucy_begin", "lucy_finish", "get_specific_energy",
                      "get_density", "get_energy_sum", "add_peeled_group", "final_begin", "final_photons",
                      "final_finish", "raytracing_photons", "image_shape", "get_sed", "get_image"):
@@ -129,6 +129,12 @@ class CApi:
     def set_grid_cylindrical(self, ctx, n1, n2, n3, w1, w2, w3):
         self.check(self._fn("set_grid_cylindrical")(ctx, C.c_int32(n1), C.c_int32(n2), C.c_int32(n3),
                                                     _ptr(w1), _ptr(w2), _ptr(w3)))
+
+    def set_grid_octree(self, ctx, refined, center, half):
+        refined = np.ascontiguousarray(refined, dtype=np.int32)
+        self.check(self._fn("set_grid_octree")(ctx, C.c_int32(len(refined)),
+                                               refined.ctypes.data_as(C.POINTER(C.c_int32)),
+                                               *[C.c_double(float(v)) for v in tuple(center) + tuple(half)]))
 
     def add_dust(self, ctx, d: FlatDust):
         t = DustTables()

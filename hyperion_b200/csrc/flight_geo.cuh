@@ -1,4 +1,4 @@
-// flight_sph.cuh -- flight kernel for spherical polar grids (Lucy and imaging iterations).
+// flight_geo.cuh -- flight kernel for the geometries of march_geo.cuh (Lucy and imaging iterations).
 // Included by hyperion_b200.cu after imaging.cuh (it uses FinalArgs).
 #pragma once
 
@@ -7,11 +7,11 @@ constexpr int SPH_FLIGHT_THREADS = 128;
 // grid_integrate (DEP) / grid_integrate_noenergy for every queued packet; persistent threads, each lane
 // refills from the queue on its own.  FINAL: a packet on its first flight with a forced first interaction
 // measures its optical depth to the grid edge first (iter_final.f90:191-209).
-template <int ND, bool DEP, bool FINAL>
+template <int GEO, int ND, bool DEP, bool FINAL>
 __global__ void __launch_bounds__(SPH_FLIGHT_THREADS)
-flight_sph_kernel(const ModelDev M, Pool P, const FinalArgs F, const uint32_t *__restrict__ q_flight,
+flight_geo_kernel(const ModelDev M, Pool P, const FinalArgs F, const uint32_t *__restrict__ q_flight,
                   const uint32_t *n_flight_ptr, uint32_t *cursor, const uint32_t iteration) {
-  const SphGrid &G = M.sph;
+  using G = Geo<GEO>;
   const uint32_t n_flight = *n_flight_ptr;
   Slot<ND> *slots = (Slot<ND> *)P.slots;
   CellRec *__restrict__ cells = M.cells;
@@ -29,8 +29,8 @@ flight_sph_kernel(const ModelDev M, Pool P, const FinalArgs F, const uint32_t *_
     if (idx < n_flight) {
       slot = q_flight[idx];
       Slot<ND> *s = slots + slot;
-      SphRay R;
-      sph_start(G, R, s->r0x, s->r0y, s->r0z, s->vx, s->vy, s->vz, s->ix, s->iy, s->iz);
+      typename G::Ray R;
+      G::start(M, R, s->r0x, s->r0y, s->r0z, s->vx, s->vy, s->vz, s->ix, s->iy, s->iz, s->ic);
       double tau = s->tau_left;
       double chi[ND], kE[ND];
 #pragma unroll
@@ -38,10 +38,10 @@ flight_sph_kernel(const ModelDev M, Pool P, const FinalArgs F, const uint32_t *_
         chi[k] = s->chi[k];
         kE[k] = s->kE[k];
       }
-      if (FINAL && tau < 0.0 && !sph_escaped(G, R)) {
-        SphRay E = R;
+      if (FINAL && tau < 0.0 && !G::escaped(M, R)) {
+        typename G::Ray E = R;
         double tau_escape = 0.0, col[ND];
-        const bool ok = sph_escape<ND, false>(G, E, chi, cells, tau_escape, col, n_peel_cross);
+        const bool ok = geo_escape<GEO, ND, false>(M, E, chi, cells, tau_escape, col, n_peel_cross);
         if (!ok) ++n_killed;  // grid_escape_tau killed its copy; the packet itself goes on unforced
         Rng rng;
         rng.init(M.seed, s->id, iteration);
@@ -77,10 +77,12 @@ flight_sph_kernel(const ModelDev M, Pool P, const FinalArgs F, const uint32_t *_
       } else if (FINAL && tau < 0.0) {
         tau = 1.0;  // escaped before the first step: the value is never used
       }
-      fin = sph_march<ND, DEP>(G, R, tau, chi, kE, cells, n_cross);
+      fin = geo_march<GEO, ND, DEP>(M, R, tau, chi, kE, cells, n_cross);
       if (fin == MARCH_INTERACT) {
         s->t = R.t;
-        s->ix = R.i1; s->iy = R.i2; s->iz = R.i3; s->ic = R.ic;
+        int ix, iy, iz, ic;
+        G::store(R, ix, iy, iz, ic);
+        s->ix = ix; s->iy = iy; s->iz = iz; s->ic = ic;
       }
       n_esc += fin == MARCH_ESCAPED ? 1u : 0u;
       n_killed += fin == MARCH_KILLED ? 1u : 0u;

@@ -19,6 +19,7 @@
 
 #include "device.cuh"
 #include "geometry_sph.cuh"
+#include "geometry_oct.cuh"
 
 using namespace hyp;
 
@@ -33,11 +34,12 @@ struct CellRec {
 enum { SC_ENERGY = 0, SC_KILLED_GEO, SC_KILLED_INT, SC_CROSS, SC_ABS, SC_SCAT, SC_ESC, SC_PHOTONS, SC_PEEL_CROSS, SC_PEELOFFS,
        SC_COUNT };
 
-enum { GEO_CAR = 0, GEO_SPH = 1 };
+enum { GEO_CAR = 0, GEO_SPH = 1, GEO_OCT = 2 };  // GEO_SPH covers both polar grids (SphGrid::kind)
 
 struct ModelDev {
   int32_t grid_type;        // GEO_*
   SphGrid sph;              // spherical polar tables (grid_type == GEO_SPH)
+  OctGrid oct;              // octree (grid_type == GEO_OCT)
   int32_t n1, n2, n3, n_dust, n_sources;
   int64_t n_cells;
   const double *w1, *w2, *w3;
@@ -297,6 +299,18 @@ __device__ bool emit_photon(const ModelDev &M, Photon<ND> &p, Rng &rng, double &
   }
   int fx, fy, fz;
   bool ok;
+  if (M.grid_type == GEO_OCT) {
+    const int node = oct_find_cell(M.oct, p.r0x, p.r0y, p.r0z);
+    if (node < 0) {
+      atomicMax(M.error_flag, ERR_NOT_IN_CELL);
+      return false;
+    }
+    p.ix = p.iy = p.iz = 0;
+    p.ic = node;
+    p.n_inter = 0;
+    p.t = 0.0;
+    return true;
+  }
   if (M.grid_type == GEO_SPH) {
     // the flight kernel applies adjust_wall when it starts the ray; the slot keeps find_cell's cell
     ok = sph_find_cell(M.sph, p.r0x, p.r0y, p.r0z, p.vx, p.vy, p.vz, fx, fy, fz);
@@ -468,12 +482,24 @@ __device__ int interact_photon(const ModelDev &M, Photon<ND> &p, Rng &rng, uint3
 // cell volume (setup_grid_geometry of each geometry module)
 __device__ __forceinline__ double cell_volume(const ModelDev &M, int64_t ic) {
   if (M.grid_type == GEO_SPH) return sph_volume(M.sph, ic);
+  if (M.grid_type == GEO_OCT) {
+    const OctNode &N = M.oct.nodes[ic];
+    return N.dx * N.dy * N.dz * 8.0;  // grid_geometry_octree.f90:250-253
+  }
   const int i1 = (int)(ic % M.n1), i2 = (int)((ic / M.n1) % M.n2), i3 = (int)(ic / ((int64_t)M.n1 * M.n2));
   return ((M.w1[i1 + 1] - M.w1[i1]) * (M.w2[i2 + 1] - M.w2[i2])) * (M.w3[i3 + 1] - M.w3[i3]);
 }
 
 // random_position_cell (grid_geometry_cartesian_3d.f90:383-394, grid_geometry_spherical_3d.f90:645-677)
 __device__ inline void random_position_cell(const ModelDev &M, int64_t ic, Rng &rng, double &x, double &y, double &z) {
+  if (M.grid_type == GEO_OCT) {
+    // grid_geometry_octree.f90:396-408
+    const OctNode &N = M.oct.nodes[ic];
+    x = (2.0 * rng.next() - 1.0) * N.dx + N.x;
+    y = (2.0 * rng.next() - 1.0) * N.dy + N.y;
+    z = (2.0 * rng.next() - 1.0) * N.dz + N.z;
+    return;
+  }
   const int i1 = (int)(ic % M.n1), i2 = (int)((ic / M.n1) % M.n2), i3 = (int)(ic / ((int64_t)M.n1 * M.n2));
   if (M.grid_type == GEO_SPH && M.sph.kind == POLAR_CYL) {
     // grid_geometry_cylindrical_3d.f90:516-547
@@ -1170,9 +1196,9 @@ __global__ void to_file_order_kernel(ModelDev M, int which, const double *__rest
   }
 }
 
-#include "march_sph.cuh"
+#include "march_geo.cuh"
 #include "imaging.cuh"
-#include "flight_sph.cuh"
+#include "flight_geo.cuh"
 
 // =============================================================================================
 // host side: context + C ABI
@@ -1216,6 +1242,12 @@ struct hyp_ctx {
   int grid_type = GEO_CAR;
   int polar_kind = POLAR_SPH;  // grid_type == GEO_SPH: spherical or cylindrical polar
   double *d_sph = nullptr;  // spherical polar tables
+  // octree (host copies until finalize)
+  std::vector<OctNode> oct_nodes;
+  std::vector<int32_t> oct_children, oct_leaves;
+  double oct_eps = 0.0;
+  OctNode *d_oct_nodes = nullptr;
+  int32_t *d_oct_children = nullptr, *d_oct_leaves = nullptr;
   int n1 = 0, n2 = 0, n3 = 0;
   int64_t n_cells = 0;
   std::vector<double> w1, w2, w3;
@@ -1225,7 +1257,7 @@ struct hyp_ctx {
   std::vector<int> source_spectrum;
   hyp_run_conf conf;
   std::vector<double> h_density, h_energy, h_min_energy;
-  bool have_density = false, have_energy = false;
+  bool have_density = false, have_energy = false, energy_from_caller = false;
   double energy_total = 0.0;
   // device
   double *d_w = nullptr;
@@ -1463,6 +1495,9 @@ void hyp_ctx_destroy(hyp_ctx *c) {
   if (c->stream) cudaStreamSynchronize(c->stream);
   free_dev(c->d_w);
   free_dev(c->d_sph);
+  free_dev(c->d_oct_nodes);
+  free_dev(c->d_oct_children);
+  free_dev(c->d_oct_leaves);
   free_dev(c->d_cells);
   free_dev(c->d_energy);
   free_dev(c->d_jfrac);
@@ -1582,6 +1617,89 @@ int hyp_set_grid_cylindrical(hyp_ctx *c, int32_t n1, int32_t n2, int32_t n3, con
   return HYP_OK;
 }
 
+int hyp_set_grid_octree(hyp_ctx *c, int32_t n_cells, const int32_t *refined, double x, double y, double z, double dx,
+                        double dy, double dz) {
+  if (!c || !refined) return fail(HYP_ERR_INVALID, "NULL argument");
+  if (c->finalized) return fail(HYP_ERR_STATE, "model is frozen");
+  if (n_cells < 1) return fail(HYP_ERR_INVALID, "octree needs at least one cell");
+  if (!(dx > 0.0 && dy > 0.0 && dz > 0.0)) return fail(HYP_ERR_INVALID, "all volumes should be greater than zero");
+  // octree_setup_indiv (grid_geometry_octree.f90:148-187), iteratively: nodes in depth-first order
+  std::vector<OctNode> nodes(n_cells);
+  std::vector<int32_t> parent(n_cells, -1), parent_sub(n_cells, 0), children;
+  for (auto &n : nodes) {
+    n.first_child = -1;
+    n.pad = 0;
+    for (int k = 0; k < 6; ++k) n.nb[k] = -1;
+  }
+  nodes[0].x = x; nodes[0].y = y; nodes[0].z = z;
+  nodes[0].dx = dx; nodes[0].dy = dy; nodes[0].dz = dz;
+  int n_filled = 1;
+  std::vector<std::pair<int, int>> stack;
+  auto refine = [&](int id) {
+    nodes[id].first_child = (int32_t)(children.size() / 8);
+    children.resize(children.size() + 8, -1);
+    stack.push_back({id, 0});
+  };
+  if (refined[0] == 1) refine(0);
+  while (!stack.empty()) {
+    const int par = stack.back().first, k = stack.back().second;
+    if (k == 8) {
+      stack.pop_back();
+      continue;
+    }
+    stack.back().second = k + 1;
+    if (n_filled >= n_cells) return fail(HYP_ERR_INVALID, "refined array is not self-consistent");
+    const int child = n_filled++;
+    children[(size_t)nodes[par].first_child * 8 + k] = child;
+    const int sx = (k & 1) ? 1 : -1, sy = (k & 2) ? 1 : -1, sz = (k & 4) ? 1 : -1;
+    nodes[child].x = nodes[par].x + sx * nodes[par].dx / 2.0;
+    nodes[child].y = nodes[par].y + sy * nodes[par].dy / 2.0;
+    nodes[child].z = nodes[par].z + sz * nodes[par].dz / 2.0;
+    nodes[child].dx = nodes[par].dx / 2.0;
+    nodes[child].dy = nodes[par].dy / 2.0;
+    nodes[child].dz = nodes[par].dz / 2.0;
+    parent[child] = par;
+    parent_sub[child] = k;
+    if (refined[child] == 1) refine(child);
+  }
+  if (n_filled != n_cells) return fail(HYP_ERR_INVALID, "refined array is not self-consistent");
+  // neighbour links: nodes are in depth-first order, so a parent's links exist before its children's.
+  // Behind wall w of child k of parent p lies a sibling if the child sits on the near side of that
+  // axis, else the matching child (same k with the axis bit flipped) of p's neighbour -- or that
+  // neighbour itself when it is a leaf (a coarser cell).
+  for (int id = 1; id < n_cells; ++id) {
+    const int par = parent[id], k = parent_sub[id];
+    for (int w = 0; w < 6; ++w) {
+      const int axis = w / 2, bit = 1 << axis, up = w & 1;
+      const bool high = (k & bit) != 0;
+      if (high != (up != 0)) {
+        nodes[id].nb[w] = children[(size_t)nodes[par].first_child * 8 + (k ^ bit)];
+      } else {
+        const int n = nodes[par].nb[w];
+        if (n < 0 || nodes[n].first_child < 0)
+          nodes[id].nb[w] = n;
+        else
+          nodes[id].nb[w] = children[(size_t)nodes[n].first_child * 8 + (k ^ bit)];
+      }
+    }
+  }
+  c->oct_leaves.clear();
+  for (int id = 0; id < n_cells; ++id)
+    if (refined[id] == 0) c->oct_leaves.push_back(id);
+  c->oct_nodes.swap(nodes);
+  c->oct_children.swap(children);
+  const double m = std::max(dx, std::max(dy, dz));
+  c->oct_eps = 3.0 * (std::nextafter(m, std::numeric_limits<double>::infinity()) - m);
+  c->grid_type = GEO_OCT;
+  c->n1 = n_cells;
+  c->n2 = c->n3 = 1;
+  c->n_cells = n_cells;
+  c->w1.assign(2, 0.0);
+  c->w2.assign(2, 0.0);
+  c->w3.assign(2, 0.0);
+  return HYP_OK;
+}
+
 int hyp_add_dust(hyp_ctx *c, const hyp_dust_tables *t) {
   if (!c || !t) return fail(HYP_ERR_INVALID, "NULL argument");
   if (c->finalized) return fail(HYP_ERR_STATE, "model is frozen");
@@ -1693,6 +1811,7 @@ int hyp_set_specific_energy(hyp_ctx *c, const double *se, const double *min_e) {
       std::fill(c->h_energy.begin() + id * c->n_cells, c->h_energy.begin() + (id + 1) * c->n_cells, c->h_min_energy[id]);
   }
   c->have_energy = true;
+  c->energy_from_caller = se != nullptr;
   if (c->finalized) {
     CUDA_TRY(cudaSetDevice(c->device));
     for (size_t i = 0; i < nd; ++i) c->M.min_energy[i] = c->h_min_energy[i];
@@ -1733,6 +1852,29 @@ int hyp_finalize_setup(hyp_ctx *c) {
   M.w2 = c->d_w + c->w1.size();
   M.w3 = M.w2 + c->w2.size();
   M.grid_type = c->grid_type;
+  if (c->grid_type == GEO_OCT) {
+    OctGrid &G = M.oct;
+    CUDA_TRY(cudaMalloc(&c->d_oct_nodes, c->oct_nodes.size() * sizeof(OctNode)));
+    CUDA_TRY(cudaMemcpy(c->d_oct_nodes, c->oct_nodes.data(), c->oct_nodes.size() * sizeof(OctNode), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMalloc(&c->d_oct_children, std::max<size_t>(c->oct_children.size(), 8) * sizeof(int32_t)));
+    CUDA_TRY(cudaMemcpy(c->d_oct_children, c->oct_children.data(), c->oct_children.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMalloc(&c->d_oct_leaves, c->oct_leaves.size() * sizeof(int32_t)));
+    CUDA_TRY(cudaMemcpy(c->d_oct_leaves, c->oct_leaves.data(), c->oct_leaves.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+    G.nodes = c->d_oct_nodes;
+    G.children = c->d_oct_children;
+    G.leaves = c->d_oct_leaves;
+    G.n_nodes = (int32_t)c->oct_nodes.size();
+    G.n_leaves = (int32_t)c->oct_leaves.size();
+    G.eps = c->oct_eps;
+    // refined nodes hold no dust (setup_grid_physics applies the mask, grid_physics_3d.f90:156-164)
+    const size_t nc = (size_t)c->n_cells;
+    for (size_t id = 0; id < c->dust.size(); ++id)
+      for (size_t ic = 0; ic < nc; ++ic)
+        if (c->oct_nodes[ic].first_child >= 0) {
+          c->h_density[id * nc + ic] = 0.0;
+          if (c->energy_from_caller) c->h_energy[id * nc + ic] = 0.0;
+        }
+  }
   if (c->grid_type == GEO_SPH) {
     // derived wall quantities of setup_grid_geometry (grid_geometry_spherical_3d.f90:137-201)
     const int n1 = c->n1, n2 = c->n2, n3 = c->n3;
@@ -1955,18 +2097,20 @@ static int run_rounds(hyp_ctx *c, int64_t first_id, int64_t n_photons, int64_t i
     CUDA_TRY(cudaMemsetAsync(P.counts + C_NI, 0, 4 * sizeof(uint32_t), st));  // C_NI, C_NE, C_CURSOR, C_CURSOR_B
     // 2. flights: the beams of new packets, then the packets that come out of an interaction
     CUDA_TRY(cudaEventRecord(c->evA, st));
-    if (c->grid_type == GEO_SPH) {
+    if (c->grid_type != GEO_CAR) {
       const FinalArgs none = FinalArgs();
+      auto geo_flight = c->grid_type == GEO_OCT ? flight_geo_kernel<GEO_OCT, ND, true, false>
+                                                : flight_geo_kernel<GEO_SPH, ND, true, false>;
       const int sph_blocks_max = c->sm_count * 12;
       if (n_new > 0) {
         int blocks = (int)std::min<int64_t>((n_new + SPH_FLIGHT_THREADS - 1) / SPH_FLIGHT_THREADS, sph_blocks_max);
-        flight_sph_kernel<ND, true, false><<<blocks, SPH_FLIGHT_THREADS, 0, st>>>(c->M, P, none, P.q_beam, P.counts + C_NB,
+        geo_flight<<<blocks, SPH_FLIGHT_THREADS, 0, st>>>(c->M, P, none, P.q_beam, P.counts + C_NB,
                                                                                  P.counts + C_CURSOR_B, (uint32_t)iteration);
         c->launches_acc += 1;
       }
       if (n_flight_prev > 0) {
         int blocks = (int)std::min<int64_t>(((int64_t)n_flight_prev + SPH_FLIGHT_THREADS - 1) / SPH_FLIGHT_THREADS, sph_blocks_max);
-        flight_sph_kernel<ND, true, false><<<blocks, SPH_FLIGHT_THREADS, 0, st>>>(c->M, P, none, P.q_flight[cur], nF,
+        geo_flight<<<blocks, SPH_FLIGHT_THREADS, 0, st>>>(c->M, P, none, P.q_flight[cur], nF,
                                                                                  P.counts + C_CURSOR, (uint32_t)iteration);
         c->launches_acc += 1;
       }
@@ -2310,6 +2454,9 @@ int launch_peel(hyp_ctx *c, const ModelDev &M, uint32_t n_jobs_max) {
   if (c->grid_type == GEO_SPH) {
     k = peel_kernel<ND, POLY, GEO_SPH>;
     ws = WallSmem{0, 0};
+  } else if (c->grid_type == GEO_OCT) {
+    k = peel_kernel<ND, POLY, GEO_OCT>;
+    ws = WallSmem{0, 0};
   }
   CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ws.bytes));
   ImagingDev I{c->d_images, c->d_views, (int)c->groups.size(), c->n_views};
@@ -2385,17 +2532,19 @@ int run_final_rounds(hyp_ctx *c, int64_t first_id, int64_t n_photons, int scatte
     }
     CUDA_TRY(cudaMemsetAsync(P.counts + C_NI, 0, 4 * sizeof(uint32_t), st));  // C_NI, C_NE, C_CURSOR, C_CURSOR_B
     CUDA_TRY(cudaEventRecord(c->evA, st));
-    if (c->grid_type == GEO_SPH) {
+    if (c->grid_type != GEO_CAR) {
       const int sph_blocks_max = c->sm_count * 12;
+      auto geo_flight = c->grid_type == GEO_OCT ? flight_geo_kernel<GEO_OCT, ND, false, true>
+                                                : flight_geo_kernel<GEO_SPH, ND, false, true>;
       if (n_new > 0) {
         int blocks = (int)std::min<int64_t>((n_new + SPH_FLIGHT_THREADS - 1) / SPH_FLIGHT_THREADS, sph_blocks_max);
-        flight_sph_kernel<ND, false, true><<<blocks, SPH_FLIGHT_THREADS, 0, st>>>(M, P, F, P.q_beam, P.counts + C_NB,
+        geo_flight<<<blocks, SPH_FLIGHT_THREADS, 0, st>>>(M, P, F, P.q_beam, P.counts + C_NB,
                                                                                  P.counts + C_CURSOR_B, iteration);
         c->launches_acc += 1;
       }
       if (n_flight_prev > 0) {
         int blocks = (int)std::min<int64_t>(((int64_t)n_flight_prev + SPH_FLIGHT_THREADS - 1) / SPH_FLIGHT_THREADS, sph_blocks_max);
-        flight_sph_kernel<ND, false, true><<<blocks, SPH_FLIGHT_THREADS, 0, st>>>(M, P, F, P.q_flight[cur], nF,
+        geo_flight<<<blocks, SPH_FLIGHT_THREADS, 0, st>>>(M, P, F, P.q_flight[cur], nF,
                                                                                  P.counts + C_CURSOR, iteration);
         c->launches_acc += 1;
       }

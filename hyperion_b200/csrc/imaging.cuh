@@ -309,7 +309,7 @@ peel_kernel(const ModelDev M, const ImagingDev I, const PeelJob<ND> *__restrict_
     if (GEO == GEO_CAR) {
       if (!place_in_grid(M, J.rx, J.ry, J.rz, vx, vy, vz, ix, iy, iz, ic)) continue;
     } else {
-      if (!sph_find_cell(M.sph, J.rx, J.ry, J.rz, vx, vy, vz, ix, iy, iz)) continue;
+      if (!Geo<GEO == GEO_CAR ? GEO_SPH : GEO>::find_cell(M, J.rx, J.ry, J.rz, vx, vy, vz, ix, iy, iz, ic)) continue;
     }
     // depth along the line of sight and image-plane coordinates (images_peeled.f90:196-211)
     const double depth = -(vx * J.rx + vy * J.ry + vz * J.rz);
@@ -329,9 +329,10 @@ peel_kernel(const ModelDev M, const ImagingDev I, const PeelJob<ND> *__restrict_
         for (int id = 0; id < ND; ++id) L.chi[id] = J.chi[id];
         escape_march<ND, POLY, PEEL_LOOKAHEAD>(L, W, M.cells, n1, n2, n3, tau, col, n_cross);
       } else {
-        SphRay R;
-        sph_start(M.sph, R, J.rx, J.ry, J.rz, vx, vy, vz, ix, iy, iz);
-        if (!sph_escape<ND, POLY>(M.sph, R, J.chi, M.cells, tau, col, n_cross)) {
+        constexpr int GG = GEO == GEO_CAR ? GEO_SPH : GEO;
+        typename Geo<GG>::Ray R;
+        Geo<GG>::start(M, R, J.rx, J.ry, J.rz, vx, vy, vz, ix, iy, iz, ic);
+        if (!geo_escape<GG, ND, POLY>(M, R, J.chi, M.cells, tau, col, n_cross)) {
           ++n_killed;  // no wall found: the reference counts the packet as killed and drops the peel-off
           continue;
         }
@@ -698,13 +699,21 @@ __global__ void raytrace_emit_kernel(const ModelDev M, PeelJob<ND> *__restrict__
       // emit_from_grid (grid_physics_3d.f90:691-753)
       rng.init(M.seed, first_dust_id + (i - n_src), ITER_RAY_DUST);
       const int id = max((int)ceil(rng.next() * (double)ND), 1) - 1;
-      const int64_t ic = max((int64_t)ceil(rng.next() * (double)M.n_cells), (int64_t)1) - 1;
+      // random_masked_cell (grid_geometry_common_3d.f90:104-115): octrees draw from their leaves
+      int64_t ic;
+      double n_masked = (double)M.n_cells;
+      if (M.grid_type == GEO_OCT) {
+        n_masked = (double)M.oct.n_leaves;
+        ic = M.oct.leaves[max((int64_t)ceil(rng.next() * n_masked), (int64_t)1) - 1];
+      } else {
+        ic = max((int64_t)ceil(rng.next() * (double)M.n_cells), (int64_t)1) - 1;
+      }
       random_position_cell(M, ic, rng, p.r0x, p.r0y, p.r0z);
       const size_t k = (size_t)ic * ND + id;
       const double vol = cell_volume(M, ic);
       const double etot = energy_abs_tot[id];
       p.energy = 0.0;
-      if (etot > 0.0) p.energy = M.specific_energy[k] * (M.cells[k].rho * vol) * (double)M.n_cells / etot;
+      if (etot > 0.0) p.energy = M.specific_energy[k] * (M.cells[k].rho * vol) * n_masked / etot;
       ok = p.energy > 0.0;
       // energy_abs_tot(dust) / n_photons_thermal * n_dust (iter_raytracing.f90:113)
       p.energy = p.energy * etot * dust_weight;

@@ -167,11 +167,23 @@ class FlatModel:
     specific_energy: Optional[np.ndarray] = None
     minimum_specific_energy: Optional[np.ndarray] = None
     peeled: List["FlatPeeledGroup"] = field(default_factory=list)
-    grid_type: str = "car"              # "car" (x, y, z walls), "sph" (r, theta, phi) or "cyl" (w, z, phi)
+    grid_type: str = "car"              # "car" (x, y, z walls), "sph" (r, theta, phi), "cyl" (w, z, phi), "oct"
+    # octree (grid_type "oct", hyperion/grid/octree_grid.py): depth-first refinement flags, centre and
+    # HALF-widths of the root cell; density is then [n_dust, n_nodes] and w1/w2/w3 are unused
+    refined: Optional[np.ndarray] = None
+    oct_center: tuple = (0.0, 0.0, 0.0)
+    oct_half: tuple = (1.0, 1.0, 1.0)
 
     def __post_init__(self):
-        self.w1, self.w2, self.w3 = _f8(self.w1), _f8(self.w2), _f8(self.w3)
         self.density = _f8(self.density)
+        if self.grid_type == "oct":
+            self.refined = np.ascontiguousarray(self.refined, dtype=np.int32)
+            if self.density.ndim == 1:
+                self.density = self.density[None]
+            if self.density.shape != (len(self.dust), len(self.refined)):
+                raise ValueError("density should have shape (n_dust, n_nodes)")
+            return
+        self.w1, self.w2, self.w3 = _f8(self.w1), _f8(self.w2), _f8(self.w3)
         n1, n2, n3 = len(self.w1) - 1, len(self.w2) - 1, len(self.w3) - 1
         if self.density.ndim == 3:
             self.density = self.density[None]
@@ -181,14 +193,34 @@ class FlatModel:
 
     @property
     def shape(self):
+        if self.grid_type == "oct":
+            return (len(self.refined),)
         return (len(self.w3) - 1, len(self.w2) - 1, len(self.w1) - 1)
 
     @property
     def n_cells(self):
-        s = self.shape
-        return s[0] * s[1] * s[2]
+        return int(np.prod(self.shape))
 
     def volumes(self):
+        if self.grid_type == "oct":
+            # node volumes in depth-first order (grid_geometry_octree.f90:160-183,250-253)
+            vol = np.zeros(len(self.refined))
+            hx, hy, hz = self.oct_half
+            stack = [[0, 8 * hx * hy * hz]]
+            vol[0] = stack[0][1]
+            idx = 0
+            pending = [(8, vol[0] / 8.)] if self.refined[0] else []
+            while pending:
+                left, v = pending[-1]
+                if left == 0:
+                    pending.pop()
+                    continue
+                pending[-1] = (left - 1, v)
+                idx += 1
+                vol[idx] = v
+                if self.refined[idx]:
+                    pending.append((8, v / 8.))
+            return vol
         if self.grid_type == "sph":
             # grid_geometry_spherical_3d.f90:147-160
             dr3, dcost, dphi = np.diff(self.w1 ** 3), -np.diff(np.cos(self.w2)), np.diff(self.w3)
@@ -206,8 +238,14 @@ def apply_model(api, ctx, model: FlatModel):
 
     ``api`` is a binding object with methods named like the header's functions
     minus the prefix (see :mod:`hyperion_b200.capi`)."""
-    n3, n2, n1 = model.shape
-    if model.grid_type == "sph":
+    if model.grid_type == "oct":
+        api.set_grid_octree(ctx, model.refined, model.oct_center, model.oct_half)
+        n1 = n2 = n3 = 0
+    else:
+        n3, n2, n1 = model.shape
+    if model.grid_type == "oct":
+        pass
+    elif model.grid_type == "sph":
         api.set_grid_spherical(ctx, n1, n2, n3, model.w1, model.w2, model.w3)
     elif model.grid_type == "cyl":
         api.set_grid_cylindrical(ctx, n1, n2, n3, model.w1, model.w2, model.w3)

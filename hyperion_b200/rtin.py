@@ -162,52 +162,63 @@ def read_rtin(filename):
     geo = f["Grid/Geometry"]
     rs.grid_type = _s(geo.attrs["grid_type"])
     rs.geometry_id = _s(geo.attrs["geometry"])
-    if rs.grid_type == "car":
-        cols, names, grid_type = ("x", "y", "z"), ("dx", "dy", "dz"), "car"
-    elif rs.grid_type == "sph_pol":
-        # grid_geometry_spherical_3d.f90:111-128
-        cols, names, grid_type = ("r", "t", "p"), ("dr", "dt", "dphi"), "sph"
-    elif rs.grid_type == "cyl_pol":
-        # grid_geometry_cylindrical_3d.f90:109-121
-        cols, names, grid_type = ("w", "z", "p"), ("dw", "dz", "dphi"), "cyl"
+    octree = None
+    if rs.grid_type == "oct":
+        # grid_geometry_octree.f90:189-262: table 'cells' (column 'refined'), root cell centre and half-widths
+        refined = np.asarray(geo["cells"][...]["refined"], dtype=np.int32)
+        octree = dict(refined=refined,
+                      oct_center=tuple(float(_num(geo.attrs[k])) for k in ("x", "y", "z")),
+                      oct_half=tuple(float(_num(geo.attrs[k])) for k in ("dx", "dy", "dz")))
+        if (len(refined) - 1) % 8 != 0:
+            raise ModelError("refined should have shape 8 * n + 1")
+        grid_type, w1, w2, w3 = "oct", None, None, None
     else:
-        raise ModelError("grid type '%s' is not implemented by this engine yet (Cartesian, spherical polar and "
-                         "cylindrical polar only)" % rs.grid_type)
-    w1 = np.asarray(geo["walls_1"][...][cols[0]], dtype=np.float64)
-    w2 = np.asarray(geo["walls_2"][...][cols[1]], dtype=np.float64)
-    w3 = np.asarray(geo["walls_3"][...][cols[2]], dtype=np.float64)
-    if grid_type == "sph":
-        if np.any(w1 < 0.):
-            raise ModelError("r walls should be positive")
-        if np.any(w2 < 0.) or np.any(w2 > np.pi):
-            raise ModelError("theta walls should be between 0 and pi")
-        if np.any(w3 < 0.) or np.any(w3 > 2 * np.pi):
-            raise ModelError("phi walls should be between 0 and 2*pi")
-    if grid_type == "cyl":
-        if np.any(w1 < 0.):
-            raise ModelError("w walls should be positive")
-        if np.any(w3 < 0.) or np.any(w3 > 2 * np.pi):
-            raise ModelError("phi walls should be between 0 and 2*pi")
-    for w, nm in zip((w1, w2, w3), names):
-        if np.any(np.diff(w) <= 0):
-            raise ModelError("all %s values should be greater than zero" % nm)
+        if rs.grid_type == "car":
+            cols, names, grid_type = ("x", "y", "z"), ("dx", "dy", "dz"), "car"
+        elif rs.grid_type == "sph_pol":
+            # grid_geometry_spherical_3d.f90:111-128
+            cols, names, grid_type = ("r", "t", "p"), ("dr", "dt", "dphi"), "sph"
+        elif rs.grid_type == "cyl_pol":
+            # grid_geometry_cylindrical_3d.f90:109-121
+            cols, names, grid_type = ("w", "z", "p"), ("dw", "dz", "dphi"), "cyl"
+        else:
+            raise ModelError("grid type '%s' is not implemented by this engine yet (Cartesian, spherical polar and "
+                             "cylindrical polar only)" % rs.grid_type)
+        w1 = np.asarray(geo["walls_1"][...][cols[0]], dtype=np.float64)
+        w2 = np.asarray(geo["walls_2"][...][cols[1]], dtype=np.float64)
+        w3 = np.asarray(geo["walls_3"][...][cols[2]], dtype=np.float64)
+        if grid_type == "sph":
+            if np.any(w1 < 0.):
+                raise ModelError("r walls should be positive")
+            if np.any(w2 < 0.) or np.any(w2 > np.pi):
+                raise ModelError("theta walls should be between 0 and pi")
+            if np.any(w3 < 0.) or np.any(w3 > 2 * np.pi):
+                raise ModelError("phi walls should be between 0 and 2*pi")
+        if grid_type == "cyl":
+            if np.any(w1 < 0.):
+                raise ModelError("w walls should be positive")
+            if np.any(w3 < 0.) or np.any(w3 > 2 * np.pi):
+                raise ModelError("phi walls should be between 0 and 2*pi")
+        for w, nm in zip((w1, w2, w3), names):
+            if np.any(np.diff(w) <= 0):
+                raise ModelError("all %s values should be greater than zero" % nm)
 
     # ---- grid physics
     q = f["Grid/Quantities"]
-    n3, n2, n1 = len(w3) - 1, len(w2) - 1, len(w1) - 1
+    grid_shape = (len(octree["refined"]),) if octree else (len(w3) - 1, len(w2) - 1, len(w1) - 1)
     if "density" in q:
         dset = q["density"]
         if "geometry" in dset.attrs and _s(dset.attrs["geometry"]) != rs.geometry_id:
             raise ModelError("geometry id of density does not match that of the grid")
         density = np.asarray(dset[...], dtype=np.float64)
-        if density.shape[1:] != (n3, n2, n1):
+        if density.shape[1:] != grid_shape:
             raise ModelError("density array has wrong shape")
         if density.shape[0] != len(dust):
             raise ModelError("density array has wrong number of dust types")
         if np.any(density < 0):
             raise ModelError("density should be positive")
     else:
-        density = np.zeros((0, n3, n2, n1))
+        density = np.zeros((0,) + grid_shape)
     se = None
     if "specific_energy" in q:
         se = np.asarray(q["specific_energy"][...], dtype=np.float64)
@@ -269,7 +280,7 @@ def read_rtin(filename):
         raise ModelError("no sources set up - need sources for last iteration")
 
     model = FlatModel(w1, w2, w3, density, dust, sources, conf, specific_energy=se, minimum_specific_energy=min_e,
-                      grid_type=grid_type)
+                      grid_type=grid_type, **(octree or {}))
     model.peeled = read_peeled_groups(f)
     if "Output" in f and "Binned" in f["Output"] and len(f["Output"]["Binned"].keys()) > 0:
         if rs.forced_first_interaction:

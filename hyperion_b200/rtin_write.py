@@ -135,16 +135,27 @@ def write_rtin(filename, model: FlatModel, n_initial_iter=5, n_initial_photons=1
 
     geo = f.create_group("Grid/Geometry")
     h = hashlib.md5()
-    for w in (model.w1, model.w2, model.w3):
-        h.update(np.ascontiguousarray(w).tobytes())
+    if model.grid_type == "oct":
+        # hyperion/grid/octree_grid.py:426-436
+        h.update(np.ascontiguousarray(model.refined).tobytes())
+        h.update(np.array(tuple(model.oct_center) + tuple(model.oct_half)).tobytes())
+    else:
+        for w in (model.w1, model.w2, model.w3):
+            h.update(np.ascontiguousarray(w).tobytes())
     gid = h.hexdigest()
     geo.attrs["geometry"] = gid
+    if model.grid_type == "oct":
+        geo.attrs["grid_type"] = "oct"
+        for k, v in zip(("x", "y", "z", "dx", "dy", "dz"), tuple(model.oct_center) + tuple(model.oct_half)):
+            geo.attrs[k] = float(v)
+        geo.create_dataset("cells", _table([("refined", np.asarray(model.refined, dtype=np.int32))]))
     # hyperion/grid/cartesian_grid.py:336-343, hyperion/grid/spherical_polar_grid.py (write)
-    cols = {"sph": ("r", "t", "p"), "cyl": ("w", "z", "p"), "car": ("x", "y", "z")}[model.grid_type]
-    geo.attrs["grid_type"] = {"sph": "sph_pol", "cyl": "cyl_pol", "car": "car"}[model.grid_type]
-    geo.create_dataset("walls_1", _table([(cols[0], model.w1)]))
-    geo.create_dataset("walls_2", _table([(cols[1], model.w2)]))
-    geo.create_dataset("walls_3", _table([(cols[2], model.w3)]))
+    if model.grid_type != "oct":
+        cols = {"sph": ("r", "t", "p"), "cyl": ("w", "z", "p"), "car": ("x", "y", "z")}[model.grid_type]
+        geo.attrs["grid_type"] = {"sph": "sph_pol", "cyl": "cyl_pol", "car": "car"}[model.grid_type]
+        geo.create_dataset("walls_1", _table([(cols[0], model.w1)]))
+        geo.create_dataset("walls_2", _table([(cols[1], model.w2)]))
+        geo.create_dataset("walls_3", _table([(cols[2], model.w3)]))
     q = f.create_group("Grid/Quantities")
     d = q.create_dataset("density", model.density)
     d.attrs["geometry"] = gid

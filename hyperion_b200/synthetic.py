@@ -231,3 +231,41 @@ def spherical_disk_model(n_r=399, n_theta=199, n_phi=1, tau_edge=10.0, dust=None
     src = FlatSource(type=1, luminosity=lsun, temperature=temperature, position=(0., 0., 0.))
     conf = FlatConf(n_initial_iter=n_iter, n_initial_photons=n_photons)
     return FlatModel(w1, w2, w3, rho, [dust], [src], conf, grid_type="sph")
+
+
+def random_octree(max_depth=5, p_refine=0.6, seed=4, min_depth=1):
+    """Depth-first refinement flags of a seeded random octree (children in x-fastest order,
+    docs/advanced/indepth_oct.rst): a node at depth < min_depth is always refined, deeper nodes with
+    probability p_refine until max_depth."""
+    rng = np.random.default_rng(seed)
+    refined = []
+
+    def build(depth):
+        r = depth < max_depth and (depth < min_depth or rng.random() < p_refine)
+        refined.append(1 if r else 0)
+        if r:
+            for _ in range(8):
+                build(depth + 1)
+
+    build(0)
+    return np.array(refined, dtype=np.int32)
+
+
+def octree_point_sources_model(refined=None, tau_edge=2.0, dust=None, n_sources=4, seed=4, lam_ref_um=0.5,
+                               n_photons=0, n_iter=1, **kw):
+    """SURVEY.md section 8d 'C4': a seeded octree over [-pc, pc]^3 with a few point sources at random
+    positions and density 1+U(0,1) per leaf (scaled so that the optical depth from the centre to a face
+    at ``lam_ref_um`` is ``tau_edge``)."""
+    if refined is None:
+        refined = random_octree(seed=seed, **kw)
+    if dust is None:
+        dust = hg_dust(n_temp=40)
+    rng = np.random.default_rng(seed + 1)
+    chi0 = chi_at(dust, c / (lam_ref_um * 1.e-4))
+    rho0 = tau_edge / (chi0 * pc * 1.5)
+    rho = (1. + rng.random((1, len(refined)))) * rho0
+    src = [FlatSource(type=1, luminosity=lsun * (0.5 + rng.random()), temperature=float(rng.uniform(3000., 9000.)),
+                      position=tuple(rng.uniform(-0.8 * pc, 0.8 * pc, 3))) for _ in range(n_sources)]
+    conf = FlatConf(n_initial_iter=n_iter, n_initial_photons=n_photons)
+    return FlatModel(None, None, None, rho, [dust], src, conf, grid_type="oct", refined=refined,
+                     oct_center=(0., 0., 0.), oct_half=(pc, pc, pc))

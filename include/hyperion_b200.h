@@ -180,6 +180,14 @@ int hyp_set_grid_spherical(hyp_ctx *ctx, int32_t n1, int32_t n2, int32_t n3,
 int hyp_set_grid_cylindrical(hyp_ctx *ctx, int32_t n1, int32_t n2, int32_t n3,
                              const double *w1, const double *w2, const double *w3);
 
+/* replaces: setup_grid_geometry + octree_setup_indiv (src/grid/grid_geometry_octree.f90:148-262).
+ * refined[n_cells]: depth-first (pre-order) refinement flags, children in x-fastest order
+ * (Grid/Geometry table 'cells', column 'refined'); (x, y, z) centre and (dx, dy, dz) HALF-widths of the root
+ * cell (group attributes).  Quantities then have one entry per NODE: density[n_dust][n_cells]; refined nodes
+ * are masked out (density forced to zero), as setup_grid_physics does. */
+int hyp_set_grid_octree(hyp_ctx *ctx, int32_t n_cells, const int32_t *refined,
+                        double x, double y, double z, double dx, double dy, double dz);
+
 /* replaces: dust_setup (src/dust/dust_type_4elem.f90:78-293); call once per dust type, in order */
 int hyp_add_dust(hyp_ctx *ctx, const hyp_dust_tables *dust);
 

@@ -1023,11 +1023,20 @@ struct orc_ctx {
   double tmin = 0, emin = 0;
   WallId imin, iext;
   // geometry kind: 0 Cartesian, 1 spherical polar (grid_geometry_spherical_3d.f90),
-  // 2 cylindrical polar (grid_geometry_cylindrical_3d.f90)
+  // 2 cylindrical polar (grid_geometry_cylindrical_3d.f90), 3 octree (grid_geometry_octree.f90)
   int grid_type = 0;
   bool radial = false;  // the 'radial' argument of the spherical find_wall (grid_propagate_3d.f90:73)
   std::vector<double> wr2, wtanp, wtant, wcost, wsint, wtant2;  // (:169-185)
   int midplane = -1;
+  // octree (grid_geometry_octree.f90:160-260): one entry per node, 1-based ids stored 0-based
+  std::vector<double> ox, oy, oz, odx, ody, odz;
+  std::vector<char> orefined;
+  std::vector<int> ochildren, oparent, oparent_subcell;  // ochildren[8*ic + k]
+  double oct_eps = 0.0;
+  // cells that hold physical quantities (geo%mask / mask_map); empty = all cells
+  std::vector<int> mask_map;
+  int n_masked = 0;
+  bool specific_energy_from_file = false;
   // dust
   int n_dust = 0;
   std::vector<Dust> d;
@@ -1073,6 +1082,7 @@ Cell new_grid_cell(const orc_ctx &g, int i1, int i2, int i3) {
 
 // escaped_cell (grid_geometry_cartesian_3d.f90:267-275)
 bool escaped(const orc_ctx &g, const Cell &c) {
+  if (g.grid_type == 3) return c.ic == g.n_cells + 1;  // grid_geometry_octree.f90:318-325
   if (c.i1 < 1 || c.i1 > g.n1) return true;
   if (g.grid_type == 1) return false;  // spherical: radial escape only (grid_geometry_spherical_3d.f90:493-500)
   if (g.grid_type == 2) return c.i2 < 1 || c.i2 > g.n2;  // cylindrical: w and z (grid_geometry_cylindrical_3d.f90:375-384)
@@ -1087,6 +1097,10 @@ void sph_adjust_wall(const orc_ctx &g, Photon &p);
 bool sph_in_correct_cell(const orc_ctx &g, const Photon &p);
 void sph_find_wall(orc_ctx &g, const Photon &p, double &tnearest, WallId &id_min);
 bool cyl_find_cell(const orc_ctx &g, const Photon &p, Cell &out);
+bool oct_find_cell(const orc_ctx &g, const Photon &p, Cell &out);
+bool oct_in_correct_cell(const orc_ctx &g, const Photon &p);
+void oct_find_wall(orc_ctx &g, const Photon &p, double &tnearest, WallId &id_min);
+Cell oct_next_cell(const orc_ctx &g, const Cell &c, const WallId &dir, const Vec &r);
 void cyl_adjust_wall(const orc_ctx &g, Photon &p);
 bool cyl_in_correct_cell(const orc_ctx &g, const Photon &p);
 void cyl_find_wall(orc_ctx &g, const Photon &p, double &tnearest, WallId &id_min);
@@ -1094,6 +1108,7 @@ void cyl_find_wall(orc_ctx &g, const Photon &p, double &tnearest, WallId &id_min
 bool find_cell(const orc_ctx &g, const Photon &p, Cell &out) {
   if (g.grid_type == 1) return sph_find_cell(g, p, out);
   if (g.grid_type == 2) return cyl_find_cell(g, p, out);
+  if (g.grid_type == 3) return oct_find_cell(g, p, out);
   int i1 = locate(g.w1.data(), g.n1 + 1, p.r.x);
   int i2 = locate(g.w2.data(), g.n2 + 1, p.r.y);
   int i3 = locate(g.w3.data(), g.n3 + 1, p.r.z);
@@ -1114,6 +1129,7 @@ void adjust_wall(const orc_ctx &g, Photon &p) {
     cyl_adjust_wall(g, p);
     return;
   }
+  if (g.grid_type == 3) return;  // the octree place_in_cell has no adjust_wall (grid_geometry_octree.f90:299-310)
   p.on_wall = false;
   p.on_wall_id = WallId();
 #define ADJ(V, R, W, I, WID)                   \
@@ -1157,6 +1173,7 @@ void place_in_cell(orc_ctx &g, Photon &p) {
 bool in_correct_cell(const orc_ctx &g, const Photon &p) {
   if (g.grid_type == 1) return sph_in_correct_cell(g, p);
   if (g.grid_type == 2) return cyl_in_correct_cell(g, p);
+  if (g.grid_type == 3) return oct_in_correct_cell(g, p);
   const double threshold = 1.e-3;
   Cell act;
   bool valid = find_cell(g, p, act);
@@ -1219,6 +1236,10 @@ void find_wall(orc_ctx &g, const Photon &p, double &tnearest, WallId &id_min) {
     cyl_find_wall(g, p, tnearest, id_min);
     return;
   }
+  if (g.grid_type == 3) {
+    oct_find_wall(g, p, tnearest, id_min);
+    return;
+  }
   g.tmin = std::numeric_limits<double>::max();
   g.emin = 0.0;
   g.imin = WallId();
@@ -1251,7 +1272,8 @@ void find_wall(orc_ctx &g, const Photon &p, double &tnearest, WallId &id_min) {
 }
 
 // next_cell_wall_id (grid_geometry_cartesian_3d.f90:303-328)
-Cell next_cell(const orc_ctx &g, const Cell &c, const WallId &dir) {
+Cell next_cell(const orc_ctx &g, const Cell &c, const WallId &dir, const Vec &r) {
+  if (g.grid_type == 3) return oct_next_cell(g, c, dir, r);
   int i1 = c.i1, i2 = c.i2, i3 = c.i3;
   if (dir.w1 == -1)
     i1 = i1 - 1;
@@ -1858,6 +1880,132 @@ Vec cyl_random_position_cell(orc_ctx &g, const Cell &c) {
   return Vec{r * std::cos(ph), r * std::sin(ph), z};
 }
 
+// ---------------------------------------------------------------------------
+// octree geometry (src/grid/grid_geometry_octree.f90); cell ids are 1-based as in the Fortran
+// ---------------------------------------------------------------------------
+// subcell_id (:98-133): 1..8, x fastest
+int oct_subcell_id(const orc_ctx &g, int cell_id, const Vec &r) {
+  const int k = cell_id - 1;
+  int s = 1;
+  if (!(r.x < g.ox[k])) s += 1;
+  if (!(r.y < g.oy[k])) s += 2;
+  if (!(r.z < g.oz[k])) s += 4;
+  return s;
+}
+
+// locate_cell (:135-146)
+int oct_locate_cell(const orc_ctx &g, const Vec &r, int cell_id) {
+  while (g.orefined[cell_id - 1]) cell_id = g.ochildren[(size_t)8 * (cell_id - 1) + oct_subcell_id(g, cell_id, r) - 1];
+  return cell_id;
+}
+
+// find_cell (:277-297)
+bool oct_find_cell(const orc_ctx &g, const Photon &p, Cell &out) {
+  if (p.r.x < g.ox[0] - g.odx[0] || p.r.x > g.ox[0] + g.odx[0]) return false;
+  if (p.r.y < g.oy[0] - g.ody[0] || p.r.y > g.oy[0] + g.ody[0]) return false;
+  if (p.r.z < g.oz[0] - g.odz[0] || p.r.z > g.oz[0] + g.odz[0]) return false;
+  out = Cell{0, 0, 0, oct_locate_cell(g, p.r, 1)};
+  return true;
+}
+
+// next_cell_int (:328-347) + next_cell_wall_id (:349-367)
+Cell oct_next_cell(const orc_ctx &g, const Cell &c, const WallId &dir, const Vec &r) {
+  // opposite_cell(subcell, wall) (:53-59)
+  static const int opposite_cell[6][8] = {{0, 1, 0, 3, 0, 5, 0, 7}, {2, 0, 4, 0, 6, 0, 8, 0}, {0, 0, 1, 2, 0, 0, 5, 6},
+                                          {3, 4, 0, 0, 7, 8, 0, 0}, {0, 0, 0, 0, 1, 2, 3, 4}, {5, 6, 7, 8, 0, 0, 0, 0}};
+  int direction;
+  if (dir.w1 == -1) direction = 1;
+  else if (dir.w1 == +1) direction = 2;
+  else if (dir.w2 == -1) direction = 3;
+  else if (dir.w2 == +1) direction = 4;
+  else if (dir.w3 == -1) direction = 5;
+  else if (dir.w3 == +1) direction = 6;
+  else return c;
+  int ic = c.ic;
+  for (;;) {
+    if (ic == 1) return Cell{0, 0, 0, g.n_cells + 1};
+    int sub = opposite_cell[direction - 1][g.oparent_subcell[ic - 1] - 1];
+    int parent = g.oparent[ic - 1];
+    if (sub > 0) return Cell{0, 0, 0, oct_locate_cell(g, r, g.ochildren[(size_t)8 * (parent - 1) + sub - 1])};
+    ic = parent;
+  }
+}
+
+// in_correct_cell (:369-394)
+bool oct_in_correct_cell(const orc_ctx &g, const Photon &p) {
+  Cell act;
+  bool valid = oct_find_cell(g, p, act);
+  if (!valid) act = Cell{0, 0, 0, -1};
+  if (!p.on_wall) return act.ic == p.icell.ic;
+  const int k = p.icell.ic - 1;
+  double frac1 = std::fabs(p.r.x - g.ox[k]) / g.odx[k];
+  double frac2 = std::fabs(p.r.y - g.oy[k]) / g.ody[k];
+  double frac3 = std::fabs(p.r.z - g.oz[k]) / g.odz[k];
+  double frac = 0.0;
+  bool ok = true;
+  if (std::abs(p.on_wall_id.w1) == 1) {
+    frac = frac1 - 1.0;
+    ok = frac2 < 1.0 && frac3 < 1.0;
+  }
+  if (std::abs(p.on_wall_id.w2) == 1) {
+    frac = frac2 - 1.0;
+    ok = frac1 < 1.0 && frac3 < 1.0;
+  }
+  if (std::abs(p.on_wall_id.w3) == 1) {
+    frac = frac3 - 1.0;
+    ok = frac1 < 1.0 && frac2 < 1.0;
+  }
+  return std::fabs(frac) < 1.e-3 && ok;
+}
+
+// find_wall (:438-537)
+void oct_find_wall(orc_ctx &g, const Photon &p, double &tmin, WallId &id_min) {
+  const double huge = std::numeric_limits<double>::max();
+  const int k = p.icell.ic - 1;
+  id_min = WallId();
+  bool pos_vx = p.v.x > 0.0, pos_vy = p.v.y > 0.0, pos_vz = p.v.z > 0.0;
+  double tx, ty, tz;
+  if (pos_vx) tx = (g.ox[k] + g.odx[k] - p.r.x) / p.v.x;
+  else if (p.v.x < 0.0) tx = (g.ox[k] - g.odx[k] - p.r.x) / p.v.x;
+  else tx = huge;
+  if (pos_vy) ty = (g.oy[k] + g.ody[k] - p.r.y) / p.v.y;
+  else if (p.v.y < 0.0) ty = (g.oy[k] - g.ody[k] - p.r.y) / p.v.y;
+  else ty = huge;
+  if (pos_vz) tz = (g.oz[k] + g.odz[k] - p.r.z) / p.v.z;
+  else if (p.v.z < 0.0) tz = (g.oz[k] - g.odz[k] - p.r.z) / p.v.z;
+  else tz = huge;
+  if (tx < tz) {
+    if (tx < ty) {
+      id_min.w1 = pos_vx ? +1 : -1;
+      tmin = tx;
+    } else {
+      id_min.w2 = pos_vy ? +1 : -1;
+      tmin = ty;
+    }
+  } else {
+    if (tz < ty) {
+      id_min.w3 = pos_vz ? +1 : -1;
+      tmin = tz;
+    } else {
+      id_min.w2 = pos_vy ? +1 : -1;
+      tmin = ty;
+    }
+  }
+  if (tmin < 0.0) {
+    if (tmin > -10 * g.oct_eps)
+      tmin = 0.0;
+    else
+      id_min = WallId();
+  }
+}
+
+// random_position_cell (:396-408)
+Vec oct_random_position_cell(orc_ctx &g, const Cell &c) {
+  double x = g.rng.random(), y = g.rng.random(), z = g.rng.random();
+  const int k = c.ic - 1;
+  return Vec{(2.0 * x - 1.0) * g.odx[k] + g.ox[k], (2.0 * y - 1.0) * g.ody[k] + g.oy[k], (2.0 * z - 1.0) * g.odz[k] + g.oz[k]};
+}
+
 // update_optconsts (dust.f90:64-79)
 void update_optconsts(orc_ctx &g, Photon &p) {
   for (int id = 0; id < g.n_dust; id++) {
@@ -2013,7 +2161,7 @@ void grid_integrate(orc_ctx &g, Photon &p, double tau_required, double &tau_achi
           g.specific_energy_sum[k] = g.specific_energy_sum[k] + tmin * p.current_kappa[id] * p.energy;
       }
       p.on_wall = true;
-      p.icell = next_cell(g, p.icell, id_min);
+      p.icell = next_cell(g, p.icell, id_min, p.r);
       p.on_wall_id = WallId{-id_min.w1, -id_min.w2, -id_min.w3};  // opposite_wall (grid_geometry_common_3d.f90:40-45)
       if (escaped(g, p.icell)) return;
     } else {
@@ -2255,7 +2403,7 @@ void grid_integrate_noenergy(orc_ctx &g, Photon &p, double tau_required, double 
       p.r.z = p.r.z + tmin * p.v.z;
       tau_achieved = tau_achieved + tau_cell;
       p.on_wall = true;
-      p.icell = next_cell(g, p.icell, id_min);
+      p.icell = next_cell(g, p.icell, id_min, p.r);
       p.on_wall_id = WallId{-id_min.w1, -id_min.w2, -id_min.w3};
       if (escaped(g, p.icell)) return;
     } else {
@@ -2339,7 +2487,7 @@ void grid_escape(orc_ctx &g, const Photon &p_orig, double tmax, double &tau, dou
     }
     if (finished) return;
     p.on_wall = true;
-    p.icell = next_cell(g, p.icell, id_min);
+    p.icell = next_cell(g, p.icell, id_min, p.r);
     p.on_wall_id = WallId{-id_min.w1, -id_min.w2, -id_min.w3};
     if (escaped(g, p.icell)) return;
   }
@@ -2606,24 +2754,34 @@ Photon emit_from_grid(orc_ctx &g) {
   Photon p;
   double xi = g.rng.random();
   p.dust_id = std::max((int)std::ceil(xi * (double)g.n_dust), 1);
-  // random_masked_cell (grid_geometry_common_3d.f90:104-115): Cartesian grids have no mask
+  // random_masked_cell (grid_geometry_common_3d.f90:104-115)
   xi = g.rng.random();
-  int ic = std::max((int)std::ceil(xi * g.n_cells), 1);
-  int i3 = (ic - 1) / (g.n1 * g.n2) + 1;
-  int i2 = (ic - 1 - (i3 - 1) * g.n1 * g.n2) / g.n1 + 1;
-  int i1 = ic - (i3 - 1) * g.n1 * g.n2 - (i2 - 1) * g.n1;
-  p.icell = new_grid_cell(g, i1, i2, i3);
+  int ic;
+  const int n_masked = g.mask_map.empty() ? g.n_cells : g.n_masked;
+  if (!g.mask_map.empty())
+    ic = g.mask_map[std::max((int)std::ceil(xi * g.n_masked), 1) - 1];
+  else
+    ic = std::max((int)std::ceil(xi * g.n_cells), 1);
   p.in_cell = true;
-  // random_position_cell (grid_geometry_cartesian_3d.f90:383-394)
-  if (g.grid_type == 1) {
-    p.r = sph_random_position_cell(g, p.icell);
-  } else if (g.grid_type == 2) {
-    p.r = cyl_random_position_cell(g, p.icell);
+  if (g.grid_type == 3) {
+    p.icell = Cell{0, 0, 0, ic};
+    p.r = oct_random_position_cell(g, p.icell);
   } else {
-    double x = g.rng.random(), y = g.rng.random(), z = g.rng.random();
-    p.r.x = x * (g.w1[i1] - g.w1[i1 - 1]) + g.w1[i1 - 1];
-    p.r.y = y * (g.w2[i2] - g.w2[i2 - 1]) + g.w2[i2 - 1];
-    p.r.z = z * (g.w3[i3] - g.w3[i3 - 1]) + g.w3[i3 - 1];
+    int i3 = (ic - 1) / (g.n1 * g.n2) + 1;
+    int i2 = (ic - 1 - (i3 - 1) * g.n1 * g.n2) / g.n1 + 1;
+    int i1 = ic - (i3 - 1) * g.n1 * g.n2 - (i2 - 1) * g.n1;
+    p.icell = new_grid_cell(g, i1, i2, i3);
+    // random_position_cell of the geometry
+    if (g.grid_type == 1) {
+      p.r = sph_random_position_cell(g, p.icell);
+    } else if (g.grid_type == 2) {
+      p.r = cyl_random_position_cell(g, p.icell);
+    } else {
+      double x = g.rng.random(), y = g.rng.random(), z = g.rng.random();
+      p.r.x = x * (g.w1[i1] - g.w1[i1 - 1]) + g.w1[i1 - 1];
+      p.r.y = y * (g.w2[i2] - g.w2[i2 - 1]) + g.w2[i2 - 1];
+      p.r.z = z * (g.w3[i3] - g.w3[i3 - 1]) + g.w3[i3 - 1];
+    }
   }
   p.a = random_sphere_angle3d(g.rng);
   p.v = angle3d_to_vector3d(p.a);
@@ -2631,7 +2789,7 @@ Photon emit_from_grid(orc_ctx &g) {
   size_t k = (size_t)(p.dust_id - 1) * g.n_cells + ic - 1;
   if (g.energy_abs_tot[p.dust_id - 1] > 0.0) {
     double mass = g.density[k] * g.volume[ic - 1];
-    p.energy = g.specific_energy[k] * mass * (double)g.n_cells / g.energy_abs_tot[p.dust_id - 1];
+    p.energy = g.specific_energy[k] * mass * (double)n_masked / g.energy_abs_tot[p.dust_id - 1];
   } else {
     p.energy = 0.0;
   }
@@ -2844,6 +3002,65 @@ int orc_set_grid_cylindrical(orc_ctx *g, int32_t n1, int32_t n2, int32_t n3, con
   return 0;
 }
 
+// setup_grid_geometry + octree_setup_indiv (grid_geometry_octree.f90:148-262): refined is the depth-first
+// list of refinement flags, (x, y, z) the centre and (dx, dy, dz) the HALF-widths of the root cell
+int orc_set_grid_octree(orc_ctx *g, int32_t n_cells, const int32_t *refined, double x, double y, double z, double dx,
+                        double dy, double dz) {
+  g->grid_type = 3;
+  g->n_cells = n_cells;
+  g->n1 = n_cells;
+  g->n2 = g->n3 = 1;
+  g->ox.assign(n_cells, 0.0);
+  g->oy = g->oz = g->odx = g->ody = g->odz = g->ox;
+  g->orefined.assign(n_cells, 0);
+  g->ochildren.assign((size_t)8 * n_cells, 0);
+  g->oparent.assign(n_cells, 0);
+  g->oparent_subcell.assign(n_cells, 0);
+  for (int i = 0; i < n_cells; i++) g->orefined[i] = refined[i] == 1;
+  g->mask_map.clear();
+  for (int i = 0; i < n_cells; i++)
+    if (refined[i] == 0) g->mask_map.push_back(i + 1);
+  g->n_masked = (int)g->mask_map.size();
+  g->ox[0] = x; g->oy[0] = y; g->oz[0] = z;
+  g->odx[0] = dx; g->ody[0] = dy; g->odz[0] = dz;
+  int n_filled = 1;
+  // iterative form of the recursion: a stack of (parent, next child index)
+  std::vector<std::pair<int, int>> stack;
+  if (g->orefined[0]) stack.push_back({1, 1});
+  while (!stack.empty()) {
+    int parent = stack.back().first, ic = stack.back().second;
+    if (ic > 8) {
+      stack.pop_back();
+      continue;
+    }
+    stack.back().second = ic + 1;
+    n_filled = n_filled + 1;
+    if (n_filled > n_cells) return fail(g, "refined array is not self-consistent");
+    int child = n_filled;
+    g->ochildren[(size_t)8 * (parent - 1) + ic - 1] = child;
+    int sx = 1, sy = 1, sz = 1;
+    if ((ic - 1) % 2 == 0) sx = -sx;
+    if (((ic - 1) / 2) % 2 == 0) sy = -sy;
+    if (((ic - 1) / 4) % 2 == 0) sz = -sz;
+    g->ox[child - 1] = g->ox[parent - 1] + sx * g->odx[parent - 1] / 2.0;
+    g->oy[child - 1] = g->oy[parent - 1] + sy * g->ody[parent - 1] / 2.0;
+    g->oz[child - 1] = g->oz[parent - 1] + sz * g->odz[parent - 1] / 2.0;
+    g->odx[child - 1] = g->odx[parent - 1] / 2.0;
+    g->ody[child - 1] = g->ody[parent - 1] / 2.0;
+    g->odz[child - 1] = g->odz[parent - 1] / 2.0;
+    g->oparent[child - 1] = parent;
+    g->oparent_subcell[child - 1] = ic;
+    if (g->orefined[child - 1]) stack.push_back({child, 1});
+  }
+  if (n_filled != n_cells) return fail(g, "refined array is not self-consistent");
+  g->volume.resize(n_cells);
+  for (int i = 0; i < n_cells; i++) g->volume[i] = g->odx[i] * g->ody[i] * g->odz[i] * 8.0;
+  for (double v : g->volume)
+    if (v == 0.0) return fail(g, "all volumes should be greater than zero");
+  g->oct_eps = spacing(std::max(dx, std::max(dy, dz))) * 3.0;
+  return 0;
+}
+
 int orc_add_dust(orc_ctx *g, const hyp_dust_tables *t) {
   try {
     g->d.emplace_back();
@@ -2899,6 +3116,7 @@ int orc_set_specific_energy(orc_ctx *g, const double *se, const double *min_e) {
   if (min_e)
     for (int id = 0; id < g->n_dust; id++) g->minimum_specific_energy[id] = min_e[id];
   g->specific_energy.resize(n);
+  g->specific_energy_from_file = se != nullptr;
   if (se) {
     g->specific_energy.assign(se, se + n);
   } else {
@@ -2914,6 +3132,18 @@ int orc_finalize_setup(orc_ctx *g, int32_t rank) {
   try {
     size_t n = (size_t)g->n_dust * g->n_cells;
     if (g->density.size() != n) return fail(g, "density not set");
+    // setup_grid_physics applies the mask (refined octree nodes hold no dust): grid_physics_3d.f90:156-164
+    if (!g->mask_map.empty() && !g->setup_done) {
+      std::vector<char> valid(g->n_cells, 0);
+      for (int ic : g->mask_map) valid[ic - 1] = 1;
+      for (int id = 0; id < g->n_dust; id++)
+        for (int ic = 0; ic < g->n_cells; ic++)
+          if (!valid[ic]) g->density[(size_t)id * g->n_cells + ic] = 0.0;
+      if (g->specific_energy_from_file)
+        for (int id = 0; id < g->n_dust; id++)
+          for (int ic = 0; ic < g->n_cells; ic++)
+            if (!valid[ic]) g->specific_energy[(size_t)id * g->n_cells + ic] = 0.0;
+    }
     if (g->specific_energy.size() != n) orc_set_specific_energy(g, nullptr, nullptr);
     g->specific_energy_sum.assign(n, 0.0);
     g->jnu_var_id.assign(n, 0);

@@ -28,3 +28,9 @@ def golden_sph():
 def golden_cyl():
     import numpy as np
     return np.load(os.path.join(ROOT, "tests", "golden", "bitlevel_cyl.npz"))
+
+
+@pytest.fixture(scope="session")
+def golden_oct():
+    import numpy as np
+    return np.load(os.path.join(ROOT, "tests", "golden", "bitlevel_oct.npz"))

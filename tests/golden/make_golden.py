@@ -107,6 +107,14 @@ def main():
     golden_outputs(cyl, "cyl")
     np.savez_compressed(os.path.join(HERE, "bitlevel_cyl.npz"), **cyl)
     print("wrote", os.path.join(HERE, "bitlevel_cyl.npz"))
+    # octree (test_bit_level.py:93-96): 25 nodes, root cell centred on the origin with half-width pc
+    refined = [1, 0, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 1, 0, 0, 0, 0, 0, 0, 0, 0]
+    oct = {"refined": np.array(refined, dtype=np.int32), "center": np.zeros(3), "half": np.array([pc, pc, pc]),
+           "density_1": dens[("density", "oct")], "density_2": dens[("density_2", "oct")],
+           "density_3": dens[("density_3", "oct")]}
+    golden_outputs(oct, "oct")
+    np.savez_compressed(os.path.join(HERE, "bitlevel_oct.npz"), **oct)
+    print("wrote", os.path.join(HERE, "bitlevel_oct.npz"))
 
 
 def golden_outputs(out, grid_type):

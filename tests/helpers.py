@@ -36,6 +36,23 @@ def bitlevel_model_sph(zc, z, evenly, multi, grid_type="sph"):
                      FlatConf(sample_sources_evenly=evenly), grid_type=grid_type)
 
 
+def bitlevel_model_oct(zc, z, evenly, multi):
+    """The same test on the octree of test_bit_level.py:93-96 (25 nodes, two refined children)."""
+    dust = kmh_dust(zc)
+    dens = [z["density_1"]] + ([z["density_2"], z["density_3"]] if multi else [])
+    srcs = [FlatSource(type=1, luminosity=float(l), temperature=float(t), position=tuple(p))
+            for l, t, p in zip(zc["source_luminosity"], zc["source_temperature"], zc["source_position"])]
+    return FlatModel(None, None, None, np.array(dens), [dust] * len(dens), srcs,
+                     FlatConf(sample_sources_evenly=evenly), grid_type="oct", refined=z["refined"],
+                     oct_center=tuple(z["center"]), oct_half=tuple(z["half"]))
+
+
+def peeloff_model_oct(zc, z, evenly):
+    m = bitlevel_model_oct(zc, z, evenly, False)
+    m.peeled = peeloff_groups()
+    return m
+
+
 def ulp_diff(a, b):
     """Distance in units in the last place, as hyperion/model/tests/test_helpers.py:59-144 measures it."""
     a = np.asarray(a, dtype=np.float64)

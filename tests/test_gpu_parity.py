@@ -10,7 +10,7 @@ estimates (|z| bounded, z^2 averaging to 1).
 import numpy as np
 import pytest
 
-from helpers import bitlevel_model, bitlevel_model_sph, kmh_dust, pc, lsun
+from helpers import bitlevel_model, bitlevel_model_oct, bitlevel_model_sph, kmh_dust, pc, lsun
 
 pytestmark = pytest.mark.gpu
 
@@ -264,3 +264,50 @@ def test_axisymmetric_grid_with_central_source(golden_car):
         b = np.mean([s[key] for s in ost])
         assert abs(a / b - 1) < 0.01, (key, a, b)
     assert all(s["killed_geo"] == 0 for s in gst) and all(s["killed_geo"] == 0 for s in ost)
+
+
+@pytest.mark.parametrize("evenly,multi", [(False, False), (True, True)])
+def test_deposits_match_oracle_octree(golden_car, golden_oct, evenly, multi):
+    """The reference's bit-level model on its octree (test_bit_level.py:93-96: 25 nodes, 22 leaves on
+    three levels).  Refined nodes carry no dust and must stay empty."""
+    model = bitlevel_model_oct(golden_car, golden_oct, evenly, multi)
+    B, N = 32, 100000   # only 22 cells: more batches keep the z statistics from being dominated by a few cells
+    g, gst = _gpu_batches(model, N, B)
+    o, ost = _oracle_batches(model, N, B)
+    leaf = golden_oct["refined"] == 0
+    assert (g[:, :, ~leaf] == 0).all() and (o[:, :, ~leaf] == 0).all()
+    z, ok = _zscores(g[:, :, leaf], o[:, :, leaf])
+    assert ok.all()
+    assert np.abs(z).max() < 5.0, np.abs(z).max()
+    assert 0.4 < (z ** 2).mean() < 1.8, (z ** 2).mean()
+    for key in ("n_crossings", "n_absorptions", "n_scatterings"):
+        a = np.mean([s[key] for s in gst])
+        b = np.mean([s[key] for s in ost])
+        assert abs(a / b - 1) < 0.01, (key, a, b)
+    assert all(s["killed_geo"] == 0 and s["killed_int"] == 0 and s["n_photons"] == N for s in gst)
+
+
+def test_deposits_match_oracle_random_deep_octree():
+    """A seeded random octree with five levels and a few thousand leaves, four point sources and
+    Henyey-Greenstein dust (the shape of BASELINE.json's octree configuration, small enough for the
+    oracle): neighbour links across coarse-fine and fine-coarse faces, descents of several levels."""
+    from hyperion_b200 import synthetic as syn
+    model = syn.octree_point_sources_model(max_depth=5, p_refine=0.45, seed=4, tau_edge=2.0)
+    leaf = model.refined == 0
+    assert 1000 < leaf.sum() < 40000
+    B, N = 8, 200000
+    g, gst = _gpu_batches(model, N, B)
+    o, ost = _oracle_batches(model, N, B)
+    z, ok = _zscores(g[:, :, leaf], o[:, :, leaf])
+    assert ok.mean() > 0.9
+    assert np.abs(z[ok]).max() < 6.0, np.abs(z[ok]).max()
+    assert 0.6 < (z[ok] ** 2).mean() < 1.5, (z[ok] ** 2).mean()
+    for key in ("n_crossings", "n_absorptions", "n_scatterings"):
+        a = np.mean([s[key] for s in gst])
+        b = np.mean([s[key] for s in ost])
+        assert abs(a / b - 1) < 0.01, (key, a, b)
+    assert all(s["killed_geo"] == 0 for s in gst)
+    # total deposited energy: sum(deposit * density) estimates the number of absorptions
+    est = (g * model.density).sum(axis=(1, 2)) * N
+    nabs = np.array([s["n_absorptions"] for s in gst])
+    assert abs(est.mean() / nabs.mean() - 1) < 0.02

@@ -197,3 +197,33 @@ def test_rtin_roundtrip_cylindrical_grid(golden_car, golden_cyl, tmp_path):
     for k in ("w1", "w2", "w3", "density"):
         assert np.array_equal(getattr(got, k), getattr(m, k))
     assert np.allclose(got.volumes().sum(), np.pi * m.w1[-1] ** 2 * (m.w2[-1] - m.w2[0]), rtol=1e-12)
+
+
+def test_rtin_roundtrip_octree(golden_car, golden_oct, tmp_path):
+    """'oct' grids: table 'cells' with the depth-first 'refined' flags, root cell attributes x, y, z,
+    dx, dy, dz (hyperion/grid/octree_grid.py:426-436); quantities are [n_dust, n_nodes]."""
+    from helpers import bitlevel_model_oct
+    m = bitlevel_model_oct(golden_car, golden_oct, False, True)
+    fn = str(tmp_path / "m.rtin")
+    rtin_write.write_rtin(fn, m)
+    got, rs, _ = rtin.read_rtin(fn)
+    assert rs.grid_type == "oct" and got.grid_type == "oct"
+    assert np.array_equal(got.refined, m.refined) and got.oct_half == m.oct_half and got.oct_center == m.oct_center
+    assert np.array_equal(got.density, m.density) and got.density.shape == (3, 25)
+    v = got.volumes()
+    assert np.allclose(v[got.refined == 0].sum(), v[0], rtol=1e-14)
+
+
+@pytest.mark.gpu
+def test_runner_octree(golden_car, golden_oct, tmp_path):
+    from helpers import peeloff_model_oct
+    m = peeloff_model_oct(golden_car, golden_oct, False)
+    fin, fout = str(tmp_path / "m.rtin"), str(tmp_path / "m.rtout")
+    rtin_write.write_rtin(fin, m, n_initial_iter=2, n_initial_photons=20000, n_last_photons=20000, raytracing=True,
+                          n_ray_photons=(5000, 5000))
+    assert runner.main(["-f", fin, fout]) == 0
+    r = h5min.File(fout)
+    se = r["iteration_00002/specific_energy"][...]
+    assert se.shape == (1, 25)
+    assert np.all(se[0][m.refined == 0] > 0)
+    assert r["Peeled/group_00001/seds"][...][0].sum() > 0
