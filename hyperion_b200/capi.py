@@ -103,7 +103,7 @@ class CApi:
         self._keep = []
         f = self._fn
         f("last_error").restype = C.c_char_p
-        for name in ("set_grid_cartesian", "set_grid_spherical", "set_grid_cylindrical", "set_grid_octree", "add_dust", "add_source", "set_run_conf", "set_density",
+        for name in ("set_grid_cartesian", "set_grid_spherical", "set_grid_cylindrical", "set_grid_octree", "set_grid_amr", "add_dust", "add_source", "set_run_conf", "set_density",
                      "set_specific_energy", "lucy_begin", "lucy_finish", "get_specific_energy",
                      "get_density", "get_energy_sum", "add_peeled_group", "final_begin", "final_photons",
                      "final_finish", "raytracing_photons", "image_shape", "get_sed", "get_image"):
@@ -135,6 +135,14 @@ class CApi:
         self.check(self._fn("set_grid_octree")(ctx, C.c_int32(len(refined)),
                                                refined.ctypes.data_as(C.POINTER(C.c_int32)),
                                                *[C.c_double(float(v)) for v in tuple(center) + tuple(half)]))
+
+    def set_grid_amr(self, ctx, levels):
+        n_grids = np.array([len(lev) for lev in levels], dtype=np.int32)
+        dims = np.array([g[:3] for lev in levels for g in lev], dtype=np.int32).ravel()
+        bounds = np.array([g[3:9] for lev in levels for g in lev], dtype=np.float64).ravel()
+        i32 = C.POINTER(C.c_int32)
+        self.check(self._fn("set_grid_amr")(ctx, C.c_int32(len(levels)), n_grids.ctypes.data_as(i32),
+                                            dims.ctypes.data_as(i32), _ptr(bounds)))
 
     def add_dust(self, ctx, d: FlatDust):
         t = DustTables()

@@ -7,6 +7,7 @@
 // HBM layout: one 16-byte record {density, energy_sum} per (cell, dust) so the
 // density read and the deposit RED of a crossing touch the same 32-byte sector.
 #include <algorithm>
+#include <array>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -20,6 +21,7 @@
 #include "device.cuh"
 #include "geometry_sph.cuh"
 #include "geometry_oct.cuh"
+#include "geometry_amr.cuh"
 
 using namespace hyp;
 
@@ -34,12 +36,13 @@ struct CellRec {
 enum { SC_ENERGY = 0, SC_KILLED_GEO, SC_KILLED_INT, SC_CROSS, SC_ABS, SC_SCAT, SC_ESC, SC_PHOTONS, SC_PEEL_CROSS, SC_PEELOFFS,
        SC_COUNT };
 
-enum { GEO_CAR = 0, GEO_SPH = 1, GEO_OCT = 2 };  // GEO_SPH covers both polar grids (SphGrid::kind)
+enum { GEO_CAR = 0, GEO_SPH = 1, GEO_OCT = 2, GEO_AMR = 3 };  // GEO_SPH covers both polar grids (SphGrid::kind)
 
 struct ModelDev {
   int32_t grid_type;        // GEO_*
   SphGrid sph;              // spherical polar tables (grid_type == GEO_SPH)
   OctGrid oct;              // octree (grid_type == GEO_OCT)
+  AmrGrid amr;              // block-structured AMR (grid_type == GEO_AMR)
   int32_t n1, n2, n3, n_dust, n_sources;
   int64_t n_cells;
   const double *w1, *w2, *w3;
@@ -299,6 +302,17 @@ __device__ bool emit_photon(const ModelDev &M, Photon<ND> &p, Rng &rng, double &
   }
   int fx, fy, fz;
   bool ok;
+  if (M.grid_type == GEO_AMR) {
+    int g;
+    if (!amr_find_cell(M.amr, p.r0x, p.r0y, p.r0z, g, p.ix, p.iy, p.iz)) {
+      atomicMax(M.error_flag, ERR_NOT_IN_CELL);
+      return false;
+    }
+    p.ic = amr_cell_id(M.amr.grids[g], p.ix, p.iy, p.iz);
+    p.n_inter = 0;
+    p.t = 0.0;
+    return true;
+  }
   if (M.grid_type == GEO_OCT) {
     const int node = oct_find_cell(M.oct, p.r0x, p.r0y, p.r0z);
     if (node < 0) {
@@ -486,12 +500,26 @@ __device__ __forceinline__ double cell_volume(const ModelDev &M, int64_t ic) {
     const OctNode &N = M.oct.nodes[ic];
     return N.dx * N.dy * N.dz * 8.0;  // grid_geometry_octree.f90:250-253
   }
+  if (M.grid_type == GEO_AMR) return amr_volume(M.amr, ic);
   const int i1 = (int)(ic % M.n1), i2 = (int)((ic / M.n1) % M.n2), i3 = (int)(ic / ((int64_t)M.n1 * M.n2));
   return ((M.w1[i1 + 1] - M.w1[i1]) * (M.w2[i2 + 1] - M.w2[i2])) * (M.w3[i3 + 1] - M.w3[i3]);
 }
 
 // random_position_cell (grid_geometry_cartesian_3d.f90:383-394, grid_geometry_spherical_3d.f90:645-677)
 __device__ inline void random_position_cell(const ModelDev &M, int64_t ic, Rng &rng, double &x, double &y, double &z) {
+  if (M.grid_type == GEO_AMR) {
+    // grid_geometry_amr.f90:729-741
+    const AmrGridDev &G = M.amr.grids[M.amr.cell_grid[ic]];
+    const int k = (int)ic - G.start_id;
+    const int i1 = k % G.n1, i2 = (k / G.n1) % G.n2, i3 = k / (G.n1 * G.n2);
+    const double x0 = amr_wall(G.xmin, G.xmax, i1, G.n1), x1 = amr_wall(G.xmin, G.xmax, i1 + 1, G.n1);
+    const double y0 = amr_wall(G.ymin, G.ymax, i2, G.n2), y1 = amr_wall(G.ymin, G.ymax, i2 + 1, G.n2);
+    const double z0 = amr_wall(G.zmin, G.zmax, i3, G.n3), z1 = amr_wall(G.zmin, G.zmax, i3 + 1, G.n3);
+    x = rng.next() * (x1 - x0) + x0;
+    y = rng.next() * (y1 - y0) + y0;
+    z = rng.next() * (z1 - z0) + z0;
+    return;
+  }
   if (M.grid_type == GEO_OCT) {
     // grid_geometry_octree.f90:396-408
     const OctNode &N = M.oct.nodes[ic];
@@ -1246,6 +1274,13 @@ struct hyp_ctx {
   std::vector<OctNode> oct_nodes;
   std::vector<int32_t> oct_children, oct_leaves;
   double oct_eps = 0.0;
+  // AMR (host copies until finalize)
+  std::vector<AmrGridDev> amr_grids;
+  std::vector<int32_t> amr_gotos, amr_cell_grid, amr_valid;
+  int amr_n_level1 = 0;
+  double amr_eps = 0.0;
+  AmrGridDev *d_amr_grids = nullptr;
+  int32_t *d_amr_gotos = nullptr, *d_amr_cell_grid = nullptr, *d_amr_valid = nullptr;
   OctNode *d_oct_nodes = nullptr;
   int32_t *d_oct_children = nullptr, *d_oct_leaves = nullptr;
   int n1 = 0, n2 = 0, n3 = 0;
@@ -1496,6 +1531,10 @@ void hyp_ctx_destroy(hyp_ctx *c) {
   free_dev(c->d_w);
   free_dev(c->d_sph);
   free_dev(c->d_oct_nodes);
+  free_dev(c->d_amr_grids);
+  free_dev(c->d_amr_gotos);
+  free_dev(c->d_amr_cell_grid);
+  free_dev(c->d_amr_valid);
   free_dev(c->d_oct_children);
   free_dev(c->d_oct_leaves);
   free_dev(c->d_cells);
@@ -1700,6 +1739,131 @@ int hyp_set_grid_octree(hyp_ctx *c, int32_t n_cells, const int32_t *refined, dou
   return HYP_OK;
 }
 
+int hyp_set_grid_amr(hyp_ctx *c, int32_t n_levels, const int32_t *n_grids, const int32_t *dims, const double *bounds) {
+  if (!c || !n_grids || !dims || !bounds) return fail(HYP_ERR_INVALID, "NULL argument");
+  if (c->finalized) return fail(HYP_ERR_STATE, "model is frozen");
+  if (n_levels < 1 || n_grids[0] < 1) return fail(HYP_ERR_INVALID, "AMR grid needs at least one level-1 grid");
+  // read_grid + setup_grid_geometry (grid_geometry_amr.f90:111-507), grids of all levels in one flat list
+  std::vector<AmrGridDev> G;
+  std::vector<int> level_of;
+  std::vector<std::array<double, 3>> width;
+  int64_t n_cells = 0, goto_total = 0;
+  double min_width = std::numeric_limits<double>::max();
+  for (int il = 0, k = 0; il < n_levels; ++il)
+    for (int ig = 0; ig < n_grids[il]; ++ig, ++k) {
+      AmrGridDev g;
+      g.n1 = dims[3 * k]; g.n2 = dims[3 * k + 1]; g.n3 = dims[3 * k + 2];
+      if (g.n1 < 1 || g.n2 < 1 || g.n3 < 1) return fail(HYP_ERR_INVALID, "grid needs at least one cell per axis");
+      g.xmin = bounds[6 * k]; g.xmax = bounds[6 * k + 1];
+      g.ymin = bounds[6 * k + 2]; g.ymax = bounds[6 * k + 3];
+      g.zmin = bounds[6 * k + 4]; g.zmax = bounds[6 * k + 5];
+      if (!(g.xmax > g.xmin && g.ymax > g.ymin && g.zmax > g.zmin))
+        return fail(HYP_ERR_INVALID, "all volumes should be greater than zero");
+      g.start_id = (int32_t)n_cells;
+      g.goto_off = goto_total;
+      n_cells += (int64_t)g.n1 * g.n2 * g.n3;
+      goto_total += (int64_t)(g.n1 + 2) * (g.n2 + 2) * (g.n3 + 2);
+      if (n_cells > 2000000000LL) return fail(HYP_ERR_INVALID, "grid too large for 32-bit cell ids");
+      std::array<double, 3> w = {(g.xmax - g.xmin) / g.n1, (g.ymax - g.ymin) / g.n2, (g.zmax - g.zmin) / g.n3};
+      for (double v : w) min_width = std::min(min_width, v);
+      G.push_back(g);
+      level_of.push_back(il);
+      width.push_back(w);
+    }
+  // grids of a level share their cell widths (:246-262)
+  for (size_t a = 0; a < G.size(); ++a)
+    for (size_t b = 0; b < a; ++b)
+      if (level_of[a] == level_of[b])
+        for (int d = 0; d < 3; ++d)
+          if (std::fabs(width[a][d] - width[b][d]) > 1.e-10 * width[a][d])
+            return fail(HYP_ERR_INVALID, "grids in one level have differing cell widths");
+  std::vector<int32_t> go((size_t)goto_total, 0);
+  auto gidx = [&](const AmrGridDev &g, int i1, int i2, int i3) {
+    return (size_t)g.goto_off + i1 + (size_t)(g.n1 + 2) * (i2 + (size_t)(g.n2 + 2) * i3);
+  };
+  auto wall = [](double a, double b, int i, int n) { return (b - a) * (double)i / (double)n + a; };
+  auto centre = [&](const AmrGridDev &g, int axis, int i) {  // 1-based cell index
+    if (axis == 0) return 0.5 * (wall(g.xmin, g.xmax, i - 1, g.n1) + wall(g.xmin, g.xmax, i, g.n1));
+    if (axis == 1) return 0.5 * (wall(g.ymin, g.ymax, i - 1, g.n2) + wall(g.ymin, g.ymax, i, g.n2));
+    return 0.5 * (wall(g.zmin, g.zmax, i - 1, g.n3) + wall(g.zmin, g.zmax, i, g.n3));
+  };
+  auto inside = [](const AmrGridDev &g, double x, double y, double z) {
+    return !(x < g.xmin || x > g.xmax || y < g.ymin || y > g.ymax || z < g.zmin || z > g.zmax);
+  };
+  // cells covered by a grid of the next finer level point to it (:355-381)
+  for (size_t a = 0; a < G.size(); ++a)
+    for (size_t b = 0; b < G.size(); ++b) {
+      if (level_of[b] != level_of[a] + 1) continue;
+      const AmrGridDev &g1 = G[a], &g2 = G[b];
+      if (g1.xmax < g2.xmin || g1.xmin > g2.xmax || g1.ymax < g2.ymin || g1.ymin > g2.ymax || g1.zmax < g2.zmin ||
+          g1.zmin > g2.zmax)
+        continue;
+      for (int i3 = 1; i3 <= g1.n3; ++i3)
+        for (int i2 = 1; i2 <= g1.n2; ++i2)
+          for (int i1 = 1; i1 <= g1.n1; ++i1)
+            if (inside(g2, centre(g1, 0, i1), centre(g1, 1, i2), centre(g1, 2, i3))) go[gidx(g1, i1, i2, i3)] = (int32_t)b + 1;
+    }
+  // ghost layer: the grid of the same or a coarser level (finest first) one half cell outside each face (:383-487)
+  for (size_t a = 0; a < G.size(); ++a) {
+    const AmrGridDev &g1 = G[a];
+    for (int lev = level_of[a]; lev >= 0; --lev)
+      for (size_t b = 0; b < G.size(); ++b) {
+        if (level_of[b] != lev || a == b) continue;
+        const AmrGridDev &g2 = G[b];
+        const std::array<double, 3> &w2 = width[b];
+        if (g1.xmax < g2.xmin - w2[0] * 0.5 || g1.xmin > g2.xmax + w2[0] * 0.5 || g1.ymax < g2.ymin - w2[1] * 0.5 ||
+            g1.ymin > g2.ymax + w2[1] * 0.5 || g1.zmax < g2.zmin - w2[2] * 0.5 || g1.zmin > g2.zmax + w2[2] * 0.5)
+          continue;
+        auto mark = [&](int i1, int i2, int i3, double x, double y, double z) {
+          int32_t &e = go[gidx(g1, i1, i2, i3)];
+          if (e == 0 && inside(g2, x, y, z)) e = (int32_t)b + 1;
+        };
+        const std::array<double, 3> &w1 = width[a];
+        for (int i3 = 1; i3 <= g1.n3; ++i3)
+          for (int i2 = 1; i2 <= g1.n2; ++i2) {
+            mark(0, i2, i3, g1.xmin - w1[0] * 0.5, centre(g1, 1, i2), centre(g1, 2, i3));
+            mark(g1.n1 + 1, i2, i3, g1.xmax + w1[0] * 0.5, centre(g1, 1, i2), centre(g1, 2, i3));
+          }
+        for (int i3 = 1; i3 <= g1.n3; ++i3)
+          for (int i1 = 1; i1 <= g1.n1; ++i1) {
+            mark(i1, 0, i3, centre(g1, 0, i1), g1.ymin - w1[1] * 0.5, centre(g1, 2, i3));
+            mark(i1, g1.n2 + 1, i3, centre(g1, 0, i1), g1.ymax + w1[1] * 0.5, centre(g1, 2, i3));
+          }
+        for (int i2 = 1; i2 <= g1.n2; ++i2)
+          for (int i1 = 1; i1 <= g1.n1; ++i1) {
+            mark(i1, i2, 0, centre(g1, 0, i1), centre(g1, 1, i2), g1.zmin - w1[2] * 0.5);
+            mark(i1, i2, g1.n3 + 1, centre(g1, 0, i1), centre(g1, 1, i2), g1.zmax + w1[2] * 0.5);
+          }
+      }
+  }
+  // cell -> grid map and the list of valid (uncovered) cells (:489-506)
+  std::vector<int32_t> cell_grid((size_t)n_cells), valid;
+  for (size_t a = 0; a < G.size(); ++a) {
+    const AmrGridDev &g = G[a];
+    for (int i3 = 1; i3 <= g.n3; ++i3)
+      for (int i2 = 1; i2 <= g.n2; ++i2)
+        for (int i1 = 1; i1 <= g.n1; ++i1) {
+          const int32_t ic = g.start_id + ((i3 - 1) * g.n2 + (i2 - 1)) * g.n1 + (i1 - 1);
+          cell_grid[ic] = (int32_t)a;
+          if (go[gidx(g, i1, i2, i3)] == 0) valid.push_back(ic);
+        }
+  }
+  c->amr_grids.swap(G);
+  c->amr_gotos.swap(go);
+  c->amr_cell_grid.swap(cell_grid);
+  c->amr_valid.swap(valid);
+  c->amr_n_level1 = n_grids[0];
+  c->amr_eps = min_width / 2.0;
+  c->grid_type = GEO_AMR;
+  c->n1 = (int)n_cells;
+  c->n2 = c->n3 = 1;
+  c->n_cells = n_cells;
+  c->w1.assign(2, 0.0);
+  c->w2.assign(2, 0.0);
+  c->w3.assign(2, 0.0);
+  return HYP_OK;
+}
+
 int hyp_add_dust(hyp_ctx *c, const hyp_dust_tables *t) {
   if (!c || !t) return fail(HYP_ERR_INVALID, "NULL argument");
   if (c->finalized) return fail(HYP_ERR_STATE, "model is frozen");
@@ -1852,6 +2016,38 @@ int hyp_finalize_setup(hyp_ctx *c) {
   M.w2 = c->d_w + c->w1.size();
   M.w3 = M.w2 + c->w2.size();
   M.grid_type = c->grid_type;
+  if (c->grid_type == GEO_AMR) {
+    AmrGrid &A = M.amr;
+    auto up = [&](auto *&dst, const auto &src) -> int {
+      CUDA_TRY(cudaMalloc(&dst, std::max<size_t>(src.size(), 1) * sizeof(src[0])));
+      CUDA_TRY(cudaMemcpy(dst, src.data(), src.size() * sizeof(src[0]), cudaMemcpyHostToDevice));
+      return HYP_OK;
+    };
+    int rc = up(c->d_amr_grids, c->amr_grids);
+    if (!rc) rc = up(c->d_amr_gotos, c->amr_gotos);
+    if (!rc) rc = up(c->d_amr_cell_grid, c->amr_cell_grid);
+    if (!rc) rc = up(c->d_amr_valid, c->amr_valid);
+    if (rc) return rc;
+    A.grids = c->d_amr_grids;
+    A.gotos = c->d_amr_gotos;
+    A.cell_grid = c->d_amr_cell_grid;
+    A.valid = c->d_amr_valid;
+    A.n_grids = (int32_t)c->amr_grids.size();
+    A.n_level1 = c->amr_n_level1;
+    A.n_cells = (int32_t)c->n_cells;
+    A.n_valid = (int32_t)c->amr_valid.size();
+    A.eps = c->amr_eps;
+    // cells covered by a finer grid hold no dust (grid_physics_3d.f90:156-164)
+    std::vector<char> ok((size_t)c->n_cells, 0);
+    for (int32_t ic : c->amr_valid) ok[ic] = 1;
+    const size_t nc = (size_t)c->n_cells;
+    for (size_t id = 0; id < c->dust.size(); ++id)
+      for (size_t ic = 0; ic < nc; ++ic)
+        if (!ok[ic]) {
+          c->h_density[id * nc + ic] = 0.0;
+          if (c->energy_from_caller) c->h_energy[id * nc + ic] = 0.0;
+        }
+  }
   if (c->grid_type == GEO_OCT) {
     OctGrid &G = M.oct;
     CUDA_TRY(cudaMalloc(&c->d_oct_nodes, c->oct_nodes.size() * sizeof(OctNode)));
@@ -2099,8 +2295,9 @@ static int run_rounds(hyp_ctx *c, int64_t first_id, int64_t n_photons, int64_t i
     CUDA_TRY(cudaEventRecord(c->evA, st));
     if (c->grid_type != GEO_CAR) {
       const FinalArgs none = FinalArgs();
-      auto geo_flight = c->grid_type == GEO_OCT ? flight_geo_kernel<GEO_OCT, ND, true, false>
-                                                : flight_geo_kernel<GEO_SPH, ND, true, false>;
+      auto geo_flight = c->grid_type == GEO_OCT   ? flight_geo_kernel<GEO_OCT, ND, true, false>
+                        : c->grid_type == GEO_AMR ? flight_geo_kernel<GEO_AMR, ND, true, false>
+                                                  : flight_geo_kernel<GEO_SPH, ND, true, false>;
       const int sph_blocks_max = c->sm_count * 12;
       if (n_new > 0) {
         int blocks = (int)std::min<int64_t>((n_new + SPH_FLIGHT_THREADS - 1) / SPH_FLIGHT_THREADS, sph_blocks_max);
@@ -2457,6 +2654,9 @@ int launch_peel(hyp_ctx *c, const ModelDev &M, uint32_t n_jobs_max) {
   } else if (c->grid_type == GEO_OCT) {
     k = peel_kernel<ND, POLY, GEO_OCT>;
     ws = WallSmem{0, 0};
+  } else if (c->grid_type == GEO_AMR) {
+    k = peel_kernel<ND, POLY, GEO_AMR>;
+    ws = WallSmem{0, 0};
   }
   CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ws.bytes));
   ImagingDev I{c->d_images, c->d_views, (int)c->groups.size(), c->n_views};
@@ -2534,8 +2734,9 @@ int run_final_rounds(hyp_ctx *c, int64_t first_id, int64_t n_photons, int scatte
     CUDA_TRY(cudaEventRecord(c->evA, st));
     if (c->grid_type != GEO_CAR) {
       const int sph_blocks_max = c->sm_count * 12;
-      auto geo_flight = c->grid_type == GEO_OCT ? flight_geo_kernel<GEO_OCT, ND, false, true>
-                                                : flight_geo_kernel<GEO_SPH, ND, false, true>;
+      auto geo_flight = c->grid_type == GEO_OCT   ? flight_geo_kernel<GEO_OCT, ND, false, true>
+                        : c->grid_type == GEO_AMR ? flight_geo_kernel<GEO_AMR, ND, false, true>
+                                                  : flight_geo_kernel<GEO_SPH, ND, false, true>;
       if (n_new > 0) {
         int blocks = (int)std::min<int64_t>((n_new + SPH_FLIGHT_THREADS - 1) / SPH_FLIGHT_THREADS, sph_blocks_max);
         geo_flight<<<blocks, SPH_FLIGHT_THREADS, 0, st>>>(M, P, F, P.q_beam, P.counts + C_NB,

@@ -77,6 +77,37 @@ struct Geo<GEO_OCT> {
   }
 };
 
+// block-structured AMR (geometry_amr.cuh)
+template <>
+struct Geo<GEO_AMR> {
+  using Ray = AmrRay;
+  struct Cross {
+    int wall;
+  };
+  static __device__ __forceinline__ bool find_cell(const ModelDev &M, double rx, double ry, double rz, double vx,
+                                                   double vy, double vz, int &ix, int &iy, int &iz, int &ic) {
+    int g;
+    if (!amr_find_cell(M.amr, rx, ry, rz, g, ix, iy, iz)) return false;
+    ic = amr_cell_id(M.amr.grids[g], ix, iy, iz);
+    return true;
+  }
+  static __device__ __forceinline__ void start(const ModelDev &M, Ray &R, double rx, double ry, double rz, double vx,
+                                               double vy, double vz, int ix, int iy, int iz, int ic) {
+    amr_start(M.amr, R, rx, ry, rz, vx, vy, vz, ix, iy, iz, ic);
+  }
+  static __device__ __forceinline__ bool escaped(const ModelDev &M, const Ray &R) { return R.ic == -2; }
+  static __device__ __forceinline__ bool find_wall(const ModelDev &M, const Ray &R, double &dt, Cross &c) {
+    if (R.ic < 0) return false;  // invalid_cell: the re-location after a grid change failed
+    amr_find_wall(M.amr.grids[R.g], R, dt, c.wall);
+    return true;
+  }
+  static __device__ __forceinline__ void step(const ModelDev &M, Ray &R, const Cross &c) { amr_step(M.amr, R, c.wall); }
+  static __device__ __forceinline__ void stop_inside(Ray &R) {}
+  static __device__ __forceinline__ void store(const Ray &R, int &ix, int &iy, int &iz, int &ic) {
+    ix = R.i1; iy = R.i2; iz = R.i3; ic = R.ic;
+  }
+};
+
 // grid_integrate / grid_integrate_noenergy (grid_propagate_3d.f90:35-375) for one packet: walk cell by
 // cell until tau_left is used up (MARCH_INTERACT, R.t = path length to the event, R.ic its cell), the
 // packet leaves the grid (MARCH_ESCAPED) or no wall is found (MARCH_KILLED).  DEP: deposit
@@ -91,6 +122,7 @@ __device__ inline int geo_march(const ModelDev &M, typename Geo<GEO>::Ray &R, do
     typename G::Cross cr;
     double rho[ND];
     const int ic = R.ic;
+    if (ic < 0) return MARCH_KILLED;  // AMR: the cell behind a grid boundary could not be located
 #pragma unroll
     for (int id = 0; id < ND; ++id) rho[id] = __ldcg(&cells[(size_t)ic * ND + id].rho);
     if (!G::find_wall(M, R, dt, cr)) return MARCH_KILLED;
@@ -134,6 +166,7 @@ __device__ inline bool geo_escape(const ModelDev &M, typename Geo<GEO>::Ray &R, 
     double dt;
     typename G::Cross cr;
     double rho[ND];
+    if (R.ic < 0) return false;
 #pragma unroll
     for (int id = 0; id < ND; ++id) rho[id] = __ldg(&cells[(size_t)R.ic * ND + id].rho);
     if (!G::find_wall(M, R, dt, cr)) return false;

@@ -173,9 +173,20 @@ class FlatModel:
     refined: Optional[np.ndarray] = None
     oct_center: tuple = (0.0, 0.0, 0.0)
     oct_half: tuple = (1.0, 1.0, 1.0)
+    # AMR (grid_type "amr", hyperion/grid/amr_grid.py): amr_levels[level] = list of grids, each
+    # (n1, n2, n3, xmin, xmax, ymin, ymax, zmin, zmax); density is [n_dust, n_cells] with the cells of
+    # all grids concatenated level-major, grid-major, x fastest (src/core/type_cell_id_amr.f90:115-133)
+    amr_levels: Optional[list] = None
 
     def __post_init__(self):
         self.density = _f8(self.density)
+        if self.grid_type == "amr":
+            n = sum(g[0] * g[1] * g[2] for lev in self.amr_levels for g in lev)
+            if self.density.ndim == 1:
+                self.density = self.density[None]
+            if self.density.shape != (len(self.dust), n):
+                raise ValueError("density should have shape (n_dust, n_cells) = %s" % ((len(self.dust), n),))
+            return
         if self.grid_type == "oct":
             self.refined = np.ascontiguousarray(self.refined, dtype=np.int32)
             if self.density.ndim == 1:
@@ -195,13 +206,31 @@ class FlatModel:
     def shape(self):
         if self.grid_type == "oct":
             return (len(self.refined),)
+        if self.grid_type == "amr":
+            return (sum(g[0] * g[1] * g[2] for lev in self.amr_levels for g in lev),)
         return (len(self.w3) - 1, len(self.w2) - 1, len(self.w1) - 1)
 
     @property
     def n_cells(self):
         return int(np.prod(self.shape))
 
+    def amr_slices(self):
+        """[(level, grid, slice into the flat cell axis, (n3, n2, n1))] in cell-id order."""
+        out, start = [], 0
+        for il, lev in enumerate(self.amr_levels):
+            for ig, g in enumerate(lev):
+                n = g[0] * g[1] * g[2]
+                out.append((il, ig, slice(start, start + n), (g[2], g[1], g[0])))
+                start += n
+        return out
+
     def volumes(self):
+        if self.grid_type == "amr":
+            vol = np.zeros(self.n_cells)
+            for il, ig, sl, _ in self.amr_slices():
+                g = self.amr_levels[il][ig]
+                vol[sl] = ((g[4] - g[3]) / g[0]) * ((g[6] - g[5]) / g[1]) * ((g[8] - g[7]) / g[2])
+            return vol
         if self.grid_type == "oct":
             # node volumes in depth-first order (grid_geometry_octree.f90:160-183,250-253)
             vol = np.zeros(len(self.refined))
@@ -238,12 +267,15 @@ def apply_model(api, ctx, model: FlatModel):
 
     ``api`` is a binding object with methods named like the header's functions
     minus the prefix (see :mod:`hyperion_b200.capi`)."""
-    if model.grid_type == "oct":
+    if model.grid_type == "amr":
+        api.set_grid_amr(ctx, model.amr_levels)
+        n1 = n2 = n3 = 0
+    elif model.grid_type == "oct":
         api.set_grid_octree(ctx, model.refined, model.oct_center, model.oct_half)
         n1 = n2 = n3 = 0
     else:
         n3, n2, n1 = model.shape
-    if model.grid_type == "oct":
+    if model.grid_type in ("oct", "amr"):
         pass
     elif model.grid_type == "sph":
         api.set_grid_spherical(ctx, n1, n2, n3, model.w1, model.w2, model.w3)

@@ -269,3 +269,55 @@ def octree_point_sources_model(refined=None, tau_edge=2.0, dust=None, n_sources=
     conf = FlatConf(n_initial_iter=n_iter, n_initial_photons=n_photons)
     return FlatModel(None, None, None, rho, [dust], src, conf, grid_type="oct", refined=refined,
                      oct_center=(0., 0., 0.), oct_half=(pc, pc, pc))
+
+
+def amr_point_sources_model(n_root=64, n_levels=3, n_patches=3, seed=5, tau_edge=2.0, dust=None, n_sources=2,
+                            lam_ref_um=0.5, n_photons=0, n_iter=1):
+    """SURVEY.md section 8d 'C5': a block-structured AMR hierarchy standing in for the yt sample:
+    one root grid of n_root^3 cells over [-pc, pc]^3; every finer level has ``n_patches`` seeded
+    non-overlapping boxes per parent patch region (refinement factor 2, aligned with parent cells and
+    nested inside a patch of the previous level).  Density 1+U(0,1) per cell, scaled so that the
+    optical depth from the centre to a face is ``tau_edge``."""
+    if dust is None:
+        dust = hg_dust(n_temp=40)
+    rng = np.random.default_rng(seed)
+    levels = [[(n_root, n_root, n_root, -pc, pc, -pc, pc, -pc, pc)]]
+    # patches as integer boxes in the index space of their level: (lo, hi) per axis
+    boxes = [[((0, 0, 0), (n_root, n_root, n_root))]]
+    for lev in range(1, n_levels):
+        new_boxes, new_grids = [], []
+        nlev = n_root * 2 ** lev
+        width = 2. * pc / nlev
+        for lo, hi in boxes[-1]:
+            # candidate sub-boxes in parent index space, refined by 2; keep those that do not touch each other
+            placed = []
+            for _ in range(8 * n_patches):
+                if len(placed) == n_patches:
+                    break
+                size = [max(2, int((hi[a] - lo[a]) * rng.uniform(0.2, 0.4))) for a in range(3)]
+                start = [int(rng.integers(lo[a] + 1, max(lo[a] + 2, hi[a] - size[a]))) for a in range(3)]
+                end = [min(start[a] + size[a], hi[a] - 1) for a in range(3)]
+                if any(end[a] - start[a] < 1 for a in range(3)):
+                    continue
+                if any(all(start[a] <= e2[a] and s2[a] <= end[a] for a in range(3)) for s2, e2 in placed):
+                    continue
+                placed.append((start, end))
+            for start, end in placed:
+                s2 = tuple(2 * v for v in start)
+                e2 = tuple(2 * v for v in end)
+                new_boxes.append((s2, e2))
+                new_grids.append((e2[0] - s2[0], e2[1] - s2[1], e2[2] - s2[2],
+                                  -pc + s2[0] * width, -pc + e2[0] * width, -pc + s2[1] * width, -pc + e2[1] * width,
+                                  -pc + s2[2] * width, -pc + e2[2] * width))
+        if not new_grids:
+            break
+        boxes.append(new_boxes)
+        levels.append(new_grids)
+    n_cells = sum(g[0] * g[1] * g[2] for lev in levels for g in lev)
+    chi0 = chi_at(dust, c / (lam_ref_um * 1.e-4))
+    rho0 = tau_edge / (chi0 * pc * 1.5)
+    rho = (1. + rng.random((1, n_cells))) * rho0
+    src = [FlatSource(type=1, luminosity=lsun * (0.5 + rng.random()), temperature=float(rng.uniform(3000., 9000.)),
+                      position=tuple(rng.uniform(-0.7 * pc, 0.7 * pc, 3))) for _ in range(n_sources)]
+    conf = FlatConf(n_initial_iter=n_iter, n_initial_photons=n_photons)
+    return FlatModel(None, None, None, rho, [dust], src, conf, grid_type="amr", amr_levels=levels)

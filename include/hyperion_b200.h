@@ -188,6 +188,14 @@ int hyp_set_grid_cylindrical(hyp_ctx *ctx, int32_t n1, int32_t n2, int32_t n3,
 int hyp_set_grid_octree(hyp_ctx *ctx, int32_t n_cells, const int32_t *refined,
                         double x, double y, double z, double dx, double dy, double dz);
 
+/* replaces: read_grid / read_level / setup_grid_geometry (src/grid/grid_geometry_amr.f90:111-507).
+ * n_grids[n_levels] grids per level (level 1 = coarsest); then per grid, level-major, in file order
+ * (Grid/Geometry/level_%05d/grid_%05d): dims[3] = n1, n2, n3 and bounds[6] = xmin, xmax, ymin, ymax, zmin, zmax.
+ * Quantities have one entry per cell of every grid, concatenated in the same order, x fastest inside a
+ * grid (src/core/type_cell_id_amr.f90:115-133): density[n_dust][n_cells]; cells covered by a finer grid
+ * are masked out. */
+int hyp_set_grid_amr(hyp_ctx *ctx, int32_t n_levels, const int32_t *n_grids, const int32_t *dims, const double *bounds);
+
 /* replaces: dust_setup (src/dust/dust_type_4elem.f90:78-293); call once per dust type, in order */
 int hyp_add_dust(hyp_ctx *ctx, const hyp_dust_tables *dust);
 

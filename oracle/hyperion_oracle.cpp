@@ -682,6 +682,7 @@ struct WallId {
 };
 struct Cell {
   int i1 = 0, i2 = 0, i3 = 0, ic = 0;
+  int ilevel = 0, igrid = 0;  // AMR only (type_cell_id_amr.f90:14-19)
 };
 const int MAX_DUST = 16;
 struct Photon {
@@ -1023,7 +1024,8 @@ struct orc_ctx {
   double tmin = 0, emin = 0;
   WallId imin, iext;
   // geometry kind: 0 Cartesian, 1 spherical polar (grid_geometry_spherical_3d.f90),
-  // 2 cylindrical polar (grid_geometry_cylindrical_3d.f90), 3 octree (grid_geometry_octree.f90)
+  // 2 cylindrical polar (grid_geometry_cylindrical_3d.f90), 3 octree (grid_geometry_octree.f90),
+  // 4 AMR (grid_geometry_amr.f90)
   int grid_type = 0;
   bool radial = false;  // the 'radial' argument of the spherical find_wall (grid_propagate_3d.f90:73)
   std::vector<double> wr2, wtanp, wtant, wcost, wsint, wtant2;  // (:169-185)
@@ -1033,6 +1035,17 @@ struct orc_ctx {
   std::vector<char> orefined;
   std::vector<int> ochildren, oparent, oparent_subcell;  // ochildren[8*ic + k]
   double oct_eps = 0.0;
+  // AMR: levels of grids (type_grid_amr.f90); goto arrays are (0:n1+1, 0:n2+1, 0:n3+1), first index fastest
+  struct AmrGrid {
+    int n1, n2, n3, n_cells, start_id;
+    double xmin, xmax, ymin, ymax, zmin, zmax, width[3], volume;
+    std::vector<double> w1, w2, w3;
+    std::vector<int> goto_grid, goto_level;
+    size_t gidx(int i1, int i2, int i3) const { return (size_t)i1 + (size_t)(n1 + 2) * (i2 + (size_t)(n2 + 2) * i3); }
+  };
+  std::vector<std::vector<AmrGrid>> levels;
+  std::vector<int> cell_ilevel, cell_igrid, cell_i1, cell_i2, cell_i3;  // preset_cell_id
+  double amr_eps = 0.0;
   // cells that hold physical quantities (geo%mask / mask_map); empty = all cells
   std::vector<int> mask_map;
   int n_masked = 0;
@@ -1082,6 +1095,7 @@ Cell new_grid_cell(const orc_ctx &g, int i1, int i2, int i3) {
 
 // escaped_cell (grid_geometry_cartesian_3d.f90:267-275)
 bool escaped(const orc_ctx &g, const Cell &c) {
+  if (g.grid_type == 4) return c.ic == -2;  // outside_cell (grid_geometry_amr.f90:592-597)
   if (g.grid_type == 3) return c.ic == g.n_cells + 1;  // grid_geometry_octree.f90:318-325
   if (c.i1 < 1 || c.i1 > g.n1) return true;
   if (g.grid_type == 1) return false;  // spherical: radial escape only (grid_geometry_spherical_3d.f90:493-500)
@@ -1098,6 +1112,10 @@ bool sph_in_correct_cell(const orc_ctx &g, const Photon &p);
 void sph_find_wall(orc_ctx &g, const Photon &p, double &tnearest, WallId &id_min);
 bool cyl_find_cell(const orc_ctx &g, const Photon &p, Cell &out);
 bool oct_find_cell(const orc_ctx &g, const Photon &p, Cell &out);
+bool amr_find_cell(const orc_ctx &g, const Photon &p, Cell &out);
+bool amr_in_correct_cell(const orc_ctx &g, const Photon &p);
+void amr_find_wall(orc_ctx &g, const Photon &p, double &tnearest, WallId &id_min);
+Cell amr_next_cell(const orc_ctx &g, const Cell &c, const WallId &dir, const Vec &r);
 bool oct_in_correct_cell(const orc_ctx &g, const Photon &p);
 void oct_find_wall(orc_ctx &g, const Photon &p, double &tnearest, WallId &id_min);
 Cell oct_next_cell(const orc_ctx &g, const Cell &c, const WallId &dir, const Vec &r);
@@ -1109,6 +1127,7 @@ bool find_cell(const orc_ctx &g, const Photon &p, Cell &out) {
   if (g.grid_type == 1) return sph_find_cell(g, p, out);
   if (g.grid_type == 2) return cyl_find_cell(g, p, out);
   if (g.grid_type == 3) return oct_find_cell(g, p, out);
+  if (g.grid_type == 4) return amr_find_cell(g, p, out);
   int i1 = locate(g.w1.data(), g.n1 + 1, p.r.x);
   int i2 = locate(g.w2.data(), g.n2 + 1, p.r.y);
   int i3 = locate(g.w3.data(), g.n3 + 1, p.r.z);
@@ -1129,7 +1148,7 @@ void adjust_wall(const orc_ctx &g, Photon &p) {
     cyl_adjust_wall(g, p);
     return;
   }
-  if (g.grid_type == 3) return;  // the octree place_in_cell has no adjust_wall (grid_geometry_octree.f90:299-310)
+  if (g.grid_type == 3 || g.grid_type == 4) return;  // octree / AMR place_in_cell have no adjust_wall
   p.on_wall = false;
   p.on_wall_id = WallId();
 #define ADJ(V, R, W, I, WID)                   \
@@ -1174,6 +1193,7 @@ bool in_correct_cell(const orc_ctx &g, const Photon &p) {
   if (g.grid_type == 1) return sph_in_correct_cell(g, p);
   if (g.grid_type == 2) return cyl_in_correct_cell(g, p);
   if (g.grid_type == 3) return oct_in_correct_cell(g, p);
+  if (g.grid_type == 4) return amr_in_correct_cell(g, p);
   const double threshold = 1.e-3;
   Cell act;
   bool valid = find_cell(g, p, act);
@@ -1240,6 +1260,10 @@ void find_wall(orc_ctx &g, const Photon &p, double &tnearest, WallId &id_min) {
     oct_find_wall(g, p, tnearest, id_min);
     return;
   }
+  if (g.grid_type == 4) {
+    amr_find_wall(g, p, tnearest, id_min);
+    return;
+  }
   g.tmin = std::numeric_limits<double>::max();
   g.emin = 0.0;
   g.imin = WallId();
@@ -1274,6 +1298,7 @@ void find_wall(orc_ctx &g, const Photon &p, double &tnearest, WallId &id_min) {
 // next_cell_wall_id (grid_geometry_cartesian_3d.f90:303-328)
 Cell next_cell(const orc_ctx &g, const Cell &c, const WallId &dir, const Vec &r) {
   if (g.grid_type == 3) return oct_next_cell(g, c, dir, r);
+  if (g.grid_type == 4) return amr_next_cell(g, c, dir, r);
   int i1 = c.i1, i2 = c.i2, i3 = c.i3;
   if (dir.w1 == -1)
     i1 = i1 - 1;
@@ -2004,6 +2029,195 @@ Vec oct_random_position_cell(orc_ctx &g, const Cell &c) {
   double x = g.rng.random(), y = g.rng.random(), z = g.rng.random();
   const int k = c.ic - 1;
   return Vec{(2.0 * x - 1.0) * g.odx[k] + g.ox[k], (2.0 * y - 1.0) * g.ody[k] + g.oy[k], (2.0 * z - 1.0) * g.odz[k] + g.oz[k]};
+}
+
+// ---------------------------------------------------------------------------
+// AMR geometry (src/grid/grid_geometry_amr.f90); level / grid ids 1-based as in the Fortran
+// ---------------------------------------------------------------------------
+bool amr_in_grid(const orc_ctx::AmrGrid &G, const Vec &r) {
+  if (r.x < G.xmin) return false;
+  if (r.x > G.xmax) return false;
+  if (r.y < G.ymin) return false;
+  if (r.y > G.ymax) return false;
+  if (r.z < G.zmin) return false;
+  if (r.z > G.zmax) return false;
+  return true;
+}
+
+// new_grid_cell_5d (type_cell_id_amr.f90:104-117)
+Cell amr_cell(const orc_ctx &g, int i1, int i2, int i3, int ilevel, int igrid) {
+  const orc_ctx::AmrGrid &G = g.levels[ilevel - 1][igrid - 1];
+  Cell c;
+  c.ic = (G.start_id - 1) + (i3 - 1) * G.n1 * G.n2 + (i2 - 1) * G.n1 + i1;
+  c.ilevel = ilevel;
+  c.igrid = igrid;
+  c.i1 = i1;
+  c.i2 = i2;
+  c.i3 = i3;
+  return c;
+}
+
+// new_grid_cell_1d (:119-129)
+Cell amr_cell_1d(const orc_ctx &g, int ic) {
+  Cell c;
+  c.ic = ic;
+  c.ilevel = g.cell_ilevel[ic - 1];
+  c.igrid = g.cell_igrid[ic - 1];
+  c.i1 = g.cell_i1[ic - 1];
+  c.i2 = g.cell_i2[ic - 1];
+  c.i3 = g.cell_i3[ic - 1];
+  return c;
+}
+
+// ipos2 (:510-519)
+int amr_ipos2(double xmin, double xmax, double x, int nbin) {
+  double eps = (xmax - xmin) * 1.e-10;
+  int i = ipos(xmin, xmax, x, nbin);
+  if (i == 0 && std::fabs(x - xmin) < eps) i = 1;
+  if (i == nbin + 1 && std::fabs(x - xmax) < eps) i = nbin;
+  return i;
+}
+
+// find_position_in_grid (:521-545); false = invalid_cell
+bool amr_find_position_in_grid(const orc_ctx &g, const Vec &r, int ilevel, int igrid, Cell &out) {
+  for (;;) {
+    const orc_ctx::AmrGrid &G = g.levels[ilevel - 1][igrid - 1];
+    int i1 = amr_ipos2(G.xmin, G.xmax, r.x, G.n1);
+    int i2 = amr_ipos2(G.ymin, G.ymax, r.y, G.n2);
+    int i3 = amr_ipos2(G.zmin, G.zmax, r.z, G.n3);
+    int ilevel_new = G.goto_level[G.gidx(i1, i2, i3)];
+    int igrid_new = G.goto_grid[G.gidx(i1, i2, i3)];
+    if (ilevel_new == 0) {
+      if (i1 < 1 || i1 > G.n1 || i2 < 1 || i2 > G.n2 || i3 < 1 || i3 > G.n3) return false;
+      out = amr_cell(g, i1, i2, i3, ilevel, igrid);
+      return true;
+    }
+    ilevel = ilevel_new;
+    igrid = igrid_new;
+  }
+}
+
+// find_cell / find_cell_position (:553-573)
+bool amr_find_cell(const orc_ctx &g, const Photon &p, Cell &out) {
+  int igrid = -1;
+  for (size_t k = 0; k < g.levels[0].size(); k++)
+    if (amr_in_grid(g.levels[0][k], p.r)) {
+      igrid = (int)k + 1;
+      break;
+    }
+  if (igrid == -1) return false;
+  return amr_find_position_in_grid(g, p.r, 1, igrid, out);
+}
+
+// next_cell_int (:599-655) + next_cell_wall_id (:657-675)
+Cell amr_next_cell(const orc_ctx &g, const Cell &cell, const WallId &dir, const Vec &intersection) {
+  int direction;
+  if (dir.w1 == -1) direction = 1;
+  else if (dir.w1 == +1) direction = 2;
+  else if (dir.w2 == -1) direction = 3;
+  else if (dir.w2 == +1) direction = 4;
+  else if (dir.w3 == -1) direction = 5;
+  else if (dir.w3 == +1) direction = 6;
+  else return cell;
+  const orc_ctx::AmrGrid &G = g.levels[cell.ilevel - 1][cell.igrid - 1];
+  int i1 = cell.i1, i2 = cell.i2, i3 = cell.i3;
+  switch (direction) {
+    case 1: i1 = i1 - 1; break;
+    case 2: i1 = i1 + 1; break;
+    case 3: i2 = i2 - 1; break;
+    case 4: i2 = i2 + 1; break;
+    case 5: i3 = i3 - 1; break;
+    case 6: i3 = i3 + 1; break;
+  }
+  if (G.goto_level[G.gidx(i1, i2, i3)] == 0) {
+    if (i1 == 0 || i1 == G.n1 + 1 || i2 == 0 || i2 == G.n2 + 1 || i3 == 0 || i3 == G.n3 + 1) {
+      Cell out;
+      out.ic = out.i1 = out.i2 = out.i3 = out.ilevel = out.igrid = -2;  // outside_cell
+      return out;
+    }
+    return amr_cell(g, i1, i2, i3, cell.ilevel, cell.igrid);
+  }
+  int ilevel = G.goto_level[G.gidx(i1, i2, i3)], igrid = G.goto_grid[G.gidx(i1, i2, i3)];
+  Vec r = intersection;
+  switch (direction) {
+    case 1: r.x = r.x - g.amr_eps; break;
+    case 2: r.x = r.x + g.amr_eps; break;
+    case 3: r.y = r.y - g.amr_eps; break;
+    case 4: r.y = r.y + g.amr_eps; break;
+    case 5: r.z = r.z - g.amr_eps; break;
+    case 6: r.z = r.z + g.amr_eps; break;
+  }
+  Cell out;
+  if (!amr_find_position_in_grid(g, r, ilevel, igrid, out)) out.ic = out.i1 = out.i2 = out.i3 = out.ilevel = out.igrid = -1;
+  return out;
+}
+
+// in_correct_cell (:677-727)
+bool amr_in_correct_cell(const orc_ctx &g, const Photon &p) {
+  const orc_ctx::AmrGrid &G = g.levels[p.icell.ilevel - 1][p.icell.igrid - 1];
+  int a1 = ipos(G.xmin, G.xmax, p.r.x, G.n1), a2 = ipos(G.ymin, G.ymax, p.r.y, G.n2), a3 = ipos(G.zmin, G.zmax, p.r.z, G.n3);
+  if (!p.on_wall) return a1 == p.icell.i1 && a2 == p.icell.i2 && a3 == p.icell.i3;
+  bool ok = true;
+  double frac;
+#define CHK(WID, R, W, I, IA)                              \
+  if (WID == -1) {                                         \
+    frac = (R - W[I - 1]) / (W[I] - W[I - 1]);             \
+    ok = ok && std::fabs(frac) < 1.e-3;                    \
+  } else if (WID == +1) {                                  \
+    frac = (R - W[I]) / (W[I] - W[I - 1]);                 \
+    ok = ok && std::fabs(frac) < 1.e-3;                    \
+  } else {                                                 \
+    ok = ok && IA == I;                                    \
+  }
+  CHK(p.on_wall_id.w1, p.r.x, G.w1, p.icell.i1, a1)
+  CHK(p.on_wall_id.w2, p.r.y, G.w2, p.icell.i2, a2)
+  CHK(p.on_wall_id.w3, p.r.z, G.w3, p.icell.i3, a3)
+#undef CHK
+  return ok;
+}
+
+// find_wall (:775-871)
+void amr_find_wall(orc_ctx &g, const Photon &p, double &tmin, WallId &id_min) {
+  const double huge = std::numeric_limits<double>::max();
+  const orc_ctx::AmrGrid &G = g.levels[p.icell.ilevel - 1][p.icell.igrid - 1];
+  id_min = WallId();
+  bool pos_vx = p.v.x > 0.0, pos_vy = p.v.y > 0.0, pos_vz = p.v.z > 0.0;
+  double tx, ty, tz;
+  if (pos_vx) tx = (G.w1[p.icell.i1] - p.r.x) / p.v.x;
+  else if (p.v.x < 0.0) tx = (G.w1[p.icell.i1 - 1] - p.r.x) / p.v.x;
+  else tx = huge;
+  if (pos_vy) ty = (G.w2[p.icell.i2] - p.r.y) / p.v.y;
+  else if (p.v.y < 0.0) ty = (G.w2[p.icell.i2 - 1] - p.r.y) / p.v.y;
+  else ty = huge;
+  if (pos_vz) tz = (G.w3[p.icell.i3] - p.r.z) / p.v.z;
+  else if (p.v.z < 0.0) tz = (G.w3[p.icell.i3 - 1] - p.r.z) / p.v.z;
+  else tz = huge;
+  if (std::min(tx, std::min(ty, tz)) < 0.0) throw OracleError{"negative t"};
+  if (tx < tz) {
+    if (tx < ty) {
+      id_min.w1 = pos_vx ? +1 : -1;
+      tmin = tx;
+    } else {
+      id_min.w2 = pos_vy ? +1 : -1;
+      tmin = ty;
+    }
+  } else {
+    if (tz < ty) {
+      id_min.w3 = pos_vz ? +1 : -1;
+      tmin = tz;
+    } else {
+      id_min.w2 = pos_vy ? +1 : -1;
+      tmin = ty;
+    }
+  }
+}
+
+// random_position_cell (:729-741)
+Vec amr_random_position_cell(orc_ctx &g, const Cell &c) {
+  const orc_ctx::AmrGrid &G = g.levels[c.ilevel - 1][c.igrid - 1];
+  double x = g.rng.random(), y = g.rng.random(), z = g.rng.random();
+  return Vec{x * (G.w1[c.i1] - G.w1[c.i1 - 1]) + G.w1[c.i1 - 1], y * (G.w2[c.i2] - G.w2[c.i2 - 1]) + G.w2[c.i2 - 1],
+             z * (G.w3[c.i3] - G.w3[c.i3 - 1]) + G.w3[c.i3 - 1]};
 }
 
 // update_optconsts (dust.f90:64-79)
@@ -2766,6 +2980,9 @@ Photon emit_from_grid(orc_ctx &g) {
   if (g.grid_type == 3) {
     p.icell = Cell{0, 0, 0, ic};
     p.r = oct_random_position_cell(g, p.icell);
+  } else if (g.grid_type == 4) {
+    p.icell = amr_cell_1d(g, ic);
+    p.r = amr_random_position_cell(g, p.icell);
   } else {
     int i3 = (ic - 1) / (g.n1 * g.n2) + 1;
     int i2 = (ic - 1 - (i3 - 1) * g.n1 * g.n2) / g.n1 + 1;
@@ -3058,6 +3275,138 @@ int orc_set_grid_octree(orc_ctx *g, int32_t n_cells, const int32_t *refined, dou
   for (double v : g->volume)
     if (v == 0.0) return fail(g, "all volumes should be greater than zero");
   g->oct_eps = spacing(std::max(dx, std::max(dy, dz))) * 3.0;
+  return 0;
+}
+
+// read_grid / setup_grid_geometry (grid_geometry_amr.f90:111-507).  n_grids[n_levels]; per grid (level-major):
+// dims[3] = n1, n2, n3 and bounds[6] = xmin, xmax, ymin, ymax, zmin, zmax
+int orc_set_grid_amr(orc_ctx *g, int32_t n_levels, const int32_t *n_grids, const int32_t *dims, const double *bounds) {
+  typedef orc_ctx::AmrGrid Grid;
+  g->grid_type = 4;
+  g->levels.assign(n_levels, std::vector<Grid>());
+  int k = 0, start_id = 1;
+  double min_width = std::numeric_limits<double>::max();
+  for (int il = 0; il < n_levels; il++) {
+    g->levels[il].resize(n_grids[il]);
+    for (int ig = 0; ig < n_grids[il]; ig++, k++) {
+      Grid &G = g->levels[il][ig];
+      G.n1 = dims[3 * k];
+      G.n2 = dims[3 * k + 1];
+      G.n3 = dims[3 * k + 2];
+      G.n_cells = G.n1 * G.n2 * G.n3;
+      G.xmin = bounds[6 * k]; G.xmax = bounds[6 * k + 1];
+      G.ymin = bounds[6 * k + 2]; G.ymax = bounds[6 * k + 3];
+      G.zmin = bounds[6 * k + 4]; G.zmax = bounds[6 * k + 5];
+      // linspace_dp (lib_array.f90:284-302)
+      auto linspace = [](double a, double b, int n, std::vector<double> &x) {
+        x.resize(n);
+        for (int i = 1; i <= n; i++) x[i - 1] = (b - a) * (double)(i - 1) / (double)(n - 1) + a;
+      };
+      linspace(G.xmin, G.xmax, G.n1 + 1, G.w1);
+      linspace(G.ymin, G.ymax, G.n2 + 1, G.w2);
+      linspace(G.zmin, G.zmax, G.n3 + 1, G.w3);
+      G.width[0] = (G.xmax - G.xmin) / (double)G.n1;
+      G.width[1] = (G.ymax - G.ymin) / (double)G.n2;
+      G.width[2] = (G.zmax - G.zmin) / (double)G.n3;
+      G.volume = G.width[0] * G.width[1] * G.width[2];
+      G.goto_grid.assign((size_t)(G.n1 + 2) * (G.n2 + 2) * (G.n3 + 2), 0);
+      G.goto_level = G.goto_grid;
+      G.start_id = start_id;
+      start_id += G.n_cells;
+      for (int a = 0; a < 3; a++)
+        if (G.width[a] < min_width) min_width = G.width[a];
+    }
+  }
+  g->n_cells = start_id - 1;
+  g->n1 = g->n_cells;
+  g->n2 = g->n3 = 1;
+  g->volume.resize(g->n_cells);
+  g->cell_ilevel.resize(g->n_cells);
+  g->cell_igrid.resize(g->n_cells);
+  g->cell_i1.resize(g->n_cells);
+  g->cell_i2.resize(g->n_cells);
+  g->cell_i3.resize(g->n_cells);
+  int ic = 0;
+  for (int il = 0; il < n_levels; il++)
+    for (size_t ig = 0; ig < g->levels[il].size(); ig++) {
+      const Grid &G = g->levels[il][ig];
+      for (int i3 = 1; i3 <= G.n3; i3++)
+        for (int i2 = 1; i2 <= G.n2; i2++)
+          for (int i1 = 1; i1 <= G.n1; i1++) {
+            g->volume[ic] = G.volume;
+            g->cell_ilevel[ic] = il + 1;
+            g->cell_igrid[ic] = (int)ig + 1;
+            g->cell_i1[ic] = i1;
+            g->cell_i2[ic] = i2;
+            g->cell_i3[ic] = i3;
+            ic++;
+          }
+    }
+  for (double v : g->volume)
+    if (v == 0.0) return fail(g, "all volumes should be greater than zero");
+  g->amr_eps = min_width / 2.0;
+  auto intersect = [](const Grid &a, const Grid &b) {
+    return !(a.xmax < b.xmin || a.xmin > b.xmax || a.ymax < b.ymin || a.ymin > b.ymax || a.zmax < b.zmin || a.zmin > b.zmax);
+  };
+  auto close = [](const Grid &a, const Grid &b) {
+    return !(a.xmax < b.xmin - b.width[0] * 0.5 || a.xmin > b.xmax + b.width[0] * 0.5 || a.ymax < b.ymin - b.width[1] * 0.5 ||
+             a.ymin > b.ymax + b.width[1] * 0.5 || a.zmax < b.zmin - b.width[2] * 0.5 || a.zmin > b.zmax + b.width[2] * 0.5);
+  };
+  // cells covered by a grid of the next level point to it (:355-381)
+  for (int il1 = n_levels - 2; il1 >= 0; il1--)
+    for (Grid &G1 : g->levels[il1])
+      for (size_t ig2 = 0; ig2 < g->levels[il1 + 1].size(); ig2++) {
+        const Grid &G2 = g->levels[il1 + 1][ig2];
+        if (!intersect(G1, G2)) continue;
+        for (int i1 = 1; i1 <= G1.n1; i1++)
+          for (int i2 = 1; i2 <= G1.n2; i2++)
+            for (int i3 = 1; i3 <= G1.n3; i3++) {
+              Vec r{0.5 * (G1.w1[i1 - 1] + G1.w1[i1]), 0.5 * (G1.w2[i2 - 1] + G1.w2[i2]), 0.5 * (G1.w3[i3 - 1] + G1.w3[i3])};
+              if (amr_in_grid(G2, r)) {
+                G1.goto_grid[G1.gidx(i1, i2, i3)] = (int)ig2 + 1;
+                G1.goto_level[G1.gidx(i1, i2, i3)] = il1 + 2;
+              }
+            }
+      }
+  // ghost cells: which grid does a packet land in one step outside the grid (:383-487)
+  for (int il1 = 0; il1 < n_levels; il1++)
+    for (size_t ig1 = 0; ig1 < g->levels[il1].size(); ig1++) {
+      Grid &G1 = g->levels[il1][ig1];
+      for (int il2 = il1; il2 >= 0; il2--)
+        for (size_t ig2 = 0; ig2 < g->levels[il2].size(); ig2++) {
+          const Grid &G2 = g->levels[il2][ig2];
+          if (!(close(G1, G2) && (ig1 != ig2 || il1 != il2))) continue;
+          auto mark = [&](int i1, int i2, int i3, const Vec &r) {
+            if (amr_in_grid(G2, r) && G1.goto_grid[G1.gidx(i1, i2, i3)] == 0) {
+              G1.goto_grid[G1.gidx(i1, i2, i3)] = (int)ig2 + 1;
+              G1.goto_level[G1.gidx(i1, i2, i3)] = il2 + 1;
+            }
+          };
+          auto cx = [&](int i) { return 0.5 * (G1.w1[i - 1] + G1.w1[i]); };
+          auto cy = [&](int i) { return 0.5 * (G1.w2[i - 1] + G1.w2[i]); };
+          auto cz = [&](int i) { return 0.5 * (G1.w3[i - 1] + G1.w3[i]); };
+          for (int i2 = 1; i2 <= G1.n2; i2++)
+            for (int i3 = 1; i3 <= G1.n3; i3++) mark(0, i2, i3, Vec{G1.xmin - G1.width[0] * 0.5, cy(i2), cz(i3)});
+          for (int i2 = 1; i2 <= G1.n2; i2++)
+            for (int i3 = 1; i3 <= G1.n3; i3++) mark(G1.n1 + 1, i2, i3, Vec{G1.xmax + G1.width[0] * 0.5, cy(i2), cz(i3)});
+          for (int i1 = 1; i1 <= G1.n1; i1++)
+            for (int i3 = 1; i3 <= G1.n3; i3++) mark(i1, 0, i3, Vec{cx(i1), G1.ymin - G1.width[1] * 0.5, cz(i3)});
+          for (int i1 = 1; i1 <= G1.n1; i1++)
+            for (int i3 = 1; i3 <= G1.n3; i3++) mark(i1, G1.n2 + 1, i3, Vec{cx(i1), G1.ymax + G1.width[1] * 0.5, cz(i3)});
+          for (int i1 = 1; i1 <= G1.n1; i1++)
+            for (int i2 = 1; i2 <= G1.n2; i2++) mark(i1, i2, 0, Vec{cx(i1), cy(i2), G1.zmin - G1.width[2] * 0.5});
+          for (int i1 = 1; i1 <= G1.n1; i1++)
+            for (int i2 = 1; i2 <= G1.n2; i2++) mark(i1, i2, G1.n3 + 1, Vec{cx(i1), cy(i2), G1.zmax + G1.width[2] * 0.5});
+        }
+    }
+  // valid cells: not covered by a finer grid (:489-506)
+  g->mask_map.clear();
+  for (int icell = 1; icell <= g->n_cells; icell++) {
+    Cell c = amr_cell_1d(*g, icell);
+    const Grid &G = g->levels[c.ilevel - 1][c.igrid - 1];
+    if (G.goto_grid[G.gidx(c.i1, c.i2, c.i3)] == 0) g->mask_map.push_back(icell);
+  }
+  g->n_masked = (int)g->mask_map.size();
   return 0;
 }
 

@@ -34,3 +34,9 @@ def golden_cyl():
 def golden_oct():
     import numpy as np
     return np.load(os.path.join(ROOT, "tests", "golden", "bitlevel_oct.npz"))
+
+
+@pytest.fixture(scope="session")
+def golden_amr():
+    import numpy as np
+    return np.load(os.path.join(ROOT, "tests", "golden", "bitlevel_amr.npz"))

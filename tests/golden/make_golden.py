@@ -36,8 +36,8 @@ def setup_all_grid_types(u, d):
     np.random.seed(141412)
     out = {}
     # AMR level 1 and 2 quantities come first
-    for shape in [(4, 6, 8)] * 3 + [(20, 6, 4)] * 3:
-        np.random.random(shape)
+    for i, shape in enumerate([(4, 6, 8)] * 3 + [(20, 6, 4)] * 3):
+        out[("amr", i)] = np.random.random(shape) * d
     shapes = {"car": (3, 5, 7), "cyl": (5, 3, 7), "sph": (3, 7, 5), "oct": (25,)}
     for k in ("density", "density_2", "density_3"):
         for g in ("car", "cyl", "sph"):
@@ -115,6 +115,15 @@ def main():
     golden_outputs(oct, "oct")
     np.savez_compressed(os.path.join(HERE, "bitlevel_oct.npz"), **oct)
     print("wrote", os.path.join(HERE, "bitlevel_oct.npz"))
+    # AMR (test_bit_level.py:64-91): level 1 = one 8x6x4 grid over [-pc, pc]^3, level 2 = one 4x6x20 grid over
+    # [-pc, 0]^3; cells concatenated level-major, x fastest (type_cell_id_amr.f90:115-133)
+    amr = {"levels": np.array([[8, 6, 4, -pc, pc, -pc, pc, -pc, pc], [4, 6, 20, -pc, 0., -pc, 0., -pc, 0.]]),
+           "n_grids": np.array([1, 1])}
+    for k in range(3):
+        amr["density_%d" % (k + 1)] = np.hstack([dens[("amr", k)].ravel(), dens[("amr", 3 + k)].ravel()])
+    golden_outputs(amr, "amr")
+    np.savez_compressed(os.path.join(HERE, "bitlevel_amr.npz"), **amr)
+    print("wrote", os.path.join(HERE, "bitlevel_amr.npz"))
 
 
 def golden_outputs(out, grid_type):
@@ -123,6 +132,14 @@ def golden_outputs(out, grid_type):
             fn = ("test_specific_energy.grid_type=%s.sample_sources_evenly=%s."
                   "multiple_densities=%s.rtout" % (grid_type, evenly, multi))
             f = h5min.File(os.path.join(DATA, fn))
+            if grid_type == "amr":
+                # one dataset per level / grid: flatten in cell-id order
+                se = []
+                for i in range(1, 6):
+                    parts = [f["iteration_%05d/level_%05d/grid_00001/specific_energy" % (i, lev)][...] for lev in (1, 2)]
+                    se.append(np.concatenate([p.reshape(p.shape[0], -1) for p in parts], axis=1))
+                out["expected_evenly=%s_multi=%s" % (evenly, multi)] = np.array(se)
+                continue
             out["expected_evenly=%s_multi=%s" % (evenly, multi)] = \
                 np.array([f["iteration_%05d/specific_energy" % i][...] for i in range(1, 6)])
     for ray in (False, True):

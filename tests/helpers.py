@@ -47,6 +47,26 @@ def bitlevel_model_oct(zc, z, evenly, multi):
                      oct_center=tuple(z["center"]), oct_half=tuple(z["half"]))
 
 
+def bitlevel_model_amr(zc, z, evenly, multi):
+    """The same test on the two-level AMR grid of test_bit_level.py:64-91."""
+    dust = kmh_dust(zc)
+    dens = [z["density_1"]] + ([z["density_2"], z["density_3"]] if multi else [])
+    srcs = [FlatSource(type=1, luminosity=float(l), temperature=float(t), position=tuple(p))
+            for l, t, p in zip(zc["source_luminosity"], zc["source_temperature"], zc["source_position"])]
+    levels, k = [], 0
+    for n in z["n_grids"]:
+        levels.append([(int(g[0]), int(g[1]), int(g[2])) + tuple(float(v) for v in g[3:]) for g in z["levels"][k:k + n]])
+        k += n
+    return FlatModel(None, None, None, np.array(dens), [dust] * len(dens), srcs,
+                     FlatConf(sample_sources_evenly=evenly), grid_type="amr", amr_levels=levels)
+
+
+def peeloff_model_amr(zc, z, evenly):
+    m = bitlevel_model_amr(zc, z, evenly, False)
+    m.peeled = peeloff_groups()
+    return m
+
+
 def peeloff_model_oct(zc, z, evenly):
     m = bitlevel_model_oct(zc, z, evenly, False)
     m.peeled = peeloff_groups()

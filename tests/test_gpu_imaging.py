@@ -9,7 +9,7 @@ from concurrent.futures import ThreadPoolExecutor
 import numpy as np
 import pytest
 
-from helpers import peeloff_model, peeloff_model_oct, peeloff_model_sph, bitlevel_model, peeloff_groups, pc
+from helpers import peeloff_model, peeloff_model_amr, peeloff_model_oct, peeloff_model_sph, bitlevel_model, peeloff_groups, pc
 
 pytestmark = pytest.mark.gpu
 
@@ -131,6 +131,22 @@ def test_peeloff_matches_oracle_octree(golden_car, golden_oct):
     """test_peeloff on the reference's octree, with raytracing: thermal packets are drawn from the
     leaves only (random_masked_cell) and weighted with the number of leaves."""
     model = peeloff_model_oct(golden_car, golden_oct, False)
+    model.specific_energy = _converged_energy(model)
+    gpu, orc = _run_both(model, 12, 60000, True, (20000, 30000))
+    print(_compare(gpu, orc))
+    for key in ("n_crossings", "n_absorptions", "n_scatterings", "n_peeloffs", "n_peel_crossings"):
+        a = np.mean([g[1][key] for g in gpu])
+        b = np.mean([o[1][key] for o in orc])
+        assert abs(a / b - 1) < 0.02, (key, a, b)
+    for key in ("n_peeloffs", "n_peel_crossings"):
+        a = np.mean([g[2][key] for g in gpu])
+        b = np.mean([o[2][key] for o in orc])
+        assert abs(a / b - 1) < 0.02, (key, a, b)
+
+
+def test_peeloff_matches_oracle_amr(golden_car, golden_amr):
+    """test_peeloff on the reference's AMR grid, with raytracing (thermal packets from uncovered cells)."""
+    model = peeloff_model_amr(golden_car, golden_amr, False)
     model.specific_energy = _converged_energy(model)
     gpu, orc = _run_both(model, 12, 60000, True, (20000, 30000))
     print(_compare(gpu, orc))

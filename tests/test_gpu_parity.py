@@ -10,7 +10,7 @@ estimates (|z| bounded, z^2 averaging to 1).
 import numpy as np
 import pytest
 
-from helpers import bitlevel_model, bitlevel_model_oct, bitlevel_model_sph, kmh_dust, pc, lsun
+from helpers import bitlevel_model, bitlevel_model_amr, bitlevel_model_oct, bitlevel_model_sph, kmh_dust, pc, lsun
 
 pytestmark = pytest.mark.gpu
 
@@ -311,3 +311,48 @@ def test_deposits_match_oracle_random_deep_octree():
     est = (g * model.density).sum(axis=(1, 2)) * N
     nabs = np.array([s["n_absorptions"] for s in gst])
     assert abs(est.mean() / nabs.mean() - 1) < 0.02
+
+
+@pytest.mark.parametrize("evenly,multi", [(False, False), (True, True)])
+def test_deposits_match_oracle_amr(golden_car, golden_amr, evenly, multi):
+    """The reference's bit-level model on its AMR grid (test_bit_level.py:64-91): a level-1 grid of
+    8 x 6 x 4 cells whose lower octant is covered by a level-2 grid of 4 x 6 x 20 cells (refinement
+    1 x 2 x 10); covered cells carry no dust and must stay empty."""
+    model = bitlevel_model_amr(golden_car, golden_amr, evenly, multi)
+    B, N = 16, 100000
+    g, gst = _gpu_batches(model, N, B)
+    o, ost = _oracle_batches(model, N, B)
+    used = o.mean(0) > 0
+    assert ((g.mean(0) > 0) == used).all()
+    assert used.sum() == (len(model.dust)) * (8 * 6 * 4 - 4 * 3 * 2 + 4 * 6 * 20)
+    z, ok = _zscores(g[:, used], o[:, used])
+    assert ok.all()
+    assert np.abs(z).max() < 5.5, np.abs(z).max()
+    assert 0.6 < (z ** 2).mean() < 1.5, (z ** 2).mean()
+    for key in ("n_crossings", "n_absorptions", "n_scatterings"):
+        a = np.mean([s[key] for s in gst])
+        b = np.mean([s[key] for s in ost])
+        assert abs(a / b - 1) < 0.01, (key, a, b)
+    assert all(s["killed_geo"] == 0 and s["killed_int"] == 0 and s["n_photons"] == N for s in gst)
+
+
+def test_deposits_match_oracle_three_level_amr():
+    """A seeded three-level AMR hierarchy (root 16^3, refinement 2, several patches per level, the
+    shape of BASELINE.json's AMR configuration at a size the oracle handles): grid-to-grid hand-over
+    through ghost links on the same level, down into finer and up into coarser grids."""
+    from hyperion_b200 import synthetic as syn
+    model = syn.amr_point_sources_model(n_root=16, n_levels=3, seed=7, tau_edge=2.0)
+    B, N = 8, 200000
+    g, gst = _gpu_batches(model, N, B)
+    o, ost = _oracle_batches(model, N, B)
+    used = o.mean(0) > 0
+    assert ((g.mean(0) > 0) == used).all()
+    z, ok = _zscores(g[:, used], o[:, used])
+    assert ok.mean() > 0.95
+    assert np.abs(z[ok]).max() < 6.0, np.abs(z[ok]).max()
+    assert 0.6 < (z[ok] ** 2).mean() < 1.5, (z[ok] ** 2).mean()
+    for key in ("n_crossings", "n_absorptions", "n_scatterings"):
+        a = np.mean([s[key] for s in gst])
+        b = np.mean([s[key] for s in ost])
+        assert abs(a / b - 1) < 0.01, (key, a, b)
+    assert all(s["killed_geo"] == 0 for s in gst) and all(s["killed_geo"] == 0 for s in ost)

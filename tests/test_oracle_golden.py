@@ -9,8 +9,8 @@ import numpy as np
 import pytest
 
 from oracle import oracle
-from helpers import (bitlevel_model, bitlevel_model_oct, bitlevel_model_sph, peeloff_model, peeloff_model_oct,
-                     peeloff_model_sph, ulp_diff)
+from helpers import (bitlevel_model, bitlevel_model_amr, bitlevel_model_oct, bitlevel_model_sph, peeloff_model,
+                     peeloff_model_amr, peeloff_model_oct, peeloff_model_sph, ulp_diff)
 
 
 @pytest.mark.parametrize("evenly", [False, True])
@@ -168,6 +168,49 @@ def test_peeloff_bitlevel_oct(golden_car, golden_oct, raytracing, evenly):
     from the leaf cells only (random_masked_cell, grid_geometry_common_3d.f90:104-115)."""
     z = golden_oct
     o = oracle.Oracle(peeloff_model_oct(golden_car, z, evenly))
+    for it in range(5):
+        o.run_lucy_iteration(1000)
+    o.final_begin()
+    o.final_photons(5000, peeloff_scattering_only=raytracing)
+    st = o.final_finish()
+    assert st.killed_geo == 0 and st.killed_int == 0
+    if raytracing:
+        o.raytracing_photons(2000, 3000)
+    for ig in (1, 2, 3):
+        for kind, get in (("seds", o.sed), ("images", o.image)):
+            expected = z["peeloff_ray=%s_evenly=%s_g%d_%s" % (raytracing, evenly, ig, kind)]
+            got = get(ig - 1)
+            assert got.shape == expected.shape
+            nz = (expected != 0) | (got != 0)
+            assert nz.any()
+            assert np.array_equal(got == 0, expected == 0), (ig, kind)
+            assert ulp_diff(got[nz], expected[nz]).max() <= 1000, (ig, kind)
+
+
+@pytest.mark.parametrize("evenly", [False, True])
+@pytest.mark.parametrize("multi", [False, True])
+def test_specific_energy_bitlevel_amr(golden_car, golden_amr, evenly, multi):
+    """AMR geometry (src/grid/grid_geometry_amr.f90): the four golden files
+    test_specific_energy.grid_type=amr.*.rtout (two levels, refinement 1 x 2 x 10), all 5 iterations;
+    bit-identical here."""
+    z = golden_amr
+    o = oracle.Oracle(bitlevel_model_amr(golden_car, z, evenly, multi))
+    expected = z["expected_evenly=%s_multi=%s" % (evenly, multi)]
+    for it in range(5):
+        st = o.run_lucy_iteration(10000)
+        got = o.get_specific_energy()
+        assert st.killed_geo == 0 and st.killed_int == 0
+        assert got.shape == expected[it].shape
+        assert ulp_diff(got, expected[it]).max() <= 1000, "iteration %d" % (it + 1)
+        assert np.array_equal(got, expected[it])
+
+
+@pytest.mark.parametrize("raytracing", [False, True])
+@pytest.mark.parametrize("evenly", [False, True])
+def test_peeloff_bitlevel_amr(golden_car, golden_amr, raytracing, evenly):
+    """test_peeloff on the AMR grid (four golden files), 1000 ULP."""
+    z = golden_amr
+    o = oracle.Oracle(peeloff_model_amr(golden_car, z, evenly))
     for it in range(5):
         o.run_lucy_iteration(1000)
     o.final_begin()
