@@ -163,7 +163,21 @@ def read_rtin(filename):
     rs.grid_type = _s(geo.attrs["grid_type"])
     rs.geometry_id = _s(geo.attrs["geometry"])
     octree = None
-    if rs.grid_type == "oct":
+    amr_levels = None
+    if rs.grid_type == "amr":
+        # grid_geometry_amr.f90:111-187: nlevels; level_%05d: ngrids; grid_%05d: n1..n3, xmin..zmax
+        amr_levels = []
+        for il in range(int(_num(geo.attrs["nlevels"]))):
+            gl = geo["level_%05d" % (il + 1)]
+            grids = []
+            for ig in range(int(_num(gl.attrs["ngrids"]))):
+                a = gl["grid_%05d" % (ig + 1)].attrs
+                grids.append(tuple(int(_num(a[k])) for k in ("n1", "n2", "n3")) +
+                             tuple(float(_num(a[k])) for k in ("xmin", "xmax", "ymin", "ymax", "zmin", "zmax")))
+            amr_levels.append(grids)
+        octree = dict(amr_levels=amr_levels)
+        grid_type, w1, w2, w3 = "amr", None, None, None
+    elif rs.grid_type == "oct":
         # grid_geometry_octree.f90:189-262: table 'cells' (column 'refined'), root cell centre and half-widths
         refined = np.asarray(geo["cells"][...]["refined"], dtype=np.int32)
         octree = dict(refined=refined,
@@ -205,8 +219,33 @@ def read_rtin(filename):
 
     # ---- grid physics
     q = f["Grid/Quantities"]
-    grid_shape = (len(octree["refined"]),) if octree else (len(w3) - 1, len(w2) - 1, len(w1) - 1)
-    if "density" in q:
+    if amr_levels is not None:
+        # one dataset per grid, [n_dust, n3, n2, n1]; flattened to [n_dust, n_cells] in cell-id order
+        def gather(name):
+            parts = []
+            for il, lev in enumerate(amr_levels):
+                for ig, g in enumerate(lev):
+                    path = "level_%05d/grid_%05d/%s" % (il + 1, ig + 1, name)
+                    if path not in q:
+                        return None
+                    a = np.asarray(q[path][...], dtype=np.float64)
+                    if a.shape[1:] != (g[2], g[1], g[0]):
+                        raise ModelError("%s array has wrong shape" % name)
+                    parts.append(a.reshape(a.shape[0], -1))
+            return np.concatenate(parts, axis=1)
+        density = gather("density")
+        if density is None:
+            density = np.zeros((0, sum(g[0] * g[1] * g[2] for lev in amr_levels for g in lev)))
+        if density.shape[0] != len(dust):
+            raise ModelError("density array has wrong number of dust types")
+        if np.any(density < 0):
+            raise ModelError("density should be positive")
+        se_amr = gather("specific_energy")
+    grid_shape = (len(octree["refined"]),) if octree and "refined" in octree else \
+        (len(w3) - 1, len(w2) - 1, len(w1) - 1) if amr_levels is None else None
+    if amr_levels is not None:
+        pass
+    elif "density" in q:
         dset = q["density"]
         if "geometry" in dset.attrs and _s(dset.attrs["geometry"]) != rs.geometry_id:
             raise ModelError("geometry id of density does not match that of the grid")
@@ -220,7 +259,9 @@ def read_rtin(filename):
     else:
         density = np.zeros((0,) + grid_shape)
     se = None
-    if "specific_energy" in q:
+    if amr_levels is not None:
+        se = se_amr
+    elif "specific_energy" in q:
         se = np.asarray(q["specific_energy"][...], dtype=np.float64)
         if np.any(se < 0):
             raise ModelError("specific_energy should be positive")

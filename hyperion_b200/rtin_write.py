@@ -135,7 +135,9 @@ def write_rtin(filename, model: FlatModel, n_initial_iter=5, n_initial_photons=1
 
     geo = f.create_group("Grid/Geometry")
     h = hashlib.md5()
-    if model.grid_type == "oct":
+    if model.grid_type == "amr":
+        h.update(np.array([v for lev in model.amr_levels for g in lev for v in g], dtype=np.float64).tobytes())
+    elif model.grid_type == "oct":
         # hyperion/grid/octree_grid.py:426-436
         h.update(np.ascontiguousarray(model.refined).tobytes())
         h.update(np.array(tuple(model.oct_center) + tuple(model.oct_half)).tobytes())
@@ -150,18 +152,38 @@ def write_rtin(filename, model: FlatModel, n_initial_iter=5, n_initial_photons=1
             geo.attrs[k] = float(v)
         geo.create_dataset("cells", _table([("refined", np.asarray(model.refined, dtype=np.int32))]))
     # hyperion/grid/cartesian_grid.py:336-343, hyperion/grid/spherical_polar_grid.py (write)
-    if model.grid_type != "oct":
+    if model.grid_type == "amr":
+        # hyperion/grid/amr_grid.py:372-412
+        geo.attrs["grid_type"] = "amr"
+        geo.attrs["nlevels"] = np.int64(len(model.amr_levels))
+        for il, lev in enumerate(model.amr_levels):
+            gl = geo.create_group("level_%05i" % (il + 1))
+            gl.attrs["ngrids"] = np.int64(len(lev))
+            for ig, g in enumerate(lev):
+                gg = gl.create_group("grid_%05i" % (ig + 1))
+                for k, v in zip(("n1", "n2", "n3"), g[:3]):
+                    gg.attrs[k] = np.int64(v)
+                for k, v in zip(("xmin", "xmax", "ymin", "ymax", "zmin", "zmax"), g[3:]):
+                    gg.attrs[k] = float(v)
+    elif model.grid_type != "oct":
         cols = {"sph": ("r", "t", "p"), "cyl": ("w", "z", "p"), "car": ("x", "y", "z")}[model.grid_type]
         geo.attrs["grid_type"] = {"sph": "sph_pol", "cyl": "cyl_pol", "car": "car"}[model.grid_type]
         geo.create_dataset("walls_1", _table([(cols[0], model.w1)]))
         geo.create_dataset("walls_2", _table([(cols[1], model.w2)]))
         geo.create_dataset("walls_3", _table([(cols[2], model.w3)]))
     q = f.create_group("Grid/Quantities")
-    d = q.create_dataset("density", model.density)
-    d.attrs["geometry"] = gid
-    if model.specific_energy is not None:
-        d = q.create_dataset("specific_energy", model.specific_energy)
+    if model.grid_type == "amr":
+        for il, ig, sl, shp in model.amr_slices():
+            qg = q.create_group("level_%05i/grid_%05i" % (il + 1, ig + 1))
+            qg.create_dataset("density", model.density[:, sl].reshape((-1,) + shp))
+            if model.specific_energy is not None:
+                qg.create_dataset("specific_energy", np.asarray(model.specific_energy)[:, sl].reshape((-1,) + shp))
+    else:
+        d = q.create_dataset("density", model.density)
         d.attrs["geometry"] = gid
+        if model.specific_energy is not None:
+            d = q.create_dataset("specific_energy", model.specific_energy)
+            d.attrs["geometry"] = gid
     if model.minimum_specific_energy is not None:
         q.attrs["minimum_specific_energy"] = np.asarray(model.minimum_specific_energy, dtype=np.float64)
 

@@ -246,17 +246,26 @@ def run(input_file, output_file, overwrite=False, device=None, log=None):
         log(" [output_grid] outputting grid arrays for iteration")
         if wanted(rs.output_n_photons):
             log(" WARNING: n_photons array is not allocated [output_grid]")
+        def put(name, arr):
+            """output_grid (src/grid/grid_generic.f90:29-130): one dataset per iteration, or, for AMR
+            grids, one per level / grid (src/grid/grid_io_amr.f90)."""
+            if model.grid_type == "amr":
+                for il, ig, sl, shp in model.amr_slices():
+                    path = "level_%05d/grid_%05d" % (il + 1, ig + 1)
+                    gg = g.require_group(path)
+                    gg.create_dataset(name, arr[:, sl].reshape((-1,) + shp).astype(io_dtype))
+            else:
+                d = g.create_dataset(name, arr.astype(io_dtype))
+                d.attrs["geometry"] = rs.geometry_id
+
         if wanted(rs.output_specific_energy):
             if se is None:
                 se = eng.get_specific_energy()
-            d = g.create_dataset("specific_energy", se.astype(io_dtype))
-            d.attrs["geometry"] = rs.geometry_id
+            put("specific_energy", se)
         if wanted(rs.output_density):
-            d = g.create_dataset("density", eng.get_density().astype(io_dtype))
-            d.attrs["geometry"] = rs.geometry_id
+            put("density", eng.get_density())
         if wanted(rs.output_density_diff):
-            d = g.create_dataset("density_diff", (eng.get_density() - density0).astype(io_dtype))
-            d.attrs["geometry"] = rs.geometry_id
+            put("density_diff", eng.get_density() - density0)
         g.attrs["killed_photons_geo"] = np.int64(st.killed_geo)
         g.attrs["killed_photons_int"] = np.int64(st.killed_int)
         if check is not None and converged:

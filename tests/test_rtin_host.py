@@ -227,3 +227,30 @@ def test_runner_octree(golden_car, golden_oct, tmp_path):
     assert se.shape == (1, 25)
     assert np.all(se[0][m.refined == 0] > 0)
     assert r["Peeled/group_00001/seds"][...][0].sum() > 0
+
+
+def test_rtin_roundtrip_amr(golden_car, golden_amr, tmp_path):
+    """'amr' grids: Grid/Geometry/level_%05d/grid_%05d attributes, one density dataset per grid
+    (hyperion/grid/amr_grid.py:372-412)."""
+    from helpers import bitlevel_model_amr
+    m = bitlevel_model_amr(golden_car, golden_amr, False, True)
+    fn = str(tmp_path / "m.rtin")
+    rtin_write.write_rtin(fn, m)
+    got, rs, _ = rtin.read_rtin(fn)
+    assert rs.grid_type == "amr" and got.grid_type == "amr"
+    assert got.amr_levels == m.amr_levels
+    assert np.array_equal(got.density, m.density) and got.density.shape == (3, 8 * 6 * 4 + 4 * 6 * 20)
+
+
+@pytest.mark.gpu
+def test_runner_amr(golden_car, golden_amr, tmp_path):
+    from helpers import peeloff_model_amr
+    m = peeloff_model_amr(golden_car, golden_amr, False)
+    fin, fout = str(tmp_path / "m.rtin"), str(tmp_path / "m.rtout")
+    rtin_write.write_rtin(fin, m, n_initial_iter=2, n_initial_photons=20000, n_last_photons=20000)
+    assert runner.main(["-f", fin, fout]) == 0
+    r = h5min.File(fout)
+    a = r["iteration_00002/level_00001/grid_00001/specific_energy"][...]
+    b = r["iteration_00002/level_00002/grid_00001/specific_energy"][...]
+    assert a.shape == (1, 4, 6, 8) and b.shape == (1, 20, 6, 4) and np.all(b > 0)
+    assert r["Peeled/group_00001/seds"][...][0].sum() > 0
