@@ -99,6 +99,7 @@ struct SourceDev {
   int32_t type, freq_type;
   double x, y, z, radius, temperature;
   int32_t limb, spectrum;  // index into spectra
+  int32_t peeloff, pad;    // whether the source is peeled off (source_emit_peeloff, source_type.f90:513-537)
   double pdf;              // normalised luminosity (for even sampling weights)
   double cdf;              // cumulative normalised luminosity
 };

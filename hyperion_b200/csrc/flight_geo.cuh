@@ -38,11 +38,15 @@ flight_geo_kernel(const ModelDev M, Pool P, const FinalArgs F, const uint32_t *_
         chi[k] = s->chi[k];
         kE[k] = s->kE[k];
       }
+      // find_nearest_source (source.f90:206-227): where, if anywhere, this flight hits a stellar surface
+      int src_hit = -1;
+      const double t_source = nearest_source(M, s->r0x, s->r0y, s->r0z, s->vx, s->vy, s->vz, src_hit);
       if (FINAL && tau < 0.0 && !G::escaped(M, R)) {
         typename G::Ray E = R;
         double tau_escape = 0.0, col[ND];
-        const bool ok = geo_escape<GEO, ND, false>(M, E, chi, cells, tau_escape, col, n_peel_cross);
-        if (!ok) ++n_killed;  // grid_escape_tau killed its copy; the packet itself goes on unforced
+        // grid_escape_tau gives up (killed) when a source lies on the way out (grid_propagate_3d.f90:410-415)
+        const bool ok = src_hit < 0 && geo_escape<GEO, ND, false>(M, E, chi, cells, tau_escape, col, n_peel_cross);
+        if (!ok && src_hit < 0) ++n_killed;  // grid_escape_tau killed its copy; the packet itself goes on unforced
         Rng rng;
         rng.init(M.seed, s->id, iteration);
         rng.blk = s->rng_blk;
@@ -77,7 +81,12 @@ flight_geo_kernel(const ModelDev M, Pool P, const FinalArgs F, const uint32_t *_
       } else if (FINAL && tau < 0.0) {
         tau = 1.0;  // escaped before the first step: the value is never used
       }
-      fin = geo_march<GEO, ND, DEP>(M, R, tau, chi, kE, cells, n_cross);
+      fin = geo_march<GEO, ND, DEP>(M, R, tau, chi, kE, cells, n_cross, t_source);
+      if (fin == MARCH_REABSORBED) {
+        // hand the packet to the interact kernel, which re-emits it from that source: t < 0 carries the id
+        s->t = -(double)(src_hit + 1);
+        fin = MARCH_INTERACT | 16;
+      }
       if (fin == MARCH_INTERACT) {
         s->t = R.t;
         int ix, iy, iz, ic;
@@ -87,7 +96,7 @@ flight_geo_kernel(const ModelDev M, Pool P, const FinalArgs F, const uint32_t *_
       n_esc += fin == MARCH_ESCAPED ? 1u : 0u;
       n_killed += fin == MARCH_KILLED ? 1u : 0u;
     }
-    queue_append(fin == MARCH_INTERACT, P.q_interact, P.counts + C_NI, slot);
+    queue_append((fin & MARCH_INTERACT) != 0, P.q_interact, P.counts + C_NI, slot);
     queue_append(fin == MARCH_ESCAPED || fin == MARCH_KILLED, P.q_emit, P.counts + C_NE, slot);
   }
   warp_add_scalar(M.scalars + SC_CROSS, (double)n_cross);

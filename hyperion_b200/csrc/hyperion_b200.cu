@@ -58,6 +58,8 @@ struct ModelDev {
   uint64_t seed;
   int64_t n_inter_max;
   int32_t kill_on_absorb, kill_on_scatter, sample_evenly, enforce_energy_range;
+  int32_t any_sphere;       // a spherical source exists: flights test for re-absorption (source.f90:206-227)
+  int64_t n_reabs_max;
   // outputs
   double *scalars;                 // [SC_COUNT], directly after the reduced sum grid
   unsigned long long *work_counter;
@@ -130,6 +132,7 @@ struct Photon {
   int32_t ix, iy, iz, ic;
   uint32_t n_inter;
   uint32_t tag;
+  double nx, ny, nz;     // outward normal at the emission point of a spherical source (0 otherwise); not stored
 };
 
 template <int ND>
@@ -258,12 +261,69 @@ __device__ __forceinline__ void set_dir(Photon<ND> &p, const Angle &a) {
   p.vz = a.cost;
 }
 
+// ran_mu_limb(1.5, 1) (source_type.f90:982-1084): mu from P = 1.5 mu^2 + mu, by the real root of the cubic
+__device__ inline double ran_mu_limb(Rng &rng) {
+  double s1 = 1.5 * (1.0 / 3.0), t1 = 1.0 * (1.0 / 2.0);
+  const double norm = s1 + t1;
+  s1 = s1 / norm;
+  t1 = t1 / norm;
+  const double xi = -rng.next();
+  const double bb = t1 / s1, dd = xi / s1;
+  const double alpha = 1.0 / 3.0, gamma = 1.0 / 27.0;
+  const double pp = -bb * bb * alpha * alpha;
+  const double q = (dd + 2.0 * bb * bb * bb * gamma) * 0.5;
+  const double p3 = pp * pp * pp;
+  double delta = q * q + p3;
+  if (delta < 0.0) {
+    const double phi = acos(-q / sqrt(fabs(p3)));
+    return 2.0 * sqrt(fabs(pp)) * cos(phi * alpha) - bb * alpha;
+  }
+  delta = sqrt(delta);
+  const double u = -q + delta, v = -q - delta;
+  const double cu = u >= 0.0 ? pow(u, alpha) : -pow(fabs(u), alpha);
+  const double cv = v >= 0.0 ? pow(v, alpha) : -pow(fabs(v), alpha);
+  return cu + cv - bb * alpha;
+}
+
+// source_distance + find_nearest_source (source_type.f90:324-357, source.f90:206-227): path length to the
+// nearest spherical source along (r, v), +inf if none is hit; `which` = its 0-based index
+__device__ inline double nearest_source(const ModelDev &M, double rx, double ry, double rz, double vx, double vy,
+                                        double vz, int &which) {
+  double nearest = __longlong_as_double(0x7ff0000000000000LL);
+  which = -1;
+  if (!M.any_sphere) return nearest;
+  for (int is = 0; is < M.n_sources; ++is) {
+    const SourceDev &S = M.sources[is];
+    if (S.type != HYP_SOURCE_SPHERE) continue;
+    const double dx = rx - S.x, dy = ry - S.y, dz = rz - S.z;
+    const double pB = 2.0 * (dx * vx + dy * vy + dz * vz);
+    const double pC = (dx * dx + dy * dy + dz * dz) - S.radius * S.radius;
+    double t1, t2;
+    quad_pascal_reduced(pB, pC, t1, t2);
+    const double tol = (double)1.e-8f * S.radius;
+    double d = __longlong_as_double(0x7ff0000000000000LL);
+    if (t1 < d && t1 > tol) d = t1;
+    if (t2 < d && t2 > tol) d = t2;
+    if (d < nearest) {
+      nearest = d;
+      which = is;
+    }
+  }
+  return nearest;
+}
+
 // emit (src/sources/source.f90:100-179): returns false on a fatal model error
 template <int ND>
-__device__ bool emit_photon(const ModelDev &M, Photon<ND> &p, Rng &rng, double &energy_emitted) {
+__device__ bool emit_photon(const ModelDev &M, Photon<ND> &p, Rng &rng, double &energy_emitted, const int reemit_src = -1,
+                            const double reemit_energy = 1.0) {
   int is = 0;
   const int ns = M.n_sources;
-  if (ns > 1) {
+  if (reemit_src >= 0) {
+    // emit(p, reemit=.true., reemit_id, reemit_energy) (source.f90:128-140): the re-absorbing source emits
+    // again; the reference still draws the source-selection number first
+    if (ns > 1) rng.next();
+    is = reemit_src;
+  } else if (ns > 1) {
     double xi = rng.next();
     if (M.sample_evenly) {
       is = min((int)(xi * ns), ns - 1);
@@ -279,14 +339,34 @@ __device__ bool emit_photon(const ModelDev &M, Photon<ND> &p, Rng &rng, double &
   }
   const SourceDev &S = M.sources[is];
   p.tag = (uint32_t)(is + 1);
-  // emit_from_point (source_type.f90:539-564)
-  p.r0x = S.x;
-  p.r0y = S.y;
-  p.r0z = S.z;
-  Angle a = random_sphere_angle(rng);
-  set_dir(p, a);
+  p.nx = p.ny = p.nz = 0.0;
+  if (S.type == HYP_SOURCE_SPHERE) {
+    // emit_from_sphere (source_type.f90:604-690): random point of the surface, direction from the
+    // cosine law (or the limb-darkened law) about the local normal
+    const Angle a_coord = random_sphere_angle(rng);
+    const double phi_local = 6.283185307179586476925286766559 * rng.next();
+    Angle a_local;
+    sincos(phi_local, &a_local.sinp, &a_local.cosp);
+    a_local.cost = S.limb ? ran_mu_limb(rng) : sqrt(rng.next());
+    a_local.sint = sqrt(1.0 - a_local.cost * a_local.cost);
+    const Angle a = rotate_angle(a_local, a_coord);
+    set_dir(p, a);
+    p.nx = a_coord.sint * a_coord.cosp;
+    p.ny = a_coord.sint * a_coord.sinp;
+    p.nz = a_coord.cost;
+    p.r0x = p.nx * S.radius + S.x;
+    p.r0y = p.ny * S.radius + S.y;
+    p.r0z = p.nz * S.radius + S.z;
+  } else {
+    // emit_from_point (source_type.f90:539-564)
+    p.r0x = S.x;
+    p.r0y = S.y;
+    p.r0z = S.z;
+    Angle a = random_sphere_angle(rng);
+    set_dir(p, a);
+  }
   p.sQ = p.sU = p.sV = 0.0;
-  p.energy = 1.0;
+  p.energy = reemit_src >= 0 ? reemit_energy : 1.0;
   if (S.freq_type == HYP_SPECTRUM_BLACKBODY) {
     p.nu = sample_planck(rng, S.temperature);
   } else {
@@ -294,8 +374,10 @@ __device__ bool emit_photon(const ModelDev &M, Photon<ND> &p, Rng &rng, double &
     p.nu = sample_powerlaw(sp.B + sp.L.o_x, sp.B + sp.L.o_cdf, sp.B + sp.L.o_invb, sp.B + sp.L.o_rm1, sp.L.n,
                            rng.next());
   }
-  if (M.sample_evenly) p.energy = p.energy * S.pdf * ns;
-  energy_emitted += p.energy;
+  if (reemit_src < 0) {
+    if (M.sample_evenly) p.energy = p.energy * S.pdf * ns;
+    energy_emitted += p.energy;
+  }
   if (!update_optconsts<ND>(M, p)) {
     atomicMax(M.error_flag, ERR_NU_RANGE);
     return false;
@@ -420,10 +502,31 @@ __device__ bool scatter_photon(const ModelDev &M, const DustDev &d, Photon<ND> &
   return true;
 }
 
+// A flight that ended on a stellar surface (Slot::t < 0 carries the source): emit(p, reemit=.true., ...) from
+// that source with the packet's energy (iter_lucy.f90:158-185, iter_final.f90:212-242).  Consecutive
+// re-absorptions are counted in bits 10-15 of the tag (n_reabs_max above 62 is treated as unlimited).
+constexpr uint32_t TAG_REABS_SHIFT = 10, TAG_REABS_MASK = 63u << 10;
+template <int ND>
+__device__ bool reemit_photon(const ModelDev &M, Photon<ND> &p, Rng &rng, uint32_t &n_killed_int) {
+  const int src = (int)(-p.t) - 1;
+  const uint32_t nre = (p.tag & TAG_REABS_MASK) >> TAG_REABS_SHIFT;
+  if (M.n_reabs_max < 63 && (int64_t)nre >= M.n_reabs_max) {
+    ++n_killed_int;
+    return false;
+  }
+  const uint32_t n_inter = p.n_inter;
+  double dummy = 0.0;
+  if (!emit_photon<ND>(M, p, rng, dummy, src, p.energy)) return false;
+  p.n_inter = n_inter;
+  p.tag = (uint32_t)(src + 1) | (min(nre + 1u, 63u) << TAG_REABS_SHIFT);
+  return true;
+}
+
 // interact (src/dust/dust_interact.f90:22-79).  Returns: 0 continue, 1 packet finished (killed).
 template <int ND>
 __device__ int interact_photon(const ModelDev &M, Photon<ND> &p, Rng &rng, uint32_t &n_abs, uint32_t &n_scat,
                                uint32_t &n_killed_int, int &dust_id, bool &was_scattered) {
+  p.tag &= ~TAG_REABS_MASK;
   // the loop guard of do_lucy (iter_lucy.f90:193-198)
   p.n_inter += 1;
   if ((int64_t)p.n_inter > M.n_inter_max) {
@@ -710,7 +813,9 @@ interact_kernel(const ModelDev M, Pool P, uint32_t *__restrict__ q_flight_next, 
       const uint64_t id = slots[slot].id;
       int dust_id = 0;
       bool scattered = false;
-      if (interact_photon<ND>(M, p, rng, n_abs, n_scat, n_kill, dust_id, scattered) == 0) {
+      const bool ok = p.t < 0.0 ? reemit_photon<ND>(M, p, rng, n_kill)
+                                : interact_photon<ND>(M, p, rng, n_abs, n_scat, n_kill, dust_id, scattered) == 0;
+      if (ok) {
         p.tau_left = -log(1.0 - rng.next());
         store_photon<ND>(slots + slot, p, rng, id);
         alive = true;
@@ -1887,7 +1992,9 @@ int hyp_add_source(hyp_ctx *c, const hyp_source *s) {
   if (!c || !s) return fail(HYP_ERR_INVALID, "NULL argument");
   if (c->finalized) return fail(HYP_ERR_STATE, "model is frozen");
   if ((int)c->sources.size() >= MAX_SOURCES) return fail(HYP_ERR_INVALID, "too many sources");
-  if (s->type != HYP_SOURCE_POINT) return fail(HYP_ERR_INVALID, "only point sources are implemented on the device");
+  if (s->type != HYP_SOURCE_POINT && s->type != HYP_SOURCE_SPHERE)
+    return fail(HYP_ERR_INVALID, "only point and spherical sources are implemented on the device");
+  if (s->type == HYP_SOURCE_SPHERE && !(s->radius > 0.0)) return fail(HYP_ERR_INVALID, "source radius should be positive");
   if (!(s->luminosity >= 0.0)) return fail(HYP_ERR_INVALID, "source luminosity should be positive");
   int spec = -1;
   if (s->spectrum_type == HYP_SPECTRUM_TABLE) {
@@ -1918,6 +2025,7 @@ int hyp_set_run_conf(hyp_ctx *c, const hyp_run_conf *conf) {
   if (c->finalized) {
     c->M.seed = (uint64_t)conf->seed;
     c->M.n_inter_max = conf->n_inter_max;
+    c->M.n_reabs_max = conf->n_reabs_max;
     c->M.kill_on_absorb = conf->kill_on_absorb;
     c->M.kill_on_scatter = conf->kill_on_scatter;
     c->M.sample_evenly = conf->sample_sources_evenly;
@@ -2171,6 +2279,8 @@ int hyp_finalize_setup(hyp_ctx *c) {
     sd[i].radius = s.radius;
     sd[i].temperature = s.temperature;
     sd[i].limb = s.limb_darkening;
+    sd[i].peeloff = s.peeloff;
+    sd[i].pad = 0;
     sd[i].spectrum = c->source_spectrum[i];
     sd[i].pdf = s.luminosity / ltot;
     cum += sd[i].pdf;
@@ -2201,6 +2311,10 @@ int hyp_finalize_setup(hyp_ctx *c) {
   M.error_flag = c->d_error;
   M.seed = (uint64_t)c->conf.seed;
   M.n_inter_max = c->conf.n_inter_max;
+  M.n_reabs_max = c->conf.n_reabs_max;
+  M.any_sphere = 0;
+  for (auto &src : c->sources)
+    if (src.type == HYP_SOURCE_SPHERE) M.any_sphere = 1;
   M.kill_on_absorb = c->conf.kill_on_absorb;
   M.kill_on_scatter = c->conf.kill_on_scatter;
   M.sample_evenly = c->conf.sample_sources_evenly;
@@ -2293,10 +2407,11 @@ static int run_rounds(hyp_ctx *c, int64_t first_id, int64_t n_photons, int64_t i
     CUDA_TRY(cudaMemsetAsync(P.counts + C_NI, 0, 4 * sizeof(uint32_t), st));  // C_NI, C_NE, C_CURSOR, C_CURSOR_B
     // 2. flights: the beams of new packets, then the packets that come out of an interaction
     CUDA_TRY(cudaEventRecord(c->evA, st));
-    if (c->grid_type != GEO_CAR) {
+    if (c->grid_type != GEO_CAR || c->M.any_sphere) {
       const FinalArgs none = FinalArgs();
       auto geo_flight = c->grid_type == GEO_OCT   ? flight_geo_kernel<GEO_OCT, ND, true, false>
                         : c->grid_type == GEO_AMR ? flight_geo_kernel<GEO_AMR, ND, true, false>
+                        : c->grid_type == GEO_CAR ? flight_geo_kernel<GEO_CAR, ND, true, false>
                                                   : flight_geo_kernel<GEO_SPH, ND, true, false>;
       const int sph_blocks_max = c->sm_count * 12;
       if (n_new > 0) {
@@ -2732,10 +2847,11 @@ int run_final_rounds(hyp_ctx *c, int64_t first_id, int64_t n_photons, int scatte
     }
     CUDA_TRY(cudaMemsetAsync(P.counts + C_NI, 0, 4 * sizeof(uint32_t), st));  // C_NI, C_NE, C_CURSOR, C_CURSOR_B
     CUDA_TRY(cudaEventRecord(c->evA, st));
-    if (c->grid_type != GEO_CAR) {
+    if (c->grid_type != GEO_CAR || c->M.any_sphere) {
       const int sph_blocks_max = c->sm_count * 12;
       auto geo_flight = c->grid_type == GEO_OCT   ? flight_geo_kernel<GEO_OCT, ND, false, true>
                         : c->grid_type == GEO_AMR ? flight_geo_kernel<GEO_AMR, ND, false, true>
+                        : c->grid_type == GEO_CAR ? flight_geo_kernel<GEO_CAR, ND, false, true>
                                                   : flight_geo_kernel<GEO_SPH, ND, false, true>;
       if (n_new > 0) {
         int blocks = (int)std::min<int64_t>((n_new + SPH_FLIGHT_THREADS - 1) / SPH_FLIGHT_THREADS, sph_blocks_max);

@@ -278,6 +278,14 @@ peel_kernel(const ModelDev M, const ImagingDev I, const PeelJob<ND> *__restrict_
     const ImageDev &im = I.images[V.group];
     const Angle a_req = V.a;
     Stokes S{1.0, 0.0, 0.0, 0.0};
+    if (J.kind == 2) {
+      // emit_from_sphere_peeloff (source_type.f90:692-707): (vpx, vpy, vpz) is the outward normal of the
+      // stellar surface at the emission point; the weights integrate to 4 pi over the sphere
+      const SourceDev &src = M.sources[J.source_id - 1];
+      const double vxr = a_req.sint * a_req.cosp, vyr = a_req.sint * a_req.sinp, vzr = a_req.cost;
+      const double mu = fmax(vxr * J.vpx + vyr * J.vpy + vzr * J.vpz, 0.0);
+      S.I = !src.peeloff ? 0.0 : (src.limb ? 2.0 * (1.5 * mu * mu + mu) : 4.0 * mu);
+    }
     if (J.kind == 1) {
       // dust_scatter_peeloff (dust_type_4elem.f90:421-444)
       const DustDev &d = M.dust[J.dust_id - 1];
@@ -318,6 +326,12 @@ peel_kernel(const ModelDev M, const ImagingDev I, const PeelJob<ND> *__restrict_
     const double x_image = dy * a_req.cosp - dx * a_req.sinp;
     const double y_image = dz * a_req.sint - dy * a_req.cost * a_req.sinp - dx * a_req.cost * a_req.cosp;
     if (!in_image(im, x_image, y_image)) continue;
+    if (!im.ignore_optical_depth && M.any_sphere) {
+      // grid_escape_*: a source on the line of sight kills the peel-off (grid_propagate_3d.f90:410-415)
+      int hit;
+      nearest_source(M, J.rx, J.ry, J.rz, vx, vy, vz, hit);
+      if (hit >= 0) continue;
+    }
     double tau = 0.0, col[ND];
 #pragma unroll
     for (int id = 0; id < ND; ++id) col[id] = 0.0;
@@ -450,6 +464,12 @@ __device__ __forceinline__ void fill_job(PeelJob<ND> *J, const Photon<ND> &p, in
   J->emiss_var_id = 0;
 }
 
+// kind of the peel-off of a packet that has just been emitted: 2 from a stellar surface, 0 isotropic
+template <int ND>
+__device__ __forceinline__ int surface_kind(const Photon<ND> &p) {
+  return (p.nx != 0.0 || p.ny != 0.0 || p.nz != 0.0) ? 2 : 0;
+}
+
 // emit + the peel-off of the fresh packet (iter_final.f90:113-123)
 template <int ND>
 __global__ void __launch_bounds__(SERVICE_THREADS)
@@ -483,7 +503,7 @@ emit_final_kernel(const ModelDev M, Pool P, const FinalArgs F, const unsigned lo
       go = emit_photon<ND>(M, p, rng, energy_emitted);
     }
     PeelJob<ND> *J = job_append<ND>(go && F.make_peeled && !F.scattering_only, F);
-    if (J) fill_job<ND>(J, p, 0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0);
+    if (J) fill_job<ND>(J, p, surface_kind(p), p.nx, p.ny, p.nz, 0.0, 0.0, 0.0, 0);
     if (go) {
       // with a forced first interaction the optical depth is drawn by the flight kernel once the
       // optical depth to the grid edge is known
@@ -510,7 +530,7 @@ interact_final_kernel(const ModelDev M, Pool P, const FinalArgs F, uint32_t *__r
     const uint32_t i = base + lane;
     const bool valid = i < n;
     uint32_t slot = 0;
-    bool alive = false, peel = false, scattered = false;
+    bool alive = false, peel = false, scattered = false, reemitted = false;
     Photon<ND> p;
     Rng rng;
     double vpx = 0, vpy = 0, vpz = 0, sQ = 0, sU = 0, sV = 0;
@@ -522,7 +542,14 @@ interact_final_kernel(const ModelDev M, Pool P, const FinalArgs F, uint32_t *__r
       id = slots[slot].id;
       vpx = p.vx; vpy = p.vy; vpz = p.vz;
       sQ = p.sQ; sU = p.sU; sV = p.sV;
-      if (interact_photon<ND>(M, p, rng, n_abs, n_scat, n_kill, dust_id, scattered) == 0) {
+      if (p.t < 0.0) {
+        // re-absorbed by a star: re-emit from its surface; always peeled (iter_final.f90:219-227)
+        if (reemit_photon<ND>(M, p, rng, n_kill)) {
+          alive = true;
+          reemitted = true;
+          peel = F.make_peeled != 0;
+        }
+      } else if (interact_photon<ND>(M, p, rng, n_abs, n_scat, n_kill, dust_id, scattered) == 0) {
         alive = true;
         if (scattered) {
           uint32_t ns = p.tag >> TAG_NSCAT_SHIFT;
@@ -535,7 +562,12 @@ interact_final_kernel(const ModelDev M, Pool P, const FinalArgs F, uint32_t *__r
       }
     }
     PeelJob<ND> *J = job_append<ND>(peel, F);
-    if (J) fill_job<ND>(J, p, scattered ? 1 : 0, vpx, vpy, vpz, sQ, sU, sV, dust_id + 1);
+    if (J) {
+      if (reemitted)
+        fill_job<ND>(J, p, surface_kind(p), p.nx, p.ny, p.nz, 0.0, 0.0, 0.0, 0);
+      else
+        fill_job<ND>(J, p, scattered ? 1 : 0, vpx, vpy, vpz, sQ, sU, sV, dust_id + 1);
+    }
     if (alive) {
       p.tau_left = -log(1.0 - rng.next());
       store_photon<ND>(slots + slot, p, rng, id);
@@ -693,7 +725,7 @@ __global__ void raytrace_emit_kernel(const ModelDev M, PeelJob<ND> *__restrict__
       rng.init(M.seed, first_source_id + i, ITER_RAY_SOURCE);
       ok = emit_photon<ND>(M, p, rng, dummy);
       p.energy = p.energy * source_weight;  // energy_total / n_photons_sources (iter_raytracing.f90:79)
-      fill_job<ND>(&J, p, 0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0);
+      fill_job<ND>(&J, p, surface_kind(p), p.nx, p.ny, p.nz, 0.0, 0.0, 0.0, 0);
       J.emiss_type = M.sources[(p.tag & TAG_SRC_MASK) - 1].freq_type;
     } else {
       // emit_from_grid (grid_physics_3d.f90:691-753)

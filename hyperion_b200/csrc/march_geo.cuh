@@ -4,10 +4,70 @@
 // Included by hyperion_b200.cu after ModelDev / CellRec are defined and before imaging.cuh.
 #pragma once
 
-enum { MARCH_ESCAPED = 1, MARCH_INTERACT = 2, MARCH_KILLED = 4 };
+enum { MARCH_ESCAPED = 1, MARCH_INTERACT = 2, MARCH_KILLED = 4, MARCH_REABSORBED = 8 };
 
 template <int GEO>
 struct Geo;
+
+// Cartesian grids, one wall search per crossing (grid_geometry_cartesian_3d.f90:424-521).  The Lucy and
+// imaging iterations of Cartesian models normally run through the specialised look-ahead kernels of
+// hyperion_b200.cu; this plain form serves models with spherical sources, whose flights must also be
+// tested against the stellar surfaces at every step.
+struct CarRay {
+  double r0x, r0y, r0z, vx, vy, vz, ivx, ivy, ivz;
+  double t;
+  int ix, iy, iz, ic;
+};
+
+template <>
+struct Geo<GEO_CAR> {
+  using Ray = CarRay;
+  struct Cross {
+    int wall;
+  };
+  static __device__ __forceinline__ bool find_cell(const ModelDev &M, double rx, double ry, double rz, double vx,
+                                                   double vy, double vz, int &ix, int &iy, int &iz, int &ic) {
+    int fx, fy, fz;
+    bool ok = place_axis(M.w1, M.n1, rx, vx, ix, fx);
+    ok = place_axis(M.w2, M.n2, ry, vy, iy, fy) && ok;
+    ok = place_axis(M.w3, M.n3, rz, vz, iz, fz) && ok;
+    if (!ok) return false;
+    ic = (fz * M.n2 + fy) * M.n1 + fx;
+    return true;
+  }
+  static __device__ __forceinline__ void start(const ModelDev &M, Ray &R, double rx, double ry, double rz, double vx,
+                                               double vy, double vz, int ix, int iy, int iz, int ic) {
+    R.r0x = rx; R.r0y = ry; R.r0z = rz;
+    R.vx = vx; R.vy = vy; R.vz = vz;
+    R.ivx = 1.0 / vx; R.ivy = 1.0 / vy; R.ivz = 1.0 / vz;
+    R.t = 0.0;
+    R.ix = ix; R.iy = iy; R.iz = iz; R.ic = ic;
+  }
+  static __device__ __forceinline__ bool escaped(const ModelDev &M, const Ray &R) {
+    return (unsigned)R.ix >= (unsigned)M.n1 || (unsigned)R.iy >= (unsigned)M.n2 || (unsigned)R.iz >= (unsigned)M.n3;
+  }
+  static __device__ __forceinline__ bool find_wall(const ModelDev &M, const Ray &R, double &dt, Cross &c) {
+    const double huge = 1.7976931348623157e308;
+    const bool px = R.vx > 0.0, py = R.vy > 0.0, pz = R.vz > 0.0;
+    const double tx = R.vx != 0.0 ? (__ldg(M.w1 + R.ix + (px ? 1 : 0)) - R.r0x) * R.ivx - R.t : huge;
+    const double ty = R.vy != 0.0 ? (__ldg(M.w2 + R.iy + (py ? 1 : 0)) - R.r0y) * R.ivy - R.t : huge;
+    const double tz = R.vz != 0.0 ? (__ldg(M.w3 + R.iz + (pz ? 1 : 0)) - R.r0z) * R.ivz - R.t : huge;
+    if (tx <= ty && tx <= tz) { c.wall = px ? 1 : 0; dt = tx; }
+    else if (ty <= tz) { c.wall = py ? 3 : 2; dt = ty; }
+    else { c.wall = pz ? 5 : 4; dt = tz; }
+    if (dt < 0.0) dt = 0.0;
+    return dt < huge;
+  }
+  static __device__ __forceinline__ void step(const ModelDev &M, Ray &R, const Cross &c) {
+    const int s = (c.wall & 1) ? 1 : -1, axis = c.wall >> 1;
+    if (axis == 0) R.ix += s; else if (axis == 1) R.iy += s; else R.iz += s;
+    R.ic = (R.iz * M.n2 + R.iy) * M.n1 + R.ix;
+  }
+  static __device__ __forceinline__ void stop_inside(Ray &R) {}
+  static __device__ __forceinline__ void store(const Ray &R, int &ix, int &iy, int &iz, int &ic) {
+    ix = R.ix; iy = R.iy; iz = R.iz; ic = R.ic;
+  }
+};
 
 // spherical and cylindrical polar grids (geometry_sph.cuh)
 template <>
@@ -112,9 +172,12 @@ struct Geo<GEO_AMR> {
 // cell until tau_left is used up (MARCH_INTERACT, R.t = path length to the event, R.ic its cell), the
 // packet leaves the grid (MARCH_ESCAPED) or no wall is found (MARCH_KILLED).  DEP: deposit
 // path length x kappa x energy in every crossed cell.
+// t_source: path length at which the flight hits a stellar surface (+inf: never); crossing it ends the march
+// with MARCH_REABSORBED before the segment is deposited, as in the reference (grid_propagate_3d.f90:140-146).
 template <int GEO, int ND, bool DEP>
 __device__ inline int geo_march(const ModelDev &M, typename Geo<GEO>::Ray &R, double &tau_left, const double (&chi)[ND],
-                                const double (&kE)[ND], CellRec *__restrict__ cells, uint32_t &n_cross) {
+                                const double (&kE)[ND], CellRec *__restrict__ cells, uint32_t &n_cross,
+                                const double t_source) {
   using G = Geo<GEO>;
   if (G::escaped(M, R)) return MARCH_ESCAPED;
   for (;;) {
@@ -132,6 +195,7 @@ __device__ inline int geo_march(const ModelDev &M, typename Geo<GEO>::Ray &R, do
     const double tau_cell = chi_rho * dt;
     ++n_cross;
     if (tau_cell < tau_left) {
+      if (R.t + dt > t_source) return MARCH_REABSORBED;
       if (DEP) {
 #pragma unroll
         for (int id = 0; id < ND; ++id)
@@ -143,6 +207,7 @@ __device__ inline int geo_march(const ModelDev &M, typename Geo<GEO>::Ray &R, do
       if (G::escaped(M, R)) return MARCH_ESCAPED;
     } else {
       const double len = dt * (tau_left / tau_cell);
+      if (R.t + len > t_source) return MARCH_REABSORBED;
       if (DEP) {
 #pragma unroll
         for (int id = 0; id < ND; ++id)

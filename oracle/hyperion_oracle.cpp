@@ -705,6 +705,7 @@ struct Photon {
   Vec v_prev{0, 0, 0};
   int emiss_type = 0, emiss_var_id = 0;
   double emiss_var_frac = 0.0;
+  Angle source_a{0, 0, 0, 0};  // position angle on a stellar surface (type_photon.f90, emit_from_sphere)
 };
 
 struct Source {
@@ -1066,7 +1067,7 @@ struct orc_ctx {
   // counters
   int64_t killed_photons_geo = 0, killed_photons_int = 0;
   int64_t n_crossings = 0, n_absorptions = 0, n_scatterings = 0, n_escaped = 0, n_photons_run = 0;
-  int64_t n_peel_crossings = 0, n_peeloffs = 0;
+  int64_t n_peel_crossings = 0, n_peeloffs = 0, n_reabsorptions = 0;
   PeeledState peeled;
   bool setup_done = false;
   std::string error;
@@ -2257,14 +2258,88 @@ void quadratic_pascal_reduced(double b, double c, double &x1, double &x2) {
   }
 }
 
+// source_distance (source_type.f90:324-357)
+double source_distance(const Source &src, const Vec &r, const Vec &v) {
+  double d = std::numeric_limits<double>::infinity();
+  if (src.type == HYP_SOURCE_SPHERE) {
+    const double tol = (double)1.e-8f;
+    Vec dr{r.x - src.position.x, r.y - src.position.y, r.z - src.position.z};
+    double pB = 2.0 * (dr.x * v.x + dr.y * v.y + dr.z * v.z);
+    double pC = (dr.x * dr.x + dr.y * dr.y + dr.z * dr.z) - src.radius * src.radius;
+    double t1, t2;
+    quadratic_pascal_reduced(pB, pC, t1, t2);
+    if (t1 < d && t1 > tol * src.radius) d = t1;
+    if (t2 < d && t2 > tol * src.radius) d = t2;
+  }
+  return d;
+}
+
 // find_nearest_source (source.f90:206-227)
 void find_nearest_source(const orc_ctx &g, const Vec &r, const Vec &v, double &nearest, int &nearest_id) {
-  (void)r;
-  (void)v;
   nearest_id = 0;
   nearest = std::numeric_limits<double>::infinity();
   if (!g.any_intersect) return;
-  // spherical sources are not part of the pinned Cartesian slice yet
+  for (size_t is = 0; is < g.s.size(); is++)
+    if (g.s[is].intersect) {
+      if (source_distance(g.s[is], r, v) < nearest) {
+        nearest = source_distance(g.s[is], r, v);
+        nearest_id = (int)is + 1;
+      }
+    }
+}
+
+// cbrt_dp (lib_algebra.f90:79-88)
+double cbrt_f(double x) {
+  const double alpha = 1.0 / 3.0;
+  return x >= 0. ? std::pow(x, alpha) : -std::pow(std::fabs(x), alpha);
+}
+
+// ran_mu_limb (source_type.f90:982-1084): P = a mu^2 + b mu
+double ran_mu_limb(Rng &rng, double a, double b) {
+  double s1 = a * (1.0 / 3.0), t1 = b * (1.0 / 2.0);
+  double norm = s1 + t1;
+  s1 = s1 / norm;
+  t1 = t1 / norm;
+  double xi = rng.random();
+  xi = -xi;
+  // cubic_real_root_v2: x^3 + bb x^2 + dd = 0
+  double bb = t1 / s1, dd = xi / s1;
+  const double alpha = 1.0 / 3.0, gamma = 1.0 / 27.0;
+  double pp = -bb * bb * alpha * alpha;
+  double q = (dd + 2.0 * bb * bb * bb * gamma) * 0.5;
+  double p3 = pp * pp * pp, q2 = q * q;
+  double delta = q2 + p3;
+  if (delta < 0) {
+    double phi = std::acos(-q / std::sqrt(std::fabs(p3)));
+    double y = +2 * std::sqrt(std::fabs(pp)) * std::cos(phi * alpha);
+    return y - bb * alpha;
+  }
+  delta = std::sqrt(delta);
+  double u = cbrt_f(-q + delta), v = cbrt_f(-q - delta);
+  return u + v - bb * alpha;
+}
+
+// emit_from_sphere (source_type.f90:604-690), no spots
+void emit_from_sphere(orc_ctx &g, const Source &src, Photon &p) {
+  Angle a_coord = random_sphere_angle3d(g.rng);
+  double phi_local = 0.0 + (TWOPI_F - 0.0) * g.rng.random();  // random_uni(phi_local, zero, twopi)
+  Angle a_local;
+  a_local.cosp = std::cos(phi_local);
+  a_local.sinp = std::sin(phi_local);
+  if (src.limb_darkening) {
+    a_local.cost = ran_mu_limb(g.rng, 1.5, 1.0);
+  } else {
+    double xi = g.rng.random();
+    a_local.cost = std::sqrt(xi);
+  }
+  a_local.sint = std::sqrt(1.0 - a_local.cost * a_local.cost);
+  p.a = rotate_angle3d(a_local, a_coord);
+  p.s = Stokes{1.0, 0.0, 0.0, 0.0};
+  Vec u = angle3d_to_vector3d(a_coord);
+  p.r = Vec{u.x * src.radius, u.y * src.radius, u.z * src.radius};
+  p.r = Vec{p.r.x + src.position.x, p.r.y + src.position.y, p.r.z + src.position.z};
+  p.last_isotropic = false;
+  p.source_a = a_coord;
 }
 
 // emit_from_point (source_type.f90:539-564)
@@ -2276,7 +2351,7 @@ void emit_from_point(orc_ctx &g, const Source &src, Photon &p) {
 }
 
 // emit (source.f90:100-179) + source_emit (source_type.f90:398-511)
-void emit(orc_ctx &g, Photon &p) {
+void emit(orc_ctx &g, Photon &p, bool reemit = false, int reemit_id = 0, double reemit_energy = 0.0) {
   p = Photon();
   int n_sources = (int)g.s.size();
   if (n_sources == 0) throw OracleError{"no sources to emit from"};
@@ -2290,10 +2365,14 @@ void emit(orc_ctx &g, Photon &p) {
   } else {
     p.source_id = 1;
   }
+  if (reemit) p.source_id = reemit_id;  // source.f90:134-140
   const Source &src = g.s[p.source_id - 1];
   switch (src.type) {
     case HYP_SOURCE_POINT:
       emit_from_point(g, src, p);
+      break;
+    case HYP_SOURCE_SPHERE:
+      emit_from_sphere(g, src, p);
       break;
     default:
       throw OracleError{"source type not restated in the oracle"};
@@ -2306,8 +2385,12 @@ void emit(orc_ctx &g, Photon &p) {
   else
     throw OracleError{"unknown spectrum type"};
   p.v = angle3d_to_vector3d(p.a);
-  if (g.conf.sample_sources_evenly) p.energy = p.energy * g.luminosity.pdf[p.source_id - 1] * n_sources;
-  g.energy_current = g.energy_current + p.energy;
+  if (reemit) {
+    p.energy = reemit_energy;
+  } else {
+    if (g.conf.sample_sources_evenly) p.energy = p.energy * g.luminosity.pdf[p.source_id - 1] * n_sources;
+    g.energy_current = g.energy_current + p.energy;
+  }
   update_optconsts(g, p);
   p.emiss_type = src.freq_type;
   p.last[0] = 's';
@@ -2550,7 +2633,22 @@ void lucy_photons(orc_ctx &g, int64_t n_photons) {
       double tau = g.rng.random_exp();
       double tau_achieved;
       grid_integrate(g, p, tau, tau_achieved);
-      if (p.reabsorbed) throw OracleError{"source re-absorption not restated in the oracle"};
+      if (p.reabsorbed) {
+        // loop until the packet finally escapes interacting with sources (iter_lucy.f90:158-185)
+        int64_t ia;
+        for (ia = 1; ia <= g.conf.n_reabs_max; ia++) {
+          emit(g, p, true, p.reabsorbed_id, p.energy);
+          g.n_reabsorptions++;
+          tau = g.rng.random_exp();
+          grid_integrate(g, p, tau, tau_achieved);
+          if (!p.reabsorbed) break;
+        }
+        if (ia == g.conf.n_reabs_max + 1) {
+          g.killed_photons_int++;
+          p.killed = true;
+          break;
+        }
+      }
       if (p.killed || escaped(g, p.icell)) {
         if (!p.killed) g.n_escaped++;
         break;
@@ -2839,8 +2937,23 @@ void peeloff_photon(orc_ctx &g, const Photon &p_orig, bool polychromatic) {
       p.v = v_req;
     } else {
       if (p.last[0] == 's' && p.last[1] == 'r') {
-        // source_emit_peeloff (source_type.f90:513-537): point sources are always isotropic
-        throw OracleError{"anisotropic source peel-off not restated in the oracle"};
+        // source_emit_peeloff (source_type.f90:513-537) -> emit_from_sphere_peeloff (:692-707)
+        const Source &src = g.s[p.source_id - 1];
+        if (src.peeloff) {
+          if (src.type != HYP_SOURCE_SPHERE) throw OracleError{"Should not be here, all other source types are isotropic"};
+          const Angle &b = p.source_a;
+          double mu = a_req.sint * a_req.cosp * b.sint * b.cosp + a_req.sint * a_req.sinp * b.sint * b.sinp + a_req.cost * b.cost;
+          mu = std::max(mu, 0.0);
+          if (src.limb_darkening)
+            p.s = Stokes{2. * (1.5 * mu * mu + mu), 0.0, 0.0, 0.0};
+          else
+            p.s = Stokes{4. * mu, 0.0, 0.0, 0.0};
+          p.a = a_req;
+        } else {
+          p.s = Stokes{0.0, 0.0, 0.0, 0.0};
+          p.a = a_req;
+        }
+        p.v = angle3d_to_vector3d(p.a);
       } else if (p.last[0] == 'd' && p.last[1] == 's') {
         dust_scatter_peeloff(g.d[p.dust_id - 1], p.nu, p.a, p.s, a_req);
         p.v = angle3d_to_vector3d(p.a);
@@ -2932,7 +3045,23 @@ void propagate_final(orc_ctx &g, Photon &p, bool peeloff_scattering_only) {
     }
     double tau_achieved;
     grid_integrate_noenergy(g, p, tau, tau_achieved);
-    if (p.reabsorbed) throw OracleError{"source re-absorption not restated in the oracle"};
+    if (p.reabsorbed) {
+      // iter_final.f90:212-242: re-emission from the stellar surface is always peeled off
+      int64_t ia;
+      for (ia = 1; ia <= g.conf.n_reabs_max; ia++) {
+        emit(g, p, true, p.reabsorbed_id, p.energy);
+        g.n_reabsorptions++;
+        if (make_peeled) peeloff_photon(g, p, false);
+        tau = g.rng.random_exp();
+        grid_integrate_noenergy(g, p, tau, tau_achieved);
+        if (!p.reabsorbed) break;
+      }
+      if (ia == g.conf.n_reabs_max + 1) {
+        g.killed_photons_int++;
+        p.killed = true;
+        break;
+      }
+    }
     if (p.killed || escaped(g, p.icell)) {
       if (!p.killed) g.n_escaped++;
       break;

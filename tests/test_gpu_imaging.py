@@ -200,3 +200,58 @@ def test_image_flux_is_additive_and_unattenuated_in_vacuum(golden_car):
     ltot = sum(s.luminosity for s in model.sources)
     assert abs(sed.sum() * dnunorm / ltot - 1) < 2e-3     # a little flux lies outside 0.01-5000 micron
     assert abs(img.sum() / sed.sum() - 1) < 1e-12
+
+
+@pytest.mark.parametrize("limb", [False, True])
+def test_stellar_surface_peeloff_flux_in_vacuum(golden_car, limb):
+    """Known answer (hyperion/model/tests/test_sed.py): a spherical source in an empty grid, seen from any
+    direction, shows its full luminosity -- the surface peel-off weights 4 mu (or the limb-darkened
+    2 (1.5 mu^2 + mu)) average to one over the visible hemisphere, and peel-offs from the far side are
+    blocked by the star itself (source_type.f90:692-707, grid_propagate_3d.f90:410-415)."""
+    from hyperion_b200.capi import Engine
+    from hyperion_b200.flatmodel import FlatPeeledGroup, FlatSource
+    from helpers import lsun
+    model = bitlevel_model(golden_car, False, False)
+    model.density[...] = 0.0
+    model.sources = [FlatSource(type=2, luminosity=lsun, temperature=5000., position=(0.1 * pc, 0.2 * pc, -0.1 * pc),
+                                radius=0.05 * pc, limb_darkening=limb)]
+    model.peeled = [FlatPeeledGroup(theta=[45., 120.], phi=[30., 200.], wavelengths=(20, 0.01, 5000.),
+                                    image=(8, 8, -2 * pc, 2 * pc, -2 * pc, 2 * pc), sed=(1, 3 * pc, 3 * pc), stokes=False)]
+    eng = Engine(0)
+    eng.load_model(model)
+    eng.final_begin()
+    N = 400000
+    eng.final_photons(0, N, False)
+    st = eng.final_finish()
+    sed, img = eng.sed(0), eng.image(0)
+    eng.close()
+    assert st.n_escaped == N
+    assert abs(st.n_peeloffs / N - 1) < 0.01          # two views, half of the surface faces each
+    nu_min, nu_max = 2.99792458e10 / (5000. * 1e-4), 2.99792458e10 / (0.01 * 1e-4)
+    dnunorm = (nu_max / nu_min) ** (0.5 / 20) - (nu_max / nu_min) ** (-0.5 / 20)
+    flux = sed.sum(axis=(0, 1, 3, 4)) * dnunorm / lsun
+    assert np.all(np.abs(flux - 1) < 0.01), flux
+    assert abs(img.sum() / sed.sum() - 1) < 1e-12
+
+
+def test_peeloff_with_stellar_source_matches_oracle(golden_car):
+    """Imaging + raytracing iterations with a star of finite radius in a dusty Cartesian grid: surface
+    peel-off, re-emission peel-offs, lines of sight blocked by the star."""
+    from hyperion_b200.flatmodel import FlatSource
+    from helpers import lsun
+    model = peeloff_model(golden_car, False)
+    model.density *= 10.
+    model.sources = [FlatSource(type=2, luminosity=lsun, temperature=5000., position=(0.05 * pc, -0.03 * pc, 0.02 * pc),
+                                radius=0.25 * pc),
+                     FlatSource(type=1, luminosity=0.5 * lsun, temperature=7000., position=(-0.5 * pc, 0.4 * pc, -0.3 * pc))]
+    model.specific_energy = _converged_energy(model, 100000)
+    gpu, orc = _run_both(model, 12, 60000, True, (20000, 30000))
+    print(_compare(gpu, orc))
+    for key in ("n_crossings", "n_absorptions", "n_scatterings", "n_peeloffs", "n_peel_crossings"):
+        a = np.mean([g[1][key] for g in gpu])
+        b = np.mean([o[1][key] for o in orc])
+        assert abs(a / b - 1) < 0.02, (key, a, b)
+    for key in ("n_peeloffs", "n_peel_crossings"):
+        a = np.mean([g[2][key] for g in gpu])
+        b = np.mean([o[2][key] for o in orc])
+        assert abs(a / b - 1) < 0.02, (key, a, b)

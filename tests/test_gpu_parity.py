@@ -356,3 +356,33 @@ def test_deposits_match_oracle_three_level_amr():
         b = np.mean([s[key] for s in ost])
         assert abs(a / b - 1) < 0.01, (key, a, b)
     assert all(s["killed_geo"] == 0 for s in gst) and all(s["killed_geo"] == 0 for s in ost)
+
+
+@pytest.mark.parametrize("geometry", ["car", "sph"])
+def test_spherical_source_with_reabsorption(golden_car, golden_sph, geometry):
+    """A star of finite radius (source type 2, src/sources/source_type.f90:604-690) in a dusty grid:
+    packets start on the stellar surface with the cosine law, and flights that come back to the
+    surface are re-emitted from it (iter_lucy.f90:158-185).  A second, limb-darkened star sits
+    off-centre.  Deposits and work counters against the oracle."""
+    from hyperion_b200.flatmodel import FlatSource
+    if geometry == "car":
+        model = bitlevel_model(golden_car, False, False)
+    else:
+        model = bitlevel_model_sph(golden_car, golden_sph, False, False)
+    model.density *= 20.
+    model.sources = [FlatSource(type=2, luminosity=lsun, temperature=5000., position=(0.05 * pc, -0.03 * pc, 0.02 * pc),
+                                radius=0.25 * pc),
+                     FlatSource(type=2, luminosity=0.3 * lsun, temperature=8000., position=(-0.5 * pc, 0.4 * pc, -0.3 * pc),
+                                radius=0.1 * pc, limb_darkening=True)]
+    B, N = 16, 100000
+    g, gst = _gpu_batches(model, N, B)
+    o, ost = _oracle_batches(model, N, B)
+    z, ok = _zscores(g, o)
+    assert ok.mean() > 0.9
+    assert np.abs(z[ok]).max() < 5.5, np.abs(z[ok]).max()
+    assert 0.6 < (z[ok] ** 2).mean() < 1.5, (z[ok] ** 2).mean()
+    for key in ("n_crossings", "n_absorptions", "n_scatterings"):
+        a = np.mean([s[key] for s in gst])
+        b = np.mean([s[key] for s in ost])
+        assert abs(a / b - 1) < 0.01, (key, a, b)
+    assert all(s["killed_geo"] == 0 and s["killed_int"] == 0 and s["n_escaped"] == N for s in gst)
