@@ -468,8 +468,9 @@ struct Dust {
   std::vector<double> specific_energy, chi_planck, kappa_planck, chi_inv_planck, kappa_inv_planck,
       chi_rosseland, kappa_rosseland;
   std::vector<double> j_nu_var, log10_j_nu_var;
-  std::vector<PdfCont> j_nu;
+  std::vector<PdfCont> j_nu, b_nu;  // b_nu: emissivity divided by opacity (dust_type_4elem.f90:286-291)
   bool zero_p2 = true;
+  bool have_b_nu = false;
 
   // dust_setup (dust_type_4elem.f90:78-293)
   void setup(const hyp_dust_tables &t) {
@@ -548,6 +549,28 @@ struct Dust {
       for (int k = 0; k < t.n_emiss_nu; k++) col[k] = t.emiss_jnu[(size_t)k * n_jnu + i];
       j_nu[i].set(t.emiss_nu, col.data(), t.n_emiss_nu, true);
     }
+    // b_nu = j_nu / kappa_nu on the emissivity frequency grid, used by the modified random walk
+    b_nu.resize(n_jnu);
+    std::vector<double> kap(t.n_emiss_nu);
+    bool kap_ok = true;
+    for (int k = 0; k < t.n_emiss_nu; k++) {
+      if (t.emiss_nu[k] < nu[0] || t.emiss_nu[k] > nu[n_nu - 1]) {
+        kap_ok = false;
+        break;
+      }
+      kap[k] = interp1d_loglog(nu.data(), kappa_nu.data(), n_nu, t.emiss_nu[k]);
+    }
+    have_b_nu = kap_ok;
+    if (kap_ok)
+      for (int i = 0; i < n_jnu; i++) {
+        for (int k = 0; k < t.n_emiss_nu; k++) col[k] = t.emiss_jnu[(size_t)k * n_jnu + i] / kap[k];
+        try {
+          b_nu[i].set(t.emiss_nu, col.data(), t.n_emiss_nu, true);
+        } catch (OracleError &) {
+          have_b_nu = false;
+          break;
+        }
+      }
   }
 
   // dust_jnu_var_pos_frac (dust_type_4elem.f90:295-320)
@@ -563,6 +586,15 @@ struct Dust {
       id = locate(j_nu_var.data(), n_jnu, v);
       frac = (std::log10(v) - log10_j_nu_var[id - 1]) / (log10_j_nu_var[id] - log10_j_nu_var[id - 1]);
     }
+  }
+
+  // dust_sample_b_nu (dust_type_4elem.f90:400-419)
+  double sample_b_nu(Rng &rng, int id, double frac) const {
+    double xi = rng.random();
+    double nu1 = b_nu[id - 1].sample_xi(xi);
+    double nu2 = b_nu[id].sample_xi(xi);
+    double v = std::log10(nu1) + frac * (std::log10(nu2) - std::log10(nu1));
+    return std::pow(10.0, v);
   }
 
   // dust_sample_j_nu (dust_type_4elem.f90:379-398)
@@ -1051,6 +1083,10 @@ struct orc_ctx {
   std::vector<int> mask_map;
   int n_masked = 0;
   bool specific_energy_from_file = false;
+  // modified random walk (grid_mrw_3d.f90:21-26, grid_physics_3d.f90:60)
+  std::vector<double> alpha_inv_planck, diff_coeff;
+  double mrw_xcdf[100], mrw_ycdf[100];
+  int64_t n_mrw_steps = 0;
   // dust
   int n_dust = 0;
   std::vector<Dust> d;
@@ -2622,6 +2658,158 @@ void precompute_jnu_var(orc_ctx &g) {
     }
 }
 
+// ---------------------------------------------------------------------------
+// modified random walk (src/grid/grid_mrw_3d.f90; Min et al. 2009, Robitaille 2010)
+// ---------------------------------------------------------------------------
+// distance_to_closest_wall of each geometry module
+double distance_to_closest_wall(const orc_ctx &g, const Photon &p) {
+  double d;
+  if (g.grid_type == 0) {  // grid_geometry_cartesian_3d.f90:396-422
+    double d1 = p.r.x - g.w1[p.icell.i1 - 1], d2 = g.w1[p.icell.i1] - p.r.x;
+    double d3 = p.r.y - g.w2[p.icell.i2 - 1], d4 = g.w2[p.icell.i2] - p.r.y;
+    double d5 = p.r.z - g.w3[p.icell.i3 - 1], d6 = g.w3[p.icell.i3] - p.r.z;
+    d = std::min(std::min(std::min(d1, d2), std::min(d3, d4)), std::min(d5, d6));
+  } else if (g.grid_type == 1) {  // grid_geometry_spherical_3d.f90:679-739
+    double r = std::sqrt(p.r.x * p.r.x + p.r.y * p.r.y + p.r.z * p.r.z);
+    double d1 = r - g.w1[p.icell.i1 - 1], d2 = g.w1[p.icell.i1] - r;
+    if (std::fabs(d1) < g.ew1[p.icell.i1 - 1]) d1 = 0.0;
+    if (std::fabs(d2) < g.ew1[p.icell.i1]) d2 = 0.0;
+    double rcyl = std::sqrt(p.r.x * p.r.x + p.r.y * p.r.y);
+    double ta = g.wtant[p.icell.i2 - 1], tb = g.wtant[p.icell.i2];
+    double d3 = std::fabs(-rcyl + ta * p.r.z) / std::sqrt(1 + ta * ta);
+    double d4 = std::fabs(-rcyl + tb * p.r.z) / std::sqrt(1 + tb * tb);
+    double d5 = std::numeric_limits<double>::max(), d6 = d5;
+    if (g.n3 > 1) {
+      double pa = g.wtanp[p.icell.i3 - 1], pb = g.wtanp[p.icell.i3];
+      d5 = std::fabs(pa * p.r.x - p.r.y) / std::sqrt(pa * pa + 1.0);
+      d6 = std::fabs(pb * p.r.x - p.r.y) / std::sqrt(pb * pb + 1.0);
+    }
+    d = std::min(std::min(std::min(d1, d2), std::min(d3, d4)), std::min(d5, d6));
+  } else if (g.grid_type == 2) {  // grid_geometry_cylindrical_3d.f90:549-590
+    double r = std::sqrt(p.r.x * p.r.x + p.r.y * p.r.y);
+    double d1 = r - g.w1[p.icell.i1 - 1], d2 = g.w1[p.icell.i1] - r;
+    double d3 = p.r.z - g.w2[p.icell.i2 - 1], d4 = g.w2[p.icell.i2] - p.r.z;
+    double d5 = std::numeric_limits<double>::max(), d6 = d5;
+    if (g.n3 > 1) {
+      double pa = g.wtanp[p.icell.i3 - 1], pb = g.wtanp[p.icell.i3];
+      d5 = std::fabs(pa * p.r.x - p.r.y) / std::sqrt(pa * pa + 1.0);
+      d6 = std::fabs(pb * p.r.x - p.r.y) / std::sqrt(pb * pb + 1.0);
+    }
+    d = std::min(std::min(std::min(d1, d2), std::min(d3, d4)), std::min(d5, d6));
+  } else if (g.grid_type == 3) {  // grid_geometry_octree.f90:410-436
+    const int k = p.icell.ic - 1;
+    double d1 = p.r.x - g.ox[k] + g.odx[k], d2 = g.ox[k] + g.odx[k] - p.r.x;
+    double d3 = p.r.y - g.oy[k] + g.ody[k], d4 = g.oy[k] + g.ody[k] - p.r.y;
+    double d5 = p.r.z - g.oz[k] + g.odz[k], d6 = g.oz[k] + g.odz[k] - p.r.z;
+    d = std::min(std::min(std::min(d1, d2), std::min(d3, d4)), std::min(d5, d6));
+  } else {  // grid_geometry_amr.f90:743-773
+    const orc_ctx::AmrGrid &G = g.levels[p.icell.ilevel - 1][p.icell.igrid - 1];
+    double d1 = p.r.x - G.w1[p.icell.i1 - 1], d2 = G.w1[p.icell.i1] - p.r.x;
+    double d3 = p.r.y - G.w2[p.icell.i2 - 1], d4 = G.w2[p.icell.i2] - p.r.y;
+    double d5 = p.r.z - G.w3[p.icell.i3 - 1], d6 = G.w3[p.icell.i3] - p.r.z;
+    d = std::min(std::min(std::min(d1, d2), std::min(d3, d4)), std::min(d5, d6));
+  }
+  if (d < 0.0) d = 0.0;
+  return d;
+}
+
+// update_alpha_inv_planck (grid_physics_3d.f90:397-418) + prepare_mrw (grid_mrw_3d.f90:29-54)
+void prepare_mrw(orc_ctx &g) {
+  // initialize_cumulative (:158-196): P(y) = 2 sum_n (-1)^(n+1) y^(n^2)
+  const int ncdf = 100;
+  for (int i = 1; i <= ncdf; i++) {
+    g.mrw_xcdf[i - 1] = (double)(i - 1) / (double)(ncdf - 1);
+    double y = 0.0;
+    if (i == ncdf) {
+      y = 0.5;
+    } else {
+      for (int64_t j = 1;; j++) {
+        double term = std::pow(g.mrw_xcdf[i - 1], (double)(j * j));
+        if (term == 0.0) break;
+        if (j % 2 == 0)
+          y = y - term;
+        else
+          y = y + term;
+      }
+    }
+    g.mrw_ycdf[i - 1] = y * 2.0;
+  }
+  const int nc = g.n_cells;
+  g.alpha_inv_planck.assign(nc, 0.0);
+  g.diff_coeff.assign(nc, 0.0);
+  for (int ic = 0; ic < nc; ic++) {
+    for (int id = 0; id < g.n_dust; id++) {
+      size_t k = (size_t)id * nc + ic;
+      if (g.density[k] > 0.0) {
+        const Dust &d = g.d[id];
+        g.alpha_inv_planck[ic] = g.alpha_inv_planck[ic] +
+                                 g.density[k] * interp1d_loglog(d.specific_energy.data(), d.chi_inv_planck.data(), d.n_e, g.specific_energy[k]);
+      }
+    }
+    double total = 0.0;
+    for (int id = 0; id < g.n_dust; id++) {
+      size_t k = (size_t)id * nc + ic;
+      const Dust &d = g.d[id];
+      // cells without dust would divide by zero below; they are never entered by the random walk
+      if (g.density[k] > 0.0)
+        total = total + g.density[k] * interp1d_loglog(d.specific_energy.data(), d.chi_inv_planck.data(), d.n_e, g.specific_energy[k]);
+    }
+    g.diff_coeff[ic] = 1.0 / 3.0 / total;
+  }
+}
+
+// sample_cumulative (:198-203): interp1d(ycdf, xcdf, xi), linear
+double mrw_sample_cumulative(orc_ctx &g) {
+  double xi = g.rng.random();
+  int ip = locate(g.mrw_ycdf, 100, xi);
+  if (ip == -1) throw OracleError{"Interpolation out of bounds"};
+  const double *x = g.mrw_ycdf, *y = g.mrw_xcdf;
+  return (xi - x[ip - 1]) / (x[ip] - x[ip - 1]) * (y[ip] - y[ip - 1]) + y[ip - 1];
+}
+
+// grid_do_mrw (:56-111) / grid_do_mrw_noenergy (:113-149)
+void grid_do_mrw(orc_ctx &g, Photon &p, bool deposit) {
+  const int nc = g.n_cells, ic = p.icell.ic;
+  double R0 = distance_to_closest_wall(g, p);
+  if (deposit) {
+    double y = mrw_sample_cumulative(g);
+    double ct = -std::log(y) / g.diff_coeff[ic - 1] * ((R0 / PI_F) * (R0 / PI_F));
+    for (int id = 0; id < g.n_dust; id++) {
+      size_t k = (size_t)id * nc + ic - 1;
+      if (g.density[k] > 0.0) {
+        const Dust &d = g.d[id];
+        double e = p.energy * ct * interp1d_loglog(d.specific_energy.data(), d.kappa_planck.data(), d.n_e, g.specific_energy[k]);
+        g.specific_energy_sum[k] = g.specific_energy_sum[k] + e;
+      }
+    }
+  }
+  // random_sphere_vector3d (type_vector3d.f90:323-333)
+  double mu = -1.0 + 2.0 * g.rng.random();
+  double phi = TWOPI_F * g.rng.random();
+  double cut = std::sqrt(1.0 - mu * mu);
+  p.r.x = p.r.x + cut * std::cos(phi) * R0;
+  p.r.y = p.r.y + cut * std::sin(phi) * R0;
+  p.r.z = p.r.z + mu * R0;
+  p.a_prev = p.a;
+  p.v_prev = p.v;
+  p.s_prev = p.s;
+  p.a = random_sphere_angle3d(g.rng);
+  p.v = angle3d_to_vector3d(p.a);
+  int id = select_dust_chi_rho(g, p);
+  size_t k = (size_t)(id - 1) * nc + ic - 1;
+  p.nu = g.d[id - 1].sample_b_nu(g.rng, g.jnu_var_id[k], g.jnu_var_frac[k]);
+  // NB: the reference does not refresh the opacities for the new frequency here
+  p.last_isotropic = true;
+  p.dust_id = id;
+  p.last[0] = deposit ? 'd' : 'm';
+  p.last[1] = 'e';
+  g.n_mrw_steps++;
+}
+
+// the MRW block at the top of the interaction loop (iter_lucy.f90:134-148, iter_final.f90:166-185);
+// returns false if the packet had to be killed
+bool mrw_steps(orc_ctx &g, Photon &p, bool deposit, bool peel);
+
 // the photon loop of do_lucy (iter_lucy.f90:127-205)
 void lucy_photons(orc_ctx &g, int64_t n_photons) {
   Photon p;
@@ -2630,6 +2818,9 @@ void lucy_photons(orc_ctx &g, int64_t n_photons) {
     emit(g, p);
     g.n_photons_run++;
     for (int64_t interactions = 1; interactions <= n_inter_max + 1; interactions++) {
+      if (g.conf.use_mrw && interactions > 1) {
+        if (!mrw_steps(g, p, true, false)) break;
+      }
       double tau = g.rng.random_exp();
       double tau_achieved;
       grid_integrate(g, p, tau, tau_achieved);
@@ -3023,11 +3214,32 @@ void peeloff_photon(orc_ctx &g, const Photon &p_orig, bool polychromatic) {
   }
 }
 
+bool mrw_steps(orc_ctx &g, Photon &p, bool deposit, bool peel) {
+  int64_t steps;
+  for (steps = 1; steps <= g.conf.n_mrw_max; steps++) {
+    if (g.alpha_inv_planck[p.icell.ic - 1] * distance_to_closest_wall(g, p) > g.conf.mrw_gamma) {
+      grid_do_mrw(g, p, deposit);
+      if (peel) peeloff_photon(g, p, false);
+    } else {
+      break;
+    }
+  }
+  if (steps == g.conf.n_mrw_max + 1) {
+    g.killed_photons_int++;
+    p.killed = true;
+    return false;
+  }
+  return true;
+}
+
 // propagate (iter_final.f90:147-273); MRW and source re-absorption are not restated
 void propagate_final(orc_ctx &g, Photon &p, bool peeloff_scattering_only) {
   const int64_t n_inter_max = g.conf.n_inter_max;
   const bool make_peeled = !g.peeled.image.empty();
   for (int64_t interactions = 1; interactions <= n_inter_max + 1; interactions++) {
+    if (interactions > 1 && g.conf.use_mrw) {
+      if (!mrw_steps(g, p, false, make_peeled && !peeloff_scattering_only)) break;
+    }
     double tau;
     if (interactions == 1 && g.conf.forced_first_interaction) {
       double tau_escape;
@@ -3653,7 +3865,12 @@ int orc_lucy_begin(orc_ctx *g) {
   g->energy_current = 0.0;
   g->killed_photons_geo = g->killed_photons_int = 0;
   g->n_crossings = g->n_absorptions = g->n_scatterings = g->n_escaped = g->n_photons_run = 0;
-  precompute_jnu_var(*g);
+  try {
+    precompute_jnu_var(*g);
+    if (g->conf.use_mrw) prepare_mrw(*g);  // iter_lucy.f90:109-112
+  } catch (OracleError &e) {
+    return fail(g, e.msg);
+  }
   return 0;
 }
 
@@ -3758,6 +3975,7 @@ int orc_final_begin(orc_ctx *g) {
   g->n_peel_crossings = g->n_peeloffs = 0;
   try {
     precompute_jnu_var(*g);
+    if (g->conf.use_mrw) prepare_mrw(*g);  // iter_final.f90:93-96
   } catch (OracleError &e) {
     return fail(g, e.msg);
   }

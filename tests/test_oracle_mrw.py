@@ -1,0 +1,48 @@
+"""Pin the oracle's modified random walk to the reference's known answers.
+
+hyperion/model/tests/test_mrw.py:10-66 (test_single_temperature): one cell of 2 cm, a 6000 K point source
+of unit luminosity, the 9-point "realistic" dust with 40 LTE emissivity states, densities from 1e-5 to
+1e12 g/cm^3, 1000 packets per iteration, up to 30 iterations with the 99-percentile convergence test,
+MRW with gamma = 2.  The reference requires the cell temperature to lie within 10 % of 18 tabulated
+values; the oracle (restated MRW + the restated dust generator of hyperion_b200/synthetic.py) lands
+within about 2 % of every one of them.
+"""
+import numpy as np
+import pytest
+
+from hyperion_b200 import synthetic as syn
+from hyperion_b200.flatmodel import FlatConf, FlatModel, FlatSource
+from hyperion_b200.runner import ConvergenceCheck
+from oracle import oracle
+
+D_REF = np.logspace(-5., 12., 18)
+T_REF = [24.75280, 24.66414, 24.52175, 21.97109, 15.53059, 10.76363, 7.810127, 6.672520, 6.902798, 16.64318,
+         53.08394, 162.0158, 438.9026, 1013.141, 2156.520, 4642.825, 9948.065, 21211.08]
+
+
+def mrw_model(density, dust):
+    w = np.array([-1., 1.])
+    conf = FlatConf(use_mrw=True, mrw_gamma=2., n_mrw_max=1000, n_inter_max=1000000000)
+    return FlatModel(w, w, w, np.full((1, 1, 1, 1), density), [dust],
+                     [FlatSource(type=1, luminosity=1., temperature=6000.)], conf)
+
+
+def temperature_of(dust, specific_energy):
+    """SphericalDust.specific_energy2temperature (hyperion/dust/dust_type.py:479-511): log-log interpolation."""
+    return 10 ** np.interp(np.log10(specific_energy), np.log10(dust.specific_energy), np.log10(dust.temperature))
+
+
+@pytest.mark.parametrize("density_ref,temperature_ref", list(zip(D_REF, T_REF)))
+def test_single_temperature(density_ref, temperature_ref):
+    dust = syn.realistic_dust(n_temp=40)
+    o = oracle.Oracle(mrw_model(density_ref, dust))
+    check = ConvergenceCheck(2., 1.02, 99.)
+    for _ in range(30):
+        st = o.run_lucy_iteration(1000)
+        se = o.get_specific_energy()
+        if check(se):
+            break
+    assert st.killed_int == 0 and st.killed_geo == 0
+    t = temperature_of(dust, se.ravel()[0])
+    assert temperature_ref / t < 1.1 and t / temperature_ref < 1.1     # the reference's criterion
+    assert abs(t / temperature_ref - 1) < 0.04                          # what the oracle actually achieves
