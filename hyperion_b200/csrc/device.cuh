@@ -87,7 +87,9 @@ __device__ __forceinline__ int lower_interval(const double *__restrict__ x, int 
 
 struct DustDev {
   DustLayout L;
-  const double *B;  // device buffer
+  const double *B;   // device buffer
+  DustMrwLayout Lm;  // b_nu samplers (modified random walk), nullptr unless the MRW is enabled
+  const double *Bm;
 };
 
 struct SpectrumDev {

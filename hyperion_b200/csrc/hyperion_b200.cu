@@ -58,6 +58,12 @@ struct ModelDev {
   uint64_t seed;
   int64_t n_inter_max;
   int32_t kill_on_absorb, kill_on_scatter, sample_evenly, enforce_energy_range;
+  // modified random walk (grid_mrw_3d.f90): per-cell alpha_inv_planck and diffusion coefficient, P(y) table
+  int32_t use_mrw;
+  int64_t n_mrw_max;
+  double mrw_gamma;
+  double *alpha_inv_planck, *diff_coeff;
+  const double *mrw_cdf;    // xcdf[100] | ycdf[100]
   int32_t any_sphere;       // a spherical source exists: flights test for re-absorption (source.f90:206-227)
   int64_t n_reabs_max;
   // outputs
@@ -66,7 +72,7 @@ struct ModelDev {
   int32_t *error_flag;
 };
 
-enum { ERR_NONE = 0, ERR_NOT_IN_CELL = 1, ERR_NU_RANGE = 2, ERR_SCATTER = 3 };
+enum { ERR_NONE = 0, ERR_NOT_IN_CELL = 1, ERR_NU_RANGE = 2, ERR_SCATTER = 3, ERR_JOBS = 4 };
 
 // =============================================================================================
 // photon pool (wavefront formulation of do_lucy's photon loop, src/main/iter_lucy.f90:119-209)
@@ -596,6 +602,151 @@ __device__ int interact_photon(const ModelDev &M, Photon<ND> &p, Rng &rng, uint3
   return 0;
 }
 
+// distance_to_closest_wall of each geometry module (e.g. grid_geometry_cartesian_3d.f90:396-422)
+template <int ND>
+__device__ inline double distance_to_closest_wall(const ModelDev &M, const Photon<ND> &p) {
+  const double x = p.r0x, y = p.r0y, z = p.r0z;
+  double d;
+  if (M.grid_type == GEO_CAR) {
+    d = fmin(fmin(fmin(x - M.w1[p.ix], M.w1[p.ix + 1] - x), fmin(y - M.w2[p.iy], M.w2[p.iy + 1] - y)),
+             fmin(z - M.w3[p.iz], M.w3[p.iz + 1] - z));
+  } else if (M.grid_type == GEO_SPH) {
+    const SphGrid &G = M.sph;
+    const double *w1 = G.T + G.o_w1, *w2 = G.T + G.o_w2;
+    const double rcyl = sqrt(x * x + y * y);
+    double d1, d2, d3, d4;
+    if (G.kind == POLAR_CYL) {
+      d1 = rcyl - w1[p.ix];
+      d2 = w1[p.ix + 1] - rcyl;
+      d3 = z - w2[p.iy];
+      d4 = w2[p.iy + 1] - z;
+    } else {
+      const double r = sqrt(x * x + y * y + z * z);
+      d1 = r - w1[p.ix];
+      d2 = w1[p.ix + 1] - r;
+      if (fabs(d1) < G.T[G.o_ew1 + p.ix]) d1 = 0.0;
+      if (fabs(d2) < G.T[G.o_ew1 + p.ix + 1]) d2 = 0.0;
+      const double ta = G.T[G.o_wtant + p.iy], tb = G.T[G.o_wtant + p.iy + 1];
+      d3 = fabs(-rcyl + ta * z) / sqrt(1.0 + ta * ta);
+      d4 = fabs(-rcyl + tb * z) / sqrt(1.0 + tb * tb);
+    }
+    double d5 = 1.7976931348623157e308, d6 = d5;
+    if (G.n3 > 1) {
+      const double pa = G.T[G.o_wtanp + p.iz], pb = G.T[G.o_wtanp + p.iz + 1];
+      d5 = fabs(pa * x - y) / sqrt(pa * pa + 1.0);
+      d6 = fabs(pb * x - y) / sqrt(pb * pb + 1.0);
+    }
+    d = fmin(fmin(fmin(d1, d2), fmin(d3, d4)), fmin(d5, d6));
+  } else if (M.grid_type == GEO_OCT) {
+    const OctNode &N = M.oct.nodes[p.ic];
+    d = fmin(fmin(fmin(x - N.x + N.dx, N.x + N.dx - x), fmin(y - N.y + N.dy, N.y + N.dy - y)),
+             fmin(z - N.z + N.dz, N.z + N.dz - z));
+  } else {
+    const AmrGridDev &G = M.amr.grids[M.amr.cell_grid[p.ic]];
+    d = fmin(fmin(fmin(x - amr_wall(G.xmin, G.xmax, p.ix, G.n1), amr_wall(G.xmin, G.xmax, p.ix + 1, G.n1) - x),
+                  fmin(y - amr_wall(G.ymin, G.ymax, p.iy, G.n2), amr_wall(G.ymin, G.ymax, p.iy + 1, G.n2) - y)),
+             fmin(z - amr_wall(G.zmin, G.zmax, p.iz, G.n3), amr_wall(G.zmin, G.zmax, p.iz + 1, G.n3) - z));
+  }
+  return d < 0.0 ? 0.0 : d;
+}
+
+__device__ __forceinline__ double mean_opacity_loglog(const DustDev &d, int64_t o_logy, double e) {
+  // interp1d_loglog on the mean-opacity table (src/dust/dust.f90:81-121)
+  const double *loge = d.B + d.L.o_loge;
+  const double le = log10(e);
+  int lo = 0, hi = d.L.n_e - 1;
+  while (hi - lo > 1) {
+    int mid = (lo + hi) >> 1;
+    if (__ldg(loge + mid) <= le) lo = mid; else hi = mid;
+  }
+  const double a = __ldg(loge + lo), b = __ldg(loge + lo + 1);
+  return loglog_at(d.B + o_logy, lo, (le - a) / (b - a));
+}
+
+
+// One step of the modified random walk in the packet's cell (grid_do_mrw / grid_do_mrw_noenergy,
+// grid_mrw_3d.f90:56-149): jump to the surface of the largest sphere that fits in the cell, deposit the
+// energy absorbed along the diffusive path (Lucy iteration), pick a new direction and a frequency from
+// the local b_nu.  As in the reference, the opacities are NOT refreshed for the new frequency here.
+template <int ND>
+__device__ inline int mrw_step(const ModelDev &M, Photon<ND> &p, Rng &rng, const bool deposit, const double R0) {
+  const size_t base = (size_t)p.ic * ND;
+  if (deposit) {
+    // sample_cumulative (:198-203): linear interpolation of x(y)
+    const double *xc = M.mrw_cdf, *yc = M.mrw_cdf + 100;
+    const double xi = rng.next();
+    const int j = lower_interval(yc, 100, xi);
+    const double y0 = __ldg(yc + j), y1 = __ldg(yc + j + 1);
+    const double yv = (xi - y0) / (y1 - y0) * (__ldg(xc + j + 1) - __ldg(xc + j)) + __ldg(xc + j);
+    const double q = R0 / 3.14159265358979323846;
+    const double ct = -log(yv) / M.diff_coeff[p.ic] * (q * q);
+#pragma unroll
+    for (int id = 0; id < ND; ++id) {
+      if (M.cells[base + id].rho > 0.0) {
+        const double e = p.energy * ct * mean_opacity_loglog(M.dust[id], M.dust[id].L.o_logkap_planck, M.specific_energy[base + id]);
+        atomicAdd(&M.cells[base + id].esum, e);
+      }
+    }
+  }
+  // random_sphere_vector3d (type_vector3d.f90:323-333)
+  const double mu = -1.0 + 2.0 * rng.next();
+  const double phi = 6.283185307179586476925286766559 * rng.next();
+  const double cut = sqrt(1.0 - mu * mu);
+  double sp, cp;
+  sincos(phi, &sp, &cp);
+  p.r0x += cut * cp * R0;
+  p.r0y += cut * sp * R0;
+  p.r0z += mu * R0;
+  const Angle a = random_sphere_angle(rng);
+  set_dir(p, a);
+  // select_dust_chi_rho with the (stale) opacities of the packet
+  int id = 0;
+  if (ND > 1) {
+    double w[ND], tot = 0.0;
+#pragma unroll
+    for (int k = 0; k < ND; ++k) {
+      tot += p.chi[k] * M.cells[base + k].rho;
+      w[k] = tot;
+    }
+    const double xi = rng.next();
+    id = ND - 1;
+#pragma unroll
+    for (int k = ND - 2; k >= 0; --k)
+      if (xi <= w[k] / tot) id = k;
+    if (xi >= 1.0) id = ND - 1;
+  }
+  // dust_sample_b_nu (dust_type_4elem.f90:400-419)
+  const DustDev &d = M.dust[id];
+  const int jid = M.jnu_id[base + id];
+  const double frac = M.jnu_frac[base + id];
+  const double x2 = rng.next();
+  const int ne = d.L.n_enu;
+  const double *enu = d.B + d.L.o_enu;
+  const double nu1 = sample_powerlaw(enu, d.Bm + d.Lm.o_bcdf + (size_t)jid * ne, d.Bm + d.Lm.o_binvb + (size_t)jid * (ne - 1),
+                                     d.Bm + d.Lm.o_brm1 + (size_t)jid * (ne - 1), ne, x2);
+  const double nu2 = sample_powerlaw(enu, d.Bm + d.Lm.o_bcdf + (size_t)(jid + 1) * ne,
+                                     d.Bm + d.Lm.o_binvb + (size_t)(jid + 1) * (ne - 1),
+                                     d.Bm + d.Lm.o_brm1 + (size_t)(jid + 1) * (ne - 1), ne, x2);
+  const double l1 = log10(nu1);
+  p.nu = pow(10.0, l1 + frac * (log10(nu2) - l1));
+  p.sQ = p.sU = p.sV = 0.0;
+  return id;
+}
+
+// The MRW block at the top of the interaction loop (iter_lucy.f90:134-148): while the cell is optically
+// thick out to its closest wall, random-walk.  Returns false if n_mrw_max steps did not get the packet out
+// (the reference kills it).
+template <int ND>
+__device__ inline bool mrw_loop(const ModelDev &M, Photon<ND> &p, Rng &rng, uint32_t &n_killed_int) {
+  for (int64_t step = 0; step < M.n_mrw_max; ++step) {
+    const double R0 = distance_to_closest_wall<ND>(M, p);
+    if (!(M.alpha_inv_planck[p.ic] * R0 > M.mrw_gamma)) return true;
+    mrw_step<ND>(M, p, rng, true, R0);
+  }
+  ++n_killed_int;
+  return false;
+}
+
 // cell volume (setup_grid_geometry of each geometry module)
 __device__ __forceinline__ double cell_volume(const ModelDev &M, int64_t ic) {
   if (M.grid_type == GEO_SPH) return sph_volume(M.sph, ic);
@@ -813,8 +964,10 @@ interact_kernel(const ModelDev M, Pool P, uint32_t *__restrict__ q_flight_next, 
       const uint64_t id = slots[slot].id;
       int dust_id = 0;
       bool scattered = false;
-      const bool ok = p.t < 0.0 ? reemit_photon<ND>(M, p, rng, n_kill)
-                                : interact_photon<ND>(M, p, rng, n_abs, n_scat, n_kill, dust_id, scattered) == 0;
+      const bool was_reabsorbed = p.t < 0.0;
+      bool ok = was_reabsorbed ? reemit_photon<ND>(M, p, rng, n_kill)
+                               : interact_photon<ND>(M, p, rng, n_abs, n_scat, n_kill, dust_id, scattered) == 0;
+      if (ok && M.use_mrw && !was_reabsorbed) ok = mrw_loop<ND>(M, p, rng, n_kill);
       if (ok) {
         p.tau_left = -log(1.0 - rng.next());
         store_photon<ND>(slots + slot, p, rng, id);
@@ -1229,24 +1382,25 @@ __global__ void lucy_begin_kernel(ModelDev M, const int reset_sums) {
   }
 }
 
+// update_alpha_inv_planck (grid_physics_3d.f90:397-418) + prepare_mrw (grid_mrw_3d.f90:29-54)
+__global__ void mrw_prepare_kernel(ModelDev M) {
+  const int nd = M.n_dust;
+  for (int64_t ic = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; ic < M.n_cells; ic += (int64_t)gridDim.x * blockDim.x) {
+    double alpha = 0.0;
+    for (int id = 0; id < nd; ++id) {
+      const double rho = M.cells[ic * nd + id].rho;
+      if (rho > 0.0) alpha += rho * mean_opacity_loglog(M.dust[id], M.dust[id].L.o_logchi_invp, M.specific_energy[ic * nd + id]);
+    }
+    M.alpha_inv_planck[ic] = alpha;
+    M.diff_coeff[ic] = 1.0 / 3.0 / alpha;
+  }
+}
+
 // gather the deposit sums into the contiguous reduction buffer
 __global__ void gather_sums_kernel(ModelDev M, double *__restrict__ sums) {
   const int64_t n = M.n_cells * M.n_dust;
   for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x)
     sums[k] = M.cells[k].esum;
-}
-
-__device__ __forceinline__ double mean_opacity_loglog(const DustDev &d, int64_t o_logy, double e) {
-  // interp1d_loglog on the mean-opacity table (src/dust/dust.f90:81-121)
-  const double *loge = d.B + d.L.o_loge;
-  const double le = log10(e);
-  int lo = 0, hi = d.L.n_e - 1;
-  while (hi - lo > 1) {
-    int mid = (lo + hi) >> 1;
-    if (__ldg(loge + mid) <= le) lo = mid; else hi = mid;
-  }
-  const double a = __ldg(loge + lo), b = __ldg(loge + lo + 1);
-  return loglog_at(d.B + o_logy, lo, (le - a) / (b - a));
 }
 
 __device__ __forceinline__ double clamp_energy(const ModelDev &M, const DustDev &d, int id, double e) {
@@ -1345,8 +1499,11 @@ struct HostDust {
   std::vector<double> buf;
   double *dev = nullptr;
   // raw columns kept for the raytracing spectra (get_chi_nu_binned / get_j_nu_binned)
-  std::vector<double> nu, chi, emiss_nu, emiss_jnu;
+  std::vector<double> nu, chi, albedo, emiss_nu, emiss_jnu;
   int n_jnu = 0;
+  // b_nu samplers for the modified random walk (built at finalize when the MRW is on)
+  DustMrwLayout Lm;
+  double *dev_mrw = nullptr;
 };
 struct HostSpectrum {
   SpectrumLayout L;
@@ -1436,6 +1593,7 @@ struct hyp_ctx {
   uint32_t *d_njobs = nullptr;
   uint32_t job_cap = 0;
   double *d_eabs = nullptr;
+  double *d_mrw_alpha = nullptr, *d_mrw_diff = nullptr, *d_mrw_cdf = nullptr;
   std::vector<double *> ray_tables;  // device copies of the binned raytracing spectra
   bool images_ready = false, ray_ready = false;
   int64_t peel_launches = 0;
@@ -1470,6 +1628,8 @@ int device_error_to_status(hyp_ctx *c) {
     case ERR_NU_RANGE:
       return fail(HYP_ERR_PHYSICS,
                   "photon frequency is outside the range defined for the dust optical properties");
+    case ERR_JOBS:
+      return fail(HYP_ERR_STATE, "peel-off queue overflow: too many random-walk steps per round (lower HYPERION_B200_POOL)");
     default:
       return fail(HYP_ERR_PHYSICS, "ERROR: in sampling mu for scattering");
   }
@@ -1658,12 +1818,18 @@ void hyp_ctx_destroy(hyp_ctx *c) {
   free_dev(c->d_jobs);
   free_dev(c->d_njobs);
   free_dev(c->d_eabs);
+  free_dev(c->d_mrw_alpha);
+  free_dev(c->d_mrw_diff);
+  free_dev(c->d_mrw_cdf);
   for (auto &t : c->ray_tables) free_dev(t);
   free_pool(c);
   if (c->h_counts) cudaFreeHost(c->h_counts);
   if (c->evA) cudaEventDestroy(c->evA);
   if (c->evB) cudaEventDestroy(c->evB);
-  for (auto &d : c->dust) free_dev(d.dev);
+  for (auto &d : c->dust) {
+    free_dev(d.dev);
+    free_dev(d.dev_mrw);
+  }
   for (auto &s : c->spectra) free_dev(s.dev);
   if (c->h_pinned) cudaFreeHost(c->h_pinned);
   if (c->ev0) cudaEventDestroy(c->ev0);
@@ -1978,6 +2144,7 @@ int hyp_add_dust(hyp_ctx *c, const hyp_dust_tables *t) {
     build_dust(*t, d.L, d.buf);
     d.nu.assign(t->nu, t->nu + t->n_nu);
     d.chi.assign(t->chi, t->chi + t->n_nu);
+    d.albedo.assign(t->albedo, t->albedo + t->n_nu);
     d.emiss_nu.assign(t->emiss_nu, t->emiss_nu + t->n_emiss_nu);
     d.emiss_jnu.assign(t->emiss_jnu, t->emiss_jnu + (size_t)t->n_emiss_nu * t->n_jnu);
     d.n_jnu = t->n_jnu;
@@ -2020,12 +2187,16 @@ int hyp_add_source(hyp_ctx *c, const hyp_source *s) {
 
 int hyp_set_run_conf(hyp_ctx *c, const hyp_run_conf *conf) {
   if (!c || !conf) return fail(HYP_ERR_INVALID, "NULL argument");
-  if (conf->use_mrw) return fail(HYP_ERR_INVALID, "the modified random walk is not implemented on the device yet");
+  if (c->finalized && conf->use_mrw && !c->M.use_mrw)
+    return fail(HYP_ERR_STATE, "the modified random walk has to be enabled before hyp_finalize_setup");
   c->conf = *conf;
   if (c->finalized) {
     c->M.seed = (uint64_t)conf->seed;
     c->M.n_inter_max = conf->n_inter_max;
     c->M.n_reabs_max = conf->n_reabs_max;
+    c->M.use_mrw = conf->use_mrw;
+    c->M.mrw_gamma = conf->mrw_gamma;
+    c->M.n_mrw_max = conf->n_mrw_max;
     c->M.kill_on_absorb = conf->kill_on_absorb;
     c->M.kill_on_scatter = conf->kill_on_scatter;
     c->M.sample_evenly = conf->sample_sources_evenly;
@@ -2246,6 +2417,20 @@ int hyp_finalize_setup(hyp_ctx *c) {
     CUDA_TRY(cudaMemcpy(d.dev, d.buf.data(), d.buf.size() * sizeof(double), cudaMemcpyHostToDevice));
     M.dust[id].L = d.L;
     M.dust[id].B = d.dev;
+    M.dust[id].Bm = nullptr;
+    if (c->conf.use_mrw) {
+      std::vector<double> mb;
+      try {
+        build_dust_mrw(d.nu.data(), d.chi.data(), d.albedo.data(), (int)d.nu.size(), d.emiss_nu.data(), d.emiss_jnu.data(),
+                       (int)d.emiss_nu.size(), d.n_jnu, d.Lm, mb);
+      } catch (std::exception &e) {
+        return fail(HYP_ERR_INVALID, e.what());
+      }
+      CUDA_TRY(cudaMalloc(&d.dev_mrw, mb.size() * sizeof(double)));
+      CUDA_TRY(cudaMemcpy(d.dev_mrw, mb.data(), mb.size() * sizeof(double), cudaMemcpyHostToDevice));
+      M.dust[id].Lm = d.Lm;
+      M.dust[id].Bm = d.dev_mrw;
+    }
     M.min_energy[id] = c->h_min_energy[id];
   }
   // spectra + sources
@@ -2312,6 +2497,20 @@ int hyp_finalize_setup(hyp_ctx *c) {
   M.seed = (uint64_t)c->conf.seed;
   M.n_inter_max = c->conf.n_inter_max;
   M.n_reabs_max = c->conf.n_reabs_max;
+  M.use_mrw = c->conf.use_mrw;
+  M.mrw_gamma = c->conf.mrw_gamma;
+  M.n_mrw_max = c->conf.n_mrw_max;
+  if (c->conf.use_mrw) {
+    double cdf[200];
+    build_mrw_cumulative(cdf, cdf + 100);
+    CUDA_TRY(cudaMalloc(&c->d_mrw_cdf, sizeof cdf));
+    CUDA_TRY(cudaMemcpy(c->d_mrw_cdf, cdf, sizeof cdf, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMalloc(&c->d_mrw_alpha, (size_t)c->n_cells * sizeof(double)));
+    CUDA_TRY(cudaMalloc(&c->d_mrw_diff, (size_t)c->n_cells * sizeof(double)));
+    M.mrw_cdf = c->d_mrw_cdf;
+    M.alpha_inv_planck = c->d_mrw_alpha;
+    M.diff_coeff = c->d_mrw_diff;
+  }
   M.any_sphere = 0;
   for (auto &src : c->sources)
     if (src.type == HYP_SOURCE_SPHERE) M.any_sphere = 1;
@@ -2339,6 +2538,11 @@ int hyp_lucy_begin(hyp_ctx *c) {
   lucy_begin_kernel<<<grid_blocks(c), 256, 0, c->stream>>>(c->M, 1);
   CUDA_TRY(cudaGetLastError());
   c->launches_acc = 1;
+  if (c->M.use_mrw) {
+    mrw_prepare_kernel<<<grid_blocks(c), 256, 0, c->stream>>>(c->M);
+    CUDA_TRY(cudaGetLastError());
+    c->launches_acc += 1;
+  }
   CUDA_TRY(cudaMemsetAsync(c->d_sums + n, 0, SC_COUNT * sizeof(double), c->stream));
   CUDA_TRY(cudaMemsetAsync(c->d_error, 0, sizeof(int32_t), c->stream));
   c->sums_gathered = false;
@@ -2795,7 +2999,7 @@ int run_final_rounds(hyp_ctx *c, int64_t first_id, int64_t n_photons, int scatte
   const uint32_t cap = (uint32_t)std::min<int64_t>(pool_target(), n_photons);
   int rc = ensure_pool(c, cap);
   if (rc) return rc;
-  rc = ensure_jobs(c, 2 * c->pool_cap);
+  rc = ensure_jobs(c, (c->M.use_mrw ? 8 : 2) * c->pool_cap);
   if (rc) return rc;
   Pool &P = c->pool;
   const WallSmem ws = wall_smem(c);
@@ -2887,7 +3091,7 @@ int run_final_rounds(hyp_ctx *c, int64_t first_id, int64_t n_photons, int scatte
     CUDA_TRY(cudaGetLastError());
     c->launches_acc += 1;
     // peel-offs of this round's emissions and interactions
-    rc = launch_peel<ND, false>(c, M, (uint32_t)std::min<int64_t>((int64_t)c->job_cap, n_new + (int64_t)cap));
+    rc = launch_peel<ND, false>(c, M, c->M.use_mrw ? c->job_cap : (uint32_t)std::min<int64_t>((int64_t)c->job_cap, n_new + (int64_t)cap));
     if (rc) return rc;
     CUDA_TRY(cudaMemsetAsync(c->d_njobs, 0, sizeof(uint32_t), st));
     CUDA_TRY(cudaMemcpyAsync(c->h_counts, P.counts, C_COUNT * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
@@ -3006,6 +3210,11 @@ int hyp_final_begin(hyp_ctx *c) {
   lucy_begin_kernel<<<grid_blocks(c), 256, 0, c->stream>>>(c->M, 0);
   CUDA_TRY(cudaGetLastError());
   c->launches_acc = 1;
+  if (c->M.use_mrw) {
+    mrw_prepare_kernel<<<grid_blocks(c), 256, 0, c->stream>>>(c->M);
+    CUDA_TRY(cudaGetLastError());
+    c->launches_acc += 1;
+  }
   CUDA_TRY(cudaMemsetAsync(c->d_imgbuf + c->imgbuf_n, 0, SC_COUNT * sizeof(double), c->stream));
   CUDA_TRY(cudaMemsetAsync(c->d_error, 0, sizeof(int32_t), c->stream));
   c->kernel_ms_acc = 0.f;

@@ -561,6 +561,34 @@ interact_final_kernel(const ModelDev M, Pool P, const FinalArgs F, uint32_t *__r
         peel = F.make_peeled && (scattered || !F.scattering_only);
       }
     }
+    if (alive && M.use_mrw && !reemitted) {
+      // grid_do_mrw_noenergy + peel-off of every random-walk step (iter_final.f90:166-185)
+      bool out = false;
+      for (int64_t step = 0; step < M.n_mrw_max; ++step) {
+        const double R0 = distance_to_closest_wall<ND>(M, p);
+        if (!(M.alpha_inv_planck[p.ic] * R0 > M.mrw_gamma)) {
+          out = true;
+          break;
+        }
+        // the interaction's own peel-off has to be queued before the state changes
+        if (peel) {
+          const uint32_t k = atomicAdd(F.n_jobs, 1u);
+          if (k < F.job_capacity) fill_job<ND>((PeelJob<ND> *)F.jobs + k, p, scattered ? 1 : 0, vpx, vpy, vpz, sQ, sU, sV, dust_id + 1);
+          else atomicMax(M.error_flag, ERR_JOBS);
+          peel = false;
+        }
+        const int id = mrw_step<ND>(M, p, rng, false, R0);
+        if (F.make_peeled && !F.scattering_only) {
+          const uint32_t k = atomicAdd(F.n_jobs, 1u);
+          if (k < F.job_capacity) fill_job<ND>((PeelJob<ND> *)F.jobs + k, p, 0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, id + 1);
+          else atomicMax(M.error_flag, ERR_JOBS);
+        }
+      }
+      if (!out) {
+        ++n_kill;
+        alive = false;
+      }
+    }
     PeelJob<ND> *J = job_append<ND>(peel, F);
     if (J) {
       if (reemitted)

@@ -35,7 +35,7 @@ struct DustLayout {
   // scattering matrix, each [n_nu][n_mu]
   int64_t o_mu, o_P1, o_P2, o_P3, o_P4, o_C1, o_C2;
   // mean opacities (length n_e), log10 of each
-  int64_t o_loge, o_logchi_ross, o_logchi_invp;
+  int64_t o_loge, o_logchi_ross, o_logchi_invp, o_logkap_planck;
   // emissivities
   int64_t o_logjvar;           // [n_jnu] log10 of the emissivity variable
   int64_t o_jvar;              // [n_jnu]
@@ -44,6 +44,13 @@ struct DustLayout {
   int64_t o_einvb;             // [n_jnu][n_enu-1]  1/(b+1)
   int64_t o_erm1;              // [n_jnu][n_enu-1]  r-1
   int64_t total;
+};
+
+// Samplers of b_nu = j_nu / kappa_nu for every emissivity state (dust_type_4elem.f90:286-291), used by the
+// modified random walk (dust_sample_b_nu, :400-419).  Layout: cdf [n_jnu][n_enu], 1/(b+1) and r-1
+// [n_jnu][n_enu-1] each, in a buffer of its own (only models that enable the MRW pay for it).
+struct DustMrwLayout {
+  int64_t o_bcdf, o_binvb, o_brm1, total;
 };
 
 struct SpectrumLayout {
@@ -166,6 +173,7 @@ inline void build_dust(const hyp_dust_tables &t, DustLayout &L, std::vector<doub
   L.o_loge = take(n_e);
   L.o_logchi_ross = take(n_e);
   L.o_logchi_invp = take(n_e);
+  L.o_logkap_planck = take(n_e);
   L.o_logjvar = take(n_jnu);
   L.o_jvar = take(n_jnu);
   L.o_enu = take(n_enu);
@@ -221,6 +229,7 @@ inline void build_dust(const hyp_dust_tables &t, DustLayout &L, std::vector<doub
     B[L.o_loge + i] = detail::safe_log10(t.specific_energy[i]);
     B[L.o_logchi_ross + i] = detail::safe_log10(t.chi_rosseland[i]);
     B[L.o_logchi_invp + i] = detail::safe_log10(t.chi_inv_planck[i]);
+    B[L.o_logkap_planck + i] = detail::safe_log10(t.kappa_planck[i]);
   }
   for (int i = 0; i < n_jnu; ++i) {
     B[L.o_jvar + i] = t.jnu_var[i];
@@ -375,5 +384,54 @@ inline void binned_chi(const double *nu, const double *chi, int n, double l0, do
     out[i] = detail::integral_loglog_range(nu, chi, n, lo, hi) / (hi - lo);
   }
 }
+
+inline void build_dust_mrw(const double *nu, const double *chi, const double *albedo, int n_nu, const double *emiss_nu,
+                           const double *emiss_jnu, int n_enu, int n_jnu, DustMrwLayout &L, std::vector<double> &buf) {
+  L.o_bcdf = 0;
+  L.o_binvb = (int64_t)n_jnu * n_enu;
+  L.o_brm1 = L.o_binvb + (int64_t)n_jnu * (n_enu - 1);
+  L.total = L.o_brm1 + (int64_t)n_jnu * (n_enu - 1);
+  buf.assign((size_t)L.total, 0.0);
+  // kappa_nu on the emissivity grid, log-log interpolation of chi (1 - albedo)
+  std::vector<double> kap(n_enu), col(n_enu);
+  for (int k = 0; k < n_enu; ++k) {
+    const double x = emiss_nu[k];
+    if (x < nu[0] || x > nu[n_nu - 1]) throw std::runtime_error("Interpolation out of bounds");
+    int j = detail::interval_of(nu, n_nu, x);
+    const double k0 = chi[j] * (1.0 - albedo[j]), k1 = chi[j + 1] * (1.0 - albedo[j + 1]);
+    if (k0 == 0.0 || k1 == 0.0) {
+      kap[k] = 0.0;
+    } else {
+      const double f = (std::log10(x) - std::log10(nu[j])) / (std::log10(nu[j + 1]) - std::log10(nu[j]));
+      kap[k] = std::pow(10.0, std::log10(k0) + f * (std::log10(k1) - std::log10(k0)));
+    }
+  }
+  for (int s = 0; s < n_jnu; ++s) {
+    for (int k = 0; k < n_enu; ++k) col[k] = emiss_jnu[(size_t)k * n_jnu + s] / kap[k];
+    detail::build_powerlaw_sampler(emiss_nu, col.data(), n_enu, buf.data() + L.o_bcdf + (size_t)s * n_enu,
+                                   buf.data() + L.o_binvb + (size_t)s * (n_enu - 1),
+                                   buf.data() + L.o_brm1 + (size_t)s * (n_enu - 1));
+  }
+}
+
+// P(y) = 2 sum_n (-1)^(n+1) y^(n^2) tabulated at 100 points (initialize_cumulative, grid_mrw_3d.f90:158-196)
+inline void build_mrw_cumulative(double *xcdf, double *ycdf) {
+  const int ncdf = 100;
+  for (int i = 1; i <= ncdf; ++i) {
+    xcdf[i - 1] = (double)(i - 1) / (double)(ncdf - 1);
+    double y = 0.0;
+    if (i == ncdf) {
+      y = 0.5;
+    } else {
+      for (long long j = 1;; ++j) {
+        const double term = std::pow(xcdf[i - 1], (double)(j * j));
+        if (term == 0.0) break;
+        y += (j % 2 == 0) ? -term : term;
+      }
+    }
+    ycdf[i - 1] = y * 2.0;
+  }
+}
+
 
 }  // namespace hyp

@@ -36,7 +36,7 @@ def _gpu_batches(model, n_per_batch, n_batches):
         stats.append(st.as_dict())
         out.append(sums / st.energy_emitted)
         # restore the initial specific energy so that every batch sees the same emissivities
-        eng.set_specific_energy(eng.ctx, None, None)
+        eng.set_specific_energy(eng.ctx, model.specific_energy, model.minimum_specific_energy)
     eng.close()
     return np.array(out), stats
 
