@@ -337,6 +337,7 @@ def run(input_file, output_file, overwrite=False, device=None, log=None):
     log(" " + "-" * 60)
     if world > 1:
         dist.barrier()
+        dist.destroy_process_group()
     return 0
 
 
