@@ -79,6 +79,7 @@ class IterStats(C.Structure):
         ("n_scatterings", C.c_int64), ("n_escaped", C.c_int64),
         ("kernel_ms", C.c_double), ("epilogue_ms", C.c_double),
         ("flight_ms", C.c_double), ("n_rounds", C.c_int64), ("n_launches", C.c_int64), ("n_peel_crossings", C.c_int64), ("n_peeloffs", C.c_int64),
+        ("n_peel_cached", C.c_int64),
     ]
 
     def as_dict(self):

@@ -45,7 +45,7 @@ flight_geo_kernel(const ModelDev M, Pool P, const FinalArgs F, const uint32_t *_
         typename G::Ray E = R;
         double tau_escape = 0.0, col[ND];
         // grid_escape_tau gives up (killed) when a source lies on the way out (grid_propagate_3d.f90:410-415)
-        const bool ok = src_hit < 0 && geo_escape<GEO, ND, false>(M, E, chi, cells, tau_escape, col, n_peel_cross);
+        const bool ok = src_hit < 0 && geo_escape<GEO, ND, false>(M, E, chi, M.rho, tau_escape, col, n_peel_cross) > 0;
         if (!ok && src_hit < 0) ++n_killed;  // grid_escape_tau killed its copy; the packet itself goes on unforced
         Rng rng;
         rng.init(M.seed, s->id, iteration);

@@ -34,7 +34,7 @@ struct CellRec {
 };
 
 enum { SC_ENERGY = 0, SC_KILLED_GEO, SC_KILLED_INT, SC_CROSS, SC_ABS, SC_SCAT, SC_ESC, SC_PHOTONS, SC_PEEL_CROSS, SC_PEELOFFS,
-       SC_COUNT };
+       SC_PEEL_CACHED, SC_COUNT };
 
 enum { GEO_CAR = 0, GEO_SPH = 1, GEO_OCT = 2, GEO_AMR = 3 };  // GEO_SPH covers both polar grids (SphGrid::kind)
 
@@ -47,6 +47,8 @@ struct ModelDev {
   int64_t n_cells;
   const double *w1, *w2, *w3;
   CellRec *cells;           // [n_cells][n_dust]
+  double *rho;              // [n_cells][n_dust] densities alone, for the marches that deposit nothing (peel-off,
+                            // imaging flights): 4 cells per 32-byte sector instead of 2
   double *specific_energy;  // [n_cells][n_dust]
   int32_t *jnu_id;          // [n_cells][n_dust]
   double *jnu_frac;         // [n_cells][n_dust]
@@ -1111,7 +1113,7 @@ __device__ __forceinline__ void deposit_warp(CellRec *__restrict__ cells, bool h
 template <int ND, int D, bool COH, bool DEP = true>
 __device__ __forceinline__ int advance_group(Lane<ND> &L, const bool on, const double *__restrict__ W,
                                              CellRec *__restrict__ cells, const int n1, const int n2, const int n3,
-                                             uint32_t &n_cross) {
+                                             uint32_t &n_cross, const double *__restrict__ rho_only = nullptr) {
   const int o2 = n1 + 1, o3 = n1 + n2 + 2;
   // stage A: geometry of the next D crossings (independent of the density) and their loads.
   // Branch-free DDA: the axis whose wall is reached first is picked with selects.
@@ -1124,7 +1126,8 @@ __device__ __forceinline__ int advance_group(Lane<ND> &L, const bool on, const d
   for (int j = 0; j < D; ++j) {
     ic_s[j] = L.ic;
 #pragma unroll
-    for (int id = 0; id < ND; ++id) rho_s[j][id] = __ldcg(&cells[(size_t)L.ic * ND + id].rho);
+    for (int id = 0; id < ND; ++id)
+      rho_s[j][id] = DEP ? __ldcg(&cells[(size_t)L.ic * ND + id].rho) : __ldg(rho_only + (size_t)L.ic * ND + id);
     const bool bx = (L.tnx <= L.tny) & (L.tnx <= L.tnz);
     const bool by = (!bx) & (L.tny <= L.tnz);
     const double t_exit = bx ? L.tnx : (by ? L.tny : L.tnz);
@@ -1429,10 +1432,12 @@ __global__ void lucy_finish_kernel(ModelDev M, const double *__restrict__ sums, 
       const double es = d.L.sublimation_specific_energy;
       if (d.L.sublimation_mode == 1) {
         M.cells[k].rho = 0.0;
+        M.rho[k] = 0.0;
         e = M.min_energy[id];
       } else if (d.L.sublimation_mode == 2) {
         const double q = mean_opacity_loglog(d, d.L.o_logchi_ross, e) / mean_opacity_loglog(d, d.L.o_logchi_ross, es);
         M.cells[k].rho = M.cells[k].rho * es / e * (q * q);
+        M.rho[k] = M.cells[k].rho;
         e = es;
       } else {
         e = es;
@@ -1461,6 +1466,7 @@ __global__ void scatter_density_kernel(ModelDev M, const double *__restrict__ in
     const int id = (int)(k / nc);
     const int64_t ic = k % nc;
     M.cells[ic * nd + id].rho = in[k];
+    M.rho[ic * nd + id] = in[k];
   }
 }
 __global__ void to_device_order_kernel(int nd, int64_t nc, const double *__restrict__ in, double *__restrict__ out) {
@@ -1559,6 +1565,7 @@ struct hyp_ctx {
   // device
   double *d_w = nullptr;
   CellRec *d_cells = nullptr;
+  double *d_rho = nullptr;
   double *d_energy = nullptr, *d_jfrac = nullptr, *d_sums = nullptr, *d_stage = nullptr;
   int32_t *d_jid = nullptr;
   SourceDev *d_sources = nullptr;
@@ -1594,6 +1601,7 @@ struct hyp_ctx {
   uint32_t job_cap = 0;
   double *d_eabs = nullptr;
   double *d_mrw_alpha = nullptr, *d_mrw_diff = nullptr, *d_mrw_cdf = nullptr;
+  double *d_src_columns = nullptr;
   std::vector<double *> ray_tables;  // device copies of the binned raytracing spectra
   bool images_ready = false, ray_ready = false;
   int64_t peel_launches = 0;
@@ -1803,6 +1811,7 @@ void hyp_ctx_destroy(hyp_ctx *c) {
   free_dev(c->d_oct_children);
   free_dev(c->d_oct_leaves);
   free_dev(c->d_cells);
+  free_dev(c->d_rho);
   free_dev(c->d_energy);
   free_dev(c->d_jfrac);
   free_dev(c->d_sums);
@@ -1821,6 +1830,7 @@ void hyp_ctx_destroy(hyp_ctx *c) {
   free_dev(c->d_mrw_alpha);
   free_dev(c->d_mrw_diff);
   free_dev(c->d_mrw_cdf);
+  free_dev(c->d_src_columns);
   for (auto &t : c->ray_tables) free_dev(t);
   free_pool(c);
   if (c->h_counts) cudaFreeHost(c->h_counts);
@@ -2477,6 +2487,7 @@ int hyp_finalize_setup(hyp_ctx *c) {
   M.sources = c->d_sources;
   // grids
   CUDA_TRY(cudaMalloc(&c->d_cells, n * sizeof(CellRec)));
+  CUDA_TRY(cudaMalloc(&c->d_rho, n * sizeof(double)));
   CUDA_TRY(cudaMalloc(&c->d_energy, n * sizeof(double)));
   CUDA_TRY(cudaMalloc(&c->d_jfrac, n * sizeof(double)));
   CUDA_TRY(cudaMalloc(&c->d_jid, n * sizeof(int32_t)));
@@ -2488,6 +2499,7 @@ int hyp_finalize_setup(hyp_ctx *c) {
   CUDA_TRY(cudaMemset(c->d_sums, 0, (n + SC_COUNT) * sizeof(double)));
   CUDA_TRY(cudaMemset(c->d_error, 0, sizeof(int32_t)));
   M.cells = c->d_cells;
+  M.rho = c->d_rho;
   M.specific_energy = c->d_energy;
   M.jnu_id = c->d_jid;
   M.jnu_frac = c->d_jfrac;
@@ -2946,8 +2958,9 @@ int ensure_jobs(hyp_ctx *c, uint32_t cap) {
   free_dev(c->d_jobs);
   free_dev(c->d_njobs);
   CUDA_TRY(cudaMalloc(&c->d_jobs, (size_t)cap * job_bytes(c->M.n_dust)));
-  CUDA_TRY(cudaMalloc(&c->d_njobs, sizeof(uint32_t)));
-  CUDA_TRY(cudaMemset(c->d_njobs, 0, sizeof(uint32_t)));
+  // [0] number of queued jobs, [2..3] the peel kernel's 64-bit work cursor
+  CUDA_TRY(cudaMalloc(&c->d_njobs, 4 * sizeof(uint32_t)));
+  CUDA_TRY(cudaMemset(c->d_njobs, 0, 4 * sizeof(uint32_t)));
   c->job_cap = cap;
   return HYP_OK;
 }
@@ -2978,13 +2991,44 @@ int launch_peel(hyp_ctx *c, const ModelDev &M, uint32_t n_jobs_max) {
     ws = WallSmem{0, 0};
   }
   CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ws.bytes));
-  ImagingDev I{c->d_images, c->d_views, (int)c->groups.size(), c->n_views};
+  ImagingDev I{c->d_images, c->d_views, (int)c->groups.size(), c->n_views, c->d_src_columns};
   const int64_t work = (int64_t)n_jobs_max * c->n_views;
-  const int blocks = (int)std::min<int64_t>((work + PEEL_THREADS - 1) / PEEL_THREADS, (int64_t)c->sm_count * 8);
-  k<<<blocks, PEEL_THREADS, ws.bytes, c->stream>>>(M, I, (const PeelJob<ND> *)c->d_jobs, c->d_njobs, ws.on);
+  int per_sm = 0;
+  CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, PEEL_THREADS, ws.bytes));
+  if (per_sm < 1) per_sm = 1;
+  const int blocks = (int)std::min<int64_t>((work + PEEL_THREADS - 1) / PEEL_THREADS, (int64_t)c->sm_count * per_sm);
+  CUDA_TRY(cudaMemsetAsync(c->d_njobs + 2, 0, 2 * sizeof(uint32_t), c->stream));
+  k<<<blocks, PEEL_THREADS, ws.bytes, c->stream>>>(M, I, (const PeelJob<ND> *)c->d_jobs, c->d_njobs,
+                                                  (unsigned long long *)(c->d_njobs + 2), ws.on);
   CUDA_TRY(cudaGetLastError());
   c->launches_acc += 1;
   return HYP_OK;
+}
+
+// (re)compute the point-source column cache; the density may have changed since the last call
+template <int ND>
+int update_source_columns(hyp_ctx *c) {
+  if (c->n_views == 0) return HYP_OK;
+  const size_t n = (size_t)c->sources.size() * c->n_views * (ND + 1);
+  if (!c->d_src_columns) CUDA_TRY(cudaMalloc(&c->d_src_columns, std::max<size_t>(n, 1) * sizeof(double)));
+  ImagingDev I{c->d_images, c->d_views, (int)c->groups.size(), c->n_views, c->d_src_columns};
+  auto k = source_columns_kernel<ND, GEO_CAR>;
+  if (c->grid_type == GEO_SPH) k = source_columns_kernel<ND, GEO_SPH>;
+  else if (c->grid_type == GEO_OCT) k = source_columns_kernel<ND, GEO_OCT>;
+  else if (c->grid_type == GEO_AMR) k = source_columns_kernel<ND, GEO_AMR>;
+  k<<<1, 128, 0, c->stream>>>(c->M, I, c->d_src_columns);
+  CUDA_TRY(cudaGetLastError());
+  c->launches_acc += 1;
+  return HYP_OK;
+}
+
+int update_source_columns_nd(hyp_ctx *c) {
+  switch (c->M.n_dust) {
+    case 1: return update_source_columns<1>(c);
+    case 2: return update_source_columns<2>(c);
+    case 3: return update_source_columns<3>(c);
+    default: return update_source_columns<4>(c);
+  }
 }
 
 ModelDev imaging_model(hyp_ctx *c) {
@@ -3170,6 +3214,7 @@ void fill_image_stats(hyp_ctx *c, const double *sc, hyp_iter_stats *st) {
   st->n_escaped = (int64_t)sc[SC_ESC];
   st->n_peel_crossings = (int64_t)sc[SC_PEEL_CROSS];
   st->n_peeloffs = (int64_t)sc[SC_PEELOFFS];
+  st->n_peel_cached = (int64_t)sc[SC_PEEL_CACHED];
   st->kernel_ms = c->kernel_ms_acc;
   st->flight_ms = c->flight_ms_acc;
   st->n_rounds = c->rounds_acc;
@@ -3217,6 +3262,8 @@ int hyp_final_begin(hyp_ctx *c) {
   }
   CUDA_TRY(cudaMemsetAsync(c->d_imgbuf + c->imgbuf_n, 0, SC_COUNT * sizeof(double), c->stream));
   CUDA_TRY(cudaMemsetAsync(c->d_error, 0, sizeof(int32_t), c->stream));
+  rc = update_source_columns_nd(c);
+  if (rc) return rc;
   c->kernel_ms_acc = 0.f;
   c->flight_ms_acc = 0.f;
   c->rounds_acc = 0;
@@ -3297,6 +3344,8 @@ int hyp_raytracing_photons(hyp_ctx *c, int64_t first_source_id, int64_t n_source
   c->kernel_ms_acc = c->flight_ms_acc = 0.f;
   c->rounds_acc = 0;
   CUDA_TRY(cudaEventRecord(c->ev0, c->stream));
+  rc = update_source_columns_nd(c);
+  if (rc) return rc;
   switch (c->M.n_dust) {
     case 1: rc = run_raytracing<1>(c, first_source_id, n_sources, n_total_sources, first_dust_id, n_dust, n_total_dust); break;
     case 2: rc = run_raytracing<2>(c, first_source_id, n_sources, n_total_sources, first_dust_id, n_dust, n_total_dust); break;

@@ -46,6 +46,12 @@ struct ImagingDev {
   const ImageDev *images;
   const ViewDev *views;
   int32_t n_groups, n_views;
+  // Column densities from every point source to the grid edge towards every view: [n_sources][n_views]
+  // records of ND columns + the number of cells crossed (-1: line of sight blocked by a star).  All
+  // packets a point source emits share these rays, so their peel-offs need no march of their own
+  // (tau = sum_d chi_d(nu) * column_d): the reference marches each of them, which on a GPU also makes
+  // every SM hammer the same cells at the same time.
+  const double *src_columns;
 };
 
 // One peel-off event.  kind 0: the last event was isotropic (emission from a point source, thermal
@@ -60,6 +66,7 @@ struct PeelJob {
   double emiss_var_frac;
   int32_t kind, source_id, dust_id, n_scat;      // ids are 1-based as in the reference
   int32_t scattered, reprocessed, emiss_type, emiss_var_id;
+  int32_t point_src, pad;  // 1-based id of the point source this job was just emitted from, else 0
 };
 
 // bits of Slot::tag / Photon::tag during the final iteration
@@ -160,18 +167,20 @@ __device__ __forceinline__ bool lane_outside(int ix, int iy, int iz, int n1, int
 // grid_escape_column_density).  COLUMN: accumulate the column density of every dust type instead of the
 // optical depth.  D crossings are resolved geometrically before their densities are consumed, so D loads
 // are in flight per lane (the cell sequence does not depend on the density).
+// At most max_groups groups are marched per call; returns true once the ray has left the grid.
 template <int ND, bool COLUMN, int D>
-__device__ __forceinline__ void escape_march(Lane<ND> &L, const double *__restrict__ W,
-                                             const CellRec *__restrict__ cells, const int n1, const int n2,
-                                             const int n3, double &tau, double (&col)[ND], uint32_t &n_cross) {
+__device__ __forceinline__ bool escape_march(Lane<ND> &L, const double *__restrict__ W,
+                                             const double *__restrict__ rho, const int n1, const int n2,
+                                             const int n3, double &tau, double (&col)[ND], uint32_t &n_cross,
+                                             const int max_groups = 0x7fffffff) {
   const int o2 = n1 + 1, o3 = n1 + n2 + 2;
   bool dead = lane_outside(L.ix, L.iy, L.iz, n1, n2, n3);
-  while (!dead) {
+  for (int g = 0; g < max_groups && !dead; ++g) {
     double ds_s[D], rho_s[D][ND];
 #pragma unroll
     for (int j = 0; j < D; ++j) {
 #pragma unroll
-      for (int id = 0; id < ND; ++id) rho_s[j][id] = __ldg(&cells[(size_t)L.ic * ND + id].rho);
+      for (int id = 0; id < ND; ++id) rho_s[j][id] = __ldg(rho + (size_t)L.ic * ND + id);
       const bool bx = (L.tnx <= L.tny) & (L.tnx <= L.tnz);
       const bool by = (!bx) & (L.tny <= L.tnz);
       const double t_exit = bx ? L.tnx : (by ? L.tny : L.tnz);
@@ -210,6 +219,7 @@ __device__ __forceinline__ void escape_march(Lane<ND> &L, const double *__restri
       }
     }
   }
+  return dead;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -260,159 +270,295 @@ __device__ __forceinline__ void bin_add(double *a, double *a2, double *an, size_
 constexpr int PEEL_THREADS = 256;
 constexpr int PEEL_LOOKAHEAD = 4;
 
+// Stokes vector a peel-off carries towards view direction a_req before attenuation:
+// isotropic events 1, stellar surfaces the limb law, scatterings the phase matrix.
+template <int ND>
+__device__ inline Stokes peel_stokes(const ModelDev &M, const PeelJob<ND> &J, const Angle &a_req) {
+  Stokes S{1.0, 0.0, 0.0, 0.0};
+  if (J.kind == 2) {
+    // emit_from_sphere_peeloff (source_type.f90:692-707): (vpx, vpy, vpz) is the outward normal of the
+    // stellar surface at the emission point; the weights integrate to 4 pi over the sphere
+    const SourceDev &src = M.sources[J.source_id - 1];
+    const double vxr = a_req.sint * a_req.cosp, vyr = a_req.sint * a_req.sinp, vzr = a_req.cost;
+    const double mu = fmax(vxr * J.vpx + vyr * J.vpy + vzr * J.vpz, 0.0);
+    S.I = !src.peeloff ? 0.0 : (src.limb ? 2.0 * (1.5 * mu * mu + mu) : 4.0 * mu);
+  } else if (J.kind == 1) {
+    // dust_scatter_peeloff (dust_type_4elem.f90:421-444)
+    const DustDev &d = M.dust[J.dust_id - 1];
+    const Angle a_prev = angle_of(J.vpx, J.vpy, J.vpz);
+    const Angle as = difference_angle(a_prev, a_req);
+    S = Stokes{1.0, J.sQ, J.sU, J.sV};
+    if (as.cost < d.L.mu_min || as.cost > d.L.mu_max) {
+      S = Stokes{0.0, 0.0, 0.0, 0.0};
+    } else {
+      const double *nu = d.B + d.L.o_nu;
+      const double *mu = d.B + d.L.o_mu;
+      const int n_mu = d.L.n_mu;
+      const int j = lower_interval(nu, d.L.n_nu, J.nu);
+      const int i = lower_interval(mu, n_mu, as.cost);
+      const double x0 = __ldg(mu + i), x1 = __ldg(mu + i + 1);
+      const double y0 = __ldg(nu + j), y1 = __ldg(nu + j + 1);
+      const double norm = 1.0 / (x1 - x0) / (y1 - y0);
+      const double wx0 = as.cost - x0, wx1 = x1 - as.cost, wy0 = J.nu - y0, wy1 = y1 - J.nu;
+      const double P1 = interp_phase(d.B + d.L.o_P1, n_mu, i, j, wx0, wx1, wy0, wy1, norm);
+      const double P2 = interp_phase(d.B + d.L.o_P2, n_mu, i, j, wx0, wx1, wy0, wy1, norm);
+      const double P3 = interp_phase(d.B + d.L.o_P3, n_mu, i, j, wx0, wx1, wy0, wy1, norm);
+      const double P4 = interp_phase(d.B + d.L.o_P4, n_mu, i, j, wx0, wx1, wy0, wy1, norm);
+      scatter_stokes(S, a_prev, as, a_req, P1, P2, P3, P4);
+    }
+  }
+  return S;
+}
+
+// image-plane coordinates of a peel-off (images_peeled.f90:196-211)
+template <int ND>
+__device__ __forceinline__ void peel_image_xy(const PeelJob<ND> &J, const ImageDev &im, const Angle &a, double &x_image,
+                                              double &y_image) {
+  const double dx = J.rx - im.rpx, dy = J.ry - im.rpy, dz = J.rz - im.rpz;
+  x_image = dy * a.cosp - dx * a.sinp;
+  y_image = dz * a.sint - dy * a.cost * a.sinp - dx * a.cost * a.cosp;
+}
+
+// image_bin / image_bin_raytraced (image_type.f90:408-606) for one finished ray
+template <int ND, bool POLY>
+__device__ inline void peel_bin(const PeelJob<ND> &J, const ImageDev &im, const ViewDev &V, const Stokes &S, const double tau,
+                                const double (&col)[ND]) {
+  if (isnan(J.energy) || isnan(S.I)) return;
+  double x_image, y_image;
+  peel_image_xy<ND>(J, im, V.a, x_image, y_image);
+  const int io = origin_slice(im, J.scattered, J.reprocessed, J.source_id, J.dust_id, J.n_scat);
+  const bool unc = im.uncertainties != 0;
+  int ixp = 0, iyp = 0, ir = 0;
+  bool in_img = false, in_sed = false;
+  if (im.compute_image) {
+    ixp = ipos_bin(im.x_min, im.x_max, x_image, im.n_x);
+    iyp = ipos_bin(im.y_min, im.y_max, y_image, im.n_y);
+    in_img = ixp >= 1 && ixp <= im.n_x && iyp >= 1 && iyp <= im.n_y;
+  }
+  if (im.compute_sed) {
+    ir = find_sed_bin(im, x_image, y_image);
+    in_sed = ir >= 1 && ir <= im.n_ap;
+  }
+  const size_t nn = (size_t)im.n_nu;
+  // offsets of (inu = 1, stokes 0) in the two cubes
+  const size_t k_img = nn * ((ixp - 1) + (size_t)im.n_x * ((iyp - 1) + (size_t)im.n_y * (V.view + (size_t)im.n_view * (io - 1))));
+  const size_t s_img = nn * im.n_x * im.n_y * im.n_view * im.n_orig;
+  const size_t k_sed = nn * ((ir - 1) + (size_t)im.n_ap * (V.view + (size_t)im.n_view * (io - 1)));
+  const size_t s_sed = nn * im.n_ap * im.n_view * im.n_orig;
+  if (POLY) {
+    // image_bin_raytraced: the whole spectrum of the ray goes into the cube, attenuated per bin
+    const double w = S.I * J.energy;
+    const double *base0 = nullptr, *base1 = nullptr;
+    if (J.emiss_type == 3) {
+      base0 = im.dust_logj[J.dust_id - 1] + (size_t)(J.emiss_var_id) * nn;  // emiss_var_id is 0-based here
+      base1 = base0 + nn;
+    } else {
+      base0 = im.src_spec + (size_t)(J.source_id - 1) * nn;
+    }
+    for (int inu = 0; inu < im.n_nu; ++inu) {
+      double v;
+      if (J.emiss_type == 3) {
+        const double l0 = __ldg(base0 + inu), l1 = __ldg(base1 + inu);
+        v = pow(10.0, (l1 - l0) * J.emiss_var_frac + l0);
+        if (isnan(v)) v = 0.0;
+      } else {
+        v = __ldg(base0 + inu);
+      }
+      v = v * w;
+#pragma unroll
+      for (int id = 0; id < ND; ++id) v = v * exp(-col[id] * __ldg(im.dust_chi + (size_t)id * nn + inu));
+      if (in_img) bin_add(im.img, im.img2, im.imgn, k_img + inu, v, unc);
+      if (in_sed) bin_add(im.sed, im.sed2, im.sedn, k_sed + inu, v, unc);
+    }
+  } else {
+    const int inu = ipos_bin(im.log10_nu_min, im.log10_nu_max, log10(J.nu), im.n_nu);
+    if (inu < 1 || inu > im.n_nu) return;
+    const double e = exp(-tau);
+    const double st[4] = {S.I * e, S.Q * e, S.U * e, S.V * e};
+    for (int is = 0; is < im.n_stokes; ++is) {
+      const double v = st[is] * J.energy * 1.0;
+      if (in_img) bin_add(im.img, im.img2, im.imgn, k_img + (inu - 1) + is * s_img, v, unc);
+      if (in_sed) bin_add(im.sed, im.sed2, im.sedn, k_sed + (inu - 1) + is * s_sed, v, unc);
+    }
+  }
+}
+
+constexpr int PEEL_GROUPS = 8;  // look-ahead groups (Cartesian) / crossings x4 (other grids) between two refill votes
+
+// Persistent threads, one (job, view) ray per lane.  A lane that finishes its ray bins it and takes the
+// next one from a global cursor while the other lanes of the warp keep marching, so rays of very different
+// length (a peel-off from the near or the far side of the grid) do not idle the warp.
 template <int ND, bool POLY, int GEO>
 __global__ void __launch_bounds__(PEEL_THREADS)
 peel_kernel(const ModelDev M, const ImagingDev I, const PeelJob<ND> *__restrict__ jobs,
-            const uint32_t *__restrict__ n_jobs_ptr, const int walls_in_smem) {
+            const uint32_t *__restrict__ n_jobs_ptr, unsigned long long *cursor, const int walls_in_smem) {
   extern __shared__ double s_walls[];
+  constexpr int GG = GEO == GEO_CAR ? GEO_SPH : GEO;  // the generic traits are not used for Cartesian grids
   const int n1 = M.n1, n2 = M.n2, n3 = M.n3;
   const double *__restrict__ W = GEO == GEO_CAR ? stage_walls(M, s_walls, walls_in_smem) : nullptr;
   const uint32_t n_jobs = *n_jobs_ptr;
   const unsigned long long total = (unsigned long long)n_jobs * (unsigned)I.n_views;
+  const unsigned lane = threadIdx.x & 31;
   uint32_t n_cross = 0, n_peel = 0, n_killed = 0;
-  const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
-  for (unsigned long long idx = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; idx < total; idx += stride) {
-    const uint32_t ip = (uint32_t)(idx / n_jobs), ij = (uint32_t)(idx % n_jobs);
-    const PeelJob<ND> &J = jobs[ij];
-    const ViewDev &V = I.views[ip];
-    const ImageDev &im = I.images[V.group];
-    const Angle a_req = V.a;
-    Stokes S{1.0, 0.0, 0.0, 0.0};
-    if (J.kind == 2) {
-      // emit_from_sphere_peeloff (source_type.f90:692-707): (vpx, vpy, vpz) is the outward normal of the
-      // stellar surface at the emission point; the weights integrate to 4 pi over the sphere
-      const SourceDev &src = M.sources[J.source_id - 1];
-      const double vxr = a_req.sint * a_req.cosp, vyr = a_req.sint * a_req.sinp, vzr = a_req.cost;
-      const double mu = fmax(vxr * J.vpx + vyr * J.vpy + vzr * J.vpz, 0.0);
-      S.I = !src.peeloff ? 0.0 : (src.limb ? 2.0 * (1.5 * mu * mu + mu) : 4.0 * mu);
-    }
-    if (J.kind == 1) {
-      // dust_scatter_peeloff (dust_type_4elem.f90:421-444)
-      const DustDev &d = M.dust[J.dust_id - 1];
-      const Angle a_prev = angle_of(J.vpx, J.vpy, J.vpz);
-      const Angle as = difference_angle(a_prev, a_req);
-      S = Stokes{1.0, J.sQ, J.sU, J.sV};
-      if (as.cost < d.L.mu_min || as.cost > d.L.mu_max) {
-        S = Stokes{0.0, 0.0, 0.0, 0.0};
-      } else {
-        const double *nu = d.B + d.L.o_nu;
-        const double *mu = d.B + d.L.o_mu;
-        const int n_mu = d.L.n_mu;
-        const int j = lower_interval(nu, d.L.n_nu, J.nu);
-        const int i = lower_interval(mu, n_mu, as.cost);
-        const double x0 = __ldg(mu + i), x1 = __ldg(mu + i + 1);
-        const double y0 = __ldg(nu + j), y1 = __ldg(nu + j + 1);
-        const double norm = 1.0 / (x1 - x0) / (y1 - y0);
-        const double wx0 = as.cost - x0, wx1 = x1 - as.cost, wy0 = J.nu - y0, wy1 = y1 - J.nu;
-        const double P1 = interp_phase(d.B + d.L.o_P1, n_mu, i, j, wx0, wx1, wy0, wy1, norm);
-        const double P2 = interp_phase(d.B + d.L.o_P2, n_mu, i, j, wx0, wx1, wy0, wy1, norm);
-        const double P3 = interp_phase(d.B + d.L.o_P3, n_mu, i, j, wx0, wx1, wy0, wy1, norm);
-        const double P4 = interp_phase(d.B + d.L.o_P4, n_mu, i, j, wx0, wx1, wy0, wy1, norm);
-        scatter_stokes(S, a_prev, as, a_req, P1, P2, P3, P4);
-      }
-    }
-    // angle3d_to_vector3d of the viewing direction
-    const double vx = a_req.sint * a_req.cosp, vy = a_req.sint * a_req.sinp, vz = a_req.cost;
-    int ix = 0, iy = 0, iz = 0, ic = 0;
-    if (GEO == GEO_CAR) {
-      if (!place_in_grid(M, J.rx, J.ry, J.rz, vx, vy, vz, ix, iy, iz, ic)) continue;
-    } else {
-      if (!Geo<GEO == GEO_CAR ? GEO_SPH : GEO>::find_cell(M, J.rx, J.ry, J.rz, vx, vy, vz, ix, iy, iz, ic)) continue;
-    }
-    // depth along the line of sight and image-plane coordinates (images_peeled.f90:196-211)
-    const double depth = -(vx * J.rx + vy * J.ry + vz * J.rz);
-    if (depth < im.d_min || depth > im.d_max) continue;
-    const double dx = J.rx - im.rpx, dy = J.ry - im.rpy, dz = J.rz - im.rpz;
-    const double x_image = dy * a_req.cosp - dx * a_req.sinp;
-    const double y_image = dz * a_req.sint - dy * a_req.cost * a_req.sinp - dx * a_req.cost * a_req.cosp;
-    if (!in_image(im, x_image, y_image)) continue;
-    if (!im.ignore_optical_depth && M.any_sphere) {
-      // grid_escape_*: a source on the line of sight kills the peel-off (grid_propagate_3d.f90:410-415)
-      int hit;
-      nearest_source(M, J.rx, J.ry, J.rz, vx, vy, vz, hit);
-      if (hit >= 0) continue;
-    }
-    double tau = 0.0, col[ND];
-#pragma unroll
-    for (int id = 0; id < ND; ++id) col[id] = 0.0;
-    if (!im.ignore_optical_depth) {
-      if (GEO == GEO_CAR) {
-        Lane<ND> L;
-        init_lane<ND>(L, J.rx, J.ry, J.rz, vx, vy, vz, ix, iy, iz, ic, W, n1 + 1, n1 + n2 + 2);
-#pragma unroll
-        for (int id = 0; id < ND; ++id) L.chi[id] = J.chi[id];
-        escape_march<ND, POLY, PEEL_LOOKAHEAD>(L, W, M.cells, n1, n2, n3, tau, col, n_cross);
-      } else {
-        constexpr int GG = GEO == GEO_CAR ? GEO_SPH : GEO;
-        typename Geo<GG>::Ray R;
-        Geo<GG>::start(M, R, J.rx, J.ry, J.rz, vx, vy, vz, ix, iy, iz, ic);
-        if (!geo_escape<GG, ND, POLY>(M, R, J.chi, M.cells, tau, col, n_cross)) {
-          ++n_killed;  // no wall found: the reference counts the packet as killed and drops the peel-off
-          continue;
-        }
-      }
-    }
-    ++n_peel;
-    if (isnan(J.energy) || isnan(S.I)) continue;
-    const int io = origin_slice(im, J.scattered, J.reprocessed, J.source_id, J.dust_id, J.n_scat);
-    const bool unc = im.uncertainties != 0;
-    int ixp = 0, iyp = 0, ir = 0;
-    bool in_img = false, in_sed = false;
-    if (im.compute_image) {
-      ixp = ipos_bin(im.x_min, im.x_max, x_image, im.n_x);
-      iyp = ipos_bin(im.y_min, im.y_max, y_image, im.n_y);
-      in_img = ixp >= 1 && ixp <= im.n_x && iyp >= 1 && iyp <= im.n_y;
-    }
-    if (im.compute_sed) {
-      ir = find_sed_bin(im, x_image, y_image);
-      in_sed = ir >= 1 && ir <= im.n_ap;
-    }
-    const size_t nn = (size_t)im.n_nu;
-    // offsets of (inu = 1, stokes 0) in the two cubes
-    const size_t k_img = nn * ((ixp - 1) + (size_t)im.n_x * ((iyp - 1) + (size_t)im.n_y * (V.view + (size_t)im.n_view * (io - 1))));
-    const size_t s_img = nn * im.n_x * im.n_y * im.n_view * im.n_orig;
-    const size_t k_sed = nn * ((ir - 1) + (size_t)im.n_ap * (V.view + (size_t)im.n_view * (io - 1)));
-    const size_t s_sed = nn * im.n_ap * im.n_view * im.n_orig;
-    if (POLY) {
-      // image_bin_raytraced: the whole spectrum of the ray goes into the cube, attenuated per bin
-      const double w = S.I * J.energy;
-      const double *base0 = nullptr, *base1 = nullptr;
-      if (J.emiss_type == 3) {
-        base0 = im.dust_logj[J.dust_id - 1] + (size_t)(J.emiss_var_id) * nn;      // emiss_var_id is 0-based here
-        base1 = base0 + nn;
-      } else {
-        base0 = im.src_spec + (size_t)(J.source_id - 1) * nn;
-      }
-      for (int inu = 0; inu < im.n_nu; ++inu) {
-        double v;
-        if (J.emiss_type == 3) {
-          const double l0 = __ldg(base0 + inu), l1 = __ldg(base1 + inu);
-          v = pow(10.0, (l1 - l0) * J.emiss_var_frac + l0);
-          if (isnan(v)) v = 0.0;
+  unsigned long long n_cached = 0;
+  bool active = false, exhausted = false;
+  uint32_t ij = 0, ip = 0;
+  Stokes S{0.0, 0.0, 0.0, 0.0};
+  double tau = 0.0, col[ND];
+  Lane<ND> L;
+  typename Geo<GG>::Ray R;
+  L.ic = 0;
+  for (;;) {
+    // ---------------- refill ----------------
+    const bool need = !active && !exhausted;
+    const unsigned m_need = __ballot_sync(0xffffffffu, need);
+    if (m_need) {
+      const int leader = __ffs(m_need) - 1;
+      unsigned long long base = 0;
+      if ((int)lane == leader) base = atomicAdd(cursor, (unsigned long long)__popc(m_need));
+      base = __shfl_sync(0xffffffffu, base, leader);
+      if (need) {
+        const unsigned long long idx = base + __popc(m_need & ((1u << lane) - 1u));
+        if (idx >= total) {
+          exhausted = true;
         } else {
-          v = __ldg(base0 + inu);
-        }
-        v = v * w;
+          // view-major order: neighbouring lanes look towards the same observer
+          ip = (uint32_t)(idx / n_jobs);
+          ij = (uint32_t)(idx % n_jobs);
+          const PeelJob<ND> &J = jobs[ij];
+          const ViewDev &V = I.views[ip];
+          const ImageDev &im = I.images[V.group];
+          const Angle a_req = V.a;
+          const double vx = a_req.sint * a_req.cosp, vy = a_req.sint * a_req.sinp, vz = a_req.cost;
+          int ix = 0, iy = 0, iz = 0, ic = 0;
+          bool ok = GEO == GEO_CAR ? place_in_grid(M, J.rx, J.ry, J.rz, vx, vy, vz, ix, iy, iz, ic)
+                                   : Geo<GG>::find_cell(M, J.rx, J.ry, J.rz, vx, vy, vz, ix, iy, iz, ic);
+          if (ok) {
+            // depth along the line of sight and image-plane coordinates (images_peeled.f90:196-211)
+            const double depth = -(vx * J.rx + vy * J.ry + vz * J.rz);
+            double x_image, y_image;
+            peel_image_xy<ND>(J, im, a_req, x_image, y_image);
+            ok = !(depth < im.d_min || depth > im.d_max) && in_image(im, x_image, y_image);
+          }
+          if (ok && !im.ignore_optical_depth && M.any_sphere) {
+            // grid_escape_*: a source on the line of sight kills the peel-off (grid_propagate_3d.f90:410-415)
+            int hit;
+            nearest_source(M, J.rx, J.ry, J.rz, vx, vy, vz, hit);
+            ok = hit < 0;
+          }
+          if (ok && J.point_src > 0 && !im.ignore_optical_depth) {
+            // the ray from this point source towards this view has been marched once already
+            const double *rec = I.src_columns + ((size_t)(J.point_src - 1) * I.n_views + ip) * (ND + 1);
+            const double nc = __ldg(rec + ND);
+            if (nc >= 0.0) {
+              tau = 0.0;
 #pragma unroll
-        for (int id = 0; id < ND; ++id) v = v * exp(-col[id] * __ldg(im.dust_chi + (size_t)id * nn + inu));
-        if (in_img) bin_add(im.img, im.img2, im.imgn, k_img + inu, v, unc);
-        if (in_sed) bin_add(im.sed, im.sed2, im.sedn, k_sed + inu, v, unc);
+              for (int id = 0; id < ND; ++id) {
+                col[id] = __ldg(rec + id);
+                tau = tau + J.chi[id] * col[id];
+              }
+              n_cached += (unsigned long long)nc;
+              ++n_peel;
+              peel_bin<ND, POLY>(J, im, V, Stokes{1.0, 0.0, 0.0, 0.0}, tau, col);
+            }
+            ok = false;
+          }
+          if (ok) {
+            S = peel_stokes<ND>(M, J, a_req);
+            tau = 0.0;
+#pragma unroll
+            for (int id = 0; id < ND; ++id) col[id] = 0.0;
+            if (GEO == GEO_CAR) {
+              init_lane<ND>(L, J.rx, J.ry, J.rz, vx, vy, vz, ix, iy, iz, ic, W, n1 + 1, n1 + n2 + 2);
+#pragma unroll
+              for (int id = 0; id < ND; ++id) L.chi[id] = J.chi[id];
+            } else {
+              Geo<GG>::start(M, R, J.rx, J.ry, J.rz, vx, vy, vz, ix, iy, iz, ic);
+            }
+            active = true;
+          }
+        }
       }
-    } else {
-      const int inu = ipos_bin(im.log10_nu_min, im.log10_nu_max, log10(J.nu), im.n_nu);
-      if (inu < 1 || inu > im.n_nu) continue;
-      const double e = exp(-tau);
-      const double st[4] = {S.I * e, S.Q * e, S.U * e, S.V * e};
-      for (int is = 0; is < im.n_stokes; ++is) {
-        const double v = st[is] * J.energy * 1.0;
-        if (in_img) bin_add(im.img, im.img2, im.imgn, k_img + (inu - 1) + is * s_img, v, unc);
-        if (in_sed) bin_add(im.sed, im.sed2, im.sedn, k_sed + (inu - 1) + is * s_sed, v, unc);
+    }
+    if (__ballot_sync(0xffffffffu, active) == 0) {
+      if (__ballot_sync(0xffffffffu, !exhausted) == 0) break;
+      continue;
+    }
+    // ---------------- march ----------------
+    if (active) {
+      const PeelJob<ND> &J = jobs[ij];
+      const ViewDev &V = I.views[ip];
+      const ImageDev &im = I.images[V.group];
+      int done;  // 0 still marching, 1 reached the edge, -1 killed
+      if (im.ignore_optical_depth) {
+        done = 1;
+      } else if (GEO == GEO_CAR) {
+        done = escape_march<ND, POLY, PEEL_LOOKAHEAD>(L, W, M.rho, n1, n2, n3, tau, col, n_cross, PEEL_GROUPS) ? 1 : 0;
+      } else {
+        done = geo_escape<GG, ND, POLY>(M, R, J.chi, M.rho, tau, col, n_cross, 4 * PEEL_GROUPS);
+      }
+      if (done) {
+        active = false;
+        if (done > 0) {
+          ++n_peel;
+          peel_bin<ND, POLY>(J, im, V, S, tau, col);
+        } else {
+          ++n_killed;  // no wall found: the reference counts the packet as killed and drops the peel-off
+        }
       }
     }
   }
-  warp_add_scalar(M.scalars + SC_PEEL_CROSS, (double)n_cross);
+  // SC_PEEL_CROSS counts what the reference would have marched; SC_PEEL_CACHED the part served by the cache
+  warp_add_scalar(M.scalars + SC_PEEL_CROSS, (double)n_cross + (double)n_cached);
+  warp_add_scalar(M.scalars + SC_PEEL_CACHED, (double)n_cached);
   warp_add_scalar(M.scalars + SC_PEELOFFS, (double)n_peel);
   if (GEO != GEO_CAR) warp_add_scalar(M.scalars + SC_KILLED_GEO, (double)n_killed);
+}
+
+// One thread per (point source, view): column density of every dust type from the source to the grid edge.
+template <int ND, int GEO>
+__global__ void source_columns_kernel(const ModelDev M, const ImagingDev I, double *__restrict__ out) {
+  constexpr int GG = GEO == GEO_CAR ? GEO_SPH : GEO;
+  const int total = M.n_sources * I.n_views;
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < total; k += gridDim.x * blockDim.x) {
+    const int is = k / I.n_views, ip = k % I.n_views;
+    const SourceDev &src = M.sources[is];
+    double *rec = out + (size_t)k * (ND + 1);
+    double col[ND], tau = 0.0;
+#pragma unroll
+    for (int id = 0; id < ND; ++id) col[id] = 0.0;
+    uint32_t n_cross = 0;
+    bool ok = src.type == HYP_SOURCE_POINT;
+    const Angle a = I.views[ip].a;
+    const double vx = a.sint * a.cosp, vy = a.sint * a.sinp, vz = a.cost;
+    int ix = 0, iy = 0, iz = 0, ic = 0;
+    if (ok) ok = GEO == GEO_CAR ? place_in_grid(M, src.x, src.y, src.z, vx, vy, vz, ix, iy, iz, ic)
+                                : Geo<GG>::find_cell(M, src.x, src.y, src.z, vx, vy, vz, ix, iy, iz, ic);
+    if (ok && M.any_sphere) {
+      int hit;
+      nearest_source(M, src.x, src.y, src.z, vx, vy, vz, hit);
+      ok = hit < 0;
+    }
+    if (ok) {
+      double chi[ND];
+#pragma unroll
+      for (int id = 0; id < ND; ++id) chi[id] = 0.0;
+      if (GEO == GEO_CAR) {
+        Lane<ND> L;
+        init_lane<ND>(L, src.x, src.y, src.z, vx, vy, vz, ix, iy, iz, ic, M.w1, M.n1 + 1, M.n1 + M.n2 + 2);
+#pragma unroll
+        for (int id = 0; id < ND; ++id) L.chi[id] = 0.0;
+        escape_march<ND, true, PEEL_LOOKAHEAD>(L, M.w1, M.rho, M.n1, M.n2, M.n3, tau, col, n_cross);
+      } else {
+        typename Geo<GG>::Ray R;
+        Geo<GG>::start(M, R, src.x, src.y, src.z, vx, vy, vz, ix, iy, iz, ic);
+        ok = geo_escape<GG, ND, true>(M, R, chi, M.rho, tau, col, n_cross) > 0;
+      }
+    }
+#pragma unroll
+    for (int id = 0; id < ND; ++id) rec[id] = col[id];
+    rec[ND] = ok ? (double)n_cross : -1.0;
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -462,6 +608,8 @@ __device__ __forceinline__ void fill_job(PeelJob<ND> *J, const Photon<ND> &p, in
   J->reprocessed = (p.tag & TAG_REPROCESSED) ? 1 : 0;
   J->emiss_type = 0;
   J->emiss_var_id = 0;
+  J->point_src = 0;
+  J->pad = 0;
 }
 
 // kind of the peel-off of a packet that has just been emitted: 2 from a stellar surface, 0 isotropic
@@ -503,7 +651,10 @@ emit_final_kernel(const ModelDev M, Pool P, const FinalArgs F, const unsigned lo
       go = emit_photon<ND>(M, p, rng, energy_emitted);
     }
     PeelJob<ND> *J = job_append<ND>(go && F.make_peeled && !F.scattering_only, F);
-    if (J) fill_job<ND>(J, p, surface_kind(p), p.nx, p.ny, p.nz, 0.0, 0.0, 0.0, 0);
+    if (J) {
+      fill_job<ND>(J, p, surface_kind(p), p.nx, p.ny, p.nz, 0.0, 0.0, 0.0, 0);
+      if (J->kind == 0) J->point_src = J->source_id;
+    }
     if (go) {
       // with a forced first interaction the optical depth is drawn by the flight kernel once the
       // optical depth to the grid edge is known
@@ -650,7 +801,7 @@ flight_final_kernel(const ModelDev M, Pool P, const FinalArgs F, const uint32_t 
           } else if (L.tau < 0.0) {
             Lane<ND> E = L;
             double tau_escape = 0.0, col[ND];
-            escape_march<ND, false, D>(E, W, cells, n1, n2, n3, tau_escape, col, n_peel_cross);
+            escape_march<ND, false, D>(E, W, M.rho, n1, n2, n3, tau_escape, col, n_peel_cross);
             Slot<ND> *s = slots + slot;
             Rng rng;
             rng.init(M.seed, s->id, iteration);
@@ -692,7 +843,7 @@ flight_final_kernel(const ModelDev M, Pool P, const FinalArgs F, const uint32_t 
     if (active && fin == 0) {
 #pragma unroll 1
       for (int g = 0; g < FLIGHT_GROUPS; ++g) {
-        fin = advance_group<ND, D, false, false>(L, true, W, cells, n1, n2, n3, n_cross);
+        fin = advance_group<ND, D, false, false>(L, true, W, cells, n1, n2, n3, n_cross, M.rho);
         if (fin) break;
       }
       if (n_cross > 0x7fffff00u) {
@@ -755,6 +906,7 @@ __global__ void raytrace_emit_kernel(const ModelDev M, PeelJob<ND> *__restrict__
       p.energy = p.energy * source_weight;  // energy_total / n_photons_sources (iter_raytracing.f90:79)
       fill_job<ND>(&J, p, surface_kind(p), p.nx, p.ny, p.nz, 0.0, 0.0, 0.0, 0);
       J.emiss_type = M.sources[(p.tag & TAG_SRC_MASK) - 1].freq_type;
+      if (J.kind == 0) J.point_src = J.source_id;
     } else {
       // emit_from_grid (grid_physics_3d.f90:691-753)
       rng.init(M.seed, first_dust_id + (i - n_src), ITER_RAY_DUST);

@@ -187,7 +187,7 @@ __device__ inline int geo_march(const ModelDev &M, typename Geo<GEO>::Ray &R, do
     const int ic = R.ic;
     if (ic < 0) return MARCH_KILLED;  // AMR: the cell behind a grid boundary could not be located
 #pragma unroll
-    for (int id = 0; id < ND; ++id) rho[id] = __ldcg(&cells[(size_t)ic * ND + id].rho);
+    for (int id = 0; id < ND; ++id) rho[id] = DEP ? __ldcg(&cells[(size_t)ic * ND + id].rho) : __ldg(M.rho + (size_t)ic * ND + id);
     if (!G::find_wall(M, R, dt, cr)) return MARCH_KILLED;
     double chi_rho = 0.0;
 #pragma unroll
@@ -222,19 +222,22 @@ __device__ inline int geo_march(const ModelDev &M, typename Geo<GEO>::Ray &R, do
 }
 
 // grid_escape_tau / grid_escape_column_density (grid_propagate_3d.f90:377-582) with tmax = huge.
-// Returns false if the packet had to be killed (no wall found).
+// At most max_steps crossings per call.  Returns 1 once the ray has left the grid, 0 if it is still inside,
+// -1 if the packet had to be killed (no wall found).
 template <int GEO, int ND, bool COLUMN>
-__device__ inline bool geo_escape(const ModelDev &M, typename Geo<GEO>::Ray &R, const double (&chi)[ND],
-                                  const CellRec *__restrict__ cells, double &tau, double (&col)[ND], uint32_t &n_cross) {
+__device__ inline int geo_escape(const ModelDev &M, typename Geo<GEO>::Ray &R, const double (&chi)[ND],
+                                 const double *__restrict__ rho_only, double &tau, double (&col)[ND], uint32_t &n_cross,
+                                 const int max_steps = 0x7fffffff) {
   using G = Geo<GEO>;
-  while (!G::escaped(M, R)) {
+  for (int step = 0; step < max_steps; ++step) {
+    if (G::escaped(M, R)) return 1;
     double dt;
     typename G::Cross cr;
     double rho[ND];
-    if (R.ic < 0) return false;
+    if (R.ic < 0) return -1;
 #pragma unroll
-    for (int id = 0; id < ND; ++id) rho[id] = __ldg(&cells[(size_t)R.ic * ND + id].rho);
-    if (!G::find_wall(M, R, dt, cr)) return false;
+    for (int id = 0; id < ND; ++id) rho[id] = __ldg(rho_only + (size_t)R.ic * ND + id);
+    if (!G::find_wall(M, R, dt, cr)) return -1;
     ++n_cross;
 #pragma unroll
     for (int id = 0; id < ND; ++id) {
@@ -246,5 +249,5 @@ __device__ inline bool geo_escape(const ModelDev &M, typename Geo<GEO>::Ray &R, 
     R.t += dt;
     G::step(M, R, cr);
   }
-  return true;
+  return G::escaped(M, R) ? 1 : 0;
 }

@@ -150,6 +150,7 @@ typedef struct {
   int64_t n_launches;         /* kernels of this library launched for the iteration */
   int64_t n_peel_crossings;   /* cell crossings of peel-off marches (grid_escape_tau / _column_density) */
   int64_t n_peeloffs;         /* peel-off contributions binned */
+  int64_t n_peel_cached;      /* part of n_peel_crossings served by the point-source column cache (not marched) */
 } hyp_iter_stats;
 
 const char *hyp_last_error(void);
@@ -225,8 +226,9 @@ int hyp_finalize_setup(hyp_ctx *ctx);
 int hyp_lucy_begin(hyp_ctx *ctx);
 int hyp_lucy_photons(hyp_ctx *ctx, int64_t first_id, int64_t n_photons, int64_t iteration);
 /* Device pointers for the host's collective: sum grid [n_dust*n_cells] fp64 followed
- * directly by 10 fp64 scalars (energy_emitted, killed_geo, killed_int, crossings,
- * absorptions, scatterings, escaped, photons, peel crossings, peel-offs); n_values = n_dust*n_cells + 10.
+ * directly by 11 fp64 scalars (energy_emitted, killed_geo, killed_int, crossings,
+ * absorptions, scatterings, escaped, photons, peel crossings, peel-offs, cached peel crossings);
+ * n_values = n_dust*n_cells + 11.
  * replaces: mp_collect_physical_arrays + mp_sync (src/mpi/mpi_routines.f90:272-361) */
 int hyp_lucy_device_buffers(hyp_ctx *ctx, void **sum_and_scalars, int64_t *n_values);
 int hyp_lucy_finish(hyp_ctx *ctx, hyp_iter_stats *stats);
@@ -255,7 +257,7 @@ int hyp_final_finish(hyp_ctx *ctx, hyp_iter_stats *stats);
 int hyp_raytracing_photons(hyp_ctx *ctx, int64_t first_source_id, int64_t n_sources, int64_t n_total_sources,
                            int64_t first_dust_id, int64_t n_dust, int64_t n_total_dust, hyp_iter_stats *stats);
 /* All image / SED accumulators of all groups as one contiguous device buffer (fp64) followed by
- * the same 10 scalars, for the host's collective.  replaces: mp_collect_images (src/mpi/mpi_routines.f90:363-471) */
+ * the same 11 scalars, for the host's collective.  replaces: mp_collect_images (src/mpi/mpi_routines.f90:363-471) */
 int hyp_image_device_buffers(hyp_ctx *ctx, void **buffer, int64_t *n_values);
 /* Shapes in file order: seds (n_stokes, n_orig, n_view, n_ap, n_wav), images (n_stokes, n_orig,
  * n_view, n_y, n_x, n_wav) (src/images/image_type.f90:291,299 reversed, as HDF5 stores them). */
