@@ -109,7 +109,17 @@ struct alignas(32) Slot {
   uint32_t tag;          // final iteration: source id | scattered | reprocessed | n_scat (see imaging.cuh)
 };
 
-enum { C_NF0 = 0, C_NF1, C_NB, C_NI, C_NE, C_CURSOR, C_CURSOR_B, C_COUNT = 8 };
+enum { C_NF0 = 0, C_NF1, C_NB, C_NI, C_NE, C_CURSOR, C_CURSOR_B, C_NP0 = 8, C_NP1, C_NITEMS, C_ITEM_CURSOR, C_COUNT = 16 };
+
+// Lists of the tile-staged flights (flight_tile.cuh)
+struct TileQ {
+  uint32_t *park_slot[2], *park_tile[2];  // flights waiting for the next round: slot id and tile id (double-buffered)
+  uint32_t *sorted;                       // slot ids of this round's flights ordered by tile
+  uint32_t *tile_count, *tile_cursor;     // [n_tiles]
+  uint4 *items;                           // work items {tile, first index in sorted, packets, -}
+  int ntx, nty, ntz, n_tiles;
+  int n_tiles_alloc;
+};
 
 struct Pool {
   void *slots;
@@ -125,6 +135,7 @@ struct Pool {
   // `window` packet offsets each; window w of the launch lives in half (w & 1).
   const uint32_t *perm;
   uint32_t window;        // power of two
+  TileQ tile;
 };
 
 // Register view of one packet in the emit / interact kernels.
@@ -200,6 +211,39 @@ __device__ __forceinline__ void queue_append(bool pred, uint32_t *__restrict__ q
   if ((int)lane == leader) base = atomicAdd(count, (uint32_t)__popc(m));
   base = __shfl_sync(0xffffffffu, base, leader);
   if (pred) q[base + __popc(m & ((1u << lane) - 1u))] = value;
+}
+
+// Tile dimensions of the tile-staged flights (flight_tile.cuh): density + sums of a tile fit in 64 KB.
+template <int ND>
+struct TileDims {
+  static constexpr int X = 16, Y = ND <= 2 ? 16 : 8, Z = ND == 1 ? 16 : 8;
+  static constexpr int CELLS = X * Y * Z;
+  // densities + sums + walls of the tile, then one prefetch record (hot part of a Slot) per thread
+  static constexpr size_t smem_bytes(int threads) {
+    return (size_t)(2 * CELLS * ND + 3 * 17 + 1) * sizeof(double) + (size_t)threads * (80 + 16 * ND);
+  }
+};
+
+template <int ND>
+__device__ __forceinline__ uint32_t tile_of_cell(const TileQ &T, int ix, int iy, int iz) {
+  using TD = TileDims<ND>;
+  return (uint32_t)(((iz / TD::Z) * T.nty + iy / TD::Y) * T.ntx + ix / TD::X);
+}
+
+// Append (slot, tile) to the park list `buf` for every lane with pred set; whole warp must call.
+__device__ __forceinline__ void park_append(const Pool &P, int buf, bool pred, uint32_t slot, uint32_t tile) {
+  const unsigned m = __ballot_sync(0xffffffffu, pred);
+  if (m == 0) return;
+  const unsigned lane = threadIdx.x & 31;
+  const int leader = __ffs(m) - 1;
+  uint32_t base = 0;
+  if ((int)lane == leader) base = atomicAdd(P.counts + C_NP0 + buf, (uint32_t)__popc(m));
+  base = __shfl_sync(0xffffffffu, base, leader);
+  if (pred) {
+    const uint32_t k = base + __popc(m & ((1u << lane) - 1u));
+    P.tile.park_slot[buf][k] = slot;
+    P.tile.park_tile[buf][k] = tile;
+  }
 }
 
 // Sum a per-lane value over the warp and add it to a global scalar.
@@ -947,7 +991,7 @@ emit_kernel(const ModelDev M, Pool P, const unsigned long long first_id, const u
 template <int ND>
 __global__ void __launch_bounds__(SERVICE_THREADS)
 interact_kernel(const ModelDev M, Pool P, uint32_t *__restrict__ q_flight_next, uint32_t *n_flight_next,
-                const uint32_t iteration) {
+                const uint32_t iteration, const int park_buf = -1) {
   const uint32_t n = P.counts[C_NI];
   const unsigned lane = threadIdx.x & 31;
   Slot<ND> *slots = (Slot<ND> *)P.slots;
@@ -956,7 +1000,7 @@ interact_kernel(const ModelDev M, Pool P, uint32_t *__restrict__ q_flight_next, 
   for (uint32_t base = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < n; base += stride) {
     const uint32_t i = base + lane;
     const bool valid = i < n;
-    uint32_t slot = 0;
+    uint32_t slot = 0, tile = 0;
     bool alive = false;
     if (valid) {
       slot = P.q_interact[i];
@@ -974,9 +1018,12 @@ interact_kernel(const ModelDev M, Pool P, uint32_t *__restrict__ q_flight_next, 
         p.tau_left = -log(1.0 - rng.next());
         store_photon<ND>(slots + slot, p, rng, id);
         alive = true;
+        if (park_buf >= 0)
+          tile = tile_of_cell<ND>(P.tile, min(max(p.ix, 0), M.n1 - 1), min(max(p.iy, 0), M.n2 - 1), min(max(p.iz, 0), M.n3 - 1));
       }
     }
-    queue_append(alive, q_flight_next, n_flight_next, slot);
+    if (park_buf >= 0) park_append(P, park_buf, alive, slot, tile);  // tile-staged flights (flight_tile.cuh)
+    else queue_append(alive, q_flight_next, n_flight_next, slot);
     queue_append(valid && !alive, P.q_emit, P.counts + C_NE, slot);
   }
   warp_add_scalar(M.scalars + SC_ABS, (double)n_abs);
@@ -1271,6 +1318,7 @@ flight_kernel(const ModelDev M, Pool P, const uint32_t *__restrict__ q_flight, c
         } else {
           slot = q_flight[idx];
           load_lane<ND>(slots + slot, L, W, n1 + 1, n1 + n2 + 2);
+          L.t = __ldcs(&slots[slot].t);  // 0 for a new flight; the path length so far for one parked by flight_tile_kernel
           active = true;
         }
       }
@@ -1492,6 +1540,7 @@ __global__ void to_file_order_kernel(ModelDev M, int which, const double *__rest
 #include "march_geo.cuh"
 #include "imaging.cuh"
 #include "flight_geo.cuh"
+#include "flight_tile.cuh"
 
 // =============================================================================================
 // host side: context + C ABI
@@ -1579,7 +1628,7 @@ struct hyp_ctx {
   float kernel_ms_acc = 0.f, flight_ms_acc = 0.f;
   int64_t rounds_acc = 0, launches_acc = 0;  // launches: this library's own kernels in the iteration
   // photon pool
-  Pool pool;
+  Pool pool = Pool();
   uint32_t pool_cap = 0;
   uint32_t *h_counts = nullptr;  // pinned: [C_COUNT] counters + next_photon (2 words)
   // emission-order sort (direction keys)
@@ -1658,6 +1707,14 @@ void free_pool(hyp_ctx *c) {
   free_dev(c->pool.q_emit);
   free_dev(c->pool.counts);
   free_dev(c->pool.next_photon);
+  for (int b = 0; b < 2; ++b) {
+    free_dev(c->pool.tile.park_slot[b]);
+    free_dev(c->pool.tile.park_tile[b]);
+  }
+  free_dev(c->pool.tile.sorted);
+  free_dev(c->pool.tile.tile_count);
+  free_dev(c->pool.tile.tile_cursor);
+  free_dev(c->pool.tile.items);
   c->pool_cap = 0;
   free_dev(c->d_keys_in);
   free_dev(c->d_keys_out);
@@ -1716,6 +1773,35 @@ int ensure_pool(hyp_ctx *c, uint32_t cap) {
   CUDA_TRY(cudaMalloc(&c->d_sort_tmp, c->sort_tmp_bytes));
   P.perm = c->d_perm;
   P.window = w;
+  return HYP_OK;
+}
+
+// Lists of the tile-staged flights (flight_tile.cuh), allocated on first use.
+int ensure_tile_queues(hyp_ctx *c, int tx, int ty, int tz) {
+  TileQ &T = c->pool.tile;
+  T.ntx = (c->n1 + tx - 1) / tx;
+  T.nty = (c->n2 + ty - 1) / ty;
+  T.ntz = (c->n3 + tz - 1) / tz;
+  T.n_tiles = T.ntx * T.nty * T.ntz;
+  if (T.sorted && T.n_tiles <= T.n_tiles_alloc) return HYP_OK;
+  for (int b = 0; b < 2; ++b) {
+    free_dev(T.park_slot[b]);
+    free_dev(T.park_tile[b]);
+  }
+  free_dev(T.sorted);
+  free_dev(T.tile_count);
+  free_dev(T.tile_cursor);
+  free_dev(T.items);
+  T.n_tiles_alloc = T.n_tiles;
+  const size_t cap = c->pool_cap;
+  for (int b = 0; b < 2; ++b) {
+    CUDA_TRY(cudaMalloc(&T.park_slot[b], cap * sizeof(uint32_t)));
+    CUDA_TRY(cudaMalloc(&T.park_tile[b], cap * sizeof(uint32_t)));
+  }
+  CUDA_TRY(cudaMalloc(&T.sorted, cap * sizeof(uint32_t)));
+  CUDA_TRY(cudaMalloc(&T.tile_count, (size_t)T.n_tiles * sizeof(uint32_t)));
+  CUDA_TRY(cudaMalloc(&T.tile_cursor, (size_t)T.n_tiles * sizeof(uint32_t)));
+  CUDA_TRY(cudaMalloc(&T.items, ((size_t)T.n_tiles + cap / TILE_CHUNK + 1) * sizeof(uint4)));
   return HYP_OK;
 }
 
@@ -2594,6 +2680,30 @@ static int run_rounds(hyp_ctx *c, int64_t first_id, int64_t n_photons, int64_t i
   const int service_blocks_max = c->sm_count * 8;
   cudaStream_t st = c->stream;
 
+  // Tile-staged flights for the packets that leave an interaction (flight_tile.cuh): opt-in with
+  // HYPERION_B200_TILES=1.  Measured on the 256^3 headline they tie with the direct kernel (both ~60 G
+  // crossings/s, profiles/r01_experiments.md), so the direct kernel stays the default.
+  bool tiles = false;
+  {
+    const char *e = getenv("HYPERION_B200_TILES");
+    tiles = c->grid_type == GEO_CAR && !c->M.any_sphere && e && atoi(e) != 0;
+  }
+  const uint32_t tile_min_flights = getenv("HYPERION_B200_TILE_MIN") ? (uint32_t)atol(getenv("HYPERION_B200_TILE_MIN")) : 1000000u;
+  const bool dbg = getenv("HYPERION_B200_TIMING") != nullptr;
+  float dbg_bucket = 0.f, dbg_tile = 0.f;
+  auto tile_flight = flight_tile_kernel<ND>;
+  const size_t tile_smem = TileDims<ND>::smem_bytes(TILE_THREADS);
+  int tile_blocks = 0;
+  if (tiles) {
+    rc = ensure_tile_queues(c, TileDims<ND>::X, TileDims<ND>::Y, TileDims<ND>::Z);
+    if (rc) return rc;
+    CUDA_TRY(cudaFuncSetAttribute(tile_flight, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem));
+    int per_sm_tile = 0;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_tile, tile_flight, TILE_THREADS, tile_smem));
+    tile_blocks = std::max(per_sm_tile, 1) * c->sm_count;
+    CUDA_TRY(cudaMemsetAsync(P.tile.tile_count, 0, (size_t)P.tile.n_tiles * sizeof(uint32_t), st));
+  }
+
   pool_init_kernel<<<c->sm_count, 256, 0, st>>>(P, cap);
   c->launches_acc += 1;
   CUDA_TRY(cudaGetLastError());
@@ -2650,7 +2760,49 @@ static int run_rounds(hyp_ctx *c, int64_t first_id, int64_t n_photons, int64_t i
       CUDA_TRY(cudaGetLastError());
       c->launches_acc += 1;
     }
-    if (n_flight_prev > 0) {
+    if (n_flight_prev > 0 && tiles && n_flight_prev < tile_min_flights) {
+      // too few flights to pay for staging every tile: finish them with the direct kernel
+      CUDA_TRY(cudaMemsetAsync(P.counts + C_NP0 + (1 - cur), 0, sizeof(uint32_t), st));
+      int blocks = (int)std::min<int64_t>(((int64_t)n_flight_prev + FLIGHT_THREADS - 1) / FLIGHT_THREADS, flight_blocks_max);
+      flight<<<blocks, FLIGHT_THREADS, wall_bytes, st>>>(c->M, P, P.tile.park_slot[cur], P.counts + C_NP0 + cur, walls_smem);
+      CUDA_TRY(cudaGetLastError());
+      c->launches_acc += 1;
+    } else if (n_flight_prev > 0 && tiles) {
+      // this round's pending flights (park list `cur`) bucketed by tile, then one tile visit each;
+      // packets that step out of their tile go to park list 1 - cur together with the re-emitted ones
+      CUDA_TRY(cudaMemsetAsync(P.counts + C_NP0 + (1 - cur), 0, sizeof(uint32_t), st));
+      const int sb = (int)std::min<int64_t>(((int64_t)n_flight_prev + 255) / 256, service_blocks_max);
+      cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr;
+      if (dbg) {
+        cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventCreate(&e2);
+        cudaEventRecord(e0, st);
+      }
+      tile_hist_kernel<<<sb, 256, 0, st>>>(P, cur);
+      tile_scan_kernel<<<1, 1024, 0, st>>>(P);
+      tile_scatter_kernel<<<sb, 256, 0, st>>>(P, cur);
+      if (dbg) cudaEventRecord(e1, st);
+      const int64_t max_items = (int64_t)P.tile.n_tiles + n_flight_prev / TILE_CHUNK + 1;
+      tile_flight<<<(int)std::min<int64_t>(max_items, tile_blocks), TILE_THREADS, tile_smem, st>>>(c->M, P, 1 - cur);
+      CUDA_TRY(cudaGetLastError());
+      c->launches_acc += 4;
+      if (dbg) {
+        // diagnostic (HYPERION_B200_TIMING): per-round times on stderr; serialises the round
+        cudaEventRecord(e2, st);
+        cudaStreamSynchronize(st);
+        float ma = 0.f, mb = 0.f;
+        cudaEventElapsedTime(&ma, e0, e1);
+        cudaEventElapsedTime(&mb, e1, e2);
+        uint32_t hc[C_COUNT];
+        cudaMemcpy(hc, P.counts, sizeof hc, cudaMemcpyDeviceToHost);
+        fprintf(stderr, "[round %lld] new %lld; %u flights in %u items: bucket %.3f ms, tile visits %.3f ms, parked %u\n",
+                (long long)round, (long long)n_new, n_flight_prev, hc[C_NITEMS], ma, mb, hc[C_NP0 + 1 - cur]);
+        dbg_bucket += ma;
+        dbg_tile += mb;
+        cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
+      }
+    } else if (tiles) {
+      CUDA_TRY(cudaMemsetAsync(P.counts + C_NP0 + (1 - cur), 0, sizeof(uint32_t), st));
+    } else if (n_flight_prev > 0) {
       int blocks = (int)std::min<int64_t>(((int64_t)n_flight_prev + FLIGHT_THREADS - 1) / FLIGHT_THREADS, flight_blocks_max);
       flight<<<blocks, FLIGHT_THREADS, wall_bytes, st>>>(c->M, P, P.q_flight[cur], nF, walls_smem);
       CUDA_TRY(cudaGetLastError());
@@ -2662,7 +2814,7 @@ static int run_rounds(hyp_ctx *c, int64_t first_id, int64_t n_photons, int64_t i
     CUDA_TRY(cudaMemsetAsync(P.counts + C_NB, 0, sizeof(uint32_t), st));
     // 3. interactions -> next round's flight queue; killed packets free their slot
     interact_kernel<ND><<<service_blocks_max, SERVICE_THREADS, 0, st>>>(c->M, P, P.q_flight[1 - cur], nF_next,
-                                                                        (uint32_t)iteration);
+                                                                        (uint32_t)iteration, tiles ? 1 - cur : -1);
     CUDA_TRY(cudaGetLastError());
     c->launches_acc += 1;
     CUDA_TRY(cudaMemcpyAsync(c->h_counts, P.counts, C_COUNT * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
@@ -2674,7 +2826,7 @@ static int run_rounds(hyp_ctx *c, int64_t first_id, int64_t n_photons, int64_t i
     cur = 1 - cur;
     memcpy(&claimed, c->h_counts + C_COUNT, sizeof claimed);
     n_emit = c->h_counts[C_NE];
-    n_flight_prev = c->h_counts[C_NF0 + cur];
+    n_flight_prev = tiles ? c->h_counts[C_NP0 + cur] : c->h_counts[C_NF0 + cur];
     const bool ids_left = claimed < (unsigned long long)n_photons;
     if (n_flight_prev == 0 && (!ids_left || n_emit == 0)) break;
   }
@@ -2682,6 +2834,7 @@ static int run_rounds(hyp_ctx *c, int64_t first_id, int64_t n_photons, int64_t i
   CUDA_TRY(cudaStreamSynchronize(st));
   float ms = 0.f;
   if (cudaEventElapsedTime(&ms, c->ev0, c->ev1) == cudaSuccess) c->kernel_ms_acc += ms;
+  if (dbg) fprintf(stderr, "[timing] bucketing %.3f ms, tile visits %.3f ms, photon loop %.3f ms\n", dbg_bucket, dbg_tile, ms);
   return HYP_OK;
 }
 

@@ -163,6 +163,53 @@ def test_split_launches_give_same_sums(golden_car):
     assert np.allclose(a, b, rtol=1e-9, atol=0)
 
 
+def _tile_case(kind):
+    from hyperion_b200 import synthetic as syn
+    from hyperion_b200.flatmodel import FlatModel, FlatSource, FlatConf
+    dust = syn.realistic_dust(n_temp=40)
+    if kind == "cube64":
+        return syn.cartesian_point_source_model(n=64, tau_edge=3.0, dust=dust), 500000
+    # ragged grid (partial tiles on every axis), non-uniform walls, off-centre sources, 1-3 dust types
+    nd = {"ragged1": 1, "ragged2": 2, "ragged3": 3}[kind]
+    rng = np.random.default_rng(7)
+    n1, n2, n3 = 40, 36, 44
+    wx = np.sort(np.hstack([-pc, pc, rng.uniform(-pc, pc, n1 - 1)]))
+    wy = np.linspace(-pc, pc, n2 + 1)
+    wz = np.sort(np.hstack([-pc, pc, rng.uniform(-pc, pc, n3 - 1)]))
+    chi0 = syn.chi_at(dust, 2.99792458e10 / 0.5e-4)
+    rho = (rng.random((nd, n3, n2, n1)) + 0.5) * (4.0 / (chi0 * pc * nd))
+    rho[:, 10:14, 5:9, 20:30] = 0.0          # a void
+    srcs = [FlatSource(type=1, luminosity=lsun, temperature=6000., position=(0.3 * pc, -0.2 * pc, 0.1 * pc)),
+            FlatSource(type=1, luminosity=2 * lsun, temperature=3000., position=(-0.5 * pc, 0.4 * pc, -0.6 * pc))]
+    return FlatModel(wx, wy, wz, rho, [dust] * nd, srcs, FlatConf(n_initial_iter=1, n_initial_photons=0)), 300000
+
+
+@pytest.mark.parametrize("kind", ["cube64", "ragged1", "ragged2", "ragged3"])
+def test_tile_staged_flights_give_same_sums(kind, monkeypatch):
+    """HYPERION_B200_TILES=1 marches the packets that leave an interaction tile by tile with density
+    and sums in shared memory (flight_tile_kernel).  A packet parked at a tile boundary resumes with
+    the same origin, walls and optical depth, so every crossing and deposit is the one the untiled
+    kernel makes: work counters are identical and the sums agree to addition order."""
+    model, N = _tile_case(kind)
+    res = []
+    monkeypatch.setenv("HYPERION_B200_TILE_MIN", "0")     # no hand-over of small rounds to the direct kernel
+    for tiles in ("0", "1"):
+        monkeypatch.setenv("HYPERION_B200_TILES", tiles)
+        eng = _engine(model)
+        eng.lucy_begin()
+        eng.lucy_photons(0, N, 1)
+        sums = eng.get_energy_sum()
+        st = eng.lucy_finish().as_dict()
+        eng.close()
+        res.append((sums, st))
+    (a, sa), (b, sb) = res
+    assert sb["n_rounds"] > sa["n_rounds"]      # the tile rounds really ran
+    for key in ("n_photons", "n_escaped", "n_crossings", "n_absorptions", "n_scatterings", "killed_int"):
+        assert sa[key] == sb[key], (key, sa[key], sb[key])
+    assert sa["n_absorptions"] + sa["n_scatterings"] > N // 2
+    assert np.allclose(a, b, rtol=1e-9, atol=0)
+
+
 def test_empty_and_vacuum_cases(golden_car):
     """Zero packets is a no-op error-free launch; zero density lets every packet escape
     without deposits."""
