@@ -41,6 +41,8 @@ class Source(C.Structure):
         ("radius", C.c_double), ("limb_darkening", C.c_int32),
         ("spectrum_type", C.c_int32), ("temperature", C.c_double),
         ("n_spec", C.c_int32), ("spec_nu", _dp), ("spec_fnu", _dp),
+        ("box", C.c_double * 6), ("theta", C.c_double), ("phi", C.c_double),
+        ("n_points", C.c_int64), ("points_xyz", _dp), ("points_lum", _dp),
     ]
 
 
@@ -162,6 +164,17 @@ class CApi:
         t.type, t.peeloff, t.luminosity = s.type, int(s.peeloff), s.luminosity
         t.x, t.y, t.z = [float(v) for v in s.position]
         t.radius, t.limb_darkening = s.radius, int(s.limb_darkening)
+        for k in range(6):
+            t.box[k] = float(s.bounds[k])
+        t.theta, t.phi = float(s.direction[0]), float(s.direction[1])
+        keep_pts = None
+        if s.points is not None:
+            xyz = np.ascontiguousarray(s.points, dtype=np.float64).reshape(-1, 3)
+            lum = np.ascontiguousarray(s.points_luminosity, dtype=np.float64)
+            if len(lum) != len(xyz):
+                raise HyperionError("point collection: positions and luminosities differ in length")
+            keep_pts = (xyz, lum)
+            t.n_points, t.points_xyz, t.points_lum = len(lum), _ptr(xyz), _ptr(lum)
         keep = None
         if s.temperature is not None:
             t.spectrum_type, t.temperature = 2, float(s.temperature)
@@ -171,7 +184,7 @@ class CApi:
             keep = (nu, fnu)
             t.spectrum_type, t.n_spec, t.spec_nu, t.spec_fnu = 1, len(nu), _ptr(nu), _ptr(fnu)
         self.check(self._fn("add_source")(ctx, C.byref(t)))
-        del keep
+        del keep, keep_pts
 
     def set_run_conf(self, ctx, c: FlatConf):
         t = RunConf()

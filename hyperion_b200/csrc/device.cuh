@@ -104,7 +104,25 @@ struct SourceDev {
   int32_t peeloff, pad;    // whether the source is peeled off (source_emit_peeloff, source_type.f90:513-537)
   double pdf;              // normalised luminosity (for even sampling weights)
   double cdf;              // cumulative normalised luminosity
+  double box[6];           // extern_box: xmin, xmax, ymin, ymax, zmin, zmax
+  double face_cdf[6];      // extern_box: cumulative face areas (set_pdf, source_type.f90:229)
+  double dir_cost, dir_sint, dir_cosp, dir_sinp;  // plane_parallel: direction of travel (angle3d_deg(theta, phi))
+  int64_t coll_off;        // point_collection: first entry in ModelDev::coll_xyz / coll_cdf
+  int64_t coll_n;
 };
+
+// sample_pdf_discrete_dp (type_pdf.f90:313-337): 0-based index of the first entry with cdf >= xi
+__device__ __forceinline__ int64_t sample_discrete(const double *__restrict__ cdf, int64_t n, double xi) {
+  if (xi <= cdf[0]) return 0;
+  if (xi >= cdf[n - 1]) return n - 1;
+  int64_t jmin = 1, jmax = n;
+  for (;;) {
+    const int64_t j = (jmax + jmin) / 2;
+    if (xi > cdf[j - 1]) jmin = j; else jmax = j;
+    if (jmax == jmin + 1) break;
+  }
+  return jmax - 1;
+}
 
 // log-log interpolation on a pre-logged table (update_optconsts, src/dust/dust.f90:64-79 +
 // interp1d_loglog, fortranlib/src/lib_array.f90:605-614): returns 0 where either node is 0.

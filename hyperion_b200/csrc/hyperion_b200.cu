@@ -66,6 +66,7 @@ struct ModelDev {
   double mrw_gamma;
   double *alpha_inv_planck, *diff_coeff;
   const double *mrw_cdf;    // xcdf[100] | ycdf[100]
+  const double *coll_xyz, *coll_cdf;  // point collections: positions [n][3] and cumulative luminosities, all sources concatenated
   int32_t any_sphere;       // a spherical source exists: flights test for re-absorption (source.f90:206-227)
   int64_t n_reabs_max;
   // outputs
@@ -409,6 +410,69 @@ __device__ bool emit_photon(const ModelDev &M, Photon<ND> &p, Rng &rng, double &
     p.r0x = p.nx * S.radius + S.x;
     p.r0y = p.ny * S.radius + S.y;
     p.r0z = p.nz * S.radius + S.z;
+  } else if (S.type == HYP_SOURCE_EXTERN_SPH) {
+    // emit_from_extern_sph (source_type.f90:748-802): from the sphere inwards; (nx, ny, nz) is the inward
+    // normal the peel-off weight refers to (source_a = -a_coord, emit_from_extern_sph_peeloff :804-820)
+    const Angle a_coord = random_sphere_angle(rng);
+    const double phi_local = 6.283185307179586476925286766559 * rng.next();
+    Angle a_local;
+    sincos(phi_local, &a_local.sinp, &a_local.cosp);
+    a_local.cost = sqrt(rng.next());
+    a_local.sint = sqrt(1.0 - a_local.cost * a_local.cost);
+    const Angle a = rotate_angle(a_local, a_coord);
+    set_dir(p, Angle{-a.cost, a.sint, -a.cosp, -a.sinp});  // minus_angle (type_angle3d.f90:443-447)
+    const double ux = a_coord.sint * a_coord.cosp, uy = a_coord.sint * a_coord.sinp, uz = a_coord.cost;
+    p.r0x = ux * S.radius + S.x;
+    p.r0y = uy * S.radius + S.y;
+    p.r0z = uz * S.radius + S.z;
+    // -a_coord as a vector: sint * (-cosp), sint * (-sinp), -cost
+    p.nx = a_coord.sint * -a_coord.cosp;
+    p.ny = a_coord.sint * -a_coord.sinp;
+    p.nz = -a_coord.cost;
+  } else if (S.type == HYP_SOURCE_EXTERN_BOX) {
+    // emit_from_extern_box (source_type.f90:822-904): face by area, cosine law about the inward normal
+    const int face = (int)sample_discrete(S.face_cdf, 6, rng.next());
+    const double phi_local = 6.283185307179586476925286766559 * rng.next();
+    Angle a_local;
+    sincos(phi_local, &a_local.sinp, &a_local.cosp);
+    a_local.cost = sqrt(rng.next());
+    a_local.sint = sqrt(1.0 - a_local.cost * a_local.cost);
+    const int ax = face >> 1;  // the face is perpendicular to this axis; the other two coordinates are uniform
+    double r[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      if (k == ax) r[k] = S.box[2 * k + (face & 1)];
+      else r[k] = S.box[2 * k] + (S.box[2 * k + 1] - S.box[2 * k]) * rng.next();
+    }
+    p.r0x = r[0]; p.r0y = r[1]; p.r0z = r[2];
+    const double sgn = (face & 1) ? -1.0 : 1.0;
+    const Angle a_coord = ax == 0 ? Angle{0.0, sgn, 1.0, 0.0} : (ax == 1 ? Angle{0.0, sgn, 0.0, 1.0} : Angle{sgn, 0.0, 1.0, 0.0});
+    set_dir(p, rotate_angle(a_local, a_coord));
+    p.nx = a_coord.sint * a_coord.cosp;
+    p.ny = a_coord.sint * a_coord.sinp;
+    p.nz = a_coord.cost;
+  } else if (S.type == HYP_SOURCE_PLANE_PARALLEL) {
+    // emit_from_plane_parallel (source_type.f90:935-980).  Such a source is never peeled off
+    // (hyperion/sources/source.py:926-929); the normal only marks the emission as non-isotropic.
+    const double r = pow(rng.next(), 0.5) * S.radius;
+    const double phi = 360.0 * rng.next();
+    const double deg2rad = 3.14159265358979323846 / 180.0;
+    const Angle a_local{cos(90.0 * deg2rad), sin(90.0 * deg2rad), cos(phi * deg2rad), sin(phi * deg2rad)};
+    const Angle dir{S.dir_cost, S.dir_sint, S.dir_cosp, S.dir_sinp};
+    const Angle a_final = rotate_angle(a_local, dir);
+    p.r0x = a_final.sint * a_final.cosp * r + S.x;
+    p.r0y = a_final.sint * a_final.sinp * r + S.y;
+    p.r0z = a_final.cost * r + S.z;
+    set_dir(p, dir);
+    p.nx = p.vx; p.ny = p.vy; p.nz = p.vz;
+  } else if (S.type == HYP_SOURCE_POINT_COLLECTION) {
+    // emit_from_point_collection (source_type.f90:570-598)
+    const int64_t k = S.coll_off + sample_discrete(M.coll_cdf + S.coll_off, S.coll_n, rng.next());
+    p.r0x = M.coll_xyz[3 * k];
+    p.r0y = M.coll_xyz[3 * k + 1];
+    p.r0z = M.coll_xyz[3 * k + 2];
+    Angle a = random_sphere_angle(rng);
+    set_dir(p, a);
   } else {
     // emit_from_point (source_type.f90:539-564)
     p.r0x = S.x;
@@ -882,8 +946,7 @@ __global__ void pool_init_kernel(Pool P, uint32_t n_slots) {
   }
 }
 
-// Direction key of packet `id` (the same draws emit_photon makes first): source, then the cube-map
-// face and a Morton code of the direction.  Packets are emitted in key order.
+// Packets are emitted in the order of a sort key (emit_keys_kernel below).
 __device__ __forceinline__ uint32_t interleave12(uint32_t a, uint32_t b) {
   // 2-D Morton code of two 12-bit integers
   auto part = [](uint32_t x) {
@@ -897,8 +960,23 @@ __device__ __forceinline__ uint32_t interleave12(uint32_t a, uint32_t b) {
   return part(a) | (part(b) << 1);
 }
 
+// Sort key of packet `id`.  mode 1: source | cube-map face | Morton code of the direction (24 bits).
+// mode 2: source | face | coarse direction (2 x KEY_COARSE_BITS) | path length to the first interaction
+// in units of the distance to the grid edge, 8 log bins per octave (6 bits) | finer direction bits.  The
+// 32 packets a beam warp claims then share a direction bin AND die within ~10 % of each other, which
+// keeps the lanes of the lockstep march busy; the price is a wider beam (more cells per warp step).
+// The key replays the packet's own random numbers (emit_photon + the first tau), so it changes the
+// order in which packets are marched and summed, never a packet's path.
+#ifndef HYP_DEFAULT_SORT
+#define HYP_DEFAULT_SORT 2
+#endif
+#ifndef KEY_COARSE_BITS
+#define KEY_COARSE_BITS 5
+#endif
+template <int ND>
 __global__ void emit_keys_kernel(const ModelDev M, const unsigned long long first_id, const uint32_t count,
-                                 const uint32_t iteration, uint32_t *__restrict__ keys, uint32_t *__restrict__ vals) {
+                                 const uint32_t iteration, uint32_t *__restrict__ keys, uint32_t *__restrict__ vals,
+                                 const int mode) {
   for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < count; k += gridDim.x * blockDim.x) {
     Rng rng;
     rng.init(M.seed, first_id + k, iteration);
@@ -922,7 +1000,35 @@ __global__ void emit_keys_kernel(const ModelDev M, const unsigned long long firs
     const double u = (f == 0 ? d[1] : d[0]) / fabs(m), v = (f == 2 ? d[1] : d[2]) / fabs(m);
     const uint32_t iu = (uint32_t)min(4095.0, (u + 1.0) * 2048.0), iv = (uint32_t)min(4095.0, (v + 1.0) * 2048.0);
     const uint32_t face = (uint32_t)(2 * f + (m < 0.0 ? 1 : 0));
-    keys[k] = ((is & 31u) << 27) | (face << 24) | interleave12(iu, iv);
+    uint32_t key = ((is & 31u) << 27) | (face << 24) | interleave12(iu, iv);
+    if (mode == 2 && M.grid_type == GEO_CAR && M.sources[is].type != HYP_SOURCE_SPHERE) {
+      // the packet as emit_kernel will make it (same id, same stream), then its first optical depth
+      Photon<ND> p;
+      Rng r2;
+      r2.init(M.seed, first_id + k, iteration);
+      double dummy = 0.0;
+      uint32_t sbin = 63;
+      if (emit_photon<ND>(M, p, r2, dummy) && p.ix >= 0 && p.ix < M.n1 && p.iy >= 0 && p.iy < M.n2 && p.iz >= 0 && p.iz < M.n3) {
+        const double tau = -log(1.0 - r2.next());
+        double chi_rho = 0.0;
+#pragma unroll
+        for (int id = 0; id < ND; ++id) chi_rho += p.chi[id] * M.cells[(size_t)p.ic * ND + id].rho;
+        // distance to the edge of the grid along the direction
+        const double tx = p.vx > 0.0 ? (M.w1[M.n1] - p.r0x) / p.vx : (p.vx < 0.0 ? (M.w1[0] - p.r0x) / p.vx : 1e300);
+        const double ty = p.vy > 0.0 ? (M.w2[M.n2] - p.r0y) / p.vy : (p.vy < 0.0 ? (M.w2[0] - p.r0y) / p.vy : 1e300);
+        const double tz = p.vz > 0.0 ? (M.w3[M.n3] - p.r0z) / p.vz : (p.vz < 0.0 ? (M.w3[0] - p.r0z) / p.vz : 1e300);
+        const double t_edge = fmin(tx, fmin(ty, tz));
+        if (chi_rho > 0.0 && t_edge > 0.0) {
+          const double frac = tau / (chi_rho * t_edge);
+          sbin = (uint32_t)min(63.0, fmax(0.0, 8.0 * log2(frac) + 48.0));
+        }
+      }
+      constexpr int CB = KEY_COARSE_BITS, FB = (18 - 2 * CB) / 2;   // coarse / fine direction bits per axis
+      const uint32_t cu = iu >> (12 - CB), cv = iv >> (12 - CB);
+      const uint32_t fu = (iu >> (12 - CB - FB)) & ((1u << FB) - 1u), fv = (iv >> (12 - CB - FB)) & ((1u << FB) - 1u);
+      key = ((is & 31u) << 27) | (face << 24) | (interleave12(cu, cv) << (6 + 2 * FB)) | (sbin << (2 * FB)) | interleave12(fu, fv);
+    }
+    keys[k] = key;
     vals[k] = k;
   }
 }
@@ -1629,6 +1735,9 @@ struct hyp_ctx {
   int64_t rounds_acc = 0, launches_acc = 0;  // launches: this library's own kernels in the iteration
   // photon pool
   Pool pool = Pool();
+  std::vector<int64_t> coll_off;              // per source: first entry of its point collection, -1 if none
+  std::vector<double> coll_xyz, coll_cdf;     // point collections of all sources
+  double *d_coll_xyz = nullptr, *d_coll_cdf = nullptr;
   uint32_t pool_cap = 0;
   uint32_t *h_counts = nullptr;  // pinned: [C_COUNT] counters + next_photon (2 words)
   // emission-order sort (direction keys)
@@ -1810,14 +1919,15 @@ int prepare_window(hyp_ctx *c, int64_t first_id, int64_t n_photons, int64_t iter
   const int64_t win = c->sort_window;
   const int64_t count = std::min<int64_t>(win, n_photons - w * win);
   if (count <= 0) return HYP_OK;
-  static const bool sorted = [] {
-    const char *e = getenv("HYPERION_B200_SORT");
-    return !(e && atoi(e) == 0);
-  }();
+  // HYPERION_B200_SORT: 0 emission in id order, 1 sorted by direction, 2 by direction bin and path length
+  const char *e = getenv("HYPERION_B200_SORT");
+  const int mode = e ? atoi(e) : HYP_DEFAULT_SORT;
+  const bool sorted = mode != 0;
   uint32_t *dst = c->d_perm + (w & 1) * win;
-  emit_keys_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(c->M, (unsigned long long)(first_id + w * win),
-                                                           (uint32_t)count, (uint32_t)iteration, c->d_keys_in,
-                                                           sorted ? c->d_vals_in : dst);
+  auto keys = c->M.n_dust == 1 ? emit_keys_kernel<1> : c->M.n_dust == 2 ? emit_keys_kernel<2>
+              : c->M.n_dust == 3 ? emit_keys_kernel<3> : emit_keys_kernel<4>;
+  keys<<<c->sm_count * 8, 256, 0, c->stream>>>(c->M, (unsigned long long)(first_id + w * win), (uint32_t)count,
+                                               (uint32_t)iteration, c->d_keys_in, sorted ? c->d_vals_in : dst, mode);
   CUDA_TRY(cudaGetLastError());
   c->launches_acc += 1;
   if (sorted)
@@ -1904,6 +2014,8 @@ void hyp_ctx_destroy(hyp_ctx *c) {
   free_dev(c->d_stage);
   free_dev(c->d_jid);
   free_dev(c->d_sources);
+  free_dev(c->d_coll_xyz);
+  free_dev(c->d_coll_cdf);
   free_dev(c->d_spectra);
   free_dev(c->d_work);
   free_dev(c->d_error);
@@ -2255,9 +2367,21 @@ int hyp_add_source(hyp_ctx *c, const hyp_source *s) {
   if (!c || !s) return fail(HYP_ERR_INVALID, "NULL argument");
   if (c->finalized) return fail(HYP_ERR_STATE, "model is frozen");
   if ((int)c->sources.size() >= MAX_SOURCES) return fail(HYP_ERR_INVALID, "too many sources");
-  if (s->type != HYP_SOURCE_POINT && s->type != HYP_SOURCE_SPHERE)
-    return fail(HYP_ERR_INVALID, "only point and spherical sources are implemented on the device");
-  if (s->type == HYP_SOURCE_SPHERE && !(s->radius > 0.0)) return fail(HYP_ERR_INVALID, "source radius should be positive");
+  if (s->type != HYP_SOURCE_POINT && s->type != HYP_SOURCE_SPHERE && s->type != HYP_SOURCE_EXTERN_SPH &&
+      s->type != HYP_SOURCE_EXTERN_BOX && s->type != HYP_SOURCE_PLANE_PARALLEL && s->type != HYP_SOURCE_POINT_COLLECTION)
+    return fail(HYP_ERR_INVALID, "spotted spheres and luminosity-map sources are not implemented on the device");
+  if ((s->type == HYP_SOURCE_SPHERE || s->type == HYP_SOURCE_EXTERN_SPH || s->type == HYP_SOURCE_PLANE_PARALLEL) && !(s->radius > 0.0))
+    return fail(HYP_ERR_INVALID, "source radius should be positive");
+  if (s->type == HYP_SOURCE_PLANE_PARALLEL && s->peeloff) return fail(HYP_ERR_INVALID, "Cannot peeloff plane parallel source");
+  if (s->type == HYP_SOURCE_EXTERN_BOX && !(s->box[1] > s->box[0] && s->box[3] > s->box[2] && s->box[5] > s->box[4]))
+    return fail(HYP_ERR_INVALID, "external box source: bounds should be increasing");
+  if (s->type == HYP_SOURCE_POINT_COLLECTION && (s->n_points < 1 || !s->points_xyz || !s->points_lum))
+    return fail(HYP_ERR_INVALID, "point collection is empty");
+  if (s->type == HYP_SOURCE_POINT_COLLECTION) {
+    double norm = 0.0;
+    for (int64_t i = 0; i < s->n_points; ++i) norm = norm + s->points_lum[i];
+    if (!(norm > 0.0)) return fail(HYP_ERR_INVALID, "[normalize_pdf_discrete] all PDF elements are zero");
+  }
   if (!(s->luminosity >= 0.0)) return fail(HYP_ERR_INVALID, "source luminosity should be positive");
   int spec = -1;
   if (s->spectrum_type == HYP_SPECTRUM_TABLE) {
@@ -2276,6 +2400,23 @@ int hyp_add_source(hyp_ctx *c, const hyp_source *s) {
   }
   hyp_source copy = *s;
   copy.spec_nu = copy.spec_fnu = nullptr;
+  copy.points_xyz = copy.points_lum = nullptr;
+  if (s->type == HYP_SOURCE_POINT_COLLECTION) {
+    // set_pdf_discrete (type_pdf.f90:222-231): normalise, accumulate, normalise the cdf
+    std::vector<double> cdf(s->points_lum, s->points_lum + s->n_points);
+    double norm = 0.0;
+    for (double v : cdf) norm = norm + v;
+    for (double &v : cdf) v = v / norm;
+    for (int64_t i = 1; i < s->n_points; ++i) cdf[i] = cdf[i - 1] + cdf[i];
+    const double last = cdf[s->n_points - 1];
+    for (double &v : cdf) v = v / last;
+    c->coll_off.push_back((int64_t)c->coll_cdf.size());
+    c->coll_cdf.insert(c->coll_cdf.end(), cdf.begin(), cdf.end());
+    c->coll_xyz.insert(c->coll_xyz.end(), s->points_xyz, s->points_xyz + 3 * s->n_points);
+    copy.luminosity = norm;  // s%luminosity = sum(luminosity_collection) (source_type.f90:268)
+  } else {
+    c->coll_off.push_back(-1);
+  }
   c->sources.push_back(copy);
   c->source_spectrum.push_back(spec);
   return HYP_OK;
@@ -2563,11 +2704,42 @@ int hyp_finalize_setup(hyp_ctx *c) {
     sd[i].peeloff = s.peeloff;
     sd[i].pad = 0;
     sd[i].spectrum = c->source_spectrum[i];
+    for (int k = 0; k < 6; ++k) sd[i].box[k] = s.box[k];
+    if (s.type == HYP_SOURCE_EXTERN_BOX) {
+      // set_pdf(s%face, (/dy*dz, dy*dz, dz*dx, dz*dx, dx*dy, dx*dy/)) (source_type.f90:229)
+      const double dx = s.box[1] - s.box[0], dy = s.box[3] - s.box[2], dz = s.box[5] - s.box[4];
+      double a[6] = {dy * dz, dy * dz, dz * dx, dz * dx, dx * dy, dx * dy};
+      double norm = 0.0;
+      for (double v : a) norm = norm + v;
+      for (double &v : a) v = v / norm;
+      for (int k = 1; k < 6; ++k) a[k] = a[k - 1] + a[k];
+      for (int k = 0; k < 6; ++k) sd[i].face_cdf[k] = a[k] / a[5];
+    } else {
+      for (int k = 0; k < 6; ++k) sd[i].face_cdf[k] = 1.0;
+    }
+    {
+      // angle3d_deg (type_angle3d.f90:127-134)
+      const double deg2rad = 3.14159265358979323846 / 180.0;
+      sd[i].dir_cost = cos(s.theta * deg2rad);
+      sd[i].dir_sint = sin(s.theta * deg2rad);
+      sd[i].dir_cosp = cos(s.phi * deg2rad);
+      sd[i].dir_sinp = sin(s.phi * deg2rad);
+    }
+    sd[i].coll_off = c->coll_off[i];
+    sd[i].coll_n = s.type == HYP_SOURCE_POINT_COLLECTION ? s.n_points : 0;
     sd[i].pdf = s.luminosity / ltot;
     cum += sd[i].pdf;
     sd[i].cdf = cum;
   }
   for (auto &s : sd) s.cdf /= cum;
+  if (!c->coll_cdf.empty()) {
+    CUDA_TRY(cudaMalloc(&c->d_coll_xyz, c->coll_xyz.size() * sizeof(double)));
+    CUDA_TRY(cudaMalloc(&c->d_coll_cdf, c->coll_cdf.size() * sizeof(double)));
+    CUDA_TRY(cudaMemcpy(c->d_coll_xyz, c->coll_xyz.data(), c->coll_xyz.size() * sizeof(double), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(c->d_coll_cdf, c->coll_cdf.data(), c->coll_cdf.size() * sizeof(double), cudaMemcpyHostToDevice));
+  }
+  M.coll_xyz = c->d_coll_xyz;
+  M.coll_cdf = c->d_coll_cdf;
   CUDA_TRY(cudaMalloc(&c->d_sources, sd.size() * sizeof(SourceDev)));
   CUDA_TRY(cudaMemcpy(c->d_sources, sd.data(), sd.size() * sizeof(SourceDev), cudaMemcpyHostToDevice));
   M.sources = c->d_sources;

@@ -653,7 +653,7 @@ emit_final_kernel(const ModelDev M, Pool P, const FinalArgs F, const unsigned lo
     PeelJob<ND> *J = job_append<ND>(go && F.make_peeled && !F.scattering_only, F);
     if (J) {
       fill_job<ND>(J, p, surface_kind(p), p.nx, p.ny, p.nz, 0.0, 0.0, 0.0, 0);
-      if (J->kind == 0) J->point_src = J->source_id;
+      if (J->kind == 0 && M.sources[J->source_id - 1].type == HYP_SOURCE_POINT) J->point_src = J->source_id;
     }
     if (go) {
       // with a forced first interaction the optical depth is drawn by the flight kernel once the
@@ -906,7 +906,7 @@ __global__ void raytrace_emit_kernel(const ModelDev M, PeelJob<ND> *__restrict__
       p.energy = p.energy * source_weight;  // energy_total / n_photons_sources (iter_raytracing.f90:79)
       fill_job<ND>(&J, p, surface_kind(p), p.nx, p.ny, p.nz, 0.0, 0.0, 0.0, 0);
       J.emiss_type = M.sources[(p.tag & TAG_SRC_MASK) - 1].freq_type;
-      if (J.kind == 0) J.point_src = J.source_id;
+      if (J.kind == 0 && M.sources[J.source_id - 1].type == HYP_SOURCE_POINT) J.point_src = J.source_id;
     } else {
       // emit_from_grid (grid_physics_3d.f90:691-753)
       rng.init(M.seed, first_dust_id + (i - n_src), ITER_RAY_DUST);

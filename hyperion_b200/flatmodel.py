@@ -102,7 +102,8 @@ class FlatDust:
 @dataclass
 class FlatSource:
     """One source (``src/sources/source_type.f90:102-282``)."""
-    type: int = 1              # 1 point, 2 sphere
+    type: int = 1              # the reference's numbering: 1 point, 2 sphere, 5 extern_sph, 6 extern_box,
+                               # 7 plane_parallel, 8 point_collection
     luminosity: float = 0.0
     position: tuple = (0.0, 0.0, 0.0)
     temperature: Optional[float] = None   # blackbody
@@ -111,6 +112,10 @@ class FlatSource:
     radius: float = 0.0
     limb_darkening: bool = False
     peeloff: bool = True
+    bounds: tuple = (0.0, 0.0, 0.0, 0.0, 0.0, 0.0)   # extern_box: xmin, xmax, ymin, ymax, zmin, zmax
+    direction: tuple = (0.0, 0.0)                    # plane_parallel: (theta, phi) in degrees
+    points: Optional[np.ndarray] = None              # point_collection: [n, 3] positions
+    points_luminosity: Optional[np.ndarray] = None   # point_collection: [n]
 
 
 @dataclass

@@ -277,15 +277,36 @@ def read_rtin(filename):
             g = g_src[name]
             a = g.attrs
             stype = _s(a["type"])
-            if stype not in ("point", "sphere"):
-                raise ModelError("source type '%s' is not implemented by this engine yet" % stype)
+            # source_read (src/sources/source_type.f90:102-282); type numbers are the reference's
+            types = {"point": 1, "sphere": 2, "extern_sph": 5, "extern_box": 6, "plane_parallel": 7,
+                     "point_collection": 8}
+            if stype == "map":
+                raise ModelError("source type 'map' is not implemented by this engine yet")
+            if stype not in types:
+                raise ModelError("unknown type in source list: " + stype)
+            if stype == "sphere" and any(isinstance(g[k], type(g)) for k in g.keys()):
+                raise ModelError("spots on spherical sources are not implemented by this engine yet")
             spec = _s(a["spectrum"])
-            kw = dict(type=1 if stype == "point" else 2, luminosity=float(_num(a["luminosity"])),
-                      position=(float(_num(a["x"])), float(_num(a["y"])), float(_num(a["z"]))),
-                      peeloff=_yes(a["peeloff"]))
-            if stype == "sphere":
+            kw = dict(type=types[stype], peeloff=_yes(a["peeloff"]))
+            if stype == "point_collection":
+                pos = np.asarray(g["position"][...], dtype=np.float64)
+                lum = np.asarray(g["luminosity"][...], dtype=np.float64).reshape(-1)
+                if pos.ndim != 2 or pos.shape[1] != 3 or pos.shape[0] != lum.shape[0]:
+                    raise ModelError("point collection: position should be (n, 3) and luminosity (n,)")
+                kw["points"], kw["points_luminosity"] = pos, lum
+                kw["luminosity"] = float(lum.sum())
+            else:
+                kw["luminosity"] = float(_num(a["luminosity"]))
+            if stype in ("point", "sphere", "extern_sph", "plane_parallel"):
+                kw["position"] = (float(_num(a["x"])), float(_num(a["y"])), float(_num(a["z"])))
+            if stype in ("sphere", "extern_sph", "plane_parallel"):
                 kw["radius"] = float(_num(a["r"]))
+            if stype == "sphere":
                 kw["limb_darkening"] = _yes(a["limb"])
+            if stype == "extern_box":
+                kw["bounds"] = tuple(float(_num(a[k])) for k in ("xmin", "xmax", "ymin", "ymax", "zmin", "zmax"))
+            if stype == "plane_parallel":
+                kw["direction"] = (float(_num(a["theta"])), float(_num(a["phi"])))
             if spec == "temperature":
                 kw["temperature"] = float(_num(a["temperature"]))
             elif spec == "spectrum":
@@ -295,8 +316,10 @@ def read_rtin(filename):
                     raise ModelError("spectrum frequency should be monotonically increasing")
                 kw["spectrum_nu"], kw["spectrum_fnu"] = nu, fnu
             elif spec == "lte":
-                raise ModelError("Point source cannot have LTE spectrum" if stype == "point"
-                                 else "Spherical source cannot have LTE spectrum")
+                raise ModelError({"point": "Point source", "sphere": "Spherical source",
+                                  "extern_sph": "External spherical source", "extern_box": "External box source",
+                                  "plane_parallel": "Plane parallel",
+                                  "point_collection": "Point source collection"}[stype] + " cannot have LTE spectrum")
             else:
                 raise ModelError("unknown spectrum specifier: " + spec)
             sources.append(FlatSource(**kw))

@@ -199,13 +199,27 @@ def write_rtin(filename, model: FlatModel, n_initial_iter=5, n_initial_photons=1
     gs = f.create_group("Sources")
     for i, s in enumerate(model.sources):
         g = gs.create_group("source_%05i" % (i + 1))
-        g.attrs["type"] = "point" if s.type == 1 else "sphere"
-        g.attrs["luminosity"] = float(s.luminosity)
+        # hyperion/sources/source.py: write() of each source class
+        stype = {1: "point", 2: "sphere", 5: "extern_sph", 6: "extern_box", 7: "plane_parallel",
+                 8: "point_collection"}[s.type]
+        g.attrs["type"] = stype
         g.attrs["peeloff"] = _yn(s.peeloff)
-        g.attrs["x"], g.attrs["y"], g.attrs["z"] = [float(v) for v in s.position]
-        if s.type == 2:
+        if stype == "point_collection":
+            g.create_dataset("position", np.ascontiguousarray(s.points, dtype=np.float64).reshape(-1, 3))
+            g.create_dataset("luminosity", np.ascontiguousarray(s.points_luminosity, dtype=np.float64))
+        else:
+            g.attrs["luminosity"] = float(s.luminosity)
+        if stype in ("point", "sphere", "extern_sph", "plane_parallel"):
+            g.attrs["x"], g.attrs["y"], g.attrs["z"] = [float(v) for v in s.position]
+        if stype in ("sphere", "extern_sph", "plane_parallel"):
             g.attrs["r"] = float(s.radius)
+        if stype == "sphere":
             g.attrs["limb"] = _yn(s.limb_darkening)
+        if stype == "extern_box":
+            for k, v in zip(("xmin", "xmax", "ymin", "ymax", "zmin", "zmax"), s.bounds):
+                g.attrs[k] = float(v)
+        if stype == "plane_parallel":
+            g.attrs["theta"], g.attrs["phi"] = float(s.direction[0]), float(s.direction[1])
         if s.temperature is not None:
             g.attrs["spectrum"] = "temperature"
             g.attrs["temperature"] = float(s.temperature)

@@ -66,19 +66,29 @@ typedef struct {
 /* One source (source_read, src/sources/source_type.f90:102-282). */
 #define HYP_SOURCE_POINT 1
 #define HYP_SOURCE_SPHERE 2
+/* 3 (sphere with spots) and 4 (luminosity map) are not implemented: rejected by hyp_add_source */
+#define HYP_SOURCE_EXTERN_SPH 5        /* emit_from_extern_sph, source_type.f90:748-820 */
+#define HYP_SOURCE_EXTERN_BOX 6        /* emit_from_extern_box, source_type.f90:822-933 */
+#define HYP_SOURCE_PLANE_PARALLEL 7    /* emit_from_plane_parallel, source_type.f90:935-980 */
+#define HYP_SOURCE_POINT_COLLECTION 8  /* emit_from_point_collection, source_type.f90:570-598 */
 #define HYP_SPECTRUM_TABLE 1
 #define HYP_SPECTRUM_BLACKBODY 2
 typedef struct {
-  int32_t type;            /* HYP_SOURCE_* */
+  int32_t type;            /* HYP_SOURCE_* (the reference's numbering, source_read) */
   int32_t peeloff;
-  double luminosity;
-  double x, y, z;
-  double radius;           /* sphere only */
+  double luminosity;       /* point collection: ignored, the sum of points_lum is used (source_type.f90:268) */
+  double x, y, z;          /* point, sphere, extern_sph, plane_parallel */
+  double radius;           /* sphere, extern_sph, plane_parallel (radius of the disk the beam starts from) */
   int32_t limb_darkening;  /* sphere only */
   int32_t spectrum_type;   /* HYP_SPECTRUM_* */
   double temperature;      /* blackbody */
   int32_t n_spec;          /* tabulated spectrum */
   const double *spec_nu, *spec_fnu;
+  double box[6];           /* extern_box: xmin, xmax, ymin, ymax, zmin, zmax */
+  double theta, phi;       /* plane_parallel: direction of travel in degrees ('theta', 'phi') */
+  int64_t n_points;        /* point collection */
+  const double *points_xyz;  /* [n_points][3] */
+  const double *points_lum;  /* [n_points] */
 } hyp_source;
 
 /* Run configuration: the root attributes of the .rtin file

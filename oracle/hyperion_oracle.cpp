@@ -738,6 +738,7 @@ struct Photon {
   int emiss_type = 0, emiss_var_id = 0;
   double emiss_var_frac = 0.0;
   Angle source_a{0, 0, 0, 0};  // position angle on a stellar surface (type_photon.f90, emit_from_sphere)
+  int face_id = 0;             // face of an external box source the packet came from (emit_from_extern_box)
 };
 
 struct Source {
@@ -751,6 +752,11 @@ struct Source {
   double temperature = 0;
   PdfCont spectrum;
   bool intersect = false;
+  double xmin = 0, xmax = 0, ymin = 0, ymax = 0, zmin = 0, zmax = 0;  // extern_box
+  PdfDiscrete face;                                                    // extern_box: area of the six faces
+  Angle direction{1.0, 0.0, 1.0, 0.0};                                 // plane_parallel
+  std::vector<Vec> position_collection;                                // point_collection
+  PdfDiscrete collection_pdf;
 };
 
 // ---------------------------------------------------------------------------
@@ -2386,6 +2392,102 @@ void emit_from_point(orc_ctx &g, const Source &src, Photon &p) {
   p.last_isotropic = true;
 }
 
+// minus_angle_dp (type_angle3d.f90:443-447)
+static Angle minus_angle(const Angle &a) { return Angle{-a.cost, a.sint, -a.cosp, -a.sinp}; }
+
+// emit_from_point_collection (source_type.f90:570-598)
+void emit_from_point_collection(orc_ctx &g, const Source &src, Photon &p) {
+  const int i_source = src.collection_pdf.sample(g.rng);
+  p.r = src.position_collection[i_source - 1];
+  p.a = random_sphere_angle3d(g.rng);
+  p.s = Stokes{1.0, 0.0, 0.0, 0.0};
+  p.last_isotropic = true;
+}
+
+// emit_from_extern_sph (source_type.f90:748-802): from the sphere inwards, cosine law about the inward normal
+void emit_from_extern_sph(orc_ctx &g, const Source &src, Photon &p) {
+  Angle a_coord = random_sphere_angle3d(g.rng);
+  double phi_local = 0.0 + (TWOPI_F - 0.0) * g.rng.random();
+  Angle a_local;
+  a_local.cosp = std::cos(phi_local);
+  a_local.sinp = std::sin(phi_local);
+  double xi = g.rng.random();
+  a_local.cost = std::sqrt(xi);
+  a_local.sint = std::sqrt(1.0 - a_local.cost * a_local.cost);
+  p.a = rotate_angle3d(a_local, a_coord);
+  p.a = minus_angle(p.a);
+  p.s = Stokes{1.0, 0.0, 0.0, 0.0};
+  Vec u = angle3d_to_vector3d(a_coord);
+  p.r = Vec{u.x * src.radius, u.y * src.radius, u.z * src.radius};
+  p.r = Vec{p.r.x + src.position.x, p.r.y + src.position.y, p.r.z + src.position.z};
+  p.last_isotropic = false;
+  p.source_a = minus_angle(a_coord);
+}
+
+// normal of face `face` of an external box pointing into the box (source_type.f90:866-896, 916-929)
+static Angle extern_box_normal(int face) {
+  switch (face) {
+    case 1: return Angle{0.0, 1.0, 1.0, 0.0};
+    case 2: return Angle{0.0, -1.0, 1.0, 0.0};
+    case 3: return Angle{0.0, 1.0, 0.0, 1.0};
+    case 4: return Angle{0.0, -1.0, 0.0, 1.0};
+    case 5: return Angle{1.0, 0.0, 1.0, 0.0};
+    default: return Angle{-1.0, 0.0, 1.0, 0.0};
+  }
+}
+
+// emit_from_extern_box (source_type.f90:822-904)
+void emit_from_extern_box(orc_ctx &g, const Source &src, Photon &p) {
+  const int face = src.face.sample(g.rng);
+  double phi_local = 0.0 + (TWOPI_F - 0.0) * g.rng.random();
+  Angle a_local;
+  a_local.cosp = std::cos(phi_local);
+  a_local.sinp = std::sin(phi_local);
+  double xi = g.rng.random();
+  a_local.cost = std::sqrt(xi);
+  a_local.sint = std::sqrt(1.0 - a_local.cost * a_local.cost);
+  auto uni = [&](double a, double b) { return a + (b - a) * g.rng.random(); };
+  switch (face) {
+    case 1:
+      p.r.x = src.xmin; p.r.y = uni(src.ymin, src.ymax); p.r.z = uni(src.zmin, src.zmax);
+      break;
+    case 2:
+      p.r.x = src.xmax; p.r.y = uni(src.ymin, src.ymax); p.r.z = uni(src.zmin, src.zmax);
+      break;
+    case 3:
+      p.r.x = uni(src.xmin, src.xmax); p.r.y = src.ymin; p.r.z = uni(src.zmin, src.zmax);
+      break;
+    case 4:
+      p.r.x = uni(src.xmin, src.xmax); p.r.y = src.ymax; p.r.z = uni(src.zmin, src.zmax);
+      break;
+    case 5:
+      p.r.x = uni(src.xmin, src.xmax); p.r.y = uni(src.ymin, src.ymax); p.r.z = src.zmin;
+      break;
+    default:
+      p.r.x = uni(src.xmin, src.xmax); p.r.y = uni(src.ymin, src.ymax); p.r.z = src.zmax;
+      break;
+  }
+  p.a = rotate_angle3d(a_local, extern_box_normal(face));
+  p.s = Stokes{1.0, 0.0, 0.0, 0.0};
+  p.last_isotropic = false;
+  p.face_id = face;
+}
+
+// emit_from_plane_parallel (source_type.f90:935-980): a beam of radius `radius` travelling along `direction`
+void emit_from_plane_parallel(orc_ctx &g, const Source &src, Photon &p) {
+  double xi = g.rng.random();
+  double r = std::pow(xi, 0.5) * src.radius;
+  double phi = 0.0 + (360.0 - 0.0) * g.rng.random();
+  Angle a_local = angle3d_deg(90.0, phi);
+  Angle a_final = rotate_angle3d(a_local, src.direction);
+  Vec u = angle3d_to_vector3d(a_final);
+  p.r = Vec{u.x * r, u.y * r, u.z * r};
+  p.r = Vec{p.r.x + src.position.x, p.r.y + src.position.y, p.r.z + src.position.z};
+  p.a = src.direction;
+  p.s = Stokes{1.0, 0.0, 0.0, 0.0};
+  p.last_isotropic = false;
+}
+
 // emit (source.f90:100-179) + source_emit (source_type.f90:398-511)
 void emit(orc_ctx &g, Photon &p, bool reemit = false, int reemit_id = 0, double reemit_energy = 0.0) {
   p = Photon();
@@ -2409,6 +2511,18 @@ void emit(orc_ctx &g, Photon &p, bool reemit = false, int reemit_id = 0, double 
       break;
     case HYP_SOURCE_SPHERE:
       emit_from_sphere(g, src, p);
+      break;
+    case HYP_SOURCE_EXTERN_SPH:
+      emit_from_extern_sph(g, src, p);
+      break;
+    case HYP_SOURCE_EXTERN_BOX:
+      emit_from_extern_box(g, src, p);
+      break;
+    case HYP_SOURCE_PLANE_PARALLEL:
+      emit_from_plane_parallel(g, src, p);
+      break;
+    case HYP_SOURCE_POINT_COLLECTION:
+      emit_from_point_collection(g, src, p);
       break;
     default:
       throw OracleError{"source type not restated in the oracle"};
@@ -3131,8 +3245,11 @@ void peeloff_photon(orc_ctx &g, const Photon &p_orig, bool polychromatic) {
         // source_emit_peeloff (source_type.f90:513-537) -> emit_from_sphere_peeloff (:692-707)
         const Source &src = g.s[p.source_id - 1];
         if (src.peeloff) {
-          if (src.type != HYP_SOURCE_SPHERE) throw OracleError{"Should not be here, all other source types are isotropic"};
-          const Angle &b = p.source_a;
+          if (src.type != HYP_SOURCE_SPHERE && src.type != HYP_SOURCE_EXTERN_SPH && src.type != HYP_SOURCE_EXTERN_BOX)
+            throw OracleError{"Should not be here, all other source types are isotropic"};
+          // emit_from_sphere_peeloff (:692-707), emit_from_extern_sph_peeloff (:804-820),
+          // emit_from_extern_box_peeloff (:906-933)
+          const Angle b = src.type == HYP_SOURCE_EXTERN_BOX ? extern_box_normal(p.face_id) : p.source_a;
           double mu = a_req.sint * a_req.cosp * b.sint * b.cosp + a_req.sint * a_req.sinp * b.sint * b.sinp + a_req.cost * b.cost;
           mu = std::max(mu, 0.0);
           if (src.limb_darkening)
@@ -3779,6 +3896,25 @@ int orc_add_source(orc_ctx *g, const hyp_source *s) {
         if (s->spec_nu[i + 1] < s->spec_nu[i])
           return fail(g, "spectrum frequency should be monotonically increasing");
       src.spectrum.set(s->spec_nu, s->spec_fnu, s->n_spec, true);
+    }
+    if (s->type == HYP_SOURCE_EXTERN_BOX) {
+      src.xmin = s->box[0]; src.xmax = s->box[1];
+      src.ymin = s->box[2]; src.ymax = s->box[3];
+      src.zmin = s->box[4]; src.zmax = s->box[5];
+      const double dx = src.xmax - src.xmin, dy = src.ymax - src.ymin, dz = src.zmax - src.zmin;
+      const double areas[6] = {dy * dz, dy * dz, dz * dx, dz * dx, dx * dy, dx * dy};  // source_type.f90:229
+      src.face.set(areas, 6);
+    } else if (s->type == HYP_SOURCE_PLANE_PARALLEL) {
+      src.direction = angle3d_deg(s->theta, s->phi);
+    } else if (s->type == HYP_SOURCE_POINT_COLLECTION) {
+      if (s->n_points < 1 || !s->points_xyz || !s->points_lum) return fail(g, "point collection is empty");
+      for (int64_t i = 0; i < s->n_points; i++)
+        src.position_collection.push_back(Vec{s->points_xyz[3 * i], s->points_xyz[3 * i + 1], s->points_xyz[3 * i + 2]});
+      src.luminosity = 0.0;
+      for (int64_t i = 0; i < s->n_points; i++) src.luminosity += s->points_lum[i];  // sum() (source_type.f90:268)
+      src.collection_pdf.set(s->points_lum, (int)s->n_points);
+    } else if (s->type != HYP_SOURCE_POINT && s->type != HYP_SOURCE_SPHERE && s->type != HYP_SOURCE_EXTERN_SPH) {
+      return fail(g, "source type not restated in the oracle");
     }
     src.intersect = (s->type == HYP_SOURCE_SPHERE);
     if (src.intersect) g->any_intersect = true;

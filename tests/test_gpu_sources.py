@@ -1,0 +1,99 @@
+"""GPU parity for the source types beyond points and spheres: external sphere / box (emitting
+inwards), plane-parallel beam, point collection (src/sources/source_type.f90:570-980).  The oracle is
+pinned for these emitters by closed-form track densities (tests/test_oracle_sources.py); here the CUDA
+engine is compared with it statistically, for the Lucy deposits and for the peeled SEDs / images
+(external sources are peeled with the 4 mu weight of emit_from_extern_*_peeloff)."""
+import numpy as np
+import pytest
+
+from helpers import bitlevel_model, peeloff_groups, pc, lsun
+from hyperion_b200.flatmodel import FlatSource
+from test_gpu_parity import _gpu_batches, _oracle_batches, _zscores
+from test_gpu_imaging import _run_both, _compare, _converged_energy
+
+pytestmark = pytest.mark.gpu
+
+
+def mixed_sources():
+    pts = np.array([[-0.5 * pc, -0.5 * pc, -0.5 * pc], [0.5 * pc, 0.25 * pc, 0.5 * pc], [0.0, 0.5 * pc, -0.25 * pc],
+                    [0.9 * pc, -0.9 * pc, 0.1 * pc]])
+    return [FlatSource(type=1, luminosity=1.0 * lsun, temperature=6000., position=(0.1 * pc, 0., -0.2 * pc)),
+            FlatSource(type=5, luminosity=2.0 * lsun, temperature=5000., position=(0.02 * pc, -0.01 * pc, 0.), radius=0.95 * pc),
+            FlatSource(type=6, luminosity=3.0 * lsun, temperature=4000.,
+                       bounds=(-0.9 * pc, 0.8 * pc, -0.7 * pc, 0.95 * pc, -0.6 * pc, 0.9 * pc)),
+            FlatSource(type=7, luminosity=1.5 * lsun, temperature=7000., position=(-0.3 * pc, 0.2 * pc, -0.8 * pc),
+                       radius=0.3 * pc, direction=(25.0, 40.0), peeloff=False),
+            FlatSource(type=8, temperature=3000., points=pts, points_luminosity=np.array([1.0, 3.0, 2.0, 0.5]) * lsun)]
+
+
+@pytest.mark.parametrize("evenly,multi", [(False, False), (True, True)])
+def test_deposits_match_oracle_mixed_sources(golden_car, evenly, multi):
+    model = bitlevel_model(golden_car, evenly, multi)
+    model.sources = mixed_sources()
+    B, N = 16, 100000
+    g, gst = _gpu_batches(model, N, B)
+    o, ost = _oracle_batches(model, N, B)
+    z, ok = _zscores(g, o)
+    assert ok.all()
+    assert np.abs(z).max() < 5.0, np.abs(z).max()
+    assert 0.6 < (z ** 2).mean() < 1.5, (z ** 2).mean()
+    rel = np.abs(g.mean(0) / o.mean(0) - 1)
+    assert np.median(rel) < 0.03
+    for key in ("n_crossings", "n_absorptions", "n_scatterings"):
+        a = np.mean([s[key] for s in gst])
+        b = np.mean([s[key] for s in ost])
+        assert abs(a / b - 1) < 0.01, (key, a, b)
+    assert all(s["killed_geo"] == 0 and s["killed_int"] == 0 and s["n_photons"] == N for s in gst)
+
+
+@pytest.mark.parametrize("kind", [5, 6, 7, 8])
+def test_each_source_type_alone(golden_car, kind):
+    """One source of each new type on its own, so that a wrong emitter cannot hide behind the others."""
+    model = bitlevel_model(golden_car, False, False)
+    model.sources = [s for s in mixed_sources() if s.type == kind]
+    B, N = 12, 100000
+    g, gst = _gpu_batches(model, N, B)
+    o, ost = _oracle_batches(model, N, B)
+    z, ok = _zscores(g, o)
+    filled = ok & (o.mean(0) > 0)
+    assert filled.sum() > 20
+    assert np.abs(z[filled]).max() < 5.0, np.abs(z[filled]).max()
+    assert 0.5 < (z[filled] ** 2).mean() < 1.6, (z[filled] ** 2).mean()
+    for key in ("n_crossings", "n_absorptions", "n_scatterings"):
+        a = np.mean([s[key] for s in gst])
+        b = np.mean([s[key] for s in ost])
+        assert abs(a / b - 1) < 0.015, (key, a, b)
+
+
+@pytest.mark.parametrize("raytracing", [False, True])
+def test_peeloff_matches_oracle_mixed_sources(golden_car, raytracing):
+    model = bitlevel_model(golden_car, False, False)
+    model.sources = mixed_sources()
+    model.peeled = peeloff_groups()
+    model.specific_energy = _converged_energy(model)
+    B = 12
+    gpu, orc = _run_both(model, B, 60000, raytracing, (20000, 30000) if raytracing else None)
+    report = _compare(gpu, orc)
+    print(report)
+    for key in ("n_crossings", "n_absorptions", "n_scatterings", "n_peeloffs", "n_peel_crossings"):
+        a = np.mean([g[1][key] for g in gpu])
+        b = np.mean([o[1][key] for o in orc])
+        assert abs(a / b - 1) < 0.02, (key, a, b)
+
+
+def test_source_argument_errors():
+    from hyperion_b200.capi import Engine, HyperionError
+    from hyperion_b200 import synthetic as syn
+    model = syn.cartesian_point_source_model(n=8, dust=syn.grey_dust())
+    for bad, msg in [(FlatSource(type=7, luminosity=lsun, temperature=5000., radius=0.1 * pc, peeloff=True),
+                      "Cannot peeloff plane parallel source"),
+                     (FlatSource(type=4, luminosity=lsun, temperature=5000.), "not implemented"),
+                     (FlatSource(type=6, luminosity=lsun, temperature=5000., bounds=(1., -1., 0., 1., 0., 1.)),
+                      "bounds should be increasing"),
+                     (FlatSource(type=8, temperature=5000., points=np.zeros((2, 3)), points_luminosity=np.zeros(2)),
+                      "all PDF elements are zero")]:
+        model.sources = [bad]
+        eng = Engine(0)
+        with pytest.raises(HyperionError, match=msg):
+            eng.load_model(model)
+        eng.close()

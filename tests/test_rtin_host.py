@@ -254,3 +254,32 @@ def test_runner_amr(golden_car, golden_amr, tmp_path):
     b = r["iteration_00002/level_00002/grid_00001/specific_energy"][...]
     assert a.shape == (1, 4, 6, 8) and b.shape == (1, 20, 6, 4) and np.all(b > 0)
     assert r["Peeled/group_00001/seds"][...][0].sum() > 0
+
+
+def test_rtin_roundtrip_all_source_types(golden_car, tmp_path):
+    """External sphere / box, plane-parallel and point-collection sources in the layout
+    hyperion/sources/source.py writes (attrs xmin..zmax, theta/phi, datasets position/luminosity)."""
+    from helpers import pc, lsun
+    from hyperion_b200.flatmodel import FlatSource
+    m = bitlevel_model(golden_car, False, False)
+    pts = np.array([[-0.5 * pc, 0.1 * pc, 0.2 * pc], [0.5 * pc, 0.25 * pc, -0.5 * pc]])
+    m.sources = [FlatSource(type=5, luminosity=2.0 * lsun, temperature=5000., position=(0.1 * pc, 0., 0.), radius=0.9 * pc),
+                 FlatSource(type=6, luminosity=3.0 * lsun, temperature=4000., bounds=(-0.9 * pc, 0.8 * pc, -0.7 * pc, 0.95 * pc, -0.6 * pc, 0.9 * pc)),
+                 FlatSource(type=7, luminosity=1.5 * lsun, temperature=7000., position=(0., 0.2 * pc, -0.9 * pc), radius=0.3 * pc,
+                            direction=(25.0, 40.0), peeloff=False),
+                 FlatSource(type=8, temperature=3000., points=pts, points_luminosity=np.array([1.0, 3.0]) * lsun)]
+    fn = str(tmp_path / "m.rtin")
+    rtin_write.write_rtin(fn, m, n_initial_iter=1, n_initial_photons=100)
+    got, rs, _ = rtin.read_rtin(fn)
+    assert [s.type for s in got.sources] == [5, 6, 7, 8]
+    a, b, c, d = got.sources
+    assert a.radius == 0.9 * pc and tuple(a.position) == (0.1 * pc, 0., 0.) and a.peeloff
+    assert tuple(b.bounds) == tuple(m.sources[1].bounds) and b.luminosity == 3.0 * lsun
+    assert tuple(c.direction) == (25.0, 40.0) and c.radius == 0.3 * pc and not c.peeloff
+    assert np.array_equal(d.points, pts) and np.array_equal(d.points_luminosity, np.array([1.0, 3.0]) * lsun)
+    assert d.luminosity == 4.0 * lsun
+    # the reference's wording for what it rejects
+    f = h5min.File(fn)
+    del f
+    m.sources = [FlatSource(type=1, luminosity=lsun, temperature=5000.)]
+    rtin_write.write_rtin(fn, m, n_initial_iter=1, n_initial_photons=100)
