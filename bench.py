@@ -242,11 +242,28 @@ def roofline_of(stats, n_dust, world, steps):
     peak, peak_kind = peaks()
     achieved = alg_bytes / (flight_ms * 1e-3) / 1e9 if flight_ms > 0 else 0.0
     return {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-            "traffic": None, "peak_kind": peak_kind, "bytes_per_crossing": 24 * n_dust,
+            "traffic": None, "algorithmic_bytes_per_step": alg_bytes / steps,
+            "peak_kind": peak_kind, "bytes_per_crossing": 24 * n_dust,
             "kernel": "flight_beam_kernel + flight_kernel (all rounds of a step)",
             "kernel_ms_per_step": flight_ms / steps, "photon_loop_ms_per_step": loop_ms / steps,
             "achieved_whole_photon_loop": alg_bytes / (loop_ms * 1e-3) / 1e9 if loop_ms > 0 else 0.0,
             "crossings_per_step": cross / steps}, cross, nabs, nscat
+
+
+def measured_traffic(workload, photons):
+    """DRAM bytes (ncu dram__bytes_read.sum + dram__bytes_write.sum) the flight kernels move per step of
+    this workload, from the newest committed capture profiles/*_traffic.json; None if no capture matches.
+    Like `achieved` it is summed over all flight launches of one step."""
+    import glob
+    for fn in sorted(glob.glob(os.path.join(ROOT, "profiles", "*_traffic.json")), reverse=True):
+        try:
+            with open(fn) as f:
+                t = json.load(f)
+        except (OSError, ValueError):
+            continue
+        if t.get("workload") == workload and int(t.get("photons_per_gpu_per_step", 0)) == int(photons):
+            return float(t["flight_dram_bytes_per_step"]), os.path.relpath(fn, ROOT)
+    return None, None
 
 
 def main():
@@ -300,6 +317,7 @@ def main():
     total_ms, stats, e2e = measure(eng, drv, stream, model, P, world, rank, a, sync_all, e2e=not a.no_e2e)
     clocks = sampler.stop() if rank == 0 else None
     roof, cross, nabs, nscat = roofline_of(stats, eng.n_dust, world, a.steps)
+    roof["traffic"], roof["traffic_source"] = measured_traffic(workload_name(a), a.photons)
     gpu_launches = int(sum(s.n_launches for s in stats))
     n_dust, n_cells = eng.n_dust, eng.n_cells
     eng.close()

@@ -70,6 +70,7 @@ class ImageConf(C.Structure):
         ("n_wav", C.c_int32), ("wav_min", C.c_double), ("wav_max", C.c_double),
         ("track_origin", C.c_int32), ("track_n_scat", C.c_int32),
         ("uncertainties", C.c_int32), ("compute_stokes", C.c_int32), ("io_bytes", C.c_int32),
+        ("binned", C.c_int32), ("n_theta", C.c_int32), ("n_phi", C.c_int32),
     ]
 
 
@@ -201,9 +202,13 @@ class CApi:
     def add_peeled_group(self, ctx, g):
         """g: :class:`hyperion_b200.flatmodel.FlatPeeledGroup`"""
         t = ImageConf()
-        theta = np.ascontiguousarray(g.theta, dtype=np.float64)
-        phi = np.ascontiguousarray(g.phi, dtype=np.float64)
-        t.n_view, t.theta, t.phi = len(theta), _ptr(theta), _ptr(phi)
+        if g.binned:
+            t.binned, t.n_theta, t.n_phi = 1, int(g.n_theta), int(g.n_phi)
+            t.n_view = int(g.n_theta) * int(g.n_phi)
+        else:
+            theta = np.ascontiguousarray(g.theta, dtype=np.float64)
+            phi = np.ascontiguousarray(g.phi, dtype=np.float64)
+            t.n_view, t.theta, t.phi = len(theta), _ptr(theta), _ptr(phi)
         t.inside_observer, t.ignore_optical_depth = int(g.inside_observer), int(g.ignore_optical_depth)
         t.peeloff_x, t.peeloff_y, t.peeloff_z = [float(v) for v in g.peeloff_origin]
         t.d_min, t.d_max = g.d_min, g.d_max

@@ -3153,7 +3153,7 @@ int ensure_images(hyp_ctx *c) {
     off += g.n_sed * copies;
     g.o_img = off;
     off += g.n_img * copies;
-    n_views += k.n_view;
+    if (!k.binned) n_views += k.n_view;
   }
   c->imgbuf_n = off;
   CUDA_TRY(cudaMalloc(&c->d_imgbuf, (off + SC_COUNT) * sizeof(double)));
@@ -3192,7 +3192,8 @@ int ensure_images(hyp_ctx *c) {
       d.img = b + g.o_img;
       if (k.uncertainties) { d.img2 = d.img + g.n_img; d.imgn = d.img2 + g.n_img; }
     }
-    for (int iv = 0; iv < k.n_view; ++iv) {
+    // a binned group has no viewing directions: packets choose their own (images_binned.f90:57-77)
+    for (int iv = 0; iv < (k.binned ? 0 : k.n_view); ++iv) {
       ViewDev v;
       v.group = (int)ig;
       v.view = iv;
@@ -3208,7 +3209,7 @@ int ensure_images(hyp_ctx *c) {
   if (!c->groups.empty()) {
     CUDA_TRY(cudaMalloc(&c->d_images, c->h_images.size() * sizeof(ImageDev)));
     CUDA_TRY(cudaMemcpy(c->d_images, c->h_images.data(), c->h_images.size() * sizeof(ImageDev), cudaMemcpyHostToDevice));
-    CUDA_TRY(cudaMalloc(&c->d_views, views.size() * sizeof(ViewDev)));
+    CUDA_TRY(cudaMalloc(&c->d_views, (views.size() + 1) * sizeof(ViewDev)));
     CUDA_TRY(cudaMemcpy(c->d_views, views.data(), views.size() * sizeof(ViewDev), cudaMemcpyHostToDevice));
   }
   c->images_ready = true;
@@ -3390,6 +3391,14 @@ int run_final_rounds(hyp_ctx *c, int64_t first_id, int64_t n_photons, int scatte
   F.algorithm = c->conf.forced_first_interaction_algorithm;
   F.baes16_xi = c->conf.baes16_xi;
   F.make_peeled = c->n_views > 0;
+  F.binned = nullptr;
+  F.n_theta = F.n_phi = 0;
+  for (size_t ig = 0; ig < c->groups.size(); ++ig)
+    if (c->groups[ig].conf.binned) {
+      F.binned = c->d_images + ig;
+      F.n_theta = c->groups[ig].conf.n_theta;
+      F.n_phi = c->groups[ig].conf.n_phi;
+    }
   const uint32_t iteration = ITER_FINAL;
 
   pool_init_kernel<<<c->sm_count, 256, 0, st>>>(P, cap);
@@ -3554,7 +3563,17 @@ int hyp_add_peeled_group(hyp_ctx *c, const hyp_image_conf *g) {
   if (!c || !g) return fail(HYP_ERR_INVALID, "NULL argument");
   if (c->images_ready) return fail(HYP_ERR_STATE, "image groups are frozen once an imaging iteration has started");
   if (g->inside_observer) return fail(HYP_ERR_INVALID, "inside observers are not implemented on the device yet");
-  if (!(g->n_view > 0) || !g->theta || !g->phi) return fail(HYP_ERR_INVALID, "n_view should be a positive integer");
+  if (g->binned) {
+    // setup_final_iteration (setup_rt.f90:318-331), binned_images_setup (images_binned.f90:41-55)
+    for (auto &o : c->groups)
+      if (o.conf.binned) return fail(HYP_ERR_INVALID, "can't have more than one binned image group");
+    if (c->conf.forced_first_interaction)
+      return fail(HYP_ERR_INVALID, "can't use binned images with forced first interaction");
+    if (g->n_theta < 1 || g->n_phi < 1 || g->n_view != g->n_theta * g->n_phi)
+      return fail(HYP_ERR_INVALID, "binned images: n_view should be n_theta * n_phi");
+  } else if (!(g->n_view > 0) || !g->theta || !g->phi) {
+    return fail(HYP_ERR_INVALID, "n_view should be a positive integer");
+  }
   if (g->n_wav < 1) return fail(HYP_ERR_INVALID, "n_nu should be >= 1");
   if (g->io_bytes != 4 && g->io_bytes != 8) return fail(HYP_ERR_INVALID, "unexpected value of io_bytes (should be 4 or 8)");
   if (g->track_origin < HYP_TRACK_NO || g->track_origin > HYP_TRACK_SCATTERINGS)
@@ -3563,8 +3582,10 @@ int hyp_add_peeled_group(hyp_ctx *c, const hyp_image_conf *g) {
   if (g->compute_sed && g->n_ap < 1) return fail(HYP_ERR_INVALID, "SED needs at least one aperture");
   HostImage h;
   h.conf = *g;
-  h.theta.assign(g->theta, g->theta + g->n_view);
-  h.phi.assign(g->phi, g->phi + g->n_view);
+  if (!g->binned) {
+    h.theta.assign(g->theta, g->theta + g->n_view);
+    h.phi.assign(g->phi, g->phi + g->n_view);
+  }
   h.conf.theta = h.conf.phi = nullptr;
   c->groups.push_back(std::move(h));
   return HYP_OK;
@@ -3631,8 +3652,10 @@ int hyp_final_finish(hyp_ctx *c, hyp_iter_stats *st) {
   if (rc) return rc;
   if (!(sc[SC_ENERGY] > 0.0)) return fail(HYP_ERR_STATE, "no photons were emitted in this iteration");
   // peeled_images_adjust_scale(energy_total / energy_current) (iter_final.f90:140-143)
-  const double scale = c->energy_total / sc[SC_ENERGY];
+  const double scale0 = c->energy_total / sc[SC_ENERGY];
   for (auto &g : c->groups) {
+    // binned_images_adjust_scale multiplies by the number of direction bins as well (images_binned.f90:35-39)
+    const double scale = g.conf.binned ? scale0 * (double)g.conf.n_theta * (double)g.conf.n_phi : scale0;
     const size_t ns[2] = {g.n_sed, g.n_img}, os[2] = {g.o_sed, g.o_img};
     for (int w = 0; w < 2; ++w) {
       if (!ns[w]) continue;

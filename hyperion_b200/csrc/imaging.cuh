@@ -572,7 +572,57 @@ struct FinalArgs {
   int32_t forced, algorithm; // forced first interaction (iter_final.f90:191-209)
   double baes16_xi;
   int32_t make_peeled;
+  // binned images (images_binned.f90): the group escaping packets are binned into, or nullptr
+  const ImageDev *binned;
+  int32_t n_theta, n_phi;
 };
+
+constexpr uint32_t TAG_NSCAT_MASK = 0x3fffu;   // n_scat saturates at 16383
+constexpr int TAG_DUST_SHIFT = 30;             // dust type of the last interaction, 0-based (p%dust_id - 1)
+
+// binned_images_bin_photon (images_binned.f90:57-77) + image_bin (image_type.f90:408-524) for a packet
+// that has just left the grid at path length t along its flight.
+template <int ND>
+__device__ inline void bin_escaped_packet(const FinalArgs &F, const Slot<ND> *__restrict__ s, const double t) {
+  const ImageDev &im = *F.binned;
+  const double energy = s->energy;
+  if (isnan(energy)) return;
+  const double vx = s->vx, vy = s->vy, vz = s->vz;
+  const double rx = s->r0x + t * vx, ry = s->r0y + t * vy, rz = s->r0z + t * vz;
+  const Angle a = angle_of(vx, vy, vz);
+  double phi = atan2(a.sinp, a.cosp);
+  if (phi < 0.0) phi = phi + 6.283185307179586476925286766559;
+  const int it = ipos_bin(-1.0, 1.0, a.cost, F.n_theta);
+  const int ip = ipos_bin(0.0, 6.283185307179586476925286766559, phi, F.n_phi);
+  if (it < 1 || it > F.n_theta || ip < 1 || ip > F.n_phi) return;
+  const int iv = F.n_phi * (it - 1) + ip - 1;  // image_id, 0-based
+  const double x_image = ry * a.cosp - rx * a.sinp;
+  const double y_image = rz * a.sint - ry * a.cost * a.sinp - rx * a.cost * a.cosp;
+  const int inu = ipos_bin(im.log10_nu_min, im.log10_nu_max, log10(s->nu), im.n_nu);
+  if (inu < 1 || inu > im.n_nu) return;
+  const uint32_t tag = s->tag;
+  const int io = origin_slice(im, (tag & TAG_SCATTERED) ? 1 : 0, (tag & TAG_REPROCESSED) ? 1 : 0, (int)(tag & TAG_SRC_MASK),
+                              (int)(tag >> TAG_DUST_SHIFT) + 1, (int)((tag >> TAG_NSCAT_SHIFT) & TAG_NSCAT_MASK));
+  const bool unc = im.uncertainties != 0;
+  const size_t nn = (size_t)im.n_nu;
+  const double st[4] = {1.0, s->sQ, s->sU, s->sV};
+  if (im.compute_image) {
+    const int ixp = ipos_bin(im.x_min, im.x_max, x_image, im.n_x), iyp = ipos_bin(im.y_min, im.y_max, y_image, im.n_y);
+    if (ixp >= 1 && ixp <= im.n_x && iyp >= 1 && iyp <= im.n_y) {
+      const size_t k = nn * ((ixp - 1) + (size_t)im.n_x * ((iyp - 1) + (size_t)im.n_y * (iv + (size_t)im.n_view * (io - 1))));
+      const size_t stride = nn * im.n_x * im.n_y * im.n_view * im.n_orig;
+      for (int is = 0; is < im.n_stokes; ++is) bin_add(im.img, im.img2, im.imgn, k + (inu - 1) + is * stride, st[is] * energy * 1.0, unc);
+    }
+  }
+  if (im.compute_sed) {
+    const int ir = find_sed_bin(im, x_image, y_image);
+    if (ir >= 1 && ir <= im.n_ap) {
+      const size_t k = nn * ((ir - 1) + (size_t)im.n_ap * (iv + (size_t)im.n_view * (io - 1)));
+      const size_t stride = nn * im.n_ap * im.n_view * im.n_orig;
+      for (int is = 0; is < im.n_stokes; ++is) bin_add(im.sed, im.sed2, im.sedn, k + (inu - 1) + is * stride, st[is] * energy * 1.0, unc);
+    }
+  }
+}
 
 // Append one job per lane with pred set; whole-warp call.
 template <int ND>
@@ -603,7 +653,7 @@ __device__ __forceinline__ void fill_job(PeelJob<ND> *J, const Photon<ND> &p, in
   J->kind = kind;
   J->source_id = (int)(p.tag & TAG_SRC_MASK);
   J->dust_id = dust_id;
-  J->n_scat = (int)(p.tag >> TAG_NSCAT_SHIFT);
+  J->n_scat = (int)((p.tag >> TAG_NSCAT_SHIFT) & TAG_NSCAT_MASK);
   J->scattered = (p.tag & TAG_SCATTERED) ? 1 : 0;
   J->reprocessed = (p.tag & TAG_REPROCESSED) ? 1 : 0;
   J->emiss_type = 0;
@@ -703,12 +753,13 @@ interact_final_kernel(const ModelDev M, Pool P, const FinalArgs F, uint32_t *__r
       } else if (interact_photon<ND>(M, p, rng, n_abs, n_scat, n_kill, dust_id, scattered) == 0) {
         alive = true;
         if (scattered) {
-          uint32_t ns = p.tag >> TAG_NSCAT_SHIFT;
-          if (ns < 0xffffu) ++ns;
+          uint32_t ns = (p.tag >> TAG_NSCAT_SHIFT) & TAG_NSCAT_MASK;
+          if (ns < TAG_NSCAT_MASK) ++ns;
           p.tag = (p.tag & 0xffffu) | (ns << TAG_NSCAT_SHIFT) | TAG_SCATTERED;
         } else {
-          p.tag = (p.tag & ~TAG_SCATTERED) | TAG_REPROCESSED;
+          p.tag = (p.tag & ~TAG_SCATTERED & ~(3u << TAG_DUST_SHIFT)) | TAG_REPROCESSED;
         }
+        p.tag = (p.tag & ~(3u << TAG_DUST_SHIFT)) | ((uint32_t)dust_id << TAG_DUST_SHIFT);  // p%dust_id (dust_interact.f90:62,68)
         peel = F.make_peeled && (scattered || !F.scattering_only);
       }
     }
@@ -852,6 +903,7 @@ flight_final_kernel(const ModelDev M, Pool P, const FinalArgs F, const uint32_t 
       }
     }
     if (fin == 2) store_flight_result<ND>(slots + slot, L);
+    if (fin == 1 && F.binned) bin_escaped_packet<ND>(F, slots + slot, L.t);   // iter_final.f90:126-129
     queue_append(fin == 2, P.q_interact, P.counts + C_NI, slot);
     queue_append(fin == 1, P.q_emit, P.counts + C_NE, slot);
     if (fin) {

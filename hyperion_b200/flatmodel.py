@@ -158,6 +158,11 @@ class FlatPeeledGroup:
     peeloff_origin: tuple = (0.0, 0.0, 0.0)
     d_min: float = -np.inf
     d_max: float = np.inf
+    # a binned group (``Output/Binned/group_00001``, BinnedImageConf, ``src/images/images_binned.f90``):
+    # theta / phi unused, escaping packets are binned into n_theta x n_phi direction bins
+    binned: bool = False
+    n_theta: int = 0
+    n_phi: int = 0
 
 
 @dataclass
@@ -172,6 +177,7 @@ class FlatModel:
     specific_energy: Optional[np.ndarray] = None
     minimum_specific_energy: Optional[np.ndarray] = None
     peeled: List["FlatPeeledGroup"] = field(default_factory=list)
+    binned: Optional["FlatPeeledGroup"] = None   # image group index len(peeled) on the engine / oracle
     grid_type: str = "car"              # "car" (x, y, z walls), "sph" (r, theta, phi), "cyl" (w, z, phi), "oct"
     # octree (grid_type "oct", hyperion/grid/octree_grid.py): depth-first refinement flags, centre and
     # HALF-widths of the root cell; density is then [n_dust, n_nodes] and w1/w2/w3 are unused
@@ -297,3 +303,5 @@ def apply_model(api, ctx, model: FlatModel):
     api.set_specific_energy(ctx, model.specific_energy, model.minimum_specific_energy)
     for g in model.peeled:
         api.add_peeled_group(ctx, g)
+    if model.binned is not None:
+        api.add_peeled_group(ctx, model.binned)

@@ -347,10 +347,47 @@ def read_rtin(filename):
                       grid_type=grid_type, **(octree or {}))
     model.peeled = read_peeled_groups(f)
     if "Output" in f and "Binned" in f["Output"] and len(f["Output"]["Binned"].keys()) > 0:
+        # setup_final_iteration (src/main/setup_rt.f90:314-331)
+        names = sorted(f["Output"]["Binned"].keys())
+        if len(names) > 1:
+            raise ModelError("can't have more than one binned image group")
         if rs.forced_first_interaction:
             raise ModelError("can't use binned images with forced first interaction")
-        raise ModelError("binned images are not implemented by this engine yet")
+        g = f["Output"]["Binned"][names[0]]
+        kw = _image_conf(g)
+        kw.update(binned=True, n_theta=int(_num(_attr(g.attrs, "n_theta", required=True))),
+                  n_phi=int(_num(_attr(g.attrs, "n_phi", required=True))))
+        model.binned = FlatPeeledGroup(**kw)
     return model, rs, f
+
+
+def _image_conf(g):
+    """The part of an image group every kind shares (``image_setup``, ``src/images/image_type.f90:153-335``)."""
+    a = g.attrs
+    kw = {}
+    if "use_filters" in a and _yes(a["use_filters"]):
+        raise ModelError("filter convolution is not implemented by this engine yet")
+    if "inu_min" in a:
+        raise ModelError("the monochromatic final iteration is not implemented by this engine yet")
+    n_wav = int(_num(_attr(a, "n_wav", required=True)))
+    if n_wav < 1:
+        raise ModelError("n_nu should be >= 1")
+    kw["wavelengths"] = (n_wav, float(_num(_attr(a, "wav_min", required=True))), float(_num(_attr(a, "wav_max", required=True))))
+    kw["stokes"] = _yes(a["compute_stokes"]) if "compute_stokes" in a else True
+    if _yes(_attr(a, "compute_image", required=True)):
+        kw["image"] = (int(_num(a["n_x"])), int(_num(a["n_y"])), float(_num(a["x_min"])), float(_num(a["x_max"])),
+                       float(_num(a["y_min"])), float(_num(a["y_max"])))
+    if _yes(_attr(a, "compute_sed", required=True)):
+        kw["sed"] = (int(_num(a["n_ap"])), float(_num(a["ap_min"])), float(_num(a["ap_max"])))
+    kw["track_origin"] = _s(_attr(a, "track_origin", required=True))
+    if kw["track_origin"] not in ("no", "basic", "yes", "detailed", "scatterings"):
+        raise ModelError("unknown track_origin flag: " + kw["track_origin"])
+    kw["track_n_scat"] = int(_num(a["track_n_scat"])) if "track_n_scat" in a else 0
+    kw["uncertainties"] = _yes(_attr(a, "uncertainties", required=True))
+    kw["io_bytes"] = int(_num(_attr(a, "io_bytes", required=True)))
+    if kw["io_bytes"] not in (4, 8):
+        raise ModelError("unexpected value of io_bytes (should be 4 or 8)")
+    return kw
 
 
 def read_peeled_groups(f):
@@ -364,10 +401,6 @@ def read_peeled_groups(f):
     for name in sorted(gp.keys()):
         g = gp[name]
         a = g.attrs
-        if "use_filters" in a and _yes(a["use_filters"]):
-            raise ModelError("filter convolution is not implemented by this engine yet")
-        if "inu_min" in a:
-            raise ModelError("the monochromatic final iteration is not implemented by this engine yet")
         n_view = int(_num(_attr(a, "n_view", required=True)))
         if not n_view > 0:
             raise ModelError("n_view should be a positive integer")
@@ -381,23 +414,6 @@ def read_peeled_groups(f):
                   peeloff_origin=tuple(float(_num(_attr(a, k, required=True))) for k in ("peeloff_x", "peeloff_y", "peeloff_z")))
         if len(kw["theta"]) != n_view:
             raise ModelError("n_view does not match the length of the angles table")
-        n_wav = int(_num(_attr(a, "n_wav", required=True)))
-        if n_wav < 1:
-            raise ModelError("n_nu should be >= 1")
-        kw["wavelengths"] = (n_wav, float(_num(_attr(a, "wav_min", required=True))), float(_num(_attr(a, "wav_max", required=True))))
-        kw["stokes"] = _yes(a["compute_stokes"]) if "compute_stokes" in a else True
-        if _yes(_attr(a, "compute_image", required=True)):
-            kw["image"] = (int(_num(a["n_x"])), int(_num(a["n_y"])), float(_num(a["x_min"])), float(_num(a["x_max"])),
-                           float(_num(a["y_min"])), float(_num(a["y_max"])))
-        if _yes(_attr(a, "compute_sed", required=True)):
-            kw["sed"] = (int(_num(a["n_ap"])), float(_num(a["ap_min"])), float(_num(a["ap_max"])))
-        kw["track_origin"] = _s(_attr(a, "track_origin", required=True))
-        if kw["track_origin"] not in ("no", "basic", "yes", "detailed", "scatterings"):
-            raise ModelError("unknown track_origin flag: " + kw["track_origin"])
-        kw["track_n_scat"] = int(_num(a["track_n_scat"])) if "track_n_scat" in a else 0
-        kw["uncertainties"] = _yes(_attr(a, "uncertainties", required=True))
-        kw["io_bytes"] = int(_num(_attr(a, "io_bytes", required=True)))
-        if kw["io_bytes"] not in (4, 8):
-            raise ModelError("unexpected value of io_bytes (should be 4 or 8)")
+        kw.update(_image_conf(g))
         groups.append(FlatPeeledGroup(**kw))
     return groups

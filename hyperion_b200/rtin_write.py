@@ -64,13 +64,17 @@ def write_dust(g, d):
 def write_peeled_group(g, p):
     """``PeeledImageConf.write`` (``hyperion/conf/conf_files.py:795-1130,1293-1345``)."""
     a = g.attrs
-    a["n_view"] = np.int64(len(p.theta))
-    g.create_dataset("angles", _table([("theta", np.asarray(p.theta, dtype=np.float64)),
-                                       ("phi", np.asarray(p.phi, dtype=np.float64))]))
-    a["inside_observer"] = _yn(p.inside_observer)
-    a["ignore_optical_depth"] = _yn(p.ignore_optical_depth)
-    a["peeloff_x"], a["peeloff_y"], a["peeloff_z"] = [float(v) for v in p.peeloff_origin]
-    a["d_min"], a["d_max"] = float(p.d_min), float(p.d_max)
+    if p.binned:
+        # BinnedImageConf (hyperion/conf/conf_files.py:1242-1275)
+        a["n_theta"], a["n_phi"] = np.int64(p.n_theta), np.int64(p.n_phi)
+    else:
+        a["n_view"] = np.int64(len(p.theta))
+        g.create_dataset("angles", _table([("theta", np.asarray(p.theta, dtype=np.float64)),
+                                           ("phi", np.asarray(p.phi, dtype=np.float64))]))
+        a["inside_observer"] = _yn(p.inside_observer)
+        a["ignore_optical_depth"] = _yn(p.ignore_optical_depth)
+        a["peeloff_x"], a["peeloff_y"], a["peeloff_z"] = [float(v) for v in p.peeloff_origin]
+        a["d_min"], a["d_max"] = float(p.d_min), float(p.d_max)
     a["compute_image"] = _yn(p.image is not None)
     if p.image is not None:
         a["n_x"], a["n_y"] = np.int64(p.image[0]), np.int64(p.image[1])
@@ -232,7 +236,9 @@ def write_rtin(filename, model: FlatModel, n_initial_iter=5, n_initial_photons=1
     go.attrs["output_density_diff"] = "none"
     go.attrs["output_specific_energy"] = output_specific_energy
     go.attrs["output_n_photons"] = "none"
-    go.create_group("Binned")
+    gb = go.create_group("Binned")
+    if model.binned is not None:
+        write_peeled_group(gb.create_group("group_00001"), model.binned)
     gp = go.create_group("Peeled")
     for i, p in enumerate(model.peeled):
         write_peeled_group(gp.create_group("group_%05i" % (i + 1)), p)

@@ -149,6 +149,8 @@ def write_peeled_output(g, eng, ig, p, n_sources, n_dust):
         d.attrs["xmin"], d.attrs["xmax"] = float(p.image[2]), float(p.image[3])
         d.attrs["ymin"], d.attrs["ymax"] = float(p.image[4]), float(p.image[5])
         origin_attrs(d)
+    if p.binned:
+        return          # binned_images_write (images_binned.f90:85-89) writes the cubes only
     g.attrs["inside_observer"] = "yes" if p.inside_observer else "no"
     g.attrs["d_min"] = float(p.d_min)
     g.attrs["d_max"] = float(p.d_max)
@@ -280,6 +282,9 @@ def run(input_file, output_file, overwrite=False, device=None, log=None):
     log(" [main] starting final iteration")
     killed_final = (0, 0)
     make_peeled = len(model.peeled) > 0
+    make_binned = model.binned is not None
+    if make_binned:
+        log(" [binned_images] setting up %d binned images " % (model.binned.n_theta * model.binned.n_phi))
     if make_peeled:
         log(" [peeled_images] setting up %d peeled image groups " % len(model.peeled))
     if rs.n_last_photons > 0:
@@ -317,8 +322,12 @@ def run(input_file, output_file, overwrite=False, device=None, log=None):
     out.attrs["killed_photons_geo_raytracing"] = np.int64(killed_ray[0])
     out.attrs["killed_photons_int_raytracing"] = np.int64(killed_ray[1])
     # mp_collect_images (mpi_routines.f90:363-471)
-    if make_peeled and world > 1:
+    if (make_peeled or make_binned) and world > 1:
         all_reduce(eng.image_buffer())
+    if make_binned:
+        # main.f90:263,326: the cubes go straight into /Binned
+        write_peeled_output(out.create_group("Binned"), eng, len(model.peeled), model.binned,
+                            len(model.sources), len(model.dust))
     if make_peeled:
         gp = out.create_group("Peeled")
         for ig, p in enumerate(model.peeled):

@@ -140,6 +140,12 @@ typedef struct {
   int32_t uncertainties;
   int32_t compute_stokes;
   int32_t io_bytes;                          /* 4 or 8: precision the caller will store */
+  /* Binned images (Output/Binned/group_00001, src/images/images_binned.f90): instead of peel-offs, every
+   * packet that escapes in the final iteration is binned by its own direction into n_theta x n_phi
+   * views (cos theta in [-1, 1], phi in [0, 2 pi]).  Then n_view must be n_theta * n_phi, theta / phi
+   * are ignored, and at most one such group may exist; it needs forced_first_interaction = 0
+   * (setup_rt.f90:327-329). */
+  int32_t binned, n_theta, n_phi;
 } hyp_image_conf;
 
 /* Per-iteration counters (killed_photons_* attrs of main.f90:225-230 plus the

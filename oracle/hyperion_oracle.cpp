@@ -3352,7 +3352,7 @@ bool mrw_steps(orc_ctx &g, Photon &p, bool deposit, bool peel) {
 // propagate (iter_final.f90:147-273); MRW and source re-absorption are not restated
 void propagate_final(orc_ctx &g, Photon &p, bool peeloff_scattering_only) {
   const int64_t n_inter_max = g.conf.n_inter_max;
-  const bool make_peeled = !g.peeled.image.empty();
+  const bool make_peeled = !g.peeled.group_id.empty();
   for (int64_t interactions = 1; interactions <= n_inter_max + 1; interactions++) {
     if (interactions > 1 && g.conf.use_mrw) {
       if (!mrw_steps(g, p, false, make_peeled && !peeloff_scattering_only)) break;
@@ -3409,15 +3409,35 @@ void propagate_final(orc_ctx &g, Photon &p, bool peeloff_scattering_only) {
   }
 }
 
+// binned_images_bin_photon (images_binned.f90:57-77): an escaping packet goes into the view its own
+// direction falls in (n_theta bins of cos theta, n_phi bins of phi)
+void binned_images_bin_photon(orc_ctx &g, Image &im, const Photon &p) {
+  const int n_theta = im.c.n_theta, n_phi = im.c.n_phi;
+  double phi = std::atan2(p.a.sinp, p.a.cosp);
+  if (phi < 0.) phi = phi + TWOPI_F;
+  const int it = ipos(-1.0, +1.0, p.a.cost, n_theta);
+  const int ip = ipos(0.0, TWOPI_F, phi, n_phi);
+  const double x_image = p.r.y * p.a.cosp - p.r.x * p.a.sinp;
+  const double y_image = p.r.z * p.a.sint - p.r.y * p.a.cost * p.a.sinp - p.r.x * p.a.cost * p.a.cosp;
+  // image_bin indexes img(:, :, :, iv, :, :); the Fortran would fault on an out-of-range view, which
+  // ipos only returns for NaN directions
+  if (it < 1 || it > n_theta || ip < 1 || ip > n_phi) return;
+  image_bin(im, p, x_image, y_image, n_phi * (it - 1) + ip);
+}
+
 // do_final (iter_final.f90:60-145), photon loop only
 void final_photons(orc_ctx &g, int64_t n_photons, bool peeloff_scattering_only) {
-  const bool make_peeled = !g.peeled.image.empty();
+  const bool make_peeled = !g.peeled.group_id.empty();
   Photon p;
   for (int64_t ip = 1; ip <= n_photons; ip++) {
     emit(g, p);
     g.n_photons_run++;
     if (make_peeled && !peeloff_scattering_only) peeloff_photon(g, p, false);
     propagate_final(g, p, peeloff_scattering_only);
+    // iter_final.f90:126-129
+    if (!p.killed)
+      for (auto &im : g.peeled.image)
+        if (im.c.binned) binned_images_bin_photon(g, im, p);
   }
 }
 
@@ -4081,13 +4101,20 @@ int orc_add_peeled_group(orc_ctx *g, const hyp_image_conf *c) {
   try {
     if (c->inside_observer) return fail(g, "inside observers are not restated in the oracle");
     if (!(c->n_view > 0)) return fail(g, "n_view should be a positive integer");
+    if (c->binned) {
+      // setup_final_iteration (setup_rt.f90:318-331) + binned_images_setup (images_binned.f90:41-55)
+      for (auto &o : g->peeled.image)
+        if (o.c.binned) return fail(g, "can't have more than one binned image group");
+      if (g->conf.forced_first_interaction) return fail(g, "can't use binned images with forced first interaction");
+      if (c->n_view != c->n_theta * c->n_phi) return fail(g, "binned images: n_view should be n_theta * n_phi");
+    }
     Image im;
     image_setup(im, *c, (int)g->s.size(), g->n_dust);
     PeeledState &P = g->peeled;
     P.image.push_back(im);
     const int ig = (int)P.image.size();
     P.r_peeloff.push_back(Vec{c->peeloff_x, c->peeloff_y, c->peeloff_z});
-    for (int iv = 1; iv <= c->n_view; iv++) {
+    for (int iv = 1; iv <= (c->binned ? 0 : c->n_view); iv++) {
       P.group_id.push_back(ig);
       P.view_id.push_back(iv);
       P.viewing_angles.push_back(angle3d_deg(c->theta[iv - 1], c->phi[iv - 1]));
@@ -4145,7 +4172,10 @@ static void fill_stats(orc_ctx *g, hyp_iter_stats *st) {
 // do_final, last part (iter_final.f90:136-143)
 int orc_final_finish(orc_ctx *g, hyp_iter_stats *st) {
   if (!(g->energy_current > 0.0)) return fail(g, "no photons were emitted in this iteration");
-  for (auto &im : g->peeled.image) image_scale(im, g->energy_total / g->energy_current);
+  // peeled_images_adjust_scale / binned_images_adjust_scale (iter_final.f90:142-143, images_binned.f90:35-39)
+  for (auto &im : g->peeled.image)
+    image_scale(im, im.c.binned ? g->energy_total / g->energy_current * (double)im.c.n_theta * (double)im.c.n_phi
+                                : g->energy_total / g->energy_current);
   fill_stats(g, st);
   return 0;
 }

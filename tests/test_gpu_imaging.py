@@ -255,3 +255,53 @@ def test_peeloff_with_stellar_source_matches_oracle(golden_car):
         a = np.mean([g[2][key] for g in gpu])
         b = np.mean([o[2][key] for o in orc])
         assert abs(a / b - 1) < 0.02, (key, a, b)
+
+
+@pytest.mark.parametrize("multi", [False, True])
+def test_binned_images_match_oracle(golden_car, multi):
+    """Binned images (images_binned.f90): every packet that escapes in the final iteration is binned by
+    its own direction (2 x 3 direction bins here), with detailed origin tracking so that the source /
+    dust ids carried in the packet tag are exercised; forced first interaction must be off."""
+    from helpers import FlatPeeledGroup
+    model = bitlevel_model(golden_car, False, multi)
+    model.conf.forced_first_interaction = False
+    model.peeled = [peeloff_groups()[1]]
+    model.binned = FlatPeeledGroup(binned=True, n_theta=2, n_phi=3, wavelengths=(4, 0.05, 200.),
+                                   image=(3, 3, -pc, pc, -pc, pc), sed=(2, 0.5 * pc, 1.8 * pc), track_origin="detailed",
+                                   uncertainties=True)
+    model.specific_energy = _converged_energy(model)
+    B = 12
+    groups = model.peeled + [model.binned]
+
+    def cubes(x):
+        return _cubes(x, groups)
+
+    from hyperion_b200.capi import Engine
+    from oracle import oracle
+    gpu, orc = [], []
+    for b in range(B):
+        eng = Engine(0)
+        eng.load_model(model)
+        eng.final_begin()
+        eng.final_photons(b * 60000, 60000, False)
+        st = eng.final_finish()
+        gpu.append((cubes(eng), st.as_dict(), None))
+        eng.close()
+
+    def one(b):
+        o = oracle.Oracle(model, rank=b)
+        o.final_begin()
+        o.final_photons(60000, False)
+        st = o.final_finish()
+        return cubes(o), st.as_dict(), None
+
+    with ThreadPoolExecutor(max_workers=8) as pool:
+        orc = list(pool.map(one, range(B)))
+    report = _compare(gpu, orc)
+    print(report)
+    assert "g1_sed" in report and "g1_img" in report and report["g1_sed"][2] > 20
+    # the binned cubes hold every escaped packet exactly once
+    for key in ("n_escaped", "n_scatterings", "n_absorptions"):
+        a = np.mean([g[1][key] for g in gpu])
+        b = np.mean([o[1][key] for o in orc])
+        assert abs(a / b - 1) < 0.02, (key, a, b)

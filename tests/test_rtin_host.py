@@ -283,3 +283,44 @@ def test_rtin_roundtrip_all_source_types(golden_car, tmp_path):
     del f
     m.sources = [FlatSource(type=1, luminosity=lsun, temperature=5000.)]
     rtin_write.write_rtin(fn, m, n_initial_iter=1, n_initial_photons=100)
+
+
+def test_rtin_roundtrip_binned_group(golden_car, tmp_path):
+    """Output/Binned/group_00001 (BinnedImageConf): n_theta / n_phi instead of viewing angles."""
+    from hyperion_b200.flatmodel import FlatPeeledGroup
+    from helpers import pc
+    m = bitlevel_model(golden_car, False, False)
+    m.conf.forced_first_interaction = False
+    m.binned = FlatPeeledGroup(binned=True, n_theta=2, n_phi=3, wavelengths=(4, 0.05, 200.),
+                               image=(3, 3, -pc, pc, -pc, pc), sed=(2, 0.5 * pc, 1.8 * pc), track_origin="basic")
+    fn = str(tmp_path / "m.rtin")
+    rtin_write.write_rtin(fn, m, n_initial_iter=1, n_initial_photons=100, n_last_photons=100)
+    got, rs, _ = rtin.read_rtin(fn)
+    b = got.binned
+    assert b is not None and b.binned and (b.n_theta, b.n_phi) == (2, 3)
+    assert b.image == m.binned.image and b.sed == m.binned.sed and b.track_origin == "basic"
+    assert got.peeled == []
+    m.conf.forced_first_interaction = True
+    rtin_write.write_rtin(fn, m, n_initial_iter=1, n_initial_photons=100, n_last_photons=100)
+    with pytest.raises(rtin.ModelError, match="can't use binned images with forced first interaction"):
+        rtin.read_rtin(fn)
+
+
+@pytest.mark.gpu
+def test_runner_writes_binned_group(golden_car, tmp_path):
+    """main.f90:263,326: the binned cubes go into /Binned/{seds,images} of the .rtout
+    (ModelOutput.get_sed(group=0) reads them, hyperion/model/model_output.py:349)."""
+    from hyperion_b200.flatmodel import FlatPeeledGroup
+    from helpers import pc
+    m = bitlevel_model(golden_car, False, False)
+    m.conf.forced_first_interaction = False
+    m.binned = FlatPeeledGroup(binned=True, n_theta=2, n_phi=3, wavelengths=(4, 0.05, 200.),
+                               image=(3, 3, -pc, pc, -pc, pc), sed=(2, 0.5 * pc, 1.8 * pc), track_origin="basic")
+    fin, fout = str(tmp_path / "m.rtin"), str(tmp_path / "m.rtout")
+    rtin_write.write_rtin(fin, m, n_initial_iter=1, n_initial_photons=20000, n_last_photons=50000)
+    assert runner.main(["-f", fin, fout]) == 0
+    r = h5min.File(fout)
+    assert "date_ended" in r.attrs
+    assert r["Binned/seds"].shape == (4, 4, 6, 2, 4) and r["Binned/images"].shape == (4, 4, 6, 3, 3, 4)
+    sed = r["Binned/seds"][...]
+    assert np.all(np.isfinite(sed)) and (sed[0, 0].sum(axis=(-1, -2)) > 0).all()
