@@ -43,6 +43,7 @@ class Source(C.Structure):
         ("n_spec", C.c_int32), ("spec_nu", _dp), ("spec_fnu", _dp),
         ("box", C.c_double * 6), ("theta", C.c_double), ("phi", C.c_double),
         ("n_points", C.c_int64), ("points_xyz", _dp), ("points_lum", _dp),
+        ("n_map", C.c_int64), ("map", _dp),
     ]
 
 
@@ -176,8 +177,14 @@ class CApi:
                 raise HyperionError("point collection: positions and luminosities differ in length")
             keep_pts = (xyz, lum)
             t.n_points, t.points_xyz, t.points_lum = len(lum), _ptr(xyz), _ptr(lum)
+        keep_map = None
+        if s.map is not None:
+            keep_map = np.ascontiguousarray(s.map, dtype=np.float64).reshape(-1)
+            t.n_map, t.map = len(keep_map), _ptr(keep_map)
         keep = None
-        if s.temperature is not None:
+        if s.lte:
+            t.spectrum_type = 3
+        elif s.temperature is not None:
             t.spectrum_type, t.temperature = 2, float(s.temperature)
         else:
             nu = np.ascontiguousarray(s.spectrum_nu, dtype=np.float64)
@@ -185,7 +192,7 @@ class CApi:
             keep = (nu, fnu)
             t.spectrum_type, t.n_spec, t.spec_nu, t.spec_fnu = 1, len(nu), _ptr(nu), _ptr(fnu)
         self.check(self._fn("add_source")(ctx, C.byref(t)))
-        del keep, keep_pts
+        del keep, keep_pts, keep_map
 
     def set_run_conf(self, ctx, c: FlatConf):
         t = RunConf()

@@ -109,6 +109,7 @@ struct SourceDev {
   double dir_cost, dir_sint, dir_cosp, dir_sinp;  // plane_parallel: direction of travel (angle3d_deg(theta, phi))
   int64_t coll_off;        // point_collection: first entry in ModelDev::coll_xyz / coll_cdf
   int64_t coll_n;
+  int64_t map_off;         // map: first entry of this source's cumulative luminosity map in ModelDev::map_cdf
 };
 
 // sample_pdf_discrete_dp (type_pdf.f90:313-337): 0-based index of the first entry with cdf >= xi

@@ -67,6 +67,7 @@ struct ModelDev {
   double *alpha_inv_planck, *diff_coeff;
   const double *mrw_cdf;    // xcdf[100] | ycdf[100]
   const double *coll_xyz, *coll_cdf;  // point collections: positions [n][3] and cumulative luminosities, all sources concatenated
+  const double *map_cdf;              // map sources: cumulative luminosity per cell (n_cells entries per source)
   int32_t any_sphere;       // a spherical source exists: flights test for re-absorption (source.f90:206-227)
   int64_t n_reabs_max;
   // outputs
@@ -365,6 +366,9 @@ __device__ inline double nearest_source(const ModelDev &M, double rx, double ry,
   return nearest;
 }
 
+__device__ inline void random_position_cell(const ModelDev &M, int64_t ic, Rng &rng, double &x, double &y, double &z);
+constexpr int TAG_DUST_SHIFT = 30;  // Photon::tag bits 30-31: dust type of the last interaction, 0-based (p%dust_id - 1)
+
 // emit (src/sources/source.f90:100-179): returns false on a fatal model error
 template <int ND>
 __device__ bool emit_photon(const ModelDev &M, Photon<ND> &p, Rng &rng, double &energy_emitted, const int reemit_src = -1,
@@ -393,6 +397,7 @@ __device__ bool emit_photon(const ModelDev &M, Photon<ND> &p, Rng &rng, double &
   const SourceDev &S = M.sources[is];
   p.tag = (uint32_t)(is + 1);
   p.nx = p.ny = p.nz = 0.0;
+  int64_t map_ic = 0;
   if (S.type == HYP_SOURCE_SPHERE) {
     // emit_from_sphere (source_type.f90:604-690): random point of the surface, direction from the
     // cosine law (or the limb-darkened law) about the local normal
@@ -465,6 +470,12 @@ __device__ bool emit_photon(const ModelDev &M, Photon<ND> &p, Rng &rng, double &
     p.r0z = a_final.cost * r + S.z;
     set_dir(p, dir);
     p.nx = p.vx; p.ny = p.vy; p.nz = p.vz;
+  } else if (S.type == HYP_SOURCE_MAP) {
+    // emit_from_map (source_type.f90:713-746): cell by luminosity, uniform position in it, isotropic
+    map_ic = sample_discrete(M.map_cdf + S.map_off, M.n_cells, rng.next());
+    random_position_cell(M, map_ic, rng, p.r0x, p.r0y, p.r0z);
+    Angle a = random_sphere_angle(rng);
+    set_dir(p, a);
   } else if (S.type == HYP_SOURCE_POINT_COLLECTION) {
     // emit_from_point_collection (source_type.f90:570-598)
     const int64_t k = S.coll_off + sample_discrete(M.coll_cdf + S.coll_off, S.coll_n, rng.next());
@@ -485,6 +496,36 @@ __device__ bool emit_photon(const ModelDev &M, Photon<ND> &p, Rng &rng, double &
   p.energy = reemit_src >= 0 ? reemit_energy : 1.0;
   if (S.freq_type == HYP_SPECTRUM_BLACKBODY) {
     p.nu = sample_planck(rng, S.temperature);
+  } else if (S.freq_type == HYP_SPECTRUM_LTE) {
+    // select_dust_specific_energy_rho (grid_physics_3d.f90:101-109; draws even for one dust type), then
+    // dust_sample_j_nu at the cell's emissivity state (source_type.f90:500-505)
+    const size_t base = (size_t)map_ic * ND;
+    double w[ND], tot = 0.0;
+#pragma unroll
+    for (int k = 0; k < ND; ++k) {
+      tot += M.specific_energy[base + k] * M.cells[base + k].rho;
+      w[k] = tot;
+    }
+    const double xi = rng.next();
+    int id = ND - 1;
+#pragma unroll
+    for (int k = ND - 2; k >= 0; --k)
+      if (xi <= w[k] / tot) id = k;
+    if (xi >= 1.0) id = ND - 1;
+    const DustDev &d = M.dust[id];
+    const int jid = M.jnu_id[base + id];
+    const double frac = M.jnu_frac[base + id];
+    const double x2 = rng.next();
+    const int ne = d.L.n_enu;
+    const double *enu = d.B + d.L.o_enu;
+    const double nu1 = sample_powerlaw(enu, d.B + d.L.o_ecdf + (size_t)jid * ne, d.B + d.L.o_einvb + (size_t)jid * (ne - 1),
+                                       d.B + d.L.o_erm1 + (size_t)jid * (ne - 1), ne, x2);
+    const double nu2 = sample_powerlaw(enu, d.B + d.L.o_ecdf + (size_t)(jid + 1) * ne,
+                                       d.B + d.L.o_einvb + (size_t)(jid + 1) * (ne - 1),
+                                       d.B + d.L.o_erm1 + (size_t)(jid + 1) * (ne - 1), ne, x2);
+    const double l1 = log10(nu1);
+    p.nu = pow(10.0, l1 + frac * (log10(nu2) - l1));
+    p.tag |= (uint32_t)id << TAG_DUST_SHIFT;
   } else {
     const SpectrumDev &sp = M.spectra[S.spectrum];
     p.nu = sample_powerlaw(sp.B + sp.L.o_x, sp.B + sp.L.o_cdf, sp.B + sp.L.o_invb, sp.B + sp.L.o_rm1, sp.L.n,
@@ -1738,6 +1779,9 @@ struct hyp_ctx {
   std::vector<int64_t> coll_off;              // per source: first entry of its point collection, -1 if none
   std::vector<double> coll_xyz, coll_cdf;     // point collections of all sources
   double *d_coll_xyz = nullptr, *d_coll_cdf = nullptr;
+  std::vector<int64_t> map_off;               // per source: first entry of its cumulative luminosity map, -1 if none
+  std::vector<double> map_cdf;                // released after the upload
+  double *d_map_cdf = nullptr;
   uint32_t pool_cap = 0;
   uint32_t *h_counts = nullptr;  // pinned: [C_COUNT] counters + next_photon (2 words)
   // emission-order sort (direction keys)
@@ -2016,6 +2060,7 @@ void hyp_ctx_destroy(hyp_ctx *c) {
   free_dev(c->d_sources);
   free_dev(c->d_coll_xyz);
   free_dev(c->d_coll_cdf);
+  free_dev(c->d_map_cdf);
   free_dev(c->d_spectra);
   free_dev(c->d_work);
   free_dev(c->d_error);
@@ -2368,8 +2413,25 @@ int hyp_add_source(hyp_ctx *c, const hyp_source *s) {
   if (c->finalized) return fail(HYP_ERR_STATE, "model is frozen");
   if ((int)c->sources.size() >= MAX_SOURCES) return fail(HYP_ERR_INVALID, "too many sources");
   if (s->type != HYP_SOURCE_POINT && s->type != HYP_SOURCE_SPHERE && s->type != HYP_SOURCE_EXTERN_SPH &&
-      s->type != HYP_SOURCE_EXTERN_BOX && s->type != HYP_SOURCE_PLANE_PARALLEL && s->type != HYP_SOURCE_POINT_COLLECTION)
-    return fail(HYP_ERR_INVALID, "spotted spheres and luminosity-map sources are not implemented on the device");
+      s->type != HYP_SOURCE_EXTERN_BOX && s->type != HYP_SOURCE_PLANE_PARALLEL && s->type != HYP_SOURCE_POINT_COLLECTION &&
+      s->type != HYP_SOURCE_MAP)
+    return fail(HYP_ERR_INVALID, "spotted spherical sources are not implemented on the device");
+  if (s->type == HYP_SOURCE_MAP) {
+    // grid_load_pdf_map (grid_geometry_common_3d.f90:47-63)
+    if (c->n_cells == 0) return fail(HYP_ERR_STATE, "set the grid before a map source");
+    if (!s->map || s->n_map != c->n_cells) return fail(HYP_ERR_INVALID, "luminosity map should have one entry per cell");
+    double norm = 0.0;
+    for (int64_t i = 0; i < s->n_map; ++i) {
+      if (!(s->map[i] >= 0.0)) return fail(HYP_ERR_INVALID, "luminosity map should be positive");
+      norm = norm + s->map[i];
+    }
+    if (!(norm > 0.0)) return fail(HYP_ERR_INVALID, "[normalize_pdf_discrete] all PDF elements are zero");
+  }
+  if (s->spectrum_type == HYP_SPECTRUM_LTE && s->type != HYP_SOURCE_MAP) {
+    static const char *who[] = {"", "Point source", "Spherical source", "Spot", "", "External spherical source",
+                                "External box source", "Plane parallel", "Point source collection"};
+    return fail(HYP_ERR_INVALID, std::string(who[s->type]) + " cannot have LTE spectrum");
+  }
   if ((s->type == HYP_SOURCE_SPHERE || s->type == HYP_SOURCE_EXTERN_SPH || s->type == HYP_SOURCE_PLANE_PARALLEL) && !(s->radius > 0.0))
     return fail(HYP_ERR_INVALID, "source radius should be positive");
   if (s->type == HYP_SOURCE_PLANE_PARALLEL && s->peeloff) return fail(HYP_ERR_INVALID, "Cannot peeloff plane parallel source");
@@ -2395,12 +2457,27 @@ int hyp_add_source(hyp_ctx *c, const hyp_source *s) {
     } catch (std::exception &e) {
       return fail(HYP_ERR_INVALID, e.what());
     }
-  } else if (s->spectrum_type != HYP_SPECTRUM_BLACKBODY) {
+  } else if (s->spectrum_type != HYP_SPECTRUM_BLACKBODY && s->spectrum_type != HYP_SPECTRUM_LTE) {
     return fail(HYP_ERR_INVALID, "unknown spectrum specifier");
   }
   hyp_source copy = *s;
   copy.spec_nu = copy.spec_fnu = nullptr;
   copy.points_xyz = copy.points_lum = nullptr;
+  copy.map = nullptr;
+  if (s->type == HYP_SOURCE_MAP) {
+    // set_pdf_discrete (type_pdf.f90:222-231) on the map
+    std::vector<double> cdf(s->map, s->map + s->n_map);
+    double norm = 0.0;
+    for (double v : cdf) norm = norm + v;
+    for (double &v : cdf) v = v / norm;
+    for (int64_t i = 1; i < s->n_map; ++i) cdf[i] = cdf[i - 1] + cdf[i];
+    const double last = cdf[s->n_map - 1];
+    for (double &v : cdf) v = v / last;
+    c->map_off.push_back((int64_t)c->map_cdf.size());
+    c->map_cdf.insert(c->map_cdf.end(), cdf.begin(), cdf.end());
+  } else {
+    c->map_off.push_back(-1);
+  }
   if (s->type == HYP_SOURCE_POINT_COLLECTION) {
     // set_pdf_discrete (type_pdf.f90:222-231): normalise, accumulate, normalise the cdf
     std::vector<double> cdf(s->points_lum, s->points_lum + s->n_points);
@@ -2725,6 +2802,7 @@ int hyp_finalize_setup(hyp_ctx *c) {
       sd[i].dir_cosp = cos(s.phi * deg2rad);
       sd[i].dir_sinp = sin(s.phi * deg2rad);
     }
+    sd[i].map_off = c->map_off[i];
     sd[i].coll_off = c->coll_off[i];
     sd[i].coll_n = s.type == HYP_SOURCE_POINT_COLLECTION ? s.n_points : 0;
     sd[i].pdf = s.luminosity / ltot;
@@ -2740,6 +2818,12 @@ int hyp_finalize_setup(hyp_ctx *c) {
   }
   M.coll_xyz = c->d_coll_xyz;
   M.coll_cdf = c->d_coll_cdf;
+  if (!c->map_cdf.empty()) {
+    CUDA_TRY(cudaMalloc(&c->d_map_cdf, c->map_cdf.size() * sizeof(double)));
+    CUDA_TRY(cudaMemcpy(c->d_map_cdf, c->map_cdf.data(), c->map_cdf.size() * sizeof(double), cudaMemcpyHostToDevice));
+    std::vector<double>().swap(c->map_cdf);
+  }
+  M.map_cdf = c->d_map_cdf;
   CUDA_TRY(cudaMalloc(&c->d_sources, sd.size() * sizeof(SourceDev)));
   CUDA_TRY(cudaMemcpy(c->d_sources, sd.data(), sd.size() * sizeof(SourceDev), cudaMemcpyHostToDevice));
   M.sources = c->d_sources;
@@ -3240,6 +3324,8 @@ int ensure_ray_tables(hyp_ctx *c) {
       if (sp >= 0) {
         const HostSpectrum &S = c->spectra[sp];
         binned_fraction(S.nu.data(), S.fnu.data(), (int)S.nu.size(), l0, l1, n_nu, &spec[(size_t)is * n_nu]);
+      } else if (c->sources[is].spectrum_type == HYP_SPECTRUM_LTE) {
+        // emiss_type 3: peeled with the dust emissivity of the emitting cell (images_peeled.f90:223-224)
       } else {
         blackbody_table(c->sources[is].temperature, bnu, bfnu);
         binned_fraction(bnu.data(), bfnu.data(), (int)bnu.size(), l0, l1, n_nu, &spec[(size_t)is * n_nu]);

@@ -578,7 +578,6 @@ struct FinalArgs {
 };
 
 constexpr uint32_t TAG_NSCAT_MASK = 0x3fffu;   // n_scat saturates at 16383
-constexpr int TAG_DUST_SHIFT = 30;             // dust type of the last interaction, 0-based (p%dust_id - 1)
 
 // binned_images_bin_photon (images_binned.f90:57-77) + image_bin (image_type.f90:408-524) for a packet
 // that has just left the grid at path length t along its flight.
@@ -958,6 +957,14 @@ __global__ void raytrace_emit_kernel(const ModelDev M, PeelJob<ND> *__restrict__
       p.energy = p.energy * source_weight;  // energy_total / n_photons_sources (iter_raytracing.f90:79)
       fill_job<ND>(&J, p, surface_kind(p), p.nx, p.ny, p.nz, 0.0, 0.0, 0.0, 0);
       J.emiss_type = M.sources[(p.tag & TAG_SRC_MASK) - 1].freq_type;
+      if (ok && J.emiss_type == HYP_SPECTRUM_LTE) {
+        // LTE map source: the spectrum is the emissivity of the dust type emit_photon picked in the cell
+        const int id = (int)(p.tag >> TAG_DUST_SHIFT);
+        const size_t k = (size_t)p.ic * ND + id;
+        J.dust_id = id + 1;
+        J.emiss_var_id = M.jnu_id[k];
+        J.emiss_var_frac = M.jnu_frac[k];
+      }
       if (J.kind == 0 && M.sources[J.source_id - 1].type == HYP_SOURCE_POINT) J.point_src = J.source_id;
     } else {
       // emit_from_grid (grid_physics_3d.f90:691-753)

@@ -102,7 +102,7 @@ class FlatDust:
 @dataclass
 class FlatSource:
     """One source (``src/sources/source_type.f90:102-282``)."""
-    type: int = 1              # the reference's numbering: 1 point, 2 sphere, 5 extern_sph, 6 extern_box,
+    type: int = 1              # the reference's numbering: 1 point, 2 sphere, 4 map, 5 extern_sph, 6 extern_box,
                                # 7 plane_parallel, 8 point_collection
     luminosity: float = 0.0
     position: tuple = (0.0, 0.0, 0.0)
@@ -116,6 +116,8 @@ class FlatSource:
     direction: tuple = (0.0, 0.0)                    # plane_parallel: (theta, phi) in degrees
     points: Optional[np.ndarray] = None              # point_collection: [n, 3] positions
     points_luminosity: Optional[np.ndarray] = None   # point_collection: [n]
+    map: Optional[np.ndarray] = None                 # map (type 4): luminosity per cell, shaped like one density array
+    lte: bool = False                                # map only: spectrum = emissivity of the dust in the emitting cell
 
 
 @dataclass

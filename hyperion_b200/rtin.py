@@ -278,10 +278,8 @@ def read_rtin(filename):
             a = g.attrs
             stype = _s(a["type"])
             # source_read (src/sources/source_type.f90:102-282); type numbers are the reference's
-            types = {"point": 1, "sphere": 2, "extern_sph": 5, "extern_box": 6, "plane_parallel": 7,
+            types = {"point": 1, "sphere": 2, "map": 4, "extern_sph": 5, "extern_box": 6, "plane_parallel": 7,
                      "point_collection": 8}
-            if stype == "map":
-                raise ModelError("source type 'map' is not implemented by this engine yet")
             if stype not in types:
                 raise ModelError("unknown type in source list: " + stype)
             if stype == "sphere" and any(isinstance(g[k], type(g)) for k in g.keys()):
@@ -297,6 +295,14 @@ def read_rtin(filename):
                 kw["luminosity"] = float(lum.sum())
             else:
                 kw["luminosity"] = float(_num(a["luminosity"]))
+            if stype == "map":
+                # grid_load_pdf_map -> read_grid_3d (src/grid/grid_geometry_common_3d.f90:47-63)
+                if amr_levels is not None:
+                    raise ModelError("map sources on AMR grids are not implemented by this engine yet")
+                lm = np.asarray(g["Luminosity map"][...], dtype=np.float64)
+                if lm.shape != grid_shape:
+                    raise ModelError("Luminosity map has wrong shape")
+                kw["map"] = lm
             if stype in ("point", "sphere", "extern_sph", "plane_parallel"):
                 kw["position"] = (float(_num(a["x"])), float(_num(a["y"])), float(_num(a["z"])))
             if stype in ("sphere", "extern_sph", "plane_parallel"):
@@ -315,6 +321,8 @@ def read_rtin(filename):
                 if np.any(np.diff(nu) < 0):
                     raise ModelError("spectrum frequency should be monotonically increasing")
                 kw["spectrum_nu"], kw["spectrum_fnu"] = nu, fnu
+            elif spec == "lte" and stype == "map":
+                kw["lte"] = True
             elif spec == "lte":
                 raise ModelError({"point": "Point source", "sphere": "Spherical source",
                                   "extern_sph": "External spherical source", "extern_box": "External box source",

@@ -204,7 +204,7 @@ def write_rtin(filename, model: FlatModel, n_initial_iter=5, n_initial_photons=1
     for i, s in enumerate(model.sources):
         g = gs.create_group("source_%05i" % (i + 1))
         # hyperion/sources/source.py: write() of each source class
-        stype = {1: "point", 2: "sphere", 5: "extern_sph", 6: "extern_box", 7: "plane_parallel",
+        stype = {1: "point", 2: "sphere", 4: "map", 5: "extern_sph", 6: "extern_box", 7: "plane_parallel",
                  8: "point_collection"}[s.type]
         g.attrs["type"] = stype
         g.attrs["peeloff"] = _yn(s.peeloff)
@@ -213,6 +213,8 @@ def write_rtin(filename, model: FlatModel, n_initial_iter=5, n_initial_photons=1
             g.create_dataset("luminosity", np.ascontiguousarray(s.points_luminosity, dtype=np.float64))
         else:
             g.attrs["luminosity"] = float(s.luminosity)
+        if stype == "map":
+            g.create_dataset("Luminosity map", np.ascontiguousarray(s.map, dtype=np.float64))
         if stype in ("point", "sphere", "extern_sph", "plane_parallel"):
             g.attrs["x"], g.attrs["y"], g.attrs["z"] = [float(v) for v in s.position]
         if stype in ("sphere", "extern_sph", "plane_parallel"):
@@ -224,7 +226,9 @@ def write_rtin(filename, model: FlatModel, n_initial_iter=5, n_initial_photons=1
                 g.attrs[k] = float(v)
         if stype == "plane_parallel":
             g.attrs["theta"], g.attrs["phi"] = float(s.direction[0]), float(s.direction[1])
-        if s.temperature is not None:
+        if s.lte:
+            g.attrs["spectrum"] = "lte"
+        elif s.temperature is not None:
             g.attrs["spectrum"] = "temperature"
             g.attrs["temperature"] = float(s.temperature)
         else:

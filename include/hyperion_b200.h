@@ -66,13 +66,15 @@ typedef struct {
 /* One source (source_read, src/sources/source_type.f90:102-282). */
 #define HYP_SOURCE_POINT 1
 #define HYP_SOURCE_SPHERE 2
-/* 3 (sphere with spots) and 4 (luminosity map) are not implemented: rejected by hyp_add_source */
+/* 3 (sphere with spots) is not implemented: rejected by hyp_add_source */
+#define HYP_SOURCE_MAP 4               /* emit_from_map, source_type.f90:713-746 */
 #define HYP_SOURCE_EXTERN_SPH 5        /* emit_from_extern_sph, source_type.f90:748-820 */
 #define HYP_SOURCE_EXTERN_BOX 6        /* emit_from_extern_box, source_type.f90:822-933 */
 #define HYP_SOURCE_PLANE_PARALLEL 7    /* emit_from_plane_parallel, source_type.f90:935-980 */
 #define HYP_SOURCE_POINT_COLLECTION 8  /* emit_from_point_collection, source_type.f90:570-598 */
 #define HYP_SPECTRUM_TABLE 1
 #define HYP_SPECTRUM_BLACKBODY 2
+#define HYP_SPECTRUM_LTE 3             /* map sources only: emissivity of the dust in the emitting cell */
 typedef struct {
   int32_t type;            /* HYP_SOURCE_* (the reference's numbering, source_read) */
   int32_t peeloff;
@@ -89,6 +91,8 @@ typedef struct {
   int64_t n_points;        /* point collection */
   const double *points_xyz;  /* [n_points][3] */
   const double *points_lum;  /* [n_points] */
+  int64_t n_map;           /* map: number of cells */
+  const double *map;       /* map: luminosity per cell, in cell-id order (the 'Luminosity map' dataset) */
 } hyp_source;
 
 /* Run configuration: the root attributes of the .rtin file

@@ -757,6 +757,7 @@ struct Source {
   Angle direction{1.0, 0.0, 1.0, 0.0};                                 // plane_parallel
   std::vector<Vec> position_collection;                                // point_collection
   PdfDiscrete collection_pdf;
+  PdfDiscrete luminosity_map;                                          // map: one entry per cell
 };
 
 // ---------------------------------------------------------------------------
@@ -2488,6 +2489,54 @@ void emit_from_plane_parallel(orc_ctx &g, const Source &src, Photon &p) {
   p.last_isotropic = false;
 }
 
+// new_grid_cell(ic, geo) + random_position_cell of the geometry module for the 1-based cell id `ic`
+void place_at_random_position_in_cell(orc_ctx &g, Photon &p, int ic) {
+  if (g.grid_type == 3) {
+    p.icell = Cell{0, 0, 0, ic};
+    p.r = oct_random_position_cell(g, p.icell);
+  } else if (g.grid_type == 4) {
+    p.icell = amr_cell_1d(g, ic);
+    p.r = amr_random_position_cell(g, p.icell);
+  } else {
+    int i3 = (ic - 1) / (g.n1 * g.n2) + 1;
+    int i2 = (ic - 1 - (i3 - 1) * g.n1 * g.n2) / g.n1 + 1;
+    int i1 = ic - (i3 - 1) * g.n1 * g.n2 - (i2 - 1) * g.n1;
+    p.icell = new_grid_cell(g, i1, i2, i3);
+    if (g.grid_type == 1) {
+      p.r = sph_random_position_cell(g, p.icell);
+    } else if (g.grid_type == 2) {
+      p.r = cyl_random_position_cell(g, p.icell);
+    } else {
+      // grid_geometry_cartesian_3d.f90:383-394
+      double x = g.rng.random(), y = g.rng.random(), z = g.rng.random();
+      p.r.x = x * (g.w1[i1] - g.w1[i1 - 1]) + g.w1[i1 - 1];
+      p.r.y = y * (g.w2[i2] - g.w2[i2 - 1]) + g.w2[i2 - 1];
+      p.r.z = z * (g.w3[i3] - g.w3[i3 - 1]) + g.w3[i3 - 1];
+    }
+  }
+}
+
+// emit_from_map (source_type.f90:713-746): cell from the luminosity map (grid_sample_pdf_map,
+// grid_geometry_common_3d.f90:65-71), uniform position inside it, isotropic direction
+void emit_from_map(orc_ctx &g, const Source &src, Photon &p) {
+  const int ic = src.luminosity_map.sample(g.rng);
+  p.in_cell = true;
+  place_at_random_position_in_cell(g, p, ic);
+  p.a = random_sphere_angle3d(g.rng);
+  p.s = Stokes{1.0, 0.0, 0.0, 0.0};
+  p.last_isotropic = true;
+}
+
+// select_dust_specific_energy_rho (grid_physics_3d.f90:101-109): always draws, even for one dust type
+int select_dust_specific_energy_rho(orc_ctx &g, const Cell &c) {
+  for (int id = 0; id < g.n_dust; id++) {
+    size_t k = (size_t)id * g.n_cells + c.ic - 1;
+    g.absorption.pdf[id] = g.specific_energy[k] * g.density[k];
+  }
+  g.absorption.find_cdf();
+  return g.absorption.sample(g.rng);
+}
+
 // emit (source.f90:100-179) + source_emit (source_type.f90:398-511)
 void emit(orc_ctx &g, Photon &p, bool reemit = false, int reemit_id = 0, double reemit_energy = 0.0) {
   p = Photon();
@@ -2524,16 +2573,27 @@ void emit(orc_ctx &g, Photon &p, bool reemit = false, int reemit_id = 0, double 
     case HYP_SOURCE_POINT_COLLECTION:
       emit_from_point_collection(g, src, p);
       break;
+    case HYP_SOURCE_MAP:
+      emit_from_map(g, src, p);
+      break;
     default:
       throw OracleError{"source type not restated in the oracle"};
   }
   p.energy = 1.0;
-  if (src.freq_type == 1)
+  if (src.freq_type == 1) {
     p.nu = src.spectrum.sample(g.rng);
-  else if (src.freq_type == 2)
+  } else if (src.freq_type == 2) {
     p.nu = g.rng.random_planck_frequency(src.temperature);
-  else
+  } else if (src.freq_type == 3) {
+    // LTE spectrum of the dust in the cell (source_type.f90:500-505)
+    p.dust_id = select_dust_specific_energy_rho(g, p.icell);
+    size_t k = (size_t)(p.dust_id - 1) * g.n_cells + p.icell.ic - 1;
+    p.emiss_var_id = g.jnu_var_id[k];
+    p.emiss_var_frac = g.jnu_var_frac[k];
+    p.nu = g.d[p.dust_id - 1].sample_j_nu(g.rng, p.emiss_var_id, p.emiss_var_frac);
+  } else {
     throw OracleError{"unknown spectrum type"};
+  }
   p.v = angle3d_to_vector3d(p.a);
   if (reemit) {
     p.energy = reemit_energy;
@@ -3455,29 +3515,7 @@ Photon emit_from_grid(orc_ctx &g) {
   else
     ic = std::max((int)std::ceil(xi * g.n_cells), 1);
   p.in_cell = true;
-  if (g.grid_type == 3) {
-    p.icell = Cell{0, 0, 0, ic};
-    p.r = oct_random_position_cell(g, p.icell);
-  } else if (g.grid_type == 4) {
-    p.icell = amr_cell_1d(g, ic);
-    p.r = amr_random_position_cell(g, p.icell);
-  } else {
-    int i3 = (ic - 1) / (g.n1 * g.n2) + 1;
-    int i2 = (ic - 1 - (i3 - 1) * g.n1 * g.n2) / g.n1 + 1;
-    int i1 = ic - (i3 - 1) * g.n1 * g.n2 - (i2 - 1) * g.n1;
-    p.icell = new_grid_cell(g, i1, i2, i3);
-    // random_position_cell of the geometry
-    if (g.grid_type == 1) {
-      p.r = sph_random_position_cell(g, p.icell);
-    } else if (g.grid_type == 2) {
-      p.r = cyl_random_position_cell(g, p.icell);
-    } else {
-      double x = g.rng.random(), y = g.rng.random(), z = g.rng.random();
-      p.r.x = x * (g.w1[i1] - g.w1[i1 - 1]) + g.w1[i1 - 1];
-      p.r.y = y * (g.w2[i2] - g.w2[i2 - 1]) + g.w2[i2 - 1];
-      p.r.z = z * (g.w3[i3] - g.w3[i3 - 1]) + g.w3[i3 - 1];
-    }
-  }
+  place_at_random_position_in_cell(g, p, ic);
   p.a = random_sphere_angle3d(g.rng);
   p.v = angle3d_to_vector3d(p.a);
   p.s = Stokes{1.0, 0.0, 0.0, 0.0};
@@ -3911,6 +3949,8 @@ int orc_add_source(orc_ctx *g, const hyp_source *s) {
     src.limb_darkening = s->limb_darkening != 0;
     src.freq_type = s->spectrum_type;
     src.temperature = s->temperature;
+    if (s->spectrum_type == HYP_SPECTRUM_LTE && s->type != HYP_SOURCE_MAP)
+      return fail(g, "only map sources can have an LTE spectrum");
     if (s->spectrum_type == HYP_SPECTRUM_TABLE) {
       for (int i = 0; i + 1 < s->n_spec; i++)
         if (s->spec_nu[i + 1] < s->spec_nu[i])
@@ -3933,6 +3973,10 @@ int orc_add_source(orc_ctx *g, const hyp_source *s) {
       src.luminosity = 0.0;
       for (int64_t i = 0; i < s->n_points; i++) src.luminosity += s->points_lum[i];  // sum() (source_type.f90:268)
       src.collection_pdf.set(s->points_lum, (int)s->n_points);
+    } else if (s->type == HYP_SOURCE_MAP) {
+      // grid_load_pdf_map (grid_geometry_common_3d.f90:47-63)
+      if (!s->map || s->n_map != g->n_cells) return fail(g, "luminosity map should have one entry per cell");
+      src.luminosity_map.set(s->map, (int)s->n_map);
     } else if (s->type != HYP_SOURCE_POINT && s->type != HYP_SOURCE_SPHERE && s->type != HYP_SOURCE_EXTERN_SPH) {
       return fail(g, "source type not restated in the oracle");
     }

@@ -23,7 +23,17 @@ def mixed_sources():
                        bounds=(-0.9 * pc, 0.8 * pc, -0.7 * pc, 0.95 * pc, -0.6 * pc, 0.9 * pc)),
             FlatSource(type=7, luminosity=1.5 * lsun, temperature=7000., position=(-0.3 * pc, 0.2 * pc, -0.8 * pc),
                        radius=0.3 * pc, direction=(25.0, 40.0), peeloff=False),
-            FlatSource(type=8, temperature=3000., points=pts, points_luminosity=np.array([1.0, 3.0, 2.0, 0.5]) * lsun)]
+            FlatSource(type=8, temperature=3000., points=pts, points_luminosity=np.array([1.0, 3.0, 2.0, 0.5]) * lsun),
+            FlatSource(type=4, luminosity=2.5 * lsun, temperature=5500., map=_luminosity_map()),
+            FlatSource(type=4, luminosity=1.5 * lsun, lte=True, map=_luminosity_map()[::-1].copy())]
+
+
+def _luminosity_map():
+    """A lumpy map on the 7 x 5 x 3 cells of the reference's bit-level grid ([z, y, x]), with dark cells."""
+    rng = np.random.default_rng(11)
+    m = rng.random((3, 5, 7)) ** 3
+    m[1, 2, :3] = 0.0
+    return m
 
 
 @pytest.mark.parametrize("evenly,multi", [(False, False), (True, True)])
@@ -46,7 +56,7 @@ def test_deposits_match_oracle_mixed_sources(golden_car, evenly, multi):
     assert all(s["killed_geo"] == 0 and s["killed_int"] == 0 and s["n_photons"] == N for s in gst)
 
 
-@pytest.mark.parametrize("kind", [5, 6, 7, 8])
+@pytest.mark.parametrize("kind", [4, 5, 6, 7, 8])
 def test_each_source_type_alone(golden_car, kind):
     """One source of each new type on its own, so that a wrong emitter cannot hide behind the others."""
     model = bitlevel_model(golden_car, False, False)
@@ -87,7 +97,10 @@ def test_source_argument_errors():
     model = syn.cartesian_point_source_model(n=8, dust=syn.grey_dust())
     for bad, msg in [(FlatSource(type=7, luminosity=lsun, temperature=5000., radius=0.1 * pc, peeloff=True),
                       "Cannot peeloff plane parallel source"),
-                     (FlatSource(type=4, luminosity=lsun, temperature=5000.), "not implemented"),
+                     (FlatSource(type=4, luminosity=lsun, temperature=5000.), "luminosity map should have one entry per cell"),
+                     (FlatSource(type=4, luminosity=lsun, temperature=5000., map=np.zeros((8, 8, 8))), "all PDF elements are zero"),
+                     (FlatSource(type=3, luminosity=lsun, temperature=5000., radius=pc), "spotted spherical sources are not implemented"),
+                     (FlatSource(type=1, luminosity=lsun, lte=True), "Point source cannot have LTE spectrum"),
                      (FlatSource(type=6, luminosity=lsun, temperature=5000., bounds=(1., -1., 0., 1., 0., 1.)),
                       "bounds should be increasing"),
                      (FlatSource(type=8, temperature=5000., points=np.zeros((2, 3)), points_luminosity=np.zeros(2)),

@@ -143,3 +143,49 @@ def test_mixed_sources_share_the_luminosity_pdf():
         assert st["n_photons"] == 40000
         # energy_current sums the weights: N exactly when sampling by luminosity, N on average when even
         assert abs(o.energy_current / 40000 - 1.0) < (1e-12 if not evenly else 0.02)
+
+
+def test_map_source_far_field():
+    """emit_from_map: cells drawn by luminosity, uniform position inside the cell.  Two lit cells
+    with weights 1 : 3 look like two point sources from afar: sum_i p_i / (4 pi d_i^2)."""
+    n = 16
+    lum = np.zeros((n, n, n))
+    lum[3, 4, 5] = 1.0        # [z, y, x]
+    lum[12, 10, 9] = 3.0
+    src = FlatSource(type=4, luminosity=lsun, temperature=4000., map=lum)
+    model, dust = _thin_model([src], n=n)
+    t = _track_density(model, dust, 600000)
+    x = 0.5 * (model.w1[1:] + model.w1[:-1])
+    zz, yy, xx = np.meshgrid(x, x, x, indexing="ij")
+    expect = np.zeros_like(t)
+    dmin = np.full(t.shape, np.inf)
+    for (iz, iy, ix), w in (((3, 4, 5), 0.25), ((12, 10, 9), 0.75)):
+        d2 = (xx - x[ix]) ** 2 + (yy - x[iy]) ** 2 + (zz - x[iz]) ** 2
+        expect += w / (4.0 * np.pi * d2)
+        dmin = np.minimum(dmin, np.sqrt(d2))
+    far = dmin > 5.0 * (model.w1[1] - model.w1[0])
+    assert far.sum() > 500
+    rel = t[far] / expect[far] - 1.0
+    assert abs(rel.mean()) < 0.01, rel.mean()
+    assert rel.std() < 0.12, rel.std()
+
+
+def test_map_source_uniform_cube_conserves_track_length():
+    """A uniform map over a cube: the mean track length of a packet is the mean chord seen from a
+    uniform interior point, i.e. total track length / N = (1 / V) int int ds dV -- checked against a
+    direct numerical average of the distance to the boundary over positions and directions."""
+    n = 8
+    src = FlatSource(type=4, luminosity=lsun, temperature=4000., map=np.ones((n, n, n)))
+    model, dust = _thin_model([src], n=n)
+    t = _track_density(model, dust, 200000)
+    vol = (model.w1[1] - model.w1[0]) ** 3
+    mean_track = t.sum() * vol
+    rng = np.random.default_rng(3)
+    m = 400000
+    p = rng.uniform(-pc, pc, (m, 3))
+    mu = rng.uniform(-1, 1, m)
+    ph = rng.uniform(0, 2 * np.pi, m)
+    v = np.stack([np.sqrt(1 - mu ** 2) * np.cos(ph), np.sqrt(1 - mu ** 2) * np.sin(ph), mu], axis=1)
+    with np.errstate(divide="ignore"):
+        d = np.min(np.where(v > 0, (pc - p) / v, (-pc - p) / v), axis=1)
+    assert abs(mean_track / d.mean() - 1.0) < 0.01

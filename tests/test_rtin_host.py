@@ -267,12 +267,14 @@ def test_rtin_roundtrip_all_source_types(golden_car, tmp_path):
                  FlatSource(type=6, luminosity=3.0 * lsun, temperature=4000., bounds=(-0.9 * pc, 0.8 * pc, -0.7 * pc, 0.95 * pc, -0.6 * pc, 0.9 * pc)),
                  FlatSource(type=7, luminosity=1.5 * lsun, temperature=7000., position=(0., 0.2 * pc, -0.9 * pc), radius=0.3 * pc,
                             direction=(25.0, 40.0), peeloff=False),
-                 FlatSource(type=8, temperature=3000., points=pts, points_luminosity=np.array([1.0, 3.0]) * lsun)]
+                 FlatSource(type=8, temperature=3000., points=pts, points_luminosity=np.array([1.0, 3.0]) * lsun),
+                 FlatSource(type=4, luminosity=lsun, lte=True, map=np.arange(105.).reshape(3, 5, 7))]
     fn = str(tmp_path / "m.rtin")
     rtin_write.write_rtin(fn, m, n_initial_iter=1, n_initial_photons=100)
     got, rs, _ = rtin.read_rtin(fn)
-    assert [s.type for s in got.sources] == [5, 6, 7, 8]
-    a, b, c, d = got.sources
+    assert [s.type for s in got.sources] == [5, 6, 7, 8, 4]
+    a, b, c, d, e = got.sources
+    assert e.lte and e.temperature is None and np.array_equal(e.map, np.arange(105.).reshape(3, 5, 7))
     assert a.radius == 0.9 * pc and tuple(a.position) == (0.1 * pc, 0., 0.) and a.peeloff
     assert tuple(b.bounds) == tuple(m.sources[1].bounds) and b.luminosity == 3.0 * lsun
     assert tuple(c.direction) == (25.0, 40.0) and c.radius == 0.3 * pc and not c.peeloff
