@@ -284,6 +284,8 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: the engine has no CPU fallback")
     torch.cuda.set_device(local)
     if world > 1:
+        # NCCL's own log lines (version banner, NCCL_DEBUG=INFO) go to stderr: stdout carries the JSON line only
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     if rank == 0:
         ge.build()

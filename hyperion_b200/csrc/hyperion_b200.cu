@@ -3256,6 +3256,7 @@ int ensure_images(hyp_ctx *c) {
     d.compute_image = k.compute_image; d.compute_sed = k.compute_sed;
     d.track_origin = k.track_origin; d.track_n_scat = k.track_n_scat;
     d.uncertainties = k.uncertainties; d.ignore_optical_depth = k.ignore_optical_depth;
+    d.inside_observer = k.inside_observer;
     d.n_sources = ns; d.n_dust = nd;
     d.x_min = k.x_min; d.x_max = k.x_max; d.y_min = k.y_min; d.y_max = k.y_max;
     d.ap_min = k.ap_min; d.ap_max = k.ap_max;
@@ -3648,7 +3649,6 @@ extern "C" {
 int hyp_add_peeled_group(hyp_ctx *c, const hyp_image_conf *g) {
   if (!c || !g) return fail(HYP_ERR_INVALID, "NULL argument");
   if (c->images_ready) return fail(HYP_ERR_STATE, "image groups are frozen once an imaging iteration has started");
-  if (g->inside_observer) return fail(HYP_ERR_INVALID, "inside observers are not implemented on the device yet");
   if (g->binned) {
     // setup_final_iteration (setup_rt.f90:318-331), binned_images_setup (images_binned.f90:41-55)
     for (auto &o : c->groups)

@@ -24,6 +24,7 @@ struct ImageDev {
   int32_t n_view, n_nu, n_x, n_y, n_ap, n_orig, n_stokes;
   int32_t compute_image, compute_sed, track_origin, track_n_scat, uncertainties, ignore_optical_depth;
   int32_t n_sources, n_dust;
+  int32_t inside_observer, pad0;  // the observer sits at (rpx, rpy, rpz) inside the grid (images_peeled.f90:95-270)
   double x_min, x_max, y_min, y_max, ap_min, ap_max;
   double log10_ap_min, log10_ap_max, log10_nu_min, log10_nu_max;
   double d_min, d_max;
@@ -172,7 +173,9 @@ template <int ND, bool COLUMN, int D>
 __device__ __forceinline__ bool escape_march(Lane<ND> &L, const double *__restrict__ W,
                                              const double *__restrict__ rho, const int n1, const int n2,
                                              const int n3, double &tau, double (&col)[ND], uint32_t &n_cross,
-                                             const int max_groups = 0x7fffffff) {
+                                             const int max_groups = 0x7fffffff,
+                                             const double tmax = 1.7976931348623157e308) {
+  // tmax: the march ends after that path length (inside observers: grid_propagate_3d.f90:440-443)
   const int o2 = n1 + 1, o3 = n1 + n2 + 2;
   bool dead = lane_outside(L.ix, L.iy, L.iz, n1, n2, n3);
   for (int g = 0; g < max_groups && !dead; ++g) {
@@ -193,9 +196,11 @@ __device__ __forceinline__ bool escape_march(Lane<ND> &L, const double *__restri
       const double wall = W[woff + (out ? 0 : i_new + fwd)];
       const double tn_new = (wall - (bx ? L.r0x : (by ? L.r0y : L.r0z))) * iv_ax;
       const bool live = !dead;
-      const bool moved = live & !out;
-      ds_s[j] = live ? t_exit - L.t : -1.0;
-      L.t = live ? t_exit : L.t;
+      const bool past = t_exit > tmax;
+      const bool moved = live & !out & !past;
+      const double t_end = past ? tmax : t_exit;
+      ds_s[j] = live ? t_end - L.t : -1.0;
+      L.t = live ? t_end : L.t;
       L.ix = (moved & bx) ? i_new : L.ix;
       L.iy = (moved & by) ? i_new : L.iy;
       L.iz = (moved & !(bx | by)) ? i_new : L.iz;
@@ -203,7 +208,7 @@ __device__ __forceinline__ bool escape_march(Lane<ND> &L, const double *__restri
       L.tny = (moved & by) ? tn_new : L.tny;
       L.tnz = (moved & !(bx | by)) ? tn_new : L.tnz;
       L.ic = moved ? (L.iz * n2 + L.iy) * n1 + L.ix : L.ic;
-      dead |= out;
+      dead |= out | past;
     }
 #pragma unroll
     for (int j = 0; j < D; ++j) {
@@ -319,13 +324,47 @@ __device__ __forceinline__ void peel_image_xy(const PeelJob<ND> &J, const ImageD
   y_image = dz * a.sint - dy * a.cost * a.sinp - dx * a.cost * a.cosp;
 }
 
+// Inside observer (images_peeled.f90:131-183, 410-421): the peel-off travels from the event to the observer at
+// (rpx, rpy, rpz); the image axes are the longitude and latitude of the arrival direction in the frame of
+// the viewing direction a_view.  Returns the direction, the distance and the image coordinates.
+template <int ND>
+__device__ __forceinline__ void peel_inside(const PeelJob<ND> &J, const ImageDev &im, const Angle &a_view, Angle &a_req,
+                                            double &dist, double &x_image, double &y_image) {
+  // vector3d_to_angle3d (type_vector3d.f90:276-299) of r_peeloff - r
+  const double wx = im.rpx - J.rx, wy = im.rpy - J.ry, wz = im.rpz - J.rz;
+  const double small_r = sqrt(wx * wx + wy * wy), big_r = sqrt(wx * wx + wy * wy + wz * wz);
+  a_req.cosp = wx / small_r;
+  a_req.sinp = wy / small_r;
+  a_req.cost = wz / big_r;
+  a_req.sint = small_r / big_r;
+  const double dx = J.rx - im.rpx, dy = J.ry - im.rpy, dz = J.rz - im.rpz;
+  dist = sqrt(dx * dx + dy * dy + dz * dz);
+  const double vax = a_req.sint * a_req.cosp, vay = a_req.sint * a_req.sinp, vaz = a_req.cost;
+  const double sx = (vax * a_view.cosp + vay * a_view.sinp) * a_view.sint + vaz * a_view.cost;
+  const double sy = -vax * a_view.sinp + vay * a_view.cosp;
+  const double sz = -(vax * a_view.cosp + vay * a_view.sinp) * a_view.cost + vaz * a_view.sint;
+  const double rad2deg = 180.0 / 3.14159265358979323846;
+  x_image = atan2(sy, sx) * rad2deg;
+  y_image = atan2(sqrt(sx * sx + sy * sy), sz) * rad2deg - 90.0;
+  // Fortran MODULO: a - floor(a / p) * p
+  const double ax = x_image - im.x_max, ay = y_image - im.y_min;
+  x_image = im.x_max + (ax - floor(ax / 360.0) * 360.0);
+  y_image = im.y_min + (ay - floor(ay / 360.0) * 360.0);
+}
+
 // image_bin / image_bin_raytraced (image_type.f90:408-606) for one finished ray
 template <int ND, bool POLY>
 __device__ inline void peel_bin(const PeelJob<ND> &J, const ImageDev &im, const ViewDev &V, const Stokes &S, const double tau,
                                 const double (&col)[ND]) {
   if (isnan(J.energy) || isnan(S.I)) return;
   double x_image, y_image;
-  peel_image_xy<ND>(J, im, V.a, x_image, y_image);
+  if (im.inside_observer) {
+    Angle a_req;
+    double dist;
+    peel_inside<ND>(J, im, V.a, a_req, dist, x_image, y_image);
+  } else {
+    peel_image_xy<ND>(J, im, V.a, x_image, y_image);
+  }
   const int io = origin_slice(im, J.scattered, J.reprocessed, J.source_id, J.dust_id, J.n_scat);
   const bool unc = im.uncertainties != 0;
   int ixp = 0, iyp = 0, ir = 0;
@@ -404,7 +443,7 @@ peel_kernel(const ModelDev M, const ImagingDev I, const PeelJob<ND> *__restrict_
   bool active = false, exhausted = false;
   uint32_t ij = 0, ip = 0;
   Stokes S{0.0, 0.0, 0.0, 0.0};
-  double tau = 0.0, col[ND];
+  double tau = 0.0, col[ND], tmax = 1.7976931348623157e308;
   Lane<ND> L;
   typename Geo<GG>::Ray R;
   L.ic = 0;
@@ -428,25 +467,32 @@ peel_kernel(const ModelDev M, const ImagingDev I, const PeelJob<ND> *__restrict_
           const PeelJob<ND> &J = jobs[ij];
           const ViewDev &V = I.views[ip];
           const ImageDev &im = I.images[V.group];
-          const Angle a_req = V.a;
+          Angle a_req = V.a;
+          const bool inside = im.inside_observer != 0;
+          double dist = 0.0, x_in = 0.0, y_in = 0.0;
+          tmax = 1.7976931348623157e308;
+          if (inside) {
+            peel_inside<ND>(J, im, V.a, a_req, dist, x_in, y_in);
+            tmax = dist;
+          }
           const double vx = a_req.sint * a_req.cosp, vy = a_req.sint * a_req.sinp, vz = a_req.cost;
           int ix = 0, iy = 0, iz = 0, ic = 0;
           bool ok = GEO == GEO_CAR ? place_in_grid(M, J.rx, J.ry, J.rz, vx, vy, vz, ix, iy, iz, ic)
                                    : Geo<GG>::find_cell(M, J.rx, J.ry, J.rz, vx, vy, vz, ix, iy, iz, ic);
           if (ok) {
             // depth along the line of sight and image-plane coordinates (images_peeled.f90:196-211)
-            const double depth = -(vx * J.rx + vy * J.ry + vz * J.rz);
-            double x_image, y_image;
-            peel_image_xy<ND>(J, im, a_req, x_image, y_image);
+            const double depth = inside ? dist : -(vx * J.rx + vy * J.ry + vz * J.rz);
+            double x_image = x_in, y_image = y_in;
+            if (!inside) peel_image_xy<ND>(J, im, a_req, x_image, y_image);
             ok = !(depth < im.d_min || depth > im.d_max) && in_image(im, x_image, y_image);
           }
           if (ok && !im.ignore_optical_depth && M.any_sphere) {
             // grid_escape_*: a source on the line of sight kills the peel-off (grid_propagate_3d.f90:410-415)
             int hit;
-            nearest_source(M, J.rx, J.ry, J.rz, vx, vy, vz, hit);
-            ok = hit < 0;
+            const double t_source = nearest_source(M, J.rx, J.ry, J.rz, vx, vy, vz, hit);
+            ok = !(t_source < tmax);
           }
-          if (ok && J.point_src > 0 && !im.ignore_optical_depth) {
+          if (ok && J.point_src > 0 && !im.ignore_optical_depth && !inside) {
             // the ray from this point source towards this view has been marched once already
             const double *rec = I.src_columns + ((size_t)(J.point_src - 1) * I.n_views + ip) * (ND + 1);
             const double nc = __ldg(rec + ND);
@@ -465,6 +511,11 @@ peel_kernel(const ModelDev M, const ImagingDev I, const PeelJob<ND> *__restrict_
           }
           if (ok) {
             S = peel_stokes<ND>(M, J, a_req);
+            if (inside) {
+              // flux at the observer (images_peeled.f90:207)
+              const double f = 4.0 * 3.14159265358979323846 * (dist * dist);
+              S.I = S.I / f; S.Q = S.Q / f; S.U = S.U / f; S.V = S.V / f;
+            }
             tau = 0.0;
 #pragma unroll
             for (int id = 0; id < ND; ++id) col[id] = 0.0;
@@ -493,9 +544,9 @@ peel_kernel(const ModelDev M, const ImagingDev I, const PeelJob<ND> *__restrict_
       if (im.ignore_optical_depth) {
         done = 1;
       } else if (GEO == GEO_CAR) {
-        done = escape_march<ND, POLY, PEEL_LOOKAHEAD>(L, W, M.rho, n1, n2, n3, tau, col, n_cross, PEEL_GROUPS) ? 1 : 0;
+        done = escape_march<ND, POLY, PEEL_LOOKAHEAD>(L, W, M.rho, n1, n2, n3, tau, col, n_cross, PEEL_GROUPS, tmax) ? 1 : 0;
       } else {
-        done = geo_escape<GG, ND, POLY>(M, R, J.chi, M.rho, tau, col, n_cross, 4 * PEEL_GROUPS);
+        done = geo_escape<GG, ND, POLY>(M, R, J.chi, M.rho, tau, col, n_cross, 4 * PEEL_GROUPS, tmax);
       }
       if (done) {
         active = false;

@@ -227,7 +227,7 @@ __device__ inline int geo_march(const ModelDev &M, typename Geo<GEO>::Ray &R, do
 template <int GEO, int ND, bool COLUMN>
 __device__ inline int geo_escape(const ModelDev &M, typename Geo<GEO>::Ray &R, const double (&chi)[ND],
                                  const double *__restrict__ rho_only, double &tau, double (&col)[ND], uint32_t &n_cross,
-                                 const int max_steps = 0x7fffffff) {
+                                 const int max_steps = 0x7fffffff, const double tmax = 1.7976931348623157e308) {
   using G = Geo<GEO>;
   for (int step = 0; step < max_steps; ++step) {
     if (G::escaped(M, R)) return 1;
@@ -239,6 +239,19 @@ __device__ inline int geo_escape(const ModelDev &M, typename Geo<GEO>::Ray &R, c
     for (int id = 0; id < ND; ++id) rho[id] = __ldg(rho_only + (size_t)R.ic * ND + id);
     if (!G::find_wall(M, R, dt, cr)) return -1;
     ++n_cross;
+    if (R.t + dt > tmax) {
+      // the ray ends inside this cell (inside observers, grid_propagate_3d.f90:440-443)
+      dt = tmax - R.t;
+#pragma unroll
+      for (int id = 0; id < ND; ++id) {
+        if (COLUMN)
+          col[id] = col[id] + rho[id] * dt;
+        else
+          tau = tau + chi[id] * rho[id] * dt;
+      }
+      R.t = tmax;
+      return 1;
+    }
 #pragma unroll
     for (int id = 0; id < ND; ++id) {
       if (COLUMN)

@@ -413,8 +413,6 @@ def read_peeled_groups(f):
         if not n_view > 0:
             raise ModelError("n_view should be a positive integer")
         inside = _yes(_attr(a, "inside_observer", required=True))
-        if inside:
-            raise ModelError("inside observers are not implemented by this engine yet")
         ang = g["angles"][...]
         kw = dict(theta=np.asarray(ang["theta"], dtype=np.float64), phi=np.asarray(ang["phi"], dtype=np.float64),
                   inside_observer=inside, ignore_optical_depth=_yes(_attr(a, "ignore_optical_depth", b"no")),

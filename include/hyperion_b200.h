@@ -129,7 +129,7 @@ typedef struct {
 typedef struct {
   int32_t n_view;
   const double *theta, *phi;                 /* [n_view] viewing angles, degrees (table 'angles') */
-  int32_t inside_observer;                   /* not implemented: rejected */
+  int32_t inside_observer;                   /* the observer sits at the peeloff origin; theta/phi = where it looks */
   int32_t ignore_optical_depth;
   double peeloff_x, peeloff_y, peeloff_z;    /* peeloff origin */
   double d_min, d_max;                       /* depth cut along the line of sight (+-inf: none) */

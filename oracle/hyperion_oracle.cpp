@@ -2393,6 +2393,9 @@ void emit_from_point(orc_ctx &g, const Source &src, Photon &p) {
   p.last_isotropic = true;
 }
 
+// Fortran MODULO(a, p) for reals: a - floor(a / p) * p (result has the sign of p)
+static double f_modulo(double a, double p) { return a - std::floor(a / p) * p; }
+
 // minus_angle_dp (type_angle3d.f90:443-447)
 static Angle minus_angle(const Angle &a) { return Angle{-a.cost, a.sint, -a.cosp, -a.sinp}; }
 
@@ -3294,7 +3297,20 @@ void peeloff_photon(orc_ctx &g, const Photon &p_orig, bool polychromatic) {
     p.s = p.s_prev;
     p.a = p.a_prev;
     p.v = p.v_prev;
-    const Angle a_req = P.viewing_angles[ip - 1];  // a_peeloff (:410-421), outside observer
+    // a_peeloff (images_peeled.f90:410-421): an inside observer is looked at from the event itself
+    const bool inside = im.c.inside_observer != 0;
+    Angle a_req = P.viewing_angles[ip - 1];
+    if (inside) {
+      // vector3d_to_angle3d (type_vector3d.f90:276-299) of r_peeloff - r
+      const Vec rp0 = P.r_peeloff[ig - 1];
+      const Vec w{rp0.x - p.r.x, rp0.y - p.r.y, rp0.z - p.r.z};
+      const double small_r = std::sqrt(w.x * w.x + w.y * w.y);
+      const double big_r = std::sqrt(w.x * w.x + w.y * w.y + w.z * w.z);
+      a_req.cosp = w.x / small_r;
+      a_req.sinp = w.y / small_r;
+      a_req.cost = w.z / big_r;
+      a_req.sint = small_r / big_r;
+    }
     const Vec v_req = angle3d_to_vector3d(a_req);
     if (p.last_isotropic) {
       p.s = Stokes{1.0, 0.0, 0.0, 0.0};
@@ -3334,12 +3350,34 @@ void peeloff_photon(orc_ctx &g, const Photon &p_orig, bool polychromatic) {
     }
     place_in_cell(g, p);
     const Vec rp = P.r_peeloff[ig - 1];
-    double d = -(v_req.x * p.r.x + v_req.y * p.r.y + v_req.z * p.r.z);
-    double tmax = std::numeric_limits<double>::max();
-    if (d < im.c.d_min || d > im.c.d_max) continue;
+    double d, tmax;
     Vec dr{p.r.x - rp.x, p.r.y - rp.y, p.r.z - rp.z};
-    double x_image = dr.y * p.a.cosp - dr.x * p.a.sinp;
-    double y_image = dr.z * p.a.sint - dr.y * p.a.cost * p.a.sinp - dr.x * p.a.cost * p.a.cosp;
+    if (inside) {
+      d = std::sqrt(dr.x * dr.x + dr.y * dr.y + dr.z * dr.z);
+      tmax = d;
+    } else {
+      d = -(v_req.x * p.r.x + v_req.y * p.r.y + v_req.z * p.r.z);
+      tmax = std::numeric_limits<double>::max();
+    }
+    if (d < im.c.d_min || d > im.c.d_max) continue;
+    double x_image, y_image;
+    if (inside) {
+      // longitude / latitude of the arrival direction in the observer's frame (images_peeled.f90:168-183)
+      const double rad2deg = 180.0 / PI;
+      const Angle a_view = P.viewing_angles[ip - 1];
+      const Vec v_a = angle3d_to_vector3d(p.a);
+      Vec v_sky;
+      v_sky.x = (v_a.x * a_view.cosp + v_a.y * a_view.sinp) * a_view.sint + v_a.z * a_view.cost;
+      v_sky.y = -v_a.x * a_view.sinp + v_a.y * a_view.cosp;
+      v_sky.z = -(v_a.x * a_view.cosp + v_a.y * a_view.sinp) * a_view.cost + v_a.z * a_view.sint;
+      x_image = std::atan2(v_sky.y, v_sky.x) * rad2deg;
+      y_image = std::atan2(std::sqrt(v_sky.x * v_sky.x + v_sky.y * v_sky.y), v_sky.z) * rad2deg - 90.0;
+      x_image = im.c.x_max + f_modulo(x_image - im.c.x_max, 360.0);
+      y_image = im.c.y_min + f_modulo(y_image - im.c.y_min, 360.0);
+    } else {
+      x_image = dr.y * p.a.cosp - dr.x * p.a.sinp;
+      y_image = dr.z * p.a.sint - dr.y * p.a.cost * p.a.sinp - dr.x * p.a.cost * p.a.cosp;
+    }
     if (!in_image(im, x_image, y_image)) continue;
     double tau = 0.0;
     bool killed = false;
@@ -3350,6 +3388,11 @@ void peeloff_photon(orc_ctx &g, const Photon &p_orig, bool polychromatic) {
     }
     if (killed) continue;
     g.n_peeloffs++;
+    if (inside) {
+      // flux through a unit area at the observer (images_peeled.f90:207)
+      const double f = 4.0 * PI * std::pow(d, 2.0);
+      p.s = Stokes{p.s.I / f, p.s.Q / f, p.s.U / f, p.s.V / f};
+    }
     if (polychromatic) {
       if (p.emiss_type == 1 || p.emiss_type == 2) {
         auto &cache = P.source_spectra[ig - 1][p.source_id - 1];
@@ -4143,7 +4186,6 @@ int orc_set_energy_sum(orc_ctx *g, const double *in) {
 // peeled_images_setup (images_peeled.f90:272-382)
 int orc_add_peeled_group(orc_ctx *g, const hyp_image_conf *c) {
   try {
-    if (c->inside_observer) return fail(g, "inside observers are not restated in the oracle");
     if (!(c->n_view > 0)) return fail(g, "n_view should be a positive integer");
     if (c->binned) {
       // setup_final_iteration (setup_rt.f90:318-331) + binned_images_setup (images_binned.f90:41-55)

@@ -305,3 +305,31 @@ def test_binned_images_match_oracle(golden_car, multi):
         a = np.mean([g[1][key] for g in gpu])
         b = np.mean([o[1][key] for o in orc])
         assert abs(a / b - 1) < 0.02, (key, a, b)
+
+
+@pytest.mark.parametrize("geometry,raytracing", [("car", False), ("car", True), ("sph", True)])
+def test_inside_observer_matches_oracle(golden_car, golden_sph, geometry, raytracing):
+    """Inside observers (images_peeled.f90:131-183): peel-offs travel to an observer inside the grid, stop
+    there, are weighted by 1 / (4 pi d^2) and land on a longitude / latitude image."""
+    from helpers import FlatPeeledGroup
+    from hyperion_b200.flatmodel import FlatSource
+    model = peeloff_model(golden_car, False) if geometry == "car" else peeloff_model_sph(golden_car, golden_sph, False)
+    if geometry == "car":
+        # a star on some lines of sight: peel-offs that would cross it before reaching the observer are dropped
+        model.sources.append(FlatSource(type=2, luminosity=2.e33, temperature=6000., position=(0.3 * pc, 0.1 * pc, -0.2 * pc),
+                                        radius=0.15 * pc))
+    inside = FlatPeeledGroup(theta=[70.], phi=[25.], wavelengths=(4, 0.05, 200.), inside_observer=True,
+                             peeloff_origin=(-0.21 * pc, 0.33 * pc, 0.12 * pc),
+                             image=(8, 4, 360., 0., -90., 90.), sed=(2, 30., 400.), track_origin="basic",
+                             d_min=0.05 * pc, d_max=5 * pc)
+    model.peeled = [peeloff_groups()[0], inside]
+    model.specific_energy = _converged_energy(model)
+    B = 12
+    gpu, orc = _run_both(model, B, 60000, raytracing, (20000, 30000) if raytracing else None)
+    report = _compare(gpu, orc)
+    print(report)
+    assert report["g1_img"][2] >= 20 and report["g1_sed"][2] >= 8
+    for key in ("n_peeloffs", "n_peel_crossings"):
+        a = np.mean([g[1][key] for g in gpu])
+        b = np.mean([o[1][key] for o in orc])
+        assert abs(a / b - 1) < 0.02, (key, a, b)
