@@ -72,6 +72,8 @@ class ImageConf(C.Structure):
         ("track_origin", C.c_int32), ("track_n_scat", C.c_int32),
         ("uncertainties", C.c_int32), ("compute_stokes", C.c_int32), ("io_bytes", C.c_int32),
         ("binned", C.c_int32), ("n_theta", C.c_int32), ("n_phi", C.c_int32),
+        ("use_filters", C.c_int32), ("filt_n", C.POINTER(C.c_int32)), ("filt_nu", _dp), ("filt_tr", _dp),
+        ("filt_nu0", _dp),
     ]
 
 
@@ -226,10 +228,21 @@ class CApi:
         if g.sed is not None:
             t.n_ap, t.ap_min, t.ap_max = g.sed
         t.n_wav, t.wav_min, t.wav_max = g.wavelengths
+        keep_f = None
+        if g.filters:
+            fn = np.array([len(f[0]) for f in g.filters], dtype=np.int32)
+            fnu = np.ascontiguousarray(np.concatenate([np.asarray(f[0], dtype=np.float64) for f in g.filters]))
+            ftr = np.ascontiguousarray(np.concatenate([np.asarray(f[1], dtype=np.float64) for f in g.filters]))
+            fnu0 = np.array([float(f[2]) for f in g.filters], dtype=np.float64)
+            keep_f = (fn, fnu, ftr, fnu0)
+            t.use_filters, t.n_wav = 1, len(g.filters)
+            t.filt_n = fn.ctypes.data_as(C.POINTER(C.c_int32))
+            t.filt_nu, t.filt_tr, t.filt_nu0 = _ptr(fnu), _ptr(ftr), _ptr(fnu0)
         t.track_origin = {"no": 0, "basic": 1, "yes": 1, "detailed": 2, "scatterings": 3}[g.track_origin]
         t.track_n_scat = g.track_n_scat
         t.uncertainties, t.compute_stokes, t.io_bytes = int(g.uncertainties), int(g.stokes), g.io_bytes
         self.check(self._fn("add_peeled_group")(ctx, C.byref(t)))
+        del keep_f
 
     def image_shape(self, ctx, group, which):
         dims = (C.c_int64 * 6)()

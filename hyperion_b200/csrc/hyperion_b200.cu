@@ -1721,6 +1721,8 @@ struct HostImage {
   double nu_min = 0, nu_max = 0;
   size_t n_sed = 0, n_img = 0;     // elements of one SED / image cube
   size_t o_sed = 0, o_img = 0;     // offsets into the image buffer: [val | sum of squares | count] each
+  std::vector<int32_t> filt_off;   // use_filters: points of channel k are [filt_off[k], filt_off[k+1])
+  std::vector<double> filt_nu, filt_tr;
 };
 
 }  // namespace
@@ -1805,6 +1807,7 @@ struct hyp_ctx {
   double *d_mrw_alpha = nullptr, *d_mrw_diff = nullptr, *d_mrw_cdf = nullptr;
   double *d_src_columns = nullptr;
   std::vector<double *> ray_tables;  // device copies of the binned raytracing spectra
+  std::vector<void *> filter_tables; // device copies of the filter curves
   bool images_ready = false, ray_ready = false;
   int64_t peel_launches = 0;
 };
@@ -2075,6 +2078,7 @@ void hyp_ctx_destroy(hyp_ctx *c) {
   free_dev(c->d_mrw_cdf);
   free_dev(c->d_src_columns);
   for (auto &t : c->ray_tables) free_dev(t);
+  for (auto &t : c->filter_tables) free_dev(t);
   free_pool(c);
   if (c->h_counts) cudaFreeHost(c->h_counts);
   if (c->evA) cudaEventDestroy(c->evA);
@@ -3257,6 +3261,21 @@ int ensure_images(hyp_ctx *c) {
     d.track_origin = k.track_origin; d.track_n_scat = k.track_n_scat;
     d.uncertainties = k.uncertainties; d.ignore_optical_depth = k.ignore_optical_depth;
     d.inside_observer = k.inside_observer;
+    d.use_filters = k.use_filters;
+    if (k.use_filters) {
+      int32_t *d_off = nullptr;
+      double *d_nu = nullptr, *d_tr = nullptr;
+      CUDA_TRY(cudaMalloc(&d_off, g.filt_off.size() * sizeof(int32_t)));
+      CUDA_TRY(cudaMalloc(&d_nu, g.filt_nu.size() * sizeof(double)));
+      CUDA_TRY(cudaMalloc(&d_tr, g.filt_tr.size() * sizeof(double)));
+      CUDA_TRY(cudaMemcpy(d_off, g.filt_off.data(), g.filt_off.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+      CUDA_TRY(cudaMemcpy(d_nu, g.filt_nu.data(), g.filt_nu.size() * sizeof(double), cudaMemcpyHostToDevice));
+      CUDA_TRY(cudaMemcpy(d_tr, g.filt_tr.data(), g.filt_tr.size() * sizeof(double), cudaMemcpyHostToDevice));
+      c->filter_tables.push_back(d_off);
+      c->filter_tables.push_back(d_nu);
+      c->filter_tables.push_back(d_tr);
+      d.filt_off = d_off; d.filt_nu = d_nu; d.filt_tr = d_tr;
+    }
     d.n_sources = ns; d.n_dust = nd;
     d.x_min = k.x_min; d.x_max = k.x_max; d.y_min = k.y_min; d.y_max = k.y_max;
     d.ap_min = k.ap_min; d.ap_max = k.ap_max;
@@ -3672,6 +3691,19 @@ int hyp_add_peeled_group(hyp_ctx *c, const hyp_image_conf *g) {
     h.theta.assign(g->theta, g->theta + g->n_view);
     h.phi.assign(g->phi, g->phi + g->n_view);
   }
+  if (g->use_filters) {
+    if (!g->filt_n || !g->filt_nu || !g->filt_tr) return fail(HYP_ERR_INVALID, "filter tables are missing");
+    h.filt_off.push_back(0);
+    for (int i = 0; i < g->n_wav; ++i) {
+      if (g->filt_n[i] < 2) return fail(HYP_ERR_INVALID, "a filter needs at least two points");
+      h.filt_off.push_back(h.filt_off.back() + g->filt_n[i]);
+    }
+    h.filt_nu.assign(g->filt_nu, g->filt_nu + h.filt_off.back());
+    h.filt_tr.assign(g->filt_tr, g->filt_tr + h.filt_off.back());
+    h.conf.wav_min = h.conf.wav_max = 1.0;   // unused with filters
+  }
+  h.conf.filt_n = nullptr;
+  h.conf.filt_nu = h.conf.filt_tr = h.conf.filt_nu0 = nullptr;
   h.conf.theta = h.conf.phi = nullptr;
   c->groups.push_back(std::move(h));
   return HYP_OK;
@@ -3768,6 +3800,9 @@ int hyp_raytracing_photons(hyp_ctx *c, int64_t first_source_id, int64_t n_source
   if (n_sources < 0 || n_dust < 0 || first_source_id < 0 || first_dust_id < 0)
     return fail(HYP_ERR_INVALID, "negative photon count");
   CUDA_TRY(cudaSetDevice(c->device));
+  for (auto &g : c->groups)
+    if (g.conf.use_filters && !g.conf.binned)
+      return fail(HYP_ERR_INVALID, "filter convolution cannot be used with raytracing");   // image_type.f90:541
   int rc = ensure_images(c);
   if (rc) return rc;
   rc = ensure_ray_tables(c);
@@ -3836,7 +3871,8 @@ static int get_cube(hyp_ctx *c, int32_t group, bool sed, double *out, double *un
   if (have_unc) CUDA_TRY(cudaMemcpyAsync(unc, c->d_imgbuf + off + n, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   CUDA_TRY(cudaStreamSynchronize(c->stream));
   const int n_nu = g.conf.n_wav;
-  const double dnunorm = std::pow(g.nu_max / g.nu_min, +0.5 / (double)n_nu) - std::pow(g.nu_max / g.nu_min, -0.5 / (double)n_nu);
+  // with filters the flux stays in F_nu dnu: the filter carries the normalisation (image_type.f90:649-657)
+  const double dnunorm = g.conf.use_filters ? 1.0 : std::pow(g.nu_max / g.nu_min, +0.5 / (double)n_nu) - std::pow(g.nu_max / g.nu_min, -0.5 / (double)n_nu);
   for (size_t i = 0; i < n; ++i) out[i] = out[i] / dnunorm;
   if (have_unc)
     for (size_t i = 0; i < n; ++i) unc[i] = std::sqrt(unc[i]) / dnunorm;

@@ -36,7 +36,31 @@ struct ImageDev {
   const double *src_spec;               // [n_sources][n_nu]
   const double *dust_chi;               // [n_dust][n_nu]
   const double *dust_logj[MAX_DUST];    // [n_jnu][n_nu] log10 of the binned emissivities
+  // filter convolution (image_type.f90:274-284,467-476): channel k has points [filt_off[k], filt_off[k+1])
+  int32_t use_filters, pad1;
+  const int32_t *filt_off;
+  const double *filt_nu, *filt_tr;
 };
+
+// interp1d_dp(x, y, xval, bounds_error=.false., fill_value=0) (lib_array.f90:616-624,704-778) with the
+// bisection of locate_dp (:917-950): x may increase or decrease
+__device__ inline double interp1d_fill0(const double *__restrict__ x, const double *__restrict__ y, int n, double xval) {
+  const bool ascnd = x[n - 1] >= x[0];
+  int jl = 0, ju = n + 1;
+  while (ju - jl > 1) {
+    const int jm = (ju + jl) / 2;
+    if (ascnd == (xval >= x[jm - 1])) jl = jm; else ju = jm;
+  }
+  int ip = jl;
+  if (xval == x[0]) ip = 1;
+  else if (xval == x[n - 1]) ip = n - 1;
+  else if (ascnd ? (xval > x[n - 1] || xval < x[0]) : (xval < x[n - 1] || xval > x[0])) return 0.0;
+  if (ip < n && ip > 0) {
+    const double frac = (xval - x[ip - 1]) / (x[ip] - x[ip - 1]);
+    return y[ip - 1] + frac * (y[ip] - y[ip - 1]);
+  }
+  return ip == n ? y[n - 1] : y[0];
+}
 
 struct ViewDev {
   int32_t group, view;  // 0-based group, 0-based view inside the group
@@ -410,14 +434,24 @@ __device__ inline void peel_bin(const PeelJob<ND> &J, const ImageDev &im, const 
       if (in_sed) bin_add(im.sed, im.sed2, im.sedn, k_sed + inu, v, unc);
     }
   } else {
-    const int inu = ipos_bin(im.log10_nu_min, im.log10_nu_max, log10(J.nu), im.n_nu);
-    if (inu < 1 || inu > im.n_nu) return;
     const double e = exp(-tau);
     const double st[4] = {S.I * e, S.Q * e, S.U * e, S.V * e};
-    for (int is = 0; is < im.n_stokes; ++is) {
-      const double v = st[is] * J.energy * 1.0;
-      if (in_img) bin_add(im.img, im.img2, im.imgn, k_img + (inu - 1) + is * s_img, v, unc);
-      if (in_sed) bin_add(im.sed, im.sed2, im.sedn, k_sed + (inu - 1) + is * s_sed, v, unc);
+    // without filters one channel, with filters every channel that transmits at this frequency
+    const int inu0 = im.use_filters ? 1 : ipos_bin(im.log10_nu_min, im.log10_nu_max, log10(J.nu), im.n_nu);
+    const int inu1 = im.use_filters ? im.n_nu : inu0;
+    for (int inu = inu0; inu <= inu1; ++inu) {
+      if (inu < 1 || inu > im.n_nu) return;
+      double transmission = 1.0;
+      if (im.use_filters) {
+        const int o = im.filt_off[inu - 1];
+        transmission = interp1d_fill0(im.filt_nu + o, im.filt_tr + o, im.filt_off[inu] - o, J.nu);
+        if (!(transmission > 0.0)) continue;
+      }
+      for (int is = 0; is < im.n_stokes; ++is) {
+        const double v = st[is] * J.energy * transmission;
+        if (in_img) bin_add(im.img, im.img2, im.imgn, k_img + (inu - 1) + is * s_img, v, unc);
+        if (in_sed) bin_add(im.sed, im.sed2, im.sedn, k_sed + (inu - 1) + is * s_sed, v, unc);
+      }
     }
   }
 }
@@ -648,28 +682,39 @@ __device__ inline void bin_escaped_packet(const FinalArgs &F, const Slot<ND> *__
   const int iv = F.n_phi * (it - 1) + ip - 1;  // image_id, 0-based
   const double x_image = ry * a.cosp - rx * a.sinp;
   const double y_image = rz * a.sint - ry * a.cost * a.sinp - rx * a.cost * a.cosp;
-  const int inu = ipos_bin(im.log10_nu_min, im.log10_nu_max, log10(s->nu), im.n_nu);
-  if (inu < 1 || inu > im.n_nu) return;
+  const int inu0 = im.use_filters ? 1 : ipos_bin(im.log10_nu_min, im.log10_nu_max, log10(s->nu), im.n_nu);
+  const int inu1 = im.use_filters ? im.n_nu : inu0;
+  if (inu0 < 1 || inu0 > im.n_nu) return;
   const uint32_t tag = s->tag;
   const int io = origin_slice(im, (tag & TAG_SCATTERED) ? 1 : 0, (tag & TAG_REPROCESSED) ? 1 : 0, (int)(tag & TAG_SRC_MASK),
                               (int)(tag >> TAG_DUST_SHIFT) + 1, (int)((tag >> TAG_NSCAT_SHIFT) & TAG_NSCAT_MASK));
   const bool unc = im.uncertainties != 0;
   const size_t nn = (size_t)im.n_nu;
   const double st[4] = {1.0, s->sQ, s->sU, s->sV};
-  if (im.compute_image) {
-    const int ixp = ipos_bin(im.x_min, im.x_max, x_image, im.n_x), iyp = ipos_bin(im.y_min, im.y_max, y_image, im.n_y);
-    if (ixp >= 1 && ixp <= im.n_x && iyp >= 1 && iyp <= im.n_y) {
-      const size_t k = nn * ((ixp - 1) + (size_t)im.n_x * ((iyp - 1) + (size_t)im.n_y * (iv + (size_t)im.n_view * (io - 1))));
-      const size_t stride = nn * im.n_x * im.n_y * im.n_view * im.n_orig;
-      for (int is = 0; is < im.n_stokes; ++is) bin_add(im.img, im.img2, im.imgn, k + (inu - 1) + is * stride, st[is] * energy * 1.0, unc);
+  for (int inu = inu0; inu <= inu1; ++inu) {
+    double transmission = 1.0;
+    if (im.use_filters) {
+      const int o = im.filt_off[inu - 1];
+      transmission = interp1d_fill0(im.filt_nu + o, im.filt_tr + o, im.filt_off[inu] - o, s->nu);
+      if (!(transmission > 0.0)) continue;
     }
-  }
-  if (im.compute_sed) {
-    const int ir = find_sed_bin(im, x_image, y_image);
-    if (ir >= 1 && ir <= im.n_ap) {
-      const size_t k = nn * ((ir - 1) + (size_t)im.n_ap * (iv + (size_t)im.n_view * (io - 1)));
-      const size_t stride = nn * im.n_ap * im.n_view * im.n_orig;
-      for (int is = 0; is < im.n_stokes; ++is) bin_add(im.sed, im.sed2, im.sedn, k + (inu - 1) + is * stride, st[is] * energy * 1.0, unc);
+    if (im.compute_image) {
+      const int ixp = ipos_bin(im.x_min, im.x_max, x_image, im.n_x), iyp = ipos_bin(im.y_min, im.y_max, y_image, im.n_y);
+      if (ixp >= 1 && ixp <= im.n_x && iyp >= 1 && iyp <= im.n_y) {
+        const size_t k = nn * ((ixp - 1) + (size_t)im.n_x * ((iyp - 1) + (size_t)im.n_y * (iv + (size_t)im.n_view * (io - 1))));
+        const size_t stride = nn * im.n_x * im.n_y * im.n_view * im.n_orig;
+        for (int is = 0; is < im.n_stokes; ++is)
+          bin_add(im.img, im.img2, im.imgn, k + (inu - 1) + is * stride, st[is] * energy * transmission, unc);
+      }
+    }
+    if (im.compute_sed) {
+      const int ir = find_sed_bin(im, x_image, y_image);
+      if (ir >= 1 && ir <= im.n_ap) {
+        const size_t k = nn * ((ir - 1) + (size_t)im.n_ap * (iv + (size_t)im.n_view * (io - 1)));
+        const size_t stride = nn * im.n_ap * im.n_view * im.n_orig;
+        for (int is = 0; is < im.n_stokes; ++is)
+          bin_add(im.sed, im.sed2, im.sedn, k + (inu - 1) + is * stride, st[is] * energy * transmission, unc);
+      }
     }
   }
 }

@@ -165,6 +165,9 @@ class FlatPeeledGroup:
     binned: bool = False
     n_theta: int = 0
     n_phi: int = 0
+    # filter convolution (``use_filters``, ``hyperion/conf/conf_files.py:862-885``): a list of
+    # (nu, normalised transmission, nu0) triples replaces the wavelength grid
+    filters: Optional[list] = None
 
 
 @dataclass

@@ -373,14 +373,26 @@ def _image_conf(g):
     """The part of an image group every kind shares (``image_setup``, ``src/images/image_type.f90:153-335``)."""
     a = g.attrs
     kw = {}
-    if "use_filters" in a and _yes(a["use_filters"]):
-        raise ModelError("filter convolution is not implemented by this engine yet")
     if "inu_min" in a:
         raise ModelError("the monochromatic final iteration is not implemented by this engine yet")
-    n_wav = int(_num(_attr(a, "n_wav", required=True)))
-    if n_wav < 1:
-        raise ModelError("n_nu should be >= 1")
-    kw["wavelengths"] = (n_wav, float(_num(_attr(a, "wav_min", required=True))), float(_num(_attr(a, "wav_max", required=True))))
+    if "use_filters" in a and _yes(a["use_filters"]):
+        # image_setup (image_type.f90:174-183, 274-284): n_filt tables filter_%05i(nu, tn) with attribute nu0
+        n_filt = int(_num(_attr(a, "n_filt", required=True)))
+        if n_filt < 1:
+            raise ModelError("n_nu should be >= 1")
+        filters = []
+        for i in range(n_filt):
+            d = g["filter_%05i" % (i + 1)]
+            t = d[...]
+            filters.append((np.asarray(t["nu"], dtype=np.float64), np.asarray(t["tn"], dtype=np.float64),
+                            float(_num(d.attrs["nu0"]))))
+        kw["filters"] = filters
+        kw["wavelengths"] = (n_filt, 1.0, 1.0)
+    else:
+        n_wav = int(_num(_attr(a, "n_wav", required=True)))
+        if n_wav < 1:
+            raise ModelError("n_nu should be >= 1")
+        kw["wavelengths"] = (n_wav, float(_num(_attr(a, "wav_min", required=True))), float(_num(_attr(a, "wav_max", required=True))))
     kw["stokes"] = _yes(a["compute_stokes"]) if "compute_stokes" in a else True
     if _yes(_attr(a, "compute_image", required=True)):
         kw["image"] = (int(_num(a["n_x"])), int(_num(a["n_y"])), float(_num(a["x_min"])), float(_num(a["x_max"])),

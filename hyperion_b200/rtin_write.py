@@ -83,9 +83,19 @@ def write_peeled_group(g, p):
     if p.sed is not None:
         a["n_ap"] = np.int64(p.sed[0])
         a["ap_min"], a["ap_max"] = float(p.sed[1]), float(p.sed[2])
-    a["use_filters"] = b"no"
-    a["n_wav"] = np.int64(p.wavelengths[0])
-    a["wav_min"], a["wav_max"] = float(p.wavelengths[1]), float(p.wavelengths[2])
+    if p.filters:
+        # _write_filters (hyperion/conf/conf_files.py:874-881) + Filter.to_hdf5_group (hyperion/filter/filter.py:90-126)
+        a["use_filters"] = b"yes"
+        a["n_filt"] = np.int64(len(p.filters))
+        for i, (nu, tn, nu0) in enumerate(p.filters):
+            d = g.create_dataset("filter_%05i" % (i + 1), _table([("nu", np.asarray(nu, dtype=np.float64)),
+                                                                   ("tr", np.asarray(tn, dtype=np.float64)),
+                                                                   ("tn", np.asarray(tn, dtype=np.float64))]))
+            d.attrs["nu0"] = float(nu0)
+    else:
+        a["use_filters"] = b"no"
+        a["n_wav"] = np.int64(p.wavelengths[0])
+        a["wav_min"], a["wav_max"] = float(p.wavelengths[1]), float(p.wavelengths[2])
     a["track_origin"] = p.track_origin
     a["track_n_scat"] = np.int64(p.track_n_scat)
     a["uncertainties"] = _yn(p.uncertainties)

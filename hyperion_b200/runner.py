@@ -136,7 +136,8 @@ def write_peeled_output(g, eng, ig, p, n_sources, n_dust):
         d = g.create_dataset("seds", val.astype(dt))
         if unc is not None:
             g.create_dataset("seds_unc", unc.astype(dt))
-        d.attrs["numin"], d.attrs["numax"] = float(nu_min), float(nu_max)
+        if not p.filters:
+            d.attrs["numin"], d.attrs["numax"] = float(nu_min), float(nu_max)
         d.attrs["apmin"], d.attrs["apmax"] = float(p.sed[1]), float(p.sed[2])
         origin_attrs(d)
     if p.image is not None:
@@ -145,10 +146,16 @@ def write_peeled_output(g, eng, ig, p, n_sources, n_dust):
         d = g.create_dataset("images", val.astype(dt))
         if unc is not None:
             g.create_dataset("images_unc", unc.astype(dt))
-        d.attrs["numin"], d.attrs["numax"] = float(nu_min), float(nu_max)
+        if not p.filters:
+            d.attrs["numin"], d.attrs["numax"] = float(nu_min), float(nu_max)
         d.attrs["xmin"], d.attrs["xmax"] = float(p.image[2]), float(p.image[3])
         d.attrs["ymin"], d.attrs["ymax"] = float(p.image[4]), float(p.image[5])
         origin_attrs(d)
+    if p.filters:
+        # image_type.f90:775-779
+        g.attrs["use_filters"] = "yes"
+        g.attrs["n_filt"] = np.int32(len(p.filters))
+        g.create_dataset("filt_nu0", np.array([f[2] for f in p.filters], dtype=np.float64))
     if p.binned:
         return          # binned_images_write (images_binned.f90:85-89) writes the cubes only
     g.attrs["inside_observer"] = "yes" if p.inside_observer else "no"
@@ -312,6 +319,8 @@ def run(input_file, output_file, overwrite=False, device=None, log=None):
     out.attrs["killed_photons_int_final"] = np.int64(killed_final[1])
     killed_ray = (0, 0)
     if rs.raytracing:
+        if any(p.filters for p in model.peeled):
+            raise ModelError("filter convolution cannot be used with raytracing")     # image_type.f90:541
         log(" [main] starting raytracing iteration")
         fs, cs = shard(n_ray[0], rank, world)
         fd, cd = shard(n_ray[1], rank, world)

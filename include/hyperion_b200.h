@@ -150,6 +150,15 @@ typedef struct {
    * are ignored, and at most one such group may exist; it needs forced_first_interaction = 0
    * (setup_rt.f90:327-329). */
   int32_t binned, n_theta, n_phi;
+  /* Filter convolution (image_setup, src/images/image_type.f90:174-183,274-284; image_bin :467-476): the
+   * n_wav channels are n_filt = n_wav filters; a packet of frequency nu adds energy x transmission(nu)
+   * to every filter whose (linearly interpolated) transmission is > 0.  wav_min / wav_max are ignored.
+   * Filters cannot be combined with raytracing (image_type.f90:541). */
+  int32_t use_filters;
+  const int32_t *filt_n;     /* [n_wav] points of each filter curve */
+  const double *filt_nu;     /* concatenated 'nu' columns of Output/Peeled/group/filter_%05i */
+  const double *filt_tr;     /* concatenated 'tn' columns (normalised transmission) */
+  const double *filt_nu0;    /* [n_wav] central frequencies (attribute nu0), written back as filt_nu0 */
 } hyp_image_conf;
 
 /* Per-iteration counters (killed_photons_* attrs of main.f90:225-230 plus the

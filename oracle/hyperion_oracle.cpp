@@ -229,6 +229,23 @@ double interp1d_loglog(const double *x, const double *y, int n, double xval, boo
   throw OracleError{"Unexpected value of ipos"};
 }
 
+// interp1d_dp = interp1d_general_dp with linear chunks (lib_array.f90:578-585,616-624,704-778)
+double interp1d_lin(const double *x, const double *y, int n, double xval, bool bounds_error = true,
+                    double fill_value = 0.0) {
+  int ip = locate(x, n, xval);
+  if (ip == -1) {
+    if (bounds_error) throw OracleError{"Interpolation out of bounds"};
+    return fill_value;
+  }
+  if (ip < n && ip > 0) {
+    double frac = (xval - x[ip - 1]) / (x[ip] - x[ip - 1]);
+    return y[ip - 1] + frac * (y[ip] - y[ip - 1]);
+  }
+  if (ip == n) return y[n - 1];
+  if (ip == 0) return y[0];
+  throw OracleError{"Unexpected value of ipos"};
+}
+
 // interp2d_dp (lib_array.f90:780-846); array(i,j) stored as a[(j-1)*nx + (i-1)]
 double interp2d(const double *x, int nx, const double *y, int ny, const double *a, double x0, double y0) {
   int i1 = locate(x, nx, x0), i2 = i1 + 1;
@@ -857,6 +874,8 @@ struct Image {
   int n_nu = 0, n_stokes = 4, n_orig = 1, n_sources = 0, n_dust = 0;
   double nu_min = 0, nu_max = 0, log10_nu_min = 0, log10_nu_max = 0, log10_ap_min = 0, log10_ap_max = 0;
   std::vector<double> img, img2, imgn, sed, sed2, sedn;
+  std::vector<std::vector<double>> filt_nu, filt_tr;   // use_filters: one transmission curve per channel
+  std::vector<double> filt_nu0;
   size_t img_index(int inu, int ix, int iy, int iv, int io, int is) const {
     return (size_t)(inu - 1) +
            (size_t)n_nu * ((ix - 1) + (size_t)c.n_x * ((iy - 1) + (size_t)c.n_y * ((iv - 1) + (size_t)c.n_view * ((io - 1) + (size_t)n_orig * is))));
@@ -894,6 +913,19 @@ void image_setup(Image &im, const hyp_image_conf &c, int n_sources, int n_dust) 
     case HYP_TRACK_BASIC: im.n_orig = 4; break;
     case HYP_TRACK_NO: im.n_orig = 1; break;
     default: throw OracleError{"unknown track_origin flag"};
+  }
+  if (c.use_filters) {
+    // image_type.f90:274-284
+    if (!c.filt_n || !c.filt_nu || !c.filt_tr || !c.filt_nu0) throw OracleError{"filter tables are missing"};
+    size_t off = 0;
+    for (int i = 0; i < im.n_nu; i++) {
+      im.filt_nu.emplace_back(c.filt_nu + off, c.filt_nu + off + c.filt_n[i]);
+      im.filt_tr.emplace_back(c.filt_tr + off, c.filt_tr + off + c.filt_n[i]);
+      im.filt_nu0.push_back(c.filt_nu0[i]);
+      off += c.filt_n[i];
+    }
+    im.c.filt_n = nullptr;
+    im.c.filt_nu = im.c.filt_tr = im.c.filt_nu0 = nullptr;
   }
   const double c_cgs = 2.99792458e10;
   // "1.e-4" is a default-real (single precision) literal in image_type.f90:262-263
@@ -968,11 +1000,28 @@ bool in_image(const Image &im, double x, double y) {
   return false;
 }
 
-// image_bin + image_bin_single (image_type.f90:408-524), no filters
+// image_bin_single (image_type.f90:478-524)
+void image_bin_single(Image &im, const Photon &p, double x_image, double y_image, int iv, int inu, int io,
+                      double transmission);
+
+// image_bin (image_type.f90:408-476)
 void image_bin(Image &im, const Photon &p, double x_image, double y_image, int iv) {
   if (std::isnan(p.energy) || std::isnan(p.s.I)) return;
-  int inu = ipos(im.log10_nu_min, im.log10_nu_max, std::log10(p.nu), im.n_nu);
   int io = origin_slice(im, p);
+  if (im.c.use_filters) {
+    for (int ifilt = 1; ifilt <= im.n_nu; ifilt++) {
+      const auto &fn = im.filt_nu[ifilt - 1];
+      double transmission = interp1d_lin(fn.data(), im.filt_tr[ifilt - 1].data(), (int)fn.size(), p.nu, false, 0.0);
+      if (transmission > 0.0) image_bin_single(im, p, x_image, y_image, iv, ifilt, io, transmission);
+    }
+  } else {
+    int inu = ipos(im.log10_nu_min, im.log10_nu_max, std::log10(p.nu), im.n_nu);
+    image_bin_single(im, p, x_image, y_image, iv, inu, io, 1.0);
+  }
+}
+
+void image_bin_single(Image &im, const Photon &p, double x_image, double y_image, int iv, int inu, int io,
+                      double transmission) {
   const double st[4] = {p.s.I, p.s.Q, p.s.U, p.s.V};
   if (inu >= 1 && inu <= im.n_nu) {
     if (im.c.compute_image) {
@@ -981,7 +1030,7 @@ void image_bin(Image &im, const Photon &p, double x_image, double y_image, int i
       if (ix >= 1 && ix <= im.c.n_x && iy >= 1 && iy <= im.c.n_y) {
         for (int is = 0; is < im.n_stokes; is++) {
           size_t k = im.img_index(inu, ix, iy, iv, io, is);
-          double v = st[is] * p.energy * 1.0;
+          double v = st[is] * p.energy * transmission;
           im.img[k] = im.img[k] + v;
           if (im.c.uncertainties) {
             im.img2[k] = im.img2[k] + v * v;
@@ -995,7 +1044,7 @@ void image_bin(Image &im, const Photon &p, double x_image, double y_image, int i
       if (ir >= 1 && ir <= im.c.n_ap) {
         for (int is = 0; is < im.n_stokes; is++) {
           size_t k = im.sed_index(inu, ir, iv, io, is);
-          double v = st[is] * p.energy * 1.0;
+          double v = st[is] * p.energy * transmission;
           im.sed[k] = im.sed[k] + v;
           if (im.c.uncertainties) {
             im.sed2[k] = im.sed2[k] + v * v;
@@ -3582,6 +3631,8 @@ Photon emit_from_grid(orc_ctx &g) {
 
 // do_raytracing (iter_raytracing.f90:31-141)
 void raytracing_photons(orc_ctx &g, int64_t n_sources, int64_t n_thermal) {
+  for (const auto &im : g.peeled.image)
+    if (im.c.use_filters && !im.c.binned) throw OracleError{"filter convolution cannot be used with raytracing"};
   precompute_jnu_var(g);
   Photon p;
   for (int64_t ip = 1; ip <= n_sources; ip++) {
@@ -3601,8 +3652,10 @@ void raytracing_photons(orc_ctx &g, int64_t n_sources, int64_t n_thermal) {
 
 // image_write (image_type.f90:608-788): the arrays as written, in memory order
 void image_written(const Image &im, bool sed, std::vector<double> &out, std::vector<double> &unc) {
-  double dnunorm = std::pow(im.nu_max / im.nu_min, +0.5 / (double)im.n_nu) -
-                   std::pow(im.nu_max / im.nu_min, -0.5 / (double)im.n_nu);
+  // with filters the flux stays in F_nu dnu: the filter carries the normalisation (image_type.f90:649-657)
+  double dnunorm = im.c.use_filters ? 1.0
+                                    : std::pow(im.nu_max / im.nu_min, +0.5 / (double)im.n_nu) -
+                                          std::pow(im.nu_max / im.nu_min, -0.5 / (double)im.n_nu);
   out = sed ? im.sed : im.img;
   if (im.c.uncertainties) {
     const std::vector<double> &s2 = sed ? im.sed2 : im.img2;

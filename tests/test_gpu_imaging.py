@@ -333,3 +333,53 @@ def test_inside_observer_matches_oracle(golden_car, golden_sph, geometry, raytra
         a = np.mean([g[1][key] for g in gpu])
         b = np.mean([o[1][key] for o in orc])
         assert abs(a / b - 1) < 0.02, (key, a, b)
+
+
+def test_filter_convolution_matches_oracle(golden_car):
+    """use_filters (image_type.f90:467-476): two overlapping smooth filters instead of a wavelength grid,
+    in a peeled group and in the binned group."""
+    from helpers import FlatPeeledGroup
+    model = peeloff_model(golden_car, False)
+    model.conf.forced_first_interaction = False
+    nu = np.logspace(12.5, 15.5, 40)
+    f1 = (nu, np.exp(-0.5 * ((np.log10(nu) - 14.5) / 0.3) ** 2), 10 ** 14.5)
+    f2 = (nu[::-1].copy(), np.exp(-0.5 * ((np.log10(nu[::-1]) - 13.6) / 0.4) ** 2) * 3.0, 10 ** 13.6)   # decreasing nu
+    g = peeloff_groups()[1]
+    g.filters = [f1, f2]
+    model.peeled = [peeloff_groups()[0], g]
+    model.binned = FlatPeeledGroup(binned=True, n_theta=1, n_phi=2, filters=[f2, f1], sed=(1, 0.5 * pc, 1.8 * pc),
+                                   track_origin="no", stokes=False)
+    model.specific_energy = _converged_energy(model)
+    B = 12
+    groups = model.peeled + [model.binned]
+    from hyperion_b200.capi import Engine
+    from oracle import oracle
+    gpu = []
+    for b in range(B):
+        eng = Engine(0)
+        eng.load_model(model)
+        eng.final_begin()
+        eng.final_photons(b * 60000, 60000, False)
+        st = eng.final_finish()
+        gpu.append((_cubes(eng, groups), st.as_dict(), None))
+        eng.close()
+
+    def one(b):
+        o = oracle.Oracle(model, rank=b)
+        o.final_begin()
+        o.final_photons(60000, False)
+        st = o.final_finish()
+        return _cubes(o, groups), st.as_dict(), None
+
+    with ThreadPoolExecutor(max_workers=8) as pool:
+        orc = list(pool.map(one, range(B)))
+    report = _compare(gpu, orc)
+    print(report)
+    assert gpu[0][0]["g1_sed"].shape[-1] == 2 and gpu[0][0]["g2_sed"].shape[-1] == 2
+    # raytracing refuses filters with the reference's message
+    from hyperion_b200.capi import HyperionError
+    eng = Engine(0)
+    eng.load_model(model)
+    with pytest.raises(HyperionError, match="filter convolution cannot be used with raytracing"):
+        eng.raytracing_photons(100, 100)
+    eng.close()

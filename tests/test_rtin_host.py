@@ -326,3 +326,21 @@ def test_runner_writes_binned_group(golden_car, tmp_path):
     assert r["Binned/seds"].shape == (4, 4, 6, 2, 4) and r["Binned/images"].shape == (4, 4, 6, 3, 3, 4)
     sed = r["Binned/seds"][...]
     assert np.all(np.isfinite(sed)) and (sed[0, 0].sum(axis=(-1, -2)) > 0).all()
+
+
+def test_rtin_roundtrip_filters_and_inside_observer(golden_car, tmp_path):
+    """use_filters / n_filt / filter_%05i tables (hyperion/conf/conf_files.py:862-885) and inside_observer."""
+    from helpers import peeloff_model, pc
+    m = peeloff_model(golden_car, False)
+    nu = np.logspace(13, 15, 10)
+    m.peeled[0].filters = [(nu, np.linspace(0.1, 1.0, 10), 3e14), (nu[:5], np.ones(5), 5e13)]
+    m.peeled[1].inside_observer = True
+    m.peeled[1].peeloff_origin = (0.1 * pc, 0.2 * pc, -0.3 * pc)
+    fn = str(tmp_path / "m.rtin")
+    rtin_write.write_rtin(fn, m, n_initial_iter=1, n_initial_photons=100, n_last_photons=100)
+    got, rs, _ = rtin.read_rtin(fn)
+    f = got.peeled[0].filters
+    assert len(f) == 2 and np.array_equal(f[0][0], nu) and np.array_equal(f[1][1], np.ones(5)) and f[0][2] == 3e14
+    assert got.peeled[0].wavelengths[0] == 2
+    assert got.peeled[1].inside_observer and got.peeled[1].peeloff_origin == (0.1 * pc, 0.2 * pc, -0.3 * pc)
+    assert got.peeled[1].filters is None and got.peeled[2].filters is None
