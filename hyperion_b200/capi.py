@@ -34,6 +34,14 @@ class DustTables(C.Structure):
     ]
 
 
+class Spot(C.Structure):
+    _fields_ = [
+        ("luminosity", C.c_double), ("longitude", C.c_double), ("latitude", C.c_double), ("radius", C.c_double),
+        ("spectrum_type", C.c_int32), ("temperature", C.c_double),
+        ("n_spec", C.c_int32), ("spec_nu", _dp), ("spec_fnu", _dp),
+    ]
+
+
 class Source(C.Structure):
     _fields_ = [
         ("type", C.c_int32), ("peeloff", C.c_int32), ("luminosity", C.c_double),
@@ -44,6 +52,7 @@ class Source(C.Structure):
         ("box", C.c_double * 6), ("theta", C.c_double), ("phi", C.c_double),
         ("n_points", C.c_int64), ("points_xyz", _dp), ("points_lum", _dp),
         ("n_map", C.c_int64), ("map", _dp),
+        ("n_spots", C.c_int32), ("spots", C.POINTER(Spot)),
     ]
 
 
@@ -179,6 +188,20 @@ class CApi:
                 raise HyperionError("point collection: positions and luminosities differ in length")
             keep_pts = (xyz, lum)
             t.n_points, t.points_xyz, t.points_lum = len(lum), _ptr(xyz), _ptr(lum)
+        keep_spots = []
+        if s.spots:
+            arr = (Spot * len(s.spots))()
+            for q, d in zip(arr, s.spots):
+                q.luminosity, q.longitude, q.latitude, q.radius = (float(d[k]) for k in ("luminosity", "longitude", "latitude", "radius"))
+                if d.get("temperature") is not None:
+                    q.spectrum_type, q.temperature = 2, float(d["temperature"])
+                else:
+                    nu = np.ascontiguousarray(d["spectrum_nu"], dtype=np.float64)
+                    fnu = np.ascontiguousarray(d["spectrum_fnu"], dtype=np.float64)
+                    keep_spots.append((nu, fnu))
+                    q.spectrum_type, q.n_spec, q.spec_nu, q.spec_fnu = 1, len(nu), _ptr(nu), _ptr(fnu)
+            keep_spots.append(arr)
+            t.n_spots, t.spots = len(s.spots), arr
         keep_map = None
         if s.map is not None:
             keep_map = np.ascontiguousarray(s.map, dtype=np.float64).reshape(-1)
@@ -194,7 +217,7 @@ class CApi:
             keep = (nu, fnu)
             t.spectrum_type, t.n_spec, t.spec_nu, t.spec_fnu = 1, len(nu), _ptr(nu), _ptr(fnu)
         self.check(self._fn("add_source")(ctx, C.byref(t)))
-        del keep, keep_pts, keep_map
+        del keep, keep_pts, keep_map, keep_spots
 
     def set_run_conf(self, ctx, c: FlatConf):
         t = RunConf()

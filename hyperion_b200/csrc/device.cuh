@@ -110,6 +110,17 @@ struct SourceDev {
   int64_t coll_off;        // point_collection: first entry in ModelDev::coll_xyz / coll_cdf
   int64_t coll_n;
   int64_t map_off;         // map: first entry of this source's cumulative luminosity map in ModelDev::map_cdf
+  int32_t spot_off, n_spots;  // sphere with spots: entries [spot_off, spot_off + n_spots] of ModelDev::spots (the last
+                              // entry is the star itself and only carries the cdf)
+};
+
+// One spot of a spherical source (source_type.f90:27-33,150-188)
+struct SpotDev {
+  double cdf;                            // cumulative luminosity over the spots and, last, the star
+  double a_cost, a_sint, a_cosp, a_sinp; // angle3d_deg(longitude, latitude)
+  double cost;                           // cos(radius)
+  double temperature;
+  int32_t freq_type, spectrum;
 };
 
 // sample_pdf_discrete_dp (type_pdf.f90:313-337): 0-based index of the first entry with cdf >= xi

@@ -68,6 +68,7 @@ struct ModelDev {
   const double *mrw_cdf;    // xcdf[100] | ycdf[100]
   const double *coll_xyz, *coll_cdf;  // point collections: positions [n][3] and cumulative luminosities, all sources concatenated
   const double *map_cdf;              // map sources: cumulative luminosity per cell (n_cells entries per source)
+  const SpotDev *spots;               // spots of all spherical sources
   int32_t any_sphere;       // a spherical source exists: flights test for re-absorption (source.f90:206-227)
   int64_t n_reabs_max;
   // outputs
@@ -398,10 +399,31 @@ __device__ bool emit_photon(const ModelDev &M, Photon<ND> &p, Rng &rng, double &
   p.tag = (uint32_t)(is + 1);
   p.nx = p.ny = p.nz = 0.0;
   int64_t map_ic = 0;
+  int ispot = -1;
   if (S.type == HYP_SOURCE_SPHERE) {
     // emit_from_sphere (source_type.f90:604-690): random point of the surface, direction from the
     // cosine law (or the limb-darkened law) about the local normal
-    const Angle a_coord = random_sphere_angle(rng);
+    Angle a_coord;
+    if (S.n_spots > 0) {
+      // source type 3 (source_type.f90:421-427): a spot or the star by luminosity; inside a spot the
+      // point is rejection-sampled (:632-637)
+      const SpotDev *sp = M.spots + S.spot_off;
+      const double xi = rng.next();
+      int k = S.n_spots;
+      if (xi <= sp[0].cdf) k = 0;
+      else if (xi < sp[S.n_spots].cdf)
+        for (k = 1; k < S.n_spots && xi > sp[k].cdf; ++k) {}
+      ispot = k < S.n_spots ? k : -1;
+      a_coord = random_sphere_angle(rng);
+      if (ispot >= 0) {
+        const SpotDev &q = sp[ispot];
+        while (!(a_coord.sint * a_coord.cosp * q.a_sint * q.a_cosp + a_coord.sint * a_coord.sinp * q.a_sint * q.a_sinp +
+                 a_coord.cost * q.a_cost > q.cost))
+          a_coord = random_sphere_angle(rng);
+      }
+    } else {
+      a_coord = random_sphere_angle(rng);
+    }
     const double phi_local = 6.283185307179586476925286766559 * rng.next();
     Angle a_local;
     sincos(phi_local, &a_local.sinp, &a_local.cosp);
@@ -494,7 +516,28 @@ __device__ bool emit_photon(const ModelDev &M, Photon<ND> &p, Rng &rng, double &
   }
   p.sQ = p.sU = p.sV = 0.0;
   p.energy = reemit_src >= 0 ? reemit_energy : 1.0;
-  if (S.freq_type == HYP_SPECTRUM_BLACKBODY) {
+  if (ispot >= 0) {
+    // the spot's own spectrum; tables are sampled with sample_pdf_log (source_type.f90:480-486,
+    // type_pdf.f90:383-400): x interpolated in the log against the cdf
+    const SpotDev &q = M.spots[S.spot_off + ispot];
+    if (q.freq_type == HYP_SPECTRUM_BLACKBODY) {
+      p.nu = sample_planck(rng, q.temperature);
+    } else {
+      const SpectrumDev &sp = M.spectra[q.spectrum];
+      const double *x = sp.B + sp.L.o_x, *cdf = sp.B + sp.L.o_cdf;
+      const int n = sp.L.n;
+      const double xi = rng.next();
+      if (xi <= cdf[0]) {
+        p.nu = x[0];
+      } else if (xi >= cdf[n - 1]) {
+        p.nu = x[n - 1];
+      } else {
+        const int i = lower_interval(cdf, n, xi);
+        const double frac = (xi - cdf[i]) / (cdf[i + 1] - cdf[i]);
+        p.nu = (x[i] == 0.0 || x[i + 1] == 0.0) ? 0.0 : pow(10.0, log10(x[i]) + frac * (log10(x[i + 1]) - log10(x[i])));
+      }
+    }
+  } else if (S.freq_type == HYP_SPECTRUM_BLACKBODY) {
     p.nu = sample_planck(rng, S.temperature);
   } else if (S.freq_type == HYP_SPECTRUM_LTE) {
     // select_dust_specific_energy_rho (grid_physics_3d.f90:101-109; draws even for one dust type), then
@@ -1784,6 +1827,9 @@ struct hyp_ctx {
   std::vector<int64_t> map_off;               // per source: first entry of its cumulative luminosity map, -1 if none
   std::vector<double> map_cdf;                // released after the upload
   double *d_map_cdf = nullptr;
+  std::vector<int> spot_off;                  // per source: first entry in spots
+  std::vector<SpotDev> spots;
+  SpotDev *d_spots = nullptr;
   uint32_t pool_cap = 0;
   uint32_t *h_counts = nullptr;  // pinned: [C_COUNT] counters + next_photon (2 words)
   // emission-order sort (direction keys)
@@ -2064,6 +2110,7 @@ void hyp_ctx_destroy(hyp_ctx *c) {
   free_dev(c->d_coll_xyz);
   free_dev(c->d_coll_cdf);
   free_dev(c->d_map_cdf);
+  free_dev(c->d_spots);
   free_dev(c->d_spectra);
   free_dev(c->d_work);
   free_dev(c->d_error);
@@ -2419,7 +2466,7 @@ int hyp_add_source(hyp_ctx *c, const hyp_source *s) {
   if (s->type != HYP_SOURCE_POINT && s->type != HYP_SOURCE_SPHERE && s->type != HYP_SOURCE_EXTERN_SPH &&
       s->type != HYP_SOURCE_EXTERN_BOX && s->type != HYP_SOURCE_PLANE_PARALLEL && s->type != HYP_SOURCE_POINT_COLLECTION &&
       s->type != HYP_SOURCE_MAP)
-    return fail(HYP_ERR_INVALID, "spotted spherical sources are not implemented on the device");
+    return fail(HYP_ERR_INVALID, "unknown type in source list");
   if (s->type == HYP_SOURCE_MAP) {
     // grid_load_pdf_map (grid_geometry_common_3d.f90:47-63)
     if (c->n_cells == 0) return fail(HYP_ERR_STATE, "set the grid before a map source");
@@ -2464,7 +2511,56 @@ int hyp_add_source(hyp_ctx *c, const hyp_source *s) {
   } else if (s->spectrum_type != HYP_SPECTRUM_BLACKBODY && s->spectrum_type != HYP_SPECTRUM_LTE) {
     return fail(HYP_ERR_INVALID, "unknown spectrum specifier");
   }
+  if (s->n_spots > 0 && s->type != HYP_SOURCE_SPHERE) return fail(HYP_ERR_INVALID, "only spherical sources can have spots");
+  if (s->n_spots > 0 && !s->spots) return fail(HYP_ERR_INVALID, "NULL argument");
   hyp_source copy = *s;
+  copy.spots = nullptr;
+  {
+    // source_read (source_type.f90:150-188): spot_pdf = (spot luminosities..., star), luminosity += spots
+    c->spot_off.push_back((int)c->spots.size());
+    if (s->n_spots > 0) {
+      std::vector<double> cdf((size_t)s->n_spots + 1);
+      for (int i = 0; i < s->n_spots; ++i) {
+        if (!(s->spots[i].luminosity >= 0.0)) return fail(HYP_ERR_INVALID, "source luminosity should be positive");
+        cdf[i] = s->spots[i].luminosity;
+        copy.luminosity = copy.luminosity + s->spots[i].luminosity;
+      }
+      cdf[s->n_spots] = s->luminosity;
+      for (int i = 1; i <= s->n_spots; ++i) cdf[i] = cdf[i - 1] + cdf[i];
+      const double norm = cdf[s->n_spots];
+      if (!(norm > 0.0)) return fail(HYP_ERR_INVALID, "[find_cdf_discrete] all PDF elements are zero");
+      const double deg = 3.14159265358979323846 / 180.0;
+      for (int i = 0; i <= s->n_spots; ++i) {
+        SpotDev q;
+        memset(&q, 0, sizeof q);
+        q.cdf = cdf[i] / norm;
+        q.spectrum = -1;
+        if (i < s->n_spots) {
+          const hyp_spot &h = s->spots[i];
+          q.a_cost = cos(h.longitude * deg); q.a_sint = sin(h.longitude * deg);   // angle3d_deg(lon, lat) (:176)
+          q.a_cosp = cos(h.latitude * deg);  q.a_sinp = sin(h.latitude * deg);
+          q.cost = cos(h.radius * deg);
+          q.freq_type = h.spectrum_type;
+          q.temperature = h.temperature;
+          if (h.spectrum_type == HYP_SPECTRUM_TABLE) {
+            try {
+              HostSpectrum sp;
+              build_spectrum(h.spec_nu, h.spec_fnu, h.n_spec, sp.L, sp.buf);
+              sp.nu.assign(h.spec_nu, h.spec_nu + h.n_spec);
+              sp.fnu.assign(h.spec_fnu, h.spec_fnu + h.n_spec);
+              q.spectrum = (int)c->spectra.size();
+              c->spectra.push_back(std::move(sp));
+            } catch (std::exception &e) {
+              return fail(HYP_ERR_INVALID, e.what());
+            }
+          } else if (h.spectrum_type != HYP_SPECTRUM_BLACKBODY) {
+            return fail(HYP_ERR_INVALID, "Spot cannot have LTE spectrum");
+          }
+        }
+        c->spots.push_back(q);
+      }
+    }
+  }
   copy.spec_nu = copy.spec_fnu = nullptr;
   copy.points_xyz = copy.points_lum = nullptr;
   copy.map = nullptr;
@@ -2807,6 +2903,8 @@ int hyp_finalize_setup(hyp_ctx *c) {
       sd[i].dir_sinp = sin(s.phi * deg2rad);
     }
     sd[i].map_off = c->map_off[i];
+    sd[i].spot_off = c->spot_off[i];
+    sd[i].n_spots = s.type == HYP_SOURCE_SPHERE ? s.n_spots : 0;
     sd[i].coll_off = c->coll_off[i];
     sd[i].coll_n = s.type == HYP_SOURCE_POINT_COLLECTION ? s.n_points : 0;
     sd[i].pdf = s.luminosity / ltot;
@@ -2828,6 +2926,11 @@ int hyp_finalize_setup(hyp_ctx *c) {
     std::vector<double>().swap(c->map_cdf);
   }
   M.map_cdf = c->d_map_cdf;
+  if (!c->spots.empty()) {
+    CUDA_TRY(cudaMalloc(&c->d_spots, c->spots.size() * sizeof(SpotDev)));
+    CUDA_TRY(cudaMemcpy(c->d_spots, c->spots.data(), c->spots.size() * sizeof(SpotDev), cudaMemcpyHostToDevice));
+  }
+  M.spots = c->d_spots;
   CUDA_TRY(cudaMalloc(&c->d_sources, sd.size() * sizeof(SourceDev)));
   CUDA_TRY(cudaMemcpy(c->d_sources, sd.data(), sd.size() * sizeof(SourceDev), cudaMemcpyHostToDevice));
   M.sources = c->d_sources;

@@ -118,6 +118,8 @@ class FlatSource:
     points_luminosity: Optional[np.ndarray] = None   # point_collection: [n]
     map: Optional[np.ndarray] = None                 # map (type 4): luminosity per cell, shaped like one density array
     lte: bool = False                                # map only: spectrum = emissivity of the dust in the emitting cell
+    # sphere only: spots, each a dict(luminosity, longitude, latitude, radius [degrees], temperature | spectrum_nu + spectrum_fnu)
+    spots: Optional[list] = None
 
 
 @dataclass

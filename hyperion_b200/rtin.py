@@ -282,8 +282,25 @@ def read_rtin(filename):
                      "point_collection": 8}
             if stype not in types:
                 raise ModelError("unknown type in source list: " + stype)
-            if stype == "sphere" and any(isinstance(g[k], type(g)) for k in g.keys()):
-                raise ModelError("spots on spherical sources are not implemented by this engine yet")
+            spots = []
+            if stype == "sphere":
+                # source_read (source_type.f90:150-188): every sub-group of a sphere is a spot
+                for k in sorted(g.keys()):
+                    if not isinstance(g[k], type(g)):
+                        continue
+                    sa = g[k].attrs
+                    d = dict(luminosity=float(_num(sa["luminosity"])), longitude=float(_num(sa["longitude"])),
+                             latitude=float(_num(sa["latitude"])), radius=float(_num(sa["radius"])))
+                    sspec = _s(sa["spectrum"])
+                    if sspec == "temperature":
+                        d["temperature"] = float(_num(sa["temperature"]))
+                    elif sspec == "spectrum":
+                        t = g[k]["spectrum"][...]
+                        d["spectrum_nu"] = np.asarray(t["nu"], dtype=np.float64)
+                        d["spectrum_fnu"] = np.asarray(t["fnu"], dtype=np.float64)
+                    else:
+                        raise ModelError("Spot cannot have LTE spectrum")
+                    spots.append(d)
             spec = _s(a["spectrum"])
             kw = dict(type=types[stype], peeloff=_yes(a["peeloff"]))
             if stype == "point_collection":
@@ -309,6 +326,8 @@ def read_rtin(filename):
                 kw["radius"] = float(_num(a["r"]))
             if stype == "sphere":
                 kw["limb_darkening"] = _yes(a["limb"])
+                if spots:
+                    kw["spots"] = spots
             if stype == "extern_box":
                 kw["bounds"] = tuple(float(_num(a[k])) for k in ("xmin", "xmax", "ymin", "ymax", "zmin", "zmax"))
             if stype == "plane_parallel":

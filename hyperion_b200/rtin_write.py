@@ -231,6 +231,19 @@ def write_rtin(filename, model: FlatModel, n_initial_iter=5, n_initial_photons=1
             g.attrs["r"] = float(s.radius)
         if stype == "sphere":
             g.attrs["limb"] = _yn(s.limb_darkening)
+            for k, d in enumerate(s.spots or []):
+                # SpotSource.write (hyperion/sources/source.py:355-365)
+                gs2 = g.create_group("Spot %i" % k)
+                gs2.attrs["type"] = "spot"
+                for key in ("luminosity", "longitude", "latitude", "radius"):
+                    gs2.attrs[key] = float(d[key])
+                gs2.attrs["peeloff"] = _yn(True)
+                if d.get("temperature") is not None:
+                    gs2.attrs["spectrum"] = "temperature"
+                    gs2.attrs["temperature"] = float(d["temperature"])
+                else:
+                    gs2.attrs["spectrum"] = "spectrum"
+                    gs2.create_dataset("spectrum", _table([("nu", d["spectrum_nu"]), ("fnu", d["spectrum_fnu"])]))
         if stype == "extern_box":
             for k, v in zip(("xmin", "xmax", "ymin", "ymax", "zmin", "zmax"), s.bounds):
                 g.attrs[k] = float(v)

@@ -66,7 +66,7 @@ typedef struct {
 /* One source (source_read, src/sources/source_type.f90:102-282). */
 #define HYP_SOURCE_POINT 1
 #define HYP_SOURCE_SPHERE 2
-/* 3 (sphere with spots) is not implemented: rejected by hyp_add_source */
+/* the reference's type 3 (sphere with spots) is HYP_SOURCE_SPHERE with n_spots > 0 */
 #define HYP_SOURCE_MAP 4               /* emit_from_map, source_type.f90:713-746 */
 #define HYP_SOURCE_EXTERN_SPH 5        /* emit_from_extern_sph, source_type.f90:748-820 */
 #define HYP_SOURCE_EXTERN_BOX 6        /* emit_from_extern_box, source_type.f90:822-933 */
@@ -75,6 +75,17 @@ typedef struct {
 #define HYP_SPECTRUM_TABLE 1
 #define HYP_SPECTRUM_BLACKBODY 2
 #define HYP_SPECTRUM_LTE 3             /* map sources only: emissivity of the dust in the emitting cell */
+/* A spot on a spherical source (source_read, src/sources/source_type.f90:150-188): a cap of angular
+ * radius `radius` around (longitude, latitude) with its own luminosity and spectrum. */
+typedef struct {
+  double luminosity;
+  double longitude, latitude, radius;   /* degrees */
+  int32_t spectrum_type;                /* HYP_SPECTRUM_TABLE / _BLACKBODY */
+  double temperature;
+  int32_t n_spec;
+  const double *spec_nu, *spec_fnu;
+} hyp_spot;
+
 typedef struct {
   int32_t type;            /* HYP_SOURCE_* (the reference's numbering, source_read) */
   int32_t peeloff;
@@ -93,6 +104,8 @@ typedef struct {
   const double *points_lum;  /* [n_points] */
   int64_t n_map;           /* map: number of cells */
   const double *map;       /* map: luminosity per cell, in cell-id order (the 'Luminosity map' dataset) */
+  int32_t n_spots;         /* sphere: spots (the reference's source type 3); luminosity is the star's own */
+  const hyp_spot *spots;
 } hyp_source;
 
 /* Run configuration: the root attributes of the .rtin file

@@ -367,6 +367,16 @@ struct PdfCont {
     }
   }
   double sample(Rng &rng) const { return sample_xi(rng.random()); }
+  // sample_pdf_cont_log_dp (type_pdf.f90:383-400): x interpolated in the log against the cdf
+  double sample_log(Rng &rng) const {
+    double xi = rng.random();
+    if (xi <= cdf[0]) return x[0];
+    if (xi >= cdf[n - 1]) return x[n - 1];
+    int ip = locate(cdf.data(), n, xi);
+    if (ip == -1) throw OracleError{"Interpolation out of bounds"};
+    if (ip < n && ip > 0) return interp1d_single_linlog(cdf[ip - 1], x[ip - 1], cdf[ip], x[ip], xi);
+    return ip == n ? x[n - 1] : x[0];
+  }
 };
 
 // ---------------------------------------------------------------------------
@@ -775,6 +785,16 @@ struct Source {
   std::vector<Vec> position_collection;                                // point_collection
   PdfDiscrete collection_pdf;
   PdfDiscrete luminosity_map;                                          // map: one entry per cell
+  // spots (source_type.f90:27-33,150-188): spot_pdf has n_spots + 1 entries, the last one is the star itself
+  struct Spot {
+    Angle a;
+    double cost = 0;
+    int freq_type = 2;
+    double temperature = 0;
+    PdfCont spectrum;
+  };
+  std::vector<Spot> spot;
+  PdfDiscrete spot_pdf;
 };
 
 // ---------------------------------------------------------------------------
@@ -2412,8 +2432,20 @@ double ran_mu_limb(Rng &rng, double a, double b) {
 }
 
 // emit_from_sphere (source_type.f90:604-690), no spots
-void emit_from_sphere(orc_ctx &g, const Source &src, Photon &p) {
-  Angle a_coord = random_sphere_angle3d(g.rng);
+void emit_from_sphere(orc_ctx &g, const Source &src, Photon &p, int spot = 0) {
+  Angle a_coord;
+  if (spot > 0) {
+    // rejection sampling of a point inside the spot (source_type.f90:632-637)
+    const Source::Spot &sp = src.spot[spot - 1];
+    for (;;) {
+      a_coord = random_sphere_angle3d(g.rng);
+      const double dot = a_coord.sint * a_coord.cosp * sp.a.sint * sp.a.cosp + a_coord.sint * a_coord.sinp * sp.a.sint * sp.a.sinp +
+                         a_coord.cost * sp.a.cost;
+      if (dot > sp.cost) break;
+    }
+  } else {
+    a_coord = random_sphere_angle3d(g.rng);
+  }
   double phi_local = 0.0 + (TWOPI_F - 0.0) * g.rng.random();  // random_uni(phi_local, zero, twopi)
   Angle a_local;
   a_local.cosp = std::cos(phi_local);
@@ -2606,12 +2638,22 @@ void emit(orc_ctx &g, Photon &p, bool reemit = false, int reemit_id = 0, double 
   }
   if (reemit) p.source_id = reemit_id;  // source.f90:134-140
   const Source &src = g.s[p.source_id - 1];
+  int ispot = 0;
   switch (src.type) {
     case HYP_SOURCE_POINT:
       emit_from_point(g, src, p);
       break;
     case HYP_SOURCE_SPHERE:
-      emit_from_sphere(g, src, p);
+      if (!src.spot.empty()) {
+        // source type 3 (source_type.f90:421-427)
+        ispot = src.spot_pdf.sample(g.rng);
+        if (ispot == (int)src.spot.size() + 1)
+          emit_from_sphere(g, src, p);
+        else
+          emit_from_sphere(g, src, p, ispot);
+      } else {
+        emit_from_sphere(g, src, p);
+      }
       break;
     case HYP_SOURCE_EXTERN_SPH:
       emit_from_extern_sph(g, src, p);
@@ -2632,7 +2674,16 @@ void emit(orc_ctx &g, Photon &p, bool reemit = false, int reemit_id = 0, double 
       throw OracleError{"source type not restated in the oracle"};
   }
   p.energy = 1.0;
-  if (src.freq_type == 1) {
+  if (ispot >= 1 && ispot <= (int)src.spot.size()) {
+    // the spot's own spectrum; tabulated ones are sampled with sample_pdf_log (source_type.f90:480-486)
+    const Source::Spot &sp = src.spot[ispot - 1];
+    if (sp.freq_type == 1)
+      p.nu = sp.spectrum.sample_log(g.rng);
+    else if (sp.freq_type == 2)
+      p.nu = g.rng.random_planck_frequency(sp.temperature);
+    else
+      throw OracleError{"Spot cannot have LTE spectrum"};
+  } else if (src.freq_type == 1) {
     p.nu = src.spectrum.sample(g.rng);
   } else if (src.freq_type == 2) {
     p.nu = g.rng.random_planck_frequency(src.temperature);
@@ -4075,6 +4126,28 @@ int orc_add_source(orc_ctx *g, const hyp_source *s) {
       src.luminosity_map.set(s->map, (int)s->n_map);
     } else if (s->type != HYP_SOURCE_POINT && s->type != HYP_SOURCE_SPHERE && s->type != HYP_SOURCE_EXTERN_SPH) {
       return fail(g, "source type not restated in the oracle");
+    }
+    if (s->type == HYP_SOURCE_SPHERE && s->n_spots > 0) {
+      // source_read (source_type.f90:150-188)
+      std::vector<double> pdf((size_t)s->n_spots + 1);
+      pdf[s->n_spots] = s->luminosity;
+      for (int i = 0; i < s->n_spots; i++) {
+        const hyp_spot &q = s->spots[i];
+        Source::Spot sp;
+        pdf[i] = q.luminosity;
+        src.luminosity = src.luminosity + q.luminosity;
+        sp.a = angle3d_deg(q.longitude, q.latitude);
+        sp.cost = std::cos(q.radius * (PI / 180.0));
+        sp.freq_type = q.spectrum_type;
+        sp.temperature = q.temperature;
+        if (q.spectrum_type == HYP_SPECTRUM_TABLE) sp.spectrum.set(q.spec_nu, q.spec_fnu, q.n_spec, true);
+        else if (q.spectrum_type != HYP_SPECTRUM_BLACKBODY) return fail(g, "Spot cannot have LTE spectrum");
+        src.spot.push_back(sp);
+      }
+      src.spot_pdf.n = s->n_spots + 1;
+      src.spot_pdf.pdf = pdf;
+      src.spot_pdf.cdf.assign(pdf.size(), 0.0);
+      src.spot_pdf.find_cdf();   // allocate_pdf + find_cdf: the pdf itself is not normalised (:160-188)
     }
     src.intersect = (s->type == HYP_SOURCE_SPHERE);
     if (src.intersect) g->any_intersect = true;

@@ -99,7 +99,7 @@ def test_source_argument_errors():
                       "Cannot peeloff plane parallel source"),
                      (FlatSource(type=4, luminosity=lsun, temperature=5000.), "luminosity map should have one entry per cell"),
                      (FlatSource(type=4, luminosity=lsun, temperature=5000., map=np.zeros((8, 8, 8))), "all PDF elements are zero"),
-                     (FlatSource(type=3, luminosity=lsun, temperature=5000., radius=pc), "spotted spherical sources are not implemented"),
+                     (FlatSource(type=3, luminosity=lsun, temperature=5000., radius=pc), "unknown type in source list"),
                      (FlatSource(type=1, luminosity=lsun, lte=True), "Point source cannot have LTE spectrum"),
                      (FlatSource(type=6, luminosity=lsun, temperature=5000., bounds=(1., -1., 0., 1., 0., 1.)),
                       "bounds should be increasing"),
@@ -110,3 +110,42 @@ def test_source_argument_errors():
         with pytest.raises(HyperionError, match=msg):
             eng.load_model(model)
         eng.close()
+
+
+def _spotted_star_model(golden_car):
+    model = bitlevel_model(golden_car, False, False)
+    model.density *= 10.
+    nu = np.logspace(13.5, 15.2, 12)
+    model.sources = [FlatSource(type=2, luminosity=lsun, temperature=5000., position=(0.05 * pc, -0.03 * pc, 0.02 * pc),
+                                radius=0.25 * pc,
+                                spots=[dict(luminosity=0.8 * lsun, longitude=60., latitude=20., radius=35., temperature=9000.),
+                                       dict(luminosity=0.5 * lsun, longitude=140., latitude=250., radius=20.,
+                                            spectrum_nu=nu, spectrum_fnu=nu ** -1.5)]),
+                     FlatSource(type=1, luminosity=0.2 * lsun, temperature=4000., position=(-0.5 * pc, 0.4 * pc, -0.3 * pc))]
+    return model
+
+
+def test_spotted_star_deposits_match_oracle(golden_car):
+    """Source type 3 (source_type.f90:150-188, 421-427, 632-637): spots with their own luminosity and
+    spectrum (blackbody, and a table sampled with sample_pdf_log) on a star that also re-absorbs."""
+    model = _spotted_star_model(golden_car)
+    B, N = 16, 100000
+    g, gst = _gpu_batches(model, N, B)
+    o, ost = _oracle_batches(model, N, B)
+    z, ok = _zscores(g, o)
+    assert ok.mean() > 0.9
+    assert np.abs(z[ok]).max() < 5.5, np.abs(z[ok]).max()
+    assert 0.6 < (z[ok] ** 2).mean() < 1.5, (z[ok] ** 2).mean()
+    for key in ("n_crossings", "n_absorptions", "n_scatterings"):
+        a = np.mean([s[key] for s in gst])
+        b = np.mean([s[key] for s in ost])
+        assert abs(a / b - 1) < 0.01, (key, a, b)
+
+
+def test_spotted_star_peeloff_matches_oracle(golden_car):
+    model = _spotted_star_model(golden_car)
+    model.peeled = peeloff_groups()
+    model.specific_energy = _converged_energy(model)
+    gpu, orc = _run_both(model, 12, 60000, True, (20000, 30000))
+    report = _compare(gpu, orc)
+    print(report)

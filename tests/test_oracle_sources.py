@@ -189,3 +189,35 @@ def test_map_source_uniform_cube_conserves_track_length():
     with np.errstate(divide="ignore"):
         d = np.min(np.where(v > 0, (pc - p) / v, (-pc - p) / v), axis=1)
     assert abs(mean_track / d.mean() - 1.0) < 0.01
+
+
+def test_spot_lights_only_its_cap():
+    """A spherical source whose luminosity sits in one spot (source type 3, source_type.f90:150-188,
+    421-427, 632-637): seen from above the spot centre the light comes from a disk of radius
+    R sin(spot radius); from the opposite side nothing is seen (the 4 mu peel-off weight vanishes)."""
+    from oracle import oracle
+    from hyperion_b200.flatmodel import FlatPeeledGroup
+    R, size = 0.4 * pc, 30.0
+    # angle3d_deg(longitude, latitude) makes the reference read the pair as (theta, phi): the cap sits
+    # around the direction (theta = longitude, phi = latitude)
+    lon, lat = 60.0, 20.0
+    star = FlatSource(type=2, luminosity=1e-12 * lsun, temperature=5000., position=(0., 0., 0.), radius=R,
+                      spots=[dict(luminosity=lsun, longitude=lon, latitude=lat, radius=size, temperature=8000.)])
+    model, _ = _thin_model([star], n=4)
+    common = dict(wavelengths=(1, 0.01, 1000.), stokes=False, image=(40, 40, -R, R, -R, R))
+    model.peeled = [FlatPeeledGroup(theta=[lon], phi=[lat], **common),
+                    FlatPeeledGroup(theta=[180. - lon], phi=[lat + 180.], **common)]
+    o = oracle.Oracle(model)
+    o.final_begin()
+    o.final_photons(40000, False)
+    o.final_finish()
+    front = o.image(0)[0, 0, 0, :, :, 0]
+    back = o.image(1)[0, 0, 0, :, :, 0]
+    x = (np.arange(40) + 0.5) / 40 * 2 * R - R
+    yy, xx = np.meshgrid(x, x, indexing="ij")
+    rr = np.sqrt(xx ** 2 + yy ** 2)
+    pix = 2 * R / 40
+    assert front.sum() > 0
+    assert front[rr > R * np.sin(np.radians(size)) + pix].sum() == 0.0
+    assert front[rr < R * np.sin(np.radians(size)) - pix].min() > 0.0
+    assert back.sum() < 1e-9 * front.sum()

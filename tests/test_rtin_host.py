@@ -344,3 +344,22 @@ def test_rtin_roundtrip_filters_and_inside_observer(golden_car, tmp_path):
     assert got.peeled[0].wavelengths[0] == 2
     assert got.peeled[1].inside_observer and got.peeled[1].peeloff_origin == (0.1 * pc, 0.2 * pc, -0.3 * pc)
     assert got.peeled[1].filters is None and got.peeled[2].filters is None
+
+
+def test_rtin_roundtrip_spots(golden_car, tmp_path):
+    """Sub-groups of a spherical source are its spots (source_read, src/sources/source_type.f90:150-188)."""
+    from helpers import pc, lsun
+    from hyperion_b200.flatmodel import FlatSource
+    m = bitlevel_model(golden_car, False, False)
+    nu = np.logspace(13.5, 15.2, 12)
+    m.sources = [FlatSource(type=2, luminosity=lsun, temperature=5000., radius=0.25 * pc,
+                            spots=[dict(luminosity=0.8 * lsun, longitude=60., latitude=20., radius=35., temperature=9000.),
+                                   dict(luminosity=0.5 * lsun, longitude=140., latitude=250., radius=20.,
+                                        spectrum_nu=nu, spectrum_fnu=nu ** -1.5)])]
+    fn = str(tmp_path / "m.rtin")
+    rtin_write.write_rtin(fn, m, n_initial_iter=1, n_initial_photons=100)
+    got, rs, _ = rtin.read_rtin(fn)
+    sp = got.sources[0].spots
+    assert len(sp) == 2 and sp[0]["temperature"] == 9000. and sp[0]["radius"] == 35.
+    assert np.array_equal(sp[1]["spectrum_nu"], nu) and sp[1]["longitude"] == 140.
+    assert got.sources[0].luminosity == lsun      # the star's own; the engine adds the spots
