@@ -315,10 +315,20 @@ def read_rtin(filename):
             if stype == "map":
                 # grid_load_pdf_map -> read_grid_3d (src/grid/grid_geometry_common_3d.f90:47-63)
                 if amr_levels is not None:
-                    raise ModelError("map sources on AMR grids are not implemented by this engine yet")
-                lm = np.asarray(g["Luminosity map"][...], dtype=np.float64)
-                if lm.shape != grid_shape:
-                    raise ModelError("Luminosity map has wrong shape")
+                    # one 'Luminosity map' dataset per level_%05i/grid_%05i (hyperion/grid/amr_grid.py:422-476),
+                    # flattened in cell-id order
+                    parts = []
+                    for il, lev in enumerate(amr_levels):
+                        for ig, gr in enumerate(lev):
+                            a_ = np.asarray(g["level_%05d/grid_%05d/Luminosity map" % (il + 1, ig + 1)][...], dtype=np.float64)
+                            if a_.shape != (gr[2], gr[1], gr[0]):
+                                raise ModelError("Luminosity map has wrong shape")
+                            parts.append(a_.reshape(-1))
+                    lm = np.concatenate(parts)
+                else:
+                    lm = np.asarray(g["Luminosity map"][...], dtype=np.float64)
+                    if lm.shape != grid_shape:
+                        raise ModelError("Luminosity map has wrong shape")
                 kw["map"] = lm
             if stype in ("point", "sphere", "extern_sph", "plane_parallel"):
                 kw["position"] = (float(_num(a["x"])), float(_num(a["y"])), float(_num(a["z"])))

@@ -223,7 +223,11 @@ def write_rtin(filename, model: FlatModel, n_initial_iter=5, n_initial_photons=1
             g.create_dataset("luminosity", np.ascontiguousarray(s.points_luminosity, dtype=np.float64))
         else:
             g.attrs["luminosity"] = float(s.luminosity)
-        if stype == "map":
+        if stype == "map" and model.grid_type == "amr":
+            flat = np.ascontiguousarray(s.map, dtype=np.float64).reshape(-1)
+            for il, ig, sl, shp in model.amr_slices():
+                g.create_dataset("level_%05i/grid_%05i/Luminosity map" % (il + 1, ig + 1), flat[sl].reshape(shp))
+        elif stype == "map":
             g.create_dataset("Luminosity map", np.ascontiguousarray(s.map, dtype=np.float64))
         if stype in ("point", "sphere", "extern_sph", "plane_parallel"):
             g.attrs["x"], g.attrs["y"], g.attrs["z"] = [float(v) for v in s.position]

@@ -149,3 +149,38 @@ def test_spotted_star_peeloff_matches_oracle(golden_car):
     gpu, orc = _run_both(model, 12, 60000, True, (20000, 30000))
     report = _compare(gpu, orc)
     print(report)
+
+
+@pytest.mark.parametrize("geometry", ["sph", "cyl", "oct", "amr"])
+def test_map_source_on_other_grids(golden_car, golden_sph, golden_cyl, golden_oct, golden_amr, geometry):
+    """emit_from_map uses random_position_cell of each geometry module; an LTE and a blackbody map."""
+    from helpers import bitlevel_model_sph, bitlevel_model_oct, bitlevel_model_amr
+    if geometry in ("sph", "cyl"):
+        model = bitlevel_model_sph(golden_car, golden_sph if geometry == "sph" else golden_cyl, False, True, geometry)
+    elif geometry == "oct":
+        model = bitlevel_model_oct(golden_car, golden_oct, False, True)
+    else:
+        model = bitlevel_model_amr(golden_car, golden_amr, False, True)
+    rng = np.random.default_rng(5)
+    shape = model.density.shape[1:]
+    # refined octree nodes / covered AMR cells hold no dust: an LTE source cannot emit from them (the
+    # reference stops in find_cdf, as the oracle does)
+    from test_gpu_parity import _engine
+    eng = _engine(model)
+    dusty = (eng.get_density().reshape(model.density.shape) > 0).all(axis=0)
+    eng.close()
+    assert 0 < dusty.sum() < dusty.size or geometry in ("sph", "cyl")
+    model.sources = [FlatSource(type=4, luminosity=2 * lsun, temperature=6000., map=rng.random(shape) ** 2),
+                     FlatSource(type=4, luminosity=lsun, lte=True, map=rng.random(shape) * dusty)]
+    B, N = 12, 100000
+    g, gst = _gpu_batches(model, N, B)
+    o, ost = _oracle_batches(model, N, B)
+    z, ok = _zscores(g, o)
+    filled = ok & (o.mean(0) > 0)
+    assert filled.sum() > 20
+    assert np.abs(z[filled]).max() < 5.5, np.abs(z[filled]).max()
+    assert 0.5 < (z[filled] ** 2).mean() < 1.6, (z[filled] ** 2).mean()
+    for key in ("n_crossings", "n_absorptions", "n_scatterings"):
+        a = np.mean([s[key] for s in gst])
+        b = np.mean([s[key] for s in ost])
+        assert abs(a / b - 1) < 0.015, (key, a, b)

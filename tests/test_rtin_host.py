@@ -363,3 +363,16 @@ def test_rtin_roundtrip_spots(golden_car, tmp_path):
     assert len(sp) == 2 and sp[0]["temperature"] == 9000. and sp[0]["radius"] == 35.
     assert np.array_equal(sp[1]["spectrum_nu"], nu) and sp[1]["longitude"] == 140.
     assert got.sources[0].luminosity == lsun      # the star's own; the engine adds the spots
+
+
+def test_rtin_roundtrip_map_source_on_amr_grid(golden_car, golden_amr, tmp_path):
+    """A luminosity map on an AMR grid is stored per level / grid like the density."""
+    from helpers import bitlevel_model_amr, lsun
+    from hyperion_b200.flatmodel import FlatSource
+    m = bitlevel_model_amr(golden_car, golden_amr, False, False)
+    lm = np.arange(float(m.n_cells)) + 1.0
+    m.sources = [FlatSource(type=4, luminosity=lsun, temperature=4000., map=lm)]
+    fn = str(tmp_path / "m.rtin")
+    rtin_write.write_rtin(fn, m, n_initial_iter=1, n_initial_photons=100)
+    got, rs, _ = rtin.read_rtin(fn)
+    assert np.array_equal(got.sources[0].map, lm)
