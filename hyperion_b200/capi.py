@@ -65,6 +65,7 @@ class RunConf(C.Structure):
         ("propagation_check_frequency", C.c_double),
         ("forced_first_interaction", C.c_int32), ("forced_first_interaction_algorithm", C.c_int32),
         ("baes16_xi", C.c_double),
+        ("specific_energy_additional", C.c_int32),
     ]
 
 
@@ -229,6 +230,7 @@ class CApi:
         t.forced_first_interaction = int(c.forced_first_interaction)
         t.forced_first_interaction_algorithm = {"wr99": 1, "baes16": 2}[c.forced_first_interaction_algorithm]
         t.baes16_xi = c.baes16_xi
+        t.specific_energy_additional = int(c.specific_energy_additional)
         self.check(self._fn("set_run_conf")(ctx, C.byref(t)))
 
     def add_peeled_group(self, ctx, g):

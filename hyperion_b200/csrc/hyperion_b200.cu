@@ -56,6 +56,7 @@ struct ModelDev {
   const SourceDev *sources;
   const SpectrumDev *spectra;
   double min_energy[MAX_DUST];
+  const double *energy_additional;  // specific_energy_type = 'additional': added after every iteration, or nullptr
   // run configuration
   uint64_t seed;
   int64_t n_inter_max;
@@ -1665,6 +1666,7 @@ __global__ void lucy_finish_kernel(ModelDev M, const double *__restrict__ sums, 
     const DustDev &d = M.dust[id];
     double e = sums[k] * scale / vol;
     if (vol == 0.0) e = 0.0;
+    if (M.energy_additional) e = e + M.energy_additional[k];   // grid_physics_3d.f90:537-545
     e = clamp_energy(M, d, id, e);
     if (d.L.sublimation_mode != 0 && e > d.L.sublimation_specific_energy) {
       const double es = d.L.sublimation_specific_energy;
@@ -1827,6 +1829,7 @@ struct hyp_ctx {
   std::vector<int64_t> map_off;               // per source: first entry of its cumulative luminosity map, -1 if none
   std::vector<double> map_cdf;                // released after the upload
   double *d_map_cdf = nullptr;
+  double *d_energy_add = nullptr;             // specific_energy_type = 'additional
   std::vector<int> spot_off;                  // per source: first entry in spots
   std::vector<SpotDev> spots;
   SpotDev *d_spots = nullptr;
@@ -2110,6 +2113,7 @@ void hyp_ctx_destroy(hyp_ctx *c) {
   free_dev(c->d_coll_xyz);
   free_dev(c->d_coll_cdf);
   free_dev(c->d_map_cdf);
+  free_dev(c->d_energy_add);
   free_dev(c->d_spots);
   free_dev(c->d_spectra);
   free_dev(c->d_work);
@@ -2647,6 +2651,19 @@ static int upload_energy(hyp_ctx *c) {
   const size_t n = (size_t)c->n_cells * c->dust.size();
   CUDA_TRY(cudaMemcpyAsync(c->d_stage, c->h_energy.data(), n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
   to_device_order_kernel<<<grid_blocks(c), 256, 0, c->stream>>>((int)c->dust.size(), c->n_cells, c->d_stage, c->d_energy);
+  if (c->conf.specific_energy_additional && c->energy_from_caller) {
+    // grid_physics_3d.f90:213-235: keep the given array as the extra heating term and start from the minimum
+    if (!c->d_energy_add) CUDA_TRY(cudaMalloc(&c->d_energy_add, n * sizeof(double)));
+    CUDA_TRY(cudaMemcpyAsync(c->d_energy_add, c->d_energy, n * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+    c->M.energy_additional = c->d_energy_add;
+    std::vector<double> start(n);
+    const size_t nd = c->dust.size();
+    for (size_t id = 0; id < nd; ++id)
+      std::fill(start.begin() + id * c->n_cells, start.begin() + (id + 1) * c->n_cells, c->h_min_energy[id]);
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    CUDA_TRY(cudaMemcpy(c->d_stage, start.data(), n * sizeof(double), cudaMemcpyHostToDevice));
+    to_device_order_kernel<<<grid_blocks(c), 256, 0, c->stream>>>((int)nd, c->n_cells, c->d_stage, c->d_energy);
+  }
   clamp_energy_kernel<<<grid_blocks(c), 256, 0, c->stream>>>(c->M);
   CUDA_TRY(cudaGetLastError());
   CUDA_TRY(cudaStreamSynchronize(c->stream));
@@ -2688,6 +2705,8 @@ int hyp_finalize_setup(hyp_ctx *c) {
     int rc = hyp_set_specific_energy(c, nullptr, nullptr);
     if (rc) return rc;
   }
+  if (c->conf.specific_energy_additional && !c->energy_from_caller)
+    return fail(HYP_ERR_INVALID, "cannot specify specific_energy_type since specific_energy was not given");
   CUDA_TRY(cudaSetDevice(c->device));
   const int nd = (int)c->dust.size();
   const size_t n = (size_t)c->n_cells * nd;

@@ -136,6 +136,7 @@ class FlatConf:
     mrw_gamma: float = 1.0
     n_mrw_max: int = 1000
     propagation_check_frequency: float = 1.e-3
+    specific_energy_additional: bool = False   # specific_energy_type = 'additional'
     n_initial_iter: int = 5
     n_initial_photons: int = 0
     forced_first_interaction: bool = True

@@ -135,7 +135,7 @@ def write_rtin(filename, model: FlatModel, n_initial_iter=5, n_initial_photons=1
     if raytracing:
         A["n_ray_photons_sources"] = float(n_ray_photons[0])
         A["n_ray_photons_dust"] = float(n_ray_photons[1])
-    A["specific_energy_type"] = "initial"
+    A["specific_energy_type"] = "additional" if c.specific_energy_additional else "initial"
     A["physics_io_bytes"] = np.int32(physics_io_bytes)
     A["copy_input"] = _yn(copy_input)
     if check_convergence is None:

@@ -199,7 +199,10 @@ def run(input_file, output_file, overwrite=False, device=None, log=None):
     if rs.pda:
         raise ModelError("the partial diffusion approximation is not implemented by this engine yet")
     if rs.specific_energy_type == "additional":
-        raise ModelError("specific_energy_type='additional' is not implemented by this engine yet")
+        # setup_initial (src/main/setup_rt.f90:191-194)
+        if rs.n_initial_iter == 0:
+            raise ModelError("Cannot use specific_energy_type='additional' if the number of specific energy iterations is 0")
+        model.conf.specific_energy_additional = True
 
     dist = None
     if world > 1:

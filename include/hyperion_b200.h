@@ -127,6 +127,10 @@ typedef struct {
   int32_t forced_first_interaction;            /* default on (hyperion/conf/conf_files.py:66) */
   int32_t forced_first_interaction_algorithm;  /* HYP_FFI_WR99 / HYP_FFI_BAES16 */
   double baes16_xi;
+  /* specific_energy_type = 'additional' (setup_grid_physics, src/grid/grid_physics_3d.f90:213-235;
+   * update_energy_abs :537-545): the specific energy passed in is an extra heating term that is added
+   * after every Lucy iteration, and the iterations start from the minimum specific energy. */
+  int32_t specific_energy_additional;
 } hyp_run_conf;
 
 #define HYP_FFI_WR99 1

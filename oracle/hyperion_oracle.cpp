@@ -1168,6 +1168,7 @@ struct orc_ctx {
   std::vector<Dust> d;
   // grid physics (grid_physics_3d.f90:34-63): (ic, id) stored at [id*n_cells + ic]
   std::vector<double> density, specific_energy, specific_energy_sum, jnu_var_frac, minimum_specific_energy;
+  std::vector<double> specific_energy_additional;  // specific_energy_type = 'additional' (grid_physics_3d.f90:55)
   std::vector<int> jnu_var_id;
   std::vector<double> energy_abs_tot;
   PdfDiscrete absorption;
@@ -2885,6 +2886,10 @@ void update_energy_abs(orc_ctx &g, double scale) {
       g.specific_energy[k] = g.specific_energy_sum[k] * scale / g.volume[ic];
       if (g.volume[ic] == 0.0) g.specific_energy[k] = 0.0;
     }
+  // additional source of heating (grid_physics_3d.f90:537-545)
+  if (!g.specific_energy_additional.empty())
+    for (size_t k = 0; k < g.specific_energy.size(); k++)
+      g.specific_energy[k] = g.specific_energy[k] + g.specific_energy_additional[k];
   update_energy_abs_tot(g);
   check_energy_abs(g);
 }
@@ -4204,6 +4209,15 @@ int orc_finalize_setup(orc_ctx *g, int32_t rank) {
             if (!valid[ic]) g->specific_energy[(size_t)id * g->n_cells + ic] = 0.0;
     }
     if (g->specific_energy.size() != n) orc_set_specific_energy(g, nullptr, nullptr);
+    if (g->conf.specific_energy_additional && !g->setup_done) {
+      // grid_physics_3d.f90:213-235,241-243
+      if (!g->specific_energy_from_file)
+        return fail(g, "cannot specify specific_energy_type since specific_energy was not given");
+      g->specific_energy_additional = g->specific_energy;
+      for (int id = 0; id < g->n_dust; id++)
+        for (int ic = 0; ic < g->n_cells; ic++)
+          g->specific_energy[(size_t)id * g->n_cells + ic] = g->minimum_specific_energy[id];
+    }
     g->specific_energy_sum.assign(n, 0.0);
     g->jnu_var_id.assign(n, 0);
     g->jnu_var_frac.assign(n, 0.0);

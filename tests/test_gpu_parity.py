@@ -433,3 +433,28 @@ def test_spherical_source_with_reabsorption(golden_car, golden_sph, geometry):
         b = np.mean([s[key] for s in ost])
         assert abs(a / b - 1) < 0.01, (key, a, b)
     assert all(s["killed_geo"] == 0 and s["killed_int"] == 0 and s["n_escaped"] == N for s in gst)
+
+
+def test_additional_specific_energy(golden_car):
+    """specific_energy_type = 'additional' (grid_physics_3d.f90:213-235, 537-545): iterations start from the
+    minimum specific energy, the given array is added after each of them.  Same packets (id-keyed RNG),
+    same starting state: E_additional = E_plain + extra, to rounding."""
+    from hyperion_b200.capi import HyperionError
+    base = bitlevel_model(golden_car, False, True)
+    extra = np.random.default_rng(2).uniform(0.5, 2.0, base.density.shape) * 1e-3
+    eng = _engine(base)
+    eng.run_lucy_iteration(200000)
+    e0 = eng.get_specific_energy()
+    eng.close()
+    add = bitlevel_model(golden_car, False, True)
+    add.specific_energy = extra
+    add.conf.specific_energy_additional = True
+    eng = _engine(add)
+    eng.run_lucy_iteration(200000)
+    e1 = eng.get_specific_energy()
+    eng.close()
+    assert np.allclose(e1, e0 + extra, rtol=1e-9, atol=0)
+    bad = bitlevel_model(golden_car, False, True)
+    bad.conf.specific_energy_additional = True
+    with pytest.raises(HyperionError, match="cannot specify specific_energy_type since specific_energy was not given"):
+        _engine(bad)

@@ -221,3 +221,25 @@ def test_spot_lights_only_its_cap():
     assert front[rr > R * np.sin(np.radians(size)) + pix].sum() == 0.0
     assert front[rr < R * np.sin(np.radians(size)) - pix].min() > 0.0
     assert back.sum() < 1e-9 * front.sum()
+
+
+def test_additional_specific_energy_is_added_after_each_iteration():
+    """specific_energy_type = 'additional' (grid_physics_3d.f90:213-235, 537-545): the iterations start from
+    the minimum specific energy and the given array is added to what the packets deposit."""
+    from oracle import oracle
+    from helpers import bitlevel_model
+    import os
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "bitlevel_car.npz"))
+    base = bitlevel_model(z, False, True)
+    extra = np.random.default_rng(2).uniform(0.5, 2.0, base.density.shape) * 1e-3
+    plain = oracle.Oracle(base)
+    plain.run_lucy_iteration(20000)
+    e0 = plain.get_specific_energy()
+    add = bitlevel_model(z, False, True)
+    add.specific_energy = extra
+    add.conf.specific_energy_additional = True
+    o = oracle.Oracle(add)
+    o.run_lucy_iteration(20000)
+    e1 = o.get_specific_energy()
+    # same random stream, same starting state (the minimum): the deposits are identical
+    assert np.allclose(e1, e0 + extra, rtol=1e-13, atol=0)
