@@ -1938,12 +1938,12 @@ size_t slot_bytes(int nd) {
   }
 }
 
-// Packets resident in the pool at once.  Large enough that a round keeps every SM busy for a
-// few milliseconds, small enough that the records (192 B each) stream through L2 without
-// displacing the cell grid.
+// Packets resident in the pool at once (never more than the launch holds).  Measured on the 256^3 headline
+// (profiles/r01_experiments.md): 2 M slots 91.7 ms per 2e7 packets, 8 M 87.5 ms, 16 M 84.9 ms, 20 M 84.6 ms --
+// fewer, fuller rounds amortise the launch tails; 16 M slots are 3 GB of the 180 GB.
 uint32_t pool_target() {
   const char *e = getenv("HYPERION_B200_POOL");
-  long v = e ? atol(e) : (1L << 21);
+  long v = e ? atol(e) : (1L << 24);
   if (v < 1024) v = 1024;
   if (v > (1L << 28)) v = 1L << 28;
   return (uint32_t)v;
