@@ -18,8 +18,14 @@
 // order in which the deposits are summed differs.
 #pragma once
 
-constexpr int TILE_THREADS = 384;
-constexpr int TILE_MIN_BLOCKS = 2;
+#ifndef TILE_THREADS_N
+#define TILE_THREADS_N 384
+#endif
+#ifndef TILE_MIN_BLOCKS_N
+#define TILE_MIN_BLOCKS_N 2
+#endif
+constexpr int TILE_THREADS = TILE_THREADS_N;
+constexpr int TILE_MIN_BLOCKS = TILE_MIN_BLOCKS_N;
 constexpr uint32_t TILE_CHUNK = 4096;   // packets per work item
 #ifndef TILE_REFILL_IDLE
 #define TILE_REFILL_IDLE 8              // idle lanes of a warp that trigger a refill
@@ -104,9 +110,10 @@ flight_tile_kernel(const ModelDev M, Pool P, const int park_buf) {
   extern __shared__ double t_smem[];
   double *__restrict__ s_rho = t_smem;
   double *__restrict__ s_esum = t_smem + TD::CELLS * ND;
-  double *__restrict__ s_w = s_esum + TD::CELLS * ND;  // [3][17] walls of the tile
+  constexpr int TW = TD::WALLS;                        // wall slots per axis
+  double *__restrict__ s_w = s_esum + TD::CELLS * ND;  // [3][TW] walls of the tile
   constexpr int REC16 = (80 + 16 * ND) / 16;            // hot part of a Slot<ND> in 16-byte units
-  uint4 *__restrict__ s_rec = (uint4 *)(s_w + 3 * 17 + 1);   // [TILE_THREADS][REC16], 16-byte aligned
+  uint4 *__restrict__ s_rec = (uint4 *)(s_w + 3 * TW + 1);   // [TILE_THREADS][REC16], 16-byte aligned
   constexpr uint32_t NO_PACKET = 0xffffffffu;
   static_assert(offsetof(Slot<ND>, ix) == 64 + 16 * ND, "hot part of Slot is contiguous");
   __shared__ uint32_t s_item, s_next;
@@ -138,8 +145,8 @@ flight_tile_kernel(const ModelDev M, Pool P, const int park_buf) {
         s_esum[c * ND + id] = 0.0;
       }
     }
-    for (int k = threadIdx.x; k < 3 * 17; k += TILE_THREADS) {
-      const int a = k / 17, j = k % 17;
+    for (int k = threadIdx.x; k < 3 * TW; k += TILE_THREADS) {
+      const int a = k / TW, j = k % TW;
       const int o = a == 0 ? 0 : (a == 1 ? n1 + 1 : n1 + n2 + 2);
       const int na = a == 0 ? n1 : (a == 1 ? n2 : n3);
       const int i0 = a == 0 ? x0 : (a == 1 ? y0 : z0);
@@ -203,8 +210,8 @@ flight_tile_kernel(const ModelDev M, Pool P, const int park_buf) {
           } else {
             // distance to the wall ahead on each axis (init_lane of the untiled kernels)
             L.tnx = vx != 0.0 ? fmax((s_w[L.lx + (vx > 0.0 ? 1 : 0)] - L.r0x) * L.ivx, 0.0) : inf;
-            L.tny = vy != 0.0 ? fmax((s_w[17 + L.ly + (vy > 0.0 ? 1 : 0)] - L.r0y) * L.ivy, 0.0) : inf;
-            L.tnz = vz != 0.0 ? fmax((s_w[34 + L.lz + (vz > 0.0 ? 1 : 0)] - L.r0z) * L.ivz, 0.0) : inf;
+            L.tny = vy != 0.0 ? fmax((s_w[TW + L.ly + (vy > 0.0 ? 1 : 0)] - L.r0y) * L.ivy, 0.0) : inf;
+            L.tnz = vz != 0.0 ? fmax((s_w[2 * TW + L.lz + (vz > 0.0 ? 1 : 0)] - L.r0z) * L.ivz, 0.0) : inf;
           }
         }
         if (!exhausted) {
@@ -278,7 +285,7 @@ flight_tile_kernel(const ModelDev M, Pool P, const int park_buf) {
             if ((unsigned)l_new >= (unsigned)t_ax) {
               fin = 4;
             } else {
-              const double wall = s_w[(bx ? 0 : (by ? 17 : 34)) + l_new + fwd];
+              const double wall = s_w[(bx ? 0 : (by ? TW : 2 * TW)) + l_new + fwd];
               const double tn_new = (wall - (bx ? L.r0x : (by ? L.r0y : L.r0z))) * iv_ax;
               L.tnx = bx ? tn_new : L.tnx;
               L.tny = by ? tn_new : L.tny;

@@ -220,11 +220,15 @@ __device__ __forceinline__ void queue_append(bool pred, uint32_t *__restrict__ q
 // Tile dimensions of the tile-staged flights (flight_tile.cuh): density + sums of a tile fit in 64 KB.
 template <int ND>
 struct TileDims {
-  static constexpr int X = 16, Y = ND <= 2 ? 16 : 8, Z = ND == 1 ? 16 : 8;
+#ifndef TILE_X
+#define TILE_X 16   // cells of a tile along x for one dust type (tuning: 32 with one 768-thread block per SM)
+#endif
+  static constexpr int X = ND == 1 ? TILE_X : 16, Y = ND <= 2 ? 16 : 8, Z = ND == 1 ? 16 : 8;
   static constexpr int CELLS = X * Y * Z;
+  static constexpr int WALLS = (X > 16 ? X : 16) + 1;
   // densities + sums + walls of the tile, then one prefetch record (hot part of a Slot) per thread
   static constexpr size_t smem_bytes(int threads) {
-    return (size_t)(2 * CELLS * ND + 3 * 17 + 1) * sizeof(double) + (size_t)threads * (80 + 16 * ND);
+    return (size_t)(2 * CELLS * ND + 3 * WALLS + 1) * sizeof(double) + (size_t)threads * (80 + 16 * ND);
   }
 };
 
