@@ -284,13 +284,23 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: the engine has no CPU fallback")
     torch.cuda.set_device(local)
     if world > 1:
-        # NCCL's own log lines (version banner, NCCL_DEBUG=INFO) go to stderr: stdout carries the JSON line only
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    if rank == 0:
+        # stdout carries the JSON line only: NCCL prints its version banner (and NCCL_DEBUG output) to fd 1
+        # when the communicator is created, so fd 1 points at stderr until the first collective is done
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            if rank == 0:
+                ge.build()
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
+            os.close(saved_stdout)
+    elif rank == 0:
         ge.build()
-    if world > 1:
-        dist.barrier()
 
     def sync_all():
         torch.cuda.synchronize()
