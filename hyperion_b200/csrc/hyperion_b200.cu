@@ -1248,6 +1248,9 @@ constexpr int FLIGHT_THREADS = 256;
 #ifndef FLIGHT_GROUPS
 #define FLIGHT_GROUPS 8      // look-ahead groups between two refill votes
 #endif
+#ifndef BEAM_SCAN_SPAN
+#define BEAM_SCAN_SPAN 16    // longest run of equal cells summed before a RED (power of two)
+#endif
 #ifndef BEAM_MAX_GROUPS
 #define BEAM_MAX_GROUPS 8    // distinct cells per warp step above which deposits go out lane by lane
 #endif
@@ -1324,7 +1327,8 @@ __device__ __forceinline__ void deposit_warp(CellRec *__restrict__ cells, bool h
   if (__ballot_sync(0xffffffffu, has) == 0) return;
   const int key = has ? c : -1 - (int)lane;  // lanes without a deposit never join a run
   const int kp = __shfl_up_sync(0xffffffffu, key, 1);
-  const bool first = lane == 0 || kp != key;
+  // runs are cut every BEAM_SCAN_SPAN lanes: log2(span) shuffle rounds instead of 5, at most 32 / span REDs more
+  const bool first = (lane % BEAM_SCAN_SPAN) == 0 || kp != key;
   const unsigned heads = __ballot_sync(0xffffffffu, first);
   const unsigned above = lane == 31 ? 0u : (heads & ~((2u << lane) - 1u));
   const unsigned end = above ? (unsigned)__ffs(above) - 2u : 31u;  // last lane of my run
@@ -1332,7 +1336,7 @@ __device__ __forceinline__ void deposit_warp(CellRec *__restrict__ cells, bool h
 #pragma unroll
   for (int id = 0; id < ND; ++id) v[id] = dv[id];
 #pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
+  for (int o = 1; o < BEAM_SCAN_SPAN; o <<= 1) {
     const bool join = lane + o <= end;
 #pragma unroll
     for (int id = 0; id < ND; ++id) {
