@@ -174,3 +174,59 @@ def test_inside_observer_sky_coordinates(backend):
         exp_lon, exp_lat = expected_lonlat(photon_dir, theta_v, phi_v)
         dlon = (lon - exp_lon + 180.) % 360. - 180.
         assert abs(dlon) < 2. and abs(lat - exp_lat) < 2., (theta_v, phi_v, lon, lat, exp_lon, exp_lat)
+
+
+# ---- filters: hyperion/model/tests/test_filters.py:19-99 ----------------------------------------------
+def _reference_filter(wav_um, tr, alpha, detector, wav0_um):
+    """Filter.to_hdf5_group (hyperion/filter/filter.py:90-126): the normalised transmission the front end
+    writes into the .rtin ('tn' column) and the central frequency nu0."""
+    c = 29979245800.
+    nu = c / (np.asarray(wav_um, dtype=float) * 1.e-4)
+    tr = np.asarray(tr, dtype=float)
+    order = np.argsort(nu)
+    nu, tr = nu[order], tr[order]
+    nu0 = c / (wav0_um * 1.e-4)
+    beta = -1 if detector == "energy" else 0
+    y = tr / nu ** (1. + alpha + beta)
+    integral = np.sum(0.5 * (y[1:] + y[:-1]) * np.diff(nu))
+    tn = tr / nu ** (1 + beta) / nu0 ** alpha / integral
+    return nu, tn * nu, nu0
+
+
+@pytest.mark.parametrize("backend", BACKENDS)
+def test_filter_image_values(backend):
+    """test_filters.py:94-99: two 6000 K unit sources in a tau = 1 cube of the test dust, three views,
+    10 x 20 pixels, filters F1 (photon detector, alpha 0, 1.15 micron) and F2 (energy detector, alpha 1,
+    2.15 micron), 1000 packets: sum of the image in MJy/sr at distance 1 = 3438.06 / 2396.48 (rtol 0.1)."""
+    f1 = _reference_filter([1, 1.1, 1.2, 1.3], [0., 1.0, 0.5, 0.], 0., "photons", 1.15)
+    f2 = _reference_filter([2, 2.1, 2.2, 2.3, 2.4], [0., 0.5, 1.0, 0.6, 0.], 1., "energy", 2.15)
+    w = np.array([-1., 1.])
+    srcs = [FlatSource(type=1, luminosity=1., temperature=6000.), FlatSource(type=1, luminosity=1., temperature=6000.)]
+    m = FlatModel(w, w, w, np.full((1, 1, 1, 1), 1.0), [_test_dust()], srcs, FlatConf())
+    m.peeled = [FlatPeeledGroup(theta=[1., 2., 3.], phi=[1., 2., 3.], filters=[f1, f2], image=(10, 20, -1., 1., -1., 1.),
+                                sed=(1, 1e-30, 1e30))]
+    if backend == "oracle":
+        from oracle import oracle
+        x = oracle.Oracle(m)
+    else:
+        from hyperion_b200.capi import Engine
+        x = Engine(0)
+        x.load_model(m)
+    x.final_begin()
+    if backend == "oracle":
+        x.final_photons(1000, False)
+    else:
+        x.final_photons(0, 1000, False)
+    x.final_finish()
+    img = x.image(0)[0, 0]            # [n_view, n_y, n_x, n_filt], stokes I, no origin tracking
+    if backend != "oracle":
+        x.close()
+    # ModelOutput.get_image(units='MJy/sr', distance=1) (hyperion/model/model_output.py:733-797)
+    pix_area_sr = (np.arctan(1.) - np.arctan(-1.)) / 10. * (np.arctan(1.) - np.arctan(-1.)) / 20.
+    nu0 = np.array([f1[2], f2[2]])
+    val = img * 1.e17 / nu0 / pix_area_sr / (4. * np.pi)
+    # the reference's criterion is 10 %; the oracle, drawing the reference's own random numbers, reproduces the
+    # two sums the real Fortran binary produced to the last digit
+    rtol = 1e-12 if backend == "oracle" else 0.1
+    assert np.isclose(val[..., 0].sum(), 3438.059082285024, rtol=rtol, atol=0)
+    assert np.isclose(val[..., 1].sum(), 2396.4803378036186, rtol=rtol, atol=0)
