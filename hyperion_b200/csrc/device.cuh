@@ -13,7 +13,7 @@
 namespace hyp {
 
 constexpr int MAX_DUST = 4;      // dust types per model handled by the kernels
-constexpr int MAX_SOURCES = 64;
+constexpr int MAX_SOURCES = 4095;   // 12 bits of the packet tag (imaging.cuh)
 
 // ---------------------------------------------------------------------------------------------
 // Philox4x32-10 counter RNG.  key = run seed, counter = (photon id lo, hi, block index, iteration):

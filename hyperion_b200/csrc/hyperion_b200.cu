@@ -373,6 +373,20 @@ __device__ inline double nearest_source(const ModelDev &M, double rx, double ry,
 }
 
 __device__ inline void random_position_cell(const ModelDev &M, int64_t ic, Rng &rng, double &x, double &y, double &z);
+
+// sample_pdf_discrete_dp on the luminosities (type_pdf.f90:313-337): first source with cdf >= xi, by bisection
+__device__ __forceinline__ int pick_source(const ModelDev &M, double xi) {
+  const int ns = M.n_sources;
+  if (xi <= M.sources[0].cdf) return 0;
+  if (xi >= M.sources[ns - 1].cdf) return ns - 1;
+  int jmin = 1, jmax = ns;
+  for (;;) {
+    const int j = (jmax + jmin) / 2;
+    if (xi > M.sources[j - 1].cdf) jmin = j; else jmax = j;
+    if (jmax == jmin + 1) break;
+  }
+  return jmax - 1;
+}
 constexpr int TAG_DUST_SHIFT = 30;  // Photon::tag bits 30-31: dust type of the last interaction, 0-based (p%dust_id - 1)
 
 // emit (src/sources/source.f90:100-179): returns false on a fatal model error
@@ -392,12 +406,7 @@ __device__ bool emit_photon(const ModelDev &M, Photon<ND> &p, Rng &rng, double &
       is = min((int)(xi * ns), ns - 1);
     } else {
       // sample_pdf_discrete_dp (type_pdf.f90:313-337): first source with cdf >= xi
-      if (xi >= M.sources[ns - 1].cdf) {
-        is = ns - 1;
-      } else {
-        is = 0;
-        while (is < ns - 1 && xi > M.sources[is].cdf) ++is;
-      }
+      is = pick_source(M, xi);
     }
   }
   const SourceDev &S = M.sources[is];
@@ -710,7 +719,7 @@ __device__ bool scatter_photon(const ModelDev &M, const DustDev &d, Photon<ND> &
 // A flight that ended on a stellar surface (Slot::t < 0 carries the source): emit(p, reemit=.true., ...) from
 // that source with the packet's energy (iter_lucy.f90:158-185, iter_final.f90:212-242).  Consecutive
 // re-absorptions are counted in bits 10-15 of the tag (n_reabs_max above 62 is treated as unlimited).
-constexpr uint32_t TAG_REABS_SHIFT = 10, TAG_REABS_MASK = 63u << 10;
+constexpr uint32_t TAG_REABS_SHIFT = 14, TAG_REABS_MASK = 63u << 14;
 template <int ND>
 __device__ bool reemit_photon(const ModelDev &M, Photon<ND> &p, Rng &rng, uint32_t &n_killed_int) {
   const int src = (int)(-p.t) - 1;
@@ -1075,10 +1084,8 @@ __global__ void emit_keys_kernel(const ModelDev M, const unsigned long long firs
       const double xi = rng.next();
       if (M.sample_evenly) {
         is = (uint32_t)min((int)(xi * ns), ns - 1);
-      } else if (xi >= M.sources[ns - 1].cdf) {
-        is = ns - 1;
       } else {
-        while ((int)is < ns - 1 && xi > M.sources[is].cdf) ++is;
+        is = (uint32_t)pick_source(M, xi);
       }
     }
     const Angle a = random_sphere_angle(rng);
@@ -3813,6 +3820,8 @@ int hyp_add_peeled_group(hyp_ctx *c, const hyp_image_conf *g) {
   if (g->io_bytes != 4 && g->io_bytes != 8) return fail(HYP_ERR_INVALID, "unexpected value of io_bytes (should be 4 or 8)");
   if (g->track_origin < HYP_TRACK_NO || g->track_origin > HYP_TRACK_SCATTERINGS)
     return fail(HYP_ERR_INVALID, "unknown track_origin flag");
+  if (g->track_origin == HYP_TRACK_SCATTERINGS && (g->track_n_scat < 0 || g->track_n_scat > 1000))
+    return fail(HYP_ERR_INVALID, "track_n_scat should be between 0 and 1000 (the packet tag counts scatterings up to 1023)");
   if (g->compute_image && (g->n_x < 1 || g->n_y < 1)) return fail(HYP_ERR_INVALID, "image needs at least one pixel");
   if (g->compute_sed && g->n_ap < 1) return fail(HYP_ERR_INVALID, "SED needs at least one aperture");
   HostImage h;

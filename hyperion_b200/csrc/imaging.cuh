@@ -95,8 +95,11 @@ struct PeelJob {
 };
 
 // bits of Slot::tag / Photon::tag during the final iteration
-constexpr uint32_t TAG_SRC_MASK = 0xffu, TAG_SCATTERED = 0x100u, TAG_REPROCESSED = 0x200u;
-constexpr int TAG_NSCAT_SHIFT = 16;
+// bits 0-11 source id (1-based, up to MAX_SOURCES), 12 scattered, 13 reprocessed, 14-19 successive re-absorptions
+// (hyperion_b200.cu), 20-29 number of scatterings (saturating), 30-31 dust type of the last interaction
+constexpr uint32_t TAG_SRC_MASK = 0xfffu, TAG_SCATTERED = 0x1000u, TAG_REPROCESSED = 0x2000u;
+constexpr int TAG_NSCAT_SHIFT = 20;
+constexpr uint32_t TAG_LOW_MASK = (1u << TAG_NSCAT_SHIFT) - 1u;
 
 // ipos_dp (fortranlib/src/lib_array.f90:954-998): 1-based bin, 0 / nbin+1 outside
 __device__ __forceinline__ int ipos_bin(double xmin, double xmax, double x, int nbin) {
@@ -662,7 +665,7 @@ struct FinalArgs {
   int32_t n_theta, n_phi;
 };
 
-constexpr uint32_t TAG_NSCAT_MASK = 0x3fffu;   // n_scat saturates at 16383
+constexpr uint32_t TAG_NSCAT_MASK = 0x3ffu;    // n_scat saturates at 1023
 
 // binned_images_bin_photon (images_binned.f90:57-77) + image_bin (image_type.f90:408-524) for a packet
 // that has just left the grid at path length t along its flight.
@@ -850,7 +853,7 @@ interact_final_kernel(const ModelDev M, Pool P, const FinalArgs F, uint32_t *__r
         if (scattered) {
           uint32_t ns = (p.tag >> TAG_NSCAT_SHIFT) & TAG_NSCAT_MASK;
           if (ns < TAG_NSCAT_MASK) ++ns;
-          p.tag = (p.tag & 0xffffu) | (ns << TAG_NSCAT_SHIFT) | TAG_SCATTERED;
+          p.tag = (p.tag & TAG_LOW_MASK) | (ns << TAG_NSCAT_SHIFT) | TAG_SCATTERED;
         } else {
           p.tag = (p.tag & ~TAG_SCATTERED & ~(3u << TAG_DUST_SHIFT)) | TAG_REPROCESSED;
         }

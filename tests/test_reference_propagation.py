@@ -1,0 +1,115 @@
+"""hyperion/model/tests/test_propagation.py restated: packets must not be killed by special alignments --
+point sources exactly at the origin or on the vertices of Cartesian / spherical / cylindrical grids
+(also for grids of size 1e20 and 1e-20), peel-offs exactly along wall directions.  Run on the oracle
+(CPU) and on the CUDA engine (gpu).  The reference marks a few variants xfail (sources on the outer
+edge, unclipped polar vertices, cylindrical aligned peel-off); those are not restated."""
+import numpy as np
+import pytest
+
+from hyperion_b200 import synthetic as syn
+from hyperion_b200.flatmodel import FlatConf, FlatModel, FlatPeeledGroup, FlatSource
+
+BACKENDS = ["oracle", pytest.param("gpu", marks=pytest.mark.gpu)]
+
+
+def _dust():
+    return syn.make_dust([3.e9, 3.e16], [0.5, 0.5], [1., 1.], n_temp=10, temp_min=0.1, temp_max=1600.)
+
+
+def _model(grid_type, walls, positions):
+    w1, w2, w3 = walls
+    shape = (1, len(w3) - 1, len(w2) - 1, len(w1) - 1)
+    srcs = [FlatSource(type=1, luminosity=1., temperature=5000., position=tuple(p)) for p in positions]
+    return FlatModel(np.asarray(w1), np.asarray(w2), np.asarray(w3), np.full(shape, 1.e-40), [_dust()], srcs, FlatConf(),
+                     grid_type=grid_type)
+
+
+def _killed(model, backend, n_initial=0, n_imaging=0):
+    if backend == "oracle":
+        from oracle import oracle
+        x = oracle.Oracle(model)
+    else:
+        from hyperion_b200.capi import Engine
+        x = Engine(0)
+        x.load_model(model)
+    killed = 0
+    if n_initial:
+        st = x.run_lucy_iteration(n_initial)
+        killed += st.killed_geo + st.killed_int
+        assert st.n_photons == n_initial
+    if n_imaging:
+        x.final_begin()
+        if backend == "oracle":
+            x.final_photons(n_imaging, False)
+        else:
+            x.final_photons(0, n_imaging, False)
+        st = x.final_finish()
+        killed += st.killed_geo + st.killed_int
+        assert st.n_peeloffs > 0
+    if backend != "oracle":
+        x.close()
+    return killed
+
+
+def _grids(scale):
+    car = (np.linspace(-10., 10., 15) * scale,) * 3
+    sph = (np.linspace(0., 10., 15) * scale, np.linspace(0., np.pi, 17), np.linspace(0., 2. * np.pi, 15))
+    cyl = (np.linspace(0., 10., 15) * scale, np.linspace(-5., 5., 17) * scale, np.linspace(0., 2. * np.pi, 15))
+    return {"car": car, "sph": sph, "cyl": cyl}
+
+
+def _vertices(grid_type, walls, scale):
+    clip = lambda v: 0.0 if abs(v) < 1.e-10 * scale else v      # the reference clips at 1e-10 for scale 1
+    out = []
+    if grid_type == "car":
+        x, y, z = walls
+        out = [(x[i], y[j], z[k]) for i in range(1, len(x) - 1) for j in range(1, len(y) - 1) for k in range(1, len(z) - 1)]
+    elif grid_type == "sph":
+        r, t, p = walls
+        for ir in range(len(r) - 1):
+            for it in range(len(t)):
+                for ip in range(len(p)):
+                    out.append((clip(r[ir] * np.cos(p[ip]) * np.sin(t[it])), clip(r[ir] * np.sin(p[ip]) * np.sin(t[it])),
+                                r[ir] * np.cos(t[it])))
+        out.append((0., 0., 0.))
+    else:
+        w, z, p = walls
+        for iw in range(len(w) - 1):
+            for iz in range(len(z)):
+                for ip in range(len(p)):
+                    out.append((clip(w[iw] * np.cos(p[ip])), clip(w[iw] * np.sin(p[ip])), z[iz]))
+        out.append((0., 0., 0.))
+    return out
+
+
+@pytest.mark.parametrize("backend", BACKENDS)
+@pytest.mark.parametrize("grid_type,scale", [("car", 1.), ("car", 1.e20), ("car", 1.e-20), ("sph", 1.), ("cyl", 1.)])
+def test_ptsource_origin(backend, grid_type, scale):
+    m = _model(grid_type, _grids(scale)[grid_type], [(0., 0., 0.)])
+    assert _killed(m, backend, n_initial=100000) == 0
+
+
+@pytest.mark.parametrize("backend", BACKENDS)
+@pytest.mark.parametrize("grid_type,scale", [("car", 1.), ("car", 1.e20), ("car", 1.e-20), ("sph", 1.), ("cyl", 1.)])
+def test_ptsource_vertices(backend, grid_type, scale):
+    walls = _grids(scale)[grid_type]
+    m = _model(grid_type, walls, _vertices(grid_type, walls, scale))
+    assert _killed(m, backend, n_initial=100000) == 0
+
+
+@pytest.mark.parametrize("backend", BACKENDS)
+@pytest.mark.parametrize("grid_type,aligned", [("car", True), ("sph", False), ("sph", True), ("cyl", False)])
+def test_ptsource_origin_peeloff(backend, grid_type, aligned):
+    """Peel-offs from a source at the origin towards a regular grid of directions (every 5 degrees), or,
+    `aligned`, exactly along the theta / phi walls of the grid."""
+    walls = _grids(1.)[grid_type]
+    if aligned and grid_type == "sph":
+        theta, phi = np.degrees(walls[1]), np.degrees(walls[2])
+    else:
+        theta, phi = np.linspace(0., 180., 37), np.linspace(0., 360., 73)
+    T, P = np.meshgrid(theta, phi)
+    m = _model(grid_type, walls, [(0., 0., 0.)])
+    half = walls[0][-1]
+    m.peeled = [FlatPeeledGroup(theta=T.ravel(), phi=P.ravel(), wavelengths=(1, 0.1, 10.), image=(1, 1, -half, half, -half, half),
+                                sed=(1, 1e-30 * half, 1e30 * half))]
+    assert _killed(m, backend, n_imaging=100) == 0
