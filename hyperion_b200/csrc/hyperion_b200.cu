@@ -2364,13 +2364,60 @@ int hyp_set_grid_amr(hyp_ctx *c, int32_t n_levels, const int32_t *n_grids, const
       level_of.push_back(il);
       width.push_back(w);
     }
-  // grids of a level share their cell widths (:246-262)
-  for (size_t a = 0; a < G.size(); ++a)
-    for (size_t b = 0; b < a; ++b)
-      if (level_of[a] == level_of[b])
-        for (int d = 0; d < 3; ++d)
-          if (std::fabs(width[a][d] - width[b][d]) > 1.e-10 * width[a][d])
-            return fail(HYP_ERR_INVALID, "grids in one level have differing cell widths");
+  // The consistency checks of setup_grid_geometry (grid_geometry_amr.f90:239-314), with its messages
+  // (hyperion/model/tests/test_amr_checks.py greps the log for them).
+  {
+    const char *axis = "xyz";
+    auto lo = [&](size_t k, int d) { return d == 0 ? G[k].xmin : (d == 1 ? G[k].ymin : G[k].zmin); };
+    auto aligned = [](double x1, double x2, double dx) {  // :184-191
+      double r = std::fmod(std::fabs(x1 - x2), dx);
+      if (r > 0.5 * dx) r = dx - r;
+      return std::fabs(r / dx) < 1.e-8;
+    };
+    std::vector<size_t> first_of;  // first grid of every level
+    for (size_t k = 0; k < G.size(); ++k)
+      if ((size_t)level_of[k] == first_of.size()) first_of.push_back(k);
+    char msg[256];
+    // grids of a level share their cell widths and sit on a common lattice
+    for (size_t k = 0; k < G.size(); ++k) {
+      const size_t ref = first_of[level_of[k]];
+      if (k == ref) continue;
+      const int igrid = (int)(k - ref) + 1, ilevel = level_of[k] + 1;
+      for (int d = 0; d < 3; ++d)
+        if (std::fabs(width[k][d] - width[ref][d]) > 1.e-10 * width[k][d]) {
+          snprintf(msg, sizeof msg, "Grids 1 and %d in level %d have differing cell widths in the %c direction (%11.4E and %11.4E respectively)",
+                   igrid, ilevel, axis[d], width[ref][d], width[k][d]);
+          return fail(HYP_ERR_INVALID, msg);
+        }
+      for (int d = 0; d < 3; ++d)
+        if (!aligned(lo(k, d), lo(ref, d), width[ref][d])) {
+          snprintf(msg, sizeof msg, "Grids 1 and %d in level %d have edges that are not separated by an integer number of cells in the %c direction",
+                   igrid, ilevel, axis[d]);
+          return fail(HYP_ERR_INVALID, msg);
+        }
+    }
+    // integer refinement factors between consecutive levels
+    for (size_t il = 0; il + 1 < first_of.size(); ++il)
+      for (int d = 0; d < 3; ++d) {
+        const double ref = width[first_of[il]][d] / width[first_of[il + 1]][d];
+        if (std::fabs(ref - std::nearbyint(ref)) > 1.e-10) {
+          snprintf(msg, sizeof msg, "Refinement factor in the %c direction between level %d and level %d is not an integer (%.3f)",
+                   axis[d], (int)il + 1, (int)il + 2, ref);
+          return fail(HYP_ERR_INVALID, msg);
+        }
+      }
+    // grids line up with the cells of the parent level
+    for (size_t k = 0; k < G.size(); ++k) {
+      if (level_of[k] == 0) continue;
+      const size_t ref = first_of[level_of[k] - 1];
+      for (int d = 0; d < 3; ++d)
+        if (!aligned(lo(k, d), lo(ref, d), width[ref][d])) {
+          snprintf(msg, sizeof msg, "Grid %d in level %d is not aligned with cells in level %d in the %c direction",
+                   (int)(k - first_of[level_of[k]]) + 1, level_of[k] + 1, level_of[k], axis[d]);
+          return fail(HYP_ERR_INVALID, msg);
+        }
+    }
+  }
   std::vector<int32_t> go((size_t)goto_total, 0);
   auto gidx = [&](const AmrGridDev &g, int i1, int i2, int i3) {
     return (size_t)g.goto_off + i1 + (size_t)(g.n1 + 2) * (i2 + (size_t)(g.n2 + 2) * i3);

@@ -27,12 +27,35 @@ from .multigpu import ShardedLucy, shard
 from .rtin import ModelError, read_rtin
 
 
+def wrap_error_text(text, width=61):
+    """The line breaking of ``error()`` (``fortranlib/src/lib_messages.f90:141-171``): cut at the last blank
+    within ``width`` characters, the blank stays at the end of the line."""
+    lines, imin, n = [], 1, len(text)          # 1-based like the Fortran
+    while True:
+        if imin + width > n:
+            imax = n
+        else:
+            imax = imin + width
+            for j in range(width, 0, -1):
+                if text[imin + j - 1] == " ":
+                    imax = imin + j
+                    break
+        lines.append(text[imin - 1:imax])
+        if imax >= n:
+            return lines
+        imin = imax + 1
+
+
 def boxed_error(where, text, stream=None):
-    """Same shape as ``error()`` of ``fortranlib/src/lib_messages.f90:126-179`` (stderr)."""
+    """``error()`` of ``fortranlib/src/lib_messages.f90:126-179``, byte for byte (list-directed writes start
+    with a blank): the reference's tests search the log for the wrapped message."""
     stream = stream or sys.stderr
-    line = "ERROR: %s [%s]" % (text, where)
-    bar = "-" * min(max(len(line) + 2, 20), 100)
-    stream.write(" %s\n %s\n %s\n" % (bar, line, bar))
+    now = datetime.datetime.now().strftime("%d %B %Y at %H:%M:%S")
+    out = [" " + "-" * 72]
+    for k, line in enumerate(wrap_error_text(text)):
+        out.append((" ERROR   : " if k == 0 else "           ") + line)
+    out += [" WHERE   : " + where, " " + "-" * 72, "", "  *** Execution aborted on " + now + " ***", ""]
+    stream.write("\n".join(out) + "\n")
     stream.flush()
 
 

@@ -113,3 +113,54 @@ def test_ptsource_origin_peeloff(backend, grid_type, aligned):
     m.peeled = [FlatPeeledGroup(theta=T.ravel(), phi=P.ravel(), wavelengths=(1, 0.1, 10.), image=(1, 1, -half, half, -half, half),
                                 sed=(1, 1e-30 * half, 1e30 * half))]
     assert _killed(m, backend, n_imaging=100) == 0
+
+
+@pytest.mark.parametrize("backend", BACKENDS)
+def test_theta_wall_viewing_angle(backend):
+    """hyperion/model/tests/test_grid_geometry.py:57-110: peel-off rays whose polar angle equals a theta
+    wall (observer at 60 degrees, wall at 60 degrees, other azimuth) must cross the cone instead of riding
+    it: the SEDs at 59, 60 and 61 degrees are all positive and essentially identical (optically thin)."""
+    r = np.array([0., 0.5, 1.0])
+    t = np.array([0., np.radians(60.), np.pi])
+    p = np.array([0., 2. * np.pi])
+    m = _model("sph", (r, t, p), [(0.3, 0., 0.05)])
+    m.density[...] = 1.e-8
+    m.sources[0].temperature = 6000.
+    m.conf.propagation_check_frequency = 1.0
+    m.peeled = [FlatPeeledGroup(theta=[59., 60., 61.], phi=[170., 170., 170.], wavelengths=(10, 0.1, 100.),
+                                sed=(1, 1e-30, 1e30), stokes=False)]
+    if backend == "oracle":
+        from oracle import oracle
+        x = oracle.Oracle(m)
+    else:
+        from hyperion_b200.capi import Engine
+        x = Engine(0)
+        x.load_model(m)
+    x.final_begin()
+    if backend == "oracle":
+        x.final_photons(5000, False)
+    else:
+        x.final_photons(0, 5000, False)
+    st = x.final_finish()
+    sed = x.sed(0)[0, 0, :, 0, :]
+    if backend != "oracle":
+        x.close()
+    tot = np.nansum(sed, axis=1)
+    # the reference's criteria (test_grid_geometry.py:107-110)
+    assert np.all(tot > 0)
+    assert np.isclose(tot[1], 0.5 * (tot[0] + tot[2]), rtol=0.1), tot
+    # direct light dominates in this optically thin model: the three totals agree far better than that
+    assert np.allclose(tot, tot.mean(), rtol=1e-3), tot
+
+
+@pytest.mark.parametrize("backend", BACKENDS)
+def test_amr_source_outside_grid(backend):
+    """test_grid_geometry.py:14-54: a source outside every level-1 grid ends the run with the controlled
+    'not emitted inside a cell' error, not with a crash."""
+    from hyperion_b200.capi import HyperionError
+    levels = [[(4, 4, 4, -1., 1., -1., 1., -1., 1.)]]
+    m = FlatModel(None, None, None, np.full((1, 64), 1.e-30), [_dust()],
+                  [FlatSource(type=1, luminosity=1., temperature=6000., position=(2., 0., 0.))], FlatConf(),
+                  grid_type="amr", amr_levels=levels)
+    with pytest.raises(HyperionError, match="not emitted inside a cell"):
+        _killed(m, backend, n_initial=100)
