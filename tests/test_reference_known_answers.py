@@ -230,3 +230,33 @@ def test_filter_image_values(backend):
     rtol = 1e-12 if backend == "oracle" else 0.1
     assert np.isclose(val[..., 0].sum(), 3438.059082285024, rtol=rtol, atol=0)
     assert np.isclose(val[..., 1].sum(), 2396.4803378036186, rtol=rtol, atol=0)
+
+
+@pytest.mark.parametrize("backend", BACKENDS)
+def test_sed_uncertainty_sum_of_squares(backend):
+    """test_sed.py:472-501: one isotropic source, no dust, one SED bin: every packet has the same weight, so
+    the sum-of-squares estimator gives sigma / flux = 1 / sqrt(N)."""
+    n = 10000
+    w = np.array([-1., 1.])
+    m = FlatModel(w, w, w, np.zeros((1, 1, 1, 1)), [_test_dust()], [FlatSource(type=1, luminosity=1., temperature=6000.)],
+                  FlatConf(seed=-1))
+    m.peeled = [FlatPeeledGroup(theta=[45.], phi=[45.], wavelengths=(1, 0.01, 5000.), sed=(1, 1.e10, 1.e10),
+                                uncertainties=True)]
+    if backend == "oracle":
+        from oracle import oracle
+        x = oracle.Oracle(m)
+    else:
+        from hyperion_b200.capi import Engine
+        x = Engine(0)
+        x.load_model(m)
+    x.final_begin()
+    if backend == "oracle":
+        x.final_photons(n, False)
+    else:
+        x.final_photons(0, n, False)
+    x.final_finish()
+    val, unc = x.sed(0, True)
+    if backend != "oracle":
+        x.close()
+    flux, sigma = np.nansum(val[0]), np.sqrt(np.nansum(unc[0] ** 2))
+    assert np.isclose(sigma / flux, 1. / np.sqrt(n), rtol=0.03)
