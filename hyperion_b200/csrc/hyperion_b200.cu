@@ -1130,8 +1130,11 @@ __global__ void emit_keys_kernel(const ModelDev M, const unsigned long long firs
 }
 
 // Fill the free slots with new packets while ids remain.
+#ifndef INTERACT_MIN_BLOCKS
+#define INTERACT_MIN_BLOCKS 8   // resident 128-thread blocks per SM the register allocation aims at (64 registers)
+#endif
 template <int ND>
-__global__ void __launch_bounds__(SERVICE_THREADS)
+__global__ void __launch_bounds__(SERVICE_THREADS, INTERACT_MIN_BLOCKS)
 emit_kernel(const ModelDev M, Pool P, const unsigned long long first_id, const unsigned long long n_photons, const uint32_t iteration) {
   const uint32_t n = P.counts[C_NE];
   const unsigned lane = threadIdx.x & 31;
@@ -1191,7 +1194,7 @@ emit_kernel(const ModelDev M, Pool P, const unsigned long long first_id, const u
 
 // Interactions of every packet whose flight ended inside the grid.
 template <int ND>
-__global__ void __launch_bounds__(SERVICE_THREADS)
+__global__ void __launch_bounds__(SERVICE_THREADS, INTERACT_MIN_BLOCKS)
 interact_kernel(const ModelDev M, Pool P, uint32_t *__restrict__ q_flight_next, uint32_t *n_flight_next,
                 const uint32_t iteration, const int park_buf = -1) {
   const uint32_t n = P.counts[C_NI];
