@@ -1794,6 +1794,8 @@ struct hyp_ctx {
   int device = 0;
   int sm_count = 148;
   cudaStream_t stream = nullptr;
+  cudaStream_t stream2 = nullptr;              // the beam kernel of a round runs here, next to the flight kernel
+  cudaEvent_t evFork = nullptr, evJoin = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
   // host model
   int grid_type = GEO_CAR;
@@ -1958,10 +1960,11 @@ size_t slot_bytes(int nd) {
 
 // Packets resident in the pool at once (never more than the launch holds).  Measured on the 256^3 headline
 // (profiles/r01_experiments.md): 2 M slots 91.7 ms per 2e7 packets, 8 M 87.5 ms, 16 M 84.9 ms, 20 M 84.6 ms --
-// fewer, fuller rounds amortise the launch tails; 16 M slots are 3 GB of the 180 GB.
+// fewer, fuller rounds amortise the launch tails; with the beam and flight kernels side by side 12 M is best
+// (77.3 ms): the second round then has both kinds of packets in quantity.  12 M slots are 2.4 GB of the 180 GB.
 uint32_t pool_target() {
   const char *e = getenv("HYPERION_B200_POOL");
-  long v = e ? atol(e) : (1L << 24);
+  long v = e ? atol(e) : 12582912L;
   if (v < 1024) v = 1024;
   if (v > (1L << 28)) v = 1L << 28;
   return (uint32_t)v;
@@ -2085,6 +2088,9 @@ int hyp_ctx_create(int device_id, hyp_ctx **out) {
   CUDA_TRY(cudaEventCreate(&c->ev1));
   CUDA_TRY(cudaEventCreate(&c->ev2));
   CUDA_TRY(cudaEventCreate(&c->ev3));
+  CUDA_TRY(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
+  CUDA_TRY(cudaEventCreateWithFlags(&c->evFork, cudaEventDisableTiming));
+  CUDA_TRY(cudaEventCreateWithFlags(&c->evJoin, cudaEventDisableTiming));
   CUDA_TRY(cudaEventCreate(&c->evA));
   CUDA_TRY(cudaEventCreate(&c->evB));
   CUDA_TRY(cudaMallocHost(&c->h_counts, (C_COUNT + 2) * sizeof(uint32_t)));
@@ -2150,6 +2156,9 @@ void hyp_ctx_destroy(hyp_ctx *c) {
   for (auto &t : c->filter_tables) free_dev(t);
   free_pool(c);
   if (c->h_counts) cudaFreeHost(c->h_counts);
+  if (c->evFork) cudaEventDestroy(c->evFork);
+  if (c->evJoin) cudaEventDestroy(c->evJoin);
+  if (c->stream2) cudaStreamDestroy(c->stream2);
   if (c->evA) cudaEventDestroy(c->evA);
   if (c->evB) cudaEventDestroy(c->evB);
   for (auto &d : c->dust) {
@@ -3135,6 +3144,10 @@ static int run_rounds(hyp_ctx *c, int64_t first_id, int64_t n_photons, int64_t i
     const char *e = getenv("HYPERION_B200_TILES");
     tiles = c->grid_type == GEO_CAR && !c->M.any_sphere && e && atoi(e) != 0;
   }
+  int overlap_b = 2, overlap_f = 2;   // measured best with a 12 M pool (profiles/r01_experiments.md); "0" = one after the other
+  if (const char *e = getenv("HYPERION_B200_OVERLAP")) {
+    if (sscanf(e, "%d,%d", &overlap_b, &overlap_f) != 2 || overlap_b < 1 || overlap_f < 1) overlap_b = overlap_f = 0;
+  }
   const uint32_t tile_min_flights = getenv("HYPERION_B200_TILE_MIN") ? (uint32_t)atol(getenv("HYPERION_B200_TILE_MIN")) : 1000000u;
   const bool dbg = getenv("HYPERION_B200_TIMING") != nullptr;
   float dbg_bucket = 0.f, dbg_tile = 0.f;
@@ -3201,7 +3214,19 @@ static int run_rounds(hyp_ctx *c, int64_t first_id, int64_t n_photons, int64_t i
       }
       CUDA_TRY(cudaGetLastError());
     } else {
-    if (n_new > 0) {
+    // The beam kernel (new packets: issue-bound, its cells live in L2) and the flight kernel (packets that
+    // left an interaction: bound by scattered REDs) want different resources and touch different packets:
+    // they run side by side on two streams, b and f blocks per SM each (HYPERION_B200_OVERLAP="b,f").
+    const bool side_by_side = overlap_b > 0 && n_new > 0 && n_flight_prev > 0 && !tiles;
+    if (side_by_side) {
+      CUDA_TRY(cudaEventRecord(c->evFork, st));
+      CUDA_TRY(cudaStreamWaitEvent(c->stream2, c->evFork, 0));
+      int blocks = (int)std::min<int64_t>((n_new + FLIGHT_THREADS - 1) / FLIGHT_THREADS, (int64_t)overlap_b * c->sm_count);
+      beam<<<blocks, FLIGHT_THREADS, wall_bytes, c->stream2>>>(c->M, P, P.q_beam, P.counts + C_NB, walls_smem);
+      CUDA_TRY(cudaGetLastError());
+      CUDA_TRY(cudaEventRecord(c->evJoin, c->stream2));
+      c->launches_acc += 1;
+    } else if (n_new > 0) {
       int blocks = (int)std::min<int64_t>((n_new + FLIGHT_THREADS - 1) / FLIGHT_THREADS, beam_blocks_max);
       beam<<<blocks, FLIGHT_THREADS, wall_bytes, st>>>(c->M, P, P.q_beam, P.counts + C_NB, walls_smem);
       CUDA_TRY(cudaGetLastError());
@@ -3250,11 +3275,13 @@ static int run_rounds(hyp_ctx *c, int64_t first_id, int64_t n_photons, int64_t i
     } else if (tiles) {
       CUDA_TRY(cudaMemsetAsync(P.counts + C_NP0 + (1 - cur), 0, sizeof(uint32_t), st));
     } else if (n_flight_prev > 0) {
-      int blocks = (int)std::min<int64_t>(((int64_t)n_flight_prev + FLIGHT_THREADS - 1) / FLIGHT_THREADS, flight_blocks_max);
+      int blocks = (int)std::min<int64_t>(((int64_t)n_flight_prev + FLIGHT_THREADS - 1) / FLIGHT_THREADS,
+                                          side_by_side ? (int64_t)overlap_f * c->sm_count : (int64_t)flight_blocks_max);
       flight<<<blocks, FLIGHT_THREADS, wall_bytes, st>>>(c->M, P, P.q_flight[cur], nF, walls_smem);
       CUDA_TRY(cudaGetLastError());
       c->launches_acc += 1;
     }
+    if (side_by_side) CUDA_TRY(cudaStreamWaitEvent(st, c->evJoin, 0));
     }
     CUDA_TRY(cudaEventRecord(c->evB, st));
     CUDA_TRY(cudaMemsetAsync(nF_next, 0, sizeof(uint32_t), st));
