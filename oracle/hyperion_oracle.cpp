@@ -3619,7 +3619,7 @@ void propagate_final(orc_ctx &g, Photon &p, bool peeloff_scattering_only) {
 
 // binned_images_bin_photon (images_binned.f90:57-77): an escaping packet goes into the view its own
 // direction falls in (n_theta bins of cos theta, n_phi bins of phi)
-void binned_images_bin_photon(orc_ctx &g, Image &im, const Photon &p) {
+void binned_images_bin_photon(Image &im, const Photon &p) {
   const int n_theta = im.c.n_theta, n_phi = im.c.n_phi;
   double phi = std::atan2(p.a.sinp, p.a.cosp);
   if (phi < 0.) phi = phi + TWOPI_F;
@@ -3645,7 +3645,7 @@ void final_photons(orc_ctx &g, int64_t n_photons, bool peeloff_scattering_only) 
     // iter_final.f90:126-129
     if (!p.killed)
       for (auto &im : g.peeled.image)
-        if (im.c.binned) binned_images_bin_photon(g, im, p);
+        if (im.c.binned) binned_images_bin_photon(im, p);
   }
 }
 
