@@ -40,6 +40,8 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-thin", action="store_true", help="skip the optically thin variant")
     ap.add_argument("--thin-tau", type=float, default=0.01)
+    ap.add_argument("--no-moderate", action="store_true", help="skip the tau = 5 variant")
+    ap.add_argument("--moderate-tau", type=float, default=5.0)
     ap.add_argument("--no-imaging", action="store_true", help="skip the imaging-iteration variant")
     ap.add_argument("--imaging-photons", type=float, default=2.0e6)
     return ap.parse_args()
@@ -110,15 +112,21 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def cpu_sample(model, n_photons, cores):
-    """Time the CPU restatement of the Fortran path (oracle/) the way the reference runs under
-    MPI: `cores` ranks seeded seed+r, equal split, deposit grids summed (src/mpi/mpi_routines.f90)."""
+def cpu_contexts(model, cores):
+    """`cores` emulated reference processes (oracle/), built ONCE: the set-up of a context (1200-state
+    emissivity tables, 256^3 arrays) is not part of the photon loop and takes longer than a sample."""
     from oracle import oracle
     oracle.build()
     t0 = time.time()
     ranks = [oracle.Oracle(model, rank=r) for r in range(cores)]
-    t_setup = time.time() - t0
+    return ranks, time.time() - t0
+
+
+def cpu_run(ranks, n_photons):
+    """Time the CPU restatement of the Fortran path (oracle/) the way the reference runs under
+    MPI: rank r seeded seed+r, equal split, deposit grids summed (src/mpi/mpi_routines.f90)."""
     from concurrent.futures import ThreadPoolExecutor
+    cores = len(ranks)
     split = [n_photons // cores + (1 if r < n_photons % cores else 0) for r in range(cores)]
     for o in ranks:
         o.lucy_begin()
@@ -131,7 +139,21 @@ def cpu_sample(model, n_photons, cores):
     for o in ranks:
         o.energy_current = e_cur
         cross += o.lucy_finish().n_crossings
-    return n_photons / dt, dt, t_setup, cross
+    return n_photons / dt, dt, cross
+
+
+def oracle_flags():
+    try:
+        with open(os.path.join(ROOT, "oracle", "Makefile")) as f:
+            for line in f:
+                if line.startswith("CXXFLAGS"):
+                    return line.split("=", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
+REFERENCE_BUDGET_S = 240.0     # wall-clock cap of the --impl reference arm (set-up included)
 
 
 def run_reference(a):
@@ -139,19 +161,24 @@ def run_reference(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    t_start = time.time()
     cores = os.cpu_count() or 1
     model = build_model(a)
+    ranks, t_setup = cpu_contexts(model, cores)
     n = int(a.cpu_photons) if a.cpu_photons else 0
     if n == 0:
-        rate, dt, _, _ = cpu_sample(model, 20000 * cores, cores)
-        n = int(max(20000 * cores, min(rate * 15.0, 5e7)))
+        rate, dt, _ = cpu_run(ranks, 20000 * cores)
+        # steps of about (budget left) / (steps + warm-up), never more than 15 s each
+        left = max(20.0, REFERENCE_BUDGET_S - (time.time() - t_start))
+        per_step = min(15.0, left / (a.warmup + a.steps + 1))
+        n = int(max(2000 * cores, min(rate * per_step, 5e7)))
     times, cross = [], 0
     for i in range(a.warmup + a.steps):
-        rate, dt, t_setup, cr = cpu_sample(model, n, cores)
+        rate, dt, cr = cpu_run(ranks, n)
         if i >= a.warmup:
             times.append(dt)
             cross += cr
-        if sum(times) > 240:
+        if time.time() - t_start > REFERENCE_BUDGET_S and times:
             break
     steps = len(times)
     T = sum(times)
@@ -163,10 +190,12 @@ def run_reference(a):
         "config": {"workload": workload_name(a), "grid": [a.grid] * 3, "n_dust": 1,
                    "photons_per_step": n, "note": "bounded CPU sample of the same model"},
         "cpu_baseline": {"value": value, "unit": "packets/s", "cores": cores, "kind": "port",
-                         "sample": "%d packets/step x %d steps on %d threads (rank r seeded seed+r, grids summed)"
-                                   % (n, steps, cores)},
+                         "sample": "%d packets/step x %d steps on %d threads (rank r seeded seed+r, grids summed); "
+                                   "contexts built once in %.1f s, not timed" % (n, steps, cores, t_setup),
+                         "compile_flags": oracle_flags()},
         "e2e": {"value": value, "unit": "packets/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "crossings_per_packet": cross / (n * steps),
+        "wall_s": time.time() - t_start,
     }
     print(json.dumps(line), flush=True)
 
@@ -199,17 +228,32 @@ def measure(eng, drv, stream, model, P, world, rank, a, sync_all, e2e=True):
     out = None
     if e2e:
         # end to end through the public API with HOST buffers: density in (pinned H2D), one
-        # iteration, specific_energy out (D2H)
+        # iteration, specific_energy out (D2H).  With N > 1 rank 0 owns the host side as in the
+        # reference (src/mpi/mpi_io.f90:213-242): it uploads, NCCL broadcasts the device buffer,
+        # every rank installs it from device memory, and only rank 0 reads the result back.
         n_el = eng.n_dust * eng.n_cells
-        h_rho = torch.empty(n_el, dtype=torch.float64).pin_memory()
-        h_rho.numpy()[:] = model.density.ravel()
-        h_out = torch.empty(n_el, dtype=torch.float64).pin_memory()
-        out_np = h_out.numpy().reshape((eng.n_dust,) + tuple(eng.shape))
+        out_np = None
+        h_rho = None
+        if rank == 0:
+            h_rho = torch.empty(n_el, dtype=torch.float64).pin_memory()
+            h_rho.numpy()[:] = model.density.ravel()
+            h_out = torch.empty(n_el, dtype=torch.float64).pin_memory()
+            out_np = h_out.numpy().reshape((eng.n_dust,) + tuple(eng.shape))
+        d_rho = torch.empty(n_el, dtype=torch.float64, device="cuda") if world > 1 else None
 
         def e2e_step(it):
-            eng.update_density(h_rho.numpy())
+            if world > 1:
+                with torch.cuda.stream(stream):
+                    if rank == 0:
+                        d_rho.copy_(h_rho, non_blocking=True)
+                    dist.broadcast(d_rho, src=0)
+                stream.synchronize()
+                eng.update_density_device(d_rho.data_ptr())
+            else:
+                eng.update_density(h_rho.numpy())
             step(it)
-            eng.get_specific_energy(out_np)
+            if rank == 0:
+                eng.get_specific_energy(out_np)
 
         e2e_step(10_000)
         sync_all()
@@ -225,7 +269,8 @@ def measure(eng, drv, stream, model, P, world, rank, a, sync_all, e2e=True):
         if world > 1:
             dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
         out = {"value": P * world * k2 / (float(ms2.item()) * 1e-3), "unit": "packets/s",
-               "h2d_bytes_per_step": int(n_el * 8), "d2h_bytes_per_step": int(n_el * 8), "steps": k2}
+               "h2d_bytes_per_step": int(n_el * 8), "d2h_bytes_per_step": int(n_el * 8), "steps": k2,
+               "host_io": "rank 0 (upload + NCCL broadcast, download on rank 0)" if world > 1 else "rank 0"}
     return total_ms, stats, out
 
 
@@ -244,7 +289,9 @@ def roofline_of(stats, n_dust, world, steps):
     return {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
             "traffic": None, "algorithmic_bytes_per_step": alg_bytes / steps,
             "peak_kind": peak_kind, "bytes_per_crossing": 24 * n_dust,
-            "kernel": "flight_beam_kernel + flight_kernel (all rounds of a step)",
+            "kernel": "wave_tile_kernel (all rounds of a step; + flight_kernel for the tail)"
+                      if any(getattr(st, "n_wave_rounds", 0) for st in stats)
+                      else "flight_beam_kernel + flight_kernel (all rounds of a step)",
             "kernel_ms_per_step": flight_ms / steps, "photon_loop_ms_per_step": loop_ms / steps,
             "achieved_whole_photon_loop": alg_bytes / (loop_ms * 1e-3) / 1e9 if loop_ms > 0 else 0.0,
             "crossings_per_step": cross / steps}, cross, nabs, nscat
@@ -264,6 +311,35 @@ def measured_traffic(workload, photons):
         if t.get("workload") == workload and int(t.get("photons_per_gpu_per_step", 0)) == int(photons):
             return float(t["flight_dram_bytes_per_step"]), os.path.relpath(fn, ROOT)
     return None, None
+
+
+def multi_gpu_check(make, Engine, local, rank, world, sync_all):
+    """32^3 model, 2e6 packets: specific_energy of the N-rank run (id shards + one all-reduce) against a
+    1-rank replay of the same ids on rank 0.  Returns "ok" or a description of the mismatch."""
+    import torch
+    import torch.distributed as dist
+    m = syn.cartesian_point_source_model(n=32, tau_edge=2.0, dust=syn.realistic_dust(n_temp=60), seed=3)
+    n = 2_000_000
+    eng, drv, _ = make(m)
+    for it in range(2):
+        drv.iteration(n, it + 1, id_offset=it * n)
+    got = eng.get_specific_energy()
+    eng.close()
+    verdict = torch.zeros(1, dtype=torch.float64, device="cuda")
+    if rank == 0:
+        one = Engine(local)
+        one.load_model(m)
+        for it in range(2):
+            one.lucy_begin()
+            one.lucy_photons(it * n, n, it + 1)
+            one.lucy_finish()
+        ref = one.get_specific_energy()
+        one.close()
+        verdict[0] = float(np.max(np.abs(got / ref - 1.0)))
+    dist.broadcast(verdict, src=0)
+    sync_all()
+    err = float(verdict.item())
+    return "ok" if err <= 1e-9 else "max relative difference %.3e" % err
 
 
 def main():
@@ -334,20 +410,22 @@ def main():
     n_dust, n_cells = eng.n_dust, eng.n_cells
     eng.close()
 
-    # the optically thin variant of the same grid (SURVEY.md 8d asks for both), rank-local timing
-    thin = None
-    if not a.no_thin:
+    # the optically thin and the moderate (tau = 5) variants of the same grid
+    def variant(tau):
         a2 = argparse.Namespace(**vars(a))
-        a2.tau = a.thin_tau
+        a2.tau = tau
         m2 = build_model(a2)
         eng2, drv2, stream2 = make(m2)
         ms2, st2, _ = measure(eng2, drv2, stream2, m2, P, world, rank, a2, sync_all, e2e=False)
         r2, c2, _, _ = roofline_of(st2, eng2.n_dust, world, a.steps)
-        thin = {"workload": workload_name(a2), "value": P * world * a.steps / (ms2 * 1e-3), "unit": "packets/s",
+        eng2.close()
+        return {"workload": workload_name(a2), "value": P * world * a.steps / (ms2 * 1e-3), "unit": "packets/s",
                 "ms_per_step": ms2 / a.steps, "roofline_achieved": r2["achieved"], "roofline_frac": r2["frac"],
                 "roofline_achieved_whole_photon_loop": r2["achieved_whole_photon_loop"],
                 "crossings_per_packet": c2 / (P * a.steps)}
-        eng2.close()
+
+    thin = variant(a.thin_tau) if not a.no_thin else None
+    moderate = variant(a.moderate_tau) if not a.no_moderate else None
 
     # the imaging iteration on the same grid (do_final + peel-off): every
     # emission and interaction is peeled towards 4 observers; unit = cell crossings at 8 B each
@@ -371,12 +449,14 @@ def main():
             st3 = eng3.final_finish()
             sync_all()
             wall = time.time() - t0
-        cr = st3.n_crossings + st3.n_peel_crossings
+        # crossings actually marched: peel-offs served by the point-source column cache read nothing
+        cr = st3.n_crossings + st3.n_peel_crossings - st3.n_peel_cached
         peak, _ = peaks()
         imaging = {"workload": "imaging_iteration_" + workload_name(a) + "_4_views_256x256x50",
                    "value": Pi / (st3.kernel_ms * 1e-3), "unit": "packets/s per GPU", "ms_per_step": st3.kernel_ms,
                    "wall_ms": wall * 1e3, "peeloffs_per_packet": st3.n_peeloffs / Pi,
-                   "crossings_per_packet": cr / Pi, "bytes_per_crossing": 8,
+                   "crossings_per_packet": cr / Pi, "peel_crossings_cached_per_packet": st3.n_peel_cached / Pi,
+                   "bytes_per_crossing": 8,
                    "roofline_achieved": 8.0 * cr / (st3.kernel_ms * 1e-3) / 1e9,
                    "roofline_frac": 8.0 * cr / (st3.kernel_ms * 1e-3) / 1e9 / peak,
                    "gpu_launches": int(st3.n_launches)}
@@ -385,15 +465,24 @@ def main():
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
         cores = os.cpu_count() or 1
+        ranks, t_setup = cpu_contexts(model, cores)
         n = int(a.cpu_photons) if a.cpu_photons else 0
         if n == 0:
-            rate, _, _, _ = cpu_sample(model, 10000 * cores, cores)
+            rate, _, _ = cpu_run(ranks, 10000 * cores)
             n = int(max(10000 * cores, min(rate * 15.0, 5e7)))
-        rate, dt, t_setup, cr = cpu_sample(model, n, cores)
+        rate, dt, cr = cpu_run(ranks, n)
+        del ranks
         cpu = {"value": rate, "unit": "packets/s", "cores": cores, "kind": "port",
                "sample": "%d packets of the same model in %.1f s on %d threads (rank r seeded seed+r, grids summed)"
                          % (n, dt, cores),
+               "compile_flags": oracle_flags(),
                "crossings_per_packet": cr / n}
+
+    # N > 1: the N-rank reduced grid must equal a 1-rank replay of the same packet ids
+    # (src/mpi/mpi_routines.f90:272-323 semantics: reduce, scale, broadcast)
+    mg_check = None
+    if world > 1:
+        mg_check = multi_gpu_check(make, Engine, local, rank, world, sync_all)
 
     if rank == 0:
         value = P * world * a.steps / (total_ms * 1e-3)
@@ -418,7 +507,9 @@ def main():
         }
         if e2e:
             line["e2e"] = e2e
-        others = [w for w in (thin, imaging) if w]
+        if mg_check is not None:
+            line["multi_gpu_check"] = mg_check
+        others = [w for w in (thin, moderate, imaging) if w]
         if others:
             line["other_workloads"] = others
         if cpu:

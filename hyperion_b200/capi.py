@@ -95,7 +95,7 @@ class IterStats(C.Structure):
         ("n_scatterings", C.c_int64), ("n_escaped", C.c_int64),
         ("kernel_ms", C.c_double), ("epilogue_ms", C.c_double),
         ("flight_ms", C.c_double), ("n_rounds", C.c_int64), ("n_launches", C.c_int64), ("n_peel_crossings", C.c_int64), ("n_peeloffs", C.c_int64),
-        ("n_peel_cached", C.c_int64),
+        ("n_peel_cached", C.c_int64), ("n_wave_rounds", C.c_int64),
     ]
 
     def as_dict(self):
@@ -358,6 +358,11 @@ class Engine(CApi):
 
     def update_density(self, density):
         self.set_density(self.ctx, self.n_dust, density)
+
+    def update_density_device(self, device_ptr):
+        """Replace the densities from a device buffer in the .rtin layout [n_dust][n3][n2][n1] (fp64) that
+        lives on this engine's GPU, e.g. one filled by an NCCL broadcast."""
+        self.check(self.lib.hyp_set_density(self.ctx, C.c_int32(self.n_dust), C.c_void_p(int(device_ptr))))
 
     def lucy_begin(self):
         self.check(self.lib.hyp_lucy_begin(self.ctx))

@@ -1,0 +1,640 @@
+// Wave engine: the Lucy photon loop (do_lucy, src/main/iter_lucy.f90:119-209) on uniformly spaced Cartesian
+// grids as a wavefront of TILE VISITS, with grid_integrate (src/grid/grid_propagate_3d.f90:35-234) reading
+// the densities from, and accumulating the specific_energy_sum deposits in, SHARED MEMORY.
+//
+// Why (profiles/r01_experiments.md): a flight that deposits straight into the HBM-resident cell records
+// issues one scattered density load and one scattered RED per crossing; that path saturates at 60-85 G
+// crossings/s wherever the records live.  Here the grid is cut into tiles of about 26^3 cells whose
+// densities (fp32) and sums (32-bit fixed point, native ATOMS.ADD) fill the 227 KB of shared memory of an
+// SM, and a crossing touches no global memory at all.
+//
+// State machine.  Every slot of the packet pool carries a KEY in `key[slot]`: the tile its packet sits in
+// (a flight is pending), WK_INTERACT (the flight reached its interaction) or WK_FREE.  A round is
+//   wave_hist / wave_scan / wave_scatter   counting sort of the slot ids by key -> `sorted`, work items
+//   wave_tile_kernel      one visit of every pending flight to its tile: march until the packet interacts,
+//                         leaves the grid or steps into the next tile; writes the slot's mutable sector
+//                         (tau, t, cell) and its next key
+//   wave_interact_kernel  interact (src/dust/dust_interact.f90:22-79) for the WK_INTERACT bucket
+//   wave_emit_kernel      emit (src/sources/source.f90:100-179) into the WK_FREE bucket while ids remain
+// The three march kernels of a round touch disjoint slots and run side by side on three streams.  When few
+// packets are left the remaining flights are finished by the direct kernels (flight_kernel / interact_kernel).
+//
+// Geometry.  Inside a visit the wall-crossing path lengths advance by the constant dt = dx |1/v| of the
+// uniformly spaced axis (the wave engine is only used when all three wall arrays are equidistant to 1e-10,
+// checked on the host); at the start of every visit they are recomputed from the wall table, so rounding does
+// not accumulate over more than one tile.  The tile is stored with a one-cell halo whose density is a
+// negative sentinel: a packet that steps out of the tile reads it and stops (-1: next tile, -2: outside the
+// grid), no index test per crossing.
+//
+// Deposits.  len * kappa * E is scaled so that the largest possible single deposit is 2^17 and rounded to an
+// integer with ERROR DIFFUSION along the packet's path: the remainder is carried to the packet's next
+// crossing, and every visit starts from a remainder drawn uniformly in [0, 1) (a hash of slot, path length
+// and iteration), so the sum a visit deposits is floor(exact + u): unbiased for deposits of any size, also
+// far below one unit.  A work item holds at most 2^14 packets and a packet crosses a cell at most once per
+// visit, so the 32-bit sums cannot overflow.  After the item the sums are converted back and added to the
+// fp64 grid with one RED per touched cell.
+#pragma once
+
+constexpr uint32_t WAVE_MAX_BINS = 11264;       // tiles + 2; the histogram kernels keep one counter per bin in shared memory
+constexpr int WAVE_SORT_THREADS = 512;
+constexpr int WAVE_SORT_SEG = 8192;             // slots per block of the counting sort
+constexpr float WAVE_DEP_MAX = 131072.0f;       // 2^17: fixed-point value of the largest possible deposit
+constexpr uint32_t WAVE_CHUNK_MAX = 16384;      // packets per work item (2^14 * 2^17 < 2^32)
+#ifndef WAVE_UNROLL
+#define WAVE_UNROLL 4                           // crossings between two hand-over votes
+#endif
+
+enum { WC_NITEMS = 0, WC_ITEM_CURSOR, WC_N_FLIGHT, WC_N_INTERACT, WC_INTERACT_START, WC_N_FREE, WC_FREE_START,
+       WC_CLAIMED_LO, WC_CLAIMED_HI, WC_COUNT = 16 };
+
+struct WaveQ {
+  uint32_t *key;         // [capacity] state of every slot
+  uint32_t *sorted;      // [capacity] slot ids ordered by key
+  uint32_t *bin_count;   // [n_tiles + 2]
+  uint32_t *bin_cursor;  // [n_tiles + 2]
+  uint4 *items;          // work items {tile, first index in sorted, packets, -}
+  uint32_t *ctl;         // [WC_COUNT]
+  uint32_t capacity;
+  int tx, ty, tz;        // cells of a tile
+  int ntx, nty, ntz, n_tiles;
+  uint32_t chunk;        // packets per work item
+  int refill;            // finished lanes of a warp that trigger a hand-over
+  uint32_t iteration;
+  double dx, dy, dz;     // cell widths
+  double diag;           // longest path through a cell
+  double dep_scale[MAX_DUST], dep_inv[MAX_DUST];
+};
+
+__device__ __forceinline__ uint32_t wave_tile_of(const WaveQ &W, int ix, int iy, int iz) {
+  return (uint32_t)(((iz / W.tz) * W.nty + iy / W.ty) * W.ntx + ix / W.tx);
+}
+
+__global__ void wave_init_kernel(WaveQ W, Pool P) {
+  const uint32_t k_free = (uint32_t)W.n_tiles + 1u;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < W.capacity; i += gridDim.x * blockDim.x) W.key[i] = k_free;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < (uint32_t)W.n_tiles + 2u; i += gridDim.x * blockDim.x)
+    W.bin_count[i] = 0;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    for (int k = 0; k < WC_COUNT; ++k) W.ctl[k] = 0;
+    for (int k = 0; k < C_COUNT; ++k) P.counts[k] = 0;
+    *P.next_photon = 0ull;
+  }
+}
+
+// ---- counting sort of the slot ids by key ------------------------------------------------------
+__global__ void __launch_bounds__(WAVE_SORT_THREADS) wave_hist_kernel(WaveQ W) {
+  extern __shared__ uint32_t s_cnt[];
+  const uint32_t nb = (uint32_t)W.n_tiles + 2u;
+  for (uint32_t k = threadIdx.x; k < nb; k += blockDim.x) s_cnt[k] = 0;
+  __syncthreads();
+  const uint32_t lo = blockIdx.x * (uint32_t)WAVE_SORT_SEG, hi = min(lo + (uint32_t)WAVE_SORT_SEG, W.capacity);
+  for (uint32_t i = lo + threadIdx.x; i < hi; i += blockDim.x) atomicAdd(&s_cnt[min(W.key[i], nb - 1u)], 1u);
+  __syncthreads();
+  for (uint32_t k = threadIdx.x; k < nb; k += blockDim.x) {
+    const uint32_t v = s_cnt[k];
+    if (v) atomicAdd(W.bin_count + k, v);
+  }
+}
+
+// One block: start of every bin in `sorted`, the work items (full chunks first so that the last blocks to
+// finish hold small items), the control words of the round.
+__global__ void __launch_bounds__(1024) wave_scan_kernel(WaveQ W, Pool P) {
+  typedef cub::BlockScan<uint32_t, 1024> Scan;
+  __shared__ typename Scan::TempStorage tmp_a, tmp_b, tmp_c;
+  __shared__ uint32_t s_full;
+  const int nt = W.n_tiles, nb = nt + 2;
+  const uint32_t chunk = W.chunk;
+  // total number of full chunks
+  uint32_t mine = 0;
+  for (int t = threadIdx.x; t < nt; t += 1024) mine += W.bin_count[t] / chunk;
+  uint32_t tot;
+  Scan(tmp_a).ExclusiveSum(mine, mine, tot);
+  if (threadIdx.x == 0) s_full = tot;
+  __syncthreads();
+  const uint32_t n_full = s_full;
+  uint32_t carry_off = 0, carry_full = 0, carry_part = 0;
+  for (int base = 0; base < nb; base += 1024) {
+    const int t = base + (int)threadIdx.x;
+    const uint32_t cnt = t < nb ? W.bin_count[t] : 0u;
+    const bool is_tile = t < nt;
+    const uint32_t nfull = is_tile ? cnt / chunk : 0u, npart = (is_tile && cnt % chunk) ? 1u : 0u;
+    uint32_t off, ifull, ipart, tot_off, tot_full, tot_part;
+    Scan(tmp_a).ExclusiveSum(cnt, off, tot_off);
+    Scan(tmp_b).ExclusiveSum(nfull, ifull, tot_full);
+    Scan(tmp_c).ExclusiveSum(npart, ipart, tot_part);
+    off += carry_off;
+    ifull += carry_full;
+    ipart += carry_part;
+    if (t < nb) {
+      W.bin_cursor[t] = off;
+      W.bin_count[t] = 0;  // ready for the next round's histogram
+      for (uint32_t k = 0; k < nfull; ++k) W.items[ifull + k] = make_uint4((uint32_t)t, off + k * chunk, chunk, 0u);
+      if (npart) W.items[n_full + ipart] = make_uint4((uint32_t)t, off + nfull * chunk, cnt - nfull * chunk, 0u);
+      if (t == nt) {
+        W.ctl[WC_N_FLIGHT] = off;
+        W.ctl[WC_N_INTERACT] = cnt;
+        W.ctl[WC_INTERACT_START] = off;
+      }
+      if (t == nt + 1) {
+        W.ctl[WC_N_FREE] = cnt;
+        W.ctl[WC_FREE_START] = off;
+      }
+    }
+    carry_off += tot_off;
+    carry_full += tot_full;
+    carry_part += tot_part;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    W.ctl[WC_NITEMS] = n_full + carry_part;
+    W.ctl[WC_ITEM_CURSOR] = 0;
+    const unsigned long long claimed = *P.next_photon;
+    W.ctl[WC_CLAIMED_LO] = (uint32_t)claimed;
+    W.ctl[WC_CLAIMED_HI] = (uint32_t)(claimed >> 32);
+  }
+}
+
+__global__ void __launch_bounds__(WAVE_SORT_THREADS) wave_scatter_kernel(WaveQ W) {
+  extern __shared__ uint32_t s_cnt[];   // [nb] counts, then [nb] bases
+  const uint32_t nb = (uint32_t)W.n_tiles + 2u;
+  uint32_t *s_base = s_cnt + nb;
+  for (uint32_t k = threadIdx.x; k < nb; k += blockDim.x) s_cnt[k] = 0;
+  __syncthreads();
+  const uint32_t lo = blockIdx.x * (uint32_t)WAVE_SORT_SEG, hi = min(lo + (uint32_t)WAVE_SORT_SEG, W.capacity);
+  for (uint32_t i = lo + threadIdx.x; i < hi; i += blockDim.x) atomicAdd(&s_cnt[min(W.key[i], nb - 1u)], 1u);
+  __syncthreads();
+  for (uint32_t k = threadIdx.x; k < nb; k += blockDim.x) {
+    const uint32_t v = s_cnt[k];
+    s_base[k] = v ? atomicAdd(W.bin_cursor + k, v) : 0u;
+    s_cnt[k] = 0;
+  }
+  __syncthreads();
+  for (uint32_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+    const uint32_t k = min(W.key[i], nb - 1u);
+    W.sorted[s_base[k] + atomicAdd(&s_cnt[k], 1u)] = i;
+  }
+}
+
+// ---- the march ---------------------------------------------------------------------------------
+// State of one flight inside a tile.  c is the shared-window ADDRESS of the packet's cell in the haloed density
+// array (base + cell index * 4 * ND); the sums lie SUM_OFF bytes behind the densities.
+template <int ND>
+struct WaveLane {
+  double tnx, tny, tnz;     // path length at which the next x / y / z wall is reached
+  double dtx, dty, dtz;     // path length between two walls of an axis (1e300 for a ray parallel to them)
+  double t, tau;
+  double chi[ND];
+  double kEs[ND];           // kappa * E in fixed-point units per length
+  float resid[ND];          // error diffusion: what rounding has left over so far
+  uint32_t c, cd;           // cd: cell whose density and sum the next crossing uses (differs from c only for the
+                            // first segment of a packet placed on a wall, grid_geometry_cartesian_3d.f90:184-232)
+  int scx, scy, scz;        // change of c for a step along +-x / +-y / +-z
+};
+
+constexpr double WAVE_FAR = 1e300;   // "never": wall distance of a ray parallel to the walls of an axis
+
+// One cell crossing (grid_propagate_3d.f90:106-232).  fin: 0 in flight, 1 left the grid, 2 interaction,
+// 4 stepped into the next tile.
+template <int ND, uint32_t SUM_OFF>
+__device__ __forceinline__ void wave_cross(WaveLane<ND> &L, int &fin, uint32_t &n_cross) {
+  float rho[ND];
+  const uint32_t a_rho = L.cd;
+#pragma unroll
+  for (int id = 0; id < ND; ++id) asm volatile("ld.shared.f32 %0, [%1+%2];" : "=f"(rho[id]) : "r"(a_rho), "n"(4 * id));
+  if (rho[0] < 0.f) {
+    fin = rho[0] < -1.5f ? 1 : 4;
+    return;
+  }
+  const bool bx = (L.tnx <= L.tny) & (L.tnx <= L.tnz);
+  const bool by = (!bx) & (L.tny <= L.tnz);
+  const double t_exit = bx ? L.tnx : (by ? L.tny : L.tnz);
+  const double ds = t_exit - L.t;
+  double chi_rho = 0.0;
+#pragma unroll
+  for (int id = 0; id < ND; ++id) chi_rho += L.chi[id] * (double)rho[id];
+  const double tau_cell = chi_rho * ds;
+  ++n_cross;
+  double len;
+  if (tau_cell < L.tau) {
+    // cross the whole cell: deposit tmin * kappa * E (grid_propagate_3d.f90:148-160)
+    len = ds;
+    L.tau -= tau_cell;
+    L.t = t_exit;
+    // tn += dt on the axis that was crossed, as a multiply-add with a 0/1 factor (one select per axis)
+    const double mx = __hiloint2double(bx ? 0x3ff00000 : 0, 0), my = __hiloint2double(by ? 0x3ff00000 : 0, 0),
+                 mz = __hiloint2double((bx | by) ? 0 : 0x3ff00000, 0);
+    L.tnx = fma(mx, L.dtx, L.tnx);
+    L.tny = fma(my, L.dty, L.tny);
+    L.tnz = fma(mz, L.dtz, L.tnz);
+    L.c += (uint32_t)(bx ? L.scx : (by ? L.scy : L.scz));
+  } else {
+    // interaction inside this cell (grid_propagate_3d.f90:186-228)
+    len = tau_cell > 0.0 ? ds * (L.tau / tau_cell) : 0.0;
+    L.t += len;
+    fin = 2;
+  }
+#pragma unroll
+  for (int id = 0; id < ND; ++id) {
+    if (rho[id] > 0.f) {
+      const float x = (float)(len * L.kEs[id]) + L.resid[id];
+      const uint32_t q = __float2uint_rd(x);
+      L.resid[id] = x - (float)q;
+      if (q) asm volatile("red.shared.add.u32 [%0+%1], %2;" ::"r"(a_rho), "n"(SUM_OFF + 4 * id), "r"(q) : "memory");
+    }
+  }
+  L.cd = L.c;
+}
+
+// uniform in [0, 1): 24 bits of a 32-bit mix (the start value of a visit's rounding remainder)
+__device__ __forceinline__ float wave_unit_hash(uint32_t a, uint32_t b, uint32_t c) {
+  uint32_t h = a * 0x9E3779B1u ^ b * 0x85EBCA77u ^ c * 0xC2B2AE3Du;
+  h ^= h >> 16; h *= 0x85EBCA6Bu; h ^= h >> 13; h *= 0xC2B2AE35u; h ^= h >> 16;
+  return (float)(h >> 8) * (1.0f / 16777216.0f);
+}
+
+// Shared memory of a block: [densities SUM_OFF bytes][sums SUM_OFF bytes][walls of the tile 3 x TW doubles].
+// SUM_OFF is a compile-time constant so that the sum of a cell is addressed as [cell + immediate].
+template <int ND, int THREADS, int MINB, uint32_t SUM_OFF>
+__global__ void __launch_bounds__(THREADS, MINB)
+wave_tile_kernel(const ModelDev M, Pool P, const WaveQ W) {
+  extern __shared__ __align__(16) unsigned char w_smem[];
+  const int TX = W.tx, TY = W.ty, TZ = W.tz;
+  const int TXh = TX + 2, TYh = TY + 2, TZh = TZ + 2;
+  float *__restrict__ s_rho = (float *)w_smem;                       // [n_h][ND], halo = sentinel
+  uint32_t *__restrict__ s_sum = (uint32_t *)(w_smem + SUM_OFF);     // [n_h][ND]
+  const int TW = max(TX, max(TY, TZ)) + 1;
+  double *__restrict__ s_w = (double *)(w_smem + 2 * SUM_OFF);       // [3][TW] walls of the tile
+  __shared__ uint32_t s_item, s_next;
+  const int n1 = M.n1, n2 = M.n2, n3 = M.n3;
+  const uint32_t n_items = W.ctl[WC_NITEMS];
+  Slot<ND> *slots = (Slot<ND> *)P.slots;
+  const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  constexpr int NWARPS = THREADS / 32;
+  const uint32_t k_interact = (uint32_t)W.n_tiles, k_free = (uint32_t)W.n_tiles + 1u;
+  const float inv_row = 1.0f / (float)TXh, inv_slab = 1.0f / (float)(TXh * TYh);
+  const uint32_t rho_base = (uint32_t)__cvta_generic_to_shared(s_rho);
+  constexpr int CB = 4 * ND;   // bytes of one cell in the density array
+  uint32_t n_cross = 0, n_esc = 0;
+  unsigned long long cross_hi = 0;
+
+  for (;;) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      s_item = atomicAdd(W.ctl + WC_ITEM_CURSOR, 1u);
+      s_next = 0;
+    }
+    __syncthreads();
+    const uint32_t item = s_item;
+    if (item >= n_items) break;
+    const uint4 it = W.items[item];
+    const int tix = (int)it.x % W.ntx, tiy = ((int)it.x / W.ntx) % W.nty, tiz = (int)it.x / (W.ntx * W.nty);
+    const int x0 = tix * TX, y0 = tiy * TY, z0 = tiz * TZ;
+    // ---------------- stage the tile: densities in (fp32), halo sentinels, sums zeroed ----------------
+    for (int row = warp; row < TYh * TZh; row += NWARPS) {
+      const int hz = row / TYh, hy = row - hz * TYh;
+      const int gy = y0 + hy - 1, gz = z0 + hz - 1;
+      const bool row_in_grid = (unsigned)gy < (unsigned)n2 && (unsigned)gz < (unsigned)n3;
+      const bool row_in_tile = hy >= 1 && hy <= TY && hz >= 1 && hz <= TZ;
+      for (int hx = lane; hx < TXh; hx += 32) {
+        const int gx = x0 + hx - 1;
+        const bool in_grid = row_in_grid && (unsigned)gx < (unsigned)n1;
+        const bool in_tile = row_in_tile && hx >= 1 && hx <= TX;
+        const int c = row * TXh + hx;
+        const size_t g = ((size_t)((size_t)gz * n2 + gy) * n1 + gx) * ND;
+#pragma unroll
+        for (int id = 0; id < ND; ++id) {
+          float v = in_grid ? -1.f : -2.f;
+          if (in_grid && in_tile) v = (float)__ldg(M.rho + g + id);
+          s_rho[c * ND + id] = v;
+          s_sum[c * ND + id] = 0u;
+        }
+      }
+    }
+    for (int k = threadIdx.x; k < 3 * TW; k += THREADS) {
+      const int a = k / TW, j = k - a * TW;
+      const int o = a == 0 ? 0 : (a == 1 ? n1 + 1 : n1 + n2 + 2);
+      const int na = a == 0 ? n1 : (a == 1 ? n2 : n3);
+      const int i0 = a == 0 ? x0 : (a == 1 ? y0 : z0);
+      s_w[k] = M.w1[o + min(i0 + j, na)];
+    }
+    __syncthreads();
+
+    // ---------------- march the packets of the work item ----------------
+    bool exhausted = false;  // warp-uniform: the item has no unclaimed packet left
+    int fin = 3;             // 3: no packet in this lane
+    uint32_t slot = 0;
+    WaveLane<ND> L;
+    L.c = L.cd = rho_base;
+    for (;;) {
+      const unsigned m_act = __ballot_sync(0xffffffffu, fin == 0);
+      const unsigned m_done = __ballot_sync(0xffffffffu, fin == 1 || fin == 2 || fin == 4);
+      if (m_act == 0 || __popc(m_done) >= W.refill) {
+        // -------- hand over the finished packets --------
+        if (fin == 1 || fin == 2 || fin == 4) {
+          // cell of the packet from its index in the haloed tile
+          const int ci = (int)(L.c - rho_base) / CB;
+          const int hz = (int)(((float)ci + 0.5f) * inv_slab);
+          const int rem = ci - hz * TXh * TYh;
+          const int hy = (int)(((float)rem + 0.5f) * inv_row);
+          const int hx = rem - hy * TXh;
+          const int gx = x0 + hx - 1, gy = y0 + hy - 1, gz = z0 + hz - 1;
+          int ic = (gz * n2 + gy) * n1 + gx;
+          uint32_t nk;
+          if (fin == 2) {
+            if (L.cd != L.c) {
+              const int di = (int)(L.cd - rho_base) / CB;
+              const int dz = (int)(((float)di + 0.5f) * inv_slab);
+              const int drem = di - dz * TXh * TYh;
+              const int dy = (int)(((float)drem + 0.5f) * inv_row);
+              const int dx = drem - dy * TXh;
+              ic = ((z0 + dz - 1) * n2 + (y0 + dy - 1)) * n1 + (x0 + dx - 1);
+            }
+            nk = k_interact;
+          } else if (fin == 1) {
+            nk = k_free;
+            ++n_esc;
+          } else {
+            const int d = (hx == 0 ? -1 : (hx == TXh - 1 ? 1 : 0)) + W.ntx * (hy == 0 ? -1 : (hy == TYh - 1 ? 1 : 0)) +
+                          W.ntx * W.nty * (hz == 0 ? -1 : (hz == TZh - 1 ? 1 : 0));
+            nk = it.x + (uint32_t)d;
+          }
+          Slot<ND> *s = slots + slot;
+          __stcs((double2 *)&s->tau_left, make_double2(L.tau, L.t));
+          __stcs((int4 *)&s->ix, make_int4(gx, gy, gz, ic));
+          W.key[slot] = nk;
+          fin = 3;
+        }
+        // -------- start the next packets --------
+        if (!exhausted) {
+          const unsigned m_need = __ballot_sync(0xffffffffu, fin == 3);
+          const int leader = __ffs(m_need) - 1;
+          uint32_t base = 0;
+          if ((int)lane == leader) base = atomicAdd(&s_next, (uint32_t)__popc(m_need));
+          base = __shfl_sync(0xffffffffu, base, leader);
+          bool failed = false;
+          int first_far = -1;   // >= 0: find_cell's cell of a packet placed on a wall, when it lies in ANOTHER tile
+          if (fin == 3) {
+            const uint32_t idx = base + __popc(m_need & ((1u << lane) - 1u));
+            if (idx >= it.z) {
+              failed = true;
+            } else {
+              slot = __ldcs(W.sorted + it.y + idx);
+              const Slot<ND> *s = slots + slot;
+              const double2 a0 = __ldcs((const double2 *)&s->r0x);  // r0x r0y
+              const double2 a1 = __ldcs((const double2 *)&s->r0z);  // r0z vx
+              const double2 a2 = __ldcs((const double2 *)&s->vy);   // vy vz
+              const double2 a3 = __ldcs((const double2 *)&s->tau_left);  // tau t
+              const int4 cc = __ldcs((const int4 *)&s->ix);
+              bool bad = false;
+#pragma unroll
+              for (int k = 0; k < ND; ++k) {
+                L.chi[k] = __ldcs(&s->chi[k]);
+                L.kEs[k] = __ldcs(&s->kE[k]) * W.dep_scale[k];
+                // fixed-point bound of the deposits (see wave_plan): kappa * E above the table maximum cannot happen
+                bad |= !(L.kEs[k] * W.diag <= (double)WAVE_DEP_MAX);
+                L.resid[k] = wave_unit_hash(slot, (uint32_t)__double2loint(a3.y) ^ (uint32_t)__double2hiint(a3.y),
+                                            W.iteration * 4u + (uint32_t)k);
+              }
+              L.tau = a3.x;
+              L.t = a3.y;
+              const int lx = cc.x - x0, ly = cc.y - y0, lz = cc.z - z0;
+              if (bad || (unsigned)lx >= (unsigned)TX || (unsigned)ly >= (unsigned)TY || (unsigned)lz >= (unsigned)TZ) {
+                // cannot happen for a packet bucketed by its own cell; never index shared memory with it
+                atomicCAS(M.error_flag, ERR_NONE, bad ? ERR_DEPOSIT : ERR_NOT_IN_CELL);
+                W.key[slot] = k_free;
+              } else {
+                const double vx = a1.y, vy = a2.x, vz = a2.y;
+                const double ivx = 1.0 / vx, ivy = 1.0 / vy, ivz = 1.0 / vz;
+                // distance to the wall ahead on each axis; a ray parallel to an axis never reaches its walls.
+                // Rounding can leave a resumed packet a few ulp past a wall it faces: clamp to its path length.
+                L.tnx = vx != 0.0 ? fmax((s_w[lx + (vx > 0.0 ? 1 : 0)] - a0.x) * ivx, L.t) : WAVE_FAR;
+                L.tny = vy != 0.0 ? fmax((s_w[TW + ly + (vy > 0.0 ? 1 : 0)] - a0.y) * ivy, L.t) : WAVE_FAR;
+                L.tnz = vz != 0.0 ? fmax((s_w[2 * TW + lz + (vz > 0.0 ? 1 : 0)] - a1.x) * ivz, L.t) : WAVE_FAR;
+                L.dtx = vx != 0.0 ? fmin(W.dx * fabs(ivx), WAVE_FAR) : WAVE_FAR;
+                L.dty = vy != 0.0 ? fmin(W.dy * fabs(ivy), WAVE_FAR) : WAVE_FAR;
+                L.dtz = vz != 0.0 ? fmin(W.dz * fabs(ivz), WAVE_FAR) : WAVE_FAR;
+                L.tnx = fmin(L.tnx, WAVE_FAR);
+                L.tny = fmin(L.tny, WAVE_FAR);
+                L.tnz = fmin(L.tnz, WAVE_FAR);
+                L.scx = vx > 0.0 ? CB : -CB;
+                L.scy = vy > 0.0 ? CB * TXh : -CB * TXh;
+                L.scz = vz > 0.0 ? CB * TXh * TYh : -CB * TXh * TYh;
+                L.c = rho_base + (uint32_t)((((lz + 1) * TYh + (ly + 1)) * TXh + lx + 1) * CB);
+                L.cd = L.c;
+                fin = 0;
+                if (cc.w != (cc.z * n2 + cc.y) * n1 + cc.x) {
+                  // first segment of a packet placed on a wall: density and deposit of find_cell's cell
+                  const int fz = cc.w / (n1 * n2), frem = cc.w - fz * n1 * n2;
+                  const int fy = frem / n1, fx = frem - fy * n1;
+                  const int qx = fx - x0, qy = fy - y0, qz = fz - z0;
+                  if ((unsigned)qx < (unsigned)TX && (unsigned)qy < (unsigned)TY && (unsigned)qz < (unsigned)TZ)
+                    L.cd = rho_base + (uint32_t)((((qz + 1) * TYh + (qy + 1)) * TXh + qx + 1) * CB);
+                  else
+                    first_far = cc.w;
+                }
+              }
+            }
+          }
+          exhausted = __any_sync(0xffffffffu, failed);
+          if (__any_sync(0xffffffffu, first_far >= 0)) {
+            // find_cell's cell belongs to another tile: that one crossing goes through global memory.  All
+            // packets of a point source on a tile boundary take this path, so the deposits of the lanes that
+            // share a cell are summed before ONE RED per cell leaves the warp.
+            const bool far = first_far >= 0;
+            double dep[ND];
+#pragma unroll
+            for (int id = 0; id < ND; ++id) dep[id] = 0.0;
+            if (far) {
+              double rho[ND], chi_rho = 0.0;
+#pragma unroll
+              for (int id = 0; id < ND; ++id) {
+                rho[id] = __ldg(M.rho + (size_t)first_far * ND + id);
+                chi_rho += L.chi[id] * rho[id];
+              }
+              const bool bx = (L.tnx <= L.tny) & (L.tnx <= L.tnz);
+              const bool by = (!bx) & (L.tny <= L.tnz);
+              const double t_exit = bx ? L.tnx : (by ? L.tny : L.tnz);
+              const double ds = t_exit - L.t;
+              const double tau_cell = chi_rho * ds;
+              ++n_cross;
+              double len;
+              if (tau_cell < L.tau) {
+                len = ds;
+                L.tau -= tau_cell;
+                L.t = t_exit;
+                if (bx) L.tnx += L.dtx;
+                if (by) L.tny += L.dty;
+                if (!(bx | by)) L.tnz += L.dtz;
+                L.c += (uint32_t)(bx ? L.scx : (by ? L.scy : L.scz));
+                L.cd = L.c;
+              } else {
+                len = tau_cell > 0.0 ? ds * (L.tau / tau_cell) : 0.0;
+                L.t += len;
+                // the interaction keeps the cell indices and find_cell's 1-D id the slot already holds
+                Slot<ND> *sw = slots + slot;
+                __stcs((double2 *)&sw->tau_left, make_double2(L.tau, L.t));
+                W.key[slot] = k_interact;
+                fin = 3;
+              }
+#pragma unroll
+              for (int id = 0; id < ND; ++id) dep[id] = rho[id] > 0.0 ? len * L.kEs[id] * W.dep_inv[id] : 0.0;
+            }
+            unsigned todo = __ballot_sync(0xffffffffu, far);
+            while (todo) {
+              const int head = __ffs(todo) - 1;
+              const int cell = __shfl_sync(0xffffffffu, first_far, head);
+              const bool mine = far && first_far == cell;
+#pragma unroll
+              for (int id = 0; id < ND; ++id) {
+                double v = mine ? dep[id] : 0.0;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                if ((int)lane == head && v != 0.0) atomicAdd(&M.cells[(size_t)cell * ND + id].esum, v);
+              }
+              todo &= ~__ballot_sync(0xffffffffu, mine);
+            }
+          }
+        }
+        if (__ballot_sync(0xffffffffu, fin == 0) == 0) {
+          if (exhausted) break;
+          continue;
+        }
+      }
+      // -------- cell crossings --------
+#pragma unroll
+      for (int u = 0; u < WAVE_UNROLL; ++u) {
+        if (fin == 0) wave_cross<ND, SUM_OFF>(L, fin, n_cross);
+      }
+    }
+    if (n_cross > 0x7fffff00u) {
+      cross_hi += n_cross;
+      n_cross = 0;
+    }
+    __syncthreads();
+
+    // ---------------- add the tile's sums to the grid ----------------
+    for (int row = warp; row < TY * TZ; row += NWARPS) {
+      const int lz = row / TY, ly = row - lz * TY;
+      const int gy = y0 + ly, gz = z0 + lz;
+      if (gy >= n2 || gz >= n3) continue;
+      for (int lx = lane; lx < TX; lx += 32) {
+        const int gx = x0 + lx;
+        if (gx >= n1) continue;
+        const int c = ((lz + 1) * TYh + (ly + 1)) * TXh + lx + 1;
+        const size_t g = ((size_t)((size_t)gz * n2 + gy) * n1 + gx) * ND;
+#pragma unroll
+        for (int id = 0; id < ND; ++id) {
+          const uint32_t v = s_sum[c * ND + id];
+          if (v) atomicAdd(&M.cells[g + id].esum, (double)v * W.dep_inv[id]);
+        }
+      }
+    }
+  }
+  warp_add_scalar(M.scalars + SC_CROSS, (double)(cross_hi + n_cross));
+  warp_add_scalar(M.scalars + SC_ESC, (double)n_esc);
+}
+
+// ---- interactions and emission of a round --------------------------------------------------------
+template <int ND>
+__global__ void __launch_bounds__(SERVICE_THREADS, INTERACT_MIN_BLOCKS)
+wave_interact_kernel(const ModelDev M, Pool P, const WaveQ W, const uint32_t iteration) {
+  const uint32_t n = W.ctl[WC_N_INTERACT], start = W.ctl[WC_INTERACT_START];
+  Slot<ND> *slots = (Slot<ND> *)P.slots;
+  uint32_t n_abs = 0, n_scat = 0, n_kill = 0;
+  const uint32_t k_free = (uint32_t)W.n_tiles + 1u;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const uint32_t slot = W.sorted[start + i];
+    Photon<ND> p;
+    Rng rng;
+    load_photon<ND>(slots + slot, p, rng, M.seed, iteration);
+    const uint64_t id = slots[slot].id;
+    int dust_id = 0;
+    bool scattered = false;
+    bool ok = interact_photon<ND>(M, p, rng, n_abs, n_scat, n_kill, dust_id, scattered) == 0;
+    if (ok && M.use_mrw) ok = mrw_loop<ND>(M, p, rng, n_kill);
+    uint32_t nk = k_free;
+    if (ok) {
+      p.tau_left = -log(1.0 - rng.next());
+      store_photon<ND>(slots + slot, p, rng, id);
+      nk = wave_tile_of(W, min(max(p.ix, 0), M.n1 - 1), min(max(p.iy, 0), M.n2 - 1), min(max(p.iz, 0), M.n3 - 1));
+    }
+    W.key[slot] = nk;
+  }
+  warp_add_scalar(M.scalars + SC_ABS, (double)n_abs);
+  warp_add_scalar(M.scalars + SC_SCAT, (double)n_scat);
+  warp_add_scalar(M.scalars + SC_KILLED_INT, (double)n_kill);
+}
+
+template <int ND>
+__global__ void __launch_bounds__(SERVICE_THREADS, INTERACT_MIN_BLOCKS)
+wave_emit_kernel(const ModelDev M, Pool P, const WaveQ W, const unsigned long long first_id,
+                 const unsigned long long n_photons, const uint32_t iteration) {
+  const uint32_t n = W.ctl[WC_N_FREE], start = W.ctl[WC_FREE_START];
+  const unsigned lane = threadIdx.x & 31;
+  Slot<ND> *slots = (Slot<ND> *)P.slots;
+  double energy_emitted = 0.0;
+  uint32_t n_run = 0, n_esc = 0;
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t base = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < n; base += stride) {
+    const uint32_t i = base + lane;
+    const bool valid = i < n;
+    // claim packet ids (warp-aggregated); packets are emitted in id order
+    const unsigned m = __ballot_sync(0xffffffffu, valid);
+    const int leader = __ffs(m) - 1;
+    unsigned long long k0 = 0;
+    if ((int)lane == leader) k0 = atomicAdd(P.next_photon, (unsigned long long)__popc(m));
+    k0 = __shfl_sync(0xffffffffu, k0, leader);
+    unsigned long long k = k0 + __popc(m & ((1u << lane) - 1u));
+    if (!valid || k >= n_photons) continue;
+    const uint32_t slot = W.sorted[start + i];
+    Photon<ND> p;
+    Rng rng;
+    bool go = true;
+    unsigned long long id = 0;
+    for (;;) {
+      id = first_id + k;
+      rng.init(M.seed, id, iteration);
+      ++n_run;
+      if (!emit_photon<ND>(M, p, rng, energy_emitted)) {
+        go = false;  // fatal model error is flagged; the host reports it after the round
+        break;
+      }
+      // a packet emitted on the outer wall moving outwards escapes immediately
+      if (p.ix < 0 || p.ix >= M.n1 || p.iy < 0 || p.iy >= M.n2 || p.iz < 0 || p.iz >= M.n3) {
+        ++n_esc;
+        k = atomicAdd(P.next_photon, 1ull);
+        if (k >= n_photons) {
+          go = false;
+          break;
+        }
+        continue;
+      }
+      break;
+    }
+    if (go) {
+      p.tau_left = -log(1.0 - rng.next());  // random_exp (lib_random.f90:227-236)
+      store_photon<ND>(slots + slot, p, rng, id);
+      W.key[slot] = wave_tile_of(W, p.ix, p.iy, p.iz);
+    }
+  }
+  warp_add_scalar(M.scalars + SC_ENERGY, energy_emitted);
+  warp_add_scalar(M.scalars + SC_PHOTONS, (double)n_run);
+  warp_add_scalar(M.scalars + SC_ESC, (double)n_esc);
+}
+
+// Hand the packets that are still in the pool to the direct kernels: flights -> q_flight[0], pending
+// interactions -> q_interact.
+__global__ void wave_handoff_kernel(Pool P, const WaveQ W) {
+  const uint32_t nf = W.ctl[WC_N_FLIGHT], ni = W.ctl[WC_N_INTERACT], is = W.ctl[WC_INTERACT_START];
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nf; i += gridDim.x * blockDim.x) P.q_flight[0][i] = W.sorted[i];
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < ni; i += gridDim.x * blockDim.x) P.q_interact[i] = W.sorted[is + i];
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    P.counts[C_NF0] = nf;
+    P.counts[C_NF0 + 1] = 0;
+    P.counts[C_NI] = ni;
+    P.counts[C_NE] = 0;
+    P.counts[C_NB] = 0;
+    P.counts[C_CURSOR] = 0;
+    P.counts[C_CURSOR_B] = 0;
+  }
+}

@@ -8,6 +8,7 @@
 // density read and the deposit RED of a crossing touch the same 32-byte sector.
 #include <algorithm>
 #include <array>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -78,7 +79,7 @@ struct ModelDev {
   int32_t *error_flag;
 };
 
-enum { ERR_NONE = 0, ERR_NOT_IN_CELL = 1, ERR_NU_RANGE = 2, ERR_SCATTER = 3, ERR_JOBS = 4 };
+enum { ERR_NONE = 0, ERR_NOT_IN_CELL = 1, ERR_NU_RANGE = 2, ERR_SCATTER = 3, ERR_JOBS = 4, ERR_DEPOSIT = 5 };
 
 // =============================================================================================
 // photon pool (wavefront formulation of do_lucy's photon loop, src/main/iter_lucy.f90:119-209)
@@ -97,9 +98,10 @@ struct alignas(32) Slot {
   // ---- hot part: what a flight needs
   double r0x, r0y, r0z;  // flight origin
   double vx, vy, vz;
+  double chi[ND], kE[ND];
+  // what a flight changes: for one dust type exactly the third 32-byte sector of the slot, written whole
   double tau_left;
   double t;              // out: path length from the origin at which the flight ended
-  double chi[ND], kE[ND];
   int32_t ix, iy, iz;    // in: cell whose walls bound the flight; out: cell of the event
   int32_t ic;            // 1-D id used for density / deposits (p%icell%ic of the reference)
   // ---- cold part: only the emit / interact kernels touch it
@@ -113,17 +115,7 @@ struct alignas(32) Slot {
   uint32_t tag;          // final iteration: source id | scattered | reprocessed | n_scat (see imaging.cuh)
 };
 
-enum { C_NF0 = 0, C_NF1, C_NB, C_NI, C_NE, C_CURSOR, C_CURSOR_B, C_NP0 = 8, C_NP1, C_NITEMS, C_ITEM_CURSOR, C_COUNT = 16 };
-
-// Lists of the tile-staged flights (flight_tile.cuh)
-struct TileQ {
-  uint32_t *park_slot[2], *park_tile[2];  // flights waiting for the next round: slot id and tile id (double-buffered)
-  uint32_t *sorted;                       // slot ids of this round's flights ordered by tile
-  uint32_t *tile_count, *tile_cursor;     // [n_tiles]
-  uint4 *items;                           // work items {tile, first index in sorted, packets, -}
-  int ntx, nty, ntz, n_tiles;
-  int n_tiles_alloc;
-};
+enum { C_NF0 = 0, C_NF1, C_NB, C_NI, C_NE, C_CURSOR, C_CURSOR_B, C_COUNT = 16 };
 
 struct Pool {
   void *slots;
@@ -139,7 +131,6 @@ struct Pool {
   // `window` packet offsets each; window w of the launch lives in half (w & 1).
   const uint32_t *perm;
   uint32_t window;        // power of two
-  TileQ tile;
 };
 
 // Register view of one packet in the emit / interact kernels.
@@ -215,43 +206,6 @@ __device__ __forceinline__ void queue_append(bool pred, uint32_t *__restrict__ q
   if ((int)lane == leader) base = atomicAdd(count, (uint32_t)__popc(m));
   base = __shfl_sync(0xffffffffu, base, leader);
   if (pred) q[base + __popc(m & ((1u << lane) - 1u))] = value;
-}
-
-// Tile dimensions of the tile-staged flights (flight_tile.cuh): density + sums of a tile fit in 64 KB.
-template <int ND>
-struct TileDims {
-#ifndef TILE_X
-#define TILE_X 16   // cells of a tile along x for one dust type (tuning: 32 with one 768-thread block per SM)
-#endif
-  static constexpr int X = ND == 1 ? TILE_X : 16, Y = ND <= 2 ? 16 : 8, Z = ND == 1 ? 16 : 8;
-  static constexpr int CELLS = X * Y * Z;
-  static constexpr int WALLS = (X > 16 ? X : 16) + 1;
-  // densities + sums + walls of the tile, then one prefetch record (hot part of a Slot) per thread
-  static constexpr size_t smem_bytes(int threads) {
-    return (size_t)(2 * CELLS * ND + 3 * WALLS + 1) * sizeof(double) + (size_t)threads * (80 + 16 * ND);
-  }
-};
-
-template <int ND>
-__device__ __forceinline__ uint32_t tile_of_cell(const TileQ &T, int ix, int iy, int iz) {
-  using TD = TileDims<ND>;
-  return (uint32_t)(((iz / TD::Z) * T.nty + iy / TD::Y) * T.ntx + ix / TD::X);
-}
-
-// Append (slot, tile) to the park list `buf` for every lane with pred set; whole warp must call.
-__device__ __forceinline__ void park_append(const Pool &P, int buf, bool pred, uint32_t slot, uint32_t tile) {
-  const unsigned m = __ballot_sync(0xffffffffu, pred);
-  if (m == 0) return;
-  const unsigned lane = threadIdx.x & 31;
-  const int leader = __ffs(m) - 1;
-  uint32_t base = 0;
-  if ((int)lane == leader) base = atomicAdd(P.counts + C_NP0 + buf, (uint32_t)__popc(m));
-  base = __shfl_sync(0xffffffffu, base, leader);
-  if (pred) {
-    const uint32_t k = base + __popc(m & ((1u << lane) - 1u));
-    P.tile.park_slot[buf][k] = slot;
-    P.tile.park_tile[buf][k] = tile;
-  }
 }
 
 // Sum a per-lane value over the warp and add it to a global scalar.
@@ -1196,7 +1150,7 @@ emit_kernel(const ModelDev M, Pool P, const unsigned long long first_id, const u
 template <int ND>
 __global__ void __launch_bounds__(SERVICE_THREADS, INTERACT_MIN_BLOCKS)
 interact_kernel(const ModelDev M, Pool P, uint32_t *__restrict__ q_flight_next, uint32_t *n_flight_next,
-                const uint32_t iteration, const int park_buf = -1) {
+                const uint32_t iteration) {
   const uint32_t n = P.counts[C_NI];
   const unsigned lane = threadIdx.x & 31;
   Slot<ND> *slots = (Slot<ND> *)P.slots;
@@ -1205,7 +1159,7 @@ interact_kernel(const ModelDev M, Pool P, uint32_t *__restrict__ q_flight_next, 
   for (uint32_t base = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < n; base += stride) {
     const uint32_t i = base + lane;
     const bool valid = i < n;
-    uint32_t slot = 0, tile = 0;
+    uint32_t slot = 0;
     bool alive = false;
     if (valid) {
       slot = P.q_interact[i];
@@ -1223,12 +1177,9 @@ interact_kernel(const ModelDev M, Pool P, uint32_t *__restrict__ q_flight_next, 
         p.tau_left = -log(1.0 - rng.next());
         store_photon<ND>(slots + slot, p, rng, id);
         alive = true;
-        if (park_buf >= 0)
-          tile = tile_of_cell<ND>(P.tile, min(max(p.ix, 0), M.n1 - 1), min(max(p.iy, 0), M.n2 - 1), min(max(p.iz, 0), M.n3 - 1));
       }
     }
-    if (park_buf >= 0) park_append(P, park_buf, alive, slot, tile);  // tile-staged flights (flight_tile.cuh)
-    else queue_append(alive, q_flight_next, n_flight_next, slot);
+    queue_append(alive, q_flight_next, n_flight_next, slot);
     queue_append(valid && !alive, P.q_emit, P.counts + C_NE, slot);
   }
   warp_add_scalar(M.scalars + SC_ABS, (double)n_abs);
@@ -1527,7 +1478,7 @@ flight_kernel(const ModelDev M, Pool P, const uint32_t *__restrict__ q_flight, c
         } else {
           slot = q_flight[idx];
           load_lane<ND>(slots + slot, L, W, n1 + 1, n1 + n2 + 2);
-          L.t = __ldcs(&slots[slot].t);  // 0 for a new flight; the path length so far for one parked by flight_tile_kernel
+          L.t = __ldcs(&slots[slot].t);  // 0 for a new flight; the path length so far for one handed over by the wave engine
           active = true;
         }
       }
@@ -1750,7 +1701,7 @@ __global__ void to_file_order_kernel(ModelDev M, int which, const double *__rest
 #include "march_geo.cuh"
 #include "imaging.cuh"
 #include "flight_geo.cuh"
-#include "flight_tile.cuh"
+#include "flight_wave.cuh"
 
 // =============================================================================================
 // host side: context + C ABI
@@ -1795,7 +1746,12 @@ struct hyp_ctx {
   int sm_count = 148;
   cudaStream_t stream = nullptr;
   cudaStream_t stream2 = nullptr;              // the beam kernel of a round runs here, next to the flight kernel
-  cudaEvent_t evFork = nullptr, evJoin = nullptr;
+  cudaStream_t stream3 = nullptr;              // wave engine: emission next to the tile visits and the interactions
+  cudaEvent_t evFork = nullptr, evJoin = nullptr, evJoin3 = nullptr;
+  WaveQ wave = WaveQ();                        // wave engine (flight_wave.cuh)
+  int wave_bins_alloc = 0;
+  bool uniform_walls = false;                  // all three wall arrays equidistant (to 1e-10 of the spacing)
+  int last_engine = 0;                         // 1: the last Lucy photon loop ran on the wave engine
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
   // host model
   int grid_type = GEO_CAR;
@@ -1840,7 +1796,7 @@ struct hyp_ctx {
   bool finalized = false;
   bool sums_gathered = false;
   float kernel_ms_acc = 0.f, flight_ms_acc = 0.f;
-  int64_t rounds_acc = 0, launches_acc = 0;  // launches: this library's own kernels in the iteration
+  int64_t rounds_acc = 0, wave_rounds_acc = 0, launches_acc = 0;  // launches: this library's own kernels in the iteration
   // photon pool
   Pool pool = Pool();
   std::vector<int64_t> coll_off;              // per source: first entry of its point collection, -1 if none
@@ -1910,6 +1866,9 @@ int device_error_to_status(hyp_ctx *c) {
     case ERR_NU_RANGE:
       return fail(HYP_ERR_PHYSICS,
                   "photon frequency is outside the range defined for the dust optical properties");
+    case ERR_DEPOSIT:
+      return fail(HYP_ERR_STATE, "internal error: a packet's kappa * energy exceeds the bound of the fixed-point deposits "
+                                 "(set HYPERION_B200_ENGINE=rounds and report)");
     case ERR_JOBS:
       return fail(HYP_ERR_STATE, "peel-off queue overflow: too many random-walk steps per round (lower HYPERION_B200_POOL)");
     default:
@@ -1932,14 +1891,14 @@ void free_pool(hyp_ctx *c) {
   free_dev(c->pool.q_emit);
   free_dev(c->pool.counts);
   free_dev(c->pool.next_photon);
-  for (int b = 0; b < 2; ++b) {
-    free_dev(c->pool.tile.park_slot[b]);
-    free_dev(c->pool.tile.park_tile[b]);
-  }
-  free_dev(c->pool.tile.sorted);
-  free_dev(c->pool.tile.tile_count);
-  free_dev(c->pool.tile.tile_cursor);
-  free_dev(c->pool.tile.items);
+  free_dev(c->wave.key);
+  free_dev(c->wave.sorted);
+  free_dev(c->wave.bin_count);
+  free_dev(c->wave.bin_cursor);
+  free_dev(c->wave.items);
+  free_dev(c->wave.ctl);
+  c->wave.capacity = 0;
+  c->wave_bins_alloc = 0;
   c->pool_cap = 0;
   free_dev(c->d_keys_in);
   free_dev(c->d_keys_out);
@@ -1999,35 +1958,6 @@ int ensure_pool(hyp_ctx *c, uint32_t cap) {
   CUDA_TRY(cudaMalloc(&c->d_sort_tmp, c->sort_tmp_bytes));
   P.perm = c->d_perm;
   P.window = w;
-  return HYP_OK;
-}
-
-// Lists of the tile-staged flights (flight_tile.cuh), allocated on first use.
-int ensure_tile_queues(hyp_ctx *c, int tx, int ty, int tz) {
-  TileQ &T = c->pool.tile;
-  T.ntx = (c->n1 + tx - 1) / tx;
-  T.nty = (c->n2 + ty - 1) / ty;
-  T.ntz = (c->n3 + tz - 1) / tz;
-  T.n_tiles = T.ntx * T.nty * T.ntz;
-  if (T.sorted && T.n_tiles <= T.n_tiles_alloc) return HYP_OK;
-  for (int b = 0; b < 2; ++b) {
-    free_dev(T.park_slot[b]);
-    free_dev(T.park_tile[b]);
-  }
-  free_dev(T.sorted);
-  free_dev(T.tile_count);
-  free_dev(T.tile_cursor);
-  free_dev(T.items);
-  T.n_tiles_alloc = T.n_tiles;
-  const size_t cap = c->pool_cap;
-  for (int b = 0; b < 2; ++b) {
-    CUDA_TRY(cudaMalloc(&T.park_slot[b], cap * sizeof(uint32_t)));
-    CUDA_TRY(cudaMalloc(&T.park_tile[b], cap * sizeof(uint32_t)));
-  }
-  CUDA_TRY(cudaMalloc(&T.sorted, cap * sizeof(uint32_t)));
-  CUDA_TRY(cudaMalloc(&T.tile_count, (size_t)T.n_tiles * sizeof(uint32_t)));
-  CUDA_TRY(cudaMalloc(&T.tile_cursor, (size_t)T.n_tiles * sizeof(uint32_t)));
-  CUDA_TRY(cudaMalloc(&T.items, ((size_t)T.n_tiles + cap / TILE_CHUNK + 1) * sizeof(uint4)));
   return HYP_OK;
 }
 
@@ -2091,6 +2021,8 @@ int hyp_ctx_create(int device_id, hyp_ctx **out) {
   CUDA_TRY(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
   CUDA_TRY(cudaEventCreateWithFlags(&c->evFork, cudaEventDisableTiming));
   CUDA_TRY(cudaEventCreateWithFlags(&c->evJoin, cudaEventDisableTiming));
+  CUDA_TRY(cudaStreamCreateWithFlags(&c->stream3, cudaStreamNonBlocking));
+  CUDA_TRY(cudaEventCreateWithFlags(&c->evJoin3, cudaEventDisableTiming));
   CUDA_TRY(cudaEventCreate(&c->evA));
   CUDA_TRY(cudaEventCreate(&c->evB));
   CUDA_TRY(cudaMallocHost(&c->h_counts, (C_COUNT + 2) * sizeof(uint32_t)));
@@ -2159,6 +2091,8 @@ void hyp_ctx_destroy(hyp_ctx *c) {
   if (c->evFork) cudaEventDestroy(c->evFork);
   if (c->evJoin) cudaEventDestroy(c->evJoin);
   if (c->stream2) cudaStreamDestroy(c->stream2);
+  if (c->evJoin3) cudaEventDestroy(c->evJoin3);
+  if (c->stream3) cudaStreamDestroy(c->stream3);
   if (c->evA) cudaEventDestroy(c->evA);
   if (c->evB) cudaEventDestroy(c->evB);
   for (auto &d : c->dust) {
@@ -2198,6 +2132,17 @@ int hyp_set_grid_cartesian(hyp_ctx *c, int32_t n1, int32_t n2, int32_t n3, const
   c->w1.assign(w1, w1 + n1 + 1);
   c->w2.assign(w2, w2 + n2 + 1);
   c->w3.assign(w3, w3 + n3 + 1);
+  // equidistant walls on all three axes (to 1e-10 of the spacing): the wave engine applies (flight_wave.cuh)
+  c->uniform_walls = true;
+  const std::vector<double> *wa[3] = {&c->w1, &c->w2, &c->w3};
+  for (int a = 0; a < 3; ++a) {
+    const std::vector<double> &w = *wa[a];
+    const int n = (int)w.size() - 1;
+    const double d = (w[n] - w[0]) / n;
+    if (!(d > 0.0) || !std::isfinite(d)) c->uniform_walls = false;
+    for (int i = 0; i < n && c->uniform_walls; ++i)
+      if (!(std::fabs((w[i + 1] - w[i]) - d) <= 1e-10 * d)) c->uniform_walls = false;
+  }
   return HYP_OK;
 }
 
@@ -2699,7 +2644,8 @@ int hyp_set_run_conf(hyp_ctx *c, const hyp_run_conf *conf) {
 
 static int upload_density(hyp_ctx *c, const double *density) {
   const size_t n = (size_t)c->n_cells * c->dust.size();
-  CUDA_TRY(cudaMemcpyAsync(c->d_stage, density, n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  // cudaMemcpyDefault: after hyp_finalize_setup the caller may pass a host or a device pointer
+  CUDA_TRY(cudaMemcpyAsync(c->d_stage, density, n * sizeof(double), cudaMemcpyDefault, c->stream));
   scatter_density_kernel<<<grid_blocks(c), 256, 0, c->stream>>>(c->M, c->d_stage);
   CUDA_TRY(cudaGetLastError());
   return HYP_OK;
@@ -3103,15 +3049,18 @@ int hyp_lucy_begin(hyp_ctx *c) {
   c->kernel_ms_acc = 0.f;
   c->flight_ms_acc = 0.f;
   c->rounds_acc = 0;
+  c->wave_rounds_acc = 0;
   return HYP_OK;
 }
 
 }  // extern "C"
 
-// The rounds of the packet pool for a fixed number of dust types.
+// The rounds of the packet pool for a fixed number of dust types.  With `handoff` set the pool already
+// holds the packets (queues filled by wave_handoff_kernel, every id claimed) and the rounds only finish them.
 template <int ND>
-static int run_rounds(hyp_ctx *c, int64_t first_id, int64_t n_photons, int64_t iteration) {
-  const uint32_t cap = (uint32_t)std::min<int64_t>(pool_target(), n_photons);
+static int run_rounds(hyp_ctx *c, int64_t first_id, int64_t n_photons, int64_t iteration, const bool handoff = false,
+                      const uint32_t handoff_flights = 0) {
+  const uint32_t cap = handoff ? c->pool_cap : (uint32_t)std::min<int64_t>(pool_target(), n_photons);
   int rc = ensure_pool(c, cap);
   if (rc) return rc;
   Pool &P = c->pool;
@@ -3136,45 +3085,24 @@ static int run_rounds(hyp_ctx *c, int64_t first_id, int64_t n_photons, int64_t i
   const int service_blocks_max = c->sm_count * 8;
   cudaStream_t st = c->stream;
 
-  // Tile-staged flights for the packets that leave an interaction (flight_tile.cuh): opt-in with
-  // HYPERION_B200_TILES=1.  Measured on the 256^3 headline they tie with the direct kernel (both ~60 G
-  // crossings/s, profiles/r01_experiments.md), so the direct kernel stays the default.
-  bool tiles = false;
-  {
-    const char *e = getenv("HYPERION_B200_TILES");
-    tiles = c->grid_type == GEO_CAR && !c->M.any_sphere && e && atoi(e) != 0;
-  }
   int overlap_b = 2, overlap_f = 2;   // measured best with a 12 M pool (profiles/r01_experiments.md); "0" = one after the other
   if (const char *e = getenv("HYPERION_B200_OVERLAP")) {
     if (sscanf(e, "%d,%d", &overlap_b, &overlap_f) != 2 || overlap_b < 1 || overlap_f < 1) overlap_b = overlap_f = 0;
   }
-  const uint32_t tile_min_flights = getenv("HYPERION_B200_TILE_MIN") ? (uint32_t)atol(getenv("HYPERION_B200_TILE_MIN")) : 1000000u;
-  const bool dbg = getenv("HYPERION_B200_TIMING") != nullptr;
-  float dbg_bucket = 0.f, dbg_tile = 0.f;
-  auto tile_flight = flight_tile_kernel<ND>;
-  const size_t tile_smem = TileDims<ND>::smem_bytes(TILE_THREADS);
-  int tile_blocks = 0;
-  if (tiles) {
-    rc = ensure_tile_queues(c, TileDims<ND>::X, TileDims<ND>::Y, TileDims<ND>::Z);
-    if (rc) return rc;
-    CUDA_TRY(cudaFuncSetAttribute(tile_flight, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem));
-    int per_sm_tile = 0;
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_tile, tile_flight, TILE_THREADS, tile_smem));
-    tile_blocks = std::max(per_sm_tile, 1) * c->sm_count;
-    CUDA_TRY(cudaMemsetAsync(P.tile.tile_count, 0, (size_t)P.tile.n_tiles * sizeof(uint32_t), st));
-  }
 
-  pool_init_kernel<<<c->sm_count, 256, 0, st>>>(P, cap);
-  c->launches_acc += 1;
-  CUDA_TRY(cudaGetLastError());
-  CUDA_TRY(cudaEventRecord(c->ev0, st));
+  if (!handoff) {
+    pool_init_kernel<<<c->sm_count, 256, 0, st>>>(P, cap);
+    c->launches_acc += 1;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaEventRecord(c->ev0, st));
+  }
   int cur = 0;
-  uint32_t n_emit = cap, n_flight_prev = 0;
-  unsigned long long claimed = 0;
+  uint32_t n_emit = handoff ? 0 : cap, n_flight_prev = handoff ? handoff_flights : 0;
+  unsigned long long claimed = handoff ? (unsigned long long)n_photons : 0;
   int64_t windows_ready = 0;
   for (int64_t round = 0;; ++round) {
     uint32_t *nF = P.counts + C_NF0 + cur, *nF_next = P.counts + C_NF0 + (1 - cur);
-    while (windows_ready * (int64_t)c->sort_window < n_photons &&
+    while (!handoff && windows_ready * (int64_t)c->sort_window < n_photons &&
            (int64_t)claimed + 2 * (int64_t)cap > windows_ready * (int64_t)c->sort_window) {
       rc = prepare_window(c, first_id, n_photons, iteration, windows_ready);
       if (rc) return rc;
@@ -3190,7 +3118,12 @@ static int run_rounds(hyp_ctx *c, int64_t first_id, int64_t n_photons, int64_t i
       CUDA_TRY(cudaGetLastError());
       c->launches_acc += 1;
     }
-    CUDA_TRY(cudaMemsetAsync(P.counts + C_NI, 0, 4 * sizeof(uint32_t), st));  // C_NI, C_NE, C_CURSOR, C_CURSOR_B
+    if (handoff && round == 0) {
+      // the interactions pending at the hand-over are already in q_interact: keep its count
+      CUDA_TRY(cudaMemsetAsync(P.counts + C_NE, 0, 3 * sizeof(uint32_t), st));  // C_NE, C_CURSOR, C_CURSOR_B
+    } else {
+      CUDA_TRY(cudaMemsetAsync(P.counts + C_NI, 0, 4 * sizeof(uint32_t), st));  // C_NI, C_NE, C_CURSOR, C_CURSOR_B
+    }
     // 2. flights: the beams of new packets, then the packets that come out of an interaction
     CUDA_TRY(cudaEventRecord(c->evA, st));
     if (c->grid_type != GEO_CAR || c->M.any_sphere) {
@@ -3217,7 +3150,7 @@ static int run_rounds(hyp_ctx *c, int64_t first_id, int64_t n_photons, int64_t i
     // The beam kernel (new packets: issue-bound, its cells live in L2) and the flight kernel (packets that
     // left an interaction: bound by scattered REDs) want different resources and touch different packets:
     // they run side by side on two streams, b and f blocks per SM each (HYPERION_B200_OVERLAP="b,f").
-    const bool side_by_side = overlap_b > 0 && n_new > 0 && n_flight_prev > 0 && !tiles;
+    const bool side_by_side = overlap_b > 0 && n_new > 0 && n_flight_prev > 0;
     if (side_by_side) {
       CUDA_TRY(cudaEventRecord(c->evFork, st));
       CUDA_TRY(cudaStreamWaitEvent(c->stream2, c->evFork, 0));
@@ -3232,49 +3165,7 @@ static int run_rounds(hyp_ctx *c, int64_t first_id, int64_t n_photons, int64_t i
       CUDA_TRY(cudaGetLastError());
       c->launches_acc += 1;
     }
-    if (n_flight_prev > 0 && tiles && n_flight_prev < tile_min_flights) {
-      // too few flights to pay for staging every tile: finish them with the direct kernel
-      CUDA_TRY(cudaMemsetAsync(P.counts + C_NP0 + (1 - cur), 0, sizeof(uint32_t), st));
-      int blocks = (int)std::min<int64_t>(((int64_t)n_flight_prev + FLIGHT_THREADS - 1) / FLIGHT_THREADS, flight_blocks_max);
-      flight<<<blocks, FLIGHT_THREADS, wall_bytes, st>>>(c->M, P, P.tile.park_slot[cur], P.counts + C_NP0 + cur, walls_smem);
-      CUDA_TRY(cudaGetLastError());
-      c->launches_acc += 1;
-    } else if (n_flight_prev > 0 && tiles) {
-      // this round's pending flights (park list `cur`) bucketed by tile, then one tile visit each;
-      // packets that step out of their tile go to park list 1 - cur together with the re-emitted ones
-      CUDA_TRY(cudaMemsetAsync(P.counts + C_NP0 + (1 - cur), 0, sizeof(uint32_t), st));
-      const int sb = (int)std::min<int64_t>(((int64_t)n_flight_prev + 255) / 256, service_blocks_max);
-      cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr;
-      if (dbg) {
-        cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventCreate(&e2);
-        cudaEventRecord(e0, st);
-      }
-      tile_hist_kernel<<<sb, 256, 0, st>>>(P, cur);
-      tile_scan_kernel<<<1, 1024, 0, st>>>(P);
-      tile_scatter_kernel<<<sb, 256, 0, st>>>(P, cur);
-      if (dbg) cudaEventRecord(e1, st);
-      const int64_t max_items = (int64_t)P.tile.n_tiles + n_flight_prev / TILE_CHUNK + 1;
-      tile_flight<<<(int)std::min<int64_t>(max_items, tile_blocks), TILE_THREADS, tile_smem, st>>>(c->M, P, 1 - cur);
-      CUDA_TRY(cudaGetLastError());
-      c->launches_acc += 4;
-      if (dbg) {
-        // diagnostic (HYPERION_B200_TIMING): per-round times on stderr; serialises the round
-        cudaEventRecord(e2, st);
-        cudaStreamSynchronize(st);
-        float ma = 0.f, mb = 0.f;
-        cudaEventElapsedTime(&ma, e0, e1);
-        cudaEventElapsedTime(&mb, e1, e2);
-        uint32_t hc[C_COUNT];
-        cudaMemcpy(hc, P.counts, sizeof hc, cudaMemcpyDeviceToHost);
-        fprintf(stderr, "[round %lld] new %lld; %u flights in %u items: bucket %.3f ms, tile visits %.3f ms, parked %u\n",
-                (long long)round, (long long)n_new, n_flight_prev, hc[C_NITEMS], ma, mb, hc[C_NP0 + 1 - cur]);
-        dbg_bucket += ma;
-        dbg_tile += mb;
-        cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
-      }
-    } else if (tiles) {
-      CUDA_TRY(cudaMemsetAsync(P.counts + C_NP0 + (1 - cur), 0, sizeof(uint32_t), st));
-    } else if (n_flight_prev > 0) {
+    if (n_flight_prev > 0) {
       int blocks = (int)std::min<int64_t>(((int64_t)n_flight_prev + FLIGHT_THREADS - 1) / FLIGHT_THREADS,
                                           side_by_side ? (int64_t)overlap_f * c->sm_count : (int64_t)flight_blocks_max);
       flight<<<blocks, FLIGHT_THREADS, wall_bytes, st>>>(c->M, P, P.q_flight[cur], nF, walls_smem);
@@ -3288,7 +3179,7 @@ static int run_rounds(hyp_ctx *c, int64_t first_id, int64_t n_photons, int64_t i
     CUDA_TRY(cudaMemsetAsync(P.counts + C_NB, 0, sizeof(uint32_t), st));
     // 3. interactions -> next round's flight queue; killed packets free their slot
     interact_kernel<ND><<<service_blocks_max, SERVICE_THREADS, 0, st>>>(c->M, P, P.q_flight[1 - cur], nF_next,
-                                                                        (uint32_t)iteration, tiles ? 1 - cur : -1);
+                                                                        (uint32_t)iteration);
     CUDA_TRY(cudaGetLastError());
     c->launches_acc += 1;
     CUDA_TRY(cudaMemcpyAsync(c->h_counts, P.counts, C_COUNT * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
@@ -3298,9 +3189,9 @@ static int run_rounds(hyp_ctx *c, int64_t first_id, int64_t n_photons, int64_t i
     if (cudaEventElapsedTime(&ms, c->evA, c->evB) == cudaSuccess) c->flight_ms_acc += ms;
     c->rounds_acc += 1;
     cur = 1 - cur;
-    memcpy(&claimed, c->h_counts + C_COUNT, sizeof claimed);
+    if (!handoff) memcpy(&claimed, c->h_counts + C_COUNT, sizeof claimed);
     n_emit = c->h_counts[C_NE];
-    n_flight_prev = tiles ? c->h_counts[C_NP0 + cur] : c->h_counts[C_NF0 + cur];
+    n_flight_prev = c->h_counts[C_NF0 + cur];
     const bool ids_left = claimed < (unsigned long long)n_photons;
     if (n_flight_prev == 0 && (!ids_left || n_emit == 0)) break;
   }
@@ -3308,7 +3199,223 @@ static int run_rounds(hyp_ctx *c, int64_t first_id, int64_t n_photons, int64_t i
   CUDA_TRY(cudaStreamSynchronize(st));
   float ms = 0.f;
   if (cudaEventElapsedTime(&ms, c->ev0, c->ev1) == cudaSuccess) c->kernel_ms_acc += ms;
-  if (dbg) fprintf(stderr, "[timing] bucketing %.3f ms, tile visits %.3f ms, photon loop %.3f ms\n", dbg_bucket, dbg_tile, ms);
+  return HYP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Wave engine (flight_wave.cuh): host side
+// ---------------------------------------------------------------------------------------------------
+namespace {
+
+// HYPERION_B200_ENGINE = "rounds" keeps the direct kernels for every model; default: the wave engine wherever
+// it applies (Cartesian grid with equidistant walls, no spherical source, tiles that fit shared memory).
+bool wave_wanted() {
+  const char *e = getenv("HYPERION_B200_ENGINE");
+  return !(e && strcmp(e, "rounds") == 0);
+}
+
+// Blocks of the tile kernel per SM: one block with 2 x 112 KB (densities, sums), or two blocks with 2 x 56 KB each
+// (one dust type only; HYPERION_B200_WAVE_CTAS=2).  The offsets are template constants of wave_tile_kernel.
+constexpr uint32_t WAVE_SUM_OFF_1 = 114688, WAVE_SUM_OFF_2 = 57344;
+
+int wave_ctas(int nd) {
+  const char *e = getenv("HYPERION_B200_WAVE_CTAS");
+  return (nd == 1 && e && atoi(e) == 2) ? 2 : 1;
+}
+
+size_t wave_smem_bytes(int tx, int ty, int tz, int ctas) {
+  const int tw = std::max(tx, std::max(ty, tz)) + 1;
+  return 2 * (size_t)(ctas == 2 ? WAVE_SUM_OFF_2 : WAVE_SUM_OFF_1) + (size_t)3 * tw * sizeof(double);
+}
+
+// Tile shape: the largest near-cubic tile whose densities fit their half of the shared memory, each axis then
+// cut into equal parts (HYPERION_B200_TILE="tx,ty,tz" overrides).
+bool wave_plan(hyp_ctx *c, int nd) {
+  WaveQ &W = c->wave;
+  if (!c->uniform_walls || c->grid_type != GEO_CAR || c->M.any_sphere) return false;
+  const int ctas = wave_ctas(nd);
+  const size_t cells_max = (size_t)(ctas == 2 ? WAVE_SUM_OFF_2 : WAVE_SUM_OFF_1) / (4 * (size_t)nd);
+  auto fits = [&](int tx, int ty, int tz) {
+    return (size_t)(tx + 2) * (ty + 2) * (tz + 2) <= cells_max && std::max(tx, std::max(ty, tz)) <= 62;
+  };
+  int tx = 0, ty = 0, tz = 0;
+  if (const char *e = getenv("HYPERION_B200_TILE")) {
+    if (sscanf(e, "%d,%d,%d", &tx, &ty, &tz) != 3 || tx < 1 || ty < 1 || tz < 1) tx = ty = tz = 0;
+  }
+  if (tx == 0) {
+    for (int t0 = 62; t0 >= 2; --t0) {
+      const int cx = std::min(t0, c->n1), cy = std::min(t0, c->n2), cz = std::min(t0, c->n3);
+      // equal parts per axis
+      const int ex = (c->n1 + (c->n1 + cx - 1) / cx - 1) / ((c->n1 + cx - 1) / cx);
+      const int ey = (c->n2 + (c->n2 + cy - 1) / cy - 1) / ((c->n2 + cy - 1) / cy);
+      const int ez = (c->n3 + (c->n3 + cz - 1) / cz - 1) / ((c->n3 + cz - 1) / cz);
+      if (fits(ex, ey, ez)) {
+        tx = ex; ty = ey; tz = ez;
+        break;
+      }
+    }
+  }
+  if (tx == 0) return false;
+  tx = std::min(tx, c->n1); ty = std::min(ty, c->n2); tz = std::min(tz, c->n3);
+  if (!fits(tx, ty, tz)) return false;
+  W.tx = tx; W.ty = ty; W.tz = tz;
+  W.ntx = (c->n1 + tx - 1) / tx;
+  W.nty = (c->n2 + ty - 1) / ty;
+  W.ntz = (c->n3 + tz - 1) / tz;
+  const int64_t nt = (int64_t)W.ntx * W.nty * W.ntz;
+  if (nt + 2 > (int64_t)WAVE_MAX_BINS) return false;
+  W.n_tiles = (int)nt;
+  W.dx = (c->w1[c->n1] - c->w1[0]) / c->n1;
+  W.dy = (c->w2[c->n2] - c->w2[0]) / c->n2;
+  W.dz = (c->w3[c->n3] - c->w3[0]) / c->n3;
+  // fixed-point scale of the deposits: the largest len * kappa * E any packet can produce maps to 2^17
+  W.diag = std::sqrt(W.dx * W.dx + W.dy * W.dy + W.dz * W.dz);
+  double e_max = 1.0;
+  if (c->conf.sample_sources_evenly && c->energy_total > 0.0)
+    for (const hyp_source &sr : c->sources) e_max = std::max(e_max, sr.luminosity / c->energy_total * (double)c->sources.size());
+  for (int id = 0; id < nd; ++id) {
+    const HostDust &d = c->dust[id];
+    double kmax = 0.0;
+    for (size_t i = 0; i < d.chi.size(); ++i) kmax = std::max(kmax, d.chi[i] * (1.0 - d.albedo[i]));
+    const double bound = W.diag * kmax * e_max * 1.001;
+    if (!(bound > 0.0) || !std::isfinite(bound)) return false;
+    W.dep_scale[id] = (double)WAVE_DEP_MAX / bound;
+    W.dep_inv[id] = bound / (double)WAVE_DEP_MAX;
+  }
+  return true;
+}
+
+int ensure_wave(hyp_ctx *c) {
+  WaveQ &W = c->wave;
+  const uint32_t cap = c->pool_cap;
+  const int nb = W.n_tiles + 2;
+  if (W.capacity >= cap && c->wave_bins_alloc >= nb) {
+    W.capacity = cap;
+    return HYP_OK;
+  }
+  free_dev(W.key); free_dev(W.sorted); free_dev(W.bin_count); free_dev(W.bin_cursor); free_dev(W.items); free_dev(W.ctl);
+  CUDA_TRY(cudaMalloc(&W.key, (size_t)cap * sizeof(uint32_t)));
+  CUDA_TRY(cudaMalloc(&W.sorted, (size_t)cap * sizeof(uint32_t)));
+  CUDA_TRY(cudaMalloc(&W.bin_count, (size_t)nb * sizeof(uint32_t)));
+  CUDA_TRY(cudaMalloc(&W.bin_cursor, (size_t)nb * sizeof(uint32_t)));
+  CUDA_TRY(cudaMalloc(&W.items, ((size_t)nb + cap / 256 + 2) * sizeof(uint4)));
+  CUDA_TRY(cudaMalloc(&W.ctl, WC_COUNT * sizeof(uint32_t)));
+  W.capacity = cap;
+  c->wave_bins_alloc = nb;
+  return HYP_OK;
+}
+
+}  // namespace
+
+template <int ND>
+static int run_wave(hyp_ctx *c, int64_t first_id, int64_t n_photons, int64_t iteration) {
+  const uint32_t cap = (uint32_t)std::min<int64_t>(pool_target(), n_photons);
+  int rc = ensure_pool(c, cap);
+  if (rc) return rc;
+  rc = ensure_wave(c);
+  if (rc) return rc;
+  Pool &P = c->pool;
+  WaveQ &W = c->wave;
+  W.capacity = cap;
+  {
+    long ch = getenv("HYPERION_B200_WAVE_CHUNK") ? atol(getenv("HYPERION_B200_WAVE_CHUNK")) : 16384L;
+    ch = std::max(256L, std::min<long>(ch, (long)WAVE_CHUNK_MAX));
+    W.chunk = (uint32_t)ch;
+  }
+  // below this many packets in flight the tiles are mostly empty: the direct kernels finish the iteration
+  const uint32_t tail_min = getenv("HYPERION_B200_WAVE_TAIL") ? (uint32_t)atol(getenv("HYPERION_B200_WAVE_TAIL")) : 400000u;
+  W.refill = getenv("HYPERION_B200_WAVE_REFILL") ? std::max(1, std::min(32, atoi(getenv("HYPERION_B200_WAVE_REFILL")))) : 8;
+  W.iteration = (uint32_t)iteration;
+  const int ctas = wave_ctas(ND);
+  constexpr int WT = ND == 1 ? 1024 : (ND == 2 ? 768 : 512);
+  void (*tile)(const ModelDev, Pool, const WaveQ) = wave_tile_kernel<ND, WT, 1, WAVE_SUM_OFF_1>;
+  int tile_threads = WT;
+  if (ND == 1 && ctas == 2) {
+    tile = wave_tile_kernel<ND, 512, 2, WAVE_SUM_OFF_2>;
+    tile_threads = 512;
+  }
+  const size_t tile_smem = wave_smem_bytes(W.tx, W.ty, W.tz, ctas);
+  CUDA_TRY(cudaFuncSetAttribute(tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem));
+  const size_t sort_smem = 2 * (size_t)(W.n_tiles + 2) * sizeof(uint32_t);
+  CUDA_TRY(cudaFuncSetAttribute(wave_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sort_smem));
+  CUDA_TRY(cudaFuncSetAttribute(wave_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sort_smem));
+  const int sort_blocks = (int)((cap + WAVE_SORT_SEG - 1) / WAVE_SORT_SEG);
+  const int service_blocks = c->sm_count * 4;
+  cudaStream_t st = c->stream, s2 = c->stream2, s3 = c->stream3;
+  const bool dbg = getenv("HYPERION_B200_TIMING") != nullptr;
+
+  wave_init_kernel<<<c->sm_count * 4, 256, 0, st>>>(W, P);
+  CUDA_TRY(cudaGetLastError());
+  c->launches_acc += 1;
+  CUDA_TRY(cudaEventRecord(c->ev0, st));
+  uint32_t *h = c->h_counts;
+  bool handoff = false;
+  uint32_t handoff_flights = 0;
+  for (int64_t round = 0;; ++round) {
+    wave_hist_kernel<<<sort_blocks, WAVE_SORT_THREADS, sort_smem / 2, st>>>(W);
+    wave_scan_kernel<<<1, 1024, 0, st>>>(W, P);
+    wave_scatter_kernel<<<sort_blocks, WAVE_SORT_THREADS, sort_smem, st>>>(W);
+    CUDA_TRY(cudaGetLastError());
+    c->launches_acc += 3;
+    CUDA_TRY(cudaMemcpyAsync(h, W.ctl, WC_COUNT * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    const uint32_t n_flight = h[WC_N_FLIGHT], n_interact = h[WC_N_INTERACT], n_free = h[WC_N_FREE];
+    const unsigned long long claimed = (unsigned long long)h[WC_CLAIMED_LO] | ((unsigned long long)h[WC_CLAIMED_HI] << 32);
+    const bool ids_left = claimed < (unsigned long long)n_photons;
+    if (dbg)
+      fprintf(stderr, "[wave %lld] flights %u in %u items, interactions %u, free %u, claimed %llu\n", (long long)round,
+              n_flight, h[WC_NITEMS], n_interact, n_free, claimed);
+    if (n_flight == 0 && n_interact == 0 && !ids_left) break;
+    if (!ids_left && n_flight + n_interact < tail_min) {
+      wave_handoff_kernel<<<c->sm_count, 256, 0, st>>>(P, W);
+      CUDA_TRY(cudaGetLastError());
+      c->launches_acc += 1;
+      handoff = true;
+      handoff_flights = n_flight;
+      break;
+    }
+    c->rounds_acc += 1;
+    c->wave_rounds_acc += 1;
+    CUDA_TRY(cudaEventRecord(c->evFork, st));
+    if (n_interact > 0) {
+      CUDA_TRY(cudaStreamWaitEvent(s2, c->evFork, 0));
+      const int blocks = (int)std::min<int64_t>(((int64_t)n_interact + SERVICE_THREADS - 1) / SERVICE_THREADS, service_blocks);
+      wave_interact_kernel<ND><<<blocks, SERVICE_THREADS, 0, s2>>>(c->M, P, W, (uint32_t)iteration);
+      CUDA_TRY(cudaGetLastError());
+      CUDA_TRY(cudaEventRecord(c->evJoin, s2));
+      c->launches_acc += 1;
+    }
+    if (n_free > 0 && ids_left) {
+      CUDA_TRY(cudaStreamWaitEvent(s3, c->evFork, 0));
+      const int blocks = (int)std::min<int64_t>(((int64_t)n_free + SERVICE_THREADS - 1) / SERVICE_THREADS, service_blocks);
+      wave_emit_kernel<ND><<<blocks, SERVICE_THREADS, 0, s3>>>(c->M, P, W, (unsigned long long)first_id,
+                                                             (unsigned long long)n_photons, (uint32_t)iteration);
+      CUDA_TRY(cudaGetLastError());
+      CUDA_TRY(cudaEventRecord(c->evJoin3, s3));
+      c->launches_acc += 1;
+    }
+    if (n_flight > 0) {
+      CUDA_TRY(cudaEventRecord(c->evA, st));
+      tile<<<(int)std::min<uint32_t>(h[WC_NITEMS], (uint32_t)(c->sm_count * ctas)), tile_threads, tile_smem, st>>>(c->M, P, W);
+      CUDA_TRY(cudaGetLastError());
+      CUDA_TRY(cudaEventRecord(c->evB, st));
+      c->launches_acc += 1;
+    }
+    if (n_interact > 0) CUDA_TRY(cudaStreamWaitEvent(st, c->evJoin, 0));
+    if (n_free > 0 && ids_left) CUDA_TRY(cudaStreamWaitEvent(st, c->evJoin3, 0));
+    if (n_flight > 0) {
+      // the tile kernel's own time (events on its stream); read after the next round's sync
+      CUDA_TRY(cudaEventSynchronize(c->evB));
+      float ms = 0.f;
+      if (cudaEventElapsedTime(&ms, c->evA, c->evB) == cudaSuccess) c->flight_ms_acc += ms;
+      if (dbg) fprintf(stderr, "[wave %lld] tile kernel %.3f ms\n", (long long)round, ms);
+    }
+  }
+  if (handoff) return run_rounds<ND>(c, first_id, n_photons, iteration, true, handoff_flights);
+  CUDA_TRY(cudaEventRecord(c->ev1, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  float ms = 0.f;
+  if (cudaEventElapsedTime(&ms, c->ev0, c->ev1) == cudaSuccess) c->kernel_ms_acc += ms;
   return HYP_OK;
 }
 
@@ -3320,11 +3427,13 @@ int hyp_lucy_photons(hyp_ctx *c, int64_t first_id, int64_t n_photons, int64_t it
   if (n_photons == 0) return HYP_OK;
   CUDA_TRY(cudaSetDevice(c->device));
   c->sums_gathered = false;
+  const bool wave = wave_wanted() && wave_plan(c, c->M.n_dust);
+  c->last_engine = wave ? 1 : 0;
   switch (c->M.n_dust) {
-    case 1: return run_rounds<1>(c, first_id, n_photons, iteration);
-    case 2: return run_rounds<2>(c, first_id, n_photons, iteration);
-    case 3: return run_rounds<3>(c, first_id, n_photons, iteration);
-    case 4: return run_rounds<4>(c, first_id, n_photons, iteration);
+    case 1: return wave ? run_wave<1>(c, first_id, n_photons, iteration) : run_rounds<1>(c, first_id, n_photons, iteration);
+    case 2: return wave ? run_wave<2>(c, first_id, n_photons, iteration) : run_rounds<2>(c, first_id, n_photons, iteration);
+    case 3: return wave ? run_wave<3>(c, first_id, n_photons, iteration) : run_rounds<3>(c, first_id, n_photons, iteration);
+    case 4: return wave ? run_wave<4>(c, first_id, n_photons, iteration) : run_rounds<4>(c, first_id, n_photons, iteration);
     default: return fail(HYP_ERR_INVALID, "unsupported number of dust types");
   }
 }
@@ -3383,6 +3492,7 @@ int hyp_lucy_finish(hyp_ctx *c, hyp_iter_stats *st) {
     st->kernel_ms = c->kernel_ms_acc;
     st->flight_ms = c->flight_ms_acc;
     st->n_rounds = c->rounds_acc;
+    st->n_wave_rounds = c->wave_rounds_acc;
     st->n_launches = c->launches_acc;
     if (cudaEventElapsedTime(&total, c->ev2, c->ev3) == cudaSuccess) st->epilogue_ms = total - c->kernel_ms_acc;
   }

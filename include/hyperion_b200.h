@@ -119,7 +119,7 @@ typedef struct {
   int32_t kill_on_scatter;
   int32_t sample_sources_evenly;
   int32_t enforce_energy_range;
-  int32_t use_mrw;                 /* not yet implemented on the device: rejected */
+  int32_t use_mrw;                 /* modified random walk (grid_mrw_3d.f90), on the device */
   double mrw_gamma;
   int64_t n_mrw_max;
   double propagation_check_frequency; /* reference self-check rate; see DESIGN.md */
@@ -197,6 +197,7 @@ typedef struct {
   int64_t n_peel_crossings;   /* cell crossings of peel-off marches (grid_escape_tau / _column_density) */
   int64_t n_peeloffs;         /* peel-off contributions binned */
   int64_t n_peel_cached;      /* part of n_peel_crossings served by the point-source column cache (not marched) */
+  int64_t n_wave_rounds;      /* rounds of n_rounds run by the wave engine (tile visits in shared memory); 0: direct kernels only */
 } hyp_iter_stats;
 
 const char *hyp_last_error(void);
@@ -254,7 +255,10 @@ int hyp_set_run_conf(hyp_ctx *ctx, const hyp_run_conf *conf);
 
 /* replaces: setup_grid_physics (src/grid/grid_physics_3d.f90:111-322).
  * density: [n_dust][n_cells]; specific_energy may be NULL (then the minimum is
- * used); minimum_specific_energy: [n_dust] or NULL (zeros). */
+ * used); minimum_specific_energy: [n_dust] or NULL (zeros).  After hyp_finalize_setup
+ * hyp_set_density replaces the densities in place and `density` may also be a device
+ * pointer on the context's GPU (e.g. a buffer filled by an NCCL broadcast from the
+ * rank that read the file, src/mpi/mpi_io.f90:213-242). */
 int hyp_set_density(hyp_ctx *ctx, int32_t n_dust, const double *density);
 int hyp_set_specific_energy(hyp_ctx *ctx, const double *specific_energy,
                             const double *minimum_specific_energy);

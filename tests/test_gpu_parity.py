@@ -163,38 +163,44 @@ def test_split_launches_give_same_sums(golden_car):
     assert np.allclose(a, b, rtol=1e-9, atol=0)
 
 
-def _tile_case(kind):
+def _wave_case(kind):
     from hyperion_b200 import synthetic as syn
     from hyperion_b200.flatmodel import FlatModel, FlatSource, FlatConf
     dust = syn.realistic_dust(n_temp=40)
     if kind == "cube64":
+        # source exactly on the walls of the central cells: every first segment uses find_cell's cell id
         return syn.cartesian_point_source_model(n=64, tau_edge=3.0, dust=dust), 500000
-    # ragged grid (partial tiles on every axis), non-uniform walls, off-centre sources, 1-3 dust types
+    # ragged uniform grid (partial tiles on every axis), off-centre sources, a void, 1-3 dust types
     nd = {"ragged1": 1, "ragged2": 2, "ragged3": 3}[kind]
     rng = np.random.default_rng(7)
     n1, n2, n3 = 40, 36, 44
-    wx = np.sort(np.hstack([-pc, pc, rng.uniform(-pc, pc, n1 - 1)]))
-    wy = np.linspace(-pc, pc, n2 + 1)
-    wz = np.sort(np.hstack([-pc, pc, rng.uniform(-pc, pc, n3 - 1)]))
+    wx = np.linspace(-pc, pc, n1 + 1)
+    wy = np.linspace(-0.8 * pc, pc, n2 + 1)
+    wz = np.linspace(-pc, 1.3 * pc, n3 + 1)
     chi0 = syn.chi_at(dust, 2.99792458e10 / 0.5e-4)
     rho = (rng.random((nd, n3, n2, n1)) + 0.5) * (4.0 / (chi0 * pc * nd))
     rho[:, 10:14, 5:9, 20:30] = 0.0          # a void
     srcs = [FlatSource(type=1, luminosity=lsun, temperature=6000., position=(0.3 * pc, -0.2 * pc, 0.1 * pc)),
-            FlatSource(type=1, luminosity=2 * lsun, temperature=3000., position=(-0.5 * pc, 0.4 * pc, -0.6 * pc))]
+            # on a wall of every axis and on a tile corner of the 8-cell tiles below
+            FlatSource(type=1, luminosity=2 * lsun, temperature=3000., position=(wx[16], wy[8], wz[24]))]
     return FlatModel(wx, wy, wz, rho, [dust] * nd, srcs, FlatConf(n_initial_iter=1, n_initial_photons=0)), 300000
 
 
-@pytest.mark.parametrize("kind", ["cube64", "ragged1", "ragged2", "ragged3"])
-def test_tile_staged_flights_give_same_sums(kind, monkeypatch):
-    """HYPERION_B200_TILES=1 marches the packets that leave an interaction tile by tile with density
-    and sums in shared memory (flight_tile_kernel).  A packet parked at a tile boundary resumes with
-    the same origin, walls and optical depth, so every crossing and deposit is the one the untiled
-    kernel makes: work counters are identical and the sums agree to addition order."""
-    model, N = _tile_case(kind)
+@pytest.mark.parametrize("kind,tile,tail", [("cube64", "", "0"), ("cube64", "16,16,16", ""), ("ragged1", "8,8,8", "0"),
+                                            ("ragged1", "", "20000"), ("ragged2", "8,8,8", "0"), ("ragged3", "7,9,8", "0")])
+def test_wave_engine_gives_same_sums_as_direct_kernels(kind, tile, tail, monkeypatch):
+    """The wave engine (flight_wave.cuh: tile visits with densities and 32-bit fixed-point sums in shared
+    memory) follows the same packets as the direct kernels (flight_kernel + flight_beam_kernel): same ids,
+    same random numbers, the same crossings up to ties at the last ulp.  Work counters agree to 1e-4, the
+    sums to the fixed-point resolution (one part in 2^17 of the largest deposit per crossing, unbiased)."""
+    model, N = _wave_case(kind)
     res = []
-    monkeypatch.setenv("HYPERION_B200_TILE_MIN", "0")     # no hand-over of small rounds to the direct kernel
-    for tiles in ("0", "1"):
-        monkeypatch.setenv("HYPERION_B200_TILES", tiles)
+    if tile:
+        monkeypatch.setenv("HYPERION_B200_TILE", tile)
+    if tail:
+        monkeypatch.setenv("HYPERION_B200_WAVE_TAIL", tail)
+    for engine in ("rounds", "wave"):
+        monkeypatch.setenv("HYPERION_B200_ENGINE", engine)
         eng = _engine(model)
         eng.lucy_begin()
         eng.lucy_photons(0, N, 1)
@@ -203,11 +209,17 @@ def test_tile_staged_flights_give_same_sums(kind, monkeypatch):
         eng.close()
         res.append((sums, st))
     (a, sa), (b, sb) = res
-    assert sb["n_rounds"] > sa["n_rounds"]      # the tile rounds really ran
-    for key in ("n_photons", "n_escaped", "n_crossings", "n_absorptions", "n_scatterings", "killed_int"):
+    assert sa["n_wave_rounds"] == 0 and sb["n_wave_rounds"] > 2      # the tile rounds really ran
+    for key in ("n_photons", "killed_int"):
         assert sa[key] == sb[key], (key, sa[key], sb[key])
+    for key in ("n_escaped", "n_crossings", "n_absorptions", "n_scatterings"):
+        assert abs(sa[key] - sb[key]) <= 1e-4 * sa[key] + 2, (key, sa[key], sb[key])
     assert sa["n_absorptions"] + sa["n_scatterings"] > N // 2
-    assert np.allclose(a, b, rtol=1e-9, atol=0)
+    assert abs(b.sum() / a.sum() - 1) < 1e-5
+    big = a > 1e-3 * a.max()
+    assert big.sum() > a.size // 20
+    assert np.allclose(a[big], b[big], rtol=2e-3, atol=0)
+    assert np.allclose(a, b, rtol=0, atol=1e-5 * a.max())
 
 
 def test_empty_and_vacuum_cases(golden_car):

@@ -25,8 +25,8 @@ eng.load_model(model)
 for it in range(a.iters):
     st = eng.run_lucy_iteration(int(a.photons), iteration=it + 1)
     alg = 24 * st.n_crossings + 12 * st.n_absorptions
-    print("iter %d: %.3f ms photon loop (%.3f ms flight kernel, %d rounds), %.3e packets/s, %.1f crossings/packet, "
-          "alg GB/s %.1f (flight kernel alone %.1f)" % (
-              it + 1, st.kernel_ms, st.flight_ms, st.n_rounds, a.photons / (st.kernel_ms * 1e-3),
+    print("iter %d: %.3f ms photon loop (%.3f ms flight kernels, %d rounds, %d on the wave engine), %.3e packets/s, "
+          "%.1f crossings/packet, alg GB/s %.1f (flight kernels alone %.1f)" % (
+              it + 1, st.kernel_ms, st.flight_ms, st.n_rounds, st.n_wave_rounds, a.photons / (st.kernel_ms * 1e-3),
               st.n_crossings / a.photons, alg / (st.kernel_ms * 1e-3) / 1e9, alg / (st.flight_ms * 1e-3) / 1e9))
 eng.close()
