@@ -59,6 +59,8 @@ struct WaveQ {
   int ntx, nty, ntz, n_tiles;
   uint32_t chunk;        // packets per work item
   int refill;            // finished lanes of a warp that trigger a hand-over
+  int queue;             // 1: lanes keep two packets queued behind the one they march (ids and records requested early)
+  uint32_t emit_max;     // packets emitted per round at most (emission then overlaps the tile visits of later rounds)
   uint32_t iteration;
   double dx, dy, dz;     // cell widths
   double diag;           // longest path through a cell
@@ -85,10 +87,17 @@ __global__ void wave_init_kernel(WaveQ W, Pool P) {
 __global__ void __launch_bounds__(WAVE_SORT_THREADS) wave_hist_kernel(WaveQ W) {
   extern __shared__ uint32_t s_cnt[];
   const uint32_t nb = (uint32_t)W.n_tiles + 2u;
+  const unsigned lane = threadIdx.x & 31;
   for (uint32_t k = threadIdx.x; k < nb; k += blockDim.x) s_cnt[k] = 0;
   __syncthreads();
   const uint32_t lo = blockIdx.x * (uint32_t)WAVE_SORT_SEG, hi = min(lo + (uint32_t)WAVE_SORT_SEG, W.capacity);
-  for (uint32_t i = lo + threadIdx.x; i < hi; i += blockDim.x) atomicAdd(&s_cnt[min(W.key[i], nb - 1u)], 1u);
+  // the keys of neighbouring slots are often equal (free slots, packets of one source): one atomic per group
+  for (uint32_t base = lo + (threadIdx.x & ~31u); base < hi; base += blockDim.x) {
+    const uint32_t i = base + lane;
+    const uint32_t k = i < hi ? min(W.key[i], nb - 1u) : 0xffffff00u + lane;
+    const unsigned m = __match_any_sync(0xffffffffu, k);
+    if (i < hi && (int)lane == __ffs(m) - 1) atomicAdd(&s_cnt[k], (uint32_t)__popc(m));
+  }
   __syncthreads();
   for (uint32_t k = threadIdx.x; k < nb; k += blockDim.x) {
     const uint32_t v = s_cnt[k];
@@ -157,11 +166,17 @@ __global__ void __launch_bounds__(1024) wave_scan_kernel(WaveQ W, Pool P) {
 __global__ void __launch_bounds__(WAVE_SORT_THREADS) wave_scatter_kernel(WaveQ W) {
   extern __shared__ uint32_t s_cnt[];   // [nb] counts, then [nb] bases
   const uint32_t nb = (uint32_t)W.n_tiles + 2u;
+  const unsigned lane = threadIdx.x & 31;
   uint32_t *s_base = s_cnt + nb;
   for (uint32_t k = threadIdx.x; k < nb; k += blockDim.x) s_cnt[k] = 0;
   __syncthreads();
   const uint32_t lo = blockIdx.x * (uint32_t)WAVE_SORT_SEG, hi = min(lo + (uint32_t)WAVE_SORT_SEG, W.capacity);
-  for (uint32_t i = lo + threadIdx.x; i < hi; i += blockDim.x) atomicAdd(&s_cnt[min(W.key[i], nb - 1u)], 1u);
+  for (uint32_t base = lo + (threadIdx.x & ~31u); base < hi; base += blockDim.x) {
+    const uint32_t i = base + lane;
+    const uint32_t k = i < hi ? min(W.key[i], nb - 1u) : 0xffffff00u + lane;
+    const unsigned m = __match_any_sync(0xffffffffu, k);
+    if (i < hi && (int)lane == __ffs(m) - 1) atomicAdd(&s_cnt[k], (uint32_t)__popc(m));
+  }
   __syncthreads();
   for (uint32_t k = threadIdx.x; k < nb; k += blockDim.x) {
     const uint32_t v = s_cnt[k];
@@ -169,9 +184,15 @@ __global__ void __launch_bounds__(WAVE_SORT_THREADS) wave_scatter_kernel(WaveQ W
     s_cnt[k] = 0;
   }
   __syncthreads();
-  for (uint32_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
-    const uint32_t k = min(W.key[i], nb - 1u);
-    W.sorted[s_base[k] + atomicAdd(&s_cnt[k], 1u)] = i;
+  for (uint32_t base = lo + (threadIdx.x & ~31u); base < hi; base += blockDim.x) {
+    const uint32_t i = base + lane;
+    const uint32_t k = i < hi ? min(W.key[i], nb - 1u) : 0xffffff00u + lane;
+    const unsigned m = __match_any_sync(0xffffffffu, k);
+    const int leader = __ffs(m) - 1;
+    uint32_t r = 0;
+    if (i < hi && (int)lane == leader) r = atomicAdd(&s_cnt[k], (uint32_t)__popc(m));
+    r = __shfl_sync(0xffffffffu, r, leader);
+    if (i < hi) W.sorted[s_base[k] + r + __popc(m & ((1u << lane) - 1u))] = i;
   }
 }
 
@@ -184,25 +205,27 @@ struct WaveLane {
   double dtx, dty, dtz;     // path length between two walls of an axis (1e300 for a ray parallel to them)
   double t, tau;
   double chi[ND];
-  double kEs[ND];           // kappa * E in fixed-point units per length
-  float resid[ND];          // error diffusion: what rounding has left over so far
+  float kEs[ND];            // kappa * E in fixed-point units per length
+  float resid[ND];          // error diffusion: what rounding has left over so far, in [0, 1)
   uint32_t c, cd;           // cd: cell whose density and sum the next crossing uses (differs from c only for the
                             // first segment of a packet placed on a wall, grid_geometry_cartesian_3d.f90:184-232)
-  int scx, scy, scz;        // change of c for a step along +-x / +-y / +-z
+  uint32_t neg;             // bit a set: the packet moves towards -axis a
 };
 
 constexpr double WAVE_FAR = 1e300;   // "never": wall distance of a ray parallel to the walls of an axis
 
 // One cell crossing (grid_propagate_3d.f90:106-232).  fin: 0 in flight, 1 left the grid, 2 interaction,
-// 4 stepped into the next tile.
+// 4 stepped into the next tile.  sx, sy, sz: bytes between neighbouring cells along x, y, z (block-uniform).
 template <int ND, uint32_t SUM_OFF>
-__device__ __forceinline__ void wave_cross(WaveLane<ND> &L, int &fin, uint32_t &n_cross) {
-  float rho[ND];
+__device__ __forceinline__ void wave_cross(WaveLane<ND> &L, int &fin, uint32_t &n_cross, const int sx, const int sy,
+                                           const int sz) {
+  uint32_t rho[ND];   // fp32 bit patterns
   const uint32_t a_rho = L.cd;
 #pragma unroll
-  for (int id = 0; id < ND; ++id) asm volatile("ld.shared.f32 %0, [%1+%2];" : "=f"(rho[id]) : "r"(a_rho), "n"(4 * id));
-  if (rho[0] < 0.f) {
-    fin = rho[0] < -1.5f ? 1 : 4;
+  for (int id = 0; id < ND; ++id) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(rho[id]) : "r"(a_rho + 4u * id));
+  if ((int)rho[0] < 0) {
+    // halo: -1.f next tile, -2.f outside the grid
+    fin = rho[0] == 0xc0000000u ? 1 : 4;
     return;
   }
   const bool bx = (L.tnx <= L.tny) & (L.tnx <= L.tnz);
@@ -211,7 +234,12 @@ __device__ __forceinline__ void wave_cross(WaveLane<ND> &L, int &fin, uint32_t &
   const double ds = t_exit - L.t;
   double chi_rho = 0.0;
 #pragma unroll
-  for (int id = 0; id < ND; ++id) chi_rho += L.chi[id] * (double)rho[id];
+  for (int id = 0; id < ND; ++id) {
+    // float -> double of a non-negative normal number by re-biasing the exponent (0 becomes 2^-127: harmless);
+    // integer instructions instead of one more trip through the narrow conversion pipe
+    const double rd = __hiloint2double((int)((rho[id] >> 3) + 0x38000000u), (int)(rho[id] << 29));
+    chi_rho = fma(L.chi[id], rd, chi_rho);
+  }
   const double tau_cell = chi_rho * ds;
   ++n_cross;
   double len;
@@ -226,23 +254,26 @@ __device__ __forceinline__ void wave_cross(WaveLane<ND> &L, int &fin, uint32_t &
     L.tnx = fma(mx, L.dtx, L.tnx);
     L.tny = fma(my, L.dty, L.tny);
     L.tnz = fma(mz, L.dtz, L.tnz);
-    L.c += (uint32_t)(bx ? L.scx : (by ? L.scy : L.scz));
+    const int mag = bx ? sx : (by ? sy : sz);
+    const uint32_t bit = bx ? 1u : (by ? 2u : 4u);
+    L.c = (L.neg & bit) ? L.c - (uint32_t)mag : L.c + (uint32_t)mag;
+    L.cd = L.c;
   } else {
-    // interaction inside this cell (grid_propagate_3d.f90:186-228)
+    // interaction inside this cell (grid_propagate_3d.f90:186-228); cd keeps the cell the packet interacted in
     len = tau_cell > 0.0 ? ds * (L.tau / tau_cell) : 0.0;
     L.t += len;
     fin = 2;
   }
+  const float lenf = (float)len;
 #pragma unroll
   for (int id = 0; id < ND; ++id) {
-    if (rho[id] > 0.f) {
-      const float x = (float)(len * L.kEs[id]) + L.resid[id];
+    if (rho[id] != 0u) {
+      const float x = fmaf(lenf, L.kEs[id], L.resid[id]);
       const uint32_t q = __float2uint_rd(x);
       L.resid[id] = x - (float)q;
-      if (q) asm volatile("red.shared.add.u32 [%0+%1], %2;" ::"r"(a_rho), "n"(SUM_OFF + 4 * id), "r"(q) : "memory");
+      if (q) asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(a_rho + (SUM_OFF + 4u * id)), "r"(q) : "memory");
     }
   }
-  L.cd = L.c;
 }
 
 // uniform in [0, 1): 24 bits of a 32-bit mix (the start value of a visit's rounding remainder)
@@ -250,6 +281,16 @@ __device__ __forceinline__ float wave_unit_hash(uint32_t a, uint32_t b, uint32_t
   uint32_t h = a * 0x9E3779B1u ^ b * 0x85EBCA77u ^ c * 0xC2B2AE3Du;
   h ^= h >> 16; h *= 0x85EBCA6Bu; h ^= h >> 13; h *= 0xC2B2AE35u; h ^= h >> 16;
   return (float)(h >> 8) * (1.0f / 16777216.0f);
+}
+
+// 1 / x to the last ulp or two for normal x != 0 (MUFU.RCP64H + two Newton steps); only used for wall distances
+__device__ __forceinline__ double wave_rcp(double x) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  double e = fma(-x, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-x, r, 1.0);
+  return fma(r, e, r);
 }
 
 // Shared memory of a block: [densities SUM_OFF bytes][sums SUM_OFF bytes][walls of the tile 3 x TW doubles].
@@ -265,17 +306,18 @@ wave_tile_kernel(const ModelDev M, Pool P, const WaveQ W) {
   const int TW = max(TX, max(TY, TZ)) + 1;
   double *__restrict__ s_w = (double *)(w_smem + 2 * SUM_OFF);       // [3][TW] walls of the tile
   __shared__ uint32_t s_item, s_next;
+  __shared__ unsigned long long s_cross, s_esc;   // work counters of the block
   const int n1 = M.n1, n2 = M.n2, n3 = M.n3;
   const uint32_t n_items = W.ctl[WC_NITEMS];
   Slot<ND> *slots = (Slot<ND> *)P.slots;
   const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   constexpr int NWARPS = THREADS / 32;
+  if (threadIdx.x == 0) s_cross = s_esc = 0ull;
   const uint32_t k_interact = (uint32_t)W.n_tiles, k_free = (uint32_t)W.n_tiles + 1u;
   const float inv_row = 1.0f / (float)TXh, inv_slab = 1.0f / (float)(TXh * TYh);
   const uint32_t rho_base = (uint32_t)__cvta_generic_to_shared(s_rho);
   constexpr int CB = 4 * ND;   // bytes of one cell in the density array
-  uint32_t n_cross = 0, n_esc = 0;
-  unsigned long long cross_hi = 0;
+  const int sx = CB, sy = CB * TXh, sz = CB * TXh * TYh;
 
   for (;;) {
     __syncthreads();
@@ -304,7 +346,7 @@ wave_tile_kernel(const ModelDev M, Pool P, const WaveQ W) {
 #pragma unroll
         for (int id = 0; id < ND; ++id) {
           float v = in_grid ? -1.f : -2.f;
-          if (in_grid && in_tile) v = (float)__ldg(M.rho + g + id);
+          if (in_grid && in_tile) v = fmaxf((float)__ldg(M.rho + g + id), 0.f);
           s_rho[c * ND + id] = v;
           s_sum[c * ND + id] = 0u;
         }
@@ -320,16 +362,25 @@ wave_tile_kernel(const ModelDev M, Pool P, const WaveQ W) {
     __syncthreads();
 
     // ---------------- march the packets of the work item ----------------
+    // Every lane keeps two packets queued behind the one it marches: `n2slot` (its slot id is being loaded
+    // from the sorted list) and `nslot` (id known, record requested into L2 with a prefetch).  Ids and records
+    // are requested one hand-over ahead of their use, so a hand-over does not wait for HBM twice.
+    constexpr uint32_t NONE = 0xffffffffu;
     bool exhausted = false;  // warp-uniform: the item has no unclaimed packet left
     int fin = 3;             // 3: no packet in this lane
-    uint32_t slot = 0;
+    uint32_t slot = 0, nslot = NONE, n2slot = NONE;
+    uint32_t n_cross = 0;
     WaveLane<ND> L;
     L.c = L.cd = rho_base;
     for (;;) {
       const unsigned m_act = __ballot_sync(0xffffffffu, fin == 0);
-      const unsigned m_done = __ballot_sync(0xffffffffu, fin == 1 || fin == 2 || fin == 4);
-      if (m_act == 0 || __popc(m_done) >= W.refill) {
+      const unsigned m_wait = __ballot_sync(0xffffffffu, fin == 1 || fin == 2 || fin == 4 || (fin == 3 && nslot != NONE));
+      if (m_act == 0 || __popc(m_wait) >= W.refill) {
         // -------- hand over the finished packets --------
+        {
+          const unsigned m_esc = __ballot_sync(0xffffffffu, fin == 1);
+          if (m_esc && lane == 0) atomicAdd(&s_esc, (unsigned long long)__popc(m_esc));
+        }
         if (fin == 1 || fin == 2 || fin == 4) {
           // cell of the packet from its index in the haloed tile
           const int ci = (int)(L.c - rho_base) / CB;
@@ -352,7 +403,6 @@ wave_tile_kernel(const ModelDev M, Pool P, const WaveQ W) {
             nk = k_interact;
           } else if (fin == 1) {
             nk = k_free;
-            ++n_esc;
           } else {
             const int d = (hx == 0 ? -1 : (hx == TXh - 1 ? 1 : 0)) + W.ntx * (hy == 0 ? -1 : (hy == TYh - 1 ? 1 : 0)) +
                           W.ntx * W.nty * (hz == 0 ? -1 : (hz == TZh - 1 ? 1 : 0));
@@ -364,89 +414,78 @@ wave_tile_kernel(const ModelDev M, Pool P, const WaveQ W) {
           W.key[slot] = nk;
           fin = 3;
         }
-        // -------- start the next packets --------
-        if (!exhausted) {
-          const unsigned m_need = __ballot_sync(0xffffffffu, fin == 3);
-          const int leader = __ffs(m_need) - 1;
-          uint32_t base = 0;
-          if ((int)lane == leader) base = atomicAdd(&s_next, (uint32_t)__popc(m_need));
-          base = __shfl_sync(0xffffffffu, base, leader);
-          bool failed = false;
+        // While the item has plenty of packets left every lane keeps its queue full; towards the end a lane only
+        // claims a packet when it has none, and walks it through the queue at once (three passes), so that the
+        // last packets are spread over all lanes.
+        const bool plenty = W.queue && *(volatile uint32_t *)&s_next + 2u * THREADS <= it.z;
+#pragma unroll 1
+        for (int pass = 0; pass < 3; ++pass) {
+          // -------- start the queued packets --------
           int first_far = -1;   // >= 0: find_cell's cell of a packet placed on a wall, when it lies in ANOTHER tile
-          if (fin == 3) {
-            const uint32_t idx = base + __popc(m_need & ((1u << lane) - 1u));
-            if (idx >= it.z) {
-              failed = true;
+          if (fin == 3 && nslot != NONE) {
+            slot = nslot;
+            nslot = NONE;
+            const Slot<ND> *s = slots + slot;
+            const double2 a0 = __ldcg((const double2 *)&s->r0x);  // r0x r0y
+            const double2 a1 = __ldcg((const double2 *)&s->r0z);  // r0z vx
+            const double2 a2 = __ldcg((const double2 *)&s->vy);   // vy vz
+            const double2 a3 = __ldcg((const double2 *)&s->tau_left);  // tau t
+            const int4 cc = __ldcg((const int4 *)&s->ix);
+            bool bad = false;
+  #pragma unroll
+            for (int k = 0; k < ND; ++k) {
+              L.chi[k] = __ldcg(&s->chi[k]);
+              L.kEs[k] = __ldcg(&s->kE[k]) * W.dep_scale[k];
+              // fixed-point bound of the deposits (see wave_plan): kappa * E above the table maximum cannot happen
+              bad |= !(L.kEs[k] * W.diag <= (double)WAVE_DEP_MAX);
+              L.resid[k] = wave_unit_hash(slot, (uint32_t)__double2loint(a3.y) ^ (uint32_t)__double2hiint(a3.y),
+                                          W.iteration * 4u + (uint32_t)k);
+            }
+            L.tau = a3.x;
+            L.t = a3.y;
+            const int lx = cc.x - x0, ly = cc.y - y0, lz = cc.z - z0;
+            if (bad || (unsigned)lx >= (unsigned)TX || (unsigned)ly >= (unsigned)TY || (unsigned)lz >= (unsigned)TZ) {
+              // cannot happen for a packet bucketed by its own cell; never index shared memory with it
+              atomicCAS(M.error_flag, ERR_NONE, bad ? ERR_DEPOSIT : ERR_NOT_IN_CELL);
+              W.key[slot] = k_free;
             } else {
-              slot = __ldcs(W.sorted + it.y + idx);
-              const Slot<ND> *s = slots + slot;
-              const double2 a0 = __ldcs((const double2 *)&s->r0x);  // r0x r0y
-              const double2 a1 = __ldcs((const double2 *)&s->r0z);  // r0z vx
-              const double2 a2 = __ldcs((const double2 *)&s->vy);   // vy vz
-              const double2 a3 = __ldcs((const double2 *)&s->tau_left);  // tau t
-              const int4 cc = __ldcs((const int4 *)&s->ix);
-              bool bad = false;
-#pragma unroll
-              for (int k = 0; k < ND; ++k) {
-                L.chi[k] = __ldcs(&s->chi[k]);
-                L.kEs[k] = __ldcs(&s->kE[k]) * W.dep_scale[k];
-                // fixed-point bound of the deposits (see wave_plan): kappa * E above the table maximum cannot happen
-                bad |= !(L.kEs[k] * W.diag <= (double)WAVE_DEP_MAX);
-                L.resid[k] = wave_unit_hash(slot, (uint32_t)__double2loint(a3.y) ^ (uint32_t)__double2hiint(a3.y),
-                                            W.iteration * 4u + (uint32_t)k);
-              }
-              L.tau = a3.x;
-              L.t = a3.y;
-              const int lx = cc.x - x0, ly = cc.y - y0, lz = cc.z - z0;
-              if (bad || (unsigned)lx >= (unsigned)TX || (unsigned)ly >= (unsigned)TY || (unsigned)lz >= (unsigned)TZ) {
-                // cannot happen for a packet bucketed by its own cell; never index shared memory with it
-                atomicCAS(M.error_flag, ERR_NONE, bad ? ERR_DEPOSIT : ERR_NOT_IN_CELL);
-                W.key[slot] = k_free;
-              } else {
-                const double vx = a1.y, vy = a2.x, vz = a2.y;
-                const double ivx = 1.0 / vx, ivy = 1.0 / vy, ivz = 1.0 / vz;
-                // distance to the wall ahead on each axis; a ray parallel to an axis never reaches its walls.
-                // Rounding can leave a resumed packet a few ulp past a wall it faces: clamp to its path length.
-                L.tnx = vx != 0.0 ? fmax((s_w[lx + (vx > 0.0 ? 1 : 0)] - a0.x) * ivx, L.t) : WAVE_FAR;
-                L.tny = vy != 0.0 ? fmax((s_w[TW + ly + (vy > 0.0 ? 1 : 0)] - a0.y) * ivy, L.t) : WAVE_FAR;
-                L.tnz = vz != 0.0 ? fmax((s_w[2 * TW + lz + (vz > 0.0 ? 1 : 0)] - a1.x) * ivz, L.t) : WAVE_FAR;
-                L.dtx = vx != 0.0 ? fmin(W.dx * fabs(ivx), WAVE_FAR) : WAVE_FAR;
-                L.dty = vy != 0.0 ? fmin(W.dy * fabs(ivy), WAVE_FAR) : WAVE_FAR;
-                L.dtz = vz != 0.0 ? fmin(W.dz * fabs(ivz), WAVE_FAR) : WAVE_FAR;
-                L.tnx = fmin(L.tnx, WAVE_FAR);
-                L.tny = fmin(L.tny, WAVE_FAR);
-                L.tnz = fmin(L.tnz, WAVE_FAR);
-                L.scx = vx > 0.0 ? CB : -CB;
-                L.scy = vy > 0.0 ? CB * TXh : -CB * TXh;
-                L.scz = vz > 0.0 ? CB * TXh * TYh : -CB * TXh * TYh;
-                L.c = rho_base + (uint32_t)((((lz + 1) * TYh + (ly + 1)) * TXh + lx + 1) * CB);
-                L.cd = L.c;
-                fin = 0;
-                if (cc.w != (cc.z * n2 + cc.y) * n1 + cc.x) {
-                  // first segment of a packet placed on a wall: density and deposit of find_cell's cell
-                  const int fz = cc.w / (n1 * n2), frem = cc.w - fz * n1 * n2;
-                  const int fy = frem / n1, fx = frem - fy * n1;
-                  const int qx = fx - x0, qy = fy - y0, qz = fz - z0;
-                  if ((unsigned)qx < (unsigned)TX && (unsigned)qy < (unsigned)TY && (unsigned)qz < (unsigned)TZ)
-                    L.cd = rho_base + (uint32_t)((((qz + 1) * TYh + (qy + 1)) * TXh + qx + 1) * CB);
-                  else
-                    first_far = cc.w;
-                }
+              const double vx = a1.y, vy = a2.x, vz = a2.y;
+              const double ivx = wave_rcp(vx), ivy = wave_rcp(vy), ivz = wave_rcp(vz);
+              // distance to the wall ahead on each axis; a ray parallel to an axis never reaches its walls.
+              // Rounding can leave a resumed packet a few ulp past a wall it faces: clamp to its path length.
+              L.tnx = vx != 0.0 ? fmin(fmax((s_w[lx + (vx > 0.0 ? 1 : 0)] - a0.x) * ivx, L.t), WAVE_FAR) : WAVE_FAR;
+              L.tny = vy != 0.0 ? fmin(fmax((s_w[TW + ly + (vy > 0.0 ? 1 : 0)] - a0.y) * ivy, L.t), WAVE_FAR) : WAVE_FAR;
+              L.tnz = vz != 0.0 ? fmin(fmax((s_w[2 * TW + lz + (vz > 0.0 ? 1 : 0)] - a1.x) * ivz, L.t), WAVE_FAR) : WAVE_FAR;
+              L.dtx = vx != 0.0 ? fmin(W.dx * fabs(ivx), WAVE_FAR) : WAVE_FAR;
+              L.dty = vy != 0.0 ? fmin(W.dy * fabs(ivy), WAVE_FAR) : WAVE_FAR;
+              L.dtz = vz != 0.0 ? fmin(W.dz * fabs(ivz), WAVE_FAR) : WAVE_FAR;
+              L.neg = (vx > 0.0 ? 0u : 1u) | (vy > 0.0 ? 0u : 2u) | (vz > 0.0 ? 0u : 4u);
+              L.c = rho_base + (uint32_t)((((lz + 1) * TYh + (ly + 1)) * TXh + lx + 1) * CB);
+              L.cd = L.c;
+              fin = 0;
+              if (cc.w != (cc.z * n2 + cc.y) * n1 + cc.x) {
+                // first segment of a packet placed on a wall: density and deposit of find_cell's cell
+                const int fz = cc.w / (n1 * n2), frem = cc.w - fz * n1 * n2;
+                const int fy = frem / n1, fx = frem - fy * n1;
+                const int qx = fx - x0, qy = fy - y0, qz = fz - z0;
+                if ((unsigned)qx < (unsigned)TX && (unsigned)qy < (unsigned)TY && (unsigned)qz < (unsigned)TZ)
+                  L.cd = rho_base + (uint32_t)((((qz + 1) * TYh + (qy + 1)) * TXh + qx + 1) * CB);
+                else
+                  first_far = cc.w;
               }
             }
           }
-          exhausted = __any_sync(0xffffffffu, failed);
           if (__any_sync(0xffffffffu, first_far >= 0)) {
             // find_cell's cell belongs to another tile: that one crossing goes through global memory.  All
             // packets of a point source on a tile boundary take this path, so the deposits of the lanes that
             // share a cell are summed before ONE RED per cell leaves the warp.
             const bool far = first_far >= 0;
             double dep[ND];
-#pragma unroll
+  #pragma unroll
             for (int id = 0; id < ND; ++id) dep[id] = 0.0;
             if (far) {
               double rho[ND], chi_rho = 0.0;
-#pragma unroll
+  #pragma unroll
               for (int id = 0; id < ND; ++id) {
                 rho[id] = __ldg(M.rho + (size_t)first_far * ND + id);
                 chi_rho += L.chi[id] * rho[id];
@@ -465,7 +504,8 @@ wave_tile_kernel(const ModelDev M, Pool P, const WaveQ W) {
                 if (bx) L.tnx += L.dtx;
                 if (by) L.tny += L.dty;
                 if (!(bx | by)) L.tnz += L.dtz;
-                L.c += (uint32_t)(bx ? L.scx : (by ? L.scy : L.scz));
+                const int mag = bx ? sx : (by ? sy : sz);
+                L.c = (L.neg & (bx ? 1u : (by ? 2u : 4u))) ? L.c - (uint32_t)mag : L.c + (uint32_t)mag;
                 L.cd = L.c;
               } else {
                 len = tau_cell > 0.0 ? ds * (L.tau / tau_cell) : 0.0;
@@ -476,39 +516,68 @@ wave_tile_kernel(const ModelDev M, Pool P, const WaveQ W) {
                 W.key[slot] = k_interact;
                 fin = 3;
               }
-#pragma unroll
-              for (int id = 0; id < ND; ++id) dep[id] = rho[id] > 0.0 ? len * L.kEs[id] * W.dep_inv[id] : 0.0;
+  #pragma unroll
+              for (int id = 0; id < ND; ++id) dep[id] = rho[id] > 0.0 ? len * ((double)L.kEs[id] * W.dep_inv[id]) : 0.0;
             }
             unsigned todo = __ballot_sync(0xffffffffu, far);
             while (todo) {
               const int head = __ffs(todo) - 1;
               const int cell = __shfl_sync(0xffffffffu, first_far, head);
               const bool mine = far && first_far == cell;
-#pragma unroll
+  #pragma unroll
               for (int id = 0; id < ND; ++id) {
                 double v = mine ? dep[id] : 0.0;
-#pragma unroll
+  #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
                 if ((int)lane == head && v != 0.0) atomicAdd(&M.cells[(size_t)cell * ND + id].esum, v);
               }
               todo &= ~__ballot_sync(0xffffffffu, mine);
             }
           }
+          // -------- move the queue up: request the record of the packet whose id has arrived --------
+          if (nslot == NONE && n2slot != NONE) {
+            nslot = n2slot;
+            n2slot = NONE;
+            const char *rec = (const char *)(slots + nslot);
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(rec));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(rec + 95));
+          }
+          // -------- claim the packets after those --------
+          if (!exhausted) {
+            const bool need = plenty ? n2slot == NONE : (fin == 3 && nslot == NONE && n2slot == NONE);
+            const unsigned m_need = __ballot_sync(0xffffffffu, need);
+            bool failed = false;
+            if (m_need) {
+              const int leader = __ffs(m_need) - 1;
+              uint32_t base = 0;
+              if ((int)lane == leader) base = atomicAdd(&s_next, (uint32_t)__popc(m_need));
+              base = __shfl_sync(0xffffffffu, base, leader);
+              if (need) {
+                const uint32_t idx = base + __popc(m_need & ((1u << lane) - 1u));
+                if (idx >= it.z) failed = true;
+                else n2slot = __ldcs(W.sorted + it.y + idx);
+              }
+            }
+            exhausted = __any_sync(0xffffffffu, failed);
+          }
+          if (__ballot_sync(0xffffffffu, fin == 3 && (nslot != NONE || n2slot != NONE)) == 0) break;
         }
         if (__ballot_sync(0xffffffffu, fin == 0) == 0) {
-          if (exhausted) break;
+          if (exhausted && __ballot_sync(0xffffffffu, nslot != NONE || n2slot != NONE) == 0) break;
           continue;
         }
       }
       // -------- cell crossings --------
 #pragma unroll
       for (int u = 0; u < WAVE_UNROLL; ++u) {
-        if (fin == 0) wave_cross<ND, SUM_OFF>(L, fin, n_cross);
+        if (fin == 0) wave_cross<ND, SUM_OFF>(L, fin, n_cross, sx, sy, sz);
       }
     }
-    if (n_cross > 0x7fffff00u) {
-      cross_hi += n_cross;
-      n_cross = 0;
+    {
+      // crossings of the item (a lane makes far fewer than 2^32 per item)
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) n_cross += __shfl_xor_sync(0xffffffffu, n_cross, o);
+      if (lane == 0 && n_cross) atomicAdd(&s_cross, (unsigned long long)n_cross);
     }
     __syncthreads();
 
@@ -530,8 +599,11 @@ wave_tile_kernel(const ModelDev M, Pool P, const WaveQ W) {
       }
     }
   }
-  warp_add_scalar(M.scalars + SC_CROSS, (double)(cross_hi + n_cross));
-  warp_add_scalar(M.scalars + SC_ESC, (double)n_esc);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (s_cross) atomicAdd(M.scalars + SC_CROSS, (double)s_cross);
+    if (s_esc) atomicAdd(M.scalars + SC_ESC, (double)s_esc);
+  }
 }
 
 // ---- interactions and emission of a round --------------------------------------------------------
@@ -569,7 +641,7 @@ template <int ND>
 __global__ void __launch_bounds__(SERVICE_THREADS, INTERACT_MIN_BLOCKS)
 wave_emit_kernel(const ModelDev M, Pool P, const WaveQ W, const unsigned long long first_id,
                  const unsigned long long n_photons, const uint32_t iteration) {
-  const uint32_t n = W.ctl[WC_N_FREE], start = W.ctl[WC_FREE_START];
+  const uint32_t n = min(W.ctl[WC_N_FREE], W.emit_max), start = W.ctl[WC_FREE_START];
   const unsigned lane = threadIdx.x & 31;
   Slot<ND> *slots = (Slot<ND> *)P.slots;
   double energy_emitted = 0.0;

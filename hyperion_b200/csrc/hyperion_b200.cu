@@ -1921,9 +1921,11 @@ size_t slot_bytes(int nd) {
 // (profiles/r01_experiments.md): 2 M slots 91.7 ms per 2e7 packets, 8 M 87.5 ms, 16 M 84.9 ms, 20 M 84.6 ms --
 // fewer, fuller rounds amortise the launch tails; with the beam and flight kernels side by side 12 M is best
 // (77.3 ms): the second round then has both kinds of packets in quantity.  12 M slots are 2.4 GB of the 180 GB.
-uint32_t pool_target() {
+// The wave engine (flight_wave.cuh) wants twice as many: its rounds are tile visits, and fuller rounds amortise
+// the staging of the tiles (12 M slots 62.8 ms per 2e7 packets, 24 M 58.9 ms, 32-48 M 58.8 ms; profiles/r02_experiments.md).
+uint32_t pool_target(bool wave = false) {
   const char *e = getenv("HYPERION_B200_POOL");
-  long v = e ? atol(e) : 12582912L;
+  long v = e ? atol(e) : (wave ? 25165824L : 12582912L);
   if (v < 1024) v = 1024;
   if (v > (1L << 28)) v = 1L << 28;
   return (uint32_t)v;
@@ -3309,7 +3311,7 @@ int ensure_wave(hyp_ctx *c) {
 
 template <int ND>
 static int run_wave(hyp_ctx *c, int64_t first_id, int64_t n_photons, int64_t iteration) {
-  const uint32_t cap = (uint32_t)std::min<int64_t>(pool_target(), n_photons);
+  const uint32_t cap = (uint32_t)std::min<int64_t>(pool_target(true), n_photons);
   int rc = ensure_pool(c, cap);
   if (rc) return rc;
   rc = ensure_wave(c);
@@ -3324,15 +3326,32 @@ static int run_wave(hyp_ctx *c, int64_t first_id, int64_t n_photons, int64_t ite
   }
   // below this many packets in flight the tiles are mostly empty: the direct kernels finish the iteration
   const uint32_t tail_min = getenv("HYPERION_B200_WAVE_TAIL") ? (uint32_t)atol(getenv("HYPERION_B200_WAVE_TAIL")) : 400000u;
-  W.refill = getenv("HYPERION_B200_WAVE_REFILL") ? std::max(1, std::min(32, atoi(getenv("HYPERION_B200_WAVE_REFILL")))) : 8;
+  W.refill = getenv("HYPERION_B200_WAVE_REFILL") ? std::max(1, std::min(32, atoi(getenv("HYPERION_B200_WAVE_REFILL")))) : 16;
+  {
+    // new packets per round: a quarter of the pool, so that emission runs next to the tile visits of the packets
+    // emitted before instead of filling the whole pool while nothing else can run
+    const long q = getenv("HYPERION_B200_WAVE_EMIT") ? atol(getenv("HYPERION_B200_WAVE_EMIT")) : (long)(cap / 4 + 1);
+    W.emit_max = (uint32_t)std::max(1024L, std::min<long>(q, (long)cap));
+  }
   W.iteration = (uint32_t)iteration;
   const int ctas = wave_ctas(ND);
+  W.queue = getenv("HYPERION_B200_WAVE_QUEUE") ? atoi(getenv("HYPERION_B200_WAVE_QUEUE")) : 1;
   constexpr int WT = ND == 1 ? 1024 : (ND == 2 ? 768 : 512);
   void (*tile)(const ModelDev, Pool, const WaveQ) = wave_tile_kernel<ND, WT, 1, WAVE_SUM_OFF_1>;
   int tile_threads = WT;
-  if (ND == 1 && ctas == 2) {
-    tile = wave_tile_kernel<ND, 512, 2, WAVE_SUM_OFF_2>;
-    tile_threads = 512;
+  if constexpr (ND == 1) {
+    // HYPERION_B200_WAVE_THREADS: 1024 threads with 64 registers (default), 896 with 72, 768 with 80
+    const int want = getenv("HYPERION_B200_WAVE_THREADS") ? atoi(getenv("HYPERION_B200_WAVE_THREADS")) : 1024;
+    if (ctas == 2) {
+      tile = wave_tile_kernel<ND, 512, 2, WAVE_SUM_OFF_2>;
+      tile_threads = 512;
+    } else if (want == 896) {
+      tile = wave_tile_kernel<ND, 896, 1, WAVE_SUM_OFF_1>;
+      tile_threads = 896;
+    } else if (want == 768) {
+      tile = wave_tile_kernel<ND, 768, 1, WAVE_SUM_OFF_1>;
+      tile_threads = 768;
+    }
   }
   const size_t tile_smem = wave_smem_bytes(W.tx, W.ty, W.tz, ctas);
   CUDA_TRY(cudaFuncSetAttribute(tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem));
@@ -3387,7 +3406,8 @@ static int run_wave(hyp_ctx *c, int64_t first_id, int64_t n_photons, int64_t ite
     }
     if (n_free > 0 && ids_left) {
       CUDA_TRY(cudaStreamWaitEvent(s3, c->evFork, 0));
-      const int blocks = (int)std::min<int64_t>(((int64_t)n_free + SERVICE_THREADS - 1) / SERVICE_THREADS, service_blocks);
+      const int64_t n_emit = std::min<int64_t>(n_free, W.emit_max);
+      const int blocks = (int)std::min<int64_t>((n_emit + SERVICE_THREADS - 1) / SERVICE_THREADS, service_blocks);
       wave_emit_kernel<ND><<<blocks, SERVICE_THREADS, 0, s3>>>(c->M, P, W, (unsigned long long)first_id,
                                                              (unsigned long long)n_photons, (uint32_t)iteration);
       CUDA_TRY(cudaGetLastError());

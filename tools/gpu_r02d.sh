@@ -1,0 +1,30 @@
+#!/bin/bash
+# Round-2 session d: wave engine with the two-deep packet queue (prefetch), aggregated sort atomics, throttled emission.
+cd "$(dirname "$0")/.."
+mkdir -p gpurun_out
+O=gpurun_out/r02d
+timeout 900 python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "wave or path_length or lucy" > ${O}_tests.log 2>&1
+tail -5 ${O}_tests.log
+run() { echo "== $*"; env "$@" timeout 300 python tools/profile_lucy.py --grid 256 --photons 2e7 --tau 1 --iters 3 2>&1 | tail -${TAILN:-1}; }
+{
+TAILN=120 run HYPERION_B200_TIMING=1
+run HYPERION_B200_WAVE_REFILL=8
+run HYPERION_B200_WAVE_REFILL=12
+run HYPERION_B200_WAVE_REFILL=20
+run HYPERION_B200_WAVE_REFILL=24
+run HYPERION_B200_WAVE_EMIT=25165824
+run HYPERION_B200_WAVE_EMIT=3000000
+run HYPERION_B200_WAVE_EMIT=10000000
+run HYPERION_B200_TILE=28,28,28
+run HYPERION_B200_WAVE_CTAS=2
+run HYPERION_B200_WAVE_TAIL=1000000
+run HYPERION_B200_POOL=12582912
+run HYPERION_B200_POOL=33554432
+} > ${O}_sweep.log 2>&1
+grep -v "^\[wave" ${O}_sweep.log | tail -40
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:wave_tile_kernel -s 6 -c 1 -o ${O}_wave_tile \
+   python tools/profile_lucy.py --grid 256 --photons 2e7 --tau 1 --iters 1 > ${O}_ncu.log 2>&1
+tail -3 ${O}_ncu.log
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 1200 --csv --log-file ${O}_launches.csv \
+   python tools/profile_lucy.py --grid 256 --photons 2e7 --tau 1 --iters 2 > ${O}_ncu2.log 2>&1
+tail -2 ${O}_ncu2.log
