@@ -43,13 +43,18 @@ constexpr uint32_t WAVE_CHUNK_MAX = 16384;      // packets per work item (2^14 *
 #ifndef WAVE_UNROLL
 #define WAVE_UNROLL 4                           // crossings between two hand-over votes
 #endif
+// throughput probes (tools/gpu_r02f.sh): 0 = product path; 1 no deposit; 2 density 1.0f instead of the shared-memory
+// load (halo test kept on the loaded word only every crossing's address...); 3 both
+#ifndef WAVE_EXPERIMENT
+#define WAVE_EXPERIMENT 0
+#endif
 
 enum { WC_NITEMS = 0, WC_ITEM_CURSOR, WC_N_FLIGHT, WC_N_INTERACT, WC_INTERACT_START, WC_N_FREE, WC_FREE_START,
        WC_CLAIMED_LO, WC_CLAIMED_HI, WC_COUNT = 16 };
 
 struct WaveQ {
   uint32_t *key;         // [capacity] state of every slot
-  uint32_t *sorted;      // [capacity] slot ids ordered by key
+  uint32_t *sorted;      // [capacity] slot ids ordered by key (this round's list; the host alternates two buffers)
   uint32_t *bin_count;   // [n_tiles + 2]
   uint32_t *bin_cursor;  // [n_tiles + 2]
   uint4 *items;          // work items {tile, first index in sorted, packets, -}
@@ -84,20 +89,16 @@ __global__ void wave_init_kernel(WaveQ W, Pool P) {
 }
 
 // ---- counting sort of the slot ids by key ------------------------------------------------------
-__global__ void __launch_bounds__(WAVE_SORT_THREADS) wave_hist_kernel(WaveQ W) {
+// The slots to sort are `src[0 .. n_src)`, or all slots 0 .. n_src-1 when src is null.  Once every packet id
+// has been claimed a free slot stays free, and the host passes the previous round's list of busy slots.
+__global__ void __launch_bounds__(WAVE_SORT_THREADS)
+wave_hist_kernel(WaveQ W, const uint32_t *__restrict__ src, const uint32_t n_src) {
   extern __shared__ uint32_t s_cnt[];
   const uint32_t nb = (uint32_t)W.n_tiles + 2u;
-  const unsigned lane = threadIdx.x & 31;
   for (uint32_t k = threadIdx.x; k < nb; k += blockDim.x) s_cnt[k] = 0;
   __syncthreads();
-  const uint32_t lo = blockIdx.x * (uint32_t)WAVE_SORT_SEG, hi = min(lo + (uint32_t)WAVE_SORT_SEG, W.capacity);
-  // the keys of neighbouring slots are often equal (free slots, packets of one source): one atomic per group
-  for (uint32_t base = lo + (threadIdx.x & ~31u); base < hi; base += blockDim.x) {
-    const uint32_t i = base + lane;
-    const uint32_t k = i < hi ? min(W.key[i], nb - 1u) : 0xffffff00u + lane;
-    const unsigned m = __match_any_sync(0xffffffffu, k);
-    if (i < hi && (int)lane == __ffs(m) - 1) atomicAdd(&s_cnt[k], (uint32_t)__popc(m));
-  }
+  const uint32_t lo = blockIdx.x * (uint32_t)WAVE_SORT_SEG, hi = min(lo + (uint32_t)WAVE_SORT_SEG, n_src);
+  for (uint32_t i = lo + threadIdx.x; i < hi; i += blockDim.x) atomicAdd(&s_cnt[min(W.key[src ? src[i] : i], nb - 1u)], 1u);
   __syncthreads();
   for (uint32_t k = threadIdx.x; k < nb; k += blockDim.x) {
     const uint32_t v = s_cnt[k];
@@ -163,20 +164,15 @@ __global__ void __launch_bounds__(1024) wave_scan_kernel(WaveQ W, Pool P) {
   }
 }
 
-__global__ void __launch_bounds__(WAVE_SORT_THREADS) wave_scatter_kernel(WaveQ W) {
+__global__ void __launch_bounds__(WAVE_SORT_THREADS)
+wave_scatter_kernel(WaveQ W, const uint32_t *__restrict__ src, const uint32_t n_src) {
   extern __shared__ uint32_t s_cnt[];   // [nb] counts, then [nb] bases
   const uint32_t nb = (uint32_t)W.n_tiles + 2u;
-  const unsigned lane = threadIdx.x & 31;
   uint32_t *s_base = s_cnt + nb;
   for (uint32_t k = threadIdx.x; k < nb; k += blockDim.x) s_cnt[k] = 0;
   __syncthreads();
-  const uint32_t lo = blockIdx.x * (uint32_t)WAVE_SORT_SEG, hi = min(lo + (uint32_t)WAVE_SORT_SEG, W.capacity);
-  for (uint32_t base = lo + (threadIdx.x & ~31u); base < hi; base += blockDim.x) {
-    const uint32_t i = base + lane;
-    const uint32_t k = i < hi ? min(W.key[i], nb - 1u) : 0xffffff00u + lane;
-    const unsigned m = __match_any_sync(0xffffffffu, k);
-    if (i < hi && (int)lane == __ffs(m) - 1) atomicAdd(&s_cnt[k], (uint32_t)__popc(m));
-  }
+  const uint32_t lo = blockIdx.x * (uint32_t)WAVE_SORT_SEG, hi = min(lo + (uint32_t)WAVE_SORT_SEG, n_src);
+  for (uint32_t i = lo + threadIdx.x; i < hi; i += blockDim.x) atomicAdd(&s_cnt[min(W.key[src ? src[i] : i], nb - 1u)], 1u);
   __syncthreads();
   for (uint32_t k = threadIdx.x; k < nb; k += blockDim.x) {
     const uint32_t v = s_cnt[k];
@@ -184,15 +180,11 @@ __global__ void __launch_bounds__(WAVE_SORT_THREADS) wave_scatter_kernel(WaveQ W
     s_cnt[k] = 0;
   }
   __syncthreads();
-  for (uint32_t base = lo + (threadIdx.x & ~31u); base < hi; base += blockDim.x) {
-    const uint32_t i = base + lane;
-    const uint32_t k = i < hi ? min(W.key[i], nb - 1u) : 0xffffff00u + lane;
-    const unsigned m = __match_any_sync(0xffffffffu, k);
-    const int leader = __ffs(m) - 1;
-    uint32_t r = 0;
-    if (i < hi && (int)lane == leader) r = atomicAdd(&s_cnt[k], (uint32_t)__popc(m));
-    r = __shfl_sync(0xffffffffu, r, leader);
-    if (i < hi) W.sorted[s_base[k] + r + __popc(m & ((1u << lane) - 1u))] = i;
+  // (warp-aggregated ranks with match_any were measured slower than one shared-memory atomic per slot)
+  for (uint32_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+    const uint32_t slot = src ? src[i] : i;
+    const uint32_t k = min(W.key[slot], nb - 1u);
+    W.sorted[s_base[k] + atomicAdd(&s_cnt[k], 1u)] = slot;
   }
 }
 
@@ -237,7 +229,11 @@ __device__ __forceinline__ void wave_cross(WaveLane<ND> &L, int &fin, uint32_t &
   for (int id = 0; id < ND; ++id) {
     // float -> double of a non-negative normal number by re-biasing the exponent (0 becomes 2^-127: harmless);
     // integer instructions instead of one more trip through the narrow conversion pipe
+#if WAVE_EXPERIMENT == 7
+    const double rd = (double)__uint_as_float(rho[id]);
+#else
     const double rd = __hiloint2double((int)((rho[id] >> 3) + 0x38000000u), (int)(rho[id] << 29));
+#endif
     chi_rho = fma(L.chi[id], rd, chi_rho);
   }
   const double tau_cell = chi_rho * ds;
@@ -271,7 +267,13 @@ __device__ __forceinline__ void wave_cross(WaveLane<ND> &L, int &fin, uint32_t &
       const float x = fmaf(lenf, L.kEs[id], L.resid[id]);
       const uint32_t q = __float2uint_rd(x);
       L.resid[id] = x - (float)q;
+#if WAVE_EXPERIMENT == 1 || WAVE_EXPERIMENT == 3
+      if (q == 0xffffffffu) asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(a_rho + (SUM_OFF + 4u * id)), "r"(q) : "memory");
+#elif WAVE_EXPERIMENT == 4
+      if (q) asm volatile("st.shared.u32 [%0], %1;" ::"r"(a_rho + (SUM_OFF + 4u * id)), "r"(q) : "memory");
+#else
       if (q) asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(a_rho + (SUM_OFF + 4u * id)), "r"(q) : "memory");
+#endif
     }
   }
 }
@@ -426,11 +428,14 @@ wave_tile_kernel(const ModelDev M, Pool P, const WaveQ W) {
             slot = nslot;
             nslot = NONE;
             const Slot<ND> *s = slots + slot;
-            const double2 a0 = __ldcg((const double2 *)&s->r0x);  // r0x r0y
-            const double2 a1 = __ldcg((const double2 *)&s->r0z);  // r0z vx
-            const double2 a2 = __ldcg((const double2 *)&s->vy);   // vy vz
-            const double2 a3 = __ldcg((const double2 *)&s->tau_left);  // tau t
-            const int4 cc = __ldcg((const int4 *)&s->ix);
+              // ld.global.cs: streaming loads that still go through L1, so that the six 16-byte loads of a record
+            // become one or two line fills instead of six L2 requests (measured: 75.5 -> 66.7 ms per step against ld.cg)
+#define WAVE_LD __ldcs
+            const double2 a0 = WAVE_LD((const double2 *)&s->r0x);  // r0x r0y
+            const double2 a1 = WAVE_LD((const double2 *)&s->r0z);  // r0z vx
+            const double2 a2 = WAVE_LD((const double2 *)&s->vy);   // vy vz
+            const double2 a3 = WAVE_LD((const double2 *)&s->tau_left);  // tau t
+            const int4 cc = WAVE_LD((const int4 *)&s->ix);
             bool bad = false;
   #pragma unroll
             for (int k = 0; k < ND; ++k) {
@@ -539,8 +544,10 @@ wave_tile_kernel(const ModelDev M, Pool P, const WaveQ W) {
             nslot = n2slot;
             n2slot = NONE;
             const char *rec = (const char *)(slots + nslot);
+#if WAVE_EXPERIMENT != 6
             asm volatile("prefetch.global.L2 [%0];" ::"l"(rec));
             asm volatile("prefetch.global.L2 [%0];" ::"l"(rec + 95));
+#endif
           }
           // -------- claim the packets after those --------
           if (!exhausted) {

@@ -93,8 +93,11 @@ enum { ERR_NONE = 0, ERR_NOT_IN_CELL = 1, ERR_NU_RANGE = 2, ERR_SCATTER = 3, ERR
 // so that the crossing loop runs converged, with few registers (high occupancy) and several
 // density loads in flight per lane, while the branchy table sampling runs in its own kernels.
 // =============================================================================================
+#ifndef SLOT_ALIGN
+#define SLOT_ALIGN 32
+#endif
 template <int ND>
-struct alignas(32) Slot {
+struct alignas(SLOT_ALIGN) Slot {
   // ---- hot part: what a flight needs
   double r0x, r0y, r0z;  // flight origin
   double vx, vy, vz;
@@ -1749,6 +1752,7 @@ struct hyp_ctx {
   cudaStream_t stream3 = nullptr;              // wave engine: emission next to the tile visits and the interactions
   cudaEvent_t evFork = nullptr, evJoin = nullptr, evJoin3 = nullptr;
   WaveQ wave = WaveQ();                        // wave engine (flight_wave.cuh)
+  uint32_t *wave_sorted[2] = {nullptr, nullptr};  // the sorted slot lists of two consecutive rounds
   int wave_bins_alloc = 0;
   bool uniform_walls = false;                  // all three wall arrays equidistant (to 1e-10 of the spacing)
   int last_engine = 0;                         // 1: the last Lucy photon loop ran on the wave engine
@@ -1892,7 +1896,9 @@ void free_pool(hyp_ctx *c) {
   free_dev(c->pool.counts);
   free_dev(c->pool.next_photon);
   free_dev(c->wave.key);
-  free_dev(c->wave.sorted);
+  free_dev(c->wave_sorted[0]);
+  free_dev(c->wave_sorted[1]);
+  c->wave.sorted = nullptr;
   free_dev(c->wave.bin_count);
   free_dev(c->wave.bin_cursor);
   free_dev(c->wave.items);
@@ -3230,8 +3236,8 @@ size_t wave_smem_bytes(int tx, int ty, int tz, int ctas) {
   return 2 * (size_t)(ctas == 2 ? WAVE_SUM_OFF_2 : WAVE_SUM_OFF_1) + (size_t)3 * tw * sizeof(double);
 }
 
-// Tile shape: the largest near-cubic tile whose densities fit their half of the shared memory, each axis then
-// cut into equal parts (HYPERION_B200_TILE="tx,ty,tz" overrides).
+// Tile shape: the largest cube whose densities fit their half of the shared memory
+// (HYPERION_B200_TILE="tx,ty,tz" overrides).
 bool wave_plan(hyp_ctx *c, int nd) {
   WaveQ &W = c->wave;
   if (!c->uniform_walls || c->grid_type != GEO_CAR || c->M.any_sphere) return false;
@@ -3245,14 +3251,12 @@ bool wave_plan(hyp_ctx *c, int nd) {
     if (sscanf(e, "%d,%d,%d", &tx, &ty, &tz) != 3 || tx < 1 || ty < 1 || tz < 1) tx = ty = tz = 0;
   }
   if (tx == 0) {
+    // the largest cube that fits (longer visits beat evenly cut axes: 28^3 tiles 58.2 ms per step of the 256^3
+    // headline, 26^3 = ten equal parts per axis 60.6 ms; profiles/r02_experiments.md)
     for (int t0 = 62; t0 >= 2; --t0) {
       const int cx = std::min(t0, c->n1), cy = std::min(t0, c->n2), cz = std::min(t0, c->n3);
-      // equal parts per axis
-      const int ex = (c->n1 + (c->n1 + cx - 1) / cx - 1) / ((c->n1 + cx - 1) / cx);
-      const int ey = (c->n2 + (c->n2 + cy - 1) / cy - 1) / ((c->n2 + cy - 1) / cy);
-      const int ez = (c->n3 + (c->n3 + cz - 1) / cz - 1) / ((c->n3 + cz - 1) / cz);
-      if (fits(ex, ey, ez)) {
-        tx = ex; ty = ey; tz = ez;
+      if (fits(cx, cy, cz)) {
+        tx = cx; ty = cy; tz = cz;
         break;
       }
     }
@@ -3295,9 +3299,11 @@ int ensure_wave(hyp_ctx *c) {
     W.capacity = cap;
     return HYP_OK;
   }
-  free_dev(W.key); free_dev(W.sorted); free_dev(W.bin_count); free_dev(W.bin_cursor); free_dev(W.items); free_dev(W.ctl);
+  free_dev(W.key); free_dev(c->wave_sorted[0]); free_dev(c->wave_sorted[1]); free_dev(W.bin_count); free_dev(W.bin_cursor); free_dev(W.items); free_dev(W.ctl);
   CUDA_TRY(cudaMalloc(&W.key, (size_t)cap * sizeof(uint32_t)));
-  CUDA_TRY(cudaMalloc(&W.sorted, (size_t)cap * sizeof(uint32_t)));
+  CUDA_TRY(cudaMalloc(&c->wave_sorted[0], (size_t)cap * sizeof(uint32_t)));
+  CUDA_TRY(cudaMalloc(&c->wave_sorted[1], (size_t)cap * sizeof(uint32_t)));
+  W.sorted = c->wave_sorted[0];
   CUDA_TRY(cudaMalloc(&W.bin_count, (size_t)nb * sizeof(uint32_t)));
   CUDA_TRY(cudaMalloc(&W.bin_cursor, (size_t)nb * sizeof(uint32_t)));
   CUDA_TRY(cudaMalloc(&W.items, ((size_t)nb + cap / 256 + 2) * sizeof(uint4)));
@@ -3325,12 +3331,13 @@ static int run_wave(hyp_ctx *c, int64_t first_id, int64_t n_photons, int64_t ite
     W.chunk = (uint32_t)ch;
   }
   // below this many packets in flight the tiles are mostly empty: the direct kernels finish the iteration
-  const uint32_t tail_min = getenv("HYPERION_B200_WAVE_TAIL") ? (uint32_t)atol(getenv("HYPERION_B200_WAVE_TAIL")) : 400000u;
+  const uint32_t tail_min = getenv("HYPERION_B200_WAVE_TAIL") ? (uint32_t)atol(getenv("HYPERION_B200_WAVE_TAIL")) : 1000000u;
   W.refill = getenv("HYPERION_B200_WAVE_REFILL") ? std::max(1, std::min(32, atoi(getenv("HYPERION_B200_WAVE_REFILL")))) : 16;
   {
-    // new packets per round: a quarter of the pool, so that emission runs next to the tile visits of the packets
-    // emitted before instead of filling the whole pool while nothing else can run
-    const long q = getenv("HYPERION_B200_WAVE_EMIT") ? atol(getenv("HYPERION_B200_WAVE_EMIT")) : (long)(cap / 4 + 1);
+    // HYPERION_B200_WAVE_EMIT: new packets per round at most.  Spreading the emission over several rounds lets it
+    // run next to tile visits, but measured slower (75.5 vs 72.8 ms per step) than filling the pool at once:
+    // the first rounds then hold fewer packets.
+    const long q = getenv("HYPERION_B200_WAVE_EMIT") ? atol(getenv("HYPERION_B200_WAVE_EMIT")) : (long)cap;
     W.emit_max = (uint32_t)std::max(1024L, std::min<long>(q, (long)cap));
   }
   W.iteration = (uint32_t)iteration;
@@ -3358,7 +3365,6 @@ static int run_wave(hyp_ctx *c, int64_t first_id, int64_t n_photons, int64_t ite
   const size_t sort_smem = 2 * (size_t)(W.n_tiles + 2) * sizeof(uint32_t);
   CUDA_TRY(cudaFuncSetAttribute(wave_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sort_smem));
   CUDA_TRY(cudaFuncSetAttribute(wave_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sort_smem));
-  const int sort_blocks = (int)((cap + WAVE_SORT_SEG - 1) / WAVE_SORT_SEG);
   const int service_blocks = c->sm_count * 4;
   cudaStream_t st = c->stream, s2 = c->stream2, s3 = c->stream3;
   const bool dbg = getenv("HYPERION_B200_TIMING") != nullptr;
@@ -3368,12 +3374,18 @@ static int run_wave(hyp_ctx *c, int64_t first_id, int64_t n_photons, int64_t ite
   c->launches_acc += 1;
   CUDA_TRY(cudaEventRecord(c->ev0, st));
   uint32_t *h = c->h_counts;
-  bool handoff = false;
-  uint32_t handoff_flights = 0;
+  bool handoff = false, compact = false;
+  uint32_t handoff_flights = 0, n_busy_prev = 0;
   for (int64_t round = 0;; ++round) {
-    wave_hist_kernel<<<sort_blocks, WAVE_SORT_THREADS, sort_smem / 2, st>>>(W);
+    // slots to sort: all of them while packets are still being emitted, afterwards the busy slots of the
+    // previous round (a slot freed after the last emission stays free)
+    const uint32_t *src = compact ? c->wave_sorted[(round + 1) & 1] : nullptr;
+    const uint32_t n_src = compact ? n_busy_prev : cap;
+    W.sorted = c->wave_sorted[round & 1];
+    const int sort_blocks = (int)std::max<uint32_t>(1u, (n_src + WAVE_SORT_SEG - 1) / WAVE_SORT_SEG);
+    wave_hist_kernel<<<sort_blocks, WAVE_SORT_THREADS, sort_smem / 2, st>>>(W, src, n_src);
     wave_scan_kernel<<<1, 1024, 0, st>>>(W, P);
-    wave_scatter_kernel<<<sort_blocks, WAVE_SORT_THREADS, sort_smem, st>>>(W);
+    wave_scatter_kernel<<<sort_blocks, WAVE_SORT_THREADS, sort_smem, st>>>(W, src, n_src);
     CUDA_TRY(cudaGetLastError());
     c->launches_acc += 3;
     CUDA_TRY(cudaMemcpyAsync(h, W.ctl, WC_COUNT * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
@@ -3385,6 +3397,9 @@ static int run_wave(hyp_ctx *c, int64_t first_id, int64_t n_photons, int64_t ite
       fprintf(stderr, "[wave %lld] flights %u in %u items, interactions %u, free %u, claimed %llu\n", (long long)round,
               n_flight, h[WC_NITEMS], n_interact, n_free, claimed);
     if (n_flight == 0 && n_interact == 0 && !ids_left) break;
+    // this round emits nothing if every id was claimed before its sort: the next sort only needs its busy slots
+    compact = !ids_left;
+    n_busy_prev = n_flight + n_interact;
     if (!ids_left && n_flight + n_interact < tail_min) {
       wave_handoff_kernel<<<c->sm_count, 256, 0, st>>>(P, W);
       CUDA_TRY(cudaGetLastError());

@@ -8,9 +8,10 @@ and ``date_ended`` only on success (the launcher treats its absence as failure,
 ``scripts/hyperion:94-104``).
 
 The photon loop itself runs on the GPU through the C ABI (``hyperion_b200.capi``); there is no
-CPU path.  Under ``torchrun`` (WORLD_SIZE > 1) every rank drives one GPU, the packets are
-sharded by id and the deposit grid is all-reduced over NCCL once per iteration
-(``hyperion_b200.multigpu``); rank 0 writes the output.
+CPU path.  Started as N ranks (``mpirun -n N hyperion_car_mpi``, ``srun``, ``torchrun``,
+``bin/hyperion_mpirun`` or ``HYPERION_B200_NGPU=N``: ``hyperion_b200.launch``) every rank drives one
+GPU, the packets are sharded by id and the deposit grid is all-reduced over NCCL once per iteration
+(``hyperion_b200.multigpu``); rank 0 owns the files, as in the reference (``src/mpi/mpi_io.f90:213-242``).
 """
 from __future__ import annotations
 
@@ -21,10 +22,14 @@ import time
 
 import numpy as np
 
-from . import __version__
+from . import __version__, launch
 from .io import h5min, h5write
 from .multigpu import ShardedLucy, shard
 from .rtin import ModelError, read_rtin
+
+
+class PeerFailure(ModelError):
+    """Raised on the ranks that did not fail themselves when another rank reported an error."""
 
 
 def wrap_error_text(text, width=61):
@@ -191,9 +196,9 @@ def run(input_file, output_file, overwrite=False, device=None, log=None):
     ModelError / HyperionError for the conditions the reference reports through ``error()``."""
     from .capi import Engine
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0")) if device is None else device
+    rank, world, local, scheme = launch.layout()
+    if device is not None:
+        local = device
     main = rank == 0
     if log is None:
         def log(s):
@@ -207,46 +212,118 @@ def run(input_file, output_file, overwrite=False, device=None, log=None):
     log(" Input:  %s" % input_file)
     log(" Output: %s" % output_file)
     log(" " + "-" * 60)
-    if not os.path.exists(input_file):
-        raise ModelError("File does not exist: %s" % input_file)
-    if main and os.path.exists(output_file):
-        if not overwrite:
-            raise ModelError("File exists: %s (use -f to overwrite)" % output_file)
-        os.remove(output_file)
-
     t_start = time.time()
-    model, rs, fin = read_rtin(input_file)
-    log(" [main] using random seed = %d" % model.conf.seed)
-    if rs.monochromatic:
-        raise ModelError("the monochromatic final iteration is not implemented by this engine yet")
-    if rs.pda:
-        raise ModelError("the partial diffusion approximation is not implemented by this engine yet")
-    if rs.specific_energy_type == "additional":
-        # setup_initial (src/main/setup_rt.f90:191-194)
-        if rs.n_initial_iter == 0:
-            raise ModelError("Cannot use specific_energy_type='additional' if the number of specific energy iterations is 0")
-        model.conf.specific_energy_additional = True
 
     dist = None
     if world > 1:
         import torch
         import torch.distributed as dist
+        n_dev = torch.cuda.device_count()
+        if n_dev < 1:
+            raise ModelError("no CUDA device is visible to rank %d" % rank)
+        local = local % n_dev
         torch.cuda.set_device(local)
         if not dist.is_initialized():
-            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            if scheme != "RANK" or "MASTER_ADDR" not in os.environ:
+                # started by mpirun / srun: the rendezvous torchrun would have provided
+                addr, port = launch.rendezvous(output_file)
+                os.environ.setdefault("MASTER_ADDR", addr)
+                os.environ.setdefault("MASTER_PORT", str(port))
+            dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local))
 
-    eng = Engine(local)
-    eng.load_model(model)
+    class _Ranks:
+        """Collectives of the run with the reference's fate sharing: ``error()`` on one rank stops the
+        job (``mpi_abort``); here every collective is preceded by an agreement on an error flag, so a
+        rank that failed never leaves its peers waiting in an all-reduce."""
+
+        def __init__(self):
+            self.stream = None
+
+        def agree(self, failure):
+            """All ranks call this with their exception or None; raises on every rank if any failed."""
+            if world == 1:
+                if failure is not None:
+                    raise failure
+                return
+            flag = torch.tensor([1 if failure is not None else 0], dtype=torch.int32, device="cuda")
+            dist.all_reduce(flag, op=dist.ReduceOp.MAX)
+            if int(flag.item()):
+                if failure is not None:
+                    raise failure
+                raise PeerFailure("another rank reported an error; stopping (see its message)")
+
+        def guarded(self, fn, *a, **k):
+            from .capi import HyperionError
+            try:
+                res = fn(*a, **k)
+                failure = None
+            except (HyperionError, ModelError, h5min.H5Error) as e:
+                res, failure = None, e
+            self.agree(failure)
+            return res
+
+        def all_reduce(self, buf):
+            with torch.cuda.stream(self.stream):
+                dist.all_reduce(buf)
+            self.stream.synchronize()
+
+        def sum_ints(self, values):
+            """Sum a few host integers over the ranks (``mp_sync`` of the killed-photon counters,
+            ``src/main/main.f90:317-323``)."""
+            if world == 1:
+                return [int(v) for v in values]
+            t = torch.tensor([int(v) for v in values], dtype=torch.int64, device="cuda")
+            dist.all_reduce(t)
+            return [int(v) for v in t.tolist()]
+
+    ranks = _Ranks()
+
+    def open_model():
+        if not os.path.exists(input_file):
+            raise ModelError("File does not exist: %s" % input_file)
+        if main and os.path.exists(output_file):
+            if not overwrite:
+                raise ModelError("File exists: %s (use -f to overwrite)" % output_file)
+            os.remove(output_file)
+        model, rs, fin = read_rtin(input_file)
+        if rs.monochromatic:
+            raise ModelError("the monochromatic final iteration is not implemented by this engine yet")
+        if rs.pda:
+            raise ModelError("the partial diffusion approximation is not implemented by this engine yet")
+        if rs.specific_energy_type == "additional":
+            # setup_initial (src/main/setup_rt.f90:191-194)
+            if rs.n_initial_iter == 0:
+                raise ModelError("Cannot use specific_energy_type='additional' if the number of specific energy iterations is 0")
+            model.conf.specific_energy_additional = True
+        return model, rs, fin
+
+    model, rs, fin = ranks.guarded(open_model)
+    log(" [main] using random seed = %d" % model.conf.seed)
+    eng = ranks.guarded(lambda: Engine(local))
+    ranks.guarded(eng.load_model, model)
     all_reduce = None
     if world > 1:
-        import torch
         stream = torch.cuda.ExternalStream(eng.stream, device=torch.device("cuda", local))
+        ranks.stream = stream
+        all_reduce = ranks.all_reduce
 
-        def all_reduce(buf):
-            with torch.cuda.stream(stream):
-                dist.all_reduce(buf)
-            stream.synchronize()
-    drv = ShardedLucy(eng, rank, world, all_reduce)
+    class _GuardedEngine:
+        """The engine as ShardedLucy sees it: every phase that can fail agrees on the outcome before the
+        collective that follows it."""
+
+        def lucy_begin(self):
+            ranks.guarded(eng.lucy_begin)
+
+        def lucy_photons(self, first, count, iteration):
+            ranks.guarded(eng.lucy_photons, first, count, iteration)
+
+        def reduction_buffer(self):
+            return eng.reduction_buffer()
+
+        def lucy_finish(self):
+            return ranks.guarded(eng.lucy_finish)
+
+    drv = ShardedLucy(_GuardedEngine() if world > 1 else eng, rank, world, all_reduce)
 
     out = h5write.File()
     out.attrs["date_started"] = started
@@ -322,8 +399,8 @@ def run(input_file, output_file, overwrite=False, device=None, log=None):
         log(" [peeled_images] setting up %d peeled image groups " % len(model.peeled))
     if rs.n_last_photons > 0:
         first, count = shard(rs.n_last_photons, rank, world)
-        eng.final_begin()
-        eng.final_photons(first, count, rs.raytracing)
+        ranks.guarded(eng.final_begin)
+        ranks.guarded(eng.final_photons, first, count, rs.raytracing)
     log(" [main] exiting final iteration")
     n_ray = (0, 0)
     if rs.raytracing:
@@ -333,7 +410,7 @@ def run(input_file, output_file, overwrite=False, device=None, log=None):
         # energy travels with the cubes, so reduce first, then scale
         if world > 1:
             all_reduce(eng.image_buffer())
-        st = eng.final_finish()
+        st = ranks.guarded(eng.final_finish)
         killed_final = (st.killed_geo, st.killed_int)
         if world > 1:
             # every rank applied the scale to the reduced cubes; keep one copy for the final sum below
@@ -350,9 +427,10 @@ def run(input_file, output_file, overwrite=False, device=None, log=None):
         log(" [main] starting raytracing iteration")
         fs, cs = shard(n_ray[0], rank, world)
         fd, cd = shard(n_ray[1], rank, world)
-        st = eng.raytracing_photons(cs, cd, first_source_id=fs, n_total_sources=n_ray[0],
-                                    first_dust_id=fd, n_total_dust=n_ray[1])
-        killed_ray = (st.killed_geo, st.killed_int)
+        st = ranks.guarded(eng.raytracing_photons, cs, cd, first_source_id=fs, n_total_sources=n_ray[0],
+                           first_dust_id=fd, n_total_dust=n_ray[1])
+        # every rank counted its own share (main.f90:317-323 syncs the counters)
+        killed_ray = tuple(ranks.sum_ints((st.killed_geo, st.killed_int)))
         log(" [main] exiting raytracing iteration")
     out.attrs["killed_photons_geo_raytracing"] = np.int64(killed_ray[0])
     out.attrs["killed_photons_int_raytracing"] = np.int64(killed_ray[1])
@@ -395,9 +473,15 @@ def main(argv=None):
     if len(argv) != 2:
         sys.stderr.write("Usage: hyperion_car|hyperion_sph [-f] input_file output_file\n")
         return 2
+    # a serial start with HYPERION_B200_NGPU=N fans out to N ranks, one per GPU (the reference's -m N)
+    if launch.layout()[3] is None and launch.wanted_gpus() > 1:
+        return launch.spawn(launch.wanted_gpus(), [sys.executable, "-m", "hyperion_b200"] + list(sys.argv[1:] if argv is None else
+                            (["-f"] if overwrite else []) + argv))
     from .capi import HyperionError
     try:
         return run(argv[0], argv[1], overwrite=overwrite)
+    except PeerFailure:
+        return 1          # the failing rank has printed the message
     except (ModelError, HyperionError, h5min.H5Error) as e:
         boxed_error("main", str(e))
         return 1

@@ -216,9 +216,9 @@ def test_wave_engine_gives_same_sums_as_direct_kernels(kind, tile, tail, monkeyp
         assert abs(sa[key] - sb[key]) <= 1e-4 * sa[key] + 2, (key, sa[key], sb[key])
     assert sa["n_absorptions"] + sa["n_scatterings"] > N // 2
     assert abs(b.sum() / a.sum() - 1) < 1e-5
-    big = a > 1e-3 * a.max()
-    assert big.sum() > a.size // 20
-    assert np.allclose(a[big], b[big], rtol=2e-3, atol=0)
+    big = a > np.median(a)
+    assert np.allclose(a[big], b[big], rtol=1e-2, atol=0)
+    assert np.median(np.abs(b[big] / a[big] - 1)) < 2e-4
     assert np.allclose(a, b, rtol=0, atol=1e-5 * a.max())
 
 
