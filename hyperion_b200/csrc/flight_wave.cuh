@@ -204,6 +204,16 @@ struct WaveLane {
   uint32_t neg;             // bit a set: the packet moves towards -axis a
 };
 
+// 1 / x to the last ulp or two for normal x != 0 (MUFU.RCP64H + two Newton steps); only used for wall distances
+__device__ __forceinline__ double wave_rcp(double x) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  double e = fma(-x, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-x, r, 1.0);
+  return fma(r, e, r);
+}
+
 constexpr double WAVE_FAR = 1e300;   // "never": wall distance of a ray parallel to the walls of an axis
 
 // One cell crossing (grid_propagate_3d.f90:106-232).  fin: 0 in flight, 1 left the grid, 2 interaction,
@@ -255,26 +265,25 @@ __device__ __forceinline__ void wave_cross(WaveLane<ND> &L, int &fin, uint32_t &
     L.c = (L.neg & bit) ? L.c - (uint32_t)mag : L.c + (uint32_t)mag;
     L.cd = L.c;
   } else {
-    // interaction inside this cell (grid_propagate_3d.f90:186-228); cd keeps the cell the packet interacted in
-    len = tau_cell > 0.0 ? ds * (L.tau / tau_cell) : 0.0;
+    // interaction inside this cell (grid_propagate_3d.f90:186-228); cd keeps the cell the packet interacted in.
+    // One lane of a warp ends its flight in most steps while the others wait: the quotient uses the short
+    // reciprocal (MUFU + two Newton steps) instead of the full division sequence.
+    len = tau_cell > 0.0 ? ds * (L.tau * wave_rcp(tau_cell)) : 0.0;
+    len = fmin(len, ds);
     L.t += len;
     fin = 2;
   }
   const float lenf = (float)len;
 #pragma unroll
   for (int id = 0; id < ND; ++id) {
-    if (rho[id] != 0u) {
-      const float x = fmaf(lenf, L.kEs[id], L.resid[id]);
-      const uint32_t q = __float2uint_rd(x);
-      L.resid[id] = x - (float)q;
-#if WAVE_EXPERIMENT == 1 || WAVE_EXPERIMENT == 3
-      if (q == 0xffffffffu) asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(a_rho + (SUM_OFF + 4u * id)), "r"(q) : "memory");
-#elif WAVE_EXPERIMENT == 4
-      if (q) asm volatile("st.shared.u32 [%0], %1;" ::"r"(a_rho + (SUM_OFF + 4u * id)), "r"(q) : "memory");
-#else
-      if (q) asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(a_rho + (SUM_OFF + 4u * id)), "r"(q) : "memory");
+    // no deposit where the density is zero (grid_propagate_3d.f90:150): branch-free, a zero path length
+    const float x = fmaf(rho[id] != 0u ? lenf : 0.f, L.kEs[id], L.resid[id]);
+    const uint32_t q = __float2uint_rd(x);
+    L.resid[id] = x - (float)q;
+#if WAVE_EXPERIMENT == 1
+    if (q == 0xffffffffu)
 #endif
-    }
+    asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(a_rho + (SUM_OFF + 4u * id)), "r"(q) : "memory");
   }
 }
 
@@ -283,16 +292,6 @@ __device__ __forceinline__ float wave_unit_hash(uint32_t a, uint32_t b, uint32_t
   uint32_t h = a * 0x9E3779B1u ^ b * 0x85EBCA77u ^ c * 0xC2B2AE3Du;
   h ^= h >> 16; h *= 0x85EBCA6Bu; h ^= h >> 13; h *= 0xC2B2AE35u; h ^= h >> 16;
   return (float)(h >> 8) * (1.0f / 16777216.0f);
-}
-
-// 1 / x to the last ulp or two for normal x != 0 (MUFU.RCP64H + two Newton steps); only used for wall distances
-__device__ __forceinline__ double wave_rcp(double x) {
-  double r;
-  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
-  double e = fma(-x, r, 1.0);
-  r = fma(r, e, r);
-  e = fma(-x, r, 1.0);
-  return fma(r, e, r);
 }
 
 // Shared memory of a block: [densities SUM_OFF bytes][sums SUM_OFF bytes][walls of the tile 3 x TW doubles].

@@ -113,7 +113,8 @@ struct alignas(SLOT_ALIGN) Slot {
   double albedo[ND];
   double rng_spare;
   uint64_t id;
-  uint32_t rng_blk, rng_has_spare;
+  uint32_t rng_blk;
+  uint32_t rng_has_spare;  // bit 0: the stream holds a spare number; bits 1-31: successive re-absorptions by sources
   uint32_t n_inter;
   uint32_t tag;          // final iteration: source id | scattered | reprocessed | n_scat (see imaging.cuh)
 };
@@ -148,6 +149,7 @@ struct Photon {
   double sQ, sU, sV;
   int32_t ix, iy, iz, ic;
   uint32_t n_inter;
+  uint32_t n_reabs = 0;  // successive re-absorptions by sources so far (iter_lucy.f90:158-185)
   uint32_t tag;
   double nx, ny, nz;     // outward normal at the emission point of a spherical source (0 otherwise); not stored
 };
@@ -172,7 +174,9 @@ __device__ __forceinline__ void load_photon(const Slot<ND> *__restrict__ s, Phot
   p.tag = s->tag;
   rng.init(seed, s->id, iteration);
   rng.blk = s->rng_blk;
-  rng.has_spare = s->rng_has_spare != 0;
+  const uint32_t hs = s->rng_has_spare;
+  rng.has_spare = (hs & 1u) != 0;
+  p.n_reabs = hs >> 1;
   rng.spare = s->rng_spare;
 }
 
@@ -194,7 +198,7 @@ __device__ __forceinline__ void store_photon(Slot<ND> *__restrict__ s, const Pho
   s->rng_spare = rng.spare;
   s->id = id;
   s->rng_blk = rng.blk;
-  s->rng_has_spare = rng.has_spare ? 1u : 0u;
+  s->rng_has_spare = (rng.has_spare ? 1u : 0u) | (p.n_reabs << 1);
   s->n_inter = p.n_inter;
   s->tag = p.tag;
 }
@@ -563,6 +567,7 @@ __device__ bool emit_photon(const ModelDev &M, Photon<ND> &p, Rng &rng, double &
     }
     p.ic = amr_cell_id(M.amr.grids[g], p.ix, p.iy, p.iz);
     p.n_inter = 0;
+    p.n_reabs = 0;
     p.t = 0.0;
     return true;
   }
@@ -575,6 +580,7 @@ __device__ bool emit_photon(const ModelDev &M, Photon<ND> &p, Rng &rng, double &
     p.ix = p.iy = p.iz = 0;
     p.ic = node;
     p.n_inter = 0;
+    p.n_reabs = 0;
     p.t = 0.0;
     return true;
   }
@@ -593,6 +599,7 @@ __device__ bool emit_photon(const ModelDev &M, Photon<ND> &p, Rng &rng, double &
   }
   p.ic = (fz * M.n2 + fy) * M.n1 + fx;
   p.n_inter = 0;
+  p.n_reabs = 0;
   p.t = 0.0;
   return true;
 }
@@ -674,14 +681,13 @@ __device__ bool scatter_photon(const ModelDev &M, const DustDev &d, Photon<ND> &
 }
 
 // A flight that ended on a stellar surface (Slot::t < 0 carries the source): emit(p, reemit=.true., ...) from
-// that source with the packet's energy (iter_lucy.f90:158-185, iter_final.f90:212-242).  Consecutive
-// re-absorptions are counted in bits 10-15 of the tag (n_reabs_max above 62 is treated as unlimited).
-constexpr uint32_t TAG_REABS_SHIFT = 14, TAG_REABS_MASK = 63u << 14;
+// that source with the packet's energy (iter_lucy.f90:158-185, iter_final.f90:212-242).  After n_reabs_max
+// successive re-emissions that were all re-absorbed the packet is killed, as in the reference.
 template <int ND>
 __device__ bool reemit_photon(const ModelDev &M, Photon<ND> &p, Rng &rng, uint32_t &n_killed_int) {
   const int src = (int)(-p.t) - 1;
-  const uint32_t nre = (p.tag & TAG_REABS_MASK) >> TAG_REABS_SHIFT;
-  if (M.n_reabs_max < 63 && (int64_t)nre >= M.n_reabs_max) {
+  const uint32_t nre = p.n_reabs;
+  if ((int64_t)nre >= M.n_reabs_max) {
     ++n_killed_int;
     return false;
   }
@@ -689,7 +695,8 @@ __device__ bool reemit_photon(const ModelDev &M, Photon<ND> &p, Rng &rng, uint32
   double dummy = 0.0;
   if (!emit_photon<ND>(M, p, rng, dummy, src, p.energy)) return false;
   p.n_inter = n_inter;
-  p.tag = (uint32_t)(src + 1) | (min(nre + 1u, 63u) << TAG_REABS_SHIFT);
+  p.n_reabs = min(nre + 1u, 0x7ffffffeu);
+  p.tag = (uint32_t)(src + 1);
   return true;
 }
 
@@ -697,7 +704,7 @@ __device__ bool reemit_photon(const ModelDev &M, Photon<ND> &p, Rng &rng, uint32
 template <int ND>
 __device__ int interact_photon(const ModelDev &M, Photon<ND> &p, Rng &rng, uint32_t &n_abs, uint32_t &n_scat,
                                uint32_t &n_killed_int, int &dust_id, bool &was_scattered) {
-  p.tag &= ~TAG_REABS_MASK;
+  p.n_reabs = 0;
   // the loop guard of do_lucy (iter_lucy.f90:193-198)
   p.n_inter += 1;
   if ((int64_t)p.n_inter > M.n_inter_max) {
@@ -3332,7 +3339,7 @@ static int run_wave(hyp_ctx *c, int64_t first_id, int64_t n_photons, int64_t ite
   }
   // below this many packets in flight the tiles are mostly empty: the direct kernels finish the iteration
   const uint32_t tail_min = getenv("HYPERION_B200_WAVE_TAIL") ? (uint32_t)atol(getenv("HYPERION_B200_WAVE_TAIL")) : 1000000u;
-  W.refill = getenv("HYPERION_B200_WAVE_REFILL") ? std::max(1, std::min(32, atoi(getenv("HYPERION_B200_WAVE_REFILL")))) : 16;
+  W.refill = getenv("HYPERION_B200_WAVE_REFILL") ? std::max(1, std::min(32, atoi(getenv("HYPERION_B200_WAVE_REFILL")))) : 12;
   {
     // HYPERION_B200_WAVE_EMIT: new packets per round at most.  Spreading the emission over several rounds lets it
     // run next to tile visits, but measured slower (75.5 vs 72.8 ms per step) than filling the pool at once:

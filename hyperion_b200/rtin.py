@@ -380,8 +380,26 @@ def read_rtin(filename):
     if not sources and rs.n_last_photons > 0:
         raise ModelError("no sources set up - need sources for last iteration")
 
+    no_dust = len(dust) == 0
+    if no_dust:
+        # setup_initial (src/main/setup_rt.f90:164-168): a model without dust skips the initial iterations and
+        # the thermal raytracing, and still images its sources.  The engine marches a vacuum: one placeholder
+        # dust type (grey, covering every frequency a source can emit) with zero density in every cell.
+        print(" WARNING: no dust present, so skipping initial iterations [main]", flush=True)
+        rs.n_initial_iter = 0
+        rs.n_initial_photons = 0
+        rs.n_ray_photons_dust = 0
+        rs.check_convergence = False
+        conf.n_initial_iter = 0
+        conf.n_initial_photons = 0
+        from .synthetic import make_dust
+        dust = [make_dust([1.e-2, 1.e30], [0., 0.], [1., 1.], n_temp=4, temp_min=0.1, temp_max=1.e5)]
+        density = np.zeros((1,) + tuple(density.shape[1:]))
+        se, min_e = None, None
+
     model = FlatModel(w1, w2, w3, density, dust, sources, conf, specific_energy=se, minimum_specific_energy=min_e,
                       grid_type=grid_type, **(octree or {}))
+    model.no_dust = no_dust
     model.peeled = read_peeled_groups(f)
     if "Output" in f and "Binned" in f["Output"] and len(f["Output"]["Binned"].keys()) > 0:
         # setup_final_iteration (src/main/setup_rt.f90:314-331)

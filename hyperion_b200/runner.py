@@ -440,12 +440,12 @@ def run(input_file, output_file, overwrite=False, device=None, log=None):
     if make_binned:
         # main.f90:263,326: the cubes go straight into /Binned
         write_peeled_output(out.create_group("Binned"), eng, len(model.peeled), model.binned,
-                            len(model.sources), len(model.dust))
+                            len(model.sources), 0 if getattr(model, "no_dust", False) else len(model.dust))
     if make_peeled:
         gp = out.create_group("Peeled")
         for ig, p in enumerate(model.peeled):
             write_peeled_output(gp.create_group("group_%05d" % (ig + 1)), eng, ig, p,
-                                len(model.sources), len(model.dust))
+                                len(model.sources), 0 if getattr(model, "no_dust", False) else len(model.dust))
 
     eng.close()
     out.attrs["cpu_time"] = float(time.time() - t_start)

@@ -376,3 +376,63 @@ def test_rtin_roundtrip_map_source_on_amr_grid(golden_car, golden_amr, tmp_path)
     rtin_write.write_rtin(fn, m, n_initial_iter=1, n_initial_photons=100)
     got, rs, _ = rtin.read_rtin(fn)
     assert np.array_equal(got.sources[0].map, lm)
+
+
+def test_model_without_dust_skips_initial_iterations(golden_car, tmp_path, capsys):
+    """setup_initial (src/main/setup_rt.f90:164-168): no dust -> warning, n_initial_iter = 0, no thermal
+    raytracing; the sources are still imaged.  The reader hands the engine a vacuum."""
+    m = bitlevel_model(golden_car, False, False)
+    m.dust = []
+    m.density = np.zeros((0,) + m.density.shape[1:])
+    m.specific_energy = None
+    m.minimum_specific_energy = None
+    fn = str(tmp_path / "nodust.rtin")
+    rtin_write.write_rtin(fn, m, n_initial_iter=3, n_initial_photons=1e4, n_last_photons=1e3)
+    got, rs, _ = rtin.read_rtin(fn)
+    assert "no dust present, so skipping initial iterations" in capsys.readouterr().out
+    assert got.no_dust and rs.n_initial_iter == 0 and rs.n_ray_photons_dust == 0 and rs.n_last_photons == 1000
+    assert len(got.dust) == 1 and got.density.shape[0] == 1 and not got.density.any()
+    nu = got.dust[0].nu
+    assert nu.min() < 1e3 and nu.max() > 1e25      # every source frequency finds an opacity
+
+
+def test_process_layouts(monkeypatch):
+    """hyperion_b200.launch: rank / world / local rank from the launcher's environment
+    (scripts/hyperion:65-92 starts `mpirun -n N hyperion_<grid>_mpi`)."""
+    from hyperion_b200 import launch
+    for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "OMPI_COMM_WORLD_RANK", "OMPI_COMM_WORLD_SIZE", "PMI_RANK", "PMI_SIZE",
+              "SLURM_PROCID", "SLURM_NTASKS", "PMIX_RANK", "PMIX_SIZE", "HYPERION_B200_NGPU"):
+        monkeypatch.delenv(k, raising=False)
+    assert launch.layout() == (0, 1, 0, None)
+    assert launch.layout({"OMPI_COMM_WORLD_RANK": "3", "OMPI_COMM_WORLD_SIZE": "8", "OMPI_COMM_WORLD_LOCAL_RANK": "3"}) == \
+        (3, 8, 3, "OMPI_COMM_WORLD_RANK")
+    assert launch.layout({"PMI_RANK": "1", "PMI_SIZE": "2"}) == (1, 2, 1, "PMI_RANK")
+    assert launch.layout({"SLURM_PROCID": "5", "SLURM_NTASKS": "6", "SLURM_LOCALID": "1"}) == (5, 6, 1, "SLURM_PROCID")
+    assert launch.layout({"RANK": "2", "WORLD_SIZE": "4", "LOCAL_RANK": "2", "OMPI_COMM_WORLD_RANK": "0",
+                          "OMPI_COMM_WORLD_SIZE": "1"})[:3] == (2, 4, 2)      # torchrun's names win
+    with pytest.raises(ValueError):
+        launch.layout({"RANK": "4", "WORLD_SIZE": "4"})
+    a = launch.rendezvous("/tmp/x.rtout", {})
+    assert a == launch.rendezvous("/tmp/x.rtout", {}) and a[0] == "127.0.0.1" and 20000 <= a[1] < 40000
+    assert launch.rendezvous("/tmp/x.rtout", {"MASTER_ADDR": "10.0.0.1", "MASTER_PORT": "1234"}) == ("10.0.0.1", 1234)
+    assert launch.wanted_gpus({"HYPERION_B200_NGPU": "4"}) == 4 and launch.wanted_gpus({}) == 1
+
+
+def test_hyperion_mpirun_starts_coordinated_ranks(tmp_path):
+    """bin/hyperion_mpirun -n N prog: N processes with RANK / WORLD_SIZE / LOCAL_RANK set; the first failure is
+    the exit status and stops the others."""
+    import os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = tmp_path / "ranks"
+    out.mkdir()
+    prog = "import os; open(os.path.join(r'%s', os.environ['RANK']), 'w').write(os.environ['WORLD_SIZE'] + ' ' + " \
+           "os.environ['LOCAL_RANK'] + ' ' + os.environ['MASTER_ADDR'] + ' ' + os.environ['MASTER_PORT'])" % out
+    rc = subprocess.call([os.path.join(root, "bin", "hyperion_mpirun"), "-n", "3", sys.executable, "-c", prog])
+    assert rc == 0
+    got = sorted(os.listdir(out))
+    assert got == ["0", "1", "2"]
+    ports = {open(out / r).read().split()[3] for r in got}
+    assert len(ports) == 1 and all(open(out / r).read().split()[:3] == ["3", r, "127.0.0.1"] for r in got)
+    rc = subprocess.call([os.path.join(root, "bin", "hyperion_mpirun"), "-n", "2", sys.executable, "-c",
+                          "import os, sys, time; time.sleep(0 if os.environ['RANK'] == '1' else 30); sys.exit(7)"])
+    assert rc == 7

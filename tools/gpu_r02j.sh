@@ -1,0 +1,12 @@
+#!/bin/bash
+cd "$(dirname "$0")/.."
+mkdir -p gpurun_out
+O=gpurun_out/r02j
+timeout 900 python -m pytest tests/test_gpu_parity.py -q -m gpu -k "wave or vacuum or path_length" > ${O}_tests.log 2>&1
+tail -3 ${O}_tests.log
+run() { echo "== $*"; env "$@" timeout 300 python tools/profile_lucy.py --grid 256 --photons 2e7 --tau ${TAU:-1} --iters 3 2>&1 | tail -${TAILN:-1}; }
+{
+run X=default
+run HYPERION_B200_WAVE_REFILL=12
+} > ${O}_sweep.log 2>&1
+grep -v "^\[wave" ${O}_sweep.log | tail -14
