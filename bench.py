@@ -43,6 +43,9 @@ def parse():
     ap.add_argument("--no-moderate", action="store_true", help="skip the tau = 5 variant")
     ap.add_argument("--moderate-tau", type=float, default=5.0)
     ap.add_argument("--no-imaging", action="store_true", help="skip the imaging-iteration variant")
+    ap.add_argument("--no-configs", action="store_true", help="skip the BASELINE.json configurations c1, c3, c4, c5")
+    ap.add_argument("--workload", default=None, choices=["c1", "c3", "c4", "c5", "tau5"],
+                    help="run ONE configuration of hyperion_b200/workloads.py as the measured workload of the line")
     ap.add_argument("--imaging-photons", type=float, default=2.0e6)
     return ap.parse_args()
 
@@ -313,6 +316,60 @@ def measured_traffic(workload, photons):
     return None, None
 
 
+def run_config(name, make, Engine, local, rank, world, sync_all):
+    """One BASELINE.json configuration (hyperion_b200/workloads.py) on this rank's GPU: per-GPU photon counts,
+    packets sharded by id, one all-reduce per Lucy iteration and one of the image cubes.  Returns the
+    other_workloads row."""
+    import torch
+    from hyperion_b200 import workloads as wl
+    from hyperion_b200.multigpu import shard
+    model, plan = wl.build(name)
+    peak, _ = peaks()
+    row = {"workload": plan["description"], "config": name, "unit": "packets/s"}
+    P = plan["photons"]
+    eng, drv, stream = make(model)
+    if "lucy" in plan["kind"]:
+        drv.iteration(world * P, 1)                       # warm-up (allocations, first-touch)
+        sync_all()
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        stats = [drv.iteration(world * P, 2 + it, id_offset=(1 + it) * world * P) for it in range(plan["iterations"])]
+        e1.record(stream)
+        sync_all()
+        ms = e0.elapsed_time(e1)
+        r, cross, _, _ = roofline_of(stats, eng.n_dust, world, len(stats))
+        row.update({"value": P * world * len(stats) / (ms * 1e-3), "ms_per_step": ms / len(stats),
+                    "photons_per_gpu_per_step": P, "lucy_iterations": len(stats),
+                    "crossings_per_packet": cross / (P * len(stats)), "bytes_per_crossing": 24 * eng.n_dust,
+                    "roofline_achieved": r["achieved"], "roofline_frac": r["frac"],
+                    "roofline_achieved_whole_photon_loop": r["achieved_whole_photon_loop"],
+                    "wave_engine_rounds": int(sum(getattr(st, "n_wave_rounds", 0) for st in stats))})
+    if "final" in plan["kind"]:
+        Pf = plan.get("final_photons", P)
+        st = None
+        for rep in range(2):       # first pass is the warm-up
+            sync_all()
+            t0 = time.time()
+            eng.final_begin()
+            first, count = shard(world * Pf, rank, world)
+            eng.final_photons(rep * world * Pf + first, count, False)
+            st = eng.final_finish()
+            sync_all()
+            wall = time.time() - t0
+        cr = st.n_crossings + st.n_peel_crossings - st.n_peel_cached
+        key = "final_" if "lucy" in plan["kind"] else ""
+        rate_ms = st.kernel_ms if world == 1 else wall * 1e3     # N > 1: wall clock between two barriers
+        row.update({key + "value": Pf * world / (rate_ms * 1e-3),
+                    key + "ms_per_step": rate_ms, key + "photons_per_gpu_per_step": Pf,
+                    key + "peeloffs_per_packet": st.n_peeloffs / Pf, key + "crossings_per_packet": cr / Pf,
+                    key + "bytes_per_crossing": 8,
+                    key + "roofline_achieved": 8.0 * cr / (st.kernel_ms * 1e-3) / 1e9,
+                    key + "roofline_frac": 8.0 * cr / (st.kernel_ms * 1e-3) / 1e9 / peak})
+    eng.close()
+    return row
+
+
 def multi_gpu_check(make, Engine, local, rank, world, sync_all):
     """32^3 model, 2e6 packets: specific_energy of the N-rank run (id shards + one all-reduce) against a
     1-rank replay of the same ids on rank 0.  Returns "ok" or a description of the mismatch."""
@@ -396,6 +453,27 @@ def main():
 
         return eng, ShardedLucy(eng, rank, world, all_reduce if world > 1 else None), stream
 
+    if a.workload:
+        sampler = ClockSampler(local)
+        if rank == 0:
+            sampler.start()
+        row = run_config(a.workload, make, Engine, local, rank, world, sync_all)
+        clocks = sampler.stop() if rank == 0 else None
+        if rank == 0:
+            key = "" if "value" in row else "final_"
+            line = {"metric": "photon_packets_per_sec", "value": row[key + "value"], "unit": "packets/s", "n_gpus": world,
+                    "steps": row.get("lucy_iterations", 1), "warmup": 1, "ms_per_step": row[key + "ms_per_step"],
+                    "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                    "config": {"workload": row["workload"], "photons_per_gpu_per_step": row[key + "photons_per_gpu_per_step"]},
+                    "roofline": {"bound": "hbm", "achieved": row[key + "roofline_achieved"], "peak": peaks()[0], "unit": "GB/s",
+                                 "frac": row[key + "roofline_frac"], "traffic": None,
+                                 "bytes_per_crossing": row[key + "bytes_per_crossing"]},
+                    "details": row, "clocks": clocks}
+            print(json.dumps(line), flush=True)
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
     model = build_model(a)
     P = int(a.photons)
     eng, drv, stream = make(model)
@@ -462,6 +540,11 @@ def main():
                    "gpu_launches": int(st3.n_launches)}
         eng3.close()
 
+    configs = []
+    if not a.no_configs:
+        for name in ("c1", "c3", "c4", "c5"):
+            configs.append(run_config(name, make, Engine, local, rank, world, sync_all))
+
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
         cores = os.cpu_count() or 1
@@ -509,7 +592,7 @@ def main():
             line["e2e"] = e2e
         if mg_check is not None:
             line["multi_gpu_check"] = mg_check
-        others = [w for w in (thin, moderate, imaging) if w]
+        others = [w for w in (thin, moderate, imaging) if w] + configs
         if others:
             line["other_workloads"] = others
         if cpu:

@@ -190,14 +190,15 @@ def cartesian_point_source_model(n=256, tau_edge=1.0, dust=None, temperature=600
 
 
 def spherical_disk_model(n_r=399, n_theta=199, n_phi=1, tau_edge=10.0, dust=None, temperature=4000.,
-                         lam_ref_um=0.5, n_photons=0, n_iter=1):
+                         lam_ref_um=0.5, n_photons=0, n_iter=1, stellar_sphere=False):
     """SURVEY.md section 8d 'C3': spherical polar (r, theta[, phi]) grid of a flared disk as the
     AnalyticalYSOModel front end lays it out (hyperion/model/analytical_yso_model.py:490-626: r walls
     [0, rmin, rmin (1 + logspace)], theta walls linspace(0, pi) + sin(2 theta)/6, which concentrates
     cells towards the midplane; hyperion/densities/flared_disk.py:286-351: rho ~ (r0/w)^(beta-p)
     exp(-(z/h)^2/2), h = h0 (w/r0)^beta).  The density is scaled so that the midplane optical depth
-    from rmin to rmax at ``lam_ref_um`` is ``tau_edge``.  A point source sits at the origin (the
-    spherical stellar source of the tutorial model is not implemented on the device yet)."""
+    from rmin to rmax at ``lam_ref_um`` is ``tau_edge``.  The star is a point source at the origin, or with
+    ``stellar_sphere`` the SphericalSource of the tutorial model (R = 2 R_sun: packets that come back to the
+    star are re-absorbed and re-emitted from its surface, src/main/iter_lucy.f90:158-185)."""
     if dust is None:
         dust = realistic_dust(n_temp=200)
     rstar = 2. * rsun
@@ -228,7 +229,10 @@ def spherical_disk_model(n_r=399, n_theta=199, n_phi=1, tau_edge=10.0, dust=None
     tau_mid = float((rho[imid] * np.diff(w1)).sum() * chi0)
     rho *= tau_edge / tau_mid
     rho = np.broadcast_to(rho[None, None], (1, n_phi, n_theta, n_r)).copy()
-    src = FlatSource(type=1, luminosity=lsun, temperature=temperature, position=(0., 0., 0.))
+    if stellar_sphere:
+        src = FlatSource(type=2, luminosity=lsun, temperature=temperature, position=(0., 0., 0.), radius=rstar)
+    else:
+        src = FlatSource(type=1, luminosity=lsun, temperature=temperature, position=(0., 0., 0.))
     conf = FlatConf(n_initial_iter=n_iter, n_initial_photons=n_photons)
     return FlatModel(w1, w2, w3, rho, [dust], [src], conf, grid_type="sph")
 
