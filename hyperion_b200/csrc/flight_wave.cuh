@@ -172,20 +172,29 @@ wave_scatter_kernel(WaveQ W, const uint32_t *__restrict__ src, const uint32_t n_
   for (uint32_t k = threadIdx.x; k < nb; k += blockDim.x) s_cnt[k] = 0;
   __syncthreads();
   const uint32_t lo = blockIdx.x * (uint32_t)WAVE_SORT_SEG, hi = min(lo + (uint32_t)WAVE_SORT_SEG, n_src);
-  for (uint32_t i = lo + threadIdx.x; i < hi; i += blockDim.x) atomicAdd(&s_cnt[min(W.key[src ? src[i] : i], nb - 1u)], 1u);
+  // one pass over the keys: the shared-memory atomic that counts a slot also returns its rank among the slots
+  // of its bin in this block; key and rank wait in registers until the block has claimed its ranges
+  constexpr int PER = WAVE_SORT_SEG / WAVE_SORT_THREADS;
+  uint32_t slot_r[PER], key_r[PER], rank_r[PER];
+#pragma unroll
+  for (int j = 0; j < PER; ++j) {
+    const uint32_t i = lo + threadIdx.x + (uint32_t)j * WAVE_SORT_THREADS;
+    key_r[j] = 0xffffffffu;
+    if (i < hi) {
+      slot_r[j] = src ? src[i] : i;
+      key_r[j] = min(W.key[slot_r[j]], nb - 1u);
+      rank_r[j] = atomicAdd(&s_cnt[key_r[j]], 1u);
+    }
+  }
   __syncthreads();
   for (uint32_t k = threadIdx.x; k < nb; k += blockDim.x) {
     const uint32_t v = s_cnt[k];
     s_base[k] = v ? atomicAdd(W.bin_cursor + k, v) : 0u;
-    s_cnt[k] = 0;
   }
   __syncthreads();
-  // (warp-aggregated ranks with match_any were measured slower than one shared-memory atomic per slot)
-  for (uint32_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
-    const uint32_t slot = src ? src[i] : i;
-    const uint32_t k = min(W.key[slot], nb - 1u);
-    W.sorted[s_base[k] + atomicAdd(&s_cnt[k], 1u)] = slot;
-  }
+#pragma unroll
+  for (int j = 0; j < PER; ++j)
+    if (key_r[j] != 0xffffffffu) W.sorted[s_base[key_r[j]] + rank_r[j]] = slot_r[j];
 }
 
 // ---- the march ---------------------------------------------------------------------------------

@@ -3420,7 +3420,8 @@ static int run_wave(hyp_ctx *c, int64_t first_id, int64_t n_photons, int64_t ite
     CUDA_TRY(cudaEventRecord(c->evFork, st));
     if (n_interact > 0) {
       CUDA_TRY(cudaStreamWaitEvent(s2, c->evFork, 0));
-      const int blocks = (int)std::min<int64_t>(((int64_t)n_interact + SERVICE_THREADS - 1) / SERVICE_THREADS, service_blocks);
+      const int blocks = (int)std::min<int64_t>(((int64_t)n_interact + SERVICE_THREADS - 1) / SERVICE_THREADS,
+                                                n_flight > 0 ? service_blocks : c->sm_count * 16);
       wave_interact_kernel<ND><<<blocks, SERVICE_THREADS, 0, s2>>>(c->M, P, W, (uint32_t)iteration);
       CUDA_TRY(cudaGetLastError());
       CUDA_TRY(cudaEventRecord(c->evJoin, s2));
@@ -3429,7 +3430,9 @@ static int run_wave(hyp_ctx *c, int64_t first_id, int64_t n_photons, int64_t ite
     if (n_free > 0 && ids_left) {
       CUDA_TRY(cudaStreamWaitEvent(s3, c->evFork, 0));
       const int64_t n_emit = std::min<int64_t>(n_free, W.emit_max);
-      const int blocks = (int)std::min<int64_t>((n_emit + SERVICE_THREADS - 1) / SERVICE_THREADS, service_blocks);
+      // next to a tile kernel the emission shares the SMs with it (4 blocks each); alone (the first round) it takes them all
+      const int blocks = (int)std::min<int64_t>((n_emit + SERVICE_THREADS - 1) / SERVICE_THREADS,
+                                                n_flight > 0 ? service_blocks : c->sm_count * 16);
       wave_emit_kernel<ND><<<blocks, SERVICE_THREADS, 0, s3>>>(c->M, P, W, (unsigned long long)first_id,
                                                              (unsigned long long)n_photons, (uint32_t)iteration);
       CUDA_TRY(cudaGetLastError());

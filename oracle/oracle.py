@@ -123,6 +123,11 @@ class Oracle(CApi):
         self.check(self.lib.orc_get_energy_sum(self.ctx, _ptr(out)))
         return out
 
+    def get_density(self):
+        out = self._grid()
+        self.check(self.lib.orc_get_density(self.ctx, _ptr(out)))
+        return out
+
     def set_energy_sum(self, a):
         a = np.ascontiguousarray(a, dtype=np.float64)
         self.check(self.lib.orc_set_energy_sum(self.ctx, _ptr(a)))
