@@ -28,8 +28,8 @@
 //
 // Deposits.  len * kappa * E is scaled so that the largest possible single deposit is 2^17 and rounded to an
 // integer with ERROR DIFFUSION along the packet's path: the remainder is carried to the packet's next
-// crossing, and every visit starts from a remainder drawn uniformly in [0, 1) (a hash of slot, path length
-// and iteration), so the sum a visit deposits is floor(exact + u): unbiased for deposits of any size, also
+// crossing, and every visit starts from a remainder drawn uniformly in [0, 1) (a hash of the packet's
+// optical depth left, path length and the iteration), so the sum a visit deposits is floor(exact + u): unbiased for deposits of any size, also
 // far below one unit.  A work item holds at most 2^14 packets and a packet crosses a cell at most once per
 // visit, so the 32-bit sums cannot overflow.  After the item the sums are converted back and added to the
 // fp64 grid with one RED per touched cell.
@@ -342,23 +342,55 @@ wave_tile_kernel(const ModelDev M, Pool P, const WaveQ W) {
     const int tix = (int)it.x % W.ntx, tiy = ((int)it.x / W.ntx) % W.nty, tiz = (int)it.x / (W.ntx * W.nty);
     const int x0 = tix * TX, y0 = tiy * TY, z0 = tiz * TZ;
     // ---------------- stage the tile: densities in (fp32), halo sentinels, sums zeroed ----------------
-    for (int row = warp; row < TYh * TZh; row += NWARPS) {
-      const int hz = row / TYh, hy = row - hz * TYh;
-      const int gy = y0 + hy - 1, gz = z0 + hz - 1;
-      const bool row_in_grid = (unsigned)gy < (unsigned)n2 && (unsigned)gz < (unsigned)n3;
-      const bool row_in_tile = hy >= 1 && hy <= TY && hz >= 1 && hz <= TZ;
-      for (int hx = lane; hx < TXh; hx += 32) {
-        const int gx = x0 + hx - 1;
-        const bool in_grid = row_in_grid && (unsigned)gx < (unsigned)n1;
-        const bool in_tile = row_in_tile && hx >= 1 && hx <= TX;
-        const int c = row * TXh + hx;
+    // four rows per warp at a time, so that their density loads are in flight together
+    for (int row0 = warp; row0 < TYh * TZh; row0 += 4 * NWARPS) {
+      float v[4][ND];
+      bool act[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int row = row0 + j * NWARPS;
+        const int hz = row / TYh, hy = row - hz * TYh;
+        const int gy = y0 + hy - 1, gz = z0 + hz - 1, hx = lane, gx = x0 + hx - 1;
+        act[j] = row < TYh * TZh && hx < TXh;
+        const bool in_grid = (unsigned)gy < (unsigned)n2 && (unsigned)gz < (unsigned)n3 && (unsigned)gx < (unsigned)n1;
+        const bool in_tile = hy >= 1 && hy <= TY && hz >= 1 && hz <= TZ && hx >= 1 && hx <= TX;
         const size_t g = ((size_t)((size_t)gz * n2 + gy) * n1 + gx) * ND;
 #pragma unroll
         for (int id = 0; id < ND; ++id) {
-          float v = in_grid ? -1.f : -2.f;
-          if (in_grid && in_tile) v = fmaxf((float)__ldg(M.rho + g + id), 0.f);
-          s_rho[c * ND + id] = v;
-          s_sum[c * ND + id] = 0u;
+          v[j][id] = in_grid ? -1.f : -2.f;
+          if (act[j] && in_grid && in_tile) v[j][id] = fmaxf((float)__ldg(M.rho + g + id), 0.f);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (act[j]) {
+          const int c = (row0 + j * NWARPS) * TXh + lane;
+#pragma unroll
+          for (int id = 0; id < ND; ++id) {
+            s_rho[c * ND + id] = v[j][id];
+            s_sum[c * ND + id] = 0u;
+          }
+        }
+      }
+    }
+    if (TXh > 32) {
+      // columns 32 .. TXh-1 of wide tiles
+      for (int row = warp; row < TYh * TZh; row += NWARPS) {
+        const int hz = row / TYh, hy = row - hz * TYh;
+        const int gy = y0 + hy - 1, gz = z0 + hz - 1;
+        for (int hx = 32 + lane; hx < TXh; hx += 32) {
+          const int gx = x0 + hx - 1;
+          const bool in_grid = (unsigned)gy < (unsigned)n2 && (unsigned)gz < (unsigned)n3 && (unsigned)gx < (unsigned)n1;
+          const bool in_tile = hy >= 1 && hy <= TY && hz >= 1 && hz <= TZ && hx >= 1 && hx <= TX;
+          const int c = row * TXh + hx;
+          const size_t g = ((size_t)((size_t)gz * n2 + gy) * n1 + gx) * ND;
+#pragma unroll
+          for (int id = 0; id < ND; ++id) {
+            float vv = in_grid ? -1.f : -2.f;
+            if (in_grid && in_tile) vv = fmaxf((float)__ldg(M.rho + g + id), 0.f);
+            s_rho[c * ND + id] = vv;
+            s_sum[c * ND + id] = 0u;
+          }
         }
       }
     }
@@ -451,7 +483,10 @@ wave_tile_kernel(const ModelDev M, Pool P, const WaveQ W) {
               L.kEs[k] = __ldcg(&s->kE[k]) * W.dep_scale[k];
               // fixed-point bound of the deposits (see wave_plan): kappa * E above the table maximum cannot happen
               bad |= !(L.kEs[k] * W.diag <= (double)WAVE_DEP_MAX);
-              L.resid[k] = wave_unit_hash(slot, (uint32_t)__double2loint(a3.y) ^ (uint32_t)__double2hiint(a3.y),
+              // seeded by what the packet itself carries (optical depth left, path length), not by its slot: the
+              // rounding of a visit is then the same whichever slot, pool size or GPU count the run uses
+              L.resid[k] = wave_unit_hash((uint32_t)__double2loint(a3.x) ^ (uint32_t)__double2hiint(a3.x),
+                                          (uint32_t)__double2loint(a3.y) ^ (uint32_t)__double2hiint(a3.y),
                                           W.iteration * 4u + (uint32_t)k);
             }
             L.tau = a3.x;
