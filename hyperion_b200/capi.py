@@ -84,6 +84,7 @@ class ImageConf(C.Structure):
         ("binned", C.c_int32), ("n_theta", C.c_int32), ("n_phi", C.c_int32),
         ("use_filters", C.c_int32), ("filt_n", C.POINTER(C.c_int32)), ("filt_nu", _dp), ("filt_tr", _dp),
         ("filt_nu0", _dp),
+        ("inu_min", C.c_int32), ("inu_max", C.c_int32),
     ]
 
 
@@ -266,6 +267,9 @@ class CApi:
         t.track_origin = {"no": 0, "basic": 1, "yes": 1, "detailed": 2, "scatterings": 3}[g.track_origin]
         t.track_n_scat = g.track_n_scat
         t.uncertainties, t.compute_stokes, t.io_bytes = int(g.uncertainties), int(g.stokes), g.io_bytes
+        t.inu_min, t.inu_max = int(getattr(g, "inu_min", 0)), int(getattr(g, "inu_max", 0))
+        if t.inu_min > 0:
+            t.n_wav = t.inu_max - t.inu_min + 1
         self.check(self._fn("add_peeled_group")(ctx, C.byref(t)))
         del keep_f
 
@@ -288,6 +292,15 @@ class CApi:
 
     def get_image(self, ctx, group, uncertainties=False):
         return self._get_cube(ctx, group, 1, uncertainties)
+
+    def set_monochromatic(self, ctx, frequencies, energy_threshold):
+        nu = np.ascontiguousarray(frequencies, dtype=np.float64)
+        self.check(self._fn("set_monochromatic")(ctx, C.c_int32(len(nu)), _ptr(nu), C.c_double(energy_threshold)))
+
+    def final_mono_photons_raw(self, ctx, inu, first_s, n_s, n_s_tot, first_d, n_d, n_d_tot, scattering_only):
+        self.check(self._fn("final_mono_photons")(ctx, C.c_int32(inu), C.c_int64(first_s), C.c_int64(n_s), C.c_int64(n_s_tot),
+                                                  C.c_int64(first_d), C.c_int64(n_d), C.c_int64(n_d_tot),
+                                                  C.c_int32(int(scattering_only))))
 
     def set_density(self, ctx, n_dust, density):
         density = np.ascontiguousarray(density, dtype=np.float64)
@@ -406,6 +419,12 @@ class Engine(CApi):
     def final_photons(self, first_id, n, peeloff_scattering_only=False):
         self.check(self.lib.hyp_final_photons(self.ctx, C.c_int64(first_id), C.c_int64(n),
                                               C.c_int32(int(peeloff_scattering_only))))
+
+    def final_mono_photons(self, inu, first_source_id, n_sources, n_total_sources, first_dust_id, n_dust, n_total_dust,
+                           peeloff_scattering_only=False):
+        """do_final_mono for frequency ``inu`` (1-based): this rank's share of the source and thermal packets."""
+        self.final_mono_photons_raw(self.ctx, inu, first_source_id, n_sources, n_total_sources, first_dust_id, n_dust,
+                                    n_total_dust, peeloff_scattering_only)
 
     def final_finish(self):
         st = IterStats()

@@ -171,6 +171,10 @@ class FlatPeeledGroup:
     # filter convolution (``use_filters``, ``hyperion/conf/conf_files.py:862-885``): a list of
     # (nu, normalised transmission, nu0) triples replaces the wavelength grid
     filters: Optional[list] = None
+    # monochromatic mode (``image_type.f90:243-258``): the channels are frequencies inu_min .. inu_max (1-based)
+    # of ``FlatModel.frequencies``; 0 = not monochromatic
+    inu_min: int = 0
+    inu_max: int = 0
 
 
 @dataclass
@@ -186,6 +190,9 @@ class FlatModel:
     minimum_specific_energy: Optional[np.ndarray] = None
     peeled: List["FlatPeeledGroup"] = field(default_factory=list)
     binned: Optional["FlatPeeledGroup"] = None   # image group index len(peeled) on the engine / oracle
+    # monochromatic mode (``set_monochromatic``; src/main/setup_rt.f90:49-56,220-222): frequencies in Hz, or None
+    frequencies: Optional[np.ndarray] = None
+    monochromatic_energy_threshold: float = 1.e-10
     grid_type: str = "car"              # "car" (x, y, z walls), "sph" (r, theta, phi), "cyl" (w, z, phi), "oct"
     # octree (grid_type "oct", hyperion/grid/octree_grid.py): depth-first refinement flags, centre and
     # HALF-widths of the root cell; density is then [n_dust, n_nodes] and w1/w2/w3 are unused
@@ -309,6 +316,8 @@ def apply_model(api, ctx, model: FlatModel):
     api.set_run_conf(ctx, model.conf)
     api.set_density(ctx, len(model.dust), model.density)
     api.set_specific_energy(ctx, model.specific_energy, model.minimum_specific_energy)
+    if model.frequencies is not None:
+        api.set_monochromatic(ctx, model.frequencies, model.monochromatic_energy_threshold)
     for g in model.peeled:
         api.add_peeled_group(ctx, g)
     if model.binned is not None:

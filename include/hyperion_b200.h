@@ -176,6 +176,10 @@ typedef struct {
   const double *filt_nu;     /* concatenated 'nu' columns of Output/Peeled/group/filter_%05i */
   const double *filt_tr;     /* concatenated 'tn' columns (normalised transmission) */
   const double *filt_nu0;    /* [n_wav] central frequencies (attribute nu0), written back as filt_nu0 */
+  /* Monochromatic mode (image_setup, src/images/image_type.f90:243-258): the n_wav channels are the
+   * frequencies inu_min .. inu_max (1-based) of hyp_set_monochromatic; wav_min / wav_max are ignored.
+   * 0 = not monochromatic. */
+  int32_t inu_min, inu_max;
 } hyp_image_conf;
 
 /* Per-iteration counters (killed_photons_* attrs of main.f90:225-230 plus the
@@ -300,6 +304,17 @@ int hyp_add_peeled_group(hyp_ctx *ctx, const hyp_image_conf *conf);
  * (iter_final.f90:140-143) after the host has all-reduced hyp_image_device_buffers. */
 int hyp_final_begin(hyp_ctx *ctx);
 int hyp_final_photons(hyp_ctx *ctx, int64_t first_id, int64_t n_photons, int32_t peeloff_scattering_only);
+/* Monochromatic mode ('monochromatic' = yes, the table /frequencies and 'monochromatic_energy_threshold' of
+ * the .rtin file; src/main/setup_rt.f90:49-56,220-222).  Call before hyp_add_peeled_group / hyp_finalize_setup. */
+int hyp_set_monochromatic(hyp_ctx *ctx, int32_t n_nu, const double *frequencies, double energy_threshold);
+/* replaces: do_final_mono (src/main/iter_final_mono.f90:58-229) for ONE frequency inu (1-based), between
+ * hyp_final_begin and hyp_final_finish: source packets [first_source_id, +n_sources) of the job's n_total_sources
+ * emitted AT that frequency with the spectrum's probability as weight, then thermal packets [first_dust_id,
+ * +n_dust) of n_total_dust drawn from the per-cell emission probability at that frequency
+ * (src/grid/grid_monochromatic.f90:50-176); every interaction is a scattering that multiplies the energy by the
+ * albedo, packets die below energy_threshold x their initial energy.  The cubes need no scaling afterwards. */
+int hyp_final_mono_photons(hyp_ctx *ctx, int32_t inu, int64_t first_source_id, int64_t n_sources, int64_t n_total_sources,
+                           int64_t first_dust_id, int64_t n_dust, int64_t n_total_dust, int32_t peeloff_scattering_only);
 int hyp_final_finish(hyp_ctx *ctx, hyp_iter_stats *stats);
 /* replaces: do_raytracing (src/main/iter_raytracing.f90:31-141): n_sources packets from the
  * sources [first_source_id ...) and n_dust packets from random cells [first_dust_id ...), each

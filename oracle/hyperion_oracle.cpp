@@ -367,6 +367,10 @@ struct PdfCont {
     }
   }
   double sample(Rng &rng) const { return sample_xi(rng.random()); }
+  // interpolate_pdf_cont_dp (type_pdf.f90:402-414) with bounds_error=.false., fill_value=0
+  double interpolate(double xv) const {
+    return log ? interp1d_loglog(x.data(), pdf.data(), n, xv, false, 0.0) : interp1d_lin(x.data(), pdf.data(), n, xv, false, 0.0);
+  }
   // sample_pdf_cont_log_dp (type_pdf.f90:383-400): x interpolated in the log against the cdf
   double sample_log(Rng &rng) const {
     double xi = rng.random();
@@ -764,6 +768,7 @@ struct Photon {
   Vec v_prev{0, 0, 0};
   int emiss_type = 0, emiss_var_id = 0;
   double emiss_var_frac = 0.0;
+  int inu = 0;   // monochromatic mode: index of the packet's frequency (1-based)
   Angle source_a{0, 0, 0, 0};  // position angle on a stellar surface (type_photon.f90, emit_from_sphere)
   int face_id = 0;             // face of an external box source the packet came from (emit_from_extern_box)
 };
@@ -896,6 +901,8 @@ struct Image {
   std::vector<double> img, img2, imgn, sed, sed2, sedn;
   std::vector<std::vector<double>> filt_nu, filt_tr;   // use_filters: one transmission curve per channel
   std::vector<double> filt_nu0;
+  bool use_exact_nu = false;                // monochromatic mode (image_type.f90:243-258)
+  std::vector<double> nu;                   // the frequencies of the channels, inu_min .. inu_max
   size_t img_index(int inu, int ix, int iy, int iv, int io, int is) const {
     return (size_t)(inu - 1) +
            (size_t)n_nu * ((ix - 1) + (size_t)c.n_x * ((iy - 1) + (size_t)c.n_y * ((iv - 1) + (size_t)c.n_view * ((io - 1) + (size_t)n_orig * is))));
@@ -916,7 +923,7 @@ struct PeeledState {
 };
 
 // image_setup (image_type.f90:153-335)
-void image_setup(Image &im, const hyp_image_conf &c, int n_sources, int n_dust) {
+void image_setup(Image &im, const hyp_image_conf &c, int n_sources, int n_dust, const std::vector<double> &frequencies) {
   im.c = c;
   im.n_sources = n_sources;
   im.n_dust = n_dust;
@@ -950,10 +957,21 @@ void image_setup(Image &im, const hyp_image_conf &c, int n_sources, int n_dust) 
   const double c_cgs = 2.99792458e10;
   // "1.e-4" is a default-real (single precision) literal in image_type.f90:262-263
   const double micron = (double)1.e-4f;
-  im.nu_min = c_cgs / (c.wav_max * micron);
-  im.nu_max = c_cgs / (c.wav_min * micron);
-  im.log10_nu_min = std::log10(im.nu_min);
-  im.log10_nu_max = std::log10(im.nu_max);
+  if (c.inu_min > 0) {
+    // image_type.f90:243-258
+    if (c.use_filters) throw OracleError{"cannot use filters in monochromatic mode"};
+    const int nf = (int)frequencies.size();
+    if (c.inu_min < 1 || c.inu_min > nf) throw OracleError{"inu_min value is out of range"};
+    if (c.inu_max < 1 || c.inu_max > nf) throw OracleError{"inu_max value is out of range"};
+    im.use_exact_nu = true;
+    im.nu.assign(frequencies.begin() + (c.inu_min - 1), frequencies.begin() + c.inu_max);
+    if (im.n_nu != (int)im.nu.size()) throw OracleError{"n_nu should match length of frequencies array"};
+  } else if (!c.use_filters) {
+    im.nu_min = c_cgs / (c.wav_max * micron);
+    im.nu_max = c_cgs / (c.wav_min * micron);
+    im.log10_nu_min = std::log10(im.nu_min);
+    im.log10_nu_max = std::log10(im.nu_max);
+  }
   if (c.compute_image) {
     size_t n = (size_t)im.n_nu * c.n_x * c.n_y * c.n_view * im.n_orig * im.n_stokes;
     im.img.assign(n, 0.0);
@@ -1034,6 +1052,8 @@ void image_bin(Image &im, const Photon &p, double x_image, double y_image, int i
       double transmission = interp1d_lin(fn.data(), im.filt_tr[ifilt - 1].data(), (int)fn.size(), p.nu, false, 0.0);
       if (transmission > 0.0) image_bin_single(im, p, x_image, y_image, iv, ifilt, io, transmission);
     }
+  } else if (im.use_exact_nu) {
+    image_bin_single(im, p, x_image, y_image, iv, p.inu - im.c.inu_min + 1, io, 1.0);   // image_type.f90:435-436
   } else {
     int inu = ipos(im.log10_nu_min, im.log10_nu_max, std::log10(p.nu), im.n_nu);
     image_bin_single(im, p, x_image, y_image, iv, inu, io, 1.0);
@@ -1176,6 +1196,12 @@ struct orc_ctx {
   std::vector<Source> s;
   PdfDiscrete luminosity;
   double energy_total = 0, energy_current = 0;
+  // monochromatic mode (settings.f90:29-31)
+  std::vector<double> frequencies;
+  double monochromatic_energy_threshold = 1e-10;
+  std::vector<double> mono_mean_prob;            // grid_monochromatic.f90:35-36
+  std::vector<PdfDiscrete> mono_emiss_pdf;
+  bool mono_run = false;
   bool any_intersect = false;
   // counters
   int64_t killed_photons_geo = 0, killed_photons_int = 0;
@@ -2622,8 +2648,19 @@ int select_dust_specific_energy_rho(orc_ctx &g, const Cell &c) {
   return g.absorption.sample(g.rng);
 }
 
+// dust_sample_emit_probability (dust_type_4elem.f90:356-377)
+double dust_sample_emit_probability(const Dust &d, int jnu_var_id, double jnu_var_frac, double nu) {
+  const double prob1 = d.j_nu[jnu_var_id - 1].interpolate(nu);
+  const double prob2 = d.j_nu[jnu_var_id].interpolate(nu);
+  if (prob1 == 0.0 || prob2 == 0.0) return 0.0;
+  const double l = std::log10(prob1) + jnu_var_frac * (std::log10(prob2) - std::log10(prob1));
+  return std::pow(10.0, l);
+}
+
+double normalized_B_nu(double nu, double T);
+
 // emit (source.f90:100-179) + source_emit (source_type.f90:398-511)
-void emit(orc_ctx &g, Photon &p, bool reemit = false, int reemit_id = 0, double reemit_energy = 0.0) {
+void emit(orc_ctx &g, Photon &p, bool reemit = false, int reemit_id = 0, double reemit_energy = 0.0, int inu = 0) {
   p = Photon();
   int n_sources = (int)g.s.size();
   if (n_sources == 0) throw OracleError{"no sources to emit from"};
@@ -2675,6 +2712,33 @@ void emit(orc_ctx &g, Photon &p, bool reemit = false, int reemit_id = 0, double 
       throw OracleError{"source type not restated in the oracle"};
   }
   p.energy = 1.0;
+  if (inu > 0) {
+    // the frequency is fixed; the energy reflects the probability of emission there (source_type.f90:436-474)
+    const double nu = g.frequencies[inu - 1];
+    p.nu = nu;
+    p.inu = inu;
+    if (ispot >= 1 && ispot <= (int)src.spot.size()) {
+      const Source::Spot &sp = src.spot[ispot - 1];
+      if (sp.freq_type == 1)
+        p.energy = sp.spectrum.interpolate(nu);
+      else if (sp.freq_type == 2)
+        p.energy = normalized_B_nu(nu, sp.temperature);
+      else
+        throw OracleError{"Spot cannot have LTE spectrum"};
+    } else if (src.freq_type == 1) {
+      p.energy = src.spectrum.interpolate(nu);
+    } else if (src.freq_type == 2) {
+      p.energy = normalized_B_nu(nu, src.temperature);
+    } else if (src.freq_type == 3) {
+      p.dust_id = select_dust_specific_energy_rho(g, p.icell);
+      size_t k = (size_t)(p.dust_id - 1) * g.n_cells + p.icell.ic - 1;
+      p.emiss_var_id = g.jnu_var_id[k];
+      p.emiss_var_frac = g.jnu_var_frac[k];
+      p.energy = dust_sample_emit_probability(g.d[p.dust_id - 1], p.emiss_var_id, p.emiss_var_frac, nu);
+    } else {
+      throw OracleError{"unknown spectrum type"};
+    }
+  } else
   if (ispot >= 1 && ispot <= (int)src.spot.size()) {
     // the spot's own spectrum; tabulated ones are sampled with sample_pdf_log (source_type.f90:480-486)
     const Source::Spot &sp = src.spot[ispot - 1];
@@ -2702,6 +2766,7 @@ void emit(orc_ctx &g, Photon &p, bool reemit = false, int reemit_id = 0, double 
   if (reemit) {
     p.energy = reemit_energy;
   } else {
+    if (inu > 0) p.energy = p.energy * g.energy_total;   // source.f90:161
     if (g.conf.sample_sources_evenly) p.energy = p.energy * g.luminosity.pdf[p.source_id - 1] * n_sources;
     g.energy_current = g.energy_current + p.energy;
   }
@@ -2810,13 +2875,14 @@ int select_dust_chi_rho(orc_ctx &g, const Photon &p) {
 }
 
 // interact (dust_interact.f90:22-79)
-void interact(orc_ctx &g, Photon &p) {
+void interact(orc_ctx &g, Photon &p, bool force_scatter = false) {
   int id = select_dust_chi_rho(g, p);
   double albedo = p.current_albedo[id - 1];
   p.a_prev = p.a;
   p.v_prev = p.v;
   p.s_prev = p.s;
-  double xi = g.rng.random();
+  // dust_interact.f90:47-52: a forced scattering draws no number
+  double xi = force_scatter ? 0.0 : g.rng.random();
   const Dust &d = g.d[id - 1];
   if (xi > albedo) {
     // dust_emit (dust_type_4elem.f90:334-354)
@@ -2845,6 +2911,7 @@ void interact(orc_ctx &g, Photon &p) {
     g.n_scatterings++;
   }
   p.v = angle3d_to_vector3d(p.a);
+  if (force_scatter) p.energy = p.energy * albedo;   // dust_interact.f90:75-77
 }
 
 // update_energy_abs_tot (grid_physics_3d.f90:605-611)
@@ -3391,6 +3458,32 @@ std::vector<double> get_chi_nu_binned(const Dust &d, const Image &im) {
 }
 
 // peeloff_photon (images_peeled.f90:95-270); inside observers are not restated
+// get_spectrum_interp (source_type.f90:1098-1116), get_j_nu_interp (dust_type_4elem.f90:708-720),
+// get_chi_nu_interp (:780-791): the raytracing spectra at the exact frequencies of a monochromatic image
+std::vector<double> get_spectrum_interp(const Source &src, const Image &im) {
+  std::vector<double> sp(im.n_nu);
+  for (int i = 0; i < im.n_nu; i++) {
+    if (src.freq_type == 1)
+      sp[i] = interp1d_loglog(src.spectrum.x.data(), src.spectrum.pdf.data(), src.spectrum.n, im.nu[i], false, 0.0);
+    else if (src.freq_type == 2)
+      sp[i] = normalized_B_nu(im.nu[i], src.temperature);
+    else
+      throw OracleError{"cannot get spectrum"};
+  }
+  return sp;
+}
+std::vector<double> get_j_nu_interp(const Dust &d, const Image &im, int ijnu) {
+  const PdfCont &j = d.j_nu[ijnu - 1];
+  std::vector<double> sp(im.n_nu);
+  for (int i = 0; i < im.n_nu; i++) sp[i] = interp1d_loglog(j.x.data(), j.pdf.data(), j.n, im.nu[i], false, 0.0);
+  return sp;
+}
+std::vector<double> get_chi_nu_interp(const Dust &d, const Image &im) {
+  std::vector<double> sp(im.n_nu);
+  for (int i = 0; i < im.n_nu; i++) sp[i] = interp1d_loglog(d.nu.data(), d.chi_nu.data(), d.n_nu, im.nu[i], false, 0.0);
+  return sp;
+}
+
 void peeloff_photon(orc_ctx &g, const Photon &p_orig, bool polychromatic) {
   PeeledState &P = g.peeled;
   const int n_peeled = (int)P.group_id.size();
@@ -3501,7 +3594,8 @@ void peeloff_photon(orc_ctx &g, const Photon &p_orig, bool polychromatic) {
     if (polychromatic) {
       if (p.emiss_type == 1 || p.emiss_type == 2) {
         auto &cache = P.source_spectra[ig - 1][p.source_id - 1];
-        if (cache.empty()) cache = get_spectrum_binned(g.s[p.source_id - 1], im);
+        if (cache.empty())
+          cache = im.use_exact_nu ? get_spectrum_interp(g.s[p.source_id - 1], im) : get_spectrum_binned(g.s[p.source_id - 1], im);
         spectrum = cache;
       } else if (p.emiss_type == 3) {
         // get_dust_emissivity (images_peeled.f90:454-500)
@@ -3510,7 +3604,7 @@ void peeloff_photon(orc_ctx &g, const Photon &p_orig, bool polychromatic) {
         if (cache.empty()) {
           cache.resize((size_t)dd.n_jnu * im.n_nu);
           for (int ij = 1; ij <= dd.n_jnu; ij++) {
-            std::vector<double> sp = get_j_nu_binned(dd, im, ij);
+            std::vector<double> sp = im.use_exact_nu ? get_j_nu_interp(dd, im, ij) : get_j_nu_binned(dd, im, ij);
             for (int inu = 0; inu < im.n_nu; inu++) cache[(size_t)(ij - 1) * im.n_nu + inu] = std::log10(sp[inu]);
           }
         }
@@ -3527,7 +3621,7 @@ void peeloff_photon(orc_ctx &g, const Photon &p_orig, bool polychromatic) {
       for (auto &v : spectrum) v = v * p.s.I * p.energy;
       for (int id = 1; id <= g.n_dust; id++) {
         auto &chi = P.dust_extinction[ig - 1][id - 1];
-        if (chi.empty()) chi = get_chi_nu_binned(g.d[id - 1], im);
+        if (chi.empty()) chi = im.use_exact_nu ? get_chi_nu_interp(g.d[id - 1], im) : get_chi_nu_binned(g.d[id - 1], im);
         for (int inu = 0; inu < im.n_nu; inu++) spectrum[inu] = spectrum[inu] * std::exp(-column[id - 1] * chi[inu]);
       }
       image_bin_raytraced(im, p, x_image, y_image, iv, spectrum);
@@ -3706,10 +3800,163 @@ void raytracing_photons(orc_ctx &g, int64_t n_sources, int64_t n_thermal) {
   }
 }
 
+// ---------------------------------------------------------------------------
+// Monochromatic final iteration (src/main/iter_final_mono.f90, src/grid/grid_monochromatic.f90)
+// ---------------------------------------------------------------------------
+
+// setup_monochromatic_grid_pdfs (grid_monochromatic.f90:50-118); returns `empty`
+bool setup_monochromatic_grid_pdfs(orc_ctx &g, int inu) {
+  const double nu = g.frequencies[inu - 1];
+  const int nc = g.n_cells;
+  g.mono_mean_prob.assign(g.n_dust, 0.0);
+  g.mono_emiss_pdf.assign(g.n_dust, PdfDiscrete());
+  std::vector<double> energy(nc), prob(nc), pe(nc);
+  for (int id = 1; id <= g.n_dust; id++) {
+    const size_t o = (size_t)(id - 1) * nc;
+    for (int ic = 0; ic < nc; ic++) {
+      if (g.energy_abs_tot[id - 1] > 0.0)
+        energy[ic] = g.specific_energy[o + ic] * g.density[o + ic] * g.volume[ic] * (double)nc / g.energy_abs_tot[id - 1];
+      else
+        energy[ic] = 0.0;
+    }
+    if (!g.mask_map.empty()) {
+      std::vector<char> in(nc, 0);
+      for (int ic : g.mask_map) in[ic - 1] = 1;
+      for (int ic = 0; ic < nc; ic++)
+        if (!in[ic]) energy[ic] = 0.0;
+    }
+    for (int ic = 0; ic < nc; ic++)
+      prob[ic] = dust_sample_emit_probability(g.d[id - 1], g.jnu_var_id[o + ic], g.jnu_var_frac[o + ic], nu);
+    double sum = 0.0;
+    for (int ic = 0; ic < nc; ic++) {
+      pe[ic] = prob[ic] * energy[ic];
+      sum = sum + pe[ic];
+    }
+    g.mono_mean_prob[id - 1] = sum / (double)nc;
+    if (g.mono_mean_prob[id - 1] > 0.0) g.mono_emiss_pdf[id - 1].set(pe.data(), nc);
+  }
+  double tot = 0.0;
+  for (double m : g.mono_mean_prob) tot = tot + m;
+  return tot == 0.0;
+}
+
+// emit_from_monochromatic_grid_pdf (grid_monochromatic.f90:120-174)
+Photon emit_from_monochromatic_grid_pdf(orc_ctx &g, int inu) {
+  Photon p;
+  p.nu = g.frequencies[inu - 1];
+  p.inu = inu;
+  update_optconsts(g, p);
+  const double xi = g.rng.random();
+  const int dust_id = std::max((int)std::ceil(xi * (double)g.n_dust), 1);
+  if (g.mono_mean_prob[dust_id - 1] == 0.0) {
+    p.energy = 0.0;
+    return p;
+  }
+  const int ic = g.mono_emiss_pdf[dust_id - 1].sample(g.rng);
+  p.in_cell = true;
+  place_at_random_position_in_cell(g, p, ic);
+  p.a = random_sphere_angle3d(g.rng);
+  p.v = angle3d_to_vector3d(p.a);
+  p.s = Stokes{1.0, 0.0, 0.0, 0.0};
+  p.energy = g.mono_mean_prob[dust_id - 1];
+  p.scattered = false;
+  p.reprocessed = true;
+  p.last_isotropic = true;
+  p.dust_id = dust_id;
+  p.last[0] = 'd';
+  p.last[1] = 'e';
+  return p;
+}
+
+// propagate of iter_final_mono.f90:231-341: every interaction is a forced scattering
+void propagate_mono(orc_ctx &g, Photon &p) {
+  const int64_t n_inter_max = g.conf.n_inter_max;
+  const bool make_peeled = !g.peeled.group_id.empty();
+  const double energy_initial = p.energy;
+  for (int64_t interactions = 1; interactions <= n_inter_max + 1; interactions++) {
+    double tau;
+    if (interactions == 1 && g.conf.forced_first_interaction) {
+      double tau_escape;
+      bool killed;
+      grid_escape(g, p, std::numeric_limits<double>::max(), tau_escape, nullptr, killed);
+      if (tau_escape > 1.e-10 && !killed) {
+        double weight;
+        forced_interaction(g, tau_escape, tau, weight);
+        p.energy = p.energy * weight;
+      } else {
+        tau = g.rng.random_exp();
+      }
+    } else {
+      tau = g.rng.random_exp();
+    }
+    double tau_achieved;
+    grid_integrate_noenergy(g, p, tau, tau_achieved);
+    if (p.reabsorbed) {
+      int64_t ia;
+      for (ia = 1; ia <= g.conf.n_reabs_max; ia++) {
+        emit(g, p, true, p.reabsorbed_id, p.energy, p.inu);
+        g.n_reabsorptions++;
+        if (make_peeled) peeloff_photon(g, p, false);
+        tau = g.rng.random_exp();
+        grid_integrate_noenergy(g, p, tau, tau_achieved);
+        if (!p.reabsorbed) break;
+      }
+      if (ia == g.conf.n_reabs_max + 1) {
+        g.killed_photons_int++;
+        p.killed = true;
+        break;
+      }
+    }
+    if (p.killed || escaped(g, p.icell)) {
+      if (!p.killed) g.n_escaped++;
+      break;
+    }
+    if (interactions == n_inter_max + 1) {
+      g.killed_photons_int++;
+      p.killed = true;
+      break;
+    }
+    interact(g, p, true);
+    p.killed = (g.conf.kill_on_scatter && p.scattered) || (p.energy < energy_initial * g.monochromatic_energy_threshold);
+    if (p.killed) break;
+    if (make_peeled) peeloff_photon(g, p, false);
+  }
+}
+
+// do_final_mono (iter_final_mono.f90:58-229) for ONE frequency: n_sources of n_total_sources source packets,
+// then n_thermal of n_total_thermal thermal packets (the weights divide by the totals)
+void final_mono_photons(orc_ctx &g, int inu, int64_t n_sources, int64_t n_total_sources, int64_t n_thermal,
+                        int64_t n_total_thermal, bool peeloff_scattering_only) {
+  if (inu < 1 || inu > (int)g.frequencies.size()) throw OracleError{"incorrect inu"};
+  const bool make_peeled = !g.peeled.group_id.empty();
+  Photon p;
+  for (int64_t ip = 1; ip <= n_sources; ip++) {
+    emit(g, p, false, 0, 0.0, inu);
+    g.n_photons_run++;
+    p.energy = p.energy / (double)n_total_sources;
+    if (make_peeled && !peeloff_scattering_only) peeloff_photon(g, p, false);
+    propagate_mono(g, p);
+  }
+  if (n_thermal > 0 && g.n_dust > 0) {
+    const bool empty = setup_monochromatic_grid_pdfs(g, inu);
+    if (!empty) {
+      for (int64_t ip = 1; ip <= n_thermal; ip++) {
+        p = emit_from_monochromatic_grid_pdf(g, inu);
+        g.n_photons_run++;
+        if (p.energy > 0.0) {
+          p.energy = p.energy * g.energy_abs_tot[p.dust_id - 1] / (double)n_total_thermal * (double)g.n_dust;
+          if (make_peeled && !peeloff_scattering_only) peeloff_photon(g, p, false);
+          propagate_mono(g, p);
+        }
+      }
+    }
+  }
+}
+
 // image_write (image_type.f90:608-788): the arrays as written, in memory order
 void image_written(const Image &im, bool sed, std::vector<double> &out, std::vector<double> &unc) {
   // with filters the flux stays in F_nu dnu: the filter carries the normalisation (image_type.f90:649-657)
-  double dnunorm = im.c.use_filters ? 1.0
+  double dnunorm = (im.c.use_filters || im.use_exact_nu) ? 1.0
                                     : std::pow(im.nu_max / im.nu_min, +0.5 / (double)im.n_nu) -
                                           std::pow(im.nu_max / im.nu_min, -0.5 / (double)im.n_nu);
   out = sed ? im.sed : im.img;
@@ -3720,8 +3967,14 @@ void image_written(const Image &im, bool sed, std::vector<double> &out, std::vec
   } else {
     unc.clear();
   }
-  for (auto &v : out) v = v / dnunorm;
-  for (auto &v : unc) v = v / dnunorm;
+  if (!im.use_exact_nu) {
+    for (auto &v : out) v = v / dnunorm;
+    for (auto &v : unc) v = v / dnunorm;
+  } else {
+    // image_type.f90:679-682,737-740: nu F_nu at the exact frequencies
+    for (size_t i = 0; i < out.size(); i++) out[i] = out[i] * im.nu[i % (size_t)im.n_nu];
+    for (size_t i = 0; i < unc.size(); i++) unc[i] = unc[i] * im.nu[i % (size_t)im.n_nu];
+  }
   if (sed) {
     const size_t n_nu = im.n_nu, n_ap = im.c.n_ap;
     const size_t outer = out.size() / (n_nu * n_ap);
@@ -4335,7 +4588,7 @@ int orc_add_peeled_group(orc_ctx *g, const hyp_image_conf *c) {
       if (c->n_view != c->n_theta * c->n_phi) return fail(g, "binned images: n_view should be n_theta * n_phi");
     }
     Image im;
-    image_setup(im, *c, (int)g->s.size(), g->n_dust);
+    image_setup(im, *c, (int)g->s.size(), g->n_dust, g->frequencies);
     PeeledState &P = g->peeled;
     P.image.push_back(im);
     const int ig = (int)P.image.size();
@@ -4395,8 +4648,34 @@ static void fill_stats(orc_ctx *g, hyp_iter_stats *st) {
   st->n_peeloffs = g->n_peeloffs;
 }
 
+int orc_set_monochromatic(orc_ctx *g, int32_t n_nu, const double *frequencies, double energy_threshold) {
+  if (n_nu < 1 || !frequencies) return fail(g, "monochromatic mode needs at least one frequency");
+  g->frequencies.assign(frequencies, frequencies + n_nu);
+  g->monochromatic_energy_threshold = energy_threshold;
+  return 0;
+}
+
+// do_final_mono for one frequency; first_*_id are unused (one sequential stream per emulated rank)
+int orc_final_mono_photons(orc_ctx *g, int32_t inu, int64_t, int64_t n_sources, int64_t n_total_sources, int64_t,
+                           int64_t n_dust, int64_t n_total_dust, int32_t peeloff_scattering_only) {
+  try {
+    g->mono_run = true;
+    update_energy_abs_tot(*g);
+    final_mono_photons(*g, inu, n_sources, n_total_sources, n_dust, n_total_dust, peeloff_scattering_only != 0);
+  } catch (OracleError &e) {
+    return fail(g, e.msg);
+  }
+  return 0;
+}
+
 // do_final, last part (iter_final.f90:136-143)
 int orc_final_finish(orc_ctx *g, hyp_iter_stats *st) {
+  if (g->mono_run) {
+    // do_final_mono scales every packet itself (iter_final_mono.f90:118,187)
+    g->mono_run = false;
+    fill_stats(g, st);
+    return 0;
+  }
   if (!(g->energy_current > 0.0)) return fail(g, "no photons were emitted in this iteration");
   // peeled_images_adjust_scale / binned_images_adjust_scale (iter_final.f90:142-143, images_binned.f90:35-39)
   for (auto &im : g->peeled.image)

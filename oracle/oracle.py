@@ -49,7 +49,8 @@ def load():
         _lib.orc_test_interp1d_loglog.restype = C.c_double
         _lib.orc_test_planck.restype = C.c_double
         _lib.orc_rng_draws.restype = C.c_uint64
-        for n in ("orc_final_begin", "orc_final_photons", "orc_final_finish", "orc_raytracing_photons"):
+        for n in ("orc_final_begin", "orc_final_photons", "orc_final_finish", "orc_raytracing_photons",
+                  "orc_set_monochromatic", "orc_final_mono_photons"):
             getattr(_lib, n).restype = C.c_int
     return _lib
 
@@ -96,6 +97,10 @@ class Oracle(CApi):
 
     def final_photons(self, n, peeloff_scattering_only=False):
         self.check(self.lib.orc_final_photons(self.ctx, C.c_int64(n), C.c_int32(int(peeloff_scattering_only))))
+
+    def final_mono_photons(self, inu, n_sources, n_total_sources, n_dust, n_total_dust, peeloff_scattering_only=False):
+        self.final_mono_photons_raw(self.ctx, inu, 0, n_sources, n_total_sources, 0, n_dust, n_total_dust,
+                                    peeloff_scattering_only)
 
     def final_finish(self):
         st = IterStats()
