@@ -93,7 +93,7 @@ flight_geo_kernel(const ModelDev M, Pool P, const FinalArgs F, const uint32_t *_
         G::store(R, ix, iy, iz, ic);
         s->ix = ix; s->iy = iy; s->iz = iz; s->ic = ic;
       }
-      if (FINAL && fin == MARCH_ESCAPED && F.binned) bin_escaped_packet<ND>(F, s, R.t);   // iter_final.f90:126-129
+      if (FINAL && fin == MARCH_ESCAPED && F.binned) bin_escaped_packet<ND>(F, s, R.t, M.mono_inu);   // iter_final.f90:126-129
       n_esc += fin == MARCH_ESCAPED ? 1u : 0u;
       n_killed += fin == MARCH_KILLED ? 1u : 0u;
     }

@@ -18,6 +18,7 @@
 
 #include <cuda_runtime.h>
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
 
 #include "device.cuh"
 #include "geometry_sph.cuh"
@@ -73,6 +74,17 @@ struct ModelDev {
   const SpotDev *spots;               // spots of all spherical sources
   int32_t any_sphere;       // a spherical source exists: flights test for re-absorption (source.f90:206-227)
   int64_t n_reabs_max;
+  // monochromatic final iteration (iter_final_mono.f90): frequency of the run (0: polychromatic), its 1-based
+  // index, the energy per source packet of every source at that frequency, the kill threshold
+  double mono_nu;
+  int32_t mono_inu;
+  const double *mono_src_w;            // [n_sources]
+  const double *mono_spot_w;           // [spots of all sources]
+  double mono_threshold;
+  double mono_lte_w;                   // energy_total / n_photons for sources with an LTE spectrum
+  const double *mono_logp[MAX_DUST];   // log10 of the emission probability per unit frequency of every emissivity state
+  const double *mono_cdf;              // [n_dust][n_cells] cumulative emission probability x energy of the cells
+  double mono_thermal_w[MAX_DUST];     // energy of a thermal packet of each dust type (0: the type does not emit)
   // outputs
   double *scalars;                 // [SC_COUNT], directly after the reduced sum grid
   unsigned long long *work_counter;
@@ -112,6 +124,7 @@ struct alignas(SLOT_ALIGN) Slot {
   double sQ, sU, sV;     // Stokes (I = 1)
   double albedo[ND];
   double rng_spare;
+  double energy0;        // monochromatic mode: energy at emission (packets die below threshold x energy0)
   uint64_t id;
   uint32_t rng_blk;
   uint32_t rng_has_spare;  // bit 0: the stream holds a spare number; bits 1-31: successive re-absorptions by sources
@@ -146,6 +159,7 @@ struct Photon {
   double tau_left;
   double chi[ND], kE[ND], albedo[ND];
   double nu, energy;
+  double energy0 = 0.0;
   double sQ, sU, sV;
   int32_t ix, iy, iz, ic;
   uint32_t n_inter;
@@ -167,7 +181,7 @@ __device__ __forceinline__ void load_photon(const Slot<ND> *__restrict__ s, Phot
     p.kE[k] = s->kE[k];
     p.albedo[k] = s->albedo[k];
   }
-  p.nu = s->nu; p.energy = s->energy;
+  p.nu = s->nu; p.energy = s->energy; p.energy0 = s->energy0;
   p.sQ = s->sQ; p.sU = s->sU; p.sV = s->sV;
   p.ix = s->ix; p.iy = s->iy; p.iz = s->iz; p.ic = s->ic;
   p.n_inter = s->n_inter;
@@ -193,7 +207,7 @@ __device__ __forceinline__ void store_photon(Slot<ND> *__restrict__ s, const Pho
     s->albedo[k] = p.albedo[k];
   }
   s->ix = p.ix; s->iy = p.iy; s->iz = p.iz; s->ic = p.ic;
-  s->nu = p.nu; s->energy = p.energy;
+  s->nu = p.nu; s->energy = p.energy; s->energy0 = p.energy0;
   s->sQ = p.sQ; s->sU = p.sU; s->sV = p.sV;
   s->rng_spare = rng.spare;
   s->id = id;
@@ -351,6 +365,18 @@ __device__ __forceinline__ int pick_source(const ModelDev &M, double xi) {
 constexpr int TAG_DUST_SHIFT = 30;  // Photon::tag bits 30-31: dust type of the last interaction, 0-based (p%dust_id - 1)
 
 // emit (src/sources/source.f90:100-179): returns false on a fatal model error
+// dust_sample_emit_probability (dust_type_4elem.f90:356-377) at the frequency of the monochromatic run: the
+// probabilities of the two bracketing emissivity states (tabulated by the host as log10, -inf for zero)
+// interpolated in the log; zero if either is zero
+__device__ __forceinline__ double mono_emit_probability(const ModelDev &M, int id, int jid, double frac) {
+  const double l1 = M.mono_logp[id][jid], l2 = M.mono_logp[id][jid + 1];
+  if (isinf(l1) || isinf(l2)) return 0.0;
+  return pow(10.0, l1 + frac * (l2 - l1));
+}
+
+template <int ND>
+__device__ bool place_emitted(const ModelDev &M, Photon<ND> &p);
+
 template <int ND>
 __device__ bool emit_photon(const ModelDev &M, Photon<ND> &p, Rng &rng, double &energy_emitted, const int reemit_src = -1,
                             const double reemit_energy = 1.0) {
@@ -491,6 +517,36 @@ __device__ bool emit_photon(const ModelDev &M, Photon<ND> &p, Rng &rng, double &
   }
   p.sQ = p.sU = p.sV = 0.0;
   p.energy = reemit_src >= 0 ? reemit_energy : 1.0;
+  if (M.mono_nu > 0.0) {
+    // monochromatic mode (source_emit with nu given, source_type.f90:436-474; emit, source.f90:161): the
+    // frequency is fixed and the energy carries the spectrum's probability there (tabulated by the host per
+    // source, times energy_total / n_photons)
+    p.nu = M.mono_nu;
+    if (reemit_src < 0) {
+      if (ispot >= 0) {
+        p.energy = M.mono_spot_w[S.spot_off + ispot];
+      } else if (S.freq_type == HYP_SPECTRUM_LTE) {
+        // select_dust_specific_energy_rho, then dust_sample_emit_probability at the cell's emissivity state
+        const size_t base = (size_t)map_ic * ND;
+        double w[ND], tot = 0.0;
+#pragma unroll
+        for (int k = 0; k < ND; ++k) {
+          tot += M.specific_energy[base + k] * M.cells[base + k].rho;
+          w[k] = tot;
+        }
+        const double xi = rng.next();
+        int id = ND - 1;
+#pragma unroll
+        for (int k = ND - 2; k >= 0; --k)
+          if (xi <= w[k] / tot) id = k;
+        if (xi >= 1.0) id = ND - 1;
+        p.energy = mono_emit_probability(M, id, M.jnu_id[base + id], M.jnu_frac[base + id]) * M.mono_lte_w;
+        p.tag |= (uint32_t)id << TAG_DUST_SHIFT;
+      } else {
+        p.energy = M.mono_src_w[is];
+      }
+    }
+  } else
   if (ispot >= 0) {
     // the spot's own spectrum; tables are sampled with sample_pdf_log (source_type.f90:480-486,
     // type_pdf.f90:383-400): x interpolated in the log against the cdf
@@ -552,7 +608,14 @@ __device__ bool emit_photon(const ModelDev &M, Photon<ND> &p, Rng &rng, double &
   if (reemit_src < 0) {
     if (M.sample_evenly) p.energy = p.energy * S.pdf * ns;
     energy_emitted += p.energy;
+    p.energy0 = p.energy;
   }
+  return place_emitted<ND>(M, p);
+}
+
+// update_optconsts + find_cell for a packet whose position, direction and frequency are set (emit, source.f90:165-171)
+template <int ND>
+__device__ bool place_emitted(const ModelDev &M, Photon<ND> &p) {
   if (!update_optconsts<ND>(M, p)) {
     atomicMax(M.error_flag, ERR_NU_RANGE);
     return false;
@@ -703,7 +766,7 @@ __device__ bool reemit_photon(const ModelDev &M, Photon<ND> &p, Rng &rng, uint32
 // interact (src/dust/dust_interact.f90:22-79).  Returns: 0 continue, 1 packet finished (killed).
 template <int ND>
 __device__ int interact_photon(const ModelDev &M, Photon<ND> &p, Rng &rng, uint32_t &n_abs, uint32_t &n_scat,
-                               uint32_t &n_killed_int, int &dust_id, bool &was_scattered) {
+                               uint32_t &n_killed_int, int &dust_id, bool &was_scattered, const bool force_scatter = false) {
   p.n_reabs = 0;
   // the loop guard of do_lucy (iter_lucy.f90:193-198)
   p.n_inter += 1;
@@ -738,7 +801,8 @@ __device__ int interact_photon(const ModelDev &M, Photon<ND> &p, Rng &rng, uint3
 #pragma unroll
   for (int k = 1; k < ND; ++k)
     if (k == id) albedo = p.albedo[k];
-  const double xi = rng.next();
+  // a forced scattering draws no number and weighs the packet with the albedo (dust_interact.f90:47-52,75-77)
+  const double xi = force_scatter ? 0.0 : rng.next();
   bool scattered;
   if (xi > albedo) {
     // dust_emit (dust_type_4elem.f90:334-354) + dust_sample_j_nu (:379-398)
@@ -770,6 +834,12 @@ __device__ int interact_photon(const ModelDev &M, Photon<ND> &p, Rng &rng, uint3
     ++n_scat;
   }
   was_scattered = scattered;
+  if (force_scatter) {
+    p.energy = p.energy * albedo;
+    // iter_final_mono.f90:334: killed without being counted
+    if ((M.kill_on_scatter && scattered) || p.energy < p.energy0 * M.mono_threshold) return 1;
+    return 0;
+  }
   if ((M.kill_on_scatter && scattered) || (M.kill_on_absorb && !scattered)) return 1;
   return 0;
 }
@@ -1846,6 +1916,14 @@ struct hyp_ctx {
   std::vector<void *> filter_tables; // device copies of the filter curves
   bool images_ready = false, ray_ready = false;
   int64_t peel_launches = 0;
+  // monochromatic mode (hyp_set_monochromatic)
+  std::vector<double> frequencies;
+  double mono_threshold = 1.e-10;
+  bool mono_run = false;                      // the cubes of this final iteration were filled by hyp_final_mono_photons
+  double *d_mono_src_w = nullptr, *d_mono_spot_w = nullptr, *d_mono_cdf = nullptr;
+  double *d_mono_logp[MAX_DUST] = {nullptr, nullptr, nullptr, nullptr};
+  void *d_scan_tmp = nullptr;
+  size_t scan_tmp_bytes = 0;
 };
 
 namespace {
@@ -1977,18 +2055,19 @@ int ensure_pool(hyp_ctx *c, uint32_t cap) {
 }
 
 // Emission order of window `w` of a launch: sort the packets of the window by direction key.
-int prepare_window(hyp_ctx *c, int64_t first_id, int64_t n_photons, int64_t iteration, int64_t w) {
+int prepare_window(hyp_ctx *c, int64_t first_id, int64_t n_photons, int64_t iteration, int64_t w,
+                   const ModelDev *Mo = nullptr, const int force_mode = -1) {
   const int64_t win = c->sort_window;
   const int64_t count = std::min<int64_t>(win, n_photons - w * win);
   if (count <= 0) return HYP_OK;
   // HYPERION_B200_SORT: 0 emission in id order, 1 sorted by direction, 2 by direction bin and path length
   const char *e = getenv("HYPERION_B200_SORT");
-  const int mode = e ? atoi(e) : HYP_DEFAULT_SORT;
+  const int mode = force_mode >= 0 ? force_mode : e ? atoi(e) : HYP_DEFAULT_SORT;
   const bool sorted = mode != 0;
   uint32_t *dst = c->d_perm + (w & 1) * win;
   auto keys = c->M.n_dust == 1 ? emit_keys_kernel<1> : c->M.n_dust == 2 ? emit_keys_kernel<2>
               : c->M.n_dust == 3 ? emit_keys_kernel<3> : emit_keys_kernel<4>;
-  keys<<<c->sm_count * 8, 256, 0, c->stream>>>(c->M, (unsigned long long)(first_id + w * win), (uint32_t)count,
+  keys<<<c->sm_count * 8, 256, 0, c->stream>>>(Mo ? *Mo : c->M, (unsigned long long)(first_id + w * win), (uint32_t)count,
                                                (uint32_t)iteration, c->d_keys_in, sorted ? c->d_vals_in : dst, mode);
   CUDA_TRY(cudaGetLastError());
   c->launches_acc += 1;
@@ -3630,6 +3709,7 @@ int ensure_images(hyp_ctx *c) {
     d.track_origin = k.track_origin; d.track_n_scat = k.track_n_scat;
     d.uncertainties = k.uncertainties; d.ignore_optical_depth = k.ignore_optical_depth;
     d.inside_observer = k.inside_observer;
+    d.inu_min = k.inu_min > 0 ? k.inu_min : 0;
     d.use_filters = k.use_filters;
     if (k.use_filters) {
       int32_t *d_off = nullptr;
@@ -3708,6 +3788,39 @@ int ensure_ray_tables(hyp_ctx *c) {
     const double l0 = d.log10_nu_min, l1 = d.log10_nu_max;
     std::vector<double> spec((size_t)ns * n_nu), chi((size_t)nd * n_nu);
     std::vector<double> bnu, bfnu;
+    if (d.inu_min > 0) {
+      // exact frequencies: get_spectrum_interp (source_type.f90:1098-1116), get_j_nu_interp / get_chi_nu_interp
+      // (dust_type_4elem.f90:708-720,780-791)
+      const double *nu = c->frequencies.data() + (d.inu_min - 1);
+      for (int is = 0; is < ns; ++is) {
+        const int sp = c->source_spectrum[is];
+        if (c->sources[is].spectrum_type == HYP_SPECTRUM_LTE) continue;
+        for (int i = 0; i < n_nu; ++i)
+          spec[(size_t)is * n_nu + i] = sp >= 0 ? pdf_loglog_at(c->spectra[sp].nu.data(), c->spectra[sp].fnu.data(),
+                                                                 (int)c->spectra[sp].nu.size(), nu[i])
+                                                : normalized_B_nu(nu[i], c->sources[is].temperature);
+      }
+      int rc = upload(spec, &d.src_spec);
+      if (rc) return rc;
+      for (int id = 0; id < nd; ++id) {
+        const HostDust &D = c->dust[id];
+        for (int i = 0; i < n_nu; ++i)
+          chi[(size_t)id * n_nu + i] = interp_loglog_fill0(D.nu.data(), D.chi.data(), (int)D.nu.size(), nu[i]);
+        const int ne = (int)D.emiss_nu.size();
+        std::vector<double> logj((size_t)D.n_jnu * n_nu), col(ne);
+        for (int st = 0; st < D.n_jnu; ++st) {
+          for (int k = 0; k < ne; ++k) col[k] = D.emiss_jnu[(size_t)k * D.n_jnu + st];
+          const double tot = detail::integral_loglog_all(D.emiss_nu.data(), col.data(), ne);
+          for (int i = 0; i < n_nu; ++i)
+            logj[(size_t)st * n_nu + i] = std::log10(interp_loglog_fill0(D.emiss_nu.data(), col.data(), ne, nu[i]) / tot);
+        }
+        rc = upload(logj, &d.dust_logj[id]);
+        if (rc) return rc;
+      }
+      rc = upload(chi, &d.dust_chi);
+      if (rc) return rc;
+      continue;
+    }
     for (int is = 0; is < ns; ++is) {
       const int sp = c->source_spectrum[is];
       if (sp >= 0) {
@@ -3840,7 +3953,8 @@ ModelDev imaging_model(hyp_ctx *c) {
 
 // rounds of the packet pool for the imaging iteration (propagate, iter_final.f90:147-273)
 template <int ND>
-int run_final_rounds(hyp_ctx *c, int64_t first_id, int64_t n_photons, int scattering_only) {
+int run_final_rounds(hyp_ctx *c, int64_t first_id, int64_t n_photons, int scattering_only, const ModelDev *Mo = nullptr,
+                     const uint32_t iteration = ITER_FINAL, const int thermal = 0) {
   const uint32_t cap = (uint32_t)std::min<int64_t>(pool_target(), n_photons);
   int rc = ensure_pool(c, cap);
   if (rc) return rc;
@@ -3856,8 +3970,9 @@ int run_final_rounds(hyp_ctx *c, int64_t first_id, int64_t n_photons, int scatte
   const int flight_blocks_max = per_sm * c->sm_count;
   const int service_blocks_max = c->sm_count * 8;
   cudaStream_t st = c->stream;
-  const ModelDev M = imaging_model(c);
+  const ModelDev M = Mo ? *Mo : imaging_model(c);
   FinalArgs F;
+  F.thermal = thermal;
   F.jobs = c->d_jobs;
   F.n_jobs = c->d_njobs;
   F.job_capacity = c->job_cap;
@@ -3874,7 +3989,6 @@ int run_final_rounds(hyp_ctx *c, int64_t first_id, int64_t n_photons, int scatte
       F.n_theta = c->groups[ig].conf.n_theta;
       F.n_phi = c->groups[ig].conf.n_phi;
     }
-  const uint32_t iteration = ITER_FINAL;
 
   pool_init_kernel<<<c->sm_count, 256, 0, st>>>(P, cap);
   c->launches_acc += 1;
@@ -3889,7 +4003,7 @@ int run_final_rounds(hyp_ctx *c, int64_t first_id, int64_t n_photons, int scatte
     uint32_t *nF = P.counts + C_NF0 + cur, *nF_next = P.counts + C_NF0 + (1 - cur);
     while (windows_ready * (int64_t)c->sort_window < n_photons &&
            (int64_t)claimed + 2 * (int64_t)cap > windows_ready * (int64_t)c->sort_window) {
-      rc = prepare_window(c, first_id, n_photons, iteration, windows_ready);
+      rc = prepare_window(c, first_id, n_photons, iteration, windows_ready, &M, thermal ? 0 : -1);
       if (rc) return rc;
       ++windows_ready;
     }
@@ -4049,6 +4163,15 @@ int hyp_add_peeled_group(hyp_ctx *c, const hyp_image_conf *g) {
     return fail(HYP_ERR_INVALID, "n_view should be a positive integer");
   }
   if (g->n_wav < 1) return fail(HYP_ERR_INVALID, "n_nu should be >= 1");
+  if (g->inu_min > 0) {
+    // image_setup (image_type.f90:243-258)
+    if (g->use_filters) return fail(HYP_ERR_INVALID, "cannot use filters in monochromatic mode");
+    const int nf = (int)c->frequencies.size();
+    if (nf == 0) return fail(HYP_ERR_STATE, "hyp_set_monochromatic has not been called");
+    if (g->inu_min < 1 || g->inu_min > nf) return fail(HYP_ERR_INVALID, "inu_min value is out of range");
+    if (g->inu_max < 1 || g->inu_max > nf) return fail(HYP_ERR_INVALID, "inu_max value is out of range");
+    if (g->n_wav != g->inu_max - g->inu_min + 1) return fail(HYP_ERR_INVALID, "n_nu should match length of frequencies array");
+  }
   if (g->io_bytes != 4 && g->io_bytes != 8) return fail(HYP_ERR_INVALID, "unexpected value of io_bytes (should be 4 or 8)");
   if (g->track_origin < HYP_TRACK_NO || g->track_origin > HYP_TRACK_SCATTERINGS)
     return fail(HYP_ERR_INVALID, "unknown track_origin flag");
@@ -4073,6 +4196,7 @@ int hyp_add_peeled_group(hyp_ctx *c, const hyp_image_conf *g) {
     h.filt_tr.assign(g->filt_tr, g->filt_tr + h.filt_off.back());
     h.conf.wav_min = h.conf.wav_max = 1.0;   // unused with filters
   }
+  if (g->inu_min > 0) h.conf.wav_min = h.conf.wav_max = 1.0;   // unused at exact frequencies
   h.conf.filt_n = nullptr;
   h.conf.filt_nu = h.conf.filt_tr = h.conf.filt_nu0 = nullptr;
   h.conf.theta = h.conf.phi = nullptr;
@@ -4120,6 +4244,155 @@ int hyp_final_photons(hyp_ctx *c, int64_t first_id, int64_t n_photons, int32_t p
   }
 }
 
+int hyp_set_monochromatic(hyp_ctx *c, int32_t n_nu, const double *frequencies, double energy_threshold) {
+  if (!c) return fail(HYP_ERR_INVALID, "NULL argument");
+  if (n_nu < 1 || !frequencies) return fail(HYP_ERR_INVALID, "monochromatic mode needs at least one frequency");
+  if (!c->groups.empty()) return fail(HYP_ERR_STATE, "hyp_set_monochromatic has to be called before hyp_add_peeled_group");
+  c->frequencies.assign(frequencies, frequencies + n_nu);
+  c->mono_threshold = energy_threshold;
+  return HYP_OK;
+}
+
+}  // extern "C"
+
+namespace {
+
+template <typename T>
+int upload_vec(const std::vector<T> &h, T *&d) {
+  free_dev(d);
+  CUDA_TRY(cudaMalloc(&d, std::max<size_t>(h.size(), 1) * sizeof(T)));
+  CUDA_TRY(cudaMemcpy(d, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+  return HYP_OK;
+}
+
+template <int ND>
+int run_final_mono(hyp_ctx *c, int32_t inu, int64_t first_source_id, int64_t n_sources, int64_t n_total_sources,
+                   int64_t first_dust_id, int64_t n_thermal, int64_t n_total_thermal, int32_t scattering_only) {
+  const double nu = c->frequencies[inu - 1];
+  const int ns = (int)c->sources.size();
+  cudaStream_t st = c->stream;
+  ModelDev M = imaging_model(c);
+  M.mono_nu = nu;
+  M.mono_inu = inu;
+  M.mono_threshold = c->mono_threshold;
+  M.use_mrw = 0;   // propagate of iter_final_mono.f90:231-341 has no random walk
+  int rc;
+  if (n_sources > 0 && ns > 0) {
+    // source_emit with nu given (source_type.f90:436-474) x energy_total (source.f90:161) / n_photons
+    // (iter_final_mono.f90:118)
+    const double wgt = c->energy_total / (double)n_total_sources;
+    std::vector<double> w(ns, 0.0), ws(std::max<size_t>(c->spots.size(), 1), 0.0);
+    for (int is = 0; is < ns; ++is) {
+      const int sp = c->source_spectrum[is];
+      if (c->sources[is].spectrum_type == HYP_SPECTRUM_LTE) continue;
+      const double prob = sp >= 0 ? pdf_loglog_at(c->spectra[sp].nu.data(), c->spectra[sp].fnu.data(),
+                                                  (int)c->spectra[sp].nu.size(), nu)
+                                  : normalized_B_nu(nu, c->sources[is].temperature);
+      w[is] = prob * wgt;
+    }
+    for (size_t k = 0; k < c->spots.size(); ++k) {
+      const SpotDev &q = c->spots[k];
+      if (q.freq_type != HYP_SPECTRUM_BLACKBODY && q.spectrum < 0) continue;   // the star's own entry after a source's spots
+      const double prob = q.freq_type == HYP_SPECTRUM_BLACKBODY
+                              ? normalized_B_nu(nu, q.temperature)
+                              : pdf_loglog_at(c->spectra[q.spectrum].nu.data(), c->spectra[q.spectrum].fnu.data(),
+                                              (int)c->spectra[q.spectrum].nu.size(), nu);
+      ws[k] = prob * wgt;
+    }
+    rc = upload_vec(w, c->d_mono_src_w);
+    if (rc) return rc;
+    rc = upload_vec(ws, c->d_mono_spot_w);
+    if (rc) return rc;
+    M.mono_src_w = c->d_mono_src_w;
+    M.mono_spot_w = c->d_mono_spot_w;
+    M.mono_lte_w = wgt;
+  }
+  // dust_sample_emit_probability's two factors: interpolate_pdf of every emissivity state at nu, as log10
+  for (int id = 0; id < ND; ++id) {
+    const HostDust &D = c->dust[id];
+    const int ne = (int)D.emiss_nu.size();
+    std::vector<double> lp(D.n_jnu), col(ne);
+    for (int s = 0; s < D.n_jnu; ++s) {
+      for (int k = 0; k < ne; ++k) col[k] = D.emiss_jnu[(size_t)k * D.n_jnu + s];
+      lp[s] = std::log10(pdf_loglog_at(D.emiss_nu.data(), col.data(), ne, nu));
+    }
+    rc = upload_vec(lp, c->d_mono_logp[id]);
+    if (rc) return rc;
+    M.mono_logp[id] = c->d_mono_logp[id];
+  }
+  if (n_sources > 0 && ns > 0) {
+    rc = run_final_rounds<ND>(c, first_source_id, n_sources, scattering_only, &M, ITER_MONO + 2u * (uint32_t)inu, 0);
+    if (rc) return rc;
+  }
+  if (n_thermal > 0) {
+    // setup_monochromatic_grid_pdfs (grid_monochromatic.f90:50-118)
+    const size_t nc = (size_t)c->n_cells;
+    if (!c->d_mono_cdf) CUDA_TRY(cudaMalloc(&c->d_mono_cdf, nc * ND * sizeof(double)));
+    CUDA_TRY(cudaMemsetAsync(c->d_mono_cdf, 0, nc * ND * sizeof(double), st));
+    const int32_t *list = c->grid_type == GEO_OCT ? c->d_oct_leaves : c->grid_type == GEO_AMR ? c->d_amr_valid : nullptr;
+    const int64_t n_list = c->grid_type == GEO_OCT ? (int64_t)c->M.oct.n_leaves
+                           : c->grid_type == GEO_AMR ? (int64_t)c->M.amr.n_valid : (int64_t)nc;
+    mono_weights_kernel<<<grid_blocks(c), 256, 0, st>>>(M, list, n_list, c->d_mono_cdf);
+    CUDA_TRY(cudaGetLastError());
+    c->launches_acc += 1;
+    size_t need = 0;
+    CUDA_TRY(cub::DeviceScan::InclusiveSum(nullptr, need, c->d_mono_cdf, c->d_mono_cdf, (int)nc, st));
+    if (need > c->scan_tmp_bytes) {
+      free_dev(c->d_scan_tmp);
+      CUDA_TRY(cudaMalloc(&c->d_scan_tmp, need));
+      c->scan_tmp_bytes = need;
+    }
+    bool any = false;
+    for (int id = 0; id < ND; ++id) {
+      double *cdf = c->d_mono_cdf + (size_t)id * nc;
+      CUDA_TRY(cub::DeviceScan::InclusiveSum(c->d_scan_tmp, need, cdf, cdf, (int)nc, st));
+      double total = 0.0;
+      CUDA_TRY(cudaMemcpyAsync(&total, cdf + nc - 1, sizeof(double), cudaMemcpyDeviceToHost, st));
+      CUDA_TRY(cudaStreamSynchronize(st));
+      M.mono_thermal_w[id] = 0.0;
+      if (total > 0.0) {
+        mono_divide_kernel<<<grid_blocks(c), 256, 0, st>>>(cdf, (int64_t)nc, total);
+        CUDA_TRY(cudaGetLastError());
+        // mean_prob x energy_abs_tot = sum over cells of prob x E rho V; x n_dust / n_photons (iter_final_mono.f90:187)
+        M.mono_thermal_w[id] = total * (double)ND / (double)n_total_thermal;
+        any = true;
+      }
+      c->launches_acc += 2;
+    }
+    M.mono_cdf = c->d_mono_cdf;
+    if (any) {
+      rc = run_final_rounds<ND>(c, first_dust_id, n_thermal, scattering_only, &M, ITER_MONO + 2u * (uint32_t)inu + 1u, 1);
+      if (rc) return rc;
+    }
+  }
+  return HYP_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int hyp_final_mono_photons(hyp_ctx *c, int32_t inu, int64_t first_source_id, int64_t n_sources, int64_t n_total_sources,
+                           int64_t first_dust_id, int64_t n_dust, int64_t n_total_dust, int32_t peeloff_scattering_only) {
+  if (!c || !c->finalized) return fail(HYP_ERR_STATE, "hyp_finalize_setup has not been called");
+  if (!c->images_ready) return fail(HYP_ERR_STATE, "hyp_final_begin has not been called");
+  if (c->frequencies.empty()) return fail(HYP_ERR_STATE, "hyp_set_monochromatic has not been called");
+  if (inu < 1 || inu > (int)c->frequencies.size()) return fail(HYP_ERR_INVALID, "incorrect inu");
+  if (n_sources < 0 || n_dust < 0 || first_source_id < 0 || first_dust_id < 0)
+    return fail(HYP_ERR_INVALID, "negative photon count");
+  if ((n_sources > 0 && n_total_sources < n_sources) || (n_dust > 0 && n_total_dust < n_dust))
+    return fail(HYP_ERR_INVALID, "the job's packet totals are smaller than this call's share");
+  CUDA_TRY(cudaSetDevice(c->device));
+  c->mono_run = true;
+  switch (c->M.n_dust) {
+    case 1: return run_final_mono<1>(c, inu, first_source_id, n_sources, n_total_sources, first_dust_id, n_dust, n_total_dust, peeloff_scattering_only);
+    case 2: return run_final_mono<2>(c, inu, first_source_id, n_sources, n_total_sources, first_dust_id, n_dust, n_total_dust, peeloff_scattering_only);
+    case 3: return run_final_mono<3>(c, inu, first_source_id, n_sources, n_total_sources, first_dust_id, n_dust, n_total_dust, peeloff_scattering_only);
+    case 4: return run_final_mono<4>(c, inu, first_source_id, n_sources, n_total_sources, first_dust_id, n_dust, n_total_dust, peeloff_scattering_only);
+    default: return fail(HYP_ERR_INVALID, "unsupported number of dust types");
+  }
+}
+
 int hyp_image_device_buffers(hyp_ctx *c, void **buffer, int64_t *n_values) {
   if (!c || !c->finalized) return fail(HYP_ERR_STATE, "hyp_finalize_setup has not been called");
   CUDA_TRY(cudaSetDevice(c->device));
@@ -4139,10 +4412,14 @@ int hyp_final_finish(hyp_ctx *c, hyp_iter_stats *st) {
   if (rc) return rc;
   rc = device_error_to_status(c);
   if (rc) return rc;
-  if (!(sc[SC_ENERGY] > 0.0)) return fail(HYP_ERR_STATE, "no photons were emitted in this iteration");
+  // do_final_mono scales every packet itself (iter_final_mono.f90:118,187)
+  const bool mono = c->mono_run;
+  c->mono_run = false;
+  if (!mono && !(sc[SC_ENERGY] > 0.0)) return fail(HYP_ERR_STATE, "no photons were emitted in this iteration");
   // peeled_images_adjust_scale(energy_total / energy_current) (iter_final.f90:140-143)
-  const double scale0 = c->energy_total / sc[SC_ENERGY];
+  const double scale0 = mono ? 1.0 : c->energy_total / sc[SC_ENERGY];
   for (auto &g : c->groups) {
+    if (mono) break;
     // binned_images_adjust_scale multiplies by the number of direction bins as well (images_binned.f90:35-39)
     const double scale = g.conf.binned ? scale0 * (double)g.conf.n_theta * (double)g.conf.n_phi : scale0;
     const size_t ns[2] = {g.n_sed, g.n_img}, os[2] = {g.o_sed, g.o_img};
@@ -4243,10 +4520,18 @@ static int get_cube(hyp_ctx *c, int32_t group, bool sed, double *out, double *un
   CUDA_TRY(cudaStreamSynchronize(c->stream));
   const int n_nu = g.conf.n_wav;
   // with filters the flux stays in F_nu dnu: the filter carries the normalisation (image_type.f90:649-657)
-  const double dnunorm = g.conf.use_filters ? 1.0 : std::pow(g.nu_max / g.nu_min, +0.5 / (double)n_nu) - std::pow(g.nu_max / g.nu_min, -0.5 / (double)n_nu);
-  for (size_t i = 0; i < n; ++i) out[i] = out[i] / dnunorm;
-  if (have_unc)
-    for (size_t i = 0; i < n; ++i) unc[i] = std::sqrt(unc[i]) / dnunorm;
+  if (g.conf.inu_min > 0) {
+    // image_type.f90:679-682,737-740: nu F_nu at the exact frequencies
+    const double *nu = c->frequencies.data() + (g.conf.inu_min - 1);
+    for (size_t i = 0; i < n; ++i) out[i] = out[i] * nu[i % (size_t)n_nu];
+    if (have_unc)
+      for (size_t i = 0; i < n; ++i) unc[i] = std::sqrt(unc[i]) * nu[i % (size_t)n_nu];
+  } else {
+    const double dnunorm = g.conf.use_filters ? 1.0 : std::pow(g.nu_max / g.nu_min, +0.5 / (double)n_nu) - std::pow(g.nu_max / g.nu_min, -0.5 / (double)n_nu);
+    for (size_t i = 0; i < n; ++i) out[i] = out[i] / dnunorm;
+    if (have_unc)
+      for (size_t i = 0; i < n; ++i) unc[i] = std::sqrt(unc[i]) / dnunorm;
+  }
   if (sed) {
     const size_t n_ap = g.conf.n_ap, outer = n / ((size_t)n_nu * n_ap);
     for (size_t o = 0; o < outer; ++o)

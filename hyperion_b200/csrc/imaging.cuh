@@ -24,7 +24,8 @@ struct ImageDev {
   int32_t n_view, n_nu, n_x, n_y, n_ap, n_orig, n_stokes;
   int32_t compute_image, compute_sed, track_origin, track_n_scat, uncertainties, ignore_optical_depth;
   int32_t n_sources, n_dust;
-  int32_t inside_observer, pad0;  // the observer sits at (rpx, rpy, rpz) inside the grid (images_peeled.f90:95-270)
+  int32_t inside_observer;  // the observer sits at (rpx, rpy, rpz) inside the grid (images_peeled.f90:95-270)
+  int32_t inu_min;          // monochromatic mode (image_type.f90:243-258): channel k is frequency inu_min + k; 0 otherwise
   double x_min, x_max, y_min, y_max, ap_min, ap_max;
   double log10_ap_min, log10_ap_max, log10_nu_min, log10_nu_max;
   double d_min, d_max;
@@ -382,7 +383,7 @@ __device__ __forceinline__ void peel_inside(const PeelJob<ND> &J, const ImageDev
 // image_bin / image_bin_raytraced (image_type.f90:408-606) for one finished ray
 template <int ND, bool POLY>
 __device__ inline void peel_bin(const PeelJob<ND> &J, const ImageDev &im, const ViewDev &V, const Stokes &S, const double tau,
-                                const double (&col)[ND]) {
+                                const double (&col)[ND], const int mono_inu) {
   if (isnan(J.energy) || isnan(S.I)) return;
   double x_image, y_image;
   if (im.inside_observer) {
@@ -440,7 +441,10 @@ __device__ inline void peel_bin(const PeelJob<ND> &J, const ImageDev &im, const 
     const double e = exp(-tau);
     const double st[4] = {S.I * e, S.Q * e, S.U * e, S.V * e};
     // without filters one channel, with filters every channel that transmits at this frequency
-    const int inu0 = im.use_filters ? 1 : ipos_bin(im.log10_nu_min, im.log10_nu_max, log10(J.nu), im.n_nu);
+    // exact frequencies: the channel of the run's frequency (image_type.f90:435-436)
+    const int inu0 = im.use_filters ? 1
+                     : im.inu_min > 0 ? mono_inu - im.inu_min + 1
+                                      : ipos_bin(im.log10_nu_min, im.log10_nu_max, log10(J.nu), im.n_nu);
     const int inu1 = im.use_filters ? im.n_nu : inu0;
     for (int inu = inu0; inu <= inu1; ++inu) {
       if (inu < 1 || inu > im.n_nu) return;
@@ -542,7 +546,7 @@ peel_kernel(const ModelDev M, const ImagingDev I, const PeelJob<ND> *__restrict_
               }
               n_cached += (unsigned long long)nc;
               ++n_peel;
-              peel_bin<ND, POLY>(J, im, V, Stokes{1.0, 0.0, 0.0, 0.0}, tau, col);
+              peel_bin<ND, POLY>(J, im, V, Stokes{1.0, 0.0, 0.0, 0.0}, tau, col, M.mono_inu);
             }
             ok = false;
           }
@@ -589,7 +593,7 @@ peel_kernel(const ModelDev M, const ImagingDev I, const PeelJob<ND> *__restrict_
         active = false;
         if (done > 0) {
           ++n_peel;
-          peel_bin<ND, POLY>(J, im, V, S, tau, col);
+          peel_bin<ND, POLY>(J, im, V, S, tau, col, M.mono_inu);
         } else {
           ++n_killed;  // no wall found: the reference counts the packet as killed and drops the peel-off
         }
@@ -663,6 +667,8 @@ struct FinalArgs {
   // binned images (images_binned.f90): the group escaping packets are binned into, or nullptr
   const ImageDev *binned;
   int32_t n_theta, n_phi;
+  // monochromatic mode: thermal = the packets of this call come from emit_from_monochromatic_grid_pdf
+  int32_t thermal;
 };
 
 constexpr uint32_t TAG_NSCAT_MASK = 0x3ffu;    // n_scat saturates at 1023
@@ -670,7 +676,8 @@ constexpr uint32_t TAG_NSCAT_MASK = 0x3ffu;    // n_scat saturates at 1023
 // binned_images_bin_photon (images_binned.f90:57-77) + image_bin (image_type.f90:408-524) for a packet
 // that has just left the grid at path length t along its flight.
 template <int ND>
-__device__ inline void bin_escaped_packet(const FinalArgs &F, const Slot<ND> *__restrict__ s, const double t) {
+__device__ inline void bin_escaped_packet(const FinalArgs &F, const Slot<ND> *__restrict__ s, const double t,
+                                          const int mono_inu) {
   const ImageDev &im = *F.binned;
   const double energy = s->energy;
   if (isnan(energy)) return;
@@ -685,7 +692,9 @@ __device__ inline void bin_escaped_packet(const FinalArgs &F, const Slot<ND> *__
   const int iv = F.n_phi * (it - 1) + ip - 1;  // image_id, 0-based
   const double x_image = ry * a.cosp - rx * a.sinp;
   const double y_image = rz * a.sint - ry * a.cost * a.sinp - rx * a.cost * a.cosp;
-  const int inu0 = im.use_filters ? 1 : ipos_bin(im.log10_nu_min, im.log10_nu_max, log10(s->nu), im.n_nu);
+  const int inu0 = im.use_filters ? 1
+                   : im.inu_min > 0 ? mono_inu - im.inu_min + 1
+                                    : ipos_bin(im.log10_nu_min, im.log10_nu_max, log10(s->nu), im.n_nu);
   const int inu1 = im.use_filters ? im.n_nu : inu0;
   if (inu0 < 1 || inu0 > im.n_nu) return;
   const uint32_t tag = s->tag;
@@ -766,6 +775,30 @@ __device__ __forceinline__ int surface_kind(const Photon<ND> &p) {
   return (p.nx != 0.0 || p.ny != 0.0 || p.nz != 0.0) ? 2 : 0;
 }
 
+// emit_from_monochromatic_grid_pdf (grid_monochromatic.f90:120-174): dust type uniformly, cell from the cumulative
+// emission probability x energy of that type, uniform position in the cell, isotropic direction; every packet of
+// a type carries the same energy (mean_prob x energy_abs_tot / n_photons x n_dust, iter_final_mono.f90:187).
+// Returns false for a type that does not emit at this frequency (the packet counts as run).
+template <int ND>
+__device__ bool emit_mono_thermal(const ModelDev &M, Photon<ND> &p, Rng &rng) {
+  p.nu = M.mono_nu;
+  const int id = max((int)ceil(rng.next() * (double)ND), 1) - 1;
+  double w = 0.0;
+#pragma unroll
+  for (int k = 0; k < ND; ++k)
+    if (k == id) w = M.mono_thermal_w[k];
+  if (!(w > 0.0)) return false;
+  const int64_t ic = sample_discrete(M.mono_cdf + (size_t)id * M.n_cells, M.n_cells, rng.next());
+  random_position_cell(M, ic, rng, p.r0x, p.r0y, p.r0z);
+  const Angle a = random_sphere_angle(rng);
+  set_dir(p, a);
+  p.nx = p.ny = p.nz = 0.0;
+  p.sQ = p.sU = p.sV = 0.0;
+  p.energy = p.energy0 = w;
+  p.tag = TAG_REPROCESSED | ((uint32_t)id << TAG_DUST_SHIFT);
+  return place_emitted<ND>(M, p);
+}
+
 // emit + the peel-off of the fresh packet (iter_final.f90:113-123)
 template <int ND>
 __global__ void __launch_bounds__(SERVICE_THREADS)
@@ -796,12 +829,16 @@ emit_final_kernel(const ModelDev M, Pool P, const FinalArgs F, const unsigned lo
       id = first_id + (k & ~(unsigned long long)(P.window - 1)) + P.perm[k & (2ull * P.window - 1)];
       rng.init(M.seed, id, iteration);
       ++n_run;
-      go = emit_photon<ND>(M, p, rng, energy_emitted);
+      go = F.thermal ? emit_mono_thermal<ND>(M, p, rng) : emit_photon<ND>(M, p, rng, energy_emitted);
     }
     PeelJob<ND> *J = job_append<ND>(go && F.make_peeled && !F.scattering_only, F);
     if (J) {
-      fill_job<ND>(J, p, surface_kind(p), p.nx, p.ny, p.nz, 0.0, 0.0, 0.0, 0);
-      if (J->kind == 0 && M.sources[J->source_id - 1].type == HYP_SOURCE_POINT) J->point_src = J->source_id;
+      if (F.thermal) {
+        fill_job<ND>(J, p, 0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, (int)(p.tag >> TAG_DUST_SHIFT) + 1);
+      } else {
+        fill_job<ND>(J, p, surface_kind(p), p.nx, p.ny, p.nz, 0.0, 0.0, 0.0, 0);
+        if (J->kind == 0 && M.sources[J->source_id - 1].type == HYP_SOURCE_POINT) J->point_src = J->source_id;
+      }
     }
     if (go) {
       // with a forced first interaction the optical depth is drawn by the flight kernel once the
@@ -848,7 +885,7 @@ interact_final_kernel(const ModelDev M, Pool P, const FinalArgs F, uint32_t *__r
           reemitted = true;
           peel = F.make_peeled != 0;
         }
-      } else if (interact_photon<ND>(M, p, rng, n_abs, n_scat, n_kill, dust_id, scattered) == 0) {
+      } else if (interact_photon<ND>(M, p, rng, n_abs, n_scat, n_kill, dust_id, scattered, M.mono_nu > 0.0) == 0) {
         alive = true;
         if (scattered) {
           uint32_t ns = (p.tag >> TAG_NSCAT_SHIFT) & TAG_NSCAT_MASK;
@@ -1001,7 +1038,7 @@ flight_final_kernel(const ModelDev M, Pool P, const FinalArgs F, const uint32_t 
       }
     }
     if (fin == 2) store_flight_result<ND>(slots + slot, L);
-    if (fin == 1 && F.binned) bin_escaped_packet<ND>(F, slots + slot, L.t);   // iter_final.f90:126-129
+    if (fin == 1 && F.binned) bin_escaped_packet<ND>(F, slots + slot, L.t, M.mono_inu);   // iter_final.f90:126-129
     queue_append(fin == 2, P.q_interact, P.counts + C_NI, slot);
     queue_append(fin == 1, P.q_emit, P.counts + C_NE, slot);
     if (fin) {
@@ -1034,6 +1071,29 @@ __global__ void energy_abs_tot_kernel(const ModelDev M, double *__restrict__ out
   for (int d = 0; d < MAX_DUST; ++d) warp_add_scalar(out + d, acc[d]);
 }
 
+// setup_monochromatic_grid_pdfs (grid_monochromatic.f90:50-118): emission probability at the run's frequency x
+// energy of every cell that holds physical quantities, per dust type; w is [n_dust][n_cells], zeroed by the caller.
+// list = the cells of geo%mask_map (octree leaves, valid AMR cells) or nullptr for all cells.
+__global__ void mono_weights_kernel(const ModelDev M, const int32_t *__restrict__ list, const int64_t n_list,
+                                    double *__restrict__ w) {
+  const int nd = M.n_dust;
+  for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < n_list; k += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t ic = list ? (int64_t)list[k] : k;
+    const double vol = cell_volume(M, ic);
+    for (int id = 0; id < nd; ++id) {
+      const size_t q = (size_t)ic * nd + id;
+      const double e = M.specific_energy[q] * M.cells[q].rho * vol;
+      w[(size_t)id * M.n_cells + ic] = e > 0.0 ? mono_emit_probability(M, id, M.jnu_id[q], M.jnu_frac[q]) * e : 0.0;
+    }
+  }
+}
+
+__global__ void mono_divide_kernel(double *__restrict__ cdf, const int64_t n, const double total) {
+  for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x)
+    cdf[k] = cdf[k] / total;
+}
+
+constexpr uint32_t ITER_MONO = 0x7f000000u;   // + 2 * inu (+ 1 for the thermal packets)
 constexpr uint32_t ITER_FINAL = 0x7fffff00u, ITER_RAY_SOURCE = 0x7fffff01u, ITER_RAY_DUST = 0x7fffff02u;
 
 // jobs [0, n_src) come from the sources, jobs [n_src, n_src + n_thermal) from random cells

@@ -376,6 +376,29 @@ inline void blackbody_table(double T, std::vector<double> &nu, std::vector<doubl
   }
 }
 
+// normalized_B_nu (source_type.f90:1088-1096) at one frequency
+inline double normalized_B_nu(double nu, double T) {
+  const double h_cgs = 6.6260689633e-27, c_cgs = 2.99792458e10, k_cgs = 1.380650424e-16, stef_boltz = 5.670400e-5;
+  const double pi = 3.14159265358979323846264338327950288419;
+  const double a = 2.0 * h_cgs / c_cgs / c_cgs / stef_boltz * pi, b = h_cgs / k_cgs;
+  const double T4 = T * T * T * T;
+  return a * nu * nu * nu / (std::exp(b * nu / T) - 1.0) / T4;
+}
+
+// interp1d_loglog(x, y, xval, bounds_error=.false., fill_value=0) (lib_array.f90:588-614): the piecewise power
+// law through an ascending table, zero outside it and where either node is zero
+inline double interp_loglog_fill0(const double *x, const double *y, int n, double xv) {
+  if (!(xv >= x[0] && xv <= x[n - 1])) return 0.0;
+  if (xv == x[n - 1]) return y[n - 1];
+  if (xv == x[0]) return y[0];
+  return detail::powerlaw_at(x, y, detail::interval_of(x, n, xv), xv);
+}
+
+// interpolate_pdf (type_pdf.f90:402-420) of a log-log PDF: the table normalised to unit integral, at xv
+inline double pdf_loglog_at(const double *x, const double *y, int n, double xv) {
+  return interp_loglog_fill0(x, y, n, xv) / detail::integral_loglog_all(x, y, n);
+}
+
 // mean extinction in each bin
 inline void binned_chi(const double *nu, const double *chi, int n, double l0, double l1, int n_nu, double *out) {
   for (int i = 0; i < n_nu; ++i) {
