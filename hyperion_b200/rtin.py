@@ -56,6 +56,8 @@ class RunSettings:
     n_initial_iter: int = 0
     n_initial_photons: int = 0
     n_last_photons: int = 0
+    n_last_photons_sources: int = 0     # monochromatic mode: per frequency (setup_rt.f90:178,241)
+    n_last_photons_dust: int = 0
     n_ray_photons_sources: int = 0
     n_ray_photons_dust: int = 0
     n_stats: int = 0
@@ -132,6 +134,11 @@ def read_rtin(filename):
         if rs.n_initial_photons == 0:
             raise ModelError("Number of initial iterations is non-zero, but number of specific_energy photons is zero")
     rs.n_last_photons = int(float(_num(_attr(A, "n_last_photons", 0))))
+    if rs.monochromatic:
+        # setup_rt.f90:49-56,178,241: the imaging iteration runs n_last_photons_sources / _dust packets per frequency
+        rs.n_last_photons = 0
+        rs.n_last_photons_sources = int(float(_num(_attr(A, "n_last_photons_sources", 0))))
+        rs.n_last_photons_dust = int(float(_num(_attr(A, "n_last_photons_dust", 0))))
     if rs.raytracing:
         rs.n_ray_photons_sources = int(float(_num(_attr(A, "n_ray_photons_sources", 0))))
         rs.n_ray_photons_dust = int(float(_num(_attr(A, "n_ray_photons_dust", 0))))
@@ -377,6 +384,13 @@ def read_rtin(filename):
     conf.baes16_xi = rs.baes16_xi
     if sources and not rs.monochromatic and rs.n_last_photons == 0 and "n_last_photons" not in A:
         raise ModelError("attribute n_last_photons is missing from the input file")
+    if rs.monochromatic:
+        if sources and "n_last_photons_sources" not in A:
+            raise ModelError("attribute n_last_photons_sources is missing from the input file")
+        if dust and "n_last_photons_dust" not in A:
+            raise ModelError("attribute n_last_photons_dust is missing from the input file")
+        if not sources:
+            rs.n_last_photons_sources = 0
     if not sources and rs.n_last_photons > 0:
         raise ModelError("no sources set up - need sources for last iteration")
 
@@ -389,6 +403,7 @@ def read_rtin(filename):
         rs.n_initial_iter = 0
         rs.n_initial_photons = 0
         rs.n_ray_photons_dust = 0
+        rs.n_last_photons_dust = 0
         rs.check_convergence = False
         conf.n_initial_iter = 0
         conf.n_initial_photons = 0
@@ -400,7 +415,13 @@ def read_rtin(filename):
     model = FlatModel(w1, w2, w3, density, dust, sources, conf, specific_energy=se, minimum_specific_energy=min_e,
                       grid_type=grid_type, **(octree or {}))
     model.no_dust = no_dust
-    model.peeled = read_peeled_groups(f)
+    if rs.monochromatic:
+        # setup_rt.f90:220-222, hyperion/model/model.py:133-137
+        if "frequencies" not in f:
+            raise ModelError("frequencies should be given if use_exact_nu is .true.")
+        model.frequencies = np.asarray(f["frequencies"][...]["nu"], dtype=np.float64)
+        model.monochromatic_energy_threshold = float(_num(_attr(A, "monochromatic_energy_threshold", 1.e-10)))
+    model.peeled = read_peeled_groups(f, rs.monochromatic)
     if "Output" in f and "Binned" in f["Output"] and len(f["Output"]["Binned"].keys()) > 0:
         # setup_final_iteration (src/main/setup_rt.f90:314-331)
         names = sorted(f["Output"]["Binned"].keys())
@@ -409,20 +430,28 @@ def read_rtin(filename):
         if rs.forced_first_interaction:
             raise ModelError("can't use binned images with forced first interaction")
         g = f["Output"]["Binned"][names[0]]
-        kw = _image_conf(g)
+        kw = _image_conf(g, rs.monochromatic)
         kw.update(binned=True, n_theta=int(_num(_attr(g.attrs, "n_theta", required=True))),
                   n_phi=int(_num(_attr(g.attrs, "n_phi", required=True))))
         model.binned = FlatPeeledGroup(**kw)
     return model, rs, f
 
 
-def _image_conf(g):
+def _image_conf(g, monochromatic=False):
     """The part of an image group every kind shares (``image_setup``, ``src/images/image_type.f90:153-335``)."""
     a = g.attrs
     kw = {}
-    if "inu_min" in a:
-        raise ModelError("the monochromatic final iteration is not implemented by this engine yet")
-    if "use_filters" in a and _yes(a["use_filters"]):
+    if monochromatic and "use_filters" in a and _yes(a["use_filters"]):
+        raise ModelError("cannot use filters in monochromatic mode")
+    if monochromatic:
+        # image_setup (image_type.f90:243-258): the channels are the frequencies inu_min .. inu_max of /frequencies
+        n_wav = int(_num(_attr(a, "n_wav", required=True)))
+        if n_wav < 1:
+            raise ModelError("n_nu should be >= 1")
+        kw["wavelengths"] = (n_wav, 1.0, 1.0)
+        kw["inu_min"] = int(_num(_attr(a, "inu_min", required=True)))
+        kw["inu_max"] = int(_num(_attr(a, "inu_max", required=True)))
+    elif "use_filters" in a and _yes(a["use_filters"]):
         # image_setup (image_type.f90:174-183, 274-284): n_filt tables filter_%05i(nu, tn) with attribute nu0
         n_filt = int(_num(_attr(a, "n_filt", required=True)))
         if n_filt < 1:
@@ -457,7 +486,7 @@ def _image_conf(g):
     return kw
 
 
-def read_peeled_groups(f):
+def read_peeled_groups(f, monochromatic=False):
     """``setup_final_iteration`` / ``peeled_images_setup`` / ``image_setup``
     (``src/main/setup_rt.f90:306-347``, ``src/images/images_peeled.f90:272-382``,
     ``src/images/image_type.f90:153-335``): one FlatPeeledGroup per ``Output/Peeled/group_%05i``."""
@@ -479,6 +508,6 @@ def read_peeled_groups(f):
                   peeloff_origin=tuple(float(_num(_attr(a, k, required=True))) for k in ("peeloff_x", "peeloff_y", "peeloff_z")))
         if len(kw["theta"]) != n_view:
             raise ModelError("n_view does not match the length of the angles table")
-        kw.update(_image_conf(g))
+        kw.update(_image_conf(g, monochromatic))
         groups.append(FlatPeeledGroup(**kw))
     return groups

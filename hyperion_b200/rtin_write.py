@@ -83,7 +83,11 @@ def write_peeled_group(g, p):
     if p.sed is not None:
         a["n_ap"] = np.int64(p.sed[0])
         a["ap_min"], a["ap_max"] = float(p.sed[1]), float(p.sed[2])
-    if p.filters:
+    if p.inu_min > 0:
+        # _write_wavelength_index_range (hyperion/conf/conf_files.py:1076-1079)
+        a["n_wav"] = np.int64(p.inu_max - p.inu_min + 1)
+        a["inu_min"], a["inu_max"] = np.int64(p.inu_min), np.int64(p.inu_max)
+    elif p.filters:
         # _write_filters (hyperion/conf/conf_files.py:874-881) + Filter.to_hdf5_group (hyperion/filter/filter.py:90-126)
         a["use_filters"] = b"yes"
         a["n_filt"] = np.int64(len(p.filters))
@@ -105,12 +109,19 @@ def write_peeled_group(g, p):
 
 def write_rtin(filename, model: FlatModel, n_initial_iter=5, n_initial_photons=10000, n_last_photons=0,
                output_specific_energy="last", copy_input=True, check_convergence=None, physics_io_bytes=8,
-               raytracing=False, n_ray_photons=(0, 0), extra_root_attrs=None):
+               raytracing=False, n_ray_photons=(0, 0), extra_root_attrs=None, n_last_photons_mono=(0, 0)):
     f = h5write.File()
     c = model.conf
     A = f.attrs
     A["python_version"] = "0.9.12"
-    A["monochromatic"] = b"no"
+    mono = model.frequencies is not None
+    A["monochromatic"] = _yn(mono)
+    if mono:
+        # Model._write_monochromatic (hyperion/model/model.py:133-137), RunConf n_photons (conf_files.py:260-268)
+        f.create_dataset("frequencies", _table([("nu", np.asarray(model.frequencies, dtype=np.float64))]))
+        A["monochromatic_energy_threshold"] = float(model.monochromatic_energy_threshold)
+        A["n_last_photons_sources"] = float(n_last_photons_mono[0])
+        A["n_last_photons_dust"] = float(n_last_photons_mono[1])
     A["raytracing"] = _yn(raytracing)
     A["n_stats"] = np.int64(0)
     A["n_inter_max"] = np.int64(c.n_inter_max)
@@ -131,7 +142,8 @@ def write_rtin(filename, model: FlatModel, n_initial_iter=5, n_initial_photons=1
     A["seed"] = np.int32(c.seed)
     A["n_initial_iter"] = np.int64(n_initial_iter)
     A["n_initial_photons"] = float(n_initial_photons)     # the front end stores what the user passed
-    A["n_last_photons"] = float(n_last_photons)
+    if not mono:
+        A["n_last_photons"] = float(n_last_photons)
     if raytracing:
         A["n_ray_photons_sources"] = float(n_ray_photons[0])
         A["n_ray_photons_dust"] = float(n_ray_photons[1])

@@ -140,7 +140,7 @@ def _copy_tree(src, dst):
             _copy_tree(child, dst.create_group(name))
 
 
-def write_peeled_output(g, eng, ig, p, n_sources, n_dust):
+def write_peeled_output(g, eng, ig, p, n_sources, n_dust, frequencies=None):
     """``image_write`` + ``peeled_images_write`` (``src/images/image_type.f90:608-788``,
     ``src/images/images_peeled.f90:384-408``): datasets ``seds`` / ``images`` (+ ``_unc``) with the
     attributes ``ModelOutput.get_sed`` / ``get_image`` read."""
@@ -148,6 +148,7 @@ def write_peeled_output(g, eng, ig, p, n_sources, n_dust):
     micron = float(np.float32(1.e-4))          # single-precision literal in image_type.f90:262-263
     n_wav, wav_min, wav_max = p.wavelengths
     nu_min, nu_max = c_cgs / (wav_max * micron), c_cgs / (wav_min * micron)
+    exact_nu = p.inu_min > 0
     dt = np.float32 if p.io_bytes == 4 else np.float64
 
     def origin_attrs(d):
@@ -164,7 +165,7 @@ def write_peeled_output(g, eng, ig, p, n_sources, n_dust):
         d = g.create_dataset("seds", val.astype(dt))
         if unc is not None:
             g.create_dataset("seds_unc", unc.astype(dt))
-        if not p.filters:
+        if not p.filters and not exact_nu:
             d.attrs["numin"], d.attrs["numax"] = float(nu_min), float(nu_max)
         d.attrs["apmin"], d.attrs["apmax"] = float(p.sed[1]), float(p.sed[2])
         origin_attrs(d)
@@ -174,7 +175,7 @@ def write_peeled_output(g, eng, ig, p, n_sources, n_dust):
         d = g.create_dataset("images", val.astype(dt))
         if unc is not None:
             g.create_dataset("images_unc", unc.astype(dt))
-        if not p.filters:
+        if not p.filters and not exact_nu:
             d.attrs["numin"], d.attrs["numax"] = float(nu_min), float(nu_max)
         d.attrs["xmin"], d.attrs["xmax"] = float(p.image[2]), float(p.image[3])
         d.attrs["ymin"], d.attrs["ymax"] = float(p.image[4]), float(p.image[5])
@@ -184,6 +185,10 @@ def write_peeled_output(g, eng, ig, p, n_sources, n_dust):
         g.attrs["use_filters"] = "yes"
         g.attrs["n_filt"] = np.int32(len(p.filters))
         g.create_dataset("filt_nu0", np.array([f[2] for f in p.filters], dtype=np.float64))
+    if exact_nu:
+        # image_type.f90:781-784
+        from .rtin_write import _table
+        g.create_dataset("frequencies", _table([("nu", np.asarray(frequencies[p.inu_min - 1:p.inu_max], dtype=np.float64))]))
     if p.binned:
         return          # binned_images_write (images_binned.f90:85-89) writes the cubes only
     g.attrs["inside_observer"] = "yes" if p.inside_observer else "no"
@@ -286,8 +291,8 @@ def run(input_file, output_file, overwrite=False, device=None, log=None):
                 raise ModelError("File exists: %s (use -f to overwrite)" % output_file)
             os.remove(output_file)
         model, rs, fin = read_rtin(input_file)
-        if rs.monochromatic:
-            raise ModelError("the monochromatic final iteration is not implemented by this engine yet")
+        if rs.monochromatic and model.binned is not None:
+            raise ModelError("Binned images cannot be computed in monochromatic mode")   # hyperion/model/model.py:115
         if rs.pda:
             raise ModelError("the partial diffusion approximation is not implemented by this engine yet")
         if rs.specific_energy_type == "additional":
@@ -397,6 +402,23 @@ def run(input_file, output_file, overwrite=False, device=None, log=None):
         log(" [binned_images] setting up %d binned images " % (model.binned.n_theta * model.binned.n_phi))
     if make_peeled:
         log(" [peeled_images] setting up %d peeled image groups " % len(model.peeled))
+    mono_counts = (0, 0)
+    if rs.monochromatic:
+        # do_final_mono (iter_final_mono.f90:58-229): n_last_photons_sources source packets and n_last_photons_dust
+        # thermal packets PER FREQUENCY, every packet already scaled, so the cubes of the ranks simply add up
+        mono_counts = (rs.n_last_photons_sources if model.sources else 0, rs.n_last_photons_dust)
+    if sum(mono_counts) > 0:
+        fs, cs = shard(mono_counts[0], rank, world)
+        fd, cd = shard(mono_counts[1], rank, world)
+        ranks.guarded(eng.final_begin)
+        for inu, nu in enumerate(model.frequencies, start=1):
+            if mono_counts[0] > 0:
+                log(" [mono] computing source photons for nu =%11.4E Hz" % nu)
+            if mono_counts[1] > 0:
+                log(" [mono] computing dust photons for nu =%11.4E Hz" % nu)
+            ranks.guarded(eng.final_mono_photons, inu, fs, cs, mono_counts[0], fd, cd, mono_counts[1], rs.raytracing)
+        st = ranks.guarded(eng.final_finish)
+        killed_final = tuple(ranks.sum_ints((st.killed_geo, st.killed_int)))
     if rs.n_last_photons > 0:
         first, count = shard(rs.n_last_photons, rank, world)
         ranks.guarded(eng.final_begin)
@@ -445,7 +467,8 @@ def run(input_file, output_file, overwrite=False, device=None, log=None):
         gp = out.create_group("Peeled")
         for ig, p in enumerate(model.peeled):
             write_peeled_output(gp.create_group("group_%05d" % (ig + 1)), eng, ig, p,
-                                len(model.sources), 0 if getattr(model, "no_dust", False) else len(model.dust))
+                                len(model.sources), 0 if getattr(model, "no_dust", False) else len(model.dust),
+                                model.frequencies)
 
     eng.close()
     out.attrs["cpu_time"] = float(time.time() - t_start)

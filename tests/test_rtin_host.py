@@ -436,3 +436,60 @@ def test_hyperion_mpirun_starts_coordinated_ranks(tmp_path):
     rc = subprocess.call([os.path.join(root, "bin", "hyperion_mpirun"), "-n", "2", sys.executable, "-c",
                           "import os, sys, time; time.sleep(0 if os.environ['RANK'] == '1' else 30); sys.exit(7)"])
     assert rc == 7
+
+
+def _mono_model(golden_car):
+    from helpers import bitlevel_model
+    from hyperion_b200.flatmodel import FlatPeeledGroup
+    m = bitlevel_model(golden_car, False, False)
+    m.frequencies = 2.99792458e10 / (np.array([0.45, 2.2, 40., 110.]) * 1e-4)
+    m.monochromatic_energy_threshold = 1e-8
+    pc = 3.08568025e18
+    m.peeled = [FlatPeeledGroup(theta=[30., 110.], phi=[40., 250.], sed=(2, 1e-3 * pc, 8. * pc),
+                                image=(4, 4, -2 * pc, 2 * pc, -2 * pc, 2 * pc), track_origin="basic",
+                                inu_min=2, inu_max=4, wavelengths=(3, 1., 1.))]
+    return m
+
+
+def test_rtin_roundtrip_monochromatic(golden_car, tmp_path):
+    """monochromatic = yes: /frequencies, monochromatic_energy_threshold, n_last_photons_sources / _dust
+    (hyperion/model/model.py:133-137, hyperion/conf/conf_files.py:260-268) and inu_min / inu_max of the image groups
+    (conf_files.py:1076-1079)."""
+    m = _mono_model(golden_car)
+    fn = str(tmp_path / "m.rtin")
+    rtin_write.write_rtin(fn, m, n_last_photons_mono=(4000, 6000), raytracing=True, n_ray_photons=(2000, 3000))
+    got, rs, _ = rtin.read_rtin(fn)
+    assert rs.monochromatic and rs.n_last_photons == 0
+    assert (rs.n_last_photons_sources, rs.n_last_photons_dust) == (4000, 6000)
+    assert np.array_equal(got.frequencies, m.frequencies) and got.monochromatic_energy_threshold == 1e-8
+    p = got.peeled[0]
+    assert (p.inu_min, p.inu_max, p.wavelengths[0]) == (2, 4, 3)
+
+
+@pytest.mark.gpu
+def test_runner_monochromatic(golden_car, tmp_path):
+    """main.f90:271-272 -> do_final_mono: the .rtout holds nu F_nu at the exact frequencies, the table
+    /Peeled/group/frequencies and no numin / numax (image_type.f90:700-705,781-784); same cubes as driving the engine
+    directly with the same packet ids."""
+    from hyperion_b200.capi import Engine
+    m = _mono_model(golden_car)
+    fin, fout = str(tmp_path / "m.rtin"), str(tmp_path / "m.rtout")
+    rtin_write.write_rtin(fin, m, n_initial_iter=2, n_initial_photons=20000, n_last_photons_mono=(20000, 30000))
+    assert runner.main(["-f", fin, fout]) == 0
+    r = h5min.File(fout)
+    g = r["Peeled/group_00001"]
+    assert g["seds"].shape == (4, 4, 2, 2, 3) and g["images"].shape == (4, 4, 2, 4, 4, 3)
+    assert "numin" not in g["seds"].attrs and "numin" not in g["images"].attrs
+    assert np.array_equal(np.asarray(g["frequencies"][...]["nu"]), m.frequencies[1:4])
+    sed = g["seds"][...]
+    assert np.all(np.isfinite(sed)) and (sed[0, 0, :, -1, :] > 0).all() and (sed[0, 1, :, -1, 1:] > 0).all()
+    eng = Engine(0)
+    eng.load_model(m)
+    for it in (1, 2):
+        eng.run_lucy_iteration(20000, it)
+    eng.final_begin()
+    for inu in (1, 2, 3, 4):
+        eng.final_mono_photons(inu, 0, 20000, 20000, 0, 30000, 30000)
+    eng.final_finish()
+    assert np.allclose(eng.sed(0), sed, rtol=1e-9, atol=1e-300)
+    eng.close()
