@@ -54,6 +54,10 @@ enum { WC_NITEMS = 0, WC_ITEM_CURSOR, WC_N_FLIGHT, WC_N_INTERACT, WC_INTERACT_ST
 
 struct WaveQ {
   uint32_t *key;         // [capacity] state of every slot
+  uint32_t *key_pos;     // [capacity] the same keys indexed by the slot's POSITION in `sorted`: once emission has
+                         // ended the next sort reads them (and the list itself) as two streams instead of gathering
+                         // key[slot] through the list, one 32-byte sector per 4-byte key
+  int by_slot;           // 1: this round's kernels also write key[slot] (the next sort still covers all slots)
   uint32_t *sorted;      // [capacity] slot ids ordered by key (this round's list; the host alternates two buffers)
   uint32_t *bin_count;   // [n_tiles + 2]
   uint32_t *bin_cursor;  // [n_tiles + 2]
@@ -98,7 +102,8 @@ wave_hist_kernel(WaveQ W, const uint32_t *__restrict__ src, const uint32_t n_src
   for (uint32_t k = threadIdx.x; k < nb; k += blockDim.x) s_cnt[k] = 0;
   __syncthreads();
   const uint32_t lo = blockIdx.x * (uint32_t)WAVE_SORT_SEG, hi = min(lo + (uint32_t)WAVE_SORT_SEG, n_src);
-  for (uint32_t i = lo + threadIdx.x; i < hi; i += blockDim.x) atomicAdd(&s_cnt[min(W.key[src ? src[i] : i], nb - 1u)], 1u);
+  const uint32_t *__restrict__ keys = src ? W.key_pos : W.key;
+  for (uint32_t i = lo + threadIdx.x; i < hi; i += blockDim.x) atomicAdd(&s_cnt[min(keys[i], nb - 1u)], 1u);
   __syncthreads();
   for (uint32_t k = threadIdx.x; k < nb; k += blockDim.x) {
     const uint32_t v = s_cnt[k];
@@ -182,7 +187,7 @@ wave_scatter_kernel(WaveQ W, const uint32_t *__restrict__ src, const uint32_t n_
     key_r[j] = 0xffffffffu;
     if (i < hi) {
       slot_r[j] = src ? src[i] : i;
-      key_r[j] = min(W.key[slot_r[j]], nb - 1u);
+      key_r[j] = min(src ? W.key_pos[i] : W.key[i], nb - 1u);
       rank_r[j] = atomicAdd(&s_cnt[key_r[j]], 1u);
     }
   }
@@ -305,8 +310,10 @@ __device__ __forceinline__ float wave_unit_hash(uint32_t a, uint32_t b, uint32_t
 
 // Shared memory of a block: [densities SUM_OFF bytes][sums SUM_OFF bytes][walls of the tile 3 x TW doubles].
 // SUM_OFF is a compile-time constant so that the sum of a cell is addressed as [cell + immediate].
-template <int ND, int THREADS, int MINB, uint32_t SUM_OFF>
-__global__ void __launch_bounds__(THREADS, MINB)
+// BOUND: the block size the register allocation is made for (1024 -> 64 registers).  Launched with THREADS < BOUND
+// the block leaves registers for the interaction / emission blocks of the round, which then run on the same SMs.
+template <int ND, int THREADS, int MINB, uint32_t SUM_OFF, int BOUND = THREADS>
+__global__ void __launch_bounds__(BOUND, MINB)
 wave_tile_kernel(const ModelDev M, Pool P, const WaveQ W) {
   extern __shared__ __align__(16) unsigned char w_smem[];
   const int TX = W.tx, TY = W.ty, TZ = W.tz;
@@ -315,6 +322,9 @@ wave_tile_kernel(const ModelDev M, Pool P, const WaveQ W) {
   uint32_t *__restrict__ s_sum = (uint32_t *)(w_smem + SUM_OFF);     // [n_h][ND]
   const int TW = max(TX, max(TY, TZ)) + 1;
   double *__restrict__ s_w = (double *)(w_smem + 2 * SUM_OFF);       // [3][TW] walls of the tile
+  // positions in `sorted` of the three packets a lane holds (marching, record requested, id requested)
+  uint32_t *__restrict__ s_pos = (uint32_t *)(s_w + 3 * TW) + threadIdx.x;
+  constexpr int PQ = THREADS;   // stride between the three entries of a lane
   __shared__ uint32_t s_item, s_next;
   __shared__ unsigned long long s_cross, s_esc;   // work counters of the block
   const int n1 = M.n1, n2 = M.n2, n3 = M.n3;
@@ -453,7 +463,8 @@ wave_tile_kernel(const ModelDev M, Pool P, const WaveQ W) {
           Slot<ND> *s = slots + slot;
           __stcs((double2 *)&s->tau_left, make_double2(L.tau, L.t));
           __stcs((int4 *)&s->ix, make_int4(gx, gy, gz, ic));
-          W.key[slot] = nk;
+          W.key_pos[s_pos[0]] = nk;
+          if (W.by_slot) W.key[slot] = nk;
           fin = 3;
         }
         // While the item has plenty of packets left every lane keeps its queue full; towards the end a lane only
@@ -467,6 +478,7 @@ wave_tile_kernel(const ModelDev M, Pool P, const WaveQ W) {
           if (fin == 3 && nslot != NONE) {
             slot = nslot;
             nslot = NONE;
+            s_pos[0] = s_pos[PQ];
             const Slot<ND> *s = slots + slot;
               // ld.global.cs: streaming loads that still go through L1, so that the six 16-byte loads of a record
             // become one or two line fills instead of six L2 requests (measured: 75.5 -> 66.7 ms per step against ld.cg)
@@ -495,6 +507,7 @@ wave_tile_kernel(const ModelDev M, Pool P, const WaveQ W) {
             if (bad || (unsigned)lx >= (unsigned)TX || (unsigned)ly >= (unsigned)TY || (unsigned)lz >= (unsigned)TZ) {
               // cannot happen for a packet bucketed by its own cell; never index shared memory with it
               atomicCAS(M.error_flag, ERR_NONE, bad ? ERR_DEPOSIT : ERR_NOT_IN_CELL);
+              W.key_pos[s_pos[0]] = k_free;
               W.key[slot] = k_free;
             } else {
               const double vx = a1.y, vy = a2.x, vz = a2.y;
@@ -561,6 +574,7 @@ wave_tile_kernel(const ModelDev M, Pool P, const WaveQ W) {
                 // the interaction keeps the cell indices and find_cell's 1-D id the slot already holds
                 Slot<ND> *sw = slots + slot;
                 __stcs((double2 *)&sw->tau_left, make_double2(L.tau, L.t));
+                W.key_pos[s_pos[0]] = k_interact;
                 W.key[slot] = k_interact;
                 fin = 3;
               }
@@ -586,6 +600,7 @@ wave_tile_kernel(const ModelDev M, Pool P, const WaveQ W) {
           if (nslot == NONE && n2slot != NONE) {
             nslot = n2slot;
             n2slot = NONE;
+            s_pos[PQ] = s_pos[2 * PQ];
             const char *rec = (const char *)(slots + nslot);
 #if WAVE_EXPERIMENT != 6
             asm volatile("prefetch.global.L2 [%0];" ::"l"(rec));
@@ -605,7 +620,10 @@ wave_tile_kernel(const ModelDev M, Pool P, const WaveQ W) {
               if (need) {
                 const uint32_t idx = base + __popc(m_need & ((1u << lane) - 1u));
                 if (idx >= it.z) failed = true;
-                else n2slot = __ldcs(W.sorted + it.y + idx);
+                else {
+                  n2slot = __ldcs(W.sorted + it.y + idx);
+                  s_pos[2 * PQ] = it.y + idx;
+                }
               }
             }
             exhausted = __any_sync(0xffffffffu, failed);
@@ -680,7 +698,8 @@ wave_interact_kernel(const ModelDev M, Pool P, const WaveQ W, const uint32_t ite
       store_photon<ND>(slots + slot, p, rng, id);
       nk = wave_tile_of(W, min(max(p.ix, 0), M.n1 - 1), min(max(p.iy, 0), M.n2 - 1), min(max(p.iz, 0), M.n3 - 1));
     }
-    W.key[slot] = nk;
+    W.key_pos[start + i] = nk;
+    if (W.by_slot) W.key[slot] = nk;
   }
   warp_add_scalar(M.scalars + SC_ABS, (double)n_abs);
   warp_add_scalar(M.scalars + SC_SCAT, (double)n_scat);

@@ -1924,6 +1924,7 @@ struct hyp_ctx {
   double *d_mono_logp[MAX_DUST] = {nullptr, nullptr, nullptr, nullptr};
   void *d_scan_tmp = nullptr;
   size_t scan_tmp_bytes = 0;
+  std::vector<cudaEvent_t> wave_ev;           // wave engine: start / end of the tile kernel of every round
 };
 
 namespace {
@@ -2189,6 +2190,7 @@ void hyp_ctx_destroy(hyp_ctx *c) {
   if (c->stream3) cudaStreamDestroy(c->stream3);
   if (c->evA) cudaEventDestroy(c->evA);
   if (c->evB) cudaEventDestroy(c->evB);
+  for (cudaEvent_t e : c->wave_ev) cudaEventDestroy(e);
   for (auto &d : c->dust) {
     free_dev(d.dev);
     free_dev(d.dev_mrw);
@@ -3310,16 +3312,27 @@ bool wave_wanted() {
 
 // Blocks of the tile kernel per SM: one block with 2 x 112 KB (densities, sums), or two blocks with 2 x 56 KB each
 // (one dust type only; HYPERION_B200_WAVE_CTAS=2).  The offsets are template constants of wave_tile_kernel.
-constexpr uint32_t WAVE_SUM_OFF_1 = 114688, WAVE_SUM_OFF_2 = 57344;
+// bytes of the density half (= of the sum half) of a tile; one dust type: 30^3 cells of 4 bytes rounded up to 128,
+// which leaves 16 KB of the SM's shared memory to the service blocks that run beside a tile block
+// (two and more dust types: blocks of 768 / 512 threads, the largest halves that still leave room for the walls and
+// the 12 bytes per thread of packet positions: 24^3 x 8, 21^3 x 12 and 19^3 x 16 bytes fit as before)
+constexpr uint32_t WAVE_SUM_OFF_ND2 = 110592, WAVE_SUM_OFF_ND34 = 111616, WAVE_SUM_OFF_2 = 53248, WAVE_SUM_OFF_ND1 = 108032;
+#ifndef WAVE_TILE_THREADS_DEFAULT
+#define WAVE_TILE_THREADS_DEFAULT 896
+#endif
+constexpr uint32_t wave_sum_off(int nd, int ctas) {
+  return ctas == 2 ? WAVE_SUM_OFF_2 : (nd == 1 ? WAVE_SUM_OFF_ND1 : (nd == 2 ? WAVE_SUM_OFF_ND2 : WAVE_SUM_OFF_ND34));
+}
 
 int wave_ctas(int nd) {
   const char *e = getenv("HYPERION_B200_WAVE_CTAS");
   return (nd == 1 && e && atoi(e) == 2) ? 2 : 1;
 }
 
-size_t wave_smem_bytes(int tx, int ty, int tz, int ctas) {
+size_t wave_smem_bytes(int tx, int ty, int tz, int ctas, int nd, int threads) {
   const int tw = std::max(tx, std::max(ty, tz)) + 1;
-  return 2 * (size_t)(ctas == 2 ? WAVE_SUM_OFF_2 : WAVE_SUM_OFF_1) + (size_t)3 * tw * sizeof(double);
+  // densities | sums | walls of the tile | positions of the three packets every lane holds
+  return 2 * (size_t)wave_sum_off(nd, ctas) + (size_t)3 * tw * sizeof(double) + (size_t)3 * threads * sizeof(uint32_t);
 }
 
 // Tile shape: the largest cube whose densities fit their half of the shared memory
@@ -3328,7 +3341,7 @@ bool wave_plan(hyp_ctx *c, int nd) {
   WaveQ &W = c->wave;
   if (!c->uniform_walls || c->grid_type != GEO_CAR || c->M.any_sphere) return false;
   const int ctas = wave_ctas(nd);
-  const size_t cells_max = (size_t)(ctas == 2 ? WAVE_SUM_OFF_2 : WAVE_SUM_OFF_1) / (4 * (size_t)nd);
+  const size_t cells_max = (size_t)wave_sum_off(nd, ctas) / (4 * (size_t)nd);
   auto fits = [&](int tx, int ty, int tz) {
     return (size_t)(tx + 2) * (ty + 2) * (tz + 2) <= cells_max && std::max(tx, std::max(ty, tz)) <= 62;
   };
@@ -3385,8 +3398,9 @@ int ensure_wave(hyp_ctx *c) {
     W.capacity = cap;
     return HYP_OK;
   }
-  free_dev(W.key); free_dev(c->wave_sorted[0]); free_dev(c->wave_sorted[1]); free_dev(W.bin_count); free_dev(W.bin_cursor); free_dev(W.items); free_dev(W.ctl);
+  free_dev(W.key); free_dev(W.key_pos); free_dev(c->wave_sorted[0]); free_dev(c->wave_sorted[1]); free_dev(W.bin_count); free_dev(W.bin_cursor); free_dev(W.items); free_dev(W.ctl);
   CUDA_TRY(cudaMalloc(&W.key, (size_t)cap * sizeof(uint32_t)));
+  CUDA_TRY(cudaMalloc(&W.key_pos, (size_t)cap * sizeof(uint32_t)));
   CUDA_TRY(cudaMalloc(&c->wave_sorted[0], (size_t)cap * sizeof(uint32_t)));
   CUDA_TRY(cudaMalloc(&c->wave_sorted[1], (size_t)cap * sizeof(uint32_t)));
   W.sorted = c->wave_sorted[0];
@@ -3430,30 +3444,57 @@ static int run_wave(hyp_ctx *c, int64_t first_id, int64_t n_photons, int64_t ite
   const int ctas = wave_ctas(ND);
   W.queue = getenv("HYPERION_B200_WAVE_QUEUE") ? atoi(getenv("HYPERION_B200_WAVE_QUEUE")) : 1;
   constexpr int WT = ND == 1 ? 1024 : (ND == 2 ? 768 : 512);
-  void (*tile)(const ModelDev, Pool, const WaveQ) = wave_tile_kernel<ND, WT, 1, WAVE_SUM_OFF_1>;
+  void (*tile)(const ModelDev, Pool, const WaveQ) = wave_tile_kernel<ND, WT, 1, wave_sum_off(ND, 1)>;
   int tile_threads = WT;
   if constexpr (ND == 1) {
-    // HYPERION_B200_WAVE_THREADS: 1024 threads with 64 registers (default), 896 with 72, 768 with 80
-    const int want = getenv("HYPERION_B200_WAVE_THREADS") ? atoi(getenv("HYPERION_B200_WAVE_THREADS")) : 1024;
+    // HYPERION_B200_WAVE_THREADS: threads of a tile block, all with the 64 registers of a 1024-thread block; below
+    // 1024 the interaction (and emission) blocks of the round find registers on the same SM
+    const int want = getenv("HYPERION_B200_WAVE_THREADS") ? atoi(getenv("HYPERION_B200_WAVE_THREADS")) : WAVE_TILE_THREADS_DEFAULT;
     if (ctas == 2) {
       tile = wave_tile_kernel<ND, 512, 2, WAVE_SUM_OFF_2>;
       tile_threads = 512;
     } else if (want == 896) {
-      tile = wave_tile_kernel<ND, 896, 1, WAVE_SUM_OFF_1>;
+      tile = wave_tile_kernel<ND, 896, 1, WAVE_SUM_OFF_ND1, 1024>;
       tile_threads = 896;
     } else if (want == 768) {
-      tile = wave_tile_kernel<ND, 768, 1, WAVE_SUM_OFF_1>;
+      tile = wave_tile_kernel<ND, 768, 1, WAVE_SUM_OFF_ND1, 1024>;
       tile_threads = 768;
+    } else if (want == 640) {
+      tile = wave_tile_kernel<ND, 640, 1, WAVE_SUM_OFF_ND1, 1024>;
+      tile_threads = 640;
     }
   }
-  const size_t tile_smem = wave_smem_bytes(W.tx, W.ty, W.tz, ctas);
+  // HYPERION_B200_WAVE_ORDER: 1 (default) the tile kernel is launched before the interactions and the emission of
+  // the round, so that its blocks take the SMs first and the service blocks fill what is left (and the SMs of tile
+  // blocks that have run out of items); 0 the other way round
+  const bool tile_first = getenv("HYPERION_B200_WAVE_ORDER") ? atoi(getenv("HYPERION_B200_WAVE_ORDER")) != 0 : true;
+  const size_t tile_smem = wave_smem_bytes(W.tx, W.ty, W.tz, ctas, ND, tile_threads);
   CUDA_TRY(cudaFuncSetAttribute(tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem));
   const size_t sort_smem = 2 * (size_t)(W.n_tiles + 2) * sizeof(uint32_t);
   CUDA_TRY(cudaFuncSetAttribute(wave_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sort_smem));
   CUDA_TRY(cudaFuncSetAttribute(wave_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sort_smem));
-  const int service_blocks = c->sm_count * 4;
   cudaStream_t st = c->stream, s2 = c->stream2, s3 = c->stream3;
   const bool dbg = getenv("HYPERION_B200_TIMING") != nullptr;
+  // HYPERION_B200_TIMING=2: every kernel of a round runs alone (a device synchronisation after each) and the summed
+  // times per kernel are printed: the step without any overlap, with warm caches and at the clocks of a real run
+  const bool serial = dbg && atoi(getenv("HYPERION_B200_TIMING")) == 2;
+  double t_acc[5] = {0, 0, 0, 0, 0};   // sort, tile, interact, emit, host gaps
+  auto lap = [&](int which, cudaStream_t s, bool begin) {
+    if (!serial) return;
+    if (begin) {
+      cudaDeviceSynchronize();
+      cudaEventRecord(c->evA, s);
+    } else {
+      cudaEventRecord(c->evB, s);
+      cudaEventSynchronize(c->evB);
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, c->evA, c->evB);
+      t_acc[which] += ms;
+    }
+  };
+  // HYPERION_B200_WAVE_SERVICE: blocks per SM of the interaction / emission kernels of a round that has tile visits
+  const int service_per_sm = getenv("HYPERION_B200_WAVE_SERVICE") ? std::max(1, atoi(getenv("HYPERION_B200_WAVE_SERVICE"))) : 8;
+  const int service_blocks = c->sm_count * service_per_sm;
 
   wave_init_kernel<<<c->sm_count * 4, 256, 0, st>>>(W, P);
   CUDA_TRY(cudaGetLastError());
@@ -3461,6 +3502,7 @@ static int run_wave(hyp_ctx *c, int64_t first_id, int64_t n_photons, int64_t ite
   CUDA_TRY(cudaEventRecord(c->ev0, st));
   uint32_t *h = c->h_counts;
   bool handoff = false, compact = false;
+  int n_tile_rounds = 0;
   uint32_t handoff_flights = 0, n_busy_prev = 0;
   for (int64_t round = 0;; ++round) {
     // slots to sort: all of them while packets are still being emitted, afterwards the busy slots of the
@@ -3469,9 +3511,11 @@ static int run_wave(hyp_ctx *c, int64_t first_id, int64_t n_photons, int64_t ite
     const uint32_t n_src = compact ? n_busy_prev : cap;
     W.sorted = c->wave_sorted[round & 1];
     const int sort_blocks = (int)std::max<uint32_t>(1u, (n_src + WAVE_SORT_SEG - 1) / WAVE_SORT_SEG);
+    lap(0, st, true);
     wave_hist_kernel<<<sort_blocks, WAVE_SORT_THREADS, sort_smem / 2, st>>>(W, src, n_src);
     wave_scan_kernel<<<1, 1024, 0, st>>>(W, P);
     wave_scatter_kernel<<<sort_blocks, WAVE_SORT_THREADS, sort_smem, st>>>(W, src, n_src);
+    lap(0, st, false);
     CUDA_TRY(cudaGetLastError());
     c->launches_acc += 3;
     CUDA_TRY(cudaMemcpyAsync(h, W.ctl, WC_COUNT * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
@@ -3485,6 +3529,7 @@ static int run_wave(hyp_ctx *c, int64_t first_id, int64_t n_photons, int64_t ite
     if (n_flight == 0 && n_interact == 0 && !ids_left) break;
     // this round emits nothing if every id was claimed before its sort: the next sort only needs its busy slots
     compact = !ids_left;
+    W.by_slot = ids_left ? 1 : 0;   // with ids left the next sort covers all slots and reads key[slot]
     n_busy_prev = n_flight + n_interact;
     if (!ids_left && n_flight + n_interact < tail_min) {
       wave_handoff_kernel<<<c->sm_count, 256, 0, st>>>(P, W);
@@ -3497,11 +3542,35 @@ static int run_wave(hyp_ctx *c, int64_t first_id, int64_t n_photons, int64_t ite
     c->rounds_acc += 1;
     c->wave_rounds_acc += 1;
     CUDA_TRY(cudaEventRecord(c->evFork, st));
+    auto launch_tile = [&]() -> int {
+      if (n_flight == 0) return HYP_OK;
+      // the tile kernel's own time: one pair of events per round, read when the photon loop has ended
+      while (c->wave_ev.size() < 2 * (size_t)(n_tile_rounds + 1)) {
+        cudaEvent_t e;
+        CUDA_TRY(cudaEventCreate(&e));
+        c->wave_ev.push_back(e);
+      }
+      lap(1, st, true);
+      CUDA_TRY(cudaEventRecord(c->wave_ev[2 * n_tile_rounds], st));
+      tile<<<(int)std::min<uint32_t>(h[WC_NITEMS], (uint32_t)(c->sm_count * ctas)), tile_threads, tile_smem, st>>>(c->M, P, W);
+      CUDA_TRY(cudaGetLastError());
+      CUDA_TRY(cudaEventRecord(c->wave_ev[2 * n_tile_rounds + 1], st));
+      lap(1, st, false);
+      ++n_tile_rounds;
+      c->launches_acc += 1;
+      return HYP_OK;
+    };
+    if (tile_first) {
+      rc = launch_tile();
+      if (rc) return rc;
+    }
     if (n_interact > 0) {
       CUDA_TRY(cudaStreamWaitEvent(s2, c->evFork, 0));
       const int blocks = (int)std::min<int64_t>(((int64_t)n_interact + SERVICE_THREADS - 1) / SERVICE_THREADS,
                                                 n_flight > 0 ? service_blocks : c->sm_count * 16);
+      lap(2, s2, true);
       wave_interact_kernel<ND><<<blocks, SERVICE_THREADS, 0, s2>>>(c->M, P, W, (uint32_t)iteration);
+      lap(2, s2, false);
       CUDA_TRY(cudaGetLastError());
       CUDA_TRY(cudaEventRecord(c->evJoin, s2));
       c->launches_acc += 1;
@@ -3512,29 +3581,36 @@ static int run_wave(hyp_ctx *c, int64_t first_id, int64_t n_photons, int64_t ite
       // next to a tile kernel the emission shares the SMs with it (4 blocks each); alone (the first round) it takes them all
       const int blocks = (int)std::min<int64_t>((n_emit + SERVICE_THREADS - 1) / SERVICE_THREADS,
                                                 n_flight > 0 ? service_blocks : c->sm_count * 16);
+      lap(3, s3, true);
       wave_emit_kernel<ND><<<blocks, SERVICE_THREADS, 0, s3>>>(c->M, P, W, (unsigned long long)first_id,
                                                              (unsigned long long)n_photons, (uint32_t)iteration);
+      lap(3, s3, false);
       CUDA_TRY(cudaGetLastError());
       CUDA_TRY(cudaEventRecord(c->evJoin3, s3));
       c->launches_acc += 1;
     }
-    if (n_flight > 0) {
-      CUDA_TRY(cudaEventRecord(c->evA, st));
-      tile<<<(int)std::min<uint32_t>(h[WC_NITEMS], (uint32_t)(c->sm_count * ctas)), tile_threads, tile_smem, st>>>(c->M, P, W);
-      CUDA_TRY(cudaGetLastError());
-      CUDA_TRY(cudaEventRecord(c->evB, st));
-      c->launches_acc += 1;
+    if (!tile_first) {
+      rc = launch_tile();
+      if (rc) return rc;
     }
     if (n_interact > 0) CUDA_TRY(cudaStreamWaitEvent(st, c->evJoin, 0));
     if (n_free > 0 && ids_left) CUDA_TRY(cudaStreamWaitEvent(st, c->evJoin3, 0));
-    if (n_flight > 0) {
-      // the tile kernel's own time (events on its stream); read after the next round's sync
-      CUDA_TRY(cudaEventSynchronize(c->evB));
-      float ms = 0.f;
-      if (cudaEventElapsedTime(&ms, c->evA, c->evB) == cudaSuccess) c->flight_ms_acc += ms;
-      if (dbg) fprintf(stderr, "[wave %lld] tile kernel %.3f ms\n", (long long)round, ms);
-    }
   }
+  auto tile_times = [&]() -> int {
+    if (n_tile_rounds == 0) return HYP_OK;
+    CUDA_TRY(cudaEventSynchronize(c->wave_ev[2 * n_tile_rounds - 1]));
+    for (int r = 0; r < n_tile_rounds; ++r) {
+      float ms = 0.f;
+      if (cudaEventElapsedTime(&ms, c->wave_ev[2 * r], c->wave_ev[2 * r + 1]) == cudaSuccess) c->flight_ms_acc += ms;
+      if (dbg) fprintf(stderr, "[wave tile round %d] %.3f ms\n", r, ms);
+    }
+    return HYP_OK;
+  };
+  rc = tile_times();
+  if (rc) return rc;
+  if (serial)
+    fprintf(stderr, "[wave serial] sort %.3f ms, tile %.3f ms, interact %.3f ms, emit %.3f ms (each kernel alone)\n", t_acc[0],
+            t_acc[1], t_acc[2], t_acc[3]);
   if (handoff) return run_rounds<ND>(c, first_id, n_photons, iteration, true, handoff_flights);
   CUDA_TRY(cudaEventRecord(c->ev1, st));
   CUDA_TRY(cudaStreamSynchronize(st));
