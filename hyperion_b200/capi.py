@@ -66,6 +66,7 @@ class RunConf(C.Structure):
         ("forced_first_interaction", C.c_int32), ("forced_first_interaction_algorithm", C.c_int32),
         ("baes16_xi", C.c_double),
         ("specific_energy_additional", C.c_int32),
+        ("use_pda", C.c_int32), ("count_photons", C.c_int32),
     ]
 
 
@@ -232,6 +233,7 @@ class CApi:
         t.forced_first_interaction_algorithm = {"wr99": 1, "baes16": 2}[c.forced_first_interaction_algorithm]
         t.baes16_xi = c.baes16_xi
         t.specific_energy_additional = int(c.specific_energy_additional)
+        t.use_pda, t.count_photons = int(c.use_pda), int(c.count_photons)
         self.check(self._fn("set_run_conf")(ctx, C.byref(t)))
 
     def add_peeled_group(self, ctx, g):
@@ -477,6 +479,27 @@ class Engine(CApi):
 
     def get_density(self, out=None):
         return self._get(self.lib.hyp_get_density, out)
+
+    def set_specific_energy_array(self, se):
+        """Replace the specific energy [n_dust, n3, n2, n1] of a loaded model (hyp_set_specific_energy)."""
+        self.set_specific_energy(self.ctx, se, None)
+
+    def solve_pda(self, n_photons=None):
+        """solve_pda (src/grid/grid_pda_3d.f90:105-169) on the current specific energy with the given packet counts
+        [n3, n2, n1] (default: those of the last Lucy iteration); returns the number of PDA cells."""
+        n = C.c_int64(0)
+        p = None
+        if n_photons is not None:
+            a = np.ascontiguousarray(n_photons, dtype=np.int64)
+            p = a.ctypes.data_as(C.c_void_p)
+        self.check(self.lib.hyp_solve_pda(self.ctx, p, C.byref(n)))
+        return n.value
+
+    def get_n_photons(self):
+        """Packets that visited each cell in the last Lucy iteration (``n_photons``, grid_physics_3d.f90:38)."""
+        out = np.empty(tuple(self.shape), dtype=np.int64)
+        self.check(self.lib.hyp_get_n_photons(self.ctx, out.ctypes.data_as(C.c_void_p)))
+        return out
 
     def get_energy_sum(self, out=None):
         return self._get(self.lib.hyp_get_energy_sum, out)

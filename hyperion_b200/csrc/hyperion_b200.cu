@@ -85,6 +85,8 @@ struct ModelDev {
   const double *mono_logp[MAX_DUST];   // log10 of the emission probability per unit frequency of every emissivity state
   const double *mono_cdf;              // [n_dust][n_cells] cumulative emission probability x energy of the cells
   double mono_thermal_w[MAX_DUST];     // energy of a thermal packet of each dust type (0: the type does not emit)
+  // per-cell packet counter (n_photons / last_photon_id, grid_physics_3d.f90:38-39), or nullptr
+  unsigned long long *n_visits, *last_id;
   // outputs
   double *scalars;                 // [SC_COUNT], directly after the reduced sum grid
   unsigned long long *work_counter;
@@ -906,6 +908,8 @@ __device__ __forceinline__ double mean_opacity_loglog(const DustDev &d, int64_t 
 }
 
 
+#include "pda.cuh"
+
 // One step of the modified random walk in the packet's cell (grid_do_mrw / grid_do_mrw_noenergy,
 // grid_mrw_3d.f90:56-149): jump to the surface of the largest sphere that fits in the cell, deposit the
 // energy absorbed along the diffusive path (Lucy iteration), pick a new direction and a frequency from
@@ -1705,7 +1709,8 @@ __device__ __forceinline__ double clamp_energy(const ModelDev &M, const DustDev 
 }
 
 // update_energy_abs (grid_physics_3d.f90:500-553) + sublimate_dust (:420-498)
-__global__ void lucy_finish_kernel(ModelDev M, const double *__restrict__ sums, double scale) {
+// mode 0: both; 1: update_energy_abs only; 2: sublimate_dust only (the PDA runs between the two, iter_lucy.f90:224-235)
+__global__ void lucy_finish_kernel(ModelDev M, const double *__restrict__ sums, double scale, const int mode = 0) {
   const int nd = M.n_dust;
   const int64_t n = M.n_cells * nd;
   for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x) {
@@ -1713,11 +1718,16 @@ __global__ void lucy_finish_kernel(ModelDev M, const double *__restrict__ sums, 
     const int64_t ic = k / nd;
     const double vol = cell_volume(M, ic);
     const DustDev &d = M.dust[id];
-    double e = sums[k] * scale / vol;
-    if (vol == 0.0) e = 0.0;
-    if (M.energy_additional) e = e + M.energy_additional[k];   // grid_physics_3d.f90:537-545
-    e = clamp_energy(M, d, id, e);
-    if (d.L.sublimation_mode != 0 && e > d.L.sublimation_specific_energy) {
+    double e;
+    if (mode == 2) {
+      e = M.specific_energy[k];
+    } else {
+      e = sums[k] * scale / vol;
+      if (vol == 0.0) e = 0.0;
+      if (M.energy_additional) e = e + M.energy_additional[k];   // grid_physics_3d.f90:537-545
+      e = clamp_energy(M, d, id, e);
+    }
+    if (mode != 1 && d.L.sublimation_mode != 0 && e > d.L.sublimation_specific_energy) {
       const double es = d.L.sublimation_specific_energy;
       if (d.L.sublimation_mode == 1) {
         M.cells[k].rho = 0.0;
@@ -1925,6 +1935,12 @@ struct hyp_ctx {
   void *d_scan_tmp = nullptr;
   size_t scan_tmp_bytes = 0;
   std::vector<cudaEvent_t> wave_ev;           // wave engine: start / end of the tile kernel of every round
+  // packet counter and partial diffusion approximation (pda.cuh)
+  unsigned long long *d_nvis = nullptr, *d_lastid = nullptr;
+  double *d_pda_geo = nullptr, *d_pda_e = nullptr, *d_pda_coef = nullptr, *d_pda_counts = nullptr;
+  int32_t *d_pda_list = nullptr;
+  unsigned long long *d_pda_ctl = nullptr;    // [0] number of PDA cells (32 bits used), [1] largest change, [2] sum of counts
+  int64_t pda_cells_last = 0, pda_sweeps_last = 0;
 };
 
 namespace {
@@ -2191,6 +2207,8 @@ void hyp_ctx_destroy(hyp_ctx *c) {
   if (c->evA) cudaEventDestroy(c->evA);
   if (c->evB) cudaEventDestroy(c->evB);
   for (cudaEvent_t e : c->wave_ev) cudaEventDestroy(e);
+  free_dev(c->d_nvis); free_dev(c->d_lastid); free_dev(c->d_pda_geo); free_dev(c->d_pda_e); free_dev(c->d_pda_coef);
+  free_dev(c->d_pda_counts); free_dev(c->d_pda_list); free_dev(c->d_pda_ctl);
   for (auto &d : c->dust) {
     free_dev(d.dev);
     free_dev(d.dev_mrw);
@@ -3075,12 +3093,13 @@ int hyp_finalize_setup(hyp_ctx *c) {
   CUDA_TRY(cudaMalloc(&c->d_energy, n * sizeof(double)));
   CUDA_TRY(cudaMalloc(&c->d_jfrac, n * sizeof(double)));
   CUDA_TRY(cudaMalloc(&c->d_jid, n * sizeof(int32_t)));
-  CUDA_TRY(cudaMalloc(&c->d_sums, (n + SC_COUNT) * sizeof(double)));
+  // [sums | scalars | n_photons as doubles]: one buffer, one collective
+  CUDA_TRY(cudaMalloc(&c->d_sums, (n + SC_COUNT + (size_t)c->n_cells) * sizeof(double)));
   CUDA_TRY(cudaMalloc(&c->d_stage, n * sizeof(double)));
   CUDA_TRY(cudaMalloc(&c->d_work, sizeof(unsigned long long)));
   CUDA_TRY(cudaMalloc(&c->d_error, sizeof(int32_t)));
   CUDA_TRY(cudaMemset(c->d_cells, 0, n * sizeof(CellRec)));
-  CUDA_TRY(cudaMemset(c->d_sums, 0, (n + SC_COUNT) * sizeof(double)));
+  CUDA_TRY(cudaMemset(c->d_sums, 0, (n + SC_COUNT + (size_t)c->n_cells) * sizeof(double)));
   CUDA_TRY(cudaMemset(c->d_error, 0, sizeof(int32_t)));
   M.cells = c->d_cells;
   M.rho = c->d_rho;
@@ -3141,6 +3160,22 @@ int hyp_lucy_begin(hyp_ctx *c) {
   }
   CUDA_TRY(cudaMemsetAsync(c->d_sums + n, 0, SC_COUNT * sizeof(double), c->stream));
   CUDA_TRY(cudaMemsetAsync(c->d_error, 0, sizeof(int32_t), c->stream));
+  // grid_reset_energy (grid_generic.f90:18-25): the packet counter exists with the PDA or the n_photons output
+  // (grid_physics_3d.f90:308-317)
+  if (c->conf.use_pda || c->conf.count_photons) {
+    if (c->conf.use_pda && (c->grid_type == GEO_OCT || c->grid_type == GEO_AMR))
+      return fail(HYP_ERR_INVALID, "PDA is not available for this grid type");   // grid_pda_disabled.f90
+    if (!c->d_nvis) {
+      CUDA_TRY(cudaMalloc(&c->d_nvis, (size_t)c->n_cells * sizeof(unsigned long long)));
+      CUDA_TRY(cudaMalloc(&c->d_lastid, (size_t)c->n_cells * sizeof(unsigned long long)));
+    }
+    CUDA_TRY(cudaMemsetAsync(c->d_nvis, 0, (size_t)c->n_cells * sizeof(unsigned long long), c->stream));
+    CUDA_TRY(cudaMemsetAsync(c->d_lastid, 0, (size_t)c->n_cells * sizeof(unsigned long long), c->stream));
+    c->M.n_visits = c->d_nvis;
+    c->M.last_id = c->d_lastid;
+  } else {
+    c->M.n_visits = c->M.last_id = nullptr;
+  }
   c->sums_gathered = false;
   c->kernel_ms_acc = 0.f;
   c->flight_ms_acc = 0.f;
@@ -3222,7 +3257,7 @@ static int run_rounds(hyp_ctx *c, int64_t first_id, int64_t n_photons, int64_t i
     }
     // 2. flights: the beams of new packets, then the packets that come out of an interaction
     CUDA_TRY(cudaEventRecord(c->evA, st));
-    if (c->grid_type != GEO_CAR || c->M.any_sphere) {
+    if (c->grid_type != GEO_CAR || c->M.any_sphere || c->M.n_visits) {
       const FinalArgs none = FinalArgs();
       auto geo_flight = c->grid_type == GEO_OCT   ? flight_geo_kernel<GEO_OCT, ND, true, false>
                         : c->grid_type == GEO_AMR ? flight_geo_kernel<GEO_AMR, ND, true, false>
@@ -3627,7 +3662,8 @@ int hyp_lucy_photons(hyp_ctx *c, int64_t first_id, int64_t n_photons, int64_t it
   if (n_photons == 0) return HYP_OK;
   CUDA_TRY(cudaSetDevice(c->device));
   c->sums_gathered = false;
-  const bool wave = wave_wanted() && wave_plan(c, c->M.n_dust);
+  // the packet counter lives in the generic march: neither the tiles nor the beams keep it
+  const bool wave = !c->M.n_visits && wave_wanted() && wave_plan(c, c->M.n_dust);
   c->last_engine = wave ? 1 : 0;
   switch (c->M.n_dust) {
     case 1: return wave ? run_wave<1>(c, first_id, n_photons, iteration) : run_rounds<1>(c, first_id, n_photons, iteration);
@@ -3638,11 +3674,166 @@ int hyp_lucy_photons(hyp_ctx *c, int64_t first_id, int64_t n_photons, int64_t it
   }
 }
 
+}  // extern "C"
+
+namespace {
+
+// cell_width / geometrical_factor of the regular grids as per-axis tables (grid_geometry_*_3d.f90 cell_width,
+// grid_pda_*_3d.f90 geometrical_factor); layout: 9 width tables (direction-major, axis-minor), then 4 wall tables
+int pda_geometry(hyp_ctx *c, PdaGeo &G) {
+  const int n1 = c->n1, n2 = c->n2, n3 = c->n3;
+  const int ns[3] = {n1, n2, n3};
+  const std::vector<double> *ws[3] = {&c->w1, &c->w2, &c->w3};
+  std::vector<double> buf;
+  size_t off_w[3][3], off_f[4];
+  auto push = [&](const std::vector<double> &v) { const size_t o = buf.size(); buf.insert(buf.end(), v.begin(), v.end()); return o; };
+  auto ones = [&](int n) { return std::vector<double>(n, 1.0); };
+  auto diff = [&](int a) { std::vector<double> v(ns[a]); for (int i = 0; i < ns[a]; ++i) v[i] = (*ws[a])[i + 1] - (*ws[a])[i]; return v; };
+  auto mid_log = [&]() {   // geo%r / geo%w (grid_geometry_spherical_3d.f90:139-143, _cylindrical_3d.f90:130-134)
+    std::vector<double> v(n1);
+    for (int i = 0; i < n1; ++i)
+      v[i] = c->w1[i] == 0.0 ? c->w1[i + 1] / 2.0 : std::pow(10.0, (std::log10(c->w1[i]) + std::log10(c->w1[i + 1])) / 2.0);
+    return v;
+  };
+  const bool car = c->grid_type == GEO_CAR, sph = c->grid_type == GEO_SPH && c->polar_kind == POLAR_SPH;
+  for (int d = 0; d < 3; ++d)
+    for (int a = 0; a < 3; ++a) {
+      std::vector<double> v = ones(ns[a]);
+      if (car) {
+        if (a == d) v = diff(a);
+      } else if (sph) {
+        if (d == 0 && a == 0) v = diff(0);
+        if (d == 1 && a == 0) v = mid_log();
+        if (d == 1 && a == 1) v = diff(1);
+        if (d == 2 && a == 0) v = mid_log();
+        if (d == 2 && a == 1) for (int i = 0; i < n2; ++i) v[i] = std::sin((c->w2[i] + c->w2[i + 1]) / 2.0);
+        if (d == 2 && a == 2) v = diff(2);
+      } else {
+        if (d == 0 && a == 0) v = diff(0);
+        if (d == 1 && a == 1) v = diff(1);
+        if (d == 2 && a == 0) v = mid_log();
+        if (d == 2 && a == 2) v = diff(2);
+      }
+      off_w[d][a] = push(v);
+    }
+  for (int w = 0; w < 4; ++w) {
+    std::vector<double> v = ones(w < 2 ? n1 : n2);
+    if (!car && w < 2)
+      for (int i = 0; i < n1; ++i) {
+        const double a = c->w1[i], b = c->w1[i + 1], x = w == 0 ? a : b;
+        v[i] = sph ? 4. * x * x / ((a + b) * (a + b)) : 2. * x / (a + b);
+      }
+    if (sph && w >= 2)
+      for (int i = 0; i < n2; ++i) {
+        const double sa = std::sin(c->w2[i]), sb = std::sin(c->w2[i + 1]);
+        v[i] = 2. * (w == 2 ? sa : sb) / (sa + sb);
+      }
+    off_f[w] = push(v);
+  }
+  free_dev(c->d_pda_geo);
+  CUDA_TRY(cudaMalloc(&c->d_pda_geo, buf.size() * sizeof(double)));
+  CUDA_TRY(cudaMemcpy(c->d_pda_geo, buf.data(), buf.size() * sizeof(double), cudaMemcpyHostToDevice));
+  for (int d = 0; d < 3; ++d)
+    for (int a = 0; a < 3; ++a) G.W[d][a] = c->d_pda_geo + off_w[d][a];
+  for (int w = 0; w < 4; ++w) G.F[w] = c->d_pda_geo + off_f[w];
+  G.n1 = n1; G.n2 = n2; G.n3 = n3;
+  G.periodic3 = car ? 0 : 1;
+  G.n_dim = (!car && n3 == 1) ? 2 : 3;
+  return HYP_OK;
+}
+
+// solve_pda (grid_pda_3d.f90:105-169) on the current specific energy.  counts: device array of n_photons as
+// doubles; n_pda_out: number of PDA cells.
+int solve_pda_device(hyp_ctx *c, const double *counts, int64_t *n_pda_out) {
+  if (c->grid_type == GEO_OCT || c->grid_type == GEO_AMR) return fail(HYP_ERR_INVALID, "PDA is not available for this grid type");
+  cudaStream_t st = c->stream;
+  const size_t nc = (size_t)c->n_cells;
+  PdaDev P;
+  memset(&P, 0, sizeof P);
+  int rc = pda_geometry(c, P.G);
+  if (rc) return rc;
+  if (!c->d_pda_ctl) CUDA_TRY(cudaMalloc(&c->d_pda_ctl, 4 * sizeof(unsigned long long)));
+  if (!c->d_pda_list) CUDA_TRY(cudaMalloc(&c->d_pda_list, nc * sizeof(int32_t)));
+  if (!c->d_pda_e) CUDA_TRY(cudaMalloc(&c->d_pda_e, 2 * nc * sizeof(double)));
+  CUDA_TRY(cudaMemsetAsync(c->d_pda_ctl, 0, 4 * sizeof(unsigned long long), st));
+  P.counts = counts;
+  P.list = c->d_pda_list;
+  P.n_list = (uint32_t *)c->d_pda_ctl;
+  P.maxdiff = c->d_pda_ctl + 1;
+  P.e_a = c->d_pda_e;
+  P.e_b = c->d_pda_e + nc;
+  // mean_n_photons = sum(n_photons) / size(n_photons); threshold max(30, ceiling(0.005 mean)) (:124-129)
+  pda_sum_counts_kernel<<<grid_blocks(c), 256, 0, st>>>(counts, (int64_t)nc, (double *)(c->d_pda_ctl + 2));
+  double total = 0.0;
+  CUDA_TRY(cudaMemcpyAsync(&total, c->d_pda_ctl + 2, sizeof(double), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  P.limit = std::max(30.0, std::ceil(0.005 * (total / (double)nc)));
+  pda_mark_kernel<<<grid_blocks(c), 256, 0, st>>>(c->M, P);
+  uint32_t n_pda = 0;
+  CUDA_TRY(cudaMemcpyAsync(&n_pda, c->d_pda_ctl, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  c->launches_acc += 2;
+  c->pda_cells_last = n_pda;
+  c->pda_sweeps_last = 0;
+  if (n_pda_out) *n_pda_out = n_pda;
+  if (n_pda == 0) return HYP_OK;   // " [pda] not necessary for this iteration"
+  free_dev(c->d_pda_coef);
+  CUDA_TRY(cudaMalloc(&c->d_pda_coef, (size_t)n_pda * 6 * sizeof(double)));
+  P.coef = c->d_pda_coef;
+  const double tolerance = n_pda < 10000 ? 1.e-5 : 1.e-4;   // tolerance_exact / tolerance_iter (:34-35,138-144)
+  const int blocks = (int)std::min<int64_t>(((int64_t)n_pda + 255) / 256, (int64_t)grid_blocks(c));
+  const int batch = 64;
+  for (int outer = 0; outer < 1000; ++outer) {
+    pda_emean_kernel<<<grid_blocks(c), 256, 0, st>>>(c->M, P);
+    pda_coef_kernel<<<blocks, 256, 0, st>>>(c->M, P);
+    c->launches_acc += 2;
+    const double *cur = P.e_a;
+    for (int64_t sweep = 0; sweep < 4000000; sweep += batch) {
+      CUDA_TRY(cudaMemsetAsync(P.maxdiff, 0, sizeof(unsigned long long), st));
+      for (int k = 0; k < batch; ++k) {
+        double *dst = cur == P.e_a ? P.e_b : P.e_a;
+        pda_sweep_kernel<<<blocks, 256, 0, st>>>(P, cur, dst, k == batch - 1 ? 1 : 0);
+        cur = dst;
+      }
+      CUDA_TRY(cudaGetLastError());
+      c->launches_acc += batch;
+      c->pda_sweeps_last += batch;
+      double worst = 0.0;
+      CUDA_TRY(cudaMemcpyAsync(&worst, P.maxdiff, sizeof(double), cudaMemcpyDeviceToHost, st));
+      CUDA_TRY(cudaStreamSynchronize(st));
+      if (worst < 1.e-9) break;
+    }
+    CUDA_TRY(cudaMemsetAsync(P.maxdiff, 0, sizeof(unsigned long long), st));
+    pda_update_energy_kernel<<<blocks, 256, 0, st>>>(c->M, P, cur);
+    CUDA_TRY(cudaGetLastError());
+    c->launches_acc += 1;
+    double maxdiff = 0.0;
+    CUDA_TRY(cudaMemcpyAsync(&maxdiff, P.maxdiff, sizeof(double), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    if (maxdiff < tolerance) break;
+  }
+  // update_energy_abs_tot + check_energy_abs (:164-166)
+  clamp_energy_kernel<<<grid_blocks(c), 256, 0, st>>>(c->M);
+  CUDA_TRY(cudaGetLastError());
+  c->launches_acc += 1;
+  return HYP_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
 static int gather_sums(hyp_ctx *c) {
   if (!c->sums_gathered) {
     gather_sums_kernel<<<grid_blocks(c), 256, 0, c->stream>>>(c->M, c->d_sums);
     CUDA_TRY(cudaGetLastError());
     c->launches_acc += 1;
+    if (c->M.n_visits) {
+      pda_counts_to_double_kernel<<<grid_blocks(c), 256, 0, c->stream>>>(
+          c->M.n_visits, c->n_cells, c->d_sums + (size_t)c->n_cells * c->dust.size() + SC_COUNT);
+      CUDA_TRY(cudaGetLastError());
+      c->launches_acc += 1;
+    }
     c->sums_gathered = true;
   }
   return HYP_OK;
@@ -3655,7 +3846,7 @@ int hyp_lucy_device_buffers(hyp_ctx *c, void **sum_and_scalars, int64_t *n_value
   if (rc) return rc;
   CUDA_TRY(cudaStreamSynchronize(c->stream));
   if (sum_and_scalars) *sum_and_scalars = c->d_sums;
-  if (n_values) *n_values = c->n_cells * (int64_t)c->dust.size() + SC_COUNT;
+  if (n_values) *n_values = c->n_cells * (int64_t)c->dust.size() + SC_COUNT + (c->M.n_visits ? c->n_cells : 0);
   return HYP_OK;
 }
 
@@ -3673,9 +3864,17 @@ int hyp_lucy_finish(hyp_ctx *c, hyp_iter_stats *st) {
   if (!(sc[SC_ENERGY] > 0.0)) return fail(HYP_ERR_STATE, "no photons were emitted in this iteration");
   // update_energy_abs(energy_total / energy_current)  (iter_lucy.f90:224)
   const double scale = c->energy_total / sc[SC_ENERGY];
-  lucy_finish_kernel<<<grid_blocks(c), 256, 0, c->stream>>>(c->M, c->d_sums, scale);
+  lucy_finish_kernel<<<grid_blocks(c), 256, 0, c->stream>>>(c->M, c->d_sums, scale, c->conf.use_pda ? 1 : 0);
   CUDA_TRY(cudaGetLastError());
   c->launches_acc += 1;
+  if (c->conf.use_pda) {
+    // iter_lucy.f90:227: the PDA between update_energy_abs and sublimate_dust, with the packet counts of all processes
+    rc = solve_pda_device(c, c->d_sums + n + SC_COUNT, nullptr);
+    if (rc) return rc;
+    lucy_finish_kernel<<<grid_blocks(c), 256, 0, c->stream>>>(c->M, c->d_sums, scale, 2);
+    CUDA_TRY(cudaGetLastError());
+    c->launches_acc += 1;
+  }
   CUDA_TRY(cudaEventRecord(c->ev3, c->stream));
   CUDA_TRY(cudaStreamSynchronize(c->stream));
   if (st) {
@@ -3726,6 +3925,36 @@ static int get_grid(hyp_ctx *c, int which, double *out) {
 int hyp_get_specific_energy(hyp_ctx *c, double *out) { return get_grid(c, 0, out); }
 int hyp_get_density(hyp_ctx *c, double *out) { return get_grid(c, 1, out); }
 int hyp_get_energy_sum(hyp_ctx *c, double *out) { return get_grid(c, 2, out); }
+
+int hyp_get_n_photons(hyp_ctx *c, int64_t *out) {
+  if (!c || !c->finalized || !out) return fail(HYP_ERR_STATE, "hyp_finalize_setup has not been called");
+  if (!c->d_nvis) return fail(HYP_ERR_STATE, "n_photons array is not allocated");   // output_grid, grid_generic.f90:44
+  CUDA_TRY(cudaSetDevice(c->device));
+  // the counts of all processes once the host has reduced the buffer (they travel behind the scalars)
+  const size_t n = (size_t)c->n_cells * c->dust.size(), nc = (size_t)c->n_cells;
+  std::vector<double> h(nc);
+  CUDA_TRY(cudaMemcpyAsync(h.data(), c->d_sums + n + SC_COUNT, nc * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  for (size_t i = 0; i < nc; ++i) out[i] = (int64_t)h[i];
+  return HYP_OK;
+}
+
+int hyp_solve_pda(hyp_ctx *c, const int64_t *n_photons, int64_t *n_pda_cells) {
+  if (!c || !c->finalized) return fail(HYP_ERR_STATE, "hyp_finalize_setup has not been called");
+  CUDA_TRY(cudaSetDevice(c->device));
+  const size_t n = (size_t)c->n_cells * c->dust.size(), nc = (size_t)c->n_cells;
+  const double *counts = c->d_sums + n + SC_COUNT;
+  if (n_photons) {
+    std::vector<double> h(nc);
+    for (size_t i = 0; i < nc; ++i) h[i] = (double)n_photons[i];
+    if (!c->d_pda_counts) CUDA_TRY(cudaMalloc(&c->d_pda_counts, nc * sizeof(double)));
+    CUDA_TRY(cudaMemcpy(c->d_pda_counts, h.data(), nc * sizeof(double), cudaMemcpyHostToDevice));
+    counts = c->d_pda_counts;
+  } else if (!c->d_nvis) {
+    return fail(HYP_ERR_STATE, "n_photons array is not allocated");
+  }
+  return solve_pda_device(c, counts, n_pda_cells);
+}
 
 }  // extern "C"
 

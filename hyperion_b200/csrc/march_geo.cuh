@@ -177,9 +177,18 @@ struct Geo<GEO_AMR> {
 template <int GEO, int ND, bool DEP>
 __device__ inline int geo_march(const ModelDev &M, typename Geo<GEO>::Ray &R, double &tau_left, const double (&chi)[ND],
                                 const double (&kE)[ND], CellRec *__restrict__ cells, uint32_t &n_cross,
-                                const double t_source) {
+                                const double t_source, const unsigned long long pid = 0ull,
+                                const bool count_start = true) {
   using G = Geo<GEO>;
   if (G::escaped(M, R)) return MARCH_ESCAPED;
+  // n_photons (grid_propagate_3d.f90:90-95,175-180): a packet counts once per cell for as long as no other packet
+  // has entered the cell since; pid = packet id + 1, 0 when no counter is kept.  The reference runs one packet at
+  // a time, so its counter is the number of DISTINCT packets per cell; here all packets are in flight together and
+  // another packet's visit can separate two visits of the same packet.  A flight that starts where the packet has
+  // just interacted is therefore not counted at all (the packet was counted when it entered that cell): what
+  // remains are packets that come back to a cell after leaving it while another packet passed through.
+  const bool counting = DEP && pid != 0ull && M.n_visits != nullptr;
+  if (counting && count_start && R.ic >= 0 && atomicExch(M.last_id + R.ic, pid) != pid) atomicAdd(M.n_visits + R.ic, 1ull);
   for (;;) {
     double dt;
     typename G::Cross cr;
@@ -205,6 +214,7 @@ __device__ inline int geo_march(const ModelDev &M, typename Geo<GEO>::Ray &R, do
       R.t += dt;
       G::step(M, R, cr);
       if (G::escaped(M, R)) return MARCH_ESCAPED;
+      if (counting && R.ic >= 0 && atomicExch(M.last_id + R.ic, pid) != pid) atomicAdd(M.n_visits + R.ic, 1ull);
     } else {
       const double len = dt * (tau_left / tau_cell);
       if (R.t + len > t_source) return MARCH_REABSORBED;

@@ -137,6 +137,8 @@ class FlatConf:
     n_mrw_max: int = 1000
     propagation_check_frequency: float = 1.e-3
     specific_energy_additional: bool = False   # specific_energy_type = 'additional'
+    use_pda: bool = False                      # 'pda' (setup_rt.f90:75; src/grid/grid_pda_3d.f90)
+    count_photons: bool = False                # keep n_photons without the PDA (output_n_photons /= 'none')
     n_initial_iter: int = 5
     n_initial_photons: int = 0
     forced_first_interaction: bool = True

@@ -109,7 +109,8 @@ def write_peeled_group(g, p):
 
 def write_rtin(filename, model: FlatModel, n_initial_iter=5, n_initial_photons=10000, n_last_photons=0,
                output_specific_energy="last", copy_input=True, check_convergence=None, physics_io_bytes=8,
-               raytracing=False, n_ray_photons=(0, 0), extra_root_attrs=None, n_last_photons_mono=(0, 0)):
+               raytracing=False, n_ray_photons=(0, 0), extra_root_attrs=None, n_last_photons_mono=(0, 0),
+               output_n_photons="none"):
     f = h5write.File()
     c = model.conf
     A = f.attrs
@@ -126,7 +127,7 @@ def write_rtin(filename, model: FlatModel, n_initial_iter=5, n_initial_photons=1
     A["n_stats"] = np.int64(0)
     A["n_inter_max"] = np.int64(c.n_inter_max)
     A["n_reabs_max"] = np.int64(c.n_reabs_max)
-    A["pda"] = b"no"
+    A["pda"] = _yn(c.use_pda)
     A["mrw"] = _yn(c.use_mrw)
     if c.use_mrw:
         A["mrw_gamma"] = float(c.mrw_gamma)
@@ -278,7 +279,7 @@ def write_rtin(filename, model: FlatModel, n_initial_iter=5, n_initial_photons=1
     go.attrs["output_density"] = "none"
     go.attrs["output_density_diff"] = "none"
     go.attrs["output_specific_energy"] = output_specific_energy
-    go.attrs["output_n_photons"] = "none"
+    go.attrs["output_n_photons"] = output_n_photons
     gb = go.create_group("Binned")
     if model.binned is not None:
         write_peeled_group(gb.create_group("group_00001"), model.binned)

@@ -293,8 +293,16 @@ def run(input_file, output_file, overwrite=False, device=None, log=None):
         model, rs, fin = read_rtin(input_file)
         if rs.monochromatic and model.binned is not None:
             raise ModelError("Binned images cannot be computed in monochromatic mode")   # hyperion/model/model.py:115
-        if rs.pda:
-            raise ModelError("the partial diffusion approximation is not implemented by this engine yet")
+        if rs.pda and not getattr(model, "no_dust", False):
+            # setup_rt.f90:296-302
+            if any(getattr(d, "version", 2) == 1 for d in model.dust):
+                raise ModelError("version 1 dust files can no longer be used when PDA is computed due to a bug - to fix "
+                                 "this, re-generate the dust file using the latest version of Hyperion")
+            if model.grid_type in ("oct", "amr"):
+                raise ModelError("PDA is not available for this grid type")      # grid_pda_disabled.f90
+            model.conf.use_pda = True
+        # the n_photons array exists with the PDA or when it is to be written (grid_physics_3d.f90:308-317)
+        model.conf.count_photons = rs.output_n_photons != "none"
         if rs.specific_energy_type == "additional":
             # setup_initial (src/main/setup_rt.f90:191-194)
             if rs.n_initial_iter == 0:
@@ -361,20 +369,22 @@ def run(input_file, output_file, overwrite=False, device=None, log=None):
             return mode == "all" or (mode == "last" and it == n_iter)
 
         log(" [output_grid] outputting grid arrays for iteration")
-        if wanted(rs.output_n_photons):
-            log(" WARNING: n_photons array is not allocated [output_grid]")
-        def put(name, arr):
+        def put(name, arr, dtype=None):
             """output_grid (src/grid/grid_generic.f90:29-130): one dataset per iteration, or, for AMR
             grids, one per level / grid (src/grid/grid_io_amr.f90)."""
             if model.grid_type == "amr":
                 for il, ig, sl, shp in model.amr_slices():
                     path = "level_%05d/grid_%05d" % (il + 1, ig + 1)
                     gg = g.require_group(path)
-                    gg.create_dataset(name, arr[:, sl].reshape((-1,) + shp).astype(io_dtype))
+                    a = arr[:, sl].reshape((-1,) + shp)
+                    gg.create_dataset(name, (a[0] if dtype is not None else a).astype(dtype or io_dtype))
             else:
-                d = g.create_dataset(name, arr.astype(io_dtype))
+                d = g.create_dataset(name, (arr[0] if dtype is not None else arr).astype(dtype or io_dtype))
                 d.attrs["geometry"] = rs.geometry_id
 
+        if wanted(rs.output_n_photons):
+            # output_grid (grid_generic.f90:40-46): one value per cell, no dust dimension
+            put("n_photons", eng.get_n_photons()[None], dtype=np.int64)
         if wanted(rs.output_specific_energy):
             if se is None:
                 se = eng.get_specific_energy()

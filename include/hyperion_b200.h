@@ -131,6 +131,13 @@ typedef struct {
    * update_energy_abs :537-545): the specific energy passed in is an extra heating term that is added
    * after every Lucy iteration, and the iterations start from the minimum specific energy. */
   int32_t specific_energy_additional;
+  /* 'pda' (setup_rt.f90:75): after every Lucy iteration the specific energy of the cells fewer than
+   * max(30, 0.005 x mean) packets visited is replaced by the solution of the diffusion equation between their
+   * better-sampled neighbours (solve_pda, src/grid/grid_pda_3d.f90:105-169; Cartesian and polar grids). */
+  int32_t use_pda;
+  /* keep the per-cell packet counter n_photons without the PDA (output_n_photons /= 'none',
+   * src/grid/grid_physics_3d.f90:308-317) */
+  int32_t count_photons;
 } hyp_run_conf;
 
 #define HYP_FFI_WR99 1
@@ -291,6 +298,15 @@ int hyp_run_lucy_iteration(hyp_ctx *ctx, int64_t n_photons, int64_t iteration, h
 /* replaces: output_grid 'specific_energy' (src/grid/grid_generic.f90:50-63): [n_dust][n_cells] */
 int hyp_get_specific_energy(hyp_ctx *ctx, double *out);
 int hyp_get_density(hyp_ctx *ctx, double *out);
+/* replaces: the n_photons dataset of output_grid (src/grid/grid_generic.f90:40-46): number of packets that visited
+ * each cell in the last Lucy iteration, [n3][n2][n1] (grid_propagate_3d.f90:90-95,175-180), summed over the
+ * processes once the host has reduced hyp_lucy_device_buffers.  Needs use_pda or count_photons. */
+int hyp_get_n_photons(hyp_ctx *ctx, int64_t *out);
+/* replaces: solve_pda (src/grid/grid_pda_3d.f90:105-169) on the current specific energy: the cells that fewer than
+ * max(30, 0.005 x mean) packets visited (and that do not lie on the edge of the grid) get the solution of the
+ * diffusion equation between their neighbours.  n_photons: [n3][n2][n1] packet counts, or NULL for the counts of the
+ * last Lucy iteration.  hyp_lucy_finish calls this itself when use_pda is set.  n_pda_cells may be NULL. */
+int hyp_solve_pda(hyp_ctx *ctx, const int64_t *n_photons, int64_t *n_pda_cells);
 /* raw deposit sums of the last iteration (specific_energy_sum, grid_physics_3d.f90:40) */
 int hyp_get_energy_sum(hyp_ctx *ctx, double *out);
 

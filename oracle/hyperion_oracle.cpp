@@ -761,6 +761,7 @@ struct Photon {
   Cell icell;
   bool last_isotropic = false, scattered = false, reprocessed = false;
   int n_scat = 0, source_id = 0, dust_id = 0;
+  int64_t id = 0;  // photon_counter at emission (source.f90:171-172)
   char last[3] = "  ";
   // state before the last interaction, used by peel-off (type_photon.f90:44-46)
   Angle a_prev{0, 0, 0, 0};
@@ -1203,6 +1204,11 @@ struct orc_ctx {
   std::vector<PdfDiscrete> mono_emiss_pdf;
   bool mono_run = false;
   bool any_intersect = false;
+  // number of packets that visited each cell (grid_physics_3d.f90:38-39,308-317), kept when the partial diffusion
+  // approximation or the n_photons output needs it
+  std::vector<int64_t> n_photons, last_photon_id;
+  int64_t photon_counter = 0;
+  int pda_exact_limit = 10000;   // grid_pda_3d.f90:126: below this many PDA cells the exact solver is used
   // counters
   int64_t killed_photons_geo = 0, killed_photons_int = 0;
   int64_t n_crossings = 0, n_absorptions = 0, n_scatterings = 0, n_escaped = 0, n_photons_run = 0;
@@ -2774,6 +2780,8 @@ void emit(orc_ctx &g, Photon &p, bool reemit = false, int reemit_id = 0, double 
   p.emiss_type = src.freq_type;
   p.last[0] = 's';
   p.last[1] = 'r';
+  g.photon_counter++;
+  p.id = g.photon_counter;
   place_in_cell(g, p);
   if (p.killed)
     throw OracleError{
@@ -2786,6 +2794,15 @@ void grid_integrate(orc_ctx &g, Photon &p, double tau_required, double &tau_achi
   tau_achieved = 0.0;
   if (!p.in_cell) throw OracleError{"photon has not been placed in a cell"};
   if (escaped(g, p.icell)) return;
+  // grid_propagate_3d.f90:90-95: a packet counts once per cell for as long as no other packet enters it
+  auto count_visit = [&]() {
+    if (g.n_photons.empty()) return;
+    if (g.last_photon_id[p.icell.ic - 1] != p.id) {
+      g.n_photons[p.icell.ic - 1]++;
+      g.last_photon_id[p.icell.ic - 1] = p.id;
+    }
+  };
+  count_visit();
   if (tau_required == 0.0) return;
   double t_source;
   int source_id;
@@ -2840,6 +2857,7 @@ void grid_integrate(orc_ctx &g, Photon &p, double tau_required, double &tau_achi
       p.icell = next_cell(g, p.icell, id_min, p.r);
       p.on_wall_id = WallId{-id_min.w1, -id_min.w2, -id_min.w3};  // opposite_wall (grid_geometry_common_3d.f90:40-45)
       if (escaped(g, p.icell)) return;
+      count_visit();   // grid_propagate_3d.f90:175-180
     } else {
       double tact = tmin * (tau_needed / tau_cell);
       t_achieved = t_achieved + tact;
@@ -2996,6 +3014,268 @@ void sublimate_dust(orc_ctx &g) {
   }
   update_energy_abs_tot(g);
   check_energy_abs(g);
+}
+
+// ---------------------------------------------------------------------------
+// Partial diffusion approximation (src/grid/grid_pda_3d.f90, grid_pda_{cartesian,spherical,cylindrical}_3d.f90)
+// ---------------------------------------------------------------------------
+double kappa_planck(const Dust &d, double e) { return interp1d_loglog(d.specific_energy.data(), d.kappa_planck.data(), d.n_e, e); }
+double chi_rosseland(const Dust &d, double e) { return interp1d_loglog(d.specific_energy.data(), d.chi_rosseland.data(), d.n_e, e); }
+
+struct PdaCell {
+  int i1, i2, i3, ic;  // 1-based, as type_grid_cell
+};
+
+int pda_cell_id(const orc_ctx &g, int i1, int i2, int i3) { return (i3 - 1) * g.n1 * g.n2 + (i2 - 1) * g.n1 + i1; }
+
+// cell_width (grid_geometry_cartesian_3d.f90:49-61, _spherical_3d.f90:60-72, _cylindrical_3d.f90:60-72)
+double pda_cell_width(const orc_ctx &g, const PdaCell &c, int idir) {
+  auto mid_log = [](const std::vector<double> &w, int i) {   // geo%r / geo%w (:139-143 / :130-134)
+    return w[i - 1] == 0.0 ? w[i] / 2.0 : std::pow(10.0, (std::log10(w[i - 1]) + std::log10(w[i])) / 2.0);
+  };
+  if (g.grid_type == 0) {
+    const std::vector<double> &w = idir == 1 ? g.w1 : (idir == 2 ? g.w2 : g.w3);
+    const int i = idir == 1 ? c.i1 : (idir == 2 ? c.i2 : c.i3);
+    return w[i] - w[i - 1];
+  }
+  if (g.grid_type == 1) {
+    const double r = mid_log(g.w1, c.i1);
+    if (idir == 1) return g.w1[c.i1] - g.w1[c.i1 - 1];
+    if (idir == 2) return r * (g.w2[c.i2] - g.w2[c.i2 - 1]);
+    const double t = (g.w2[c.i2 - 1] + g.w2[c.i2]) / 2.0;
+    return r * std::sin(t) * (g.w3[c.i3] - g.w3[c.i3 - 1]);
+  }
+  if (idir == 1) return g.w1[c.i1] - g.w1[c.i1 - 1];
+  if (idir == 2) return g.w2[c.i2] - g.w2[c.i2 - 1];
+  return mid_log(g.w1, c.i1) * (g.w3[c.i3] - g.w3[c.i3 - 1]);
+}
+
+// geometrical_factor (grid_pda_*_3d.f90)
+double pda_geometrical_factor(const orc_ctx &g, int wall, const PdaCell &c) {
+  if (g.grid_type == 1) {
+    const double a = g.w1[c.i1 - 1], b = g.w1[c.i1];
+    if (wall == 1) return 4. * a * a / ((a + b) * (a + b));
+    if (wall == 2) return 4. * b * b / ((a + b) * (a + b));
+    const double sa = std::sin(g.w2[c.i2 - 1]), sb = std::sin(g.w2[c.i2]);
+    if (wall == 3) return 2. * sa / (sa + sb);
+    if (wall == 4) return 2. * sb / (sa + sb);
+    return 1.0;
+  }
+  if (g.grid_type == 2) {
+    const double a = g.w1[c.i1 - 1], b = g.w1[c.i1];
+    if (wall == 1) return 2. * a / (a + b);
+    if (wall == 2) return 2. * b / (a + b);
+    return 1.0;
+  }
+  return 1.0;
+}
+
+// next_cell(cell, wall) (next_cell_int; the polar grids wrap in phi)
+PdaCell pda_next_cell(const orc_ctx &g, const PdaCell &c, int wall) {
+  PdaCell n = c;
+  switch (wall) {
+    case 1: n.i1--; break;
+    case 2: n.i1++; break;
+    case 3: n.i2--; break;
+    case 4: n.i2++; break;
+    case 5:
+      n.i3--;
+      if (g.grid_type != 0 && n.i3 == 0) n.i3 = g.n3;
+      break;
+    default:
+      n.i3++;
+      if (g.grid_type != 0 && n.i3 == g.n3 + 1) n.i3 = 1;
+  }
+  n.ic = pda_cell_id(g, n.i1, n.i2, n.i3);
+  return n;
+}
+
+struct PdaState {
+  std::vector<double> e_mean;
+  int n_dim = 3;
+};
+
+double pda_density_sum(const orc_ctx &g, int ic) {
+  double s = 0.0;
+  for (int id = 0; id < g.n_dust; id++) s = s + g.density[(size_t)id * g.n_cells + ic - 1];
+  return s;
+}
+
+// update_e_mean (grid_pda_3d.f90:92-103)
+void pda_update_e_mean(const orc_ctx &g, PdaState &P, int ic) {
+  P.e_mean[ic - 1] = 0.;
+  const double rs = pda_density_sum(g, ic);
+  if (rs > 0.0) {
+    for (int id = 0; id < g.n_dust; id++) {
+      const size_t k = (size_t)id * g.n_cells + ic - 1;
+      P.e_mean[ic - 1] = P.e_mean[ic - 1] + g.density[k] * g.specific_energy[k] / kappa_planck(g.d[id], g.specific_energy[k]);
+    }
+    P.e_mean[ic - 1] = P.e_mean[ic - 1] / rs;
+  }
+}
+
+// update_specific_energy (grid_pda_3d.f90:52-90)
+void pda_update_specific_energy(orc_ctx &g, const PdaState &P, int ic) {
+  for (int id = 0; id < g.n_dust; id++) {
+    const Dust &d = g.d[id];
+    const size_t k = (size_t)id * g.n_cells + ic - 1;
+    double s = g.specific_energy[k];
+    const double smin = d.specific_energy[0], smax = d.specific_energy[d.n_e - 1];
+    if (P.e_mean[ic - 1] < smin / kappa_planck(d, smin)) {
+      s = smin;
+    } else if (P.e_mean[ic - 1] > smax / kappa_planck(d, smax)) {
+      s = smax;
+    } else {
+      for (;;) {
+        const double s_prev = s;
+        s = P.e_mean[ic - 1] * kappa_planck(d, s);
+        if (std::max(s / s_prev, s_prev / s) - 1.0 < 1.e-5) break;
+      }
+    }
+    g.specific_energy[k] = s;
+  }
+}
+
+// dtau_rosseland (grid_pda_3d.f90:171-181)
+double pda_dtau_rosseland(const orc_ctx &g, const PdaCell &c, int idir) {
+  double t = 0.0;
+  for (int id = 0; id < g.n_dust; id++) {
+    const size_t k = (size_t)id * g.n_cells + c.ic - 1;
+    t = t + g.density[k] * chi_rosseland(g.d[id], g.specific_energy[k]) * pda_cell_width(g, c, idir);
+  }
+  return t;
+}
+
+// lineq_gausselim_dp (fortranlib/src/lib_algebra.f90:166-200); a is stored column-major, a(i, j) at [i + n * j]
+void lineq_gausselim(std::vector<double> &a, std::vector<double> &b, int n) {
+  auto A = [&](int i, int j) -> double & { return a[(size_t)(i - 1) + (size_t)n * (j - 1)]; };
+  for (int i = 1; i <= n - 1; i++) {
+    if (A(i, i) == 0.0) throw OracleError{"Zero pivot value"};
+    for (int j = i + 1; j <= n; j++)
+      if (A(i, j) != 0.0) {
+        const double frac = A(i, j) / A(i, i);
+        b[j - 1] = b[j - 1] - frac * b[i - 1];
+        for (int k = i; k <= n; k++) A(k, j) = A(k, j) - frac * A(k, i);
+      }
+  }
+  for (int i = n; i >= 2; i--)
+    for (int j = i - 1; j >= 1; j--)
+      if (A(i, j) != 0.0) {
+        const double frac = A(i, j) / A(i, i);
+        b[j - 1] = b[j - 1] - frac * b[i - 1];
+        for (int k = i; k <= n; k++) A(k, j) = A(k, j) - frac * A(k, i);
+      }
+  for (int i = 1; i <= n; i++) b[i - 1] = b[i - 1] / A(i, i);
+}
+
+// solve_pda_indiv_exact (grid_pda_3d.f90:183-248)
+void solve_pda_indiv_exact(orc_ctx &g, PdaState &P, const std::vector<PdaCell> &cells, const std::vector<int> &id_pda_cell) {
+  const int n = (int)cells.size();
+  for (const PdaCell &c : cells) pda_update_e_mean(g, P, c.ic);
+  std::vector<double> a((size_t)n * n, 0.0), b(n, 0.0);
+  for (int id_curr = 1; id_curr <= n; id_curr++) {
+    const PdaCell &curr = cells[id_curr - 1];
+    for (int wall = 1; wall <= P.n_dim * 2; wall++) {
+      const int direction = (wall + 1) / 2;
+      const PdaCell next = pda_next_cell(g, curr, wall);
+      double dtau_sum = pda_dtau_rosseland(g, curr, direction) + pda_dtau_rosseland(g, next, direction);
+      if (dtau_sum < 1e-100) dtau_sum = 1e-100;
+      double coefficient = 1. / dtau_sum / pda_cell_width(g, curr, direction);
+      coefficient = coefficient * pda_geometrical_factor(g, wall, curr);
+      a[(size_t)(id_curr - 1) + (size_t)n * (id_curr - 1)] -= coefficient;
+      if (id_pda_cell[next.ic - 1] > 0) {
+        const int id_next = id_pda_cell[next.ic - 1];
+        a[(size_t)(id_next - 1) + (size_t)n * (id_curr - 1)] += coefficient;
+      } else {
+        b[id_curr - 1] = b[id_curr - 1] - coefficient * P.e_mean[next.ic - 1];
+      }
+    }
+  }
+  lineq_gausselim(a, b, n);
+  for (int id_curr = 1; id_curr <= n; id_curr++) {
+    const int ic = cells[id_curr - 1].ic;
+    P.e_mean[ic - 1] = b[id_curr - 1];
+    pda_update_specific_energy(g, P, ic);
+  }
+}
+
+// solve_pda_indiv_iterative (grid_pda_3d.f90:250-325): Gauss-Seidel sweeps in cell order
+void solve_pda_indiv_iterative(orc_ctx &g, PdaState &P, const std::vector<PdaCell> &cells) {
+  const double tolerance_iter = 1.e-4;
+  for (const PdaCell &c : cells) pda_update_e_mean(g, P, c.ic);
+  for (;;) {
+    double max_e_diff = 0.;
+    for (const PdaCell &curr : cells) {
+      double a = 0.0, b = 0.0;
+      for (int wall = 1; wall <= P.n_dim * 2; wall++) {
+        const int direction = (wall + 1) / 2;
+        const PdaCell next = pda_next_cell(g, curr, wall);
+        double coefficient = 1. / (pda_dtau_rosseland(g, curr, direction) + pda_dtau_rosseland(g, next, direction)) /
+                             pda_cell_width(g, curr, direction);
+        coefficient = coefficient * pda_geometrical_factor(g, wall, curr);
+        a = a - coefficient;
+        b = b - coefficient * P.e_mean[next.ic - 1];
+      }
+      const double e_new = b / a;
+      const double e_diff = std::fabs(e_new - P.e_mean[curr.ic - 1]) / P.e_mean[curr.ic - 1];
+      if (e_diff > max_e_diff) max_e_diff = e_diff;
+      P.e_mean[curr.ic - 1] = e_new;
+    }
+    if (max_e_diff < tolerance_iter) break;
+  }
+  for (const PdaCell &c : cells) pda_update_specific_energy(g, P, c.ic);
+}
+
+// solve_pda (grid_pda_3d.f90:105-169).  Returns the number of PDA cells; exact_limit is the reference's 10000.
+int solve_pda(orc_ctx &g, int exact_limit = 10000) {
+  if (g.grid_type > 2) throw OracleError{"PDA is not available for this grid type"};   // grid_pda_disabled.f90
+  if (g.n_photons.empty()) throw OracleError{"n_photons array is not allocated"};
+  const int nc = g.n_cells;
+  double tot = 0.0;
+  for (int64_t v : g.n_photons) tot = tot + (double)v;
+  const double mean_n_photons = tot / (double)nc;
+  const double threshold_pda = 0.005;
+  const int64_t limit = std::max<int64_t>(30, (int64_t)std::ceil(threshold_pda * mean_n_photons));
+  std::vector<char> do_pda(nc, 0);
+  for (int ic = 1; ic <= nc; ic++) do_pda[ic - 1] = g.n_photons[ic - 1] < limit && pda_density_sum(g, ic) > 0.0;
+  // check_allowed_pda: no PDA in the cells on the edge of the grid (the polar grids are periodic in phi)
+  for (int i3 = 1; i3 <= g.n3; i3++)
+    for (int i2 = 1; i2 <= g.n2; i2++)
+      for (int i1 = 1; i1 <= g.n1; i1++)
+        if (i1 == 1 || i1 == g.n1 || i2 == 1 || i2 == g.n2 || (g.grid_type == 0 && (i3 == 1 || i3 == g.n3)))
+          do_pda[pda_cell_id(g, i1, i2, i3) - 1] = 0;
+  int n_pda = 0;
+  for (char c : do_pda) n_pda += c;
+  if (n_pda == 0) return 0;
+  const double tolerance = n_pda < exact_limit ? 1.e-5 : 1.e-4;
+  PdaState P;
+  P.n_dim = (g.grid_type != 0 && g.n3 == 1) ? 2 : 3;
+  P.e_mean.assign(nc, 0.0);
+  for (int ic = 1; ic <= nc; ic++) pda_update_e_mean(g, P, ic);
+  std::vector<PdaCell> cells;
+  std::vector<int> id_pda_cell(nc, -1);
+  for (int i3 = 1; i3 <= g.n3; i3++)
+    for (int i2 = 1; i2 <= g.n2; i2++)
+      for (int i1 = 1; i1 <= g.n1; i1++) {
+        const int ic = pda_cell_id(g, i1, i2, i3);
+        if (do_pda[ic - 1]) {
+          cells.push_back(PdaCell{i1, i2, i3, ic});
+          id_pda_cell[ic - 1] = (int)cells.size();
+        }
+      }
+  for (;;) {
+    const std::vector<double> prev = g.specific_energy;
+    if (n_pda < exact_limit)
+      solve_pda_indiv_exact(g, P, cells, id_pda_cell);
+    else
+      solve_pda_indiv_iterative(g, P, cells);
+    double maxdiff = 0.0;
+    for (size_t k = 0; k < prev.size(); k++) maxdiff = std::max(maxdiff, std::fabs(g.specific_energy[k] - prev[k]) / prev[k]);
+    if (maxdiff < tolerance) break;
+  }
+  update_energy_abs_tot(g);
+  check_energy_abs(g);
+  return n_pda;
 }
 
 // precompute_jnu_var (grid_physics_3d.f90:613-629)
@@ -4501,6 +4781,15 @@ int orc_lucy_begin(orc_ctx *g) {
   g->energy_current = 0.0;
   g->killed_photons_geo = g->killed_photons_int = 0;
   g->n_crossings = g->n_absorptions = g->n_scatterings = g->n_escaped = g->n_photons_run = 0;
+  // grid_reset_energy (grid_generic.f90:18-25); the arrays exist with the PDA or the n_photons output
+  // (grid_physics_3d.f90:308-317)
+  if (g->conf.use_pda || g->conf.count_photons) {
+    g->n_photons.assign(g->n_cells, 0);
+    g->last_photon_id.assign(g->n_cells, 0);
+  } else {
+    g->n_photons.clear();
+    g->last_photon_id.clear();
+  }
   try {
     precompute_jnu_var(*g);
     if (g->conf.use_mrw) prepare_mrw(*g);  // iter_lucy.f90:109-112
@@ -4530,6 +4819,7 @@ void orc_set_energy_current(orc_ctx *g, double e) { g->energy_current = e; }
 int orc_lucy_finish(orc_ctx *g, hyp_iter_stats *st) {
   try {
     update_energy_abs(*g, g->energy_total / g->energy_current);
+    if (g->conf.use_pda) solve_pda(*g, g->pda_exact_limit);   // iter_lucy.f90:227
     sublimate_dust(*g);
   } catch (OracleError &e) {
     return fail(g, e.msg);
@@ -4559,6 +4849,34 @@ int orc_run_lucy_iteration(orc_ctx *g, int64_t n_photons, hyp_iter_stats *st) {
 int orc_get_specific_energy(orc_ctx *g, double *out) {
   memcpy(out, g->specific_energy.data(), g->specific_energy.size() * sizeof(double));
   return 0;
+}
+// n_photons (grid_physics_3d.f90:38), zeros when it is not kept; the arrays of emulated ranks add up
+// (mp_collect_physical_arrays, mpi_routines.f90:303-311)
+int orc_get_n_photons(orc_ctx *g, int64_t *out) {
+  for (int ic = 0; ic < g->n_cells; ic++) out[ic] = g->n_photons.empty() ? 0 : g->n_photons[ic];
+  return 0;
+}
+int orc_set_n_photons(orc_ctx *g, const int64_t *in) {
+  g->n_photons.assign(in, in + g->n_cells);
+  return 0;
+}
+int orc_put_specific_energy(orc_ctx *g, const double *se) {
+  g->specific_energy.assign(se, se + (size_t)g->n_dust * g->n_cells);
+  return 0;
+}
+// test hook: the reference's switch between the exact and the iterative solver (10000 PDA cells)
+int orc_set_pda_exact_limit(orc_ctx *g, int32_t n) {
+  g->pda_exact_limit = n;
+  return 0;
+}
+// solve_pda on the current state; returns the number of PDA cells, or -1
+int orc_solve_pda(orc_ctx *g) {
+  try {
+    return solve_pda(*g, g->pda_exact_limit);
+  } catch (OracleError &e) {
+    fail(g, e.msg);
+    return -1;
+  }
 }
 int orc_get_density(orc_ctx *g, double *out) {
   memcpy(out, g->density.data(), g->density.size() * sizeof(double));

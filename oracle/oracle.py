@@ -128,6 +128,30 @@ class Oracle(CApi):
         self.check(self.lib.orc_get_energy_sum(self.ctx, _ptr(out)))
         return out
 
+    def get_n_photons(self):
+        out = np.empty(tuple(self.shape), dtype=np.int64)
+        self.check(self.lib.orc_get_n_photons(self.ctx, out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def set_n_photons(self, a):
+        a = np.ascontiguousarray(a, dtype=np.int64)
+        self.check(self.lib.orc_set_n_photons(self.ctx, a.ctypes.data_as(C.c_void_p)))
+
+    def put_specific_energy(self, a):
+        """Overwrite the specific energy (test hook; the minimum specific energies stay)."""
+        a = np.ascontiguousarray(a, dtype=np.float64)
+        self.check(self.lib.orc_put_specific_energy(self.ctx, _ptr(a)))
+
+    def set_pda_exact_limit(self, n):
+        self.check(self.lib.orc_set_pda_exact_limit(self.ctx, C.c_int32(n)))
+
+    def solve_pda(self):
+        """solve_pda on the current specific energy and n_photons; returns the number of PDA cells."""
+        n = self.lib.orc_solve_pda(self.ctx)
+        if n < 0:
+            self.check(1)
+        return n
+
     def get_density(self):
         out = self._grid()
         self.check(self.lib.orc_get_density(self.ctx, _ptr(out)))

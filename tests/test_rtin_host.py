@@ -493,3 +493,42 @@ def test_runner_monochromatic(golden_car, tmp_path):
     eng.final_finish()
     assert np.allclose(eng.sed(0), sed, rtol=1e-9, atol=1e-300)
     eng.close()
+
+
+def test_rtin_roundtrip_pda_and_n_photons(golden_car, tmp_path):
+    """'pda' (setup_rt.f90:75) and Output/output_n_photons (:273-278)."""
+    from helpers import bitlevel_model
+    m = bitlevel_model(golden_car, False, False)
+    m.conf.use_pda = True
+    fn = str(tmp_path / "m.rtin")
+    rtin_write.write_rtin(fn, m, output_n_photons="last")
+    got, rs, _ = rtin.read_rtin(fn)
+    assert rs.pda and rs.output_n_photons == "last"
+
+
+@pytest.mark.gpu
+def test_runner_pda_and_n_photons(golden_car, tmp_path):
+    """main.f90 with pda = yes and output_n_photons = all: every iteration group holds the n_photons dataset
+    (output_grid, grid_generic.f90:40-46), one value per cell, and the run ends normally."""
+    from helpers import bitlevel_model
+    import copy
+    m = bitlevel_model(golden_car, False, False)
+    m.conf.use_pda = True
+    fin, fout = str(tmp_path / "m.rtin"), str(tmp_path / "m.rtout")
+    kw = dict(n_initial_iter=2, n_initial_photons=3000, output_n_photons="all", output_specific_energy="all")
+    # the reference's kmh_lite.hdf5 is a version-1 dust file: refused with the PDA (setup_rt.f90:296-302)
+    assert m.dust[0].version == 1
+    rtin_write.write_rtin(fin, m, **kw)
+    assert runner.main(["-f", fin, fout]) == 1
+    d = copy.deepcopy(m.dust[0])
+    d.version = 2
+    m.dust = [d]
+    rtin_write.write_rtin(fin, m, **kw)
+    assert runner.main(["-f", fin, fout]) == 0
+    r = h5min.File(fout)
+    for it in (1, 2):
+        g = r["iteration_%05d" % it]
+        n = g["n_photons"][...]
+        assert n.shape == m.density.shape[1:] and n.dtype == np.int64
+        assert n.max() <= 3000 * 1.05 and n.sum() > 3000
+        assert g["specific_energy"].shape == m.density.shape
