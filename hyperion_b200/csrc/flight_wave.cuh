@@ -50,7 +50,7 @@ constexpr uint32_t WAVE_CHUNK_MAX = 16384;      // packets per work item (2^14 *
 #endif
 
 enum { WC_NITEMS = 0, WC_ITEM_CURSOR, WC_N_FLIGHT, WC_N_INTERACT, WC_INTERACT_START, WC_N_FREE, WC_FREE_START,
-       WC_CLAIMED_LO, WC_CLAIMED_HI, WC_COUNT = 16 };
+       WC_CLAIMED_LO, WC_CLAIMED_HI, WC_N_EMIT, WC_COUNT = 16 };
 
 struct WaveQ {
   uint32_t *key;         // [capacity] state of every slot
@@ -113,7 +113,7 @@ wave_hist_kernel(WaveQ W, const uint32_t *__restrict__ src, const uint32_t n_src
 
 // One block: start of every bin in `sorted`, the work items (full chunks first so that the last blocks to
 // finish hold small items), the control words of the round.
-__global__ void __launch_bounds__(1024) wave_scan_kernel(WaveQ W, Pool P) {
+__global__ void __launch_bounds__(1024) wave_scan_kernel(WaveQ W, Pool P, const unsigned long long n_photons) {
   typedef cub::BlockScan<uint32_t, 1024> Scan;
   __shared__ typename Scan::TempStorage tmp_a, tmp_b, tmp_c;
   __shared__ uint32_t s_full;
@@ -166,6 +166,12 @@ __global__ void __launch_bounds__(1024) wave_scan_kernel(WaveQ W, Pool P) {
     const unsigned long long claimed = *P.next_photon;
     W.ctl[WC_CLAIMED_LO] = (uint32_t)claimed;
     W.ctl[WC_CLAIMED_HI] = (uint32_t)(claimed >> 32);
+    // the ids of this round's emission are handed out here, in one piece: free slot i of the round emits packet
+    // claimed + i (one atomic per warp on one address was 13 % of the emission kernel's stalls)
+    const unsigned long long left = n_photons > claimed ? n_photons - claimed : 0ull;
+    const uint32_t n_emit = (uint32_t)min((unsigned long long)min(W.ctl[WC_N_FREE], W.emit_max), left);
+    W.ctl[WC_N_EMIT] = n_emit;
+    *P.next_photon = claimed + n_emit;
   }
 }
 
@@ -710,7 +716,8 @@ template <int ND>
 __global__ void __launch_bounds__(SERVICE_THREADS, INTERACT_MIN_BLOCKS)
 wave_emit_kernel(const ModelDev M, Pool P, const WaveQ W, const unsigned long long first_id,
                  const unsigned long long n_photons, const uint32_t iteration) {
-  const uint32_t n = min(W.ctl[WC_N_FREE], W.emit_max), start = W.ctl[WC_FREE_START];
+  const uint32_t n = W.ctl[WC_N_EMIT], start = W.ctl[WC_FREE_START];
+  const unsigned long long k_base = (unsigned long long)W.ctl[WC_CLAIMED_LO] | ((unsigned long long)W.ctl[WC_CLAIMED_HI] << 32);
   const unsigned lane = threadIdx.x & 31;
   Slot<ND> *slots = (Slot<ND> *)P.slots;
   double energy_emitted = 0.0;
@@ -719,13 +726,8 @@ wave_emit_kernel(const ModelDev M, Pool P, const WaveQ W, const unsigned long lo
   for (uint32_t base = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < n; base += stride) {
     const uint32_t i = base + lane;
     const bool valid = i < n;
-    // claim packet ids (warp-aggregated); packets are emitted in id order
-    const unsigned m = __ballot_sync(0xffffffffu, valid);
-    const int leader = __ffs(m) - 1;
-    unsigned long long k0 = 0;
-    if ((int)lane == leader) k0 = atomicAdd(P.next_photon, (unsigned long long)__popc(m));
-    k0 = __shfl_sync(0xffffffffu, k0, leader);
-    unsigned long long k = k0 + __popc(m & ((1u << lane) - 1u));
+    // packet ids: the scan kernel has reserved [k_base, k_base + n) for this round; packets are emitted in id order
+    unsigned long long k = k_base + i;
     if (!valid || k >= n_photons) continue;
     const uint32_t slot = W.sorted[start + i];
     Photon<ND> p;

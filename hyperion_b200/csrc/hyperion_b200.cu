@@ -3353,7 +3353,7 @@ bool wave_wanted() {
 // the 12 bytes per thread of packet positions: 24^3 x 8, 21^3 x 12 and 19^3 x 16 bytes fit as before)
 constexpr uint32_t WAVE_SUM_OFF_ND2 = 110592, WAVE_SUM_OFF_ND34 = 111616, WAVE_SUM_OFF_2 = 53248, WAVE_SUM_OFF_ND1 = 108032;
 #ifndef WAVE_TILE_THREADS_DEFAULT
-#define WAVE_TILE_THREADS_DEFAULT 896
+#define WAVE_TILE_THREADS_DEFAULT 1024
 #endif
 constexpr uint32_t wave_sum_off(int nd, int ctas) {
   return ctas == 2 ? WAVE_SUM_OFF_2 : (nd == 1 ? WAVE_SUM_OFF_ND1 : (nd == 2 ? WAVE_SUM_OFF_ND2 : WAVE_SUM_OFF_ND34));
@@ -3528,7 +3528,7 @@ static int run_wave(hyp_ctx *c, int64_t first_id, int64_t n_photons, int64_t ite
     }
   };
   // HYPERION_B200_WAVE_SERVICE: blocks per SM of the interaction / emission kernels of a round that has tile visits
-  const int service_per_sm = getenv("HYPERION_B200_WAVE_SERVICE") ? std::max(1, atoi(getenv("HYPERION_B200_WAVE_SERVICE"))) : 8;
+  const int service_per_sm = getenv("HYPERION_B200_WAVE_SERVICE") ? std::max(1, atoi(getenv("HYPERION_B200_WAVE_SERVICE"))) : 16;
   const int service_blocks = c->sm_count * service_per_sm;
 
   wave_init_kernel<<<c->sm_count * 4, 256, 0, st>>>(W, P);
@@ -3548,7 +3548,7 @@ static int run_wave(hyp_ctx *c, int64_t first_id, int64_t n_photons, int64_t ite
     const int sort_blocks = (int)std::max<uint32_t>(1u, (n_src + WAVE_SORT_SEG - 1) / WAVE_SORT_SEG);
     lap(0, st, true);
     wave_hist_kernel<<<sort_blocks, WAVE_SORT_THREADS, sort_smem / 2, st>>>(W, src, n_src);
-    wave_scan_kernel<<<1, 1024, 0, st>>>(W, P);
+    wave_scan_kernel<<<1, 1024, 0, st>>>(W, P, (unsigned long long)n_photons);
     wave_scatter_kernel<<<sort_blocks, WAVE_SORT_THREADS, sort_smem, st>>>(W, src, n_src);
     lap(0, st, false);
     CUDA_TRY(cudaGetLastError());

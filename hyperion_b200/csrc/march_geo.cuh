@@ -178,7 +178,7 @@ template <int GEO, int ND, bool DEP>
 __device__ inline int geo_march(const ModelDev &M, typename Geo<GEO>::Ray &R, double &tau_left, const double (&chi)[ND],
                                 const double (&kE)[ND], CellRec *__restrict__ cells, uint32_t &n_cross,
                                 const double t_source, const unsigned long long pid = 0ull,
-                                const bool count_start = true) {
+                                const bool count_start = true, int max_steps = 0x7fffffff) {
   using G = Geo<GEO>;
   if (G::escaped(M, R)) return MARCH_ESCAPED;
   // n_photons (grid_propagate_3d.f90:90-95,175-180): a packet counts once per cell for as long as no other packet
@@ -189,7 +189,9 @@ __device__ inline int geo_march(const ModelDev &M, typename Geo<GEO>::Ray &R, do
   // remains are packets that come back to a cell after leaving it while another packet passed through.
   const bool counting = DEP && pid != 0ull && M.n_visits != nullptr;
   if (counting && count_start && R.ic >= 0 && atomicExch(M.last_id + R.ic, pid) != pid) atomicAdd(M.n_visits + R.ic, 1ull);
-  for (;;) {
+  // max_steps: crossings after which the march returns 0 (still in flight; call again with count_start = false)
+  for (;; --max_steps) {
+    if (max_steps <= 0) return 0;
     double dt;
     typename G::Cross cr;
     double rho[ND];
