@@ -93,3 +93,47 @@ def test_failure_on_one_rank_stops_all(golden_car, tmp_path):
     assert p.returncode != 0
     assert "File exists" in p.stderr
     assert open(fout).read() == "occupied"
+
+
+@pytest.mark.skipif(_n_gpus() < 2, reason="needs 2 GPUs")
+def test_two_rank_monochromatic_and_pda_run(golden_car, tmp_path):
+    """The round-2 paths through two ranks: the monochromatic final iteration (every packet already scaled, the cubes
+    of the ranks add up, iter_final_mono.f90:118,187) with raytracing, and Lucy iterations with the PDA, whose packet
+    counts travel with the reduced grid (mpi_routines.f90:303-311).  SEDs and images equal the 1-rank run to rounding;
+    n_photons and the PDA cells may differ by a few counts, so the specific energy is
+    compared on the cells both runs sampled."""
+    import copy
+    from helpers import bitlevel_model
+    from hyperion_b200 import rtin_write
+    from hyperion_b200.flatmodel import FlatPeeledGroup
+    from hyperion_b200.io import h5min
+    m = bitlevel_model(golden_car, False, False)
+    d = copy.deepcopy(m.dust[0])
+    d.version = 2
+    m.dust = [d]
+    m.conf.use_pda = True
+    m.frequencies = 2.99792458e10 / (np.array([0.45, 2.2, 40.]) * 1e-4)
+    pc = 3.08568025e18
+    m.peeled = [FlatPeeledGroup(theta=[30., 110.], phi=[40., 250.], sed=(2, 1e-3 * pc, 8. * pc),
+                                image=(4, 4, -2 * pc, 2 * pc, -2 * pc, 2 * pc), track_origin="basic",
+                                inu_min=1, inu_max=3, wavelengths=(3, 1., 1.))]
+    fin = str(tmp_path / "m.rtin")
+    rtin_write.write_rtin(fin, m, n_initial_iter=2, n_initial_photons=100000, n_last_photons_mono=(40000, 60000),
+                          raytracing=True, n_ray_photons=(20000, 30000), output_n_photons="last")
+    env = {k: v for k, v in os.environ.items()
+           if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "MASTER_ADDR", "MASTER_PORT", "HYPERION_B200_NGPU")}
+    out1, out2 = str(tmp_path / "one.rtout"), str(tmp_path / "two.rtout")
+    car = os.path.join(ROOT, "bin", "hyperion_car")
+    subprocess.check_call([car, "-f", fin, out1], env=env, stdout=subprocess.DEVNULL)
+    subprocess.check_call([car, "-f", fin, out2], env=dict(env, HYPERION_B200_NGPU="2"), stdout=subprocess.DEVNULL)
+    a, b = h5min.File(out1), h5min.File(out2)
+    for k in ("seds", "images"):
+        x, y = a["Peeled/group_00001/" + k][...], b["Peeled/group_00001/" + k][...]
+        nz = (x != 0) | (y != 0)
+        # the images start from specific energies that agree to the PDA's tolerance, not to rounding
+        assert nz.sum() > 20 and (np.abs(x[nz] - y[nz]) / np.maximum(np.abs(x[nz]), np.abs(y[nz]))).max() < 2e-2, k
+    n1, n2 = a["iteration_00002/n_photons"][...], b["iteration_00002/n_photons"][...]
+    assert abs(n1.sum() / n2.sum() - 1.) < 1e-2
+    e1, e2 = a["iteration_00002/specific_energy"][...][0], b["iteration_00002/specific_energy"][...][0]
+    both = (n1 >= 40) & (n2 >= 40)
+    assert both.sum() > 20 and np.abs(e1[both] / e2[both] - 1.).max() < 1e-9
