@@ -50,14 +50,15 @@ constexpr uint32_t WAVE_CHUNK_MAX = 16384;      // packets per work item (2^14 *
 #endif
 
 enum { WC_NITEMS = 0, WC_ITEM_CURSOR, WC_N_FLIGHT, WC_N_INTERACT, WC_INTERACT_START, WC_N_FREE, WC_FREE_START,
-       WC_CLAIMED_LO, WC_CLAIMED_HI, WC_N_EMIT, WC_COUNT = 16 };
+       WC_CLAIMED_LO, WC_CLAIMED_HI, WC_N_EMIT, WC_BY_SLOT, WC_COUNT = 16 };
 
 struct WaveQ {
   uint32_t *key;         // [capacity] state of every slot
   uint32_t *key_pos;     // [capacity] the same keys indexed by the slot's POSITION in `sorted`: once emission has
                          // ended the next sort reads them (and the list itself) as two streams instead of gathering
                          // key[slot] through the list, one 32-byte sector per 4-byte key
-  int by_slot;           // 1: this round's kernels also write key[slot] (the next sort still covers all slots)
+                         // (ctl[WC_BY_SLOT], set by the scan kernel: 1 while packet ids are left, i.e. while the next
+                         // sort still covers all slots and reads key[slot])
   uint32_t *sorted;      // [capacity] slot ids ordered by key (this round's list; the host alternates two buffers)
   uint32_t *bin_count;   // [n_tiles + 2]
   uint32_t *bin_cursor;  // [n_tiles + 2]
@@ -171,6 +172,7 @@ __global__ void __launch_bounds__(1024) wave_scan_kernel(WaveQ W, Pool P, const 
     const unsigned long long left = n_photons > claimed ? n_photons - claimed : 0ull;
     const uint32_t n_emit = (uint32_t)min((unsigned long long)min(W.ctl[WC_N_FREE], W.emit_max), left);
     W.ctl[WC_N_EMIT] = n_emit;
+    W.ctl[WC_BY_SLOT] = left > 0ull ? 1u : 0u;
     *P.next_photon = claimed + n_emit;
   }
 }
@@ -335,6 +337,7 @@ wave_tile_kernel(const ModelDev M, Pool P, const WaveQ W) {
   __shared__ unsigned long long s_cross, s_esc;   // work counters of the block
   const int n1 = M.n1, n2 = M.n2, n3 = M.n3;
   const uint32_t n_items = W.ctl[WC_NITEMS];
+  const bool by_slot = W.ctl[WC_BY_SLOT] != 0u;
   Slot<ND> *slots = (Slot<ND> *)P.slots;
   const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   constexpr int NWARPS = THREADS / 32;
@@ -470,7 +473,7 @@ wave_tile_kernel(const ModelDev M, Pool P, const WaveQ W) {
           __stcs((double2 *)&s->tau_left, make_double2(L.tau, L.t));
           __stcs((int4 *)&s->ix, make_int4(gx, gy, gz, ic));
           W.key_pos[s_pos[0]] = nk;
-          if (W.by_slot) W.key[slot] = nk;
+          if (by_slot) W.key[slot] = nk;
           fin = 3;
         }
         // While the item has plenty of packets left every lane keeps its queue full; towards the end a lane only
@@ -685,6 +688,7 @@ template <int ND>
 __global__ void __launch_bounds__(SERVICE_THREADS, INTERACT_MIN_BLOCKS)
 wave_interact_kernel(const ModelDev M, Pool P, const WaveQ W, const uint32_t iteration) {
   const uint32_t n = W.ctl[WC_N_INTERACT], start = W.ctl[WC_INTERACT_START];
+  const bool by_slot = W.ctl[WC_BY_SLOT] != 0u;
   Slot<ND> *slots = (Slot<ND> *)P.slots;
   uint32_t n_abs = 0, n_scat = 0, n_kill = 0;
   const uint32_t k_free = (uint32_t)W.n_tiles + 1u;
@@ -705,7 +709,7 @@ wave_interact_kernel(const ModelDev M, Pool P, const WaveQ W, const uint32_t ite
       nk = wave_tile_of(W, min(max(p.ix, 0), M.n1 - 1), min(max(p.iy, 0), M.n2 - 1), min(max(p.iz, 0), M.n3 - 1));
     }
     W.key_pos[start + i] = nk;
-    if (W.by_slot) W.key[slot] = nk;
+    if (by_slot) W.key[slot] = nk;
   }
   warp_add_scalar(M.scalars + SC_ABS, (double)n_abs);
   warp_add_scalar(M.scalars + SC_SCAT, (double)n_scat);

@@ -1907,7 +1907,7 @@ struct hyp_ctx {
   uint32_t *d_keys_in = nullptr, *d_keys_out = nullptr, *d_vals_in = nullptr, *d_perm = nullptr;
   void *d_sort_tmp = nullptr;
   size_t sort_tmp_bytes = 0;
-  cudaEvent_t evA = nullptr, evB = nullptr;
+  cudaEvent_t evA = nullptr, evB = nullptr, evCtl = nullptr;
   // imaging (final / raytracing iterations)
   std::vector<HostImage> groups;
   double *d_imgbuf = nullptr;       // all cubes of all groups, then SC_COUNT scalars
@@ -1976,7 +1976,7 @@ int device_error_to_status(hyp_ctx *c) {
       return fail(HYP_ERR_STATE, "internal error: a packet's kappa * energy exceeds the bound of the fixed-point deposits "
                                  "(set HYPERION_B200_ENGINE=rounds and report)");
     case ERR_JOBS:
-      return fail(HYP_ERR_STATE, "peel-off queue overflow: too many random-walk steps per round (lower HYPERION_B200_POOL)");
+      return fail(HYP_ERR_STATE, "internal error: the peel-off queue of a round overflowed");
     default:
       return fail(HYP_ERR_PHYSICS, "ERROR: in sampling mu for scattering");
   }
@@ -2135,6 +2135,7 @@ int hyp_ctx_create(int device_id, hyp_ctx **out) {
   CUDA_TRY(cudaStreamCreateWithFlags(&c->stream3, cudaStreamNonBlocking));
   CUDA_TRY(cudaEventCreateWithFlags(&c->evJoin3, cudaEventDisableTiming));
   CUDA_TRY(cudaEventCreate(&c->evA));
+  CUDA_TRY(cudaEventCreateWithFlags(&c->evCtl, cudaEventDisableTiming));
   CUDA_TRY(cudaEventCreate(&c->evB));
   CUDA_TRY(cudaMallocHost(&c->h_counts, (C_COUNT + 2) * sizeof(uint32_t)));
   memset(&c->pool, 0, sizeof c->pool);
@@ -2205,6 +2206,7 @@ void hyp_ctx_destroy(hyp_ctx *c) {
   if (c->evJoin3) cudaEventDestroy(c->evJoin3);
   if (c->stream3) cudaStreamDestroy(c->stream3);
   if (c->evA) cudaEventDestroy(c->evA);
+  if (c->evCtl) cudaEventDestroy(c->evCtl);
   if (c->evB) cudaEventDestroy(c->evB);
   for (cudaEvent_t e : c->wave_ev) cudaEventDestroy(e);
   free_dev(c->d_nvis); free_dev(c->d_lastid); free_dev(c->d_pda_geo); free_dev(c->d_pda_e); free_dev(c->d_pda_coef);
@@ -3537,6 +3539,8 @@ static int run_wave(hyp_ctx *c, int64_t first_id, int64_t n_photons, int64_t ite
   CUDA_TRY(cudaEventRecord(c->ev0, st));
   uint32_t *h = c->h_counts;
   bool handoff = false, compact = false;
+  const bool speculative = getenv("HYPERION_B200_WAVE_SPEC") ? atoi(getenv("HYPERION_B200_WAVE_SPEC")) != 0 : false;
+  bool stop_next = false, spec_emit = true;
   int n_tile_rounds = 0;
   uint32_t handoff_flights = 0, n_busy_prev = 0;
   for (int64_t round = 0;; ++round) {
@@ -3554,19 +3558,98 @@ static int run_wave(hyp_ctx *c, int64_t first_id, int64_t n_photons, int64_t ite
     CUDA_TRY(cudaGetLastError());
     c->launches_acc += 3;
     CUDA_TRY(cudaMemcpyAsync(h, W.ctl, WC_COUNT * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaStreamSynchronize(st));
-    const uint32_t n_flight = h[WC_N_FLIGHT], n_interact = h[WC_N_INTERACT], n_free = h[WC_N_FREE];
-    const unsigned long long claimed = (unsigned long long)h[WC_CLAIMED_LO] | ((unsigned long long)h[WC_CLAIMED_HI] << 32);
-    const bool ids_left = claimed < (unsigned long long)n_photons;
-    if (dbg)
-      fprintf(stderr, "[wave %lld] flights %u in %u items, interactions %u, free %u, claimed %llu\n", (long long)round,
-              n_flight, h[WC_NITEMS], n_interact, n_free, claimed);
-    if (n_flight == 0 && n_interact == 0 && !ids_left) break;
+    CUDA_TRY(cudaEventRecord(c->evCtl, st));
+    // The kernels of a round read their counts from device memory, so they CAN be launched before the host has seen
+    // the counts of this round's sort (HYPERION_B200_WAVE_SPEC=1): the GPU then does not wait for the host between
+    // the sort and the tile kernel, and what the host decides from the counts (end of the loop, hand-off to the
+    // direct kernels, which slots the next sort covers) takes effect one round later.  Measured: 55.8 against
+    // 55.4 ms per step (one more round, full-size grids for empty kernels), so the default waits for the counts.
+    uint32_t n_flight = 0, n_interact = 0, n_free = 0;
+    bool ids_left = true;
+    auto read_counts = [&]() -> int {
+      CUDA_TRY(cudaEventSynchronize(c->evCtl));
+      n_flight = h[WC_N_FLIGHT]; n_interact = h[WC_N_INTERACT]; n_free = h[WC_N_FREE];
+      const unsigned long long claimed = (unsigned long long)h[WC_CLAIMED_LO] | ((unsigned long long)h[WC_CLAIMED_HI] << 32);
+      ids_left = claimed < (unsigned long long)n_photons;
+      if (dbg)
+        fprintf(stderr, "[wave %lld] flights %u in %u items, interactions %u, free %u, claimed %llu\n", (long long)round,
+                n_flight, h[WC_NITEMS], n_interact, n_free, claimed);
+      return HYP_OK;
+    };
+    // known = the host has this round's counts: empty kernels are skipped and the grids sized to the work
+    auto launch_round = [&](const bool known) -> int {
+      const bool want_tile = !known || n_flight > 0, want_interact = !known || n_interact > 0;
+      const bool want_emit = known ? (n_free > 0 && ids_left) : spec_emit;
+      CUDA_TRY(cudaEventRecord(c->evFork, st));
+      auto launch_tile = [&]() -> int {
+        if (!want_tile) return HYP_OK;
+        // the tile kernel's own time: one pair of events per round, read when the photon loop has ended
+        while (c->wave_ev.size() < 2 * (size_t)(n_tile_rounds + 1)) {
+          cudaEvent_t e;
+          CUDA_TRY(cudaEventCreate(&e));
+          c->wave_ev.push_back(e);
+        }
+        const uint32_t grid_max = (uint32_t)(c->sm_count * ctas);
+        lap(1, st, true);
+        CUDA_TRY(cudaEventRecord(c->wave_ev[2 * n_tile_rounds], st));
+        tile<<<(int)(known ? std::min<uint32_t>(h[WC_NITEMS], grid_max) : grid_max), tile_threads, tile_smem, st>>>(c->M, P, W);
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaEventRecord(c->wave_ev[2 * n_tile_rounds + 1], st));
+        lap(1, st, false);
+        ++n_tile_rounds;
+        c->launches_acc += 1;
+        return HYP_OK;
+      };
+      if (tile_first) {
+        rc = launch_tile();
+        if (rc) return rc;
+      }
+      if (want_interact) {
+        CUDA_TRY(cudaStreamWaitEvent(s2, c->evFork, 0));
+        const int blocks = known ? (int)std::min<int64_t>(((int64_t)n_interact + SERVICE_THREADS - 1) / SERVICE_THREADS, service_blocks)
+                                 : service_blocks;
+        lap(2, s2, true);
+        wave_interact_kernel<ND><<<blocks, SERVICE_THREADS, 0, s2>>>(c->M, P, W, (uint32_t)iteration);
+        lap(2, s2, false);
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaEventRecord(c->evJoin, s2));
+        c->launches_acc += 1;
+      }
+      if (want_emit) {
+        CUDA_TRY(cudaStreamWaitEvent(s3, c->evFork, 0));
+        const int64_t n_emit = known ? std::min<int64_t>(n_free, W.emit_max) : (int64_t)W.emit_max;
+        const int blocks = (int)std::min<int64_t>((n_emit + SERVICE_THREADS - 1) / SERVICE_THREADS, service_blocks);
+        lap(3, s3, true);
+        wave_emit_kernel<ND><<<blocks, SERVICE_THREADS, 0, s3>>>(c->M, P, W, (unsigned long long)first_id,
+                                                               (unsigned long long)n_photons, (uint32_t)iteration);
+        lap(3, s3, false);
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaEventRecord(c->evJoin3, s3));
+        c->launches_acc += 1;
+      }
+      if (!tile_first) {
+        rc = launch_tile();
+        if (rc) return rc;
+      }
+      if (want_interact) CUDA_TRY(cudaStreamWaitEvent(st, c->evJoin, 0));
+      if (want_emit) CUDA_TRY(cudaStreamWaitEvent(st, c->evJoin3, 0));
+      return HYP_OK;
+    };
+    bool launched = false;
+    if (speculative && !stop_next) {
+      rc = launch_round(false);
+      if (rc) return rc;
+      launched = true;
+    }
+    rc = read_counts();
+    if (rc) return rc;
+    if (n_flight == 0 && n_interact == 0 && !ids_left) break;   // (kernels launched ahead found nothing to do)
     // this round emits nothing if every id was claimed before its sort: the next sort only needs its busy slots
     compact = !ids_left;
-    W.by_slot = ids_left ? 1 : 0;   // with ids left the next sort covers all slots and reads key[slot]
+    spec_emit = ids_left;
     n_busy_prev = n_flight + n_interact;
-    if (!ids_left && n_flight + n_interact < tail_min) {
+    const bool tail = !ids_left && n_flight + n_interact < tail_min;
+    if (tail && !launched) {
       wave_handoff_kernel<<<c->sm_count, 256, 0, st>>>(P, W);
       CUDA_TRY(cudaGetLastError());
       c->launches_acc += 1;
@@ -3574,62 +3657,13 @@ static int run_wave(hyp_ctx *c, int64_t first_id, int64_t n_photons, int64_t ite
       handoff_flights = n_flight;
       break;
     }
+    stop_next = tail;   // launched ahead: this round runs on the wave engine, the hand-off follows the next sort
     c->rounds_acc += 1;
     c->wave_rounds_acc += 1;
-    CUDA_TRY(cudaEventRecord(c->evFork, st));
-    auto launch_tile = [&]() -> int {
-      if (n_flight == 0) return HYP_OK;
-      // the tile kernel's own time: one pair of events per round, read when the photon loop has ended
-      while (c->wave_ev.size() < 2 * (size_t)(n_tile_rounds + 1)) {
-        cudaEvent_t e;
-        CUDA_TRY(cudaEventCreate(&e));
-        c->wave_ev.push_back(e);
-      }
-      lap(1, st, true);
-      CUDA_TRY(cudaEventRecord(c->wave_ev[2 * n_tile_rounds], st));
-      tile<<<(int)std::min<uint32_t>(h[WC_NITEMS], (uint32_t)(c->sm_count * ctas)), tile_threads, tile_smem, st>>>(c->M, P, W);
-      CUDA_TRY(cudaGetLastError());
-      CUDA_TRY(cudaEventRecord(c->wave_ev[2 * n_tile_rounds + 1], st));
-      lap(1, st, false);
-      ++n_tile_rounds;
-      c->launches_acc += 1;
-      return HYP_OK;
-    };
-    if (tile_first) {
-      rc = launch_tile();
+    if (!launched) {
+      rc = launch_round(true);
       if (rc) return rc;
     }
-    if (n_interact > 0) {
-      CUDA_TRY(cudaStreamWaitEvent(s2, c->evFork, 0));
-      const int blocks = (int)std::min<int64_t>(((int64_t)n_interact + SERVICE_THREADS - 1) / SERVICE_THREADS,
-                                                n_flight > 0 ? service_blocks : c->sm_count * 16);
-      lap(2, s2, true);
-      wave_interact_kernel<ND><<<blocks, SERVICE_THREADS, 0, s2>>>(c->M, P, W, (uint32_t)iteration);
-      lap(2, s2, false);
-      CUDA_TRY(cudaGetLastError());
-      CUDA_TRY(cudaEventRecord(c->evJoin, s2));
-      c->launches_acc += 1;
-    }
-    if (n_free > 0 && ids_left) {
-      CUDA_TRY(cudaStreamWaitEvent(s3, c->evFork, 0));
-      const int64_t n_emit = std::min<int64_t>(n_free, W.emit_max);
-      // next to a tile kernel the emission shares the SMs with it (4 blocks each); alone (the first round) it takes them all
-      const int blocks = (int)std::min<int64_t>((n_emit + SERVICE_THREADS - 1) / SERVICE_THREADS,
-                                                n_flight > 0 ? service_blocks : c->sm_count * 16);
-      lap(3, s3, true);
-      wave_emit_kernel<ND><<<blocks, SERVICE_THREADS, 0, s3>>>(c->M, P, W, (unsigned long long)first_id,
-                                                             (unsigned long long)n_photons, (uint32_t)iteration);
-      lap(3, s3, false);
-      CUDA_TRY(cudaGetLastError());
-      CUDA_TRY(cudaEventRecord(c->evJoin3, s3));
-      c->launches_acc += 1;
-    }
-    if (!tile_first) {
-      rc = launch_tile();
-      if (rc) return rc;
-    }
-    if (n_interact > 0) CUDA_TRY(cudaStreamWaitEvent(st, c->evJoin, 0));
-    if (n_free > 0 && ids_left) CUDA_TRY(cudaStreamWaitEvent(st, c->evJoin3, 0));
   }
   auto tile_times = [&]() -> int {
     if (n_tile_rounds == 0) return HYP_OK;
@@ -4263,7 +4297,11 @@ int run_final_rounds(hyp_ctx *c, int64_t first_id, int64_t n_photons, int scatte
   const uint32_t cap = (uint32_t)std::min<int64_t>(pool_target(), n_photons);
   int rc = ensure_pool(c, cap);
   if (rc) return rc;
-  rc = ensure_jobs(c, (c->M.use_mrw ? 8 : 2) * c->pool_cap);
+  // peel-off queue of a round: one job per emission and per interaction, plus two per random-walk step; a walk
+  // that finds the queue nearly full is interrupted and resumed next round (interact_final_kernel), so the size
+  // only sets how many steps fit in a round.  HYPERION_B200_JOBS: capacity in units of the packet pool (>= 4).
+  const int job_mult = c->M.use_mrw ? std::max(4, getenv("HYPERION_B200_JOBS") ? atoi(getenv("HYPERION_B200_JOBS")) : 8) : 2;
+  rc = ensure_jobs(c, (uint32_t)job_mult * c->pool_cap);
   if (rc) return rc;
   Pool &P = c->pool;
   const WallSmem ws = wall_smem(c);
@@ -4280,7 +4318,8 @@ int run_final_rounds(hyp_ctx *c, int64_t first_id, int64_t n_photons, int scatte
   F.thermal = thermal;
   F.jobs = c->d_jobs;
   F.n_jobs = c->d_njobs;
-  F.job_capacity = c->job_cap;
+  F.job_capacity = (uint32_t)job_mult * c->pool_cap;
+  F.job_margin = 2u * std::min<uint32_t>((uint32_t)(c->sm_count * 8 * SERVICE_THREADS), c->pool_cap);
   F.scattering_only = scattering_only;
   F.forced = c->conf.forced_first_interaction;
   F.algorithm = c->conf.forced_first_interaction_algorithm;

@@ -99,6 +99,9 @@ struct PeelJob {
 // bits 0-11 source id (1-based, up to MAX_SOURCES), 12 scattered, 13 reprocessed, 14-19 successive re-absorptions
 // (hyperion_b200.cu), 20-29 number of scatterings (saturating), 30-31 dust type of the last interaction
 constexpr uint32_t TAG_SRC_MASK = 0xfffu, TAG_SCATTERED = 0x1000u, TAG_REPROCESSED = 0x2000u;
+// the packet is in the middle of a modified random walk that was interrupted because the peel-off queue of the
+// round was full: its next "flight" has optical depth zero and the interaction kernel resumes the walk
+constexpr uint32_t TAG_MRW_PAUSED = 0x4000u;
 constexpr int TAG_NSCAT_SHIFT = 20;
 constexpr uint32_t TAG_LOW_MASK = (1u << TAG_NSCAT_SHIFT) - 1u;
 
@@ -660,6 +663,7 @@ struct FinalArgs {
   void *jobs;            // PeelJob<ND>[job_capacity]
   uint32_t *n_jobs;
   uint32_t job_capacity;
+  uint32_t job_margin;       // jobs the threads of an interaction kernel can add between a look at n_jobs and their append
   int32_t scattering_only;   // main.f90:274: with raytracing on, only scattered light is peeled here
   int32_t forced, algorithm; // forced first interaction (iter_final.f90:191-209)
   double baes16_xi;
@@ -866,7 +870,7 @@ interact_final_kernel(const ModelDev M, Pool P, const FinalArgs F, uint32_t *__r
     const uint32_t i = base + lane;
     const bool valid = i < n;
     uint32_t slot = 0;
-    bool alive = false, peel = false, scattered = false, reemitted = false;
+    bool alive = false, peel = false, scattered = false, reemitted = false, resume = false, paused = false;
     Photon<ND> p;
     Rng rng;
     double vpx = 0, vpy = 0, vpz = 0, sQ = 0, sU = 0, sV = 0;
@@ -878,6 +882,12 @@ interact_final_kernel(const ModelDev M, Pool P, const FinalArgs F, uint32_t *__r
       id = slots[slot].id;
       vpx = p.vx; vpy = p.vy; vpz = p.vz;
       sQ = p.sQ; sU = p.sU; sV = p.sV;
+      resume = (p.tag & TAG_MRW_PAUSED) != 0u;
+      if (resume) {
+        // no interaction: the random walk this packet was in goes on where it stopped
+        p.tag &= ~TAG_MRW_PAUSED;
+        alive = true;
+      } else
       if (p.t < 0.0) {
         // re-absorbed by a star: re-emit from its surface; always peeled (iter_final.f90:219-227)
         if (reemit_photon<ND>(M, p, rng, n_kill)) {
@@ -901,10 +911,17 @@ interact_final_kernel(const ModelDev M, Pool P, const FinalArgs F, uint32_t *__r
     if (alive && M.use_mrw && !reemitted) {
       // grid_do_mrw_noenergy + peel-off of every random-walk step (iter_final.f90:166-185)
       bool out = false;
-      for (int64_t step = 0; step < M.n_mrw_max; ++step) {
+      int64_t step = resume ? (int64_t)p.energy0 : 0;   // (energy0 is free outside the monochromatic mode)
+      for (; step < M.n_mrw_max; ++step) {
         const double R0 = distance_to_closest_wall<ND>(M, p);
         if (!(M.alpha_inv_planck[p.ic] * R0 > M.mrw_gamma)) {
           out = true;
+          break;
+        }
+        // every step queues up to two peel-offs: when the queue of this round is nearly full the walk is interrupted
+        // and resumed next round (the packet takes a flight of optical depth zero in between)
+        if (*(volatile uint32_t *)F.n_jobs + F.job_margin > F.job_capacity) {
+          paused = true;
           break;
         }
         // the interaction's own peel-off has to be queued before the state changes
@@ -921,7 +938,10 @@ interact_final_kernel(const ModelDev M, Pool P, const FinalArgs F, uint32_t *__r
           else atomicMax(M.error_flag, ERR_JOBS);
         }
       }
-      if (!out) {
+      if (paused) {
+        p.energy0 = (double)step;
+        p.tag |= TAG_MRW_PAUSED;
+      } else if (!out) {
         ++n_kill;
         alive = false;
       }
@@ -934,7 +954,7 @@ interact_final_kernel(const ModelDev M, Pool P, const FinalArgs F, uint32_t *__r
         fill_job<ND>(J, p, scattered ? 1 : 0, vpx, vpy, vpz, sQ, sU, sV, dust_id + 1);
     }
     if (alive) {
-      p.tau_left = -log(1.0 - rng.next());
+      p.tau_left = paused ? 0.0 : -log(1.0 - rng.next());
       store_photon<ND>(slots + slot, p, rng, id);
     }
     queue_append(alive, q_flight_next, n_flight_next, slot);

@@ -218,7 +218,7 @@ __device__ inline int geo_march(const ModelDev &M, typename Geo<GEO>::Ray &R, do
       if (G::escaped(M, R)) return MARCH_ESCAPED;
       if (counting && R.ic >= 0 && atomicExch(M.last_id + R.ic, pid) != pid) atomicAdd(M.n_visits + R.ic, 1ull);
     } else {
-      const double len = dt * (tau_left / tau_cell);
+      const double len = tau_cell > 0.0 ? dt * (tau_left / tau_cell) : 0.0;   // (a flight of optical depth zero ends at once)
       if (R.t + len > t_source) return MARCH_REABSORBED;
       if (DEP) {
 #pragma unroll

@@ -49,9 +49,11 @@ def test_blackbody_point_source_in_vacuum_is_exact(golden_car):
     eng.close()
 
 
-def _dusty(golden_car, golden_sph=None):
+def _dusty(golden_car, golden_sph=None, kind="sph"):
     from oracle import oracle
-    m = bitlevel_model_sph(golden_car, golden_sph, False, False) if golden_sph is not None else \
+    from helpers import bitlevel_model_oct, bitlevel_model_amr
+    make = {"sph": bitlevel_model_sph, "oct": bitlevel_model_oct, "amr": bitlevel_model_amr}[kind]
+    m = make(golden_car, golden_sph, False, False) if golden_sph is not None else \
         bitlevel_model(golden_car, False, False)
     m.density *= 10.0
     o = oracle.Oracle(m)
@@ -78,10 +80,13 @@ def _z(a, b, zmax=5.5, z2max=1.8):
     assert np.abs(z).max() < zmax and (z ** 2).mean() < z2max
 
 
-@pytest.mark.parametrize("case", ["sources", "thermal", "raytracing", "spherical"])
-def test_mono_matches_oracle(golden_car, golden_sph, case):
+@pytest.mark.parametrize("case", ["sources", "thermal", "raytracing", "spherical", "octree", "amr"])
+def test_mono_matches_oracle(golden_car, golden_sph, golden_oct, golden_amr, case):
+    """octree / amr: the thermal packets come from the cells that hold physical quantities only (leaves, cells not
+    covered by a finer grid: geo%mask_map in setup_monochromatic_grid_pdfs)."""
     from oracle import oracle
-    m = _dusty(golden_car, golden_sph if case == "spherical" else None)
+    other = {"spherical": (golden_sph, "sph"), "octree": (golden_oct, "oct"), "amr": (golden_amr, "amr")}.get(case)
+    m = _dusty(golden_car, other[0], other[1]) if other else _dusty(golden_car)
     B = 10
     ns, nd = (30000, 0) if case == "sources" else (0, 30000) if case == "thermal" else (20000, 20000)
     ray = case == "raytracing"

@@ -79,3 +79,38 @@ def test_mrw_imaging_matches_oracle():
         a = np.mean([g[1][key] for g in gpu])
         b = np.mean([o[1][key] for o in orc])
         assert abs(a / b - 1) < 0.05, (key, a, b)
+
+
+def test_interrupted_random_walks_give_the_same_images(monkeypatch):
+    """The peel-off queue of a round holds two jobs per random-walk step; a walk that finds it nearly full is
+    interrupted, the packet takes a flight of optical depth zero and the walk resumes in the next round.  With the
+    smallest queue (HYPERION_B200_JOBS=4 pools instead of 8) and a medium in which most interactions are random
+    walks of many steps, walks ARE interrupted, and since every packet keeps its own random-number stream the cubes
+    must equal those of the run with the large queue to rounding."""
+    from hyperion_b200.capi import Engine
+    from hyperion_b200.flatmodel import FlatPeeledGroup
+    grp = FlatPeeledGroup(theta=[40., 130.], phi=[20., 250.], wavelengths=(6, 1., 3000.),
+                          image=(3, 3, -1.5, 1.5, -1.5, 1.5), sed=(2, 0.5, 2.), stokes=False, track_origin="basic")
+    model = _dense_model(density=600., peeled=[grp])
+
+    def run(jobs):
+        monkeypatch.setenv("HYPERION_B200_JOBS", str(jobs))
+        eng = Engine(0)
+        eng.load_model(model)
+        eng.final_begin()
+        eng.final_photons(0, 20000, False)
+        st = eng.final_finish()
+        out = eng.sed(0).copy(), eng.image(0).copy(), st.as_dict()
+        eng.close()
+        return out
+
+    big, small = run(64), run(4)
+    print("peel-offs per packet %.1f, rounds %d (large queue) / %d (small queue)" %
+          (big[2]["n_peeloffs"] / 20000. / 2., big[2]["n_rounds"], small[2]["n_rounds"]))
+    assert big[2]["n_peeloffs"] > 20 * 20000          # long walks: tens of peeled steps per packet and view
+    assert small[2]["n_rounds"] > big[2]["n_rounds"]  # walks were interrupted
+    for k in ("n_peeloffs", "n_absorptions", "n_scatterings", "killed_int"):
+        assert big[2][k] == small[2][k], k
+    for a, b in zip(big[:2], small[:2]):
+        nz = a != 0
+        assert np.array_equal(nz, b != 0) and np.abs(b[nz] / a[nz] - 1.).max() < 1e-9
