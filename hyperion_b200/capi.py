@@ -122,7 +122,7 @@ class CApi:
         self._keep = []
         f = self._fn
         f("last_error").restype = C.c_char_p
-        for name in ("set_grid_cartesian", "set_grid_spherical", "set_grid_cylindrical", "set_grid_octree", "set_grid_amr", "add_dust", "add_source", "set_run_conf", "set_density",
+        for name in ("set_grid_cartesian", "set_grid_spherical", "set_grid_cylindrical", "set_grid_octree", "set_grid_amr", "set_grid_voronoi", "add_dust", "add_source", "set_run_conf", "set_density",
                      "set_specific_energy", "lucy_begin", "lucy_finish", "get_specific_energy",
                      "get_density", "get_energy_sum", "add_peeled_group", "final_begin", "final_photons",
                      "final_finish", "raytracing_photons", "image_shape", "get_sed", "get_image"):
@@ -154,6 +154,12 @@ class CApi:
         self.check(self._fn("set_grid_octree")(ctx, C.c_int32(len(refined)),
                                                refined.ctypes.data_as(C.POINTER(C.c_int32)),
                                                *[C.c_double(float(v)) for v in tuple(center) + tuple(half)]))
+
+    def set_grid_voronoi(self, ctx, v):
+        i32 = C.POINTER(C.c_int32)
+        self.check(self._fn("set_grid_voronoi")(ctx, C.c_int32(len(v["volume"])), _ptr(v["coordinates"]), _ptr(v["bb_min"]),
+                                                _ptr(v["bb_max"]), _ptr(v["volume"]), v["sparse_idx"].ctypes.data_as(i32),
+                                                v["sparse_neighs"].ctypes.data_as(i32), _ptr(v["box"])))
 
     def set_grid_amr(self, ctx, levels):
         n_grids = np.array([len(lev) for lev in levels], dtype=np.int32)

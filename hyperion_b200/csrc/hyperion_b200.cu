@@ -24,6 +24,7 @@
 #include "geometry_sph.cuh"
 #include "geometry_oct.cuh"
 #include "geometry_amr.cuh"
+#include "geometry_vor.cuh"
 
 using namespace hyp;
 
@@ -38,13 +39,14 @@ struct CellRec {
 enum { SC_ENERGY = 0, SC_KILLED_GEO, SC_KILLED_INT, SC_CROSS, SC_ABS, SC_SCAT, SC_ESC, SC_PHOTONS, SC_PEEL_CROSS, SC_PEELOFFS,
        SC_PEEL_CACHED, SC_COUNT };
 
-enum { GEO_CAR = 0, GEO_SPH = 1, GEO_OCT = 2, GEO_AMR = 3 };  // GEO_SPH covers both polar grids (SphGrid::kind)
+enum { GEO_CAR = 0, GEO_SPH = 1, GEO_OCT = 2, GEO_AMR = 3, GEO_VOR = 4 };  // GEO_SPH covers both polar grids (SphGrid::kind)
 
 struct ModelDev {
   int32_t grid_type;        // GEO_*
   SphGrid sph;              // spherical polar tables (grid_type == GEO_SPH)
   OctGrid oct;              // octree (grid_type == GEO_OCT)
   AmrGrid amr;              // block-structured AMR (grid_type == GEO_AMR)
+  VorGrid vor;              // Voronoi mesh (grid_type == GEO_VOR)
   int32_t n1, n2, n3, n_dust, n_sources;
   int64_t n_cells;
   const double *w1, *w2, *w3;
@@ -636,6 +638,19 @@ __device__ bool place_emitted(const ModelDev &M, Photon<ND> &p) {
     p.t = 0.0;
     return true;
   }
+  if (M.grid_type == GEO_VOR) {
+    const int cell = vor_find_cell(M.vor, p.r0x, p.r0y, p.r0z);
+    if (cell < 0) {
+      atomicMax(M.error_flag, ERR_NOT_IN_CELL);
+      return false;
+    }
+    p.ix = p.iy = p.iz = 0;
+    p.ic = cell;
+    p.n_inter = 0;
+    p.n_reabs = 0;
+    p.t = 0.0;
+    return true;
+  }
   if (M.grid_type == GEO_OCT) {
     const int node = oct_find_cell(M.oct, p.r0x, p.r0y, p.r0z);
     if (node < 0) {
@@ -1001,6 +1016,7 @@ __device__ __forceinline__ double cell_volume(const ModelDev &M, int64_t ic) {
     return N.dx * N.dy * N.dz * 8.0;  // grid_geometry_octree.f90:250-253
   }
   if (M.grid_type == GEO_AMR) return amr_volume(M.amr, ic);
+  if (M.grid_type == GEO_VOR) return M.vor.volume[ic];
   const int i1 = (int)(ic % M.n1), i2 = (int)((ic / M.n1) % M.n2), i3 = (int)(ic / ((int64_t)M.n1 * M.n2));
   return ((M.w1[i1 + 1] - M.w1[i1]) * (M.w2[i2 + 1] - M.w2[i2])) * (M.w3[i3 + 1] - M.w3[i3]);
 }
@@ -1018,6 +1034,19 @@ __device__ inline void random_position_cell(const ModelDev &M, int64_t ic, Rng &
     x = rng.next() * (x1 - x0) + x0;
     y = rng.next() * (y1 - y0) + y0;
     z = rng.next() * (z1 - z0) + z0;
+    return;
+  }
+  if (M.grid_type == GEO_VOR) {
+    // grid_geometry_voronoi.f90:285-312: rejection sampling in the cell's bounding box
+    const double *bb = M.vor.bb + 6 * (size_t)ic;
+    for (int i = 0; i < 1000000; ++i) {
+      x = rng.next() * (bb[1] - bb[0]) + bb[0];
+      y = rng.next() * (bb[3] - bb[2]) + bb[2];
+      z = rng.next() * (bb[5] - bb[4]) + bb[4];
+      int i0, i1;
+      vor_nearest(M.vor, x, y, z, 1, i0, i1);
+      if (i0 == (int)ic) return;
+    }
     return;
   }
   if (M.grid_type == GEO_OCT) {
@@ -1861,6 +1890,13 @@ struct hyp_ctx {
   int32_t *d_amr_gotos = nullptr, *d_amr_cell_grid = nullptr, *d_amr_valid = nullptr;
   OctNode *d_oct_nodes = nullptr;
   int32_t *d_oct_children = nullptr, *d_oct_leaves = nullptr;
+  // Voronoi mesh (host copies until finalize)
+  std::vector<double> vor_sites, vor_bb, vor_volume;
+  std::vector<int32_t> vor_nidx, vor_neigh, vor_valid, vor_b_start, vor_b_sites;
+  double vor_box[6] = {0, 0, 0, 0, 0, 0};
+  int vor_nb = 1;
+  double *d_vor_f64 = nullptr;    // sites | bounding boxes | volumes
+  int32_t *d_vor_i32 = nullptr;   // nidx | neigh | valid | b_start | b_sites
   int n1 = 0, n2 = 0, n3 = 0;
   int64_t n_cells = 0;
   std::vector<double> w1, w2, w3;
@@ -2170,6 +2206,8 @@ void hyp_ctx_destroy(hyp_ctx *c) {
   free_dev(c->d_amr_valid);
   free_dev(c->d_oct_children);
   free_dev(c->d_oct_leaves);
+  free_dev(c->d_vor_f64);
+  free_dev(c->d_vor_i32);
   free_dev(c->d_cells);
   free_dev(c->d_rho);
   free_dev(c->d_energy);
@@ -2578,6 +2616,64 @@ int hyp_set_grid_amr(hyp_ctx *c, int32_t n_levels, const int32_t *n_grids, const
   return HYP_OK;
 }
 
+int hyp_set_grid_voronoi(hyp_ctx *c, int32_t n_cells, const double *coords, const double *bb_min, const double *bb_max,
+                         const double *volume, const int32_t *sparse_idx, const int32_t *sparse_neighs, const double *box) {
+  if (!c || !coords || !bb_min || !bb_max || !volume || !sparse_idx || !sparse_neighs || !box)
+    return fail(HYP_ERR_INVALID, "NULL argument");
+  if (c->finalized) return fail(HYP_ERR_STATE, "model is frozen");
+  if (n_cells < 1) return fail(HYP_ERR_INVALID, "Voronoi grid needs at least one cell");
+  for (int a = 0; a < 3; ++a)
+    if (!(box[2 * a + 1] > box[2 * a])) return fail(HYP_ERR_INVALID, "Voronoi grid: empty bounding box");
+  if (sparse_idx[0] != 0) return fail(HYP_ERR_INVALID, "sparse_idx should start at 0");
+  for (int i = 0; i < n_cells; ++i)
+    if (sparse_idx[i + 1] < sparse_idx[i]) return fail(HYP_ERR_INVALID, "sparse_idx should not decrease");
+  for (int q = 0; q < sparse_idx[n_cells]; ++q)
+    if (sparse_neighs[q] < -6 || sparse_neighs[q] >= n_cells) return fail(HYP_ERR_INVALID, "sparse_neighs out of range");
+  // setup_grid_geometry (grid_geometry_voronoi.f90:92-187)
+  c->vor_sites.assign(coords, coords + 3 * (size_t)n_cells);
+  c->vor_bb.resize(6 * (size_t)n_cells);
+  c->vor_volume.resize(n_cells);
+  c->vor_valid.clear();
+  for (int i = 0; i < n_cells; ++i) {
+    for (int a = 0; a < 3; ++a) {
+      c->vor_bb[6 * (size_t)i + 2 * a] = bb_min[3 * (size_t)i + a];
+      c->vor_bb[6 * (size_t)i + 2 * a + 1] = bb_max[3 * (size_t)i + a];
+    }
+    if (volume[i] > 0.0) c->vor_valid.push_back(i);          // geo%mask = geo%volume > 0
+    c->vor_volume[i] = volume[i] < 0.0 ? 0.0 : volume[i];
+  }
+  c->vor_nidx.assign(sparse_idx, sparse_idx + n_cells + 1);
+  c->vor_neigh.assign(sparse_neighs, sparse_neighs + sparse_idx[n_cells]);
+  for (int a = 0; a < 6; ++a) c->vor_box[a] = box[a];
+  // nearest-site search: sites bucketed on a uniform grid over the box, about two sites per bucket
+  const int per_axis = std::max(1, (int)std::cbrt((double)n_cells / 2.0));
+  c->vor_nb = per_axis;
+  const int nb = per_axis * per_axis * per_axis;
+  std::vector<int> bucket(n_cells);
+  c->vor_b_start.assign(nb + 1, 0);
+  for (int i = 0; i < n_cells; ++i) {
+    int b[3];
+    for (int a = 0; a < 3; ++a) {
+      const double w = (box[2 * a + 1] - box[2 * a]) / per_axis;
+      b[a] = std::min(std::max((int)((coords[3 * (size_t)i + a] - box[2 * a]) / w), 0), per_axis - 1);
+    }
+    bucket[i] = (b[2] * per_axis + b[1]) * per_axis + b[0];
+    c->vor_b_start[bucket[i] + 1]++;
+  }
+  for (int k = 0; k < nb; ++k) c->vor_b_start[k + 1] += c->vor_b_start[k];
+  c->vor_b_sites.assign(n_cells, 0);
+  std::vector<int> fill(c->vor_b_start.begin(), c->vor_b_start.end() - 1);
+  for (int i = 0; i < n_cells; ++i) c->vor_b_sites[fill[bucket[i]]++] = i;
+  c->grid_type = GEO_VOR;
+  c->n1 = n_cells;
+  c->n2 = c->n3 = 1;
+  c->n_cells = n_cells;
+  c->w1.assign(2, 0.0);
+  c->w2.assign(2, 0.0);
+  c->w3.assign(2, 0.0);
+  return HYP_OK;
+}
+
 int hyp_add_dust(hyp_ctx *c, const hyp_dust_tables *t) {
   if (!c || !t) return fail(HYP_ERR_INVALID, "NULL argument");
   if (c->finalized) return fail(HYP_ERR_STATE, "model is frozen");
@@ -2843,6 +2939,8 @@ int hyp_finalize_setup(hyp_ctx *c) {
   }
   if (c->conf.specific_energy_additional && !c->energy_from_caller)
     return fail(HYP_ERR_INVALID, "cannot specify specific_energy_type since specific_energy was not given");
+  if (c->grid_type == GEO_VOR && c->conf.use_mrw)   // distance_to_closest_wall, grid_geometry_voronoi.f90:314-320
+    return fail(HYP_ERR_INVALID, "not implemented for Voronoi grid");
   CUDA_TRY(cudaSetDevice(c->device));
   const int nd = (int)c->dust.size();
   const size_t n = (size_t)c->n_cells * nd;
@@ -2894,6 +2992,49 @@ int hyp_finalize_setup(hyp_ctx *c) {
         if (!ok[ic]) {
           c->h_density[id * nc + ic] = 0.0;
           if (c->energy_from_caller) c->h_energy[id * nc + ic] = 0.0;
+        }
+  }
+  if (c->grid_type == GEO_VOR) {
+    VorGrid &V = M.vor;
+    const size_t n = (size_t)c->n_cells;
+    std::vector<double> f;
+    f.insert(f.end(), c->vor_sites.begin(), c->vor_sites.end());
+    f.insert(f.end(), c->vor_bb.begin(), c->vor_bb.end());
+    f.insert(f.end(), c->vor_volume.begin(), c->vor_volume.end());
+    CUDA_TRY(cudaMalloc(&c->d_vor_f64, f.size() * sizeof(double)));
+    CUDA_TRY(cudaMemcpy(c->d_vor_f64, f.data(), f.size() * sizeof(double), cudaMemcpyHostToDevice));
+    V.sites = c->d_vor_f64;
+    V.bb = c->d_vor_f64 + 3 * n;
+    V.volume = c->d_vor_f64 + 9 * n;
+    std::vector<int32_t> I;
+    size_t off[5];
+    const std::vector<int32_t> *parts[5] = {&c->vor_nidx, &c->vor_neigh, &c->vor_valid, &c->vor_b_start, &c->vor_b_sites};
+    for (int k = 0; k < 5; ++k) {
+      off[k] = I.size();
+      I.insert(I.end(), parts[k]->begin(), parts[k]->end());
+    }
+    CUDA_TRY(cudaMalloc(&c->d_vor_i32, std::max<size_t>(I.size(), 1) * sizeof(int32_t)));
+    CUDA_TRY(cudaMemcpy(c->d_vor_i32, I.data(), I.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+    V.nidx = c->d_vor_i32 + off[0];
+    V.neigh = c->d_vor_i32 + off[1];
+    V.valid = c->d_vor_i32 + off[2];
+    V.b_start = c->d_vor_i32 + off[3];
+    V.b_sites = c->d_vor_i32 + off[4];
+    for (int a = 0; a < 6; ++a) V.box[a] = c->vor_box[a];
+    for (int a = 0; a < 3; ++a) {
+      V.nb[a] = c->vor_nb;
+      V.bw[a] = (c->vor_box[2 * a + 1] - c->vor_box[2 * a]) / c->vor_nb;
+    }
+    V.n_cells = (int32_t)n;
+    V.n_valid = (int32_t)c->vor_valid.size();
+    // cells without volume hold no dust (geo%mask, grid_physics_3d.f90:156-164)
+    std::vector<char> ok(n, 0);
+    for (int32_t ic : c->vor_valid) ok[ic] = 1;
+    for (size_t id = 0; id < c->dust.size(); ++id)
+      for (size_t ic = 0; ic < n; ++ic)
+        if (!ok[ic]) {
+          c->h_density[id * n + ic] = 0.0;
+          if (c->energy_from_caller) c->h_energy[id * n + ic] = 0.0;
         }
   }
   if (c->grid_type == GEO_OCT) {
@@ -3165,7 +3306,7 @@ int hyp_lucy_begin(hyp_ctx *c) {
   // grid_reset_energy (grid_generic.f90:18-25): the packet counter exists with the PDA or the n_photons output
   // (grid_physics_3d.f90:308-317)
   if (c->conf.use_pda || c->conf.count_photons) {
-    if (c->conf.use_pda && (c->grid_type == GEO_OCT || c->grid_type == GEO_AMR))
+    if (c->conf.use_pda && (c->grid_type == GEO_OCT || c->grid_type == GEO_AMR || c->grid_type == GEO_VOR))
       return fail(HYP_ERR_INVALID, "PDA is not available for this grid type");   // grid_pda_disabled.f90
     if (!c->d_nvis) {
       CUDA_TRY(cudaMalloc(&c->d_nvis, (size_t)c->n_cells * sizeof(unsigned long long)));
@@ -3263,6 +3404,7 @@ static int run_rounds(hyp_ctx *c, int64_t first_id, int64_t n_photons, int64_t i
       const FinalArgs none = FinalArgs();
       auto geo_flight = c->grid_type == GEO_OCT   ? flight_geo_kernel<GEO_OCT, ND, true, false>
                         : c->grid_type == GEO_AMR ? flight_geo_kernel<GEO_AMR, ND, true, false>
+                        : c->grid_type == GEO_VOR ? flight_geo_kernel<GEO_VOR, ND, true, false>
                         : c->grid_type == GEO_CAR ? flight_geo_kernel<GEO_CAR, ND, true, false>
                                                   : flight_geo_kernel<GEO_SPH, ND, true, false>;
       const int sph_blocks_max = c->sm_count * 12;
@@ -3779,7 +3921,8 @@ int pda_geometry(hyp_ctx *c, PdaGeo &G) {
 // solve_pda (grid_pda_3d.f90:105-169) on the current specific energy.  counts: device array of n_photons as
 // doubles; n_pda_out: number of PDA cells.
 int solve_pda_device(hyp_ctx *c, const double *counts, int64_t *n_pda_out) {
-  if (c->grid_type == GEO_OCT || c->grid_type == GEO_AMR) return fail(HYP_ERR_INVALID, "PDA is not available for this grid type");
+  if (c->grid_type == GEO_OCT || c->grid_type == GEO_AMR || c->grid_type == GEO_VOR)
+    return fail(HYP_ERR_INVALID, "PDA is not available for this grid type");
   cudaStream_t st = c->stream;
   const size_t nc = (size_t)c->n_cells;
   PdaDev P;
@@ -4242,6 +4385,9 @@ int launch_peel(hyp_ctx *c, const ModelDev &M, uint32_t n_jobs_max) {
   } else if (c->grid_type == GEO_AMR) {
     k = peel_kernel<ND, POLY, GEO_AMR>;
     ws = WallSmem{0, 0};
+  } else if (c->grid_type == GEO_VOR) {
+    k = peel_kernel<ND, POLY, GEO_VOR>;
+    ws = WallSmem{0, 0};
   }
   CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ws.bytes));
   ImagingDev I{c->d_images, c->d_views, (int)c->groups.size(), c->n_views, c->d_src_columns};
@@ -4269,6 +4415,7 @@ int update_source_columns(hyp_ctx *c) {
   if (c->grid_type == GEO_SPH) k = source_columns_kernel<ND, GEO_SPH>;
   else if (c->grid_type == GEO_OCT) k = source_columns_kernel<ND, GEO_OCT>;
   else if (c->grid_type == GEO_AMR) k = source_columns_kernel<ND, GEO_AMR>;
+  else if (c->grid_type == GEO_VOR) k = source_columns_kernel<ND, GEO_VOR>;
   k<<<1, 128, 0, c->stream>>>(c->M, I, c->d_src_columns);
   CUDA_TRY(cudaGetLastError());
   c->launches_acc += 1;
@@ -4366,6 +4513,7 @@ int run_final_rounds(hyp_ctx *c, int64_t first_id, int64_t n_photons, int scatte
       const int sph_blocks_max = c->sm_count * 12;
       auto geo_flight = c->grid_type == GEO_OCT   ? flight_geo_kernel<GEO_OCT, ND, false, true>
                         : c->grid_type == GEO_AMR ? flight_geo_kernel<GEO_AMR, ND, false, true>
+                        : c->grid_type == GEO_VOR ? flight_geo_kernel<GEO_VOR, ND, false, true>
                         : c->grid_type == GEO_CAR ? flight_geo_kernel<GEO_CAR, ND, false, true>
                                                   : flight_geo_kernel<GEO_SPH, ND, false, true>;
       if (n_new > 0) {
@@ -4673,9 +4821,12 @@ int run_final_mono(hyp_ctx *c, int32_t inu, int64_t first_source_id, int64_t n_s
     const size_t nc = (size_t)c->n_cells;
     if (!c->d_mono_cdf) CUDA_TRY(cudaMalloc(&c->d_mono_cdf, nc * ND * sizeof(double)));
     CUDA_TRY(cudaMemsetAsync(c->d_mono_cdf, 0, nc * ND * sizeof(double), st));
-    const int32_t *list = c->grid_type == GEO_OCT ? c->d_oct_leaves : c->grid_type == GEO_AMR ? c->d_amr_valid : nullptr;
-    const int64_t n_list = c->grid_type == GEO_OCT ? (int64_t)c->M.oct.n_leaves
-                           : c->grid_type == GEO_AMR ? (int64_t)c->M.amr.n_valid : (int64_t)nc;
+    const int32_t *list = c->grid_type == GEO_OCT   ? c->d_oct_leaves
+                          : c->grid_type == GEO_AMR ? c->d_amr_valid
+                          : c->grid_type == GEO_VOR ? c->M.vor.valid : nullptr;
+    const int64_t n_list = c->grid_type == GEO_OCT   ? (int64_t)c->M.oct.n_leaves
+                           : c->grid_type == GEO_AMR ? (int64_t)c->M.amr.n_valid
+                           : c->grid_type == GEO_VOR ? (int64_t)c->M.vor.n_valid : (int64_t)nc;
     mono_weights_kernel<<<grid_blocks(c), 256, 0, st>>>(M, list, n_list, c->d_mono_cdf);
     CUDA_TRY(cudaGetLastError());
     c->launches_acc += 1;

@@ -1158,6 +1158,9 @@ __global__ void raytrace_emit_kernel(const ModelDev M, PeelJob<ND> *__restrict__
       } else if (M.grid_type == GEO_AMR) {
         n_masked = (double)M.amr.n_valid;
         ic = M.amr.valid[max((int64_t)ceil(rng.next() * n_masked), (int64_t)1) - 1];
+      } else if (M.grid_type == GEO_VOR) {
+        n_masked = (double)M.vor.n_valid;
+        ic = M.vor.valid[max((int64_t)ceil(rng.next() * n_masked), (int64_t)1) - 1];
       } else {
         ic = max((int64_t)ceil(rng.next() * (double)M.n_cells), (int64_t)1) - 1;
       }

@@ -137,6 +137,40 @@ struct Geo<GEO_OCT> {
   }
 };
 
+// Voronoi meshes (geometry_vor.cuh)
+template <>
+struct Geo<GEO_VOR> {
+  using Ray = VorRay;
+  struct Cross {
+    int next;
+  };
+  static __device__ __forceinline__ bool find_cell(const ModelDev &M, double rx, double ry, double rz, double vx,
+                                                   double vy, double vz, int &ix, int &iy, int &iz, int &ic) {
+    ix = iy = iz = 0;
+    ic = vor_find_cell(M.vor, rx, ry, rz);
+    return ic >= 0;
+  }
+  static __device__ __forceinline__ void start(const ModelDev &M, Ray &R, double rx, double ry, double rz, double vx,
+                                               double vy, double vz, int ix, int iy, int iz, int ic) {
+    R.r0x = rx; R.r0y = ry; R.r0z = rz;
+    R.vx = vx; R.vy = vy; R.vz = vz;
+    R.t = 0.0;
+    R.ic = ic;
+  }
+  static __device__ __forceinline__ bool escaped(const ModelDev &M, const Ray &R) { return R.ic == M.vor.n_cells; }
+  static __device__ __forceinline__ bool find_wall(const ModelDev &M, const Ray &R, double &dt, Cross &c) {
+    return vor_find_wall(M.vor, R, dt, c.next);
+  }
+  static __device__ __forceinline__ void step(const ModelDev &M, Ray &R, const Cross &c) {
+    R.ic = c.next;
+  }
+  static __device__ __forceinline__ void stop_inside(Ray &R) {}
+  static __device__ __forceinline__ void store(const Ray &R, int &ix, int &iy, int &iz, int &ic) {
+    ix = iy = iz = 0;
+    ic = R.ic;
+  }
+};
+
 // block-structured AMR (geometry_amr.cuh)
 template <>
 struct Geo<GEO_AMR> {

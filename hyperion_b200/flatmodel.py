@@ -205,9 +205,27 @@ class FlatModel:
     # (n1, n2, n3, xmin, xmax, ymin, ymax, zmin, zmax); density is [n_dust, n_cells] with the cells of
     # all grids concatenated level-major, grid-major, x fastest (src/core/type_cell_id_amr.f90:115-133)
     amr_levels: Optional[list] = None
+    # Voronoi mesh (grid_type "vor", hyperion/grid/voronoi_grid.py:417-478): a dict with the columns of the 'cells'
+    # table -- "coordinates", "bb_min", "bb_max" [n, 3], "volume" [n] -- the neighbour lists "sparse_neighs" /
+    # "sparse_idx" in the file's numbering (>= 0: cell, -1 .. -6: the walls xmin, xmax, ymin, ymax, zmin, zmax of
+    # the box) and "box" = (xmin, xmax, ymin, ymax, zmin, zmax); density is [n_dust, n_cells]
+    voronoi: Optional[dict] = None
 
     def __post_init__(self):
         self.density = _f8(self.density)
+        if self.grid_type == "vor":
+            v = self.voronoi
+            for k in ("coordinates", "bb_min", "bb_max"):
+                v[k] = np.ascontiguousarray(v[k], dtype=np.float64).reshape(-1, 3)
+            v["volume"] = _f8(v["volume"])
+            v["sparse_neighs"] = np.ascontiguousarray(v["sparse_neighs"], dtype=np.int32)
+            v["sparse_idx"] = np.ascontiguousarray(v["sparse_idx"], dtype=np.int32)
+            v["box"] = _f8(v["box"])
+            if self.density.ndim == 1:
+                self.density = self.density[None]
+            if self.density.shape != (len(self.dust), len(v["volume"])):
+                raise ValueError("density should have shape (n_dust, n_cells)")
+            return
         if self.grid_type == "amr":
             n = sum(g[0] * g[1] * g[2] for lev in self.amr_levels for g in lev)
             if self.density.ndim == 1:
@@ -232,6 +250,8 @@ class FlatModel:
 
     @property
     def shape(self):
+        if self.grid_type == "vor":
+            return (len(self.voronoi["volume"]),)
         if self.grid_type == "oct":
             return (len(self.refined),)
         if self.grid_type == "amr":
@@ -253,6 +273,8 @@ class FlatModel:
         return out
 
     def volumes(self):
+        if self.grid_type == "vor":
+            return np.maximum(self.voronoi["volume"], 0.0)
         if self.grid_type == "amr":
             vol = np.zeros(self.n_cells)
             for il, ig, sl, _ in self.amr_slices():
@@ -301,9 +323,12 @@ def apply_model(api, ctx, model: FlatModel):
     elif model.grid_type == "oct":
         api.set_grid_octree(ctx, model.refined, model.oct_center, model.oct_half)
         n1 = n2 = n3 = 0
+    elif model.grid_type == "vor":
+        api.set_grid_voronoi(ctx, model.voronoi)
+        n1 = n2 = n3 = 0
     else:
         n3, n2, n1 = model.shape
-    if model.grid_type in ("oct", "amr"):
+    if model.grid_type in ("oct", "amr", "vor"):
         pass
     elif model.grid_type == "sph":
         api.set_grid_spherical(ctx, n1, n2, n3, model.w1, model.w2, model.w3)

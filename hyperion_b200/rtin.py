@@ -193,6 +193,21 @@ def read_rtin(filename):
         if (len(refined) - 1) % 8 != 0:
             raise ModelError("refined should have shape 8 * n + 1")
         grid_type, w1, w2, w3 = "oct", None, None, None
+    elif rs.grid_type == "vor":
+        # grid_geometry_voronoi.f90:92-187: table 'cells' (columns 'coordinates', 'bb_min', 'bb_max', 'volume'),
+        # 'sparse_neighs' / 'sparse_idx', the box as attributes
+        cells = geo["cells"][...]
+        mesh = dict(coordinates=np.asarray(cells["coordinates"], dtype=np.float64),
+                    bb_min=np.asarray(cells["bb_min"], dtype=np.float64),
+                    bb_max=np.asarray(cells["bb_max"], dtype=np.float64),
+                    volume=np.asarray(cells["volume"], dtype=np.float64),
+                    sparse_neighs=np.asarray(geo["sparse_neighs"][...], dtype=np.int32),
+                    sparse_idx=np.asarray(geo["sparse_idx"][...], dtype=np.int32),
+                    box=np.array([float(_num(geo.attrs[k])) for k in ("xmin", "xmax", "ymin", "ymax", "zmin", "zmax")]))
+        if len(mesh["sparse_idx"]) != len(mesh["volume"]) + 1:
+            raise ModelError("sparse_idx should have one entry per cell plus one")
+        octree = dict(voronoi=mesh)
+        grid_type, w1, w2, w3 = "vor", None, None, None
     else:
         if rs.grid_type == "car":
             cols, names, grid_type = ("x", "y", "z"), ("dx", "dy", "dz"), "car"
@@ -203,8 +218,7 @@ def read_rtin(filename):
             # grid_geometry_cylindrical_3d.f90:109-121
             cols, names, grid_type = ("w", "z", "p"), ("dw", "dz", "dphi"), "cyl"
         else:
-            raise ModelError("grid type '%s' is not implemented by this engine yet (Cartesian, spherical polar and "
-                             "cylindrical polar only)" % rs.grid_type)
+            raise ModelError("unknown grid type '%s'" % rs.grid_type)
         w1 = np.asarray(geo["walls_1"][...][cols[0]], dtype=np.float64)
         w2 = np.asarray(geo["walls_2"][...][cols[1]], dtype=np.float64)
         w3 = np.asarray(geo["walls_3"][...][cols[2]], dtype=np.float64)
@@ -249,6 +263,7 @@ def read_rtin(filename):
             raise ModelError("density should be positive")
         se_amr = gather("specific_energy")
     grid_shape = (len(octree["refined"]),) if octree and "refined" in octree else \
+        (len(octree["voronoi"]["volume"]),) if octree and "voronoi" in octree else \
         (len(w3) - 1, len(w2) - 1, len(w1) - 1) if amr_levels is None else None
     if amr_levels is not None:
         pass

@@ -168,6 +168,9 @@ def write_rtin(filename, model: FlatModel, n_initial_iter=5, n_initial_photons=1
         # hyperion/grid/octree_grid.py:426-436
         h.update(np.ascontiguousarray(model.refined).tobytes())
         h.update(np.array(tuple(model.oct_center) + tuple(model.oct_half)).tobytes())
+    elif model.grid_type == "vor":
+        # hyperion/grid/voronoi_grid.py (get_geometry_id): the sites
+        h.update(np.ascontiguousarray(model.voronoi["coordinates"]).tobytes())
     else:
         for w in (model.w1, model.w2, model.w3):
             h.update(np.ascontiguousarray(w).tobytes())
@@ -178,6 +181,18 @@ def write_rtin(filename, model: FlatModel, n_initial_iter=5, n_initial_photons=1
         for k, v in zip(("x", "y", "z", "dx", "dy", "dz"), tuple(model.oct_center) + tuple(model.oct_half)):
             geo.attrs[k] = float(v)
         geo.create_dataset("cells", _table([("refined", np.asarray(model.refined, dtype=np.int32))]))
+    if model.grid_type == "vor":
+        # hyperion/grid/voronoi_grid.py:417-478
+        v = model.voronoi
+        geo.attrs["grid_type"] = "vor"
+        for k, x in zip(("xmin", "xmax", "ymin", "ymax", "zmin", "zmax"), v["box"]):
+            geo.attrs[k] = float(x)
+        vol = np.array(v["volume"], dtype=np.float64)
+        vol[~(vol > 0.) | ~np.isfinite(vol)] = -1.
+        geo.create_dataset("cells", _table([("coordinates", v["coordinates"]), ("volume", vol),
+                                            ("bb_min", v["bb_min"]), ("bb_max", v["bb_max"])]))
+        geo.create_dataset("sparse_neighs", np.asarray(v["sparse_neighs"], dtype=np.int32))
+        geo.create_dataset("sparse_idx", np.asarray(v["sparse_idx"], dtype=np.int32))
     # hyperion/grid/cartesian_grid.py:336-343, hyperion/grid/spherical_polar_grid.py (write)
     if model.grid_type == "amr":
         # hyperion/grid/amr_grid.py:372-412
@@ -192,7 +207,7 @@ def write_rtin(filename, model: FlatModel, n_initial_iter=5, n_initial_photons=1
                     gg.attrs[k] = np.int64(v)
                 for k, v in zip(("xmin", "xmax", "ymin", "ymax", "zmin", "zmax"), g[3:]):
                     gg.attrs[k] = float(v)
-    elif model.grid_type != "oct":
+    elif model.grid_type not in ("oct", "vor"):
         cols = {"sph": ("r", "t", "p"), "cyl": ("w", "z", "p"), "car": ("x", "y", "z")}[model.grid_type]
         geo.attrs["grid_type"] = {"sph": "sph_pol", "cyl": "cyl_pol", "car": "car"}[model.grid_type]
         geo.create_dataset("walls_1", _table([(cols[0], model.w1)]))

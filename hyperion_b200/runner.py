@@ -298,7 +298,7 @@ def run(input_file, output_file, overwrite=False, device=None, log=None):
             if any(getattr(d, "version", 2) == 1 for d in model.dust):
                 raise ModelError("version 1 dust files can no longer be used when PDA is computed due to a bug - to fix "
                                  "this, re-generate the dust file using the latest version of Hyperion")
-            if model.grid_type in ("oct", "amr"):
+            if model.grid_type in ("oct", "amr", "vor"):
                 raise ModelError("PDA is not available for this grid type")      # grid_pda_disabled.f90
             model.conf.use_pda = True
         # the n_photons array exists with the PDA or when it is to be written (grid_physics_3d.f90:308-317)

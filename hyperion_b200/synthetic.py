@@ -325,3 +325,62 @@ def amr_point_sources_model(n_root=64, n_levels=3, n_patches=3, seed=5, tau_edge
                       position=tuple(rng.uniform(-0.7 * pc, 0.7 * pc, 3))) for _ in range(n_sources)]
     conf = FlatConf(n_initial_iter=n_iter, n_initial_photons=n_photons)
     return FlatModel(None, None, None, rho, [dust], src, conf, grid_type="amr", amr_levels=levels)
+
+
+def voronoi_mesh(sites, box):
+    """The Voronoi tessellation of ``sites`` [n, 3] clipped to ``box`` = (xmin, xmax, ymin, ymax, zmin, zmax) in the
+    layout ``VoronoiGrid.write`` gives the Fortran code (hyperion/grid/voronoi_grid.py:417-478; the front end computes
+    it with voro++): cell volumes, bounding boxes and neighbour lists, walls of the box numbered -1 .. -6.
+    Made with scipy: the sites are mirrored in the six walls, so that every cell of the unbounded tessellation of
+    sites + mirror images is exactly the clipped cell, and a neighbour that is a mirror image in wall w means the
+    cell touches that wall."""
+    from scipy.spatial import ConvexHull, Voronoi
+    sites = np.asarray(sites, dtype=np.float64)
+    n = len(sites)
+    box = np.asarray(box, dtype=np.float64)
+    pts = [sites]
+    for w in range(6):
+        m = sites.copy()
+        m[:, w // 2] = 2.0 * box[w] - m[:, w // 2]
+        pts.append(m)
+    vor = Voronoi(np.concatenate(pts))
+    neigh = [[] for _ in range(n)]
+    for a, b in vor.ridge_points:
+        for i, j in ((a, b), (b, a)):
+            if i < n:
+                neigh[i].append(j if j < n else -(j // n))        # mirror block k (1..6) -> wall -k
+    volume, bb_min, bb_max = np.zeros(n), np.zeros((n, 3)), np.zeros((n, 3))
+    for i in range(n):
+        reg = vor.regions[vor.point_region[i]]
+        if -1 in reg or len(reg) < 4:
+            raise ValueError("open Voronoi cell: is a site outside the box?")
+        v = vor.vertices[reg]
+        volume[i] = ConvexHull(v).volume
+        bb_min[i], bb_max[i] = v.min(0), v.max(0)
+    idx = np.concatenate([[0], np.cumsum([len(set(x)) for x in neigh])]).astype(np.int32)
+    flat = np.concatenate([sorted(set(x), reverse=True) for x in neigh]).astype(np.int32)
+    return dict(coordinates=sites, bb_min=bb_min, bb_max=bb_max, volume=volume, sparse_neighs=flat, sparse_idx=idx, box=box)
+
+
+def lattice_voronoi(w1, w2, w3):
+    """The Voronoi mesh whose cells are the cells of a Cartesian grid: sites at the cell centres, the six face
+    neighbours (or walls of the box) of every cell, in x-fastest order."""
+    w1, w2, w3 = [np.asarray(w, dtype=np.float64) for w in (w1, w2, w3)]
+    n1, n2, n3 = len(w1) - 1, len(w2) - 1, len(w3) - 1
+    c1, c2, c3 = [0.5 * (w[1:] + w[:-1]) for w in (w1, w2, w3)]
+    Z, Y, X = np.meshgrid(c3, c2, c1, indexing="ij")
+    sites = np.stack([X.ravel(), Y.ravel(), Z.ravel()], axis=1)
+    lo = np.stack(np.meshgrid(w3[:-1], w2[:-1], w1[:-1], indexing="ij")[::-1], axis=-1).reshape(-1, 3)
+    hi = np.stack(np.meshgrid(w3[1:], w2[1:], w1[1:], indexing="ij")[::-1], axis=-1).reshape(-1, 3)
+    neigh = []
+    for i3 in range(n3):
+        for i2 in range(n2):
+            for i1 in range(n1):
+                ic = (i3 * n2 + i2) * n1 + i1
+                neigh.append([ic - 1 if i1 > 0 else -1, ic + 1 if i1 < n1 - 1 else -2,
+                              ic - n1 if i2 > 0 else -3, ic + n1 if i2 < n2 - 1 else -4,
+                              ic - n1 * n2 if i3 > 0 else -5, ic + n1 * n2 if i3 < n3 - 1 else -6])
+    idx = (6 * np.arange(len(neigh) + 1)).astype(np.int32)
+    return dict(coordinates=sites, bb_min=lo, bb_max=hi, volume=np.prod(hi - lo, axis=1),
+                sparse_neighs=np.array(neigh, dtype=np.int32).ravel(), sparse_idx=idx,
+                box=np.array([w1[0], w1[-1], w2[0], w2[-1], w3[0], w3[-1]]))

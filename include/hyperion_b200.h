@@ -255,6 +255,16 @@ int hyp_set_grid_octree(hyp_ctx *ctx, int32_t n_cells, const int32_t *refined,
  * are masked out. */
 int hyp_set_grid_amr(hyp_ctx *ctx, int32_t n_levels, const int32_t *n_grids, const int32_t *dims, const double *bounds);
 
+/* replaces: setup_grid_geometry (src/grid/grid_geometry_voronoi.f90:92-187).
+ * The 'cells' table and neighbour lists VoronoiGrid.write stores (hyperion/grid/voronoi_grid.py:417-478):
+ * coords / bb_min / bb_max [n_cells][3] (sites and bounding boxes), volume[n_cells] (cells with volume <= 0 are
+ * masked out), sparse_idx[n_cells + 1] / sparse_neighs[sparse_idx[n_cells]] (CSR neighbour lists in the file's
+ * numbering: >= 0 a cell, -1 .. -6 the walls xmin, xmax, ymin, ymax, zmin, zmax), box[6] = xmin, xmax, ymin, ymax,
+ * zmin, zmax.  Quantities have one entry per cell: density[n_dust][n_cells].  No PDA and no modified random walk
+ * on this grid (grid_pda_disabled.f90; distance_to_closest_wall, grid_geometry_voronoi.f90:314-320). */
+int hyp_set_grid_voronoi(hyp_ctx *ctx, int32_t n_cells, const double *coords, const double *bb_min, const double *bb_max,
+                         const double *volume, const int32_t *sparse_idx, const int32_t *sparse_neighs, const double *box);
+
 /* replaces: dust_setup (src/dust/dust_type_4elem.f90:78-293); call once per dust type, in order */
 int hyp_add_dust(hyp_ctx *ctx, const hyp_dust_tables *dust);
 

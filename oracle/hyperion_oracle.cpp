@@ -1176,6 +1176,14 @@ struct orc_ctx {
   std::vector<std::vector<AmrGrid>> levels;
   std::vector<int> cell_ilevel, cell_igrid, cell_i1, cell_i2, cell_i3;  // preset_cell_id
   double amr_eps = 0.0;
+  // Voronoi mesh (grid_geometry_voronoi.f90, type_grid_voronoi.f90): sites, neighbour lists in the file's C-style
+  // numbering (>= 0: cell, -1 .. -6: the walls of the box), bounding boxes, the box; grid_type 5
+  std::vector<double> vx, vy, vz, vbb;      // vbb: xmin, xmax, ymin, ymax, zmin, zmax per cell
+  std::vector<int> vidx, vneigh;
+  double vbox[6] = {0, 0, 0, 0, 0, 0};
+  // nearest-site search (the reference's kd-tree): sites bucketed on a uniform grid over the box
+  int vg[3] = {1, 1, 1};
+  std::vector<int> vg_start, vg_sites;
   // cells that hold physical quantities (geo%mask / mask_map); empty = all cells
   std::vector<int> mask_map;
   int n_masked = 0;
@@ -1243,6 +1251,7 @@ Cell new_grid_cell(const orc_ctx &g, int i1, int i2, int i3) {
 bool escaped(const orc_ctx &g, const Cell &c) {
   if (g.grid_type == 4) return c.ic == -2;  // outside_cell (grid_geometry_amr.f90:592-597)
   if (g.grid_type == 3) return c.ic == g.n_cells + 1;  // grid_geometry_octree.f90:318-325
+  if (g.grid_type == 5) return c.ic == g.n_cells + 1;  // grid_geometry_voronoi.f90:249-255
   if (c.i1 < 1 || c.i1 > g.n1) return true;
   if (g.grid_type == 1) return false;  // spherical: radial escape only (grid_geometry_spherical_3d.f90:493-500)
   if (g.grid_type == 2) return c.i2 < 1 || c.i2 > g.n2;  // cylindrical: w and z (grid_geometry_cylindrical_3d.f90:375-384)
@@ -1269,7 +1278,12 @@ void cyl_adjust_wall(const orc_ctx &g, Photon &p);
 bool cyl_in_correct_cell(const orc_ctx &g, const Photon &p);
 void cyl_find_wall(orc_ctx &g, const Photon &p, double &tnearest, WallId &id_min);
 
+bool vor_find_cell(const orc_ctx &g, const Photon &p, Cell &out);
+bool vor_in_correct_cell(const orc_ctx &g, const Photon &p);
+void vor_find_wall(orc_ctx &g, const Photon &p, double &tnearest, WallId &id_min);
+
 bool find_cell(const orc_ctx &g, const Photon &p, Cell &out) {
+  if (g.grid_type == 5) return vor_find_cell(g, p, out);
   if (g.grid_type == 1) return sph_find_cell(g, p, out);
   if (g.grid_type == 2) return cyl_find_cell(g, p, out);
   if (g.grid_type == 3) return oct_find_cell(g, p, out);
@@ -1294,7 +1308,7 @@ void adjust_wall(const orc_ctx &g, Photon &p) {
     cyl_adjust_wall(g, p);
     return;
   }
-  if (g.grid_type == 3 || g.grid_type == 4) return;  // octree / AMR place_in_cell have no adjust_wall
+  if (g.grid_type >= 3) return;  // octree / AMR / Voronoi place_in_cell have no adjust_wall
   p.on_wall = false;
   p.on_wall_id = WallId();
 #define ADJ(V, R, W, I, WID)                   \
@@ -1340,6 +1354,7 @@ bool in_correct_cell(const orc_ctx &g, const Photon &p) {
   if (g.grid_type == 2) return cyl_in_correct_cell(g, p);
   if (g.grid_type == 3) return oct_in_correct_cell(g, p);
   if (g.grid_type == 4) return amr_in_correct_cell(g, p);
+  if (g.grid_type == 5) return vor_in_correct_cell(g, p);
   const double threshold = 1.e-3;
   Cell act;
   bool valid = find_cell(g, p, act);
@@ -1410,6 +1425,10 @@ void find_wall(orc_ctx &g, const Photon &p, double &tnearest, WallId &id_min) {
     amr_find_wall(g, p, tnearest, id_min);
     return;
   }
+  if (g.grid_type == 5) {
+    vor_find_wall(g, p, tnearest, id_min);
+    return;
+  }
   g.tmin = std::numeric_limits<double>::max();
   g.emin = 0.0;
   g.imin = WallId();
@@ -1443,6 +1462,8 @@ void find_wall(orc_ctx &g, const Photon &p, double &tnearest, WallId &id_min) {
 
 // next_cell_wall_id (grid_geometry_cartesian_3d.f90:303-328)
 Cell next_cell(const orc_ctx &g, const Cell &c, const WallId &dir, const Vec &r) {
+  // next_cell_wall_id (grid_geometry_voronoi.f90:266-272): the wall id is the id of the cell behind it
+  if (g.grid_type == 5) return Cell{0, 0, 0, dir.w1};
   if (g.grid_type == 3) return oct_next_cell(g, c, dir, r);
   if (g.grid_type == 4) return amr_next_cell(g, c, dir, r);
   int i1 = c.i1, i2 = c.i2, i3 = c.i3;
@@ -2171,10 +2192,121 @@ void oct_find_wall(orc_ctx &g, const Photon &p, double &tmin, WallId &id_min) {
 }
 
 // random_position_cell (:396-408)
+Vec vor_random_position_cell(orc_ctx &g, const Cell &c);
 Vec oct_random_position_cell(orc_ctx &g, const Cell &c) {
   double x = g.rng.random(), y = g.rng.random(), z = g.rng.random();
   const int k = c.ic - 1;
   return Vec{(2.0 * x - 1.0) * g.odx[k] + g.ox[k], (2.0 * y - 1.0) * g.ody[k] + g.oy[k], (2.0 * z - 1.0) * g.odz[k] + g.oz[k]};
+}
+
+// ---------------------------------------------------------------------------
+// Voronoi geometry (src/grid/grid_geometry_voronoi.f90); cell ids 1-based as in the Fortran, n_cells + 1 = outside
+// ---------------------------------------------------------------------------
+// The k <= 2 nearest sites of a point (kdtree2_n_nearest): buckets of a uniform grid are searched in shells around
+// the point's bucket until no unvisited bucket can hold a closer site.
+void vor_nearest(const orc_ctx &g, double x, double y, double z, int k, int *idx) {
+  double best[2] = {std::numeric_limits<double>::max(), std::numeric_limits<double>::max()};
+  idx[0] = idx[1] = 0;
+  double w[3], lo[3] = {g.vbox[0], g.vbox[2], g.vbox[4]}, pos[3] = {x, y, z};
+  int b[3];
+  for (int a = 0; a < 3; a++) {
+    w[a] = (g.vbox[2 * a + 1] - g.vbox[2 * a]) / g.vg[a];
+    b[a] = std::min(std::max((int)((pos[a] - lo[a]) / w[a]), 0), g.vg[a] - 1);
+  }
+  const double wmin = std::min(w[0], std::min(w[1], w[2]));
+  const int rmax = std::max(g.vg[0], std::max(g.vg[1], g.vg[2]));
+  for (int r = 0; r <= rmax; r++) {
+    // every site in a bucket of shell r or beyond is at least (r - 1) * wmin away (the point lies anywhere in its bucket)
+    if (r > 0) {
+      const double reach = (double)(r - 1) * wmin;
+      if (best[k - 1] <= reach * reach) break;
+    }
+    for (int k3 = b[2] - r; k3 <= b[2] + r; k3++) {
+      if (k3 < 0 || k3 >= g.vg[2]) continue;
+      for (int k2 = b[1] - r; k2 <= b[1] + r; k2++) {
+        if (k2 < 0 || k2 >= g.vg[1]) continue;
+        for (int k1 = b[0] - r; k1 <= b[0] + r; k1++) {
+          if (k1 < 0 || k1 >= g.vg[0]) continue;
+          if (std::max(std::abs(k1 - b[0]), std::max(std::abs(k2 - b[1]), std::abs(k3 - b[2]))) != r) continue;
+          const int cell = (k3 * g.vg[1] + k2) * g.vg[0] + k1;
+          for (int q = g.vg_start[cell]; q < g.vg_start[cell + 1]; q++) {
+            const int i = g.vg_sites[q];
+            const double dx = g.vx[i] - x, dy = g.vy[i] - y, dz = g.vz[i] - z;
+            const double d2 = dx * dx + dy * dy + dz * dz;
+            if (d2 < best[0]) {
+              best[1] = best[0]; idx[1] = idx[0];
+              best[0] = d2; idx[0] = i + 1;
+            } else if (d2 < best[1]) {
+              best[1] = d2; idx[1] = i + 1;
+            }
+          }
+        }
+      }
+    }
+  }
+}
+
+// find_cell (:195-228)
+bool vor_find_cell(const orc_ctx &g, const Photon &p, Cell &out) {
+  if (p.r.x < g.vbox[0] || p.r.x > g.vbox[1]) return false;
+  if (p.r.y < g.vbox[2] || p.r.y > g.vbox[3]) return false;
+  if (p.r.z < g.vbox[4] || p.r.z > g.vbox[5]) return false;
+  int idx[2];
+  vor_nearest(g, p.r.x, p.r.y, p.r.z, 1, idx);
+  out = Cell{0, 0, 0, idx[0]};
+  return true;
+}
+
+// in_correct_cell (:274-283): the cell is one of the two nearest sites
+bool vor_in_correct_cell(const orc_ctx &g, const Photon &p) {
+  int idx[2];
+  vor_nearest(g, p.r.x, p.r.y, p.r.z, 2, idx);
+  return p.icell.ic == idx[0] || p.icell.ic == idx[1];
+}
+
+// find_wall (:322-402): the planes that bisect the segments to the neighbouring sites, and the walls of the box
+void vor_find_wall(orc_ctx &g, const Photon &p, double &tmin, WallId &id_min) {
+  g.tmin = std::numeric_limits<double>::max();
+  g.emin = 0.0;
+  g.imin = WallId();
+  const int ic = p.icell.ic - 1;
+  for (int q = g.vidx[ic]; q < g.vidx[ic + 1]; q++) {
+    const int nb = g.vneigh[q] + 1;   // the Fortran numbering: cells from 1, walls 0 .. -5
+    if (nb <= 0 && nb >= -5) {
+      switch (nb) {
+        case 0: if (p.v.x < 0.0) insert_t(g, (g.vbox[0] - p.r.x) / p.v.x, 1, g.n_cells + 1, 0.0); break;
+        case -1: if (p.v.x > 0.0) insert_t(g, (g.vbox[1] - p.r.x) / p.v.x, 1, g.n_cells + 1, 0.0); break;
+        case -2: if (p.v.y < 0.0) insert_t(g, (g.vbox[2] - p.r.y) / p.v.y, 1, g.n_cells + 1, 0.0); break;
+        case -3: if (p.v.y > 0.0) insert_t(g, (g.vbox[3] - p.r.y) / p.v.y, 1, g.n_cells + 1, 0.0); break;
+        case -4: if (p.v.z < 0.0) insert_t(g, (g.vbox[4] - p.r.z) / p.v.z, 1, g.n_cells + 1, 0.0); break;
+        default: if (p.v.z > 0.0) insert_t(g, (g.vbox[5] - p.r.z) / p.v.z, 1, g.n_cells + 1, 0.0); break;
+      }
+      continue;
+    }
+    if (nb == -p.on_wall_id.w2) continue;   // the wall the packet stands on (w2 keeps the previous cell)
+    const double nx = g.vx[nb - 1] - g.vx[ic], ny = g.vy[nb - 1] - g.vy[ic], nz = g.vz[nb - 1] - g.vz[ic];
+    const double mx = 0.5 * (g.vx[nb - 1] + g.vx[ic]), my = 0.5 * (g.vy[nb - 1] + g.vy[ic]), mz = 0.5 * (g.vz[nb - 1] + g.vz[ic]);
+    const double t = (nx * (mx - p.r.x) + ny * (my - p.r.y) + nz * (mz - p.r.z)) / (nx * p.v.x + ny * p.v.y + nz * p.v.z);
+    insert_t(g, t, 1, nb, 0.0);
+  }
+  tmin = g.tmin;
+  id_min = g.imin;
+  id_min.w2 = p.icell.ic;   // "use w2 to store previous cell"
+}
+
+// random_position_cell (:285-312): rejection sampling in the cell's bounding box
+Vec vor_random_position_cell(orc_ctx &g, const Cell &c) {
+  const double *bb = &g.vbb[(size_t)6 * (c.ic - 1)];
+  for (int i = 0; i < 1000000; i++) {
+    Vec pos;
+    pos.x = g.rng.random() * (bb[1] - bb[0]) + bb[0];   // random_uni (lib_random.f90)
+    pos.y = g.rng.random() * (bb[3] - bb[2]) + bb[2];
+    pos.z = g.rng.random() * (bb[5] - bb[4]) + bb[4];
+    int idx[2];
+    vor_nearest(g, pos.x, pos.y, pos.z, 1, idx);
+    if (idx[0] == c.ic) return pos;
+  }
+  throw OracleError{"too many samples"};
 }
 
 // ---------------------------------------------------------------------------
@@ -2608,7 +2740,10 @@ void emit_from_plane_parallel(orc_ctx &g, const Source &src, Photon &p) {
 
 // new_grid_cell(ic, geo) + random_position_cell of the geometry module for the 1-based cell id `ic`
 void place_at_random_position_in_cell(orc_ctx &g, Photon &p, int ic) {
-  if (g.grid_type == 3) {
+  if (g.grid_type == 5) {
+    p.icell = Cell{0, 0, 0, ic};
+    p.r = vor_random_position_cell(g, p.icell);
+  } else if (g.grid_type == 3) {
     p.icell = Cell{0, 0, 0, ic};
     p.r = oct_random_position_cell(g, p.icell);
   } else if (g.grid_type == 4) {
@@ -3325,6 +3460,8 @@ double distance_to_closest_wall(const orc_ctx &g, const Photon &p) {
       d6 = std::fabs(pb * p.r.x - p.r.y) / std::sqrt(pb * pb + 1.0);
     }
     d = std::min(std::min(std::min(d1, d2), std::min(d3, d4)), std::min(d5, d6));
+  } else if (g.grid_type == 5) {
+    throw OracleError{"not implemented for Voronoi grid"};   // distance_to_closest_wall, grid_geometry_voronoi.f90:314-320
   } else if (g.grid_type == 3) {  // grid_geometry_octree.f90:410-436
     const int k = p.icell.ic - 1;
     double d1 = p.r.x - g.ox[k] + g.odx[k], d2 = g.ox[k] + g.odx[k] - p.r.x;
@@ -4422,6 +4559,51 @@ int orc_set_grid_cylindrical(orc_ctx *g, int32_t n1, int32_t n2, int32_t n3, con
 
 // setup_grid_geometry + octree_setup_indiv (grid_geometry_octree.f90:148-262): refined is the depth-first
 // list of refinement flags, (x, y, z) the centre and (dx, dy, dz) the HALF-widths of the root cell
+// setup_grid_geometry (grid_geometry_voronoi.f90:92-187)
+int orc_set_grid_voronoi(orc_ctx *g, int32_t n_cells, const double *coords, const double *bb_min, const double *bb_max,
+                         const double *volume, const int32_t *sparse_idx, const int32_t *sparse_neighs, const double *box) {
+  g->grid_type = 5;
+  g->n_cells = n_cells;
+  g->n1 = n_cells;
+  g->n2 = g->n3 = 1;
+  g->vx.resize(n_cells); g->vy.resize(n_cells); g->vz.resize(n_cells);
+  g->vbb.resize((size_t)6 * n_cells);
+  g->volume.assign(n_cells, 0.0);
+  g->mask_map.clear();
+  for (int i = 0; i < n_cells; i++) {
+    g->vx[i] = coords[3 * i]; g->vy[i] = coords[3 * i + 1]; g->vz[i] = coords[3 * i + 2];
+    for (int a = 0; a < 3; a++) {
+      g->vbb[(size_t)6 * i + 2 * a] = bb_min[3 * i + a];
+      g->vbb[(size_t)6 * i + 2 * a + 1] = bb_max[3 * i + a];
+    }
+    if (volume[i] > 0.0) g->mask_map.push_back(i + 1);       // geo%mask = geo%volume > 0
+    g->volume[i] = volume[i] < 0.0 ? 0.0 : volume[i];
+  }
+  g->n_masked = (int)g->mask_map.size();
+  g->vidx.assign(sparse_idx, sparse_idx + n_cells + 1);
+  g->vneigh.assign(sparse_neighs, sparse_neighs + sparse_idx[n_cells]);
+  for (int a = 0; a < 6; a++) g->vbox[a] = box[a];
+  // buckets of about two sites
+  const int per_axis = std::max(1, (int)std::cbrt((double)n_cells / 2.0));
+  for (int a = 0; a < 3; a++) g->vg[a] = per_axis;
+  const int nb = per_axis * per_axis * per_axis;
+  std::vector<int> bucket(n_cells);
+  g->vg_start.assign(nb + 1, 0);
+  for (int i = 0; i < n_cells; i++) {
+    const double pos[3] = {g->vx[i], g->vy[i], g->vz[i]};
+    int b[3];
+    for (int a = 0; a < 3; a++)
+      b[a] = std::min(std::max((int)((pos[a] - box[2 * a]) / ((box[2 * a + 1] - box[2 * a]) / per_axis)), 0), per_axis - 1);
+    bucket[i] = (b[2] * per_axis + b[1]) * per_axis + b[0];
+    g->vg_start[bucket[i] + 1]++;
+  }
+  for (int k = 0; k < nb; k++) g->vg_start[k + 1] += g->vg_start[k];
+  g->vg_sites.assign(n_cells, 0);
+  std::vector<int> fill(g->vg_start.begin(), g->vg_start.end() - 1);
+  for (int i = 0; i < n_cells; i++) g->vg_sites[fill[bucket[i]]++] = i;
+  return 0;
+}
+
 int orc_set_grid_octree(orc_ctx *g, int32_t n_cells, const int32_t *refined, double x, double y, double z, double dx,
                         double dy, double dz) {
   g->grid_type = 3;

@@ -61,6 +61,31 @@ def bitlevel_model_amr(zc, z, evenly, multi):
                      FlatConf(sample_sources_evenly=evenly), grid_type="amr", amr_levels=levels)
 
 
+def bitlevel_model_vor(zc, evenly, multi, n_sites=160, seed=11):
+    """The bit-level test's dust, sources and box on a seeded random Voronoi mesh (the reference has no Voronoi
+    fixture: its test_voronoi_basics only checks that a 1000-site run completes).  Densities follow the
+    Cartesian fixture's values at the sites' positions."""
+    from hyperion_b200 import synthetic as syn
+    rng = np.random.default_rng(seed)
+    box = np.array([zc["w1"][0], zc["w1"][-1], zc["w2"][0], zc["w2"][-1], zc["w3"][0], zc["w3"][-1]])
+    sites = np.stack([rng.uniform(box[2 * a], box[2 * a + 1], n_sites) for a in range(3)], axis=1)
+    mesh = syn.voronoi_mesh(sites, box)
+    idx = [np.clip(np.searchsorted(zc[w], sites[:, a]) - 1, 0, len(zc[w]) - 2) for a, w in enumerate(("w1", "w2", "w3"))]
+    dust = kmh_dust(zc)
+    names = ["density_1"] + (["density_2", "density_3"] if multi else [])
+    dens = [zc[k][idx[2], idx[1], idx[0]] for k in names]
+    srcs = [FlatSource(type=1, luminosity=float(l), temperature=float(t), position=tuple(p))
+            for l, t, p in zip(zc["source_luminosity"], zc["source_temperature"], zc["source_position"])]
+    return FlatModel(None, None, None, np.array(dens), [dust] * len(dens), srcs,
+                     FlatConf(sample_sources_evenly=evenly), grid_type="vor", voronoi=mesh)
+
+
+def peeloff_model_vor(zc, evenly):
+    m = bitlevel_model_vor(zc, evenly, False)
+    m.peeled = peeloff_groups()
+    return m
+
+
 def peeloff_model_amr(zc, z, evenly):
     m = bitlevel_model_amr(zc, z, evenly, False)
     m.peeled = peeloff_groups()

@@ -229,6 +229,36 @@ def test_runner_octree(golden_car, golden_oct, tmp_path):
     assert r["Peeled/group_00001/seds"][...][0].sum() > 0
 
 
+def test_rtin_roundtrip_voronoi(golden_car, tmp_path):
+    """'vor' grids: table 'cells' (coordinates, volume, bb_min, bb_max), 'sparse_neighs' / 'sparse_idx', the box as
+    attributes (hyperion/grid/voronoi_grid.py:417-478); quantities are [n_dust, n_cells]."""
+    from helpers import bitlevel_model_vor
+    m = bitlevel_model_vor(golden_car, False, True)
+    m.voronoi["volume"][5] = 0.0
+    fn = str(tmp_path / "m.rtin")
+    rtin_write.write_rtin(fn, m)
+    got, rs, _ = rtin.read_rtin(fn)
+    assert rs.grid_type == "vor" and got.grid_type == "vor"
+    for k in ("coordinates", "bb_min", "bb_max", "sparse_neighs", "sparse_idx", "box"):
+        assert np.array_equal(got.voronoi[k], m.voronoi[k]), k
+    assert got.voronoi["volume"][5] == -1.0 and np.array_equal(np.delete(got.voronoi["volume"], 5), np.delete(m.voronoi["volume"], 5))
+    assert np.array_equal(got.density, m.density) and got.density.shape == (3, 160)
+
+
+@pytest.mark.gpu
+def test_runner_voronoi(golden_car, tmp_path):
+    from helpers import peeloff_model_vor
+    m = peeloff_model_vor(golden_car, False)
+    fin, fout = str(tmp_path / "m.rtin"), str(tmp_path / "m.rtout")
+    rtin_write.write_rtin(fin, m, n_initial_iter=2, n_initial_photons=20000, n_last_photons=20000, raytracing=True,
+                          n_ray_photons=(5000, 5000))
+    assert runner.main(["-f", fin, fout]) == 0
+    r = h5min.File(fout)
+    se = r["iteration_00002/specific_energy"][...]
+    assert se.shape == (1, 160) and np.all(se > 0)
+    assert r["Peeled/group_00001/seds"][...][0].sum() > 0
+
+
 def test_rtin_roundtrip_amr(golden_car, golden_amr, tmp_path):
     """'amr' grids: Grid/Geometry/level_%05d/grid_%05d attributes, one density dataset per grid
     (hyperion/grid/amr_grid.py:372-412)."""
