@@ -161,6 +161,21 @@ class CApi:
                                                 _ptr(v["bb_max"]), _ptr(v["volume"]), v["sparse_idx"].ctypes.data_as(i32),
                                                 v["sparse_neighs"].ctypes.data_as(i32), _ptr(v["box"])))
 
+    def set_specific_energy_spectrum_bins(self, ctx, edges):
+        edges = np.ascontiguousarray(edges, dtype=np.float64)
+        f = self._fn("set_specific_energy_spectrum_bins")
+        f.restype = C.c_int
+        self.check(f(ctx, C.c_int32(len(edges)), _ptr(edges)))
+        self.n_nu_bins = len(edges) - 1
+
+    def get_specific_energy_spectrum(self):
+        """[n_bins, n_dust, cells...] as the reference writes /specific_energy_spectrum."""
+        out = np.empty((self.n_nu_bins, self.n_dust) + tuple(self.shape), dtype=np.float64)
+        f = self._fn("get_specific_energy_spectrum")
+        f.restype = C.c_int
+        self.check(f(self.ctx, _ptr(out)))
+        return out
+
     def set_grid_amr(self, ctx, levels):
         n_grids = np.array([len(lev) for lev in levels], dtype=np.int32)
         dims = np.array([g[:3] for lev in levels for g in lev], dtype=np.int32).ravel()

@@ -210,6 +210,9 @@ class FlatModel:
     # "sparse_idx" in the file's numbering (>= 0: cell, -1 .. -6: the walls xmin, xmax, ymin, ymax, zmin, zmax of
     # the box) and "box" = (xmin, xmax, ymin, ymax, zmin, zmax); density is [n_dust, n_cells]
     voronoi: Optional[dict] = None
+    # frequency-resolved specific energy (Model.set_specific_energy_spectrum_bins, /specific_energy_spectrum_bin_edges
+    # of the .rtin): n + 1 strictly increasing frequencies; None = not computed
+    spectrum_bin_edges: Optional[np.ndarray] = None
 
     def __post_init__(self):
         self.density = _f8(self.density)
@@ -341,6 +344,8 @@ def apply_model(api, ctx, model: FlatModel):
     for s in model.sources:
         api.add_source(ctx, s)
     api.set_run_conf(ctx, model.conf)
+    if model.spectrum_bin_edges is not None:
+        api.set_specific_energy_spectrum_bins(ctx, model.spectrum_bin_edges)
     api.set_density(ctx, len(model.dust), model.density)
     api.set_specific_energy(ctx, model.specific_energy, model.minimum_specific_energy)
     if model.frequencies is not None:

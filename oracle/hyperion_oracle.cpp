@@ -1198,6 +1198,11 @@ struct orc_ctx {
   // grid physics (grid_physics_3d.f90:34-63): (ic, id) stored at [id*n_cells + ic]
   std::vector<double> density, specific_energy, specific_energy_sum, jnu_var_frac, minimum_specific_energy;
   std::vector<double> specific_energy_additional;  // specific_energy_type = 'additional' (grid_physics_3d.f90:55)
+  // frequency-resolved specific energy (grid_physics_3d.f90:41-56): [bin][dust][cell], the file's order;
+  // empty unless bin edges were given (compute_specific_energy_spectrum)
+  std::vector<double> nu_bin_edges, log_nu_bin_edges, specific_energy_spectrum, specific_energy_sum_spectrum;
+  std::vector<double> j_nu_bin_frac;               // [dust][state][bin] (setup_j_nu_bin_fractions, :325-348)
+  int n_nu_bins = 0, n_jnu_max = 0;
   std::vector<int> jnu_var_id;
   std::vector<double> energy_abs_tot;
   PdfDiscrete absorption;
@@ -2927,6 +2932,10 @@ void emit(orc_ctx &g, Photon &p, bool reemit = false, int reemit_id = 0, double 
 void grid_integrate(orc_ctx &g, Photon &p, double tau_required, double &tau_achieved) {
   const double frac_check = g.conf.propagation_check_frequency;
   tau_achieved = 0.0;
+  // grid_propagate_3d.f90:61-71: the frequency bin of the packet, found once per call; -1 outside the edges
+  int idx = -1;
+  if (g.n_nu_bins > 0) idx = locate(g.log_nu_bin_edges.data(), g.n_nu_bins + 1, std::log10(p.nu));
+  const size_t nsp = (size_t)g.n_dust * g.n_cells;
   if (!p.in_cell) throw OracleError{"photon has not been placed in a cell"};
   if (escaped(g, p.icell)) return;
   // grid_propagate_3d.f90:90-95: a packet counts once per cell for as long as no other packet enters it
@@ -2985,8 +2994,13 @@ void grid_integrate(orc_ctx &g, Photon &p, double tau_required, double &tau_achi
       tau_achieved = tau_achieved + tau_cell;
       for (int id = 0; id < g.n_dust; id++) {
         size_t k = (size_t)id * nc + ic - 1;
-        if (g.density[k] > 0.0)
+        if (g.density[k] > 0.0) {
           g.specific_energy_sum[k] = g.specific_energy_sum[k] + tmin * p.current_kappa[id] * p.energy;
+          if (idx > 0) {   // :155-158
+            double &b = g.specific_energy_sum_spectrum[(size_t)(idx - 1) * nsp + k];
+            b = b + tmin * p.current_kappa[id] * p.energy;
+          }
+        }
       }
       p.on_wall = true;
       p.icell = next_cell(g, p.icell, id_min, p.r);
@@ -3012,6 +3026,14 @@ void grid_integrate(orc_ctx &g, Photon &p, double tau_required, double &tau_achi
         if (g.density[k] > 0.0)
           g.specific_energy_sum[k] = g.specific_energy_sum[k] + tact * p.current_kappa[id] * p.energy;
       }
+      if (idx > 0)   // :217-225
+        for (int id = 0; id < g.n_dust; id++) {
+          size_t k = (size_t)id * nc + ic - 1;
+          if (g.density[k] > 0.0) {
+            double &b = g.specific_energy_sum_spectrum[(size_t)(idx - 1) * nsp + k];
+            b = b + tact * p.current_kappa[id] * p.energy;
+          }
+        }
       return;
     }
   }
@@ -3105,13 +3127,28 @@ void update_energy_abs(orc_ctx &g, double scale) {
       size_t k = (size_t)id * g.n_cells + ic;
       g.specific_energy[k] = g.specific_energy_sum[k] * scale / g.volume[ic];
       if (g.volume[ic] == 0.0) g.specific_energy[k] = 0.0;
+      for (int ib = 0; ib < g.n_nu_bins; ib++) {   // :516-524
+        const size_t kb = (size_t)ib * g.n_dust * g.n_cells + k;
+        g.specific_energy_spectrum[kb] = g.specific_energy_sum_spectrum[kb] * scale / g.volume[ic];
+        if (g.volume[ic] == 0.0) g.specific_energy_spectrum[kb] = 0.0;
+      }
     }
+  // (specific_energy_additional_spectrum is a copy of the spectrum array at a moment when it is all zeros,
+  // grid_physics_3d.f90:143,223-225: adding it, :543-545, changes nothing)
   // additional source of heating (grid_physics_3d.f90:537-545)
   if (!g.specific_energy_additional.empty())
     for (size_t k = 0; k < g.specific_energy.size(); k++)
       g.specific_energy[k] = g.specific_energy[k] + g.specific_energy_additional[k];
   update_energy_abs_tot(g);
   check_energy_abs(g);
+}
+
+// scale_specific_energy_spectrum (grid_physics_3d.f90:350-365); ic 0-based
+void scale_specific_energy_spectrum(orc_ctx &g, int ic, int id, double factor) {
+  for (int ib = 0; ib < g.n_nu_bins; ib++) {
+    double &b = g.specific_energy_spectrum[((size_t)ib * g.n_dust + id) * g.n_cells + ic];
+    b = b * factor;
+  }
 }
 
 // sublimate_dust (grid_physics_3d.f90:420-498)
@@ -3126,6 +3163,8 @@ void sublimate_dust(orc_ctx &g) {
           if (e[ic] > d.sublimation_specific_energy) {
             rho[ic] = 0.;
             e[ic] = g.minimum_specific_energy[id];
+            for (int ib = 0; ib < g.n_nu_bins; ib++)   // :442-446
+              g.specific_energy_spectrum[((size_t)ib * g.n_dust + id) * g.n_cells + ic] = g.minimum_specific_energy[id];
           }
         break;
       case 2:
@@ -3136,12 +3175,16 @@ void sublimate_dust(orc_ctx &g) {
                                          d.sublimation_specific_energy);
             double q = cr1 / cr2;
             rho[ic] = rho[ic] * d.sublimation_specific_energy / e[ic] * (q * q);
+            scale_specific_energy_spectrum(g, ic, id, d.sublimation_specific_energy / e[ic]);
             e[ic] = d.sublimation_specific_energy;
           }
         break;
       case 3:
         for (int ic = 0; ic < g.n_cells; ic++)
-          if (e[ic] > d.sublimation_specific_energy) e[ic] = d.sublimation_specific_energy;
+          if (e[ic] > d.sublimation_specific_energy) {
+            scale_specific_energy_spectrum(g, ic, id, d.sublimation_specific_energy / e[ic]);
+            e[ic] = d.sublimation_specific_energy;
+          }
         break;
       default:
         break;
@@ -3255,6 +3298,7 @@ void pda_update_specific_energy(orc_ctx &g, const PdaState &P, int ic) {
     const Dust &d = g.d[id];
     const size_t k = (size_t)id * g.n_cells + ic - 1;
     double s = g.specific_energy[k];
+    const double s_old = s;
     const double smin = d.specific_energy[0], smax = d.specific_energy[d.n_e - 1];
     if (P.e_mean[ic - 1] < smin / kappa_planck(d, smin)) {
       s = smin;
@@ -3268,6 +3312,7 @@ void pda_update_specific_energy(orc_ctx &g, const PdaState &P, int ic) {
       }
     }
     g.specific_energy[k] = s;
+    if (s_old > 0.0) scale_specific_energy_spectrum(g, ic - 1, id, s / s_old);   // :63-67
   }
 }
 
@@ -3546,6 +3591,18 @@ void grid_do_mrw(orc_ctx &g, Photon &p, bool deposit) {
         const Dust &d = g.d[id];
         double e = p.energy * ct * interp1d_loglog(d.specific_energy.data(), d.kappa_planck.data(), d.n_e, g.specific_energy[k]);
         g.specific_energy_sum[k] = g.specific_energy_sum[k] + e;
+        // deposit_specific_energy_spectrum (grid_physics_3d.f90:367-395): spread over the bins like the local
+        // emissivity, interpolated between the two adjacent emissivity states
+        if (g.n_nu_bins > 0) {
+          const int iv = g.jnu_var_id[k];
+          const double fr = g.jnu_var_frac[k];
+          const double *f1 = &g.j_nu_bin_frac[((size_t)id * g.n_jnu_max + iv - 1) * g.n_nu_bins];
+          const double *f2 = f1 + g.n_nu_bins;
+          for (int ib = 0; ib < g.n_nu_bins; ib++) {
+            double &b = g.specific_energy_sum_spectrum[(size_t)ib * g.n_dust * nc + k];
+            b = b + e * ((1.0 - fr) * f1[ib] + fr * f2[ib]);
+          }
+        }
       }
     }
   }
@@ -4934,6 +4991,31 @@ int orc_finalize_setup(orc_ctx *g, int32_t rank) {
           g->specific_energy[(size_t)id * g->n_cells + ic] = g->minimum_specific_energy[id];
     }
     g->specific_energy_sum.assign(n, 0.0);
+    if (g->n_nu_bins > 0 && !g->setup_done) {
+      // grid_physics_3d.f90:135-143,199-207,229-233,249-252: zeros when the specific energy comes from the file,
+      // the minimum specific energy otherwise (and with specific_energy_type = 'additional')
+      g->specific_energy_spectrum.assign(n * g->n_nu_bins, 0.0);
+      g->specific_energy_sum_spectrum.assign(n * g->n_nu_bins, 0.0);
+      if (!g->specific_energy_from_file || g->conf.specific_energy_additional)
+        for (int ib = 0; ib < g->n_nu_bins; ib++)
+          for (int id = 0; id < g->n_dust; id++)
+            for (int ic = 0; ic < g->n_cells; ic++)
+              g->specific_energy_spectrum[((size_t)ib * g->n_dust + id) * g->n_cells + ic] = g->minimum_specific_energy[id];
+      // setup_j_nu_bin_fractions (:325-348), get_j_nu_bin_fractions (dust_type_4elem.f90:752-778)
+      g->n_jnu_max = 0;
+      for (int id = 0; id < g->n_dust; id++) g->n_jnu_max = std::max(g->n_jnu_max, g->d[id].n_jnu);
+      g->j_nu_bin_frac.assign((size_t)g->n_dust * g->n_jnu_max * g->n_nu_bins, 0.0);
+      for (int id = 0; id < g->n_dust; id++)
+        for (int iv = 0; iv < g->d[id].n_jnu; iv++) {
+          const PdfCont &j = g->d[id].j_nu[iv];
+          double *frac = &g->j_nu_bin_frac[((size_t)id * g->n_jnu_max + iv) * g->n_nu_bins];
+          for (int ib = 0; ib < g->n_nu_bins; ib++)
+            frac[ib] = integral_loglog_subset(j.x.data(), j.pdf.data(), j.n, g->nu_bin_edges[ib], g->nu_bin_edges[ib + 1]);
+          const double norm = integral_general(j.x.data(), j.pdf.data(), j.n, trapezium_loglog);
+          if (norm > 0.0)
+            for (int ib = 0; ib < g->n_nu_bins; ib++) frac[ib] = frac[ib] / norm;
+        }
+    }
     g->jnu_var_id.assign(n, 0);
     g->jnu_var_frac.assign(n, 0.0);
     g->energy_abs_tot.assign(g->n_dust, 0.0);
@@ -4960,6 +5042,7 @@ int orc_finalize_setup(orc_ctx *g, int32_t rank) {
 // do_lucy, first part (iter_lucy.f90:99-112)
 int orc_lucy_begin(orc_ctx *g) {
   std::fill(g->specific_energy_sum.begin(), g->specific_energy_sum.end(), 0.0);
+  std::fill(g->specific_energy_sum_spectrum.begin(), g->specific_energy_sum_spectrum.end(), 0.0);   // grid_generic.f90:26
   g->energy_current = 0.0;
   g->killed_photons_geo = g->killed_photons_int = 0;
   g->n_crossings = g->n_absorptions = g->n_scatterings = g->n_escaped = g->n_photons_run = 0;
@@ -5070,6 +5153,32 @@ int orc_get_energy_sum(orc_ctx *g, double *out) {
 }
 int orc_set_energy_sum(orc_ctx *g, const double *in) {
   memcpy(g->specific_energy_sum.data(), in, g->specific_energy_sum.size() * sizeof(double));
+  return 0;
+}
+// specific_energy_spectrum_bin_edges (setup_rt.f90:98-104, grid_physics_3d.f90:124-129,278-283)
+int orc_set_specific_energy_spectrum_bins(orc_ctx *g, int32_t n_edges, const double *edges) {
+  if (n_edges < 2) return fail(g, "specific_energy_spectrum_bin_edges should have at least two values");
+  for (int i = 1; i < n_edges; i++)
+    if (edges[i] <= edges[i - 1]) return fail(g, "specific_energy_spectrum_bin_edges should be strictly increasing");
+  g->nu_bin_edges.assign(edges, edges + n_edges);
+  g->log_nu_bin_edges.resize(n_edges);
+  for (int i = 0; i < n_edges; i++) g->log_nu_bin_edges[i] = std::log10(edges[i]);
+  g->n_nu_bins = n_edges - 1;
+  return 0;
+}
+// [n_bins][n_dust][n_cells], as output_grid writes it (grid_generic.f90:68-84)
+int orc_get_specific_energy_spectrum(orc_ctx *g, double *out) {
+  if (g->n_nu_bins == 0) return fail(g, "specific_energy_spectrum array is not allocated");
+  memcpy(out, g->specific_energy_spectrum.data(), g->specific_energy_spectrum.size() * sizeof(double));
+  return 0;
+}
+// the sums of emulated ranks add up (mp_collect_physical_arrays, mpi_routines.f90:292-301)
+int orc_get_energy_sum_spectrum(orc_ctx *g, double *out) {
+  memcpy(out, g->specific_energy_sum_spectrum.data(), g->specific_energy_sum_spectrum.size() * sizeof(double));
+  return 0;
+}
+int orc_set_energy_sum_spectrum(orc_ctx *g, const double *in) {
+  memcpy(g->specific_energy_sum_spectrum.data(), in, g->specific_energy_sum_spectrum.size() * sizeof(double));
   return 0;
 }
 

@@ -128,6 +128,15 @@ class Oracle(CApi):
         self.check(self.lib.orc_get_energy_sum(self.ctx, _ptr(out)))
         return out
 
+    def get_energy_sum_spectrum(self):
+        out = np.empty((self.n_nu_bins, self.n_dust) + tuple(self.shape), dtype=np.float64)
+        self.check(self.lib.orc_get_energy_sum_spectrum(self.ctx, _ptr(out)))
+        return out
+
+    def set_energy_sum_spectrum(self, a):
+        a = np.ascontiguousarray(a, dtype=np.float64)
+        self.check(self.lib.orc_set_energy_sum_spectrum(self.ctx, _ptr(a)))
+
     def get_n_photons(self):
         out = np.empty(tuple(self.shape), dtype=np.int64)
         self.check(self.lib.orc_get_n_photons(self.ctx, out.ctypes.data_as(C.c_void_p)))
@@ -184,6 +193,10 @@ def run_lucy_ranks(model: FlatModel, n_photons, n_ranks=1, n_iter=1, first_rank=
                 o.lucy_begin()
             list(pool.map(lambda a: a[0].lucy_photons(a[1]), zip(ranks, split)))
             total = sum(o.get_energy_sum() for o in ranks) if n_ranks > 1 else None
+            if n_ranks > 1 and model.spectrum_bin_edges is not None:
+                total_nu = sum(o.get_energy_sum_spectrum() for o in ranks)
+                for o in ranks:
+                    o.set_energy_sum_spectrum(total_nu)
             e_cur = sum(o.energy_current for o in ranks)
             sts = []
             for o in ranks:
