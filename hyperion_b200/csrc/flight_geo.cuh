@@ -81,9 +81,14 @@ flight_geo_kernel(const ModelDev M, Pool P, const FinalArgs F, const uint32_t *_
       } else if (FINAL && tau < 0.0) {
         tau = 1.0;  // escaped before the first step: the value is never used
       }
+      double *spec = nullptr;
+      if (DEP && M.spec_sums) {
+        const int b = spectrum_bin(M, s->nu);
+        if (b >= 0) spec = M.spec_sums + (size_t)b * (size_t)M.n_cells * ND;
+      }
       fin = geo_march<GEO, ND, DEP>(M, R, tau, chi, kE, cells, n_cross, t_source, (DEP && M.n_visits) ? s->id + 1ull : 0ull,
                                     // first flight of a packet, or of its re-emission by a star that absorbed it
-                                    s->n_inter == 0u || (s->rng_has_spare >> 1) != 0u);
+                                    s->n_inter == 0u || (s->rng_has_spare >> 1) != 0u, 0x7fffffff, spec);
       if (fin == MARCH_REABSORBED) {
         // hand the packet to the interact kernel, which re-emits it from that source: t < 0 carries the id
         s->t = -(double)(src_hit + 1);

@@ -89,11 +89,31 @@ struct ModelDev {
   double mono_thermal_w[MAX_DUST];     // energy of a thermal packet of each dust type (0: the type does not emit)
   // per-cell packet counter (n_photons / last_photon_id, grid_physics_3d.f90:38-39), or nullptr
   unsigned long long *n_visits, *last_id;
+  // frequency-resolved specific energy (grid_physics_3d.f90:41-56), or nullptr: deposit sums and specific energies as
+  // n_spec_bins planes in device order [cell][dust]; log10 of the n_spec_bins + 1 bin edges; the fraction of every
+  // emissivity state's spectrum per bin [dust][spec_jmax][bin] (setup_j_nu_bin_fractions, :325-348)
+  double *spec_sums, *spec_energy;
+  const double *spec_log_edges, *spec_jfrac;
+  int32_t n_spec_bins, spec_jmax;
   // outputs
   double *scalars;                 // [SC_COUNT], directly after the reduced sum grid
   unsigned long long *work_counter;
   int32_t *error_flag;
 };
+
+// locate(log_nu_bin_edges, log10(nu)) (grid_propagate_3d.f90:71), 0-based; -1 outside the outer edges
+__device__ __forceinline__ int spectrum_bin(const ModelDev &M, double nu) {
+  const double lg = log10(nu);
+  const int nb = M.n_spec_bins;
+  const double *e = M.spec_log_edges;
+  if (lg < __ldg(e) || lg > __ldg(e + nb)) return -1;
+  int lo = 0, hi = nb;          // e[lo] <= lg, lg <= e[hi]
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (lg >= __ldg(e + mid)) lo = mid; else hi = mid;
+  }
+  return lo;
+}
 
 enum { ERR_NONE = 0, ERR_NOT_IN_CELL = 1, ERR_NU_RANGE = 2, ERR_SCATTER = 3, ERR_JOBS = 4, ERR_DEPOSIT = 5 };
 
@@ -946,6 +966,17 @@ __device__ inline int mrw_step(const ModelDev &M, Photon<ND> &p, Rng &rng, const
       if (M.cells[base + id].rho > 0.0) {
         const double e = p.energy * ct * mean_opacity_loglog(M.dust[id], M.dust[id].L.o_logkap_planck, M.specific_energy[base + id]);
         atomicAdd(&M.cells[base + id].esum, e);
+        if (M.spec_sums) {
+          // deposit_specific_energy_spectrum (grid_physics_3d.f90:367-395): spread like the local emissivity
+          const int iv = M.jnu_id[base + id];
+          const double fr = M.jnu_frac[base + id];
+          const double *f1 = M.spec_jfrac + ((size_t)id * M.spec_jmax + iv) * M.n_spec_bins, *f2 = f1 + M.n_spec_bins;
+          const size_t plane = (size_t)M.n_cells * ND;
+          for (int b = 0; b < M.n_spec_bins; ++b) {
+            const double w = (1.0 - fr) * __ldg(f1 + b) + fr * __ldg(f2 + b);
+            if (w != 0.0) atomicAdd(M.spec_sums + (size_t)b * plane + base + id, e * w);
+          }
+        }
       }
     }
   }
@@ -1748,16 +1779,28 @@ __global__ void lucy_finish_kernel(ModelDev M, const double *__restrict__ sums, 
     const double vol = cell_volume(M, ic);
     const DustDev &d = M.dust[id];
     double e;
+    const int nb = M.spec_sums ? M.n_spec_bins : 0;
     if (mode == 2) {
       e = M.specific_energy[k];
     } else {
       e = sums[k] * scale / vol;
       if (vol == 0.0) e = 0.0;
+      // update_energy_abs, spectrum part (:516-524); the additional spectrum is all zeros (:143,223-225)
+      for (int b = 0; b < nb; ++b) {
+        double eb = M.spec_sums[(size_t)b * n + k] * scale / vol;
+        if (vol == 0.0) eb = 0.0;
+        M.spec_energy[(size_t)b * n + k] = eb;
+      }
       if (M.energy_additional) e = e + M.energy_additional[k];   // grid_physics_3d.f90:537-545
       e = clamp_energy(M, d, id, e);
     }
     if (mode != 1 && d.L.sublimation_mode != 0 && e > d.L.sublimation_specific_energy) {
       const double es = d.L.sublimation_specific_energy;
+      // the spectrum follows: reset to the minimum (:442-446) or rescaled with its shape kept (:463,479)
+      for (int b = 0; b < nb; ++b) {
+        double &eb = M.spec_energy[(size_t)b * n + k];
+        eb = d.L.sublimation_mode == 1 ? M.min_energy[id] : eb * (es / e);
+      }
       if (d.L.sublimation_mode == 1) {
         M.cells[k].rho = 0.0;
         M.rho[k] = 0.0;
@@ -1890,6 +1933,9 @@ struct hyp_ctx {
   int32_t *d_amr_gotos = nullptr, *d_amr_cell_grid = nullptr, *d_amr_valid = nullptr;
   OctNode *d_oct_nodes = nullptr;
   int32_t *d_oct_children = nullptr, *d_oct_leaves = nullptr;
+  // frequency-resolved specific energy
+  std::vector<double> spec_edges;
+  double *d_spec_energy = nullptr, *d_spec_tab = nullptr;   // [bins][n] ; log edges | j_nu_bin_frac
   // Voronoi mesh (host copies until finalize)
   std::vector<double> vor_sites, vor_bb, vor_volume;
   std::vector<int32_t> vor_nidx, vor_neigh, vor_valid, vor_b_start, vor_b_sites;
@@ -2208,6 +2254,8 @@ void hyp_ctx_destroy(hyp_ctx *c) {
   free_dev(c->d_oct_leaves);
   free_dev(c->d_vor_f64);
   free_dev(c->d_vor_i32);
+  free_dev(c->d_spec_energy);
+  free_dev(c->d_spec_tab);
   free_dev(c->d_cells);
   free_dev(c->d_rho);
   free_dev(c->d_energy);
@@ -3237,12 +3285,52 @@ int hyp_finalize_setup(hyp_ctx *c) {
   CUDA_TRY(cudaMalloc(&c->d_jfrac, n * sizeof(double)));
   CUDA_TRY(cudaMalloc(&c->d_jid, n * sizeof(int32_t)));
   // [sums | scalars | n_photons as doubles]: one buffer, one collective
-  CUDA_TRY(cudaMalloc(&c->d_sums, (n + SC_COUNT + (size_t)c->n_cells) * sizeof(double)));
+  const size_t n_spec = c->spec_edges.empty() ? 0 : c->spec_edges.size() - 1;
+  CUDA_TRY(cudaMalloc(&c->d_sums, (n + SC_COUNT + (size_t)c->n_cells + n_spec * n) * sizeof(double)));
   CUDA_TRY(cudaMalloc(&c->d_stage, n * sizeof(double)));
   CUDA_TRY(cudaMalloc(&c->d_work, sizeof(unsigned long long)));
   CUDA_TRY(cudaMalloc(&c->d_error, sizeof(int32_t)));
   CUDA_TRY(cudaMemset(c->d_cells, 0, n * sizeof(CellRec)));
-  CUDA_TRY(cudaMemset(c->d_sums, 0, (n + SC_COUNT + (size_t)c->n_cells) * sizeof(double)));
+  CUDA_TRY(cudaMemset(c->d_sums, 0, (n + SC_COUNT + (size_t)c->n_cells + n_spec * n) * sizeof(double)));
+  M.spec_sums = M.spec_energy = nullptr;
+  M.spec_log_edges = M.spec_jfrac = nullptr;
+  M.n_spec_bins = M.spec_jmax = 0;
+  if (n_spec) {
+    // setup_grid_physics (grid_physics_3d.f90:124-143,199-207,229-233,249-252,269-284)
+    M.n_spec_bins = (int32_t)n_spec;
+    M.spec_sums = c->d_sums + n + SC_COUNT + (size_t)c->n_cells;
+    CUDA_TRY(cudaMalloc(&c->d_spec_energy, n_spec * n * sizeof(double)));
+    std::vector<double> e0(n_spec * n, 0.0);
+    if (!c->energy_from_caller || c->conf.specific_energy_additional)
+      for (size_t b = 0; b < n_spec; ++b)
+        for (size_t k = 0; k < n; ++k) e0[b * n + k] = c->h_min_energy[k % nd];
+    CUDA_TRY(cudaMemcpy(c->d_spec_energy, e0.data(), e0.size() * sizeof(double), cudaMemcpyHostToDevice));
+    M.spec_energy = c->d_spec_energy;
+    int jmax = 0;
+    for (const HostDust &d : c->dust) jmax = std::max(jmax, d.n_jnu);
+    M.spec_jmax = jmax;
+    std::vector<double> tab(n_spec + 1 + (size_t)nd * jmax * n_spec, 0.0);
+    for (size_t i = 0; i <= n_spec; ++i) tab[i] = std::log10(c->spec_edges[i]);
+    // get_j_nu_bin_fractions (dust_type_4elem.f90:752-778)
+    for (int id = 0; id < nd; ++id) {
+      const HostDust &D = c->dust[id];
+      const int ne = (int)D.emiss_nu.size();
+      std::vector<double> col(ne);
+      for (int iv = 0; iv < D.n_jnu; ++iv) {
+        for (int k = 0; k < ne; ++k) col[k] = D.emiss_jnu[(size_t)k * D.n_jnu + iv];
+        const double norm = detail::integral_loglog_all(D.emiss_nu.data(), col.data(), ne);
+        double *frac = &tab[n_spec + 1 + ((size_t)id * jmax + iv) * n_spec];
+        for (size_t b = 0; b < n_spec; ++b) {
+          frac[b] = detail::integral_loglog_range(D.emiss_nu.data(), col.data(), ne, c->spec_edges[b], c->spec_edges[b + 1]);
+          if (norm > 0.0) frac[b] /= norm;
+        }
+      }
+    }
+    CUDA_TRY(cudaMalloc(&c->d_spec_tab, tab.size() * sizeof(double)));
+    CUDA_TRY(cudaMemcpy(c->d_spec_tab, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice));
+    M.spec_log_edges = c->d_spec_tab;
+    M.spec_jfrac = c->d_spec_tab + n_spec + 1;
+  }
   CUDA_TRY(cudaMemset(c->d_error, 0, sizeof(int32_t)));
   M.cells = c->d_cells;
   M.rho = c->d_rho;
@@ -3302,6 +3390,8 @@ int hyp_lucy_begin(hyp_ctx *c) {
     c->launches_acc += 1;
   }
   CUDA_TRY(cudaMemsetAsync(c->d_sums + n, 0, SC_COUNT * sizeof(double), c->stream));
+  if (c->M.spec_sums)   // grid_reset_energy (grid_generic.f90:26)
+    CUDA_TRY(cudaMemsetAsync(c->M.spec_sums, 0, (size_t)c->M.n_spec_bins * n * sizeof(double), c->stream));
   CUDA_TRY(cudaMemsetAsync(c->d_error, 0, sizeof(int32_t), c->stream));
   // grid_reset_energy (grid_generic.f90:18-25): the packet counter exists with the PDA or the n_photons output
   // (grid_physics_3d.f90:308-317)
@@ -3400,7 +3490,7 @@ static int run_rounds(hyp_ctx *c, int64_t first_id, int64_t n_photons, int64_t i
     }
     // 2. flights: the beams of new packets, then the packets that come out of an interaction
     CUDA_TRY(cudaEventRecord(c->evA, st));
-    if (c->grid_type != GEO_CAR || c->M.any_sphere || c->M.n_visits) {
+    if (c->grid_type != GEO_CAR || c->M.any_sphere || c->M.n_visits || c->M.spec_sums) {
       const FinalArgs none = FinalArgs();
       auto geo_flight = c->grid_type == GEO_OCT   ? flight_geo_kernel<GEO_OCT, ND, true, false>
                         : c->grid_type == GEO_AMR ? flight_geo_kernel<GEO_AMR, ND, true, false>
@@ -3839,7 +3929,7 @@ int hyp_lucy_photons(hyp_ctx *c, int64_t first_id, int64_t n_photons, int64_t it
   CUDA_TRY(cudaSetDevice(c->device));
   c->sums_gathered = false;
   // the packet counter lives in the generic march: neither the tiles nor the beams keep it
-  const bool wave = !c->M.n_visits && wave_wanted() && wave_plan(c, c->M.n_dust);
+  const bool wave = !c->M.n_visits && !c->M.spec_sums && wave_wanted() && wave_plan(c, c->M.n_dust);
   c->last_engine = wave ? 1 : 0;
   switch (c->M.n_dust) {
     case 1: return wave ? run_wave<1>(c, first_id, n_photons, iteration) : run_rounds<1>(c, first_id, n_photons, iteration);
@@ -4023,7 +4113,11 @@ int hyp_lucy_device_buffers(hyp_ctx *c, void **sum_and_scalars, int64_t *n_value
   if (rc) return rc;
   CUDA_TRY(cudaStreamSynchronize(c->stream));
   if (sum_and_scalars) *sum_and_scalars = c->d_sums;
-  if (n_values) *n_values = c->n_cells * (int64_t)c->dust.size() + SC_COUNT + (c->M.n_visits ? c->n_cells : 0);
+  // [sums | scalars | n_photons | spectrum sums]: the tail only as far as it is in use
+  if (n_values)
+    *n_values = c->n_cells * (int64_t)c->dust.size() + SC_COUNT +
+                (c->M.spec_sums ? c->n_cells + (int64_t)c->M.n_spec_bins * c->n_cells * (int64_t)c->dust.size()
+                                : (c->M.n_visits ? c->n_cells : 0));
   return HYP_OK;
 }
 
@@ -4102,6 +4196,34 @@ static int get_grid(hyp_ctx *c, int which, double *out) {
 int hyp_get_specific_energy(hyp_ctx *c, double *out) { return get_grid(c, 0, out); }
 int hyp_get_density(hyp_ctx *c, double *out) { return get_grid(c, 1, out); }
 int hyp_get_energy_sum(hyp_ctx *c, double *out) { return get_grid(c, 2, out); }
+
+int hyp_set_specific_energy_spectrum_bins(hyp_ctx *c, int32_t n_edges, const double *edges) {
+  if (!c || !edges) return fail(HYP_ERR_INVALID, "NULL argument");
+  if (c->finalized) return fail(HYP_ERR_STATE, "model is frozen");
+  if (n_edges < 2) return fail(HYP_ERR_INVALID, "specific_energy_spectrum_bin_edges should have at least two values");
+  for (int i = 0; i < n_edges; ++i)
+    if (!(edges[i] > 0.0)) return fail(HYP_ERR_INVALID, "specific_energy_spectrum_bin_edges should be positive");
+  for (int i = 1; i < n_edges; ++i)
+    if (edges[i] <= edges[i - 1])   // grid_physics_3d.f90:126-128
+      return fail(HYP_ERR_INVALID, "specific_energy_spectrum_bin_edges should be strictly increasing");
+  c->spec_edges.assign(edges, edges + n_edges);
+  return HYP_OK;
+}
+
+int hyp_get_specific_energy_spectrum(hyp_ctx *c, double *out) {
+  if (!c || !c->finalized) return fail(HYP_ERR_STATE, "hyp_finalize_setup has not been called");
+  if (!out) return fail(HYP_ERR_INVALID, "NULL argument");
+  if (!c->M.spec_energy) return fail(HYP_ERR_STATE, "specific_energy_spectrum array is not allocated");   // grid_generic.f90:86
+  CUDA_TRY(cudaSetDevice(c->device));
+  const size_t n = (size_t)c->n_cells * c->dust.size();
+  for (int b = 0; b < c->M.n_spec_bins; ++b) {
+    to_file_order_kernel<<<grid_blocks(c), 256, 0, c->stream>>>(c->M, 2, c->M.spec_energy + (size_t)b * n, c->d_stage);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(out + (size_t)b * n, c->d_stage, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+  }
+  return HYP_OK;
+}
 
 int hyp_get_n_photons(hyp_ctx *c, int64_t *out) {
   if (!c || !c->finalized || !out) return fail(HYP_ERR_STATE, "hyp_finalize_setup has not been called");

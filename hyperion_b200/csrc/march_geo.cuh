@@ -212,7 +212,8 @@ template <int GEO, int ND, bool DEP>
 __device__ inline int geo_march(const ModelDev &M, typename Geo<GEO>::Ray &R, double &tau_left, const double (&chi)[ND],
                                 const double (&kE)[ND], CellRec *__restrict__ cells, uint32_t &n_cross,
                                 const double t_source, const unsigned long long pid = 0ull,
-                                const bool count_start = true, int max_steps = 0x7fffffff) {
+                                const bool count_start = true, int max_steps = 0x7fffffff,
+                                double *__restrict__ spec = nullptr) {
   using G = Geo<GEO>;
   if (G::escaped(M, R)) return MARCH_ESCAPED;
   // n_photons (grid_propagate_3d.f90:90-95,175-180): a packet counts once per cell for as long as no other packet
@@ -245,6 +246,12 @@ __device__ inline int geo_march(const ModelDev &M, typename Geo<GEO>::Ray &R, do
 #pragma unroll
         for (int id = 0; id < ND; ++id)
           if (rho[id] > 0.0) atomicAdd(&cells[(size_t)ic * ND + id].esum, dt * kE[id]);
+        // the packet's frequency bin of specific_energy_sum_spectrum (grid_propagate_3d.f90:155-158)
+        if (spec) {
+#pragma unroll
+          for (int id = 0; id < ND; ++id)
+            if (rho[id] > 0.0) atomicAdd(spec + (size_t)ic * ND + id, dt * kE[id]);
+        }
       }
       tau_left -= tau_cell;
       R.t += dt;
@@ -258,6 +265,11 @@ __device__ inline int geo_march(const ModelDev &M, typename Geo<GEO>::Ray &R, do
 #pragma unroll
         for (int id = 0; id < ND; ++id)
           if (rho[id] > 0.0) atomicAdd(&cells[(size_t)ic * ND + id].esum, len * kE[id]);
+        if (spec) {   // grid_propagate_3d.f90:217-225
+#pragma unroll
+          for (int id = 0; id < ND; ++id)
+            if (rho[id] > 0.0) atomicAdd(spec + (size_t)ic * ND + id, len * kE[id]);
+        }
       }
       R.t += len;
       tau_left = 0.0;

@@ -177,6 +177,9 @@ __global__ void pda_update_energy_kernel(const ModelDev M, const PdaDev P, const
         }
       }
       M.specific_energy[k] = s;
+      // the spectrum keeps its shape (grid_pda_3d.f90:63-67)
+      if (M.spec_sums && s_old > 0.0)
+        for (int b = 0; b < M.n_spec_bins; ++b) M.spec_energy[((size_t)b * M.n_cells * nd) + k] *= s / s_old;
       worst = fmax(worst, fabs(s - s_old) / s_old);
     }
   }

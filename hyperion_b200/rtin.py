@@ -78,6 +78,7 @@ class RunSettings:
     output_density: str = "none"
     output_density_diff: str = "none"
     output_n_photons: str = "none"
+    output_specific_energy_spectrum: str = "none"
     geometry_id: str = ""
     grid_type: str = "car"
     extra: dict = field(default_factory=dict)
@@ -394,6 +395,22 @@ def read_rtin(filename):
                 raise ModelError("%s should be one of all/last/none" % key)
             setattr(rs, key, val)
 
+    # setup_initial (src/main/setup_rt.f90:78-104): the frequency-resolved specific energy is computed whenever it is
+    # written, and then needs its bin edges (table column 'nu' at the root of the file)
+    spectrum_bin_edges = None
+    if "output_specific_energy_spectrum" in out:
+        val = _s(out["output_specific_energy_spectrum"])
+        if val not in ("all", "last", "none"):
+            raise ModelError("output_specific_energy_spectrum should be one of all/last/none")
+        rs.output_specific_energy_spectrum = val
+    if rs.output_specific_energy_spectrum != "none":
+        if "specific_energy_spectrum_bin_edges" not in f:
+            raise ModelError("specific_energy_spectrum_bin_edges should be present in the input when "
+                             "output_specific_energy_spectrum is enabled")
+        spectrum_bin_edges = np.asarray(f["specific_energy_spectrum_bin_edges"][...]["nu"], dtype=np.float64)
+        if np.any(np.diff(spectrum_bin_edges) <= 0):     # setup_grid_physics, grid_physics_3d.f90:126-128
+            raise ModelError("specific_energy_spectrum_bin_edges should be strictly increasing")
+
     conf.forced_first_interaction = rs.forced_first_interaction
     conf.forced_first_interaction_algorithm = rs.forced_first_interaction_algorithm
     conf.baes16_xi = rs.baes16_xi
@@ -430,6 +447,7 @@ def read_rtin(filename):
     model = FlatModel(w1, w2, w3, density, dust, sources, conf, specific_energy=se, minimum_specific_energy=min_e,
                       grid_type=grid_type, **(octree or {}))
     model.no_dust = no_dust
+    model.spectrum_bin_edges = spectrum_bin_edges
     if rs.monochromatic:
         # setup_rt.f90:220-222, hyperion/model/model.py:133-137
         if "frequencies" not in f:

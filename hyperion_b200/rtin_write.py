@@ -110,7 +110,7 @@ def write_peeled_group(g, p):
 def write_rtin(filename, model: FlatModel, n_initial_iter=5, n_initial_photons=10000, n_last_photons=0,
                output_specific_energy="last", copy_input=True, check_convergence=None, physics_io_bytes=8,
                raytracing=False, n_ray_photons=(0, 0), extra_root_attrs=None, n_last_photons_mono=(0, 0),
-               output_n_photons="none"):
+               output_n_photons="none", output_specific_energy_spectrum="none"):
     f = h5write.File()
     c = model.conf
     A = f.attrs
@@ -295,6 +295,12 @@ def write_rtin(filename, model: FlatModel, n_initial_iter=5, n_initial_photons=1
     go.attrs["output_density_diff"] = "none"
     go.attrs["output_specific_energy"] = output_specific_energy
     go.attrs["output_n_photons"] = output_n_photons
+    if output_specific_energy_spectrum != "none" or model.spectrum_bin_edges is not None:
+        # hyperion/model/model.py (set_specific_energy_spectrum_bins / write): option + table of bin edges
+        go.attrs["output_specific_energy_spectrum"] = output_specific_energy_spectrum
+    if model.spectrum_bin_edges is not None:
+        f.create_dataset("specific_energy_spectrum_bin_edges",
+                         _table([("nu", np.asarray(model.spectrum_bin_edges, dtype=np.float64))]))
     gb = go.create_group("Binned")
     if model.binned is not None:
         write_peeled_group(gb.create_group("group_00001"), model.binned)

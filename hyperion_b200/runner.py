@@ -389,6 +389,18 @@ def run(input_file, output_file, overwrite=False, device=None, log=None):
             if se is None:
                 se = eng.get_specific_energy()
             put("specific_energy", se)
+        if wanted(rs.output_specific_energy_spectrum):
+            # output_grid (grid_generic.f90:68-88): the bin edges (1-D) and the spectrum [n_bins, n_dust, cells]
+            g.create_dataset("specific_energy_spectrum_bin_edges", np.asarray(model.spectrum_bin_edges, dtype=np.float64))
+            se_nu = eng.get_specific_energy_spectrum()
+            if model.grid_type == "amr":
+                for il, ig, sl, shp in model.amr_slices():
+                    gg = g.require_group("level_%05d/grid_%05d" % (il + 1, ig + 1))
+                    gg.create_dataset("specific_energy_spectrum",
+                                      se_nu[:, :, sl].reshape(se_nu.shape[:2] + shp).astype(io_dtype))
+            else:
+                d = g.create_dataset("specific_energy_spectrum", se_nu.astype(io_dtype))
+                d.attrs["geometry"] = rs.geometry_id
         if wanted(rs.output_density):
             put("density", eng.get_density())
         if wanted(rs.output_density_diff):

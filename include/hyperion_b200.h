@@ -265,6 +265,17 @@ int hyp_set_grid_amr(hyp_ctx *ctx, int32_t n_levels, const int32_t *n_grids, con
 int hyp_set_grid_voronoi(hyp_ctx *ctx, int32_t n_cells, const double *coords, const double *bb_min, const double *bb_max,
                          const double *volume, const int32_t *sparse_idx, const int32_t *sparse_neighs, const double *box);
 
+/* replaces: the specific_energy_spectrum_bin_edges input (src/main/setup_rt.f90:98-104) and the spectrum part of
+ * setup_grid_physics (src/grid/grid_physics_3d.f90:124-143,269-284).  n_edges strictly increasing frequencies (Hz):
+ * the Lucy iterations then also keep the deposits per frequency bin of the absorbed packets
+ * (grid_propagate_3d.f90:155-158,217-225; MRW deposits by the local emissivity, grid_physics_3d.f90:367-395).
+ * Call before hyp_finalize_setup.  With several processes the per-bin sums travel behind the scalars and the packet
+ * counts in hyp_lucy_device_buffers (mp_collect_physical_arrays, src/mpi/mpi_routines.f90:292-301). */
+int hyp_set_specific_energy_spectrum_bins(hyp_ctx *ctx, int32_t n_edges, const double *edges);
+
+/* replaces: output_grid 'specific_energy_spectrum' (src/grid/grid_generic.f90:68-84): out[n_bins][n_dust][n_cells] */
+int hyp_get_specific_energy_spectrum(hyp_ctx *ctx, double *out);
+
 /* replaces: dust_setup (src/dust/dust_type_4elem.f90:78-293); call once per dust type, in order */
 int hyp_add_dust(hyp_ctx *ctx, const hyp_dust_tables *dust);
 

@@ -259,6 +259,27 @@ def test_runner_voronoi(golden_car, tmp_path):
     assert r["Peeled/group_00001/seds"][...][0].sum() > 0
 
 
+def test_rtin_spectrum_bin_edges(golden_car, tmp_path):
+    """setup_initial (src/main/setup_rt.f90:78-104): the option, the table of bin edges, and the reference's messages."""
+    m = bitlevel_model(golden_car, False, False)
+    m.spectrum_bin_edges = np.logspace(6., 18., 13)
+    fn = str(tmp_path / "m.rtin")
+    rtin_write.write_rtin(fn, m, output_specific_energy_spectrum="all")
+    got, rs, _ = rtin.read_rtin(fn)
+    assert rs.output_specific_energy_spectrum == "all" and np.array_equal(got.spectrum_bin_edges, m.spectrum_bin_edges)
+    rtin_write.write_rtin(fn, m)                       # edges given, option off: nothing is computed
+    got, rs, _ = rtin.read_rtin(fn)
+    assert rs.output_specific_energy_spectrum == "none" and got.spectrum_bin_edges is None
+    m.spectrum_bin_edges = None
+    rtin_write.write_rtin(fn, m, output_specific_energy_spectrum="last")
+    with pytest.raises(rtin.ModelError, match="specific_energy_spectrum_bin_edges should be present in the input"):
+        rtin.read_rtin(fn)
+    m.spectrum_bin_edges = np.array([1e10, 1e12, 1e11])
+    rtin_write.write_rtin(fn, m, output_specific_energy_spectrum="last")
+    with pytest.raises(rtin.ModelError, match="should be strictly increasing"):
+        rtin.read_rtin(fn)
+
+
 def test_rtin_roundtrip_amr(golden_car, golden_amr, tmp_path):
     """'amr' grids: Grid/Geometry/level_%05d/grid_%05d attributes, one density dataset per grid
     (hyperion/grid/amr_grid.py:372-412)."""
