@@ -137,3 +137,34 @@ def test_two_rank_monochromatic_and_pda_run(golden_car, tmp_path):
     e1, e2 = a["iteration_00002/specific_energy"][...][0], b["iteration_00002/specific_energy"][...][0]
     both = (n1 >= 40) & (n2 >= 40)
     assert both.sum() > 20 and np.abs(e1[both] / e2[both] - 1.).max() < 1e-9
+
+
+@pytest.mark.skipif(_n_gpus() < 2, reason="needs 2 GPUs")
+def test_two_rank_spectrum_run_on_a_voronoi_mesh(golden_car, tmp_path):
+    """The frequency-resolved sums travel behind the scalars of the one reduction per iteration
+    (mp_collect_physical_arrays, mpi_routines.f90:292-301; the reference's test_..._mpi_matches_serial,
+    test_specific_energy_spectrum.py:373-392), here on a Voronoi mesh through bin/hyperion_vor[_mpi]."""
+    from helpers import bitlevel_model_vor
+    from hyperion_b200 import rtin_write
+    from hyperion_b200.io import h5min
+    m = bitlevel_model_vor(golden_car, False, True)
+    m.spectrum_bin_edges = np.logspace(6., 18., 13)
+    fin = str(tmp_path / "m.rtin")
+    rtin_write.write_rtin(fin, m, n_initial_iter=2, n_initial_photons=100000, output_specific_energy="all",
+                          output_specific_energy_spectrum="all")
+    env = {k: v for k, v in os.environ.items()
+           if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "MASTER_ADDR", "MASTER_PORT", "HYPERION_B200_NGPU")}
+    out1, out2 = str(tmp_path / "one.rtout"), str(tmp_path / "two.rtout")
+    subprocess.check_call([os.path.join(ROOT, "bin", "hyperion_vor"), "-f", fin, out1], env=env, stdout=subprocess.DEVNULL)
+    subprocess.check_call([os.path.join(ROOT, "bin", "hyperion_mpirun"), "-n", "2", os.path.join(ROOT, "bin", "hyperion_vor_mpi"),
+                           "-f", fin, out2], env=env, stdout=subprocess.DEVNULL)
+    a, b = h5min.File(out1), h5min.File(out2)
+    for it in (1, 2):
+        for name in ("specific_energy", "specific_energy_spectrum"):
+            x, y = a["iteration_%05d/%s" % (it, name)][...], b["iteration_%05d/%s" % (it, name)][...]
+            assert x.shape == y.shape == ((3, 160) if name == "specific_energy" else (12, 3, 160))
+            nz = (x != 0) | (y != 0)
+            assert (np.abs(x[nz] - y[nz]) / np.maximum(np.abs(x[nz]), np.abs(y[nz]))).max() < 1e-9, (it, name)
+        se, se_nu = b["iteration_%05d/specific_energy" % it][...], b["iteration_%05d/specific_energy_spectrum" % it][...]
+        heated = se > se.min() * (1 + 1e-6)
+        np.testing.assert_allclose(se_nu.sum(axis=0)[heated], se[heated], rtol=1e-9)
