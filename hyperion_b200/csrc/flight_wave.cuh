@@ -223,8 +223,10 @@ struct WaveLane {
   float resid[ND];          // error diffusion: what rounding has left over so far, in [0, 1)
   uint32_t c, cd;           // cd: cell whose density and sum the next crossing uses (differs from c only for the
                             // first segment of a packet placed on a wall, grid_geometry_cartesian_3d.f90:184-232)
-  uint32_t neg;             // bit a set: the packet moves towards -axis a
+  // (the direction signs of the packet live in the three top bits of the lane's crossing counter, WAVE_NEG_SHIFT: as
+  // a member of their own the compiler spilled them and every crossing began with a load from local memory)
 };
+constexpr uint32_t WAVE_NEG_SHIFT = 29, WAVE_CROSS_MASK = (1u << WAVE_NEG_SHIFT) - 1u;
 
 // 1 / x to the last ulp or two for normal x != 0 (MUFU.RCP64H + two Newton steps); only used for wall distances
 __device__ __forceinline__ double wave_rcp(double x) {
@@ -283,8 +285,8 @@ __device__ __forceinline__ void wave_cross(WaveLane<ND> &L, int &fin, uint32_t &
     L.tny = fma(my, L.dty, L.tny);
     L.tnz = fma(mz, L.dtz, L.tnz);
     const int mag = bx ? sx : (by ? sy : sz);
-    const uint32_t bit = bx ? 1u : (by ? 2u : 4u);
-    L.c = (L.neg & bit) ? L.c - (uint32_t)mag : L.c + (uint32_t)mag;
+    const uint32_t bit = bx ? (1u << WAVE_NEG_SHIFT) : (by ? (2u << WAVE_NEG_SHIFT) : (4u << WAVE_NEG_SHIFT));
+    L.c = (n_cross & bit) ? L.c - (uint32_t)mag : L.c + (uint32_t)mag;
     L.cd = L.c;
   } else {
     // interaction inside this cell (grid_propagate_3d.f90:186-228); cd keeps the cell the packet interacted in.
@@ -320,11 +322,13 @@ __device__ __forceinline__ float wave_unit_hash(uint32_t a, uint32_t b, uint32_t
 // SUM_OFF is a compile-time constant so that the sum of a cell is addressed as [cell + immediate].
 // BOUND: the block size the register allocation is made for (1024 -> 64 registers).  Launched with THREADS < BOUND
 // the block leaves registers for the interaction / emission blocks of the round, which then run on the same SMs.
-template <int ND, int THREADS, int MINB, uint32_t SUM_OFF, int BOUND = THREADS>
+// CUBE: edge of a cubic tile known at compile time (the strides between cells are then immediates of the crossing
+// loop instead of constant-bank loads and a multiply per crossing); 0: any shape, from WaveQ.
+template <int ND, int THREADS, int MINB, uint32_t SUM_OFF, int BOUND = THREADS, int CUBE = 0>
 __global__ void __launch_bounds__(BOUND, MINB)
 wave_tile_kernel(const ModelDev M, Pool P, const WaveQ W) {
   extern __shared__ __align__(16) unsigned char w_smem[];
-  const int TX = W.tx, TY = W.ty, TZ = W.tz;
+  const int TX = CUBE ? CUBE : W.tx, TY = CUBE ? CUBE : W.ty, TZ = CUBE ? CUBE : W.tz;
   const int TXh = TX + 2, TYh = TY + 2, TZh = TZ + 2;
   float *__restrict__ s_rho = (float *)w_smem;                       // [n_h][ND], halo = sentinel
   uint32_t *__restrict__ s_sum = (uint32_t *)(w_smem + SUM_OFF);     // [n_h][ND]
@@ -529,7 +533,8 @@ wave_tile_kernel(const ModelDev M, Pool P, const WaveQ W) {
               L.dtx = vx != 0.0 ? fmin(W.dx * fabs(ivx), WAVE_FAR) : WAVE_FAR;
               L.dty = vy != 0.0 ? fmin(W.dy * fabs(ivy), WAVE_FAR) : WAVE_FAR;
               L.dtz = vz != 0.0 ? fmin(W.dz * fabs(ivz), WAVE_FAR) : WAVE_FAR;
-              L.neg = (vx > 0.0 ? 0u : 1u) | (vy > 0.0 ? 0u : 2u) | (vz > 0.0 ? 0u : 4u);
+              n_cross = (n_cross & WAVE_CROSS_MASK) |
+                        (((vx > 0.0 ? 0u : 1u) | (vy > 0.0 ? 0u : 2u) | (vz > 0.0 ? 0u : 4u)) << WAVE_NEG_SHIFT);
               L.c = rho_base + (uint32_t)((((lz + 1) * TYh + (ly + 1)) * TXh + lx + 1) * CB);
               L.cd = L.c;
               fin = 0;
@@ -575,7 +580,7 @@ wave_tile_kernel(const ModelDev M, Pool P, const WaveQ W) {
                 if (by) L.tny += L.dty;
                 if (!(bx | by)) L.tnz += L.dtz;
                 const int mag = bx ? sx : (by ? sy : sz);
-                L.c = (L.neg & (bx ? 1u : (by ? 2u : 4u))) ? L.c - (uint32_t)mag : L.c + (uint32_t)mag;
+                L.c = ((n_cross >> WAVE_NEG_SHIFT) & (bx ? 1u : (by ? 2u : 4u))) ? L.c - (uint32_t)mag : L.c + (uint32_t)mag;
                 L.cd = L.c;
               } else {
                 len = tau_cell > 0.0 ? ds * (L.tau / tau_cell) : 0.0;
@@ -651,7 +656,8 @@ wave_tile_kernel(const ModelDev M, Pool P, const WaveQ W) {
       }
     }
     {
-      // crossings of the item (a lane makes far fewer than 2^32 per item)
+      // crossings of the item (a lane makes far fewer than 2^29 per item)
+      n_cross &= WAVE_CROSS_MASK;
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) n_cross += __shfl_xor_sync(0xffffffffu, n_cross, o);
       if (lane == 0 && n_cross) atomicAdd(&s_cross, (unsigned long long)n_cross);

@@ -3722,6 +3722,8 @@ static int run_wave(hyp_ctx *c, int64_t first_id, int64_t n_photons, int64_t ite
     if (ctas == 2) {
       tile = wave_tile_kernel<ND, 512, 2, WAVE_SUM_OFF_2>;
       tile_threads = 512;
+    } else if (want == 1024 && W.tx == 28 && W.ty == 28 && W.tz == 28 && !getenv("HYPERION_B200_WAVE_NOCUBE")) {
+      tile = wave_tile_kernel<ND, 1024, 1, WAVE_SUM_OFF_ND1, 1024, 28>;   // the default tile of large grids
     } else if (want == 896) {
       tile = wave_tile_kernel<ND, 896, 1, WAVE_SUM_OFF_ND1, 1024>;
       tile_threads = 896;
