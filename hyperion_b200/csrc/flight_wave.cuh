@@ -210,6 +210,16 @@ wave_scatter_kernel(WaveQ W, const uint32_t *__restrict__ src, const uint32_t n_
     if (key_r[j] != 0xffffffffu) W.sorted[s_base[key_r[j]] + rank_r[j]] = slot_r[j];
 }
 
+#ifndef WAVE_SIGNED_STRIDES
+#define WAVE_SIGNED_STRIDES 1
+#endif
+#ifndef WAVE_PRED_TN
+#define WAVE_PRED_TN 0
+#endif
+#ifndef WAVE_MAGIC_FLOOR
+#define WAVE_MAGIC_FLOOR 0
+#endif
+
 // ---- the march ---------------------------------------------------------------------------------
 // State of one flight inside a tile.  c is the shared-window ADDRESS of the packet's cell in the haloed density
 // array (base + cell index * 4 * ND); the sums lie SUM_OFF bytes behind the densities.
@@ -225,6 +235,9 @@ struct WaveLane {
                             // first segment of a packet placed on a wall, grid_geometry_cartesian_3d.f90:184-232)
   // (the direction signs of the packet live in the three top bits of the lane's crossing counter, WAVE_NEG_SHIFT: as
   // a member of their own the compiler spilled them and every crossing began with a load from local memory)
+#if WAVE_SIGNED_STRIDES
+  int ssx, ssy, ssz;        // bytes to the next cell along the packet's direction on each axis (signed)
+#endif
 };
 constexpr uint32_t WAVE_NEG_SHIFT = 29, WAVE_CROSS_MASK = (1u << WAVE_NEG_SHIFT) - 1u;
 
@@ -278,15 +291,32 @@ __device__ __forceinline__ void wave_cross(WaveLane<ND> &L, int &fin, uint32_t &
     len = ds;
     L.tau -= tau_cell;
     L.t = t_exit;
+#if WAVE_PRED_TN == 2
+    // tn += dt on the axis that was crossed: one PREDICATED add per axis (written in PTX: from C the compiler makes
+    // an unconditional add and two selects of every axis)
+    asm("{ .reg .pred p; setp.ne.s32 p, %1, 0; @p add.f64 %0, %0, %2; }" : "+d"(L.tnx) : "r"((int)bx), "d"(L.dtx));
+    asm("{ .reg .pred p; setp.ne.s32 p, %1, 0; @p add.f64 %0, %0, %2; }" : "+d"(L.tny) : "r"((int)by), "d"(L.dty));
+    asm("{ .reg .pred p; setp.eq.s32 p, %1, 0; @p add.f64 %0, %0, %2; }" : "+d"(L.tnz) : "r"((int)(bx | by)), "d"(L.dtz));
+#elif WAVE_PRED_TN
+    // tn += dt on the axis that was crossed: one predicated add per axis
+    if (bx) L.tnx += L.dtx;
+    if (by) L.tny += L.dty;
+    if (!(bx | by)) L.tnz += L.dtz;
+#else
     // tn += dt on the axis that was crossed, as a multiply-add with a 0/1 factor (one select per axis)
     const double mx = __hiloint2double(bx ? 0x3ff00000 : 0, 0), my = __hiloint2double(by ? 0x3ff00000 : 0, 0),
                  mz = __hiloint2double((bx | by) ? 0 : 0x3ff00000, 0);
     L.tnx = fma(mx, L.dtx, L.tnx);
     L.tny = fma(my, L.dty, L.tny);
     L.tnz = fma(mz, L.dtz, L.tnz);
+#endif
+#if WAVE_SIGNED_STRIDES
+    L.c += (uint32_t)(bx ? L.ssx : (by ? L.ssy : L.ssz));
+#else
     const int mag = bx ? sx : (by ? sy : sz);
     const uint32_t bit = bx ? (1u << WAVE_NEG_SHIFT) : (by ? (2u << WAVE_NEG_SHIFT) : (4u << WAVE_NEG_SHIFT));
     L.c = (n_cross & bit) ? L.c - (uint32_t)mag : L.c + (uint32_t)mag;
+#endif
     L.cd = L.c;
   } else {
     // interaction inside this cell (grid_propagate_3d.f90:186-228); cd keeps the cell the packet interacted in.
@@ -302,8 +332,15 @@ __device__ __forceinline__ void wave_cross(WaveLane<ND> &L, int &fin, uint32_t &
   for (int id = 0; id < ND; ++id) {
     // no deposit where the density is zero (grid_propagate_3d.f90:150): branch-free, a zero path length
     const float x = fmaf(rho[id] != 0u ? lenf : 0.f, L.kEs[id], L.resid[id]);
+#if WAVE_MAGIC_FLOOR
+    // floor(x) for 0 <= x < 2^23 without the conversion pipe: x + 2^23 rounded DOWN holds floor(x) in its mantissa
+    const float xf = __fadd_rd(x, 8388608.0f);
+    const uint32_t q = __float_as_uint(xf) - 0x4B000000u;
+    L.resid[id] = x - (xf - 8388608.0f);
+#else
     const uint32_t q = __float2uint_rd(x);
     L.resid[id] = x - (float)q;
+#endif
 #if WAVE_EXPERIMENT == 1
     if (q == 0xffffffffu)
 #endif
@@ -434,12 +471,15 @@ wave_tile_kernel(const ModelDev M, Pool P, const WaveQ W) {
     bool exhausted = false;  // warp-uniform: the item has no unclaimed packet left
     int fin = 3;             // 3: no packet in this lane
     uint32_t slot = 0, nslot = NONE, n2slot = NONE;
+    // whether nslot / n2slot hold a packet: kept apart from the values, so that no decision of the hand-over waits
+    // for the load of an id from the sorted list (it used to: 4 % of the stall samples on the test n2slot != NONE)
+    bool has1 = false, has2 = false;
     uint32_t n_cross = 0;
     WaveLane<ND> L;
     L.c = L.cd = rho_base;
     for (;;) {
       const unsigned m_act = __ballot_sync(0xffffffffu, fin == 0);
-      const unsigned m_wait = __ballot_sync(0xffffffffu, fin == 1 || fin == 2 || fin == 4 || (fin == 3 && nslot != NONE));
+      const unsigned m_wait = __ballot_sync(0xffffffffu, fin == 1 || fin == 2 || fin == 4 || (fin == 3 && has1));
       if (m_act == 0 || __popc(m_wait) >= W.refill) {
         // -------- hand over the finished packets --------
         {
@@ -488,9 +528,9 @@ wave_tile_kernel(const ModelDev M, Pool P, const WaveQ W) {
         for (int pass = 0; pass < 3; ++pass) {
           // -------- start the queued packets --------
           int first_far = -1;   // >= 0: find_cell's cell of a packet placed on a wall, when it lies in ANOTHER tile
-          if (fin == 3 && nslot != NONE) {
+          if (fin == 3 && has1) {
             slot = nslot;
-            nslot = NONE;
+            has1 = false;
             s_pos[0] = s_pos[PQ];
             const Slot<ND> *s = slots + slot;
               // ld.global.cs: streaming loads that still go through L1, so that the six 16-byte loads of a record
@@ -535,6 +575,11 @@ wave_tile_kernel(const ModelDev M, Pool P, const WaveQ W) {
               L.dtz = vz != 0.0 ? fmin(W.dz * fabs(ivz), WAVE_FAR) : WAVE_FAR;
               n_cross = (n_cross & WAVE_CROSS_MASK) |
                         (((vx > 0.0 ? 0u : 1u) | (vy > 0.0 ? 0u : 2u) | (vz > 0.0 ? 0u : 4u)) << WAVE_NEG_SHIFT);
+#if WAVE_SIGNED_STRIDES
+              L.ssx = vx > 0.0 ? sx : -sx;
+              L.ssy = vy > 0.0 ? sy : -sy;
+              L.ssz = vz > 0.0 ? sz : -sz;
+#endif
               L.c = rho_base + (uint32_t)((((lz + 1) * TYh + (ly + 1)) * TXh + lx + 1) * CB);
               L.cd = L.c;
               fin = 0;
@@ -611,9 +656,10 @@ wave_tile_kernel(const ModelDev M, Pool P, const WaveQ W) {
             }
           }
           // -------- move the queue up: request the record of the packet whose id has arrived --------
-          if (nslot == NONE && n2slot != NONE) {
+          if (!has1 && has2) {
             nslot = n2slot;
-            n2slot = NONE;
+            has1 = true;
+            has2 = false;
             s_pos[PQ] = s_pos[2 * PQ];
             const char *rec = (const char *)(slots + nslot);
 #if WAVE_EXPERIMENT != 6
@@ -623,7 +669,7 @@ wave_tile_kernel(const ModelDev M, Pool P, const WaveQ W) {
           }
           // -------- claim the packets after those --------
           if (!exhausted) {
-            const bool need = plenty ? n2slot == NONE : (fin == 3 && nslot == NONE && n2slot == NONE);
+            const bool need = plenty ? !has2 : (fin == 3 && !has1 && !has2);
             const unsigned m_need = __ballot_sync(0xffffffffu, need);
             bool failed = false;
             if (m_need) {
@@ -636,16 +682,17 @@ wave_tile_kernel(const ModelDev M, Pool P, const WaveQ W) {
                 if (idx >= it.z) failed = true;
                 else {
                   n2slot = __ldcs(W.sorted + it.y + idx);
+                  has2 = true;
                   s_pos[2 * PQ] = it.y + idx;
                 }
               }
             }
             exhausted = __any_sync(0xffffffffu, failed);
           }
-          if (__ballot_sync(0xffffffffu, fin == 3 && (nslot != NONE || n2slot != NONE)) == 0) break;
+          if (__ballot_sync(0xffffffffu, fin == 3 && (has1 || has2)) == 0) break;
         }
         if (__ballot_sync(0xffffffffu, fin == 0) == 0) {
-          if (exhausted && __ballot_sync(0xffffffffu, nslot != NONE || n2slot != NONE) == 0) break;
+          if (exhausted && __ballot_sync(0xffffffffu, has1 || has2) == 0) break;
           continue;
         }
       }
