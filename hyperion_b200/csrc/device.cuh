@@ -156,6 +156,34 @@ __device__ __forceinline__ double sample_powerlaw(const double *__restrict__ x, 
   return pow(f * __ldg(rm1 + i) + 1.0, __ldg(invb + i)) * __ldg(x + i);
 }
 
+// The same draw xi from two samplers that share x and lie row by row in one table (the emissivity states jid and
+// jid + 1 of dust_sample_j_nu, dust_type_4elem.f90:379-398): the two bisections advance in lock-step, so that their
+// dependent loads (the latency of a re-emission) are in flight two at a time instead of one after the other.
+__device__ __forceinline__ void sample_powerlaw_pair(const double *__restrict__ x, const double *__restrict__ cdfA,
+                                                     const double *__restrict__ invbA, const double *__restrict__ rm1A,
+                                                     const double *__restrict__ cdfB, const double *__restrict__ invbB,
+                                                     const double *__restrict__ rm1B, int n, double xi, double &outA,
+                                                     double &outB) {
+  const double a0 = __ldg(cdfA), a1 = __ldg(cdfA + n - 1), b0 = __ldg(cdfB), b1 = __ldg(cdfB + n - 1);
+  int loA = 0, hiA = n - 1, loB = 0, hiB = n - 1;
+  while (hiA - loA > 1 || hiB - loB > 1) {
+    const int mA = (loA + hiA) >> 1, mB = (loB + hiB) >> 1;
+    const double a = __ldg(cdfA + mA), b = __ldg(cdfB + mB);
+    if (hiA - loA > 1) {
+      if (a <= xi) loA = mA; else hiA = mA;
+    }
+    if (hiB - loB > 1) {
+      if (b <= xi) loB = mB; else hiB = mB;
+    }
+  }
+  const double cA0 = __ldg(cdfA + loA), cA1 = __ldg(cdfA + loA + 1), cB0 = __ldg(cdfB + loB), cB1 = __ldg(cdfB + loB + 1);
+  const double rA = __ldg(rm1A + loA), iA = __ldg(invbA + loA), xA = __ldg(x + loA);
+  const double rB = __ldg(rm1B + loB), iB = __ldg(invbB + loB), xB = __ldg(x + loB);
+  const double fA = (xi - cA0) / (cA1 - cA0), fB = (xi - cB0) / (cB1 - cB0);
+  outA = xi <= a0 ? __ldg(x) : (xi >= a1 ? __ldg(x + n - 1) : pow(fA * rA + 1.0, iA) * xA);
+  outB = xi <= b0 ? __ldg(x) : (xi >= b1 ? __ldg(x + n - 1) : pow(fB * rB + 1.0, iB) * xB);
+}
+
 // Planck-law frequency sampling (random_planck_frequency_dp, lib_random.f90:297-347).
 __device__ __forceinline__ double sample_planck(Rng &rng, double T) {
   const double k = 1.3806503e-23, h = 6.626068e-34;

@@ -320,11 +320,17 @@ __device__ __forceinline__ void wave_cross(WaveLane<ND> &L, int &fin, uint32_t &
     L.cd = L.c;
   } else {
     // interaction inside this cell (grid_propagate_3d.f90:186-228); cd keeps the cell the packet interacted in.
-    // One lane of a warp ends its flight in most steps while the others wait: the quotient uses the short
-    // reciprocal (MUFU + two Newton steps) instead of the full division sequence.
+    // One lane of a warp ends its flight in most steps while the others wait, so this branch is kept to one move:
+    // the path length to the interaction point and its deposit are left to the interaction kernel
+    // (wave_partial_step), which gets the optical depth left at the entry wall with a minus sign.
+#if WAVE_DEFER_PARTIAL
+    len = 0.0;
+#else
+    // the quotient uses the short reciprocal (MUFU + two Newton steps) instead of the full division sequence
     len = tau_cell > 0.0 ? ds * (L.tau * wave_rcp(tau_cell)) : 0.0;
     len = fmin(len, ds);
     L.t += len;
+#endif
     fin = 2;
   }
   const float lenf = (float)len;
@@ -514,7 +520,7 @@ wave_tile_kernel(const ModelDev M, Pool P, const WaveQ W) {
             nk = it.x + (uint32_t)d;
           }
           Slot<ND> *s = slots + slot;
-          __stcs((double2 *)&s->tau_left, make_double2(L.tau, L.t));
+          __stcs((double2 *)&s->tau_left, make_double2((WAVE_DEFER_PARTIAL && fin == 2) ? -L.tau : L.tau, L.t));
           __stcs((int4 *)&s->ix, make_int4(gx, gy, gz, ic));
           W.key_pos[s_pos[0]] = nk;
           if (by_slot) W.key[slot] = nk;
@@ -753,6 +759,7 @@ wave_interact_kernel(const ModelDev M, Pool P, const WaveQ W, const uint32_t ite
     const uint64_t id = slots[slot].id;
     int dust_id = 0;
     bool scattered = false;
+    if (WAVE_DEFER_PARTIAL && p.tau_left < 0.0) wave_partial_step<ND>(M, p);
     bool ok = interact_photon<ND>(M, p, rng, n_abs, n_scat, n_kill, dust_id, scattered) == 0;
     if (ok && M.use_mrw) ok = mrw_loop<ND>(M, p, rng, n_kill);
     uint32_t nk = k_free;

@@ -174,6 +174,10 @@ struct Pool {
   uint32_t window;        // power of two
 };
 
+#ifndef WAVE_DEFER_PARTIAL
+#define WAVE_DEFER_PARTIAL 1
+#endif
+
 // Register view of one packet in the emit / interact kernels.
 template <int ND>
 struct Photon {
@@ -616,11 +620,11 @@ __device__ bool emit_photon(const ModelDev &M, Photon<ND> &p, Rng &rng, double &
     const double x2 = rng.next();
     const int ne = d.L.n_enu;
     const double *enu = d.B + d.L.o_enu;
-    const double nu1 = sample_powerlaw(enu, d.B + d.L.o_ecdf + (size_t)jid * ne, d.B + d.L.o_einvb + (size_t)jid * (ne - 1),
-                                       d.B + d.L.o_erm1 + (size_t)jid * (ne - 1), ne, x2);
-    const double nu2 = sample_powerlaw(enu, d.B + d.L.o_ecdf + (size_t)(jid + 1) * ne,
-                                       d.B + d.L.o_einvb + (size_t)(jid + 1) * (ne - 1),
-                                       d.B + d.L.o_erm1 + (size_t)(jid + 1) * (ne - 1), ne, x2);
+    double nu1, nu2;
+    sample_powerlaw_pair(enu, d.B + d.L.o_ecdf + (size_t)jid * ne, d.B + d.L.o_einvb + (size_t)jid * (ne - 1),
+                         d.B + d.L.o_erm1 + (size_t)jid * (ne - 1), d.B + d.L.o_ecdf + (size_t)(jid + 1) * ne,
+                         d.B + d.L.o_einvb + (size_t)(jid + 1) * (ne - 1), d.B + d.L.o_erm1 + (size_t)(jid + 1) * (ne - 1),
+                         ne, x2, nu1, nu2);
     const double l1 = log10(nu1);
     p.nu = pow(10.0, l1 + frac * (log10(nu2) - l1));
     p.tag |= (uint32_t)id << TAG_DUST_SHIFT;
@@ -801,6 +805,27 @@ __device__ bool reemit_photon(const ModelDev &M, Photon<ND> &p, Rng &rng, uint32
 }
 
 // interact (src/dust/dust_interact.f90:22-79).  Returns: 0 continue, 1 packet finished (killed).
+// The last, partial cell of a flight that ended on the wave engine (flight_wave.cuh): the tile kernel only notices
+// that the optical depth runs out inside the cell and hands the packet over with tau_left = -(optical depth left at
+// the cell's entry wall); the path length to the interaction point and its deposit (grid_propagate_3d.f90:186-228)
+// are made here, once per interaction, instead of in a divergent branch of the crossing loop.  The density is rounded
+// to fp32 as the tile kernel stages it, so that both see the same optical depth of the cell.
+template <int ND>
+__device__ __forceinline__ void wave_partial_step(const ModelDev &M, Photon<ND> &p) {
+  double rho[ND], chi_rho = 0.0;
+#pragma unroll
+  for (int k = 0; k < ND; ++k) {
+    rho[k] = (double)fmaxf((float)__ldcg(&M.cells[(size_t)p.ic * ND + k].rho), 0.f);
+    chi_rho = fma(p.chi[k], rho[k], chi_rho);
+  }
+  const double len = chi_rho > 0.0 ? -p.tau_left / chi_rho : 0.0;
+#pragma unroll
+  for (int k = 0; k < ND; ++k)
+    if (rho[k] > 0.0) atomicAdd(&M.cells[(size_t)p.ic * ND + k].esum, len * p.kE[k]);
+  p.t += len;
+  p.tau_left = 0.0;
+}
+
 template <int ND>
 __device__ int interact_photon(const ModelDev &M, Photon<ND> &p, Rng &rng, uint32_t &n_abs, uint32_t &n_scat,
                                uint32_t &n_killed_int, int &dust_id, bool &was_scattered, const bool force_scatter = false) {
@@ -849,11 +874,11 @@ __device__ int interact_photon(const ModelDev &M, Photon<ND> &p, Rng &rng, uint3
     const double x2 = rng.next();
     const int ne = d.L.n_enu;
     const double *enu = d.B + d.L.o_enu;
-    const double nu1 = sample_powerlaw(enu, d.B + d.L.o_ecdf + (size_t)jid * ne, d.B + d.L.o_einvb + (size_t)jid * (ne - 1),
-                                       d.B + d.L.o_erm1 + (size_t)jid * (ne - 1), ne, x2);
-    const double nu2 = sample_powerlaw(enu, d.B + d.L.o_ecdf + (size_t)(jid + 1) * ne,
-                                       d.B + d.L.o_einvb + (size_t)(jid + 1) * (ne - 1),
-                                       d.B + d.L.o_erm1 + (size_t)(jid + 1) * (ne - 1), ne, x2);
+    double nu1, nu2;
+    sample_powerlaw_pair(enu, d.B + d.L.o_ecdf + (size_t)jid * ne, d.B + d.L.o_einvb + (size_t)jid * (ne - 1),
+                         d.B + d.L.o_erm1 + (size_t)jid * (ne - 1), d.B + d.L.o_ecdf + (size_t)(jid + 1) * ne,
+                         d.B + d.L.o_einvb + (size_t)(jid + 1) * (ne - 1), d.B + d.L.o_erm1 + (size_t)(jid + 1) * (ne - 1),
+                         ne, x2, nu1, nu2);
     const double l1 = log10(nu1);
     p.nu = pow(10.0, l1 + frac * (log10(nu2) - l1));
     p.sQ = p.sU = p.sV = 0.0;
@@ -1314,6 +1339,8 @@ interact_kernel(const ModelDev M, Pool P, uint32_t *__restrict__ q_flight_next, 
       int dust_id = 0;
       bool scattered = false;
       const bool was_reabsorbed = p.t < 0.0;
+      // (packets the wave engine handed over in the middle of their last cell)
+      if (WAVE_DEFER_PARTIAL && !was_reabsorbed && p.tau_left < 0.0) wave_partial_step<ND>(M, p);
       bool ok = was_reabsorbed ? reemit_photon<ND>(M, p, rng, n_kill)
                                : interact_photon<ND>(M, p, rng, n_abs, n_scat, n_kill, dust_id, scattered) == 0;
       if (ok && M.use_mrw && !was_reabsorbed) ok = mrw_loop<ND>(M, p, rng, n_kill);
