@@ -3,12 +3,15 @@
 #pragma once
 
 constexpr int SPH_FLIGHT_THREADS = 128;
+#ifndef GEO_FLIGHT_MIN_BLOCKS
+#define GEO_FLIGHT_MIN_BLOCKS 1
+#endif
 
 // grid_integrate (DEP) / grid_integrate_noenergy for every queued packet; persistent threads, each lane
 // refills from the queue on its own.  FINAL: a packet on its first flight with a forced first interaction
 // measures its optical depth to the grid edge first (iter_final.f90:191-209).
 template <int GEO, int ND, bool DEP, bool FINAL>
-__global__ void __launch_bounds__(SPH_FLIGHT_THREADS)
+__global__ void __launch_bounds__(SPH_FLIGHT_THREADS, GEO_FLIGHT_MIN_BLOCKS)
 flight_geo_kernel(const ModelDev M, Pool P, const FinalArgs F, const uint32_t *__restrict__ q_flight,
                   const uint32_t *n_flight_ptr, uint32_t *cursor, const uint32_t iteration) {
   using G = Geo<GEO>;
