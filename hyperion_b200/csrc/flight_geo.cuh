@@ -3,15 +3,20 @@
 #pragma once
 
 constexpr int SPH_FLIGHT_THREADS = 128;
-#ifndef GEO_FLIGHT_MIN_BLOCKS
-#define GEO_FLIGHT_MIN_BLOCKS 1
+// Resident blocks per SM the register allocation of the spherical / cylindrical march is made for: its find_wall is
+// 470 instructions of fp64 arithmetic per crossing and the kernel is bound by instruction issue at the 4 blocks (16
+// warps) that 110 registers allow; 6 / 7 / 8 blocks (80 / 72 / 64 registers, a few spills) measure 16 / 21 / 22 % faster on
+// the c3 disk.  The
+// other geometries wait for dependent loads and lose 3-4 % with the same bound, so they keep their registers.
+#ifndef GEO_SPH_MIN_BLOCKS
+#define GEO_SPH_MIN_BLOCKS 8
 #endif
 
 // grid_integrate (DEP) / grid_integrate_noenergy for every queued packet; persistent threads, each lane
 // refills from the queue on its own.  FINAL: a packet on its first flight with a forced first interaction
 // measures its optical depth to the grid edge first (iter_final.f90:191-209).
 template <int GEO, int ND, bool DEP, bool FINAL>
-__global__ void __launch_bounds__(SPH_FLIGHT_THREADS, GEO_FLIGHT_MIN_BLOCKS)
+__global__ void __launch_bounds__(SPH_FLIGHT_THREADS, GEO == GEO_SPH ? GEO_SPH_MIN_BLOCKS : 1)
 flight_geo_kernel(const ModelDev M, Pool P, const FinalArgs F, const uint32_t *__restrict__ q_flight,
                   const uint32_t *n_flight_ptr, uint32_t *cursor, const uint32_t iteration) {
   using G = Geo<GEO>;
