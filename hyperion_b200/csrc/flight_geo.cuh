@@ -8,6 +8,9 @@ constexpr int SPH_FLIGHT_THREADS = 128;
 // warps) that 110 registers allow; 6 / 7 / 8 blocks (80 / 72 / 64 registers, a few spills) measure 16 / 21 / 22 % faster on
 // the c3 disk.  The
 // other geometries wait for dependent loads and lose 3-4 % with the same bound, so they keep their registers.
+#ifndef GEO_TREE_MIN_BLOCKS
+#define GEO_TREE_MIN_BLOCKS 1
+#endif
 #ifndef GEO_SPH_MIN_BLOCKS
 #define GEO_SPH_MIN_BLOCKS 8
 #endif
@@ -16,7 +19,7 @@ constexpr int SPH_FLIGHT_THREADS = 128;
 // refills from the queue on its own.  FINAL: a packet on its first flight with a forced first interaction
 // measures its optical depth to the grid edge first (iter_final.f90:191-209).
 template <int GEO, int ND, bool DEP, bool FINAL>
-__global__ void __launch_bounds__(SPH_FLIGHT_THREADS, GEO == GEO_SPH ? GEO_SPH_MIN_BLOCKS : 1)
+__global__ void __launch_bounds__(SPH_FLIGHT_THREADS, GEO == GEO_SPH ? GEO_SPH_MIN_BLOCKS : (GEO == GEO_CAR ? 1 : GEO_TREE_MIN_BLOCKS))
 flight_geo_kernel(const ModelDev M, Pool P, const FinalArgs F, const uint32_t *__restrict__ q_flight,
                   const uint32_t *n_flight_ptr, uint32_t *cursor, const uint32_t iteration) {
   using G = Geo<GEO>;

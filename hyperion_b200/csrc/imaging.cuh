@@ -473,11 +473,14 @@ constexpr int PEEL_GROUPS = 8;  // look-ahead groups (Cartesian) / crossings x4 
 // length (a peel-off from the near or the far side of the grid) do not idle the warp.
 // (the polar grids get the register allocation of PEEL_SPH_MIN_BLOCKS resident blocks: their find_wall is bound by
 // instruction issue at the 2 blocks of 256 threads that 128 registers allow, as in flight_geo.cuh)
+#ifndef PEEL_MIN_BLOCKS
+#define PEEL_MIN_BLOCKS 1
+#endif
 #ifndef PEEL_SPH_MIN_BLOCKS
 #define PEEL_SPH_MIN_BLOCKS 3
 #endif
 template <int ND, bool POLY, int GEO>
-__global__ void __launch_bounds__(PEEL_THREADS, GEO == GEO_SPH ? PEEL_SPH_MIN_BLOCKS : 1)
+__global__ void __launch_bounds__(PEEL_THREADS, GEO == GEO_SPH ? PEEL_SPH_MIN_BLOCKS : PEEL_MIN_BLOCKS)
 peel_kernel(const ModelDev M, const ImagingDev I, const PeelJob<ND> *__restrict__ jobs,
             const uint32_t *__restrict__ n_jobs_ptr, unsigned long long *cursor, const int walls_in_smem) {
   extern __shared__ double s_walls[];
