@@ -9,6 +9,10 @@
 // recursion.
 #pragma once
 
+#ifndef OCT_LDG
+#define OCT_LDG 1
+#endif
+
 namespace hyp {
 
 struct OctNode {
@@ -32,13 +36,34 @@ struct OctRay {
   int ic;  // node id, n_nodes = outside
 };
 
+// a node through the read-only path, as five 16-byte loads
+__device__ __forceinline__ OctNode oct_load(const OctNode *p) {
+  union {
+    OctNode n;
+    int4 q[5];
+  } u;
+  static_assert(sizeof(OctNode) == 80, "OctNode is five 16-byte words");
+#pragma unroll
+  for (int k = 0; k < 5; ++k) u.q[k] = __ldg((const int4 *)p + k);
+  return u.n;
+}
+
 // locate_cell: descend from `node` to the leaf that contains (x, y, z)
 __device__ __forceinline__ int oct_descend(const OctGrid &G, int node, double x, double y, double z) {
   for (;;) {
     const OctNode *N = G.nodes + node;
+#if OCT_LDG
+    const int4 tail = __ldg((const int4 *)N + 4);   // nb[4], nb[5], first_child, pad
+    const int fc = tail.z;
+    if (fc < 0) return node;
+    const double2 xy = __ldg((const double2 *)N);
+    const double nz = __ldg(&N->z);
+    const int sub = (x < xy.x ? 0 : 1) + (y < xy.y ? 0 : 2) + (z < nz ? 0 : 4);
+#else
     const int fc = N->first_child;
     if (fc < 0) return node;
     const int sub = (x < N->x ? 0 : 1) + (y < N->y ? 0 : 2) + (z < N->z ? 0 : 4);
+#endif
     node = __ldg(G.children + (size_t)fc * 8 + sub);
   }
 }

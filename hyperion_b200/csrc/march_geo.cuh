@@ -117,7 +117,11 @@ struct Geo<GEO_OCT> {
   }
   static __device__ __forceinline__ bool escaped(const ModelDev &M, const Ray &R) { return oct_escaped(M.oct, R); }
   static __device__ __forceinline__ bool find_wall(const ModelDev &M, const Ray &R, double &dt, Cross &c) {
+#if OCT_LDG
+    const OctNode N = oct_load(M.oct.nodes + R.ic);
+#else
     const OctNode N = M.oct.nodes[R.ic];
+#endif
     int wall;
     if (!oct_find_wall(M.oct, R, N, dt, wall)) return false;
     c.nb = N.nb[wall];
