@@ -12,6 +12,9 @@
 #ifndef OCT_LDG
 #define OCT_LDG 1
 #endif
+#ifndef OCT_PREFETCH
+#define OCT_PREFETCH 1
+#endif
 
 namespace hyp {
 
@@ -53,6 +56,11 @@ __device__ __forceinline__ int oct_descend(const OctGrid &G, int node, double x,
   for (;;) {
     const OctNode *N = G.nodes + node;
 #if OCT_LDG
+#if OCT_PREFETCH
+    // the march reads the whole node next; an 80-byte node straddles two 128-byte lines more often than not, so
+    // ask for the line of its first word now, beside the load of its last word
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(N));
+#endif
     const int4 tail = __ldg((const int4 *)N + 4);   // nb[4], nb[5], first_child, pad
     const int fc = tail.z;
     if (fc < 0) return node;
