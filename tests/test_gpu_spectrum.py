@@ -177,3 +177,18 @@ def test_spectrum_through_the_file_boundary(golden_car, tmp_path):
     np.testing.assert_allclose(r["iteration_00002/specific_energy_spectrum_bin_edges"][...], EDGES, rtol=1e-12)
     assert se_nu.shape == (12, 3, 3, 5, 7)
     _assert_sums(se, se_nu, se.min(), rtol=1e-9)
+
+
+def test_spectrum_with_additional_specific_energy(golden_car):
+    m = bitlevel_model(golden_car, False, False)
+    extra = np.full(m.density.shape, 3.e-2)
+    m.specific_energy = extra
+    m.conf.specific_energy_additional = True
+    m.spectrum_bin_edges = EDGES
+    eng = _run(m, 200000, n_iter=2)
+    se, se_nu = eng.get_specific_energy(), eng.get_specific_energy_spectrum()
+    eng.close()
+    mc = se - extra
+    heated = mc > 1e-3 * mc.max()
+    assert heated.sum() > 50
+    np.testing.assert_allclose(se_nu.sum(axis=0)[heated], mc[heated], rtol=1e-8)

@@ -112,3 +112,31 @@ def test_mrw_is_refused_with_the_reference_message(golden_car):
     with pytest.raises(HyperionError, match="not implemented for Voronoi grid"):
         eng.load_model(model)
     eng.close()
+
+
+def test_source_outside_the_box_reports_reference_message(golden_car):
+    from hyperion_b200.capi import Engine, HyperionError
+    m = bitlevel_model_vor(golden_car, False, False)
+    m.sources[0].position = (10 * m.voronoi["box"][1], 0., 0.)
+    eng = Engine(0)
+    eng.load_model(m)
+    with pytest.raises(HyperionError, match="photon was not emitted inside a cell"):
+        eng.run_lucy_iteration(20000)
+    eng.close()
+
+
+def test_masked_cells_stay_empty(golden_car):
+    """Cells the front end marked invalid (volume -1) hold no dust and take no thermal raytracing packets."""
+    from hyperion_b200.capi import Engine
+    m = peeloff_model_vor(golden_car, False)
+    m.voronoi["volume"][[3, 17]] = -1.0
+    eng = Engine(0)
+    eng.load_model(m)
+    eng.run_lucy_iteration(100000)
+    assert np.all(eng.get_density()[0][[3, 17]] == 0)
+    eng.final_begin()
+    eng.final_photons(0, 20000, True)
+    eng.final_finish()
+    st = eng.raytracing_photons(5000, 20000)
+    assert st.killed_geo == 0 and eng.sed(0).sum() > 0
+    eng.close()

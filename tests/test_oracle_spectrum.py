@@ -181,3 +181,20 @@ def test_spectrum_on_other_grids(golden_car, golden_amr, grid):
     se, se_nu = o.get_specific_energy(), o.get_specific_energy_spectrum()
     assert se_nu.shape == (12,) + se.shape
     _assert_sums(se, se_nu, se.min())
+
+
+def test_spectrum_with_additional_specific_energy(golden_car):
+    """specific_energy_type = 'additional': the extra heating is added to the specific energy after every iteration;
+    its spectrum is a copy of the (all-zero) spectrum array (grid_physics_3d.f90:143,223-225,543-545), so the bins
+    hold the Monte-Carlo part only."""
+    m = bitlevel_model(golden_car, False, False)
+    extra = np.full(m.density.shape, 3.e-2)
+    m.specific_energy = extra
+    m.conf.specific_energy_additional = True
+    m.spectrum_bin_edges = EDGES
+    o = _run(m, 5000, n_iter=2)
+    se, se_nu = o.get_specific_energy(), o.get_specific_energy_spectrum()
+    mc = se - extra
+    heated = mc > 1e-3 * mc.max()
+    assert heated.sum() > 50
+    np.testing.assert_allclose(se_nu.sum(axis=0)[heated], mc[heated], rtol=1e-9)

@@ -139,3 +139,23 @@ def test_masked_cells_and_mrw(golden_car):
     with pytest.raises(Exception, match="not implemented for Voronoi grid"):
         o = oracle.Oracle(model)
         o.run_lucy_iteration(2000)
+
+
+def test_source_outside_the_box_and_single_cell(golden_car):
+    """find_cell outside the box kills the packet at emission (place_in_cell, :230-241 -> emit, source.f90:177);
+    a mesh of one site is the box itself: all six walls, no neighbour."""
+    m = bitlevel_model_vor(golden_car, False, False)
+    m.sources[0].position = (10 * m.voronoi["box"][1], 0., 0.)
+    with pytest.raises(Exception, match="photon was not emitted inside a cell"):
+        oracle.Oracle(m).run_lucy_iteration(2000)
+    one = bitlevel_model(golden_car, False, False)
+    w = [np.array([one.w1[0], one.w1[-1]]), np.array([one.w2[0], one.w2[-1]]), np.array([one.w3[0], one.w3[-1]])]
+    rho = np.full((1, 1, 1, 1), float(one.density.mean()))
+    car = FlatModel(w[0], w[1], w[2], rho, one.dust, one.sources, one.conf)
+    vor = FlatModel(None, None, None, rho.reshape(1, 1), one.dust, one.sources, one.conf, grid_type="vor",
+                    voronoi=syn.lattice_voronoi(*w))
+    assert sorted(vor.voronoi["sparse_neighs"]) == [-6, -5, -4, -3, -2, -1]
+    a, b = oracle.Oracle(car), oracle.Oracle(vor)
+    sa, sb = a.run_lucy_iteration(5000), b.run_lucy_iteration(5000)
+    assert sa.n_crossings == sb.n_crossings and sa.n_absorptions == sb.n_absorptions
+    np.testing.assert_allclose(b.get_specific_energy().ravel(), a.get_specific_energy().ravel(), rtol=1e-12)
