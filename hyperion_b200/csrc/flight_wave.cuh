@@ -216,6 +216,9 @@ wave_scatter_kernel(WaveQ W, const uint32_t *__restrict__ src, const uint32_t n_
 #ifndef WAVE_PRED_TN
 #define WAVE_PRED_TN 0
 #endif
+#ifndef WAVE_TRIM
+#define WAVE_TRIM 1
+#endif
 #ifndef WAVE_MAGIC_FLOOR
 #define WAVE_MAGIC_FLOOR 0
 #endif
@@ -495,9 +498,10 @@ wave_tile_kernel(const ModelDev M, Pool P, const WaveQ W) {
         if (fin == 1 || fin == 2 || fin == 4) {
           // cell of the packet from its index in the haloed tile
           const int ci = (int)(L.c - rho_base) / CB;
-          const int hz = (int)(((float)ci + 0.5f) * inv_slab);
+          // (with a compile-time tile the divisions are by constants: multiply-high and shift)
+          const int hz = (CUBE && WAVE_TRIM) ? ci / ((CUBE + 2) * (CUBE + 2)) : (int)(((float)ci + 0.5f) * inv_slab);
           const int rem = ci - hz * TXh * TYh;
-          const int hy = (int)(((float)rem + 0.5f) * inv_row);
+          const int hy = (CUBE && WAVE_TRIM) ? rem / (CUBE + 2) : (int)(((float)rem + 0.5f) * inv_row);
           const int hx = rem - hy * TXh;
           const int gx = x0 + hx - 1, gy = y0 + hy - 1, gz = z0 + hz - 1;
           int ic = (gz * n2 + gy) * n1 + gx;
@@ -573,9 +577,17 @@ wave_tile_kernel(const ModelDev M, Pool P, const WaveQ W) {
               const double ivx = wave_rcp(vx), ivy = wave_rcp(vy), ivz = wave_rcp(vz);
               // distance to the wall ahead on each axis; a ray parallel to an axis never reaches its walls.
               // Rounding can leave a resumed packet a few ulp past a wall it faces: clamp to its path length.
+#if WAVE_TRIM
+              // (an infinite distance -- a direction component below 1e-300 -- is as good as WAVE_FAR here: the
+              // increments below stay finite, so no 0 x inf can arise in the crossing's multiply-add)
+              L.tnx = vx != 0.0 ? fmax((s_w[lx + (vx > 0.0 ? 1 : 0)] - a0.x) * ivx, L.t) : WAVE_FAR;
+              L.tny = vy != 0.0 ? fmax((s_w[TW + ly + (vy > 0.0 ? 1 : 0)] - a0.y) * ivy, L.t) : WAVE_FAR;
+              L.tnz = vz != 0.0 ? fmax((s_w[2 * TW + lz + (vz > 0.0 ? 1 : 0)] - a1.x) * ivz, L.t) : WAVE_FAR;
+#else
               L.tnx = vx != 0.0 ? fmin(fmax((s_w[lx + (vx > 0.0 ? 1 : 0)] - a0.x) * ivx, L.t), WAVE_FAR) : WAVE_FAR;
               L.tny = vy != 0.0 ? fmin(fmax((s_w[TW + ly + (vy > 0.0 ? 1 : 0)] - a0.y) * ivy, L.t), WAVE_FAR) : WAVE_FAR;
               L.tnz = vz != 0.0 ? fmin(fmax((s_w[2 * TW + lz + (vz > 0.0 ? 1 : 0)] - a1.x) * ivz, L.t), WAVE_FAR) : WAVE_FAR;
+#endif
               L.dtx = vx != 0.0 ? fmin(W.dx * fabs(ivx), WAVE_FAR) : WAVE_FAR;
               L.dty = vy != 0.0 ? fmin(W.dy * fabs(ivy), WAVE_FAR) : WAVE_FAR;
               L.dtz = vz != 0.0 ? fmin(W.dz * fabs(ivz), WAVE_FAR) : WAVE_FAR;
